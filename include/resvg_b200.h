@@ -1,0 +1,139 @@
+/*
+ * resvg_b200.h — C ABI of the B200-native resvg pixel hot path.
+ *
+ * This is the drop-in seam described in SURVEY.md §8(b): the reference renderer
+ * (crates/resvg/src/{render,path,clip,mask}.rs and crates/resvg/src/filter/mod.rs) depends only on
+ * (1) a finite list of tiny-skia Pixmap/Mask calls and (2) the filter primitive functions of
+ * crates/resvg/src/filter/*.rs.  Every entry point below replaces one of those and cites it.
+ *
+ * Conventions
+ *   - every function returns an rb_status (0 = RB_OK); nothing throws across the boundary;
+ *   - all pixel data is tightly packed premultiplied RGBA8888, R first, no stride — the resvg pixmap
+ *     contract (crates/c-api/resvg.h:482-483);
+ *   - an rb_layer is a device-resident Pixmap, an rb_mask a device-resident tiny-skia Mask (u8 plane);
+ *   - work is enqueued on the context's CUDA stream; only *_download / rb_ctx_synchronize block;
+ *   - there is no CPU fallback: without a usable CUDA device rb_ctx_create fails with RB_ERR_CUDA.
+ */
+#ifndef RESVG_B200_H
+#define RESVG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rb_ctx rb_ctx;
+typedef struct rb_layer rb_layer;
+typedef struct rb_mask rb_mask;
+
+typedef enum {
+    RB_OK = 0,
+    RB_ERR_INVALID = 1, /* bad argument (null, zero size, size mismatch) — reference: Option::None / warn+skip */
+    RB_ERR_CUDA = 2,    /* CUDA runtime error; see rb_last_error() */
+    RB_ERR_OOM = 3,
+    RB_ERR_UNSUPPORTED = 4
+} rb_status;
+
+/* ------------------------------------------------------------------------------------------------
+ * Context / memory
+ * ---------------------------------------------------------------------------------------------- */
+int rb_ctx_create(int device, rb_ctx **out);
+void rb_ctx_destroy(rb_ctx *ctx);
+int rb_ctx_synchronize(rb_ctx *ctx);
+const char *rb_last_error(rb_ctx *ctx);
+void *rb_ctx_stream(rb_ctx *ctx); /* cudaStream_t */
+int rb_ctx_device(rb_ctx *ctx);
+/* CUDA-event timer on the context's stream (bench.py times kernels with it). */
+int rb_timer_begin(rb_ctx *ctx);
+int rb_timer_end(rb_ctx *ctx, float *elapsed_ms); /* synchronises */
+/* Number of kernel launches issued through this context since creation (bench "gpu_launches"). */
+uint64_t rb_ctx_launch_count(rb_ctx *ctx);
+/* Pinned host memory for upload/download staging. */
+int rb_host_alloc(size_t bytes, void **out);
+void rb_host_free(void *p);
+
+/* tiny_skia::Pixmap::new — zeroed premultiplied RGBA8 (render.rs:108, filter/mod.rs:101-103). */
+int rb_layer_create(rb_ctx *ctx, uint32_t width, uint32_t height, rb_layer **out);
+void rb_layer_destroy(rb_layer *layer);
+uint32_t rb_layer_width(const rb_layer *layer);
+uint32_t rb_layer_height(const rb_layer *layer);
+void *rb_layer_device_ptr(rb_layer *layer);
+/* PixmapMut::from_bytes / Pixmap::data (c-api/lib.rs:887-890): host <-> device copies. */
+int rb_layer_upload(rb_layer *layer, const uint8_t *host_rgba);
+int rb_layer_download(rb_layer *layer, uint8_t *host_rgba);
+/* Pixmap::fill(color) with an already premultiplied RGBA8 colour (filter/mod.rs:112, 824). */
+int rb_layer_fill(rb_layer *layer, uint8_t r, uint8_t g, uint8_t b, uint8_t a);
+/* Pixmap::clone (filter/mod.rs:531): dst and src must have equal size. */
+int rb_layer_copy(rb_layer *dst, const rb_layer *src);
+
+/* ------------------------------------------------------------------------------------------------
+ * Filter helpers — crates/resvg/src/filter/mod.rs
+ * ---------------------------------------------------------------------------------------------- */
+int rb_layer_multiply_alpha(rb_layer *layer);   /* mod.rs:129-136 */
+int rb_layer_demultiply_alpha(rb_layer *layer); /* mod.rs:139-146 */
+int rb_layer_into_linear_rgb(rb_layer *layer);  /* mod.rs:120-124, fused demultiply+LUT+multiply */
+int rb_layer_into_srgb(rb_layer *layer);        /* mod.rs:114-118 */
+
+/* ------------------------------------------------------------------------------------------------
+ * Filter primitives — one per file of crates/resvg/src/filter/
+ * ---------------------------------------------------------------------------------------------- */
+/* box_blur::apply(sigma_x, sigma_y, src) — box_blur.rs:23 */
+int rb_filter_box_blur(rb_layer *layer, double sigma_x, double sigma_y);
+/* iir_blur::apply(sigma_x, sigma_y, src) — iir_blur.rs:47 */
+int rb_filter_iir_blur(rb_layer *layer, double sigma_x, double sigma_y);
+/* morphology::apply(operator, rx, ry, src) — morphology.rs:15.  op: 0 erode, 1 dilate */
+int rb_filter_morphology(rb_layer *layer, int op, float rx, float ry);
+/* convolve_matrix::apply(matrix, src) — convolve_matrix.rs:15.
+ * kernel is row-major (usvg ConvolveMatrixData::get(x,y) = data[y*columns+x]); edge_mode 0 none,
+ * 1 duplicate, 2 wrap. */
+int rb_filter_convolve_matrix(rb_layer *layer, const float *kernel, uint32_t columns, uint32_t rows,
+                              uint32_t target_x, uint32_t target_y, float divisor, float bias,
+                              int edge_mode, int preserve_alpha);
+/* color_matrix::apply(kind, src) — color_matrix.rs:11.
+ * kind 0 matrix (20 floats), 1 saturate (1), 2 hueRotate (1, degrees), 3 luminanceToAlpha. */
+int rb_filter_color_matrix(rb_layer *layer, int kind, const float *params);
+/* component_transfer::apply(fe, src) — component_transfer.rs:10.
+ * type 0 identity, 1 table, 2 discrete, 3 linear, 4 gamma; order r,g,b,a. */
+typedef struct {
+    int32_t type;
+    int32_t n_values;
+    const float *values;
+    float slope, intercept;
+    float amplitude, exponent, offset;
+} rb_transfer_fn;
+int rb_filter_component_transfer(rb_layer *layer, const rb_transfer_fn funcs[4]);
+/* composite::arithmetic(k1..k4, src1, src2, dest) — composite.rs:14 */
+int rb_filter_composite_arithmetic(rb_layer *dest, const rb_layer *src1, const rb_layer *src2,
+                                   float k1, float k2, float k3, float k4);
+/* displacement_map::apply(fe, sx, sy, src, map, dest) — displacement_map.rs:15.  channel 0..3 = R,G,B,A */
+int rb_filter_displacement_map(rb_layer *dest, const rb_layer *src, const rb_layer *map,
+                               int x_channel, int y_channel, float scale, float sx, float sy);
+/* lighting — lighting.rs:132 / :175.  The light source is the one already transformed by
+ * transform_light_source (filter/mod.rs:1063-1098). */
+typedef struct {
+    int32_t kind;              /* 0 distant, 1 point, 2 spot */
+    float azimuth, elevation;  /* distant, degrees */
+    float x, y, z;             /* point / spot */
+    float points_at_x, points_at_y, points_at_z;
+    float specular_exponent;   /* spot */
+    int32_t has_cone;
+    float limiting_cone_angle; /* degrees */
+} rb_light_source;
+int rb_filter_diffuse_lighting(rb_layer *dest, const rb_layer *src, float surface_scale,
+                               float diffuse_constant, uint8_t r, uint8_t g, uint8_t b,
+                               const rb_light_source *light);
+int rb_filter_specular_lighting(rb_layer *dest, const rb_layer *src, float surface_scale,
+                                float specular_constant, float specular_exponent,
+                                uint8_t r, uint8_t g, uint8_t b, const rb_light_source *light);
+/* turbulence::apply(...) — turbulence.rs:33 (result is unpremultiplied; caller multiplies alpha as
+ * filter/mod.rs:1015 does). */
+int rb_filter_turbulence(rb_layer *dest, double offset_x, double offset_y, double sx, double sy,
+                         double base_frequency_x, double base_frequency_y, uint32_t num_octaves,
+                         int32_t seed, int stitch_tiles, int fractal_noise);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RESVG_B200_H */

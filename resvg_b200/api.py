@@ -1,0 +1,269 @@
+"""Thin Python mirror of the reference's operator interface over the C ABI.
+
+Names follow the reference: ``Layer`` plays tiny_skia::Pixmap, the functions in ``filters`` carry the
+names and argument order of crates/resvg/src/filter/*.rs (``box_blur.apply(sigma_x, sigma_y, src)`` →
+``filters.box_blur(sigma_x, sigma_y, layer)``).  Everything executes on the GPU through
+libresvg_b200.so; numpy is only the host-side container for pixels.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import LightSource, TransferFn, lib
+
+
+class ResvgB200Error(RuntimeError):
+    pass
+
+
+_STATUS = {1: "invalid argument", 2: "CUDA error", 3: "out of memory", 4: "unsupported"}
+
+
+class Context:
+    """One per GPU (rb_ctx): owns the CUDA stream every operation is enqueued on."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        st = lib.rb_ctx_create(device, C.byref(h))
+        if st != 0:
+            raise ResvgB200Error(
+                f"rb_ctx_create(device={device}) failed: {_STATUS.get(st, st)} — resvg_b200 needs a CUDA GPU "
+                "(there is no CPU fallback)"
+            )
+        self._h = h
+        self.device = device
+
+    def check(self, st: int, what: str = ""):
+        if st != 0:
+            msg = lib.rb_last_error(self._h)
+            raise ResvgB200Error(f"{what}: {_STATUS.get(st, st)} ({msg.decode() if msg else ''})")
+
+    def synchronize(self):
+        self.check(lib.rb_ctx_synchronize(self._h), "synchronize")
+
+    def timer_begin(self):
+        self.check(lib.rb_timer_begin(self._h), "timer_begin")
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        self.check(lib.rb_timer_end(self._h, C.byref(ms)), "timer_end")
+        return ms.value
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib.rb_ctx_launch_count(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(lib.rb_ctx_stream(self._h) or 0)
+
+    def layer(self, width: int, height: int) -> "Layer":
+        return Layer(self, width, height)
+
+    def layer_from(self, rgba: np.ndarray) -> "Layer":
+        assert rgba.dtype == np.uint8 and rgba.ndim == 3 and rgba.shape[2] == 4
+        l = Layer(self, rgba.shape[1], rgba.shape[0])
+        l.upload(rgba)
+        return l
+
+    def close(self):
+        if self._h:
+            lib.rb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PinnedBuffer:
+    """Page-locked host staging buffer exposed as a numpy uint8 array."""
+
+    def __init__(self, nbytes: int):
+        p = C.c_void_p()
+        if lib.rb_host_alloc(nbytes, C.byref(p)) != 0:
+            raise ResvgB200Error("rb_host_alloc failed")
+        self._p = p
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p.value))
+
+    def close(self):
+        if self._p:
+            self.array = None
+            lib.rb_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Layer:
+    """Device-resident premultiplied RGBA8 pixmap (tiny_skia::Pixmap)."""
+
+    def __init__(self, ctx: Context, width: int, height: int):
+        h = C.c_void_p()
+        ctx.check(lib.rb_layer_create(ctx._h, width, height, C.byref(h)), "layer_create")
+        self._h = h
+        self.ctx = ctx
+        self.width = width
+        self.height = height
+
+    def upload(self, rgba: np.ndarray):
+        a = np.ascontiguousarray(rgba, dtype=np.uint8)
+        assert a.size == self.width * self.height * 4
+        self.ctx.check(lib.rb_layer_upload(self._h, a.ctypes.data), "upload")
+        self.ctx.synchronize()  # `a` may be a temporary
+
+    def upload_ptr(self, ptr: int):
+        self.ctx.check(lib.rb_layer_upload(self._h, ptr), "upload")
+
+    def download(self) -> np.ndarray:
+        out = np.empty((self.height, self.width, 4), dtype=np.uint8)
+        self.ctx.check(lib.rb_layer_download(self._h, out.ctypes.data), "download")
+        return out
+
+    def download_ptr(self, ptr: int):
+        self.ctx.check(lib.rb_layer_download(self._h, ptr), "download")
+
+    def fill(self, r: int, g: int, b: int, a: int):
+        self.ctx.check(lib.rb_layer_fill(self._h, r, g, b, a), "fill")
+
+    def copy_from(self, other: "Layer"):
+        self.ctx.check(lib.rb_layer_copy(self._h, other._h), "copy")
+
+    def clone(self) -> "Layer":
+        l = Layer(self.ctx, self.width, self.height)
+        l.copy_from(self)
+        return l
+
+    def close(self):
+        if self._h:
+            lib.rb_layer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _f32(values):
+    arr = np.ascontiguousarray(values, dtype=np.float32)
+    return arr, arr.ctypes.data_as(_ffi.f32p)
+
+
+def make_transfer(kind="identity", values=(), slope=1.0, intercept=0.0, amplitude=1.0, exponent=1.0, offset=0.0):
+    """usvg::filter::TransferFunction → (rb_transfer_fn, keep-alive)."""
+    types = {"identity": 0, "table": 1, "discrete": 2, "linear": 3, "gamma": 4}
+    arr, ptr = _f32(list(values))
+    t = TransferFn(types[kind], len(arr), ptr if len(arr) else None, slope, intercept, amplitude, exponent, offset)
+    return t, arr
+
+
+def make_light(kind="distant", azimuth=0.0, elevation=0.0, x=0.0, y=0.0, z=0.0, points_at=(0.0, 0.0, 0.0),
+               specular_exponent=1.0, limiting_cone_angle=None):
+    kinds = {"distant": 0, "point": 1, "spot": 2}
+    return LightSource(kinds[kind], azimuth, elevation, x, y, z, points_at[0], points_at[1], points_at[2],
+                       specular_exponent, 0 if limiting_cone_angle is None else 1,
+                       0.0 if limiting_cone_angle is None else limiting_cone_angle)
+
+
+class filters:
+    """crates/resvg/src/filter/* on the GPU.  Static methods, reference names and argument order."""
+
+    @staticmethod
+    def multiply_alpha(l: Layer):
+        l.ctx.check(lib.rb_layer_multiply_alpha(l._h), "multiply_alpha")
+
+    @staticmethod
+    def demultiply_alpha(l: Layer):
+        l.ctx.check(lib.rb_layer_demultiply_alpha(l._h), "demultiply_alpha")
+
+    @staticmethod
+    def into_linear_rgb(l: Layer):
+        l.ctx.check(lib.rb_layer_into_linear_rgb(l._h), "into_linear_rgb")
+
+    @staticmethod
+    def into_srgb(l: Layer):
+        l.ctx.check(lib.rb_layer_into_srgb(l._h), "into_srgb")
+
+    @staticmethod
+    def box_blur(sigma_x: float, sigma_y: float, src: Layer):
+        src.ctx.check(lib.rb_filter_box_blur(src._h, sigma_x, sigma_y), "box_blur")
+
+    @staticmethod
+    def iir_blur(sigma_x: float, sigma_y: float, src: Layer):
+        src.ctx.check(lib.rb_filter_iir_blur(src._h, sigma_x, sigma_y), "iir_blur")
+
+    @staticmethod
+    def morphology(operator: str, rx: float, ry: float, src: Layer):
+        src.ctx.check(lib.rb_filter_morphology(src._h, {"erode": 0, "dilate": 1}[operator], rx, ry), "morphology")
+
+    @staticmethod
+    def convolve_matrix(kernel, columns, rows, target_x, target_y, divisor, bias, edge_mode, preserve_alpha,
+                        src: Layer):
+        arr, ptr = _f32(kernel)
+        assert arr.size == columns * rows
+        em = {"none": 0, "duplicate": 1, "wrap": 2}[edge_mode]
+        src.ctx.check(
+            lib.rb_filter_convolve_matrix(src._h, ptr, columns, rows, target_x, target_y, divisor, bias, em,
+                                          1 if preserve_alpha else 0),
+            "convolve_matrix",
+        )
+
+    @staticmethod
+    def color_matrix(kind: str, params, src: Layer):
+        k = {"matrix": 0, "saturate": 1, "hueRotate": 2, "luminanceToAlpha": 3}[kind]
+        arr, ptr = _f32(params if len(params) else [0.0])
+        src.ctx.check(lib.rb_filter_color_matrix(src._h, k, ptr), "color_matrix")
+
+    @staticmethod
+    def component_transfer(funcs, src: Layer):
+        """funcs: four (rb_transfer_fn, keepalive) pairs from make_transfer, order r,g,b,a."""
+        arr = (TransferFn * 4)(*[f[0] for f in funcs])
+        src.ctx.check(lib.rb_filter_component_transfer(src._h, arr), "component_transfer")
+
+    @staticmethod
+    def arithmetic(k1, k2, k3, k4, src1: Layer, src2: Layer, dest: Layer):
+        dest.ctx.check(lib.rb_filter_composite_arithmetic(dest._h, src1._h, src2._h, k1, k2, k3, k4), "arithmetic")
+
+    @staticmethod
+    def displacement_map(x_channel: int, y_channel: int, scale: float, sx: float, sy: float, src: Layer, map_: Layer,
+                         dest: Layer):
+        dest.ctx.check(
+            lib.rb_filter_displacement_map(dest._h, src._h, map_._h, x_channel, y_channel, scale, sx, sy),
+            "displacement_map",
+        )
+
+    @staticmethod
+    def diffuse_lighting(surface_scale, diffuse_constant, color, light: LightSource, src: Layer, dest: Layer):
+        dest.ctx.check(
+            lib.rb_filter_diffuse_lighting(dest._h, src._h, surface_scale, diffuse_constant, color[0], color[1],
+                                           color[2], C.byref(light)),
+            "diffuse_lighting",
+        )
+
+    @staticmethod
+    def specular_lighting(surface_scale, specular_constant, specular_exponent, color, light: LightSource, src: Layer,
+                          dest: Layer):
+        dest.ctx.check(
+            lib.rb_filter_specular_lighting(dest._h, src._h, surface_scale, specular_constant, specular_exponent,
+                                            color[0], color[1], color[2], C.byref(light)),
+            "specular_lighting",
+        )
+
+    @staticmethod
+    def turbulence(offset_x, offset_y, sx, sy, base_frequency_x, base_frequency_y, num_octaves, seed, stitch_tiles,
+                   fractal_noise, dest: Layer):
+        dest.ctx.check(
+            lib.rb_filter_turbulence(dest._h, offset_x, offset_y, sx, sy, base_frequency_x, base_frequency_y,
+                                     num_octaves, seed, 1 if stitch_tiles else 0, 1 if fractal_noise else 0),
+            "turbulence",
+        )

@@ -1,0 +1,197 @@
+// context.cu — context, device memory and host<->device plumbing of the resvg_b200 C ABI.
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "rb_internal.h"
+
+int rb_filters_init(rb_ctx *ctx);
+
+int rb_fail(rb_ctx *ctx, int code, const char *what)
+{
+    if (ctx) ctx->err = what ? what : "";
+    return code;
+}
+
+int rb_cuda_fail(rb_ctx *ctx, cudaError_t e, const char *what)
+{
+    if (ctx) {
+        ctx->err = std::string(what ? what : "") + ": " + cudaGetErrorString(e);
+        fprintf(stderr, "[resvg_b200] CUDA error: %s\n", ctx->err.c_str());
+    }
+    return e == cudaErrorMemoryAllocation ? RB_ERR_OOM : RB_ERR_CUDA;
+}
+
+int rb_scratch(rb_ctx *ctx, size_t bytes, void **out)
+{
+    if (bytes > ctx->scratch_bytes) {
+        // The old block may still be in use by enqueued kernels.
+        RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->scratch) RB_CUDA(ctx, cudaFree(ctx->scratch));
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        size_t want = bytes + bytes / 8 + 4096;
+        RB_CUDA(ctx, cudaMalloc(&ctx->scratch, want));
+        ctx->scratch_bytes = want;
+    }
+    *out = ctx->scratch;
+    return RB_OK;
+}
+
+extern "C" int rb_ctx_create(int device, rb_ctx **out)
+{
+    if (!out) return RB_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        fprintf(stderr, "[resvg_b200] no usable CUDA device (%s); there is no CPU fallback\n",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return RB_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) return RB_ERR_INVALID;
+    rb_ctx *ctx = new rb_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return RB_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return RB_ERR_CUDA; }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RB_ERR_CUDA; }
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    // Keep freed layer memory in the stream-ordered pool: isolated groups allocate one layer each
+    // (render.rs:108), so layer create/destroy must not hit the driver.
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thresh = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+    }
+    int st = rb_filters_init(ctx);
+    if (st != RB_OK) { rb_ctx_destroy(ctx); return st; }
+    *out = ctx;
+    return RB_OK;
+}
+
+extern "C" void rb_ctx_destroy(rb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int rb_ctx_synchronize(rb_ctx *ctx)
+{
+    if (!ctx) return RB_ERR_INVALID;
+    RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RB_OK;
+}
+
+extern "C" const char *rb_last_error(rb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" void *rb_ctx_stream(rb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" int rb_ctx_device(rb_ctx *ctx) { return ctx ? ctx->device : -1; }
+extern "C" uint64_t rb_ctx_launch_count(rb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int rb_timer_begin(rb_ctx *ctx)
+{
+    if (!ctx) return RB_ERR_INVALID;
+    RB_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    return RB_OK;
+}
+
+extern "C" int rb_timer_end(rb_ctx *ctx, float *ms)
+{
+    if (!ctx || !ms) return RB_ERR_INVALID;
+    RB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    RB_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    RB_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return RB_OK;
+}
+
+extern "C" int rb_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return RB_ERR_INVALID;
+    return cudaMallocHost(out, bytes) == cudaSuccess ? RB_OK : RB_ERR_OOM;
+}
+extern "C" void rb_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+// ---- layers -------------------------------------------------------------------------------------
+
+extern "C" int rb_layer_create(rb_ctx *ctx, uint32_t w, uint32_t h, rb_layer **out)
+{
+    if (!ctx || !out) return RB_ERR_INVALID;
+    *out = nullptr;
+    // tiny-skia Pixmap::new: zero size or a row wider than i32::MAX/4 fails.
+    if (w == 0 || h == 0 || w > 0x1fffffffu) return rb_fail(ctx, RB_ERR_INVALID, "invalid layer size");
+    size_t bytes = (size_t)w * h * 4;
+    void *d = nullptr;
+    cudaSetDevice(ctx->device);
+    RB_CUDA(ctx, cudaMallocAsync(&d, bytes, ctx->stream));
+    RB_CUDA(ctx, cudaMemsetAsync(d, 0, bytes, ctx->stream));
+    rb_layer *l = new rb_layer{ctx, w, h, (uint8_t *)d};
+    *out = l;
+    return RB_OK;
+}
+
+extern "C" void rb_layer_destroy(rb_layer *l)
+{
+    if (!l) return;
+    cudaFreeAsync(l->d, l->ctx->stream);
+    delete l;
+}
+
+extern "C" uint32_t rb_layer_width(const rb_layer *l) { return l ? l->w : 0; }
+extern "C" uint32_t rb_layer_height(const rb_layer *l) { return l ? l->h : 0; }
+extern "C" void *rb_layer_device_ptr(rb_layer *l) { return l ? l->d : nullptr; }
+
+extern "C" int rb_layer_upload(rb_layer *l, const uint8_t *host)
+{
+    if (!l || !host) return RB_ERR_INVALID;
+    RB_CUDA(l->ctx, cudaMemcpyAsync(l->d, host, (size_t)l->w * l->h * 4, cudaMemcpyHostToDevice, l->ctx->stream));
+    return RB_OK;
+}
+
+extern "C" int rb_layer_download(rb_layer *l, uint8_t *host)
+{
+    if (!l || !host) return RB_ERR_INVALID;
+    RB_CUDA(l->ctx, cudaMemcpyAsync(host, l->d, (size_t)l->w * l->h * 4, cudaMemcpyDeviceToHost, l->ctx->stream));
+    RB_CUDA(l->ctx, cudaStreamSynchronize(l->ctx->stream));
+    return RB_OK;
+}
+
+__global__ void __launch_bounds__(256) k_fill_u32(uint32_t *__restrict__ px, size_t n, uint32_t v)
+{
+    size_t n4 = n >> 2;
+    uint4 *p4 = reinterpret_cast<uint4 *>(px);
+    uint4 vv = make_uint4(v, v, v, v);
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) p4[i] = vv;
+    size_t tail = n & 3;
+    if (blockIdx.x == 0 && threadIdx.x < tail) px[(n4 << 2) + threadIdx.x] = v;
+}
+
+extern "C" int rb_layer_fill(rb_layer *l, uint8_t r, uint8_t g, uint8_t b, uint8_t a)
+{
+    if (!l) return RB_ERR_INVALID;
+    rb_ctx *ctx = l->ctx;
+    size_t n = (size_t)l->w * l->h;
+    uint32_t v = (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16) | ((uint32_t)a << 24);
+    k_fill_u32<<<rb_grid_1d(ctx, (n + 3) / 4, 256), 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(l->d), n, v);
+    RB_LAUNCHED(ctx, "fill");
+    return RB_OK;
+}
+
+extern "C" int rb_layer_copy(rb_layer *dst, const rb_layer *src)
+{
+    if (!dst || !src || dst->w != src->w || dst->h != src->h) return RB_ERR_INVALID;
+    RB_CUDA(dst->ctx, cudaMemcpyAsync(dst->d, src->d, (size_t)src->w * src->h * 4, cudaMemcpyDeviceToDevice,
+                                      dst->ctx->stream));
+    return RB_OK;
+}

@@ -1,0 +1,1416 @@
+// filters.cu — sm_100a kernels for every primitive of crates/resvg/src/filter/ plus the
+// colour-space / alpha helpers of filter/mod.rs.  One C-ABI entry point per reference function
+// (include/resvg_b200.h).  All kernels are HBM-bound RGBA8 streaming kernels except turbulence (FP64
+// ALU bound) and the IIR blur (sequential FP64 recurrences).
+//
+// Arithmetic follows the reference operation for operation; this file is
+// compiled with -fmad=false so no a*b+c is contracted.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "rb_internal.h"
+
+// =================================================================================================
+// Pointwise infrastructure: 4 pixels (one 16-byte vector) per thread per step, grid-stride.
+// =================================================================================================
+
+// i / 255.0f for i in 0..255, computed with IEEE division so it equals Rust's `c as f32 / 255.0`.
+__device__ __forceinline__ void rb_fill_div255(float *lut)
+{
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = __fdiv_rn((float)i, 255.0f);
+}
+
+template <class Op>
+__global__ void __launch_bounds__(256) k_pointwise(uint32_t *__restrict__ px, size_t n, Op op)
+{
+    __shared__ float div255[256];
+    rb_fill_div255(div255);
+    __syncthreads();
+    size_t n4 = n >> 2;
+    uint4 *v = reinterpret_cast<uint4 *>(px);
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        uint4 p = v[i];
+        p.x = op(p.x, div255);
+        p.y = op(p.y, div255);
+        p.z = op(p.z, div255);
+        p.w = op(p.w, div255);
+        v[i] = p;
+    }
+    // tail (n % 4 pixels)
+    size_t tail = n & 3;
+    if (blockIdx.x == 0 && threadIdx.x < tail) {
+        size_t i = (n4 << 2) + threadIdx.x;
+        px[i] = op(px[i], div255);
+    }
+}
+
+template <class Op>
+static int launch_pointwise(rb_layer *l, Op op, const char *name)
+{
+    if (!l) return RB_ERR_INVALID;
+    rb_ctx *ctx = l->ctx;
+    size_t n = (size_t)l->w * l->h;
+    int grid = rb_grid_1d(ctx, (n + 3) / 4, 256);
+    k_pointwise<Op><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(l->d), n, op);
+    RB_LAUNCHED(ctx, name);
+    return RB_OK;
+}
+
+// ---- filter/mod.rs:129-136 ----
+struct OpMultiplyAlpha {
+    __device__ __forceinline__ uint32_t operator()(uint32_t p, const float *div255) const
+    {
+        float a = div255[RB_A(p)];
+        uint32_t b = rb_f2u8((float)RB_B(p) * a + 0.5f);
+        uint32_t g = rb_f2u8((float)RB_G(p) * a + 0.5f);
+        uint32_t r = rb_f2u8((float)RB_R(p) * a + 0.5f);
+        return rb_pack(r, g, b, RB_A(p));
+    }
+};
+
+// ---- filter/mod.rs:139-146 ----
+__device__ __forceinline__ uint32_t rb_demul_px(uint32_t p, const float *div255)
+{
+    float a = div255[RB_A(p)];
+    uint32_t b = rb_f2u8(__fdiv_rn((float)RB_B(p), a) + 0.5f);
+    uint32_t g = rb_f2u8(__fdiv_rn((float)RB_G(p), a) + 0.5f);
+    uint32_t r = rb_f2u8(__fdiv_rn((float)RB_R(p), a) + 0.5f);
+    return rb_pack(r, g, b, RB_A(p));
+}
+struct OpDemultiplyAlpha {
+    __device__ __forceinline__ uint32_t operator()(uint32_t p, const float *div255) const
+    {
+        return rb_demul_px(p, div255);
+    }
+};
+
+// ---- filter/mod.rs:114-124: demultiply -> LUT -> multiply fused into one 8 B/px pass ----
+__constant__ uint8_t c_srgb_to_linear[256];
+__constant__ uint8_t c_linear_to_srgb[256];
+
+template <bool TO_LINEAR>
+__global__ void __launch_bounds__(256) k_cs_convert(uint32_t *__restrict__ px, size_t n)
+{
+    __shared__ float div255[256];
+    __shared__ uint8_t lut[256];
+    rb_fill_div255(div255);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        lut[i] = TO_LINEAR ? c_srgb_to_linear[i] : c_linear_to_srgb[i];
+    __syncthreads();
+    OpMultiplyAlpha mul;
+    auto conv = [&](uint32_t p) -> uint32_t {
+        uint32_t a = RB_A(p);
+        if (a == 0 && (p & 0xffffffu) == 0) return 0u; // 0/0 = NaN -> 0, LUT[0] = 0, 0*0+0.5 -> 0
+        uint32_t q = rb_demul_px(p, div255);
+        q = rb_pack(lut[RB_R(q)], lut[RB_G(q)], lut[RB_B(q)], a);
+        return mul(q, div255);
+    };
+    size_t n4 = n >> 2;
+    uint4 *v = reinterpret_cast<uint4 *>(px);
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        uint4 p = v[i];
+        p.x = conv(p.x);
+        p.y = conv(p.y);
+        p.z = conv(p.z);
+        p.w = conv(p.w);
+        v[i] = p;
+    }
+    size_t tail = n & 3;
+    if (blockIdx.x == 0 && threadIdx.x < tail) {
+        size_t i = (n4 << 2) + threadIdx.x;
+        px[i] = conv(px[i]);
+    }
+}
+
+static const uint8_t h_srgb_to_linear[256] = {
+    0,   0,   0,   0,   0,   0,   0,   1,   1,   1,   1,   1,   1,   1,   1,   1,   1,   1,   2,   2,   2,   2,
+    2,   2,   2,   2,   3,   3,   3,   3,   3,   3,   4,   4,   4,   4,   4,   5,   5,   5,   5,   6,   6,   6,
+    6,   7,   7,   7,   8,   8,   8,   8,   9,   9,   9,   10,  10,  10,  11,  11,  12,  12,  12,  13,  13,  13,
+    14,  14,  15,  15,  16,  16,  17,  17,  17,  18,  18,  19,  19,  20,  20,  21,  22,  22,  23,  23,  24,  24,
+    25,  25,  26,  27,  27,  28,  29,  29,  30,  30,  31,  32,  32,  33,  34,  35,  35,  36,  37,  37,  38,  39,
+    40,  41,  41,  42,  43,  44,  45,  45,  46,  47,  48,  49,  50,  51,  51,  52,  53,  54,  55,  56,  57,  58,
+    59,  60,  61,  62,  63,  64,  65,  66,  67,  68,  69,  70,  71,  72,  73,  74,  76,  77,  78,  79,  80,  81,
+    82,  84,  85,  86,  87,  88,  90,  91,  92,  93,  95,  96,  97,  99,  100, 101, 103, 104, 105, 107, 108, 109,
+    111, 112, 114, 115, 116, 118, 119, 121, 122, 124, 125, 127, 128, 130, 131, 133, 134, 136, 138, 139, 141, 142,
+    144, 146, 147, 149, 151, 152, 154, 156, 157, 159, 161, 163, 164, 166, 168, 170, 171, 173, 175, 177, 179, 181,
+    183, 184, 186, 188, 190, 192, 194, 196, 198, 200, 202, 204, 206, 208, 210, 212, 214, 216, 218, 220, 222, 224,
+    226, 229, 231, 233, 235, 237, 239, 242, 244, 246, 248, 250, 253, 255,
+};
+static const uint8_t h_linear_to_srgb[256] = {
+    0,   13,  22,  28,  34,  38,  42,  46,  50,  53,  56,  59,  61,  64,  66,  69,  71,  73,  75,  77,  79,  81,
+    83,  85,  86,  88,  90,  92,  93,  95,  96,  98,  99,  101, 102, 104, 105, 106, 108, 109, 110, 112, 113, 114,
+    115, 117, 118, 119, 120, 121, 122, 124, 125, 126, 127, 128, 129, 130, 131, 132, 133, 134, 135, 136, 137, 138,
+    139, 140, 141, 142, 143, 144, 145, 146, 147, 148, 148, 149, 150, 151, 152, 153, 154, 155, 155, 156, 157, 158,
+    159, 159, 160, 161, 162, 163, 163, 164, 165, 166, 167, 167, 168, 169, 170, 170, 171, 172, 173, 173, 174, 175,
+    175, 176, 177, 178, 178, 179, 180, 180, 181, 182, 182, 183, 184, 185, 185, 186, 187, 187, 188, 189, 189, 190,
+    190, 191, 192, 192, 193, 194, 194, 195, 196, 196, 197, 197, 198, 199, 199, 200, 200, 201, 202, 202, 203, 203,
+    204, 205, 205, 206, 206, 207, 208, 208, 209, 209, 210, 210, 211, 212, 212, 213, 213, 214, 214, 215, 215, 216,
+    216, 217, 218, 218, 219, 219, 220, 220, 221, 221, 222, 222, 223, 223, 224, 224, 225, 226, 226, 227, 227, 228,
+    228, 229, 229, 230, 230, 231, 231, 232, 232, 233, 233, 234, 234, 235, 235, 236, 236, 237, 237, 238, 238, 238,
+    239, 239, 240, 240, 241, 241, 242, 242, 243, 243, 244, 244, 245, 245, 246, 246, 246, 247, 247, 248, 248, 249,
+    249, 250, 250, 251, 251, 251, 252, 252, 253, 253, 254, 254, 255, 255,
+};
+
+int rb_filters_init(rb_ctx *ctx)
+{
+    RB_CUDA(ctx, cudaMemcpyToSymbol(c_srgb_to_linear, h_srgb_to_linear, 256));
+    RB_CUDA(ctx, cudaMemcpyToSymbol(c_linear_to_srgb, h_linear_to_srgb, 256));
+    return RB_OK;
+}
+
+extern "C" int rb_layer_multiply_alpha(rb_layer *l) { return launch_pointwise(l, OpMultiplyAlpha(), "multiply_alpha"); }
+extern "C" int rb_layer_demultiply_alpha(rb_layer *l)
+{
+    return launch_pointwise(l, OpDemultiplyAlpha(), "demultiply_alpha");
+}
+
+template <bool TO_LINEAR>
+static int launch_cs(rb_layer *l)
+{
+    if (!l) return RB_ERR_INVALID;
+    rb_ctx *ctx = l->ctx;
+    size_t n = (size_t)l->w * l->h;
+    int grid = rb_grid_1d(ctx, (n + 3) / 4, 256);
+    k_cs_convert<TO_LINEAR><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(l->d), n);
+    RB_LAUNCHED(ctx, "cs_convert");
+    return RB_OK;
+}
+extern "C" int rb_layer_into_linear_rgb(rb_layer *l) { return launch_cs<true>(l); }
+extern "C" int rb_layer_into_srgb(rb_layer *l) { return launch_cs<false>(l); }
+
+// =================================================================================================
+// box_blur.rs — five iterations of (vertical box, horizontal box), every pass quantised to u8.
+// Each pass equals a zero-padded window sum (fv = lv = RGBA8::default(), box_blur.rs:105-106,
+// 222-223) followed by `round(sum as f32 * iarr) as u8` with the magic-constant rounding (:327-331).
+// =================================================================================================
+
+__device__ __forceinline__ uint32_t rb_box_quant(uint4 s, float iarr)
+{
+    // round(): x += 12582912.0; x -= 12582912.0  (box_blur.rs:327-331) — explicit _rn intrinsics so the
+    // pair is never folded.
+    float r = __fsub_rn(__fadd_rn(__fmul_rn((float)(int)s.x, iarr), 12582912.0f), 12582912.0f);
+    float g = __fsub_rn(__fadd_rn(__fmul_rn((float)(int)s.y, iarr), 12582912.0f), 12582912.0f);
+    float b = __fsub_rn(__fadd_rn(__fmul_rn((float)(int)s.z, iarr), 12582912.0f), 12582912.0f);
+    float a = __fsub_rn(__fadd_rn(__fmul_rn((float)(int)s.w, iarr), 12582912.0f), 12582912.0f);
+    return rb_pack(rb_f2u8(r), rb_f2u8(g), rb_f2u8(b), rb_f2u8(a));
+}
+
+__device__ __forceinline__ void rb_acc(uint4 &s, uint32_t p)
+{
+    s.x += RB_R(p);
+    s.y += RB_G(p);
+    s.z += RB_B(p);
+    s.w += RB_A(p);
+}
+__device__ __forceinline__ void rb_dec(uint4 &s, uint32_t p)
+{
+    s.x -= RB_R(p);
+    s.y -= RB_G(p);
+    s.z -= RB_B(p);
+    s.w -= RB_A(p);
+}
+
+// Horizontal pass.  One block = one 1024-pixel tile of one row (halo H >= r on both sides, H % 4 == 0).
+// 256 threads x 4 consecutive pixels: per-channel local prefix, warp-shuffle scan of the thread totals,
+// cross-warp fix-up through shared memory; exclusive prefix sums X[] land in shared memory and every
+// output is X[i+r+1] - X[i-r].
+constexpr int BOXH_THREADS = 256;
+constexpr int BOXH_TILE = BOXH_THREADS * 4;
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(BOXH_THREADS)
+k_box_blur_h(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h, int r, float iarr,
+             int halo, int out_len)
+{
+    __shared__ uint4 X[BOXH_TILE + 1];
+    __shared__ uint4 warp_tot[BOXH_THREADS / 32];
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int tile_x0 = blockIdx.x * out_len - halo;
+
+    for (int y = blockIdx.y; y < h; y += gridDim.y) {
+        const uint32_t *row = src + (size_t)y * w;
+        int px0 = tile_x0 + 4 * t;
+        uint32_t p[4];
+        if (ALIGNED && px0 >= 0 && px0 + 3 < w) {
+            uint4 v = *reinterpret_cast<const uint4 *>(row + px0);
+            p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int x = px0 + k;
+                p[k] = (x >= 0 && x < w) ? row[x] : 0u;
+            }
+        }
+        uint4 s[4];
+        uint4 run = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            rb_acc(run, p[k]);
+            s[k] = run;
+        }
+        // warp inclusive scan of thread totals
+        uint4 inc = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t ax = __shfl_up_sync(0xffffffffu, inc.x, d);
+            uint32_t ay = __shfl_up_sync(0xffffffffu, inc.y, d);
+            uint32_t az = __shfl_up_sync(0xffffffffu, inc.z, d);
+            uint32_t aw = __shfl_up_sync(0xffffffffu, inc.w, d);
+            if (lane >= d) { inc.x += ax; inc.y += ay; inc.z += az; inc.w += aw; }
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        uint4 base = make_uint4(inc.x - run.x, inc.y - run.y, inc.z - run.z, inc.w - run.w);
+        for (int k = 0; k < wid; k++) {
+            uint4 wt = warp_tot[k];
+            base.x += wt.x; base.y += wt.y; base.z += wt.z; base.w += wt.w;
+        }
+        if (t == 0) X[0] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            X[4 * t + 1 + k] = make_uint4(base.x + s[k].x, base.y + s[k].y, base.z + s[k].z, base.w + s[k].w);
+        __syncthreads();
+        uint32_t *orow = dst + (size_t)y * w;
+        for (int j = t; j < out_len; j += BOXH_THREADS) {
+            int gx = blockIdx.x * out_len + j;
+            if (gx >= w) break;
+            int i = halo + j;
+            uint4 hi = X[i + r + 1], lo = X[i - r];
+            uint4 sum = make_uint4(hi.x - lo.x, hi.y - lo.y, hi.z - lo.z, hi.w - lo.w);
+            orow[gx] = rb_box_quant(sum, iarr);
+        }
+        __syncthreads();
+    }
+}
+
+// Horizontal pass fallback for radii too large for the 1024-pixel tile (2*halo >= tile): one thread per
+// row with a running window.  Only reachable with sigma > ~190.
+__global__ void k_box_blur_h_big(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h,
+                                 int r, float iarr)
+{
+    int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= h) return;
+    const uint32_t *row = src + (size_t)y * w;
+    uint32_t *orow = dst + (size_t)y * w;
+    uint4 s = make_uint4(0, 0, 0, 0);
+    for (int x = 0; x <= min(r, w - 1); x++) rb_acc(s, row[x]);
+    for (int x = 0; x < w; x++) {
+        orow[x] = rb_box_quant(s, iarr);
+        int add = x + r + 1, sub = x - r;
+        if (add < w) rb_acc(s, row[add]);
+        if (sub >= 0) rb_dec(s, row[sub]);
+    }
+}
+
+// Vertical pass.  One thread = one pixel column over a chunk of rows: window sum initialised from the
+// 2r+1 rows around the chunk start (zero outside the image), then slid down the chunk.  Adjacent
+// threads touch adjacent pixels, so every row access of a warp is one 128-byte line; the trailing-edge
+// re-read of row y-r comes out of L2.
+constexpr int BOXV_THREADS = 128;
+
+__global__ void __launch_bounds__(BOXV_THREADS)
+k_box_blur_v(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h, int r, float iarr,
+             int chunk)
+{
+    int x = blockIdx.x * BOXV_THREADS + threadIdx.x;
+    if (x >= w) return;
+    for (int y0 = blockIdx.y * chunk; y0 < h; y0 += gridDim.y * chunk) {
+        int y1 = min(y0 + chunk, h);
+        uint4 s = make_uint4(0, 0, 0, 0);
+        int lo = max(0, y0 - r), hi = min(h - 1, y0 + r);
+        for (int yy = lo; yy <= hi; yy++) rb_acc(s, __ldg(src + (size_t)yy * w + x));
+        for (int y = y0; y < y1; y++) {
+            dst[(size_t)y * w + x] = rb_box_quant(s, iarr);
+            int add = y + r + 1, sub = y - r;
+            if (add < h) rb_acc(s, __ldg(src + (size_t)add * w + x));
+            if (sub >= 0) rb_dec(s, __ldg(src + (size_t)sub * w + x));
+        }
+    }
+}
+
+// box_blur.rs:37-71 (host side; f32 arithmetic as in the reference)
+static void create_box_gauss(float sigma, int sizes[5])
+{
+    if (sigma > 0.0f) {
+        const float n_float = 5.0f;
+        float w_ideal = sqrtf(12.0f * sigma * sigma / n_float) + 1.0f;
+        float wf = floorf(w_ideal);
+        int wl = wf >= 2147483647.0f ? 2147483647 : (int)wf;
+        if (wl % 2 == 0) wl -= 1;
+        int wu = wl + 2;
+        float wl_float = (float)wl;
+        float m_ideal = (12.0f * sigma * sigma - n_float * wl_float * wl_float - 4.0f * n_float * wl_float
+                         - 3.0f * n_float)
+                        / (-4.0f * wl_float - 4.0f);
+        float mr = roundf(m_ideal);
+        long m = !(mr > 0.0f) ? 0 : (mr > 1e9f ? 1000000000L : (long)mr);
+        for (int i = 0; i < 5; i++) sizes[i] = (i < m) ? wl : wu;
+    } else {
+        for (int i = 0; i < 5; i++) sizes[i] = 1;
+    }
+}
+
+extern "C" int rb_filter_box_blur(rb_layer *l, double sigma_x, double sigma_y)
+{
+    if (!l) return RB_ERR_INVALID;
+    rb_ctx *ctx = l->ctx;
+    int w = (int)l->w, h = (int)l->h;
+    size_t bytes = (size_t)w * h * 4;
+    int bh[5], bv[5];
+    create_box_gauss((float)sigma_x, bh);
+    create_box_gauss((float)sigma_y, bv);
+
+    void *scratch = nullptr;
+    int st = rb_scratch(ctx, bytes, &scratch);
+    if (st != RB_OK) return st;
+    uint32_t *cur = reinterpret_cast<uint32_t *>(l->d);
+    uint32_t *other = reinterpret_cast<uint32_t *>(scratch);
+    const bool aligned = (w % 4) == 0;
+
+    for (int it = 0; it < 5; it++) {
+        int rv = (bv[it] - 1) / 2, rh = (bh[it] - 1) / 2;
+        if (rv > 0) { // box_blur_vert (radius 0 = copy, i.e. nothing to do with ping-pong buffers)
+            float iarr = 1.0f / (float)(rv + rv + 1);
+            int chunk = 128;
+            dim3 grid((w + BOXV_THREADS - 1) / BOXV_THREADS, (h + chunk - 1) / chunk);
+            if (grid.y > 65535) grid.y = 65535;
+            k_box_blur_v<<<grid, BOXV_THREADS, 0, ctx->stream>>>(cur, other, w, h, rv, iarr, chunk);
+            RB_LAUNCHED(ctx, "box_blur_v");
+            uint32_t *t = cur; cur = other; other = t;
+        }
+        if (rh > 0) { // box_blur_horz
+            float iarr = 1.0f / (float)(rh + rh + 1);
+            int halo = (rh + 3) & ~3;
+            int out_len = BOXH_TILE - 2 * halo;
+            if (out_len >= 256) {
+                dim3 grid((w + out_len - 1) / out_len, h > 65535 ? 65535 : h);
+                if (aligned)
+                    k_box_blur_h<true><<<grid, BOXH_THREADS, 0, ctx->stream>>>(cur, other, w, h, rh, iarr, halo, out_len);
+                else
+                    k_box_blur_h<false><<<grid, BOXH_THREADS, 0, ctx->stream>>>(cur, other, w, h, rh, iarr, halo, out_len);
+            } else {
+                k_box_blur_h_big<<<(h + 63) / 64, 64, 0, ctx->stream>>>(cur, other, w, h, rh, iarr);
+            }
+            RB_LAUNCHED(ctx, "box_blur_h");
+            uint32_t *t = cur; cur = other; other = t;
+        }
+    }
+    if (cur != reinterpret_cast<uint32_t *>(l->d)) {
+        RB_CUDA(ctx, cudaMemcpyAsync(l->d, cur, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return RB_OK;
+}
+
+// =================================================================================================
+// iir_blur.rs — recursive Gaussian, f64, 4 steps, strictly sequential along each line so the result
+// is bit-identical to the reference.  Planar f64 scratch: the row recurrences run on a transposed
+// plane B[ch][x][y] (thread = (y, ch), step x => a warp touches 32 consecutive doubles), the column
+// recurrences on A[ch][y][x] (thread = (x, ch)).
+// =================================================================================================
+
+// rgba -> planes.  TRANSPOSED: out[ch][x][y], else out[ch][y][x].
+template <bool TRANSPOSED>
+__global__ void k_iir_load(const uint32_t *__restrict__ src, double *__restrict__ out, int w, int h)
+{
+    __shared__ uint32_t tile[32][33];
+    int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    size_t plane = (size_t)w * h;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int x = x0 + threadIdx.x, y = y0 + j;
+        tile[j][threadIdx.x] = (x < w && y < h) ? src[(size_t)y * w + x] : 0u;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        if (TRANSPOSED) {
+            int x = x0 + j, y = y0 + threadIdx.x;
+            if (x < w && y < h) {
+                uint32_t p = tile[threadIdx.x][j];
+                size_t o = (size_t)x * h + y;
+                out[o] = __ddiv_rn((double)RB_R(p), 255.0);
+                out[plane + o] = __ddiv_rn((double)RB_G(p), 255.0);
+                out[2 * plane + o] = __ddiv_rn((double)RB_B(p), 255.0);
+                out[3 * plane + o] = __ddiv_rn((double)RB_A(p), 255.0);
+            }
+        } else {
+            int x = x0 + threadIdx.x, y = y0 + j;
+            if (x < w && y < h) {
+                uint32_t p = tile[j][threadIdx.x];
+                size_t o = (size_t)y * w + x;
+                out[o] = __ddiv_rn((double)RB_R(p), 255.0);
+                out[plane + o] = __ddiv_rn((double)RB_G(p), 255.0);
+                out[2 * plane + o] = __ddiv_rn((double)RB_B(p), 255.0);
+                out[3 * plane + o] = __ddiv_rn((double)RB_A(p), 255.0);
+            }
+        }
+    }
+}
+
+// Recurrence along the slow axis of a plane [len][lines]: thread = one line of one channel plane.
+// iir_blur.rs:84-101 / 111-130: steps x { forward b[i] += nu*b[i-1]; backward b[i-1] += nu*b[i] }.
+__global__ void k_iir_sweep(double *__restrict__ buf, int lines, int len, size_t plane, double dnu, int steps)
+{
+    int line = blockIdx.x * blockDim.x + threadIdx.x;
+    if (line >= lines) return;
+    double *b = buf + (size_t)blockIdx.y * plane + line;
+    size_t stride = (size_t)lines;
+    for (int s = 0; s < steps; s++) {
+        double prev = b[0];
+        for (int i = 1; i < len; i++) {
+            double v = __dadd_rn(b[(size_t)i * stride], __dmul_rn(dnu, prev));
+            b[(size_t)i * stride] = v;
+            prev = v;
+        }
+        // prev == b[len-1]
+        for (int i = len - 1; i > 0; i--) {
+            double v = __dadd_rn(b[(size_t)(i - 1) * stride], __dmul_rn(dnu, prev));
+            b[(size_t)(i - 1) * stride] = v;
+            prev = v;
+        }
+    }
+}
+
+// [ch][x][y] -> [ch][y][x]
+__global__ void k_iir_transpose(const double *__restrict__ in, double *__restrict__ out, int w, int h)
+{
+    __shared__ double tile[32][33];
+    size_t plane = (size_t)w * h;
+    const double *ip = in + blockIdx.z * plane;
+    double *op = out + blockIdx.z * plane;
+    int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int x = x0 + j, y = y0 + threadIdx.x;
+        if (x < w && y < h) tile[j][threadIdx.x] = ip[(size_t)x * h + y];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int x = x0 + threadIdx.x, y = y0 + j;
+        if (x < w && y < h) op[(size_t)y * w + x] = tile[threadIdx.x][j];
+    }
+}
+
+// planes [ch][y][x] -> rgba: v *= post_scale; (v * 255.0) as u8   (iir_blur.rs:73-76, 137-139)
+__global__ void k_iir_store(const double *__restrict__ in, uint32_t *__restrict__ dst, size_t n, double post_scale)
+{
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t r = rb_d2u8(__dmul_rn(__dmul_rn(in[i], post_scale), 255.0));
+        uint32_t g = rb_d2u8(__dmul_rn(__dmul_rn(in[n + i], post_scale), 255.0));
+        uint32_t b = rb_d2u8(__dmul_rn(__dmul_rn(in[2 * n + i], post_scale), 255.0));
+        uint32_t a = rb_d2u8(__dmul_rn(__dmul_rn(in[3 * n + i], post_scale), 255.0));
+        dst[i] = rb_pack(r, g, b, a);
+    }
+}
+
+static double powi_f64(double a, int b)
+{
+    // compiler-rt __powidf2, which Rust's f64::powi lowers to
+    bool recip = b < 0;
+    double r = 1.0;
+    while (true) {
+        if (b & 1) r *= a;
+        b /= 2;
+        if (b == 0) break;
+        a *= a;
+    }
+    return recip ? 1.0 / r : r;
+}
+
+extern "C" int rb_filter_iir_blur(rb_layer *l, double sigma_x, double sigma_y)
+{
+    if (!l) return RB_ERR_INVALID;
+    rb_ctx *ctx = l->ctx;
+    int w = (int)l->w, h = (int)l->h;
+    size_t n = (size_t)w * h;
+    const int steps = 4;
+    double lambda_x = 1.0, dnu_x = 1.0, lambda_y = 1.0, dnu_y = 1.0;
+    bool do_x = sigma_x > 0.0, do_y = sigma_y > 0.0;
+    if (do_x) { // iir_blur.rs:142-146
+        lambda_x = (sigma_x * sigma_x) / (2.0 * (double)steps);
+        dnu_x = (1.0 + 2.0 * lambda_x - sqrt(1.0 + 4.0 * lambda_x)) / (2.0 * lambda_x);
+    }
+    if (do_y) {
+        lambda_y = (sigma_y * sigma_y) / (2.0 * (double)steps);
+        dnu_y = (1.0 + 2.0 * lambda_y - sqrt(1.0 + 4.0 * lambda_y)) / (2.0 * lambda_y);
+    }
+    double post_scale = powi_f64(sqrt(dnu_x * dnu_y) / sqrt(lambda_x * lambda_y), 2 * steps);
+
+    void *scratch = nullptr;
+    int st = rb_scratch(ctx, n * 4 * sizeof(double) * 2, &scratch);
+    if (st != RB_OK) return st;
+    double *A = reinterpret_cast<double *>(scratch);
+    double *B = A + n * 4;
+    uint32_t *px = reinterpret_cast<uint32_t *>(l->d);
+    dim3 tb(32, 8), tg((w + 31) / 32, (h + 31) / 32);
+    if (do_x) {
+        k_iir_load<true><<<tg, tb, 0, ctx->stream>>>(px, B, w, h);
+        RB_LAUNCHED(ctx, "iir_load_t");
+        dim3 g((h + 127) / 128, 4);
+        k_iir_sweep<<<g, 128, 0, ctx->stream>>>(B, h, w, n, dnu_x, steps);
+        RB_LAUNCHED(ctx, "iir_sweep_x");
+        dim3 tg3(tg.x, tg.y, 4);
+        k_iir_transpose<<<tg3, tb, 0, ctx->stream>>>(B, A, w, h);
+        RB_LAUNCHED(ctx, "iir_transpose");
+    } else {
+        k_iir_load<false><<<tg, tb, 0, ctx->stream>>>(px, A, w, h);
+        RB_LAUNCHED(ctx, "iir_load");
+    }
+    if (do_y) {
+        dim3 g((w + 127) / 128, 4);
+        k_iir_sweep<<<g, 128, 0, ctx->stream>>>(A, w, h, n, dnu_y, steps);
+        RB_LAUNCHED(ctx, "iir_sweep_y");
+    }
+    k_iir_store<<<rb_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>(A, px, n, post_scale);
+    RB_LAUNCHED(ctx, "iir_store");
+    return RB_OK;
+}
+
+// =================================================================================================
+// morphology.rs:15-73 — window [x - cols/2, x - cols/2 + cols - 1] (asymmetric for even cols), samples
+// outside the image skipped.  Per-channel min/max is separable, so two 1-D passes give exactly the
+// reference's 2-D window result.
+// =================================================================================================
+__device__ __forceinline__ uint32_t rb_minmax4(uint32_t a, uint32_t b, bool dilate)
+{
+    return dilate ? __vmaxu4(a, b) : __vminu4(a, b);
+}
+
+// step = 1 (horizontal) or w (vertical); pos/len index the filtered axis.
+template <bool VERTICAL>
+__global__ void k_morph_pass(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h, int lo,
+                             int count, bool dilate)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    uint32_t acc = dilate ? 0u : 0xffffffffu;
+    if (VERTICAL) {
+        int a = max(0, y - lo), b = min(h - 1, y - lo + count - 1);
+        for (int t = a; t <= b; t++) acc = rb_minmax4(acc, __ldg(src + (size_t)t * w + x), dilate);
+    } else {
+        int a = max(0, x - lo), b = min(w - 1, x - lo + count - 1);
+        const uint32_t *row = src + (size_t)y * w;
+        for (int t = a; t <= b; t++) acc = rb_minmax4(acc, __ldg(row + t), dilate);
+    }
+    dst[(size_t)y * w + x] = acc;
+}
+
+static inline uint32_t f2u32_sat(float v)
+{
+    if (!(v > 0.0f)) return 0;
+    if (v >= 4294967296.0f) return 0xFFFFFFFFu;
+    return (uint32_t)v;
+}
+
+extern "C" int rb_filter_morphology(rb_layer *l, int op, float rx, float ry)
+{
+    if (!l || (op != 0 && op != 1)) return RB_ERR_INVALID;
+    rb_ctx *ctx = l->ctx;
+    int w = (int)l->w, h = (int)l->h;
+    // morphology.rs:17-20 (u32 arithmetic: `ceil() as u32 * 2` wraps in release builds)
+    uint32_t cx = f2u32_sat(ceilf(rx)) * 2u, cy = f2u32_sat(ceilf(ry)) * 2u;
+    uint32_t columns = cx < (uint32_t)w ? cx : (uint32_t)w;
+    uint32_t rows = cy < (uint32_t)h ? cy : (uint32_t)h;
+    int target_x = (int)f2u32_sat(floorf((float)columns / 2.0f));
+    int target_y = (int)f2u32_sat(floorf((float)rows / 2.0f));
+    size_t bytes = (size_t)w * h * 4;
+    void *scratch = nullptr;
+    int st = rb_scratch(ctx, bytes, &scratch);
+    if (st != RB_OK) return st;
+    uint32_t *px = reinterpret_cast<uint32_t *>(l->d), *tmp = reinterpret_cast<uint32_t *>(scratch);
+    dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+    // An empty window (columns == 0 or rows == 0) leaves the init value: 255 (erode) / 0 (dilate);
+    // the two passes reproduce that because an empty 1-D window yields the identity element.
+    k_morph_pass<false><<<grid, block, 0, ctx->stream>>>(px, tmp, w, h, target_x, (int)columns, op == 1);
+    RB_LAUNCHED(ctx, "morph_h");
+    k_morph_pass<true><<<grid, block, 0, ctx->stream>>>(tmp, px, w, h, target_y, (int)rows, op == 1);
+    RB_LAUNCHED(ctx, "morph_v");
+    return RB_OK;
+}
+
+// =================================================================================================
+// convolve_matrix.rs:15-111
+// =================================================================================================
+struct ConvParams {
+    int columns, rows, target_x, target_y;
+    float divisor, bias;
+    int edge_mode, preserve_alpha;
+};
+
+__global__ void k_convolve(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h,
+                           const float *__restrict__ kernel, ConvParams P)
+{
+    __shared__ float div255[256];
+    rb_fill_div255(div255);
+    // flipped kernel in shared memory: kf[oy*columns + ox] = get(columns-ox-1, rows-oy-1)
+    extern __shared__ float kf[];
+    int ksize = P.columns * P.rows;
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < ksize; i += blockDim.x * blockDim.y) {
+        int oy = i / P.columns, ox = i - oy * P.columns;
+        kf[i] = kernel[(P.rows - oy - 1) * P.columns + (P.columns - ox - 1)];
+    }
+    __syncthreads();
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    float nr = 0.0f, ng = 0.0f, nb = 0.0f, na = 0.0f;
+    for (int oy = 0; oy < P.rows; oy++) {
+        int ty = y - P.target_y + oy;
+        if (P.edge_mode == 0) {
+            if (ty < 0 || ty > h - 1) continue;
+        } else if (P.edge_mode == 1) {
+            ty = max(0, min(h - 1, ty));
+        } else {
+            ty %= h;
+            if (ty < 0) ty += h;
+        }
+        const uint32_t *row = src + (size_t)ty * w;
+        for (int ox = 0; ox < P.columns; ox++) {
+            int tx = x - P.target_x + ox;
+            if (P.edge_mode == 0) {
+                if (tx < 0 || tx > w - 1) continue;
+            } else if (P.edge_mode == 1) {
+                tx = max(0, min(w - 1, tx));
+            } else {
+                tx %= w;
+                if (tx < 0) tx += w;
+            }
+            float k = kf[oy * P.columns + ox];
+            uint32_t p = __ldg(row + tx);
+            nr = nr + div255[RB_R(p)] * k;
+            ng = ng + div255[RB_G(p)] * k;
+            nb = nb + div255[RB_B(p)] * k;
+            if (!P.preserve_alpha) na = na + div255[RB_A(p)] * k;
+        }
+    }
+    uint32_t in_p = src[(size_t)y * w + x];
+    if (P.preserve_alpha) na = div255[RB_A(in_p)];
+    else na = __fdiv_rn(na, P.divisor) + P.bias;
+    float ba = rb_f32_bound(0.0f, na, 1.0f);
+    float ch[3] = {nr, ng, nb};
+    uint32_t o[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float v = __fdiv_rn(ch[c], P.divisor) + P.bias * na;
+        if (P.preserve_alpha) v = rb_f32_bound(0.0f, v, 1.0f) * ba;
+        else v = rb_f32_bound(0.0f, v, ba);
+        o[c] = rb_f2u8(v * 255.0f + 0.5f);
+    }
+    dst[(size_t)y * w + x] = rb_pack(o[0], o[1], o[2], rb_f2u8(ba * 255.0f + 0.5f));
+}
+
+extern "C" int rb_filter_convolve_matrix(rb_layer *l, const float *kernel, uint32_t columns, uint32_t rows,
+                                         uint32_t target_x, uint32_t target_y, float divisor, float bias,
+                                         int edge_mode, int preserve_alpha)
+{
+    if (!l || !kernel || columns == 0 || rows == 0 || edge_mode < 0 || edge_mode > 2) return RB_ERR_INVALID;
+    if ((size_t)columns * rows > 8192) return RB_ERR_UNSUPPORTED;
+    rb_ctx *ctx = l->ctx;
+    int w = (int)l->w, h = (int)l->h;
+    size_t bytes = (size_t)w * h * 4;
+    size_t kbytes = (size_t)columns * rows * sizeof(float);
+    void *scratch = nullptr;
+    int st = rb_scratch(ctx, bytes + 256 + kbytes, &scratch);
+    if (st != RB_OK) return st;
+    uint32_t *tmp = reinterpret_cast<uint32_t *>(scratch);
+    float *dk = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(scratch) + ((bytes + 255) & ~(size_t)255));
+    // Pageable-host async copy is staged by the runtime before returning, so `kernel` may be freed by the caller.
+    RB_CUDA(ctx, cudaMemcpyAsync(dk, kernel, kbytes, cudaMemcpyHostToDevice, ctx->stream));
+    ConvParams P{(int)columns, (int)rows, (int)target_x, (int)target_y, divisor, bias, edge_mode, preserve_alpha ? 1 : 0};
+    dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+    k_convolve<<<grid, block, kbytes, ctx->stream>>>(reinterpret_cast<uint32_t *>(l->d), tmp, w, h, dk, P);
+    RB_LAUNCHED(ctx, "convolve");
+    RB_CUDA(ctx, cudaMemcpyAsync(l->d, tmp, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return RB_OK;
+}
+
+// =================================================================================================
+// color_matrix.rs:11-110
+// =================================================================================================
+__device__ __forceinline__ uint32_t rb_from_normalized(float c) { return rb_f2u8(rb_f32_bound(0.0f, c, 1.0f) * 255.0f); }
+
+struct OpColorMatrixFull {
+    float m[20];
+    __device__ __forceinline__ uint32_t operator()(uint32_t p, const float *d) const
+    {
+        float r = d[RB_R(p)], g = d[RB_G(p)], b = d[RB_B(p)], a = d[RB_A(p)];
+        float nr = r * m[0] + g * m[1] + b * m[2] + a * m[3] + m[4];
+        float ng = r * m[5] + g * m[6] + b * m[7] + a * m[8] + m[9];
+        float nb = r * m[10] + g * m[11] + b * m[12] + a * m[13] + m[14];
+        float na = r * m[15] + g * m[16] + b * m[17] + a * m[18] + m[19];
+        return rb_pack(rb_from_normalized(nr), rb_from_normalized(ng), rb_from_normalized(nb), rb_from_normalized(na));
+    }
+};
+struct OpColorMatrix3x3 {
+    float m[9];
+    __device__ __forceinline__ uint32_t operator()(uint32_t p, const float *d) const
+    {
+        float r = d[RB_R(p)], g = d[RB_G(p)], b = d[RB_B(p)];
+        float nr = r * m[0] + g * m[1] + b * m[2];
+        float ng = r * m[3] + g * m[4] + b * m[5];
+        float nb = r * m[6] + g * m[7] + b * m[8];
+        return rb_pack(rb_from_normalized(nr), rb_from_normalized(ng), rb_from_normalized(nb), RB_A(p));
+    }
+};
+struct OpLuminanceToAlpha {
+    __device__ __forceinline__ uint32_t operator()(uint32_t p, const float *d) const
+    {
+        float r = d[RB_R(p)], g = d[RB_G(p)], b = d[RB_B(p)];
+        float na = r * 0.2125f + g * 0.7154f + b * 0.0721f;
+        return rb_pack(0, 0, 0, rb_from_normalized(na));
+    }
+};
+
+extern "C" int rb_filter_color_matrix(rb_layer *l, int kind, const float *params)
+{
+    if (!l) return RB_ERR_INVALID;
+    if (kind == 0) {
+        if (!params) return RB_ERR_INVALID;
+        OpColorMatrixFull op;
+        memcpy(op.m, params, sizeof(op.m));
+        return launch_pointwise(l, op, "color_matrix");
+    } else if (kind == 1 || kind == 2) {
+        if (!params) return RB_ERR_INVALID;
+        OpColorMatrix3x3 op;
+        float *m = op.m;
+        if (kind == 1) { // color_matrix.rs:29-41 — the 3x3 is built in f32 on the host exactly as there
+            volatile float v = params[0] > 0.0f ? params[0] : 0.0f;
+            m[0] = 0.213f + 0.787f * v; m[1] = 0.715f - 0.715f * v; m[2] = 0.072f - 0.072f * v;
+            m[3] = 0.213f - 0.213f * v; m[4] = 0.715f + 0.285f * v; m[5] = 0.072f - 0.072f * v;
+            m[6] = 0.213f - 0.213f * v; m[7] = 0.715f - 0.715f * v; m[8] = 0.072f + 0.928f * v;
+        } else { // :54-69; glibc cosf/sinf are what Rust's f32::cos/sin lower to on Linux
+            float angle = params[0] * 0.017453292519943295769236907684886f;
+            volatile float a1 = cosf(angle), a2 = sinf(angle);
+            m[0] = 0.213f + 0.787f * a1 - 0.213f * a2;
+            m[1] = 0.715f - 0.715f * a1 - 0.715f * a2;
+            m[2] = 0.072f - 0.072f * a1 + 0.928f * a2;
+            m[3] = 0.213f - 0.213f * a1 + 0.143f * a2;
+            m[4] = 0.715f + 0.285f * a1 + 0.140f * a2;
+            m[5] = 0.072f - 0.072f * a1 - 0.283f * a2;
+            m[6] = 0.213f - 0.213f * a1 - 0.787f * a2;
+            m[7] = 0.715f - 0.715f * a1 + 0.715f * a2;
+            m[8] = 0.072f + 0.928f * a1 + 0.072f * a2;
+        }
+        return launch_pointwise(l, op, "color_matrix");
+    } else if (kind == 3) {
+        return launch_pointwise(l, OpLuminanceToAlpha(), "color_matrix");
+    }
+    return RB_ERR_INVALID;
+}
+
+// =================================================================================================
+// component_transfer.rs:10-72 — every transfer function maps u8 -> u8, so the host evaluates it for
+// the 256 inputs (same f32 arithmetic, glibc powf) and the device applies four 256-entry LUTs.
+// =================================================================================================
+struct OpLut4 {
+    uint32_t lut[4][64]; // 4 x 256 bytes, packed
+    __device__ __forceinline__ uint32_t get(int ch, uint32_t v) const { return (lut[ch][v >> 2] >> ((v & 3) * 8)) & 0xffu; }
+};
+
+__global__ void __launch_bounds__(256) k_lut4(uint32_t *__restrict__ px, size_t n, OpLut4 L)
+{
+    __shared__ uint8_t s[4][256];
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) s[i >> 8][i & 255] = (uint8_t)L.get(i >> 8, i & 255);
+    __syncthreads();
+    auto ap = [&](uint32_t p) { return rb_pack(s[0][RB_R(p)], s[1][RB_G(p)], s[2][RB_B(p)], s[3][RB_A(p)]); };
+    size_t n4 = n >> 2;
+    uint4 *v = reinterpret_cast<uint4 *>(px);
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        uint4 p = v[i];
+        p.x = ap(p.x); p.y = ap(p.y); p.z = ap(p.z); p.w = ap(p.w);
+        v[i] = p;
+    }
+    size_t tail = n & 3;
+    if (blockIdx.x == 0 && threadIdx.x < tail) {
+        size_t i = (n4 << 2) + threadIdx.x;
+        px[i] = ap(px[i]);
+    }
+}
+
+static inline float h_f32_bound(float mn, float v, float mx) { return v > mx ? mx : (v >= mn ? v : mn); }
+static inline uint8_t h_f2u8(float v) { return !(v > 0.0f) ? 0 : (v >= 255.0f ? 255 : (uint8_t)v); }
+static inline size_t h_f2usize(float v) { return !(v > 0.0f) ? 0 : (v >= 1.8e19f ? (size_t)-1 : (size_t)v); }
+
+// component_transfer.rs:40-72
+static uint8_t transfer_u8(const rb_transfer_fn &f, uint8_t cu)
+{
+    volatile float c = (float)cu / 255.0f;
+    switch (f.type) {
+    case 1: {
+        size_t n = (size_t)f.n_values - 1;
+        size_t k = h_f2usize(floorf(c * (float)n));
+        if (k > n) k = n;
+        if (k == n) c = f.values[k];
+        else {
+            float vk = f.values[k], vk1 = f.values[k + 1];
+            float kf = (float)k, nf = (float)n;
+            volatile float t0 = kf / nf;
+            volatile float t1 = c - t0;
+            volatile float t2 = t1 * nf;
+            volatile float t3 = vk1 - vk;
+            volatile float t4 = t2 * t3;
+            c = vk + t4;
+        }
+        break;
+    }
+    case 2: {
+        size_t n = (size_t)f.n_values;
+        size_t k = h_f2usize(floorf(c * (float)n));
+        c = f.values[k < n - 1 ? k : n - 1];
+        break;
+    }
+    case 3: {
+        volatile float t = f.slope * c;
+        c = t + f.intercept;
+        break;
+    }
+    case 4: {
+        volatile float t = f.amplitude * powf(c, f.exponent);
+        c = t + f.offset;
+        break;
+    }
+    default: break;
+    }
+    return h_f2u8(h_f32_bound(0.0f, c, 1.0f) * 255.0f);
+}
+
+extern "C" int rb_filter_component_transfer(rb_layer *l, const rb_transfer_fn funcs[4])
+{
+    if (!l || !funcs) return RB_ERR_INVALID;
+    OpLut4 L;
+    uint8_t lut[4][256];
+    for (int ch = 0; ch < 4; ch++) {
+        const rb_transfer_fn &f = funcs[ch];
+        bool dummy = f.type == 0 || ((f.type == 1 || f.type == 2) && f.n_values == 0); // :30-38
+        if (!dummy && (f.type == 1 || f.type == 2) && !f.values) return RB_ERR_INVALID;
+        if (f.type < 0 || f.type > 4) return RB_ERR_INVALID;
+        for (int v = 0; v < 256; v++) lut[ch][v] = dummy ? (uint8_t)v : transfer_u8(f, (uint8_t)v);
+    }
+    memcpy(L.lut, lut, sizeof(lut));
+    rb_ctx *ctx = l->ctx;
+    size_t n = (size_t)l->w * l->h;
+    k_lut4<<<rb_grid_1d(ctx, (n + 3) / 4, 256), 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(l->d), n, L);
+    RB_LAUNCHED(ctx, "component_transfer");
+    return RB_OK;
+}
+
+// =================================================================================================
+// composite.rs:14-50 — arithmetic operator, 12 B/px (two reads, one write)
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+k_arithmetic(const uint32_t *__restrict__ s1, const uint32_t *__restrict__ s2, uint32_t *__restrict__ dst, size_t n,
+             float k1, float k2, float k3, float k4)
+{
+    __shared__ float div255[256];
+    rb_fill_div255(div255);
+    __syncthreads();
+    auto calc = [&](uint32_t c1, uint32_t c2, float mx) {
+        float i1 = div255[c1], i2 = div255[c2];
+        float result = k1 * i1 * i2 + k2 * i1 + k3 * i2 + k4;
+        return rb_f32_bound(0.0f, result, mx);
+    };
+    auto px = [&](uint32_t a, uint32_t b, uint32_t old) -> uint32_t {
+        float al = calc(RB_A(a), RB_A(b), 1.0f);
+        if (rb_approx_zero_ulps(al)) return old; // `continue`: destination pixel left untouched
+        uint32_t r = rb_f2u8(calc(RB_R(a), RB_R(b), al) * 255.0f);
+        uint32_t g = rb_f2u8(calc(RB_G(a), RB_G(b), al) * 255.0f);
+        uint32_t bl = rb_f2u8(calc(RB_B(a), RB_B(b), al) * 255.0f);
+        return rb_pack(r, g, bl, rb_f2u8(al * 255.0f));
+    };
+    size_t n4 = n >> 2;
+    const uint4 *v1 = reinterpret_cast<const uint4 *>(s1), *v2 = reinterpret_cast<const uint4 *>(s2);
+    uint4 *vd = reinterpret_cast<uint4 *>(dst);
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        uint4 a = v1[i], b = v2[i], d = vd[i];
+        d.x = px(a.x, b.x, d.x); d.y = px(a.y, b.y, d.y); d.z = px(a.z, b.z, d.z); d.w = px(a.w, b.w, d.w);
+        vd[i] = d;
+    }
+    size_t tail = n & 3;
+    if (blockIdx.x == 0 && threadIdx.x < tail) {
+        size_t i = (n4 << 2) + threadIdx.x;
+        dst[i] = px(s1[i], s2[i], dst[i]);
+    }
+}
+
+extern "C" int rb_filter_composite_arithmetic(rb_layer *dest, const rb_layer *src1, const rb_layer *src2, float k1,
+                                              float k2, float k3, float k4)
+{
+    if (!dest || !src1 || !src2) return RB_ERR_INVALID;
+    if (src1->w != dest->w || src2->w != dest->w || src1->h != dest->h || src2->h != dest->h) return RB_ERR_INVALID;
+    rb_ctx *ctx = dest->ctx;
+    size_t n = (size_t)dest->w * dest->h;
+    k_arithmetic<<<rb_grid_1d(ctx, (n + 3) / 4, 256), 256, 0, ctx->stream>>>(
+        reinterpret_cast<const uint32_t *>(src1->d), reinterpret_cast<const uint32_t *>(src2->d),
+        reinterpret_cast<uint32_t *>(dest->d), n, k1, k2, k3, k4);
+    RB_LAUNCHED(ctx, "composite_arithmetic");
+    return RB_OK;
+}
+
+// =================================================================================================
+// displacement_map.rs:15-62 — gather
+// =================================================================================================
+__global__ void k_displace(const uint32_t *__restrict__ src, const uint32_t *__restrict__ map,
+                           uint32_t *__restrict__ dst, int w, int h, int xch, int ych, float scale, float sx, float sy)
+{
+    __shared__ float div255[256];
+    rb_fill_div255(div255);
+    __syncthreads();
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    uint32_t m = map[(size_t)y * w + x];
+    float dx = div255[(m >> (8 * xch)) & 0xffu] - 0.5f;
+    float dy = div255[(m >> (8 * ych)) & 0xffu] - 0.5f;
+    // f32::round = half away from zero = roundf; `as i32` saturates (cvt.rzi.s32.f32), NaN -> 0
+    int ox = __float2int_rz(roundf((float)x + dx * sx * scale));
+    int oy = __float2int_rz(roundf((float)y + dy * sy * scale));
+    if (ox >= 0 && ox < w && oy >= 0 && oy < h) dst[(size_t)y * w + x] = __ldg(src + (size_t)oy * w + ox);
+}
+
+extern "C" int rb_filter_displacement_map(rb_layer *dest, const rb_layer *src, const rb_layer *map, int xch, int ych,
+                                          float scale, float sx, float sy)
+{
+    if (!dest || !src || !map || xch < 0 || xch > 3 || ych < 0 || ych > 3) return RB_ERR_INVALID;
+    if (src->w != dest->w || map->w != dest->w || src->h != dest->h || map->h != dest->h) return RB_ERR_INVALID;
+    if (dest->d == src->d) return RB_ERR_INVALID;
+    rb_ctx *ctx = dest->ctx;
+    int w = (int)dest->w, h = (int)dest->h;
+    dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+    k_displace<<<grid, block, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(src->d),
+                                                reinterpret_cast<const uint32_t *>(map->d),
+                                                reinterpret_cast<uint32_t *>(dest->d), w, h, xch, ych, scale, sx, sy);
+    RB_LAUNCHED(ctx, "displacement_map");
+    return RB_OK;
+}
+
+// =================================================================================================
+// lighting.rs — diffuse / specular lighting from the alpha-channel surface normal
+// =================================================================================================
+struct LightParams {
+    int specular;
+    float surface_scale, constant, exponent;
+    int exp_is_one;
+    float lr, lg, lb; // lighting colour as f32 of the u8 channels
+    int kind;
+    float lvx, lvy, lvz;        // distant light vector (host, glibc cosf/sinf)
+    float x, y, z;              // point/spot origin
+    float dirx, diry, dirz;     // spot: normalised (points_at - origin), host
+    float spot_exponent;
+    int has_cone;
+    float cone_cos;             // cos(limiting_cone_angle) (host)
+};
+
+struct V3 { float x, y, z; };
+__device__ __forceinline__ float v3dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float v3len(V3 a) { return __fsqrt_rn(a.x * a.x + a.y * a.y + a.z * a.z); }
+
+// powf through FP64: correctly rounded in all but vanishingly rare cases, which is what glibc's powf
+// (used by the reference on Linux) delivers; any residual difference is inside the 1/255 tolerance.
+__device__ __forceinline__ float rb_powf(float a, float b) { return (float)pow((double)a, (double)b); }
+
+__global__ void k_lighting(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h, LightParams P)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    auto A = [&](int dx, int dy) -> int { return (int)RB_A(__ldg(src + (size_t)(y + dy) * w + (x + dx))); };
+    const int bx = (x == 0) ? 0 : (x == w - 1 ? 2 : 1);
+    const int by = (y == 0) ? 0 : (y == h - 1 ? 2 : 1);
+    const float F12 = 1.0f / 2.0f, F13 = 1.0f / 3.0f, F14 = 1.0f / 4.0f, F23 = 2.0f / 3.0f;
+    float fx, fy;
+    int nx, ny;
+    // lighting.rs:340-485
+    if (bx == 0 && by == 0) {
+        int c = A(0, 0), r = A(1, 0), b = A(0, 1), br = A(1, 1);
+        fx = F23; fy = F23;
+        nx = -2 * c + 2 * r - b + br;
+        ny = -2 * c - r + 2 * b + br;
+    } else if (bx == 2 && by == 0) {
+        int l = A(-1, 0), c = A(0, 0), bl = A(-1, 1), b = A(0, 1);
+        fx = F23; fy = F23;
+        nx = -2 * l + 2 * c - bl + b;
+        ny = -l - 2 * c + bl + 2 * b;
+    } else if (bx == 0 && by == 2) {
+        int t = A(0, -1), tr = A(1, -1), c = A(0, 0), r = A(1, 0);
+        fx = F23; fy = F23;
+        nx = -t + tr - 2 * c + 2 * r;
+        ny = -2 * t - tr + 2 * c + r;
+    } else if (bx == 2 && by == 2) {
+        int tl = A(-1, -1), t = A(0, -1), l = A(-1, 0), c = A(0, 0);
+        fx = F23; fy = F23;
+        nx = -tl + t - 2 * l + 2 * c;
+        ny = -tl - 2 * t + l + 2 * c;
+    } else if (by == 0) {
+        int l = A(-1, 0), c = A(0, 0), r = A(1, 0), bl = A(-1, 1), b = A(0, 1), br = A(1, 1);
+        fx = F13; fy = F12;
+        nx = -2 * l + 2 * r - bl + br;
+        ny = -l - 2 * c - r + bl + 2 * b + br;
+    } else if (by == 2) {
+        int tl = A(-1, -1), t = A(0, -1), tr = A(1, -1), l = A(-1, 0), c = A(0, 0), r = A(1, 0);
+        fx = F13; fy = F12;
+        nx = -tl + tr - 2 * l + 2 * r;
+        ny = -tl - 2 * t - tr + l + 2 * c + r;
+    } else if (bx == 0) {
+        int t = A(0, -1), tr = A(1, -1), c = A(0, 0), r = A(1, 0), b = A(0, 1), br = A(1, 1);
+        fx = F12; fy = F13;
+        nx = -t + tr - 2 * c + 2 * r - b + br;
+        ny = -2 * t - tr + 2 * b + br;
+    } else if (bx == 2) {
+        int tl = A(-1, -1), t = A(0, -1), l = A(-1, 0), c = A(0, 0), bl = A(-1, 1), b = A(0, 1);
+        fx = F12; fy = F13;
+        nx = -tl + t - 2 * l + 2 * c - bl + b;
+        ny = -tl - 2 * t + bl + 2 * b;
+    } else {
+        int tl = A(-1, -1), t = A(0, -1), tr = A(1, -1), l = A(-1, 0), r = A(1, 0);
+        int bl = A(-1, 1), b = A(0, 1), br = A(1, 1);
+        fx = F14; fy = F14;
+        nx = -tl + tr - 2 * l + 2 * r - bl + br;
+        ny = -tl - 2 * t - tr + bl + 2 * b + br;
+    }
+    float nnx = (float)(-nx), nny = (float)(-ny);
+
+    // light vector (lighting.rs:257-271)
+    V3 lv = {P.lvx, P.lvy, P.lvz};
+    if (P.kind != 0) {
+        float nz = __fdiv_rn((float)A(0, 0), 255.0f) * P.surface_scale;
+        V3 v = {P.x - (float)x, P.y - (float)y, P.z - nz};
+        float len = v3len(v);
+        if (!rb_approx_zero_ulps(len)) {
+            v.x = __fdiv_rn(v.x, len);
+            v.y = __fdiv_rn(v.y, len);
+            v.z = __fdiv_rn(v.z, len);
+        }
+        lv = v;
+    }
+    // light colour (lighting.rs:309-338)
+    float cr = P.lr, cg = P.lg, cb = P.lb;
+    if (P.kind == 2) {
+        V3 dir = {P.dirx, P.diry, P.dirz};
+        float mls = -v3dot(lv, dir);
+        bool black = (mls <= 0.0f) || (P.has_cone && mls < P.cone_cos);
+        if (black) {
+            cr = cg = cb = 0.0f;
+        } else {
+            float factor = rb_powf(mls, P.spot_exponent);
+            cr = (float)rb_f2u8(rb_f32_bound(0.0f, P.lr * factor, 255.0f) + 0.5f);
+            cg = (float)rb_f2u8(rb_f32_bound(0.0f, P.lg * factor, 255.0f) + 0.5f);
+            cb = (float)rb_f2u8(rb_f32_bound(0.0f, P.lb * factor, 255.0f) + 0.5f);
+        }
+    }
+    // light factor (lighting.rs:141-153, 185-219)
+    bool nzero = rb_approx_zero_ulps(nnx) && rb_approx_zero_ulps(nny);
+    float factor;
+    if (!P.specular) {
+        float k;
+        if (nzero) k = lv.z;
+        else {
+            float s = __fdiv_rn(P.surface_scale, 255.0f);
+            float ax = nnx * s, ay = nny * s;
+            ax *= fx;
+            ay *= fy;
+            V3 n = {ax, ay, 1.0f};
+            k = __fdiv_rn(v3dot(n, lv), v3len(n));
+        }
+        factor = P.constant * k;
+    } else {
+        V3 hv = {lv.x + 0.0f, lv.y + 0.0f, lv.z + 1.0f};
+        float hl = v3len(hv);
+        if (rb_approx_zero_ulps(hl)) factor = 0.0f;
+        else {
+            float ndh;
+            if (nzero) ndh = __fdiv_rn(hv.z, hl);
+            else {
+                float s = __fdiv_rn(P.surface_scale, 255.0f);
+                float ax = nnx * s, ay = nny * s;
+                ax *= fx;
+                ay *= fy;
+                V3 n = {ax, ay, 1.0f};
+                ndh = __fdiv_rn(__fdiv_rn(v3dot(n, hv), v3len(n)), hl);
+            }
+            float k = P.exp_is_one ? ndh : rb_powf(ndh, P.exponent);
+            factor = P.constant * k;
+        }
+    }
+    uint32_t r = rb_f2u8(rb_f32_bound(0.0f, cr * factor, 255.0f) + 0.5f);
+    uint32_t g = rb_f2u8(rb_f32_bound(0.0f, cg * factor, 255.0f) + 0.5f);
+    uint32_t b = rb_f2u8(rb_f32_bound(0.0f, cb * factor, 255.0f) + 0.5f);
+    uint32_t a = P.specular ? max(max(r, g), b) : 255u;
+    dst[(size_t)y * w + x] = rb_pack(r, g, b, a);
+}
+
+static bool h_approx_eq_ulps(float a, float b, int32_t ulps)
+{
+    if (a == b) return true;
+    if (std::signbit(a) != std::signbit(b)) return false;
+    int32_t ai, bi;
+    memcpy(&ai, &a, 4);
+    memcpy(&bi, &b, 4);
+    int32_t diff = (int32_t)((uint32_t)ai - (uint32_t)bi);
+    return diff >= -ulps && diff <= ulps;
+}
+
+static int launch_lighting(rb_layer *dest, const rb_layer *src, int specular, float surface_scale, float constant,
+                           float exponent, uint8_t r, uint8_t g, uint8_t b, const rb_light_source *light)
+{
+    if (!dest || !src || !light) return RB_ERR_INVALID;
+    if (dest->w != src->w || dest->h != src->h || dest->d == src->d) return RB_ERR_INVALID;
+    if (light->kind < 0 || light->kind > 2) return RB_ERR_INVALID;
+    if (src->w < 3 || src->h < 3) return RB_OK; // lighting.rs:236-238
+    const float TO_RAD = 0.017453292519943295769236907684886f;
+    LightParams P;
+    memset(&P, 0, sizeof(P));
+    P.specular = specular;
+    P.surface_scale = surface_scale;
+    P.constant = constant;
+    P.exponent = exponent;
+    P.exp_is_one = h_approx_eq_ulps(exponent, 1.0f, 4) ? 1 : 0;
+    P.lr = (float)r; P.lg = (float)g; P.lb = (float)b;
+    P.kind = light->kind;
+    if (light->kind == 0) { // lighting.rs:244-253
+        float az = light->azimuth * TO_RAD, el = light->elevation * TO_RAD;
+        volatile float ca = cosf(az), sa = sinf(az), ce = cosf(el), se = sinf(el);
+        P.lvx = ca * ce;
+        P.lvy = sa * ce;
+        P.lvz = se;
+    } else {
+        P.lvx = P.lvy = P.lvz = 1.0f;
+        P.x = light->x; P.y = light->y; P.z = light->z;
+    }
+    if (light->kind == 2) { // lighting.rs:313-317 — per-primitive constants
+        volatile float dx = light->points_at_x - light->x, dy = light->points_at_y - light->y,
+                       dz = light->points_at_z - light->z;
+        volatile float xx = dx * dx, yy = dy * dy, zz = dz * dz;
+        volatile float sxy = xx + yy;
+        volatile float sum = sxy + zz;
+        float len = sqrtf(sum);
+        bool zero = (len == 0.0f) || (!std::signbit(len) && [&] { int32_t bi; memcpy(&bi, &len, 4); return bi <= 4; }());
+        if (!zero) { P.dirx = dx / len; P.diry = dy / len; P.dirz = dz / len; }
+        else { P.dirx = dx; P.diry = dy; P.dirz = dz; }
+        P.spot_exponent = light->specular_exponent;
+        P.has_cone = light->has_cone;
+        P.cone_cos = light->has_cone ? cosf(light->limiting_cone_angle * TO_RAD) : 0.0f;
+    }
+    rb_ctx *ctx = dest->ctx;
+    int w = (int)dest->w, h = (int)dest->h;
+    dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+    k_lighting<<<grid, block, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(src->d),
+                                                reinterpret_cast<uint32_t *>(dest->d), w, h, P);
+    RB_LAUNCHED(ctx, "lighting");
+    return RB_OK;
+}
+
+extern "C" int rb_filter_diffuse_lighting(rb_layer *dest, const rb_layer *src, float surface_scale,
+                                          float diffuse_constant, uint8_t r, uint8_t g, uint8_t b,
+                                          const rb_light_source *light)
+{
+    return launch_lighting(dest, src, 0, surface_scale, diffuse_constant, 1.0f, r, g, b, light);
+}
+extern "C" int rb_filter_specular_lighting(rb_layer *dest, const rb_layer *src, float surface_scale,
+                                           float specular_constant, float specular_exponent, uint8_t r, uint8_t g,
+                                           uint8_t b, const rb_light_source *light)
+{
+    return launch_lighting(dest, src, 1, surface_scale, specular_constant, specular_exponent, r, g, b, light);
+}
+
+// =================================================================================================
+// turbulence.rs — Perlin turbulence in f64.  Lattice/gradient tables are built on the host exactly as
+// turbulence.rs:93-140 and staged in shared memory (2 KB + 32.9 KB).
+// =================================================================================================
+#define TB_BSIZE 0x100
+#define TB_BLEN (TB_BSIZE + TB_BSIZE + 2)
+#define TB_PERLIN_N 0x1000
+
+struct TurbParams {
+    double offset_x, offset_y, sx, sy, bfx, bfy;
+    int octaves, stitch, fractal;
+};
+
+__device__ __forceinline__ double tb_s_curve(double t)
+{
+    return __dmul_rn(__dmul_rn(t, t), __dsub_rn(3.0, __dmul_rn(2.0, t)));
+}
+__device__ __forceinline__ double tb_lerp(double t, double a, double b)
+{
+    return __dadd_rn(a, __dmul_rn(t, __dsub_rn(b, a)));
+}
+
+__global__ void __launch_bounds__(256)
+k_turbulence(uint32_t *__restrict__ dst, int w, int h, const int *__restrict__ g_lat, const double *__restrict__ g_grad,
+             TurbParams P)
+{
+    extern __shared__ double s_grad[]; // 4*514*2 doubles, then 514 ints
+    int *s_lat = reinterpret_cast<int *>(s_grad + 4 * TB_BLEN * 2);
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 4 * TB_BLEN * 2; i += blockDim.x * blockDim.y)
+        s_grad[i] = g_grad[i];
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < TB_BLEN; i += blockDim.x * blockDim.y) s_lat[i] = g_lat[i];
+    __syncthreads();
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+
+    // turbulence.rs:47 — point in user space
+    const double px = __ddiv_rn(__dadd_rn((double)x, P.offset_x), P.sx);
+    const double py = __ddiv_rn(__dadd_rn((double)y, P.offset_y), P.sy);
+    // turbulence.rs:158-195 — stitching set-up (identical for the four channels)
+    double bfx = P.bfx, bfy = P.bfy;
+    int st_w = 0, st_h = 0, wrap_x = 0, wrap_y = 0;
+    if (P.stitch) {
+        const double tw = (double)w, th = (double)h;
+        // !approx_zero_ulps(4) for f64
+        long long bx_bits = __double_as_longlong(bfx), by_bits = __double_as_longlong(bfy);
+        bool zx = (bfx == 0.0) || (bx_bits >= 0 && bx_bits <= 4);
+        bool zy = (bfy == 0.0) || (by_bits >= 0 && by_bits <= 4);
+        if (!zx) {
+            double lo = __ddiv_rn(floor(__dmul_rn(tw, bfx)), tw), hi = __ddiv_rn(ceil(__dmul_rn(tw, bfx)), tw);
+            bfx = (__ddiv_rn(bfx, lo) < __ddiv_rn(hi, bfx)) ? lo : hi;
+        }
+        if (!zy) {
+            double lo = __ddiv_rn(floor(__dmul_rn(th, bfy)), th), hi = __ddiv_rn(ceil(__dmul_rn(th, bfy)), th);
+            bfy = (__ddiv_rn(bfy, lo) < __ddiv_rn(hi, bfy)) ? lo : hi;
+        }
+        st_w = __double2int_rz(__dadd_rn(__dmul_rn(tw, bfx), 0.5));
+        st_h = __double2int_rz(__dadd_rn(__dmul_rn(th, bfy), 0.5));
+        wrap_x = __double2int_rz(__dadd_rn(__dadd_rn(__dmul_rn((double)x, bfx), (double)TB_PERLIN_N), (double)st_w));
+        wrap_y = __double2int_rz(__dadd_rn(__dadd_rn(__dmul_rn((double)y, bfy), (double)TB_PERLIN_N), (double)st_h));
+    }
+    uint32_t out[4];
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ch++) {
+        const double *grad = s_grad + ch * TB_BLEN * 2;
+        double sum = 0.0;
+        double vx = __dmul_rn(px, bfx), vy = __dmul_rn(py, bfy);
+        double ratio = 1.0;
+        int sw = st_w, sh = st_h, wx = wrap_x, wy = wrap_y;
+        for (int o = 0; o < P.octaves; o++) {
+            // noise2 — turbulence.rs:224-285
+            double t = __dadd_rn(vx, (double)TB_PERLIN_N);
+            int bx0 = __double2int_rz(t);
+            int bx1 = (int)((unsigned)bx0 + 1u);
+            double rx0 = __dsub_rn(t, (double)__double2ll_rz(t));
+            double rx1 = __dsub_rn(rx0, 1.0);
+            t = __dadd_rn(vy, (double)TB_PERLIN_N);
+            int by0 = __double2int_rz(t);
+            int by1 = (int)((unsigned)by0 + 1u);
+            double ry0 = __dsub_rn(t, (double)__double2ll_rz(t));
+            double ry1 = __dsub_rn(ry0, 1.0);
+            if (P.stitch) {
+                if (bx0 >= wx) bx0 = (int)((unsigned)bx0 - (unsigned)sw);
+                if (bx1 >= wx) bx1 = (int)((unsigned)bx1 - (unsigned)sw);
+                if (by0 >= wy) by0 = (int)((unsigned)by0 - (unsigned)sh);
+                if (by1 >= wy) by1 = (int)((unsigned)by1 - (unsigned)sh);
+            }
+            bx0 &= 0xff; bx1 &= 0xff; by0 &= 0xff; by1 &= 0xff;
+            int i = s_lat[bx0], j = s_lat[bx1];
+            int b00 = s_lat[i + by0], b10 = s_lat[j + by0], b01 = s_lat[i + by1], b11 = s_lat[j + by1];
+            double sxc = tb_s_curve(rx0), syc = tb_s_curve(ry0);
+            const double *q = grad + b00 * 2;
+            double u = __dadd_rn(__dmul_rn(rx0, q[0]), __dmul_rn(ry0, q[1]));
+            q = grad + b10 * 2;
+            double v = __dadd_rn(__dmul_rn(rx1, q[0]), __dmul_rn(ry0, q[1]));
+            double a = tb_lerp(sxc, u, v);
+            q = grad + b01 * 2;
+            u = __dadd_rn(__dmul_rn(rx0, q[0]), __dmul_rn(ry1, q[1]));
+            q = grad + b11 * 2;
+            v = __dadd_rn(__dmul_rn(rx1, q[0]), __dmul_rn(ry1, q[1]));
+            double b = tb_lerp(sxc, u, v);
+            double nz = tb_lerp(syc, a, b);
+            if (P.fractal) sum = __dadd_rn(sum, __ddiv_rn(nz, ratio));
+            else sum = __dadd_rn(sum, __ddiv_rn(fabs(nz), ratio));
+            vx = __dmul_rn(vx, 2.0);
+            vy = __dmul_rn(vy, 2.0);
+            ratio = __dmul_rn(ratio, 2.0);
+            if (P.stitch) {
+                sw = (int)((unsigned)sw * 2u);
+                wx = (int)(2u * (unsigned)wx - (unsigned)TB_PERLIN_N);
+                sh = (int)((unsigned)sh * 2u);
+                wy = (int)(2u * (unsigned)wy - (unsigned)TB_PERLIN_N);
+            }
+        }
+        double n = P.fractal ? __ddiv_rn(__dadd_rn(__dmul_rn(sum, 255.0), 255.0), 2.0) : __dmul_rn(sum, 255.0);
+        out[ch] = rb_f2u8(rb_f32_bound(0.0f, (float)n, 255.0f) + 0.5f);
+    }
+    dst[(size_t)y * w + x] = rb_pack(out[0], out[1], out[2], out[3]);
+}
+
+// turbulence.rs:287-294
+static int32_t tb_random(int32_t seed)
+{
+    int32_t result = (int32_t)((uint32_t)16807 * (uint32_t)(seed % 127773) - (uint32_t)2836 * (uint32_t)(seed / 127773));
+    if (result <= 0) result = (int32_t)((uint32_t)result + 2147483647u);
+    return result;
+}
+
+// turbulence.rs:93-140
+static void tb_init(int32_t seed, int32_t *lattice, double *gradient)
+{
+    const int32_t RAND_M = 2147483647;
+    if (seed <= 0) seed = (int32_t)(-(int64_t)seed % (RAND_M - 1)) + 1;
+    if (seed > RAND_M - 1) seed = RAND_M - 1;
+    memset(lattice, 0, sizeof(int32_t) * TB_BLEN);
+    memset(gradient, 0, sizeof(double) * 4 * TB_BLEN * 2);
+    for (int k = 0; k < 4; k++) {
+        for (int i = 0; i < TB_BSIZE; i++) {
+            lattice[i] = i;
+            double *g = gradient + ((size_t)k * TB_BLEN + i) * 2;
+            for (int j = 0; j < 2; j++) {
+                seed = tb_random(seed);
+                g[j] = (double)((seed % (TB_BSIZE + TB_BSIZE)) - TB_BSIZE) / (double)TB_BSIZE;
+            }
+            volatile double xx = g[0] * g[0], yy = g[1] * g[1];
+            double s = sqrt(xx + yy);
+            g[0] /= s;
+            g[1] /= s;
+        }
+    }
+    for (int i = TB_BSIZE - 1; i >= 1; i--) {
+        int32_t k = lattice[i];
+        seed = tb_random(seed);
+        int j = seed % TB_BSIZE;
+        lattice[i] = lattice[j];
+        lattice[j] = k;
+    }
+    for (int i = 0; i < TB_BSIZE + 2; i++) {
+        lattice[TB_BSIZE + i] = lattice[i];
+        for (int k = 0; k < 4; k++)
+            for (int j = 0; j < 2; j++)
+                gradient[((size_t)k * TB_BLEN + TB_BSIZE + i) * 2 + j] = gradient[((size_t)k * TB_BLEN + i) * 2 + j];
+    }
+}
+
+extern "C" int rb_filter_turbulence(rb_layer *dest, double offset_x, double offset_y, double sx, double sy,
+                                    double bfx, double bfy, uint32_t num_octaves, int32_t seed, int stitch_tiles,
+                                    int fractal_noise)
+{
+    if (!dest) return RB_ERR_INVALID;
+    rb_ctx *ctx = dest->ctx;
+    int w = (int)dest->w, h = (int)dest->h;
+    const size_t grad_bytes = sizeof(double) * 4 * TB_BLEN * 2, lat_bytes = sizeof(int32_t) * TB_BLEN;
+    std::vector<double> grad(4 * TB_BLEN * 2);
+    std::vector<int32_t> lat(TB_BLEN);
+    tb_init(seed, lat.data(), grad.data());
+    void *scratch = nullptr;
+    int st = rb_scratch(ctx, grad_bytes + lat_bytes, &scratch);
+    if (st != RB_OK) return st;
+    double *dg = reinterpret_cast<double *>(scratch);
+    int *dl = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(scratch) + grad_bytes);
+    RB_CUDA(ctx, cudaMemcpyAsync(dg, grad.data(), grad_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    RB_CUDA(ctx, cudaMemcpyAsync(dl, lat.data(), lat_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    TurbParams P{offset_x, offset_y, sx, sy, bfx, bfy, (int)num_octaves, stitch_tiles ? 1 : 0, fractal_noise ? 1 : 0};
+    static bool attr_set = false;
+    if (!attr_set) {
+        RB_CUDA(ctx, cudaFuncSetAttribute(k_turbulence, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(grad_bytes + lat_bytes)));
+        attr_set = true;
+    }
+    dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+    k_turbulence<<<grid, block, grad_bytes + lat_bytes, ctx->stream>>>(reinterpret_cast<uint32_t *>(dest->d), w, h, dl,
+                                                                         dg, P);
+    RB_LAUNCHED(ctx, "turbulence");
+    return RB_OK;
+}

@@ -1,0 +1,61 @@
+// rb_internal.h — shared declarations of the resvg_b200 CUDA library (not part of the public ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/resvg_b200.h"
+
+struct rb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    int sm_count = 148;
+    // scratch reused by multi-pass filters (grown on demand, freed with the context)
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+struct rb_layer {
+    rb_ctx *ctx;
+    uint32_t w, h;
+    uint8_t *d; // w*h*4 bytes, premultiplied RGBA8
+};
+
+struct rb_mask {
+    rb_ctx *ctx;
+    uint32_t w, h;
+    uint8_t *d; // w*h bytes
+};
+
+int rb_fail(rb_ctx *ctx, int code, const char *what);
+int rb_cuda_fail(rb_ctx *ctx, cudaError_t e, const char *what);
+// Ensures ctx->scratch holds at least `bytes`; returns RB_OK or an error status.
+int rb_scratch(rb_ctx *ctx, size_t bytes, void **out);
+
+#define RB_CUDA(ctx, call)                                              \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return rb_cuda_fail((ctx), e__, #call); \
+    } while (0)
+
+// Call after every kernel launch: counts the launch and surfaces launch-configuration errors.
+#define RB_LAUNCHED(ctx, name)                                           \
+    do {                                                                 \
+        (ctx)->launches++;                                               \
+        cudaError_t e__ = cudaGetLastError();                            \
+        if (e__ != cudaSuccess) return rb_cuda_fail((ctx), e__, (name)); \
+    } while (0)
+
+static inline int rb_grid_1d(const rb_ctx *ctx, size_t work_items, int block, int max_waves = 8)
+{
+    size_t blocks = (work_items + block - 1) / block;
+    size_t cap = (size_t)ctx->sm_count * (2048 / block) * max_waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}

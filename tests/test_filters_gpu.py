@@ -1,0 +1,260 @@
+"""GPU parity: every CUDA filter kernel against the CPU oracle (oracle/filters.c) on the same inputs.
+
+Bars (BASELINE.json north_star): bit-exact for integer / u8 / LUT stages and for every f32/f64 stage
+whose operation order is reproduced exactly; <= 1/255 per channel only where the device evaluates
+`powf` (spot-light cone exponent, specular exponent) differently from glibc.
+"""
+import numpy as np
+import pytest
+
+from tests.util import assert_exact, assert_within, random_premul, random_rgba, smooth_alpha
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(1, 1), (3, 2), (7, 5), (64, 48), (257, 131), (300, 300), (1029, 67)]
+
+
+def _run(ctx, img, fn):
+    import resvg_b200 as rb
+
+    l = ctx.layer_from(img)
+    fn(rb.filters, l)
+    out = l.download()
+    l.close()
+    return out
+
+
+@pytest.mark.parametrize("w,h", SIZES)
+def test_alpha_and_colorspace_helpers(ctx, oracle, w, h):
+    img = random_premul(w, h, 1)
+    assert_exact(_run(ctx, img, lambda f, l: f.demultiply_alpha(l)), oracle.demultiply_alpha(img), "demultiply")
+    un = random_rgba(w, h, 2)
+    assert_exact(_run(ctx, un, lambda f, l: f.multiply_alpha(l)), oracle.multiply_alpha(un), "multiply")
+    assert_exact(_run(ctx, img, lambda f, l: f.into_linear_rgb(l)), oracle.into_linear_rgb(img), "into_linear")
+    assert_exact(_run(ctx, img, lambda f, l: f.into_srgb(l)), oracle.into_srgb(img), "into_srgb")
+    # non-premultiplied garbage must follow the same saturating arithmetic
+    assert_exact(_run(ctx, un, lambda f, l: f.into_linear_rgb(l)), oracle.into_linear_rgb(un), "into_linear(unpremul)")
+    assert_exact(_run(ctx, un, lambda f, l: f.demultiply_alpha(l)), oracle.demultiply_alpha(un), "demultiply(unpremul)")
+
+
+def test_colorspace_round_trip_full_range(ctx, oracle):
+    # every (c, a) pair with c <= a
+    a, c = np.meshgrid(np.arange(256), np.arange(256), indexing="ij")
+    img = np.zeros((256, 256, 4), dtype=np.uint8)
+    img[..., 3] = a
+    img[..., 0] = np.minimum(c, a)
+    img[..., 1] = np.minimum(255 - c, a)
+    img[..., 2] = np.minimum((c * 7) % 256, a)
+    assert_exact(_run(ctx, img, lambda f, l: f.into_linear_rgb(l)), oracle.into_linear_rgb(img))
+    assert_exact(_run(ctx, img, lambda f, l: f.into_srgb(l)), oracle.into_srgb(img))
+
+
+@pytest.mark.parametrize("w,h", SIZES)
+@pytest.mark.parametrize("sx,sy", [(2.0, 2.0), (4.0, 3.0), (8.0, 0.0), (0.0, 16.0), (64.0, 64.0), (2.5, 40.0)])
+def test_box_blur(ctx, oracle, w, h, sx, sy):
+    img = random_premul(w, h, 3, sparse=True)
+    assert_exact(_run(ctx, img, lambda f, l: f.box_blur(sx, sy, l)), oracle.box_blur(sx, sy, img), f"box {sx},{sy}")
+
+
+def test_box_blur_radius_larger_than_image(ctx, oracle):
+    img = random_premul(40, 9, 4)
+    assert_exact(_run(ctx, img, lambda f, l: f.box_blur(30.0, 30.0, l)), oracle.box_blur(30.0, 30.0, img))
+    # radius too large for the tiled horizontal kernel -> fallback kernel
+    img = random_premul(700, 16, 5)
+    assert_exact(_run(ctx, img, lambda f, l: f.box_blur(300.0, 2.0, l)), oracle.box_blur(300.0, 2.0, img))
+
+
+def test_box_blur_large(ctx, oracle):
+    img = random_premul(2048, 1024, 6, sparse=True)
+    for s in (2.0, 8.0, 64.0):
+        assert_exact(_run(ctx, img, lambda f, l: f.box_blur(s, s, l)), oracle.box_blur(s, s, img), f"box {s}")
+
+
+@pytest.mark.parametrize("w,h", SIZES)
+@pytest.mark.parametrize("sx,sy", [(0.5, 0.5), (1.0, 1.9), (1.9, 0.0), (0.0, 1.2)])
+def test_iir_blur(ctx, oracle, w, h, sx, sy):
+    img = random_premul(w, h, 7, sparse=True)
+    # Sequential recurrences in the reference order: bit-exact.
+    assert_exact(_run(ctx, img, lambda f, l: f.iir_blur(sx, sy, l)), oracle.iir_blur(sx, sy, img), f"iir {sx},{sy}")
+
+
+@pytest.mark.parametrize("w,h", SIZES)
+@pytest.mark.parametrize("op", ["erode", "dilate"])
+@pytest.mark.parametrize("rx,ry", [(1.0, 1.0), (3.0, 2.0), (0.4, 7.5), (32.0, 8.0)])
+def test_morphology(ctx, oracle, w, h, op, rx, ry):
+    if w * h > 100000 and rx * ry > 100:
+        pytest.skip("oracle is O(rx*ry) per pixel")
+    img = random_premul(w, h, 8, sparse=True)
+    assert_exact(_run(ctx, img, lambda f, l: f.morphology(op, rx, ry, l)), oracle.morphology(op, rx, ry, img),
+                 f"morph {op} {rx},{ry}")
+
+
+KERNELS = {
+    "sharpen3": ([0, -1, 0, -1, 5, -1, 0, -1, 0], 3, 3, 1, 1, 1.0, 0.0),
+    "emboss3": ([-2, -1, 0, -1, 1, 1, 0, 1, 2], 3, 3, 1, 1, 1.0, 0.5),
+    "blur5": ([1] * 25, 5, 5, 2, 2, 25.0, 0.0),
+    "asym": ([1, 2, 3, 4, 5, 6], 3, 2, 0, 1, 3.0, 0.1),
+    "wide": ([0.5, -1, 2, 0.25, 1, 1, -0.5], 7, 1, 6, 0, 2.0, 0.0),
+}
+
+
+@pytest.mark.parametrize("w,h", [(3, 2), (64, 48), (257, 131)])
+@pytest.mark.parametrize("kname", list(KERNELS))
+@pytest.mark.parametrize("edge", ["none", "duplicate", "wrap"])
+@pytest.mark.parametrize("preserve", [False, True])
+def test_convolve_matrix(ctx, oracle, w, h, kname, edge, preserve):
+    k, cols, rows, tx, ty, div, bias = KERNELS[kname]
+    img = random_premul(w, h, 9)
+    got = _run(ctx, img, lambda f, l: f.convolve_matrix(k, cols, rows, tx, ty, div, bias, edge, preserve, l))
+    assert_exact(got, oracle.convolve_matrix(k, cols, rows, tx, ty, div, bias, edge, preserve, img),
+                 f"convolve {kname} {edge} {preserve}")
+
+
+@pytest.mark.parametrize("w,h", [(7, 5), (257, 131)])
+def test_color_matrix(ctx, oracle, w, h):
+    img = random_rgba(w, h, 10)
+    rng = np.random.default_rng(11)
+    m = (rng.random(20) * 2 - 0.7).astype(np.float32)
+    cases = [("matrix", m), ("saturate", [0.3]), ("saturate", [1.7]), ("hueRotate", [90.0]), ("hueRotate", [-37.5]),
+             ("luminanceToAlpha", [])]
+    for kind, params in cases:
+        got = _run(ctx, img, lambda f, l: f.color_matrix(kind, params, l))
+        assert_exact(got, oracle.color_matrix(kind, params, img), f"color_matrix {kind}")
+
+
+@pytest.mark.parametrize("w,h", [(7, 5), (257, 131)])
+def test_component_transfer(ctx, oracle, w, h):
+    import resvg_b200 as rb
+
+    img = random_rgba(w, h, 12)
+    specs = [
+        dict(kind="table", values=[0.0, 1.0, 0.2, 0.9]),
+        dict(kind="discrete", values=[0.1, 0.5, 0.9]),
+        dict(kind="linear", slope=1.5, intercept=-0.2),
+        dict(kind="gamma", amplitude=0.9, exponent=2.2, offset=0.05),
+        dict(kind="identity"),
+        dict(kind="table", values=[]),
+        dict(kind="table", values=[0.7]),
+    ]
+    for i in range(len(specs)):
+        four = [specs[(i + j) % len(specs)] for j in range(4)]
+        got = _run(ctx, img, lambda f, l: f.component_transfer([rb.make_transfer(**s) for s in four], l))
+        want = oracle.component_transfer([oracle.make_transfer(**s) for s in four], img)
+        assert_exact(got, want, f"component_transfer {i}")
+
+
+@pytest.mark.parametrize("w,h", [(7, 5), (257, 131), (1029, 67)])
+@pytest.mark.parametrize("k", [(0.5, 0.5, 0.5, 0.0), (1.0, 0.0, 0.0, 0.0), (0.0, 1.0, -1.0, 0.1), (0.0, 0.0, 0.0, 0.0),
+                               (-0.3, 0.2, 1.4, -0.05)])
+def test_composite_arithmetic(ctx, oracle, w, h, k):
+    import resvg_b200 as rb
+
+    a, b = random_premul(w, h, 13, sparse=True), random_premul(w, h, 14, sparse=True)
+    la, lb, ld = ctx.layer_from(a), ctx.layer_from(b), ctx.layer(w, h)
+    rb.filters.arithmetic(*k, la, lb, ld)
+    assert_exact(ld.download(), oracle.arithmetic(*k, a, b), f"arithmetic {k}")
+
+
+@pytest.mark.parametrize("w,h", [(7, 5), (257, 131)])
+@pytest.mark.parametrize("xch,ych,scale,s", [(0, 1, 20.0, 1.0), (3, 3, 50.0, 1.5), (2, 0, -7.3, 0.5)])
+def test_displacement_map(ctx, oracle, w, h, xch, ych, scale, s):
+    import resvg_b200 as rb
+
+    src, mp = random_premul(w, h, 15), random_rgba(w, h, 16)
+    ls, lm, ld = ctx.layer_from(src), ctx.layer_from(mp), ctx.layer(w, h)
+    rb.filters.displacement_map(xch, ych, scale, s * scale, s * scale, ls, lm, ld)
+    assert_exact(ld.download(), oracle.displacement_map(xch, ych, scale, s * scale, s * scale, src, mp), "displacement")
+
+
+LIGHTS = {
+    "distant": dict(kind="distant", azimuth=45.0, elevation=60.0),
+    "distant_flat": dict(kind="distant", azimuth=200.0, elevation=5.0),
+    "point": dict(kind="point", x=40.0, y=30.0, z=25.0),
+    "spot": dict(kind="spot", x=10.0, y=10.0, z=40.0, points_at=(60.0, 50.0, 0.0), specular_exponent=8.0),
+    "spot_cone": dict(kind="spot", x=10.0, y=10.0, z=40.0, points_at=(60.0, 50.0, 0.0), specular_exponent=1.0,
+                      limiting_cone_angle=25.0),
+}
+
+
+@pytest.mark.parametrize("w,h", [(2, 9), (3, 3), (64, 48), (257, 131)])
+@pytest.mark.parametrize("lname", list(LIGHTS))
+def test_diffuse_lighting(ctx, oracle, w, h, lname):
+    import resvg_b200 as rb
+
+    src = smooth_alpha(w, h, 17)
+    ls, ld = ctx.layer_from(src), ctx.layer(w, h)
+    rb.filters.diffuse_lighting(5.0, 1.2, (255, 200, 90), rb.make_light(**LIGHTS[lname]), ls, ld)
+    want = oracle.diffuse_lighting(5.0, 1.2, (255, 200, 90), oracle.make_light(**LIGHTS[lname]), src)
+    if lname == "spot":  # device powf for the cone exponent: <= 1/255
+        assert_within(ld.download(), want, 1, f"diffuse {lname}")
+    else:
+        assert_exact(ld.download(), want, f"diffuse {lname}")
+
+
+@pytest.mark.parametrize("w,h", [(3, 3), (64, 48), (257, 131)])
+@pytest.mark.parametrize("lname", list(LIGHTS))
+@pytest.mark.parametrize("exponent", [1.0, 20.0])
+def test_specular_lighting(ctx, oracle, w, h, lname, exponent):
+    import resvg_b200 as rb
+
+    src = smooth_alpha(w, h, 18)
+    ls, ld = ctx.layer_from(src), ctx.layer(w, h)
+    rb.filters.specular_lighting(5.0, 1.1, exponent, (255, 255, 255), rb.make_light(**LIGHTS[lname]), ls, ld)
+    want = oracle.specular_lighting(5.0, 1.1, exponent, (255, 255, 255), oracle.make_light(**LIGHTS[lname]), src)
+    if exponent != 1.0 or lname == "spot":  # powf on the device: tolerance 1/255 (north star, highp float stages)
+        assert_within(ld.download(), want, 1, f"specular {lname} {exponent}")
+    else:
+        assert_exact(ld.download(), want, f"specular {lname} {exponent}")
+
+
+@pytest.mark.parametrize("w,h", [(7, 5), (200, 120)])
+@pytest.mark.parametrize("bf,octaves,fractal,stitch", [
+    ((0.05, 0.05), 1, False, False), ((0.01, 0.03), 4, True, False), ((0.05, 0.02), 3, False, True),
+    ((0.1, 0.1), 2, True, True), ((0.0, 0.04), 2, True, True)])
+def test_turbulence(ctx, oracle, w, h, bf, octaves, fractal, stitch):
+    import resvg_b200 as rb
+
+    ld = ctx.layer(w, h)
+    args = (6.0 - 1.5, 6.0 - 0.25, 1.5, 1.5, bf[0], bf[1], octaves, 7, stitch, fractal)
+    rb.filters.turbulence(*args, ld)
+    assert_exact(ld.download(), oracle.turbulence(*args, w, h), f"turbulence {bf} {octaves} {fractal} {stitch}")
+    for seed in (0, -5, 12345):
+        args2 = (0.0, 0.0, 1.0, 2.0, bf[0], bf[1], octaves, seed, stitch, fractal)
+        rb.filters.turbulence(*args2, ld)
+        assert_exact(ld.download(), oracle.turbulence(*args2, w, h), f"turbulence seed {seed}")
+
+
+def test_filter_chain_matches_oracle(ctx, oracle):
+    """C3 chain at a size the oracle finishes in seconds."""
+    import resvg_b200 as rb
+
+    f = rb.filters
+    w, h = 512, 384
+    img = random_premul(w, h, 19, sparse=True)
+    l = ctx.layer_from(img)
+    f.into_linear_rgb(l)
+    f.box_blur(8.0, 8.0, l)
+    f.morphology("dilate", 3.0, 3.0, l)
+    sharpen = [0, -1, 0, -1, 5, -1, 0, -1, 0]
+    f.convolve_matrix(sharpen, 3, 3, 1, 1, 1.0, 0.0, "duplicate", False, l)
+    t = ctx.layer(w, h)
+    f.turbulence(0.0, 0.0, 1.0, 1.0, 0.02, 0.02, 3, 7, False, True, t)
+    f.multiply_alpha(t)
+    c = ctx.layer(w, h)
+    f.arithmetic(0.5, 0.5, 0.5, 0.0, l, t, c)
+    lit = ctx.layer(w, h)
+    f.diffuse_lighting(5.0, 1.0, (255, 255, 255), rb.make_light(kind="distant", azimuth=45.0, elevation=60.0), c, lit)
+    f.box_blur(64.0, 64.0, lit)
+    f.into_srgb(lit)
+    got = lit.download()
+
+    o = oracle
+    x = o.into_linear_rgb(img)
+    x = o.box_blur(8.0, 8.0, x)
+    x = o.morphology("dilate", 3.0, 3.0, x)
+    x = o.convolve_matrix(sharpen, 3, 3, 1, 1, 1.0, 0.0, "duplicate", False, x)
+    tt = o.multiply_alpha(o.turbulence(0.0, 0.0, 1.0, 1.0, 0.02, 0.02, 3, 7, False, True, w, h))
+    cc = o.arithmetic(0.5, 0.5, 0.5, 0.0, x, tt)
+    ll = o.diffuse_lighting(5.0, 1.0, (255, 255, 255), o.make_light(kind="distant", azimuth=45.0, elevation=60.0), cc)
+    ll = o.into_srgb(o.box_blur(64.0, 64.0, ll))
+    assert_exact(got, ll, "filter chain")
