@@ -133,6 +133,79 @@ int rb_filter_turbulence(rb_layer *dest, double offset_x, double offset_y, doubl
                          double base_frequency_x, double base_frequency_y, uint32_t num_octaves,
                          int32_t seed, int stitch_tiles, int fractal_noise);
 
+/* ------------------------------------------------------------------------------------------------
+ * Rasteriser — the tiny-skia calls made by crates/resvg/src/{path,render,clip,mask}.rs
+ * ---------------------------------------------------------------------------------------------- */
+/* path verbs (tiny_skia_path::PathVerb) */
+enum { RB_VERB_MOVE = 0, RB_VERB_LINE = 1, RB_VERB_QUAD = 2, RB_VERB_CUBIC = 3, RB_VERB_CLOSE = 4 };
+/* tiny_skia::BlendMode in declaration order (render.rs:145-164 maps usvg::BlendMode onto it) */
+enum {
+    RB_BLEND_CLEAR = 0, RB_BLEND_SOURCE, RB_BLEND_DESTINATION, RB_BLEND_SOURCE_OVER, RB_BLEND_DESTINATION_OVER,
+    RB_BLEND_SOURCE_IN, RB_BLEND_DESTINATION_IN, RB_BLEND_SOURCE_OUT, RB_BLEND_DESTINATION_OUT,
+    RB_BLEND_SOURCE_ATOP, RB_BLEND_DESTINATION_ATOP, RB_BLEND_XOR, RB_BLEND_PLUS, RB_BLEND_MODULATE,
+    RB_BLEND_SCREEN, RB_BLEND_OVERLAY, RB_BLEND_DARKEN, RB_BLEND_LIGHTEN, RB_BLEND_COLOR_DODGE,
+    RB_BLEND_COLOR_BURN, RB_BLEND_HARD_LIGHT, RB_BLEND_SOFT_LIGHT, RB_BLEND_DIFFERENCE, RB_BLEND_EXCLUSION,
+    RB_BLEND_MULTIPLY, RB_BLEND_HUE, RB_BLEND_SATURATION, RB_BLEND_COLOR, RB_BLEND_LUMINOSITY
+};
+enum { RB_SHADER_SOLID = 0, RB_SHADER_LINEAR = 1, RB_SHADER_RADIAL = 2, RB_SHADER_PATTERN = 3 };
+enum { RB_SPREAD_PAD = 0, RB_SPREAD_REFLECT = 1, RB_SPREAD_REPEAT = 2 };
+enum { RB_QUALITY_NEAREST = 0, RB_QUALITY_BILINEAR = 1, RB_QUALITY_BICUBIC = 2 };
+enum { RB_FILL_WINDING = 0, RB_FILL_EVENODD = 1 };
+
+/* Transform layout everywhere: ts[6] = {sx, ky, kx, sy, tx, ty} = tiny_skia::Transform::from_row order, i.e.
+ * resvg_transform {a,b,c,d,e,f} (crates/c-api/lib.rs:67-81). NULL means identity. */
+
+/* tiny_skia::Paint as path.rs builds it (path.rs:45-71, 118-177): shader + blend mode + anti_alias. */
+typedef struct {
+    int32_t shader;                 /* RB_SHADER_* */
+    float color[4];                 /* solid: non-premultiplied r,g,b,a = Color::from_rgba8 (c / 255) */
+    float x0, y0, r0, x1, y1, r1;   /* LinearGradient::new(start,end) / RadialGradient::new(start,r0,end,r1) */
+    int32_t n_stops;
+    const float *stops;             /* n_stops x {offset, r, g, b, a}, non-premultiplied */
+    int32_t spread;                 /* RB_SPREAD_* */
+    float ts[6];                    /* gradient.transform() / pattern transform */
+    const rb_layer *pattern;        /* Pattern::new(pixmap, spread, quality, opacity, ts) */
+    int32_t quality;
+    float opacity;
+    int32_t blend_mode;             /* RB_BLEND_* */
+    int32_t anti_alias;
+    int32_t force_hq;
+} rb_paint;
+
+/* PixmapMut::fill_path(path, paint, rule, transform, None) — path.rs:73.  Host: transform, chop, clip, edge
+ * build; device: coverage + shade + blend.  Equivalent to a one-draw batch. */
+int rb_fill_path(rb_layer *layer, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
+                 const rb_paint *paint, int32_t fill_rule, const float ts[6]);
+
+/* Batched drawing: many fill_path calls against one layer executed by ONE tile-binned kernel launch that
+ * keeps every destination tile on chip across all the draws that touch it (painter's order preserved). */
+typedef struct rb_batch rb_batch;
+int rb_batch_begin(rb_layer *target, rb_batch **out);
+int rb_batch_fill_path(rb_batch *batch, const uint8_t *verbs, int32_t n_verbs, const float *points,
+                       int32_t n_points, const rb_paint *paint, int32_t fill_rule, const float ts[6]);
+/* Builds edges on host threads (n_threads <= 0: all cores), uploads, launches.  The batch can be re-submitted. */
+int rb_batch_submit(rb_batch *batch, int32_t n_threads);
+void rb_batch_destroy(rb_batch *batch);
+/* statistics of the last submit: [0] draws, [1] line edges, [2] (draw,tile) pairs, [3] non-empty tiles,
+ * [4] bytes uploaded, [5] host build microseconds */
+int rb_batch_stats(rb_batch *batch, uint64_t stats[6]);
+
+/* PixmapMut::draw_pixmap(x, y, src, PixmapPaint{opacity, blend_mode, Nearest}, identity, None) —
+ * render.rs:133, clip.rs:88, filter/mod.rs (9 call sites): the layer composite. */
+int rb_draw_layer(rb_layer *dst, const rb_layer *src, int32_t x, int32_t y, float opacity, int32_t blend_mode);
+
+/* tiny_skia::Mask — clip.rs:25-27, mask.rs:17-45 */
+int rb_mask_create(rb_ctx *ctx, uint32_t width, uint32_t height, rb_mask **out); /* Mask::new (zeroed) */
+void rb_mask_destroy(rb_mask *mask);
+int rb_mask_download(rb_mask *mask, uint8_t *host);
+int rb_mask_upload(rb_mask *mask, const uint8_t *host);
+int rb_mask_from_layer(rb_mask *mask, const rb_layer *layer, int32_t luminance); /* Mask::from_pixmap */
+int rb_mask_invert(rb_mask *mask);                                                /* Mask::invert */
+int rb_layer_apply_mask(rb_layer *layer, const rb_mask *mask);                    /* Pixmap::apply_mask */
+/* Mask::fill_path(path, rule, anti_alias, transform) */
+int rb_mask_fill_path(rb_mask *mask, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
+                      int32_t fill_rule, int32_t anti_alias, const float ts[6]);
+
 #ifdef __cplusplus
 }
 #endif

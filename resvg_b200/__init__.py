@@ -5,7 +5,8 @@ The compute lives in ``libresvg_b200.so`` (hand-written sm_100a CUDA behind the 
 raises at import time if the library is missing — there is no CPU fallback.
 """
 from . import _ffi  # noqa: F401  (raises ImportError if the CUDA library is not built)
-from .api import (Context, Layer, PinnedBuffer, ResvgB200Error, filters, make_light,  # noqa: F401
-                  make_transfer)
+from .api import (Batch, Context, Layer, Mask, PinnedBuffer, ResvgB200Error, apply_mask,  # noqa: F401
+                  draw_layer, fill_path, filters, make_light, make_paint, make_transfer)
 
-__all__ = ["Context", "Layer", "PinnedBuffer", "ResvgB200Error", "filters", "make_light", "make_transfer"]
+__all__ = ["Batch", "Context", "Layer", "Mask", "PinnedBuffer", "ResvgB200Error", "apply_mask", "draw_layer",
+           "fill_path", "filters", "make_light", "make_paint", "make_transfer"]

@@ -54,6 +54,18 @@ class LightSource(C.Structure):
 
 _vp, _i, _u32, _f, _d, _u8 = C.c_void_p, C.c_int, C.c_uint32, C.c_float, C.c_double, C.c_uint8
 
+
+class Paint(C.Structure):
+    """rb_paint (include/resvg_b200.h)."""
+    _fields_ = [
+        ("shader", C.c_int32), ("color", C.c_float * 4),
+        ("x0", _f), ("y0", _f), ("r0", _f), ("x1", _f), ("y1", _f), ("r1", _f),
+        ("n_stops", C.c_int32), ("stops", f32p), ("spread", C.c_int32), ("ts", C.c_float * 6),
+        ("pattern", _vp), ("quality", C.c_int32), ("opacity", _f),
+        ("blend_mode", C.c_int32), ("anti_alias", C.c_int32), ("force_hq", C.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/resvg_b200.h one to one
 SIGNATURES = {
     "rb_ctx_create": (_i, [_i, c_void_pp]),
@@ -91,6 +103,21 @@ SIGNATURES = {
     "rb_filter_diffuse_lighting": (_i, [_vp, _vp, _f, _f, _u8, _u8, _u8, C.POINTER(LightSource)]),
     "rb_filter_specular_lighting": (_i, [_vp, _vp, _f, _f, _f, _u8, _u8, _u8, C.POINTER(LightSource)]),
     "rb_filter_turbulence": (_i, [_vp, _d, _d, _d, _d, _d, _d, _u32, C.c_int32, _i, _i]),
+    "rb_fill_path": (_i, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.POINTER(Paint), C.c_int32, f32p]),
+    "rb_batch_begin": (_i, [_vp, c_void_pp]),
+    "rb_batch_fill_path": (_i, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.POINTER(Paint), C.c_int32, f32p]),
+    "rb_batch_submit": (_i, [_vp, C.c_int32]),
+    "rb_batch_destroy": (None, [_vp]),
+    "rb_batch_stats": (_i, [_vp, C.POINTER(C.c_uint64)]),
+    "rb_draw_layer": (_i, [_vp, _vp, C.c_int32, C.c_int32, _f, C.c_int32]),
+    "rb_mask_create": (_i, [_vp, _u32, _u32, c_void_pp]),
+    "rb_mask_destroy": (None, [_vp]),
+    "rb_mask_download": (_i, [_vp, _vp]),
+    "rb_mask_upload": (_i, [_vp, _vp]),
+    "rb_mask_from_layer": (_i, [_vp, _vp, C.c_int32]),
+    "rb_mask_invert": (_i, [_vp]),
+    "rb_layer_apply_mask": (_i, [_vp, _vp]),
+    "rb_mask_fill_path": (_i, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32, f32p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _ffi
-from ._ffi import LightSource, TransferFn, lib
+from ._ffi import LightSource, Paint, TransferFn, lib
 
 
 class ResvgB200Error(RuntimeError):
@@ -267,3 +267,162 @@ class filters:
                                      num_octaves, seed, 1 if stitch_tiles else 0, 1 if fractal_noise else 0),
             "turbulence",
         )
+
+
+# --------------------------------------------------------------------------------------------------
+# rasteriser: tiny-skia Paint / fill_path / draw_pixmap / Mask over the C ABI
+# --------------------------------------------------------------------------------------------------
+BLEND = {n: i for i, n in enumerate([
+    "clear", "source", "destination", "source_over", "destination_over", "source_in", "destination_in",
+    "source_out", "destination_out", "source_atop", "destination_atop", "xor", "plus", "modulate", "screen",
+    "overlay", "darken", "lighten", "color_dodge", "color_burn", "hard_light", "soft_light", "difference",
+    "exclusion", "multiply", "hue", "saturation", "color", "luminosity"])}
+SPREAD = {"pad": 0, "reflect": 1, "repeat": 2}
+QUALITY = {"nearest": 0, "bilinear": 1, "bicubic": 2}
+IDENTITY = (1.0, 0.0, 0.0, 1.0, 0.0, 0.0)
+
+
+def _ts(ts):
+    return (C.c_float * 6)(*[float(v) for v in ts])
+
+
+def make_paint(spec, blend="source_over", anti_alias=True):
+    """Build an rb_paint from a plain dict:
+    {"kind": "solid", "color": (r,g,b,a)} | {"kind": "linear"|"radial", x0,y0,[r0],x1,y1,[r1], stops, spread, ts}
+    | {"kind": "pattern", "layer": Layer, spread, quality, opacity, ts}."""
+    p = Paint()
+    p.blend_mode = BLEND[blend] if isinstance(blend, str) else int(blend)
+    p.anti_alias = 1 if anti_alias else 0
+    p.ts[:] = IDENTITY
+    kind = spec["kind"]
+    if kind == "solid":
+        p.shader = 0
+        p.color[:] = [float(np.float32(c)) for c in spec["color"]]
+    elif kind in ("linear", "radial"):
+        p.shader = 1 if kind == "linear" else 2
+        p.x0, p.y0, p.x1, p.y1 = spec["x0"], spec["y0"], spec["x1"], spec["y1"]
+        p.r0, p.r1 = spec.get("r0", 0.0), spec.get("r1", 0.0)
+        stops = np.ascontiguousarray(spec["stops"], dtype=np.float32).reshape(-1, 5)
+        p.n_stops = stops.shape[0]
+        p.stops = stops.ctypes.data_as(_ffi.f32p)
+        p.spread = SPREAD[spec.get("spread", "pad")]
+        p.ts[:] = spec.get("ts", IDENTITY)
+        p._keep = stops
+    elif kind == "pattern":
+        p.shader = 3
+        p.pattern = spec["layer"]._h
+        p.spread = SPREAD[spec.get("spread", "repeat")]
+        p.quality = QUALITY[spec.get("quality", "bicubic")]
+        p.opacity = spec.get("opacity", 1.0)
+        p.ts[:] = spec.get("ts", IDENTITY)
+        p._keep = spec["layer"]
+    else:
+        raise ValueError(kind)
+    return p
+
+
+def _path(verbs, pts):
+    v = np.ascontiguousarray(verbs, dtype=np.uint8)
+    p = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 2)
+    return v, p
+
+
+def fill_path(layer: Layer, verbs, pts, paint: Paint, rule="nonzero", ts=IDENTITY):
+    """PixmapMut::fill_path(path, paint, rule, transform, None)."""
+    v, p = _path(verbs, pts)
+    layer.ctx.check(lib.rb_fill_path(layer._h, v.ctypes.data, len(v), p.ctypes.data, len(p), C.byref(paint),
+                                     1 if rule == "evenodd" else 0, _ts(ts)), "fill_path")
+
+
+class Batch:
+    """Many fill_path calls against one layer, executed by one tile-binned kernel launch."""
+
+    def __init__(self, layer: Layer):
+        h = C.c_void_p()
+        layer.ctx.check(lib.rb_batch_begin(layer._h, C.byref(h)), "batch_begin")
+        self._h = h
+        self.layer = layer
+        self._keep = []
+
+    def fill_path(self, verbs, pts, paint: Paint, rule="nonzero", ts=IDENTITY):
+        v, p = _path(verbs, pts)
+        self.layer.ctx.check(lib.rb_batch_fill_path(self._h, v.ctypes.data, len(v), p.ctypes.data, len(p),
+                                                    C.byref(paint), 1 if rule == "evenodd" else 0, _ts(ts)),
+                             "batch_fill_path")
+        if getattr(paint, "_keep", None) is not None and paint.shader == 3:
+            self._keep.append(paint._keep)
+
+    def submit(self, n_threads: int = 0):
+        self.layer.ctx.check(lib.rb_batch_submit(self._h, n_threads), "batch_submit")
+
+    def stats(self):
+        s = (C.c_uint64 * 6)()
+        lib.rb_batch_stats(self._h, s)
+        return dict(draws=s[0], edges=s[1], pairs=s[2], tiles=s[3], upload_bytes=s[4], host_us=s[5])
+
+    def close(self):
+        if self._h:
+            lib.rb_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def draw_layer(dst: Layer, src: Layer, x=0, y=0, opacity=1.0, blend="source_over"):
+    """PixmapMut::draw_pixmap(x, y, src, PixmapPaint{opacity, blend_mode, Nearest}, identity, None)."""
+    b = BLEND[blend] if isinstance(blend, str) else int(blend)
+    dst.ctx.check(lib.rb_draw_layer(dst._h, src._h, int(x), int(y), float(opacity), b), "draw_layer")
+
+
+class Mask:
+    """tiny_skia::Mask on the device."""
+
+    def __init__(self, ctx: Context, width: int, height: int):
+        h = C.c_void_p()
+        ctx.check(lib.rb_mask_create(ctx._h, width, height, C.byref(h)), "mask_create")
+        self._h, self.ctx, self.width, self.height = h, ctx, width, height
+
+    @staticmethod
+    def from_layer(layer: Layer, kind="alpha") -> "Mask":
+        m = Mask(layer.ctx, layer.width, layer.height)
+        layer.ctx.check(lib.rb_mask_from_layer(m._h, layer._h, 1 if kind == "luminance" else 0), "mask_from_layer")
+        return m
+
+    def invert(self):
+        self.ctx.check(lib.rb_mask_invert(self._h), "mask_invert")
+
+    def fill_path(self, verbs, pts, rule="nonzero", anti_alias=True, ts=IDENTITY):
+        v, p = _path(verbs, pts)
+        self.ctx.check(lib.rb_mask_fill_path(self._h, v.ctypes.data, len(v), p.ctypes.data, len(p),
+                                             1 if rule == "evenodd" else 0, 1 if anti_alias else 0, _ts(ts)),
+                       "mask_fill_path")
+
+    def download(self) -> np.ndarray:
+        out = np.empty((self.height, self.width), dtype=np.uint8)
+        self.ctx.check(lib.rb_mask_download(self._h, out.ctypes.data), "mask_download")
+        return out
+
+    def upload(self, m: np.ndarray):
+        a = np.ascontiguousarray(m, dtype=np.uint8)
+        self.ctx.check(lib.rb_mask_upload(self._h, a.ctypes.data), "mask_upload")
+        self.ctx.synchronize()
+
+    def close(self):
+        if self._h:
+            lib.rb_mask_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def apply_mask(layer: Layer, mask: Mask):
+    """Pixmap::apply_mask(mask)."""
+    layer.ctx.check(lib.rb_layer_apply_mask(layer._h, mask._h), "apply_mask")

@@ -1,0 +1,286 @@
+"""GPU parity of the rasteriser: CUDA tile kernel vs the CPU oracle (oracle/raster.c) on the same seeded paths.
+
+Bars: coverage, the u16 "lowp" pipeline, masks and the non-AA path are bit-exact; the f32 "highp" pipeline
+(two-point-conical gradients, highp-only blend modes, layer composites, pattern sampling) is within 1/255.
+"""
+import numpy as np
+import pytest
+
+from tests import oracle_raster as R
+from tests.pathgen import SplitMix64, random_paint_spec, random_path, random_stops
+from tests.util import assert_exact, assert_within, random_premul
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_fill(ctx, base, verbs, pts, spec, rule="nonzero", ts=R.IDENTITY, blend="source_over", aa=True):
+    import resvg_b200 as rb
+
+    l = ctx.layer_from(base)
+    rb.fill_path(l, verbs, pts, rb.make_paint(spec, blend, aa), rule, ts)
+    return l.download()
+
+
+def _cpu_fill(base, verbs, pts, spec, rule="nonzero", ts=R.IDENTITY, blend="source_over", aa=True):
+    px = base.copy()
+    R.fill_path(px, verbs, pts, R.make_paint(spec, blend, aa), rule, ts)
+    return px
+
+
+SOLID = {"kind": "solid", "color": (0.2, 0.6, 0.9, 0.7)}
+OPAQUE = {"kind": "solid", "color": (1.0, 0.5, 0.0, 1.0)}
+
+
+@pytest.mark.parametrize("w,h", [(64, 16), (300, 300), (257, 131), (70, 500), (1, 1), (5, 3)])
+@pytest.mark.parametrize("rule", ["nonzero", "evenodd"])
+@pytest.mark.parametrize("aa", [True, False])
+def test_coverage_random_paths(ctx, w, h, rule, aa):
+    """Coverage through an opaque solid on a transparent layer: alpha == coverage, so this pins scan conversion."""
+    rng = SplitMix64(1000 + w * 7 + h)
+    base = np.zeros((h, w, 4), np.uint8)
+    for i in range(12):
+        r = rng.log_uniform(2, max(w, h))
+        verbs, pts = random_path(rng, rng.uniform(0, w), rng.uniform(0, h), r)
+        got = _gpu_fill(ctx, base, verbs, pts, OPAQUE, rule, aa=aa)
+        want = _cpu_fill(base, verbs, pts, OPAQUE, rule, aa=aa)
+        assert_exact(got, want, f"path {i} {w}x{h} {rule} aa={aa}")
+
+
+def test_coverage_structured_shapes(ctx):
+    """Axis-aligned rectangles, shared vertical edges, thin slivers and self-retracing contours: the cases where
+    spans abut inside one pixel (the 63-vs-64 rule) and where edges tie."""
+    w, h = 200, 120
+    base = np.zeros((h, w, 4), np.uint8)
+    M, L, Z = 0, 1, 4
+
+    def rect(x, y, rw, rh, ccw=False):
+        p = [(x, y), (x + rw, y), (x + rw, y + rh), (x, y + rh)]
+        if ccw:
+            p = p[::-1]
+        return [M, L, L, L, Z], p
+
+    shapes = []
+    for (x, y, rw, rh) in [(10.25, 10.25, 50.5, 30.5), (0.75, 0.75, 198.5, 118.5), (20, 20, 0.1, 60), (30.5, 7.3, 90.2, 0.2)]:
+        shapes.append(rect(x, y, rw, rh))
+    # two rectangles sharing an edge inside a pixel, same and opposite orientation
+    for ccw in (False, True):
+        v1, p1 = rect(10.3, 40.6, 40.33, 30.1)
+        v2, p2 = rect(50.63, 35.2, 33.3, 50.7, ccw)
+        shapes.append((v1 + v2, p1 + p2))
+    # stroke-like outline: outer rect + inner rect reversed + excursions through the corner
+    v1, p1 = rect(100.75, 20.75, 80.5, 60.5)
+    v2, p2 = rect(102.25, 22.25, 77.5, 57.5, True)
+    shapes.append((v1 + v2, p1 + p2))
+    # retraced spike (zero-area excursion) inside a filled region
+    shapes.append(([M, L, L, L, L, L, Z], [(20.2, 80.1), (90.7, 80.1), (90.7, 110.9), (55.3, 110.9), (55.3, 85.0), (55.3, 110.9), (20.2, 110.9)][:7]))
+    for i, (v, p) in enumerate(shapes):
+        for rule in ("nonzero", "evenodd"):
+            for ts in (R.IDENTITY, (1.5, 0, 0, 1.5, 0.37, 0.21), (0.8, 0.3, -0.2, 1.1, 20, 5)):
+                got = _gpu_fill(ctx, base, v, p, OPAQUE, rule, ts)
+                want = _cpu_fill(base, v, p, OPAQUE, rule, ts)
+                assert_exact(got, want, f"shape {i} {rule} {ts}")
+
+
+def test_paths_leaving_the_canvas_are_clipped_identically(ctx):
+    w, h = 160, 96
+    rng = SplitMix64(77)
+    base = random_premul(w, h, 5)
+    for i in range(40):
+        cx, cy = rng.uniform(-40, w + 40), rng.uniform(-40, h + 40)
+        verbs, pts = random_path(rng, cx, cy, rng.log_uniform(20, 300))
+        rule = "evenodd" if i % 2 else "nonzero"
+        got = _gpu_fill(ctx, base, verbs, pts, SOLID, rule, aa=(i % 5 != 0))
+        want = _cpu_fill(base, verbs, pts, SOLID, rule, aa=(i % 5 != 0))
+        assert_exact(got, want, f"clipped path {i}")
+
+
+LOWP_BLENDS = ["clear", "source", "source_over", "destination_over", "source_in", "destination_in", "source_out",
+               "destination_out", "source_atop", "destination_atop", "xor", "plus", "modulate", "screen", "overlay",
+               "darken", "lighten", "hard_light", "difference", "exclusion", "multiply"]
+HIGHP_BLENDS = ["color_dodge", "color_burn", "soft_light", "hue", "saturation", "color", "luminosity"]
+
+
+@pytest.mark.parametrize("blend", LOWP_BLENDS)
+def test_lowp_blend_modes_exact(ctx, blend):
+    w, h = 96, 64
+    rng = SplitMix64(31)
+    base = random_premul(w, h, 6)
+    for i, spec in enumerate([SOLID, OPAQUE, {"kind": "linear", "x0": 5, "y0": 5, "x1": 90, "y1": 50,
+                                              "stops": random_stops(rng, 4), "spread": "reflect"}]):
+        verbs, pts = random_path(rng, 48, 32, 40)
+        got = _gpu_fill(ctx, base, verbs, pts, spec, blend=blend)
+        want = _cpu_fill(base, verbs, pts, spec, blend=blend)
+        assert_exact(got, want, f"{blend} paint {i}")
+
+
+@pytest.mark.parametrize("blend", HIGHP_BLENDS)
+def test_highp_blend_modes_within_one(ctx, blend):
+    w, h = 96, 64
+    rng = SplitMix64(32)
+    base = random_premul(w, h, 7)
+    verbs, pts = random_path(rng, 48, 32, 40)
+    for spec in (SOLID, OPAQUE):
+        got = _gpu_fill(ctx, base, verbs, pts, spec, blend=blend)
+        want = _cpu_fill(base, verbs, pts, spec, blend=blend)
+        assert_within(got, want, 1, blend)  # f32 pipeline: tolerance 1/255 (north star)
+
+
+def test_gradients(ctx):
+    w, h = 200, 150
+    rng = SplitMix64(33)
+    base = random_premul(w, h, 8)
+    for i in range(40):
+        cx, cy, r = rng.uniform(20, 180), rng.uniform(20, 130), rng.log_uniform(10, 120)
+        verbs, pts = random_path(rng, cx, cy, r)
+        spec = random_paint_spec(rng, cx, cy, r, solid=0.0, linear=0.5)
+        if i % 3 == 0:
+            spec["ts"] = (0.9, 0.2, -0.3, 1.2, 3.0, -2.0)
+        if i % 4 == 0:
+            for s in spec["stops"]:
+                s[4] = 1.0
+        ts = (1.0, 0, 0, 1.0, 0, 0) if i % 2 else (1.3, 0.1, -0.1, 0.9, 4, 2)
+        got = _gpu_fill(ctx, base, verbs, pts, spec, ts=ts)
+        want = _cpu_fill(base, verbs, pts, spec, ts=ts)
+        if spec["kind"] == "linear" or (abs(spec["x0"] - spec["x1"]) < 1e-9 and abs(spec["y0"] - spec["y1"]) < 1e-9):
+            assert_exact(got, want, f"gradient {i} {spec['kind']}")  # lowp pipeline
+        else:
+            assert_within(got, want, 1, f"gradient {i} two-point conical")  # highp f32
+
+
+def test_simple_radial_and_focal_variants(ctx):
+    w, h = 128, 128
+    base = np.zeros((h, w, 4), np.uint8)
+    verbs, pts = [0, 1, 1, 1, 4], [(4, 4), (124, 4), (124, 124), (4, 124)]
+    stops = [[0, 1, 1, 1, 1], [0.5, 0.2, 0.8, 0.3, 0.6], [1, 0, 0, 0, 1]]
+    cases = [
+        dict(x0=64, y0=64, r0=0, x1=64, y1=64, r1=50),      # simple radial: lowp, exact
+        dict(x0=64, y0=64, r0=10, x1=64, y1=64, r1=50),     # concentric with fr
+        dict(x0=50, y0=60, r0=0, x1=64, y1=64, r1=50),      # focal inside
+        dict(x0=64, y0=14, r0=0, x1=64, y1=64, r1=50),      # focal on circle
+        dict(x0=20, y0=20, r0=5, x1=90, y1=90, r1=30),      # general two point
+        dict(x0=20, y0=64, r0=20, x1=100, y1=64, r1=20),    # strip
+    ]
+    for i, c in enumerate(cases):
+        for spread in ("pad", "reflect", "repeat"):
+            spec = dict(kind="radial", stops=stops, spread=spread, **c)
+            got = _gpu_fill(ctx, base, verbs, pts, spec)
+            want = _cpu_fill(base, verbs, pts, spec)
+            if i == 0:
+                assert_exact(got, want, f"radial {i} {spread}")
+            else:
+                assert_within(got, want, 1, f"radial {i} {spread}")
+
+
+def test_batch_painters_order_matches_sequential_oracle(ctx):
+    """200 overlapping translucent paths in one batch (one kernel launch) == 200 sequential oracle fills."""
+    import resvg_b200 as rb
+
+    w, h = 333, 217
+    rng = SplitMix64(34)
+    want = np.zeros((h, w, 4), np.uint8)
+    l = ctx.layer(w, h)
+    b = rb.Batch(l)
+    blends = ["source_over", "source_over", "source_over", "multiply", "screen", "xor", "plus", "darken"]
+    for i in range(200):
+        cx, cy, r = rng.uniform(0, w), rng.uniform(0, h), rng.log_uniform(4, 150)
+        verbs, pts = random_path(rng, cx, cy, r)
+        spec = random_paint_spec(rng, cx, cy, r, solid=0.6, linear=0.4)
+        rule = "evenodd" if rng.u() < 0.5 else "nonzero"
+        aa = rng.u() < 0.9
+        blend = blends[rng.randint(0, len(blends) - 1)]
+        b.fill_path(verbs, pts, rb.make_paint(spec, blend, aa), rule)
+        R.fill_path(want, verbs, pts, R.make_paint(spec, blend, aa), rule)
+    b.submit()
+    st = b.stats()
+    assert st["draws"] >= 190 and st["edges"] > 1000
+    assert_exact(l.download(), want, "batch of 200")
+    assert ctx.launch_count > 0
+
+
+def test_large_canvas_draw_tiler_split(ctx):
+    """A canvas wider than 8191 px is drawn as DrawTiler tiles (8191 + rest); paths across the seam must match."""
+    import resvg_b200 as rb
+
+    w, h = 8300, 40
+    rng = SplitMix64(35)
+    want = np.zeros((h, w, 4), np.uint8)
+    l = ctx.layer(w, h)
+    b = rb.Batch(l)
+    for i in range(30):
+        cx = rng.uniform(8100, 8290) if i % 2 else rng.uniform(0, w)
+        verbs, pts = random_path(rng, cx, rng.uniform(0, h), rng.log_uniform(5, 120))
+        spec = random_paint_spec(rng, cx, 20, 60, solid=0.7, linear=0.3)
+        b.fill_path(verbs, pts, rb.make_paint(spec), "nonzero")
+        R.fill_path(want, verbs, pts, R.make_paint(spec), "nonzero")
+    b.submit()
+    assert_exact(l.download(), want, "draw tiler seam")
+
+
+@pytest.mark.parametrize("blend", LOWP_BLENDS + HIGHP_BLENDS)
+def test_draw_layer_all_blend_modes(ctx, blend):
+    import resvg_b200 as rb
+
+    dst, src = random_premul(150, 90, 9, sparse=True), random_premul(100, 70, 10, sparse=True)
+    for (x, y, op) in [(0, 0, 1.0), (20, 10, 0.5), (-30, -20, 0.85), (100, 60, 1.0)]:
+        ld, ls = ctx.layer_from(dst), ctx.layer_from(src)
+        rb.draw_layer(ld, ls, x, y, op, blend)
+        want = dst.copy()
+        R.draw_pixmap(want, x, y, src, op, blend)
+        # layer composites run the f32 pipeline; identical operation order gives identical bytes except where
+        # division/sqrt sequences differ (dodge/burn/soft-light/non-separable): tolerance 1/255 there
+        if blend in HIGHP_BLENDS:
+            assert_within(ld.download(), want, 1, f"draw_layer {blend} {x},{y},{op}")
+        else:
+            assert_exact(ld.download(), want, f"draw_layer {blend} {x},{y},{op}")
+
+
+def test_masks(ctx):
+    import resvg_b200 as rb
+
+    w, h = 131, 77
+    px = random_premul(w, h, 11, sparse=True)
+    l = ctx.layer_from(px)
+    for kind in ("alpha", "luminance"):
+        m = rb.Mask.from_layer(l, kind)
+        assert_exact(m.download(), R.mask_from_pixmap(px, kind), f"mask_from_pixmap {kind}")
+    m = rb.Mask.from_layer(l, "luminance")
+    m.invert()
+    want_m = R.mask_from_pixmap(px, "luminance")
+    R.mask_invert(want_m)
+    assert_exact(m.download(), want_m, "invert")
+    other = random_premul(w, h, 12)
+    lo = ctx.layer_from(other)
+    rb.apply_mask(lo, m)
+    want = other.copy()
+    R.apply_mask(want, want_m)
+    assert_exact(lo.download(), want, "apply_mask")
+    # Mask::fill_path
+    rng = SplitMix64(36)
+    gm = rb.Mask(ctx, w, h)
+    cm = np.zeros((h, w), np.uint8)
+    for i in range(6):
+        verbs, pts = random_path(rng, rng.uniform(0, w), rng.uniform(0, h), rng.log_uniform(10, 80))
+        gm.fill_path(verbs, pts, "evenodd" if i % 2 else "nonzero", i % 3 != 0, (1.2, 0, 0, 1.2, 1.5, 0.5))
+        R.mask_fill_path(cm, verbs, pts, "evenodd" if i % 2 else "nonzero", i % 3 != 0, (1.2, 0, 0, 1.2, 1.5, 0.5))
+    assert_exact(gm.download(), cm, "mask fill_path")
+
+
+def test_pattern_fill(ctx):
+    import resvg_b200 as rb
+
+    w, h = 120, 90
+    tile = random_premul(17, 13, 13)
+    lt = ctx.layer_from(tile)
+    base = random_premul(w, h, 14)
+    rng = SplitMix64(37)
+    verbs, pts = random_path(rng, 60, 45, 50)
+    for quality in ("nearest", "bilinear", "bicubic"):
+        for spread in ("repeat", "pad", "reflect"):
+            for ts in ((1, 0, 0, 1, 3, 4), (1.7, 0.2, -0.1, 1.4, 5.5, 2.25)):
+                gspec = dict(kind="pattern", layer=lt, spread=spread, quality=quality, opacity=0.8, ts=ts)
+                cspec = dict(kind="pattern", pixmap=tile, spread=spread, quality=quality, opacity=0.8, ts=ts)
+                l = ctx.layer_from(base)
+                rb.fill_path(l, verbs, pts, rb.make_paint(gspec))
+                want = base.copy()
+                R.fill_path(want, verbs, pts, R.make_paint(cspec))
+                assert_within(l.download(), want, 1, f"pattern {quality} {spread} {ts}")
