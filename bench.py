@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py — Mpixels/s rendered on the BASELINE.json workloads (resvg pixel hot path on B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload paths8k]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload `paths8k` (BASELINE.json configs[1]): one 8192x8192 canvas, 100k random cubic/quad/line
+paths, non-zero + even-odd, solid + linear + radial paints.  A *step* is one full render of the scene (clear + every
+path).  With N GPUs every rank renders its own scene (document-parallel, weak scaling, no collective on the data
+path); `value` = N * canvas Mpx / max-over-ranks device time.
+
+Printed JSON keys follow the driver's contract; see DESIGN.md §Measurement for how each number is obtained.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (width, height, n_paths, seed)
+    "paths8k": (8192, 8192, 100_000, 0x5EED0002),
+    "paths2k": (2048, 2048, 6_000, 0x5EED0002),  # smoke-sized variant for quick checks (not a bench line)
+}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_lib():
+    from tests import oracle_raster as R  # the CPU checker: only cpu_baseline / --impl reference use it
+    return R
+
+
+def cpu_render_sample(R, scene, n_sample, canvas=None):
+    """Oracle (CPU restatement of the reference path) over the first n_sample paths; returns seconds."""
+    from resvg_b200 import scenes
+    sub = scenes.subset(scene, n_sample)
+    paints = scenes.to_paint_array(sub, R.Paint)
+    w, h = scene["width"], scene["height"]
+    px = canvas if canvas is not None else np.zeros((h, w, 4), np.uint8)
+    t0 = time.perf_counter()
+    R.lib.orc_fill_paths(px.ctypes.data, w, h, sub["n_paths"], sub["verb_off"].ctypes.data, sub["pt_off"].ctypes.data,
+                         sub["verbs"].ctypes.data, sub["pts"].ctypes.data, C.addressof(paints), sub["rules"].ctypes.data,
+                         R.ts_arr(R.IDENTITY))
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path (oracle restatement; Rust cannot be built here) on all host cores."""
+    if rank != 0:
+        return
+    from resvg_b200 import scenes
+    R = oracle_lib()
+    W, H, n_paths, seed = WORKLOADS[args.workload]
+    cores = min(os.cpu_count() or 1, 32)
+    n_sample = max(200, min(n_paths, int(args.cpu_sample)))
+    scs = [scenes.paths_scene(W, H, n_paths, seed + t) for t in range(min(cores, 4))]
+    canvases = [np.zeros((H, W, 4), np.uint8) for _ in range(cores)]
+
+    def step():
+        ths = [threading.Thread(target=cpu_render_sample, args=(R, scs[t % len(scs)], n_sample, canvases[t])) for t in range(cores)]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        return time.perf_counter() - t0
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    times = [step() for _ in range(max(1, min(args.steps, 3)))]
+    dt = statistics.mean(times)
+    mpx = cores * (W * H / 1e6) * (n_sample / n_paths)
+    v = mpx / dt
+    sample = f"{cores} threads x first {n_sample} of {n_paths} paths of the {W}x{H} scene per step (full canvas); value scaled by {n_sample}/{n_paths}"
+    print(json.dumps({
+        "impl": "reference", "metric": "Mpixels/s rendered", "value": v, "unit": "Mpx/s", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16 fixed point + f32", "data": "synthetic",
+        "config": {"workload": args.workload, "canvas": [W, H], "paths": n_paths},
+        "cpu_baseline": {"value": v, "unit": "Mpx/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="paths8k", choices=list(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=12000, help="paths in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA GPU: resvg_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import resvg_b200 as rb
+    from resvg_b200 import _ffi, scenes
+
+    W, H, n_paths, seed = WORKLOADS[args.workload]
+    canvas_mpx = W * H / 1e6
+    ctx = rb.Context(local_rank)
+    scene = scenes.paths_scene(W, H, n_paths, seed + rank)  # every rank renders its own document
+    paints = scenes.to_paint_array(scene, _ffi.Paint)
+    scene["paints"] = paints
+
+    layer = ctx.layer(W, H)
+    batch = rb.Batch(layer)
+    batch.fill_paths(scene)
+    batch.prepare(0)  # host edge build + binning + H2D: inputs are resident in HBM before the timed region
+    st = batch.stats()
+    ctx.synchronize()
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ctx.synchronize()
+
+    def step():
+        layer.fill(0, 0, 0, 0)
+        batch.run()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        step()
+    ms_total = ctx.timer_end()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = ctx.launch_count - launches0
+    ms_step = ms_total / args.steps
+
+    # dominant kernel alone (k_raster_tiles), for the roofline
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        batch.run()
+    ms_kernel = ctx.timer_end() / args.steps
+    layer.fill(0, 0, 0, 0)
+    n_rmw, n_store = batch.run_counting()
+    alg_bytes = 8 * n_rmw + 4 * n_store + 16 * st["edges"]
+
+    # end to end through the C ABI with host buffers: record + edge build + H2D + kernel + D2H, every step
+    pinned = rb.PinnedBuffer(W * H * 4)
+    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    e2e_h2d = 0
+
+    def e2e_step():
+        nonlocal e2e_h2d
+        layer.fill(0, 0, 0, 0)
+        b = rb.Batch(layer)
+        b.fill_paths(scene)
+        b.submit(0)
+        e2e_h2d = b.stats()["upload_bytes"]
+        b.close()
+        layer.download_ptr(pinned.array.ctypes.data)  # synchronises
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ctx.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+
+    t = torch.tensor([ms_step, ms_kernel, e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step, ms_kernel, e2e_s = [float(x) for x in t.tolist()]
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(args.workload, {}).get("k_raster_tiles_dram_bytes")
+        except Exception:
+            pass
+        out = {
+            "metric": "Mpixels/s rendered", "value": world * canvas_mpx / (ms_step * 1e-3), "unit": "Mpx/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/u16 fixed point + f32", "data": "synthetic",
+            "config": {"workload": args.workload, "canvas": [W, H], "paths": n_paths, "fills_only": True,
+                       "sharding": "one scene (document) per GPU, no collective",
+                       "l2": "inputs (256 MiB canvas + %.0f MiB edges/bins) exceed the 126 MB L2" % (st["upload_bytes"] / 2**20),
+                       "draws": st["draws"], "line_edges": st["edges"], "draw_tile_pairs": st["pairs"], "tiles": st["tiles"]},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_raster_tiles", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes": alg_bytes, "kernel_ms": ms_kernel,
+                         "model": "8 B per blended px + 4 B per opaque-stored px + 16 B per line edge"},
+            "e2e": {"value": world * canvas_mpx / e2e_s, "unit": "Mpx/s", "h2d_bytes_per_step": int(e2e_h2d),
+                    "d2h_bytes_per_step": W * H * 4, "ms_per_step": e2e_s * 1e3, "host_build_ms": st["host_us"] / 1e3,
+                    "steps": e2e_steps},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            R = oracle_lib()
+            n_sample = max(200, min(n_paths, int(args.cpu_sample)))
+            dt = cpu_render_sample(R, scene, n_sample)
+            out["cpu_baseline"] = {
+                "value": canvas_mpx / (dt * n_paths / n_sample), "unit": "Mpx/s", "cores": 1, "kind": "port",
+                "sample": f"first {n_sample} of {n_paths} paths of the same scene on the full canvas, {dt:.2f} s; "
+                          f"value = canvas Mpx / (t * {n_paths}/{n_sample}); oracle restatement of the resvg/tiny-skia CPU path"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -183,8 +183,20 @@ typedef struct rb_batch rb_batch;
 int rb_batch_begin(rb_layer *target, rb_batch **out);
 int rb_batch_fill_path(rb_batch *batch, const uint8_t *verbs, int32_t n_verbs, const float *points,
                        int32_t n_points, const rb_paint *paint, int32_t fill_rule, const float ts[6]);
-/* Builds edges on host threads (n_threads <= 0: all cores), uploads, launches.  The batch can be re-submitted. */
+/* Bulk form of rb_batch_fill_path: n_paths paths in packed arrays; verb_off / point_off hold n_paths + 1 prefix
+ * offsets into verbs / points (points counted in x,y pairs); one paint and one fill rule per path. */
+int rb_batch_fill_paths(rb_batch *batch, int32_t n_paths, const uint32_t *verb_off, const uint32_t *point_off,
+                        const uint8_t *verbs, const float *points, const rb_paint *paints, const uint8_t *fill_rules,
+                        const float ts[6]);
+/* Builds edges on host threads (n_threads <= 0: all cores), uploads, launches, frees the device copy. */
 int rb_batch_submit(rb_batch *batch, int32_t n_threads);
+/* Split form: prepare = host edge build + binning + upload (device copy stays resident in the batch);
+ * run = the kernel launch only, repeatable (e.g. after clearing the layer). */
+int rb_batch_prepare(rb_batch *batch, int32_t n_threads);
+int rb_batch_run(rb_batch *batch);
+/* rb_batch_run with pixel counters (roofline accounting): out[0] = pixels read-modify-written, out[1] = pixels
+ * stored without a read (full coverage + opaque solid paint).  Synchronises the stream. */
+int rb_batch_run_counting(rb_batch *batch, uint64_t out[2]);
 void rb_batch_destroy(rb_batch *batch);
 /* statistics of the last submit: [0] draws, [1] line edges, [2] (draw,tile) pairs, [3] non-empty tiles,
  * [4] bytes uploaded, [5] host build microseconds */
@@ -205,6 +217,14 @@ int rb_layer_apply_mask(rb_layer *layer, const rb_mask *mask);                  
 /* Mask::fill_path(path, rule, anti_alias, transform) */
 int rb_mask_fill_path(rb_mask *mask, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
                       int32_t fill_rule, int32_t anti_alias, const float ts[6]);
+
+/* Host-only introspection (no device work; used by the CPU test-suite): the line edges {x, dx, first_y,
+ * last_y, winding} and blitter bounds geom = {sect.x, sect.y, sect.w, sect.h, shift, start_y, stop_y} the device
+ * would receive for one path on a cw x ch tile.  Returns the edge count, 0 if nothing is drawn, < 0 on error. */
+int rb_debug_build_edges(const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
+                         int32_t anti_alias, int32_t cw, int32_t ch, const float ts[6], int32_t *out_edges,
+                         int32_t *out_meta /* optional: {prev segment index | -1, inserts-before flag} per edge */,
+                         int32_t max_edges, int32_t geom[7]);
 
 #ifdef __cplusplus
 }

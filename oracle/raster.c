@@ -2244,3 +2244,14 @@ int orc_path_coverage(uint8_t *cov, uint32_t w, uint32_t h, const uint8_t *verbs
     memset(cov, 0, (size_t)w * h);
     return coverage_common(cov, w, h, verbs, n_verbs, pts, n_pts, fill_rule, anti_alias, ts, 0);
 }
+
+/* Painter's-order loop over packed paths: the CPU baseline / checker for a whole scene in one call. */
+int orc_fill_paths(uint8_t *px, uint32_t w, uint32_t h, int32_t n_paths, const uint32_t *verb_off, const uint32_t *pt_off,
+                   const uint8_t *verbs, const float *pts, const orc_paint *paints, const uint8_t *rules, const float ts[6])
+{
+    int drawn = 0;
+    for (int32_t i = 0; i < n_paths; i++)
+        drawn += orc_fill_path(px, w, h, verbs + verb_off[i], (int32_t)(verb_off[i + 1] - verb_off[i]),
+                               pts + 2 * (size_t)pt_off[i], (int32_t)(pt_off[i + 1] - pt_off[i]), &paints[i], rules[i], ts);
+    return drawn;
+}

@@ -60,6 +60,9 @@ typedef struct {
 /* PixmapMut::fill_path(path, paint, rule, transform, None) */
 int orc_fill_path(uint8_t *px, uint32_t w, uint32_t h, const uint8_t *verbs, int32_t n_verbs, const float *pts,
                   int32_t n_pts, const orc_paint *paint, int32_t fill_rule, const float ts[6]);
+/* n_paths fill_path calls in painter's order over packed arrays (verb_off / pt_off: n_paths + 1 offsets) */
+int orc_fill_paths(uint8_t *px, uint32_t w, uint32_t h, int32_t n_paths, const uint32_t *verb_off, const uint32_t *pt_off,
+                   const uint8_t *verbs, const float *pts, const orc_paint *paints, const uint8_t *rules, const float ts[6]);
 /* PixmapMut::fill_rect(rect, paint, transform, None) */
 int orc_fill_rect(uint8_t *px, uint32_t w, uint32_t h, float x, float y, float rw, float rh, const orc_paint *paint,
                   const float ts[6]);

@@ -106,7 +106,11 @@ SIGNATURES = {
     "rb_fill_path": (_i, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.POINTER(Paint), C.c_int32, f32p]),
     "rb_batch_begin": (_i, [_vp, c_void_pp]),
     "rb_batch_fill_path": (_i, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.POINTER(Paint), C.c_int32, f32p]),
+    "rb_batch_fill_paths": (_i, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, f32p]),
     "rb_batch_submit": (_i, [_vp, C.c_int32]),
+    "rb_batch_prepare": (_i, [_vp, C.c_int32]),
+    "rb_batch_run": (_i, [_vp]),
+    "rb_batch_run_counting": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "rb_batch_destroy": (None, [_vp]),
     "rb_batch_stats": (_i, [_vp, C.POINTER(C.c_uint64)]),
     "rb_draw_layer": (_i, [_vp, _vp, C.c_int32, C.c_int32, _f, C.c_int32]),
@@ -118,6 +122,8 @@ SIGNATURES = {
     "rb_mask_invert": (_i, [_vp]),
     "rb_layer_apply_mask": (_i, [_vp, _vp]),
     "rb_mask_fill_path": (_i, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32, f32p]),
+    "rb_debug_build_edges": (_i, [_vp, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, f32p, _vp, _vp,
+                                  C.c_int32, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -352,8 +352,30 @@ class Batch:
         if getattr(paint, "_keep", None) is not None and paint.shader == 3:
             self._keep.append(paint._keep)
 
+    def fill_paths(self, scene, ts=IDENTITY):
+        """Bulk recording from packed arrays: scene has verb_off, pt_off (uint32, n+1), verbs (uint8), pts (float32
+        (m, 2)), paints (ctypes array of rb_paint), rules (uint8)."""
+        n = len(scene["rules"])
+        self.layer.ctx.check(
+            lib.rb_batch_fill_paths(self._h, n, scene["verb_off"].ctypes.data, scene["pt_off"].ctypes.data,
+                                    scene["verbs"].ctypes.data, scene["pts"].ctypes.data,
+                                    C.addressof(scene["paints"]), scene["rules"].ctypes.data, _ts(ts)),
+            "batch_fill_paths")
+
     def submit(self, n_threads: int = 0):
         self.layer.ctx.check(lib.rb_batch_submit(self._h, n_threads), "batch_submit")
+
+    def prepare(self, n_threads: int = 0):
+        self.layer.ctx.check(lib.rb_batch_prepare(self._h, n_threads), "batch_prepare")
+
+    def run(self):
+        self.layer.ctx.check(lib.rb_batch_run(self._h), "batch_run")
+
+    def run_counting(self):
+        """One run with the pixel counters on → (pixels blended read-modify-write, pixels stored write-only)."""
+        out = (C.c_uint64 * 2)()
+        self.layer.ctx.check(lib.rb_batch_run_counting(self._h, out), "batch_run_counting")
+        return int(out[0]), int(out[1])
 
     def stats(self):
         s = (C.c_uint64 * 6)()

@@ -39,7 +39,11 @@ constexpr int ROW_POS = TW * 4;   // sub-sample positions per row
 constexpr int CNT_ROWS = TH * 4;
 constexpr int CNT_BYTES = CNT_ROWS * ROW_POS * 4;
 
-struct DevEdge { int32_t x, dx; uint32_t ypack; int32_t winding; }; // ypack = first_y | last_y << 16
+// ypack = first_y | last_y << 16.  meta: bit 0 = upward edge (winding -1), bit 1 = continuation segment of a
+// curve, bit 2 = insert_new_edges places it before equal-x active edges, bits 4.. = index of the previous
+// segment of the same curve (valid when bit 1 is set).
+struct DevEdge { int32_t x, dx; uint32_t ypack; uint32_t meta; };
+__host__ __device__ __forceinline__ int edge_winding(uint32_t meta) { return (meta & 1u) ? -1 : 1; }
 struct DevDraw {
     uint32_t edge_off, edge_cnt;
     int32_t ox, oy;         // DrawTiler tile origin inside the layer
@@ -414,29 +418,65 @@ __device__ __forceinline__ uint32_t blend_pixel(const DevPaint &P, const DevStop
 // =================================================================================================
 
 // Rare path: crossings of both directions share one sub-sample position strictly inside a fully covered
-// pixel on the 4th sub-row, so whether the span breaks there depends on the walker's edge order
-// (ascending FDot16 x, then sorted-list order).  One lane replays just that position.
+// pixel on the 4th sub-row, so whether the span breaks there depends on the scanline walker's list order
+// (tiny-skia scan/path.rs walk_edges).  One lane replays just that position.  The walker's order is: ascending
+// FDot16 x; among equal x, edges that were already active keep the order they had on the previous scanline
+// (i.e. ascending previous x — a curve's next segment inherits its curve's slot), and an edge that becomes
+// active on this scanline goes after them, or before them when insert_new_edges' forward scan stops at them
+// (DevEdge meta bit 2).  Two new edges keep their sorted order.
+__device__ __forceinline__ int edge_x_at(const DevEdge &E, int y)
+{
+    return (int)((uint32_t)E.x + (uint32_t)(y - (int)(E.ypack & 0xffffu)) * (uint32_t)E.dx);
+}
+
+// Walker list order of two edges that cross sub-scanline y.  kind: 0 = was active on y-1 ("survivor", keyed by
+// its previous x), 1 = new edge placed after equal-x survivors, 2 = new edge placed before them.
+__device__ bool walker_less(const DevEdge *__restrict__ edges, const DevEdge &A, uint32_t ia, const DevEdge &B, uint32_t ib, int y)
+{
+    for (int depth = 0; depth < 2; depth++) {
+        const int xa = edge_x_at(A, y), xb = edge_x_at(B, y);
+        if (xa != xb) return xa < xb;
+        const int fya = (int)(A.ypack & 0xffffu), fyb = (int)(B.ypack & 0xffffu);
+        int ka, kb, pa = 0, pb = 0;
+        if (y > fya) { ka = 0; pa = (int)((uint32_t)xa - (uint32_t)A.dx); }
+        else if (A.meta & 2u) { const DevEdge P = edges[A.meta >> 4]; ka = 0; pa = edge_x_at(P, (int)(P.ypack >> 16)); }
+        else ka = (A.meta & 4u) ? 2 : 1;
+        if (y > fyb) { kb = 0; pb = (int)((uint32_t)xb - (uint32_t)B.dx); }
+        else if (B.meta & 2u) { const DevEdge P = edges[B.meta >> 4]; kb = 0; pb = edge_x_at(P, (int)(P.ypack >> 16)); }
+        else kb = (B.meta & 4u) ? 2 : 1;
+        if (ka == 0 && kb == 0) {
+            if (pa != pb) return pa < pb;
+            // coincident lines: their order was fixed on the scanline where the later one joined the list
+            if (y > fya && y > fyb) { y = max(fya, fyb); continue; }
+            return ia < ib;
+        }
+        if (ka == 0) return kb == 1;
+        if (kb == 0) return ka == 2;
+        return ia < ib;
+    }
+    return ia < ib;
+}
+
 __device__ bool exact_span_break(const DevEdge *__restrict__ edges, uint32_t n, int y, int target_r, int w_before)
 {
-    int xs[16], ws[16];
-    uint32_t idx[16];
+    uint32_t c[12];
     int cnt = 0;
     for (uint32_t e = 0; e < n; e++) {
-        DevEdge E = edges[e];
+        const DevEdge E = edges[e];
         int fy = (int)(E.ypack & 0xffffu), ly = (int)(E.ypack >> 16);
         if (fy > y) break; // sorted by first_y
         if (ly < y) continue;
-        int x = (int)((uint32_t)E.x + (uint32_t)(y - fy) * (uint32_t)E.dx);
+        int x = edge_x_at(E, y);
         int r = (int)((uint32_t)x + 0x8000u) >> 16;
         if (r != target_r) continue;
-        if (cnt == 16) return true;
+        if (cnt == 12) return true;
         int j = cnt++;
-        while (j > 0 && (xs[j - 1] > x)) { xs[j] = xs[j - 1]; ws[j] = ws[j - 1]; idx[j] = idx[j - 1]; j--; }
-        xs[j] = x; ws[j] = E.winding; idx[j] = e;
+        while (j > 0 && walker_less(edges, E, e, edges[c[j - 1]], c[j - 1], y)) { c[j] = c[j - 1]; j--; }
+        c[j] = e;
     }
     int w = w_before;
     for (int i = 0; i < cnt; i++) {
-        w += ws[i];
+        w += edge_winding(edges[c[i]].meta);
         if (w == 0) return true;
     }
     return false;
@@ -447,7 +487,7 @@ __global__ void __launch_bounds__(RT_THREADS)
 k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint32_t *__restrict__ tile_ids,
                const uint32_t *__restrict__ tile_off, const uint32_t *__restrict__ tile_draws,
                const DevDraw *__restrict__ draws, const DevEdge *__restrict__ edges, const DevPaint *__restrict__ paints,
-               const DevStop *__restrict__ stops)
+               const DevStop *__restrict__ stops, unsigned long long *__restrict__ px_stats)
 {
     extern __shared__ int cnt[]; // [CNT_ROWS][ROW_POS]: low 16 bits = downward (+1) crossings, high 16 = upward
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -472,6 +512,7 @@ k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint3
     for (int i = tid; i < CNT_ROWS * ROW_POS / 4; i += RT_THREADS) reinterpret_cast<int4 *>(cnt)[i] = make_int4(0, 0, 0, 0);
     __syncthreads();
 
+    uint32_t n_partial = 0, n_full = 0; // pixels blended / pixels stored at full coverage (for the roofline model)
     const uint32_t d_begin = tile_off[tile], d_end = tile_off[tile + 1];
     for (uint32_t di = d_begin; di < d_end; di++) {
         const DevDraw D = draws[tile_draws[di]];
@@ -493,7 +534,7 @@ k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint3
             const int ys = max(fy, sub_top), ye = min(ly, sub_bot - 1);
             if (ys > ye) continue;
             uint32_t x = (uint32_t)E.x + (uint32_t)(ys - fy) * (uint32_t)E.dx;
-            const int inc = E.winding > 0 ? 1 : 0x10000;
+            const int inc = (E.meta & 1u) ? 0x10000 : 1;
             int *row = cnt + (ys - row0) * ROW_POS;
             for (int y = ys; y <= ye; y++) {
                 int r = (int)(x + 0x8000u) >> 16;
@@ -615,13 +656,24 @@ k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint3
 #pragma unroll
                     for (int j = 0; j < 2; j++) {
                         uint32_t c = cov[i][j];
-                        if (c) dst[i][j] = blend_pixel(P, stops, dst[i][j], c, tlx + 2 * lane + j, tly + wid + 8 * i);
+                        if (c) {
+                            dst[i][j] = blend_pixel(P, stops, dst[i][j], c, tlx + 2 * lane + j, tly + wid + 8 * i);
+                            if (c == 255 && P.has_memset) n_full++; else n_partial++;
+                        }
                     }
             }
         }
         __syncthreads(); // histogram rows are zero again before the next draw scatters into them
     }
 
+    if (px_stats) {
+        n_partial = __reduce_add_sync(0xffffffffu, n_partial);
+        n_full = __reduce_add_sync(0xffffffffu, n_full);
+        if (lane == 0) {
+            atomicAdd(px_stats, (unsigned long long)n_partial);
+            atomicAdd(px_stats + 1, (unsigned long long)n_full);
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         int gy = Y0 + wid + 8 * i, gx = X0 + 2 * lane;
@@ -659,6 +711,15 @@ struct rb_batch {
     rb_mask *mask = nullptr;
     std::vector<RecordedDraw> recs;
     uint64_t stats[6] = {0, 0, 0, 0, 0, 0};
+    // device-resident form produced by rb_batch_prepare
+    uint8_t *dev = nullptr;
+    const DevEdge *d_edges = nullptr;
+    const DevDraw *d_draws = nullptr;
+    const DevPaint *d_paints = nullptr;
+    const DevStop *d_stops = nullptr;
+    const uint32_t *d_toff = nullptr, *d_tdraws = nullptr, *d_tids = nullptr;
+    unsigned n_tile_ids = 0;
+    int tiles_x = 0;
 };
 
 static constexpr int kMaxDim = 8191; // tiny-skia DrawTiler::MAX_DIMENSIONS
@@ -764,7 +825,22 @@ extern "C" int rb_batch_fill_path(rb_batch *b, const uint8_t *verbs, int32_t n_v
     return batch_add(b, verbs, n_verbs, points, n_points, paint, fill_rule, ts);
 }
 
-extern "C" void rb_batch_destroy(rb_batch *b) { delete b; }
+static void batch_release(rb_batch *b)
+{
+    if (b->dev) {
+        rb_ctx *ctx = b->mask ? b->mask->ctx : b->layer->ctx;
+        cudaFreeAsync(b->dev, ctx->stream);
+        b->dev = nullptr;
+    }
+    b->n_tile_ids = 0;
+}
+
+extern "C" void rb_batch_destroy(rb_batch *b)
+{
+    if (!b) return;
+    batch_release(b);
+    delete b;
+}
 
 extern "C" int rb_batch_stats(rb_batch *b, uint64_t stats[6])
 {
@@ -773,13 +849,13 @@ extern "C" int rb_batch_stats(rb_batch *b, uint64_t stats[6])
     return RB_OK;
 }
 
-extern "C" int rb_batch_submit(rb_batch *b, int32_t n_threads)
+extern "C" int rb_batch_prepare(rb_batch *b, int32_t n_threads)
 {
     if (!b) return RB_ERR_INVALID;
+    batch_release(b);
     const bool mask_target = b->mask != nullptr;
     rb_ctx *ctx = mask_target ? b->mask->ctx : b->layer->ctx;
     const int W = (int)(mask_target ? b->mask->w : b->layer->w), H = (int)(mask_target ? b->mask->h : b->layer->h);
-    void *target = mask_target ? (void *)b->mask->d : (void *)b->layer->d;
     memset(b->stats, 0, sizeof(b->stats));
     if (b->recs.empty()) return RB_OK;
     auto t0 = std::chrono::steady_clock::now();
@@ -820,7 +896,8 @@ extern "C" int rb_batch_submit(rb_batch *b, int32_t n_threads)
                 DevEdge d;
                 d.x = e.x; d.dx = e.dx;
                 d.ypack = ((uint32_t)e.first_y & 0xffffu) | ((uint32_t)e.last_y << 16);
-                d.winding = e.winding;
+                d.meta = (e.winding < 0 ? 1u : 0u) | (e.prev >= 0 ? 2u : 0u) | (e.before ? 4u : 0u)
+                         | (e.prev >= 0 ? ((uint32_t)e.prev << 4) : 0u);
                 edges[eo++] = d;
             }
             for (auto p : o.paints) { p.stop_off += sbase; paints.push_back(p); }
@@ -884,6 +961,50 @@ extern "C" int rb_batch_submit(rb_batch *b, int32_t n_threads)
     uint32_t *d_tids = (uint32_t *)p;     RB_CUDA(ctx, up(tile_ids.data(), tile_ids.size() * 4, b_tids));
     // pageable sources: the runtime has staged the data by the time cudaMemcpyAsync returns
 
+    b->dev = dev;
+    b->d_edges = d_edges; b->d_draws = d_draws; b->d_paints = d_paints; b->d_stops = d_stops;
+    b->d_toff = d_toff; b->d_tdraws = d_tdraws; b->d_tids = d_tids;
+    b->n_tile_ids = (unsigned)tile_ids.size();
+    b->tiles_x = tiles_x;
+    b->stats[0] = draws.size();
+    b->stats[1] = edges.size();
+    b->stats[2] = n_pairs;
+    b->stats[3] = tile_ids.size();
+    b->stats[4] = total;
+    b->stats[5] = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+    return RB_OK;
+}
+
+static int batch_run(rb_batch *b, unsigned long long *px_stats);
+extern "C" int rb_batch_run(rb_batch *b) { return batch_run(b, nullptr); }
+
+// Runs the batch once with the coverage counters on: out[0] = pixels read-modify-written (partial coverage or
+// non-opaque paint), out[1] = pixels stored without reading (full coverage, opaque solid).  Synchronises.
+extern "C" int rb_batch_run_counting(rb_batch *b, uint64_t out[2])
+{
+    if (!b || !out) return RB_ERR_INVALID;
+    rb_ctx *ctx = b->mask ? b->mask->ctx : b->layer->ctx;
+    unsigned long long *d = nullptr;
+    RB_CUDA(ctx, cudaMallocAsync((void **)&d, 16, ctx->stream));
+    RB_CUDA(ctx, cudaMemsetAsync(d, 0, 16, ctx->stream));
+    int st = batch_run(b, d);
+    unsigned long long h[2] = {0, 0};
+    RB_CUDA(ctx, cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RB_CUDA(ctx, cudaFreeAsync(d, ctx->stream));
+    out[0] = h[0];
+    out[1] = h[1];
+    return st;
+}
+
+static int batch_run(rb_batch *b, unsigned long long *px_stats)
+{
+    if (!b) return RB_ERR_INVALID;
+    if (!b->dev || b->n_tile_ids == 0) return RB_OK; // nothing to draw
+    const bool mask_target = b->mask != nullptr;
+    rb_ctx *ctx = mask_target ? b->mask->ctx : b->layer->ctx;
+    const int W = (int)(mask_target ? b->mask->w : b->layer->w), H = (int)(mask_target ? b->mask->h : b->layer->h);
+    void *target = mask_target ? (void *)b->mask->d : (void *)b->layer->d;
     static bool attr_set = false;
     if (!attr_set) {
         RB_CUDA(ctx, cudaFuncSetAttribute(k_raster_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CNT_BYTES));
@@ -891,20 +1012,35 @@ extern "C" int rb_batch_submit(rb_batch *b, int32_t n_threads)
         attr_set = true;
     }
     if (mask_target)
-        k_raster_tiles<true><<<(unsigned)tile_ids.size(), RT_THREADS, CNT_BYTES, ctx->stream>>>(
-            target, W, H, tiles_x, d_tids, d_toff, d_tdraws, d_draws, d_edges, d_paints, d_stops);
+        k_raster_tiles<true><<<b->n_tile_ids, RT_THREADS, CNT_BYTES, ctx->stream>>>(
+            target, W, H, b->tiles_x, b->d_tids, b->d_toff, b->d_tdraws, b->d_draws, b->d_edges, b->d_paints, b->d_stops, px_stats);
     else
-        k_raster_tiles<false><<<(unsigned)tile_ids.size(), RT_THREADS, CNT_BYTES, ctx->stream>>>(
-            target, W, H, tiles_x, d_tids, d_toff, d_tdraws, d_draws, d_edges, d_paints, d_stops);
+        k_raster_tiles<false><<<b->n_tile_ids, RT_THREADS, CNT_BYTES, ctx->stream>>>(
+            target, W, H, b->tiles_x, b->d_tids, b->d_toff, b->d_tdraws, b->d_draws, b->d_edges, b->d_paints, b->d_stops, px_stats);
     RB_LAUNCHED(ctx, "raster_tiles");
-    RB_CUDA(ctx, cudaFreeAsync(dev, ctx->stream));
+    return RB_OK;
+}
 
-    b->stats[0] = draws.size();
-    b->stats[1] = edges.size();
-    b->stats[2] = n_pairs;
-    b->stats[3] = tile_ids.size();
-    b->stats[4] = total;
-    b->stats[5] = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+extern "C" int rb_batch_submit(rb_batch *b, int32_t n_threads)
+{
+    int st = rb_batch_prepare(b, n_threads);
+    if (st == RB_OK) st = rb_batch_run(b);
+    if (b) batch_release(b);
+    return st;
+}
+
+// Bulk recording: n_paths paths in packed arrays (verb_off / point_off have n_paths + 1 entries).
+extern "C" int rb_batch_fill_paths(rb_batch *b, int32_t n_paths, const uint32_t *verb_off, const uint32_t *point_off,
+                                   const uint8_t *verbs, const float *points, const rb_paint *paints,
+                                   const uint8_t *fill_rules, const float ts[6])
+{
+    if (!b || n_paths < 0 || !verb_off || !point_off || !verbs || !points || !paints || !fill_rules) return RB_ERR_INVALID;
+    b->recs.reserve(b->recs.size() + (size_t)n_paths);
+    for (int32_t i = 0; i < n_paths; i++) {
+        int st = rb_batch_fill_path(b, verbs + verb_off[i], (int32_t)(verb_off[i + 1] - verb_off[i]), points + 2 * (size_t)point_off[i],
+                                    (int32_t)(point_off[i + 1] - point_off[i]), &paints[i], fill_rules[i], ts);
+        if (st != RB_OK) return st;
+    }
     return RB_OK;
 }
 
@@ -1068,4 +1204,33 @@ extern "C" int rb_layer_apply_mask(rb_layer *l, const rb_mask *m)
     k_apply_mask<<<rb_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(l->d), m->d, n);
     RB_LAUNCHED(ctx, "apply_mask");
     return RB_OK;
+}
+
+// =================================================================================================
+// host-only introspection used by the CPU test-suite (no device work): the line-edge list and blitter
+// bounds the device would receive for one path on a (cw x ch) DrawTiler tile.
+// =================================================================================================
+extern "C" int rb_debug_build_edges(const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
+                                    int32_t anti_alias, int32_t cw, int32_t ch, const float ts[6], int32_t *out_edges,
+                                    int32_t *out_meta, int32_t max_edges, int32_t geom[7])
+{
+    if (!verbs || !points || !out_edges || !geom) return -1;
+    std::vector<rbh::Pt> pts((size_t)n_points);
+    memcpy(pts.data(), points, sizeof(float) * 2 * (size_t)n_points);
+    if (ts) rbh::map_points(rbh::Xform::from(ts), pts.data(), n_points);
+    std::vector<rbh::Edge> edges;
+    rbh::DrawGeom g;
+    if (!rbh::build_draw(verbs, n_verbs, pts.data(), n_points, anti_alias != 0, cw, ch, edges, &g)) return 0;
+    if ((int64_t)edges.size() > max_edges) return -2;
+    for (size_t i = 0; i < edges.size(); i++) {
+        out_edges[i * 5 + 0] = edges[i].x;
+        out_edges[i * 5 + 1] = edges[i].dx;
+        out_edges[i * 5 + 2] = edges[i].first_y;
+        out_edges[i * 5 + 3] = edges[i].last_y;
+        out_edges[i * 5 + 4] = edges[i].winding;
+        if (out_meta) { out_meta[i * 2 + 0] = edges[i].prev; out_meta[i * 2 + 1] = edges[i].before; }
+    }
+    geom[0] = g.sect.x; geom[1] = g.sect.y; geom[2] = g.sect.w; geom[3] = g.sect.h;
+    geom[4] = g.shift; geom[5] = g.start_y; geom[6] = g.stop_y;
+    return (int)edges.size();
 }

@@ -241,6 +241,9 @@ struct Sink {
         e->first_y = top;
         e->last_y = bot - 1;
         e->winding = winding;
+        e->prev = -1;
+        e->before = 0;
+        e->order = (uint32_t)(out->size() - base);
         return true;
     }
 
@@ -322,6 +325,7 @@ struct Sink {
         b = shl(y1 - y0, 10);
         int32_t qy = shl(y0, 10), qdy = wadd(b, a >> sh), qddy = a >> (sh - 1);
         int32_t lastx = shl(x2, 10), lasty = shl(y2, 10);
+        int32_t link = -1;
         while (count > 0) {
             int32_t nx, ny;
             if (--count > 0) {
@@ -331,7 +335,12 @@ struct Sink {
                 qdy = wadd(qdy, qddy);
             } else { nx = lastx; ny = lasty; }
             Edge e;
-            if (emit(qx >> 10, qy >> 10, nx >> 10, ny >> 10, w, &e)) { out->push_back(e); kinds.push_back(1); }
+            if (emit(qx >> 10, qy >> 10, nx >> 10, ny >> 10, w, &e)) {
+                e.prev = link;
+                link = (int32_t)e.order;
+                out->push_back(e);
+                kinds.push_back(1);
+            }
             qx = nx; qy = ny;
         }
     }
@@ -368,6 +377,7 @@ struct Sink {
         int32_t cy = shl(y0, 10), cdy = wadd(wadd(b, c >> sh), d >> (2 * sh)), cddy = wadd(wmul(2, c), wmul(3, d) >> (sh - 1)),
                 cdddy = wmul(3, d) >> (sh - 1);
         int32_t lastx = shl(x3, 10), lasty = shl(y3, 10);
+        int32_t link = -1;
         while (count < 0) {
             int32_t nx, ny;
             if (++count < 0) {
@@ -380,7 +390,12 @@ struct Sink {
             } else { nx = lastx; ny = lasty; }
             if (ny < cy) ny = cy;
             Edge e;
-            if (emit(cx >> 10, cy >> 10, nx >> 10, ny >> 10, w, &e)) { out->push_back(e); kinds.push_back(1); }
+            if (emit(cx >> 10, cy >> 10, nx >> 10, ny >> 10, w, &e)) {
+                e.prev = link;
+                link = (int32_t)e.order;
+                out->push_back(e);
+                kinds.push_back(1);
+            }
             cx = nx; cy = ny;
         }
     }
@@ -724,6 +739,30 @@ bool build_draw(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, boo
         if (a.first_y != e.first_y) return a.first_y < e.first_y;
         return a.x < e.x;
     });
+    {
+        // `order` values may have gaps (combine_vertical pops), so map through a table sized by the maximum
+        Edge *e = out.data() + sink.base;
+        uint32_t max_order = 0;
+        for (size_t i = 0; i < n; i++) max_order = std::max(max_order, e[i].order);
+        std::vector<int32_t> pos((size_t)max_order + 1, -1);
+        for (size_t i = 0; i < n; i++) pos[e[i].order] = (int32_t)i;
+        for (size_t i = 0; i < n; i++) if (e[i].prev >= 0) e[i].prev = pos[(size_t)e[i].prev];
+        // insert_new_edges batches: the non-continuation edges sharing one first_y, in sorted order
+        size_t i = 0;
+        while (i < n) {
+            size_t j = i;
+            bool have_first = false;
+            int32_t first_x = 0;
+            while (j < n && e[j].first_y == e[i].first_y) {
+                if (e[j].prev < 0) {
+                    if (!have_first) { have_first = true; first_x = e[j].x; }
+                    else if (e[j].x > first_x) e[j].before = 1;
+                }
+                j++;
+            }
+            i = j;
+        }
+    }
     int32_t start_y = shl(ir.y, shift), stop_y = shl(ir.y + ir.h, shift);
     if (!inside) {
         start_y = std::max(start_y, 0);

@@ -40,6 +40,14 @@ struct Edge {
     int32_t first_y; // inclusive
     int32_t last_y;  // inclusive
     int32_t winding; // +1 / -1
+    // Bookkeeping for the one place where the scanline walker's list order is observable (two crossings
+    // with the identical FDot16 x): `prev` = index (within the draw, after sorting) of the previous segment
+    // of the same curve, -1 for an edge that enters the walker through insert_new_edges; `before` = 1 when
+    // insert_new_edges would place it in front of already-active edges with the same x (scan/path.rs:
+    // every new edge but the first of its scanline batch stops at the first active edge with x >= its x).
+    int32_t prev;
+    int32_t before;
+    uint32_t order;  // emission order (internal)
 };
 
 struct IRect { int32_t x, y, w, h; };

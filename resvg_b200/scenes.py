@@ -1,0 +1,162 @@
+"""Synthetic workloads of BASELINE.json, generated deterministically (SplitMix64, counter based so it vectorises).
+
+``paths_scene`` is config C2 of SURVEY.md §8(d): N random closed paths of cubic / quadratic / line segments on a
+W x H canvas, non-zero and even-odd fills, solid / linear / radial paints, 95 % anti-aliased.  The result is a plain
+dict of packed numpy arrays (the layout rb_batch_fill_paths consumes); ``to_rb_paints`` / ``to_paint_array`` turn the
+neutral paint table into a ctypes array of the caller's paint struct (the library's rb_paint, or the CPU checker's
+struct in tests/bench).
+"""
+import ctypes as C
+
+import numpy as np
+
+_GAMMA = np.uint64(0x9E3779B97F4A7C15)
+_M1 = np.uint64(0xBF58476D1CE4E5B9)
+_M2 = np.uint64(0x94D049BB133111EB)
+
+
+def splitmix64_uniform(seed: int, n: int) -> np.ndarray:
+    """First n outputs of SplitMix64(seed) mapped to [0, 1) doubles."""
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + (np.arange(1, n + 1, dtype=np.uint64) * _GAMMA)
+        z = (z ^ (z >> np.uint64(30))) * _M1
+        z = (z ^ (z >> np.uint64(27))) * _M2
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
+
+
+STREAM = 160  # uniforms reserved per path
+
+MOVE, LINE, QUAD, CUBIC, CLOSE = 0, 1, 2, 3, 4
+
+
+def paths_scene(width=8192, height=8192, n_paths=100_000, seed=0x5EED0002, rmin=8.0, rmax=256.0,
+                stroke_share=0.0):
+    """C2 'paths8k'.  stroke_share is reserved for the stroker (paths that are stroked are emitted by
+    ``add_strokes`` once the outline exists); with 0.0 every path is a fill."""
+    u = splitmix64_uniform(seed, n_paths * STREAM).reshape(n_paths, STREAM)
+    cx = u[:, 0] * width
+    cy = u[:, 1] * height
+    radius = np.exp(np.log(rmin) + u[:, 2] * (np.log(rmax) - np.log(rmin)))
+    n_seg = 3 + np.minimum((u[:, 3] * 10).astype(np.int64), 9)  # 3..12
+    evenodd = (u[:, 4] < 0.5).astype(np.uint8)
+    paint_kind = np.where(u[:, 5] < 0.5, 0, np.where(u[:, 5] < 0.8, 1, 2)).astype(np.int32)  # solid/linear/radial
+    anti_alias = (u[:, 6] < 0.95).astype(np.int32)
+
+    # segments: per segment one kind draw + 6 coordinate draws, starting at column 32
+    seg_kind_u = u[:, 32:32 + 12]
+    seg_kind = np.where(seg_kind_u < 0.5, CUBIC, np.where(seg_kind_u < 0.8, QUAD, LINE)).astype(np.uint8)
+    coords = u[:, 48:48 + 12 * 6].reshape(n_paths, 12, 3, 2) * 2.0 - 1.0
+    start = u[:, 44:46] * 2.0 - 1.0
+    seg_valid = np.arange(12)[None, :] < n_seg[:, None]
+    pts_per_seg = np.where(seg_kind == CUBIC, 3, np.where(seg_kind == QUAD, 2, 1)) * seg_valid
+    n_pts = 1 + pts_per_seg.sum(axis=1)
+    n_verbs = 2 + n_seg  # move + segments + close
+    pt_off = np.zeros(n_paths + 1, np.uint32)
+    verb_off = np.zeros(n_paths + 1, np.uint32)
+    pt_off[1:] = np.cumsum(n_pts)
+    verb_off[1:] = np.cumsum(n_verbs)
+
+    verbs = np.empty(int(verb_off[-1]), np.uint8)
+    pts = np.empty((int(pt_off[-1]), 2), np.float32)
+    centre = np.stack([cx, cy], axis=1)
+    # move
+    verbs[verb_off[:-1]] = MOVE
+    pts[pt_off[:-1]] = (centre + radius[:, None] * start).astype(np.float32)
+    verbs[verb_off[1:] - 1] = CLOSE
+    seg_pt_start = 1 + np.concatenate([np.zeros((n_paths, 1), np.int64), np.cumsum(pts_per_seg, axis=1)[:, :-1]], axis=1)
+    for s in range(12):
+        m = seg_valid[:, s]
+        idx = np.nonzero(m)[0]
+        verbs[verb_off[idx] + 1 + s] = seg_kind[idx, s]
+        for k in range(3):
+            mk = pts_per_seg[idx, s] > k
+            ii = idx[mk]
+            dst = pt_off[ii].astype(np.int64) + seg_pt_start[ii, s] + k
+            pts[dst] = (centre[ii] + radius[ii, None] * coords[ii, s, k]).astype(np.float32)
+
+    # paints
+    color = np.empty((n_paths, 4), np.float32)
+    color[:, 0] = np.floor(u[:, 8] * 256) / 255.0
+    color[:, 1] = np.floor(u[:, 9] * 256) / 255.0
+    color[:, 2] = np.floor(u[:, 10] * 256) / 255.0
+    color[:, 3] = (32 + np.floor(u[:, 11] * 224)) / 255.0
+    spread = np.minimum((u[:, 12] * 3).astype(np.int32), 2)
+    n_stops = np.where(paint_kind == 0, 0, 2 + np.minimum((u[:, 13] * 7).astype(np.int64), 6)).astype(np.int32)  # 2..8
+    stop_off = np.zeros(n_paths + 1, np.int64)
+    stop_off[1:] = np.cumsum(n_stops)
+    stops = np.zeros((int(stop_off[-1]), 5), np.float32)
+    su = u[:, 120:160].reshape(n_paths, 8, 5)
+    for k in range(8):
+        m = n_stops > k
+        idx = np.nonzero(m)[0]
+        dst = stop_off[idx] + k
+        ns = n_stops[idx].astype(np.float64)
+        # increasing offsets: (k + jitter) / n
+        stops[dst, 0] = ((k + su[idx, k, 0] * 0.999) / ns).astype(np.float32)
+        stops[dst, 1] = np.floor(su[idx, k, 1] * 256) / 255.0
+        stops[dst, 2] = np.floor(su[idx, k, 2] * 256) / 255.0
+        stops[dst, 3] = np.floor(su[idx, k, 3] * 256) / 255.0
+        stops[dst, 4] = (32 + np.floor(su[idx, k, 4] * 224)) / 255.0
+    ang = u[:, 14] * 2 * np.pi
+    foc = u[:, 15] * 0.8 * radius
+    geom = np.zeros((n_paths, 6), np.float32)  # x0,y0,r0,x1,y1,r1
+    lin = paint_kind == 1
+    geom[lin, 0] = (cx - radius * np.cos(ang))[lin]
+    geom[lin, 1] = (cy - radius * np.sin(ang))[lin]
+    geom[lin, 3] = (cx + radius * np.cos(ang))[lin]
+    geom[lin, 4] = (cy + radius * np.sin(ang))[lin]
+    rad = paint_kind == 2
+    geom[rad, 0] = (cx + foc * np.cos(ang))[rad]
+    geom[rad, 1] = (cy + foc * np.sin(ang))[rad]
+    geom[rad, 2] = 0.0
+    geom[rad, 3] = cx[rad]
+    geom[rad, 4] = cy[rad]
+    geom[rad, 5] = radius[rad]
+    return dict(width=width, height=height, n_paths=n_paths, verb_off=verb_off, pt_off=pt_off, verbs=verbs, pts=pts,
+                rules=evenodd, paint_kind=paint_kind, color=color, geom=geom, spread=spread, n_stops=n_stops,
+                stop_off=stop_off, stops=stops, anti_alias=anti_alias, radius=radius.astype(np.float32))
+
+
+def to_paint_array(scene, paint_struct, blend_mode=3):
+    """ctypes array of `paint_struct` (fields: shader, color, x0..r1, n_stops, stops, spread, ts, blend_mode,
+    anti_alias ...) filled from the neutral tables without a Python loop."""
+    n = scene["n_paths"]
+    arr = (paint_struct * n)()
+    view = np.frombuffer(arr, dtype=np.uint8).reshape(n, C.sizeof(paint_struct))
+
+    def put(field, values, dtype):
+        f = getattr(paint_struct, field)
+        raw = np.ascontiguousarray(values, dtype=dtype)
+        raw = raw.reshape(n, -1).view(np.uint8)
+        view[:, f.offset:f.offset + raw.shape[1]] = raw
+
+    put("shader", scene["paint_kind"], np.int32)
+    put("color", scene["color"], np.float32)
+    g = scene["geom"]
+    for i, name in enumerate(["x0", "y0", "r0", "x1", "y1", "r1"]):
+        put(name, g[:, i], np.float32)
+    put("n_stops", scene["n_stops"], np.int32)
+    base = scene["stops"].ctypes.data
+    ptr = np.where(scene["n_stops"] > 0, base + scene["stop_off"][:-1] * 20, 0).astype(np.uint64)
+    put("stops", ptr, np.uint64)
+    put("spread", scene["spread"], np.int32)
+    put("ts", np.tile(np.array([1, 0, 0, 1, 0, 0], np.float32), (n, 1)), np.float32)
+    put("blend_mode", np.full(n, blend_mode, np.int32), np.int32)
+    put("anti_alias", scene["anti_alias"], np.int32)
+    if hasattr(paint_struct, "opacity"):
+        put("opacity", np.ones(n, np.float32), np.float32)
+    return arr
+
+
+def subset(scene, n):
+    """First n paths of a scene (same canvas): the bounded sample the CPU baseline is timed on."""
+    n = min(n, scene["n_paths"])
+    out = dict(scene)
+    out["n_paths"] = n
+    out["verb_off"] = scene["verb_off"][: n + 1].copy()
+    out["pt_off"] = scene["pt_off"][: n + 1].copy()
+    for k in ("rules", "paint_kind", "color", "geom", "spread", "n_stops", "anti_alias", "radius"):
+        out[k] = scene[k][:n].copy()
+    out["stop_off"] = scene["stop_off"][: n + 1].copy()
+    return out

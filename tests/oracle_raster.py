@@ -38,6 +38,7 @@ def _sig(name, res, args):
 
 
 _sig("orc_fill_path", _i, [_vp, _u32, _u32, _vp, _i, _vp, _i, C.POINTER(Paint), _i, f32p])
+_sig("orc_fill_paths", _i, [_vp, _u32, _u32, _i, _vp, _vp, _vp, _vp, _vp, _vp, f32p])
 _sig("orc_fill_rect", _i, [_vp, _u32, _u32, _f, _f, _f, _f, C.POINTER(Paint), f32p])
 _sig("orc_draw_pixmap", _i, [_vp, _u32, _u32, _i, _i, _vp, _u32, _u32, _f, _i, _i, f32p])
 _sig("orc_pixmap_fill", None, [_vp, _u32, _u32, _f, _f, _f, _f])
