@@ -84,7 +84,7 @@ def test_device_model_structured_shapes():
     v1, p1 = rect(40.75, 10.75, 40.5, 40.5)
     v2, p2 = rect(42.25, 12.25, 37.5, 37.5, True)
     shapes.append((v1 + v2, p1 + p2))
-    shapes.append(([M, L, L, L, L, L, Z], [(5.2, 40.1), (60.7, 40.1), (60.7, 60.9), (35.3, 60.9), (35.3, 45.0), (35.3, 60.9), (5.2, 60.9)]))
+    shapes.append(([M, L, L, L, L, L, L, Z], [(5.2, 40.1), (60.7, 40.1), (60.7, 60.9), (35.3, 60.9), (35.3, 45.0), (35.3, 60.9), (5.2, 60.9)]))
     for i, (v, p) in enumerate(shapes):
         for rule in ("nonzero", "evenodd"):
             for ts in (D.IDENTITY, (1.5, 0, 0, 1.5, 0.37, 0.21)):

@@ -72,7 +72,7 @@ def test_coverage_structured_shapes(ctx):
     v2, p2 = rect(102.25, 22.25, 77.5, 57.5, True)
     shapes.append((v1 + v2, p1 + p2))
     # retraced spike (zero-area excursion) inside a filled region
-    shapes.append(([M, L, L, L, L, L, Z], [(20.2, 80.1), (90.7, 80.1), (90.7, 110.9), (55.3, 110.9), (55.3, 85.0), (55.3, 110.9), (20.2, 110.9)][:7]))
+    shapes.append(([M, L, L, L, L, L, L, Z], [(20.2, 80.1), (90.7, 80.1), (90.7, 110.9), (55.3, 110.9), (55.3, 85.0), (55.3, 110.9), (20.2, 110.9)]))
     for i, (v, p) in enumerate(shapes):
         for rule in ("nonzero", "evenodd"):
             for ts in (R.IDENTITY, (1.5, 0, 0, 1.5, 0.37, 0.21), (0.8, 0.3, -0.2, 1.1, 20, 5)):
