@@ -218,6 +218,10 @@ int rb_layer_apply_mask(rb_layer *layer, const rb_mask *mask);                  
 int rb_mask_fill_path(rb_mask *mask, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
                       int32_t fill_rule, int32_t anti_alias, const float ts[6]);
 
+/* Test hook: route every batch through the any-winding fallback kernel (k_raster_tiles_wide) instead of the packed
+ * one, which the host otherwise selects only when a draw could reach |winding| > 127. */
+void rb_debug_force_wide_kernel(int on);
+
 /* Host-only introspection (no device work; used by the CPU test-suite): the line edges {x, dx, first_y,
  * last_y, winding} and blitter bounds geom = {sect.x, sect.y, sect.w, sect.h, shift, start_y, stop_y} the device
  * would receive for one path on a cw x ch tile.  Returns the edge count, 0 if nothing is drawn, < 0 on error. */

@@ -230,7 +230,7 @@ __device__ __forceinline__ uint32_t store_pf(PF o) { return rb_pack(unnorm(o.r),
 // =================================================================================================
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 
-__device__ float gradient_t(const DevPaint &P, int px, int py, bool &masked)
+__device__ __noinline__ float gradient_t(const DevPaint &P, int px, int py, bool &masked)
 {
     float x = (float)px + 0.5f, y = (float)py + 0.5f;
     if (P.has_ts) {
@@ -299,7 +299,7 @@ __device__ __forceinline__ PF gather(const DevPaint &P, float x, float y)
 __device__ __forceinline__ float bicubic_near(float t) { return mad(t, mad(t, mad(-21.0f / 18.0f, t, 27.0f / 18.0f), 9.0f / 18.0f), 1.0f / 18.0f); }
 __device__ __forceinline__ float bicubic_far(float t) { return (t * t) * mad(7.0f / 18.0f, t, -6.0f / 18.0f); }
 
-__device__ PF shade_pattern(const DevPaint &P, int px, int py)
+__device__ __noinline__ PF shade_pattern(const DevPaint &P, int px, int py)
 {
     float x = (float)px + 0.5f, y = (float)py + 0.5f;
     if (P.has_ts) {
@@ -373,7 +373,7 @@ __device__ __forceinline__ PF shadef(const DevPaint &P, const DevStop *__restric
 }
 
 // RasterPipelineBlitter: full-coverage pixels run the blit_rect program, others blit_anti_h.
-__device__ __forceinline__ uint32_t blend_pixel(const DevPaint &P, const DevStop *__restrict__ stops, uint32_t dst, uint32_t cov,
+__device__ __noinline__ uint32_t blend_pixel(const DevPaint &P, const DevStop *__restrict__ stops, uint32_t dst, uint32_t cov,
                                                 int x, int y)
 {
     if (cov == 255 && P.has_memset) return P.memset_color;
@@ -457,7 +457,7 @@ __device__ bool walker_less(const DevEdge *__restrict__ edges, const DevEdge &A,
     return ia < ib;
 }
 
-__device__ bool exact_span_break(const DevEdge *__restrict__ edges, uint32_t n, int y, int target_r, int w_before)
+__device__ __noinline__ bool exact_span_break(const DevEdge *__restrict__ edges, uint32_t n, int y, int target_r, int w_before)
 {
     uint32_t c[12];
     int cnt = 0;
@@ -482,9 +482,10 @@ __device__ bool exact_span_break(const DevEdge *__restrict__ edges, uint32_t n, 
     return false;
 }
 
+// ---- fallback kernel: one 32-bit counter pair per sub-sample (any winding magnitude) ----------------------------
 template <bool MASK>
 __global__ void __launch_bounds__(RT_THREADS)
-k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint32_t *__restrict__ tile_ids,
+k_raster_tiles_wide(void *__restrict__ target, int W, int H, int tiles_x, const uint32_t *__restrict__ tile_ids,
                const uint32_t *__restrict__ tile_off, const uint32_t *__restrict__ tile_draws,
                const DevDraw *__restrict__ draws, const DevEdge *__restrict__ edges, const DevPaint *__restrict__ paints,
                const DevStop *__restrict__ stops, unsigned long long *__restrict__ px_stats)
@@ -694,6 +695,234 @@ k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint3
     }
 }
 
+
+// =================================================================================================
+// main kernel: packed winding histogram
+//
+// Per pixel row the four sub-scanlines share ONE 32-bit word per sub-sample position: a crossing on
+// sub-row s adds (+-1) << 8s.  The word is then the balanced base-256 number sum_s net_s * 256^s, and
+// because integer addition is linear, ONE warp-shuffle prefix sum over the raw words yields the packed
+// windings W_s(c) of all four sub-rows at once; adding 0x80808080 turns the balanced digits into plain
+// unsigned bytes W_s + 128 (valid while |W_s| <= 127 — the host routes batches that could exceed that to
+// k_raster_tiles_wide).  Byte-SIMD compares then give the 4x4 inside mask of each pixel.  Only the 4th
+// sub-row keeps separate up/down crossing counts (cnt3) for the abutting-span rule.
+// =================================================================================================
+constexpr int FAST_SMEM = 2 * TH * ROW_POS * 4; // wsum + cnt3
+
+// coverage of one pixel from its 4 biased packed windings (positions 4p..4p+3)
+__device__ __forceinline__ uint32_t pixel_inside_counts(const uint32_t *b, bool evenodd)
+{
+    uint32_t sum4 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t m = evenodd ? (b[k] & 0x01010101u) : (__vcmpne4(b[k], 0x80808080u) & 0x01010101u);
+        sum4 += m;
+    }
+    return sum4; // byte s = number of inside sub-samples on sub-row s
+}
+
+template <bool MASK>
+__global__ void __launch_bounds__(RT_THREADS, 3)
+k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint32_t *__restrict__ tile_ids,
+               const uint32_t *__restrict__ tile_off, const uint32_t *__restrict__ tile_draws,
+               const DevDraw *__restrict__ draws, const DevEdge *__restrict__ edges, const DevPaint *__restrict__ paints,
+               const DevStop *__restrict__ stops, unsigned long long *__restrict__ px_stats)
+{
+    extern __shared__ int smem[];
+    int *wsum = smem;                 // [TH][ROW_POS] packed nets of the 4 sub-rows (AA) / plain net (non-AA, 64 used)
+    int *cnt3 = smem + TH * ROW_POS;  // [TH][ROW_POS] sub-row 3: low 16 bits downward crossings, high 16 upward
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t tile = tile_ids[blockIdx.x];
+    const int X0 = (int)(tile % (uint32_t)tiles_x) * TW, Y0 = (int)(tile / (uint32_t)tiles_x) * TH;
+
+    uint32_t dst[4]; // [row i][col j] -> dst[2*i + j]
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        int gy = Y0 + wid + 8 * (q >> 1), gx = X0 + 2 * lane + (q & 1);
+        uint32_t v = 0;
+        if (gy < H && gx < W) {
+            size_t o = (size_t)gy * W + gx;
+            v = MASK ? (uint32_t) reinterpret_cast<const uint8_t *>(target)[o] : reinterpret_cast<const uint32_t *>(target)[o];
+        }
+        dst[q] = v;
+    }
+    for (int i = tid; i < 2 * TH * ROW_POS / 4; i += RT_THREADS) reinterpret_cast<int4 *>(smem)[i] = make_int4(0, 0, 0, 0);
+    __syncthreads();
+
+    uint32_t n_partial = 0, n_full = 0;
+    const uint32_t d_begin = tile_off[tile], d_end = tile_off[tile + 1];
+    DevDraw Dn;
+    if (d_begin < d_end) Dn = draws[tile_draws[d_begin]];
+#pragma unroll 1
+    for (uint32_t di = d_begin; di < d_end; di++) {
+        const DevDraw D = Dn;
+        if (di + 1 < d_end) Dn = draws[tile_draws[di + 1]]; // prefetch: hides the dependent index -> record load
+        const int tlx = X0 - D.ox, tly = Y0 - D.oy;
+        const int py0 = max(0, D.sy - tly), py1 = min(TH, D.sy + D.sh - tly);
+        const int pxa = max(0, D.sx - tlx), pxb = min(TW, D.sx + D.sw - tlx);
+        if (py0 >= py1 || pxa >= pxb) continue;
+        const int sh = D.shift;
+        const int lo_pos = pxa << sh, hi_pos = pxb << sh;
+        const int sub_top = (tly + py0) << sh, sub_bot = (tly + py1) << sh;
+        const int row0 = tly << sh, col0 = tlx << sh;
+        const DevEdge *E0 = edges + D.edge_off;
+
+        // ---- edge pass ----------------------------------------------------------------------------
+        int did = 0;
+#pragma unroll 1
+        for (uint32_t e = tid; e < D.edge_cnt; e += RT_THREADS) {
+            const DevEdge E = E0[e];
+            const int fy = (int)(E.ypack & 0xffffu), ly = (int)(E.ypack >> 16);
+            if (fy >= sub_bot) break;
+            const int ys = max(fy, sub_top), ye = min(ly, sub_bot - 1);
+            if (ys > ye) continue;
+            uint32_t x = (uint32_t)E.x + (uint32_t)(ys - fy) * (uint32_t)E.dx;
+            const bool up = (E.meta & 1u) != 0;
+#pragma unroll 1
+            for (int y = ys; y <= ye; y++) {
+                int r = (int)(x + 0x8000u) >> 16;
+                int pos = max(r - col0, lo_pos);
+                x += (uint32_t)E.dx;
+                if (pos >= hi_pos) continue;
+                did = 1;
+                const int rel = y - row0;
+                if (sh == 2) {
+                    const int s = rel & 3, idx = (rel >> 2) * ROW_POS + pos;
+                    const int one = 1 << (8 * s);
+                    atomicAdd(wsum + idx, up ? -one : one);
+                    if (s == 3) atomicAdd(cnt3 + idx, up ? 0x10000 : 1);
+                } else {
+                    atomicAdd(wsum + rel * ROW_POS + pos, up ? -1 : 1);
+                }
+            }
+        }
+        if (!__syncthreads_or(did)) continue; // the draw's bounds overlap this tile but none of its spans do
+
+        // ---- scan pass ----------------------------------------------------------------------------
+        uint32_t cov[4] = {0, 0, 0, 0};
+        const bool evenodd = D.rule != 0;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const int prow = wid + 8 * i;
+            if (prow < py0 || prow >= py1) continue;
+            if (sh == 2) {
+                int4 *rp = reinterpret_cast<int4 *>(wsum + prow * ROW_POS + lane * 8);
+                const int4 a = rp[0], b = rp[1];
+                const int any = a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w;
+                if (!__any_sync(0xffffffffu, any != 0)) continue;
+                uint32_t wv[8] = {(uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w,
+                                  (uint32_t)b.x, (uint32_t)b.y, (uint32_t)b.z, (uint32_t)b.w};
+#pragma unroll
+                for (int k = 1; k < 8; k++) wv[k] += wv[k - 1];
+                uint32_t incl = wv[7];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const uint32_t base = incl - wv[7] + 0x80808080u;
+#pragma unroll
+                for (int k = 0; k < 8; k++) wv[k] += base; // biased: byte s = W_s + 128
+                if (any) { rp[0] = make_int4(0, 0, 0, 0); rp[1] = make_int4(0, 0, 0, 0); }
+                int4 *cp = reinterpret_cast<int4 *>(cnt3 + prow * ROW_POS + lane * 8);
+                const int4 ca = cp[0], cb = cp[1];
+                const int c3[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+                if (ca.x | ca.y | ca.z | ca.w | cb.x | cb.y | cb.z | cb.w) { cp[0] = make_int4(0, 0, 0, 0); cp[1] = make_int4(0, 0, 0, 0); }
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    const uint32_t sum4 = pixel_inside_counts(wv + 4 * p, evenodd);
+                    uint32_t c = 16u * __dp4a(sum4, 0x00010101u, 0u);
+                    const uint32_t n3 = sum4 >> 24;
+                    if (n3 == 4) {
+                        bool brk = false;
+#pragma unroll
+                        for (int k = 1; k < 4; k++) {
+                            const int ck = c3[4 * p + k];
+                            if (ck == 0) continue;
+                            if (evenodd) { brk = true; continue; }
+                            const int before = (int)(wv[4 * p + k - 1] >> 24) - 128, after = (int)(wv[4 * p + k] >> 24) - 128;
+                            if ((ck & 0xffff) && ((uint32_t)ck >> 16))
+                                brk = brk || exact_span_break(E0, D.edge_cnt, row0 + prow * 4 + 3, col0 + lane * 8 + 4 * p + k, before);
+                            else if ((before ^ after) < 0) brk = true;
+                        }
+                        c += brk ? 64u : 63u;
+                    } else c += 16u * n3;
+                    cov[2 * i + p] = min(c, 255u);
+                }
+            } else {
+                int2 *rp = reinterpret_cast<int2 *>(wsum + prow * ROW_POS + lane * 2);
+                const int2 a = *rp;
+                if (!__any_sync(0xffffffffu, (a.x | a.y) != 0)) continue;
+                int w0 = a.x, w1 = a.x + a.y;
+                int incl = w1;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    int v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const int base = incl - w1;
+                w0 += base; w1 += base;
+                cov[2 * i] = (evenodd ? (w0 & 1) : (w0 != 0)) ? 255u : 0u;
+                cov[2 * i + 1] = (evenodd ? (w1 & 1) : (w1 != 0)) ? 255u : 0u;
+                if (a.x | a.y) *rp = make_int2(0, 0);
+            }
+        }
+        if (2 * lane >= pxb) { cov[0] = 0; cov[2] = 0; }
+        if (2 * lane + 1 >= pxb) { cov[1] = 0; cov[3] = 0; }
+
+        // ---- blend pass ---------------------------------------------------------------------------
+        if (cov[0] | cov[1] | cov[2] | cov[3]) {
+            if (MASK) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t c = cov[q];
+                    if (c == 255) dst[q] = 255;
+                    else if (c) dst[q] = div255(dst[q] * (255 - c) + 255u * c);
+                }
+            } else {
+                const DevPaint &P = paints[D.paint];
+                const bool memset_ok = P.has_memset != 0;
+                const uint32_t memset_color = P.memset_color;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t c = cov[q];
+                    if (!c) continue;
+                    if (c == 255 && memset_ok) { dst[q] = memset_color; n_full++; }
+                    else { dst[q] = blend_pixel(P, stops, dst[q], c, tlx + 2 * lane + (q & 1), tly + wid + 8 * (q >> 1)); n_partial++; }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    if (px_stats) {
+        n_partial = __reduce_add_sync(0xffffffffu, n_partial);
+        n_full = __reduce_add_sync(0xffffffffu, n_full);
+        if (lane == 0) {
+            atomicAdd(px_stats, (unsigned long long)n_partial);
+            atomicAdd(px_stats + 1, (unsigned long long)n_full);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        int gy = Y0 + wid + 8 * i, gx = X0 + 2 * lane;
+        if (gy >= H) continue;
+        size_t o = (size_t)gy * W + gx;
+        if (MASK) {
+            uint8_t *t = reinterpret_cast<uint8_t *>(target);
+            if (gx < W) t[o] = (uint8_t)dst[2 * i];
+            if (gx + 1 < W) t[o + 1] = (uint8_t)dst[2 * i + 1];
+        } else {
+            uint32_t *t = reinterpret_cast<uint32_t *>(target);
+            if (gx + 1 < W && (W & 1) == 0) *reinterpret_cast<uint2 *>(t + o) = make_uint2(dst[2 * i], dst[2 * i + 1]);
+            else {
+                if (gx < W) t[o] = dst[2 * i];
+                if (gx + 1 < W) t[o + 1] = dst[2 * i + 1];
+            }
+        }
+    }
+}
+
 // =================================================================================================
 // batch: host-side recording, edge building, binning, upload, launch
 // =================================================================================================
@@ -720,11 +949,34 @@ struct rb_batch {
     const uint32_t *d_toff = nullptr, *d_tdraws = nullptr, *d_tids = nullptr;
     unsigned n_tile_ids = 0;
     int tiles_x = 0;
+    bool wide = false; // some draw may reach |winding| > 127: use k_raster_tiles_wide
 };
 
 static constexpr int kMaxDim = 8191; // tiny-skia DrawTiler::MAX_DIMENSIONS
 
+// Upper bound of |winding| for a draw: edges simultaneously active on one scanline.  Chains (an edge plus its
+// curve continuations) never overlap themselves in y, so the chain count bounds it; only when that is not tight
+// enough is the exact maximum swept.
+static bool draw_may_exceed_packed_winding(const rbh::Edge *e, size_t n)
+{
+    size_t chains = 0;
+    for (size_t i = 0; i < n; i++) chains += e[i].prev < 0 ? 1 : 0;
+    if (chains < 128) return false;
+    std::vector<int32_t> ends;
+    ends.reserve(n);
+    for (size_t i = 0; i < n; i++) ends.push_back(e[i].last_y);
+    std::sort(ends.begin(), ends.end());
+    size_t active = 0, j = 0, worst = 0;
+    for (size_t i = 0; i < n; i++) { // e is sorted by first_y
+        while (j < n && ends[j] < e[i].first_y) { j++; active--; }
+        active++;
+        worst = std::max(worst, active);
+    }
+    return worst >= 128;
+}
+
 struct ThreadOut {
+    bool wide = false;
     std::vector<rbh::Edge> edges;
     std::vector<DevDraw> draws;
     std::vector<DevPaint> paints;
@@ -756,6 +1008,7 @@ static void build_range(const rb_batch *b, size_t begin, size_t end, int W, int 
                 size_t e0 = out->edges.size();
                 if (!rbh::build_draw(r.verbs.data(), (int)r.verbs.size(), pts, (int)r.pts.size(), aa, tw, th, out->edges, &g))
                     continue;
+                if (draw_may_exceed_packed_winding(out->edges.data() + e0, out->edges.size() - e0)) out->wide = true;
                 DevDraw d;
                 memset(&d, 0, sizeof(d));
                 d.edge_off = (uint32_t)e0;
@@ -875,6 +1128,8 @@ extern "C" int rb_batch_prepare(rb_batch *b, int32_t n_threads)
         for (auto &t : th) t.join();
     }
     size_t n_edges = 0, n_draws = 0, n_paints = 0, n_stops = 0;
+    b->wide = false;
+    for (auto &o : outs) b->wide = b->wide || o.wide;
     for (auto &o : outs) { n_edges += o.edges.size(); n_draws += o.draws.size(); n_paints += o.paints.size(); n_stops += o.stops.size(); }
     if (n_draws == 0) return RB_OK;
     if (n_edges > 0xfffffff0ull) return rb_fail(ctx, RB_ERR_UNSUPPORTED, "too many edges in one batch");
@@ -976,6 +1231,9 @@ extern "C" int rb_batch_prepare(rb_batch *b, int32_t n_threads)
 }
 
 static int batch_run(rb_batch *b, unsigned long long *px_stats);
+static bool g_force_wide = false;
+// Test hook: route every batch through the any-winding fallback kernel.
+extern "C" void rb_debug_force_wide_kernel(int on) { g_force_wide = on != 0; }
 extern "C" int rb_batch_run(rb_batch *b) { return batch_run(b, nullptr); }
 
 // Runs the batch once with the coverage counters on: out[0] = pixels read-modify-written (partial coverage or
@@ -1007,16 +1265,22 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
     void *target = mask_target ? (void *)b->mask->d : (void *)b->layer->d;
     static bool attr_set = false;
     if (!attr_set) {
-        RB_CUDA(ctx, cudaFuncSetAttribute(k_raster_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CNT_BYTES));
-        RB_CUDA(ctx, cudaFuncSetAttribute(k_raster_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CNT_BYTES));
+        RB_CUDA(ctx, cudaFuncSetAttribute(k_raster_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM));
+        RB_CUDA(ctx, cudaFuncSetAttribute(k_raster_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM));
+        RB_CUDA(ctx, cudaFuncSetAttribute(k_raster_tiles_wide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CNT_BYTES));
+        RB_CUDA(ctx, cudaFuncSetAttribute(k_raster_tiles_wide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CNT_BYTES));
         attr_set = true;
     }
-    if (mask_target)
-        k_raster_tiles<true><<<b->n_tile_ids, RT_THREADS, CNT_BYTES, ctx->stream>>>(
-            target, W, H, b->tiles_x, b->d_tids, b->d_toff, b->d_tdraws, b->d_draws, b->d_edges, b->d_paints, b->d_stops, px_stats);
-    else
-        k_raster_tiles<false><<<b->n_tile_ids, RT_THREADS, CNT_BYTES, ctx->stream>>>(
-            target, W, H, b->tiles_x, b->d_tids, b->d_toff, b->d_tdraws, b->d_draws, b->d_edges, b->d_paints, b->d_stops, px_stats);
+#define RB_RASTER_ARGS target, W, H, b->tiles_x, b->d_tids, b->d_toff, b->d_tdraws, b->d_draws, b->d_edges, b->d_paints, b->d_stops, px_stats
+    const bool wide = b->wide || g_force_wide;
+    if (wide) {
+        if (mask_target) k_raster_tiles_wide<true><<<b->n_tile_ids, RT_THREADS, CNT_BYTES, ctx->stream>>>(RB_RASTER_ARGS);
+        else k_raster_tiles_wide<false><<<b->n_tile_ids, RT_THREADS, CNT_BYTES, ctx->stream>>>(RB_RASTER_ARGS);
+    } else {
+        if (mask_target) k_raster_tiles<true><<<b->n_tile_ids, RT_THREADS, FAST_SMEM, ctx->stream>>>(RB_RASTER_ARGS);
+        else k_raster_tiles<false><<<b->n_tile_ids, RT_THREADS, FAST_SMEM, ctx->stream>>>(RB_RASTER_ARGS);
+    }
+#undef RB_RASTER_ARGS
     RB_LAUNCHED(ctx, "raster_tiles");
     return RB_OK;
 }

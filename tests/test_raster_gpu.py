@@ -284,3 +284,51 @@ def test_pattern_fill(ctx):
                 want = base.copy()
                 R.fill_path(want, verbs, pts, R.make_paint(cspec))
                 assert_within(l.download(), want, 1, f"pattern {quality} {spread} {ts}")
+
+
+def test_wide_fallback_kernel_matches_too(ctx):
+    """The any-winding fallback kernel (selected by the host when |winding| could exceed 127) gives the same bytes."""
+    import resvg_b200 as rb
+    from resvg_b200 import _ffi
+
+    w, h = 300, 180
+    rng = SplitMix64(41)
+    want = np.zeros((h, w, 4), np.uint8)
+    recs = []
+    for i in range(60):
+        cx, cy, r = rng.uniform(0, w), rng.uniform(0, h), rng.log_uniform(4, 150)
+        verbs, pts = random_path(rng, cx, cy, r)
+        spec = random_paint_spec(rng, cx, cy, r, solid=0.6, linear=0.4)
+        rule = "evenodd" if rng.u() < 0.5 else "nonzero"
+        recs.append((verbs, pts, spec, rule, rng.u() < 0.9))
+        R.fill_path(want, verbs, pts, R.make_paint(spec, "source_over", recs[-1][4]), rule)
+    _ffi.lib.rb_debug_force_wide_kernel(1)
+    try:
+        l = ctx.layer(w, h)
+        b = rb.Batch(l)
+        for verbs, pts, spec, rule, aa in recs:
+            b.fill_path(verbs, pts, rb.make_paint(spec, "source_over", aa), rule)
+        b.submit()
+        got = l.download()
+    finally:
+        _ffi.lib.rb_debug_force_wide_kernel(0)
+    assert_exact(got, want, "wide kernel")
+
+
+def test_many_overlapping_loops_select_wide_kernel(ctx):
+    """A path winding around the same point 140 times exceeds the packed kernel's +-127 range: the host must route
+    it to the fallback kernel and the result must still be exact."""
+    import resvg_b200 as rb
+
+    w, h = 96, 96
+    verbs, pts = [], []
+    for k in range(140):
+        d = 0.05 * k
+        verbs += [0, 1, 1, 1, 4]
+        pts += [(10 + d, 10 + d), (80 - d, 12 + d), (78 - d, 82 - d), (12 + d, 80 - d)]
+    spec = {"kind": "solid", "color": (0.1, 0.7, 0.3, 0.8)}
+    l = ctx.layer(w, h)
+    rb.fill_path(l, verbs, pts, rb.make_paint(spec), "nonzero")
+    want = np.zeros((h, w, 4), np.uint8)
+    R.fill_path(want, verbs, pts, R.make_paint(spec), "nonzero")
+    assert_exact(l.download(), want, "140 nested loops")
