@@ -707,7 +707,8 @@ k_raster_tiles_wide(void *__restrict__ target, int W, int H, int tiles_x, const 
 // k_raster_tiles_wide).  Byte-SIMD compares then give the 4x4 inside mask of each pixel.  Only the 4th
 // sub-row keeps separate up/down crossing counts (cnt3) for the abutting-span rule.
 // =================================================================================================
-constexpr int FAST_SMEM = 2 * TH * ROW_POS * 4; // wsum + cnt3
+constexpr int FAST_HIST = 2 * TH * ROW_POS;       // ints in one histogram buffer: wsum + cnt3
+constexpr int FAST_SMEM = 2 * FAST_HIST * 4;      // double buffered
 
 // coverage of one pixel from its 4 biased packed windings (positions 4p..4p+3)
 __device__ __forceinline__ uint32_t pixel_inside_counts(const uint32_t *b, bool evenodd)
@@ -729,8 +730,13 @@ k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint3
                const DevStop *__restrict__ stops, unsigned long long *__restrict__ px_stats)
 {
     extern __shared__ int smem[];
-    int *wsum = smem;                 // [TH][ROW_POS] packed nets of the 4 sub-rows (AA) / plain net (non-AA, 64 used)
-    int *cnt3 = smem + TH * ROW_POS;  // [TH][ROW_POS] sub-row 3: low 16 bits downward crossings, high 16 upward
+    __shared__ uint16_t s_list[2][RT_THREADS];
+    __shared__ int s_count[3]; // rotated: iteration n counts in [n % 3] and clears [(n + 1) % 3] before its barrier
+    // Two histogram buffers used alternately by successive draws, so the scan of one draw and the scatter of the
+    // next may overlap and a draw costs two block barriers instead of four.  Each buffer: wsum[TH][ROW_POS] packed
+    // nets of the 4 sub-rows (AA) / plain net (non-AA), then cnt3[TH][ROW_POS] (sub-row 3: low 16 bits downward
+    // crossings, high 16 upward).
+    int hbuf = 0, lbuf = 0, cbuf = 0;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t tile = tile_ids[blockIdx.x];
     const int X0 = (int)(tile % (uint32_t)tiles_x) * TW, Y0 = (int)(tile / (uint32_t)tiles_x) * TH;
@@ -746,7 +752,8 @@ k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint3
         }
         dst[q] = v;
     }
-    for (int i = tid; i < 2 * TH * ROW_POS / 4; i += RT_THREADS) reinterpret_cast<int4 *>(smem)[i] = make_int4(0, 0, 0, 0);
+    for (int i = tid; i < 2 * FAST_HIST / 4; i += RT_THREADS) reinterpret_cast<int4 *>(smem)[i] = make_int4(0, 0, 0, 0);
+    if (tid < 3) s_count[tid] = 0;
     __syncthreads();
 
     uint32_t n_partial = 0, n_full = 0;
@@ -766,37 +773,58 @@ k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint3
         const int sub_top = (tly + py0) << sh, sub_bot = (tly + py1) << sh;
         const int row0 = tly << sh, col0 = tlx << sh;
         const DevEdge *E0 = edges + D.edge_off;
+        int *wsum = smem + hbuf * FAST_HIST, *cnt3 = wsum + TH * ROW_POS;
 
         // ---- edge pass ----------------------------------------------------------------------------
+        // (a) every thread tests one edge of a 256-edge chunk against the tile's sub-scanline range and the
+        //     survivors are compacted into s_list; (b) the (edge, sub-row) pairs of the survivors are spread
+        //     over all 256 threads, each evaluating x(y) = x + (y - first_y) * dx in closed form — so a long
+        //     edge costs the CTA ceil(rows / 256) steps instead of `rows` serial steps of one thread.
         int did = 0;
+        const int rows_log2 = sh == 2 ? 6 : 4; // sub-rows per tile: 64 (AA) / 16 (non-AA)
 #pragma unroll 1
-        for (uint32_t e = tid; e < D.edge_cnt; e += RT_THREADS) {
-            const DevEdge E = E0[e];
-            const int fy = (int)(E.ypack & 0xffffu), ly = (int)(E.ypack >> 16);
-            if (fy >= sub_bot) break;
-            const int ys = max(fy, sub_top), ye = min(ly, sub_bot - 1);
-            if (ys > ye) continue;
-            uint32_t x = (uint32_t)E.x + (uint32_t)(ys - fy) * (uint32_t)E.dx;
-            const bool up = (E.meta & 1u) != 0;
+        for (uint32_t chunk = 0; chunk < D.edge_cnt; chunk += RT_THREADS) {
+            const uint32_t e = chunk + tid;
+            const int cnext = cbuf == 2 ? 0 : cbuf + 1;
+            if (tid == 0) s_count[cnext] = 0; // last read two iterations ago; first touched after the next barrier
+            bool past = false;
+            if (e < D.edge_cnt) {
+                const uint32_t yp = E0[e].ypack;
+                const int fy = (int)(yp & 0xffffu), ly = (int)(yp >> 16);
+                past = fy >= sub_bot;
+                if (!past && ly >= sub_top) s_list[lbuf][atomicAdd(&s_count[cbuf], 1)] = (uint16_t)tid;
+            }
+            const int chunk_past = __syncthreads_and(past || e >= D.edge_cnt); // also publishes s_list
+            const int n_act = s_count[cbuf];
+            const uint16_t *list = s_list[lbuf];
+            lbuf ^= 1;
+            cbuf = cnext;
 #pragma unroll 1
-            for (int y = ys; y <= ye; y++) {
-                int r = (int)(x + 0x8000u) >> 16;
-                int pos = max(r - col0, lo_pos);
-                x += (uint32_t)E.dx;
+            for (int i = tid; i < (n_act << rows_log2); i += RT_THREADS) {
+                const DevEdge E = E0[chunk + list[i >> rows_log2]];
+                const int rel = (py0 << sh) + (i & ((1 << rows_log2) - 1)); // tile-local sub-row
+                const int y = row0 + rel;
+                const int fy = (int)(E.ypack & 0xffffu), ly = (int)(E.ypack >> 16);
+                if (y < fy || y > ly || y >= sub_bot) continue;
+                const uint32_t x = (uint32_t)E.x + (uint32_t)(y - fy) * (uint32_t)E.dx;
+                const int r = (int)(x + 0x8000u) >> 16;
+                const int pos = max(r - col0, lo_pos);
                 if (pos >= hi_pos) continue;
                 did = 1;
-                const int rel = y - row0;
+                const bool up = (E.meta & 1u) != 0;
                 if (sh == 2) {
-                    const int s = rel & 3, idx = (rel >> 2) * ROW_POS + pos;
-                    const int one = 1 << (8 * s);
+                    const int sr = rel & 3, idx = (rel >> 2) * ROW_POS + pos;
+                    const int one = 1 << (8 * sr);
                     atomicAdd(wsum + idx, up ? -one : one);
-                    if (s == 3) atomicAdd(cnt3 + idx, up ? 0x10000 : 1);
+                    if (sr == 3) atomicAdd(cnt3 + idx, up ? 0x10000 : 1);
                 } else {
                     atomicAdd(wsum + rel * ROW_POS + pos, up ? -1 : 1);
                 }
             }
+            if (chunk_past) break; // edges are sorted by first_y: nothing further can reach this tile
         }
         if (!__syncthreads_or(did)) continue; // the draw's bounds overlap this tile but none of its spans do
+        hbuf ^= 1; // the next draw scatters into the other buffer while stragglers still scan this one
 
         // ---- scan pass ----------------------------------------------------------------------------
         uint32_t cov[4] = {0, 0, 0, 0};
@@ -883,16 +911,37 @@ k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint3
                 const DevPaint &P = paints[D.paint];
                 const bool memset_ok = P.has_memset != 0;
                 const uint32_t memset_color = P.memset_color;
+                // solid colour through the u16 pipeline with Source / SourceOver: the common case, kept inline
+                const bool solid_fast = P.kind == 0 && P.lowp && (P.blend == 1 || P.blend == 3);
+                const uint32_t sr = P.solid16[0], sg = P.solid16[1], sb = P.solid16[2], sa = P.solid16[3];
+                const bool src_over = P.blend == 3;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const uint32_t c = cov[q];
                     if (!c) continue;
-                    if (c == 255 && memset_ok) { dst[q] = memset_color; n_full++; }
-                    else { dst[q] = blend_pixel(P, stops, dst[q], c, tlx + 2 * lane + (q & 1), tly + wid + 8 * (q >> 1)); n_partial++; }
+                    if (c == 255 && memset_ok) { dst[q] = memset_color; n_full++; continue; }
+                    n_partial++;
+                    if (solid_fast) {
+                        const uint32_t d = dst[q];
+                        uint32_t r, g, b2, a;
+                        if (src_over) { // scale_1_float (coverage folded into the source), then source_over
+                            const uint32_t pr = c == 255 ? sr : div255(sr * c), pg = c == 255 ? sg : div255(sg * c);
+                            const uint32_t pb = c == 255 ? sb : div255(sb * c), pa = c == 255 ? sa : div255(sa * c);
+                            const uint32_t ia = 255 - pa;
+                            r = pr + div255(RB_R(d) * ia); g = pg + div255(RB_G(d) * ia);
+                            b2 = pb + div255(RB_B(d) * ia); a = pa + div255(RB_A(d) * ia);
+                        } else {        // Source: lerp_1_float(dst, src, coverage)
+                            const uint32_t ic = 255 - c;
+                            r = div255(RB_R(d) * ic + sr * c); g = div255(RB_G(d) * ic + sg * c);
+                            b2 = div255(RB_B(d) * ic + sb * c); a = div255(RB_A(d) * ic + sa * c);
+                        }
+                        dst[q] = rb_pack(r & 0xffu, g & 0xffu, b2 & 0xffu, a & 0xffu);
+                    } else {
+                        dst[q] = blend_pixel(P, stops, dst[q], c, tlx + 2 * lane + (q & 1), tly + wid + 8 * (q >> 1));
+                    }
                 }
             }
         }
-        __syncthreads();
     }
 
     if (px_stats) {
