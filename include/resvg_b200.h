@@ -218,6 +218,18 @@ int rb_layer_apply_mask(rb_layer *layer, const rb_mask *mask);                  
 int rb_mask_fill_path(rb_mask *mask, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
                       int32_t fill_rule, int32_t anti_alias, const float ts[6]);
 
+/* ------------------------------------------------------------------------------------------------
+ * Host geometry: tiny_skia_path::Path::stroke(&Stroke, res_scale) — the outline PixmapMut::stroke_path fills
+ * (path.rs:113; usvg Stroke::to_tiny_skia tree/mod.rs:638-664).  Pure host code (the north star keeps stroking on the
+ * host).  cap: 0 butt, 1 round, 2 square; join: 0 miter, 1 miter-clip, 2 round, 3 bevel.  res_scale =
+ * PathStroker::compute_resolution_scale(transform).  Outputs are malloc'ed; release them with rb_path_free.
+ * Returns RB_ERR_INVALID when the stroke is empty (the reference's None).
+ * ---------------------------------------------------------------------------------------------- */
+int rb_path_stroke(const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points, float width,
+                   float miter_limit, int32_t cap, int32_t join, float res_scale, uint8_t **out_verbs,
+                   int32_t *out_n_verbs, float **out_points, int32_t *out_n_points);
+void rb_path_free(void *p);
+
 /* Test hook: route every batch through the any-winding fallback kernel (k_raster_tiles_wide) instead of the packed
  * one, which the host otherwise selects only when a draw could reach |winding| > 127. */
 void rb_debug_force_wide_kernel(int on);

@@ -1347,7 +1347,8 @@ static void clip_color(float *r, float *g, float *b, float a)
     float *ch[3] = {r, g, b};
     for (int i = 0; i < 3; i++) {
         float c = *ch[i];
-        if (!(mn >= 0.0f)) c = l + (c - l) * l / (l - mn);
+        /* tiny-skia tests `mx >= 0` here (Skia tests mn); pinned by painting/mix-blend-mode/color.png */
+        if (!(mx >= 0.0f)) c = l + (c - l) * l / (l - mn);
         if (mx > a) c = l + (c - l) * (a - l) / (mx - l);
         *ch[i] = fmaxf(c, 0.0f);
     }
@@ -2176,7 +2177,9 @@ void orc_mask_from_pixmap(const uint8_t *px, uint32_t w, uint32_t h, int32_t typ
         if (type == 0) { mask[i] = p[3]; continue; }
         float r = (float)p[0] / 255.0f, g = (float)p[1] / 255.0f, b = (float)p[2] / 255.0f, a = (float)p[3] / 255.0f;
         if (p[3] != 0) { r /= a; g /= a; b /= a; }
-        float luma = r * 0.2125f + g * 0.7154f + b * 0.0721f;
+        /* Rec. 709 coefficients; pinned by masking/mask/simple-case.png (0 of 240 probe pixels differ,
+         * whereas the 0.2125/0.7154/0.0721 set used by filter/color_matrix.rs gives 39 mismatches) */
+        float luma = r * 0.2126f + g * 0.7152f + b * 0.0722f;
         float v = (luma * a) * 255.0f;
         v = v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v);
         mask[i] = f2u8(ceilf(v));

@@ -122,6 +122,9 @@ SIGNATURES = {
     "rb_mask_invert": (_i, [_vp]),
     "rb_layer_apply_mask": (_i, [_vp, _vp]),
     "rb_mask_fill_path": (_i, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32, f32p]),
+    "rb_path_stroke": (_i, [_vp, C.c_int32, _vp, C.c_int32, _f, _f, C.c_int32, C.c_int32, _f, c_void_pp,
+                            C.POINTER(C.c_int32), c_void_pp, C.POINTER(C.c_int32)]),
+    "rb_path_free": (None, [_vp]),
     "rb_debug_force_wide_kernel": (None, [_i]),
     "rb_debug_build_edges": (_i, [_vp, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, f32p, _vp, _vp,
                                   C.c_int32, _vp]),

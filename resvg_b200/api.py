@@ -448,3 +448,28 @@ class Mask:
 def apply_mask(layer: Layer, mask: Mask):
     """Pixmap::apply_mask(mask)."""
     layer.ctx.check(lib.rb_layer_apply_mask(layer._h, mask._h), "apply_mask")
+
+
+CAPS = {"butt": 0, "round": 1, "square": 2}
+JOINS = {"miter": 0, "miter-clip": 1, "round": 2, "bevel": 3}
+
+
+def stroke_path(verbs, pts, width, miter_limit=4.0, cap="butt", join="miter", res_scale=1.0):
+    """tiny_skia_path::Path::stroke → (verbs uint8, points float32 (n, 2)) or None when the stroke is empty.
+    Host-only (no GPU needed)."""
+    v, p = _path(verbs, pts)
+    ov, op = C.c_void_p(), C.c_void_p()
+    nv, np_ = C.c_int32(), C.c_int32()
+    st = lib.rb_path_stroke(v.ctypes.data, len(v), p.ctypes.data, len(p), float(width), float(miter_limit),
+                            CAPS[cap] if isinstance(cap, str) else int(cap),
+                            JOINS[join] if isinstance(join, str) else int(join), float(res_scale),
+                            C.byref(ov), C.byref(nv), C.byref(op), C.byref(np_))
+    if st != 0:
+        return None
+    try:
+        out_v = np.ctypeslib.as_array((C.c_uint8 * nv.value).from_address(ov.value)).copy()
+        out_p = np.ctypeslib.as_array((C.c_float * (np_.value * 2)).from_address(op.value)).copy().reshape(-1, 2)
+    finally:
+        lib.rb_path_free(ov)
+        lib.rb_path_free(op)
+    return out_v, out_p

@@ -173,7 +173,7 @@ __device__ __forceinline__ void set_lum(float &r, float &g, float &b, float l)
 }
 __device__ __forceinline__ float clip_ch(float c, float mn, float mx, float l, float a)
 {
-    if (!(mn >= 0.0f)) c = l + __fdiv_rn((c - l) * l, l - mn);
+    if (!(mx >= 0.0f)) c = l + __fdiv_rn((c - l) * l, l - mn); // tiny-skia tests mx (pinned by mix-blend-mode goldens)
     if (mx > a) c = l + __fdiv_rn((c - l) * (a - l), mx - l);
     return fmaxf(c, 0.0f);
 }
@@ -1469,7 +1469,7 @@ __global__ void __launch_bounds__(256) k_mask_from_layer(const uint32_t *__restr
         float r = __fdiv_rn((float)RB_R(p), 255.0f), g = __fdiv_rn((float)RB_G(p), 255.0f), b = __fdiv_rn((float)RB_B(p), 255.0f);
         float a = __fdiv_rn((float)av, 255.0f);
         if (av != 0) { r = __fdiv_rn(r, a); g = __fdiv_rn(g, a); b = __fdiv_rn(b, a); }
-        float luma = r * 0.2125f + g * 0.7154f + b * 0.0721f;
+        float luma = r * 0.2126f + g * 0.7152f + b * 0.0722f; // Rec. 709 (pinned by masking/mask goldens)
         float v = (luma * a) * 255.0f;
         v = v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v); // f32::clamp
         m[i] = (uint8_t)rb_f2u8(ceilf(v));
