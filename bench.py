@@ -95,17 +95,44 @@ def oracle_lib():
 
 
 def cpu_render_sample(R, scene, n_sample, canvas=None):
-    """Oracle (CPU restatement of the reference path) over the first n_sample paths; returns seconds."""
+    """Oracle (CPU restatement of the reference path) over the first n_sample draws; returns seconds of CPU work:
+    host stroking of the stroke draws (the same host stroker both arms use) + the oracle's fill of every draw."""
+    import resvg_b200 as rb
     from resvg_b200 import scenes
     sub = scenes.subset(scene, n_sample)
+    n = sub["n_paths"]
+    t_stroke = 0.0
+    sw = sub["stroke_width"]
+    if (sw > 0).any():
+        verbs, pts, voff, poff = [], [], [0], [0]
+        caps, joins = ["butt", "round", "square"], ["miter", "miter-clip", "round", "bevel"]
+        for i in range(n):
+            v = sub["verbs"][sub["verb_off"][i]:sub["verb_off"][i + 1]]
+            p = sub["pts"][sub["pt_off"][i]:sub["pt_off"][i + 1]]
+            if sw[i] > 0:
+                t0 = time.perf_counter()
+                out = rb.stroke_path(v, p, float(sw[i]), float(sub["stroke_miter"][i]), caps[sub["stroke_cap"][i]],
+                                     joins[sub["stroke_join"][i]], 1.0)
+                t_stroke += time.perf_counter() - t0
+                if out is None:
+                    v, p = v[:0], p[:0]
+                else:
+                    v, p = out
+                sub["rules"][i] = 0
+            verbs.append(v); pts.append(p)
+            voff.append(voff[-1] + len(v)); poff.append(poff[-1] + len(p))
+        sub["verbs"] = np.ascontiguousarray(np.concatenate(verbs), np.uint8)
+        sub["pts"] = np.ascontiguousarray(np.concatenate(pts), np.float32)
+        sub["verb_off"] = np.array(voff, np.uint32)
+        sub["pt_off"] = np.array(poff, np.uint32)
     paints = scenes.to_paint_array(sub, R.Paint)
     w, h = scene["width"], scene["height"]
     px = canvas if canvas is not None else np.zeros((h, w, 4), np.uint8)
     t0 = time.perf_counter()
-    R.lib.orc_fill_paths(px.ctypes.data, w, h, sub["n_paths"], sub["verb_off"].ctypes.data, sub["pt_off"].ctypes.data,
+    R.lib.orc_fill_paths(px.ctypes.data, w, h, n, sub["verb_off"].ctypes.data, sub["pt_off"].ctypes.data,
                          sub["verbs"].ctypes.data, sub["pts"].ctypes.data, C.addressof(paints), sub["rules"].ctypes.data,
                          R.ts_arr(R.IDENTITY))
-    return time.perf_counter() - t0
+    return time.perf_counter() - t0 + t_stroke
 
 
 def run_reference(args, rank, world):
@@ -116,8 +143,9 @@ def run_reference(args, rank, world):
     R = oracle_lib()
     W, H, n_paths, seed = WORKLOADS[args.workload]
     cores = min(os.cpu_count() or 1, 32)
-    n_sample = max(200, min(n_paths, int(args.cpu_sample)))
     scs = [scenes.paths_scene(W, H, n_paths, seed + t) for t in range(min(cores, 4))]
+    n_draws = scs[0]["n_paths"]
+    n_sample = max(200, min(n_draws, int(args.cpu_sample)))
     canvases = [np.zeros((H, W, 4), np.uint8) for _ in range(cores)]
 
     def step():
@@ -133,9 +161,9 @@ def run_reference(args, rank, world):
         step()
     times = [step() for _ in range(max(1, min(args.steps, 3)))]
     dt = statistics.mean(times)
-    mpx = cores * (W * H / 1e6) * (n_sample / n_paths)
+    mpx = cores * (W * H / 1e6) * (n_sample / n_draws)
     v = mpx / dt
-    sample = f"{cores} threads x first {n_sample} of {n_paths} paths of the {W}x{H} scene per step (full canvas); value scaled by {n_sample}/{n_paths}"
+    sample = f"{cores} threads x first {n_sample} of {n_draws} draws of the {W}x{H} scene per step (full canvas); value scaled by {n_sample}/{n_draws}"
     print(json.dumps({
         "impl": "reference", "metric": "Mpixels/s rendered", "value": v, "unit": "Mpx/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -183,8 +211,9 @@ def main():
     canvas_mpx = W * H / 1e6
     ctx = rb.Context(local_rank)
     scene = scenes.paths_scene(W, H, n_paths, seed + rank)  # every rank renders its own document
-    paints = scenes.to_paint_array(scene, _ffi.Paint)
-    scene["paints"] = paints
+    scene["paints"] = scenes.to_paint_array(scene, _ffi.Paint)
+    scene["strokes"] = scenes.to_stroke_array(scene, _ffi.Stroke)
+    n_draws_in = scene["n_paths"]
 
     layer = ctx.layer(W, H)
     batch = rb.Batch(layer)
@@ -269,7 +298,9 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/u16 fixed point + f32", "data": "synthetic",
-            "config": {"workload": args.workload, "canvas": [W, H], "paths": n_paths, "fills_only": True,
+            "config": {"workload": args.workload, "canvas": [W, H], "paths": n_paths, "draw_calls": int(n_draws_in),
+                       "mix": "70% fill / 20% fill+stroke / 10% stroke; nonzero+evenodd; 50% solid / 30% linear / 20% radial; 95% AA",
+                       "stroke": "width log-U[1,16] px, miter/round/bevel joins, butt/round/square caps; hairlines (<=1 px) and dashes not implemented yet",
                        "sharding": "one scene (document) per GPU, no collective",
                        "l2": "inputs (256 MiB canvas + %.0f MiB edges/bins) exceed the 126 MB L2" % (st["upload_bytes"] / 2**20),
                        "draws": st["draws"], "line_edges": st["edges"], "draw_tile_pairs": st["pairs"], "tiles": st["tiles"]},
@@ -285,12 +316,12 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             R = oracle_lib()
-            n_sample = max(200, min(n_paths, int(args.cpu_sample)))
+            n_sample = max(200, min(n_draws_in, int(args.cpu_sample)))
             dt = cpu_render_sample(R, scene, n_sample)
             out["cpu_baseline"] = {
-                "value": canvas_mpx / (dt * n_paths / n_sample), "unit": "Mpx/s", "cores": 1, "kind": "port",
-                "sample": f"first {n_sample} of {n_paths} paths of the same scene on the full canvas, {dt:.2f} s; "
-                          f"value = canvas Mpx / (t * {n_paths}/{n_sample}); oracle restatement of the resvg/tiny-skia CPU path"}
+                "value": canvas_mpx / (dt * n_draws_in / n_sample), "unit": "Mpx/s", "cores": 1, "kind": "port",
+                "sample": f"first {n_sample} of {n_draws_in} draws of the same scene on the full canvas, {dt:.2f} s; "
+                          f"value = canvas Mpx / (t * {n_draws_in}/{n_sample}); oracle restatement of the resvg/tiny-skia CPU path"}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -183,6 +183,21 @@ typedef struct rb_batch rb_batch;
 int rb_batch_begin(rb_layer *target, rb_batch **out);
 int rb_batch_fill_path(rb_batch *batch, const uint8_t *verbs, int32_t n_verbs, const float *points,
                        int32_t n_points, const rb_paint *paint, int32_t fill_rule, const float ts[6]);
+/* tiny_skia::Stroke as usvg fills it (tree/mod.rs:638-664); dashes are applied by the caller (path.dash) */
+typedef struct {
+    float width, miter_limit;
+    int32_t cap;  /* 0 butt, 1 round, 2 square */
+    int32_t join; /* 0 miter, 1 miter-clip, 2 round, 3 bevel */
+} rb_stroke;
+/* PixmapMut::stroke_path(path, paint, stroke, transform, None) — path.rs:113: outline on the host (rb_path_stroke),
+ * then a Winding fill.  Hairline strokes (anti-aliased, transformed width <= 1 px) return RB_ERR_UNSUPPORTED. */
+int rb_batch_stroke_path(rb_batch *batch, const uint8_t *verbs, int32_t n_verbs, const float *points,
+                         int32_t n_points, const rb_paint *paint, const rb_stroke *stroke, const float ts[6]);
+/* Bulk recording of fills and strokes: strokes may be NULL; entry i is stroked when strokes[i].width > 0, filled
+ * with fill_rules[i] otherwise. */
+int rb_batch_draw_paths(rb_batch *batch, int32_t n_paths, const uint32_t *verb_off, const uint32_t *point_off,
+                        const uint8_t *verbs, const float *points, const rb_paint *paints, const uint8_t *fill_rules,
+                        const rb_stroke *strokes, const float ts[6]);
 /* Bulk form of rb_batch_fill_path: n_paths paths in packed arrays; verb_off / point_off hold n_paths + 1 prefix
  * offsets into verbs / points (points counted in x,y pairs); one paint and one fill rule per path. */
 int rb_batch_fill_paths(rb_batch *batch, int32_t n_paths, const uint32_t *verb_off, const uint32_t *point_off,

@@ -66,6 +66,11 @@ class Paint(C.Structure):
     ]
 
 
+class Stroke(C.Structure):
+    """rb_stroke"""
+    _fields_ = [("width", C.c_float), ("miter_limit", C.c_float), ("cap", C.c_int32), ("join", C.c_int32)]
+
+
 # name -> (restype, argtypes); mirrors include/resvg_b200.h one to one
 SIGNATURES = {
     "rb_ctx_create": (_i, [_i, c_void_pp]),
@@ -106,6 +111,8 @@ SIGNATURES = {
     "rb_fill_path": (_i, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.POINTER(Paint), C.c_int32, f32p]),
     "rb_batch_begin": (_i, [_vp, c_void_pp]),
     "rb_batch_fill_path": (_i, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.POINTER(Paint), C.c_int32, f32p]),
+    "rb_batch_stroke_path": (_i, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.POINTER(Paint), _vp, f32p]),
+    "rb_batch_draw_paths": (_i, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, f32p]),
     "rb_batch_fill_paths": (_i, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, f32p]),
     "rb_batch_submit": (_i, [_vp, C.c_int32]),
     "rb_batch_prepare": (_i, [_vp, C.c_int32]),

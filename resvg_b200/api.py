@@ -356,11 +356,21 @@ class Batch:
         """Bulk recording from packed arrays: scene has verb_off, pt_off (uint32, n+1), verbs (uint8), pts (float32
         (m, 2)), paints (ctypes array of rb_paint), rules (uint8)."""
         n = len(scene["rules"])
+        strokes = scene.get("strokes")
         self.layer.ctx.check(
-            lib.rb_batch_fill_paths(self._h, n, scene["verb_off"].ctypes.data, scene["pt_off"].ctypes.data,
+            lib.rb_batch_draw_paths(self._h, n, scene["verb_off"].ctypes.data, scene["pt_off"].ctypes.data,
                                     scene["verbs"].ctypes.data, scene["pts"].ctypes.data,
-                                    C.addressof(scene["paints"]), scene["rules"].ctypes.data, _ts(ts)),
-            "batch_fill_paths")
+                                    C.addressof(scene["paints"]), scene["rules"].ctypes.data,
+                                    C.addressof(strokes) if strokes is not None else None, _ts(ts)),
+            "batch_draw_paths")
+
+    def stroke_path(self, verbs, pts, paint: Paint, width, miter_limit=4.0, cap="butt", join="miter", ts=IDENTITY):
+        """PixmapMut::stroke_path."""
+        v, p = _path(verbs, pts)
+        st = _ffi.Stroke(float(width), float(miter_limit), CAPS[cap] if isinstance(cap, str) else int(cap),
+                         JOINS[join] if isinstance(join, str) else int(join))
+        self.layer.ctx.check(lib.rb_batch_stroke_path(self._h, v.ctypes.data, len(v), p.ctypes.data, len(p),
+                                                      C.byref(paint), C.byref(st), _ts(ts)), "batch_stroke_path")
 
     def submit(self, n_threads: int = 0):
         self.layer.ctx.check(lib.rb_batch_submit(self._h, n_threads), "batch_submit")

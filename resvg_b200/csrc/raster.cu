@@ -977,11 +977,13 @@ k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint3
 // =================================================================================================
 struct RecordedDraw {
     std::vector<uint8_t> verbs;
-    std::vector<rbh::Pt> pts; // device space (transform applied)
+    std::vector<rbh::Pt> pts; // fills: device space (transform applied); strokes: local space until stroked
     rb_paint paint;
     std::vector<float> stops;
     rbh::Xform ctm;
     int rule;
+    bool is_stroke = false;
+    rb_stroke stroke;
 };
 
 struct rb_batch {
@@ -1032,11 +1034,50 @@ struct ThreadOut {
     std::vector<DevStop> stops;
 };
 
+extern "C" int rb_path_stroke(const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points, float width,
+                              float miter_limit, int32_t cap, int32_t join, float res_scale, uint8_t **out_verbs,
+                              int32_t *out_n_verbs, float **out_points, int32_t *out_n_points);
+extern "C" void rb_path_free(void *p);
+
+// painter.rs stroke_path: PathStroker::compute_resolution_scale(ts)
+static float resolution_scale(const rbh::Xform &t)
+{
+    float sx = sqrtf(t.sx * t.sx + t.kx * t.kx), sy = sqrtf(t.ky * t.ky + t.sy * t.sy);
+    if (std::isfinite(sx) && std::isfinite(sy)) {
+        float s = std::max(sx, sy);
+        if (s > 0) return s;
+    }
+    return 1.0f;
+}
+
 static void build_range(const rb_batch *b, size_t begin, size_t end, int W, int H, bool mask_target, ThreadOut *out)
 {
     std::vector<rbh::Pt> tmp;
+    RecordedDraw stroked;
     for (size_t i = begin; i < end; i++) {
-        const RecordedDraw &r = b->recs[i];
+        const RecordedDraw *rp = &b->recs[i];
+        if (rp->is_stroke) {
+            // stroke_path: the outline is computed in local coordinates, then filled (Winding) under the transform
+            uint8_t *ov = nullptr;
+            float *op = nullptr;
+            int32_t nv = 0, np = 0;
+            if (rb_path_stroke(rp->verbs.data(), (int32_t)rp->verbs.size(), &rp->pts[0].x, (int32_t)rp->pts.size(),
+                               rp->stroke.width, rp->stroke.miter_limit, rp->stroke.cap, rp->stroke.join,
+                               resolution_scale(rp->ctm), &ov, &nv, &op, &np) != RB_OK)
+                continue;
+            stroked.verbs.assign(ov, ov + nv);
+            stroked.pts.resize((size_t)np);
+            memcpy(stroked.pts.data(), op, sizeof(float) * 2 * (size_t)np);
+            rb_path_free(ov);
+            rb_path_free(op);
+            rbh::map_points(rp->ctm, stroked.pts.data(), np);
+            stroked.paint = rp->paint;
+            stroked.stops = rp->stops;
+            stroked.ctm = rp->ctm;
+            stroked.rule = 0;
+            rp = &stroked;
+        }
+        const RecordedDraw &r = *rp;
         const bool aa = r.paint.anti_alias != 0;
         // DrawTiler: tiles of at most 8191x8191 in row-major order; a single tile for ordinary canvases.
         for (int ty = 0; ty < H; ty += kMaxDim) {
@@ -1135,6 +1176,34 @@ static void batch_release(rb_batch *b)
         b->dev = nullptr;
     }
     b->n_tile_ids = 0;
+}
+
+// PixmapMut::stroke_path(path, paint, stroke, transform, None) — path.rs:113.  Thin anti-aliased strokes that
+// tiny-skia draws as hairlines (both transformed stroke-width vectors no longer than 1 px) are not implemented yet
+// and are reported as RB_ERR_UNSUPPORTED instead of being drawn differently.
+extern "C" int rb_batch_stroke_path(rb_batch *b, const uint8_t *verbs, int32_t n_verbs, const float *points,
+                                    int32_t n_points, const rb_paint *paint, const rb_stroke *stroke, const float ts[6])
+{
+    if (!stroke || !paint) return RB_ERR_INVALID;
+    if (stroke->width < 0.0f) return RB_OK;
+    if (stroke->cap < 0 || stroke->cap > 2 || stroke->join < 0 || stroke->join > 3) return RB_ERR_INVALID;
+    const rbh::Xform ctm = ts ? rbh::Xform::from(ts) : rbh::Xform();
+    {
+        // treat_as_hairline
+        auto fast_len = [](float x, float y) { x = fabsf(x); y = fabsf(y); return std::max(x, y) + std::min(x, y) * 0.5f; };
+        const float w = stroke->width;
+        if (w == 0.0f) return RB_ERR_UNSUPPORTED;
+        if (paint->anti_alias && fast_len(ctm.sx * w, ctm.ky * w) <= 1.0f && fast_len(ctm.kx * w, ctm.sy * w) <= 1.0f)
+            return RB_ERR_UNSUPPORTED;
+    }
+    static const float ident[6] = {1, 0, 0, 1, 0, 0};
+    int st = rb_batch_fill_path(b, verbs, n_verbs, points, n_points, paint, 0, ident); // keep local coordinates
+    if (st != RB_OK) return st;
+    RecordedDraw &r = b->recs.back();
+    r.ctm = ctm;
+    r.is_stroke = true;
+    r.stroke = *stroke;
+    return RB_OK;
 }
 
 extern "C" void rb_batch_destroy(rb_batch *b)
@@ -1343,18 +1412,29 @@ extern "C" int rb_batch_submit(rb_batch *b, int32_t n_threads)
 }
 
 // Bulk recording: n_paths paths in packed arrays (verb_off / point_off have n_paths + 1 entries).
-extern "C" int rb_batch_fill_paths(rb_batch *b, int32_t n_paths, const uint32_t *verb_off, const uint32_t *point_off,
+extern "C" int rb_batch_draw_paths(rb_batch *b, int32_t n_paths, const uint32_t *verb_off, const uint32_t *point_off,
                                    const uint8_t *verbs, const float *points, const rb_paint *paints,
-                                   const uint8_t *fill_rules, const float ts[6])
+                                   const uint8_t *fill_rules, const rb_stroke *strokes, const float ts[6])
 {
     if (!b || n_paths < 0 || !verb_off || !point_off || !verbs || !points || !paints || !fill_rules) return RB_ERR_INVALID;
     b->recs.reserve(b->recs.size() + (size_t)n_paths);
     for (int32_t i = 0; i < n_paths; i++) {
-        int st = rb_batch_fill_path(b, verbs + verb_off[i], (int32_t)(verb_off[i + 1] - verb_off[i]), points + 2 * (size_t)point_off[i],
-                                    (int32_t)(point_off[i + 1] - point_off[i]), &paints[i], fill_rules[i], ts);
+        const uint8_t *v = verbs + verb_off[i];
+        const float *p = points + 2 * (size_t)point_off[i];
+        const int32_t nv = (int32_t)(verb_off[i + 1] - verb_off[i]), np = (int32_t)(point_off[i + 1] - point_off[i]);
+        int st;
+        if (strokes && strokes[i].width > 0.0f) st = rb_batch_stroke_path(b, v, nv, p, np, &paints[i], &strokes[i], ts);
+        else st = rb_batch_fill_path(b, v, nv, p, np, &paints[i], fill_rules[i], ts);
         if (st != RB_OK) return st;
     }
     return RB_OK;
+}
+
+extern "C" int rb_batch_fill_paths(rb_batch *b, int32_t n_paths, const uint32_t *verb_off, const uint32_t *point_off,
+                                   const uint8_t *verbs, const float *points, const rb_paint *paints,
+                                   const uint8_t *fill_rules, const float ts[6])
+{
+    return rb_batch_draw_paths(b, n_paths, verb_off, point_off, verbs, points, paints, fill_rules, nullptr, ts);
 }
 
 extern "C" int rb_fill_path(rb_layer *layer, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,

@@ -30,10 +30,22 @@ STREAM = 160  # uniforms reserved per path
 MOVE, LINE, QUAD, CUBIC, CLOSE = 0, 1, 2, 3, 4
 
 
-def paths_scene(width=8192, height=8192, n_paths=100_000, seed=0x5EED0002, rmin=8.0, rmax=256.0,
-                stroke_share=0.0):
-    """C2 'paths8k'.  stroke_share is reserved for the stroker (paths that are stroked are emitted by
-    ``add_strokes`` once the outline exists); with 0.0 every path is a fill."""
+def _gather_ranges(off, idx):
+    """Indices selecting the concatenation of ranges off[i]:off[i+1] for i in idx, plus the new offsets."""
+    lens = (off[1:] - off[:-1]).astype(np.int64)[idx]
+    new_off = np.zeros(len(idx) + 1, np.uint32)
+    new_off[1:] = np.cumsum(lens)
+    starts = off[:-1].astype(np.int64)[idx]
+    pos = np.arange(int(new_off[-1]), dtype=np.int64) - np.repeat(new_off[:-1].astype(np.int64), lens)
+    return np.repeat(starts, lens) + pos, new_off
+
+
+def paths_scene(width=8192, height=8192, n_paths=100_000, seed=0x5EED0002, rmin=8.0, rmax=256.0, strokes=True,
+                stroke_wmin=1.0, stroke_wmax=16.0):
+    """C2 'paths8k': n_paths random closed paths; 70 % are filled, 20 % filled then stroked, 10 % stroked only
+    (strokes=True).  The returned arrays hold one entry per DRAW (a filled+stroked path is two entries).  Stroke
+    width is log-uniform [stroke_wmin, stroke_wmax]; the default lower bound of 1 px keeps every stroke on the general
+    stroker path (tiny-skia's hairline special case for widths <= 1 px is not implemented yet)."""
     u = splitmix64_uniform(seed, n_paths * STREAM).reshape(n_paths, STREAM)
     cx = u[:, 0] * width
     cy = u[:, 1] * height
@@ -113,9 +125,43 @@ def paths_scene(width=8192, height=8192, n_paths=100_000, seed=0x5EED0002, rmin=
     geom[rad, 3] = cx[rad]
     geom[rad, 4] = cy[rad]
     geom[rad, 5] = radius[rad]
-    return dict(width=width, height=height, n_paths=n_paths, verb_off=verb_off, pt_off=pt_off, verbs=verbs, pts=pts,
-                rules=evenodd, paint_kind=paint_kind, color=color, geom=geom, spread=spread, n_stops=n_stops,
-                stop_off=stop_off, stops=stops, anti_alias=anti_alias, radius=radius.astype(np.float32))
+    sc = dict(width=width, height=height, n_paths=n_paths, n_source_paths=n_paths, verb_off=verb_off, pt_off=pt_off,
+              verbs=verbs, pts=pts, rules=evenodd, paint_kind=paint_kind, color=color, geom=geom, spread=spread,
+              n_stops=n_stops, stop_off=stop_off, stops=stops, anti_alias=anti_alias, radius=radius.astype(np.float32),
+              stroke_width=np.zeros(n_paths, np.float32), stroke_miter=np.full(n_paths, 4.0, np.float32),
+              stroke_cap=np.zeros(n_paths, np.int32), stroke_join=np.zeros(n_paths, np.int32))
+    if not strokes:
+        return sc
+    # draw list: fill (kind < 0.9), then stroke (kind >= 0.7), in path order
+    kind = u[:, 7]
+    has_fill, has_stroke = kind < 0.9, kind >= 0.7
+    n_entries = has_fill.astype(np.int64) + has_stroke.astype(np.int64)
+    src = np.repeat(np.arange(n_paths), n_entries)
+    first = np.zeros(len(src), bool)
+    first[np.cumsum(n_entries) - n_entries] = True
+    is_stroke = np.where(first, ~has_fill[src], True)
+    vi, new_voff = _gather_ranges(verb_off, src)
+    pi, new_poff = _gather_ranges(pt_off, src)
+    out = dict(sc)
+    out.update(n_paths=len(src), verb_off=new_voff, pt_off=new_poff, verbs=verbs[vi], pts=pts[pi], rules=evenodd[src],
+               anti_alias=anti_alias[src], radius=sc["radius"][src])
+    # stroke draws are painted with their own solid colour; fills keep the path's paint
+    pk = paint_kind[src].copy()
+    col = color[src].copy()
+    scol = np.stack([np.floor(u[:, 16] * 256) / 255.0, np.floor(u[:, 17] * 256) / 255.0, np.floor(u[:, 18] * 256) / 255.0,
+                     (32 + np.floor(u[:, 19] * 224)) / 255.0], axis=1).astype(np.float32)
+    pk[is_stroke] = 0
+    col[is_stroke] = scol[src][is_stroke]
+    ns = n_stops[src].copy()
+    ns[is_stroke] = 0
+    so = stop_off[:-1][src].copy()  # offsets into the unchanged stop pool (not a prefix sum any more)
+    sw = np.exp(np.log(stroke_wmin) + u[:, 20] * (np.log(stroke_wmax) - np.log(stroke_wmin))).astype(np.float32)
+    out.update(paint_kind=pk, color=col, geom=geom[src], spread=spread[src], n_stops=ns, stop_start=so,
+               stroke_width=np.where(is_stroke, sw[src], 0.0).astype(np.float32),
+               stroke_miter=np.full(len(src), 4.0, np.float32),
+               stroke_cap=np.minimum((u[:, 21] * 3).astype(np.int32), 2)[src],
+               stroke_join=np.array([0, 2, 3], np.int32)[np.minimum((u[:, 22] * 3).astype(np.int64), 2)][src])
+    return out
 
 
 def to_paint_array(scene, paint_struct, blend_mode=3):
@@ -138,7 +184,8 @@ def to_paint_array(scene, paint_struct, blend_mode=3):
         put(name, g[:, i], np.float32)
     put("n_stops", scene["n_stops"], np.int32)
     base = scene["stops"].ctypes.data
-    ptr = np.where(scene["n_stops"] > 0, base + scene["stop_off"][:-1] * 20, 0).astype(np.uint64)
+    start = scene["stop_start"] if "stop_start" in scene else scene["stop_off"][:-1]
+    ptr = np.where(scene["n_stops"] > 0, base + start * 20, 0).astype(np.uint64)
     put("stops", ptr, np.uint64)
     put("spread", scene["spread"], np.int32)
     put("ts", np.tile(np.array([1, 0, 0, 1, 0, 0], np.float32), (n, 1)), np.float32)
@@ -149,6 +196,18 @@ def to_paint_array(scene, paint_struct, blend_mode=3):
     return arr
 
 
+def to_stroke_array(scene, stroke_struct):
+    """ctypes array of rb_stroke {width, miter_limit, cap, join}; width 0 marks a fill entry."""
+    n = scene["n_paths"]
+    arr = (stroke_struct * n)()
+    view = np.frombuffer(arr, dtype=np.uint8).reshape(n, C.sizeof(stroke_struct))
+    for name, dt in (("width", np.float32), ("miter_limit", np.float32), ("cap", np.int32), ("join", np.int32)):
+        f = getattr(stroke_struct, name)
+        key = {"width": "stroke_width", "miter_limit": "stroke_miter", "cap": "stroke_cap", "join": "stroke_join"}[name]
+        view[:, f.offset:f.offset + 4] = np.ascontiguousarray(scene[key], dtype=dt).reshape(n, 1).view(np.uint8)
+    return arr
+
+
 def subset(scene, n):
     """First n paths of a scene (same canvas): the bounded sample the CPU baseline is timed on."""
     n = min(n, scene["n_paths"])
@@ -156,7 +215,9 @@ def subset(scene, n):
     out["n_paths"] = n
     out["verb_off"] = scene["verb_off"][: n + 1].copy()
     out["pt_off"] = scene["pt_off"][: n + 1].copy()
-    for k in ("rules", "paint_kind", "color", "geom", "spread", "n_stops", "anti_alias", "radius"):
-        out[k] = scene[k][:n].copy()
+    for k in ("rules", "paint_kind", "color", "geom", "spread", "n_stops", "anti_alias", "radius", "stroke_width",
+              "stroke_miter", "stroke_cap", "stroke_join", "stop_start"):
+        if k in scene:
+            out[k] = scene[k][:n].copy()
     out["stop_off"] = scene["stop_off"][: n + 1].copy()
     return out

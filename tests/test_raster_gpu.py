@@ -3,6 +3,8 @@
 Bars: coverage, the u16 "lowp" pipeline, masks and the non-AA path are bit-exact; the f32 "highp" pipeline
 (two-point-conical gradients, highp-only blend modes, layer composites, pattern sampling) is within 1/255.
 """
+import math
+
 import numpy as np
 import pytest
 
@@ -332,3 +334,31 @@ def test_many_overlapping_loops_select_wide_kernel(ctx):
     want = np.zeros((h, w, 4), np.uint8)
     R.fill_path(want, verbs, pts, R.make_paint(spec), "nonzero")
     assert_exact(l.download(), want, "140 nested loops")
+
+
+def test_batch_stroke_path_matches_host_stroker_plus_oracle_fill(ctx):
+    """PixmapMut::stroke_path through the batch API (host stroker inside prepare, device fill) == the same outline
+    filled by the oracle."""
+    import resvg_b200 as rb
+
+    w, h = 320, 240
+    rng = SplitMix64(51)
+    want = np.zeros((h, w, 4), np.uint8)
+    l = ctx.layer(w, h)
+    b = rb.Batch(l)
+    caps, joins = ["butt", "round", "square"], ["miter", "round", "bevel", "miter-clip"]
+    for i in range(60):
+        cx, cy, r = rng.uniform(0, w), rng.uniform(0, h), rng.log_uniform(8, 120)
+        verbs, pts = random_path(rng, cx, cy, r)
+        if i % 3 == 0:
+            verbs = verbs[:-1]  # open contour: caps
+        spec = random_paint_spec(rng, cx, cy, r, solid=0.7, linear=0.3)
+        width, cap, join = rng.log_uniform(1.2, 14), caps[i % 3], joins[i % 4]
+        ts = (1.0, 0.0, 0.0, 1.0, 0.0, 0.0) if i % 2 else (1.3, 0.2, -0.1, 0.8, 3.0, -2.0)
+        b.stroke_path(verbs, pts, rb.make_paint(spec), width, 4.0, cap, join, ts)
+        res = math.hypot(ts[0], ts[2]), math.hypot(ts[1], ts[3])
+        out = rb.stroke_path(verbs, pts, width, 4.0, cap, join, max(res))
+        if out is not None:
+            R.fill_path(want, out[0], out[1], R.make_paint(spec), "nonzero", ts)
+    b.submit()
+    assert_exact(l.download(), want, "stroke batch")
