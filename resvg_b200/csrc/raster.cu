@@ -758,12 +758,11 @@ k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint3
 
     uint32_t n_partial = 0, n_full = 0;
     const uint32_t d_begin = tile_off[tile], d_end = tile_off[tile + 1];
-    DevDraw Dn;
-    if (d_begin < d_end) Dn = draws[tile_draws[d_begin]];
+    uint32_t next_draw = d_begin < d_end ? tile_draws[d_begin] : 0u;
 #pragma unroll 1
     for (uint32_t di = d_begin; di < d_end; di++) {
-        const DevDraw D = Dn;
-        if (di + 1 < d_end) Dn = draws[tile_draws[di + 1]]; // prefetch: hides the dependent index -> record load
+        const DevDraw D = draws[next_draw];
+        if (di + 1 < d_end) next_draw = tile_draws[di + 1]; // index prefetch: one dependent load less per draw
         const int tlx = X0 - D.ox, tly = Y0 - D.oy;
         const int py0 = max(0, D.sy - tly), py1 = min(TH, D.sy + D.sh - tly);
         const int pxa = max(0, D.sx - tlx), pxb = min(TW, D.sx + D.sw - tlx);
@@ -781,7 +780,6 @@ k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint3
         //     over all 256 threads, each evaluating x(y) = x + (y - first_y) * dx in closed form — so a long
         //     edge costs the CTA ceil(rows / 256) steps instead of `rows` serial steps of one thread.
         int did = 0;
-        const int rows_log2 = sh == 2 ? 6 : 4; // sub-rows per tile: 64 (AA) / 16 (non-AA)
 #pragma unroll 1
         for (uint32_t chunk = 0; chunk < D.edge_cnt; chunk += RT_THREADS) {
             const uint32_t e = chunk + tid;
@@ -796,29 +794,33 @@ k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint3
             }
             const int chunk_past = __syncthreads_and(past || e >= D.edge_cnt); // also publishes s_list
             const int n_act = s_count[cbuf];
+            if (px_stats && tid == 0) atomicAdd(px_stats + 5, (unsigned long long)n_act);
             const uint16_t *list = s_list[lbuf];
             lbuf ^= 1;
             cbuf = cnext;
+            // one warp per surviving edge, lanes = consecutive sub-rows of that edge inside the tile
 #pragma unroll 1
-            for (int i = tid; i < (n_act << rows_log2); i += RT_THREADS) {
-                const DevEdge E = E0[chunk + list[i >> rows_log2]];
-                const int rel = (py0 << sh) + (i & ((1 << rows_log2) - 1)); // tile-local sub-row
-                const int y = row0 + rel;
+            for (int a = wid; a < n_act; a += RT_THREADS / 32) {
+                const DevEdge E = E0[chunk + list[a]];
                 const int fy = (int)(E.ypack & 0xffffu), ly = (int)(E.ypack >> 16);
-                if (y < fy || y > ly || y >= sub_bot) continue;
-                const uint32_t x = (uint32_t)E.x + (uint32_t)(y - fy) * (uint32_t)E.dx;
-                const int r = (int)(x + 0x8000u) >> 16;
-                const int pos = max(r - col0, lo_pos);
-                if (pos >= hi_pos) continue;
-                did = 1;
+                const int ys = max(fy, sub_top), ye = min(ly, sub_bot - 1);
                 const bool up = (E.meta & 1u) != 0;
-                if (sh == 2) {
-                    const int sr = rel & 3, idx = (rel >> 2) * ROW_POS + pos;
-                    const int one = 1 << (8 * sr);
-                    atomicAdd(wsum + idx, up ? -one : one);
-                    if (sr == 3) atomicAdd(cnt3 + idx, up ? 0x10000 : 1);
-                } else {
-                    atomicAdd(wsum + rel * ROW_POS + pos, up ? -1 : 1);
+#pragma unroll 1
+                for (int y = ys + lane; y <= ye; y += 32) {
+                    const uint32_t x = (uint32_t)E.x + (uint32_t)(y - fy) * (uint32_t)E.dx;
+                    const int r = (int)(x + 0x8000u) >> 16;
+                    const int pos = max(r - col0, lo_pos);
+                    if (pos >= hi_pos) continue;
+                    did = 1;
+                    const int rel = y - row0;
+                    if (sh == 2) {
+                        const int sr = rel & 3, idx = (rel >> 2) * ROW_POS + pos;
+                        const int one = 1 << (8 * sr);
+                        atomicAdd(wsum + idx, up ? -one : one);
+                        if (sr == 3) atomicAdd(cnt3 + idx, up ? 0x10000 : 1);
+                    } else {
+                        atomicAdd(wsum + rel * ROW_POS + pos, up ? -1 : 1);
+                    }
                 }
             }
             if (chunk_past) break; // edges are sorted by first_y: nothing further can reach this tile
