@@ -205,12 +205,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import resvg_b200 as rb
-    from resvg_b200 import _ffi, scenes
+    from resvg_b200 import _ffi, scenes, shard
 
     W, H, n_paths, seed = WORKLOADS[args.workload]
     canvas_mpx = W * H / 1e6
     ctx = rb.Context(local_rank)
-    scene = scenes.paths_scene(W, H, n_paths, seed + rank)  # every rank renders its own document
+    scene = scenes.paths_scene(W, H, n_paths, shard.scene_seed(seed, rank))  # every rank renders its own document
+    n_threads = 0 if world == 1 else shard.host_threads(world)
     scene["paints"] = scenes.to_paint_array(scene, _ffi.Paint)
     scene["strokes"] = scenes.to_stroke_array(scene, _ffi.Stroke)
     n_draws_in = scene["n_paths"]
@@ -218,7 +219,7 @@ def main():
     layer = ctx.layer(W, H)
     batch = rb.Batch(layer)
     batch.fill_paths(scene)
-    batch.prepare(0)  # host edge build + binning + H2D: inputs are resident in HBM before the timed region
+    batch.prepare(n_threads)  # host edge build + binning + H2D: inputs are resident in HBM before the timed region
     st = batch.stats()
     ctx.synchronize()
 
@@ -266,7 +267,7 @@ def main():
         layer.fill(0, 0, 0, 0)
         b = rb.Batch(layer)
         b.fill_paths(scene)
-        b.submit(0)
+        b.submit(n_threads)
         e2e_h2d = b.stats()["upload_bytes"]
         b.close()
         layer.download_ptr(pinned.array.ctypes.data)  # synchronises
@@ -279,10 +280,7 @@ def main():
     ctx.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
 
-    t = torch.tensor([ms_step, ms_kernel, e2e_s], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step, ms_kernel, e2e_s = [float(x) for x in t.tolist()]
+    ms_step, ms_kernel, e2e_s = shard.max_over_ranks([ms_step, ms_kernel, e2e_s], world, f"cuda:{local_rank}")
 
     if rank == 0:
         peak, peak_src = measured_peaks()
@@ -294,7 +292,7 @@ def main():
         except Exception:
             pass
         out = {
-            "metric": "Mpixels/s rendered", "value": world * canvas_mpx / (ms_step * 1e-3), "unit": "Mpx/s",
+            "metric": "Mpixels/s rendered", "value": shard.aggregate_throughput(canvas_mpx, world, ms_step * 1e-3), "unit": "Mpx/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/u16 fixed point + f32", "data": "synthetic",
@@ -310,7 +308,7 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes": alg_bytes, "kernel_ms": ms_kernel,
                          "model": "8 B per blended px + 4 B per opaque-stored px + 16 B per line edge"},
-            "e2e": {"value": world * canvas_mpx / e2e_s, "unit": "Mpx/s", "h2d_bytes_per_step": int(e2e_h2d),
+            "e2e": {"value": shard.aggregate_throughput(canvas_mpx, world, e2e_s), "unit": "Mpx/s", "h2d_bytes_per_step": int(e2e_h2d),
                     "d2h_bytes_per_step": W * H * 4, "ms_per_step": e2e_s * 1e3, "host_build_ms": st["host_us"] / 1e3,
                     "steps": e2e_steps},
         }

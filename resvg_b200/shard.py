@@ -1,0 +1,62 @@
+"""Document-parallel sharding of the pixel path across GPUs.
+
+resvg renders one tree into one pixmap (crates/resvg/src/lib.rs:34); independent documents share nothing, so the
+multi-GPU form of the path is one process per GPU, each rendering its own documents, with NO collective on the data
+path.  torch.distributed is used for the timing protocol only (barrier, max-over-ranks), which is what this module
+holds so that it can be exercised on CPU with the gloo backend (tests/test_shard_gloo.py) and on GPUs with nccl
+(bench.py).
+"""
+from __future__ import annotations
+
+import os
+
+
+def env_rank():
+    """(rank, local_rank, world) as torchrun exports them; (0, 0, 1) for a plain launch."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+def documents_for_rank(n_documents: int, rank: int, world: int):
+    """Round-robin assignment of document indices: rank r renders documents r, r + world, ..."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    return list(range(rank, n_documents, world))
+
+
+def scene_seed(base_seed: int, rank: int, index: int = 0, world: int = 1) -> int:
+    """Seed of the synthetic document `index` of `rank` (distinct per rank so ranks do not render one scene)."""
+    return int(base_seed) + rank + index * world
+
+
+def host_threads(world: int) -> int:
+    """Host edge-build threads per rank: the ranks of one node share its cores."""
+    return max(1, (os.cpu_count() or 1) // max(1, world))
+
+
+def max_over_ranks(values, world: int, device=None):
+    """Element-wise maximum over ranks of a small list of floats (device timings); identity for world == 1."""
+    if world == 1:
+        return [float(v) for v in values]
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t.tolist()]
+
+
+def gather_ints(values, world: int, device=None):
+    """All ranks' integer tuples (checksums, counters), as a list indexed by rank."""
+    if world == 1:
+        return [[int(v) for v in values]]
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(values), dtype=torch.int64, device=device)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [[int(v) for v in o.tolist()] for o in out]
+
+
+def aggregate_throughput(units_per_rank: float, world: int, seconds: float) -> float:
+    """Whole-job throughput under weak scaling: every rank processed `units_per_rank` in `seconds` (max over ranks)."""
+    return world * units_per_rank / seconds

@@ -1,0 +1,48 @@
+"""Worker of tests/test_shard_gloo.py: one rank of the document-parallel path on CPU (gloo).
+
+Each rank builds ITS document (resvg_b200.shard.scene_seed), renders it with the oracle (there is no GPU here; on the
+GPU box bench.py runs the same protocol with the CUDA path and nccl), then the ranks exchange checksums and reduce
+their timings exactly as bench.py does.  Rank 0 writes a JSON report.
+"""
+import json
+import os
+import sys
+import zlib
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    out_path, W, H, n_paths, seed = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5])
+    import torch.distributed as dist
+    import bench
+    from resvg_b200 import scenes, shard
+
+    rank, _, world = shard.env_rank()
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("gloo")
+    try:
+        scene = scenes.paths_scene(W, H, n_paths, shard.scene_seed(seed, rank))
+        px = np.zeros((H, W, 4), np.uint8)
+        dt = bench.cpu_render_sample(bench.oracle_lib(), scene, scene["n_paths"], px)
+        crc = zlib.crc32(px.tobytes())
+        dist.barrier()
+        per_rank = shard.gather_ints([crc, scene["n_paths"], int(px[..., 3].astype(np.int64).sum())], world)
+        fake_ms = 10.0 + 5.0 * rank  # deterministic "device times": the reduction must return the slowest rank's
+        (ms,) = shard.max_over_ranks([fake_ms], world)
+        (real,) = shard.max_over_ranks([dt], world)
+        docs = shard.documents_for_rank(7, rank, world)
+        all_docs = shard.gather_ints(docs + [-1] * (4 - len(docs)), world)
+        if rank == 0:
+            with open(out_path, "w") as f:
+                json.dump({"world": world, "per_rank": per_rank, "ms": ms, "render_s": real, "docs": all_docs,
+                           "value": shard.aggregate_throughput(W * H / 1e6, world, ms * 1e-3)}, f)
+    finally:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,57 @@
+"""World-size-2 CPU (gloo) run of the multi-GPU protocol: document-parallel sharding, no data-path collective
+(SURVEY.md §8(e)); only checksums and timings cross ranks."""
+import json
+import os
+import subprocess
+import sys
+import zlib
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from resvg_b200 import scenes, shard  # noqa: E402
+
+
+def test_document_assignment_is_a_partition():
+    for world in (1, 2, 3, 8):
+        seen = sorted(d for r in range(world) for d in shard.documents_for_rank(11, r, world))
+        assert seen == list(range(11))
+    with pytest.raises(ValueError):
+        shard.documents_for_rank(4, 2, 2)
+    assert shard.scene_seed(7, 0) != shard.scene_seed(7, 1)
+    assert len({shard.scene_seed(7, r, i, 4) for r in range(4) for i in range(5)}) == 20
+    assert shard.aggregate_throughput(67.108864, 8, 0.05) == pytest.approx(8 * 67.108864 / 0.05)
+    assert shard.max_over_ranks([1.5, 2.5], 1) == [1.5, 2.5]
+    assert shard.host_threads(1) >= shard.host_threads(2) >= 1
+
+
+@pytest.mark.timeout(300)
+def test_two_ranks_gloo(tmp_path):
+    import bench
+    W, H, n_paths, seed = 192, 160, 60, 4242
+    out = tmp_path / "report.json"
+    port = 29500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tests", "dist_worker.py"), str(out), str(W), str(H), str(n_paths), str(seed)]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    rep = json.loads(out.read_text())
+    assert rep["world"] == 2
+    # every rank rendered its own document: same result as rendering the two documents serially here
+    R = bench.oracle_lib()
+    want = []
+    for rank in range(2):
+        scene = scenes.paths_scene(W, H, n_paths, shard.scene_seed(seed, rank))
+        px = np.zeros((H, W, 4), np.uint8)
+        bench.cpu_render_sample(R, scene, scene["n_paths"], px)
+        want.append([zlib.crc32(px.tobytes()), scene["n_paths"], int(px[..., 3].astype(np.int64).sum())])
+    assert rep["per_rank"] == want
+    assert want[0][0] != want[1][0]
+    assert rep["ms"] == 15.0  # max over ranks, not rank 0's 10 ms
+    assert rep["value"] == pytest.approx(2 * (W * H / 1e6) / 15e-3)
+    assert rep["docs"] == [[0, 2, 4, 6], [1, 3, 5, -1]]
