@@ -257,6 +257,16 @@ int rb_debug_build_edges(const uint8_t *verbs, int32_t n_verbs, const float *poi
                          int32_t *out_meta /* optional: {prev segment index | -1, inserts-before flag} per edge */,
                          int32_t max_edges, int32_t geom[7]);
 
+/* Host-only batch (no target, no device work): records like any batch; rb_batch_prepare runs the host build (edges,
+ * binning, block layout) for a width x height canvas and keeps the block on the host.  For the CPU test-suite and for
+ * profiling the host half.  rb_debug_batch_phases: microseconds of the last host build — [0] edge build, [1] layout +
+ * tile counting, [2] pack, [3] tile lists, [4] staging allocation/wait, [5] total.  rb_debug_batch_block copies one
+ * array of the block out (which: 0 draws (48 B), 1 tile offsets, 2 tile draw lists, 3 tile ids, 4 edges (16 B)) and
+ * returns its element count. */
+int rb_debug_batch_begin_host(uint32_t width, uint32_t height, rb_batch **out);
+int rb_debug_batch_phases(rb_batch *batch, uint64_t phases[6]);
+int64_t rb_debug_batch_block(rb_batch *batch, int32_t which, void *out, uint64_t max_bytes);
+
 #ifdef __cplusplus
 }
 #endif

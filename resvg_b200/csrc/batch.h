@@ -1,0 +1,81 @@
+// batch.h — a recorded batch of fill_path / stroke_path calls and its device-consumable form.
+//
+// The host half (batch_host.cpp) records draws, builds edges on host threads, bins draws into device tiles and
+// lays everything out in ONE contiguous block (pinned staging) that raster.cu uploads with a single copy and the
+// tile kernel consumes in place.
+#pragma once
+
+#include <stdint.h>
+
+#include <vector>
+
+#include "raster_host.h"
+
+struct rb_ctx;
+struct rb_layer;
+struct rb_mask;
+
+constexpr int TW = 64; // device tile width  (pixels)
+constexpr int TH = 16; // device tile height (pixels)
+
+// ypack = first_y | last_y << 16.  meta: bit 0 = upward edge (winding -1), bit 1 = continuation segment of a
+// curve, bit 2 = insert_new_edges places it before equal-x active edges, bits 4.. = index of the previous
+// segment of the same curve (valid when bit 1 is set).
+struct DevEdge { int32_t x, dx; uint32_t ypack; uint32_t meta; };
+struct DevDraw {
+    uint32_t edge_off, edge_cnt;
+    int32_t ox, oy;         // DrawTiler tile origin inside the layer
+    int32_t sx, sy, sw, sh; // pixels the blitter may touch (DrawTiler-tile local)
+    int32_t shift, rule;    // 2 = AA / 0 = non-AA; 0 winding / 1 even-odd
+    uint32_t paint, pad;
+};
+
+struct RecordedDraw {
+    uint32_t verb_off, n_verbs; // into rb_batch::verbs
+    uint32_t pt_off, n_pts;     // into rb_batch::pts — fills: device space (transform applied); strokes: local space
+    uint32_t stop_off, n_stops; // into rb_batch::stops (5 floats per stop)
+    rb_paint paint;
+    rbh::Xform ctm;
+    int rule;
+    bool is_stroke;
+    rb_stroke stroke;
+};
+
+// Byte offsets of the arrays inside the contiguous block (identical on host staging and device).
+struct BatchLayout {
+    size_t o_edges = 0, o_draws = 0, o_paints = 0, o_stops = 0, o_toff = 0, o_tdraws = 0, o_tids = 0, total = 0;
+    size_t n_edges = 0, n_draws = 0, n_paints = 0, n_stops = 0, n_tiles = 0, n_pairs = 0, n_tile_ids = 0;
+    int tiles_x = 0;
+    bool wide = false; // some draw may reach |winding| > 127: use k_raster_tiles_wide
+};
+
+// phases of the last host build, microseconds: [0] edge build (threads), [1] layout + count, [2] pack (threads),
+// [3] binning, [4] staging allocation / wait, [5] total
+enum { RB_PHASES = 6 };
+
+struct rb_batch {
+    rb_layer *layer = nullptr;
+    rb_mask *mask = nullptr;
+    int host_w = 0, host_h = 0; // host-only batches (rb_debug_batch_begin_host): no target, no upload
+    std::vector<uint8_t> verbs;
+    std::vector<rbh::Pt> pts;
+    std::vector<float> stops;
+    std::vector<RecordedDraw> recs;
+    uint64_t stats[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t phases[RB_PHASES] = {0, 0, 0, 0, 0, 0};
+    // device-resident form produced by rb_batch_prepare
+    BatchLayout lay;
+    uint8_t *dev = nullptr;
+    void *host_block = nullptr; // host-only batches: malloc'ed copy of the block
+};
+
+// Staging allocator: returns `bytes` of host memory the block is assembled in (pinned, owned by the context; or
+// malloc'ed for host-only batches).
+typedef void *(*rb_stage_alloc)(void *user, size_t bytes);
+
+// Edge build + binning + layout.  Returns RB_OK with lay.n_draws == 0 when nothing is to be drawn.
+int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threads, rb_stage_alloc alloc, void *user,
+                        void **block);
+
+int rb_batch_record(rb_batch *b, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
+                    const rb_paint *paint, int32_t rule, const float ts[6]);

@@ -1,0 +1,570 @@
+// batch_host.cpp — host half of a draw batch: recording (tiny-skia's fill_path / stroke_path arguments), edge
+// building on host threads, tile binning, and the layout of the single block the device consumes.
+//
+// The reference does this work inside every PixmapMut::fill_path call (tiny-skia painter.rs → scan/path*.rs:
+// transform, clip, build edges, sort) right before walking the edges; here it is done for a whole batch at once,
+// in parallel over draws, and the result is shipped to the GPU in one copy.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "batch.h"
+
+extern "C" int rb_path_stroke(const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points, float width,
+                              float miter_limit, int32_t cap, int32_t join, float res_scale, uint8_t **out_verbs,
+                              int32_t *out_n_verbs, float **out_points, int32_t *out_n_points);
+extern "C" void rb_path_free(void *p);
+
+namespace {
+
+using rbh::DevPaint;
+using rbh::DevStop;
+
+constexpr int kMaxDim = 8191;    // tiny-skia DrawTiler::MAX_DIMENSIONS
+constexpr size_t kChunk = 128;   // draws per work item
+
+typedef std::chrono::steady_clock Clock;
+inline uint64_t us_since(Clock::time_point t0)
+{
+    return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(Clock::now() - t0).count();
+}
+
+// Runs fn(item, worker) for item in [0, n) on `nt` threads with dynamic scheduling.
+template <class F>
+void parallel_for(int nt, size_t n, F fn)
+{
+    if (nt <= 1 || n <= 1) {
+        for (size_t i = 0; i < n; i++) fn(i, 0);
+        return;
+    }
+    std::atomic<size_t> next(0);
+    std::vector<std::thread> th;
+    th.reserve((size_t)nt);
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([&, t]() {
+            for (;;) {
+                size_t i = next.fetch_add(1, std::memory_order_relaxed);
+                if (i >= n) break;
+                fn(i, t);
+            }
+        });
+    for (auto &t : th) t.join();
+}
+
+// Upper bound of |winding| for a draw: edges simultaneously active on one scanline.  Chains (an edge plus its
+// curve continuations) never overlap themselves in y, so the chain count bounds it; only when that is not tight
+// enough is the exact maximum swept.
+bool draw_may_exceed_packed_winding(const rbh::Edge *e, size_t n)
+{
+    if (n < 128) return false;
+    size_t chains = 0;
+    for (size_t i = 0; i < n; i++) chains += e[i].prev < 0 ? 1 : 0;
+    if (chains < 128) return false;
+    std::vector<int32_t> ends;
+    ends.reserve(n);
+    for (size_t i = 0; i < n; i++) ends.push_back(e[i].last_y);
+    std::sort(ends.begin(), ends.end());
+    size_t active = 0, j = 0, worst = 0;
+    for (size_t i = 0; i < n; i++) { // e is sorted by first_y
+        while (j < n && ends[j] < e[i].first_y) { j++; active--; }
+        active++;
+        worst = std::max(worst, active);
+    }
+    return worst >= 128;
+}
+
+// painter.rs stroke_path: PathStroker::compute_resolution_scale(ts)
+float resolution_scale(const rbh::Xform &t)
+{
+    float sx = sqrtf(t.sx * t.sx + t.kx * t.kx), sy = sqrtf(t.ky * t.ky + t.sy * t.sy);
+    if (std::isfinite(sx) && std::isfinite(sy)) {
+        float s = std::max(sx, sy);
+        if (s > 0) return s;
+    }
+    return 1.0f;
+}
+
+// Per-worker output; the big vectors are recycled across builds (their pages stay mapped).
+struct Worker {
+    std::vector<DevEdge> edges;
+    std::vector<DevDraw> draws;   // edge_off relative to the chunk's first edge
+    std::vector<DevPaint> paints; // stop_off relative to the chunk's first stop
+    std::vector<DevStop> stops;
+    std::vector<rbh::Edge> scratch;
+    std::vector<rbh::Pt> tmp, spts;
+    std::vector<uint8_t> sverbs;
+    bool wide = false;
+    void reset() { edges.clear(); draws.clear(); paints.clear(); stops.clear(); wide = false; }
+};
+
+std::mutex g_pool_mu;
+std::vector<std::unique_ptr<Worker>> g_pool;
+
+std::unique_ptr<Worker> borrow_worker()
+{
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    if (g_pool.empty()) return std::unique_ptr<Worker>(new Worker());
+    std::unique_ptr<Worker> w = std::move(g_pool.back());
+    g_pool.pop_back();
+    return w;
+}
+void return_worker(std::unique_ptr<Worker> w)
+{
+    w->reset();
+    std::lock_guard<std::mutex> g(g_pool_mu);
+    if (g_pool.size() < 256) g_pool.push_back(std::move(w));
+}
+
+struct ChunkInfo {
+    int worker = 0;
+    size_t e0 = 0, ne = 0, d0 = 0, nd = 0, p0 = 0, np = 0, s0 = 0, ns = 0; // ranges in the worker's vectors
+    size_t ge = 0, gd = 0, gp = 0, gs = 0;                                  // global bases
+};
+
+inline DevEdge pack_edge(const rbh::Edge &e)
+{
+    DevEdge d;
+    d.x = e.x;
+    d.dx = e.dx;
+    d.ypack = ((uint32_t)e.first_y & 0xffffu) | ((uint32_t)e.last_y << 16);
+    d.meta = (e.winding < 0 ? 1u : 0u) | (e.prev >= 0 ? 2u : 0u) | (e.before ? 4u : 0u) | (e.prev >= 0 ? ((uint32_t)e.prev << 4) : 0u);
+    return d;
+}
+
+#ifdef RB_HOST_PROFILE
+#include <x86intrin.h>
+std::atomic<uint64_t> g_prof[4];
+} namespace rbh { extern std::atomic<uint64_t> g_bd_prof[4]; } using rbh::g_bd_prof; namespace {
+struct Tick { uint64_t &acc; uint64_t t0; Tick(uint64_t &a) : acc(a), t0(__rdtsc()) {} ~Tick() { acc += __rdtsc() - t0; } };
+#define PROF(i) Tick tick__(prof_local[i])
+#else
+#define PROF(i)
+#endif
+
+void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool mask_target, Worker *out, ChunkInfo *ci)
+{
+    ci->e0 = out->edges.size();
+    ci->d0 = out->draws.size();
+    ci->p0 = out->paints.size();
+    ci->s0 = out->stops.size();
+#ifdef RB_HOST_PROFILE
+    uint64_t prof_local[4] = {0, 0, 0, 0};
+    struct Flush { uint64_t *p; ~Flush() { for (int i = 0; i < 4; i++) g_prof[i] += p[i]; } } flush__{prof_local};
+#endif
+    for (size_t i = begin; i < end; i++) {
+        const RecordedDraw &r = b->recs[i];
+        const uint8_t *verbs = b->verbs.data() + r.verb_off;
+        const rbh::Pt *rpts = b->pts.data() + r.pt_off;
+        int n_verbs = (int)r.n_verbs, n_pts = (int)r.n_pts, rule = r.rule;
+        if (r.is_stroke) {
+            // stroke_path: the outline is computed in local coordinates, then filled (Winding) under the transform
+            uint8_t *ov = nullptr;
+            float *op = nullptr;
+            int32_t nv = 0, np = 0;
+            int sst;
+            {
+                PROF(0);
+                sst = rb_path_stroke(verbs, n_verbs, &rpts[0].x, n_pts, r.stroke.width, r.stroke.miter_limit, r.stroke.cap,
+                                     r.stroke.join, resolution_scale(r.ctm), &ov, &nv, &op, &np);
+            }
+            if (sst != RB_OK) continue;
+            out->sverbs.assign(ov, ov + nv);
+            out->spts.resize((size_t)np);
+            memcpy(out->spts.data(), op, sizeof(float) * 2 * (size_t)np);
+            rb_path_free(ov);
+            rb_path_free(op);
+            rbh::map_points(r.ctm, out->spts.data(), np);
+            verbs = out->sverbs.data();
+            rpts = out->spts.data();
+            n_verbs = nv;
+            n_pts = np;
+            rule = 0;
+        }
+        const bool aa = r.paint.anti_alias != 0;
+        // DrawTiler: tiles of at most 8191x8191 in row-major order; a single tile for ordinary canvases.
+        for (int ty = 0; ty < H; ty += kMaxDim) {
+            for (int tx = 0; tx < W; tx += kMaxDim) {
+                const int tw = std::min(W - tx, kMaxDim), th = std::min(H - ty, kMaxDim);
+                const rbh::Pt *pts = rpts;
+                rbh::Xform ctm = r.ctm;
+                if (tx || ty) {
+                    out->tmp.assign(rpts, rpts + n_pts);
+                    rbh::Xform tr;
+                    tr.tx = -(float)tx;
+                    tr.ty = -(float)ty;
+                    rbh::map_points(tr, out->tmp.data(), n_pts);
+                    pts = out->tmp.data();
+                    ctm = rbh::post_concat(ctm, tr);
+                }
+                rbh::DrawGeom g;
+                out->scratch.clear();
+                bool ok;
+                {
+                    PROF(1);
+                    ok = rbh::build_draw(verbs, n_verbs, pts, n_pts, aa, tw, th, out->scratch, &g);
+                }
+                if (!ok) continue;
+                const size_t ne = out->scratch.size();
+                DevDraw d;
+                memset(&d, 0, sizeof(d));
+                d.edge_off = (uint32_t)(out->edges.size() - ci->e0);
+                d.edge_cnt = (uint32_t)ne;
+                d.ox = tx; d.oy = ty;
+                d.sx = g.sect.x; d.sy = g.sect.y; d.sw = g.sect.w; d.sh = g.sect.h;
+                d.shift = g.shift;
+                d.rule = rule;
+                if (!mask_target) {
+                    DevPaint p;
+                    rb_paint rp = r.paint;
+                    rp.stops = r.n_stops ? b->stops.data() + r.stop_off : nullptr;
+                    const size_t s_before = out->stops.size();
+                    if (!rbh::prepare_paint(&rp, ctm, &p, out->stops)) continue;
+                    if (out->stops.size() != s_before) p.stop_off = (uint32_t)(p.stop_off - ci->s0);
+                    d.paint = (uint32_t)(out->paints.size() - ci->p0);
+                    out->paints.push_back(p);
+                }
+                PROF(2);
+                if (draw_may_exceed_packed_winding(out->scratch.data(), ne)) out->wide = true;
+                const size_t eo = out->edges.size();
+                out->edges.resize(eo + ne);
+                DevEdge *dst = out->edges.data() + eo;
+                const rbh::Edge *src = out->scratch.data();
+                for (size_t k = 0; k < ne; k++) dst[k] = pack_edge(src[k]);
+                out->draws.push_back(d);
+            }
+        }
+    }
+    ci->ne = out->edges.size() - ci->e0;
+    ci->nd = out->draws.size() - ci->d0;
+    ci->np = out->paints.size() - ci->p0;
+    ci->ns = out->stops.size() - ci->s0;
+}
+
+inline void tile_range(const DevDraw &d, int &x0, int &x1, int &y0, int &y1)
+{
+    x0 = (d.ox + d.sx) / TW; x1 = (d.ox + d.sx + d.sw - 1) / TW;
+    y0 = (d.oy + d.sy) / TH; y1 = (d.oy + d.sy + d.sh - 1) / TH;
+}
+
+} // namespace
+
+int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threads, rb_stage_alloc alloc, void *user,
+                        void **block)
+{
+    memset(b->stats, 0, sizeof(b->stats));
+    memset(b->phases, 0, sizeof(b->phases));
+    b->lay = BatchLayout();
+    *block = nullptr;
+    const size_t n = b->recs.size();
+    if (n == 0) return RB_OK;
+    const auto t0 = Clock::now();
+
+    // ---- 1. edges + paints on host threads (dynamic chunks; painter's order = chunk order) ------------------
+    const size_t n_chunks = (n + kChunk - 1) / kChunk;
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min<int>(nt, (int)n_chunks));
+    std::vector<std::unique_ptr<Worker>> workers;
+    for (int t = 0; t < nt; t++) workers.push_back(borrow_worker());
+    struct Return {
+        std::vector<std::unique_ptr<Worker>> &w;
+        ~Return() { for (auto &x : w) if (x) return_worker(std::move(x)); }
+    } give_back{workers};
+    std::vector<ChunkInfo> chunks(n_chunks);
+    parallel_for(nt, n_chunks, [&](size_t c, int t) {
+        chunks[c].worker = t;
+        build_chunk(b, c * kChunk, std::min(n, (c + 1) * kChunk), W, H, mask_target, workers[(size_t)t].get(), &chunks[c]);
+    });
+    b->phases[0] = us_since(t0);
+#ifdef RB_HOST_PROFILE
+    fprintf(stderr, "[host profile] Mcycles: stroke %.0f build_draw %.0f pack %.0f\n", g_prof[0].load() / 1e6, g_prof[1].load() / 1e6, g_prof[2].load() / 1e6);
+    for (auto &g : g_prof) g = 0;
+    fprintf(stderr, "[host profile] build_draw Mcycles: emit %.0f sort %.0f links %.0f\n", g_bd_prof[0].load() / 1e6, g_bd_prof[1].load() / 1e6, g_bd_prof[2].load() / 1e6);
+    for (auto &g : g_bd_prof) g = 0;
+#endif
+
+    // ---- 2. layout --------------------------------------------------------------------------------------------
+    const auto t1 = Clock::now();
+    BatchLayout L;
+    for (auto &c : chunks) {
+        c.ge = L.n_edges; c.gd = L.n_draws; c.gp = L.n_paints; c.gs = L.n_stops;
+        L.n_edges += c.ne; L.n_draws += c.nd; L.n_paints += c.np; L.n_stops += c.ns;
+    }
+    for (auto &w : workers) L.wide = L.wide || w->wide;
+    if (L.n_draws == 0) return RB_OK;
+    if (L.n_edges > 0xfffffff0ull) return RB_ERR_UNSUPPORTED;
+    L.tiles_x = (W + TW - 1) / TW;
+    const int tiles_y = (H + TH - 1) / TH;
+    L.n_tiles = (size_t)L.tiles_x * tiles_y;
+
+    // tile ranges of every draw, computed from the workers' draws in painter's order; counts per tile
+    struct TR { uint16_t x0, x1, y0, y1; };
+    std::vector<TR> tr(L.n_draws);
+    parallel_for(nt, n_chunks, [&](size_t ci, int) {
+        const ChunkInfo &c = chunks[ci];
+        const DevDraw *src = workers[(size_t)c.worker]->draws.data() + c.d0;
+        for (size_t k = 0; k < c.nd; k++) {
+            int x0, x1, y0, y1;
+            tile_range(src[k], x0, x1, y0, y1);
+            tr[c.gd + k] = TR{(uint16_t)x0, (uint16_t)x1, (uint16_t)y0, (uint16_t)y1};
+        }
+    });
+    // binning is parallel over bands of tile rows: a band owns its tiles' counters and cursors
+    constexpr int kBand = 8;
+    const size_t n_bands = (size_t)(tiles_y + kBand - 1) / kBand;
+    std::vector<uint32_t> tile_cnt(L.n_tiles + 1, 0);
+    parallel_for(nt, n_bands, [&](size_t band, int) {
+        const int by0 = (int)band * kBand, by1 = std::min(tiles_y, by0 + kBand) - 1;
+        for (size_t di = 0; di < L.n_draws; di++) {
+            const TR r = tr[di];
+            if (r.y1 < by0 || r.y0 > by1) continue;
+            for (int y = std::max<int>(r.y0, by0); y <= std::min<int>(r.y1, by1); y++) {
+                uint32_t *row = tile_cnt.data() + (size_t)y * L.tiles_x + 1;
+                for (int x = r.x0; x <= r.x1; x++) row[x]++;
+            }
+        }
+    });
+    for (size_t i = 0; i < L.n_tiles; i++) tile_cnt[i + 1] += tile_cnt[i];
+    L.n_pairs = tile_cnt[L.n_tiles];
+    // non-empty tiles, heaviest first (longest-processing-time-first over the CTA slots)
+    std::vector<uint32_t> tile_ids;
+    tile_ids.reserve(L.n_tiles);
+    for (size_t i = 0; i < L.n_tiles; i++) if (tile_cnt[i + 1] > tile_cnt[i]) tile_ids.push_back((uint32_t)i);
+    std::stable_sort(tile_ids.begin(), tile_ids.end(), [&](uint32_t a, uint32_t c) {
+        return tile_cnt[a + 1] - tile_cnt[a] > tile_cnt[c + 1] - tile_cnt[c];
+    });
+    L.n_tile_ids = tile_ids.size();
+
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t off = 0;
+    L.o_draws = off;  off += al(L.n_draws * sizeof(DevDraw));
+    L.o_paints = off; off += al(std::max<size_t>(L.n_paints, 1) * sizeof(DevPaint));
+    L.o_stops = off;  off += al(std::max<size_t>(L.n_stops, 1) * sizeof(DevStop));
+    L.o_toff = off;   off += al((L.n_tiles + 1) * 4);
+    L.o_tids = off;   off += al(L.n_tile_ids * 4);
+    L.o_tdraws = off; off += al(L.n_pairs * 4);
+    L.o_edges = off;  off += al(L.n_edges * sizeof(DevEdge));
+    L.total = off;
+    b->phases[1] = us_since(t1);
+
+    const auto t2 = Clock::now();
+    uint8_t *blk = (uint8_t *)alloc(user, L.total);
+    if (!blk) return RB_ERR_OOM;
+    b->phases[4] = us_since(t2);
+
+    // ---- 3. pack into the block (threads) ------------------------------------------------------------------------
+    const auto t3 = Clock::now();
+    DevEdge *o_edges = (DevEdge *)(blk + L.o_edges);
+    DevDraw *o_draws = (DevDraw *)(blk + L.o_draws);
+    DevPaint *o_paints = (DevPaint *)(blk + L.o_paints);
+    DevStop *o_stops = (DevStop *)(blk + L.o_stops);
+    parallel_for(nt, n_chunks, [&](size_t ci, int) {
+        const ChunkInfo &c = chunks[ci];
+        const Worker &w = *workers[(size_t)c.worker];
+        if (c.ne) memcpy(o_edges + c.ge, w.edges.data() + c.e0, c.ne * sizeof(DevEdge));
+        if (c.ns) memcpy(o_stops + c.gs, w.stops.data() + c.s0, c.ns * sizeof(DevStop));
+        for (size_t k = 0; k < c.np; k++) {
+            DevPaint p = w.paints[c.p0 + k];
+            p.stop_off += (uint32_t)c.gs;
+            o_paints[c.gp + k] = p;
+        }
+        for (size_t k = 0; k < c.nd; k++) {
+            DevDraw d = w.draws[c.d0 + k];
+            d.edge_off += (uint32_t)c.ge;
+            d.paint += (uint32_t)c.gp;
+            o_draws[c.gd + k] = d;
+        }
+    });
+    memcpy(blk + L.o_toff, tile_cnt.data(), (L.n_tiles + 1) * 4);
+    memcpy(blk + L.o_tids, tile_ids.data(), L.n_tile_ids * 4);
+    b->phases[2] = us_since(t3);
+
+    // ---- 4. fill the per-tile draw lists (counting sort keeps painter's order inside each tile) -------------------
+    const auto t4 = Clock::now();
+    uint32_t *tile_draws = (uint32_t *)(blk + L.o_tdraws);
+    parallel_for(nt, n_bands, [&](size_t band, int) {
+        const int by0 = (int)band * kBand, by1 = std::min(tiles_y, by0 + kBand) - 1;
+        const size_t first = (size_t)by0 * L.tiles_x, cnt = (size_t)(by1 - by0 + 1) * L.tiles_x;
+        std::vector<uint32_t> cursor(tile_cnt.begin() + first, tile_cnt.begin() + first + cnt);
+        for (size_t di = 0; di < L.n_draws; di++) {
+            const TR r = tr[di];
+            if (r.y1 < by0 || r.y0 > by1) continue;
+            for (int y = std::max<int>(r.y0, by0); y <= std::min<int>(r.y1, by1); y++) {
+                uint32_t *row = cursor.data() + (size_t)(y - by0) * L.tiles_x;
+                for (int x = r.x0; x <= r.x1; x++) tile_draws[row[x]++] = (uint32_t)di;
+            }
+        }
+    });
+    b->phases[3] = us_since(t4);
+
+    b->lay = L;
+    *block = blk;
+    b->stats[0] = L.n_draws;
+    b->stats[1] = L.n_edges;
+    b->stats[2] = L.n_pairs;
+    b->stats[3] = L.n_tile_ids;
+    b->stats[4] = L.total;
+    b->stats[5] = b->phases[5] = us_since(t0);
+    return RB_OK;
+}
+
+// ---- recording --------------------------------------------------------------------------------------------------------
+int rb_batch_record(rb_batch *b, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
+                    const rb_paint *paint, int32_t rule, const float ts[6])
+{
+    if (!b || !verbs || !points || n_verbs <= 0 || n_points <= 0 || !paint) return RB_ERR_INVALID;
+    // validate the verb/point bookkeeping so the builder never reads past the arrays
+    int need = 0;
+    for (int i = 0; i < n_verbs; i++) {
+        switch (verbs[i]) {
+        case 0: case 1: need += 1; break;
+        case 2: need += 2; break;
+        case 3: need += 3; break;
+        case 4: break;
+        default: return RB_ERR_INVALID;
+        }
+    }
+    if (need != n_points || verbs[0] != 0) return RB_ERR_INVALID;
+    if (b->verbs.size() + (size_t)n_verbs > 0xfffffff0ull || b->pts.size() + (size_t)n_points > 0xfffffff0ull) return RB_ERR_UNSUPPORTED;
+    RecordedDraw r;
+    memset(&r, 0, sizeof(r));
+    r.verb_off = (uint32_t)b->verbs.size();
+    r.n_verbs = (uint32_t)n_verbs;
+    r.pt_off = (uint32_t)b->pts.size();
+    r.n_pts = (uint32_t)n_points;
+    b->verbs.insert(b->verbs.end(), verbs, verbs + n_verbs);
+    b->pts.resize(b->pts.size() + (size_t)n_points);
+    memcpy(b->pts.data() + r.pt_off, points, sizeof(float) * 2 * (size_t)n_points);
+    r.ctm = ts ? rbh::Xform::from(ts) : rbh::Xform();
+    rbh::map_points(r.ctm, b->pts.data() + r.pt_off, n_points); // painter.rs: path.transform(ts), shader.transform(ts)
+    r.paint = *paint;
+    if (paint->stops && paint->n_stops > 0) {
+        r.stop_off = (uint32_t)b->stops.size();
+        r.n_stops = (uint32_t)paint->n_stops;
+        b->stops.insert(b->stops.end(), paint->stops, paint->stops + (size_t)paint->n_stops * 5);
+    }
+    r.paint.stops = nullptr;
+    r.rule = rule ? 1 : 0;
+    r.is_stroke = false;
+    b->recs.push_back(r);
+    return RB_OK;
+}
+
+extern "C" int rb_batch_fill_path(rb_batch *b, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
+                                  const rb_paint *paint, int32_t fill_rule, const float ts[6])
+{
+    if (paint && (paint->shader < 0 || paint->shader > 3 || paint->blend_mode < 0 || paint->blend_mode > 28)) return RB_ERR_INVALID;
+    if (paint && (paint->shader == 1 || paint->shader == 2) && paint->n_stops > rbh::kMaxStops) return RB_ERR_UNSUPPORTED;
+    return rb_batch_record(b, verbs, n_verbs, points, n_points, paint, fill_rule, ts);
+}
+
+// PixmapMut::stroke_path(path, paint, stroke, transform, None) — path.rs:113.  Thin anti-aliased strokes that
+// tiny-skia draws as hairlines (both transformed stroke-width vectors no longer than 1 px) are not implemented yet
+// and are reported as RB_ERR_UNSUPPORTED instead of being drawn differently.
+extern "C" int rb_batch_stroke_path(rb_batch *b, const uint8_t *verbs, int32_t n_verbs, const float *points,
+                                    int32_t n_points, const rb_paint *paint, const rb_stroke *stroke, const float ts[6])
+{
+    if (!stroke || !paint) return RB_ERR_INVALID;
+    if (stroke->width < 0.0f) return RB_OK;
+    if (stroke->cap < 0 || stroke->cap > 2 || stroke->join < 0 || stroke->join > 3) return RB_ERR_INVALID;
+    const rbh::Xform ctm = ts ? rbh::Xform::from(ts) : rbh::Xform();
+    {
+        // treat_as_hairline
+        auto fast_len = [](float x, float y) { x = fabsf(x); y = fabsf(y); return std::max(x, y) + std::min(x, y) * 0.5f; };
+        const float w = stroke->width;
+        if (w == 0.0f) return RB_ERR_UNSUPPORTED;
+        if (paint->anti_alias && fast_len(ctm.sx * w, ctm.ky * w) <= 1.0f && fast_len(ctm.kx * w, ctm.sy * w) <= 1.0f)
+            return RB_ERR_UNSUPPORTED;
+    }
+    static const float ident[6] = {1, 0, 0, 1, 0, 0};
+    int st = rb_batch_fill_path(b, verbs, n_verbs, points, n_points, paint, 0, ident); // keep local coordinates
+    if (st != RB_OK) return st;
+    RecordedDraw &r = b->recs.back();
+    r.ctm = ctm;
+    r.is_stroke = true;
+    r.stroke = *stroke;
+    return RB_OK;
+}
+
+// Bulk recording: n_paths paths in packed arrays (verb_off / point_off have n_paths + 1 entries).
+extern "C" int rb_batch_draw_paths(rb_batch *b, int32_t n_paths, const uint32_t *verb_off, const uint32_t *point_off,
+                                   const uint8_t *verbs, const float *points, const rb_paint *paints,
+                                   const uint8_t *fill_rules, const rb_stroke *strokes, const float ts[6])
+{
+    if (!b || n_paths < 0 || !verb_off || !point_off || !verbs || !points || !paints || !fill_rules) return RB_ERR_INVALID;
+    if (n_paths > 0) {
+        b->recs.reserve(b->recs.size() + (size_t)n_paths);
+        b->verbs.reserve(b->verbs.size() + (verb_off[n_paths] - verb_off[0]));
+        b->pts.reserve(b->pts.size() + (point_off[n_paths] - point_off[0]));
+    }
+    for (int32_t i = 0; i < n_paths; i++) {
+        const uint8_t *v = verbs + verb_off[i];
+        const float *p = points + 2 * (size_t)point_off[i];
+        const int32_t nv = (int32_t)(verb_off[i + 1] - verb_off[i]), np = (int32_t)(point_off[i + 1] - point_off[i]);
+        int st;
+        if (strokes && strokes[i].width > 0.0f) st = rb_batch_stroke_path(b, v, nv, p, np, &paints[i], &strokes[i], ts);
+        else st = rb_batch_fill_path(b, v, nv, p, np, &paints[i], fill_rules[i], ts);
+        if (st != RB_OK) return st;
+    }
+    return RB_OK;
+}
+
+extern "C" int rb_batch_fill_paths(rb_batch *b, int32_t n_paths, const uint32_t *verb_off, const uint32_t *point_off,
+                                   const uint8_t *verbs, const float *points, const rb_paint *paints,
+                                   const uint8_t *fill_rules, const float ts[6])
+{
+    return rb_batch_draw_paths(b, n_paths, verb_off, point_off, verbs, points, paints, fill_rules, nullptr, ts);
+}
+
+extern "C" int rb_batch_stats(rb_batch *b, uint64_t stats[6])
+{
+    if (!b || !stats) return RB_ERR_INVALID;
+    memcpy(stats, b->stats, sizeof(b->stats));
+    return RB_OK;
+}
+
+// ---- host-only batches (CPU test-suite / host-build profiling; no device work) ------------------------------------------
+extern "C" int rb_debug_batch_begin_host(uint32_t width, uint32_t height, rb_batch **out)
+{
+    if (!out || width == 0 || height == 0) return RB_ERR_INVALID;
+    rb_batch *b = new rb_batch();
+    b->host_w = (int)width;
+    b->host_h = (int)height;
+    *out = b;
+    return RB_OK;
+}
+
+extern "C" int rb_debug_batch_phases(rb_batch *b, uint64_t phases[RB_PHASES])
+{
+    if (!b || !phases) return RB_ERR_INVALID;
+    memcpy(phases, b->phases, sizeof(b->phases));
+    return RB_OK;
+}
+
+// Copies the arrays of a host-only batch's block out for inspection: which = 0 draws (DevDraw), 1 tile offsets,
+// 2 tile draw lists, 3 tile ids, 4 edges (DevEdge).  Returns the element count; copies at most max_bytes.
+extern "C" int64_t rb_debug_batch_block(rb_batch *b, int32_t which, void *out, uint64_t max_bytes)
+{
+    if (!b || !b->host_block) return -1;
+    const BatchLayout &L = b->lay;
+    const uint8_t *blk = (const uint8_t *)b->host_block;
+    size_t off, cnt, esz;
+    switch (which) {
+    case 0: off = L.o_draws; cnt = L.n_draws; esz = sizeof(DevDraw); break;
+    case 1: off = L.o_toff; cnt = L.n_tiles + 1; esz = 4; break;
+    case 2: off = L.o_tdraws; cnt = L.n_pairs; esz = 4; break;
+    case 3: off = L.o_tids; cnt = L.n_tile_ids; esz = 4; break;
+    case 4: off = L.o_edges; cnt = L.n_edges; esz = sizeof(DevEdge); break;
+    default: return -1;
+    }
+    if (out) memcpy(out, blk + off, std::min<uint64_t>(max_bytes, (uint64_t)cnt * esz));
+    return (int64_t)cnt;
+}

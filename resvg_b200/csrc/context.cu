@@ -38,6 +38,40 @@ int rb_scratch(rb_ctx *ctx, size_t bytes, void **out)
     return RB_OK;
 }
 
+int rb_staging(rb_ctx *ctx, size_t bytes, void **out)
+{
+    if (ctx->staging_in_flight) {
+        RB_CUDA(ctx, cudaEventSynchronize(ctx->staging_ev));
+        ctx->staging_in_flight = false;
+    }
+    if (bytes > ctx->staging_bytes) {
+        if (ctx->staging) RB_CUDA(ctx, cudaFreeHost(ctx->staging));
+        ctx->staging = nullptr;
+        ctx->staging_bytes = 0;
+        size_t want = bytes + bytes / 4 + (1u << 20);
+        RB_CUDA(ctx, cudaHostAlloc(&ctx->staging, want, cudaHostAllocDefault));
+        ctx->staging_bytes = want;
+    }
+    *out = ctx->staging;
+    return RB_OK;
+}
+
+void rb_ctx_retain(rb_ctx *ctx) { ctx->refs.fetch_add(1, std::memory_order_relaxed); }
+
+void rb_ctx_release(rb_ctx *ctx)
+{
+    if (ctx->refs.fetch_sub(1, std::memory_order_acq_rel) != 1) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->staging) cudaFreeHost(ctx->staging);
+    if (ctx->staging_ev) cudaEventDestroy(ctx->staging_ev);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
 extern "C" int rb_ctx_create(int device, rb_ctx **out)
 {
     if (!out) return RB_ERR_INVALID;
@@ -59,6 +93,7 @@ extern "C" int rb_ctx_create(int device, rb_ctx **out)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RB_ERR_CUDA; }
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
+    cudaEventCreateWithFlags(&ctx->staging_ev, cudaEventDisableTiming);
     // Keep freed layer memory in the stream-ordered pool: isolated groups allocate one layer each
     // (render.rs:108), so layer create/destroy must not hit the driver.
     cudaMemPool_t pool;
@@ -72,16 +107,13 @@ extern "C" int rb_ctx_create(int device, rb_ctx **out)
     return RB_OK;
 }
 
+// Drops the owner's reference; the context is torn down when the last layer / mask / batch created from it is gone.
 extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    if (ctx->scratch) cudaFree(ctx->scratch);
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    delete ctx;
+    rb_ctx_release(ctx);
 }
 
 extern "C" int rb_ctx_synchronize(rb_ctx *ctx)
@@ -136,6 +168,7 @@ extern "C" int rb_layer_create(rb_ctx *ctx, uint32_t w, uint32_t h, rb_layer **o
     RB_CUDA(ctx, cudaMallocAsync(&d, bytes, ctx->stream));
     RB_CUDA(ctx, cudaMemsetAsync(d, 0, bytes, ctx->stream));
     rb_layer *l = new rb_layer{ctx, w, h, (uint8_t *)d};
+    rb_ctx_retain(ctx);
     *out = l;
     return RB_OK;
 }
@@ -144,6 +177,7 @@ extern "C" void rb_layer_destroy(rb_layer *l)
 {
     if (!l) return;
     cudaFreeAsync(l->d, l->ctx->stream);
+    rb_ctx_release(l->ctx);
     delete l;
 }
 

@@ -25,6 +25,7 @@
 #include <thread>
 #include <vector>
 
+#include "batch.h"
 #include "common.cuh"
 #include "raster_host.h"
 #include "rb_internal.h"
@@ -32,25 +33,12 @@
 using rbh::DevPaint;
 using rbh::DevStop;
 
-constexpr int TW = 64;            // tile width  (pixels)
-constexpr int TH = 16;            // tile height (pixels)
 constexpr int RT_THREADS = 256;   // 8 warps; warp w owns pixel rows w and w+8, lane l owns columns 2l, 2l+1
 constexpr int ROW_POS = TW * 4;   // sub-sample positions per row
 constexpr int CNT_ROWS = TH * 4;
 constexpr int CNT_BYTES = CNT_ROWS * ROW_POS * 4;
 
-// ypack = first_y | last_y << 16.  meta: bit 0 = upward edge (winding -1), bit 1 = continuation segment of a
-// curve, bit 2 = insert_new_edges places it before equal-x active edges, bits 4.. = index of the previous
-// segment of the same curve (valid when bit 1 is set).
-struct DevEdge { int32_t x, dx; uint32_t ypack; uint32_t meta; };
 __host__ __device__ __forceinline__ int edge_winding(uint32_t meta) { return (meta & 1u) ? -1 : 1; }
-struct DevDraw {
-    uint32_t edge_off, edge_cnt;
-    int32_t ox, oy;         // DrawTiler tile origin inside the layer
-    int32_t sx, sy, sw, sh; // pixels the blitter may touch (DrawTiler-tile local)
-    int32_t shift, rule;    // 2 = AA / 0 = non-AA; 0 winding / 1 even-odd
-    uint32_t paint, pad;
-};
 
 // =================================================================================================
 // pipeline arithmetic (tiny-skia pipeline/lowp.rs, highp.rs; Skia SkRasterPipeline_opts.h)
@@ -975,378 +963,78 @@ k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint3
 }
 
 // =================================================================================================
-// batch: host-side recording, edge building, binning, upload, launch
+// batch: upload + launch (recording, edge building and binning live in batch_host.cpp)
 // =================================================================================================
-struct RecordedDraw {
-    std::vector<uint8_t> verbs;
-    std::vector<rbh::Pt> pts; // fills: device space (transform applied); strokes: local space until stroked
-    rb_paint paint;
-    std::vector<float> stops;
-    rbh::Xform ctm;
-    int rule;
-    bool is_stroke = false;
-    rb_stroke stroke;
-};
-
-struct rb_batch {
-    rb_layer *layer = nullptr;
-    rb_mask *mask = nullptr;
-    std::vector<RecordedDraw> recs;
-    uint64_t stats[6] = {0, 0, 0, 0, 0, 0};
-    // device-resident form produced by rb_batch_prepare
-    uint8_t *dev = nullptr;
-    const DevEdge *d_edges = nullptr;
-    const DevDraw *d_draws = nullptr;
-    const DevPaint *d_paints = nullptr;
-    const DevStop *d_stops = nullptr;
-    const uint32_t *d_toff = nullptr, *d_tdraws = nullptr, *d_tids = nullptr;
-    unsigned n_tile_ids = 0;
-    int tiles_x = 0;
-    bool wide = false; // some draw may reach |winding| > 127: use k_raster_tiles_wide
-};
-
-static constexpr int kMaxDim = 8191; // tiny-skia DrawTiler::MAX_DIMENSIONS
-
-// Upper bound of |winding| for a draw: edges simultaneously active on one scanline.  Chains (an edge plus its
-// curve continuations) never overlap themselves in y, so the chain count bounds it; only when that is not tight
-// enough is the exact maximum swept.
-static bool draw_may_exceed_packed_winding(const rbh::Edge *e, size_t n)
-{
-    size_t chains = 0;
-    for (size_t i = 0; i < n; i++) chains += e[i].prev < 0 ? 1 : 0;
-    if (chains < 128) return false;
-    std::vector<int32_t> ends;
-    ends.reserve(n);
-    for (size_t i = 0; i < n; i++) ends.push_back(e[i].last_y);
-    std::sort(ends.begin(), ends.end());
-    size_t active = 0, j = 0, worst = 0;
-    for (size_t i = 0; i < n; i++) { // e is sorted by first_y
-        while (j < n && ends[j] < e[i].first_y) { j++; active--; }
-        active++;
-        worst = std::max(worst, active);
-    }
-    return worst >= 128;
-}
-
-struct ThreadOut {
-    bool wide = false;
-    std::vector<rbh::Edge> edges;
-    std::vector<DevDraw> draws;
-    std::vector<DevPaint> paints;
-    std::vector<DevStop> stops;
-};
-
-extern "C" int rb_path_stroke(const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points, float width,
-                              float miter_limit, int32_t cap, int32_t join, float res_scale, uint8_t **out_verbs,
-                              int32_t *out_n_verbs, float **out_points, int32_t *out_n_points);
-extern "C" void rb_path_free(void *p);
-
-// painter.rs stroke_path: PathStroker::compute_resolution_scale(ts)
-static float resolution_scale(const rbh::Xform &t)
-{
-    float sx = sqrtf(t.sx * t.sx + t.kx * t.kx), sy = sqrtf(t.ky * t.ky + t.sy * t.sy);
-    if (std::isfinite(sx) && std::isfinite(sy)) {
-        float s = std::max(sx, sy);
-        if (s > 0) return s;
-    }
-    return 1.0f;
-}
-
-static void build_range(const rb_batch *b, size_t begin, size_t end, int W, int H, bool mask_target, ThreadOut *out)
-{
-    std::vector<rbh::Pt> tmp;
-    RecordedDraw stroked;
-    for (size_t i = begin; i < end; i++) {
-        const RecordedDraw *rp = &b->recs[i];
-        if (rp->is_stroke) {
-            // stroke_path: the outline is computed in local coordinates, then filled (Winding) under the transform
-            uint8_t *ov = nullptr;
-            float *op = nullptr;
-            int32_t nv = 0, np = 0;
-            if (rb_path_stroke(rp->verbs.data(), (int32_t)rp->verbs.size(), &rp->pts[0].x, (int32_t)rp->pts.size(),
-                               rp->stroke.width, rp->stroke.miter_limit, rp->stroke.cap, rp->stroke.join,
-                               resolution_scale(rp->ctm), &ov, &nv, &op, &np) != RB_OK)
-                continue;
-            stroked.verbs.assign(ov, ov + nv);
-            stroked.pts.resize((size_t)np);
-            memcpy(stroked.pts.data(), op, sizeof(float) * 2 * (size_t)np);
-            rb_path_free(ov);
-            rb_path_free(op);
-            rbh::map_points(rp->ctm, stroked.pts.data(), np);
-            stroked.paint = rp->paint;
-            stroked.stops = rp->stops;
-            stroked.ctm = rp->ctm;
-            stroked.rule = 0;
-            rp = &stroked;
-        }
-        const RecordedDraw &r = *rp;
-        const bool aa = r.paint.anti_alias != 0;
-        // DrawTiler: tiles of at most 8191x8191 in row-major order; a single tile for ordinary canvases.
-        for (int ty = 0; ty < H; ty += kMaxDim) {
-            for (int tx = 0; tx < W; tx += kMaxDim) {
-                const int tw = std::min(W - tx, kMaxDim), th = std::min(H - ty, kMaxDim);
-                const rbh::Pt *pts = r.pts.data();
-                rbh::Xform ctm = r.ctm;
-                if (tx || ty) {
-                    tmp = r.pts;
-                    rbh::Xform tr;
-                    tr.tx = -(float)tx;
-                    tr.ty = -(float)ty;
-                    rbh::map_points(tr, tmp.data(), (int)tmp.size());
-                    pts = tmp.data();
-                    ctm = rbh::post_concat(ctm, tr);
-                }
-                rbh::DrawGeom g;
-                size_t e0 = out->edges.size();
-                if (!rbh::build_draw(r.verbs.data(), (int)r.verbs.size(), pts, (int)r.pts.size(), aa, tw, th, out->edges, &g))
-                    continue;
-                if (draw_may_exceed_packed_winding(out->edges.data() + e0, out->edges.size() - e0)) out->wide = true;
-                DevDraw d;
-                memset(&d, 0, sizeof(d));
-                d.edge_off = (uint32_t)e0;
-                d.edge_cnt = (uint32_t)(out->edges.size() - e0);
-                d.ox = tx; d.oy = ty;
-                d.sx = g.sect.x; d.sy = g.sect.y; d.sw = g.sect.w; d.sh = g.sect.h;
-                d.shift = g.shift;
-                d.rule = r.rule;
-                if (!mask_target) {
-                    DevPaint p;
-                    rb_paint rp = r.paint;
-                    rp.stops = r.stops.empty() ? nullptr : r.stops.data();
-                    if (!rbh::prepare_paint(&rp, ctm, &p, out->stops)) { out->edges.resize(e0); continue; }
-                    d.paint = (uint32_t)out->paints.size();
-                    out->paints.push_back(p);
-                }
-                out->draws.push_back(d);
-            }
-        }
-    }
-}
+static rb_ctx *batch_ctx(const rb_batch *b) { return b->mask ? b->mask->ctx : (b->layer ? b->layer->ctx : nullptr); }
 
 extern "C" int rb_batch_begin(rb_layer *target, rb_batch **out)
 {
     if (!target || !out) return RB_ERR_INVALID;
     rb_batch *b = new rb_batch();
     b->layer = target;
+    rb_ctx_retain(target->ctx);
     *out = b;
     return RB_OK;
-}
-
-static int batch_add(rb_batch *b, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
-                     const rb_paint *paint, int32_t rule, const float ts[6])
-{
-    if (!b || !verbs || !points || n_verbs <= 0 || n_points <= 0 || !paint) return RB_ERR_INVALID;
-    // validate the verb/point bookkeeping so the builder never reads past the arrays
-    int need = 0;
-    for (int i = 0; i < n_verbs; i++) {
-        switch (verbs[i]) {
-        case 0: case 1: need += 1; break;
-        case 2: need += 2; break;
-        case 3: need += 3; break;
-        case 4: break;
-        default: return RB_ERR_INVALID;
-        }
-    }
-    if (need != n_points || verbs[0] != 0) return RB_ERR_INVALID;
-    b->recs.emplace_back();
-    RecordedDraw &r = b->recs.back();
-    r.verbs.assign(verbs, verbs + n_verbs);
-    r.pts.resize((size_t)n_points);
-    memcpy(r.pts.data(), points, sizeof(float) * 2 * (size_t)n_points);
-    r.ctm = ts ? rbh::Xform::from(ts) : rbh::Xform();
-    rbh::map_points(r.ctm, r.pts.data(), n_points); // painter.rs: path.transform(ts), shader.transform(ts)
-    r.paint = *paint;
-    if (paint->stops && paint->n_stops > 0) r.stops.assign(paint->stops, paint->stops + (size_t)paint->n_stops * 5);
-    r.paint.stops = nullptr;
-    r.rule = rule ? 1 : 0;
-    return RB_OK;
-}
-
-extern "C" int rb_batch_fill_path(rb_batch *b, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
-                                  const rb_paint *paint, int32_t fill_rule, const float ts[6])
-{
-    if (paint && (paint->shader < 0 || paint->shader > 3 || paint->blend_mode < 0 || paint->blend_mode > 28)) return RB_ERR_INVALID;
-    if (paint && (paint->shader == 1 || paint->shader == 2) && paint->n_stops > rbh::kMaxStops) return RB_ERR_UNSUPPORTED;
-    return batch_add(b, verbs, n_verbs, points, n_points, paint, fill_rule, ts);
 }
 
 static void batch_release(rb_batch *b)
 {
     if (b->dev) {
-        rb_ctx *ctx = b->mask ? b->mask->ctx : b->layer->ctx;
-        cudaFreeAsync(b->dev, ctx->stream);
+        cudaFreeAsync(b->dev, batch_ctx(b)->stream);
         b->dev = nullptr;
     }
-    b->n_tile_ids = 0;
-}
-
-// PixmapMut::stroke_path(path, paint, stroke, transform, None) — path.rs:113.  Thin anti-aliased strokes that
-// tiny-skia draws as hairlines (both transformed stroke-width vectors no longer than 1 px) are not implemented yet
-// and are reported as RB_ERR_UNSUPPORTED instead of being drawn differently.
-extern "C" int rb_batch_stroke_path(rb_batch *b, const uint8_t *verbs, int32_t n_verbs, const float *points,
-                                    int32_t n_points, const rb_paint *paint, const rb_stroke *stroke, const float ts[6])
-{
-    if (!stroke || !paint) return RB_ERR_INVALID;
-    if (stroke->width < 0.0f) return RB_OK;
-    if (stroke->cap < 0 || stroke->cap > 2 || stroke->join < 0 || stroke->join > 3) return RB_ERR_INVALID;
-    const rbh::Xform ctm = ts ? rbh::Xform::from(ts) : rbh::Xform();
-    {
-        // treat_as_hairline
-        auto fast_len = [](float x, float y) { x = fabsf(x); y = fabsf(y); return std::max(x, y) + std::min(x, y) * 0.5f; };
-        const float w = stroke->width;
-        if (w == 0.0f) return RB_ERR_UNSUPPORTED;
-        if (paint->anti_alias && fast_len(ctm.sx * w, ctm.ky * w) <= 1.0f && fast_len(ctm.kx * w, ctm.sy * w) <= 1.0f)
-            return RB_ERR_UNSUPPORTED;
+    if (b->host_block) {
+        free(b->host_block);
+        b->host_block = nullptr;
     }
-    static const float ident[6] = {1, 0, 0, 1, 0, 0};
-    int st = rb_batch_fill_path(b, verbs, n_verbs, points, n_points, paint, 0, ident); // keep local coordinates
-    if (st != RB_OK) return st;
-    RecordedDraw &r = b->recs.back();
-    r.ctm = ctm;
-    r.is_stroke = true;
-    r.stroke = *stroke;
-    return RB_OK;
+    b->lay = BatchLayout();
 }
 
 extern "C" void rb_batch_destroy(rb_batch *b)
 {
     if (!b) return;
+    rb_ctx *ctx = batch_ctx(b);
     batch_release(b);
     delete b;
+    if (ctx) rb_ctx_release(ctx);
 }
 
-extern "C" int rb_batch_stats(rb_batch *b, uint64_t stats[6])
+struct StageReq { rb_ctx *ctx; int status; };
+static void *stage_pinned(void *user, size_t bytes)
 {
-    if (!b || !stats) return RB_ERR_INVALID;
-    memcpy(stats, b->stats, sizeof(b->stats));
-    return RB_OK;
+    StageReq *r = (StageReq *)user;
+    void *p = nullptr;
+    r->status = rb_staging(r->ctx, bytes, &p);
+    return r->status == RB_OK ? p : nullptr;
 }
+static void *stage_malloc(void *, size_t bytes) { return malloc(bytes); }
 
+// Host build (threads) into the context's pinned staging block, then ONE host-to-device copy.
 extern "C" int rb_batch_prepare(rb_batch *b, int32_t n_threads)
 {
     if (!b) return RB_ERR_INVALID;
     batch_release(b);
+    void *blk = nullptr;
+    if (!b->layer && !b->mask) { // host-only batch (rb_debug_batch_begin_host)
+        int st = rb_batch_host_build(b, b->host_w, b->host_h, false, n_threads, stage_malloc, nullptr, &blk);
+        b->host_block = blk;
+        return st;
+    }
     const bool mask_target = b->mask != nullptr;
-    rb_ctx *ctx = mask_target ? b->mask->ctx : b->layer->ctx;
+    rb_ctx *ctx = batch_ctx(b);
     const int W = (int)(mask_target ? b->mask->w : b->layer->w), H = (int)(mask_target ? b->mask->h : b->layer->h);
-    memset(b->stats, 0, sizeof(b->stats));
-    if (b->recs.empty()) return RB_OK;
-    auto t0 = std::chrono::steady_clock::now();
-
-    // ---- 1. edges + paints on host threads -----------------------------------------------------------
-    size_t n = b->recs.size();
-    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
-    nt = std::max(1, std::min<int>(nt, (int)((n + 255) / 256)));
-    std::vector<ThreadOut> outs((size_t)nt);
-    if (nt == 1) build_range(b, 0, n, W, H, mask_target, &outs[0]);
-    else {
-        std::vector<std::thread> th;
-        for (int t = 0; t < nt; t++) {
-            size_t lo = n * (size_t)t / (size_t)nt, hi = n * (size_t)(t + 1) / (size_t)nt;
-            th.emplace_back(build_range, b, lo, hi, W, H, mask_target, &outs[(size_t)t]);
-        }
-        for (auto &t : th) t.join();
-    }
-    size_t n_edges = 0, n_draws = 0, n_paints = 0, n_stops = 0;
-    b->wide = false;
-    for (auto &o : outs) b->wide = b->wide || o.wide;
-    for (auto &o : outs) { n_edges += o.edges.size(); n_draws += o.draws.size(); n_paints += o.paints.size(); n_stops += o.stops.size(); }
-    if (n_draws == 0) return RB_OK;
-    if (n_edges > 0xfffffff0ull) return rb_fail(ctx, RB_ERR_UNSUPPORTED, "too many edges in one batch");
-
-    // ---- 2. concatenate (painter's order = thread order) and pack -------------------------------------
-    std::vector<DevEdge> edges(n_edges);
-    std::vector<DevDraw> draws;
-    draws.reserve(n_draws);
-    std::vector<DevPaint> paints;
-    paints.reserve(n_paints);
-    std::vector<DevStop> stops;
-    stops.reserve(n_stops);
-    {
-        size_t eo = 0;
-        for (auto &o : outs) {
-            uint32_t ebase = (uint32_t)eo, pbase = (uint32_t)paints.size(), sbase = (uint32_t)stops.size();
-            for (size_t i = 0; i < o.edges.size(); i++) {
-                const rbh::Edge &e = o.edges[i];
-                DevEdge d;
-                d.x = e.x; d.dx = e.dx;
-                d.ypack = ((uint32_t)e.first_y & 0xffffu) | ((uint32_t)e.last_y << 16);
-                d.meta = (e.winding < 0 ? 1u : 0u) | (e.prev >= 0 ? 2u : 0u) | (e.before ? 4u : 0u)
-                         | (e.prev >= 0 ? ((uint32_t)e.prev << 4) : 0u);
-                edges[eo++] = d;
-            }
-            for (auto p : o.paints) { p.stop_off += sbase; paints.push_back(p); }
-            for (auto &s : o.stops) stops.push_back(s);
-            for (auto d : o.draws) { d.edge_off += ebase; d.paint += pbase; draws.push_back(d); }
-        }
-    }
-
-    // ---- 3. bin draws into device tiles (counting sort keeps painter's order inside each tile) --------
-    const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
-    const size_t n_tiles = (size_t)tiles_x * tiles_y;
-    std::vector<uint32_t> tile_off(n_tiles + 1, 0);
-    auto tile_range = [&](const DevDraw &d, int &x0, int &x1, int &y0, int &y1) {
-        x0 = (d.ox + d.sx) / TW; x1 = (d.ox + d.sx + d.sw - 1) / TW;
-        y0 = (d.oy + d.sy) / TH; y1 = (d.oy + d.sy + d.sh - 1) / TH;
-    };
-    for (const DevDraw &d : draws) {
-        int x0, x1, y0, y1;
-        tile_range(d, x0, x1, y0, y1);
-        for (int y = y0; y <= y1; y++)
-            for (int x = x0; x <= x1; x++) tile_off[(size_t)y * tiles_x + x + 1]++;
-    }
-    for (size_t i = 0; i < n_tiles; i++) tile_off[i + 1] += tile_off[i];
-    const size_t n_pairs = tile_off[n_tiles];
-    std::vector<uint32_t> tile_draws(n_pairs), cursor(tile_off.begin(), tile_off.end() - 1);
-    for (uint32_t di = 0; di < (uint32_t)draws.size(); di++) {
-        int x0, x1, y0, y1;
-        tile_range(draws[di], x0, x1, y0, y1);
-        for (int y = y0; y <= y1; y++)
-            for (int x = x0; x <= x1; x++) tile_draws[cursor[(size_t)y * tiles_x + x]++] = di;
-    }
-    // non-empty tiles, heaviest first (longest-processing-time-first over the CTA slots)
-    std::vector<uint32_t> tile_ids;
-    for (size_t i = 0; i < n_tiles; i++) if (tile_off[i + 1] > tile_off[i]) tile_ids.push_back((uint32_t)i);
-    std::stable_sort(tile_ids.begin(), tile_ids.end(), [&](uint32_t a, uint32_t c) {
-        return tile_off[a + 1] - tile_off[a] > tile_off[c + 1] - tile_off[c];
-    });
-    auto t1 = std::chrono::steady_clock::now();
-
-    // ---- 4. upload + launch -----------------------------------------------------------------------------
-    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    size_t b_edges = al(edges.size() * sizeof(DevEdge)), b_draws = al(draws.size() * sizeof(DevDraw));
-    size_t b_paints = al(std::max<size_t>(paints.size(), 1) * sizeof(DevPaint)), b_stops = al(std::max<size_t>(stops.size(), 1) * sizeof(DevStop));
-    size_t b_toff = al(tile_off.size() * 4), b_tdraws = al(tile_draws.size() * 4), b_tids = al(tile_ids.size() * 4);
-    size_t total = b_edges + b_draws + b_paints + b_stops + b_toff + b_tdraws + b_tids;
-    uint8_t *dev = nullptr;
     cudaSetDevice(ctx->device);
-    RB_CUDA(ctx, cudaMallocAsync((void **)&dev, total, ctx->stream));
-    uint8_t *p = dev;
-    auto up = [&](const void *src, size_t bytes, size_t slot) -> cudaError_t {
-        cudaError_t e = bytes ? cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
-        p += slot;
-        return e;
-    };
-    DevEdge *d_edges = (DevEdge *)p;      RB_CUDA(ctx, up(edges.data(), edges.size() * sizeof(DevEdge), b_edges));
-    DevDraw *d_draws = (DevDraw *)p;      RB_CUDA(ctx, up(draws.data(), draws.size() * sizeof(DevDraw), b_draws));
-    DevPaint *d_paints = (DevPaint *)p;   RB_CUDA(ctx, up(paints.data(), paints.size() * sizeof(DevPaint), b_paints));
-    DevStop *d_stops = (DevStop *)p;      RB_CUDA(ctx, up(stops.data(), stops.size() * sizeof(DevStop), b_stops));
-    uint32_t *d_toff = (uint32_t *)p;     RB_CUDA(ctx, up(tile_off.data(), tile_off.size() * 4, b_toff));
-    uint32_t *d_tdraws = (uint32_t *)p;   RB_CUDA(ctx, up(tile_draws.data(), tile_draws.size() * 4, b_tdraws));
-    uint32_t *d_tids = (uint32_t *)p;     RB_CUDA(ctx, up(tile_ids.data(), tile_ids.size() * 4, b_tids));
-    // pageable sources: the runtime has staged the data by the time cudaMemcpyAsync returns
-
+    StageReq req{ctx, RB_OK};
+    int st = rb_batch_host_build(b, W, H, mask_target, n_threads, stage_pinned, &req, &blk);
+    if (req.status != RB_OK) return req.status;
+    if (st != RB_OK) return rb_fail(ctx, st, "batch host build failed");
+    if (!blk || b->lay.n_draws == 0) return RB_OK;
+    uint8_t *dev = nullptr;
+    RB_CUDA(ctx, cudaMallocAsync((void **)&dev, b->lay.total, ctx->stream));
     b->dev = dev;
-    b->d_edges = d_edges; b->d_draws = d_draws; b->d_paints = d_paints; b->d_stops = d_stops;
-    b->d_toff = d_toff; b->d_tdraws = d_tdraws; b->d_tids = d_tids;
-    b->n_tile_ids = (unsigned)tile_ids.size();
-    b->tiles_x = tiles_x;
-    b->stats[0] = draws.size();
-    b->stats[1] = edges.size();
-    b->stats[2] = n_pairs;
-    b->stats[3] = tile_ids.size();
-    b->stats[4] = total;
-    b->stats[5] = (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count();
+    RB_CUDA(ctx, cudaMemcpyAsync(dev, blk, b->lay.total, cudaMemcpyHostToDevice, ctx->stream));
+    RB_CUDA(ctx, cudaEventRecord(ctx->staging_ev, ctx->stream));
+    ctx->staging_in_flight = true;
     return RB_OK;
 }
 
@@ -1361,7 +1049,8 @@ extern "C" int rb_batch_run(rb_batch *b) { return batch_run(b, nullptr); }
 extern "C" int rb_batch_run_counting(rb_batch *b, uint64_t out[2])
 {
     if (!b || !out) return RB_ERR_INVALID;
-    rb_ctx *ctx = b->mask ? b->mask->ctx : b->layer->ctx;
+    rb_ctx *ctx = batch_ctx(b);
+    if (!ctx) return RB_ERR_INVALID;
     unsigned long long *d = nullptr;
     RB_CUDA(ctx, cudaMallocAsync((void **)&d, 16, ctx->stream));
     RB_CUDA(ctx, cudaMemsetAsync(d, 0, 16, ctx->stream));
@@ -1378,7 +1067,7 @@ extern "C" int rb_batch_run_counting(rb_batch *b, uint64_t out[2])
 static int batch_run(rb_batch *b, unsigned long long *px_stats)
 {
     if (!b) return RB_ERR_INVALID;
-    if (!b->dev || b->n_tile_ids == 0) return RB_OK; // nothing to draw
+    if (!b->dev || b->lay.n_tile_ids == 0) return RB_OK; // nothing to draw
     const bool mask_target = b->mask != nullptr;
     rb_ctx *ctx = mask_target ? b->mask->ctx : b->layer->ctx;
     const int W = (int)(mask_target ? b->mask->w : b->layer->w), H = (int)(mask_target ? b->mask->h : b->layer->h);
@@ -1391,14 +1080,18 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
         RB_CUDA(ctx, cudaFuncSetAttribute(k_raster_tiles_wide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CNT_BYTES));
         attr_set = true;
     }
-#define RB_RASTER_ARGS target, W, H, b->tiles_x, b->d_tids, b->d_toff, b->d_tdraws, b->d_draws, b->d_edges, b->d_paints, b->d_stops, px_stats
-    const bool wide = b->wide || g_force_wide;
+    const BatchLayout &L = b->lay;
+    const unsigned n_tile_ids = (unsigned)L.n_tile_ids;
+#define RB_RASTER_ARGS target, W, H, L.tiles_x, (const uint32_t *)(b->dev + L.o_tids), (const uint32_t *)(b->dev + L.o_toff), \
+    (const uint32_t *)(b->dev + L.o_tdraws), (const DevDraw *)(b->dev + L.o_draws), (const DevEdge *)(b->dev + L.o_edges),    \
+    (const DevPaint *)(b->dev + L.o_paints), (const DevStop *)(b->dev + L.o_stops), px_stats
+    const bool wide = L.wide || g_force_wide;
     if (wide) {
-        if (mask_target) k_raster_tiles_wide<true><<<b->n_tile_ids, RT_THREADS, CNT_BYTES, ctx->stream>>>(RB_RASTER_ARGS);
-        else k_raster_tiles_wide<false><<<b->n_tile_ids, RT_THREADS, CNT_BYTES, ctx->stream>>>(RB_RASTER_ARGS);
+        if (mask_target) k_raster_tiles_wide<true><<<n_tile_ids, RT_THREADS, CNT_BYTES, ctx->stream>>>(RB_RASTER_ARGS);
+        else k_raster_tiles_wide<false><<<n_tile_ids, RT_THREADS, CNT_BYTES, ctx->stream>>>(RB_RASTER_ARGS);
     } else {
-        if (mask_target) k_raster_tiles<true><<<b->n_tile_ids, RT_THREADS, FAST_SMEM, ctx->stream>>>(RB_RASTER_ARGS);
-        else k_raster_tiles<false><<<b->n_tile_ids, RT_THREADS, FAST_SMEM, ctx->stream>>>(RB_RASTER_ARGS);
+        if (mask_target) k_raster_tiles<true><<<n_tile_ids, RT_THREADS, FAST_SMEM, ctx->stream>>>(RB_RASTER_ARGS);
+        else k_raster_tiles<false><<<n_tile_ids, RT_THREADS, FAST_SMEM, ctx->stream>>>(RB_RASTER_ARGS);
     }
 #undef RB_RASTER_ARGS
     RB_LAUNCHED(ctx, "raster_tiles");
@@ -1411,32 +1104,6 @@ extern "C" int rb_batch_submit(rb_batch *b, int32_t n_threads)
     if (st == RB_OK) st = rb_batch_run(b);
     if (b) batch_release(b);
     return st;
-}
-
-// Bulk recording: n_paths paths in packed arrays (verb_off / point_off have n_paths + 1 entries).
-extern "C" int rb_batch_draw_paths(rb_batch *b, int32_t n_paths, const uint32_t *verb_off, const uint32_t *point_off,
-                                   const uint8_t *verbs, const float *points, const rb_paint *paints,
-                                   const uint8_t *fill_rules, const rb_stroke *strokes, const float ts[6])
-{
-    if (!b || n_paths < 0 || !verb_off || !point_off || !verbs || !points || !paints || !fill_rules) return RB_ERR_INVALID;
-    b->recs.reserve(b->recs.size() + (size_t)n_paths);
-    for (int32_t i = 0; i < n_paths; i++) {
-        const uint8_t *v = verbs + verb_off[i];
-        const float *p = points + 2 * (size_t)point_off[i];
-        const int32_t nv = (int32_t)(verb_off[i + 1] - verb_off[i]), np = (int32_t)(point_off[i + 1] - point_off[i]);
-        int st;
-        if (strokes && strokes[i].width > 0.0f) st = rb_batch_stroke_path(b, v, nv, p, np, &paints[i], &strokes[i], ts);
-        else st = rb_batch_fill_path(b, v, nv, p, np, &paints[i], fill_rules[i], ts);
-        if (st != RB_OK) return st;
-    }
-    return RB_OK;
-}
-
-extern "C" int rb_batch_fill_paths(rb_batch *b, int32_t n_paths, const uint32_t *verb_off, const uint32_t *point_off,
-                                   const uint8_t *verbs, const float *points, const rb_paint *paints,
-                                   const uint8_t *fill_rules, const float ts[6])
-{
-    return rb_batch_draw_paths(b, n_paths, verb_off, point_off, verbs, points, paints, fill_rules, nullptr, ts);
 }
 
 extern "C" int rb_fill_path(rb_layer *layer, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
@@ -1461,7 +1128,7 @@ extern "C" int rb_mask_fill_path(rb_mask *mask, const uint8_t *verbs, int32_t n_
     memset(&paint, 0, sizeof(paint));
     paint.anti_alias = anti_alias;
     paint.blend_mode = RB_BLEND_SOURCE_OVER;
-    int st = batch_add(&b, verbs, n_verbs, points, n_points, &paint, fill_rule, ts);
+    int st = rb_batch_record(&b, verbs, n_verbs, points, n_points, &paint, fill_rule, ts);
     if (st != RB_OK) return st;
     return rb_batch_submit(&b, 1);
 }
@@ -1518,12 +1185,14 @@ extern "C" int rb_mask_create(rb_ctx *ctx, uint32_t w, uint32_t h, rb_mask **out
     RB_CUDA(ctx, cudaMallocAsync(&d, (size_t)w * h, ctx->stream));
     RB_CUDA(ctx, cudaMemsetAsync(d, 0, (size_t)w * h, ctx->stream));
     *out = new rb_mask{ctx, w, h, (uint8_t *)d};
+    rb_ctx_retain(ctx);
     return RB_OK;
 }
 extern "C" void rb_mask_destroy(rb_mask *m)
 {
     if (!m) return;
     cudaFreeAsync(m->d, m->ctx->stream);
+    rb_ctx_release(m->ctx);
     delete m;
 }
 extern "C" int rb_mask_download(rb_mask *m, uint8_t *host)

@@ -6,6 +6,10 @@
 // ever sees independent `Edge {x, dx, first_y, last_y, winding}` records it can evaluate in closed form:
 // x(y) = x + (y - first_y) * dx (wrapping i32).
 #include "raster_host.h"
+#ifdef RB_HOST_PROFILE
+#include <x86intrin.h>
+#include <atomic>
+#endif
 
 #include <math.h>
 #include <string.h>
@@ -652,9 +656,18 @@ static bool contains(IRect o, IRect in)
 }
 static inline bool short_overflow(int32_t v, int s) { return ((int32_t)(int16_t)shl(v, s) >> s) != v; }
 
+#ifdef RB_HOST_PROFILE
+std::atomic<uint64_t> g_bd_prof[4];
+#define BD_T(i) do { uint64_t now__ = __rdtsc(); g_bd_prof[i] += now__ - bd_t__; bd_t__ = now__; } while (0)
+#else
+#define BD_T(i)
+#endif
 bool build_draw(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, bool anti_alias, int32_t cw, int32_t ch,
                 std::vector<Edge> &out, DrawGeom *g)
 {
+#ifdef RB_HOST_PROFILE
+    uint64_t bd_t__ = __rdtsc();
+#endif
     if (n_pts == 0) return false;
     float l = pts[0].x, r = l, t = pts[0].y, b = t;
     for (int i = 1; i < n_pts; i++) {
@@ -732,6 +745,7 @@ bool build_draw(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, boo
         }
         open = true;
     }
+    BD_T(0);
     size_t n = out.size() - sink.base;
     if (n < 2) { out.resize(sink.base); return false; }
     // scan/path.rs: sort by (first_y, x); stable = builder order among ties
@@ -739,6 +753,7 @@ bool build_draw(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, boo
         if (a.first_y != e.first_y) return a.first_y < e.first_y;
         return a.x < e.x;
     });
+    BD_T(1);
     {
         // `order` values may have gaps (combine_vertical pops), so map through a table sized by the maximum
         Edge *e = out.data() + sink.base;
@@ -763,6 +778,7 @@ bool build_draw(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, boo
             i = j;
         }
     }
+    BD_T(2);
     int32_t start_y = shl(ir.y, shift), stop_y = shl(ir.y + ir.h, shift);
     if (!inside) {
         start_y = std::max(start_y, 0);

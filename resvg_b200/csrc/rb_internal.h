@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 
 #include "../../include/resvg_b200.h"
@@ -18,7 +19,19 @@ struct rb_ctx {
     // scratch reused by multi-pass filters (grown on demand, freed with the context)
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
+    // pinned host staging for batch uploads (grown on demand); staging_ev marks the last copy that read it
+    void *staging = nullptr;
+    size_t staging_bytes = 0;
+    cudaEvent_t staging_ev = nullptr;
+    bool staging_in_flight = false;
+    // owner + every live layer / mask / batch: the context outlives them whatever the destruction order
+    std::atomic<int> refs{1};
 };
+
+void rb_ctx_retain(rb_ctx *ctx);
+void rb_ctx_release(rb_ctx *ctx);
+// Pinned staging block of at least `bytes`, safe to overwrite (waits for the previous upload out of it).
+int rb_staging(rb_ctx *ctx, size_t bytes, void **out);
 
 struct rb_layer {
     rb_ctx *ctx;
