@@ -27,8 +27,14 @@ struct DevDraw {
     int32_t ox, oy;         // DrawTiler tile origin inside the layer
     int32_t sx, sy, sw, sh; // pixels the blitter may touch (DrawTiler-tile local)
     int32_t shift, rule;    // 2 = AA / 0 = non-AA; 0 winding / 1 even-odd
-    uint32_t paint, pad;
+    uint32_t paint;
+    // per-draw tile-row edge lists (built on the device by k_row_lists): tile row r of the draw covers layer pixel
+    // rows [8 (r0 + r), 8 (r0 + r) + 8); its edges are row_edges[list_off + row_off[row_base + r] ..
+    // list_off + row_off[row_base + r + 1])
+    uint32_t list_off, row_base, r0, n_rows;
+    uint32_t pad;
 };
+static_assert(sizeof(DevDraw) == 64, "DevDraw is uploaded as is");
 
 struct RecordedDraw {
     uint32_t verb_off, n_verbs; // into rb_batch::verbs
@@ -47,6 +53,12 @@ struct BatchLayout {
     size_t n_edges = 0, n_draws = 0, n_paints = 0, n_stops = 0, n_tiles = 0, n_pairs = 0, n_tile_ids = 0;
     int tiles_x = 0;
     bool wide = false; // some draw may reach |winding| > 127: use k_raster_tiles_wide
+    // warp-tile path (k_raster_warp): device-built structures, sizes known on the host
+    int wtiles_x = 0, wtiles_y = 0;
+    size_t n_row_off = 0;   // entries of row_off: sum over draws of (n_rows + 1)
+    size_t n_list = 0;      // entries of row_edges: sum over edges of the tile rows they touch
+    size_t n_row_ent = 0;   // sum over draws of n_rows
+    size_t n_wpairs = 0;    // (draw, warp tile) pairs
 };
 
 // phases of the last host build, microseconds: [0] edge build (threads), [1] layout + count, [2] pack (threads),
@@ -66,6 +78,7 @@ struct rb_batch {
     // device-resident form produced by rb_batch_prepare
     BatchLayout lay;
     uint8_t *dev = nullptr;
+    uint8_t *dev_scratch = nullptr; // row lists + warp-tile bins (device-built)
     void *host_block = nullptr; // host-only batches: malloc'ed copy of the block
 };
 

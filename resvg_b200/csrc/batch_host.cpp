@@ -128,7 +128,11 @@ struct ChunkInfo {
     int worker = 0;
     size_t e0 = 0, ne = 0, d0 = 0, nd = 0, p0 = 0, np = 0, s0 = 0, ns = 0; // ranges in the worker's vectors
     size_t ge = 0, gd = 0, gp = 0, gs = 0;                                  // global bases
+    // warp-tile path: totals of this chunk and their global bases
+    size_t n_list = 0, n_row_off = 0, n_row_ent = 0, n_wpairs = 0, g_list = 0, g_row_off = 0;
 };
+
+bool g_force_wide = false;
 
 inline DevEdge pack_edge(const rbh::Edge &e)
 {
@@ -238,7 +242,24 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
                 out->edges.resize(eo + ne);
                 DevEdge *dst = out->edges.data() + eo;
                 const rbh::Edge *src = out->scratch.data();
-                for (size_t k = 0; k < ne; k++) dst[k] = pack_edge(src[k]);
+                // warp-tile rows of the draw (layer pixel rows / 8) and the size of its tile-row edge lists
+                const int r0 = (ty + g.sect.y) >> 3, r1 = (ty + g.sect.y + g.sect.h - 1) >> 3, nr = r1 - r0 + 1;
+                const int c0 = (tx + g.sect.x) / 32, c1 = (tx + g.sect.x + g.sect.w - 1) / 32;
+                size_t n_list = 0;
+                for (size_t k = 0; k < ne; k++) {
+                    dst[k] = pack_edge(src[k]);
+                    const int ra = std::min(std::max((((src[k].first_y >> g.shift) + ty) >> 3) - r0, 0), nr - 1);
+                    const int rb = std::min(std::max((((src[k].last_y >> g.shift) + ty) >> 3) - r0, 0), nr - 1);
+                    n_list += (size_t)(rb - ra + 1);
+                }
+                d.r0 = (uint32_t)r0;
+                d.n_rows = (uint32_t)nr;
+                d.list_off = (uint32_t)ci->n_list;   // chunk-relative until the pack phase
+                d.row_base = (uint32_t)ci->n_row_off;
+                ci->n_list += n_list;
+                ci->n_row_off += (size_t)nr + 1;
+                ci->n_row_ent += (size_t)nr;
+                ci->n_wpairs += (size_t)nr * (size_t)(c1 - c0 + 1);
                 out->draws.push_back(d);
             }
         }
@@ -296,19 +317,24 @@ int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threa
     BatchLayout L;
     for (auto &c : chunks) {
         c.ge = L.n_edges; c.gd = L.n_draws; c.gp = L.n_paints; c.gs = L.n_stops;
+        c.g_list = L.n_list; c.g_row_off = L.n_row_off;
         L.n_edges += c.ne; L.n_draws += c.nd; L.n_paints += c.np; L.n_stops += c.ns;
+        L.n_list += c.n_list; L.n_row_off += c.n_row_off; L.n_row_ent += c.n_row_ent; L.n_wpairs += c.n_wpairs;
     }
     for (auto &w : workers) L.wide = L.wide || w->wide;
+    L.wide = L.wide || g_force_wide;
     if (L.n_draws == 0) return RB_OK;
-    if (L.n_edges > 0xfffffff0ull) return RB_ERR_UNSUPPORTED;
+    if (L.n_edges > 0xfffffff0ull || L.n_list > 0xfffffff0ull || L.n_wpairs > 0xfffffff0ull) return RB_ERR_UNSUPPORTED;
+    L.wtiles_x = (W + 31) / 32;
+    L.wtiles_y = (H + 7) / 8;
     L.tiles_x = (W + TW - 1) / TW;
-    const int tiles_y = (H + TH - 1) / TH;
+    const int tiles_y = L.wide ? (H + TH - 1) / TH : 0; // the 64x16 bins are only used by k_raster_tiles_wide
     L.n_tiles = (size_t)L.tiles_x * tiles_y;
 
     // tile ranges of every draw, computed from the workers' draws in painter's order; counts per tile
     struct TR { uint16_t x0, x1, y0, y1; };
-    std::vector<TR> tr(L.n_draws);
-    parallel_for(nt, n_chunks, [&](size_t ci, int) {
+    std::vector<TR> tr(L.wide ? L.n_draws : 0);
+    if (L.wide) parallel_for(nt, n_chunks, [&](size_t ci, int) {
         const ChunkInfo &c = chunks[ci];
         const DevDraw *src = workers[(size_t)c.worker]->draws.data() + c.d0;
         for (size_t k = 0; k < c.nd; k++) {
@@ -380,6 +406,8 @@ int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threa
             DevDraw d = w.draws[c.d0 + k];
             d.edge_off += (uint32_t)c.ge;
             d.paint += (uint32_t)c.gp;
+            d.list_off += (uint32_t)c.g_list;
+            d.row_base += (uint32_t)c.g_row_off;
             o_draws[c.gd + k] = d;
         }
     });
@@ -409,8 +437,8 @@ int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threa
     *block = blk;
     b->stats[0] = L.n_draws;
     b->stats[1] = L.n_edges;
-    b->stats[2] = L.n_pairs;
-    b->stats[3] = L.n_tile_ids;
+    b->stats[2] = L.wide ? L.n_pairs : L.n_wpairs;
+    b->stats[3] = L.wide ? L.n_tile_ids : (size_t)L.wtiles_x * L.wtiles_y;
     b->stats[4] = L.total;
     b->stats[5] = b->phases[5] = us_since(t0);
     return RB_OK;
@@ -530,6 +558,9 @@ extern "C" int rb_batch_stats(rb_batch *b, uint64_t stats[6])
     memcpy(stats, b->stats, sizeof(b->stats));
     return RB_OK;
 }
+
+// Test hook: route every batch prepared from now on through the any-winding fallback kernel (k_raster_tiles_wide).
+extern "C" void rb_debug_force_wide_kernel(int on) { g_force_wide = on != 0; }
 
 // ---- host-only batches (CPU test-suite / host-build profiling; no device work) ------------------------------------------
 extern "C" int rb_debug_batch_begin_host(uint32_t width, uint32_t height, rb_batch **out)

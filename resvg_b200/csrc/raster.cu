@@ -262,7 +262,10 @@ __device__ __forceinline__ PF gradient_color(const DevPaint &P, const DevStop *_
 {
     const DevStop *st = stops + P.stop_off;
     int idx = 0;
-    if (!P.two_stop) for (int i = 1; i < P.len; i++) idx += (t >= st[i].t0) ? 1 : 0;
+    if (!P.two_stop) {
+#pragma unroll 1
+        for (int i = 1; i < P.len; i++) idx += (t >= st[i].t0) ? 1 : 0;
+    }
     const float4 f = *reinterpret_cast<const float4 *>(st[idx].f);
     const float4 b = *reinterpret_cast<const float4 *>(st[idx].b);
     PF c = {mad(t, f.x, b.x), mad(t, f.y, b.y), mad(t, f.z, b.z), mad(t, f.w, b.w)};
@@ -333,10 +336,9 @@ __device__ __noinline__ PF shade_pattern(const DevPaint &P, int px, int py)
     return c;
 }
 
-__device__ __forceinline__ P16 shade16(const DevPaint &P, const DevStop *__restrict__ stops, int x, int y)
+__device__ __noinline__ P16 shade16_gradient(const DevPaint &P, const DevStop *__restrict__ stops, int x, int y)
 {
     P16 o;
-    if (P.kind == 0) { o.r = P.solid16[0]; o.g = P.solid16[1]; o.b = P.solid16[2]; o.a = P.solid16[3]; return o; }
     bool masked;
     float t = gradient_t(P, x, y, masked);
     PF c = gradient_color(P, stops, t);
@@ -346,6 +348,12 @@ __device__ __forceinline__ P16 shade16(const DevPaint &P, const DevStop *__restr
     o.a = min(__float2uint_rz(clamp01(c.a) * 255.0f + 0.5f), 65535u);
     if (P.premul_after) { o.r = div255(o.r * o.a); o.g = div255(o.g * o.a); o.b = div255(o.b * o.a); }
     return o;
+}
+
+__device__ __forceinline__ P16 shade16(const DevPaint &P, const DevStop *__restrict__ stops, int x, int y)
+{
+    if (P.kind == 0) { P16 o = {P.solid16[0], P.solid16[1], P.solid16[2], P.solid16[3]}; return o; }
+    return shade16_gradient(P, stops, x, y);
 }
 
 __device__ __forceinline__ PF shadef(const DevPaint &P, const DevStop *__restrict__ stops, int x, int y)
@@ -962,6 +970,8 @@ k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint3
     }
 }
 
+#include "raster_warp.cuh"
+
 // =================================================================================================
 // batch: upload + launch (recording, edge building and binning live in batch_host.cpp)
 // =================================================================================================
@@ -983,6 +993,10 @@ static void batch_release(rb_batch *b)
         cudaFreeAsync(b->dev, batch_ctx(b)->stream);
         b->dev = nullptr;
     }
+    if (b->dev_scratch) {
+        cudaFreeAsync(b->dev_scratch, batch_ctx(b)->stream);
+        b->dev_scratch = nullptr;
+    }
     if (b->host_block) {
         free(b->host_block);
         b->host_block = nullptr;
@@ -997,6 +1011,24 @@ extern "C" void rb_batch_destroy(rb_batch *b)
     batch_release(b);
     delete b;
     if (ctx) rb_ctx_release(ctx);
+}
+
+// Device-built structures of the warp-tile path (sizes come from the host build).
+struct WarpScratch { size_t o_row_off, o_row_edges, o_boxes, o_row_cnt, o_row_draws, o_tile_off, o_tile_pairs, total; };
+static WarpScratch warp_scratch_layout(const BatchLayout &L)
+{
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    WarpScratch w;
+    size_t off = 0;
+    w.o_row_off = off;    off += al((L.n_row_off + 1) * 4);
+    w.o_row_edges = off;  off += al((L.n_list + 1) * sizeof(DevEdge));
+    w.o_boxes = off;      off += al(L.n_draws * sizeof(DrawBox));
+    w.o_row_cnt = off;    off += al(((size_t)L.wtiles_y + 2) * 4);
+    w.o_row_draws = off;  off += al((L.n_row_ent + 1) * sizeof(RowEnt));
+    w.o_tile_off = off;   off += al(((size_t)L.wtiles_x * L.wtiles_y + 2) * 4);
+    w.o_tile_pairs = off; off += al((L.n_wpairs + 1) * 4);
+    w.total = off;
+    return w;
 }
 
 struct StageReq { rb_ctx *ctx; int status; };
@@ -1035,13 +1067,14 @@ extern "C" int rb_batch_prepare(rb_batch *b, int32_t n_threads)
     RB_CUDA(ctx, cudaMemcpyAsync(dev, blk, b->lay.total, cudaMemcpyHostToDevice, ctx->stream));
     RB_CUDA(ctx, cudaEventRecord(ctx->staging_ev, ctx->stream));
     ctx->staging_in_flight = true;
+    if (!b->lay.wide) {
+        const WarpScratch ws = warp_scratch_layout(b->lay);
+        RB_CUDA(ctx, cudaMallocAsync((void **)&b->dev_scratch, ws.total, ctx->stream));
+    }
     return RB_OK;
 }
 
 static int batch_run(rb_batch *b, unsigned long long *px_stats);
-static bool g_force_wide = false;
-// Test hook: route every batch through the any-winding fallback kernel.
-extern "C" void rb_debug_force_wide_kernel(int on) { g_force_wide = on != 0; }
 extern "C" int rb_batch_run(rb_batch *b) { return batch_run(b, nullptr); }
 
 // Runs the batch once with the coverage counters on: out[0] = pixels read-modify-written (partial coverage or
@@ -1067,7 +1100,7 @@ extern "C" int rb_batch_run_counting(rb_batch *b, uint64_t out[2])
 static int batch_run(rb_batch *b, unsigned long long *px_stats)
 {
     if (!b) return RB_ERR_INVALID;
-    if (!b->dev || b->lay.n_tile_ids == 0) return RB_OK; // nothing to draw
+    if (!b->dev || b->lay.n_draws == 0) return RB_OK; // nothing to draw
     const bool mask_target = b->mask != nullptr;
     rb_ctx *ctx = mask_target ? b->mask->ctx : b->layer->ctx;
     const int W = (int)(mask_target ? b->mask->w : b->layer->w), H = (int)(mask_target ? b->mask->h : b->layer->h);
@@ -1081,11 +1114,47 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
         attr_set = true;
     }
     const BatchLayout &L = b->lay;
+    if (!L.wide) {
+        // warp-tile path: bin the draws, build the per-draw tile-row edge lists, rasterise
+        const WarpScratch ws = warp_scratch_layout(L);
+        uint8_t *sc = b->dev_scratch;
+        const DevDraw *d_draws = (const DevDraw *)(b->dev + L.o_draws);
+        const DevEdge *d_edges = (const DevEdge *)(b->dev + L.o_edges);
+        uint32_t *row_off = (uint32_t *)(sc + ws.o_row_off), *row_cnt = (uint32_t *)(sc + ws.o_row_cnt);
+        uint32_t *tile_off = (uint32_t *)(sc + ws.o_tile_off), *tile_pairs = (uint32_t *)(sc + ws.o_tile_pairs);
+        DevEdge *row_edges = (DevEdge *)(sc + ws.o_row_edges);
+        DrawBox *boxes = (DrawBox *)(sc + ws.o_boxes);
+        RowEnt *row_draws = (RowEnt *)(sc + ws.o_row_draws);
+        const uint32_t n_draws = (uint32_t)L.n_draws, n_wtiles = (uint32_t)((size_t)L.wtiles_x * L.wtiles_y);
+        RB_CUDA(ctx, cudaMemsetAsync(row_cnt, 0, ((size_t)L.wtiles_y + 2) * 4, ctx->stream));
+        RB_CUDA(ctx, cudaMemsetAsync(tile_off, 0, ((size_t)n_wtiles + 2) * 4, ctx->stream));
+        k_bin_count<<<(n_draws + 255) / 256, 256, 0, ctx->stream>>>(d_draws, n_draws, L.wtiles_x, boxes, row_cnt, tile_off);
+        RB_LAUNCHED(ctx, "bin_count");
+        k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(row_cnt, (uint32_t)L.wtiles_y);
+        RB_LAUNCHED(ctx, "scan_rows");
+        k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(tile_off, n_wtiles);
+        RB_LAUNCHED(ctx, "scan_tiles");
+        k_bin_rows<<<L.wtiles_y, 256, 0, ctx->stream>>>(boxes, n_draws, row_cnt, row_draws);
+        RB_LAUNCHED(ctx, "bin_rows");
+        k_bin_tiles<<<(n_wtiles + 7) / 8, 256, 0, ctx->stream>>>(row_draws, row_cnt, tile_off, L.wtiles_x, n_wtiles, tile_pairs);
+        RB_LAUNCHED(ctx, "bin_tiles");
+        k_row_lists<<<n_draws, RL_THREADS, 0, ctx->stream>>>(d_draws, d_edges, row_off, row_edges);
+        RB_LAUNCHED(ctx, "row_lists");
+        const unsigned grid = (n_wtiles + WT_WARPS - 1) / WT_WARPS;
+        if (mask_target)
+            k_raster_warp<true><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(target, W, H, L.wtiles_x, n_wtiles, tile_off, tile_pairs, d_draws, row_off,
+                row_edges, d_edges, (const DevPaint *)(b->dev + L.o_paints), (const DevStop *)(b->dev + L.o_stops), px_stats);
+        else
+            k_raster_warp<false><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(target, W, H, L.wtiles_x, n_wtiles, tile_off, tile_pairs, d_draws, row_off,
+                row_edges, d_edges, (const DevPaint *)(b->dev + L.o_paints), (const DevStop *)(b->dev + L.o_stops), px_stats);
+        RB_LAUNCHED(ctx, "raster_warp");
+        return RB_OK;
+    }
     const unsigned n_tile_ids = (unsigned)L.n_tile_ids;
 #define RB_RASTER_ARGS target, W, H, L.tiles_x, (const uint32_t *)(b->dev + L.o_tids), (const uint32_t *)(b->dev + L.o_toff), \
     (const uint32_t *)(b->dev + L.o_tdraws), (const DevDraw *)(b->dev + L.o_draws), (const DevEdge *)(b->dev + L.o_edges),    \
     (const DevPaint *)(b->dev + L.o_paints), (const DevStop *)(b->dev + L.o_stops), px_stats
-    const bool wide = L.wide || g_force_wide;
+    const bool wide = true; // the packed 64x16 kernel is superseded by k_raster_warp; kept for A/B measurements
     if (wide) {
         if (mask_target) k_raster_tiles_wide<true><<<n_tile_ids, RT_THREADS, CNT_BYTES, ctx->stream>>>(RB_RASTER_ARGS);
         else k_raster_tiles_wide<false><<<n_tile_ids, RT_THREADS, CNT_BYTES, ctx->stream>>>(RB_RASTER_ARGS);

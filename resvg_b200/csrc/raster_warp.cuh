@@ -1,0 +1,722 @@
+// raster_warp.cuh — the fill-path kernel proper (included by raster.cu after the pipeline code).
+//
+// One WARP owns one 32x8-pixel tile of the layer for a whole batch: its 256 destination pixels live in registers
+// (8 per lane), it walks the tile's draw list in painter's order, and no block-level barrier exists anywhere.
+// Per (draw, tile):
+//   scatter   lanes = edges of the draw's list for this tile row (built on the device by k_row_lists); every
+//             crossing x(y) is added into a packed per-position counter (one 32-bit word per sub-sample position,
+//             byte s = net crossings on sub-row s of the pixel row) and marked in a per-sub-row bit mask;
+//   scan      lanes = the 32 sub-scanlines; a lane visits only the marked positions of its sub-row (ffs), keeps the
+//             running winding in a full int, records the positions where inside/outside toggles, and a 128-bit
+//             prefix-xor turns those into the inside mask of the sub-row — work proportional to crossings, not to
+//             sub-samples;
+//   coverage  lanes = 8-pixel groups; nibble popcounts of the four sub-row masks give tiny-skia's coverage
+//             (16 per sub-sample, 64/64/64/63 for full pixels, abutting-span exception from the sub-row-3 marks);
+//   blend     the reference's pipeline per covered pixel (pipeline code in raster.cu).
+//
+// Only per-position NET crossings are packed into bytes, so the limit is |net crossings at one sub-sample| <= 127;
+// the host routes draws that could exceed it to k_raster_tiles_wide.
+#pragma once
+
+constexpr int WT_W = 32;           // warp-tile width  (pixels)
+constexpr int WT_H = 8;            // warp-tile height (pixels)
+constexpr int WT_POS = WT_W * 4;   // sub-sample positions per row
+constexpr int WT_SUB = WT_H * 4;   // sub-scanlines per tile
+constexpr int WT_WARPS = 4;        // warps per CTA (independent of each other)
+
+struct WarpTileSmem {
+    int wsum[WT_H * WT_POS];        // packed net crossings: [pixel row][position], byte s = sub-row s
+    uint32_t tmask[WT_SUB][4];      // positions with at least one crossing, per sub-row
+    uint32_t dmask[WT_H][2][4];     // sub-row 3 of every pixel row: positions with downward [0] / upward [1] crossings
+    uint32_t inside[WT_SUB][4];     // scan result: inside mask per sub-row
+    uint32_t flip[WT_H][4];         // sub-row 3: positions where the winding passes through zero between two non-zero values
+    int bd[WT_SUB + 4];             // difference array of the backdrop: edges wholly left of the tile add +-1 over their rows
+};
+
+// ---- rare path ---------------------------------------------------------------------------------------------------
+// Crossings of both directions share one sub-sample position strictly inside a fully covered pixel on the 4th
+// sub-row, so whether the span breaks there depends on the scanline walker's list order (tiny-skia scan/path.rs
+// walk_edges).  One lane replays that position from the tile row's edge list.  `list` entries carry their own slot
+// (index in the draw's edge array) in meta >> 4; `edges` is the draw's edge array (meta >> 4 = previous segment).
+struct WalkEdge { DevEdge e; uint32_t slot; uint32_t prev_meta; };
+
+// insert_new_edges on the scanline where a (non-continuation) edge joins the walker's list: the first new edge of
+// that scanline (smallest x among the edges starting there) goes after equal-x actives, every later one before them.
+// Those edges need not reach this tile row, so the whole draw is scanned — only when two crossings really tie.
+__device__ __noinline__ bool inserted_before(const DevEdge *__restrict__ edges, uint32_t n_edges, const DevEdge &E)
+{
+    const uint32_t fy = E.ypack & 0xffffu;
+    for (uint32_t k = 0; k < n_edges; k++) {
+        const DevEdge O = edges[k];
+        if ((O.ypack & 0xffffu) != fy || (O.meta & 2u) || (O.ypack >> 16) < fy) continue;
+        if (O.x < E.x) return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ bool sorted_before(const DevEdge &A, uint32_t sa, const DevEdge &B, uint32_t sb)
+{
+    // order of the walker's initial sort: (first_y, x), ties in builder order
+    const int fa = (int)(A.ypack & 0xffffu), fb = (int)(B.ypack & 0xffffu);
+    if (fa != fb) return fa < fb;
+    if (A.x != B.x) return A.x < B.x;
+    return sa < sb;
+}
+
+// kind: 0 = was active on y-1 ("survivor", keyed by its previous x), 1 = new edge placed after equal-x survivors,
+// 2 = new edge placed before them (insert_new_edges stops at the first active edge with x >= its x for every new
+// edge but the first of its scanline batch).
+__device__ bool walker_less_l(const DevEdge *__restrict__ edges, uint32_t n_edges, const WalkEdge &A, const WalkEdge &B, int y)
+{
+    for (int depth = 0; depth < 2; depth++) {
+        const int xa = edge_x_at(A.e, y), xb = edge_x_at(B.e, y);
+        if (xa != xb) return xa < xb;
+        const int fya = (int)(A.e.ypack & 0xffffu), fyb = (int)(B.e.ypack & 0xffffu);
+        int ka, kb, pa = 0, pb = 0;
+        if (y > fya) { ka = 0; pa = (int)((uint32_t)xa - (uint32_t)A.e.dx); }
+        else if (A.prev_meta & 2u) { const DevEdge P = edges[A.prev_meta >> 4]; ka = 0; pa = edge_x_at(P, (int)(P.ypack >> 16)); }
+        else ka = inserted_before(edges, n_edges, A.e) ? 2 : 1;
+        if (y > fyb) { kb = 0; pb = (int)((uint32_t)xb - (uint32_t)B.e.dx); }
+        else if (B.prev_meta & 2u) { const DevEdge P = edges[B.prev_meta >> 4]; kb = 0; pb = edge_x_at(P, (int)(P.ypack >> 16)); }
+        else kb = inserted_before(edges, n_edges, B.e) ? 2 : 1;
+        if (ka == 0 && kb == 0) {
+            if (pa != pb) return pa < pb;
+            // coincident lines: their order was fixed on the scanline where the later one joined the list
+            if (y > fya && y > fyb) { y = max(fya, fyb); continue; }
+            return sorted_before(A.e, A.slot, B.e, B.slot);
+        }
+        if (ka == 0) return kb == 1;
+        if (kb == 0) return ka == 2;
+        return sorted_before(A.e, A.slot, B.e, B.slot);
+    }
+    return sorted_before(A.e, A.slot, B.e, B.slot);
+}
+
+__device__ __noinline__ bool exact_span_break_list(const DevEdge *__restrict__ all_edges, const DevDraw *__restrict__ draws, uint32_t draw,
+                                                   const DevEdge *__restrict__ list, uint32_t n, int y, int target_r, int lo_r)
+{
+    const DevEdge *edges = all_edges + draws[draw].edge_off;
+    const uint32_t n_edges = draws[draw].edge_cnt;
+    // winding before the position (crossings left of it; positions are clamped to lo_r on the left) and the
+    // candidates at it
+    WalkEdge c[12];
+    int cnt = 0, w = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const DevEdge E = list[i];
+        const int fy = (int)(E.ypack & 0xffffu), ly = (int)(E.ypack >> 16);
+        if (fy > y || ly < y) continue;
+        const int r = max((int)((uint32_t)edge_x_at(E, y) + 0x8000u) >> 16, lo_r);
+        if (r < target_r) { w += edge_winding(E.meta); continue; }
+        if (r != target_r) continue;
+        if (cnt == 12) return true;
+        WalkEdge we;
+        we.e = E;
+        we.slot = E.meta >> 4;
+        we.prev_meta = edges[we.slot].meta;
+        int j = cnt++;
+        while (j > 0 && walker_less_l(edges, n_edges, we, c[j - 1], y)) { c[j] = c[j - 1]; j--; }
+        c[j] = we;
+    }
+    for (int i = 0; i < cnt; i++) {
+        w += edge_winding(c[i].e.meta);
+        if (w == 0) return true;
+    }
+    return false;
+}
+
+// ---- per-draw tile-row edge lists ----------------------------------------------------------------------------------
+// One CTA per draw.  Tile row r of a draw = layer pixel rows [8 (r0 + r), 8 (r0 + r) + 8); an edge is copied into the
+// list of every tile row its sub-scanline range touches (meta: bit 0 upward, bit 1 continuation, bits 4.. own slot).
+constexpr int RL_THREADS = 128;
+constexpr int RL_MAX_ROWS = 1026;
+
+__device__ __forceinline__ int draw_row_of(const DevDraw &D, int suby)
+{
+    const int r = (((suby >> D.shift) + D.oy) >> 3) - D.r0;
+    return min(max(r, 0), (int)D.n_rows - 1);
+}
+
+__global__ void __launch_bounds__(RL_THREADS)
+k_row_lists(const DevDraw *__restrict__ draws, const DevEdge *__restrict__ edges, uint32_t *__restrict__ row_off,
+            DevEdge *__restrict__ row_edges)
+{
+    __shared__ uint32_t cnt[RL_MAX_ROWS + 2];
+    __shared__ uint32_t warp_tot[RL_THREADS / 32];
+    const DevDraw D = draws[blockIdx.x];
+    const int tid = threadIdx.x, nr = (int)D.n_rows;
+    const DevEdge *E0 = edges + D.edge_off;
+    for (int i = tid; i <= nr; i += RL_THREADS) cnt[i] = 0;
+    __syncthreads();
+    if (nr > 1) {
+        for (uint32_t e = tid; e < D.edge_cnt; e += RL_THREADS) {
+            const uint32_t yp = E0[e].ypack;
+            const int fy = (int)(yp & 0xffffu), ly = (int)(yp >> 16);
+            if (fy > ly) continue; // empty slot
+            const int ra = draw_row_of(D, fy), rb = draw_row_of(D, ly);
+            for (int r = ra; r <= rb; r++) atomicAdd(&cnt[r], 1u);
+        }
+    } else {
+        uint32_t c = 0;
+        for (uint32_t e = tid; e < D.edge_cnt; e += RL_THREADS) {
+            const uint32_t yp = E0[e].ypack;
+            c += (yp & 0xffffu) <= (yp >> 16) ? 1u : 0u;
+        }
+        if (c) atomicAdd(&cnt[0], c);
+    }
+    __syncthreads();
+    // exclusive scan of cnt[0..nr) -> cnt; contiguous chunks per thread + warp shuffles
+    {
+        const int per = (nr + RL_THREADS - 1) / RL_THREADS;
+        const int lo = tid * per, hi = min(lo + per, nr);
+        uint32_t s = 0;
+        for (int i = lo; i < hi; i++) s += cnt[i];
+        uint32_t incl = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((tid & 31) >= d) incl += v;
+        }
+        if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+        __syncthreads();
+        uint32_t base = incl - s;
+        for (int w = 0; w < (tid >> 5); w++) base += warp_tot[w];
+        for (int i = lo; i < hi; i++) { uint32_t c = cnt[i]; cnt[i] = base; base += c; }
+        if (hi == nr && lo < nr) cnt[nr] = base;
+        if (nr == 0 && tid == 0) cnt[0] = 0;
+    }
+    __syncthreads();
+    for (int i = tid; i <= nr; i += RL_THREADS) row_off[D.row_base + i] = cnt[i];
+    __syncthreads();
+    DevEdge *out = row_edges + D.list_off;
+    for (uint32_t e = tid; e < D.edge_cnt; e += RL_THREADS) {
+        DevEdge E = E0[e];
+        const int fy = (int)(E.ypack & 0xffffu), ly = (int)(E.ypack >> 16);
+        if (fy > ly) continue;
+        E.meta = (E.meta & 3u) | (e << 4);
+        const int ra = draw_row_of(D, fy), rb = draw_row_of(D, ly);
+        for (int r = ra; r <= rb; r++) out[atomicAdd(&cnt[r], 1u)] = E;
+    }
+}
+
+// ---- binning draws into warp tiles (painter's order kept without sorting) ------------------------------------------
+struct DrawBox { uint32_t rows, cols; }; // r0 | r1 << 16, c0 | c1 << 16 (inclusive warp-tile coordinates)
+
+__global__ void __launch_bounds__(256)
+k_bin_count(const DevDraw *__restrict__ draws, uint32_t n_draws, int wtiles_x, DrawBox *__restrict__ boxes,
+            uint32_t *__restrict__ row_cnt, uint32_t *__restrict__ tile_cnt)
+{
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_draws) return;
+    const DevDraw D = draws[d];
+    const uint32_t c0 = (uint32_t)(D.ox + D.sx) / WT_W, c1 = (uint32_t)(D.ox + D.sx + D.sw - 1) / WT_W;
+    const uint32_t r0 = D.r0, r1 = D.r0 + D.n_rows - 1;
+    boxes[d] = DrawBox{r0 | (r1 << 16), c0 | (c1 << 16)};
+    for (uint32_t r = r0; r <= r1; r++) {
+        atomicAdd(&row_cnt[r], 1u);
+        uint32_t *t = tile_cnt + (size_t)r * wtiles_x;
+        for (uint32_t c = c0; c <= c1; c++) atomicAdd(&t[c], 1u);
+    }
+}
+
+// In-place exclusive scan of a[0..n) by ONE CTA of 1024 threads; a[n] receives the total.
+__global__ void __launch_bounds__(1024)
+k_exclusive_scan(uint32_t *__restrict__ a, uint32_t n)
+{
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t per = (n + 1023u) / 1024u;
+    const uint32_t lo = min(tid * per, n), hi = min(lo + per, n);
+    uint32_t s = 0;
+    for (uint32_t i = lo; i < hi; i++) s += a[i];
+    uint32_t incl = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((tid & 31u) >= (uint32_t)d) incl += v;
+    }
+    if ((tid & 31u) == 31u) warp_tot[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+        uint32_t v = warp_tot[tid], t = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t u = __shfl_up_sync(0xffffffffu, t, d);
+            if (tid >= (uint32_t)d) t += u;
+        }
+        warp_tot[tid] = t - v;
+    }
+    __syncthreads();
+    uint32_t base = incl - s + warp_tot[tid >> 5];
+    for (uint32_t i = lo; i < hi; i++) { uint32_t c = a[i]; a[i] = base; base += c; }
+    if (tid == 1023) a[n] = base;
+}
+
+struct RowEnt { uint32_t draw, cols; };
+
+// One CTA per warp-tile row: the draws touching the row, in draw order.
+__global__ void __launch_bounds__(256)
+k_bin_rows(const DrawBox *__restrict__ boxes, uint32_t n_draws, const uint32_t *__restrict__ row_off, RowEnt *__restrict__ row_draws)
+{
+    __shared__ uint32_t warp_cnt[8];
+    const uint32_t R = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    uint32_t out = row_off[R];
+    if (row_off[R + 1] == out) return;
+    for (uint32_t base = 0; base < n_draws; base += 256) {
+        const uint32_t d = base + tid;
+        DrawBox b = DrawBox{0, 0};
+        bool ok = false;
+        if (d < n_draws) {
+            b = boxes[d];
+            ok = (b.rows & 0xffffu) <= R && R <= (b.rows >> 16);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) warp_cnt[wid] = __popc(m);
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < 8; w++) {
+            const uint32_t c = warp_cnt[w];
+            if (w < wid) before += c;
+            total += c;
+        }
+        if (ok) row_draws[out + before + __popc(m & ((1u << lane) - 1u))] = RowEnt{d, b.cols};
+        out += total;
+        __syncthreads();
+    }
+}
+
+// One warp per warp tile: filters its row's draw list by column range, keeping the order.
+__global__ void __launch_bounds__(256)
+k_bin_tiles(const RowEnt *__restrict__ row_draws, const uint32_t *__restrict__ row_off, const uint32_t *__restrict__ tile_off,
+            int wtiles_x, uint32_t n_wtiles, uint32_t *__restrict__ tile_pairs)
+{
+    const uint32_t t = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+    if (t >= n_wtiles) return;
+    uint32_t out = tile_off[t];
+    if (tile_off[t + 1] == out) return;
+    const uint32_t R = t / (uint32_t)wtiles_x, Cc = t % (uint32_t)wtiles_x;
+    const uint32_t lo = row_off[R], hi = row_off[R + 1];
+    for (uint32_t i = lo; i < hi; i += 32) {
+        bool ok = false;
+        RowEnt e = RowEnt{0, 0};
+        if (i + lane < hi) {
+            e = row_draws[i + lane];
+            ok = (e.cols & 0xffffu) <= Cc && Cc <= (e.cols >> 16);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (ok) tile_pairs[out + __popc(m & ((1u << lane) - 1u))] = e.draw;
+        out += __popc(m);
+    }
+}
+
+// ---- the tile kernel ---------------------------------------------------------------------------------------------------
+// The per-pair path is executed once per (draw, tile) by warps that are all at different points of it, so its code
+// has to stay within the 32 KB L1.5 instruction cache: loops are kept rolled (the 8 pixels of a lane rotate through
+// one copy of the blend code), non-anti-aliased draws reuse the anti-aliased machinery (a crossing on pixel row r at
+// pixel p is entered on the four sub-rows of r at position 4p, which yields exactly 0 / 255), and rare work lives in
+// __noinline__ functions.
+struct WarpDraw { // what one lane holds about one upcoming (draw, tile) pair
+    int tlx, tly;          // tile origin in the draw's DrawTiler-tile-local pixels
+    uint32_t bounds;       // py0 | py1 << 8 | pxa << 16 | pxb << 24 (tile-local pixel bounds of the blitter rectangle)
+    uint32_t flags;        // shift | rule << 4 | valid << 8
+    uint32_t list_begin, n_list, paint;
+};
+
+template <bool MASK>
+__global__ void __launch_bounds__(WT_WARPS * 32, 6)
+k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_wtiles, const uint32_t *__restrict__ tile_off,
+              const uint32_t *__restrict__ tile_pairs, const DevDraw *__restrict__ draws, const uint32_t *__restrict__ row_off,
+              const DevEdge *__restrict__ row_edges, const DevEdge *__restrict__ edges, const DevPaint *__restrict__ paints,
+              const DevStop *__restrict__ stops, unsigned long long *__restrict__ px_stats)
+{
+    __shared__ WarpTileSmem s_all[WT_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    WarpTileSmem &S = s_all[wid];
+    const uint32_t tile = blockIdx.x * WT_WARPS + wid;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(&S);
+        for (int i = lane; i < (int)(sizeof(WarpTileSmem) / 16); i += 32) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (tile >= n_wtiles) return;
+    const uint32_t d_begin = tile_off[tile], d_end = tile_off[tile + 1];
+    if (d_begin == d_end) return;
+    const int X0 = (int)(tile % (uint32_t)wtiles_x) * WT_W, Y0 = (int)(tile / (uint32_t)wtiles_x) * WT_H;
+    const int prow = lane >> 2, pj = lane & 3; // this lane's pixels: row prow, columns 8 pj .. 8 pj + 7
+
+    uint32_t dst0 = 0, dst1 = 0, dst2 = 0, dst3 = 0, dst4 = 0, dst5 = 0, dst6 = 0, dst7 = 0;
+    {
+        const int gy = Y0 + prow, gx = X0 + 8 * pj;
+        if (gy < H) {
+            const size_t o = (size_t)gy * W + gx;
+            if (MASK) {
+                const uint8_t *t = reinterpret_cast<const uint8_t *>(target);
+                if (gx + 0 < W) dst0 = t[o + 0];
+                if (gx + 1 < W) dst1 = t[o + 1];
+                if (gx + 2 < W) dst2 = t[o + 2];
+                if (gx + 3 < W) dst3 = t[o + 3];
+                if (gx + 4 < W) dst4 = t[o + 4];
+                if (gx + 5 < W) dst5 = t[o + 5];
+                if (gx + 6 < W) dst6 = t[o + 6];
+                if (gx + 7 < W) dst7 = t[o + 7];
+            } else {
+                const uint32_t *t = reinterpret_cast<const uint32_t *>(target);
+                if (gx + 8 <= W && (W & 3) == 0) {
+                    const uint4 a = *reinterpret_cast<const uint4 *>(t + o), b = *reinterpret_cast<const uint4 *>(t + o + 4);
+                    dst0 = a.x; dst1 = a.y; dst2 = a.z; dst3 = a.w; dst4 = b.x; dst5 = b.y; dst6 = b.z; dst7 = b.w;
+                } else {
+                    if (gx + 0 < W) dst0 = t[o + 0];
+                    if (gx + 1 < W) dst1 = t[o + 1];
+                    if (gx + 2 < W) dst2 = t[o + 2];
+                    if (gx + 3 < W) dst3 = t[o + 3];
+                    if (gx + 4 < W) dst4 = t[o + 4];
+                    if (gx + 5 < W) dst5 = t[o + 5];
+                    if (gx + 6 < W) dst6 = t[o + 6];
+                    if (gx + 7 < W) dst7 = t[o + 7];
+                }
+            }
+        }
+    }
+    __syncwarp();
+
+    uint32_t n_partial = 0, n_full = 0;
+#pragma unroll 1
+    for (uint32_t gbase = d_begin; gbase < d_end; gbase += 32) {
+        // ---- every lane prepares one upcoming pair ---------------------------------------------------------------
+        WarpDraw mine;
+        mine.flags = 0; mine.n_list = 0; mine.list_begin = 0; mine.tlx = 0; mine.tly = 0; mine.bounds = 0; mine.paint = 0;
+        const int n_group = (int)min(32u, d_end - gbase);
+        if (lane < n_group) {
+            const DevDraw D = draws[tile_pairs[gbase + lane]];
+            const int tlx = X0 - D.ox, tly = Y0 - D.oy;
+            const int py0 = max(0, D.sy - tly), py1 = min(WT_H, D.sy + D.sh - tly);
+            const int pxa = max(0, D.sx - tlx), pxb = min(WT_W, D.sx + D.sw - tlx);
+            mine.tlx = tlx; mine.tly = tly;
+            mine.bounds = (uint32_t)py0 | ((uint32_t)py1 << 8) | ((uint32_t)pxa << 16) | ((uint32_t)pxb << 24);
+            const bool valid = py0 < py1 && pxa < pxb;
+            mine.flags = (uint32_t)D.shift | ((uint32_t)D.rule << 4) | (valid ? 0x100u : 0u);
+            mine.paint = D.paint;
+            if (valid) {
+                const uint32_t r = (uint32_t)(Y0 >> 3) - D.r0;
+                const uint32_t lb = row_off[D.row_base + r], le = row_off[D.row_base + r + 1];
+                mine.list_begin = D.list_off + lb;
+                mine.n_list = le - lb;
+            }
+        }
+        // first edges of the group's first pair
+        DevEdge pre;
+        pre.x = 0; pre.dx = 0; pre.ypack = 0xffffu; pre.meta = 0; // fy > ly: empty
+        {
+            const uint32_t lb0 = __shfl_sync(0xffffffffu, mine.list_begin, 0), n0 = __shfl_sync(0xffffffffu, mine.n_list, 0);
+            if ((uint32_t)lane < n0) pre = row_edges[lb0 + lane];
+        }
+#pragma unroll 1
+        for (int k = 0; k < n_group; k++) {
+            const uint32_t flags = __shfl_sync(0xffffffffu, mine.flags, k);
+            const uint32_t list_begin = __shfl_sync(0xffffffffu, mine.list_begin, k);
+            const uint32_t n_list = __shfl_sync(0xffffffffu, mine.n_list, k);
+            const uint32_t paint_idx = __shfl_sync(0xffffffffu, mine.paint, k);
+            DevEdge E = pre;
+            // prefetch the first edges of the next pair while this one is processed
+            pre.ypack = 0xffffu;
+            if (k + 1 < n_group) {
+                const uint32_t lbn = __shfl_sync(0xffffffffu, mine.list_begin, k + 1), nn = __shfl_sync(0xffffffffu, mine.n_list, k + 1);
+                if ((uint32_t)lane < nn) pre = row_edges[lbn + lane];
+            }
+            if (!(flags & 0x100u) || n_list == 0) continue;
+            const int tlx = __shfl_sync(0xffffffffu, mine.tlx, k), tly = __shfl_sync(0xffffffffu, mine.tly, k);
+            const uint32_t bounds = __shfl_sync(0xffffffffu, mine.bounds, k);
+            const int py0 = (int)(bounds & 0xffu), py1 = (int)((bounds >> 8) & 0xffu);
+            const int pxa = (int)((bounds >> 16) & 0xffu), pxb = (int)(bounds >> 24);
+            const int sh = (int)(flags & 0xfu); // 2: draw units are quarter pixels; 0: whole pixels
+            const int up4 = 2 - sh;             // draw units -> the tile's quarter-pixel units
+            const bool evenodd = (flags & 0x10u) != 0;
+            const int lo_pos = pxa << sh, hi_pos = pxb << sh;  // draw units
+            const int lo4 = pxa << 2, hi4 = pxb << 2;          // quarter pixels
+            const int sub_top = (tly + py0) << sh, sub_bot = (tly + py1) << sh;
+            const int row0 = tly << sh, col0 = tlx << sh;
+
+            // ---- scatter ---------------------------------------------------------------------------------------------
+            // An edge's rounded x is monotonic in y, so its two end crossings inside the tile classify it: wholly right of
+            // the blitter range -> no effect; wholly left -> it only shifts the winding the rows start with (two adds into
+            // a difference array instead of one crossing per sub-row); otherwise its crossings are scattered, the
+            // (edge, sub-row) pairs of all such edges spread evenly over the lanes.
+            bool did = false, any_left = false;
+#pragma unroll 1
+            for (uint32_t cb = 0; cb < n_list; cb += 32) {
+                if (cb) {
+                    E.ypack = 0xffffu;
+                    if (cb + lane < n_list) E = row_edges[list_begin + cb + lane];
+                }
+                const int fy = (int)(E.ypack & 0xffffu), ly = (int)(E.ypack >> 16);
+                const int ys = max(fy, sub_top), ye = min(ly, sub_bot - 1);
+                int n = max(ye - ys + 1, 0); // 0: nothing (also empty lanes: fy = 0xffff, ly = 0)
+                const uint32_t upbit = E.meta & 1u;
+                const uint32_t xs = (uint32_t)E.x + (uint32_t)(ys - fy) * (uint32_t)E.dx;
+                if (n > 0) {
+                    const uint32_t xe = xs + (uint32_t)(n - 1) * (uint32_t)E.dx;
+                    const int ra = ((int)(xs + 0x8000u) >> 16) - col0, rb = ((int)(xe + 0x8000u) >> 16) - col0;
+                    if (min(ra, rb) >= hi_pos) n = 0;
+                    else if (max(ra, rb) <= lo_pos) {
+                        atomicAdd(&S.bd[(ys - row0) << up4], upbit ? -1 : 1);
+                        atomicAdd(&S.bd[(ye + 1 - row0) << up4], upbit ? 1 : -1);
+                        any_left = true;
+                        n = 0;
+                    }
+                }
+                int incl = n;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += u;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (total) did = true;
+                const uint32_t ysup = (uint32_t)ys | (upbit << 16);
+#pragma unroll 1
+                for (int base = 0; base < total; base += 32) {
+                    const int i = base + lane;
+                    int e = 0; // first lane whose inclusive count exceeds i
+#pragma unroll
+                    for (int step = 16; step; step >>= 1) {
+                        const int v = __shfl_sync(0xffffffffu, incl, e + step - 1);
+                        if (v <= i) e += step;
+                    }
+                    e = min(e, 31);
+                    const uint32_t exs = __shfl_sync(0xffffffffu, xs, e), edx = __shfl_sync(0xffffffffu, (uint32_t)E.dx, e);
+                    const uint32_t eys = __shfl_sync(0xffffffffu, ysup, e);
+                    const int eexcl = __shfl_sync(0xffffffffu, incl - n, e);
+                    if (i < total) {
+                        const int kk = i - eexcl, y = (int)(eys & 0xffffu) + kk;
+                        const bool eup = (eys >> 16) != 0;
+                        const uint32_t x = exs + (uint32_t)kk * edx;
+                        const int r = (int)(x + 0x8000u) >> 16;
+                        const int pos = max(r - col0, lo_pos);
+                        if (pos < hi_pos) {
+                            const int rel = y - row0;
+                            if (sh == 2) {
+                                const int sr = rel & 3, pr = rel >> 2;
+                                const int one = 1 << (8 * sr);
+                                const uint32_t bit = 1u << (pos & 31);
+                                atomicAdd(&S.wsum[pr * WT_POS + pos], eup ? -one : one);
+                                atomicOr(&S.tmask[rel][pos >> 5], bit);
+                                if (sr == 3) atomicOr(&S.dmask[pr][eup ? 1 : 0][pos >> 5], bit);
+                            } else {
+                                const int p4 = pos << 2;
+                                const uint32_t bit = 1u << (p4 & 31);
+                                atomicAdd(&S.wsum[rel * WT_POS + p4], eup ? -0x01010101 : 0x01010101);
+                                atomicOr(&S.tmask[4 * rel + 0][p4 >> 5], bit);
+                                atomicOr(&S.tmask[4 * rel + 1][p4 >> 5], bit);
+                                atomicOr(&S.tmask[4 * rel + 2][p4 >> 5], bit);
+                                atomicOr(&S.tmask[4 * rel + 3][p4 >> 5], bit);
+                            }
+                        }
+                    }
+                }
+            }
+            any_left = __any_sync(0xffffffffu, any_left);
+            if (!did && !any_left) continue; // bounds overlap the tile but no span does
+            __syncwarp();
+            // winding every sub-scanline starts with at the left end of the blitter range
+            int backdrop = 0;
+            if (any_left) {
+                const int v = S.bd[lane];
+                int incl = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += u;
+                }
+                backdrop = incl;
+                if (v) S.bd[lane] = 0;
+                if (lane == 0) S.bd[32] = 0;
+            }
+
+            // ---- scan: lane = sub-scanline ------------------------------------------------------------------------------
+            {
+                const int sr = lane & 3, dshift = 8 * sr;
+                int w = backdrop;
+                uint32_t carry = 0;
+                const bool in0 = evenodd ? (w & 1) : (w != 0);
+#pragma unroll 1
+                for (int q = 0; q < 4; q++) {
+                    uint32_t m = S.tmask[lane][q];
+                    uint32_t T = (in0 && q == (lo4 >> 5)) ? (1u << (lo4 & 31)) : 0u, F = 0;
+                    const int *wrow = &S.wsum[prow * WT_POS + 32 * q]; // prow == lane >> 2
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int d = (int)((((uint32_t)wrow[b] + 0x80808080u) >> dshift) & 0xffu) - 128;
+                        const int wn = w + d;
+                        const bool ib = evenodd ? (w & 1) : (w != 0), ia = evenodd ? (wn & 1) : (wn != 0);
+                        if (ib != ia) T ^= 1u << b;
+                        if (w != 0 && wn != 0 && (w ^ wn) < 0) F |= 1u << b;
+                        w = wn;
+                    }
+                    // inside mask = prefix xor of the toggles, restricted to [lo4, hi4)
+                    uint32_t x = T;
+                    x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16;
+                    x ^= carry;
+                    carry = (x >> 31) ? 0xffffffffu : 0u;
+                    const int a = hi4 - 32 * q;
+                    const uint32_t keep = a >= 32 ? 0xffffffffu : (a <= 0 ? 0u : ((1u << a) - 1u));
+                    S.inside[lane][q] = x & keep;
+                    if (sr == 3) S.flip[prow][q] = F;
+                }
+            }
+            __syncwarp();
+
+            // ---- coverage: lane = 8 pixels of one row ------------------------------------------------------------------------
+            uint32_t c0 = 0, c1 = 0, dec = 0; // sample counts (0..16) of pixels 0..3 / 4..7, one per byte; 63-instead-of-64 flags
+            {
+                const uint32_t I0 = S.inside[4 * prow + 0][pj], I1 = S.inside[4 * prow + 1][pj];
+                const uint32_t I2 = S.inside[4 * prow + 2][pj], I3 = S.inside[4 * prow + 3][pj];
+                if (I0 | I1 | I2 | I3) {
+                    auto nib = [](uint32_t v) {
+                        v = v - ((v >> 1) & 0x55555555u);
+                        return (v & 0x33333333u) + ((v >> 2) & 0x33333333u);
+                    };
+                    const uint32_t n0 = nib(I0), n1 = nib(I1), n2 = nib(I2), n3 = nib(I3);
+                    const uint32_t lo = (n0 & 0x0f0f0f0fu) + (n1 & 0x0f0f0f0fu) + (n2 & 0x0f0f0f0fu) + (n3 & 0x0f0f0f0fu);
+                    const uint32_t hi = ((n0 >> 4) & 0x0f0f0f0fu) + ((n1 >> 4) & 0x0f0f0f0fu) + ((n2 >> 4) & 0x0f0f0f0fu) + ((n3 >> 4) & 0x0f0f0f0fu);
+                    c0 = __byte_perm(lo, hi, 0x5140); // pixels 0, 1, 2, 3
+                    c1 = __byte_perm(lo, hi, 0x7362); // pixels 4, 5, 6, 7
+                    const uint32_t full3 = I3 & (I3 >> 1) & (I3 >> 2) & (I3 >> 3) & 0x11111111u;
+                    uint32_t brk = 0; // bit 4k: the span breaks inside pixel k on sub-row 3
+                    if (full3) {
+                        const uint32_t dn = S.dmask[prow][0][pj], upm = S.dmask[prow][1][pj];
+                        const uint32_t inner = (dn | upm) & 0xeeeeeeeeu; // crossings strictly inside a pixel
+                        if (inner) {
+                            if (evenodd) {
+                                brk = ((inner >> 1) | (inner >> 2) | (inner >> 3)) & 0x11111111u;
+                            } else {
+                                const uint32_t mixed = dn & upm & 0xeeeeeeeeu;
+                                const uint32_t f2 = S.flip[prow][pj] & 0xeeeeeeeeu & ~mixed;
+                                brk = ((f2 >> 1) | (f2 >> 2) | (f2 >> 3)) & 0x11111111u;
+                                uint32_t mx = mixed;
+                                while (mx) { // both directions at one position: the walker's order decides
+                                    const int b = __ffs(mx) - 1;
+                                    mx &= mx - 1;
+                                    const uint32_t pixbit = 1u << (b & ~3);
+                                    if (!(full3 & pixbit) || (brk & pixbit)) continue;
+                                    if (exact_span_break_list(edges, draws, tile_pairs[gbase + k], row_edges + list_begin, n_list,
+                                                              row0 + prow * 4 + 3, col0 + 32 * pj + b, col0 + lo_pos))
+                                        brk |= pixbit;
+                                }
+                            }
+                        }
+                    }
+                    dec = full3 & ~brk;
+                }
+            }
+            __syncwarp();
+
+            // ---- clear the marks this draw left -------------------------------------------------------------------------------
+#pragma unroll 1
+            for (int q = 0; q < 4; q++) {
+                uint32_t m = S.tmask[lane][q];
+                if (!m) continue;
+                S.tmask[lane][q] = 0;
+                int *wrow = &S.wsum[prow * WT_POS + 32 * q];
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    wrow[b] = 0;
+                }
+            }
+            if (lane < 16) reinterpret_cast<uint4 *>(S.dmask)[lane] = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+
+            // ---- blend: the lane's 8 pixels rotate through one copy of the code ---------------------------------------------------
+            if (c0 | c1) {
+                const DevPaint &P = paints[paint_idx];
+                const bool memset_ok = !MASK && P.has_memset != 0;
+                const uint32_t memset_color = P.memset_color;
+                // u16 pipeline with Source / SourceOver over a solid colour or a gradient: the common programs, kept inline
+                const bool simple = !MASK && P.kind != 2 && P.lowp && (P.blend == 1 || P.blend == 3);
+                const bool is_solid = P.kind == 0;
+                uint32_t sr = P.solid16[0], sg = P.solid16[1], sb = P.solid16[2], sa = P.solid16[3];
+                const bool src_over = P.blend == 3;
+#pragma unroll 1
+                for (int q = 0; q < 8; q++) {
+                    const uint32_t c = min(16u * (c0 & 0xffu) - (dec & 1u), 255u);
+                    c0 = __funnelshift_r(c0, c1, 8);
+                    c1 >>= 8;
+                    dec >>= 4;
+                    uint32_t d = dst0;
+                    if (c) {
+                        if (MASK) {
+                            d = c == 255 ? 255u : div255(d * (255 - c) + 255u * c);
+                        } else if (c == 255 && memset_ok) {
+                            d = memset_color;
+                            n_full++;
+                        } else if (simple) {
+                            n_partial++;
+                            if (!is_solid) {
+                                const P16 g16 = shade16_gradient(P, stops, tlx + 8 * pj + q, tly + prow);
+                                sr = g16.r; sg = g16.g; sb = g16.b; sa = g16.a;
+                            }
+                            uint32_t r, g, b2, a;
+                            if (src_over) { // scale_1_float (coverage folded into the source), then source_over
+                                const uint32_t pr = c == 255 ? sr : div255(sr * c), pg = c == 255 ? sg : div255(sg * c);
+                                const uint32_t pb = c == 255 ? sb : div255(sb * c), pa = c == 255 ? sa : div255(sa * c);
+                                const uint32_t ia = 255 - pa;
+                                r = pr + div255(RB_R(d) * ia); g = pg + div255(RB_G(d) * ia);
+                                b2 = pb + div255(RB_B(d) * ia); a = pa + div255(RB_A(d) * ia);
+                            } else {        // Source: lerp_1_float(dst, src, coverage)
+                                const uint32_t ic = 255 - c;
+                                r = div255(RB_R(d) * ic + sr * c); g = div255(RB_G(d) * ic + sg * c);
+                                b2 = div255(RB_B(d) * ic + sb * c); a = div255(RB_A(d) * ic + sa * c);
+                            }
+                            d = rb_pack(r & 0xffu, g & 0xffu, b2 & 0xffu, a & 0xffu);
+                        } else {
+                            n_partial++;
+                            d = blend_pixel(P, stops, d, c, tlx + 8 * pj + q, tly + prow);
+                        }
+                    }
+                    dst0 = dst1; dst1 = dst2; dst2 = dst3; dst3 = dst4; dst4 = dst5; dst5 = dst6; dst6 = dst7; dst7 = d;
+                }
+            }
+        }
+    }
+
+    if (px_stats) {
+        n_partial = __reduce_add_sync(0xffffffffu, n_partial);
+        n_full = __reduce_add_sync(0xffffffffu, n_full);
+        if (lane == 0) {
+            atomicAdd(px_stats, (unsigned long long)n_partial);
+            atomicAdd(px_stats + 1, (unsigned long long)n_full);
+        }
+    }
+    {
+        const int gy = Y0 + prow, gx = X0 + 8 * pj;
+        if (gy < H) {
+            const size_t o = (size_t)gy * W + gx;
+            if (MASK) {
+                uint8_t *t = reinterpret_cast<uint8_t *>(target);
+                if (gx + 0 < W) t[o + 0] = (uint8_t)dst0;
+                if (gx + 1 < W) t[o + 1] = (uint8_t)dst1;
+                if (gx + 2 < W) t[o + 2] = (uint8_t)dst2;
+                if (gx + 3 < W) t[o + 3] = (uint8_t)dst3;
+                if (gx + 4 < W) t[o + 4] = (uint8_t)dst4;
+                if (gx + 5 < W) t[o + 5] = (uint8_t)dst5;
+                if (gx + 6 < W) t[o + 6] = (uint8_t)dst6;
+                if (gx + 7 < W) t[o + 7] = (uint8_t)dst7;
+            } else {
+                uint32_t *t = reinterpret_cast<uint32_t *>(target);
+                if (gx + 8 <= W && (W & 3) == 0) {
+                    *reinterpret_cast<uint4 *>(t + o) = make_uint4(dst0, dst1, dst2, dst3);
+                    *reinterpret_cast<uint4 *>(t + o + 4) = make_uint4(dst4, dst5, dst6, dst7);
+                } else {
+                    if (gx + 0 < W) t[o + 0] = dst0;
+                    if (gx + 1 < W) t[o + 1] = dst1;
+                    if (gx + 2 < W) t[o + 2] = dst2;
+                    if (gx + 3 < W) t[o + 3] = dst3;
+                    if (gx + 4 < W) t[o + 4] = dst4;
+                    if (gx + 5 < W) t[o + 5] = dst5;
+                    if (gx + 6 < W) t[o + 6] = dst6;
+                    if (gx + 7 < W) t[o + 7] = dst7;
+                }
+            }
+        }
+    }
+}
