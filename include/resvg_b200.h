@@ -257,6 +257,9 @@ int rb_debug_build_edges(const uint8_t *verbs, int32_t n_verbs, const float *poi
                          int32_t *out_meta /* optional: {prev segment index | -1, inserts-before flag} per edge */,
                          int32_t max_edges, int32_t geom[7]);
 
+/* Test hook: expand curves into line edges on the host (as the fallback path does) instead of on the device. */
+void rb_debug_host_expand(int on);
+
 /* Host-only batch (no target, no device work): records like any batch; rb_batch_prepare runs the host build (edges,
  * binning, block layout) for a width x height canvas and keeps the block on the host.  For the CPU test-suite and for
  * profiling the host half.  rb_debug_batch_phases: microseconds of the last host build — [0] edge build, [1] layout +

@@ -32,9 +32,12 @@ struct DevDraw {
     // rows [8 (r0 + r), 8 (r0 + r) + 8); its edges are row_edges[list_off + row_off[row_base + r] ..
     // list_off + row_off[row_base + r + 1])
     uint32_t list_off, row_base, r0, n_rows;
-    uint32_t pad;
+    uint32_t list_cap;      // entries reserved for this draw's lists
+    // item mode (curves expanded on the device): edge_off / edge_cnt address the draw's SLOTS in the device-side
+    // edge array; the uploaded line edges (meta >> 4 = slot) and curve records (item = first slot) are here:
+    uint32_t line_off, line_cnt, curve_off, curve_cnt;
 };
-static_assert(sizeof(DevDraw) == 64, "DevDraw is uploaded as is");
+static_assert(sizeof(DevDraw) == 80, "DevDraw is uploaded as is");
 
 struct RecordedDraw {
     uint32_t verb_off, n_verbs; // into rb_batch::verbs
@@ -49,8 +52,12 @@ struct RecordedDraw {
 
 // Byte offsets of the arrays inside the contiguous block (identical on host staging and device).
 struct BatchLayout {
-    size_t o_edges = 0, o_draws = 0, o_paints = 0, o_stops = 0, o_toff = 0, o_tdraws = 0, o_tids = 0, total = 0;
+    size_t o_edges = 0, o_draws = 0, o_paints = 0, o_stops = 0, o_toff = 0, o_tdraws = 0, o_tids = 0, o_curves = 0, total = 0;
     size_t n_edges = 0, n_draws = 0, n_paints = 0, n_stops = 0, n_tiles = 0, n_pairs = 0, n_tile_ids = 0;
+    // item mode: the block carries final line edges (n_edges of them) and curve records; the device expands the
+    // curves into an edge array of n_slots entries
+    bool items = false;
+    size_t n_curves = 0, n_slots = 0;
     int tiles_x = 0;
     bool wide = false; // some draw may reach |winding| > 127: use k_raster_tiles_wide
     // warp-tile path (k_raster_warp): device-built structures, sizes known on the host

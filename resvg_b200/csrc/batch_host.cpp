@@ -99,11 +99,14 @@ struct Worker {
     std::vector<DevDraw> draws;   // edge_off relative to the chunk's first edge
     std::vector<DevPaint> paints; // stop_off relative to the chunk's first stop
     std::vector<DevStop> stops;
+    std::vector<rbh::CurveRec> curves; // item mode: recorded curves, `item` = draw-relative slot of the first segment
     std::vector<rbh::Edge> scratch;
+    std::vector<rbh::CurveRec> cscratch;
+    std::vector<int32_t> ends;
     std::vector<rbh::Pt> tmp, spts;
     std::vector<uint8_t> sverbs;
     bool wide = false;
-    void reset() { edges.clear(); draws.clear(); paints.clear(); stops.clear(); wide = false; }
+    void reset() { edges.clear(); draws.clear(); paints.clear(); stops.clear(); curves.clear(); wide = false; }
 };
 
 std::mutex g_pool_mu;
@@ -130,9 +133,12 @@ struct ChunkInfo {
     size_t ge = 0, gd = 0, gp = 0, gs = 0;                                  // global bases
     // warp-tile path: totals of this chunk and their global bases
     size_t n_list = 0, n_row_off = 0, n_row_ent = 0, n_wpairs = 0, g_list = 0, g_row_off = 0;
+    // item mode: recorded curves and the slots of the device-side edge array
+    size_t c0 = 0, nc = 0, gc = 0, n_slots = 0, g_slots = 0;
 };
 
 bool g_force_wide = false;
+bool g_host_expand = false;
 
 inline DevEdge pack_edge(const rbh::Edge &e)
 {
@@ -154,8 +160,24 @@ struct Tick { uint64_t &acc; uint64_t t0; Tick(uint64_t &a) : acc(a), t0(__rdtsc
 #define PROF(i)
 #endif
 
-void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool mask_target, Worker *out, ChunkInfo *ci)
+// Upper bound of simultaneously active edges from the y ranges of the chains (a line, or a whole curve): used in item
+// mode, where the curve segments do not exist on the host.  `iv` holds (first_y, last_y) pairs.
+bool chains_may_exceed_packed_winding(std::vector<int32_t> &iv)
 {
+    const size_t n = iv.size() / 2;
+    if (n < 128) return false;
+    std::vector<std::pair<int32_t, int32_t>> ev;
+    ev.reserve(2 * n);
+    for (size_t i = 0; i < n; i++) { ev.emplace_back(iv[2 * i], 1); ev.emplace_back(iv[2 * i + 1] + 1, -1); }
+    std::sort(ev.begin(), ev.end());
+    int active = 0, worst = 0;
+    for (auto &e : ev) { active += e.second; worst = std::max(worst, active); }
+    return worst >= 128;
+}
+
+void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool mask_target, bool items, Worker *out, ChunkInfo *ci)
+{
+    ci->c0 = out->curves.size();
     ci->e0 = out->edges.size();
     ci->d0 = out->draws.size();
     ci->p0 = out->paints.size();
@@ -211,17 +233,17 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
                 }
                 rbh::DrawGeom g;
                 out->scratch.clear();
+                out->cscratch.clear();
                 bool ok;
                 {
                     PROF(1);
-                    ok = rbh::build_draw(verbs, n_verbs, pts, n_pts, aa, tw, th, out->scratch, &g);
+                    ok = items ? rbh::build_draw_items(verbs, n_verbs, pts, n_pts, aa, tw, th, out->scratch, out->cscratch, &g)
+                               : rbh::build_draw(verbs, n_verbs, pts, n_pts, aa, tw, th, out->scratch, &g);
                 }
                 if (!ok) continue;
-                const size_t ne = out->scratch.size();
+                const size_t ne = out->scratch.size(), ncv = out->cscratch.size();
                 DevDraw d;
                 memset(&d, 0, sizeof(d));
-                d.edge_off = (uint32_t)(out->edges.size() - ci->e0);
-                d.edge_cnt = (uint32_t)ne;
                 d.ox = tx; d.oy = ty;
                 d.sx = g.sect.x; d.sy = g.sect.y; d.sw = g.sect.w; d.sh = g.sect.h;
                 d.shift = g.shift;
@@ -237,25 +259,71 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
                     out->paints.push_back(p);
                 }
                 PROF(2);
-                if (draw_may_exceed_packed_winding(out->scratch.data(), ne)) out->wide = true;
+                // warp-tile rows of the draw (layer pixel rows / 8) and the size of its tile-row edge lists
+                const int r0 = (ty + g.sect.y) >> 3, r1 = (ty + g.sect.y + g.sect.h - 1) >> 3, nr = r1 - r0 + 1;
+                const int c0 = (tx + g.sect.x) / 32, c1 = (tx + g.sect.x + g.sect.w - 1) / 32;
+                auto row_of = [&](int32_t suby) { return std::min(std::max((((suby >> g.shift) + ty) >> 3) - r0, 0), nr - 1); };
+                size_t n_list = 0;
                 const size_t eo = out->edges.size();
                 out->edges.resize(eo + ne);
                 DevEdge *dst = out->edges.data() + eo;
                 const rbh::Edge *src = out->scratch.data();
-                // warp-tile rows of the draw (layer pixel rows / 8) and the size of its tile-row edge lists
-                const int r0 = (ty + g.sect.y) >> 3, r1 = (ty + g.sect.y + g.sect.h - 1) >> 3, nr = r1 - r0 + 1;
-                const int c0 = (tx + g.sect.x) / 32, c1 = (tx + g.sect.x + g.sect.w - 1) / 32;
-                size_t n_list = 0;
-                for (size_t k = 0; k < ne; k++) {
-                    dst[k] = pack_edge(src[k]);
-                    const int ra = std::min(std::max((((src[k].first_y >> g.shift) + ty) >> 3) - r0, 0), nr - 1);
-                    const int rb = std::min(std::max((((src[k].last_y >> g.shift) + ty) >> 3) - r0, 0), nr - 1);
-                    n_list += (size_t)(rb - ra + 1);
+                d.edge_off = (uint32_t)(eo - ci->e0);
+                if (!items) {
+                    if (draw_may_exceed_packed_winding(src, ne)) out->wide = true;
+                    d.edge_cnt = (uint32_t)ne;
+                    for (size_t k = 0; k < ne; k++) {
+                        dst[k] = pack_edge(src[k]);
+                        n_list += (size_t)(row_of(src[k].last_y) - row_of(src[k].first_y) + 1);
+                    }
+                } else {
+                    // slots of the device-side edge array in emission order: one per line, 2^shift per curve
+                    const size_t co = out->curves.size();
+                    out->curves.resize(co + ncv);
+                    rbh::CurveRec *cdst = out->curves.data() + co;
+                    const rbh::CurveRec *csrc = out->cscratch.data();
+                    out->ends.clear();
+                    uint32_t slot = 0;
+                    size_t il = 0, ic = 0;
+                    while (il < ne || ic < ncv) {
+                        if (ic >= ncv || (il < ne && src[il].order < csrc[ic].item)) {
+                            const rbh::Edge &e = src[il];
+                            DevEdge de;
+                            de.x = e.x; de.dx = e.dx;
+                            de.ypack = ((uint32_t)e.first_y & 0xffffu) | ((uint32_t)e.last_y << 16);
+                            de.meta = (e.winding < 0 ? 1u : 0u) | (slot << 4);
+                            dst[il++] = de;
+                            n_list += (size_t)(row_of(e.last_y) - row_of(e.first_y) + 1);
+                            out->ends.push_back(e.first_y); out->ends.push_back(e.last_y);
+                            slot += 1;
+                        } else {
+                            rbh::CurveRec c = csrc[ic];
+                            const int sh = (int)((c.info >> 4) & 0xfu);
+                            const int ylast = (c.info & 1u) ? c.p[7] : c.p[5];
+                            const int32_t top = (c.p[1] + 32) >> 6, bot = (ylast + 32) >> 6;
+                            c.item = slot;
+                            cdst[ic++] = c;
+                            // its segments partition [top, bot): at most one extra list entry per tile-row boundary
+                            n_list += ((size_t)1 << sh) + (size_t)(row_of(bot - 1) - row_of(top)) + 2;
+                            out->ends.push_back(top); out->ends.push_back(bot - 1);
+                            slot += 1u << sh;
+                        }
+                    }
+                    if (slot >= (1u << 28)) continue; // meta keeps slot indices in 28 bits
+                    if (chains_may_exceed_packed_winding(out->ends)) out->wide = true;
+                    d.edge_cnt = slot;                     // slots of this draw in the device edge array
+                    d.edge_off = (uint32_t)ci->n_slots;    // chunk-relative slot base
+                    d.line_off = (uint32_t)(eo - ci->e0);
+                    d.line_cnt = (uint32_t)ne;
+                    d.curve_off = (uint32_t)(co - ci->c0);
+                    d.curve_cnt = (uint32_t)ncv;
+                    ci->n_slots += slot;
                 }
                 d.r0 = (uint32_t)r0;
                 d.n_rows = (uint32_t)nr;
                 d.list_off = (uint32_t)ci->n_list;   // chunk-relative until the pack phase
                 d.row_base = (uint32_t)ci->n_row_off;
+                d.list_cap = (uint32_t)n_list;
                 ci->n_list += n_list;
                 ci->n_row_off += (size_t)nr + 1;
                 ci->n_row_ent += (size_t)nr;
@@ -264,6 +332,7 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
             }
         }
     }
+    ci->nc = out->curves.size() - ci->c0;
     ci->ne = out->edges.size() - ci->e0;
     ci->nd = out->draws.size() - ci->d0;
     ci->np = out->paints.size() - ci->p0;
@@ -290,6 +359,8 @@ int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threa
     const auto t0 = Clock::now();
 
     // ---- 1. edges + paints on host threads (dynamic chunks; painter's order = chunk order) ------------------
+    // Item mode first (lines final, curves recorded for the device to expand); when a draw could exceed the packed
+    // winding range — or a debug hook asks for it — everything is rebuilt with the curves expanded on the host.
     const size_t n_chunks = (n + kChunk - 1) / kChunk;
     int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
     nt = std::max(1, std::min<int>(nt, (int)n_chunks));
@@ -300,29 +371,39 @@ int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threa
         ~Return() { for (auto &x : w) if (x) return_worker(std::move(x)); }
     } give_back{workers};
     std::vector<ChunkInfo> chunks(n_chunks);
-    parallel_for(nt, n_chunks, [&](size_t c, int t) {
-        chunks[c].worker = t;
-        build_chunk(b, c * kChunk, std::min(n, (c + 1) * kChunk), W, H, mask_target, workers[(size_t)t].get(), &chunks[c]);
-    });
+    bool items = !g_force_wide && !g_host_expand;
+    bool any_wide = false;
+    for (;;) {
+        for (auto &c : chunks) c = ChunkInfo();
+        for (auto &w : workers) w->reset();
+        parallel_for(nt, n_chunks, [&](size_t c, int t) {
+            chunks[c].worker = t;
+            build_chunk(b, c * kChunk, std::min(n, (c + 1) * kChunk), W, H, mask_target, items, workers[(size_t)t].get(), &chunks[c]);
+        });
+        any_wide = false;
+        for (auto &w : workers) any_wide = any_wide || w->wide;
+        if (items && any_wide) { items = false; continue; }
+        break;
+    }
     b->phases[0] = us_since(t0);
 #ifdef RB_HOST_PROFILE
     fprintf(stderr, "[host profile] Mcycles: stroke %.0f build_draw %.0f pack %.0f\n", g_prof[0].load() / 1e6, g_prof[1].load() / 1e6, g_prof[2].load() / 1e6);
     for (auto &g : g_prof) g = 0;
-    fprintf(stderr, "[host profile] build_draw Mcycles: emit %.0f sort %.0f links %.0f\n", g_bd_prof[0].load() / 1e6, g_bd_prof[1].load() / 1e6, g_bd_prof[2].load() / 1e6);
-    for (auto &g : g_bd_prof) g = 0;
 #endif
 
     // ---- 2. layout --------------------------------------------------------------------------------------------
     const auto t1 = Clock::now();
     BatchLayout L;
+    L.items = items;
     for (auto &c : chunks) {
         c.ge = L.n_edges; c.gd = L.n_draws; c.gp = L.n_paints; c.gs = L.n_stops;
-        c.g_list = L.n_list; c.g_row_off = L.n_row_off;
+        c.g_list = L.n_list; c.g_row_off = L.n_row_off; c.gc = L.n_curves; c.g_slots = L.n_slots;
         L.n_edges += c.ne; L.n_draws += c.nd; L.n_paints += c.np; L.n_stops += c.ns;
         L.n_list += c.n_list; L.n_row_off += c.n_row_off; L.n_row_ent += c.n_row_ent; L.n_wpairs += c.n_wpairs;
+        L.n_curves += c.nc; L.n_slots += c.n_slots;
     }
-    for (auto &w : workers) L.wide = L.wide || w->wide;
-    L.wide = L.wide || g_force_wide;
+    L.wide = any_wide || g_force_wide;
+    if (L.n_slots > 0xfffffff0ull) return RB_ERR_UNSUPPORTED;
     if (L.n_draws == 0) return RB_OK;
     if (L.n_edges > 0xfffffff0ull || L.n_list > 0xfffffff0ull || L.n_wpairs > 0xfffffff0ull) return RB_ERR_UNSUPPORTED;
     L.wtiles_x = (W + 31) / 32;
@@ -377,6 +458,7 @@ int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threa
     L.o_toff = off;   off += al((L.n_tiles + 1) * 4);
     L.o_tids = off;   off += al(L.n_tile_ids * 4);
     L.o_tdraws = off; off += al(L.n_pairs * 4);
+    L.o_curves = off; off += al(std::max<size_t>(L.n_curves, 1) * sizeof(rbh::CurveRec));
     L.o_edges = off;  off += al(L.n_edges * sizeof(DevEdge));
     L.total = off;
     b->phases[1] = us_since(t1);
@@ -392,10 +474,12 @@ int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threa
     DevDraw *o_draws = (DevDraw *)(blk + L.o_draws);
     DevPaint *o_paints = (DevPaint *)(blk + L.o_paints);
     DevStop *o_stops = (DevStop *)(blk + L.o_stops);
+    rbh::CurveRec *o_curves = (rbh::CurveRec *)(blk + L.o_curves);
     parallel_for(nt, n_chunks, [&](size_t ci, int) {
         const ChunkInfo &c = chunks[ci];
         const Worker &w = *workers[(size_t)c.worker];
         if (c.ne) memcpy(o_edges + c.ge, w.edges.data() + c.e0, c.ne * sizeof(DevEdge));
+        if (c.nc) memcpy(o_curves + c.gc, w.curves.data() + c.c0, c.nc * sizeof(rbh::CurveRec));
         if (c.ns) memcpy(o_stops + c.gs, w.stops.data() + c.s0, c.ns * sizeof(DevStop));
         for (size_t k = 0; k < c.np; k++) {
             DevPaint p = w.paints[c.p0 + k];
@@ -404,7 +488,13 @@ int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threa
         }
         for (size_t k = 0; k < c.nd; k++) {
             DevDraw d = w.draws[c.d0 + k];
-            d.edge_off += (uint32_t)c.ge;
+            if (L.items) {
+                d.edge_off += (uint32_t)c.g_slots;
+                d.line_off += (uint32_t)c.ge;
+                d.curve_off += (uint32_t)c.gc;
+            } else {
+                d.edge_off += (uint32_t)c.ge;
+            }
             d.paint += (uint32_t)c.gp;
             d.list_off += (uint32_t)c.g_list;
             d.row_base += (uint32_t)c.g_row_off;
@@ -436,7 +526,7 @@ int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threa
     b->lay = L;
     *block = blk;
     b->stats[0] = L.n_draws;
-    b->stats[1] = L.n_edges;
+    b->stats[1] = L.items ? L.n_slots : L.n_edges; // line edges (item mode: upper bound = slots of the device edge array)
     b->stats[2] = L.wide ? L.n_pairs : L.n_wpairs;
     b->stats[3] = L.wide ? L.n_tile_ids : (size_t)L.wtiles_x * L.wtiles_y;
     b->stats[4] = L.total;
@@ -561,6 +651,9 @@ extern "C" int rb_batch_stats(rb_batch *b, uint64_t stats[6])
 
 // Test hook: route every batch prepared from now on through the any-winding fallback kernel (k_raster_tiles_wide).
 extern "C" void rb_debug_force_wide_kernel(int on) { g_force_wide = on != 0; }
+
+// Test hook: expand curves on the host (the device then only bins and rasterises), to cross-check the device expansion.
+extern "C" void rb_debug_host_expand(int on) { g_host_expand = on != 0; }
 
 // ---- host-only batches (CPU test-suite / host-build profiling; no device work) ------------------------------------------
 extern "C" int rb_debug_batch_begin_host(uint32_t width, uint32_t height, rb_batch **out)

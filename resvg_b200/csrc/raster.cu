@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "batch.h"
+#include "edge_math.h"
 #include "common.cuh"
 #include "raster_host.h"
 #include "rb_internal.h"
@@ -1014,7 +1015,7 @@ extern "C" void rb_batch_destroy(rb_batch *b)
 }
 
 // Device-built structures of the warp-tile path (sizes come from the host build).
-struct WarpScratch { size_t o_row_off, o_row_edges, o_boxes, o_row_cnt, o_row_draws, o_tile_off, o_tile_pairs, total; };
+struct WarpScratch { size_t o_row_off, o_row_edges, o_boxes, o_row_cnt, o_row_draws, o_tile_off, o_tile_pairs, o_edges, o_flag, total; };
 static WarpScratch warp_scratch_layout(const BatchLayout &L)
 {
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -1027,6 +1028,8 @@ static WarpScratch warp_scratch_layout(const BatchLayout &L)
     w.o_row_draws = off;  off += al((L.n_row_ent + 1) * sizeof(RowEnt));
     w.o_tile_off = off;   off += al(((size_t)L.wtiles_x * L.wtiles_y + 2) * 4);
     w.o_tile_pairs = off; off += al((L.n_wpairs + 1) * 4);
+    w.o_edges = off;      off += al(((L.items ? L.n_slots : 0) + 1) * sizeof(DevEdge));
+    w.o_flag = off;       off += 256;
     w.total = off;
     return w;
 }
@@ -1094,6 +1097,12 @@ extern "C" int rb_batch_run_counting(rb_batch *b, uint64_t out[2])
     RB_CUDA(ctx, cudaFreeAsync(d, ctx->stream));
     out[0] = h[0];
     out[1] = h[1];
+    if (st == RB_OK && b->dev_scratch && !b->lay.wide) {
+        // the list builder counts entries it had to drop (the host's capacity bound makes that impossible)
+        unsigned int dropped = 0;
+        RB_CUDA(ctx, cudaMemcpy(&dropped, b->dev_scratch + warp_scratch_layout(b->lay).o_flag, 4, cudaMemcpyDeviceToHost));
+        if (dropped) return rb_fail(ctx, RB_ERR_CUDA, "tile-row edge list overflow");
+    }
     return st;
 }
 
@@ -1119,7 +1128,10 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
         const WarpScratch ws = warp_scratch_layout(L);
         uint8_t *sc = b->dev_scratch;
         const DevDraw *d_draws = (const DevDraw *)(b->dev + L.o_draws);
-        const DevEdge *d_edges = (const DevEdge *)(b->dev + L.o_edges);
+        // item mode: o_edges holds the uploaded line edges; the edge array proper is expanded into the scratch block
+        const DevEdge *d_lines = (const DevEdge *)(b->dev + L.o_edges);
+        DevEdge *d_edges = L.items ? (DevEdge *)(sc + ws.o_edges) : (DevEdge *)(b->dev + L.o_edges);
+        unsigned int *d_flag = (unsigned int *)(sc + ws.o_flag);
         uint32_t *row_off = (uint32_t *)(sc + ws.o_row_off), *row_cnt = (uint32_t *)(sc + ws.o_row_cnt);
         uint32_t *tile_off = (uint32_t *)(sc + ws.o_tile_off), *tile_pairs = (uint32_t *)(sc + ws.o_tile_pairs);
         DevEdge *row_edges = (DevEdge *)(sc + ws.o_row_edges);
@@ -1128,6 +1140,7 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
         const uint32_t n_draws = (uint32_t)L.n_draws, n_wtiles = (uint32_t)((size_t)L.wtiles_x * L.wtiles_y);
         RB_CUDA(ctx, cudaMemsetAsync(row_cnt, 0, ((size_t)L.wtiles_y + 2) * 4, ctx->stream));
         RB_CUDA(ctx, cudaMemsetAsync(tile_off, 0, ((size_t)n_wtiles + 2) * 4, ctx->stream));
+        RB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, 4, ctx->stream));
         k_bin_count<<<(n_draws + 255) / 256, 256, 0, ctx->stream>>>(d_draws, n_draws, L.wtiles_x, boxes, row_cnt, tile_off);
         RB_LAUNCHED(ctx, "bin_count");
         k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(row_cnt, (uint32_t)L.wtiles_y);
@@ -1138,7 +1151,8 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
         RB_LAUNCHED(ctx, "bin_rows");
         k_bin_tiles<<<(n_wtiles + 7) / 8, 256, 0, ctx->stream>>>(row_draws, row_cnt, tile_off, L.wtiles_x, n_wtiles, tile_pairs);
         RB_LAUNCHED(ctx, "bin_tiles");
-        k_row_lists<<<n_draws, RL_THREADS, 0, ctx->stream>>>(d_draws, d_edges, row_off, row_edges);
+        k_row_lists<<<n_draws, RL_THREADS, 0, ctx->stream>>>(d_draws, d_lines, (const rbh::CurveRec *)(b->dev + L.o_curves), d_edges, row_off,
+                                                              row_edges, L.items ? 1 : 0, d_flag);
         RB_LAUNCHED(ctx, "row_lists");
         const unsigned grid = (n_wtiles + WT_WARPS - 1) / WT_WARPS;
         if (mask_target)

@@ -6,6 +6,8 @@
 // ever sees independent `Edge {x, dx, first_y, last_y, winding}` records it can evaluate in closed form:
 // x(y) = x + (y - first_y) * dx (wrapping i32).
 #include "raster_host.h"
+
+#include "edge_math.h"
 #ifdef RB_HOST_PROFILE
 #include <x86intrin.h>
 #include <atomic>
@@ -35,18 +37,8 @@ static inline int32_t d2i(double v)
     if (v <= -2147483648.0) return INT32_MIN;
     return (int32_t)v;
 }
-static inline int32_t shl(int32_t v, int s) { return (int32_t)((uint32_t)v << s); }
-static inline int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
-static inline int32_t wsub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
-static inline int32_t wmul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
-static inline int32_t fdot6_round(int32_t n) { return wadd(n, 32) >> 6; }
-static inline int32_t fdot16_mul(int32_t a, int32_t b) { return (int32_t)(((int64_t)a * (int64_t)b) >> 16); }
-static inline int32_t fdot6_div(int32_t a, int32_t b)
-{
-    if (a >= -32768 && a <= 32767) return shl(a, 16) / b;
-    int64_t v = ((int64_t)a * 65536) / (int64_t)b;
-    return (int32_t)std::min<int64_t>(std::max<int64_t>(v, INT32_MIN), INT32_MAX);
-}
+using rbe::shl;
+using rbe::fdot6_round;
 static constexpr float kNearlyZero = 1.0f / 4096.0f;
 static inline bool nearly_zero(float v, float tol = kNearlyZero) { return fabsf(v) <= tol; }
 
@@ -232,22 +224,26 @@ struct Sink {
     int shift;
     std::vector<uint8_t> kinds; // per emitted edge: 0 = from a line, 1 = from a curve (combine_vertical only
                                 // ever looks at a preceding *line* edge)
+    // item mode: curves are recorded (FDot6 control points + subdivision count) instead of being expanded; `order`
+    // of a line / `item` of a curve is then the emission index shared by both kinds
+    std::vector<CurveRec> *curves = nullptr;
+    uint32_t n_items = 0;
+
+    uint32_t next_order() { return curves ? n_items++ : (uint32_t)(out->size() - base); }
 
     // LineEdge::new / update tail: FDot6 end points, y0 <= y1
     bool emit(int32_t x0, int32_t y0, int32_t x1, int32_t y1, int winding, Edge *e)
     {
-        int32_t top = fdot6_round(y0), bot = fdot6_round(y1);
-        if (top == bot) return false;
-        int32_t slope = fdot6_div(wsub(x1, x0), wsub(y1, y0));
-        int32_t dy = wsub(wadd(shl(top, 6), 32), y0);
-        e->x = shl(wadd(x0, fdot16_mul(slope, dy)), 10);
-        e->dx = slope;
-        e->first_y = top;
-        e->last_y = bot - 1;
+        rbe::RawEdge r;
+        if (!rbe::line_edge(x0, y0, x1, y1, &r)) return false;
+        e->x = r.x;
+        e->dx = r.dx;
+        e->first_y = r.first_y;
+        e->last_y = r.last_y;
         e->winding = winding;
         e->prev = -1;
         e->before = 0;
-        e->order = (uint32_t)(out->size() - base);
+        e->order = 0;
         return true;
     }
 
@@ -264,6 +260,7 @@ struct Sink {
             if (c == 2) { out->pop_back(); kinds.pop_back(); return; }
             if (c == 1) return;
         }
+        e.order = next_order();
         out->push_back(e);
         kinds.push_back(0);
     }
@@ -297,16 +294,17 @@ struct Sink {
         return 0;
     }
 
-    static inline int32_t cheap_distance(int32_t dx, int32_t dy)
+    void push_segment(const rbe::RawEdge &r, int w, int32_t *link)
     {
-        dx = dx < 0 ? -dx : dx;
-        dy = dy < 0 ? -dy : dy;
-        return dx > dy ? dx + (dy >> 1) : dy + (dx >> 1);
-    }
-    static inline int diff_to_shift(int32_t dx, int32_t dy, int shift_aa)
-    {
-        int32_t dist = (cheap_distance(dx, dy) + 16) >> (3 + shift_aa);
-        return (32 - (dist ? __builtin_clz((uint32_t)dist) : 32)) / 2;
+        Edge e;
+        e.x = r.x; e.dx = r.dx; e.first_y = r.first_y; e.last_y = r.last_y;
+        e.winding = w;
+        e.prev = *link;
+        e.before = 0;
+        e.order = (uint32_t)(out->size() - base);
+        *link = (int32_t)e.order;
+        out->push_back(e);
+        kinds.push_back(1);
     }
 
     // QuadraticEdge::new + every update(): emits one line edge per non-degenerate segment.
@@ -318,44 +316,18 @@ struct Sink {
         int w = 1;
         if (y0 > y2) { std::swap(x0, x2); std::swap(y0, y2); w = -1; }
         if (fdot6_round(y0) == fdot6_round(y2)) return;
-        int sh = diff_to_shift((shl(x1, 1) - x0 - x2) >> 2, (shl(y1, 1) - y0 - y2) >> 2, shift);
-        if (sh == 0) sh = 1;
-        else if (sh > 6) sh = 6;
-        int count = 1 << sh;
-        int cshift = sh - 1;
-        int32_t a = shl(x0 - x1 - x1 + x2, 9), b = shl(x1 - x0, 10);
-        int32_t qx = shl(x0, 10), qdx = wadd(b, a >> sh), qddx = a >> (sh - 1);
-        a = shl(y0 - y1 - y1 + y2, 9);
-        b = shl(y1 - y0, 10);
-        int32_t qy = shl(y0, 10), qdy = wadd(b, a >> sh), qddy = a >> (sh - 1);
-        int32_t lastx = shl(x2, 10), lasty = shl(y2, 10);
-        int32_t link = -1;
-        while (count > 0) {
-            int32_t nx, ny;
-            if (--count > 0) {
-                nx = wadd(qx, qdx >> cshift);
-                qdx = wadd(qdx, qddx);
-                ny = wadd(qy, qdy >> cshift);
-                qdy = wadd(qdy, qddy);
-            } else { nx = lastx; ny = lasty; }
-            Edge e;
-            if (emit(qx >> 10, qy >> 10, nx >> 10, ny >> 10, w, &e)) {
-                e.prev = link;
-                link = (int32_t)e.order;
-                out->push_back(e);
-                kinds.push_back(1);
-            }
-            qx = nx; qy = ny;
+        const int sh = rbe::quad_shift(x0, y0, x1, y1, x2, y2, shift);
+        if (curves) {
+            CurveRec c;
+            c.p[0] = x0; c.p[1] = y0; c.p[2] = x1; c.p[3] = y1; c.p[4] = x2; c.p[5] = y2; c.p[6] = 0; c.p[7] = 0;
+            c.info = 0u | ((uint32_t)sh << 4) | (w < 0 ? 0x100u : 0u);
+            c.item = n_items++;
+            curves->push_back(c);
+            kinds.push_back(1);
+            return;
         }
-    }
-
-    static inline int32_t cubic_delta(int32_t a, int32_t b, int32_t c, int32_t d)
-    {
-        int32_t one = wmul(a * 8 - b * 15 + 6 * c + d, 19) >> 9;
-        int32_t two = wmul(a + 6 * b - c * 15 + d * 8, 19) >> 9;
-        one = one < 0 ? -one : one;
-        two = two < 0 ? -two : two;
-        return std::max(one, two);
+        int32_t link = -1;
+        rbe::quad_expand(x0, y0, x1, y1, x2, y2, sh, [&](const rbe::RawEdge &r) { push_segment(r, w, &link); });
     }
 
     // CubicEdge::new + every update()
@@ -367,41 +339,18 @@ struct Sink {
         int w = 1;
         if (y0 > y3) { std::swap(x0, x3); std::swap(x1, x2); std::swap(y0, y3); std::swap(y1, y2); w = -1; }
         if (fdot6_round(y0) == fdot6_round(y3)) return;
-        int sh = diff_to_shift(cubic_delta(x0, x1, x2, x3), cubic_delta(y0, y1, y2, y3), 2) + 1;
-        if (sh > 6) sh = 6;
-        int up = 6, down = sh + up - 10;
-        if (down < 0) { down = 0; up = 10 - sh; }
-        int count = -(1 << sh);
-        int32_t b = shl(3 * (x1 - x0), up), c = shl(3 * (x0 - x1 - x1 + x2), up), d = shl(x3 + 3 * (x1 - x2) - x0, up);
-        int32_t cx = shl(x0, 10), cdx = wadd(wadd(b, c >> sh), d >> (2 * sh)), cddx = wadd(wmul(2, c), wmul(3, d) >> (sh - 1)),
-                cdddx = wmul(3, d) >> (sh - 1);
-        b = shl(3 * (y1 - y0), up);
-        c = shl(3 * (y0 - y1 - y1 + y2), up);
-        d = shl(y3 + 3 * (y1 - y2) - y0, up);
-        int32_t cy = shl(y0, 10), cdy = wadd(wadd(b, c >> sh), d >> (2 * sh)), cddy = wadd(wmul(2, c), wmul(3, d) >> (sh - 1)),
-                cdddy = wmul(3, d) >> (sh - 1);
-        int32_t lastx = shl(x3, 10), lasty = shl(y3, 10);
-        int32_t link = -1;
-        while (count < 0) {
-            int32_t nx, ny;
-            if (++count < 0) {
-                nx = wadd(cx, cdx >> down);
-                cdx = wadd(cdx, cddx >> sh);
-                cddx = wadd(cddx, cdddx);
-                ny = wadd(cy, cdy >> down);
-                cdy = wadd(cdy, cddy >> sh);
-                cddy = wadd(cddy, cdddy);
-            } else { nx = lastx; ny = lasty; }
-            if (ny < cy) ny = cy;
-            Edge e;
-            if (emit(cx >> 10, cy >> 10, nx >> 10, ny >> 10, w, &e)) {
-                e.prev = link;
-                link = (int32_t)e.order;
-                out->push_back(e);
-                kinds.push_back(1);
-            }
-            cx = nx; cy = ny;
+        const int sh = rbe::cubic_shift(x0, y0, x1, y1, x2, y2, x3, y3);
+        if (curves) {
+            CurveRec c;
+            c.p[0] = x0; c.p[1] = y0; c.p[2] = x1; c.p[3] = y1; c.p[4] = x2; c.p[5] = y2; c.p[6] = x3; c.p[7] = y3;
+            c.info = 1u | ((uint32_t)sh << 4) | (w < 0 ? 0x100u : 0u);
+            c.item = n_items++;
+            curves->push_back(c);
+            kinds.push_back(1);
+            return;
         }
+        int32_t link = -1;
+        rbe::cubic_expand(x0, y0, x1, y1, x2, y2, x3, y3, sh, [&](const rbe::RawEdge &r) { push_segment(r, w, &link); });
     }
 };
 
@@ -662,12 +611,11 @@ std::atomic<uint64_t> g_bd_prof[4];
 #else
 #define BD_T(i)
 #endif
-bool build_draw(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, bool anti_alias, int32_t cw, int32_t ch,
-                std::vector<Edge> &out, DrawGeom *g)
+// Shared front end of both builders: bounds and clip decisions of tiny-skia's fill_path (painter.rs, scan/path.rs,
+// scan/path_aa.rs), then PathEdgeIter + EdgeClipper feeding `sink`.  Returns false when nothing is to be drawn.
+static bool walk_path(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, bool anti_alias, int32_t cw, int32_t ch,
+                      Sink &sink, DrawGeom *g, IRect *ir_out, bool *inside_out)
 {
-#ifdef RB_HOST_PROFILE
-    uint64_t bd_t__ = __rdtsc();
-#endif
     if (n_pts == 0) return false;
     float l = pts[0].x, r = l, t = pts[0].y, b = t;
     for (int i = 1; i < n_pts; i++) {
@@ -698,11 +646,8 @@ bool build_draw(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, boo
     }
     IRect s;
     if (!sect(ir, clip, &s)) return false;
-    bool inside = ir.x >= 0 && ir.y >= 0 && contains(clip, ir);
+    const bool inside = ir.x >= 0 && ir.y >= 0 && contains(clip, ir);
 
-    Sink sink;
-    sink.out = &out;
-    sink.base = out.size();
     sink.shift = shift;
     Clipper cl{&sink, Clip{0.0f, 0.0f, (float)cw, (float)ch}};
 
@@ -745,9 +690,46 @@ bool build_draw(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, boo
         }
         open = true;
     }
+    g->sect = s;
+    g->shift = shift;
+    *ir_out = ir;
+    *inside_out = inside;
+    return true;
+}
+
+static bool finish_geom(const IRect &ir, bool inside, int32_t ch, DrawGeom *g)
+{
+    int32_t start_y = shl(ir.y, g->shift), stop_y = shl(ir.y + ir.h, g->shift);
+    if (!inside) {
+        start_y = std::max(start_y, 0);
+        stop_y = std::min(stop_y, shl(ch, g->shift));
+    }
+    if (start_y < 0 || stop_y <= start_y) return false;
+    g->start_y = start_y;
+    g->stop_y = stop_y;
+    return true;
+}
+
+bool build_draw(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, bool anti_alias, int32_t cw, int32_t ch,
+                std::vector<Edge> &out, DrawGeom *g)
+{
+#ifdef RB_HOST_PROFILE
+    uint64_t bd_t__ = __rdtsc();
+#endif
+    Sink sink;
+    sink.out = &out;
+    sink.base = out.size();
+    IRect ir;
+    bool inside;
+    if (!walk_path(verbs, n_verbs, pts, n_pts, anti_alias, cw, ch, sink, g, &ir, &inside)) { out.resize(sink.base); return false; }
     BD_T(0);
     size_t n = out.size() - sink.base;
-    if (n < 2) { out.resize(sink.base); return false; }
+    {
+        // BasicEdgeBuilder::build: fewer than two edge objects (a curve is one) -> nothing to draw
+        size_t objects = 0;
+        for (size_t i = sink.base; i < out.size() && objects < 2; i++) objects += out[i].prev < 0 ? 1 : 0;
+        if (objects < 2) { out.resize(sink.base); return false; }
+    }
     // scan/path.rs: sort by (first_y, x); stable = builder order among ties
     std::stable_sort(out.begin() + (long)sink.base, out.end(), [](const Edge &a, const Edge &e) {
         if (a.first_y != e.first_y) return a.first_y < e.first_y;
@@ -779,16 +761,27 @@ bool build_draw(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, boo
         }
     }
     BD_T(2);
-    int32_t start_y = shl(ir.y, shift), stop_y = shl(ir.y + ir.h, shift);
-    if (!inside) {
-        start_y = std::max(start_y, 0);
-        stop_y = std::min(stop_y, shl(ch, shift));
-    }
-    if (start_y < 0 || stop_y <= start_y) { out.resize(sink.base); return false; }
-    g->sect = s;
-    g->shift = shift;
-    g->start_y = start_y;
-    g->stop_y = stop_y;
+    if (!finish_geom(ir, inside, ch, g)) { out.resize(sink.base); return false; }
+    return true;
+}
+
+// Item form of build_draw for the device-side expansion: line edges are final (appended to `lines`, order = emission
+// index), curves are recorded with their FDot6 control points (appended to `curves`, item = emission index).
+bool build_draw_items(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, bool anti_alias, int32_t cw, int32_t ch,
+                      std::vector<Edge> &lines, std::vector<CurveRec> &curves, DrawGeom *g)
+{
+    Sink sink;
+    sink.out = &lines;
+    sink.base = lines.size();
+    sink.curves = &curves;
+    const size_t cbase = curves.size();
+    IRect ir;
+    bool inside;
+    bool ok = walk_path(verbs, n_verbs, pts, n_pts, anti_alias, cw, ch, sink, g, &ir, &inside);
+    // BasicEdgeBuilder::build: fewer than two edge objects (a curve is one) -> nothing to draw
+    if (ok && (lines.size() - sink.base) + (curves.size() - cbase) < 2) ok = false;
+    if (ok) ok = finish_geom(ir, inside, ch, g);
+    if (!ok) { lines.resize(sink.base); curves.resize(cbase); return false; }
     return true;
 }
 

@@ -59,10 +59,19 @@ struct DrawGeom {
     int32_t start_y, stop_y; // walker range in (super-sampled) scanlines
 };
 
+// A recorded quadratic / cubic edge for the device-side expansion: FDot6 control points (y ascending),
+// info = kind (0 quad, 1 cubic) | log2 subdivisions << 4 | upward << 8; item = emission index among the draw's items.
+struct CurveRec { int32_t p[8]; uint32_t info; uint32_t item; };
+
 // Builds the sorted line-edge list for `path` (device space, tile-local) against clip (0,0,cw,ch).
 // Appends to `out`; returns false when nothing is to be drawn.
 bool build_draw(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, bool anti_alias, int32_t cw, int32_t ch,
                 std::vector<Edge> &out, DrawGeom *geom);
+
+// Same front end, but curves are only recorded (see CurveRec); `lines` receives the final line edges with
+// order = emission index.  Nothing is sorted: the device orders nothing either.
+bool build_draw_items(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, bool anti_alias, int32_t cw, int32_t ch,
+                      std::vector<Edge> &lines, std::vector<CurveRec> &curves, DrawGeom *geom);
 
 // ---- shaders ------------------------------------------------------------------------------------
 constexpr int kMaxStops = 32;

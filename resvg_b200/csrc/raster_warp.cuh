@@ -136,16 +136,48 @@ __device__ __forceinline__ int draw_row_of(const DevDraw &D, int suby)
     return min(max(r, 0), (int)D.n_rows - 1);
 }
 
+// Item mode: the draw's edge array is first materialised from the uploaded items — line edges are copied to their
+// slots, every recorded curve is forward-differenced by one thread into the line edges tiny-skia's update() calls
+// would produce (edge_math.h, shared with the host builder), unused slots are marked empty (first_y > last_y).
 __global__ void __launch_bounds__(RL_THREADS)
-k_row_lists(const DevDraw *__restrict__ draws, const DevEdge *__restrict__ edges, uint32_t *__restrict__ row_off,
-            DevEdge *__restrict__ row_edges)
+k_row_lists(const DevDraw *__restrict__ draws, const DevEdge *__restrict__ lines, const rbh::CurveRec *__restrict__ curves,
+            DevEdge *__restrict__ edges, uint32_t *__restrict__ row_off, DevEdge *__restrict__ row_edges, int items,
+            unsigned int *__restrict__ overflow)
 {
     __shared__ uint32_t cnt[RL_MAX_ROWS + 2];
     __shared__ uint32_t warp_tot[RL_THREADS / 32];
     const DevDraw D = draws[blockIdx.x];
     const int tid = threadIdx.x, nr = (int)D.n_rows;
-    const DevEdge *E0 = edges + D.edge_off;
+    DevEdge *E0 = edges + D.edge_off;
     for (int i = tid; i <= nr; i += RL_THREADS) cnt[i] = 0;
+    if (items) {
+        for (uint32_t i = tid; i < D.line_cnt; i += RL_THREADS) {
+            DevEdge L = lines[D.line_off + i];
+            const uint32_t slot = L.meta >> 4;
+            L.meta &= 1u;
+            E0[slot] = L;
+        }
+        for (uint32_t i = tid; i < D.curve_cnt; i += RL_THREADS) {
+            const rbh::CurveRec C = curves[D.curve_off + i];
+            const int sh = (int)((C.info >> 4) & 0xfu);
+            const uint32_t up = (C.info >> 8) & 1u, first = C.item, n_slots = 1u << sh;
+            uint32_t k = 0;
+            auto emit = [&](const rbe::RawEdge &r) {
+                DevEdge e;
+                e.x = r.x;
+                e.dx = r.dx;
+                e.ypack = ((uint32_t)r.first_y & 0xffffu) | ((uint32_t)r.last_y << 16);
+                e.meta = up | (k ? (2u | ((first + k - 1) << 4)) : 0u);
+                if (k < n_slots) E0[first + k] = e;
+                k++;
+            };
+            if (C.info & 1u) rbe::cubic_expand(C.p[0], C.p[1], C.p[2], C.p[3], C.p[4], C.p[5], C.p[6], C.p[7], sh, emit);
+            else rbe::quad_expand(C.p[0], C.p[1], C.p[2], C.p[3], C.p[4], C.p[5], sh, emit);
+            DevEdge none;
+            none.x = 0; none.dx = 0; none.ypack = 0xffffu; none.meta = 0;
+            for (; k < n_slots; k++) E0[first + k] = none;
+        }
+    }
     __syncthreads();
     if (nr > 1) {
         for (uint32_t e = tid; e < D.edge_cnt; e += RL_THREADS) {
@@ -194,7 +226,11 @@ k_row_lists(const DevDraw *__restrict__ draws, const DevEdge *__restrict__ edges
         if (fy > ly) continue;
         E.meta = (E.meta & 3u) | (e << 4);
         const int ra = draw_row_of(D, fy), rb = draw_row_of(D, ly);
-        for (int r = ra; r <= rb; r++) out[atomicAdd(&cnt[r], 1u)] = E;
+        for (int r = ra; r <= rb; r++) {
+            const uint32_t at = atomicAdd(&cnt[r], 1u);
+            if (at < D.list_cap) out[at] = E;
+            else atomicAdd(overflow, 1u); // cannot happen: the host's bound covers every segment
+        }
     }
 }
 

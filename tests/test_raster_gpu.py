@@ -317,6 +317,39 @@ def test_wide_fallback_kernel_matches_too(ctx):
     assert_exact(got, want, "wide kernel")
 
 
+def test_device_curve_expansion_matches_host_expansion(ctx):
+    """Curves are forward-differenced on the device by default; expanding them on the host (the fallback builder) must
+    give the same pixels, and both must equal the oracle."""
+    import resvg_b200 as rb
+    from resvg_b200 import _ffi
+
+    w, h = 300, 260
+    rng = SplitMix64(991)
+    want = np.zeros((h, w, 4), np.uint8)
+    recs = []
+    for _ in range(60):
+        cx, cy, r = rng.uniform(-20, w + 20), rng.uniform(-20, h + 20), rng.log_uniform(5, 200)
+        verbs, pts = random_path(rng, cx, cy, r)
+        spec = random_paint_spec(rng, cx, cy, r, solid=0.7, linear=0.3)
+        rule = "evenodd" if rng.u() < 0.5 else "nonzero"
+        recs.append((verbs, pts, spec, rule, rng.u() < 0.9))
+        R.fill_path(want, verbs, pts, R.make_paint(spec, "source_over", recs[-1][4]), rule)
+    got = []
+    for host_expand in (0, 1):
+        _ffi.lib.rb_debug_host_expand(host_expand)
+        try:
+            l = ctx.layer(w, h)
+            b = rb.Batch(l)
+            for verbs, pts, spec, rule, aa in recs:
+                b.fill_path(verbs, pts, rb.make_paint(spec, "source_over", aa), rule)
+            b.submit()
+            got.append(l.download())
+        finally:
+            _ffi.lib.rb_debug_host_expand(0)
+    assert_exact(got[0], want, "device expansion")
+    assert_exact(got[1], want, "host expansion")
+
+
 def test_many_overlapping_loops_select_wide_kernel(ctx):
     """A path winding around the same point 140 times exceeds the packed kernel's +-127 range: the host must route
     it to the fallback kernel and the result must still be exact."""
