@@ -194,7 +194,8 @@ typedef struct {
 int rb_batch_stroke_path(rb_batch *batch, const uint8_t *verbs, int32_t n_verbs, const float *points,
                          int32_t n_points, const rb_paint *paint, const rb_stroke *stroke, const float ts[6]);
 /* Bulk recording of fills and strokes: strokes may be NULL; entry i is stroked when strokes[i].width > 0, filled
- * with fill_rules[i] otherwise. */
+ * with fill_rules[i] otherwise.  Recorded BY REFERENCE: every array (and the stops the paints point to) must stay
+ * valid and unchanged until the next rb_batch_prepare / rb_batch_submit on this batch has returned. */
 int rb_batch_draw_paths(rb_batch *batch, int32_t n_paths, const uint32_t *verb_off, const uint32_t *point_off,
                         const uint8_t *verbs, const float *points, const rb_paint *paints, const uint8_t *fill_rules,
                         const rb_stroke *strokes, const float ts[6]);
@@ -212,6 +213,9 @@ int rb_batch_run(rb_batch *batch);
 /* rb_batch_run with pixel counters (roofline accounting): out[0] = pixels read-modify-written, out[1] = pixels
  * stored without a read (full coverage + opaque solid paint).  Synchronises the stream. */
 int rb_batch_run_counting(rb_batch *batch, uint64_t out[2]);
+/* Device time (CUDA events on the context's stream) of the last rb_batch_run / submit on this context:
+ * ms[0] = binning + edge-list pre-pass kernels, ms[1] = the raster kernel.  Synchronises. */
+int rb_ctx_last_run_ms(rb_ctx *ctx, float ms[2]);
 void rb_batch_destroy(rb_batch *batch);
 /* statistics of the last submit: [0] draws, [1] line edges, [2] (draw,tile) pairs, [3] non-empty tiles,
  * [4] bytes uploaded, [5] host build microseconds */

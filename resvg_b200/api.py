@@ -50,6 +50,12 @@ class Context:
         self.check(lib.rb_timer_end(self._h, C.byref(ms)), "timer_end")
         return ms.value
 
+    def last_run_ms(self):
+        """(pre-pass ms, raster kernel ms) of the last batch run on this context, from CUDA events."""
+        ms = (C.c_float * 2)()
+        self.check(lib.rb_ctx_last_run_ms(self._h, ms), "last_run_ms")
+        return float(ms[0]), float(ms[1])
+
     @property
     def launch_count(self) -> int:
         return int(lib.rb_ctx_launch_count(self._h))
@@ -354,9 +360,11 @@ class Batch:
 
     def fill_paths(self, scene, ts=IDENTITY):
         """Bulk recording from packed arrays: scene has verb_off, pt_off (uint32, n+1), verbs (uint8), pts (float32
-        (m, 2)), paints (ctypes array of rb_paint), rules (uint8)."""
+        (m, 2)), paints (ctypes array of rb_paint), rules (uint8).  Recorded by reference: the arrays are kept alive
+        by this batch and must not be modified before submit() / prepare() has returned."""
         n = len(scene["rules"])
         strokes = scene.get("strokes")
+        self._keep.append(dict(scene))
         self.layer.ctx.check(
             lib.rb_batch_draw_paths(self._h, n, scene["verb_off"].ctypes.data, scene["pt_off"].ctypes.data,
                                     scene["verbs"].ctypes.data, scene["pts"].ctypes.data,

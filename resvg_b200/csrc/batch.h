@@ -50,6 +50,20 @@ struct RecordedDraw {
     rb_stroke stroke;
 };
 
+// rb_batch_draw_paths records by reference: the caller's packed arrays are used in place by the host build.
+struct BulkSeg {
+    int32_t n;
+    const uint32_t *verb_off, *point_off;
+    const uint8_t *verbs;
+    const float *points;
+    const rb_paint *paints;
+    const uint8_t *fill_rules;
+    const rb_stroke *strokes; // may be null
+    rbh::Xform ctm;
+};
+// Draws in call order: a span is either a run of individually recorded draws (recs[first ..]) or one bulk segment.
+struct DrawSpan { size_t start, count; int bulk; size_t first; };
+
 // Byte offsets of the arrays inside the contiguous block (identical on host staging and device).
 struct BatchLayout {
     size_t o_edges = 0, o_draws = 0, o_paints = 0, o_stops = 0, o_toff = 0, o_tdraws = 0, o_tids = 0, o_curves = 0, total = 0;
@@ -80,6 +94,9 @@ struct rb_batch {
     std::vector<rbh::Pt> pts;
     std::vector<float> stops;
     std::vector<RecordedDraw> recs;
+    std::vector<BulkSeg> bulk;
+    std::vector<DrawSpan> spans;
+    size_t n_total = 0; // draws recorded so far (recs + bulk)
     uint64_t stats[6] = {0, 0, 0, 0, 0, 0};
     uint64_t phases[RB_PHASES] = {0, 0, 0, 0, 0, 0};
     // device-resident form produced by rb_batch_prepare
@@ -94,8 +111,9 @@ struct rb_batch {
 typedef void *(*rb_stage_alloc)(void *user, size_t bytes);
 
 // Edge build + binning + layout.  Returns RB_OK with lay.n_draws == 0 when nothing is to be drawn.
+// Draws [begin, end) of the batch only (end = 0: all of them).
 int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threads, rb_stage_alloc alloc, void *user,
-                        void **block);
+                        void **block, size_t begin = 0, size_t end = 0);
 
 int rb_batch_record(rb_batch *b, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
                     const rb_paint *paint, int32_t rule, const float ts[6]);

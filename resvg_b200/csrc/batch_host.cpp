@@ -23,6 +23,9 @@ extern "C" int rb_path_stroke(const uint8_t *verbs, int32_t n_verbs, const float
                               float miter_limit, int32_t cap, int32_t join, float res_scale, uint8_t **out_verbs,
                               int32_t *out_n_verbs, float **out_points, int32_t *out_n_points);
 extern "C" void rb_path_free(void *p);
+int rb_path_stroke_view(const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points, float width,
+                        float miter_limit, int32_t cap, int32_t join, float res_scale, const uint8_t **out_verbs,
+                        int32_t *out_n_verbs, const float **out_points, int32_t *out_n_points);
 
 namespace {
 
@@ -103,7 +106,7 @@ struct Worker {
     std::vector<rbh::Edge> scratch;
     std::vector<rbh::CurveRec> cscratch;
     std::vector<int32_t> ends;
-    std::vector<rbh::Pt> tmp, spts;
+    std::vector<rbh::Pt> tmp, spts, bpts;
     std::vector<uint8_t> sverbs;
     bool wide = false;
     void reset() { edges.clear(); draws.clear(); paints.clear(); stops.clear(); curves.clear(); wide = false; }
@@ -186,28 +189,62 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
     uint64_t prof_local[4] = {0, 0, 0, 0};
     struct Flush { uint64_t *p; ~Flush() { for (int i = 0; i < 4; i++) g_prof[i] += p[i]; } } flush__{prof_local};
 #endif
+    size_t span_i = 0;
+    RecordedDraw bulk_rec;
     for (size_t i = begin; i < end; i++) {
-        const RecordedDraw &r = b->recs[i];
-        const uint8_t *verbs = b->verbs.data() + r.verb_off;
-        const rbh::Pt *rpts = b->pts.data() + r.pt_off;
+        // locate the draw: an individually recorded one, or entry k of a bulk segment (used in place)
+        while (i >= b->spans[span_i].start + b->spans[span_i].count) span_i++;
+        while (i < b->spans[span_i].start) span_i--;
+        const DrawSpan &sp = b->spans[span_i];
+        const RecordedDraw *rp;
+        const uint8_t *verbs;
+        const rbh::Pt *rpts;
+        const float *stops_src;
+        if (sp.bulk < 0) {
+            rp = &b->recs[sp.first + (i - sp.start)];
+            verbs = b->verbs.data() + rp->verb_off;
+            rpts = b->pts.data() + rp->pt_off;
+            stops_src = rp->n_stops ? b->stops.data() + rp->stop_off : nullptr;
+        } else {
+            const BulkSeg &bs = b->bulk[(size_t)sp.bulk];
+            const size_t k = i - sp.start;
+            RecordedDraw &r = bulk_rec;
+            r.verb_off = 0; r.pt_off = 0; r.stop_off = 0;
+            r.n_verbs = bs.verb_off[k + 1] - bs.verb_off[k];
+            r.n_pts = bs.point_off[k + 1] - bs.point_off[k];
+            r.paint = bs.paints[k];
+            r.n_stops = (r.paint.stops && r.paint.n_stops > 0) ? (uint32_t)r.paint.n_stops : 0u;
+            stops_src = r.n_stops ? r.paint.stops : nullptr;
+            r.ctm = bs.ctm;
+            r.is_stroke = bs.strokes && bs.strokes[k].width > 0.0f;
+            if (r.is_stroke) r.stroke = bs.strokes[k];
+            r.rule = r.is_stroke ? 0 : (bs.fill_rules[k] ? 1 : 0);
+            verbs = bs.verbs + bs.verb_off[k];
+            rpts = reinterpret_cast<const rbh::Pt *>(bs.points) + bs.point_off[k];
+            if (!r.is_stroke && !bs.ctm.is_identity()) { // painter.rs: path.transform(ts)
+                out->bpts.assign(rpts, rpts + r.n_pts);
+                rbh::map_points(bs.ctm, out->bpts.data(), (int)r.n_pts);
+                rpts = out->bpts.data();
+            }
+            rp = &r;
+        }
+        const RecordedDraw &r = *rp;
         int n_verbs = (int)r.n_verbs, n_pts = (int)r.n_pts, rule = r.rule;
         if (r.is_stroke) {
             // stroke_path: the outline is computed in local coordinates, then filled (Winding) under the transform
-            uint8_t *ov = nullptr;
-            float *op = nullptr;
+            const uint8_t *ov = nullptr;
+            const float *op = nullptr;
             int32_t nv = 0, np = 0;
             int sst;
             {
                 PROF(0);
-                sst = rb_path_stroke(verbs, n_verbs, &rpts[0].x, n_pts, r.stroke.width, r.stroke.miter_limit, r.stroke.cap,
-                                     r.stroke.join, resolution_scale(r.ctm), &ov, &nv, &op, &np);
+                sst = rb_path_stroke_view(verbs, n_verbs, &rpts[0].x, n_pts, r.stroke.width, r.stroke.miter_limit, r.stroke.cap,
+                                          r.stroke.join, resolution_scale(r.ctm), &ov, &nv, &op, &np);
             }
             if (sst != RB_OK) continue;
             out->sverbs.assign(ov, ov + nv);
             out->spts.resize((size_t)np);
             memcpy(out->spts.data(), op, sizeof(float) * 2 * (size_t)np);
-            rb_path_free(ov);
-            rb_path_free(op);
             rbh::map_points(r.ctm, out->spts.data(), np);
             verbs = out->sverbs.data();
             rpts = out->spts.data();
@@ -251,7 +288,7 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
                 if (!mask_target) {
                     DevPaint p;
                     rb_paint rp = r.paint;
-                    rp.stops = r.n_stops ? b->stops.data() + r.stop_off : nullptr;
+                    rp.stops = stops_src;
                     const size_t s_before = out->stops.size();
                     if (!rbh::prepare_paint(&rp, ctm, &p, out->stops)) continue;
                     if (out->stops.size() != s_before) p.stop_off = (uint32_t)(p.stop_off - ci->s0);
@@ -348,14 +385,15 @@ inline void tile_range(const DevDraw &d, int &x0, int &x1, int &y0, int &y1)
 } // namespace
 
 int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threads, rb_stage_alloc alloc, void *user,
-                        void **block)
+                        void **block, size_t begin, size_t end)
 {
     memset(b->stats, 0, sizeof(b->stats));
     memset(b->phases, 0, sizeof(b->phases));
     b->lay = BatchLayout();
     *block = nullptr;
-    const size_t n = b->recs.size();
-    if (n == 0) return RB_OK;
+    if (end == 0 || end > b->n_total) end = b->n_total;
+    if (begin >= end) return RB_OK;
+    const size_t n = end - begin;
     const auto t0 = Clock::now();
 
     // ---- 1. edges + paints on host threads (dynamic chunks; painter's order = chunk order) ------------------
@@ -378,7 +416,7 @@ int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threa
         for (auto &w : workers) w->reset();
         parallel_for(nt, n_chunks, [&](size_t c, int t) {
             chunks[c].worker = t;
-            build_chunk(b, c * kChunk, std::min(n, (c + 1) * kChunk), W, H, mask_target, items, workers[(size_t)t].get(), &chunks[c]);
+            build_chunk(b, begin + c * kChunk, begin + std::min(n, (c + 1) * kChunk), W, H, mask_target, items, workers[(size_t)t].get(), &chunks[c]);
         });
         any_wide = false;
         for (auto &w : workers) any_wide = any_wide || w->wide;
@@ -573,6 +611,9 @@ int rb_batch_record(rb_batch *b, const uint8_t *verbs, int32_t n_verbs, const fl
     r.rule = rule ? 1 : 0;
     r.is_stroke = false;
     b->recs.push_back(r);
+    if (!b->spans.empty() && b->spans.back().bulk < 0) b->spans.back().count++;
+    else b->spans.push_back(DrawSpan{b->n_total, 1, -1, b->recs.size() - 1});
+    b->n_total++;
     return RB_OK;
 }
 
@@ -612,26 +653,48 @@ extern "C" int rb_batch_stroke_path(rb_batch *b, const uint8_t *verbs, int32_t n
     return RB_OK;
 }
 
-// Bulk recording: n_paths paths in packed arrays (verb_off / point_off have n_paths + 1 entries).
+// Bulk recording: n_paths paths in packed arrays (verb_off / point_off have n_paths + 1 entries).  Same checks and
+// semantics as n calls of rb_batch_fill_path / rb_batch_stroke_path, but BY REFERENCE: the arrays (including the
+// gradient stops the paints point to) are read in place by rb_batch_prepare / submit and must stay valid and unchanged
+// until that call has returned.
 extern "C" int rb_batch_draw_paths(rb_batch *b, int32_t n_paths, const uint32_t *verb_off, const uint32_t *point_off,
                                    const uint8_t *verbs, const float *points, const rb_paint *paints,
                                    const uint8_t *fill_rules, const rb_stroke *strokes, const float ts[6])
 {
     if (!b || n_paths < 0 || !verb_off || !point_off || !verbs || !points || !paints || !fill_rules) return RB_ERR_INVALID;
-    if (n_paths > 0) {
-        b->recs.reserve(b->recs.size() + (size_t)n_paths);
-        b->verbs.reserve(b->verbs.size() + (verb_off[n_paths] - verb_off[0]));
-        b->pts.reserve(b->pts.size() + (point_off[n_paths] - point_off[0]));
-    }
+    if (n_paths == 0) return RB_OK;
+    const rbh::Xform ctm = ts ? rbh::Xform::from(ts) : rbh::Xform();
     for (int32_t i = 0; i < n_paths; i++) {
-        const uint8_t *v = verbs + verb_off[i];
-        const float *p = points + 2 * (size_t)point_off[i];
-        const int32_t nv = (int32_t)(verb_off[i + 1] - verb_off[i]), np = (int32_t)(point_off[i + 1] - point_off[i]);
-        int st;
-        if (strokes && strokes[i].width > 0.0f) st = rb_batch_stroke_path(b, v, nv, p, np, &paints[i], &strokes[i], ts);
-        else st = rb_batch_fill_path(b, v, nv, p, np, &paints[i], fill_rules[i], ts);
-        if (st != RB_OK) return st;
+        const uint32_t va = verb_off[i], vb = verb_off[i + 1], pa = point_off[i], pb = point_off[i + 1];
+        const rb_paint &paint = paints[i];
+        if (vb <= va || pb <= pa) return RB_ERR_INVALID;
+        if (paint.shader < 0 || paint.shader > 3 || paint.blend_mode < 0 || paint.blend_mode > 28) return RB_ERR_INVALID;
+        if ((paint.shader == 1 || paint.shader == 2) && paint.n_stops > rbh::kMaxStops) return RB_ERR_UNSUPPORTED;
+        // the verb/point bookkeeping must be right or the builder would read past the arrays
+        uint32_t need = 0;
+        for (uint32_t k = va; k < vb; k++) {
+            const uint8_t v = verbs[k];
+            if (v > 4) return RB_ERR_INVALID;
+            need += v == 4 ? 0u : (v <= 1 ? 1u : v);
+        }
+        if (need != pb - pa || verbs[va] != 0) return RB_ERR_INVALID;
+        if (strokes && strokes[i].width > 0.0f) {
+            const rb_stroke &sk = strokes[i];
+            if (sk.cap < 0 || sk.cap > 2 || sk.join < 0 || sk.join > 3) return RB_ERR_INVALID;
+            // treat_as_hairline: not implemented (see rb_batch_stroke_path)
+            auto fast_len = [](float x, float y) { x = fabsf(x); y = fabsf(y); return std::max(x, y) + std::min(x, y) * 0.5f; };
+            if (paint.anti_alias && fast_len(ctm.sx * sk.width, ctm.ky * sk.width) <= 1.0f && fast_len(ctm.kx * sk.width, ctm.sy * sk.width) <= 1.0f)
+                return RB_ERR_UNSUPPORTED;
+        }
     }
+    BulkSeg bs;
+    bs.n = n_paths;
+    bs.verb_off = verb_off; bs.point_off = point_off; bs.verbs = verbs; bs.points = points;
+    bs.paints = paints; bs.fill_rules = fill_rules; bs.strokes = strokes;
+    bs.ctm = ctm;
+    b->bulk.push_back(bs);
+    b->spans.push_back(DrawSpan{b->n_total, (size_t)n_paths, (int)b->bulk.size() - 1, 0});
+    b->n_total += (size_t)n_paths;
     return RB_OK;
 }
 

@@ -66,6 +66,7 @@ void rb_ctx_release(rb_ctx *ctx)
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->staging) cudaFreeHost(ctx->staging);
     if (ctx->staging_ev) cudaEventDestroy(ctx->staging_ev);
+    for (auto &e : ctx->ev_run) if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -94,6 +95,7 @@ extern "C" int rb_ctx_create(int device, rb_ctx **out)
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
     cudaEventCreateWithFlags(&ctx->staging_ev, cudaEventDisableTiming);
+    for (auto &e : ctx->ev_run) cudaEventCreate(&e);
     // Keep freed layer memory in the stream-ordered pool: isolated groups allocate one layer each
     // (render.rs:108), so layer create/destroy must not hit the driver.
     cudaMemPool_t pool;

@@ -1044,14 +1044,14 @@ static void *stage_pinned(void *user, size_t bytes)
 }
 static void *stage_malloc(void *, size_t bytes) { return malloc(bytes); }
 
-// Host build (threads) into the context's pinned staging block, then ONE host-to-device copy.
-extern "C" int rb_batch_prepare(rb_batch *b, int32_t n_threads)
+// Host build (threads) of draws [begin, end) into the context's pinned staging block, then ONE host-to-device copy.
+static int batch_prepare_range(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
 {
     if (!b) return RB_ERR_INVALID;
     batch_release(b);
     void *blk = nullptr;
     if (!b->layer && !b->mask) { // host-only batch (rb_debug_batch_begin_host)
-        int st = rb_batch_host_build(b, b->host_w, b->host_h, false, n_threads, stage_malloc, nullptr, &blk);
+        int st = rb_batch_host_build(b, b->host_w, b->host_h, false, n_threads, stage_malloc, nullptr, &blk, begin, end);
         b->host_block = blk;
         return st;
     }
@@ -1060,7 +1060,7 @@ extern "C" int rb_batch_prepare(rb_batch *b, int32_t n_threads)
     const int W = (int)(mask_target ? b->mask->w : b->layer->w), H = (int)(mask_target ? b->mask->h : b->layer->h);
     cudaSetDevice(ctx->device);
     StageReq req{ctx, RB_OK};
-    int st = rb_batch_host_build(b, W, H, mask_target, n_threads, stage_pinned, &req, &blk);
+    int st = rb_batch_host_build(b, W, H, mask_target, n_threads, stage_pinned, &req, &blk, begin, end);
     if (req.status != RB_OK) return req.status;
     if (st != RB_OK) return rb_fail(ctx, st, "batch host build failed");
     if (!blk || b->lay.n_draws == 0) return RB_OK;
@@ -1076,6 +1076,8 @@ extern "C" int rb_batch_prepare(rb_batch *b, int32_t n_threads)
     }
     return RB_OK;
 }
+
+extern "C" int rb_batch_prepare(rb_batch *b, int32_t n_threads) { return batch_prepare_range(b, n_threads, 0, 0); }
 
 static int batch_run(rb_batch *b, unsigned long long *px_stats);
 extern "C" int rb_batch_run(rb_batch *b) { return batch_run(b, nullptr); }
@@ -1138,6 +1140,7 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
         DrawBox *boxes = (DrawBox *)(sc + ws.o_boxes);
         RowEnt *row_draws = (RowEnt *)(sc + ws.o_row_draws);
         const uint32_t n_draws = (uint32_t)L.n_draws, n_wtiles = (uint32_t)((size_t)L.wtiles_x * L.wtiles_y);
+        RB_CUDA(ctx, cudaEventRecord(ctx->ev_run[0], ctx->stream));
         RB_CUDA(ctx, cudaMemsetAsync(row_cnt, 0, ((size_t)L.wtiles_y + 2) * 4, ctx->stream));
         RB_CUDA(ctx, cudaMemsetAsync(tile_off, 0, ((size_t)n_wtiles + 2) * 4, ctx->stream));
         RB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, 4, ctx->stream));
@@ -1154,6 +1157,7 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
         k_row_lists<<<n_draws, RL_THREADS, 0, ctx->stream>>>(d_draws, d_lines, (const rbh::CurveRec *)(b->dev + L.o_curves), d_edges, row_off,
                                                               row_edges, L.items ? 1 : 0, d_flag);
         RB_LAUNCHED(ctx, "row_lists");
+        RB_CUDA(ctx, cudaEventRecord(ctx->ev_run[1], ctx->stream));
         const unsigned grid = (n_wtiles + WT_WARPS - 1) / WT_WARPS;
         if (mask_target)
             k_raster_warp<true><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(target, W, H, L.wtiles_x, n_wtiles, tile_off, tile_pairs, d_draws, row_off,
@@ -1162,6 +1166,7 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
             k_raster_warp<false><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(target, W, H, L.wtiles_x, n_wtiles, tile_off, tile_pairs, d_draws, row_off,
                 row_edges, d_edges, (const DevPaint *)(b->dev + L.o_paints), (const DevStop *)(b->dev + L.o_stops), px_stats);
         RB_LAUNCHED(ctx, "raster_warp");
+        RB_CUDA(ctx, cudaEventRecord(ctx->ev_run[2], ctx->stream));
         return RB_OK;
     }
     const unsigned n_tile_ids = (unsigned)L.n_tile_ids;
@@ -1181,11 +1186,39 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
     return RB_OK;
 }
 
+// Device time of the context's last batch run: ms[0] = binning + edge-list pre-pass, ms[1] = the raster kernel.
+extern "C" int rb_ctx_last_run_ms(rb_ctx *ctx, float ms[2])
+{
+    if (!ctx || !ms) return RB_ERR_INVALID;
+    RB_CUDA(ctx, cudaEventSynchronize(ctx->ev_run[2]));
+    RB_CUDA(ctx, cudaEventElapsedTime(&ms[0], ctx->ev_run[0], ctx->ev_run[1]));
+    RB_CUDA(ctx, cudaEventElapsedTime(&ms[1], ctx->ev_run[1], ctx->ev_run[2]));
+    return RB_OK;
+}
+
+// Large batches are submitted in a few consecutive parts (painter's order is kept: part k + 1 is rasterised after part
+// k on the same stream), so the GPU works on one part while the host threads build the edges of the next.
 extern "C" int rb_batch_submit(rb_batch *b, int32_t n_threads)
 {
-    int st = rb_batch_prepare(b, n_threads);
-    if (st == RB_OK) st = rb_batch_run(b);
-    if (b) batch_release(b);
+    if (!b) return RB_ERR_INVALID;
+    const size_t n = b->n_total;
+    size_t parts = 1;
+    if (n >= 32768 && (b->layer || b->mask)) {
+        parts = 8;
+        if (const char *e = getenv("RB_SUBMIT_PARTS")) parts = (size_t)std::max(1, atoi(e));
+    }
+    int st = RB_OK;
+    uint64_t total[6] = {0, 0, 0, 0, 0, 0};
+    for (size_t k = 0; k < parts && st == RB_OK; k++) {
+        const size_t lo = n * k / parts, hi = n * (k + 1) / parts;
+        if (parts == 1) st = batch_prepare_range(b, n_threads, 0, 0);
+        else if (lo < hi) st = batch_prepare_range(b, n_threads, lo, hi);
+        else continue;
+        if (st == RB_OK) st = rb_batch_run(b);
+        for (int i = 0; i < 6; i++) total[i] += b->stats[i];
+        batch_release(b);
+    }
+    memcpy(b->stats, total, sizeof(total));
     return st;
 }
 

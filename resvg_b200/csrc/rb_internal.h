@@ -13,6 +13,7 @@ struct rb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_run[3] = {nullptr, nullptr, nullptr}; // last batch run: start, after the pre-pass, after the raster kernel
     std::string err;
     uint64_t launches = 0;
     int sm_count = 148;

@@ -464,6 +464,22 @@ struct Stroker {
     int recursion_depth = 0;
     bool found_tangents = false, join_completed = false;
 
+    // Back to the freshly constructed state, keeping the builders' storage.
+    void reset()
+    {
+        first_normal = prev_normal = first_unit_normal = prev_unit_normal = first_pt = prev_pt = first_outer_pt = P{0, 0};
+        first_outer_idx = 0;
+        segment_count = -1;
+        prev_is_line = false;
+        stroke_type = 1;
+        recursion_depth = 0;
+        found_tangents = false;
+        join_completed = false;
+        inner.clear();
+        outer.clear();
+        cusper.clear();
+    }
+
     bool set_normal_unitnormal(P before, P after, float scale, P &normal, P &unit)
     {
         if (!set_length(unit, (after.x - before.x) * scale, (after.y - before.y) * scale, 1.0f)) return false;
@@ -984,14 +1000,18 @@ bool has_valid_tangent(const uint8_t *verbs, int n_verbs, int vi, const P *pts, 
 // Path::stroke(&Stroke{width, miter_limit, line_cap, line_join}, res_scale).  cap: 0 butt, 1 round, 2 square;
 // join: 0 miter, 1 miter-clip, 2 round, 3 bevel.  Outputs are malloc'ed (free with rb_path_free); returns RB_OK, or
 // RB_ERR_INVALID when the stroke is empty (Option::None in the reference).
-extern "C" int rb_path_stroke(const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points, float width,
-                              float miter_limit, int32_t cap, int32_t join, float res_scale, uint8_t **out_verbs,
-                              int32_t *out_n_verbs, float **out_points, int32_t *out_n_points)
+// Internal form: the outline stays in a thread-local stroker (valid until the next call on this thread).
+int rb_path_stroke_view(const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points, float width,
+                        float miter_limit, int32_t cap, int32_t join, float res_scale, const uint8_t **out_verbs,
+                        int32_t *out_n_verbs, const float **out_points, int32_t *out_n_points)
 {
+    (void)n_points;
     if (!verbs || !points || !out_verbs || !out_points || !out_n_verbs || !out_n_points) return RB_ERR_INVALID;
     *out_verbs = nullptr; *out_points = nullptr; *out_n_verbs = 0; *out_n_points = 0;
     if (!(width > 0.0f) || !std::isfinite(width) || n_verbs <= 0) return RB_ERR_INVALID;
-    Stroker s;
+    static thread_local Stroker tls;
+    Stroker &s = tls;
+    s.reset();
     Join j = (Join)join;
     float inv_miter = 0.0f;
     if (j == JoinMiter) {
@@ -1060,12 +1080,30 @@ extern "C" int rb_path_stroke(const uint8_t *verbs, int32_t n_verbs, const float
     }
     s.finish_contour(false, last_is_line);
     if (s.outer.verbs.size() <= 1) return RB_ERR_INVALID;
-    size_t nv = s.outer.verbs.size(), np = s.outer.pts.size();
+    *out_verbs = s.outer.verbs.data();
+    *out_n_verbs = (int32_t)s.outer.verbs.size();
+    *out_points = reinterpret_cast<const float *>(s.outer.pts.data());
+    *out_n_points = (int32_t)s.outer.pts.size();
+    return RB_OK;
+}
+
+extern "C" int rb_path_stroke(const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points, float width,
+                              float miter_limit, int32_t cap, int32_t join, float res_scale, uint8_t **out_verbs,
+                              int32_t *out_n_verbs, float **out_points, int32_t *out_n_points)
+{
+    if (!out_verbs || !out_points || !out_n_verbs || !out_n_points) return RB_ERR_INVALID;
+    *out_verbs = nullptr; *out_points = nullptr; *out_n_verbs = 0; *out_n_points = 0;
+    const uint8_t *vv;
+    const float *pp;
+    int32_t cv = 0, cp = 0;
+    int st = rb_path_stroke_view(verbs, n_verbs, points, n_points, width, miter_limit, cap, join, res_scale, &vv, &cv, &pp, &cp);
+    if (st != RB_OK) return st;
+    size_t nv = (size_t)cv, np = (size_t)cp;
     uint8_t *ov = (uint8_t *)malloc(nv);
     float *op = (float *)malloc(np * sizeof(P));
     if (!ov || !op) { free(ov); free(op); return RB_ERR_OOM; }
-    memcpy(ov, s.outer.verbs.data(), nv);
-    memcpy(op, s.outer.pts.data(), np * sizeof(P));
+    memcpy(ov, vv, nv);
+    memcpy(op, pp, np * sizeof(P));
     *out_verbs = ov; *out_points = op; *out_n_verbs = (int32_t)nv; *out_n_points = (int32_t)np;
     return RB_OK;
 }
