@@ -135,6 +135,50 @@ def cpu_render_sample(R, scene, n_sample, canvas=None):
     return time.perf_counter() - t0 + t_stroke
 
 
+def kernel_table(rb, ctx, layer, W, H, peak, reps=3):
+    """Device time of every other kernel of the path on a W x H layer holding the rendered scene (CUDA events on the
+    library's stream), with its algorithmic bytes per pixel -> GB/s and fraction of the HBM peak.
+    Inputs are 256 MiB layers (> L2), so no flush is needed between repetitions."""
+    F = rb.filters
+    a, b = ctx.layer(W, H), ctx.layer(W, H)
+    a.copy_from(layer)
+    b.copy_from(layer)
+    mask = rb.Mask.from_layer(layer, "alpha")
+    light = rb.make_light("distant", azimuth=30.0, elevation=40.0)
+    ident = [rb.make_transfer("gamma", amplitude=1.0, exponent=0.9, offset=0.01)] * 3 + [rb.make_transfer("identity")]
+    rows = [
+        ("k_fill_u32 (Pixmap::fill)", 4, lambda: a.fill(0, 0, 0, 0)),
+        ("layer copy (Pixmap::clone)", 8, lambda: a.copy_from(layer)),
+        ("k_pointwise<demultiply>", 8, lambda: F.demultiply_alpha(a)),
+        ("k_pointwise<multiply>", 8, lambda: F.multiply_alpha(a)),
+        ("k_cs_convert (into_linear_rgb)", 8, lambda: F.into_linear_rgb(a)),
+        ("k_pointwise<color_matrix saturate>", 8, lambda: F.color_matrix("saturate", [0.5], a)),
+        ("k_lut4 (component_transfer gamma)", 8, lambda: F.component_transfer(ident, a)),
+        ("box_blur sigma 4 (3 H + 3 V passes)", 48, lambda: F.box_blur(4.0, 4.0, a)),
+        ("box_blur sigma 20 (3 H + 3 V passes)", 48, lambda: F.box_blur(20.0, 20.0, a)),
+        ("iir_blur sigma 1.5 (f64 planes)", 8, lambda: F.iir_blur(1.5, 1.5, a)),
+        ("morphology dilate r=3 (H + V)", 16, lambda: F.morphology("dilate", 3.0, 3.0, a)),
+        ("k_convolve 3x3", 8, lambda: F.convolve_matrix([0, -1, 0, -1, 5, -1, 0, -1, 0], 3, 3, 1, 1, 1.0, 0.0, "duplicate", False, a)),
+        ("k_arithmetic", 12, lambda: F.arithmetic(0.1, 0.5, 0.5, 0.0, layer, b, a)),
+        ("k_displace", 12, lambda: F.displacement_map(0, 1, 12.0, 1.0, 1.0, layer, b, a)),
+        ("k_lighting diffuse distant", 8, lambda: F.diffuse_lighting(2.0, 1.0, (255, 255, 255), light, layer, a)),
+        ("k_turbulence 2 octaves", 4, lambda: F.turbulence(0.0, 0.0, 1.0, 1.0, 0.01, 0.01, 2, 1, False, True, a)),
+        ("k_draw_layer source_over", 12, lambda: rb.draw_layer(a, layer, 0, 0, 0.75, "source_over")),
+        ("k_mask_from_layer luminance", 5, lambda: rb.Mask.from_layer(layer, "luminance")),
+        ("k_apply_mask", 9, lambda: rb.apply_mask(a, mask)),
+    ]
+    out = []
+    for name, bpp, fn in rows:
+        fn()
+        ctx.timer_begin()
+        for _ in range(reps):
+            fn()
+        ms = ctx.timer_end() / reps
+        gbs = bpp * W * H / (ms * 1e-3) / 1e9
+        out.append({"kernel": name, "ms": round(ms, 4), "bytes_per_px": bpp, "GB/s": round(gbs, 1), "frac": round(gbs / peak, 4)})
+    return out
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path (oracle restatement; Rust cannot be built here) on all host cores."""
     if rank != 0:
@@ -183,6 +227,7 @@ def main():
     ap.add_argument("--workload", default="paths8k", choices=list(WORKLOADS))
     ap.add_argument("--cpu-sample", type=int, default=12000, help="paths in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-table", action="store_true", help="skip the per-kernel roofline table of the filter / compositing kernels")
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
 
@@ -324,6 +369,8 @@ def main():
                     "host_build_and_enqueue_ms": e2e_phase[1] / e2e_steps * 1e3, "gpu_wait_and_d2h_ms": e2e_phase[2] / e2e_steps * 1e3,
                     "steps": e2e_steps},
         }
+        if world == 1 and not args.no_kernel_table:
+            out["kernels"] = kernel_table(rb, ctx, layer, W, H, peak)
         if world == 1 and not args.no_cpu_baseline:
             R = oracle_lib()
             n_sample = max(200, min(n_draws_in, int(args.cpu_sample)))

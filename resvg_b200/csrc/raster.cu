@@ -264,8 +264,13 @@ __device__ __forceinline__ PF gradient_color(const DevPaint &P, const DevStop *_
     const DevStop *st = stops + P.stop_off;
     int idx = 0;
     if (!P.two_stop) {
+        if (P.len <= 8) {
+            const float4 a = *reinterpret_cast<const float4 *>(P.t0s), b = *reinterpret_cast<const float4 *>(P.t0s + 4);
+            idx = (t >= a.y) + (t >= a.z) + (t >= a.w) + (t >= b.x) + (t >= b.y) + (t >= b.z) + (t >= b.w);
+        } else {
 #pragma unroll 1
-        for (int i = 1; i < P.len; i++) idx += (t >= st[i].t0) ? 1 : 0;
+            for (int i = 1; i < P.len; i++) idx += (t >= st[i].t0) ? 1 : 0;
+        }
     }
     const float4 f = *reinterpret_cast<const float4 *>(st[idx].f);
     const float4 b = *reinterpret_cast<const float4 *>(st[idx].b);

@@ -358,8 +358,11 @@ struct WarpDraw { // what one lane holds about one upcoming (draw, tile) pair
     uint32_t list_begin, n_list, paint;
 };
 
+#ifndef RW_MIN_CTAS
+#define RW_MIN_CTAS 6
+#endif
 template <bool MASK>
-__global__ void __launch_bounds__(WT_WARPS * 32, 6)
+__global__ void __launch_bounds__(WT_WARPS * 32, RW_MIN_CTAS)
 k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_wtiles, const uint32_t *__restrict__ tile_off,
               const uint32_t *__restrict__ tile_pairs, const DevDraw *__restrict__ draws, const uint32_t *__restrict__ row_off,
               const DevEdge *__restrict__ row_edges, const DevEdge *__restrict__ edges, const DevPaint *__restrict__ paints,
@@ -565,6 +568,7 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
                 backdrop = incl;
                 if (v) S.bd[lane] = 0;
                 if (lane == 0) S.bd[32] = 0;
+                if (!did && !__any_sync(0xffffffffu, backdrop != 0)) continue; // the edges left of the tile cancel out
             }
 
             // ---- scan: lane = sub-scanline ------------------------------------------------------------------------------
