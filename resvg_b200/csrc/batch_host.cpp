@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -41,6 +43,71 @@ inline uint64_t us_since(Clock::time_point t0)
     return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(Clock::now() - t0).count();
 }
 
+// Persistent worker threads: a large submit runs a few dozen short parallel phases, and creating 16 threads for each
+// of them costs more than some of the phases themselves.  The pool is created on first use and never torn down
+// (its threads sleep on a condition variable and die with the process).
+class Pool {
+public:
+    static Pool &get()
+    {
+        static Pool *p = new Pool();
+        return *p;
+    }
+    int size() const { return (int)threads_.size(); }
+    // Runs body(t) for t in [0, nt) on nt pool threads and waits for all of them.
+    void run(int nt, const std::function<void(int)> &body)
+    {
+        std::lock_guard<std::mutex> one_job(run_mu_);
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            job_ = &body;
+            job_threads_ = nt;
+            remaining_ = nt;
+            generation_++;
+        }
+        cv_job_.notify_all();
+        std::unique_lock<std::mutex> g(mu_);
+        cv_done_.wait(g, [&] { return remaining_ == 0; });
+        job_ = nullptr;
+    }
+
+private:
+    Pool()
+    {
+        int n = (int)std::thread::hardware_concurrency();
+        if (n < 1) n = 1;
+        for (int t = 0; t < n; t++) {
+            threads_.emplace_back([this, t] { loop(t); });
+            threads_.back().detach();
+        }
+    }
+    void loop(int t)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)> *job = nullptr;
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                cv_job_.wait(g, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (t < job_threads_) job = job_;
+            }
+            if (!job) continue;
+            (*job)(t);
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                if (--remaining_ == 0) cv_done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex mu_, run_mu_;
+    std::condition_variable cv_job_, cv_done_;
+    const std::function<void(int)> *job_ = nullptr;
+    int job_threads_ = 0, remaining_ = 0;
+    uint64_t generation_ = 0;
+};
+
 // Runs fn(item, worker) for item in [0, n) on `nt` threads with dynamic scheduling.
 template <class F>
 void parallel_for(int nt, size_t n, F fn)
@@ -49,18 +116,16 @@ void parallel_for(int nt, size_t n, F fn)
         for (size_t i = 0; i < n; i++) fn(i, 0);
         return;
     }
+    Pool &pool = Pool::get();
+    nt = std::min(nt, pool.size());
     std::atomic<size_t> next(0);
-    std::vector<std::thread> th;
-    th.reserve((size_t)nt);
-    for (int t = 0; t < nt; t++)
-        th.emplace_back([&, t]() {
-            for (;;) {
-                size_t i = next.fetch_add(1, std::memory_order_relaxed);
-                if (i >= n) break;
-                fn(i, t);
-            }
-        });
-    for (auto &t : th) t.join();
+    pool.run(nt, [&](int t) {
+        for (;;) {
+            size_t i = next.fetch_add(1, std::memory_order_relaxed);
+            if (i >= n) break;
+            fn(i, t);
+        }
+    });
 }
 
 // Upper bound of |winding| for a draw: edges simultaneously active on one scanline.  Chains (an edge plus its

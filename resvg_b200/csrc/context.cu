@@ -64,6 +64,7 @@ void rb_ctx_release(rb_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->px_tables) cudaFree(ctx->px_tables);
     if (ctx->staging) cudaFreeHost(ctx->staging);
     if (ctx->staging_ev) cudaEventDestroy(ctx->staging_ev);
     for (auto &e : ctx->ev_run) if (e) cudaEventDestroy(e);

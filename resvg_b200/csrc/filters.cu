@@ -156,23 +156,95 @@ static const uint8_t h_linear_to_srgb[256] = {
     249, 250, 250, 251, 251, 251, 252, 252, 253, 253, 254, 254, 255, 255,
 };
 
+// demultiply, and demultiply -> LUT -> multiply, are pure functions of (alpha, channel): they are tabulated once per
+// context BY THE ARITHMETIC ABOVE (one thread per (alpha, channel) pair, so the tables are exact by construction) and
+// the per-pixel kernels become three shared-memory lookups — IEEE divisions no longer bound the pass.
+constexpr int PX_TABLE = 256 * 256;
+
+__global__ void __launch_bounds__(256) k_build_px_tables(uint8_t *__restrict__ demul, uint8_t *__restrict__ to_linear,
+                                                         uint8_t *__restrict__ to_srgb)
+{
+    __shared__ float div255[256];
+    rb_fill_div255(div255);
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; // alpha << 8 | channel
+    if (i >= (uint32_t)PX_TABLE) return;
+    const uint32_t a = i >> 8, c = i & 0xffu;
+    const uint32_t p = rb_pack(c, c, c, a);
+    const uint32_t q = rb_demul_px(p, div255);
+    demul[i] = (uint8_t)RB_R(q);
+    OpMultiplyAlpha mul;
+    const uint32_t dl = c_srgb_to_linear[RB_R(q)], ds = c_linear_to_srgb[RB_R(q)];
+    to_linear[i] = (uint8_t)RB_R(mul(rb_pack(dl, dl, dl, a), div255));
+    to_srgb[i] = (uint8_t)RB_R(mul(rb_pack(ds, ds, ds, a), div255));
+}
+
+__global__ void __launch_bounds__(256) k_px_table(uint32_t *__restrict__ px, size_t n, const uint8_t *__restrict__ table)
+{
+    extern __shared__ uint8_t tab[];
+    for (int i = threadIdx.x; i < PX_TABLE / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(tab)[i] = reinterpret_cast<const uint4 *>(table)[i];
+    __syncthreads();
+    auto conv = [&](uint32_t p) -> uint32_t {
+        const uint8_t *row = tab + ((p >> 16) & 0xff00u);
+        return rb_pack(row[RB_R(p)], row[RB_G(p)], row[RB_B(p)], RB_A(p));
+    };
+    size_t n4 = n >> 2;
+    uint4 *v = reinterpret_cast<uint4 *>(px);
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        uint4 p = v[i];
+        p.x = conv(p.x);
+        p.y = conv(p.y);
+        p.z = conv(p.z);
+        p.w = conv(p.w);
+        v[i] = p;
+    }
+    size_t tail = n & 3;
+    if (blockIdx.x == 0 && threadIdx.x < tail) {
+        size_t i = (n4 << 2) + threadIdx.x;
+        px[i] = conv(px[i]);
+    }
+}
+
 int rb_filters_init(rb_ctx *ctx)
 {
     RB_CUDA(ctx, cudaMemcpyToSymbol(c_srgb_to_linear, h_srgb_to_linear, 256));
     RB_CUDA(ctx, cudaMemcpyToSymbol(c_linear_to_srgb, h_linear_to_srgb, 256));
+    RB_CUDA(ctx, cudaMalloc((void **)&ctx->px_tables, 3 * PX_TABLE));
+    k_build_px_tables<<<PX_TABLE / 256, 256, 0, ctx->stream>>>(ctx->px_tables, ctx->px_tables + PX_TABLE, ctx->px_tables + 2 * PX_TABLE);
+    RB_CUDA(ctx, cudaGetLastError());
+    RB_CUDA(ctx, cudaFuncSetAttribute(k_px_table, cudaFuncAttributeMaxDynamicSharedMemorySize, PX_TABLE));
+    return RB_OK;
+}
+
+static int launch_px_table(rb_layer *l, int which, const char *name)
+{
+    if (!l) return RB_ERR_INVALID;
+    rb_ctx *ctx = l->ctx;
+    size_t n = (size_t)l->w * l->h;
+    if (n < 65536) return -1; // small layers: not worth staging a 64 KB table per CTA
+    int grid = (int)std::min<size_t>((size_t)ctx->sm_count * 3, (n / 4 + 255) / 256);
+    k_px_table<<<grid, 256, PX_TABLE, ctx->stream>>>(reinterpret_cast<uint32_t *>(l->d), n, ctx->px_tables + (size_t)which * PX_TABLE);
+    RB_LAUNCHED(ctx, name);
     return RB_OK;
 }
 
 extern "C" int rb_layer_multiply_alpha(rb_layer *l) { return launch_pointwise(l, OpMultiplyAlpha(), "multiply_alpha"); }
 extern "C" int rb_layer_demultiply_alpha(rb_layer *l)
 {
-    return launch_pointwise(l, OpDemultiplyAlpha(), "demultiply_alpha");
+    int st = launch_px_table(l, 0, "demultiply_alpha");
+    return st >= 0 ? st : launch_pointwise(l, OpDemultiplyAlpha(), "demultiply_alpha");
 }
 
 template <bool TO_LINEAR>
 static int launch_cs(rb_layer *l)
 {
     if (!l) return RB_ERR_INVALID;
+    {
+        int st = launch_px_table(l, TO_LINEAR ? 1 : 2, "cs_convert");
+        if (st >= 0) return st;
+    }
     rb_ctx *ctx = l->ctx;
     size_t n = (size_t)l->w * l->h;
     int grid = rb_grid_1d(ctx, (n + 3) / 4, 256);

@@ -1259,21 +1259,38 @@ extern "C" int rb_mask_fill_path(rb_mask *mask, const uint8_t *verbs, int32_t n_
 // (gather is highp-only): s = src/255 [* opacity]; blend with dst/255; store round(clamp*255).
 // 12 B/px: src read, dst read, dst write.
 // =================================================================================================
+__device__ __forceinline__ uint32_t draw_layer_px(uint32_t sp, uint32_t dp, float opacity, int blend)
+{
+    PF s = load_pf(sp);
+    if (opacity != 1.0f) { s.r *= opacity; s.g *= opacity; s.b *= opacity; s.a *= opacity; }
+    return store_pf(blendf(blend, s, load_pf(dp)));
+}
+
+// grid.y strides over the rows of the clipped rectangle, threads run along x.  VEC: source and destination rows are
+// 16-byte aligned at x0 and the width is a multiple of 4 (the whole-layer composite of render.rs:133): 4 px per thread.
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 k_draw_layer(uint32_t *__restrict__ dst, int dw, const uint32_t *__restrict__ src, int sw, int x0, int y0, int x1, int y1,
              int ox, int oy, float opacity, int blend)
 {
-    int w = x1 - x0;
-    size_t n = (size_t)w * (y1 - y0);
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        int y = y0 + (int)(i / (size_t)w), x = x0 + (int)(i % (size_t)w);
-        uint32_t sp = __ldg(src + (size_t)(y - oy) * sw + (x - ox));
-        uint32_t *dp = dst + (size_t)y * dw + x;
-        PF s = load_pf(sp);
-        if (opacity != 1.0f) { s.r *= opacity; s.g *= opacity; s.b *= opacity; s.a *= opacity; }
-        PF d = load_pf(*dp);
-        *dp = store_pf(blendf(blend, s, d));
+    const int w = x1 - x0;
+    for (int y = y0 + blockIdx.y; y < y1; y += gridDim.y) {
+        const uint32_t *srow = src + (size_t)(y - oy) * sw + (x0 - ox);
+        uint32_t *drow = dst + (size_t)y * dw + x0;
+        if (VEC) {
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (w >> 2); i += gridDim.x * blockDim.x) {
+                const uint4 s4 = __ldg(reinterpret_cast<const uint4 *>(srow) + i);
+                uint4 d4 = reinterpret_cast<uint4 *>(drow)[i];
+                d4.x = draw_layer_px(s4.x, d4.x, opacity, blend);
+                d4.y = draw_layer_px(s4.y, d4.y, opacity, blend);
+                d4.z = draw_layer_px(s4.z, d4.z, opacity, blend);
+                d4.w = draw_layer_px(s4.w, d4.w, opacity, blend);
+                reinterpret_cast<uint4 *>(drow)[i] = d4;
+            }
+        } else {
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w; i += gridDim.x * blockDim.x)
+                drow[i] = draw_layer_px(__ldg(srow + i), drow[i], opacity, blend);
+        }
     }
 }
 
@@ -1288,9 +1305,16 @@ extern "C" int rb_draw_layer(rb_layer *dst, const rb_layer *src, int32_t x, int3
     if (x1 <= x0 || y1 <= y0) return RB_OK;
     size_t n = (size_t)(x1 - x0) * (size_t)(y1 - y0);
     int blend = blend_mode == RB_BLEND_CLEAR ? RB_BLEND_CLEAR : blend_mode;
-    k_draw_layer<<<rb_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(dst->d), (int)dst->w,
-                                                                    reinterpret_cast<const uint32_t *>(src->d), (int)src->w,
-                                                                    (int)x0, (int)y0, (int)x1, (int)y1, x, y, opacity, blend);
+    (void)n;
+    const int cw = (int)(x1 - x0), ch = (int)(y1 - y0);
+    const bool vec = (cw & 3) == 0 && (x0 & 3) == 0 && ((x0 - x) & 3) == 0 && (dst->w & 3) == 0 && (src->w & 3) == 0;
+    const int per_row = vec ? cw / 4 : cw;
+    dim3 grid((unsigned)std::min(std::max((per_row + 255) / 256, 1), 64), (unsigned)std::min(ch, 16384));
+#define RB_DL_ARGS reinterpret_cast<uint32_t *>(dst->d), (int)dst->w, reinterpret_cast<const uint32_t *>(src->d), (int)src->w, \
+    (int)x0, (int)y0, (int)x1, (int)y1, x, y, opacity, blend
+    if (vec) k_draw_layer<true><<<grid, 256, 0, ctx->stream>>>(RB_DL_ARGS);
+    else k_draw_layer<false><<<grid, 256, 0, ctx->stream>>>(RB_DL_ARGS);
+#undef RB_DL_ARGS
     RB_LAUNCHED(ctx, "draw_layer");
     return RB_OK;
 }
@@ -1331,34 +1355,65 @@ extern "C" int rb_mask_upload(rb_mask *m, const uint8_t *host)
 }
 
 // Mask::from_pixmap: 5 B/px
+__device__ __forceinline__ uint32_t mask_px(uint32_t p, int luminance)
+{
+    const uint32_t av = RB_A(p);
+    if (!luminance) return av;
+    float r = __fdiv_rn((float)RB_R(p), 255.0f), g = __fdiv_rn((float)RB_G(p), 255.0f), b = __fdiv_rn((float)RB_B(p), 255.0f);
+    const float a = __fdiv_rn((float)av, 255.0f);
+    if (av != 0) { r = __fdiv_rn(r, a); g = __fdiv_rn(g, a); b = __fdiv_rn(b, a); }
+    const float luma = r * 0.2126f + g * 0.7152f + b * 0.0722f; // Rec. 709 (pinned by masking/mask goldens)
+    float v = (luma * a) * 255.0f;
+    v = v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v); // f32::clamp
+    return rb_f2u8(ceilf(v));
+}
+// 4 pixels per thread: one 16-byte load, one 4-byte store (layers and masks are 256-byte aligned).
 __global__ void __launch_bounds__(256) k_mask_from_layer(const uint32_t *__restrict__ px, uint8_t *__restrict__ m, size_t n, int luminance)
 {
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        uint32_t p = px[i];
-        uint32_t av = RB_A(p);
-        if (!luminance) { m[i] = (uint8_t)av; continue; }
-        float r = __fdiv_rn((float)RB_R(p), 255.0f), g = __fdiv_rn((float)RB_G(p), 255.0f), b = __fdiv_rn((float)RB_B(p), 255.0f);
-        float a = __fdiv_rn((float)av, 255.0f);
-        if (av != 0) { r = __fdiv_rn(r, a); g = __fdiv_rn(g, a); b = __fdiv_rn(b, a); }
-        float luma = r * 0.2126f + g * 0.7152f + b * 0.0722f; // Rec. 709 (pinned by masking/mask goldens)
-        float v = (luma * a) * 255.0f;
-        v = v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v); // f32::clamp
-        m[i] = (uint8_t)rb_f2u8(ceilf(v));
+    const size_t n4 = n >> 2, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const uint4 p = reinterpret_cast<const uint4 *>(px)[i];
+        reinterpret_cast<uint32_t *>(m)[i] = mask_px(p.x, luminance) | (mask_px(p.y, luminance) << 8) | (mask_px(p.z, luminance) << 16)
+                                             | (mask_px(p.w, luminance) << 24);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const size_t i = (n4 << 2) + threadIdx.x;
+        m[i] = (uint8_t)mask_px(px[i], luminance);
     }
 }
 __global__ void __launch_bounds__(256) k_mask_invert(uint8_t *__restrict__ m, size_t n)
 {
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m[i] = (uint8_t)(255 - m[i]);
+    const size_t n16 = n >> 4, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        uint4 v = reinterpret_cast<uint4 *>(m)[i];
+        v.x = ~v.x; v.y = ~v.y; v.z = ~v.z; v.w = ~v.w;
+        reinterpret_cast<uint4 *>(m)[i] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 15)) {
+        const size_t i = (n16 << 4) + threadIdx.x;
+        m[i] = (uint8_t)(255 - m[i]);
+    }
 }
 // LoadMaskU8, LoadDestination, DestinationIn, Store (lowp): c' = div255(c * m).  9 B/px.
+__device__ __forceinline__ uint32_t apply_mask_px(uint32_t p, uint32_t k)
+{
+    return rb_pack(div255(RB_R(p) * k), div255(RB_G(p) * k), div255(RB_B(p) * k), div255(RB_A(p) * k));
+}
 __global__ void __launch_bounds__(256) k_apply_mask(uint32_t *__restrict__ px, const uint8_t *__restrict__ m, size_t n)
 {
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        uint32_t p = px[i], k = m[i];
-        px[i] = rb_pack(div255(RB_R(p) * k), div255(RB_G(p) * k), div255(RB_B(p) * k), div255(RB_A(p) * k));
+    const size_t n4 = n >> 2, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        uint4 p = reinterpret_cast<uint4 *>(px)[i];
+        const uint32_t k = reinterpret_cast<const uint32_t *>(m)[i];
+        p.x = apply_mask_px(p.x, k & 0xffu);
+        p.y = apply_mask_px(p.y, (k >> 8) & 0xffu);
+        p.z = apply_mask_px(p.z, (k >> 16) & 0xffu);
+        p.w = apply_mask_px(p.w, k >> 24);
+        reinterpret_cast<uint4 *>(px)[i] = p;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const size_t i = (n4 << 2) + threadIdx.x;
+        px[i] = apply_mask_px(px[i], m[i]);
     }
 }
 
@@ -1367,7 +1422,7 @@ extern "C" int rb_mask_from_layer(rb_mask *m, const rb_layer *l, int32_t luminan
     if (!m || !l || m->w != l->w || m->h != l->h) return RB_ERR_INVALID;
     rb_ctx *ctx = m->ctx;
     size_t n = (size_t)m->w * m->h;
-    k_mask_from_layer<<<rb_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(l->d), m->d, n, luminance);
+    k_mask_from_layer<<<rb_grid_1d(ctx, (n + 3) / 4, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(l->d), m->d, n, luminance);
     RB_LAUNCHED(ctx, "mask_from_layer");
     return RB_OK;
 }
@@ -1376,7 +1431,7 @@ extern "C" int rb_mask_invert(rb_mask *m)
     if (!m) return RB_ERR_INVALID;
     rb_ctx *ctx = m->ctx;
     size_t n = (size_t)m->w * m->h;
-    k_mask_invert<<<rb_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>(m->d, n);
+    k_mask_invert<<<rb_grid_1d(ctx, (n + 15) / 16, 256), 256, 0, ctx->stream>>>(m->d, n);
     RB_LAUNCHED(ctx, "mask_invert");
     return RB_OK;
 }
@@ -1386,7 +1441,7 @@ extern "C" int rb_layer_apply_mask(rb_layer *l, const rb_mask *m)
     if (m->w != l->w || m->h != l->h) return RB_OK; // tiny-skia: warn and return
     rb_ctx *ctx = l->ctx;
     size_t n = (size_t)m->w * m->h;
-    k_apply_mask<<<rb_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(l->d), m->d, n);
+    k_apply_mask<<<rb_grid_1d(ctx, (n + 3) / 4, 256), 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(l->d), m->d, n);
     RB_LAUNCHED(ctx, "apply_mask");
     return RB_OK;
 }

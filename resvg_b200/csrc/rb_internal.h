@@ -20,6 +20,7 @@ struct rb_ctx {
     // scratch reused by multi-pass filters (grown on demand, freed with the context)
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
+    uint8_t *px_tables = nullptr; // 3 x 64 KB: demultiply, into_linear_rgb, into_srgb as functions of (alpha, channel)
     // pinned host staging for batch uploads (grown on demand); staging_ev marks the last copy that read it
     void *staging = nullptr;
     size_t staging_bytes = 0;

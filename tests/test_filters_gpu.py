@@ -12,6 +12,8 @@ from tests.util import assert_exact, assert_within, random_premul, random_rgba, 
 pytestmark = pytest.mark.gpu
 
 SIZES = [(1, 1), (3, 2), (7, 5), (64, 48), (257, 131), (300, 300), (1029, 67)]
+# layers of >= 65536 px take the table-driven demultiply / colour-space kernels
+SIZES_HELPERS = SIZES + [(256, 256), (517, 301)]
 
 
 def _run(ctx, img, fn):
@@ -24,7 +26,7 @@ def _run(ctx, img, fn):
     return out
 
 
-@pytest.mark.parametrize("w,h", SIZES)
+@pytest.mark.parametrize("w,h", SIZES_HELPERS)
 def test_alpha_and_colorspace_helpers(ctx, oracle, w, h):
     img = random_premul(w, h, 1)
     assert_exact(_run(ctx, img, lambda f, l: f.demultiply_alpha(l)), oracle.demultiply_alpha(img), "demultiply")
@@ -35,6 +37,20 @@ def test_alpha_and_colorspace_helpers(ctx, oracle, w, h):
     # non-premultiplied garbage must follow the same saturating arithmetic
     assert_exact(_run(ctx, un, lambda f, l: f.into_linear_rgb(l)), oracle.into_linear_rgb(un), "into_linear(unpremul)")
     assert_exact(_run(ctx, un, lambda f, l: f.demultiply_alpha(l)), oracle.demultiply_alpha(un), "demultiply(unpremul)")
+
+
+def test_every_alpha_channel_pair_through_the_tables(ctx, oracle):
+    """All 65536 (alpha, channel) pairs, premultiplied or not, on a layer large enough for the table kernels."""
+    a, c = np.meshgrid(np.arange(256), np.arange(256), indexing="ij")
+    img = np.zeros((256, 512, 4), dtype=np.uint8)
+    img[:, :256, 3] = a
+    img[:, :256, 0] = c
+    img[:, :256, 1] = 255 - c
+    img[:, :256, 2] = (c * 7) % 256
+    img[:, 256:] = img[:, :256][:, ::-1]
+    assert_exact(_run(ctx, img, lambda f, l: f.demultiply_alpha(l)), oracle.demultiply_alpha(img), "demultiply")
+    assert_exact(_run(ctx, img, lambda f, l: f.into_linear_rgb(l)), oracle.into_linear_rgb(img), "into_linear")
+    assert_exact(_run(ctx, img, lambda f, l: f.into_srgb(l)), oracle.into_srgb(img), "into_srgb")
 
 
 def test_colorspace_round_trip_full_range(ctx, oracle):
