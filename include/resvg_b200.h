@@ -183,11 +183,16 @@ typedef struct rb_batch rb_batch;
 int rb_batch_begin(rb_layer *target, rb_batch **out);
 int rb_batch_fill_path(rb_batch *batch, const uint8_t *verbs, int32_t n_verbs, const float *points,
                        int32_t n_points, const rb_paint *paint, int32_t fill_rule, const float ts[6]);
-/* tiny_skia::Stroke as usvg fills it (tree/mod.rs:638-664); dashes are applied by the caller (path.dash) */
+/* tiny_skia::Stroke as usvg fills it (tree/mod.rs:638-664).  dash_array = StrokeDash::new(array, offset) arguments
+ * (NULL / n_dash 0: no dashing; an array StrokeDash::new rejects — odd or < 2 entries, a negative entry, sum <= 0 —
+ * leaves the stroke solid, as usvg does). */
 typedef struct {
     float width, miter_limit;
     int32_t cap;  /* 0 butt, 1 round, 2 square */
     int32_t join; /* 0 miter, 1 miter-clip, 2 round, 3 bevel */
+    const float *dash_array;
+    int32_t n_dash;
+    float dash_offset;
 } rb_stroke;
 /* PixmapMut::stroke_path(path, paint, stroke, transform, None) — path.rs:113: outline on the host (rb_path_stroke),
  * then a Winding fill.  Hairline strokes (anti-aliased, transformed width <= 1 px) return RB_ERR_UNSUPPORTED. */
@@ -248,6 +253,12 @@ int rb_path_stroke(const uint8_t *verbs, int32_t n_verbs, const float *points, i
                    float miter_limit, int32_t cap, int32_t join, float res_scale, uint8_t **out_verbs,
                    int32_t *out_n_verbs, float **out_points, int32_t *out_n_points);
 void rb_path_free(void *p);
+/* tiny_skia_path::Path::dash(&StrokeDash::new(dash_array, dash_offset)?, res_scale) — the path stroke_path strokes when
+ * the stroke is dashed (tiny-skia painter.rs stroke_path).  Host code.  RB_ERR_INVALID: the dash specification is
+ * rejected or nothing is left of the path. */
+int rb_path_dash(const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points, const float *dash_array,
+                 int32_t n_dash, float dash_offset, float res_scale, uint8_t **out_verbs, int32_t *out_n_verbs,
+                 float **out_points, int32_t *out_n_points);
 
 /* Test hook: route every batch through the any-winding fallback kernel (k_raster_tiles_wide) instead of the packed
  * one, which the host otherwise selects only when a draw could reach |winding| > 127. */

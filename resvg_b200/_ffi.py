@@ -68,7 +68,8 @@ class Paint(C.Structure):
 
 class Stroke(C.Structure):
     """rb_stroke"""
-    _fields_ = [("width", C.c_float), ("miter_limit", C.c_float), ("cap", C.c_int32), ("join", C.c_int32)]
+    _fields_ = [("width", C.c_float), ("miter_limit", C.c_float), ("cap", C.c_int32), ("join", C.c_int32),
+                ("dash_array", f32p), ("n_dash", C.c_int32), ("dash_offset", C.c_float)]
 
 
 # name -> (restype, argtypes); mirrors include/resvg_b200.h one to one
@@ -132,6 +133,8 @@ SIGNATURES = {
     "rb_path_stroke": (_i, [_vp, C.c_int32, _vp, C.c_int32, _f, _f, C.c_int32, C.c_int32, _f, c_void_pp,
                             C.POINTER(C.c_int32), c_void_pp, C.POINTER(C.c_int32)]),
     "rb_path_free": (None, [_vp]),
+    "rb_path_dash": (_i, [_vp, C.c_int32, _vp, C.c_int32, _vp, C.c_int32, _f, _f, c_void_pp, C.POINTER(C.c_int32), c_void_pp,
+                          C.POINTER(C.c_int32)]),
     "rb_debug_force_wide_kernel": (None, [_i]),
     "rb_debug_build_edges": (_i, [_vp, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, f32p, _vp, _vp,
                                   C.c_int32, _vp]),

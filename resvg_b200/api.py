@@ -372,11 +372,17 @@ class Batch:
                                     C.addressof(strokes) if strokes is not None else None, _ts(ts)),
             "batch_draw_paths")
 
-    def stroke_path(self, verbs, pts, paint: Paint, width, miter_limit=4.0, cap="butt", join="miter", ts=IDENTITY):
-        """PixmapMut::stroke_path."""
+    def stroke_path(self, verbs, pts, paint: Paint, width, miter_limit=4.0, cap="butt", join="miter", ts=IDENTITY,
+                    dash=None, dash_offset=0.0):
+        """PixmapMut::stroke_path; dash = the StrokeDash::new array (None: solid)."""
         v, p = _path(verbs, pts)
         st = _ffi.Stroke(float(width), float(miter_limit), CAPS[cap] if isinstance(cap, str) else int(cap),
                          JOINS[join] if isinstance(join, str) else int(join))
+        if dash is not None and len(dash):
+            arr, ptr = _f32(dash)
+            st.dash_array = ptr
+            st.n_dash = arr.size
+            st.dash_offset = float(dash_offset)
         self.layer.ctx.check(lib.rb_batch_stroke_path(self._h, v.ctypes.data, len(v), p.ctypes.data, len(p),
                                                       C.byref(paint), C.byref(st), _ts(ts)), "batch_stroke_path")
 
@@ -470,6 +476,26 @@ def apply_mask(layer: Layer, mask: Mask):
 
 CAPS = {"butt": 0, "round": 1, "square": 2}
 JOINS = {"miter": 0, "miter-clip": 1, "round": 2, "bevel": 3}
+
+
+def dash_path(verbs, pts, dash_array, dash_offset=0.0, res_scale=1.0):
+    """tiny_skia_path::Path::dash(StrokeDash::new(dash_array, dash_offset)?, res_scale) → (verbs, points) or None when
+    the specification is rejected or nothing is left.  Host-only."""
+    v, p = _path(verbs, pts)
+    arr, ptr = _f32(dash_array)
+    ov, op = C.c_void_p(), C.c_void_p()
+    nv, np_ = C.c_int32(), C.c_int32()
+    st = lib.rb_path_dash(v.ctypes.data, len(v), p.ctypes.data, len(p), C.cast(ptr, C.c_void_p), arr.size, float(dash_offset),
+                          float(res_scale), C.byref(ov), C.byref(nv), C.byref(op), C.byref(np_))
+    if st != 0:
+        return None
+    try:
+        out_v = np.ctypeslib.as_array((C.c_uint8 * nv.value).from_address(ov.value)).copy()
+        out_p = np.ctypeslib.as_array((C.c_float * (np_.value * 2)).from_address(op.value)).copy().reshape(-1, 2)
+    finally:
+        lib.rb_path_free(ov)
+        lib.rb_path_free(op)
+    return out_v, out_p
 
 
 def stroke_path(verbs, pts, width, miter_limit=4.0, cap="butt", join="miter", res_scale=1.0):

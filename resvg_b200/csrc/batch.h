@@ -47,7 +47,8 @@ struct RecordedDraw {
     rbh::Xform ctm;
     int rule;
     bool is_stroke;
-    rb_stroke stroke;
+    rb_stroke stroke;           // dash_array points into rb_batch::dashes (dash_off) for individually recorded draws
+    uint32_t dash_off;
 };
 
 // rb_batch_draw_paths records by reference: the caller's packed arrays are used in place by the host build.
@@ -93,6 +94,7 @@ struct rb_batch {
     std::vector<uint8_t> verbs;
     std::vector<rbh::Pt> pts;
     std::vector<float> stops;
+    std::vector<float> dashes;
     std::vector<RecordedDraw> recs;
     std::vector<BulkSeg> bulk;
     std::vector<DrawSpan> spans;

@@ -25,6 +25,9 @@ extern "C" int rb_path_stroke(const uint8_t *verbs, int32_t n_verbs, const float
                               float miter_limit, int32_t cap, int32_t join, float res_scale, uint8_t **out_verbs,
                               int32_t *out_n_verbs, float **out_points, int32_t *out_n_points);
 extern "C" void rb_path_free(void *p);
+int rb_path_dash_into(const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points, const float *dash_array,
+                      int32_t n_dash, float dash_offset, float res_scale, std::vector<uint8_t> &ov, std::vector<float> &op,
+                      bool *spec_valid);
 int rb_path_stroke_view(const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points, float width,
                         float miter_limit, int32_t cap, int32_t join, float res_scale, const uint8_t **out_verbs,
                         int32_t *out_n_verbs, const float **out_points, int32_t *out_n_points);
@@ -172,6 +175,8 @@ struct Worker {
     std::vector<rbh::CurveRec> cscratch;
     std::vector<int32_t> ends;
     std::vector<rbh::Pt> tmp, spts, bpts;
+    std::vector<uint8_t> dverbs;
+    std::vector<float> dpts;
     std::vector<uint8_t> sverbs;
     bool wide = false;
     void reset() { edges.clear(); draws.clear(); paints.clear(); stops.clear(); curves.clear(); wide = false; }
@@ -301,6 +306,21 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
             const float *op = nullptr;
             int32_t nv = 0, np = 0;
             int sst;
+            if (r.stroke.n_dash > 0) {
+                // painter.rs stroke_path: the path is dashed first; a rejected dash specification leaves it solid
+                const float *da = sp.bulk < 0 ? b->dashes.data() + r.dash_off : r.stroke.dash_array;
+                bool valid = false;
+                int dst_ = da ? rb_path_dash_into(verbs, n_verbs, &rpts[0].x, n_pts, da, r.stroke.n_dash, r.stroke.dash_offset,
+                                                  resolution_scale(r.ctm), out->dverbs, out->dpts, &valid)
+                              : RB_ERR_INVALID;
+                if (valid) {
+                    if (dst_ != RB_OK) continue; // "path dashing failed": nothing is drawn
+                    verbs = out->dverbs.data();
+                    n_verbs = (int)out->dverbs.size();
+                    rpts = reinterpret_cast<const rbh::Pt *>(out->dpts.data());
+                    n_pts = (int)(out->dpts.size() / 2);
+                }
+            }
             {
                 PROF(0);
                 sst = rb_path_stroke_view(verbs, n_verbs, &rpts[0].x, n_pts, r.stroke.width, r.stroke.miter_limit, r.stroke.cap,
@@ -715,6 +735,10 @@ extern "C" int rb_batch_stroke_path(rb_batch *b, const uint8_t *verbs, int32_t n
     r.ctm = ctm;
     r.is_stroke = true;
     r.stroke = *stroke;
+    r.stroke.dash_array = nullptr;
+    r.dash_off = (uint32_t)b->dashes.size();
+    if (stroke->dash_array && stroke->n_dash > 0) b->dashes.insert(b->dashes.end(), stroke->dash_array, stroke->dash_array + stroke->n_dash);
+    else r.stroke.n_dash = 0;
     return RB_OK;
 }
 

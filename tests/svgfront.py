@@ -865,7 +865,15 @@ class Converter:
                 st["miter"] = _f(ml)
                 da = d.attr(el, "stroke-dasharray")
                 if da and da != "none":
-                    raise Unsupported("dash")
+                    # usvg style.rs conv_dasharray: a negative value or a zero sum means no dashing; an odd list is repeated
+                    fs = d.attr(el, "font-size")
+                    font = float(parse_length(fs, 12.0, ref=diag)) if fs and re.match(rf"^{NUM}", fs.strip()) else 12.0
+                    vals = [_f(parse_length(x, 0.0, ref=diag, font=font)) for x in re.split(r"[\s,]+", da.strip()) if x]
+                    if vals and not any(v < 0 or (v == 0 and math.copysign(1.0, v) < 0) for v in vals) and abs(sum(vals)) > 1e-12:
+                        if len(vals) % 2:
+                            vals = vals + vals
+                        st["dash"] = vals
+                        st["dash_offset"] = _f(parse_length(d.attr(el, "stroke-dashoffset"), 0.0, ref=diag, font=font))
         node["stroke"] = st
         ts = parse_transform(el.attrib.get("transform"))
         g = {"t": "g", "ts": list(ts), "children": [node]}
@@ -1277,7 +1285,14 @@ class Renderer:
 
             if fast_len(v0) <= 1.0 and fast_len(v1) <= 1.0:
                 raise Unsupported("hairline stroke")
-        out = self.stroke_path(n["verbs"], n["pts"], s["width"], s["miter"], s["cap"], s["join"], res_scale)
+        src_verbs, src_pts = n["verbs"], n["pts"]
+        if s.get("dash"):
+            import resvg_b200 as rb
+            dashed = rb.dash_path(src_verbs, src_pts, s["dash"], s.get("dash_offset", 0.0), res_scale)
+            if dashed is None:
+                return  # StrokeDash::new accepted the list (the front end filtered the others) but nothing is left
+            src_verbs, src_pts = dashed
+        out = self.stroke_path(src_verbs, src_pts, s["width"], s["miter"], s["cap"], s["join"], res_scale)
         if out is None:
             return
         verbs, pts = out

@@ -91,3 +91,26 @@ def test_device_model_structured_shapes():
                 want = R.path_coverage(w, h, v, p, rule, True, ts)
                 got = D.coverage(v, p, w, h, rule, True, ts)
                 assert np.array_equal(got, want), (i, rule, ts, np.argwhere(got != want)[:4].tolist())
+
+
+def test_dasher_lengths_and_rejections():
+    """tiny_skia_path::Path::dash on a straight line: the on-intervals come out where the pattern says; StrokeDash::new
+    rejections (odd count, negative entry, zero sum) yield no path."""
+    import resvg_b200 as rb
+
+    verbs, pts = [0, 1], [(0.0, 0.0), (100.0, 0.0)]
+    v, p = rb.dash_path(verbs, pts, [10.0, 5.0], 0.0)
+    assert list(v[:4]) == [0, 1, 0, 1]
+    xs = p[:, 0].reshape(-1, 2)
+    assert np.allclose(xs[:, 0], np.arange(0, 100, 15.0)) and np.allclose(xs[:-1, 1], np.arange(10, 100, 15.0))
+    assert xs[-1, 1] == 100.0  # the last dash is cut at the end of the contour
+    v2, p2 = rb.dash_path(verbs, pts, [10.0, 5.0], 12.0)  # starts inside the gap
+    assert np.allclose(p2[:2, 0], [3.0, 13.0])
+    v3, p3 = rb.dash_path(verbs, pts, [10.0, 5.0], -5.0)  # negative offsets wrap
+    assert np.allclose(p3[:2, 0], [0.0, 5.0]) or np.allclose(p3[:2, 0], [5.0, 15.0])
+    for bad in ([4.0], [4.0, 4.0, 4.0], [5.0, -1.0], [0.0, 0.0]):
+        assert rb.dash_path(verbs, pts, bad, 0.0) is None
+    # closed contour: the first dash joins up with the last one (no move_to in between)
+    sq_v, sq_p = [0, 1, 1, 1, 4], [(0.0, 0.0), (40.0, 0.0), (40.0, 40.0), (0.0, 40.0)]
+    v4, p4 = rb.dash_path(sq_v, sq_p, [30.0, 10.0], 0.0)
+    assert int((v4 == 0).sum()) == 4 and len(v4) > 8

@@ -317,6 +317,41 @@ def test_wide_fallback_kernel_matches_too(ctx):
     assert_exact(got, want, "wide kernel")
 
 
+def test_batch_dashed_strokes(ctx):
+    """stroke_path with a dash array: dash (tiny_skia_path::Path::dash) -> stroke -> fill inside the batch builder must
+    equal the same host steps done one by one and filled by the oracle; rejected dash lists leave the stroke solid."""
+    import resvg_b200 as rb
+
+    w, h = 300, 220
+    rng = SplitMix64(77)
+    want = np.zeros((h, w, 4), np.uint8)
+    l = ctx.layer(w, h)
+    b = rb.Batch(l)
+    dashes = [([6.0, 3.0], 0.0), ([10.0, 2.0, 1.0, 2.0], 4.5), ([3.0, 3.0], -7.0), ([0.0, 5.0], 0.0), ([4.0], 0.0),
+              ([5.0, -1.0], 0.0), ([0.0, 0.0], 0.0), ([12.5, 7.25], 100.0)]
+    caps = ["butt", "round", "square"]
+    for i in range(48):
+        cx, cy, r = rng.uniform(20, w - 20), rng.uniform(20, h - 20), rng.log_uniform(10, 90)
+        verbs, pts = random_path(rng, cx, cy, r)
+        if i % 2 == 0:
+            verbs = verbs[:-1]
+        spec = random_paint_spec(rng, cx, cy, r, solid=1.0, linear=0.0)
+        dash, off = dashes[i % len(dashes)]
+        width, cap = rng.log_uniform(1.5, 8), caps[i % 3]
+        b.stroke_path(verbs, pts, rb.make_paint(spec), width, 4.0, cap, "round", dash=dash, dash_offset=off)
+        src = (np.asarray(verbs, np.uint8), np.asarray(pts, np.float32))
+        valid = len(dash) >= 2 and len(dash) % 2 == 0 and min(dash) >= 0 and sum(dash) > 0
+        if valid:
+            src = rb.dash_path(verbs, pts, dash, off, 1.0)
+            if src is None:
+                continue
+        out = rb.stroke_path(src[0], src[1], width, 4.0, cap, "round", 1.0)
+        if out is not None:
+            R.fill_path(want, out[0], out[1], R.make_paint(spec), "nonzero")
+    b.submit()
+    assert_exact(l.download(), want, "dashed strokes")
+
+
 def test_device_curve_expansion_matches_host_expansion(ctx):
     """Curves are forward-differenced on the device by default; expanding them on the host (the fallback builder) must
     give the same pixels, and both must equal the oracle."""
