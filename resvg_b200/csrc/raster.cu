@@ -18,6 +18,8 @@
 // 63 on sub-row 3 when one span covers it, but 4*16 = 64 when two spans abut strictly inside it; partially
 // covered pixels receive 16 per sub-sample; the four sub-rows are summed and 256 is folded to 255.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -796,7 +798,6 @@ k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint3
             }
             const int chunk_past = __syncthreads_and(past || e >= D.edge_cnt); // also publishes s_list
             const int n_act = s_count[cbuf];
-            if (px_stats && tid == 0) atomicAdd(px_stats + 5, (unsigned long long)n_act);
             const uint16_t *list = s_list[lbuf];
             lbuf ^= 1;
             cbuf = cnext;
@@ -1020,13 +1021,14 @@ extern "C" void rb_batch_destroy(rb_batch *b)
 }
 
 // Device-built structures of the warp-tile path (sizes come from the host build).
-struct WarpScratch { size_t o_row_off, o_row_edges, o_boxes, o_row_cnt, o_row_draws, o_tile_off, o_tile_pairs, o_edges, o_flag, total; };
+struct WarpScratch { size_t o_row_off, o_row_cols, o_row_edges, o_boxes, o_row_cnt, o_row_draws, o_tile_off, o_tile_pairs, o_edges, o_flag, total; };
 static WarpScratch warp_scratch_layout(const BatchLayout &L)
 {
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     WarpScratch w;
     size_t off = 0;
     w.o_row_off = off;    off += al((L.n_row_off + 1) * 4);
+    w.o_row_cols = off;   off += al((L.n_row_off + 1) * 4);
     w.o_row_edges = off;  off += al((L.n_list + 1) * sizeof(DevEdge));
     w.o_boxes = off;      off += al(L.n_draws * sizeof(DrawBox));
     w.o_row_cnt = off;    off += al(((size_t)L.wtiles_y + 2) * 4);
@@ -1095,15 +1097,18 @@ extern "C" int rb_batch_run_counting(rb_batch *b, uint64_t out[2])
     rb_ctx *ctx = batch_ctx(b);
     if (!ctx) return RB_ERR_INVALID;
     unsigned long long *d = nullptr;
-    RB_CUDA(ctx, cudaMallocAsync((void **)&d, 16, ctx->stream));
-    RB_CUDA(ctx, cudaMemsetAsync(d, 0, 16, ctx->stream));
+    RB_CUDA(ctx, cudaMallocAsync((void **)&d, 64, ctx->stream));
+    RB_CUDA(ctx, cudaMemsetAsync(d, 0, 64, ctx->stream));
     int st = batch_run(b, d);
-    unsigned long long h[2] = {0, 0};
-    RB_CUDA(ctx, cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    RB_CUDA(ctx, cudaMemcpyAsync(h, d, 64, cudaMemcpyDeviceToHost, ctx->stream));
     RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     RB_CUDA(ctx, cudaFreeAsync(d, ctx->stream));
     out[0] = h[0];
     out[1] = h[1];
+    if (getenv("RB_RASTER_DIAG"))
+        fprintf(stderr, "[raster diag] pairs %llu, skipped(bounds/empty) %llu, skipped(no span) %llu, with coverage %llu, list entries %llu, crossings %llu, "
+                        "blended px %llu, stored px %llu\n", h[2], h[3], h[4], h[5], h[6], h[7], h[0], h[1]);
     if (st == RB_OK && b->dev_scratch && !b->lay.wide) {
         // the list builder counts entries it had to drop (the host's capacity bound makes that impossible)
         unsigned int dropped = 0;
@@ -1140,6 +1145,7 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
         DevEdge *d_edges = L.items ? (DevEdge *)(sc + ws.o_edges) : (DevEdge *)(b->dev + L.o_edges);
         unsigned int *d_flag = (unsigned int *)(sc + ws.o_flag);
         uint32_t *row_off = (uint32_t *)(sc + ws.o_row_off), *row_cnt = (uint32_t *)(sc + ws.o_row_cnt);
+        uint32_t *row_cols = (uint32_t *)(sc + ws.o_row_cols);
         uint32_t *tile_off = (uint32_t *)(sc + ws.o_tile_off), *tile_pairs = (uint32_t *)(sc + ws.o_tile_pairs);
         DevEdge *row_edges = (DevEdge *)(sc + ws.o_row_edges);
         DrawBox *boxes = (DrawBox *)(sc + ws.o_boxes);
@@ -1149,19 +1155,19 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
         RB_CUDA(ctx, cudaMemsetAsync(row_cnt, 0, ((size_t)L.wtiles_y + 2) * 4, ctx->stream));
         RB_CUDA(ctx, cudaMemsetAsync(tile_off, 0, ((size_t)n_wtiles + 2) * 4, ctx->stream));
         RB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, 4, ctx->stream));
-        k_bin_count<<<(n_draws + 255) / 256, 256, 0, ctx->stream>>>(d_draws, n_draws, L.wtiles_x, boxes, row_cnt, tile_off);
+        k_row_lists<<<n_draws, RL_THREADS, 0, ctx->stream>>>(d_draws, d_lines, (const rbh::CurveRec *)(b->dev + L.o_curves), d_edges, row_off,
+                                                              row_edges, row_cols, L.items ? 1 : 0, d_flag);
+        RB_LAUNCHED(ctx, "row_lists");
+        k_bin_count<<<(n_draws + 255) / 256, 256, 0, ctx->stream>>>(d_draws, n_draws, L.wtiles_x, row_cols, boxes, row_cnt, tile_off);
         RB_LAUNCHED(ctx, "bin_count");
         k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(row_cnt, (uint32_t)L.wtiles_y);
         RB_LAUNCHED(ctx, "scan_rows");
         k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(tile_off, n_wtiles);
         RB_LAUNCHED(ctx, "scan_tiles");
-        k_bin_rows<<<L.wtiles_y, 256, 0, ctx->stream>>>(boxes, n_draws, row_cnt, row_draws);
+        k_bin_rows<<<L.wtiles_y, 256, 0, ctx->stream>>>(boxes, n_draws, row_cols, row_cnt, row_draws);
         RB_LAUNCHED(ctx, "bin_rows");
         k_bin_tiles<<<(n_wtiles + 7) / 8, 256, 0, ctx->stream>>>(row_draws, row_cnt, tile_off, L.wtiles_x, n_wtiles, tile_pairs);
         RB_LAUNCHED(ctx, "bin_tiles");
-        k_row_lists<<<n_draws, RL_THREADS, 0, ctx->stream>>>(d_draws, d_lines, (const rbh::CurveRec *)(b->dev + L.o_curves), d_edges, row_off,
-                                                              row_edges, L.items ? 1 : 0, d_flag);
-        RB_LAUNCHED(ctx, "row_lists");
         RB_CUDA(ctx, cudaEventRecord(ctx->ev_run[1], ctx->stream));
         const unsigned grid = (n_wtiles + WT_WARPS - 1) / WT_WARPS;
         if (mask_target)

@@ -141,15 +141,16 @@ __device__ __forceinline__ int draw_row_of(const DevDraw &D, int suby)
 // would produce (edge_math.h, shared with the host builder), unused slots are marked empty (first_y > last_y).
 __global__ void __launch_bounds__(RL_THREADS)
 k_row_lists(const DevDraw *__restrict__ draws, const DevEdge *__restrict__ lines, const rbh::CurveRec *__restrict__ curves,
-            DevEdge *__restrict__ edges, uint32_t *__restrict__ row_off, DevEdge *__restrict__ row_edges, int items,
-            unsigned int *__restrict__ overflow)
+            DevEdge *__restrict__ edges, uint32_t *__restrict__ row_off, DevEdge *__restrict__ row_edges, uint32_t *__restrict__ row_cols,
+            int items, unsigned int *__restrict__ overflow)
 {
     __shared__ uint32_t cnt[RL_MAX_ROWS + 2];
+    __shared__ int xlo[RL_MAX_ROWS + 2], xhi[RL_MAX_ROWS + 2]; // extent of the crossings of each tile row, in pixels
     __shared__ uint32_t warp_tot[RL_THREADS / 32];
     const DevDraw D = draws[blockIdx.x];
     const int tid = threadIdx.x, nr = (int)D.n_rows;
     DevEdge *E0 = edges + D.edge_off;
-    for (int i = tid; i <= nr; i += RL_THREADS) cnt[i] = 0;
+    for (int i = tid; i <= nr; i += RL_THREADS) { cnt[i] = 0; xlo[i] = INT_MAX; xhi[i] = INT_MIN; }
     if (items) {
         for (uint32_t i = tid; i < D.line_cnt; i += RL_THREADS) {
             DevEdge L = lines[D.line_off + i];
@@ -179,23 +180,38 @@ k_row_lists(const DevDraw *__restrict__ draws, const DevEdge *__restrict__ lines
         }
     }
     __syncthreads();
-    if (nr > 1) {
+    {
+        // Per tile row: how many edges touch it, and between which pixel columns they cross it.  Outside that extent the
+        // winding is zero (contours are closed), so only the warp tiles inside it are paired with this draw.
+        const int sub_lo = D.sy << D.shift, sub_hi = ((D.sy + D.sh) << D.shift) - 1; // sub-scanlines the blitter may touch
         for (uint32_t e = tid; e < D.edge_cnt; e += RL_THREADS) {
-            const uint32_t yp = E0[e].ypack;
-            const int fy = (int)(yp & 0xffffu), ly = (int)(yp >> 16);
+            const DevEdge E = E0[e];
+            const int fy = (int)(E.ypack & 0xffffu), ly = (int)(E.ypack >> 16);
             if (fy > ly) continue; // empty slot
             const int ra = draw_row_of(D, fy), rb = draw_row_of(D, ly);
-            for (int r = ra; r <= rb; r++) atomicAdd(&cnt[r], 1u);
+            for (int r = ra; r <= rb; r++) {
+                atomicAdd(&cnt[r], 1u);
+                // sub-scanlines of tile row r: layer pixel rows [8 (r0 + r), +8) in the draw's units
+                const int top = max(max((((int)(D.r0 + r) << 3) - D.oy) << D.shift, sub_lo), fy);
+                const int bot = min(min((((((int)(D.r0 + r) + 1) << 3) - D.oy) << D.shift) - 1, sub_hi), ly);
+                if (top > bot) continue;
+                const int xa = (int)((uint32_t)E.x + (uint32_t)(top - fy) * (uint32_t)E.dx), xb = (int)((uint32_t)E.x + (uint32_t)(bot - fy) * (uint32_t)E.dx);
+                const int pa = (((int)((uint32_t)xa + 0x8000u) >> 16) >> D.shift), pb = (((int)((uint32_t)xb + 0x8000u) >> 16) >> D.shift);
+                atomicMin(&xlo[r], min(pa, pb));
+                atomicMax(&xhi[r], max(pa, pb));
+            }
         }
-    } else {
-        uint32_t c = 0;
-        for (uint32_t e = tid; e < D.edge_cnt; e += RL_THREADS) {
-            const uint32_t yp = E0[e].ypack;
-            c += (yp & 0xffffu) <= (yp >> 16) ? 1u : 0u;
-        }
-        if (c) atomicAdd(&cnt[0], c);
     }
     __syncthreads();
+    for (int i = tid; i < nr; i += RL_THREADS) {
+        // warp-tile columns [c0, c1] of row i that can receive coverage, clipped to the blitter rectangle; c0 > c1: none
+        uint32_t cols = 1u;
+        if (xlo[i] <= xhi[i]) {
+            const int px0 = max(xlo[i], D.sx), px1 = min(xhi[i], D.sx + D.sw - 1);
+            if (px0 <= px1) cols = (uint32_t)((D.ox + px0) / WT_W) | ((uint32_t)((D.ox + px1) / WT_W) << 16);
+        }
+        row_cols[D.row_base + i] = cols;
+    }
     // exclusive scan of cnt[0..nr) -> cnt; contiguous chunks per thread + warp shuffles
     {
         const int per = (nr + RL_THREADS - 1) / RL_THREADS;
@@ -235,19 +251,23 @@ k_row_lists(const DevDraw *__restrict__ draws, const DevEdge *__restrict__ lines
 }
 
 // ---- binning draws into warp tiles (painter's order kept without sorting) ------------------------------------------
-struct DrawBox { uint32_t rows, cols; }; // r0 | r1 << 16, c0 | c1 << 16 (inclusive warp-tile coordinates)
+struct DrawBox { uint32_t rows, row_base; }; // r0 | r1 << 16 (inclusive warp-tile rows); where its row_cols entries start
 
+// row_cols[row_base + r] = c0 | c1 << 16: the warp-tile columns of the draw's tile row r that can receive coverage
+// (from k_row_lists; c0 > c1 when the row is empty).
 __global__ void __launch_bounds__(256)
-k_bin_count(const DevDraw *__restrict__ draws, uint32_t n_draws, int wtiles_x, DrawBox *__restrict__ boxes,
-            uint32_t *__restrict__ row_cnt, uint32_t *__restrict__ tile_cnt)
+k_bin_count(const DevDraw *__restrict__ draws, uint32_t n_draws, int wtiles_x, const uint32_t *__restrict__ row_cols,
+            DrawBox *__restrict__ boxes, uint32_t *__restrict__ row_cnt, uint32_t *__restrict__ tile_cnt)
 {
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n_draws) return;
     const DevDraw D = draws[d];
-    const uint32_t c0 = (uint32_t)(D.ox + D.sx) / WT_W, c1 = (uint32_t)(D.ox + D.sx + D.sw - 1) / WT_W;
     const uint32_t r0 = D.r0, r1 = D.r0 + D.n_rows - 1;
-    boxes[d] = DrawBox{r0 | (r1 << 16), c0 | (c1 << 16)};
+    boxes[d] = DrawBox{r0 | (r1 << 16), D.row_base};
     for (uint32_t r = r0; r <= r1; r++) {
+        const uint32_t cols = row_cols[D.row_base + (r - r0)];
+        const uint32_t c0 = cols & 0xffffu, c1 = cols >> 16;
+        if (c0 > c1) continue;
         atomicAdd(&row_cnt[r], 1u);
         uint32_t *t = tile_cnt + (size_t)r * wtiles_x;
         for (uint32_t c = c0; c <= c1; c++) atomicAdd(&t[c], 1u);
@@ -291,7 +311,8 @@ struct RowEnt { uint32_t draw, cols; };
 
 // One CTA per warp-tile row: the draws touching the row, in draw order.
 __global__ void __launch_bounds__(256)
-k_bin_rows(const DrawBox *__restrict__ boxes, uint32_t n_draws, const uint32_t *__restrict__ row_off, RowEnt *__restrict__ row_draws)
+k_bin_rows(const DrawBox *__restrict__ boxes, uint32_t n_draws, const uint32_t *__restrict__ row_cols, const uint32_t *__restrict__ row_off,
+           RowEnt *__restrict__ row_draws)
 {
     __shared__ uint32_t warp_cnt[8];
     const uint32_t R = blockIdx.x, tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
@@ -299,11 +320,14 @@ k_bin_rows(const DrawBox *__restrict__ boxes, uint32_t n_draws, const uint32_t *
     if (row_off[R + 1] == out) return;
     for (uint32_t base = 0; base < n_draws; base += 256) {
         const uint32_t d = base + tid;
-        DrawBox b = DrawBox{0, 0};
+        uint32_t cols = 1u;
         bool ok = false;
         if (d < n_draws) {
-            b = boxes[d];
-            ok = (b.rows & 0xffffu) <= R && R <= (b.rows >> 16);
+            const DrawBox b = boxes[d];
+            if ((b.rows & 0xffffu) <= R && R <= (b.rows >> 16)) {
+                cols = row_cols[b.row_base + (R - (b.rows & 0xffffu))];
+                ok = (cols & 0xffffu) <= (cols >> 16);
+            }
         }
         const uint32_t m = __ballot_sync(0xffffffffu, ok);
         if (lane == 0) warp_cnt[wid] = __popc(m);
@@ -315,7 +339,7 @@ k_bin_rows(const DrawBox *__restrict__ boxes, uint32_t n_draws, const uint32_t *
             if (w < wid) before += c;
             total += c;
         }
-        if (ok) row_draws[out + before + __popc(m & ((1u << lane) - 1u))] = RowEnt{d, b.cols};
+        if (ok) row_draws[out + before + __popc(m & ((1u << lane) - 1u))] = RowEnt{d, cols};
         out += total;
         __syncthreads();
     }
@@ -461,7 +485,9 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
                 const uint32_t lbn = __shfl_sync(0xffffffffu, mine.list_begin, k + 1), nn = __shfl_sync(0xffffffffu, mine.n_list, k + 1);
                 if ((uint32_t)lane < nn) pre = row_edges[lbn + lane];
             }
-            if (!(flags & 0x100u) || n_list == 0) continue;
+            if (px_stats && lane == 0) atomicAdd(px_stats + 2, 1ull);
+            if (!(flags & 0x100u) || n_list == 0) { if (px_stats && lane == 0) atomicAdd(px_stats + 3, 1ull); continue; }
+            if (px_stats && lane == 0) atomicAdd(px_stats + 6, (unsigned long long)n_list);
             const int tlx = __shfl_sync(0xffffffffu, mine.tlx, k), tly = __shfl_sync(0xffffffffu, mine.tly, k);
             const uint32_t bounds = __shfl_sync(0xffffffffu, mine.bounds, k);
             const int py0 = (int)(bounds & 0xffu), py1 = (int)((bounds >> 8) & 0xffu);
@@ -510,6 +536,7 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
                 }
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
                 if (total) did = true;
+                if (px_stats && lane == 0) atomicAdd(px_stats + 7, (unsigned long long)total);
                 const uint32_t ysup = (uint32_t)ys | (upbit << 16);
 #pragma unroll 1
                 for (int base = 0; base < total; base += 32) {
@@ -553,7 +580,7 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
                 }
             }
             any_left = __any_sync(0xffffffffu, any_left);
-            if (!did && !any_left) continue; // bounds overlap the tile but no span does
+            if (!did && !any_left) { if (px_stats && lane == 0) atomicAdd(px_stats + 4, 1ull); continue; } // bounds overlap the tile but no span does
             __syncwarp();
             // winding every sub-scanline starts with at the left end of the blitter range
             int backdrop = 0;
@@ -568,7 +595,7 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
                 backdrop = incl;
                 if (v) S.bd[lane] = 0;
                 if (lane == 0) S.bd[32] = 0;
-                if (!did && !__any_sync(0xffffffffu, backdrop != 0)) continue; // the edges left of the tile cancel out
+                if (!did && !__any_sync(0xffffffffu, backdrop != 0)) { if (px_stats && lane == 0) atomicAdd(px_stats + 4, 1ull); continue; } // the edges left of the tile cancel out
             }
 
             // ---- scan: lane = sub-scanline ------------------------------------------------------------------------------
@@ -667,6 +694,7 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
             __syncwarp();
 
             // ---- blend: the lane's 8 pixels rotate through one copy of the code ---------------------------------------------------
+            if (px_stats && __any_sync(0xffffffffu, (c0 | c1) != 0) && lane == 0) atomicAdd(px_stats + 5, 1ull);
             if (c0 | c1) {
                 const DevPaint &P = paints[paint_idx];
                 const bool memset_ok = !MASK && P.has_memset != 0;
