@@ -364,16 +364,21 @@ __device__ __forceinline__ P16 shade16(const DevPaint &P, const DevStop *__restr
     return shade16_gradient(P, stops, x, y);
 }
 
-__device__ __forceinline__ PF shadef(const DevPaint &P, const DevStop *__restrict__ stops, int x, int y)
+__device__ __noinline__ PF shadef_gradient(const DevPaint &P, const DevStop *__restrict__ stops, int x, int y)
 {
-    if (P.kind == 0) { PF c = {P.premul[0], P.premul[1], P.premul[2], P.premul[3]}; return c; }
-    if (P.kind == 2) return shade_pattern(P, x, y);
     bool masked;
     float t = gradient_t(P, x, y, masked);
     PF c = gradient_color(P, stops, t);
     if (P.premul_after) { c.r *= c.a; c.g *= c.a; c.b *= c.a; }
     if (masked) c.r = c.g = c.b = c.a = 0.0f;
     return c;
+}
+
+__device__ __forceinline__ PF shadef(const DevPaint &P, const DevStop *__restrict__ stops, int x, int y)
+{
+    if (P.kind == 0) { PF c = {P.premul[0], P.premul[1], P.premul[2], P.premul[3]}; return c; }
+    if (P.kind == 2) return shade_pattern(P, x, y);
+    return shadef_gradient(P, stops, x, y);
 }
 
 // RasterPipelineBlitter: full-coverage pixels run the blit_rect program, others blit_anti_h.

@@ -702,6 +702,8 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
                 // u16 pipeline with Source / SourceOver over a solid colour or a gradient: the common programs, kept inline
                 const bool simple = !MASK && P.kind != 2 && P.lowp && (P.blend == 1 || P.blend == 3);
                 const bool is_solid = P.kind == 0;
+                // f32 pipeline with Source / SourceOver over a gradient (two-point conical gradients are f32-only)
+                const bool simple_hp = !MASK && P.kind == 1 && !P.lowp && (P.blend == 1 || P.blend == 3);
                 uint32_t sr = P.solid16[0], sg = P.solid16[1], sb = P.solid16[2], sa = P.solid16[3];
                 const bool src_over = P.blend == 3;
 #pragma unroll 1
@@ -736,6 +738,22 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
                                 b2 = div255(RB_B(d) * ic + sb * c); a = div255(RB_A(d) * ic + sa * c);
                             }
                             d = rb_pack(r & 0xffu, g & 0xffu, b2 & 0xffu, a & 0xffu);
+                        } else if (simple_hp) {
+                            n_partial++;
+                            const PF dd = load_pf(d);
+                            PF sc = shadef_gradient(P, stops, tlx + 8 * pj + q, tly + prow), o;
+                            const float cf = (float)c * (1.0f / 255.0f);
+                            if (src_over) { // scale_1_float, then source_over: d * (1 - sa) + s
+                                if (c != 255) { sc.r *= cf; sc.g *= cf; sc.b *= cf; sc.a *= cf; }
+                                const float ia = 1.0f - sc.a;
+                                o.r = mad(dd.r, ia, sc.r); o.g = mad(dd.g, ia, sc.g); o.b = mad(dd.b, ia, sc.b); o.a = mad(dd.a, ia, sc.a);
+                            } else if (c == 255) {
+                                o = sc;
+                            } else {        // Source: lerp_1_float(dst, src, coverage)
+                                o.r = mad(sc.r - dd.r, cf, dd.r); o.g = mad(sc.g - dd.g, cf, dd.g);
+                                o.b = mad(sc.b - dd.b, cf, dd.b); o.a = mad(sc.a - dd.a, cf, dd.a);
+                            }
+                            d = store_pf(o);
                         } else {
                             n_partial++;
                             d = blend_pixel(P, stops, d, c, tlx + 8 * pj + q, tly + prow);
