@@ -111,8 +111,11 @@ def cpu_render_sample(R, scene, n_sample, canvas=None):
             p = sub["pts"][sub["pt_off"][i]:sub["pt_off"][i + 1]]
             if sw[i] > 0:
                 t0 = time.perf_counter()
-                out = rb.stroke_path(v, p, float(sw[i]), float(sub["stroke_miter"][i]), caps[sub["stroke_cap"][i]],
-                                     joins[sub["stroke_join"][i]], 1.0)
+                src = (v, p)
+                if "n_dash" in sub and sub["n_dash"][i] > 0:
+                    src = rb.dash_path(v, p, sub["dash"][i][: sub["n_dash"][i]], 0.0, 1.0)
+                out = None if src is None else rb.stroke_path(src[0], src[1], float(sw[i]), float(sub["stroke_miter"][i]),
+                                                               caps[sub["stroke_cap"][i]], joins[sub["stroke_join"][i]], 1.0)
                 t_stroke += time.perf_counter() - t0
                 if out is None:
                     v, p = v[:0], p[:0]
@@ -356,7 +359,7 @@ def main():
             "dtype": "u8/u16 fixed point + f32", "data": "synthetic",
             "config": {"workload": args.workload, "canvas": [W, H], "paths": n_paths, "draw_calls": int(n_draws_in),
                        "mix": "70% fill / 20% fill+stroke / 10% stroke; nonzero+evenodd; 50% solid / 30% linear / 20% radial; 95% AA",
-                       "stroke": "width log-U[1,16] px, miter/round/bevel joins, butt/round/square caps; hairlines (<=1 px) and dashes not implemented yet",
+                       "stroke": "width log-U[1,16] px (hairlines <= 1 px are not implemented yet), miter/round/bevel joins, butt/round/square caps, 10% dashed (2-4 intervals U[2,32])",
                        "sharding": "one scene (document) per GPU, no collective",
                        "l2": "inputs (256 MiB canvas + %.0f MiB edges/bins) exceed the 126 MB L2" % (st["upload_bytes"] / 2**20),
                        "draws": st["draws"], "line_edges": st["edges"], "draw_tile_pairs": st["pairs"], "tiles": st["tiles"]},

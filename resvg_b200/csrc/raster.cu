@@ -1218,8 +1218,9 @@ extern "C" int rb_batch_submit(rb_batch *b, int32_t n_threads)
 {
     if (!b) return RB_ERR_INVALID;
     const size_t n = b->n_total;
-    size_t parts = 1;
-    if (n >= 32768 && (b->layer || b->mask)) {
+    size_t parts = 1, split_from = 32768;
+    if (const char *e = getenv("RB_SUBMIT_SPLIT_FROM")) split_from = (size_t)std::max(1, atoi(e)); // tests
+    if (n >= split_from && (b->layer || b->mask)) {
         parts = 8;
         if (const char *e = getenv("RB_SUBMIT_PARTS")) parts = (size_t)std::max(1, atoi(e));
     }

@@ -41,9 +41,10 @@ def _gather_ranges(off, idx):
 
 
 def paths_scene(width=8192, height=8192, n_paths=100_000, seed=0x5EED0002, rmin=8.0, rmax=256.0, strokes=True,
-                stroke_wmin=1.0, stroke_wmax=16.0):
+                stroke_wmin=1.0, stroke_wmax=16.0, dashed=0.1):
     """C2 'paths8k': n_paths random closed paths; 70 % are filled, 20 % filled then stroked, 10 % stroked only
-    (strokes=True).  The returned arrays hold one entry per DRAW (a filled+stroked path is two entries).  Stroke
+    (strokes=True), a fraction `dashed` of the strokes with a dash array of 2-4 intervals U[2, 32] (an odd list is
+    repeated, as usvg does).  The returned arrays hold one entry per DRAW (a filled+stroked path is two entries).  Stroke
     width is log-uniform [stroke_wmin, stroke_wmax]; the default lower bound of 1 px keeps every stroke on the general
     stroker path (tiny-skia's hairline special case for widths <= 1 px is not implemented yet)."""
     u = splitmix64_uniform(seed, n_paths * STREAM).reshape(n_paths, STREAM)
@@ -161,6 +162,15 @@ def paths_scene(width=8192, height=8192, n_paths=100_000, seed=0x5EED0002, rmin=
                stroke_miter=np.full(len(src), 4.0, np.float32),
                stroke_cap=np.minimum((u[:, 21] * 3).astype(np.int32), 2)[src],
                stroke_join=np.array([0, 2, 3], np.int32)[np.minimum((u[:, 22] * 3).astype(np.int64), 2)][src])
+    # dash arrays: up to 6 floats per draw (3 intervals are repeated to 6); n_dash = 0 for solid strokes and fills
+    cnt = 2 + np.minimum((u[:, 24] * 3).astype(np.int64), 2)
+    vals = (2.0 + 30.0 * u[:, 25:29]).astype(np.float32)
+    dash = np.zeros((n_paths, 6), np.float32)
+    dash[:, :4] = vals
+    three = cnt == 3
+    dash[three, 3:6] = vals[three, :3]
+    n_dash = np.where(u[:, 23] < dashed, np.where(three, 6, cnt), 0).astype(np.int32)
+    out.update(dash=np.ascontiguousarray(dash[src]), n_dash=np.where(is_stroke, n_dash[src], 0).astype(np.int32))
     return out
 
 
@@ -197,10 +207,18 @@ def to_paint_array(scene, paint_struct, blend_mode=3):
 
 
 def to_stroke_array(scene, stroke_struct):
-    """ctypes array of rb_stroke {width, miter_limit, cap, join}; width 0 marks a fill entry."""
+    """ctypes array of rb_stroke {width, miter_limit, cap, join, dash_array, n_dash, dash_offset}; width 0 marks a fill
+    entry.  dash_array points into scene["dash"], which must outlive the array."""
     n = scene["n_paths"]
     arr = (stroke_struct * n)()
     view = np.frombuffer(arr, dtype=np.uint8).reshape(n, C.sizeof(stroke_struct))
+    if "n_dash" in scene and hasattr(stroke_struct, "n_dash"):
+        nd = np.ascontiguousarray(scene["n_dash"], np.int32)
+        f = stroke_struct.n_dash
+        view[:, f.offset:f.offset + 4] = nd.reshape(n, 1).view(np.uint8)
+        ptr = np.where(nd > 0, scene["dash"].ctypes.data + np.arange(n, dtype=np.uint64) * 24, 0).astype(np.uint64)
+        f = stroke_struct.dash_array
+        view[:, f.offset:f.offset + 8] = ptr.reshape(n, 1).view(np.uint8)
     for name, dt in (("width", np.float32), ("miter_limit", np.float32), ("cap", np.int32), ("join", np.int32)):
         f = getattr(stroke_struct, name)
         key = {"width": "stroke_width", "miter_limit": "stroke_miter", "cap": "stroke_cap", "join": "stroke_join"}[name]
@@ -216,7 +234,7 @@ def subset(scene, n):
     out["verb_off"] = scene["verb_off"][: n + 1].copy()
     out["pt_off"] = scene["pt_off"][: n + 1].copy()
     for k in ("rules", "paint_kind", "color", "geom", "spread", "n_stops", "anti_alias", "radius", "stroke_width",
-              "stroke_miter", "stroke_cap", "stroke_join", "stop_start"):
+              "stroke_miter", "stroke_cap", "stroke_join", "stop_start", "dash", "n_dash"):
         if k in scene:
             out[k] = scene[k][:n].copy()
     out["stop_off"] = scene["stop_off"][: n + 1].copy()

@@ -317,6 +317,34 @@ def test_wide_fallback_kernel_matches_too(ctx):
     assert_exact(got, want, "wide kernel")
 
 
+@pytest.mark.parametrize("split", [False, True])
+def test_bench_scene_bulk_api_matches_oracle(ctx, split, monkeypatch):
+    """The C2 bench scene (fills, strokes, dashes, gradients) at a small size, recorded through the by-reference bulk
+    API exactly as bench.py does — once as a single submit, once forced through the multi-part pipelined submit — must
+    equal the oracle rendering of the same draws."""
+    import bench
+    import resvg_b200 as rb
+    from resvg_b200 import _ffi, scenes
+
+    if split:
+        monkeypatch.setenv("RB_SUBMIT_SPLIT_FROM", "64")
+        monkeypatch.setenv("RB_SUBMIT_PARTS", "5")
+    w, h = 640, 480
+    scene = scenes.paths_scene(w, h, 700, 0xC2, rmin=6.0, rmax=90.0)
+    scene["paints"] = scenes.to_paint_array(scene, _ffi.Paint)
+    scene["strokes"] = scenes.to_stroke_array(scene, _ffi.Stroke)
+    assert (scene["n_dash"] > 0).sum() > 5 and (scene["stroke_width"] > 0).sum() > 100
+    l = ctx.layer(w, h)
+    b = rb.Batch(l)
+    b.fill_paths(scene)
+    b.submit()
+    got = l.download()
+    want = np.zeros((h, w, 4), np.uint8)
+    bench.cpu_render_sample(bench.oracle_lib(), scene, scene["n_paths"], want)
+    assert_within(got, want, 1, "bench scene")  # two-point conical gradients run the f32 pipeline
+    assert (got != want).any(axis=-1).mean() < 0.02
+
+
 def test_batch_dashed_strokes(ctx):
     """stroke_path with a dash array: dash (tiny_skia_path::Path::dash) -> stroke -> fill inside the batch builder must
     equal the same host steps done one by one and filled by the oracle; rejected dash lists leave the stroke solid."""
