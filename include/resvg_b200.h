@@ -194,8 +194,10 @@ typedef struct {
     int32_t n_dash;
     float dash_offset;
 } rb_stroke;
-/* PixmapMut::stroke_path(path, paint, stroke, transform, None) — path.rs:113: outline on the host (rb_path_stroke),
- * then a Winding fill.  Hairline strokes (anti-aliased, transformed width <= 1 px) return RB_ERR_UNSUPPORTED. */
+/* PixmapMut::stroke_path(path, paint, stroke, transform, None) — path.rs:113: dash, then outline on the host
+ * (rb_path_stroke) and a Winding fill; or, when tiny-skia's treat_as_hairline says so (width 0, or an anti-aliased
+ * stroke whose transformed width is at most one pixel), the anti-aliased hairline walker (scan/hairline_aa.rs) with
+ * the paint's alpha modulated by the width.  Batches holding hairlines must be executed with rb_batch_submit. */
 int rb_batch_stroke_path(rb_batch *batch, const uint8_t *verbs, int32_t n_verbs, const float *points,
                          int32_t n_points, const rb_paint *paint, const rb_stroke *stroke, const float ts[6]);
 /* Bulk recording of fills and strokes: strokes may be NULL; entry i is stroked when strokes[i].width > 0, filled
@@ -253,6 +255,11 @@ int rb_path_stroke(const uint8_t *verbs, int32_t n_verbs, const float *points, i
                    float miter_limit, int32_t cap, int32_t join, float res_scale, uint8_t **out_verbs,
                    int32_t *out_n_verbs, float **out_points, int32_t *out_n_points);
 void rb_path_free(void *p);
+/* The ordered blits {x, y, alpha} (int32 triples, malloc'ed) of tiny-skia's anti-aliased hairline walker
+ * (scan/hairline_aa.rs via hairline::stroke_path_impl) for a path already in device space, clipped to clip_w x clip_h;
+ * cap: 0 butt, 1 round, 2 square.  Host code; the batch uses the same walker internally. */
+int rb_path_hairline(const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points, int32_t cap,
+                     int32_t clip_w, int32_t clip_h, int32_t **out_blits, int32_t *out_n);
 /* tiny_skia_path::Path::dash(&StrokeDash::new(dash_array, dash_offset)?, res_scale) — the path stroke_path strokes when
  * the stroke is dashed (tiny-skia painter.rs stroke_path).  Host code.  RB_ERR_INVALID: the dash specification is
  * rejected or nothing is left of the path. */

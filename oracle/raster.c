@@ -2106,6 +2106,20 @@ int orc_fill_path(uint8_t *px, uint32_t w, uint32_t h, const uint8_t *verbs, int
     return r;
 }
 
+/* Blitter::blit_anti_h with one pixel per call: the hairline walkers (scan/hairline_aa.rs) emit their coverage this way,
+ * two pixels per step, every one a separate blend through the RasterPipelineBlitter (alpha 255 = the full-coverage
+ * program).  blits = n x {x, y, alpha}; ts is the paint's (= the draw's) transform. */
+int orc_blit_coverage(uint8_t *px, uint32_t w, uint32_t h, int32_t n, const int32_t *blits, const orc_paint *paint, const float ts[6])
+{
+    pix_blitter_t b;
+    if (!pix_blitter_init(&b, px, w, h, paint, ts ? ts_from(ts) : ts_identity())) return 0;
+    for (int32_t i = 0; i < n; i++) {
+        const uint8_t c = (uint8_t)blits[3 * i + 2];
+        b.base.blit_row(&b.base, blits[3 * i], blits[3 * i + 1], &c, 1);
+    }
+    return 1;
+}
+
 /* scan::fill_rect (non-AA): Rect::round() then intersect */
 static int fill_int_rect(uint8_t *px, uint32_t w, uint32_t h, int32_t x, int32_t y, int32_t rw, int32_t rh,
                          const orc_paint *paint, xform ctm)

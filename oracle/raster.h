@@ -64,6 +64,9 @@ int orc_fill_path(uint8_t *px, uint32_t w, uint32_t h, const uint8_t *verbs, int
 int orc_fill_paths(uint8_t *px, uint32_t w, uint32_t h, int32_t n_paths, const uint32_t *verb_off, const uint32_t *pt_off,
                    const uint8_t *verbs, const float *pts, const orc_paint *paints, const uint8_t *rules, const float ts[6]);
 /* PixmapMut::fill_rect(rect, paint, transform, None) */
+/* n single-pixel coverage blits {x, y, alpha} blended in order (Blitter::blit_anti_h; used for hairline strokes) */
+int orc_blit_coverage(uint8_t *px, uint32_t w, uint32_t h, int32_t n, const int32_t *blits, const orc_paint *paint, const float ts[6]);
+
 int orc_fill_rect(uint8_t *px, uint32_t w, uint32_t h, float x, float y, float rw, float rh, const orc_paint *paint,
                   const float ts[6]);
 /* PixmapMut::draw_pixmap(x, y, src, PixmapPaint{opacity, blend_mode, quality}, transform, None) */

@@ -133,6 +133,7 @@ SIGNATURES = {
     "rb_path_stroke": (_i, [_vp, C.c_int32, _vp, C.c_int32, _f, _f, C.c_int32, C.c_int32, _f, c_void_pp,
                             C.POINTER(C.c_int32), c_void_pp, C.POINTER(C.c_int32)]),
     "rb_path_free": (None, [_vp]),
+    "rb_path_hairline": (_i, [_vp, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_void_pp, C.POINTER(C.c_int32)]),
     "rb_path_dash": (_i, [_vp, C.c_int32, _vp, C.c_int32, _vp, C.c_int32, _f, _f, c_void_pp, C.POINTER(C.c_int32), c_void_pp,
                           C.POINTER(C.c_int32)]),
     "rb_debug_force_wide_kernel": (None, [_i]),

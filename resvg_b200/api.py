@@ -478,6 +478,22 @@ CAPS = {"butt": 0, "round": 1, "square": 2}
 JOINS = {"miter": 0, "miter-clip": 1, "round": 2, "bevel": 3}
 
 
+def hairline_blits(verbs, pts, cap="butt", clip_w=1, clip_h=1):
+    """The ordered {x, y, alpha} blits of tiny-skia's anti-aliased hairline walker for a path in device space
+    → int32 array (n, 3).  Host-only."""
+    v, p = _path(verbs, pts)
+    out, n = C.c_void_p(), C.c_int32()
+    st = lib.rb_path_hairline(v.ctypes.data, len(v), p.ctypes.data, len(p), CAPS[cap] if isinstance(cap, str) else int(cap),
+                              int(clip_w), int(clip_h), C.byref(out), C.byref(n))
+    if st != 0:
+        return np.zeros((0, 3), np.int32)
+    try:
+        arr = np.ctypeslib.as_array((C.c_int32 * (max(n.value, 1) * 3)).from_address(out.value)).copy()[: n.value * 3]
+    finally:
+        lib.rb_path_free(out)
+    return arr.reshape(-1, 3)
+
+
 def dash_path(verbs, pts, dash_array, dash_offset=0.0, res_scale=1.0):
     """tiny_skia_path::Path::dash(StrokeDash::new(dash_array, dash_offset)?, res_scale) → (verbs, points) or None when
     the specification is rejected or nothing is left.  Host-only."""

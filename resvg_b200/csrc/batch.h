@@ -99,6 +99,7 @@ struct rb_batch {
     std::vector<BulkSeg> bulk;
     std::vector<DrawSpan> spans;
     size_t n_total = 0; // draws recorded so far (recs + bulk)
+    size_t n_hair = 0;  // how many of them are hairline strokes (drawn by k_hair_blits, between the fill runs)
     uint64_t stats[6] = {0, 0, 0, 0, 0, 0};
     uint64_t phases[RB_PHASES] = {0, 0, 0, 0, 0, 0};
     // device-resident form produced by rb_batch_prepare
@@ -116,6 +117,22 @@ typedef void *(*rb_stage_alloc)(void *user, size_t bytes);
 // Draws [begin, end) of the batch only (end = 0: all of them).
 int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threads, rb_stage_alloc alloc, void *user,
                         void **block, size_t begin = 0, size_t end = 0);
+
+// ---- hairline strokes (hairline.cpp): blits grouped per pixel, applied in order by one thread per pixel ----------------
+struct HairGroup { uint32_t x, y, first, count; };            // layer pixel and its range of blits
+struct HairDevBlit { uint32_t alpha, paint; int32_t ox, oy; }; // coverage, DevPaint index, DrawTiler tile origin
+struct HairBuilt {
+    std::vector<HairGroup> groups;
+    std::vector<HairDevBlit> blits;
+    std::vector<rbh::DevPaint> paints;
+    std::vector<rbh::DevStop> stops;
+};
+// painter.rs treat_as_hairline: the coverage the hairline is modulated with, or < 0 when the stroke is a real outline.
+float rb_hairline_coverage(const rb_paint &paint, const rb_stroke &stroke, const rbh::Xform &ctm);
+// Is draw i of the batch a hairline stroke?
+bool rb_batch_draw_is_hairline(const rb_batch *b, size_t i);
+// Builds the blits of the consecutive hairline draws [begin, end).
+int rb_batch_hair_build(const rb_batch *b, size_t begin, size_t end, int W, int H, HairBuilt *out);
 
 int rb_batch_record(rb_batch *b, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
                     const rb_paint *paint, int32_t rule, const float ts[6]);

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "batch.h"
+#include "hairline.h"
 
 extern "C" int rb_path_stroke(const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points, float width,
                               float miter_limit, int32_t cap, int32_t join, float res_scale, uint8_t **out_verbs,
@@ -233,6 +234,182 @@ struct Tick { uint64_t &acc; uint64_t t0; Tick(uint64_t &a) : acc(a), t0(__rdtsc
 #define PROF(i)
 #endif
 
+} // namespace
+
+// painter.rs treat_as_hairline
+float rb_hairline_coverage(const rb_paint &paint, const rb_stroke &stroke, const rbh::Xform &ctm)
+{
+    auto fast_len = [](float x, float y) { x = fabsf(x); y = fabsf(y); if (x < y) std::swap(x, y); return x + y * 0.5f; };
+    const float w = stroke.width;
+    if (w == 0.0f) return 1.0f;
+    if (!paint.anti_alias) return -1.0f;
+    // the two stroke-width vectors mapped by the transform (translation ignored)
+    const float len0 = fast_len(ctm.sx * w, ctm.ky * w), len1 = fast_len(ctm.kx * w, ctm.sy * w);
+    if (len0 <= 1.0f && len1 <= 1.0f) return (len0 + len1) * 0.5f;
+    return -1.0f;
+}
+
+namespace {
+
+struct DrawRef {
+    const uint8_t *verbs;
+    const rbh::Pt *pts;
+    int n_verbs, n_pts;
+    rb_paint paint;
+    const float *stops;
+    rbh::Xform ctm;
+    bool is_stroke;
+    rb_stroke stroke; // dash_array resolved
+};
+// The recorded form of draw i (fill points of bulk segments are NOT transformed here).
+DrawRef resolve_draw(const rb_batch *b, size_t i)
+{
+    size_t lo = 0, hi = b->spans.size() - 1;
+    while (lo < hi) { // last span with start <= i
+        const size_t mid = (lo + hi + 1) >> 1;
+        if (b->spans[mid].start <= i) lo = mid; else hi = mid - 1;
+    }
+    const DrawSpan &sp = b->spans[lo];
+    DrawRef d;
+    if (sp.bulk < 0) {
+        const RecordedDraw &r = b->recs[sp.first + (i - sp.start)];
+        d.verbs = b->verbs.data() + r.verb_off;
+        d.pts = b->pts.data() + r.pt_off;
+        d.n_verbs = (int)r.n_verbs;
+        d.n_pts = (int)r.n_pts;
+        d.paint = r.paint;
+        d.stops = r.n_stops ? b->stops.data() + r.stop_off : nullptr;
+        d.ctm = r.ctm;
+        d.is_stroke = r.is_stroke;
+        d.stroke = r.stroke;
+        d.stroke.dash_array = r.stroke.n_dash > 0 ? b->dashes.data() + r.dash_off : nullptr;
+    } else {
+        const BulkSeg &bs = b->bulk[(size_t)sp.bulk];
+        const size_t k = i - sp.start;
+        d.verbs = bs.verbs + bs.verb_off[k];
+        d.pts = reinterpret_cast<const rbh::Pt *>(bs.points) + bs.point_off[k];
+        d.n_verbs = (int)(bs.verb_off[k + 1] - bs.verb_off[k]);
+        d.n_pts = (int)(bs.point_off[k + 1] - bs.point_off[k]);
+        d.paint = bs.paints[k];
+        d.stops = (d.paint.stops && d.paint.n_stops > 0) ? d.paint.stops : nullptr;
+        d.ctm = bs.ctm;
+        d.is_stroke = bs.strokes && bs.strokes[k].width > 0.0f;
+        if (d.is_stroke) d.stroke = bs.strokes[k];
+        else memset(&d.stroke, 0, sizeof(d.stroke));
+    }
+    return d;
+}
+
+} // namespace
+
+bool rb_batch_draw_is_hairline(const rb_batch *b, size_t i)
+{
+    if (b->n_hair == 0) return false;
+    const DrawRef d = resolve_draw(b, i);
+    return d.is_stroke && rb_hairline_coverage(d.paint, d.stroke, d.ctm) >= 0.0f;
+}
+
+// stroke_path for a hairline (tiny-skia painter.rs): dash, transform into device space, modulate the paint's alpha by
+// the hairline coverage, walk every DrawTiler tile, then group the blits by pixel keeping their order.
+int rb_batch_hair_build(const rb_batch *b, size_t begin, size_t end, int W, int H, HairBuilt *out)
+{
+    struct Raw { uint32_t x, y, alpha, paint; int32_t ox, oy; };
+    std::vector<Raw> raw;
+    std::vector<rbh::HairBlit> blits;
+    std::vector<uint8_t> dverbs;
+    std::vector<float> dpts;
+    std::vector<rbh::Pt> dev, tmp;
+    std::vector<float> stops_scaled;
+    for (size_t i = begin; i < end; i++) {
+        DrawRef d = resolve_draw(b, i);
+        if (!d.is_stroke) continue;
+        const float coverage = rb_hairline_coverage(d.paint, d.stroke, d.ctm);
+        if (coverage < 0.0f) continue;
+        const uint8_t *verbs = d.verbs;
+        const rbh::Pt *pts = d.pts;
+        int n_verbs = d.n_verbs, n_pts = d.n_pts;
+        if (d.stroke.n_dash > 0 && d.stroke.dash_array) {
+            bool valid = false;
+            float sx = sqrtf(d.ctm.sx * d.ctm.sx + d.ctm.kx * d.ctm.kx), sy = sqrtf(d.ctm.ky * d.ctm.ky + d.ctm.sy * d.ctm.sy);
+            float res = (std::isfinite(sx) && std::isfinite(sy) && std::max(sx, sy) > 0) ? std::max(sx, sy) : 1.0f;
+            int st = rb_path_dash_into(verbs, n_verbs, &pts[0].x, n_pts, d.stroke.dash_array, d.stroke.n_dash, d.stroke.dash_offset, res,
+                                       dverbs, dpts, &valid);
+            if (valid) {
+                if (st != RB_OK) continue;
+                verbs = dverbs.data();
+                n_verbs = (int)dverbs.size();
+                pts = reinterpret_cast<const rbh::Pt *>(dpts.data());
+                n_pts = (int)(dpts.size() / 2);
+            }
+        }
+        dev.assign(pts, pts + n_pts);
+        rbh::map_points(d.ctm, dev.data(), n_pts);
+        // coverage < 1 is folded into the paint's alpha when the blend mode pre-scales coverage (painter.rs: "the old
+        // technique"): scale = (coverage * 256) as i32; alpha' = (255 * scale) >> 8; shader.apply_opacity(alpha' / 255)
+        rb_paint paint = d.paint;
+        paint.stops = d.stops;
+        if (coverage != 1.0f) {
+            const int m = paint.blend_mode;
+            const bool pre_scales = m == 2 || m == 4 || m == 12 || m == 8 || m == 9 || m == 3 || m == 11;
+            if (pre_scales) {
+                const int scale = (int)(coverage * 256.0f);
+                const float opacity = (float)((255 * scale) >> 8) / 255.0f;
+                if (paint.shader == 0) paint.color[3] = std::min(std::max(paint.color[3] * opacity, 0.0f), 1.0f);
+                else if (paint.shader == 3) paint.opacity = std::min(std::max(paint.opacity * opacity, 0.0f), 1.0f);
+                else if (paint.stops && paint.n_stops > 0) {
+                    stops_scaled.assign(paint.stops, paint.stops + (size_t)paint.n_stops * 5);
+                    for (int k = 0; k < paint.n_stops; k++)
+                        stops_scaled[(size_t)k * 5 + 4] = std::min(std::max(stops_scaled[(size_t)k * 5 + 4] * opacity, 0.0f), 1.0f);
+                    paint.stops = stops_scaled.data();
+                }
+            }
+        }
+        for (int ty = 0; ty < H; ty += kMaxDim) {
+            for (int tx = 0; tx < W; tx += kMaxDim) {
+                const int tw = std::min(W - tx, kMaxDim), th = std::min(H - ty, kMaxDim);
+                const rbh::Pt *p = dev.data();
+                rbh::Xform ctm = d.ctm;
+                if (tx || ty) {
+                    tmp = dev;
+                    rbh::Xform tr;
+                    tr.tx = -(float)tx;
+                    tr.ty = -(float)ty;
+                    rbh::map_points(tr, tmp.data(), n_pts);
+                    p = tmp.data();
+                    ctm = rbh::post_concat(ctm, tr);
+                }
+                blits.clear();
+                rbh::hairline_blits(verbs, n_verbs, &p[0].x, n_pts, d.stroke.cap, tw, th, blits);
+                if (blits.empty()) continue;
+                rbh::DevPaint P;
+                if (!rbh::prepare_paint(&paint, ctm, &P, out->stops)) continue;
+                const uint32_t pi = (uint32_t)out->paints.size();
+                out->paints.push_back(P);
+                for (const rbh::HairBlit &hb : blits)
+                    raw.push_back(Raw{(uint32_t)(hb.x + tx), (uint32_t)(hb.y + ty), hb.alpha, pi, tx, ty});
+            }
+        }
+    }
+    // group by pixel, keeping the blit order inside each group
+    std::vector<uint32_t> order(raw.size());
+    for (size_t i = 0; i < raw.size(); i++) order[i] = (uint32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) {
+        const uint64_t ka = (uint64_t)raw[a].y * (uint64_t)W + raw[a].x, kc = (uint64_t)raw[c].y * (uint64_t)W + raw[c].x;
+        return ka < kc;
+    });
+    out->blits.reserve(raw.size());
+    for (size_t k = 0; k < order.size(); k++) {
+        const Raw &r = raw[order[k]];
+        if (out->groups.empty() || out->groups.back().x != r.x || out->groups.back().y != r.y)
+            out->groups.push_back(HairGroup{r.x, r.y, (uint32_t)out->blits.size(), 0});
+        out->groups.back().count++;
+        out->blits.push_back(HairDevBlit{r.alpha, r.paint, r.ox, r.oy});
+    }
+    return RB_OK;
+}
+
+namespace {
+
 // Upper bound of simultaneously active edges from the y ranges of the chains (a line, or a whole curve): used in item
 // mode, where the curve segments do not exist on the host.  `iv` holds (first_y, last_y) pairs.
 bool chains_may_exceed_packed_winding(std::vector<int32_t> &iv)
@@ -300,6 +477,10 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
         }
         const RecordedDraw &r = *rp;
         int n_verbs = (int)r.n_verbs, n_pts = (int)r.n_pts, rule = r.rule;
+        if (r.is_stroke && b->n_hair) {
+            rb_stroke sk = r.stroke;
+            if (rb_hairline_coverage(r.paint, sk, r.ctm) >= 0.0f) continue; // hairlines are drawn by their own pass
+        }
         if (r.is_stroke) {
             // stroke_path: the outline is computed in local coordinates, then filled (Winding) under the transform
             const uint8_t *ov = nullptr;
@@ -716,18 +897,11 @@ extern "C" int rb_batch_fill_path(rb_batch *b, const uint8_t *verbs, int32_t n_v
 extern "C" int rb_batch_stroke_path(rb_batch *b, const uint8_t *verbs, int32_t n_verbs, const float *points,
                                     int32_t n_points, const rb_paint *paint, const rb_stroke *stroke, const float ts[6])
 {
-    if (!stroke || !paint) return RB_ERR_INVALID;
+    if (!stroke || !paint || !b) return RB_ERR_INVALID;
     if (stroke->width < 0.0f) return RB_OK;
     if (stroke->cap < 0 || stroke->cap > 2 || stroke->join < 0 || stroke->join > 3) return RB_ERR_INVALID;
     const rbh::Xform ctm = ts ? rbh::Xform::from(ts) : rbh::Xform();
-    {
-        // treat_as_hairline
-        auto fast_len = [](float x, float y) { x = fabsf(x); y = fabsf(y); return std::max(x, y) + std::min(x, y) * 0.5f; };
-        const float w = stroke->width;
-        if (w == 0.0f) return RB_ERR_UNSUPPORTED;
-        if (paint->anti_alias && fast_len(ctm.sx * w, ctm.ky * w) <= 1.0f && fast_len(ctm.kx * w, ctm.sy * w) <= 1.0f)
-            return RB_ERR_UNSUPPORTED;
-    }
+    const bool hair = rb_hairline_coverage(*paint, *stroke, ctm) >= 0.0f;
     static const float ident[6] = {1, 0, 0, 1, 0, 0};
     int st = rb_batch_fill_path(b, verbs, n_verbs, points, n_points, paint, 0, ident); // keep local coordinates
     if (st != RB_OK) return st;
@@ -739,6 +913,7 @@ extern "C" int rb_batch_stroke_path(rb_batch *b, const uint8_t *verbs, int32_t n
     r.dash_off = (uint32_t)b->dashes.size();
     if (stroke->dash_array && stroke->n_dash > 0) b->dashes.insert(b->dashes.end(), stroke->dash_array, stroke->dash_array + stroke->n_dash);
     else r.stroke.n_dash = 0;
+    if (hair) b->n_hair++;
     return RB_OK;
 }
 
@@ -753,6 +928,7 @@ extern "C" int rb_batch_draw_paths(rb_batch *b, int32_t n_paths, const uint32_t 
     if (!b || n_paths < 0 || !verb_off || !point_off || !verbs || !points || !paints || !fill_rules) return RB_ERR_INVALID;
     if (n_paths == 0) return RB_OK;
     const rbh::Xform ctm = ts ? rbh::Xform::from(ts) : rbh::Xform();
+    size_t n_hair = 0;
     for (int32_t i = 0; i < n_paths; i++) {
         const uint32_t va = verb_off[i], vb = verb_off[i + 1], pa = point_off[i], pb = point_off[i + 1];
         const rb_paint &paint = paints[i];
@@ -770,12 +946,10 @@ extern "C" int rb_batch_draw_paths(rb_batch *b, int32_t n_paths, const uint32_t 
         if (strokes && strokes[i].width > 0.0f) {
             const rb_stroke &sk = strokes[i];
             if (sk.cap < 0 || sk.cap > 2 || sk.join < 0 || sk.join > 3) return RB_ERR_INVALID;
-            // treat_as_hairline: not implemented (see rb_batch_stroke_path)
-            auto fast_len = [](float x, float y) { x = fabsf(x); y = fabsf(y); return std::max(x, y) + std::min(x, y) * 0.5f; };
-            if (paint.anti_alias && fast_len(ctm.sx * sk.width, ctm.ky * sk.width) <= 1.0f && fast_len(ctm.kx * sk.width, ctm.sy * sk.width) <= 1.0f)
-                return RB_ERR_UNSUPPORTED;
+            if (rb_hairline_coverage(paint, sk, ctm) >= 0.0f) n_hair++;
         }
     }
+    b->n_hair += n_hair;
     BulkSeg bs;
     bs.n = n_paths;
     bs.verb_off = verb_off; bs.point_off = point_off; bs.verbs = verbs; bs.points = points;

@@ -1089,7 +1089,12 @@ static int batch_prepare_range(rb_batch *b, int32_t n_threads, size_t begin, siz
     return RB_OK;
 }
 
-extern "C" int rb_batch_prepare(rb_batch *b, int32_t n_threads) { return batch_prepare_range(b, n_threads, 0, 0); }
+extern "C" int rb_batch_prepare(rb_batch *b, int32_t n_threads)
+{
+    // the resident prepare / run split covers scan-converted draws only; hairline strokes need rb_batch_submit
+    if (b && b->n_hair) return rb_fail(batch_ctx(b), RB_ERR_UNSUPPORTED, "rb_batch_prepare: the batch holds hairline strokes, use rb_batch_submit");
+    return batch_prepare_range(b, n_threads, 0, 0);
+}
 
 static int batch_run(rb_batch *b, unsigned long long *px_stats);
 extern "C" int rb_batch_run(rb_batch *b) { return batch_run(b, nullptr); }
@@ -1212,12 +1217,89 @@ extern "C" int rb_ctx_last_run_ms(rb_ctx *ctx, float ms[2])
     return RB_OK;
 }
 
+// ---- hairline strokes: one thread per touched pixel applies that pixel's blits in the order the walker produced them ----
+__global__ void __launch_bounds__(128)
+k_hair_blits(uint32_t *__restrict__ px, int W, const HairGroup *__restrict__ groups, uint32_t n_groups, const HairDevBlit *__restrict__ blits,
+             const DevPaint *__restrict__ paints, const DevStop *__restrict__ stops)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const HairGroup G = groups[g];
+    uint32_t *p = px + (size_t)G.y * W + G.x;
+    uint32_t d = *p;
+    for (uint32_t k = 0; k < G.count; k++) {
+        const HairDevBlit B = blits[G.first + k];
+        d = blend_pixel(paints[B.paint], stops, d, B.alpha, (int)G.x - B.ox, (int)G.y - B.oy);
+    }
+    *p = d;
+}
+
+static int hair_run(rb_batch *b, size_t lo, size_t hi)
+{
+    if (!b->layer) return RB_OK; // Mask::fill_path never strokes
+    rb_ctx *ctx = b->layer->ctx;
+    HairBuilt hb;
+    int st = rb_batch_hair_build(b, lo, hi, (int)b->layer->w, (int)b->layer->h, &hb);
+    if (st != RB_OK) return rb_fail(ctx, st, "hairline build failed");
+    if (hb.groups.empty()) return RB_OK;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_groups = 0, o_blits = o_groups + al(hb.groups.size() * sizeof(HairGroup));
+    const size_t o_paints = o_blits + al(hb.blits.size() * sizeof(HairDevBlit));
+    const size_t o_stops = o_paints + al(hb.paints.size() * sizeof(DevPaint));
+    const size_t total = o_stops + al(std::max<size_t>(hb.stops.size(), 1) * sizeof(DevStop));
+    void *stage = nullptr;
+    st = rb_staging(ctx, total, &stage);
+    if (st != RB_OK) return st;
+    uint8_t *h = (uint8_t *)stage;
+    memcpy(h + o_groups, hb.groups.data(), hb.groups.size() * sizeof(HairGroup));
+    memcpy(h + o_blits, hb.blits.data(), hb.blits.size() * sizeof(HairDevBlit));
+    memcpy(h + o_paints, hb.paints.data(), hb.paints.size() * sizeof(DevPaint));
+    if (!hb.stops.empty()) memcpy(h + o_stops, hb.stops.data(), hb.stops.size() * sizeof(DevStop));
+    uint8_t *dev = nullptr;
+    cudaSetDevice(ctx->device);
+    RB_CUDA(ctx, cudaMallocAsync((void **)&dev, total, ctx->stream));
+    RB_CUDA(ctx, cudaMemcpyAsync(dev, h, total, cudaMemcpyHostToDevice, ctx->stream));
+    RB_CUDA(ctx, cudaEventRecord(ctx->staging_ev, ctx->stream));
+    ctx->staging_in_flight = true;
+    const uint32_t n = (uint32_t)hb.groups.size();
+    k_hair_blits<<<(n + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(b->layer->d), (int)b->layer->w, (const HairGroup *)(dev + o_groups), n,
+                                                        (const HairDevBlit *)(dev + o_blits), (const DevPaint *)(dev + o_paints),
+                                                        (const DevStop *)(dev + o_stops));
+    RB_LAUNCHED(ctx, "hair_blits");
+    RB_CUDA(ctx, cudaFreeAsync(dev, ctx->stream));
+    return RB_OK;
+}
+
 // Large batches are submitted in a few consecutive parts (painter's order is kept: part k + 1 is rasterised after part
 // k on the same stream), so the GPU works on one part while the host threads build the edges of the next.
+static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t last, uint64_t total[6]);
+
+// Hairline strokes are not scan-converted: the batch is cut into runs of ordinary draws (tile kernel) and runs of
+// hairlines (k_hair_blits), executed in painter's order on the context's stream.
 extern "C" int rb_batch_submit(rb_batch *b, int32_t n_threads)
 {
     if (!b) return RB_ERR_INVALID;
-    const size_t n = b->n_total;
+    uint64_t total[6] = {0, 0, 0, 0, 0, 0};
+    int st = RB_OK;
+    if (b->n_hair == 0) st = submit_fill_run(b, n_threads, 0, b->n_total, total);
+    else {
+        size_t i = 0;
+        while (i < b->n_total && st == RB_OK) {
+            const bool hair = rb_batch_draw_is_hairline(b, i);
+            size_t j = i + 1;
+            while (j < b->n_total && rb_batch_draw_is_hairline(b, j) == hair) j++;
+            st = hair ? hair_run(b, i, j) : submit_fill_run(b, n_threads, i, j, total);
+            i = j;
+        }
+    }
+    memcpy(b->stats, total, sizeof(total));
+    return st;
+}
+
+static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t last, uint64_t total[6])
+{
+    const size_t n = last - first;
+    if (n == 0) return RB_OK;
     size_t parts = 1, split_from = 32768;
     if (const char *e = getenv("RB_SUBMIT_SPLIT_FROM")) split_from = (size_t)std::max(1, atoi(e)); // tests
     if (n >= split_from && (b->layer || b->mask)) {
@@ -1225,17 +1307,14 @@ extern "C" int rb_batch_submit(rb_batch *b, int32_t n_threads)
         if (const char *e = getenv("RB_SUBMIT_PARTS")) parts = (size_t)std::max(1, atoi(e));
     }
     int st = RB_OK;
-    uint64_t total[6] = {0, 0, 0, 0, 0, 0};
     for (size_t k = 0; k < parts && st == RB_OK; k++) {
-        const size_t lo = n * k / parts, hi = n * (k + 1) / parts;
-        if (parts == 1) st = batch_prepare_range(b, n_threads, 0, 0);
-        else if (lo < hi) st = batch_prepare_range(b, n_threads, lo, hi);
-        else continue;
+        const size_t lo = first + n * k / parts, hi = first + n * (k + 1) / parts;
+        if (lo >= hi) continue;
+        st = batch_prepare_range(b, n_threads, lo, hi);
         if (st == RB_OK) st = rb_batch_run(b);
         for (int i = 0; i < 6; i++) total[i] += b->stats[i];
         batch_release(b);
     }
-    memcpy(b->stats, total, sizeof(total));
     return st;
 }
 

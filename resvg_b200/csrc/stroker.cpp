@@ -1000,6 +1000,12 @@ bool has_valid_tangent(const uint8_t *verbs, int n_verbs, int vi, const P *pts, 
 // Path::stroke(&Stroke{width, miter_limit, line_cap, line_join}, res_scale).  cap: 0 butt, 1 round, 2 square;
 // join: 0 miter, 1 miter-clip, 2 round, 3 bevel.  Outputs are malloc'ed (free with rb_path_free); returns RB_OK, or
 // RB_ERR_INVALID when the stroke is empty (Option::None in the reference).
+// path_geometry helpers shared with the hairline walker (hairline.cpp)
+namespace rbs {
+int cubic_max_curvature_ts(const float pts[8], float t[3]) { return cubic_max_curvature(reinterpret_cast<const P *>(pts), t); }
+void chop_cubic_at_t(const float src[8], float t, float dst[14]) { chop_cubic(reinterpret_cast<const P *>(src), t, reinterpret_cast<P *>(dst)); }
+}
+
 // Internal form: the outline stays in a thread-local stroker (valid until the next call on this thread).
 int rb_path_stroke_view(const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points, float width,
                         float miter_limit, int32_t cap, int32_t join, float res_scale, const uint8_t **out_verbs,

@@ -33,6 +33,57 @@ class OracleBackend:
             spec = dict(spec, pixmap=spec["layer"])
         self.R.fill_path(l, verbs, pts, self.R.make_paint(spec, blend, aa), rule, ts)
 
+    def stroke_hairline(self, l, verbs, pts, spec, ts, blend, width, cap, dash=None, dash_offset=0.0):
+        """tiny-skia painter.rs stroke_path for a stroke treat_as_hairline accepts (anti-aliased, transformed width <= 1
+        px): dash, transform into device space, fold the hairline coverage into the paint's alpha, walk the segments
+        (shared host geometry, like the stroker) and blend every blit with the oracle's pipeline."""
+        import math
+
+        import resvg_b200 as rb
+        f = np.float32
+
+        def fast_len(x, y):
+            x, y = abs(f(x)), abs(f(y))
+            if x < y:
+                x, y = y, x
+            return f(x + y * f(0.5))
+
+        w = f(width)
+        len0, len1 = fast_len(f(ts[0]) * w, f(ts[1]) * w), fast_len(f(ts[2]) * w, f(ts[3]) * w)
+        coverage = f((len0 + len1) * f(0.5))
+        v, p = np.asarray(verbs, np.uint8), np.asarray(pts, np.float32).reshape(-1, 2)
+        if dash:
+            sx, sy = math.hypot(ts[0], ts[2]), math.hypot(ts[1], ts[3])
+            res = max(sx, sy) if (math.isfinite(sx) and math.isfinite(sy) and max(sx, sy) > 0) else 1.0
+            out = rb.dash_path(v, p, dash, dash_offset, res)
+            if out is None:
+                return
+            v, p = out
+        sx_, ky, kx, sy_, tx, ty = [f(t) for t in ts]
+        dev = np.stack([p[:, 0] * sx_ + p[:, 1] * kx + tx, p[:, 0] * ky + p[:, 1] * sy_ + ty], axis=1).astype(np.float32) \
+            if tuple(ts) != (1.0, 0.0, 0.0, 1.0, 0.0, 0.0) else p
+        if spec["kind"] == "pattern":
+            spec = dict(spec, pixmap=spec["layer"])
+        pre_scales = blend in ("destination", "destination_over", "plus", "destination_out", "source_atop", "source_over", "xor")
+        if coverage != 1.0 and pre_scales:
+            scale = int(f(coverage) * f(256.0))
+            opacity = f(f((255 * scale) >> 8) / f(255.0))
+            clamp = lambda a: float(min(max(f(a) * opacity, f(0.0)), f(1.0)))
+            if spec["kind"] == "solid":
+                c = list(spec["color"])
+                c[3] = clamp(c[3])
+                spec = dict(spec, color=c)
+            elif spec["kind"] == "pattern":
+                spec = dict(spec, opacity=clamp(spec.get("opacity", 1.0)))
+            else:
+                st = np.array(spec["stops"], dtype=np.float32).reshape(-1, 5).copy()
+                st[:, 4] = [clamp(a) for a in st[:, 4]]
+                spec = dict(spec, stops=st)
+        h, wpx = l.shape[:2]
+        blits = rb.hairline_blits(v, dev, cap, wpx, h)
+        if len(blits):
+            self.R.blit_coverage(l, blits, self.R.make_paint(spec, blend, True), ts)
+
     def draw_layer(self, dst, src, x, y, opacity=1.0, blend="source_over"):
         self.R.draw_pixmap(dst, x, y, src, opacity, blend)
 
@@ -108,6 +159,12 @@ class GpuBackend:
 
     def fill_path(self, l, verbs, pts, spec, rule, ts, blend="source_over", aa=True):
         self.rb.fill_path(l, verbs, pts, self.rb.make_paint(spec, blend, aa), rule, ts)
+
+    def stroke_hairline(self, l, verbs, pts, spec, ts, blend, width, cap, dash=None, dash_offset=0.0):
+        b = self.rb.Batch(l)
+        b.stroke_path(verbs, pts, self.rb.make_paint(spec, blend, True), width, 4.0, cap, "miter", ts, dash, dash_offset)
+        b.submit()
+        b.close()
 
     def draw_layer(self, dst, src, x, y, opacity=1.0, blend="source_over"):
         self.rb.draw_layer(dst, src, x, y, opacity, blend)

@@ -39,6 +39,7 @@ def _sig(name, res, args):
 
 _sig("orc_fill_path", _i, [_vp, _u32, _u32, _vp, _i, _vp, _i, C.POINTER(Paint), _i, f32p])
 _sig("orc_fill_paths", _i, [_vp, _u32, _u32, _i, _vp, _vp, _vp, _vp, _vp, _vp, f32p])
+_sig("orc_blit_coverage", _i, [_vp, _u32, _u32, _i, _vp, C.POINTER(Paint), f32p])
 _sig("orc_fill_rect", _i, [_vp, _u32, _u32, _f, _f, _f, _f, C.POINTER(Paint), f32p])
 _sig("orc_draw_pixmap", _i, [_vp, _u32, _u32, _i, _i, _vp, _u32, _u32, _f, _i, _i, f32p])
 _sig("orc_pixmap_fill", None, [_vp, _u32, _u32, _f, _f, _f, _f])
@@ -105,6 +106,13 @@ def fill_path(px, verbs, pts, paint, rule="nonzero", ts=IDENTITY):
     h, w = px.shape[:2]
     return lib.orc_fill_path(px.ctypes.data, w, h, v.ctypes.data, len(v), p.ctypes.data, len(p), C.byref(paint),
                              1 if rule == "evenodd" else 0, ts_arr(ts))
+
+
+def blit_coverage(px, blits, paint, ts=IDENTITY):
+    """blits: (n, 3) int32 {x, y, alpha}, blended in order."""
+    b = np.ascontiguousarray(blits, dtype=np.int32).reshape(-1, 3)
+    h, w = px.shape[:2]
+    return lib.orc_blit_coverage(px.ctypes.data, w, h, len(b), b.ctypes.data, C.byref(paint), ts_arr(ts))
 
 
 def fill_rect(px, x, y, rw, rh, paint, ts=IDENTITY):

@@ -1284,7 +1284,11 @@ class Renderer:
                 return max(v) + min(v) / 2.0
 
             if fast_len(v0) <= 1.0 and fast_len(v1) <= 1.0:
-                raise Unsupported("hairline stroke")
+                paint = self.resolve_paint(s["paint"], s.get("opacity", 1.0), ts)
+                if paint is not None:
+                    self.be.stroke_hairline(layer, n["verbs"], n["pts"], paint, ts, blend, s["width"], s["cap"],
+                                            s.get("dash"), s.get("dash_offset", 0.0))
+                return
         src_verbs, src_pts = n["verbs"], n["pts"]
         if s.get("dash"):
             import resvg_b200 as rb

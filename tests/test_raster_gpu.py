@@ -345,6 +345,43 @@ def test_bench_scene_bulk_api_matches_oracle(ctx, split, monkeypatch):
     assert (got != want).any(axis=-1).mean() < 0.02
 
 
+def test_hairline_strokes_in_painters_order(ctx):
+    """Strokes tiny-skia treats as hairlines (anti-aliased, transformed width <= 1 px) interleaved with ordinary fills:
+    the library must cut the batch into fill runs and hairline runs and keep painter's order.  Checked against the
+    oracle back end (same host walker, oracle blending), lowp exactly."""
+    import resvg_b200 as rb
+    from tests.backends import OracleBackend
+
+    w, h = 260, 200
+    rng = SplitMix64(4711)
+    ob = OracleBackend()
+    want = np.zeros((h, w, 4), np.uint8)
+    l = ctx.layer(w, h)
+    b = rb.Batch(l)
+    caps = ["butt", "round", "square"]
+    n_hair = 0
+    for i in range(90):
+        cx, cy, r = rng.uniform(-10, w + 10), rng.uniform(-10, h + 10), rng.log_uniform(6, 120)
+        verbs, pts = random_path(rng, cx, cy, r)
+        if i % 2:
+            verbs = verbs[:-1]  # open contour
+        spec = random_paint_spec(rng, cx, cy, r, solid=0.7, linear=0.3)
+        if i % 3 == 0:  # an ordinary fill between the hairlines
+            b.fill_path(verbs, pts, rb.make_paint(spec), "nonzero")
+            R.fill_path(want, verbs, pts, R.make_paint(spec), "nonzero")
+            continue
+        ts = [(1.0, 0.0, 0.0, 1.0, 0.0, 0.0), (0.6, 0.1, -0.2, 0.7, 4.0, 3.0), (1.4, 0.0, 0.0, 0.5, -3.0, 9.0)][i % 3]
+        width = rng.uniform(0.05, 0.6)
+        cap = caps[i % 3]
+        dash, off = ([7.0, 4.0], 2.0) if i % 5 == 0 else (None, 0.0)
+        b.stroke_path(verbs, pts, rb.make_paint(spec), width, 4.0, cap, "miter", ts, dash, off)
+        ob.stroke_hairline(want, verbs, pts, spec, ts, "source_over", width, cap, dash, off)
+        n_hair += 1
+    assert n_hair > 40
+    b.submit()
+    assert_exact(l.download(), want, "hairlines")
+
+
 def test_batch_dashed_strokes(ctx):
     """stroke_path with a dash array: dash (tiny_skia_path::Path::dash) -> stroke -> fill inside the batch builder must
     equal the same host steps done one by one and filled by the oracle; rejected dash lists leave the stroke solid."""
