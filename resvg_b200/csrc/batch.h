@@ -75,6 +75,7 @@ struct BatchLayout {
     size_t n_curves = 0, n_slots = 0;
     int tiles_x = 0;
     bool wide = false; // some draw may reach |winding| > 127: use k_raster_tiles_wide
+    bool has_hair = false; // some draw is a hairline stroke (its "edges" are blits)
     // warp-tile path (k_raster_warp): device-built structures, sizes known on the host
     int wtiles_x = 0, wtiles_y = 0;
     size_t n_row_off = 0;   // entries of row_off: sum over draws of (n_rows + 1)
@@ -108,6 +109,9 @@ struct rb_batch {
     uint8_t *dev_scratch = nullptr; // row lists + warp-tile bins (device-built)
     void *host_block = nullptr; // host-only batches: malloc'ed copy of the block
 };
+
+// rb_batch_host_build: the range holds hairline strokes the chosen builder cannot draw inline (internal status).
+enum { RB_NEEDS_RUN_SPLIT = 104 };
 
 // Staging allocator: returns `bytes` of host memory the block is assembled in (pinned, owned by the context; or
 // malloc'ed for host-only batches).

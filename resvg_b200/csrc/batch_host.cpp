@@ -177,10 +177,12 @@ struct Worker {
     std::vector<int32_t> ends;
     std::vector<rbh::Pt> tmp, spts, bpts;
     std::vector<uint8_t> dverbs;
-    std::vector<float> dpts;
+    std::vector<float> dpts, hstops;
+    std::vector<rbh::HairBlit> hblits;
+    std::vector<uint32_t> hrank;
     std::vector<uint8_t> sverbs;
-    bool wide = false;
-    void reset() { edges.clear(); draws.clear(); paints.clear(); stops.clear(); curves.clear(); wide = false; }
+    bool wide = false, skipped_hair = false, has_hair = false;
+    void reset() { edges.clear(); draws.clear(); paints.clear(); stops.clear(); curves.clear(); wide = false; skipped_hair = false; has_hair = false; }
 };
 
 std::mutex g_pool_mu;
@@ -302,6 +304,27 @@ DrawRef resolve_draw(const rb_batch *b, size_t i)
 
 } // namespace
 
+// painter.rs stroke_path, hairline branch: coverage < 1 is folded into the paint's alpha when the blend mode pre-scales
+// coverage ("the old technique"): scale = (coverage * 256) as i32; alpha' = (255 * scale) >> 8;
+// shader.apply_opacity(alpha' / 255).  `scaled` receives the modified gradient stops when there are any.
+static void hairline_modulate_paint(rb_paint *paint, float coverage, std::vector<float> &scaled)
+{
+    if (coverage == 1.0f) return;
+    const int m = paint->blend_mode;
+    const bool pre_scales = m == 2 || m == 4 || m == 12 || m == 8 || m == 9 || m == 3 || m == 11;
+    if (!pre_scales) return;
+    const int scale = (int)(coverage * 256.0f);
+    const float opacity = (float)((255 * scale) >> 8) / 255.0f;
+    auto mul = [&](float a) { return std::min(std::max(a * opacity, 0.0f), 1.0f); };
+    if (paint->shader == 0) paint->color[3] = mul(paint->color[3]);
+    else if (paint->shader == 3) paint->opacity = mul(paint->opacity);
+    else if (paint->stops && paint->n_stops > 0) {
+        scaled.assign(paint->stops, paint->stops + (size_t)paint->n_stops * 5);
+        for (int k = 0; k < paint->n_stops; k++) scaled[(size_t)k * 5 + 4] = mul(scaled[(size_t)k * 5 + 4]);
+        paint->stops = scaled.data();
+    }
+}
+
 bool rb_batch_draw_is_hairline(const rb_batch *b, size_t i)
 {
     if (b->n_hair == 0) return false;
@@ -344,26 +367,9 @@ int rb_batch_hair_build(const rb_batch *b, size_t begin, size_t end, int W, int 
         }
         dev.assign(pts, pts + n_pts);
         rbh::map_points(d.ctm, dev.data(), n_pts);
-        // coverage < 1 is folded into the paint's alpha when the blend mode pre-scales coverage (painter.rs: "the old
-        // technique"): scale = (coverage * 256) as i32; alpha' = (255 * scale) >> 8; shader.apply_opacity(alpha' / 255)
         rb_paint paint = d.paint;
         paint.stops = d.stops;
-        if (coverage != 1.0f) {
-            const int m = paint.blend_mode;
-            const bool pre_scales = m == 2 || m == 4 || m == 12 || m == 8 || m == 9 || m == 3 || m == 11;
-            if (pre_scales) {
-                const int scale = (int)(coverage * 256.0f);
-                const float opacity = (float)((255 * scale) >> 8) / 255.0f;
-                if (paint.shader == 0) paint.color[3] = std::min(std::max(paint.color[3] * opacity, 0.0f), 1.0f);
-                else if (paint.shader == 3) paint.opacity = std::min(std::max(paint.opacity * opacity, 0.0f), 1.0f);
-                else if (paint.stops && paint.n_stops > 0) {
-                    stops_scaled.assign(paint.stops, paint.stops + (size_t)paint.n_stops * 5);
-                    for (int k = 0; k < paint.n_stops; k++)
-                        stops_scaled[(size_t)k * 5 + 4] = std::min(std::max(stops_scaled[(size_t)k * 5 + 4] * opacity, 0.0f), 1.0f);
-                    paint.stops = stops_scaled.data();
-                }
-            }
-        }
+        hairline_modulate_paint(&paint, coverage, stops_scaled);
         for (int ty = 0; ty < H; ty += kMaxDim) {
             for (int tx = 0; tx < W; tx += kMaxDim) {
                 const int tw = std::min(W - tx, kMaxDim), th = std::min(H - ty, kMaxDim);
@@ -425,7 +431,8 @@ bool chains_may_exceed_packed_winding(std::vector<int32_t> &iv)
     return worst >= 128;
 }
 
-void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool mask_target, bool items, Worker *out, ChunkInfo *ci)
+void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool mask_target, bool items, bool hair_inline, Worker *out,
+                 ChunkInfo *ci)
 {
     ci->c0 = out->curves.size();
     ci->e0 = out->edges.size();
@@ -478,8 +485,100 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
         const RecordedDraw &r = *rp;
         int n_verbs = (int)r.n_verbs, n_pts = (int)r.n_pts, rule = r.rule;
         if (r.is_stroke && b->n_hair) {
-            rb_stroke sk = r.stroke;
-            if (rb_hairline_coverage(r.paint, sk, r.ctm) >= 0.0f) continue; // hairlines are drawn by their own pass
+            const float coverage = rb_hairline_coverage(r.paint, r.stroke, r.ctm);
+            if (coverage >= 0.0f) {
+                // A hairline stroke: not scan-converted.  Its ordered blits become the draw's "edge list" (k_row_lists keeps
+                // their order per tile row through the rank stored with each), and the tile kernel applies them one by one.
+                if (mask_target) continue;
+                if (!hair_inline) { out->skipped_hair = true; continue; } // the caller draws them in separate passes
+                if (r.stroke.n_dash > 0) {
+                    const float *da = sp.bulk < 0 ? b->dashes.data() + r.dash_off : r.stroke.dash_array;
+                    bool valid = false;
+                    int dst_ = da ? rb_path_dash_into(verbs, n_verbs, &rpts[0].x, n_pts, da, r.stroke.n_dash, r.stroke.dash_offset,
+                                                      resolution_scale(r.ctm), out->dverbs, out->dpts, &valid)
+                                  : RB_ERR_INVALID;
+                    if (valid) {
+                        if (dst_ != RB_OK) continue;
+                        verbs = out->dverbs.data();
+                        n_verbs = (int)out->dverbs.size();
+                        rpts = reinterpret_cast<const rbh::Pt *>(out->dpts.data());
+                        n_pts = (int)(out->dpts.size() / 2);
+                    }
+                }
+                out->spts.assign(rpts, rpts + n_pts);
+                rbh::map_points(r.ctm, out->spts.data(), n_pts);
+                rb_paint hp = r.paint;
+                hp.stops = stops_src;
+                hairline_modulate_paint(&hp, coverage, out->hstops);
+                for (int ty = 0; ty < H; ty += kMaxDim) {
+                    for (int tx = 0; tx < W; tx += kMaxDim) {
+                        const int tw = std::min(W - tx, kMaxDim), th = std::min(H - ty, kMaxDim);
+                        const rbh::Pt *p = out->spts.data();
+                        rbh::Xform ctm = r.ctm;
+                        if (tx || ty) {
+                            out->tmp = out->spts;
+                            rbh::Xform tr;
+                            tr.tx = -(float)tx;
+                            tr.ty = -(float)ty;
+                            rbh::map_points(tr, out->tmp.data(), n_pts);
+                            p = out->tmp.data();
+                            ctm = rbh::post_concat(ctm, tr);
+                        }
+                        out->hblits.clear();
+                        rbh::hairline_blits(verbs, n_verbs, &p[0].x, n_pts, r.stroke.cap, tw, th, out->hblits);
+                        const size_t nb = out->hblits.size();
+                        if (nb == 0 || nb >= (1u << 28)) continue;
+                        int x0 = INT32_MAX, y0 = INT32_MAX, x1 = INT32_MIN, y1 = INT32_MIN;
+                        for (const rbh::HairBlit &hb : out->hblits) {
+                            x0 = std::min(x0, hb.x); x1 = std::max(x1, hb.x);
+                            y0 = std::min(y0, hb.y); y1 = std::max(y1, hb.y);
+                        }
+                        DevDraw d;
+                        memset(&d, 0, sizeof(d));
+                        d.ox = tx; d.oy = ty;
+                        d.sx = x0; d.sy = y0; d.sw = x1 - x0 + 1; d.sh = y1 - y0 + 1;
+                        d.shift = 2;
+                        d.rule = 2; // hairline
+                        DevPaint P;
+                        const size_t s_before = out->stops.size();
+                        if (!rbh::prepare_paint(&hp, ctm, &P, out->stops)) continue;
+                        if (out->stops.size() != s_before) P.stop_off = (uint32_t)(P.stop_off - ci->s0);
+                        d.paint = (uint32_t)(out->paints.size() - ci->p0);
+                        out->paints.push_back(P);
+                        const int r0 = (ty + y0) >> 3, r1 = (ty + y1) >> 3, nr = r1 - r0 + 1;
+                        const int c0 = (tx + x0) / 32, c1 = (tx + x1) / 32;
+                        out->hrank.assign((size_t)nr, 0u);
+                        const size_t eo = out->edges.size();
+                        out->edges.resize(eo + nb);
+                        DevEdge *dst = out->edges.data() + eo;
+                        for (size_t k = 0; k < nb; k++) {
+                            const rbh::HairBlit &hb = out->hblits[k];
+                            DevEdge e; // a blit in an edge-sized record: layer pixel, coverage, rank inside its tile row
+                            e.x = (int32_t)((uint32_t)(hb.x + tx) | ((uint32_t)(hb.y + ty) << 16));
+                            e.dx = (int32_t)hb.alpha;
+                            e.ypack = out->hrank[(size_t)(((ty + hb.y) >> 3) - r0)]++;
+                            e.meta = 0;
+                            dst[k] = e;
+                        }
+                        d.edge_off = items ? (uint32_t)ci->n_slots : (uint32_t)(eo - ci->e0);
+                        d.edge_cnt = 0;
+                        d.line_off = (uint32_t)(eo - ci->e0);
+                        d.line_cnt = (uint32_t)nb;
+                        d.r0 = (uint32_t)r0;
+                        d.n_rows = (uint32_t)nr;
+                        d.list_off = (uint32_t)ci->n_list;
+                        d.row_base = (uint32_t)ci->n_row_off;
+                        d.list_cap = (uint32_t)nb;
+                        ci->n_list += nb;
+                        ci->n_row_off += (size_t)nr + 1;
+                        ci->n_row_ent += (size_t)nr;
+                        ci->n_wpairs += (size_t)nr * (size_t)(c1 - c0 + 1);
+                        out->draws.push_back(d);
+                        out->has_hair = true;
+                    }
+                }
+                continue;
+            }
         }
         if (r.is_stroke) {
             // stroke_path: the outline is computed in local coordinates, then filled (Winding) under the transform
@@ -682,13 +781,17 @@ int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threa
         for (auto &w : workers) w->reset();
         parallel_for(nt, n_chunks, [&](size_t c, int t) {
             chunks[c].worker = t;
-            build_chunk(b, begin + c * kChunk, begin + std::min(n, (c + 1) * kChunk), W, H, mask_target, items, workers[(size_t)t].get(), &chunks[c]);
+            build_chunk(b, begin + c * kChunk, begin + std::min(n, (c + 1) * kChunk), W, H, mask_target, items, /*hair_inline=*/items,
+                        workers[(size_t)t].get(), &chunks[c]);
         });
         any_wide = false;
         for (auto &w : workers) any_wide = any_wide || w->wide;
         if (items && any_wide) { items = false; continue; }
         break;
     }
+    // hairline strokes are only drawn inline by the tile kernel fed with items; with the fallback builder the caller has
+    // to cut the batch into fill runs and hairline runs (rb_batch_submit does)
+    for (auto &w : workers) if (w->skipped_hair) return RB_NEEDS_RUN_SPLIT;
     b->phases[0] = us_since(t0);
 #ifdef RB_HOST_PROFILE
     fprintf(stderr, "[host profile] Mcycles: stroke %.0f build_draw %.0f pack %.0f\n", g_prof[0].load() / 1e6, g_prof[1].load() / 1e6, g_prof[2].load() / 1e6);
@@ -707,6 +810,7 @@ int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threa
         L.n_curves += c.nc; L.n_slots += c.n_slots;
     }
     L.wide = any_wide || g_force_wide;
+    for (auto &w : workers) L.has_hair = L.has_hair || w->has_hair;
     if (L.n_slots > 0xfffffff0ull) return RB_ERR_UNSUPPORTED;
     if (L.n_draws == 0) return RB_OK;
     if (L.n_edges > 0xfffffff0ull || L.n_list > 0xfffffff0ull || L.n_wpairs > 0xfffffff0ull) return RB_ERR_UNSUPPORTED;
@@ -798,6 +902,7 @@ int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threa
                 d.curve_off += (uint32_t)c.gc;
             } else {
                 d.edge_off += (uint32_t)c.ge;
+                d.line_off += (uint32_t)c.ge; // hairline draws keep their blits in the edge array in this mode too
             }
             d.paint += (uint32_t)c.gp;
             d.list_off += (uint32_t)c.g_list;

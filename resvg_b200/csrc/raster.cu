@@ -1074,6 +1074,7 @@ static int batch_prepare_range(rb_batch *b, int32_t n_threads, size_t begin, siz
     StageReq req{ctx, RB_OK};
     int st = rb_batch_host_build(b, W, H, mask_target, n_threads, stage_pinned, &req, &blk, begin, end);
     if (req.status != RB_OK) return req.status;
+    if (st == RB_NEEDS_RUN_SPLIT) return st;
     if (st != RB_OK) return rb_fail(ctx, st, "batch host build failed");
     if (!blk || b->lay.n_draws == 0) return RB_OK;
     uint8_t *dev = nullptr;
@@ -1091,9 +1092,11 @@ static int batch_prepare_range(rb_batch *b, int32_t n_threads, size_t begin, siz
 
 extern "C" int rb_batch_prepare(rb_batch *b, int32_t n_threads)
 {
-    // the resident prepare / run split covers scan-converted draws only; hairline strokes need rb_batch_submit
-    if (b && b->n_hair) return rb_fail(batch_ctx(b), RB_ERR_UNSUPPORTED, "rb_batch_prepare: the batch holds hairline strokes, use rb_batch_submit");
-    return batch_prepare_range(b, n_threads, 0, 0);
+    int st = batch_prepare_range(b, n_threads, 0, 0);
+    // hairline strokes + the fallback builder: only rb_batch_submit can interleave the two kinds of passes
+    if (st == RB_NEEDS_RUN_SPLIT)
+        return rb_fail(batch_ctx(b), RB_ERR_UNSUPPORTED, "rb_batch_prepare: hairline strokes in a batch that needs the fallback builder, use rb_batch_submit");
+    return st;
 }
 
 static int batch_run(rb_batch *b, unsigned long long *px_stats);
@@ -1180,12 +1183,12 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
         RB_LAUNCHED(ctx, "bin_tiles");
         RB_CUDA(ctx, cudaEventRecord(ctx->ev_run[1], ctx->stream));
         const unsigned grid = (n_wtiles + WT_WARPS - 1) / WT_WARPS;
-        if (mask_target)
-            k_raster_warp<true><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(target, W, H, L.wtiles_x, n_wtiles, tile_off, tile_pairs, d_draws, row_off,
-                row_edges, d_edges, (const DevPaint *)(b->dev + L.o_paints), (const DevStop *)(b->dev + L.o_stops), px_stats);
-        else
-            k_raster_warp<false><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(target, W, H, L.wtiles_x, n_wtiles, tile_off, tile_pairs, d_draws, row_off,
-                row_edges, d_edges, (const DevPaint *)(b->dev + L.o_paints), (const DevStop *)(b->dev + L.o_stops), px_stats);
+#define RB_WARP_ARGS target, W, H, L.wtiles_x, n_wtiles, tile_off, tile_pairs, d_draws, row_off, row_edges, d_edges,                   \
+    (const DevPaint *)(b->dev + L.o_paints), (const DevStop *)(b->dev + L.o_stops), px_stats
+        if (mask_target) k_raster_warp<true, false><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
+        else if (L.has_hair) k_raster_warp<false, true><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
+        else k_raster_warp<false, false><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
+#undef RB_WARP_ARGS
         RB_LAUNCHED(ctx, "raster_warp");
         RB_CUDA(ctx, cudaEventRecord(ctx->ev_run[2], ctx->stream));
         return RB_OK;
@@ -1272,7 +1275,7 @@ static int hair_run(rb_batch *b, size_t lo, size_t hi)
 
 // Large batches are submitted in a few consecutive parts (painter's order is kept: part k + 1 is rasterised after part
 // k on the same stream), so the GPU works on one part while the host threads build the edges of the next.
-static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t last, uint64_t total[6]);
+static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t last, uint64_t total[6], size_t *stopped_at);
 
 // Hairline strokes are not scan-converted: the batch is cut into runs of ordinary draws (tile kernel) and runs of
 // hairlines (k_hair_blits), executed in painter's order on the context's stream.
@@ -1281,14 +1284,18 @@ extern "C" int rb_batch_submit(rb_batch *b, int32_t n_threads)
     if (!b) return RB_ERR_INVALID;
     uint64_t total[6] = {0, 0, 0, 0, 0, 0};
     int st = RB_OK;
-    if (b->n_hair == 0) st = submit_fill_run(b, n_threads, 0, b->n_total, total);
-    else {
-        size_t i = 0;
+    // Hairline strokes ride along as draws of their own kind (their blits are applied by the tile kernel), except with
+    // the any-winding fallback kernel, which does not know them: then the batch is cut into fill runs and hairline runs.
+    size_t resume = 0;
+    st = submit_fill_run(b, n_threads, 0, b->n_total, total, &resume);
+    if (st == RB_NEEDS_RUN_SPLIT) {
+        st = RB_OK;
+        size_t i = resume; // everything before was drawn already
         while (i < b->n_total && st == RB_OK) {
             const bool hair = rb_batch_draw_is_hairline(b, i);
             size_t j = i + 1;
             while (j < b->n_total && rb_batch_draw_is_hairline(b, j) == hair) j++;
-            st = hair ? hair_run(b, i, j) : submit_fill_run(b, n_threads, i, j, total);
+            st = hair ? hair_run(b, i, j) : submit_fill_run(b, n_threads, i, j, total, &resume);
             i = j;
         }
     }
@@ -1296,9 +1303,10 @@ extern "C" int rb_batch_submit(rb_batch *b, int32_t n_threads)
     return st;
 }
 
-static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t last, uint64_t total[6])
+static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t last, uint64_t total[6], size_t *stopped_at)
 {
     const size_t n = last - first;
+    *stopped_at = first;
     if (n == 0) return RB_OK;
     size_t parts = 1, split_from = 32768;
     if (const char *e = getenv("RB_SUBMIT_SPLIT_FROM")) split_from = (size_t)std::max(1, atoi(e)); // tests
@@ -1310,6 +1318,7 @@ static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t 
     for (size_t k = 0; k < parts && st == RB_OK; k++) {
         const size_t lo = first + n * k / parts, hi = first + n * (k + 1) / parts;
         if (lo >= hi) continue;
+        *stopped_at = lo;
         st = batch_prepare_range(b, n_threads, lo, hi);
         if (st == RB_OK) st = rb_batch_run(b);
         for (int i = 0; i < 6; i++) total[i] += b->stats[i];

@@ -151,6 +151,38 @@ k_row_lists(const DevDraw *__restrict__ draws, const DevEdge *__restrict__ lines
     const int tid = threadIdx.x, nr = (int)D.n_rows;
     DevEdge *E0 = edges + D.edge_off;
     for (int i = tid; i <= nr; i += RL_THREADS) { cnt[i] = 0; xlo[i] = INT_MAX; xhi[i] = INT_MIN; }
+    if (D.rule == 2) {
+        // A hairline stroke: `lines` holds its ordered blits (x | y << 16 in layer pixels, coverage, rank inside the tile
+        // row).  They are copied into the tile-row lists at row start + rank, i.e. in the order the walker produced them.
+        __syncthreads();
+        const DevEdge *B0 = lines + D.line_off;
+        for (uint32_t i = tid; i < D.line_cnt; i += RL_THREADS) {
+            const uint32_t xy = (uint32_t)B0[i].x;
+            const int r = (int)((xy >> 16) >> 3) - (int)D.r0, x = (int)(xy & 0xffffu);
+            atomicAdd(&cnt[r], 1u);
+            atomicMin(&xlo[r], x);
+            atomicMax(&xhi[r], x);
+        }
+        __syncthreads();
+        if (tid == 0) { // rows are few (a hairline is thin): a serial scan is fine
+            uint32_t run = 0;
+            for (int i = 0; i < nr; i++) { const uint32_t c = cnt[i]; cnt[i] = run; run += c; }
+            cnt[nr] = run;
+        }
+        __syncthreads();
+        for (int i = tid; i <= nr; i += RL_THREADS) row_off[D.row_base + i] = cnt[i];
+        for (int i = tid; i < nr; i += RL_THREADS)
+            row_cols[D.row_base + i] = xlo[i] <= xhi[i] ? ((uint32_t)(xlo[i] / WT_W) | ((uint32_t)(xhi[i] / WT_W) << 16)) : 1u;
+        DevEdge *out = row_edges + D.list_off;
+        for (uint32_t i = tid; i < D.line_cnt; i += RL_THREADS) {
+            const DevEdge B = B0[i];
+            const int r = (int)(((uint32_t)B.x >> 16) >> 3) - (int)D.r0;
+            const uint32_t at = cnt[r] + B.ypack;
+            if (at < D.list_cap) out[at] = B;
+            else atomicAdd(overflow, 1u);
+        }
+        return;
+    }
     if (items) {
         for (uint32_t i = tid; i < D.line_cnt; i += RL_THREADS) {
             DevEdge L = lines[D.line_off + i];
@@ -385,7 +417,8 @@ struct WarpDraw { // what one lane holds about one upcoming (draw, tile) pair
 #ifndef RW_MIN_CTAS
 #define RW_MIN_CTAS 6
 #endif
-template <bool MASK>
+// HAIR: the batch holds hairline strokes (a second instantiation, so that batches without them run the leaner code).
+template <bool MASK, bool HAIR>
 __global__ void __launch_bounds__(WT_WARPS * 32, RW_MIN_CTAS)
 k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_wtiles, const uint32_t *__restrict__ tile_off,
               const uint32_t *__restrict__ tile_pairs, const DevDraw *__restrict__ draws, const uint32_t *__restrict__ row_off,
@@ -456,7 +489,7 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
             mine.tlx = tlx; mine.tly = tly;
             mine.bounds = (uint32_t)py0 | ((uint32_t)py1 << 8) | ((uint32_t)pxa << 16) | ((uint32_t)pxb << 24);
             const bool valid = py0 < py1 && pxa < pxb;
-            mine.flags = (uint32_t)D.shift | ((uint32_t)D.rule << 4) | (valid ? 0x100u : 0u);
+            mine.flags = (uint32_t)D.shift | ((uint32_t)(D.rule & 1) << 4) | (valid ? 0x100u : 0u) | (D.rule == 2 ? 0x200u : 0u);
             mine.paint = D.paint;
             if (valid) {
                 const uint32_t r = (uint32_t)(Y0 >> 3) - D.r0;
@@ -489,6 +522,47 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
             if (!(flags & 0x100u) || n_list == 0) { if (px_stats && lane == 0) atomicAdd(px_stats + 3, 1ull); continue; }
             if (px_stats && lane == 0) atomicAdd(px_stats + 6, (unsigned long long)n_list);
             const int tlx = __shfl_sync(0xffffffffu, mine.tlx, k), tly = __shfl_sync(0xffffffffu, mine.tly, k);
+            if (HAIR && (flags & 0x200u)) {
+                // ---- hairline stroke: apply the row's blits that fall into this tile, one after the other -----------------
+                if (!MASK) {
+                    const DevPaint &P = paints[paint_idx];
+#pragma unroll 1
+                    for (uint32_t cb = 0; cb < n_list; cb += 32) {
+                        if (cb) {
+                            E.ypack = 0xffffu;
+                            E.x = -1;
+                            if (cb + lane < n_list) E = row_edges[list_begin + cb + lane];
+                        }
+                        const bool have = cb + lane < n_list;
+                        const int bx = (int)((uint32_t)E.x & 0xffffu) - X0, by = (int)((uint32_t)E.x >> 16) - Y0;
+                        const bool hit = have && bx >= 0 && bx < WT_W && by >= 0 && by < WT_H;
+                        const uint32_t packed = (uint32_t)(bx & 31) | ((uint32_t)(by & 7) << 5) | ((uint32_t)E.dx << 8);
+                        uint32_t todo = __ballot_sync(0xffffffffu, hit);
+                        while (todo) {
+                            const int src = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const uint32_t v = __shfl_sync(0xffffffffu, packed, src);
+                            const int px_ = (int)(v & 31u), py_ = (int)((v >> 5) & 7u);
+                            if (lane == (py_ << 2 | px_ >> 3)) {
+                                const uint32_t a = v >> 8;
+                                const int lx = tlx + px_, ly = tly + py_;
+                                if (a == 255) n_full++; else n_partial++;
+                                switch (px_ & 7) {
+                                case 0: dst0 = blend_pixel(P, stops, dst0, a, lx, ly); break;
+                                case 1: dst1 = blend_pixel(P, stops, dst1, a, lx, ly); break;
+                                case 2: dst2 = blend_pixel(P, stops, dst2, a, lx, ly); break;
+                                case 3: dst3 = blend_pixel(P, stops, dst3, a, lx, ly); break;
+                                case 4: dst4 = blend_pixel(P, stops, dst4, a, lx, ly); break;
+                                case 5: dst5 = blend_pixel(P, stops, dst5, a, lx, ly); break;
+                                case 6: dst6 = blend_pixel(P, stops, dst6, a, lx, ly); break;
+                                default: dst7 = blend_pixel(P, stops, dst7, a, lx, ly); break;
+                                }
+                            }
+                        }
+                    }
+                }
+                continue;
+            }
             const uint32_t bounds = __shfl_sync(0xffffffffu, mine.bounds, k);
             const int py0 = (int)(bounds & 0xffu), py1 = (int)((bounds >> 8) & 0xffu);
             const int pxa = (int)((bounds >> 16) & 0xffu), pxb = (int)(bounds >> 24);

@@ -345,11 +345,14 @@ def test_bench_scene_bulk_api_matches_oracle(ctx, split, monkeypatch):
     assert (got != want).any(axis=-1).mean() < 0.02
 
 
-def test_hairline_strokes_in_painters_order(ctx):
-    """Strokes tiny-skia treats as hairlines (anti-aliased, transformed width <= 1 px) interleaved with ordinary fills:
-    the library must cut the batch into fill runs and hairline runs and keep painter's order.  Checked against the
-    oracle back end (same host walker, oracle blending), lowp exactly."""
+@pytest.mark.parametrize("mode", ["inline", "wide-kernel"])
+def test_hairline_strokes_in_painters_order(ctx, mode):
+    """Strokes tiny-skia treats as hairlines (anti-aliased, transformed width <= 1 px) interleaved with ordinary fills,
+    painter's order kept.  "inline": their blits are applied by the tile kernel as a draw kind of its own;
+    "wide-kernel": the fallback kernel does not know them, so the batch is cut into fill runs and hairline runs.
+    Checked against the oracle back end (same host walker, oracle blending), exactly."""
     import resvg_b200 as rb
+    from resvg_b200 import _ffi
     from tests.backends import OracleBackend
 
     w, h = 260, 200
@@ -378,8 +381,12 @@ def test_hairline_strokes_in_painters_order(ctx):
         ob.stroke_hairline(want, verbs, pts, spec, ts, "source_over", width, cap, dash, off)
         n_hair += 1
     assert n_hair > 40
-    b.submit()
-    assert_exact(l.download(), want, "hairlines")
+    _ffi.lib.rb_debug_force_wide_kernel(1 if mode == "wide-kernel" else 0)
+    try:
+        b.submit()
+    finally:
+        _ffi.lib.rb_debug_force_wide_kernel(0)
+    assert_exact(l.download(), want, f"hairlines ({mode})")
 
 
 def test_batch_dashed_strokes(ctx):
