@@ -95,14 +95,17 @@ def oracle_lib():
 
 
 def cpu_render_sample(R, scene, n_sample, canvas=None):
-    """Oracle (CPU restatement of the reference path) over the first n_sample draws; returns seconds of CPU work:
-    host stroking of the stroke draws (the same host stroker both arms use) + the oracle's fill of every draw."""
+    """Oracle (CPU restatement of the reference path) over the first n_sample draws; returns seconds of CPU work: host
+    dashing / stroking / hairline walking of the stroke draws (the same host geometry both arms use) + the oracle's
+    fill of every outline and its blend of every hairline blit, in painter's order."""
     import resvg_b200 as rb
     from resvg_b200 import scenes
     sub = scenes.subset(scene, n_sample)
     n = sub["n_paths"]
-    t_stroke = 0.0
+    w, h = scene["width"], scene["height"]
+    t_geom = 0.0
     sw = sub["stroke_width"]
+    hair = {}  # draw index -> (blits, modulated alpha)
     if (sw > 0).any():
         verbs, pts, voff, poff = [], [], [0], [0]
         caps, joins = ["butt", "round", "square"], ["miter", "miter-clip", "round", "bevel"]
@@ -114,9 +117,25 @@ def cpu_render_sample(R, scene, n_sample, canvas=None):
                 src = (v, p)
                 if "n_dash" in sub and sub["n_dash"][i] > 0:
                     src = rb.dash_path(v, p, sub["dash"][i][: sub["n_dash"][i]], 0.0, 1.0)
-                out = None if src is None else rb.stroke_path(src[0], src[1], float(sw[i]), float(sub["stroke_miter"][i]),
-                                                               caps[sub["stroke_cap"][i]], joins[sub["stroke_join"][i]], 1.0)
-                t_stroke += time.perf_counter() - t0
+                out = None
+                if src is not None and sub["anti_alias"][i] and sw[i] <= 1.0:
+                    # treat_as_hairline (identity transform: both mapped width vectors have length w)
+                    parts = []
+                    for ty in range(0, h, 8191):  # DrawTiler
+                        for tx in range(0, w, 8191):
+                            bl = rb.hairline_blits(src[0], src[1] - np.float32([tx, ty]), caps[sub["stroke_cap"][i]],
+                                                   min(w - tx, 8191), min(h - ty, 8191))
+                            if len(bl):
+                                bl[:, 0] += tx
+                                bl[:, 1] += ty
+                                parts.append(bl)
+                    scale = int(np.float32(sw[i]) * np.float32(256.0))
+                    hair[i] = (np.concatenate(parts) if parts else np.zeros((0, 3), np.int32),
+                               np.float32((255 * scale) >> 8) / np.float32(255.0) if sw[i] != 1.0 else np.float32(1.0))
+                elif src is not None:
+                    out = rb.stroke_path(src[0], src[1], float(sw[i]), float(sub["stroke_miter"][i]),
+                                         caps[sub["stroke_cap"][i]], joins[sub["stroke_join"][i]], 1.0)
+                t_geom += time.perf_counter() - t0
                 if out is None:
                     v, p = v[:0], p[:0]
                 else:
@@ -129,13 +148,28 @@ def cpu_render_sample(R, scene, n_sample, canvas=None):
         sub["verb_off"] = np.array(voff, np.uint32)
         sub["pt_off"] = np.array(poff, np.uint32)
     paints = scenes.to_paint_array(sub, R.Paint)
-    w, h = scene["width"], scene["height"]
     px = canvas if canvas is not None else np.zeros((h, w, 4), np.uint8)
+    psz = C.sizeof(R.Paint)
+    ident = R.ts_arr(R.IDENTITY)
+
+    def fill_run(a, b):
+        if b > a:
+            R.lib.orc_fill_paths(px.ctypes.data, w, h, b - a, sub["verb_off"].ctypes.data + 4 * a, sub["pt_off"].ctypes.data + 4 * a,
+                                 sub["verbs"].ctypes.data, sub["pts"].ctypes.data, C.addressof(paints) + psz * a,
+                                 sub["rules"].ctypes.data + a, ident)
+
     t0 = time.perf_counter()
-    R.lib.orc_fill_paths(px.ctypes.data, w, h, n, sub["verb_off"].ctypes.data, sub["pt_off"].ctypes.data,
-                         sub["verbs"].ctypes.data, sub["pts"].ctypes.data, C.addressof(paints), sub["rules"].ctypes.data,
-                         R.ts_arr(R.IDENTITY))
-    return time.perf_counter() - t0 + t_stroke
+    start = 0
+    for i in sorted(hair):
+        fill_run(start, i)
+        blits, opacity = hair[i]
+        if len(blits):
+            paint = paints[i]  # stroke draws are solid: Shader::apply_opacity scales the colour's alpha
+            paint.color[3] = float(min(max(np.float32(paint.color[3]) * opacity, np.float32(0)), np.float32(1)))
+            R.lib.orc_blit_coverage(px.ctypes.data, w, h, len(blits), blits.ctypes.data, C.byref(paint), ident)
+        start = i + 1
+    fill_run(start, n)
+    return time.perf_counter() - t0 + t_geom
 
 
 def kernel_table(rb, ctx, layer, W, H, peak, reps=3):
@@ -359,7 +393,7 @@ def main():
             "dtype": "u8/u16 fixed point + f32", "data": "synthetic",
             "config": {"workload": args.workload, "canvas": [W, H], "paths": n_paths, "draw_calls": int(n_draws_in),
                        "mix": "70% fill / 20% fill+stroke / 10% stroke; nonzero+evenodd; 50% solid / 30% linear / 20% radial; 95% AA",
-                       "stroke": "width log-U[1,16] px (hairlines <= 1 px are not implemented yet), miter/round/bevel joins, butt/round/square caps, 10% dashed (2-4 intervals U[2,32])",
+                       "stroke": "width log-U[0.5,16] px (<= 1 px: anti-aliased hairlines), miter/round/bevel joins, butt/round/square caps, 10% dashed (2-4 intervals U[2,32])",
                        "sharding": "one scene (document) per GPU, no collective",
                        "l2": "inputs (256 MiB canvas + %.0f MiB edges/bins) exceed the 126 MB L2" % (st["upload_bytes"] / 2**20),
                        "draws": st["draws"], "line_edges": st["edges"], "draw_tile_pairs": st["pairs"], "tiles": st["tiles"]},

@@ -547,19 +547,25 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
                         out->paints.push_back(P);
                         const int r0 = (ty + y0) >> 3, r1 = (ty + y1) >> 3, nr = r1 - r0 + 1;
                         const int c0 = (tx + x0) / 32, c1 = (tx + x1) / 32;
-                        out->hrank.assign((size_t)nr, 0u);
+                        // the draw's "tile rows" are its warp-tile CELLS (row-major over its bounding box), so that a tile
+                        // finds exactly its own blits; rank = order of the blit inside its cell
+                        const int ncols = c1 - c0 + 1;
+                        out->hrank.assign((size_t)nr * (size_t)ncols, 0u);
                         const size_t eo = out->edges.size();
                         out->edges.resize(eo + nb);
                         DevEdge *dst = out->edges.data() + eo;
                         for (size_t k = 0; k < nb; k++) {
                             const rbh::HairBlit &hb = out->hblits[k];
-                            DevEdge e; // a blit in an edge-sized record: layer pixel, coverage, rank inside its tile row
+                            const size_t cell = (size_t)(((ty + hb.y) >> 3) - r0) * (size_t)ncols + (size_t)(((tx + hb.x) >> 5) - c0);
+                            DevEdge e; // a blit in an edge-sized record: layer pixel, coverage, rank inside its cell, cell
                             e.x = (int32_t)((uint32_t)(hb.x + tx) | ((uint32_t)(hb.y + ty) << 16));
                             e.dx = (int32_t)hb.alpha;
-                            e.ypack = out->hrank[(size_t)(((ty + hb.y) >> 3) - r0)]++;
-                            e.meta = 0;
+                            e.ypack = out->hrank[cell]++;
+                            e.meta = (uint32_t)cell;
                             dst[k] = e;
                         }
+                        d.curve_off = (uint32_t)c0; // hairline draws: first cell column / cells per row
+                        d.curve_cnt = (uint32_t)ncols;
                         d.edge_off = items ? (uint32_t)ci->n_slots : (uint32_t)(eo - ci->e0);
                         d.edge_cnt = 0;
                         d.line_off = (uint32_t)(eo - ci->e0);
@@ -570,7 +576,7 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
                         d.row_base = (uint32_t)ci->n_row_off;
                         d.list_cap = (uint32_t)nb;
                         ci->n_list += nb;
-                        ci->n_row_off += (size_t)nr + 1;
+                        ci->n_row_off += (size_t)nr * (size_t)ncols + 1;
                         ci->n_row_ent += (size_t)nr;
                         ci->n_wpairs += (size_t)nr * (size_t)(c1 - c0 + 1);
                         out->draws.push_back(d);
@@ -899,7 +905,7 @@ int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threa
             if (L.items) {
                 d.edge_off += (uint32_t)c.g_slots;
                 d.line_off += (uint32_t)c.ge;
-                d.curve_off += (uint32_t)c.gc;
+                if (d.rule != 2) d.curve_off += (uint32_t)c.gc; // hairline draws keep their first cell column there
             } else {
                 d.edge_off += (uint32_t)c.ge;
                 d.line_off += (uint32_t)c.ge; // hairline draws keep their blits in the edge array in this mode too

@@ -152,32 +152,49 @@ k_row_lists(const DevDraw *__restrict__ draws, const DevEdge *__restrict__ lines
     DevEdge *E0 = edges + D.edge_off;
     for (int i = tid; i <= nr; i += RL_THREADS) { cnt[i] = 0; xlo[i] = INT_MAX; xhi[i] = INT_MIN; }
     if (D.rule == 2) {
-        // A hairline stroke: `lines` holds its ordered blits (x | y << 16 in layer pixels, coverage, rank inside the tile
-        // row).  They are copied into the tile-row lists at row start + rank, i.e. in the order the walker produced them.
+        // A hairline stroke: `lines` holds its ordered blits (x | y << 16 in layer pixels, coverage, rank inside its
+        // warp-tile cell, cell index).  The draw's list table has one entry per CELL of its bounding box (row-major,
+        // curve_cnt cells per row) instead of one per tile row; blits are copied to cell start + rank, i.e. in the
+        // order the walker produced them.
+        const uint32_t n_cells = D.n_rows * D.curve_cnt;
+        uint32_t *cell_off = row_off + D.row_base;
+        for (uint32_t i = tid; i <= n_cells; i += RL_THREADS) cell_off[i] = 0;
         __syncthreads();
         const DevEdge *B0 = lines + D.line_off;
         for (uint32_t i = tid; i < D.line_cnt; i += RL_THREADS) {
-            const uint32_t xy = (uint32_t)B0[i].x;
-            const int r = (int)((xy >> 16) >> 3) - (int)D.r0, x = (int)(xy & 0xffffu);
-            atomicAdd(&cnt[r], 1u);
+            const DevEdge B = B0[i];
+            const int r = (int)(((uint32_t)B.x >> 16) >> 3) - (int)D.r0, x = (int)((uint32_t)B.x & 0xffffu);
+            atomicAdd(&cell_off[B.meta], 1u);
             atomicMin(&xlo[r], x);
             atomicMax(&xhi[r], x);
         }
         __syncthreads();
-        if (tid == 0) { // rows are few (a hairline is thin): a serial scan is fine
-            uint32_t run = 0;
-            for (int i = 0; i < nr; i++) { const uint32_t c = cnt[i]; cnt[i] = run; run += c; }
-            cnt[nr] = run;
+        {
+            // exclusive scan of the cell counts (global memory; contiguous chunks per thread + warp shuffles)
+            const uint32_t per = (n_cells + RL_THREADS - 1) / RL_THREADS;
+            const uint32_t lo = min((uint32_t)tid * per, n_cells), hi = min(lo + per, n_cells);
+            uint32_t sum = 0;
+            for (uint32_t i = lo; i < hi; i++) sum += cell_off[i];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((tid & 31) >= d) incl += v;
+            }
+            if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+            __syncthreads();
+            uint32_t base = incl - sum;
+            for (int w = 0; w < (tid >> 5); w++) base += warp_tot[w];
+            for (uint32_t i = lo; i < hi; i++) { const uint32_t c = cell_off[i]; cell_off[i] = base; base += c; }
+            if (tid == RL_THREADS - 1) cell_off[n_cells] = base;
         }
         __syncthreads();
-        for (int i = tid; i <= nr; i += RL_THREADS) row_off[D.row_base + i] = cnt[i];
         for (int i = tid; i < nr; i += RL_THREADS)
             row_cols[D.row_base + i] = xlo[i] <= xhi[i] ? ((uint32_t)(xlo[i] / WT_W) | ((uint32_t)(xhi[i] / WT_W) << 16)) : 1u;
         DevEdge *out = row_edges + D.list_off;
         for (uint32_t i = tid; i < D.line_cnt; i += RL_THREADS) {
             const DevEdge B = B0[i];
-            const int r = (int)(((uint32_t)B.x >> 16) >> 3) - (int)D.r0;
-            const uint32_t at = cnt[r] + B.ypack;
+            const uint32_t at = cell_off[B.meta] + B.ypack;
             if (at < D.list_cap) out[at] = B;
             else atomicAdd(overflow, 1u);
         }
@@ -492,7 +509,8 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
             mine.flags = (uint32_t)D.shift | ((uint32_t)(D.rule & 1) << 4) | (valid ? 0x100u : 0u) | (D.rule == 2 ? 0x200u : 0u);
             mine.paint = D.paint;
             if (valid) {
-                const uint32_t r = (uint32_t)(Y0 >> 3) - D.r0;
+                uint32_t r = (uint32_t)(Y0 >> 3) - D.r0;
+                if (D.rule == 2) r = r * D.curve_cnt + ((uint32_t)(X0 >> 5) - D.curve_off); // hairline: its cell of the bounding box
                 const uint32_t lb = row_off[D.row_base + r], le = row_off[D.row_base + r + 1];
                 mine.list_begin = D.list_off + lb;
                 mine.n_list = le - lb;
@@ -525,41 +543,66 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
             if (HAIR && (flags & 0x200u)) {
                 // ---- hairline stroke: apply the row's blits that fall into this tile, one after the other -----------------
                 if (!MASK) {
+                    // Blits of one pixel must be applied in list order, different pixels are independent: every chunk of
+                    // 32 blits is dealt into per-owner-lane queues (order kept by ranking the lanes that share an owner),
+                    // then all owner lanes work through their queues at once.  The queues live in the (idle) wsum array.
                     const DevPaint &P = paints[paint_idx];
+                    const bool memset_ok = P.has_memset != 0;
+                    const uint32_t memset_color = P.memset_color;
+                    const bool solid_so = P.kind == 0 && P.lowp && P.blend == 3; // solid colour, SourceOver, u16 pipeline
+                    const uint32_t sr = P.solid16[0], sg = P.solid16[1], sb = P.solid16[2], sa = P.solid16[3];
+                    uint32_t *queue = reinterpret_cast<uint32_t *>(S.wsum); // [owner lane][32]
+                    int *qcnt = S.bd;
 #pragma unroll 1
                     for (uint32_t cb = 0; cb < n_list; cb += 32) {
                         if (cb) {
-                            E.ypack = 0xffffu;
                             E.x = -1;
                             if (cb + lane < n_list) E = row_edges[list_begin + cb + lane];
                         }
                         const bool have = cb + lane < n_list;
                         const int bx = (int)((uint32_t)E.x & 0xffffu) - X0, by = (int)((uint32_t)E.x >> 16) - Y0;
                         const bool hit = have && bx >= 0 && bx < WT_W && by >= 0 && by < WT_H;
-                        const uint32_t packed = (uint32_t)(bx & 31) | ((uint32_t)(by & 7) << 5) | ((uint32_t)E.dx << 8);
-                        uint32_t todo = __ballot_sync(0xffffffffu, hit);
-                        while (todo) {
-                            const int src = __ffs(todo) - 1;
-                            todo &= todo - 1;
-                            const uint32_t v = __shfl_sync(0xffffffffu, packed, src);
-                            const int px_ = (int)(v & 31u), py_ = (int)((v >> 5) & 7u);
-                            if (lane == (py_ << 2 | px_ >> 3)) {
-                                const uint32_t a = v >> 8;
-                                const int lx = tlx + px_, ly = tly + py_;
-                                if (a == 255) n_full++; else n_partial++;
-                                switch (px_ & 7) {
-                                case 0: dst0 = blend_pixel(P, stops, dst0, a, lx, ly); break;
-                                case 1: dst1 = blend_pixel(P, stops, dst1, a, lx, ly); break;
-                                case 2: dst2 = blend_pixel(P, stops, dst2, a, lx, ly); break;
-                                case 3: dst3 = blend_pixel(P, stops, dst3, a, lx, ly); break;
-                                case 4: dst4 = blend_pixel(P, stops, dst4, a, lx, ly); break;
-                                case 5: dst5 = blend_pixel(P, stops, dst5, a, lx, ly); break;
-                                case 6: dst6 = blend_pixel(P, stops, dst6, a, lx, ly); break;
-                                default: dst7 = blend_pixel(P, stops, dst7, a, lx, ly); break;
-                                }
+                        const uint32_t owner = hit ? (uint32_t)(by << 2 | bx >> 3) : 32u + (uint32_t)lane;
+                        const uint32_t same = __match_any_sync(0xffffffffu, owner);
+                        qcnt[lane] = 0;
+                        __syncwarp();
+                        if (hit) {
+                            const uint32_t rank = __popc(same & ((1u << lane) - 1u));
+                            queue[owner * 32 + rank] = (uint32_t)(bx & 7) | ((uint32_t)E.dx << 8);
+                            if (rank == 0) qcnt[owner] = __popc(same);
+                        }
+                        __syncwarp();
+                        const int mine_cnt = qcnt[lane];
+                        for (int i = 0; i < mine_cnt; i++) {
+                            const uint32_t v = queue[lane * 32 + i];
+                            queue[lane * 32 + i] = 0;
+                            const uint32_t qi = v & 7u, c = v >> 8;
+                            uint32_t d;
+                            switch (qi) {
+                            case 0: d = dst0; break; case 1: d = dst1; break; case 2: d = dst2; break; case 3: d = dst3; break;
+                            case 4: d = dst4; break; case 5: d = dst5; break; case 6: d = dst6; break; default: d = dst7; break;
+                            }
+                            if (c == 255 && memset_ok) { d = memset_color; n_full++; }
+                            else if (solid_so) {
+                                n_partial++;
+                                const uint32_t pr = c == 255 ? sr : div255(sr * c), pg = c == 255 ? sg : div255(sg * c);
+                                const uint32_t pb = c == 255 ? sb : div255(sb * c), pa = c == 255 ? sa : div255(sa * c);
+                                const uint32_t ia = 255 - pa;
+                                d = rb_pack((pr + div255(RB_R(d) * ia)) & 0xffu, (pg + div255(RB_G(d) * ia)) & 0xffu,
+                                            (pb + div255(RB_B(d) * ia)) & 0xffu, (pa + div255(RB_A(d) * ia)) & 0xffu);
+                            } else {
+                                n_partial++;
+                                d = blend_pixel(P, stops, d, c, tlx + 8 * pj + (int)qi, tly + prow);
+                            }
+                            switch (qi) {
+                            case 0: dst0 = d; break; case 1: dst1 = d; break; case 2: dst2 = d; break; case 3: dst3 = d; break;
+                            case 4: dst4 = d; break; case 5: dst5 = d; break; case 6: dst6 = d; break; default: dst7 = d; break;
                             }
                         }
+                        __syncwarp();
                     }
+                    qcnt[lane] = 0;
+                    __syncwarp();
                 }
                 continue;
             }

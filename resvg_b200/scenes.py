@@ -41,12 +41,11 @@ def _gather_ranges(off, idx):
 
 
 def paths_scene(width=8192, height=8192, n_paths=100_000, seed=0x5EED0002, rmin=8.0, rmax=256.0, strokes=True,
-                stroke_wmin=1.0, stroke_wmax=16.0, dashed=0.1):
+                stroke_wmin=0.5, stroke_wmax=16.0, dashed=0.1):
     """C2 'paths8k': n_paths random closed paths; 70 % are filled, 20 % filled then stroked, 10 % stroked only
     (strokes=True), a fraction `dashed` of the strokes with a dash array of 2-4 intervals U[2, 32] (an odd list is
     repeated, as usvg does).  The returned arrays hold one entry per DRAW (a filled+stroked path is two entries).  Stroke
-    width is log-uniform [stroke_wmin, stroke_wmax]; the default lower bound of 1 px keeps every stroke on the general
-    stroker path (tiny-skia's hairline special case for widths <= 1 px is not implemented yet)."""
+    width is log-uniform [stroke_wmin, stroke_wmax]; anti-aliased strokes of at most 1 px are hairlines for tiny-skia."""
     u = splitmix64_uniform(seed, n_paths * STREAM).reshape(n_paths, STREAM)
     cx = u[:, 0] * width
     cy = u[:, 1] * height
