@@ -345,6 +345,44 @@ def test_bench_scene_bulk_api_matches_oracle(ctx, split, monkeypatch):
     assert (got != want).any(axis=-1).mean() < 0.02
 
 
+def test_full_size_scene_is_independent_of_how_the_batch_is_cut(ctx, monkeypatch):
+    """BASELINE.json's full-size C2 scene (8192 x 8192, 120 k draws incl. strokes, dashes, hairlines): the image must not
+    depend on how rb_batch_submit cuts the batch into pipelined parts, nor on a resident prepare + run, and a second
+    run over the cleared layer must reproduce it bit for bit (the tile kernel has no order-dependent arithmetic)."""
+    import zlib
+
+    import resvg_b200 as rb
+    from resvg_b200 import _ffi, scenes
+
+    w = h = 8192
+    scene = scenes.paths_scene(w, h, 100_000, 0x5EED0002)
+    scene["paints"] = scenes.to_paint_array(scene, _ffi.Paint)
+    scene["strokes"] = scenes.to_stroke_array(scene, _ffi.Stroke)
+    l = ctx.layer(w, h)
+    pinned = rb.PinnedBuffer(w * h * 4)
+
+    def render(parts):
+        l.fill(0, 0, 0, 0)
+        b = rb.Batch(l)
+        b.fill_paths(scene)
+        if parts == 0:
+            b.prepare()
+            b.run()
+        else:
+            monkeypatch.setenv("RB_SUBMIT_PARTS", str(parts))
+            b.submit()
+        b.close()
+        l.download_ptr(pinned.array.ctypes.data)
+        return zlib.crc32(pinned.array), int(pinned.array[3::4][:: 4097].astype(np.int64).sum())
+
+    ref = render(1)
+    assert ref[1] > 0
+    for parts in (3, 8, 0, 1):
+        assert render(parts) == ref, f"parts={parts}"
+    pinned.close()
+    l.close()
+
+
 @pytest.mark.parametrize("mode", ["inline", "wide-kernel"])
 def test_hairline_strokes_in_painters_order(ctx, mode):
     """Strokes tiny-skia treats as hairlines (anti-aliased, transformed width <= 1 px) interleaved with ordinary fills,
