@@ -1,15 +1,15 @@
-// raster.cu — device half of the fill path: tile-binned, painter-ordered coverage + shade + blend.
+// raster.cu — device half of the fill path: the reference's pipeline arithmetic, the any-winding fallback kernel, the
+// batch upload / launch glue, layer compositing and masks.  The main tile kernel lives in raster_warp.cuh.
 //
 // Replaces tiny-skia's per-scanline edge walk + SuperBlitter + RasterPipelineBlitter
 // (scan/path.rs, scan/path_aa.rs, alpha_runs.rs, pipeline/{blitter,lowp,highp}.rs), reached from
 // crates/resvg/src/path.rs:73.  B200 design:
-//   * the layer is cut into 64x16-pixel tiles; one CTA owns one tile for the whole batch and keeps its
-//     destination pixels in REGISTERS (4 px/thread), so a tile is read from HBM once and written once no
-//     matter how many paths cover it (the reference re-reads/re-writes the destination for every path);
-//   * per draw, threads scatter each edge's per-sub-scanline crossing into a shared-memory histogram with
-//     shared atomics; the signed winding at every one of the 4x4 sub-samples is then a warp-shuffle prefix
-//     sum along the row, from which the reference's coverage value follows exactly (see coverage rules
-//     below), including its 64/64/64/63 full-pixel rule and the abutting-span exception;
+//   * the layer is cut into tiles (32x8 px per WARP in k_raster_warp, 64x16 px per CTA in the fallback); the owner
+//     keeps the tile's destination pixels in REGISTERS for a whole batch of draws, so a tile is read from HBM once
+//     and written once no matter how many paths cover it (the reference re-reads/re-writes it for every path);
+//   * per draw, edge crossings are scattered into shared memory and the signed winding of every one of the 4x4
+//     sub-samples follows by a prefix sum along the row, from which the reference's coverage value follows exactly
+//     (coverage rules below), including its 64/64/64/63 full-pixel rule and the abutting-span exception;
 //   * shading and blending are straight-line per-pixel code (u16 "lowp" or f32 "highp" arithmetic).
 //
 // Coverage rules restated from tiny-skia SuperBlitter::blit_h / AlphaRuns::add: on sub-scanline s a
@@ -705,283 +705,6 @@ k_raster_tiles_wide(void *__restrict__ target, int W, int H, int tiles_x, const 
 }
 
 
-// =================================================================================================
-// main kernel: packed winding histogram
-//
-// Per pixel row the four sub-scanlines share ONE 32-bit word per sub-sample position: a crossing on
-// sub-row s adds (+-1) << 8s.  The word is then the balanced base-256 number sum_s net_s * 256^s, and
-// because integer addition is linear, ONE warp-shuffle prefix sum over the raw words yields the packed
-// windings W_s(c) of all four sub-rows at once; adding 0x80808080 turns the balanced digits into plain
-// unsigned bytes W_s + 128 (valid while |W_s| <= 127 — the host routes batches that could exceed that to
-// k_raster_tiles_wide).  Byte-SIMD compares then give the 4x4 inside mask of each pixel.  Only the 4th
-// sub-row keeps separate up/down crossing counts (cnt3) for the abutting-span rule.
-// =================================================================================================
-constexpr int FAST_HIST = 2 * TH * ROW_POS;       // ints in one histogram buffer: wsum + cnt3
-constexpr int FAST_SMEM = 2 * FAST_HIST * 4;      // double buffered
-
-// coverage of one pixel from its 4 biased packed windings (positions 4p..4p+3)
-__device__ __forceinline__ uint32_t pixel_inside_counts(const uint32_t *b, bool evenodd)
-{
-    uint32_t sum4 = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        uint32_t m = evenodd ? (b[k] & 0x01010101u) : (__vcmpne4(b[k], 0x80808080u) & 0x01010101u);
-        sum4 += m;
-    }
-    return sum4; // byte s = number of inside sub-samples on sub-row s
-}
-
-template <bool MASK>
-__global__ void __launch_bounds__(RT_THREADS, 3)
-k_raster_tiles(void *__restrict__ target, int W, int H, int tiles_x, const uint32_t *__restrict__ tile_ids,
-               const uint32_t *__restrict__ tile_off, const uint32_t *__restrict__ tile_draws,
-               const DevDraw *__restrict__ draws, const DevEdge *__restrict__ edges, const DevPaint *__restrict__ paints,
-               const DevStop *__restrict__ stops, unsigned long long *__restrict__ px_stats)
-{
-    extern __shared__ int smem[];
-    __shared__ uint16_t s_list[2][RT_THREADS];
-    __shared__ int s_count[3]; // rotated: iteration n counts in [n % 3] and clears [(n + 1) % 3] before its barrier
-    // Two histogram buffers used alternately by successive draws, so the scan of one draw and the scatter of the
-    // next may overlap and a draw costs two block barriers instead of four.  Each buffer: wsum[TH][ROW_POS] packed
-    // nets of the 4 sub-rows (AA) / plain net (non-AA), then cnt3[TH][ROW_POS] (sub-row 3: low 16 bits downward
-    // crossings, high 16 upward).
-    int hbuf = 0, lbuf = 0, cbuf = 0;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t tile = tile_ids[blockIdx.x];
-    const int X0 = (int)(tile % (uint32_t)tiles_x) * TW, Y0 = (int)(tile / (uint32_t)tiles_x) * TH;
-
-    uint32_t dst[4]; // [row i][col j] -> dst[2*i + j]
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        int gy = Y0 + wid + 8 * (q >> 1), gx = X0 + 2 * lane + (q & 1);
-        uint32_t v = 0;
-        if (gy < H && gx < W) {
-            size_t o = (size_t)gy * W + gx;
-            v = MASK ? (uint32_t) reinterpret_cast<const uint8_t *>(target)[o] : reinterpret_cast<const uint32_t *>(target)[o];
-        }
-        dst[q] = v;
-    }
-    for (int i = tid; i < 2 * FAST_HIST / 4; i += RT_THREADS) reinterpret_cast<int4 *>(smem)[i] = make_int4(0, 0, 0, 0);
-    if (tid < 3) s_count[tid] = 0;
-    __syncthreads();
-
-    uint32_t n_partial = 0, n_full = 0;
-    const uint32_t d_begin = tile_off[tile], d_end = tile_off[tile + 1];
-    uint32_t next_draw = d_begin < d_end ? tile_draws[d_begin] : 0u;
-#pragma unroll 1
-    for (uint32_t di = d_begin; di < d_end; di++) {
-        const DevDraw D = draws[next_draw];
-        if (di + 1 < d_end) next_draw = tile_draws[di + 1]; // index prefetch: one dependent load less per draw
-        const int tlx = X0 - D.ox, tly = Y0 - D.oy;
-        const int py0 = max(0, D.sy - tly), py1 = min(TH, D.sy + D.sh - tly);
-        const int pxa = max(0, D.sx - tlx), pxb = min(TW, D.sx + D.sw - tlx);
-        if (py0 >= py1 || pxa >= pxb) continue;
-        const int sh = D.shift;
-        const int lo_pos = pxa << sh, hi_pos = pxb << sh;
-        const int sub_top = (tly + py0) << sh, sub_bot = (tly + py1) << sh;
-        const int row0 = tly << sh, col0 = tlx << sh;
-        const DevEdge *E0 = edges + D.edge_off;
-        int *wsum = smem + hbuf * FAST_HIST, *cnt3 = wsum + TH * ROW_POS;
-
-        // ---- edge pass ----------------------------------------------------------------------------
-        // (a) every thread tests one edge of a 256-edge chunk against the tile's sub-scanline range and the
-        //     survivors are compacted into s_list; (b) the (edge, sub-row) pairs of the survivors are spread
-        //     over all 256 threads, each evaluating x(y) = x + (y - first_y) * dx in closed form — so a long
-        //     edge costs the CTA ceil(rows / 256) steps instead of `rows` serial steps of one thread.
-        int did = 0;
-#pragma unroll 1
-        for (uint32_t chunk = 0; chunk < D.edge_cnt; chunk += RT_THREADS) {
-            const uint32_t e = chunk + tid;
-            const int cnext = cbuf == 2 ? 0 : cbuf + 1;
-            if (tid == 0) s_count[cnext] = 0; // last read two iterations ago; first touched after the next barrier
-            bool past = false;
-            if (e < D.edge_cnt) {
-                const uint32_t yp = E0[e].ypack;
-                const int fy = (int)(yp & 0xffffu), ly = (int)(yp >> 16);
-                past = fy >= sub_bot;
-                if (!past && ly >= sub_top) s_list[lbuf][atomicAdd(&s_count[cbuf], 1)] = (uint16_t)tid;
-            }
-            const int chunk_past = __syncthreads_and(past || e >= D.edge_cnt); // also publishes s_list
-            const int n_act = s_count[cbuf];
-            const uint16_t *list = s_list[lbuf];
-            lbuf ^= 1;
-            cbuf = cnext;
-            // one warp per surviving edge, lanes = consecutive sub-rows of that edge inside the tile
-#pragma unroll 1
-            for (int a = wid; a < n_act; a += RT_THREADS / 32) {
-                const DevEdge E = E0[chunk + list[a]];
-                const int fy = (int)(E.ypack & 0xffffu), ly = (int)(E.ypack >> 16);
-                const int ys = max(fy, sub_top), ye = min(ly, sub_bot - 1);
-                const bool up = (E.meta & 1u) != 0;
-#pragma unroll 1
-                for (int y = ys + lane; y <= ye; y += 32) {
-                    const uint32_t x = (uint32_t)E.x + (uint32_t)(y - fy) * (uint32_t)E.dx;
-                    const int r = (int)(x + 0x8000u) >> 16;
-                    const int pos = max(r - col0, lo_pos);
-                    if (pos >= hi_pos) continue;
-                    did = 1;
-                    const int rel = y - row0;
-                    if (sh == 2) {
-                        const int sr = rel & 3, idx = (rel >> 2) * ROW_POS + pos;
-                        const int one = 1 << (8 * sr);
-                        atomicAdd(wsum + idx, up ? -one : one);
-                        if (sr == 3) atomicAdd(cnt3 + idx, up ? 0x10000 : 1);
-                    } else {
-                        atomicAdd(wsum + rel * ROW_POS + pos, up ? -1 : 1);
-                    }
-                }
-            }
-            if (chunk_past) break; // edges are sorted by first_y: nothing further can reach this tile
-        }
-        if (!__syncthreads_or(did)) continue; // the draw's bounds overlap this tile but none of its spans do
-        hbuf ^= 1; // the next draw scatters into the other buffer while stragglers still scan this one
-
-        // ---- scan pass ----------------------------------------------------------------------------
-        uint32_t cov[4] = {0, 0, 0, 0};
-        const bool evenodd = D.rule != 0;
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const int prow = wid + 8 * i;
-            if (prow < py0 || prow >= py1) continue;
-            if (sh == 2) {
-                int4 *rp = reinterpret_cast<int4 *>(wsum + prow * ROW_POS + lane * 8);
-                const int4 a = rp[0], b = rp[1];
-                const int any = a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w;
-                if (!__any_sync(0xffffffffu, any != 0)) continue;
-                uint32_t wv[8] = {(uint32_t)a.x, (uint32_t)a.y, (uint32_t)a.z, (uint32_t)a.w,
-                                  (uint32_t)b.x, (uint32_t)b.y, (uint32_t)b.z, (uint32_t)b.w};
-#pragma unroll
-                for (int k = 1; k < 8; k++) wv[k] += wv[k - 1];
-                uint32_t incl = wv[7];
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += v;
-                }
-                const uint32_t base = incl - wv[7] + 0x80808080u;
-#pragma unroll
-                for (int k = 0; k < 8; k++) wv[k] += base; // biased: byte s = W_s + 128
-                if (any) { rp[0] = make_int4(0, 0, 0, 0); rp[1] = make_int4(0, 0, 0, 0); }
-                int4 *cp = reinterpret_cast<int4 *>(cnt3 + prow * ROW_POS + lane * 8);
-                const int4 ca = cp[0], cb = cp[1];
-                const int c3[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-                if (ca.x | ca.y | ca.z | ca.w | cb.x | cb.y | cb.z | cb.w) { cp[0] = make_int4(0, 0, 0, 0); cp[1] = make_int4(0, 0, 0, 0); }
-#pragma unroll
-                for (int p = 0; p < 2; p++) {
-                    const uint32_t sum4 = pixel_inside_counts(wv + 4 * p, evenodd);
-                    uint32_t c = 16u * __dp4a(sum4, 0x00010101u, 0u);
-                    const uint32_t n3 = sum4 >> 24;
-                    if (n3 == 4) {
-                        bool brk = false;
-#pragma unroll
-                        for (int k = 1; k < 4; k++) {
-                            const int ck = c3[4 * p + k];
-                            if (ck == 0) continue;
-                            if (evenodd) { brk = true; continue; }
-                            const int before = (int)(wv[4 * p + k - 1] >> 24) - 128, after = (int)(wv[4 * p + k] >> 24) - 128;
-                            if ((ck & 0xffff) && ((uint32_t)ck >> 16))
-                                brk = brk || exact_span_break(E0, D.edge_cnt, row0 + prow * 4 + 3, col0 + lane * 8 + 4 * p + k, before);
-                            else if ((before ^ after) < 0) brk = true;
-                        }
-                        c += brk ? 64u : 63u;
-                    } else c += 16u * n3;
-                    cov[2 * i + p] = min(c, 255u);
-                }
-            } else {
-                int2 *rp = reinterpret_cast<int2 *>(wsum + prow * ROW_POS + lane * 2);
-                const int2 a = *rp;
-                if (!__any_sync(0xffffffffu, (a.x | a.y) != 0)) continue;
-                int w0 = a.x, w1 = a.x + a.y;
-                int incl = w1;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    int v = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += v;
-                }
-                const int base = incl - w1;
-                w0 += base; w1 += base;
-                cov[2 * i] = (evenodd ? (w0 & 1) : (w0 != 0)) ? 255u : 0u;
-                cov[2 * i + 1] = (evenodd ? (w1 & 1) : (w1 != 0)) ? 255u : 0u;
-                if (a.x | a.y) *rp = make_int2(0, 0);
-            }
-        }
-        if (2 * lane >= pxb) { cov[0] = 0; cov[2] = 0; }
-        if (2 * lane + 1 >= pxb) { cov[1] = 0; cov[3] = 0; }
-
-        // ---- blend pass ---------------------------------------------------------------------------
-        if (cov[0] | cov[1] | cov[2] | cov[3]) {
-            if (MASK) {
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t c = cov[q];
-                    if (c == 255) dst[q] = 255;
-                    else if (c) dst[q] = div255(dst[q] * (255 - c) + 255u * c);
-                }
-            } else {
-                const DevPaint &P = paints[D.paint];
-                const bool memset_ok = P.has_memset != 0;
-                const uint32_t memset_color = P.memset_color;
-                // solid colour through the u16 pipeline with Source / SourceOver: the common case, kept inline
-                const bool solid_fast = P.kind == 0 && P.lowp && (P.blend == 1 || P.blend == 3);
-                const uint32_t sr = P.solid16[0], sg = P.solid16[1], sb = P.solid16[2], sa = P.solid16[3];
-                const bool src_over = P.blend == 3;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t c = cov[q];
-                    if (!c) continue;
-                    if (c == 255 && memset_ok) { dst[q] = memset_color; n_full++; continue; }
-                    n_partial++;
-                    if (solid_fast) {
-                        const uint32_t d = dst[q];
-                        uint32_t r, g, b2, a;
-                        if (src_over) { // scale_1_float (coverage folded into the source), then source_over
-                            const uint32_t pr = c == 255 ? sr : div255(sr * c), pg = c == 255 ? sg : div255(sg * c);
-                            const uint32_t pb = c == 255 ? sb : div255(sb * c), pa = c == 255 ? sa : div255(sa * c);
-                            const uint32_t ia = 255 - pa;
-                            r = pr + div255(RB_R(d) * ia); g = pg + div255(RB_G(d) * ia);
-                            b2 = pb + div255(RB_B(d) * ia); a = pa + div255(RB_A(d) * ia);
-                        } else {        // Source: lerp_1_float(dst, src, coverage)
-                            const uint32_t ic = 255 - c;
-                            r = div255(RB_R(d) * ic + sr * c); g = div255(RB_G(d) * ic + sg * c);
-                            b2 = div255(RB_B(d) * ic + sb * c); a = div255(RB_A(d) * ic + sa * c);
-                        }
-                        dst[q] = rb_pack(r & 0xffu, g & 0xffu, b2 & 0xffu, a & 0xffu);
-                    } else {
-                        dst[q] = blend_pixel(P, stops, dst[q], c, tlx + 2 * lane + (q & 1), tly + wid + 8 * (q >> 1));
-                    }
-                }
-            }
-        }
-    }
-
-    if (px_stats) {
-        n_partial = __reduce_add_sync(0xffffffffu, n_partial);
-        n_full = __reduce_add_sync(0xffffffffu, n_full);
-        if (lane == 0) {
-            atomicAdd(px_stats, (unsigned long long)n_partial);
-            atomicAdd(px_stats + 1, (unsigned long long)n_full);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        int gy = Y0 + wid + 8 * i, gx = X0 + 2 * lane;
-        if (gy >= H) continue;
-        size_t o = (size_t)gy * W + gx;
-        if (MASK) {
-            uint8_t *t = reinterpret_cast<uint8_t *>(target);
-            if (gx < W) t[o] = (uint8_t)dst[2 * i];
-            if (gx + 1 < W) t[o + 1] = (uint8_t)dst[2 * i + 1];
-        } else {
-            uint32_t *t = reinterpret_cast<uint32_t *>(target);
-            if (gx + 1 < W && (W & 1) == 0) *reinterpret_cast<uint2 *>(t + o) = make_uint2(dst[2 * i], dst[2 * i + 1]);
-            else {
-                if (gx < W) t[o] = dst[2 * i];
-                if (gx + 1 < W) t[o + 1] = dst[2 * i + 1];
-            }
-        }
-    }
-}
-
 #include "raster_warp.cuh"
 
 // =================================================================================================
@@ -1141,8 +864,6 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
     void *target = mask_target ? (void *)b->mask->d : (void *)b->layer->d;
     static bool attr_set = false;
     if (!attr_set) {
-        RB_CUDA(ctx, cudaFuncSetAttribute(k_raster_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM));
-        RB_CUDA(ctx, cudaFuncSetAttribute(k_raster_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM));
         RB_CUDA(ctx, cudaFuncSetAttribute(k_raster_tiles_wide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CNT_BYTES));
         RB_CUDA(ctx, cudaFuncSetAttribute(k_raster_tiles_wide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CNT_BYTES));
         attr_set = true;
@@ -1197,14 +918,9 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
 #define RB_RASTER_ARGS target, W, H, L.tiles_x, (const uint32_t *)(b->dev + L.o_tids), (const uint32_t *)(b->dev + L.o_toff), \
     (const uint32_t *)(b->dev + L.o_tdraws), (const DevDraw *)(b->dev + L.o_draws), (const DevEdge *)(b->dev + L.o_edges),    \
     (const DevPaint *)(b->dev + L.o_paints), (const DevStop *)(b->dev + L.o_stops), px_stats
-    const bool wide = true; // the packed 64x16 kernel is superseded by k_raster_warp; kept for A/B measurements
-    if (wide) {
-        if (mask_target) k_raster_tiles_wide<true><<<n_tile_ids, RT_THREADS, CNT_BYTES, ctx->stream>>>(RB_RASTER_ARGS);
-        else k_raster_tiles_wide<false><<<n_tile_ids, RT_THREADS, CNT_BYTES, ctx->stream>>>(RB_RASTER_ARGS);
-    } else {
-        if (mask_target) k_raster_tiles<true><<<n_tile_ids, RT_THREADS, FAST_SMEM, ctx->stream>>>(RB_RASTER_ARGS);
-        else k_raster_tiles<false><<<n_tile_ids, RT_THREADS, FAST_SMEM, ctx->stream>>>(RB_RASTER_ARGS);
-    }
+    // the any-winding fallback: CTA per 64x16 tile, host-expanded edges, host-built bins
+    if (mask_target) k_raster_tiles_wide<true><<<n_tile_ids, RT_THREADS, CNT_BYTES, ctx->stream>>>(RB_RASTER_ARGS);
+    else k_raster_tiles_wide<false><<<n_tile_ids, RT_THREADS, CNT_BYTES, ctx->stream>>>(RB_RASTER_ARGS);
 #undef RB_RASTER_ARGS
     RB_LAUNCHED(ctx, "raster_tiles");
     return RB_OK;
