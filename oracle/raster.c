@@ -1062,11 +1062,15 @@ static void fill_path_impl(const path_t *path, int fill_rule, irect clip, int32_
 static int path_bounds(const path_t *p, rectf *out)
 {
     if (p->n_pts == 0) return 0;
-    float l = p->pts[0].x, r = l, t = p->pts[0].y, b = t;
-    for (int i = 1; i < p->n_pts; i++) {
+    /* tiny_skia_path::Path cannot hold a non-finite point (Rect::from_points fails in PathBuilder::finish): such a
+     * path never reaches fill_path.  fmin/fmax would silently skip a NaN, so every point is tested. */
+    float l = p->pts[0].x, r = l, t = p->pts[0].y, b = t, probe = 0.0f;
+    for (int i = 0; i < p->n_pts; i++) {
         l = fminf(l, p->pts[i].x); r = fmaxf(r, p->pts[i].x);
         t = fminf(t, p->pts[i].y); b = fmaxf(b, p->pts[i].y);
+        probe += p->pts[i].x * 0.0f + p->pts[i].y * 0.0f; /* NaN as soon as one coordinate is NaN or infinite */
     }
+    if (!(probe == 0.0f)) return 0;
     if (!(isfinite(l) && isfinite(r) && isfinite(t) && isfinite(b))) return 0;
     out->l = l; out->t = t; out->r = r; out->b = b;
     return 1;

@@ -89,6 +89,7 @@ struct BatchLayout {
 enum { RB_PHASES = 6 };
 
 struct rb_batch {
+    rb_ctx *ctx = nullptr; // retained for the batch's lifetime: destroying it must not look at the (maybe gone) target
     rb_layer *layer = nullptr;
     rb_mask *mask = nullptr;
     int host_w = 0, host_h = 0; // host-only batches (rb_debug_batch_begin_host): no target, no upload

@@ -449,8 +449,12 @@ void hairline_blits(const uint8_t *verbs, int n_verbs, const float *points, int 
     Sink s{&out, clip_w, clip_h};
     Cull cull{false, R{0, 0, 0, 0}, R{0, 0, 0, 0}};
     {
-        float l = pts[0].x, t = pts[0].y, r = l, b = t;
-        for (int i = 1; i < n_pts; i++) { l = std::min(l, pts[i].x); t = std::min(t, pts[i].y); r = std::max(r, pts[i].x); b = std::max(b, pts[i].y); }
+        float l = pts[0].x, t = pts[0].y, r = l, b = t, probe = 0.0f;
+        for (int i = 0; i < n_pts; i++) {
+            l = std::min(l, pts[i].x); t = std::min(t, pts[i].y); r = std::max(r, pts[i].x); b = std::max(b, pts[i].y);
+            probe += pts[i].x * 0.0f + pts[i].y * 0.0f; // a Path never holds a non-finite point
+        }
+        if (!(probe == 0.0f)) return;
         if (!(std::isfinite(l) && std::isfinite(t) && std::isfinite(r) && std::isfinite(b))) return;
         const float o = cap == 0 ? 1.0f : 2.0f;
         const double fl = floor((double)l - o), ft = floor((double)t - o), cr = ceil((double)r + o), cb = ceil((double)b + o); // round_out

@@ -710,13 +710,14 @@ k_raster_tiles_wide(void *__restrict__ target, int W, int H, int tiles_x, const 
 // =================================================================================================
 // batch: upload + launch (recording, edge building and binning live in batch_host.cpp)
 // =================================================================================================
-static rb_ctx *batch_ctx(const rb_batch *b) { return b->mask ? b->mask->ctx : (b->layer ? b->layer->ctx : nullptr); }
+static rb_ctx *batch_ctx(const rb_batch *b) { return b->ctx ? b->ctx : (b->mask ? b->mask->ctx : (b->layer ? b->layer->ctx : nullptr)); }
 
 extern "C" int rb_batch_begin(rb_layer *target, rb_batch **out)
 {
     if (!target || !out) return RB_ERR_INVALID;
     rb_batch *b = new rb_batch();
     b->layer = target;
+    b->ctx = target->ctx;
     rb_ctx_retain(target->ctx);
     *out = b;
     return RB_OK;

@@ -617,11 +617,15 @@ static bool walk_path(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pt
                       Sink &sink, DrawGeom *g, IRect *ir_out, bool *inside_out)
 {
     if (n_pts == 0) return false;
-    float l = pts[0].x, r = l, t = pts[0].y, b = t;
-    for (int i = 1; i < n_pts; i++) {
+    // tiny_skia_path::Path cannot hold a non-finite point (PathBuilder::finish fails): such a path is never drawn.
+    // min / max would silently skip a NaN, so every point is probed.
+    float l = pts[0].x, r = l, t = pts[0].y, b = t, probe = 0.0f;
+    for (int i = 0; i < n_pts; i++) {
         l = std::min(l, pts[i].x); r = std::max(r, pts[i].x);
         t = std::min(t, pts[i].y); b = std::max(b, pts[i].y);
+        probe += pts[i].x * 0.0f + pts[i].y * 0.0f; // NaN as soon as one coordinate is NaN or infinite
     }
+    if (!(probe == 0.0f)) return false;
     if (!(std::isfinite(l) && std::isfinite(r) && std::isfinite(t) && std::isfinite(b))) return false;
     if (nearly_zero(r - l) || nearly_zero(b - t)) return false; // painter.rs: empty paths, h/v lines
     const IRect clip{0, 0, cw, ch};

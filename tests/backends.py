@@ -80,9 +80,14 @@ class OracleBackend:
                 st[:, 4] = [clamp(a) for a in st[:, 4]]
                 spec = dict(spec, stops=st)
         h, wpx = l.shape[:2]
-        blits = rb.hairline_blits(v, dev, cap, wpx, h)
-        if len(blits):
-            self.R.blit_coverage(l, blits, self.R.make_paint(spec, blend, True), ts)
+        paint = self.R.make_paint(spec, blend, True)
+        for ty in range(0, h, 8191):  # DrawTiler: the painter draws layers larger than 8191 px tile by tile
+            for tx in range(0, wpx, 8191):
+                blits = rb.hairline_blits(v, dev - np.float32([tx, ty]), cap, min(wpx - tx, 8191), min(h - ty, 8191))
+                if len(blits):
+                    blits[:, 0] += tx
+                    blits[:, 1] += ty
+                    self.R.blit_coverage(l, blits, paint, ts)
 
     def draw_layer(self, dst, src, x, y, opacity=1.0, blend="source_over"):
         self.R.draw_pixmap(dst, x, y, src, opacity, blend)
