@@ -211,6 +211,11 @@ int rb_batch_draw_paths(rb_batch *batch, int32_t n_paths, const uint32_t *verb_o
 int rb_batch_fill_paths(rb_batch *batch, int32_t n_paths, const uint32_t *verb_off, const uint32_t *point_off,
                         const uint8_t *verbs, const float *points, const rb_paint *paints, const uint8_t *fill_rules,
                         const float ts[6]);
+/* The draws recorded after this call are rendered as if the rectangle (x, y, w, h) of the target were a pixmap of its
+ * own (what resvg::render gets for one document): coordinates are relative to its origin, nothing is drawn outside it.
+ * One batch can thus render many small documents into one atlas layer (document-parallel thumbnailing, BASELINE
+ * config 5).  w = h = 0 restores the whole target. */
+int rb_batch_set_viewport(rb_batch *batch, int32_t x, int32_t y, uint32_t w, uint32_t h);
 /* Builds edges on host threads (n_threads <= 0: all cores), uploads, launches, frees the device copy. */
 int rb_batch_submit(rb_batch *batch, int32_t n_threads);
 /* Split form: prepare = host edge build + binning + upload (device copy stays resident in the batch);

@@ -140,6 +140,7 @@ SIGNATURES = {
     "rb_debug_build_edges": (_i, [_vp, C.c_int32, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, f32p, _vp, _vp,
                                   C.c_int32, _vp]),
     "rb_ctx_last_run_ms": (_i, [_vp, _vp]),
+    "rb_batch_set_viewport": (_i, [_vp, C.c_int32, C.c_int32, _u32, _u32]),
     "rb_debug_host_expand": (None, [_i]),
     "rb_debug_batch_begin_host": (_i, [_u32, _u32, c_void_pp]),
     "rb_debug_batch_phases": (_i, [_vp, _vp]),

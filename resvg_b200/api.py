@@ -386,6 +386,11 @@ class Batch:
         self.layer.ctx.check(lib.rb_batch_stroke_path(self._h, v.ctypes.data, len(v), p.ctypes.data, len(p),
                                                       C.byref(paint), C.byref(st), _ts(ts)), "batch_stroke_path")
 
+    def set_viewport(self, x=0, y=0, w=0, h=0):
+        """Render the draws recorded next into the rectangle (x, y, w, h) of the layer as if it were a pixmap of its own
+        (w = h = 0: the whole layer again)."""
+        self.layer.ctx.check(lib.rb_batch_set_viewport(self._h, int(x), int(y), int(w), int(h)), "batch_set_viewport")
+
     def submit(self, n_threads: int = 0):
         self.layer.ctx.check(lib.rb_batch_submit(self._h, n_threads), "batch_submit")
 

@@ -63,7 +63,8 @@ struct BulkSeg {
     rbh::Xform ctm;
 };
 // Draws in call order: a span is either a run of individually recorded draws (recs[first ..]) or one bulk segment.
-struct DrawSpan { size_t start, count; int bulk; size_t first; };
+// vp_*: the viewport the span's draws are rendered into (vp_w == 0: the whole target), see rb_batch_set_viewport.
+struct DrawSpan { size_t start, count; int bulk; size_t first; int32_t vp_x, vp_y, vp_w, vp_h; };
 
 // Byte offsets of the arrays inside the contiguous block (identical on host staging and device).
 struct BatchLayout {
@@ -100,6 +101,7 @@ struct rb_batch {
     std::vector<RecordedDraw> recs;
     std::vector<BulkSeg> bulk;
     std::vector<DrawSpan> spans;
+    int32_t vp_x = 0, vp_y = 0, vp_w = 0, vp_h = 0; // current viewport for the draws recorded next (vp_w == 0: whole target)
     size_t n_total = 0; // draws recorded so far (recs + bulk)
     size_t n_hair = 0;  // how many of them are hairline strokes (drawn by k_hair_blits, between the fill runs)
     uint64_t stats[6] = {0, 0, 0, 0, 0, 0};

@@ -262,6 +262,7 @@ struct DrawRef {
     rbh::Xform ctm;
     bool is_stroke;
     rb_stroke stroke; // dash_array resolved
+    int32_t vp_x, vp_y, vp_w, vp_h;
 };
 // The recorded form of draw i (fill points of bulk segments are NOT transformed here).
 DrawRef resolve_draw(const rb_batch *b, size_t i)
@@ -273,6 +274,7 @@ DrawRef resolve_draw(const rb_batch *b, size_t i)
     }
     const DrawSpan &sp = b->spans[lo];
     DrawRef d;
+    d.vp_x = sp.vp_x; d.vp_y = sp.vp_y; d.vp_w = sp.vp_w; d.vp_h = sp.vp_h;
     if (sp.bulk < 0) {
         const RecordedDraw &r = b->recs[sp.first + (i - sp.start)];
         d.verbs = b->verbs.data() + r.verb_off;
@@ -370,9 +372,16 @@ int rb_batch_hair_build(const rb_batch *b, size_t begin, size_t end, int W, int 
         rb_paint paint = d.paint;
         paint.stops = d.stops;
         hairline_modulate_paint(&paint, coverage, stops_scaled);
-        for (int ty = 0; ty < H; ty += kMaxDim) {
-            for (int tx = 0; tx < W; tx += kMaxDim) {
-                const int tw = std::min(W - tx, kMaxDim), th = std::min(H - ty, kMaxDim);
+        int VX = 0, VY = 0, VW = W, VH = H;
+        if (d.vp_w > 0) {
+            VX = d.vp_x; VY = d.vp_y;
+            if (VX < 0 || VY < 0 || VX >= W || VY >= H) continue;
+            VW = std::min(d.vp_w, W - VX);
+            VH = std::min(d.vp_h, H - VY);
+        }
+        for (int ty = 0; ty < VH; ty += kMaxDim) {
+            for (int tx = 0; tx < VW; tx += kMaxDim) {
+                const int tw = std::min(VW - tx, kMaxDim), th = std::min(VH - ty, kMaxDim);
                 const rbh::Pt *p = dev.data();
                 rbh::Xform ctm = d.ctm;
                 if (tx || ty) {
@@ -392,7 +401,7 @@ int rb_batch_hair_build(const rb_batch *b, size_t begin, size_t end, int W, int 
                 const uint32_t pi = (uint32_t)out->paints.size();
                 out->paints.push_back(P);
                 for (const rbh::HairBlit &hb : blits)
-                    raw.push_back(Raw{(uint32_t)(hb.x + tx), (uint32_t)(hb.y + ty), hb.alpha, pi, tx, ty});
+                    raw.push_back(Raw{(uint32_t)(hb.x + VX + tx), (uint32_t)(hb.y + VY + ty), hb.alpha, pi, VX + tx, VY + ty});
             }
         }
     }
@@ -450,6 +459,14 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
         while (i >= b->spans[span_i].start + b->spans[span_i].count) span_i++;
         while (i < b->spans[span_i].start) span_i--;
         const DrawSpan &sp = b->spans[span_i];
+        // the rectangle of the target this draw is rendered into, as if it were a pixmap of its own
+        int VX = 0, VY = 0, VW = W, VH = H;
+        if (sp.vp_w > 0) {
+            VX = sp.vp_x; VY = sp.vp_y; VW = sp.vp_w; VH = sp.vp_h;
+            if (VX < 0 || VY < 0 || VX >= W || VY >= H) continue;
+            VW = std::min(VW, W - VX);
+            VH = std::min(VH, H - VY);
+        }
         const RecordedDraw *rp;
         const uint8_t *verbs;
         const rbh::Pt *rpts;
@@ -510,9 +527,10 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
                 rb_paint hp = r.paint;
                 hp.stops = stops_src;
                 hairline_modulate_paint(&hp, coverage, out->hstops);
-                for (int ty = 0; ty < H; ty += kMaxDim) {
-                    for (int tx = 0; tx < W; tx += kMaxDim) {
-                        const int tw = std::min(W - tx, kMaxDim), th = std::min(H - ty, kMaxDim);
+                for (int ty = 0; ty < VH; ty += kMaxDim) {
+                    for (int tx = 0; tx < VW; tx += kMaxDim) {
+                        const int tw = std::min(VW - tx, kMaxDim), th = std::min(VH - ty, kMaxDim);
+                        const int ox = VX + tx, oy = VY + ty; // tile origin inside the target
                         const rbh::Pt *p = out->spts.data();
                         rbh::Xform ctm = r.ctm;
                         if (tx || ty) {
@@ -535,7 +553,7 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
                         }
                         DevDraw d;
                         memset(&d, 0, sizeof(d));
-                        d.ox = tx; d.oy = ty;
+                        d.ox = ox; d.oy = oy;
                         d.sx = x0; d.sy = y0; d.sw = x1 - x0 + 1; d.sh = y1 - y0 + 1;
                         d.shift = 2;
                         d.rule = 2; // hairline
@@ -545,8 +563,8 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
                         if (out->stops.size() != s_before) P.stop_off = (uint32_t)(P.stop_off - ci->s0);
                         d.paint = (uint32_t)(out->paints.size() - ci->p0);
                         out->paints.push_back(P);
-                        const int r0 = (ty + y0) >> 3, r1 = (ty + y1) >> 3, nr = r1 - r0 + 1;
-                        const int c0 = (tx + x0) / 32, c1 = (tx + x1) / 32;
+                        const int r0 = (oy + y0) >> 3, r1 = (oy + y1) >> 3, nr = r1 - r0 + 1;
+                        const int c0 = (ox + x0) / 32, c1 = (ox + x1) / 32;
                         // the draw's "tile rows" are its warp-tile CELLS (row-major over its bounding box), so that a tile
                         // finds exactly its own blits; rank = order of the blit inside its cell
                         const int ncols = c1 - c0 + 1;
@@ -556,9 +574,9 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
                         DevEdge *dst = out->edges.data() + eo;
                         for (size_t k = 0; k < nb; k++) {
                             const rbh::HairBlit &hb = out->hblits[k];
-                            const size_t cell = (size_t)(((ty + hb.y) >> 3) - r0) * (size_t)ncols + (size_t)(((tx + hb.x) >> 5) - c0);
+                            const size_t cell = (size_t)(((oy + hb.y) >> 3) - r0) * (size_t)ncols + (size_t)(((ox + hb.x) >> 5) - c0);
                             DevEdge e; // a blit in an edge-sized record: layer pixel, coverage, rank inside its cell, cell
-                            e.x = (int32_t)((uint32_t)(hb.x + tx) | ((uint32_t)(hb.y + ty) << 16));
+                            e.x = (int32_t)((uint32_t)(hb.x + ox) | ((uint32_t)(hb.y + oy) << 16));
                             e.dx = (int32_t)hb.alpha;
                             e.ypack = out->hrank[cell]++;
                             e.meta = (uint32_t)cell;
@@ -625,9 +643,10 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
         }
         const bool aa = r.paint.anti_alias != 0;
         // DrawTiler: tiles of at most 8191x8191 in row-major order; a single tile for ordinary canvases.
-        for (int ty = 0; ty < H; ty += kMaxDim) {
-            for (int tx = 0; tx < W; tx += kMaxDim) {
-                const int tw = std::min(W - tx, kMaxDim), th = std::min(H - ty, kMaxDim);
+        for (int ty = 0; ty < VH; ty += kMaxDim) {
+            for (int tx = 0; tx < VW; tx += kMaxDim) {
+                const int tw = std::min(VW - tx, kMaxDim), th = std::min(VH - ty, kMaxDim);
+                const int ox = VX + tx, oy = VY + ty; // tile origin inside the target
                 const rbh::Pt *pts = rpts;
                 rbh::Xform ctm = r.ctm;
                 if (tx || ty) {
@@ -652,7 +671,7 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
                 const size_t ne = out->scratch.size(), ncv = out->cscratch.size();
                 DevDraw d;
                 memset(&d, 0, sizeof(d));
-                d.ox = tx; d.oy = ty;
+                d.ox = ox; d.oy = oy;
                 d.sx = g.sect.x; d.sy = g.sect.y; d.sw = g.sect.w; d.sh = g.sect.h;
                 d.shift = g.shift;
                 d.rule = rule;
@@ -668,9 +687,9 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
                 }
                 PROF(2);
                 // warp-tile rows of the draw (layer pixel rows / 8) and the size of its tile-row edge lists
-                const int r0 = (ty + g.sect.y) >> 3, r1 = (ty + g.sect.y + g.sect.h - 1) >> 3, nr = r1 - r0 + 1;
-                const int c0 = (tx + g.sect.x) / 32, c1 = (tx + g.sect.x + g.sect.w - 1) / 32;
-                auto row_of = [&](int32_t suby) { return std::min(std::max((((suby >> g.shift) + ty) >> 3) - r0, 0), nr - 1); };
+                const int r0 = (oy + g.sect.y) >> 3, r1 = (oy + g.sect.y + g.sect.h - 1) >> 3, nr = r1 - r0 + 1;
+                const int c0 = (ox + g.sect.x) / 32, c1 = (ox + g.sect.x + g.sect.w - 1) / 32;
+                auto row_of = [&](int32_t suby) { return std::min(std::max((((suby >> g.shift) + oy) >> 3) - r0, 0), nr - 1); };
                 size_t n_list = 0;
                 const size_t eo = out->edges.size();
                 out->edges.resize(eo + ne);
@@ -988,8 +1007,10 @@ int rb_batch_record(rb_batch *b, const uint8_t *verbs, int32_t n_verbs, const fl
     r.rule = rule ? 1 : 0;
     r.is_stroke = false;
     b->recs.push_back(r);
-    if (!b->spans.empty() && b->spans.back().bulk < 0) b->spans.back().count++;
-    else b->spans.push_back(DrawSpan{b->n_total, 1, -1, b->recs.size() - 1});
+    if (!b->spans.empty() && b->spans.back().bulk < 0 && b->spans.back().vp_x == b->vp_x && b->spans.back().vp_y == b->vp_y
+        && b->spans.back().vp_w == b->vp_w && b->spans.back().vp_h == b->vp_h)
+        b->spans.back().count++;
+    else b->spans.push_back(DrawSpan{b->n_total, 1, -1, b->recs.size() - 1, b->vp_x, b->vp_y, b->vp_w, b->vp_h});
     b->n_total++;
     return RB_OK;
 }
@@ -1067,7 +1088,7 @@ extern "C" int rb_batch_draw_paths(rb_batch *b, int32_t n_paths, const uint32_t 
     bs.paints = paints; bs.fill_rules = fill_rules; bs.strokes = strokes;
     bs.ctm = ctm;
     b->bulk.push_back(bs);
-    b->spans.push_back(DrawSpan{b->n_total, (size_t)n_paths, (int)b->bulk.size() - 1, 0});
+    b->spans.push_back(DrawSpan{b->n_total, (size_t)n_paths, (int)b->bulk.size() - 1, 0, b->vp_x, b->vp_y, b->vp_w, b->vp_h});
     b->n_total += (size_t)n_paths;
     return RB_OK;
 }
@@ -1083,6 +1104,16 @@ extern "C" int rb_batch_stats(rb_batch *b, uint64_t stats[6])
 {
     if (!b || !stats) return RB_ERR_INVALID;
     memcpy(stats, b->stats, sizeof(b->stats));
+    return RB_OK;
+}
+
+// The draws recorded after this call are rendered as if the rectangle (x, y, w, h) of the target were a pixmap of its
+// own: coordinates are relative to its origin and nothing is drawn outside it.  This is how many small documents are
+// rendered into one atlas layer by a single batch (document-parallel thumbnailing).  w == 0 restores the whole target.
+extern "C" int rb_batch_set_viewport(rb_batch *b, int32_t x, int32_t y, uint32_t w, uint32_t h)
+{
+    if (!b || x < 0 || y < 0 || w > 0x7fffffffu || h > 0x7fffffffu || ((w == 0) != (h == 0))) return RB_ERR_INVALID;
+    b->vp_x = x; b->vp_y = y; b->vp_w = (int32_t)w; b->vp_h = (int32_t)h;
     return RB_OK;
 }
 

@@ -427,6 +427,59 @@ def test_hairline_strokes_in_painters_order(ctx, mode):
     assert_exact(l.download(), want, f"hairlines ({mode})")
 
 
+@pytest.mark.parametrize("mode", ["items", "wide-kernel"])
+def test_viewports_render_many_documents_into_one_atlas(ctx, mode):
+    """rb_batch_set_viewport: 35 small 'documents' (fills, strokes, hairlines, gradients leaving their cell) rendered by ONE
+    batch into the cells of an atlas layer == the oracle rendering every document into a pixmap of its own; the gutter
+    between the cells stays untouched."""
+    import resvg_b200 as rb
+    from resvg_b200 import _ffi
+    from tests.backends import OracleBackend
+
+    cw, ch, gap, nx, ny = 61, 47, 3, 7, 5
+    W, H = gap + nx * (cw + gap), gap + ny * (ch + gap)
+    rng = SplitMix64(2025)
+    ob = OracleBackend()
+    base = random_premul(W, H, 9)
+    want = base.copy()
+    l = ctx.layer_from(base)
+    b = rb.Batch(l)
+    for j in range(ny):
+        for i in range(nx):
+            x0, y0 = gap + i * (cw + gap), gap + j * (ch + gap)
+            doc = np.ascontiguousarray(want[y0:y0 + ch, x0:x0 + cw])
+            b.set_viewport(x0, y0, cw, ch)
+            for k in range(5):
+                cx, cy, r = rng.uniform(-10, cw + 10), rng.uniform(-10, ch + 10), rng.log_uniform(5, 70)
+                verbs, pts = random_path(rng, cx, cy, r)
+                spec = random_paint_spec(rng, cx, cy, r, solid=0.6, linear=0.4)
+                if k == 3:
+                    width = rng.uniform(0.1, 0.8)
+                    b.stroke_path(verbs, pts, rb.make_paint(spec), width, 4.0, "square", "miter")
+                    ob.stroke_hairline(doc, verbs, pts, spec, R.IDENTITY, "source_over", width, "square")
+                elif k == 4:
+                    b.stroke_path(verbs, pts, rb.make_paint(spec), 3.5, 4.0, "round", "round")
+                    out = rb.stroke_path(verbs, pts, 3.5, 4.0, "round", "round", 1.0)
+                    if out is not None:
+                        R.fill_path(doc, out[0], out[1], R.make_paint(spec), "nonzero")
+                else:
+                    rule = "evenodd" if k % 2 else "nonzero"
+                    b.fill_path(verbs, pts, rb.make_paint(spec), rule)
+                    R.fill_path(doc, verbs, pts, R.make_paint(spec), rule)
+            want[y0:y0 + ch, x0:x0 + cw] = doc
+    b.set_viewport()  # back to the whole layer: one shape across everything
+    big_v, big_p = [0, 1, 1, 4], [(5.0, 5.0), (W - 9.5, 20.25), (40.0, H - 7.75)]
+    big = {"kind": "solid", "color": (0.1, 0.9, 0.4, 0.35)}
+    b.fill_path(big_v, big_p, rb.make_paint(big), "nonzero")
+    R.fill_path(want, big_v, big_p, R.make_paint(big), "nonzero")
+    _ffi.lib.rb_debug_force_wide_kernel(1 if mode == "wide-kernel" else 0)
+    try:
+        b.submit()
+    finally:
+        _ffi.lib.rb_debug_force_wide_kernel(0)
+    assert_exact(l.download(), want, f"atlas ({mode})")
+
+
 def test_batch_dashed_strokes(ctx):
     """stroke_path with a dash array: dash (tiny_skia_path::Path::dash) -> stroke -> fill inside the batch builder must
     equal the same host steps done one by one and filled by the oracle; rejected dash lists leave the stroke solid."""
