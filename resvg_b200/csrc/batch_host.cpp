@@ -504,6 +504,7 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
         if (r.is_stroke && b->n_hair) {
             const float coverage = rb_hairline_coverage(r.paint, r.stroke, r.ctm);
             if (coverage >= 0.0f) {
+                PROF(3);
                 // A hairline stroke: not scan-converted.  Its ordered blits become the draw's "edge list" (k_row_lists keeps
                 // their order per tile row through the rank stored with each), and the tile kernel applies them one by one.
                 if (mask_target) continue;
@@ -819,7 +820,7 @@ int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threa
     for (auto &w : workers) if (w->skipped_hair) return RB_NEEDS_RUN_SPLIT;
     b->phases[0] = us_since(t0);
 #ifdef RB_HOST_PROFILE
-    fprintf(stderr, "[host profile] Mcycles: stroke %.0f build_draw %.0f pack %.0f\n", g_prof[0].load() / 1e6, g_prof[1].load() / 1e6, g_prof[2].load() / 1e6);
+    fprintf(stderr, "[host profile] Mcycles: stroke %.0f build_draw %.0f pack %.0f hairline %.0f\n", g_prof[0].load() / 1e6, g_prof[1].load() / 1e6, g_prof[2].load() / 1e6, g_prof[3].load() / 1e6);
     for (auto &g : g_prof) g = 0;
 #endif
 

@@ -524,24 +524,47 @@ __global__ void k_iir_load(const uint32_t *__restrict__ src, double *__restrict_
 
 // Recurrence along the slow axis of a plane [len][lines]: thread = one line of one channel plane.
 // iir_blur.rs:84-101 / 111-130: steps x { forward b[i] += nu*b[i-1]; backward b[i-1] += nu*b[i] }.
+// Only 4 * lines threads exist (one per recurrence), so the memory system is kept busy by each thread issuing the
+// loads of the next IIR_AHEAD elements before it runs the (strictly sequential, unchanged) arithmetic over them.
+constexpr int IIR_AHEAD = 16;
 __global__ void k_iir_sweep(double *__restrict__ buf, int lines, int len, size_t plane, double dnu, int steps)
 {
     int line = blockIdx.x * blockDim.x + threadIdx.x;
     if (line >= lines) return;
     double *b = buf + (size_t)blockIdx.y * plane + line;
-    size_t stride = (size_t)lines;
+    const size_t stride = (size_t)lines;
     for (int s = 0; s < steps; s++) {
         double prev = b[0];
-        for (int i = 1; i < len; i++) {
-            double v = __dadd_rn(b[(size_t)i * stride], __dmul_rn(dnu, prev));
-            b[(size_t)i * stride] = v;
-            prev = v;
+        int i = 1;
+        for (; i + IIR_AHEAD <= len; i += IIR_AHEAD) {
+            double v[IIR_AHEAD];
+#pragma unroll
+            for (int k = 0; k < IIR_AHEAD; k++) v[k] = b[(size_t)(i + k) * stride];
+#pragma unroll
+            for (int k = 0; k < IIR_AHEAD; k++) {
+                prev = __dadd_rn(v[k], __dmul_rn(dnu, prev));
+                b[(size_t)(i + k) * stride] = prev;
+            }
+        }
+        for (; i < len; i++) {
+            prev = __dadd_rn(b[(size_t)i * stride], __dmul_rn(dnu, prev));
+            b[(size_t)i * stride] = prev;
         }
         // prev == b[len-1]
-        for (int i = len - 1; i > 0; i--) {
-            double v = __dadd_rn(b[(size_t)(i - 1) * stride], __dmul_rn(dnu, prev));
-            b[(size_t)(i - 1) * stride] = v;
-            prev = v;
+        i = len - 1;
+        for (; i - IIR_AHEAD >= 0; i -= IIR_AHEAD) {
+            double v[IIR_AHEAD];
+#pragma unroll
+            for (int k = 0; k < IIR_AHEAD; k++) v[k] = b[(size_t)(i - 1 - k) * stride];
+#pragma unroll
+            for (int k = 0; k < IIR_AHEAD; k++) {
+                prev = __dadd_rn(v[k], __dmul_rn(dnu, prev));
+                b[(size_t)(i - 1 - k) * stride] = prev;
+            }
+        }
+        for (; i > 0; i--) {
+            prev = __dadd_rn(b[(size_t)(i - 1) * stride], __dmul_rn(dnu, prev));
+            b[(size_t)(i - 1) * stride] = prev;
         }
     }
 }

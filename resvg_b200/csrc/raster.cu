@@ -1172,12 +1172,13 @@ extern "C" int rb_mask_upload(rb_mask *m, const uint8_t *host)
 }
 
 // Mask::from_pixmap: 5 B/px
-__device__ __forceinline__ uint32_t mask_px(uint32_t p, int luminance)
+// div255[c] = c / 255.0f (IEEE division, as Rust's `c as f32 / 255.0`), tabulated per block
+__device__ __forceinline__ uint32_t mask_px(uint32_t p, int luminance, const float *div255)
 {
     const uint32_t av = RB_A(p);
     if (!luminance) return av;
-    float r = __fdiv_rn((float)RB_R(p), 255.0f), g = __fdiv_rn((float)RB_G(p), 255.0f), b = __fdiv_rn((float)RB_B(p), 255.0f);
-    const float a = __fdiv_rn((float)av, 255.0f);
+    float r = div255[RB_R(p)], g = div255[RB_G(p)], b = div255[RB_B(p)];
+    const float a = div255[av];
     if (av != 0) { r = __fdiv_rn(r, a); g = __fdiv_rn(g, a); b = __fdiv_rn(b, a); }
     const float luma = r * 0.2126f + g * 0.7152f + b * 0.0722f; // Rec. 709 (pinned by masking/mask goldens)
     float v = (luma * a) * 255.0f;
@@ -1187,15 +1188,18 @@ __device__ __forceinline__ uint32_t mask_px(uint32_t p, int luminance)
 // 4 pixels per thread: one 16-byte load, one 4-byte store (layers and masks are 256-byte aligned).
 __global__ void __launch_bounds__(256) k_mask_from_layer(const uint32_t *__restrict__ px, uint8_t *__restrict__ m, size_t n, int luminance)
 {
+    __shared__ float div255[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) div255[i] = __fdiv_rn((float)i, 255.0f);
+    __syncthreads();
     const size_t n4 = n >> 2, stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         const uint4 p = reinterpret_cast<const uint4 *>(px)[i];
-        reinterpret_cast<uint32_t *>(m)[i] = mask_px(p.x, luminance) | (mask_px(p.y, luminance) << 8) | (mask_px(p.z, luminance) << 16)
-                                             | (mask_px(p.w, luminance) << 24);
+        reinterpret_cast<uint32_t *>(m)[i] = mask_px(p.x, luminance, div255) | (mask_px(p.y, luminance, div255) << 8)
+                                             | (mask_px(p.z, luminance, div255) << 16) | (mask_px(p.w, luminance, div255) << 24);
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
         const size_t i = (n4 << 2) + threadIdx.x;
-        m[i] = (uint8_t)mask_px(px[i], luminance);
+        m[i] = (uint8_t)mask_px(px[i], luminance, div255);
     }
 }
 __global__ void __launch_bounds__(256) k_mask_invert(uint8_t *__restrict__ m, size_t n)
