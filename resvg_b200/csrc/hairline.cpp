@@ -6,7 +6,8 @@
 // SkScan_Hairline.cpp / SkScan_Antihair.cpp.  A hairline is not scan-converted: every path segment is walked in
 // fixed point along its major axis and blitted two pixels at a time, each blit being a separate blend, so a pixel
 // touched twice is blended twice.  The host therefore produces the ordered list of (x, y, alpha) blits; the device
-// applies them per pixel in that order (k_hair_blits in raster.cu).
+// applies them per pixel in that order (the hairline branch of k_raster_warp; k_hair_blits in raster.cu when the
+// fallback builder is in use).
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
