@@ -750,7 +750,7 @@ extern "C" void rb_batch_destroy(rb_batch *b)
 }
 
 // Device-built structures of the warp-tile path (sizes come from the host build).
-struct WarpScratch { size_t o_row_off, o_row_cols, o_row_edges, o_boxes, o_row_cnt, o_row_draws, o_tile_off, o_tile_pairs, o_edges, o_flag, total; };
+struct WarpScratch { size_t o_row_off, o_row_cols, o_row_edges, o_boxes, o_row_cnt, o_row_draws, o_tile_off, o_tile_pairs, o_edges, o_flag, o_scan, total; };
 static WarpScratch warp_scratch_layout(const BatchLayout &L)
 {
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -766,6 +766,7 @@ static WarpScratch warp_scratch_layout(const BatchLayout &L)
     w.o_tile_pairs = off; off += al((L.n_wpairs + 1) * 4);
     w.o_edges = off;      off += al(((L.items ? L.n_slots : 0) + 1) * sizeof(DevEdge));
     w.o_flag = off;       off += 256;
+    w.o_scan = off;       off += al((((size_t)L.wtiles_x * L.wtiles_y + SCAN_PER_CTA) / SCAN_PER_CTA + 1) * 4);
     w.total = off;
     return w;
 }
@@ -895,10 +896,22 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
         RB_LAUNCHED(ctx, "row_lists");
         k_bin_count<<<(n_draws + 255) / 256, 256, 0, ctx->stream>>>(d_draws, n_draws, L.wtiles_x, row_cols, boxes, row_cnt, tile_off);
         RB_LAUNCHED(ctx, "bin_count");
-        k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(row_cnt, (uint32_t)L.wtiles_y);
-        RB_LAUNCHED(ctx, "scan_rows");
-        k_exclusive_scan<<<1, 1024, 0, ctx->stream>>>(tile_off, n_wtiles);
-        RB_LAUNCHED(ctx, "scan_tiles");
+        uint32_t *scan_tmp = (uint32_t *)(sc + ws.o_scan);
+        auto exclusive_scan = [&](uint32_t *a, uint32_t n) -> int {
+            const uint32_t nb = (n + SCAN_PER_CTA - 1) / SCAN_PER_CTA;
+            if (nb > (uint32_t)SCAN_PER_CTA) return rb_fail(ctx, RB_ERR_UNSUPPORTED, "layer too large for the tile table scan");
+            k_scan_local<<<nb, SCAN_THREADS, 0, ctx->stream>>>(a, n, scan_tmp);
+            RB_LAUNCHED(ctx, "scan_local");
+            k_scan_sums<<<1, SCAN_THREADS, 0, ctx->stream>>>(scan_tmp, nb, a, n);
+            RB_LAUNCHED(ctx, "scan_sums");
+            if (nb > 1) {
+                k_scan_add<<<nb, SCAN_THREADS, 0, ctx->stream>>>(a, n, scan_tmp);
+                RB_LAUNCHED(ctx, "scan_add");
+            }
+            return RB_OK;
+        };
+        { int st = exclusive_scan(row_cnt, (uint32_t)L.wtiles_y); if (st != RB_OK) return st; }
+        { int st = exclusive_scan(tile_off, n_wtiles); if (st != RB_OK) return st; }
         k_bin_rows<<<L.wtiles_y, 256, 0, ctx->stream>>>(boxes, n_draws, row_cols, row_cnt, row_draws);
         RB_LAUNCHED(ctx, "bin_rows");
         k_bin_tiles<<<(n_wtiles + 7) / 8, 256, 0, ctx->stream>>>(row_draws, row_cnt, tile_off, L.wtiles_x, n_wtiles, tile_pairs);

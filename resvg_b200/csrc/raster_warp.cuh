@@ -323,37 +323,81 @@ k_bin_count(const DevDraw *__restrict__ draws, uint32_t n_draws, int wtiles_x, c
     }
 }
 
-// In-place exclusive scan of a[0..n) by ONE CTA of 1024 threads; a[n] receives the total.
-__global__ void __launch_bounds__(1024)
-k_exclusive_scan(uint32_t *__restrict__ a, uint32_t n)
+// In-place exclusive scan of a[0..n), a[n] = total, in three small launches: every CTA scans 4096 consecutive
+// elements (coalesced 16-byte loads, 4 per thread) and publishes its sum; one CTA scans the sums; every CTA adds its
+// offset.  (The tile table has 262 144 entries for an 8192 x 8192 layer: a single CTA took 0.45 ms.)
+constexpr int SCAN_THREADS = 1024, SCAN_PER_CTA = SCAN_THREADS * 4;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *warp_tot, uint32_t *total)
 {
-    __shared__ uint32_t warp_tot[32];
     const uint32_t tid = threadIdx.x;
-    const uint32_t per = (n + 1023u) / 1024u;
-    const uint32_t lo = min(tid * per, n), hi = min(lo + per, n);
-    uint32_t s = 0;
-    for (uint32_t i = lo; i < hi; i++) s += a[i];
-    uint32_t incl = s;
+    uint32_t incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-        if ((tid & 31u) >= (uint32_t)d) incl += v;
+        uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+        if ((tid & 31u) >= (uint32_t)d) incl += u;
     }
     if ((tid & 31u) == 31u) warp_tot[tid >> 5] = incl;
     __syncthreads();
     if (tid < 32) {
-        uint32_t v = warp_tot[tid], t = v;
+        uint32_t w = warp_tot[tid], t = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             uint32_t u = __shfl_up_sync(0xffffffffu, t, d);
             if (tid >= (uint32_t)d) t += u;
         }
-        warp_tot[tid] = t - v;
+        warp_tot[tid] = t - w;
+        if (tid == 31) *total = t;
     }
     __syncthreads();
-    uint32_t base = incl - s + warp_tot[tid >> 5];
-    for (uint32_t i = lo; i < hi; i++) { uint32_t c = a[i]; a[i] = base; base += c; }
-    if (tid == 1023) a[n] = base;
+    return incl - v + warp_tot[tid >> 5];
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_local(uint32_t *__restrict__ a, uint32_t n, uint32_t *__restrict__ block_sums)
+{
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t total;
+    const uint32_t base = blockIdx.x * SCAN_PER_CTA + threadIdx.x * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = base + k < n ? a[base + k] : 0u;
+    const uint32_t sum = v[0] + v[1] + v[2] + v[3];
+    uint32_t off = block_exclusive_scan(sum, warp_tot, &total);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (base + k < n) a[base + k] = off;
+        off += v[k];
+    }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// scans the block sums (at most SCAN_PER_CTA of them, i.e. n <= 16 M entries) and writes the grand total to a[n]
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_sums(uint32_t *__restrict__ block_sums, uint32_t n_blocks, uint32_t *__restrict__ a, uint32_t n)
+{
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t total;
+    const uint32_t base = threadIdx.x * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = base + k < n_blocks ? block_sums[base + k] : 0u;
+    uint32_t off = block_exclusive_scan(v[0] + v[1] + v[2] + v[3], warp_tot, &total);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (base + k < n_blocks) block_sums[base + k] = off;
+        off += v[k];
+    }
+    if (threadIdx.x == 0) a[n] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_add(uint32_t *__restrict__ a, uint32_t n, const uint32_t *__restrict__ block_sums)
+{
+    const uint32_t add = block_sums[blockIdx.x];
+    const uint32_t base = blockIdx.x * SCAN_PER_CTA + threadIdx.x * 4;
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (base + k < n) a[base + k] += add;
 }
 
 struct RowEnt { uint32_t draw, cols; };
