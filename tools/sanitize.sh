@@ -1,0 +1,7 @@
+#!/bin/bash
+# compute-sanitizer passes over the GPU tests (run through gpurun on a B200).
+set -u
+compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_raster_gpu.py tests/test_edge_cases_gpu.py -q -x -k "not full_size" || exit 1
+compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_filters_gpu.py -q -x -k "box or iir or helpers or morph or convolve" || exit 1
+compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_raster_gpu.py -q -x \
+    -k "structured or hairline or batch_painters or coverage_random_paths or viewports or masks" || exit 1
