@@ -221,6 +221,23 @@ def kernel_table(rb, ctx, layer, W, H, peak, reps=3):
         ("k_mask_from_layer luminance", 5, lambda: rb.Mask.from_layer(layer, "luminance")),
         ("k_apply_mask", 9, lambda: rb.apply_mask(a, mask)),
     ]
+    def c3_chain():
+        # blur 8 -> dilate 3 -> sharpen 3x3 -> arithmetic with turbulence(0.02, 3 oct) -> diffuse
+        # lighting (distant 45/60) -> blur 64, in linearRGB
+        F.into_linear_rgb(a)
+        F.box_blur(8.0, 8.0, a)
+        F.morphology("dilate", 3.0, 3.0, a)
+        F.convolve_matrix([0, -1, 0, -1, 5, -1, 0, -1, 0], 3, 3, 1, 1, 1.0, 0.0, "duplicate", False, a)
+        F.turbulence(0.0, 0.0, 1.0, 1.0, 0.02, 0.02, 3, 7, False, False, b)
+        F.multiply_alpha(b)
+        F.arithmetic(0.5, 0.5, 0.5, 0.0, a, b, c)
+        F.diffuse_lighting(5.0, 1.0, (255, 255, 255), rb.make_light("distant", azimuth=45.0, elevation=60.0), c, a)
+        F.box_blur(64.0, 64.0, a)
+        F.into_srgb(a)
+
+    c = ctx.layer(W, H)
+    rows.append(("C3 filter chain (blur 8, dilate 3, sharpen, arithmetic x turbulence, diffuse light, blur 64; 10 primitives)",
+                 8 + 80 + 16 + 8 + 4 + 8 + 12 + 8 + 80 + 8, c3_chain))
     out = []
     for name, bpp, fn in rows:
         fn()

@@ -104,6 +104,13 @@ typedef struct {
     float amplitude, exponent, offset;
 } rb_transfer_fn;
 int rb_filter_component_transfer(rb_layer *layer, const rb_transfer_fn funcs[4]);
+/* box_blur::apply on n sub-pixmaps at once: rectangle i = rects[4i..4i+3] = (x, y, w, h) of the layer is blurred as a
+ * pixmap of its own (windows clipped to it) with sigma_x[i], sigma_y[i]; everything else is untouched.  One launch per
+ * pass for all rectangles (per-document filters on an atlas).  Rectangles must lie inside the layer and not overlap. */
+int rb_filter_box_blur_cells(rb_layer *layer, int32_t n, const int32_t *rects, const double *sigma_x, const double *sigma_y);
+/* apply_drop_shadow's flood step, filter/mod.rs:606-617: every pixel := the colour (r, g, b, a) with its opacity scaled
+ * by the pixel's alpha / 255, premultiplied (Color::apply_opacity, premultiply, to_color_u8). */
+int rb_filter_flood_alpha(rb_layer *layer, uint8_t r, uint8_t g, uint8_t b, uint8_t a);
 /* composite::arithmetic(k1..k4, src1, src2, dest) — composite.rs:14 */
 int rb_filter_composite_arithmetic(rb_layer *dest, const rb_layer *src1, const rb_layer *src2,
                                    float k1, float k2, float k3, float k4);
@@ -216,6 +223,13 @@ int rb_batch_fill_paths(rb_batch *batch, int32_t n_paths, const uint32_t *verb_o
  * One batch can thus render many small documents into one atlas layer (document-parallel thumbnailing, BASELINE
  * config 5).  w = h = 0 restores the whole target. */
 int rb_batch_set_viewport(rb_batch *batch, int32_t x, int32_t y, uint32_t w, uint32_t h);
+/* Bulk form of { rb_batch_set_viewport; rb_batch_draw_paths } per document (BASELINE config 5: one resvg::render per
+ * icon): document k owns doc_count[k] paths starting at doc_first[k] of the packed arrays (same layout and lifetime rules
+ * as rb_batch_draw_paths) and is rendered into viewports[4k..4k+3] = (x, y, w, h).  The current viewport is unchanged. */
+int rb_batch_draw_documents(rb_batch *batch, int32_t n_docs, const int32_t *viewports, const uint32_t *doc_first,
+                            const uint32_t *doc_count, const uint32_t *verb_off, const uint32_t *point_off,
+                            const uint8_t *verbs, const float *points, const rb_paint *paints, const uint8_t *fill_rules,
+                            const rb_stroke *strokes, const float ts[6]);
 /* Builds edges on host threads (n_threads <= 0: all cores), uploads, launches, frees the device copy. */
 int rb_batch_submit(rb_batch *batch, int32_t n_threads);
 /* Split form: prepare = host edge build + binning + upload (device copy stays resident in the batch);
@@ -236,6 +250,12 @@ int rb_batch_stats(rb_batch *batch, uint64_t stats[6]);
 /* PixmapMut::draw_pixmap(x, y, src, PixmapPaint{opacity, blend_mode, Nearest}, identity, None) —
  * render.rs:133, clip.rs:88, filter/mod.rs (9 call sites): the layer composite. */
 int rb_draw_layer(rb_layer *dst, const rb_layer *src, int32_t x, int32_t y, float opacity, int32_t blend_mode);
+/* Atlas form of the layer composite (render.rs:108-133 per document; the offset / merge draws of filter/mod.rs): for every
+ * rectangle i = rects[4i..4i+3] = (x, y, w, h) of `dst`, the w x h pixels of `src` at src_xy[2i..2i+1] (NULL: the same
+ * position) are drawn with opacity[i], as draw_pixmap of that sub-pixmap would; rectangles are clipped to both layers; one
+ * launch for all documents of an atlas (see rb_batch_set_viewport).  Destination rectangles must not overlap. */
+int rb_draw_layer_rects(rb_layer *dst, const rb_layer *src, int32_t n, const int32_t *rects, const int32_t *src_xy,
+                        const float *opacity, int32_t blend_mode);
 
 /* tiny_skia::Mask — clip.rs:25-27, mask.rs:17-45 */
 int rb_mask_create(rb_ctx *ctx, uint32_t width, uint32_t height, rb_mask **out); /* Mask::new (zeroed) */

@@ -6,7 +6,7 @@ raises at import time if the library is missing — there is no CPU fallback.
 """
 from . import _ffi  # noqa: F401  (raises ImportError if the CUDA library is not built)
 from .api import (Batch, Context, Layer, Mask, PinnedBuffer, ResvgB200Error, apply_mask,  # noqa: F401
-                  draw_layer, fill_path, filters, make_light, make_paint, make_transfer, stroke_path, dash_path, hairline_blits)
+                  draw_layer, draw_layer_rects, fill_path, filters, make_light, make_paint, make_transfer, stroke_path, dash_path, hairline_blits)
 
-__all__ = ["Batch", "Context", "Layer", "Mask", "PinnedBuffer", "ResvgB200Error", "apply_mask", "draw_layer",
+__all__ = ["Batch", "Context", "Layer", "Mask", "PinnedBuffer", "ResvgB200Error", "apply_mask", "draw_layer", "draw_layer_rects",
            "fill_path", "filters", "make_light", "make_paint", "make_transfer", "stroke_path", "dash_path", "hairline_blits"]

@@ -141,6 +141,10 @@ SIGNATURES = {
                                   C.c_int32, _vp]),
     "rb_ctx_last_run_ms": (_i, [_vp, _vp]),
     "rb_batch_set_viewport": (_i, [_vp, C.c_int32, C.c_int32, _u32, _u32]),
+    "rb_batch_draw_documents": (_i, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, f32p]),
+    "rb_draw_layer_rects": (_i, [_vp, _vp, C.c_int32, _vp, _vp, _vp, C.c_int32]),
+    "rb_filter_box_blur_cells": (_i, [_vp, C.c_int32, _vp, _vp, _vp]),
+    "rb_filter_flood_alpha": (_i, [_vp, _u8, _u8, _u8, _u8]),
     "rb_debug_host_expand": (None, [_i]),
     "rb_debug_batch_begin_host": (_i, [_u32, _u32, c_void_pp]),
     "rb_debug_batch_phases": (_i, [_vp, _vp]),

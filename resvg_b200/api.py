@@ -237,6 +237,19 @@ class filters:
         src.ctx.check(lib.rb_filter_component_transfer(src._h, arr), "component_transfer")
 
     @staticmethod
+    def box_blur_cells(rects, sigma_x, sigma_y, src: Layer):
+        """box_blur::apply on every rectangle (x, y, w, h) of the layer as a pixmap of its own (rb_filter_box_blur_cells)."""
+        r = np.ascontiguousarray(rects, np.int32).reshape(-1, 4)
+        sx = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma_x, np.float64), (len(r),)))
+        sy = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma_y, np.float64), (len(r),)))
+        src.ctx.check(lib.rb_filter_box_blur_cells(src._h, len(r), r.ctypes.data, sx.ctypes.data, sy.ctypes.data), "box_blur_cells")
+
+    @staticmethod
+    def flood_alpha(color, opacity_u8: int, src: Layer):
+        """apply_drop_shadow's flood (filter/mod.rs:606-617): colour (r, g, b as u8) with opacity_u8 scaled by every pixel's alpha."""
+        src.ctx.check(lib.rb_filter_flood_alpha(src._h, int(color[0]), int(color[1]), int(color[2]), int(opacity_u8)), "flood_alpha")
+
+    @staticmethod
     def arithmetic(k1, k2, k3, k4, src1: Layer, src2: Layer, dest: Layer):
         dest.ctx.check(lib.rb_filter_composite_arithmetic(dest._h, src1._h, src2._h, k1, k2, k3, k4), "arithmetic")
 
@@ -386,6 +399,22 @@ class Batch:
         self.layer.ctx.check(lib.rb_batch_stroke_path(self._h, v.ctypes.data, len(v), p.ctypes.data, len(p),
                                                       C.byref(paint), C.byref(st), _ts(ts)), "batch_stroke_path")
 
+    def draw_documents(self, scene, viewports, doc_first, doc_count, ts=IDENTITY):
+        """One document per viewport (rb_batch_draw_documents): document k = doc_count[k] paths from doc_first[k] of the
+        packed scene arrays (same layout and lifetime rules as fill_paths), rendered into viewports[k] = (x, y, w, h)."""
+        vp = np.ascontiguousarray(viewports, np.int32).reshape(-1, 4)
+        first = np.ascontiguousarray(doc_first, np.uint32)
+        count = np.ascontiguousarray(doc_count, np.uint32)
+        assert len(first) == len(vp) == len(count)
+        strokes = scene.get("strokes")
+        self._keep.append((dict(scene), vp, first, count))
+        self.layer.ctx.check(
+            lib.rb_batch_draw_documents(self._h, len(vp), vp.ctypes.data, first.ctypes.data, count.ctypes.data,
+                                        scene["verb_off"].ctypes.data, scene["pt_off"].ctypes.data, scene["verbs"].ctypes.data,
+                                        scene["pts"].ctypes.data, C.addressof(scene["paints"]), scene["rules"].ctypes.data,
+                                        C.addressof(strokes) if strokes is not None else None, _ts(ts)),
+            "batch_draw_documents")
+
     def set_viewport(self, x=0, y=0, w=0, h=0):
         """Render the draws recorded next into the rectangle (x, y, w, h) of the layer as if it were a pixmap of its own
         (w = h = 0: the whole layer again)."""
@@ -427,6 +456,18 @@ def draw_layer(dst: Layer, src: Layer, x=0, y=0, opacity=1.0, blend="source_over
     """PixmapMut::draw_pixmap(x, y, src, PixmapPaint{opacity, blend_mode, Nearest}, identity, None)."""
     b = BLEND[blend] if isinstance(blend, str) else int(blend)
     dst.ctx.check(lib.rb_draw_layer(dst._h, src._h, int(x), int(y), float(opacity), b), "draw_layer")
+
+
+def draw_layer_rects(dst: Layer, src: Layer, rects, opacity, blend="source_over", src_xy=None):
+    """Region-wise draw_pixmap for atlases (rb_draw_layer_rects): rects (n, 4) = x, y, w, h in dst; src_xy (n, 2) = where
+    the pixels come from in src (None: the same position); opacity (n,) or a scalar."""
+    r = np.ascontiguousarray(rects, np.int32).reshape(-1, 4)
+    o = np.ascontiguousarray(np.broadcast_to(np.asarray(opacity, np.float32), (len(r),)))
+    s = None if src_xy is None else np.ascontiguousarray(src_xy, np.int32).reshape(-1, 2)
+    assert s is None or len(s) == len(r)
+    b = BLEND[blend] if isinstance(blend, str) else int(blend)
+    dst.ctx.check(lib.rb_draw_layer_rects(dst._h, src._h, len(r), r.ctypes.data, s.ctypes.data if s is not None else None,
+                                          o.ctypes.data, b), "draw_layer_rects")
 
 
 class Mask:

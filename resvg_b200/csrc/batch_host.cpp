@@ -1118,6 +1118,30 @@ extern "C" int rb_batch_set_viewport(rb_batch *b, int32_t x, int32_t y, uint32_t
     return RB_OK;
 }
 
+// Bulk form of { rb_batch_set_viewport; rb_batch_draw_paths } per document: document k owns doc_count[k] paths starting at
+// doc_first[k] of the packed arrays and is rendered into viewports[4k .. 4k + 3] = (x, y, w, h).  The batch's current
+// viewport is restored afterwards.
+extern "C" int rb_batch_draw_documents(rb_batch *b, int32_t n_docs, const int32_t *viewports, const uint32_t *doc_first,
+                                       const uint32_t *doc_count, const uint32_t *verb_off, const uint32_t *point_off,
+                                       const uint8_t *verbs, const float *points, const rb_paint *paints,
+                                       const uint8_t *fill_rules, const rb_stroke *strokes, const float ts[6])
+{
+    if (!b || n_docs < 0 || (n_docs > 0 && (!viewports || !doc_first || !doc_count))) return RB_ERR_INVALID;
+    const int32_t ox = b->vp_x, oy = b->vp_y, ow = b->vp_w, oh = b->vp_h;
+    int st = RB_OK;
+    for (int32_t k = 0; k < n_docs && st == RB_OK; k++) {
+        const uint32_t a = doc_first[k], n = doc_count[k];
+        if (n > 0x7fffffffu || viewports[4 * k + 2] <= 0 || viewports[4 * k + 3] <= 0) { st = RB_ERR_INVALID; break; }
+        if (n == 0) continue;
+        st = rb_batch_set_viewport(b, viewports[4 * k], viewports[4 * k + 1], (uint32_t)viewports[4 * k + 2], (uint32_t)viewports[4 * k + 3]);
+        if (st == RB_OK)
+            st = rb_batch_draw_paths(b, (int32_t)n, verb_off + a, point_off + a, verbs, points, paints + a, fill_rules + a,
+                                     strokes ? strokes + a : nullptr, ts);
+    }
+    b->vp_x = ox; b->vp_y = oy; b->vp_w = ow; b->vp_h = oh;
+    return st;
+}
+
 // Test hook: route every batch prepared from now on through the any-winding fallback kernel (k_raster_tiles_wide).
 extern "C" void rb_debug_force_wide_kernel(int on) { g_force_wide = on != 0; }
 

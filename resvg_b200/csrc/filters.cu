@@ -8,6 +8,9 @@
 #include <math.h>
 #include <string.h>
 
+#include <algorithm>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "common.cuh"
@@ -215,6 +218,7 @@ int rb_filters_init(rb_ctx *ctx)
     k_build_px_tables<<<PX_TABLE / 256, 256, 0, ctx->stream>>>(ctx->px_tables, ctx->px_tables + PX_TABLE, ctx->px_tables + 2 * PX_TABLE);
     RB_CUDA(ctx, cudaGetLastError());
     RB_CUDA(ctx, cudaFuncSetAttribute(k_px_table, cudaFuncAttributeMaxDynamicSharedMemorySize, PX_TABLE));
+
     return RB_OK;
 }
 
@@ -405,6 +409,197 @@ k_box_blur_v(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w
     }
 }
 
+// ---- fast passes for radii up to BOX2_MAX_R ---------------------------------------------------------------------------------
+// Sliding-window sums with the four channel sums packed two per 32-bit register (16 bits each).  The reference's
+// `round(sum as f32 * iarr) as u8` (box_blur.rs:148, 327-331: iarr = 1.0 / d as f32 with d = 2r + 1, round = add and
+// subtract 1.5 * 2^23) equals the exactly rounded quotient sum / d: d is odd, so sum / d is at least 1 / (2d) >= 0.002
+// away from every half-integer, while the two f32 roundings move the product by less than 255 * 2^-22 = 6e-5.  Hence
+// q = floor((sum + r) / d), evaluated as ((sum + r) * M) >> 24 with M = ceil(2^24 / d): exact while (sum + r) * d < 2^24,
+// i.e. for every d <= 255, and the product stays below 2^32 because (sum + r) / d < 256.  The window sums carry the + r
+// bias from the start.  The CPU test-suite checks the identity against the float formula for every radius and every
+// possible sum; the GPU tests compare whole blurs with the CPU checker across the radius range.
+constexpr int BOX2_MAX_R = 120;
+
+__device__ __forceinline__ void box2_add(uint32_t &rb, uint32_t &ga, uint32_t p) { rb += p & 0x00ff00ffu; ga += (p >> 8) & 0x00ff00ffu; }
+__device__ __forceinline__ void box2_sub(uint32_t &rb, uint32_t &ga, uint32_t p) { rb -= p & 0x00ff00ffu; ga -= (p >> 8) & 0x00ff00ffu; }
+__device__ __forceinline__ uint32_t box2_out(uint32_t rb, uint32_t ga, uint32_t M)
+{
+    const uint32_t r = ((rb & 0xffffu) * M) >> 24, b = ((rb >> 16) * M) >> 24;
+    const uint32_t g = ((ga & 0xffffu) * M) >> 24, a = ((ga >> 16) * M) >> 24;
+    return r | (g << 8) | (b << 16) | (a << 24);
+}
+
+// Both kernels work on a list of CELLS: rectangles of the buffer that are blurred as if each were a pixmap of its own
+// (windows are clipped to the cell), every cell with its own radii — a whole layer is one cell; an atlas of small
+// documents (rb_filter_box_blur_cells) has one cell per document that carries a blur.  blockIdx.z = cell.
+struct BoxCell {
+    int32_t x, y, w, h;
+    int32_t rv[5], rh[5];
+};
+__device__ __forceinline__ uint32_t box2_magic(int r) { return ((1u << 24) + (uint32_t)(2 * r)) / (uint32_t)(2 * r + 1); } // ceil(2^24 / d)
+
+// Vertical: one thread = two adjacent columns (8-byte accesses; VEC2 needs even cell x / width / pitch) or one column,
+// over `rows` consecutive rows of the cell.  Radius 0 copies (the passes ping-pong between two buffers).
+constexpr int BOX2V_THREADS = 128;
+template <bool VEC2>
+__global__ void __launch_bounds__(BOX2V_THREADS)
+k_box_blur_v2(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int pitch, const BoxCell *__restrict__ cells, int it,
+              int rows)
+{
+    using T = typename std::conditional<VEC2, uint2, uint32_t>::type;
+    constexpr int PER = VEC2 ? 2 : 1;
+    const BoxCell c = cells[blockIdx.z];
+    const int r = c.rv[it], h = c.h;
+    const int x = (blockIdx.x * BOX2V_THREADS + threadIdx.x) * PER;
+    const int y0 = blockIdx.y * rows, y1 = min(y0 + rows, h);
+    if (x >= c.w || y0 >= h) return;
+    const size_t org = (size_t)c.y * pitch + c.x + x;
+    const T *s2 = reinterpret_cast<const T *>(src + org);
+    T *d2 = reinterpret_cast<T *>(dst + org);
+    const size_t step = (size_t)pitch / PER; // in T
+    if (r == 0) {
+        for (int y = y0; y < y1; y++) d2[(size_t)y * step] = s2[(size_t)y * step];
+        return;
+    }
+    const uint32_t M = box2_magic(r);
+    const uint32_t bias = (uint32_t)r | ((uint32_t)r << 16);
+    uint32_t rb0 = bias, ga0 = bias, rb1 = bias, ga1 = bias;
+    auto add = [&](T p) {
+        if constexpr (VEC2) { box2_add(rb0, ga0, p.x); box2_add(rb1, ga1, p.y); }
+        else box2_add(rb0, ga0, p);
+    };
+    auto sub = [&](T p) {
+        if constexpr (VEC2) { box2_sub(rb0, ga0, p.x); box2_sub(rb1, ga1, p.y); }
+        else box2_sub(rb0, ga0, p);
+    };
+    for (int yy = max(0, y0 - r); yy <= min(h - 1, y0 + r); yy++) add(__ldg(s2 + (size_t)yy * step));
+#pragma unroll 4
+    for (int y = y0; y < y1; y++) {
+        if constexpr (VEC2) d2[(size_t)y * step] = make_uint2(box2_out(rb0, ga0, M), box2_out(rb1, ga1, M));
+        else d2[(size_t)y * step] = box2_out(rb0, ga0, M);
+        const int ya = y + r + 1, ys = y - r;
+        if (ya < h) add(__ldg(s2 + (size_t)ya * step));
+        if (ys >= 0) sub(__ldg(s2 + (size_t)ys * step));
+    }
+}
+
+// Horizontal: one warp = one segment of `seg` pixels (a power of two, 32 .. 1024) of one row of a cell, staged in shared
+// memory with a skewed layout (index + index / 32) so that both the coalesced load/store phase (lane stride 1) and the
+// sliding phase (lane stride seg / 32: every lane slides over its own seg / 32 outputs) are free of bank conflicts.
+// Warps never synchronise with each other.
+constexpr int BOX2H_WARPS = 8, BOX2H_SEG = 1024;
+__device__ __forceinline__ int box2_skew(int i) { return i + (i >> 5); }
+__global__ void __launch_bounds__(BOX2H_WARPS * 32)
+k_box_blur_h2(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int pitch, const BoxCell *__restrict__ cells, int it,
+              int rows, int seg, int max_r)
+{
+    extern __shared__ uint32_t box_smem[];
+    const BoxCell c = cells[blockIdx.z];
+    const int r = c.rh[it], w = c.w, h = c.h;
+    const int x0 = blockIdx.x * seg;
+    if (x0 >= w || (int)(blockIdx.y * rows) >= h) return;
+    const int in_words = box2_skew(seg + 2 * max_r + 1) + 1, out_words = box2_skew(seg) + 1; // layout sized for the largest radius
+    const int n_in = seg + 2 * r + 1;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t *in = box_smem + (size_t)wid * (in_words + out_words);
+    uint32_t *out = in + in_words;
+    const int row_end = min((int)(blockIdx.y + 1) * rows, h);
+    const int per = seg >> 5;
+    const uint32_t M = box2_magic(r);
+    const uint32_t bias = (uint32_t)r | ((uint32_t)r << 16);
+    const size_t org = (size_t)c.y * pitch + c.x;
+    for (int y = blockIdx.y * rows + wid; y < row_end; y += BOX2H_WARPS) {
+        const uint32_t *row = src + org + (size_t)y * pitch;
+        uint32_t *orow = dst + org + (size_t)y * pitch;
+        if (r == 0) {
+            for (int i = lane; i < seg; i += 32)
+                if (x0 + i < w) orow[x0 + i] = row[x0 + i];
+            continue;
+        }
+        for (int i = lane; i < n_in; i += 32) {
+            const int gx = x0 - r + i;
+            in[box2_skew(i)] = (gx >= 0 && gx < w) ? __ldg(row + gx) : 0u;
+        }
+        __syncwarp();
+        {
+            const int j0 = lane * per; // this lane's outputs: j0 .. j0 + per - 1; output j sums in[j .. j + 2r]
+            uint32_t rb = bias, ga = bias;
+            for (int t = 0; t <= 2 * r; t++) box2_add(rb, ga, in[box2_skew(j0 + t)]);
+#pragma unroll 4
+            for (int k = 0; k < per; k++) {
+                const int j = j0 + k;
+                out[box2_skew(j)] = box2_out(rb, ga, M);
+                box2_add(rb, ga, in[box2_skew(j + 2 * r + 1)]);
+                box2_sub(rb, ga, in[box2_skew(j)]);
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < seg; i += 32) {
+            const int gx = x0 + i;
+            if (gx < w) orow[gx] = out[box2_skew(i)];
+        }
+        __syncwarp();
+    }
+}
+
+// Runs the 5 x (vertical, horizontal) passes over a list of cells, ping-ponging between `a` (holding the input) and `b`;
+// returns the buffer holding the result in *result.  `dev_cells` is the device copy of `cells`.  A pass whose radius is 0
+// in every cell is skipped (box_blur.rs:86-89 copies); in a pass some cells need, the others copy.
+static int box2_run_cells(rb_ctx *ctx, uint32_t *a, uint32_t *b, int pitch, const BoxCell *cells, int n_cells, const BoxCell *dev_cells,
+                          uint32_t **result)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        RB_CUDA(ctx, cudaFuncSetAttribute(k_box_blur_h2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+    }
+    int max_w = 0, max_h = 0;
+    bool vec2 = (pitch % 2) == 0;
+    for (int i = 0; i < n_cells; i++) {
+        max_w = std::max(max_w, (int)cells[i].w);
+        max_h = std::max(max_h, (int)cells[i].h);
+        vec2 = vec2 && (cells[i].x % 2) == 0 && (cells[i].w % 2) == 0;
+    }
+    int seg = 32;
+    while (seg < BOX2H_SEG && seg < max_w) seg <<= 1;
+    uint32_t *cur = a, *other = b;
+    for (int it = 0; it < 5; it++) {
+        int rv = 0, rh = 0;
+        for (int i = 0; i < n_cells; i++) {
+            rv = std::max(rv, (int)cells[i].rv[it]);
+            rh = std::max(rh, (int)cells[i].rh[it]);
+        }
+        if (rv > 0) {
+            // a chunk of `rows` rows pays 2r + 1 warm-up rows: keep that below ~1/6; then pick the column width per thread
+            // (8-byte or 4-byte accesses) that still puts ~1536 threads on every SM
+            int rows = 64;
+            while (rows < 512 && rows < 6 * (2 * rv + 1)) rows <<= 1;
+            const int chunks = (max_h + rows - 1) / rows;
+            const bool two = vec2 && (long long)(max_w / 2) * chunks * n_cells >= 1536LL * ctx->sm_count;
+            const int gx = (max_w / (two ? 2 : 1) + BOX2V_THREADS - 1) / BOX2V_THREADS;
+            dim3 grid(gx, chunks, n_cells);
+            if (two) k_box_blur_v2<true><<<grid, BOX2V_THREADS, 0, ctx->stream>>>(cur, other, pitch, dev_cells, it, rows);
+            else k_box_blur_v2<false><<<grid, BOX2V_THREADS, 0, ctx->stream>>>(cur, other, pitch, dev_cells, it, rows);
+            RB_LAUNCHED(ctx, "box_blur_v2");
+            std::swap(cur, other);
+        }
+        if (rh > 0) {
+            // rows are independent: cut the cell into enough CTAs (8 warps = 8 rows at a time) for ~8 per SM
+            const int gx = (max_w + seg - 1) / seg;
+            int rows = 256;
+            while (rows > 8 && (long long)gx * ((max_h + rows - 1) / rows) * n_cells < 8LL * ctx->sm_count) rows >>= 1;
+            const int in_words = seg + 2 * rh + 1 + ((seg + 2 * rh + 1) >> 5) + 1, out_words = seg + (seg >> 5) + 1;
+            const size_t smem = (size_t)BOX2H_WARPS * (in_words + out_words) * 4;
+            dim3 grid(gx, (max_h + rows - 1) / rows, n_cells);
+            k_box_blur_h2<<<grid, BOX2H_WARPS * 32, smem, ctx->stream>>>(cur, other, pitch, dev_cells, it, rows, seg, rh);
+            RB_LAUNCHED(ctx, "box_blur_h2");
+            std::swap(cur, other);
+        }
+    }
+    *result = cur;
+    return RB_OK;
+}
+
 // box_blur.rs:37-71 (host side; f32 arithmetic as in the reference)
 static void create_box_gauss(float sigma, int sizes[5])
 {
@@ -438,12 +633,25 @@ extern "C" int rb_filter_box_blur(rb_layer *l, double sigma_x, double sigma_y)
     create_box_gauss((float)sigma_y, bv);
 
     void *scratch = nullptr;
-    int st = rb_scratch(ctx, bytes, &scratch);
+    int st = rb_scratch(ctx, bytes + 256, &scratch);
     if (st != RB_OK) return st;
     uint32_t *cur = reinterpret_cast<uint32_t *>(l->d);
     uint32_t *other = reinterpret_cast<uint32_t *>(scratch);
     const bool aligned = (w % 4) == 0;
 
+    BoxCell cell{0, 0, w, h, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+    int max_r = 0;
+    for (int it = 0; it < 5; it++) {
+        cell.rv[it] = (bv[it] - 1) / 2;
+        cell.rh[it] = (bh[it] - 1) / 2;
+        max_r = std::max(max_r, std::max(cell.rv[it], cell.rh[it]));
+    }
+    if (max_r <= BOX2_MAX_R) { // integer-quotient passes; the layer is one cell
+        BoxCell *dev_cell = reinterpret_cast<BoxCell *>(reinterpret_cast<uint8_t *>(scratch) + ((bytes + 255) & ~(size_t)255));
+        RB_CUDA(ctx, cudaMemcpyAsync(dev_cell, &cell, sizeof(cell), cudaMemcpyHostToDevice, ctx->stream));
+        st = box2_run_cells(ctx, cur, other, w, &cell, 1, dev_cell, &cur);
+        if (st != RB_OK) return st;
+    } else
     for (int it = 0; it < 5; it++) {
         int rv = (bv[it] - 1) / 2, rh = (bh[it] - 1) / 2;
         if (rv > 0) { // box_blur_vert (radius 0 = copy, i.e. nothing to do with ping-pong buffers)
@@ -474,6 +682,52 @@ extern "C" int rb_filter_box_blur(rb_layer *l, double sigma_x, double sigma_y)
     }
     if (cur != reinterpret_cast<uint32_t *>(l->d)) {
         RB_CUDA(ctx, cudaMemcpyAsync(l->d, cur, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return RB_OK;
+}
+
+// Atlas form: rectangle i of the layer is blurred as a pixmap of its own (box_blur::apply on a sub-pixmap, windows
+// clipped to the rectangle) with its own standard deviations; pixels outside the rectangles are untouched.  One launch
+// per pass for all rectangles.  Rectangles must not overlap.
+extern "C" int rb_filter_box_blur_cells(rb_layer *l, int32_t n, const int32_t *rects, const double *sigma_x, const double *sigma_y)
+{
+    if (!l || n < 0 || (n > 0 && (!rects || !sigma_x || !sigma_y))) return RB_ERR_INVALID;
+    if (n == 0) return RB_OK;
+    if (n > 65535) return RB_ERR_UNSUPPORTED;
+    rb_ctx *ctx = l->ctx;
+    const int w = (int)l->w, h = (int)l->h;
+    std::vector<BoxCell> cells;
+    cells.reserve((size_t)n);
+    for (int32_t i = 0; i < n; i++) {
+        const int32_t x = rects[4 * i], y = rects[4 * i + 1], cw = rects[4 * i + 2], ch = rects[4 * i + 3];
+        if (x < 0 || y < 0 || cw <= 0 || ch <= 0 || (int64_t)x + cw > w || (int64_t)y + ch > h) return RB_ERR_INVALID;
+        int bh[5], bv[5];
+        create_box_gauss((float)sigma_x[i], bh);
+        create_box_gauss((float)sigma_y[i], bv);
+        BoxCell c{x, y, cw, ch, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+        bool any = false;
+        for (int it = 0; it < 5; it++) {
+            c.rv[it] = (bv[it] - 1) / 2;
+            c.rh[it] = (bh[it] - 1) / 2;
+            if (c.rv[it] > BOX2_MAX_R || c.rh[it] > BOX2_MAX_R) return RB_ERR_UNSUPPORTED;
+            any = any || c.rv[it] > 0 || c.rh[it] > 0;
+        }
+        if (any) cells.push_back(c);
+    }
+    if (cells.empty()) return RB_OK;
+    const size_t bytes = (size_t)w * h * 4, tbytes = cells.size() * sizeof(BoxCell);
+    void *scratch = nullptr;
+    int st = rb_scratch(ctx, bytes + 256 + tbytes, &scratch);
+    if (st != RB_OK) return st;
+    BoxCell *dev_cells = reinterpret_cast<BoxCell *>(reinterpret_cast<uint8_t *>(scratch) + ((bytes + 255) & ~(size_t)255));
+    RB_CUDA(ctx, cudaMemcpyAsync(dev_cells, cells.data(), tbytes, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t *px = reinterpret_cast<uint32_t *>(l->d), *res = nullptr;
+    st = box2_run_cells(ctx, px, reinterpret_cast<uint32_t *>(scratch), w, cells.data(), (int)cells.size(), dev_cells, &res);
+    if (st != RB_OK) return st;
+    if (res != px) { // odd number of passes: bring the cells back (only they were written)
+        for (const BoxCell &c : cells)
+            RB_CUDA(ctx, cudaMemcpy2DAsync(px + (size_t)c.y * w + c.x, (size_t)w * 4, res + (size_t)c.y * w + c.x, (size_t)w * 4,
+                                           (size_t)c.w * 4, (size_t)c.h, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     return RB_OK;
 }
@@ -694,6 +948,56 @@ __global__ void k_morph_pass(const uint32_t *__restrict__ src, uint32_t *__restr
     dst[(size_t)y * w + x] = acc;
 }
 
+// Both passes in one launch for windows up to MORPH_MAXC per axis: a CTA stages the footprint of a 64x32 output tile
+// in shared memory (pixels outside the image = the identity element, which is what clipping the window to the image
+// amounts to), filters it horizontally into a second shared array and vertically from there: 8 B/px of HBM traffic
+// instead of 16, and every window tap is a shared-memory read.  Pixels are staged as two u16x2 words (r,b | g,a) because
+// sm_100 has a native 16x2 min/max (VIMNMX.U16x2) while the 8x4 form is emulated with seven logic instructions.
+constexpr int MORPH_TW = 64, MORPH_TH = 32, MORPH_MAXC = 16;
+__device__ __forceinline__ uint2 morph_mm(uint2 a, uint2 b, bool dilate)
+{
+    return dilate ? make_uint2(__vmaxu2(a.x, b.x), __vmaxu2(a.y, b.y)) : make_uint2(__vminu2(a.x, b.x), __vminu2(a.y, b.y));
+}
+__global__ void __launch_bounds__(256)
+k_morph_tile(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h, int lox, int cx, int loy, int cy,
+             bool dilate)
+{
+    extern __shared__ uint2 morph_sm[];
+    const int SW = MORPH_TW + cx - 1, SH = MORPH_TH + cy - 1;
+    uint2 *A = morph_sm, *B = morph_sm + SH * SW;
+    const uint32_t iw = dilate ? 0u : 0x00ff00ffu;
+    const uint2 ident = make_uint2(iw, iw);
+    const int X0 = blockIdx.x * MORPH_TW, Y0 = blockIdx.y * MORPH_TH;
+    {   // staging: 2 rows of 128 threads (SW <= 79)
+        const int sx = threadIdx.x & 127, gx = X0 - lox + sx;
+        if (sx < SW)
+            for (int sy = threadIdx.x >> 7; sy < SH; sy += 2) {
+                const int gy = Y0 - loy + sy;
+                uint2 v = ident;
+                if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+                    const uint32_t p = __ldg(src + (size_t)gy * w + gx);
+                    v = make_uint2(p & 0x00ff00ffu, (p >> 8) & 0x00ff00ffu);
+                }
+                A[sy * SW + sx] = v;
+            }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SH * MORPH_TW; i += 256) {
+        const uint2 *a = A + (i >> 6) * SW + (i & 63);
+        uint2 acc = ident;
+        for (int t = 0; t < cx; t++) acc = morph_mm(acc, a[t], dilate);
+        B[i] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < MORPH_TH * MORPH_TW; i += 256) {
+        const int y = i >> 6, x = i & 63;
+        const uint2 *b = B + i;
+        uint2 acc = ident;
+        for (int t = 0; t < cy; t++) acc = morph_mm(acc, b[t * MORPH_TW], dilate);
+        if (X0 + x < w && Y0 + y < h) dst[(size_t)(Y0 + y) * w + X0 + x] = acc.x | (acc.y << 8);
+    }
+}
+
 static inline uint32_t f2u32_sat(float v)
 {
     if (!(v > 0.0f)) return 0;
@@ -713,6 +1017,25 @@ extern "C" int rb_filter_morphology(rb_layer *l, int op, float rx, float ry)
     int target_x = (int)f2u32_sat(floorf((float)columns / 2.0f));
     int target_y = (int)f2u32_sat(floorf((float)rows / 2.0f));
     size_t bytes = (size_t)w * h * 4;
+    if (columns >= 1 && rows >= 1 && columns <= (uint32_t)MORPH_MAXC && rows <= (uint32_t)MORPH_MAXC) {
+        // fused tile kernel; its output block becomes the layer's storage
+        uint32_t *out = nullptr;
+        RB_CUDA(ctx, cudaMallocAsync((void **)&out, bytes, ctx->stream));
+        const int SW = MORPH_TW + (int)columns - 1, SH = MORPH_TH + (int)rows - 1;
+        const size_t smem = (size_t)(SH * SW + SH * MORPH_TW) * 8;
+        dim3 grid((w + MORPH_TW - 1) / MORPH_TW, (h + MORPH_TH - 1) / MORPH_TH);
+        static bool attr_set = false;
+        if (!attr_set) {
+            RB_CUDA(ctx, cudaFuncSetAttribute(k_morph_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            attr_set = true;
+        }
+        k_morph_tile<<<grid, 256, smem, ctx->stream>>>(reinterpret_cast<const uint32_t *>(l->d), out, w, h, target_x,
+                                                       (int)columns, target_y, (int)rows, op == 1);
+        RB_LAUNCHED(ctx, "morph_tile");
+        RB_CUDA(ctx, cudaFreeAsync(l->d, ctx->stream));
+        l->d = reinterpret_cast<uint8_t *>(out);
+        return RB_OK;
+    }
     void *scratch = nullptr;
     int st = rb_scratch(ctx, bytes, &scratch);
     if (st != RB_OK) return st;
@@ -735,6 +1058,25 @@ struct ConvParams {
     float divisor, bias;
     int edge_mode, preserve_alpha;
 };
+
+__device__ __forceinline__ uint32_t conv_finish(float nr, float ng, float nb, float na, uint32_t in_p, const float *div255,
+                                                const ConvParams &P)
+{
+    const bool unit = P.divisor == 1.0f; // x / 1.0 == x: skip the IEEE division sequence for the usual divisor
+    if (P.preserve_alpha) na = div255[RB_A(in_p)];
+    else na = (unit ? na : __fdiv_rn(na, P.divisor)) + P.bias;
+    float ba = rb_f32_bound(0.0f, na, 1.0f);
+    float ch[3] = {nr, ng, nb};
+    uint32_t o[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float v = (unit ? ch[c] : __fdiv_rn(ch[c], P.divisor)) + P.bias * na;
+        if (P.preserve_alpha) v = rb_f32_bound(0.0f, v, 1.0f) * ba;
+        else v = rb_f32_bound(0.0f, v, ba);
+        o[c] = rb_f2u8(v * 255.0f + 0.5f);
+    }
+    return rb_pack(o[0], o[1], o[2], rb_f2u8(ba * 255.0f + 0.5f));
+}
 
 __global__ void k_convolve(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h,
                            const float *__restrict__ kernel, ConvParams P)
@@ -782,20 +1124,115 @@ __global__ void k_convolve(const uint32_t *__restrict__ src, uint32_t *__restric
             if (!P.preserve_alpha) na = na + div255[RB_A(p)] * k;
         }
     }
-    uint32_t in_p = src[(size_t)y * w + x];
-    if (P.preserve_alpha) na = div255[RB_A(in_p)];
-    else na = __fdiv_rn(na, P.divisor) + P.bias;
-    float ba = rb_f32_bound(0.0f, na, 1.0f);
-    float ch[3] = {nr, ng, nb};
-    uint32_t o[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        float v = __fdiv_rn(ch[c], P.divisor) + P.bias * na;
-        if (P.preserve_alpha) v = rb_f32_bound(0.0f, v, 1.0f) * ba;
-        else v = rb_f32_bound(0.0f, v, ba);
-        o[c] = rb_f2u8(v * 255.0f + 0.5f);
+    dst[(size_t)y * w + x] = conv_finish(nr, ng, nb, na, src[(size_t)y * w + x], div255, P);
+}
+
+// Fast path for the common 3x3 / 5x5 matrices.  A CTA of 32x8 threads produces a 32x32 tile: the tile's footprint is
+// staged in shared memory as float4 (the c/255 table is consulted once per staged pixel instead of once per tap; edge
+// modes `duplicate` / `wrap` are applied while staging, so the taps never test coordinates), every thread keeps the
+// flipped matrix in registers and computes 4 vertically adjacent outputs so a staged row is reused by up to ROWS
+// outputs.  Accumulation order and arithmetic are those of k_convolve (convolve_matrix.rs:56-82).  Edge mode `none`
+// skips taps instead of adding zeros, so CTAs whose footprint leaves the image take the generic per-pixel route there.
+constexpr int CONV_TW = 32, CONV_TH = 32, CONV_PER = 4;
+
+__device__ __forceinline__ void conv_generic_px(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h,
+                                                const float *kf, const float *div255, const ConvParams &P, int x, int y)
+{
+    float nr = 0.0f, ng = 0.0f, nb = 0.0f, na = 0.0f;
+    for (int oy = 0; oy < P.rows; oy++) {
+        int ty = y - P.target_y + oy;
+        if (ty < 0 || ty > h - 1) continue;
+        const uint32_t *row = src + (size_t)ty * w;
+        for (int ox = 0; ox < P.columns; ox++) {
+            int tx = x - P.target_x + ox;
+            if (tx < 0 || tx > w - 1) continue;
+            float k = kf[oy * P.columns + ox];
+            uint32_t p = __ldg(row + tx);
+            nr = nr + div255[RB_R(p)] * k;
+            ng = ng + div255[RB_G(p)] * k;
+            nb = nb + div255[RB_B(p)] * k;
+            if (!P.preserve_alpha) na = na + div255[RB_A(p)] * k;
+        }
     }
-    dst[(size_t)y * w + x] = rb_pack(o[0], o[1], o[2], rb_f2u8(ba * 255.0f + 0.5f));
+    dst[(size_t)y * w + x] = conv_finish(nr, ng, nb, na, src[(size_t)y * w + x], div255, P);
+}
+
+template <int COLS, int ROWS>
+__global__ void __launch_bounds__(256)
+k_convolve_tile(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h,
+                const float *__restrict__ kernel, ConvParams P)
+{
+    constexpr int SW = CONV_TW + COLS - 1, SH = CONV_TH + ROWS - 1;
+    __shared__ float div255[256];
+    __shared__ float kf[COLS * ROWS];
+    __shared__ float4 tile[SH * SW];
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    rb_fill_div255(div255);
+    if (tid < COLS * ROWS) {
+        int oy = tid / COLS, ox = tid - oy * COLS;
+        kf[tid] = kernel[(ROWS - oy - 1) * COLS + (COLS - ox - 1)];
+    }
+    __syncthreads();
+    const int X0 = blockIdx.x * CONV_TW, Y0 = blockIdx.y * CONV_TH;
+    const int fx0 = X0 - P.target_x, fy0 = Y0 - P.target_y;
+    const bool interior = fx0 >= 0 && fy0 >= 0 && fx0 + SW <= w && fy0 + SH <= h;
+    if (!interior && P.edge_mode == 0) {
+        for (int j = 0; j < CONV_PER; j++) {
+            int x = X0 + threadIdx.x, y = Y0 + threadIdx.y + 8 * j;
+            if (x < w && y < h) conv_generic_px(src, dst, w, h, kf, div255, P, x, y);
+        }
+        return;
+    }
+    for (int i = tid; i < SH * SW; i += 256) {
+        int sy = i / SW, sx = i - sy * SW;
+        int tx = fx0 + sx, ty = fy0 + sy;
+        if (!interior) {
+            if (P.edge_mode == 1) {
+                tx = max(0, min(w - 1, tx));
+                ty = max(0, min(h - 1, ty));
+            } else {
+                tx %= w;
+                if (tx < 0) tx += w;
+                ty %= h;
+                if (ty < 0) ty += h;
+            }
+        }
+        uint32_t p = __ldg(src + (size_t)ty * w + tx);
+        tile[i] = make_float4(div255[RB_R(p)], div255[RB_G(p)], div255[RB_B(p)], div255[RB_A(p)]);
+    }
+    __syncthreads();
+    float k[COLS * ROWS];
+#pragma unroll
+    for (int i = 0; i < COLS * ROWS; i++) k[i] = kf[i];
+    const int lx = threadIdx.x, ly = threadIdx.y * CONV_PER;
+    float nr[CONV_PER], ng[CONV_PER], nb[CONV_PER], na[CONV_PER];
+#pragma unroll
+    for (int j = 0; j < CONV_PER; j++) nr[j] = ng[j] = nb[j] = na[j] = 0.0f;
+    // Staged row r feeds output j with matrix row oy = r - j; for every output the taps arrive in (oy, ox) order.
+#pragma unroll
+    for (int r = 0; r < CONV_PER + ROWS - 1; r++) {
+        float4 v[COLS];
+#pragma unroll
+        for (int ox = 0; ox < COLS; ox++) v[ox] = tile[(ly + r) * SW + lx + ox];
+#pragma unroll
+        for (int j = 0; j < CONV_PER; j++) {
+            const int oy = r - j;
+            if (oy < 0 || oy >= ROWS) continue;
+#pragma unroll
+            for (int ox = 0; ox < COLS; ox++) {
+                const float kk = k[oy * COLS + ox];
+                nr[j] = nr[j] + v[ox].x * kk;
+                ng[j] = ng[j] + v[ox].y * kk;
+                nb[j] = nb[j] + v[ox].z * kk;
+                if (!P.preserve_alpha) na[j] = na[j] + v[ox].w * kk;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CONV_PER; j++) {
+        const int x = X0 + lx, y = Y0 + ly + j;
+        if (x < w && y < h) dst[(size_t)y * w + x] = conv_finish(nr[j], ng[j], nb[j], na[j], src[(size_t)y * w + x], div255, P);
+    }
 }
 
 extern "C" int rb_filter_convolve_matrix(rb_layer *l, const float *kernel, uint32_t columns, uint32_t rows,
@@ -808,18 +1245,29 @@ extern "C" int rb_filter_convolve_matrix(rb_layer *l, const float *kernel, uint3
     int w = (int)l->w, h = (int)l->h;
     size_t bytes = (size_t)w * h * 4;
     size_t kbytes = (size_t)columns * rows * sizeof(float);
+    // The result is written into a fresh pool block that then becomes the layer's storage (no copy back).
     void *scratch = nullptr;
-    int st = rb_scratch(ctx, bytes + 256 + kbytes, &scratch);
+    int st = rb_scratch(ctx, kbytes + 256, &scratch);
     if (st != RB_OK) return st;
-    uint32_t *tmp = reinterpret_cast<uint32_t *>(scratch);
-    float *dk = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(scratch) + ((bytes + 255) & ~(size_t)255));
+    float *dk = reinterpret_cast<float *>(scratch);
     // Pageable-host async copy is staged by the runtime before returning, so `kernel` may be freed by the caller.
     RB_CUDA(ctx, cudaMemcpyAsync(dk, kernel, kbytes, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t *out = nullptr;
+    RB_CUDA(ctx, cudaMallocAsync((void **)&out, bytes, ctx->stream));
     ConvParams P{(int)columns, (int)rows, (int)target_x, (int)target_y, divisor, bias, edge_mode, preserve_alpha ? 1 : 0};
-    dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
-    k_convolve<<<grid, block, kbytes, ctx->stream>>>(reinterpret_cast<uint32_t *>(l->d), tmp, w, h, dk, P);
-    RB_LAUNCHED(ctx, "convolve");
-    RB_CUDA(ctx, cudaMemcpyAsync(l->d, tmp, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    const uint32_t *in = reinterpret_cast<const uint32_t *>(l->d);
+    if ((columns == 3 && rows == 3) || (columns == 5 && rows == 5)) {
+        dim3 block(32, 8), grid((w + CONV_TW - 1) / CONV_TW, (h + CONV_TH - 1) / CONV_TH);
+        if (columns == 3) k_convolve_tile<3, 3><<<grid, block, 0, ctx->stream>>>(in, out, w, h, dk, P);
+        else k_convolve_tile<5, 5><<<grid, block, 0, ctx->stream>>>(in, out, w, h, dk, P);
+        RB_LAUNCHED(ctx, "convolve_tile");
+    } else {
+        dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+        k_convolve<<<grid, block, kbytes, ctx->stream>>>(in, out, w, h, dk, P);
+        RB_LAUNCHED(ctx, "convolve");
+    }
+    RB_CUDA(ctx, cudaFreeAsync(l->d, ctx->stream));
+    l->d = reinterpret_cast<uint8_t *>(out);
     return RB_OK;
 }
 
@@ -995,6 +1443,60 @@ extern "C" int rb_filter_component_transfer(rb_layer *l, const rb_transfer_fn fu
 }
 
 // =================================================================================================
+// filter/mod.rs:606-617 (apply_drop_shadow's flood): every pixel becomes the flood colour with its opacity scaled by the
+// pixel's alpha, premultiplied — a function of the alpha byte alone, tabulated on the host with tiny-skia's f32
+// arithmetic (Color::from_rgba8, apply_opacity, premultiply, to_color_u8) and applied as one table lookup.  8 B/px.
+// =================================================================================================
+struct AlphaLut {
+    uint32_t v[256];
+};
+__global__ void __launch_bounds__(256) k_alpha_lut(uint32_t *__restrict__ px, size_t n, AlphaLut L)
+{
+    __shared__ uint32_t s[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s[i] = L.v[i];
+    __syncthreads();
+    size_t n4 = n >> 2;
+    uint4 *v = reinterpret_cast<uint4 *>(px);
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        uint4 p = v[i];
+        p.x = s[p.x >> 24]; p.y = s[p.y >> 24]; p.z = s[p.z >> 24]; p.w = s[p.w >> 24];
+        v[i] = p;
+    }
+    size_t tail = n & 3;
+    if (blockIdx.x == 0 && threadIdx.x < tail) {
+        size_t i = (n4 << 2) + threadIdx.x;
+        px[i] = s[px[i] >> 24];
+    }
+}
+
+extern "C" int rb_filter_flood_alpha(rb_layer *l, uint8_t r, uint8_t g, uint8_t b, uint8_t a)
+{
+    if (!l) return RB_ERR_INVALID;
+    AlphaLut L;
+    volatile float cr = (float)r / 255.0f, cg = (float)g / 255.0f, cb = (float)b / 255.0f, ca = (float)a / 255.0f;
+    for (int i = 0; i < 256; i++) {
+        volatile float op = (float)i / 255.0f;
+        volatile float al = h_f32_bound(0.0f, ca * op, 1.0f); // Color::apply_opacity
+        float pr = cr, pg = cg, pb = cb;                      // Color::premultiply
+        if (al != 1.0f) {
+            volatile float t;
+            t = cr * al; pr = h_f32_bound(0.0f, t, 1.0f);
+            t = cg * al; pg = h_f32_bound(0.0f, t, 1.0f);
+            t = cb * al; pb = h_f32_bound(0.0f, t, 1.0f);
+        }
+        volatile float qr = pr * 255.0f, qg = pg * 255.0f, qb = pb * 255.0f, qa = al * 255.0f; // to_color_u8
+        L.v[i] = (uint32_t)h_f2u8(qr + 0.5f) | ((uint32_t)h_f2u8(qg + 0.5f) << 8) | ((uint32_t)h_f2u8(qb + 0.5f) << 16) |
+                 ((uint32_t)h_f2u8(qa + 0.5f) << 24);
+    }
+    rb_ctx *ctx = l->ctx;
+    size_t n = (size_t)l->w * l->h;
+    k_alpha_lut<<<rb_grid_1d(ctx, (n + 3) / 4, 256), 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(l->d), n, L);
+    RB_LAUNCHED(ctx, "flood_alpha");
+    return RB_OK;
+}
+
+// =================================================================================================
 // composite.rs:14-50 — arithmetic operator, 12 B/px (two reads, one write)
 // =================================================================================================
 __global__ void __launch_bounds__(256)
@@ -1111,10 +1613,19 @@ __device__ __forceinline__ float rb_powf(float a, float b) { return (float)pow((
 
 __global__ void k_lighting(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h, LightParams P)
 {
+    // the CTA's 34x10 alpha footprint is staged once (the border variants below never touch a neighbour outside the image,
+    // so what is staged for those positions does not matter)
+    __shared__ uint8_t s_alpha[10][36];
+    for (int i = threadIdx.y * 32 + threadIdx.x; i < 340; i += 256) {
+        const int sy = i / 34, sx = i - sy * 34;
+        const int gx = (int)(blockIdx.x * 32) - 1 + sx, gy = (int)(blockIdx.y * 8) - 1 + sy;
+        s_alpha[sy][sx] = (gx >= 0 && gx < w && gy >= 0 && gy < h) ? (uint8_t)RB_A(__ldg(src + (size_t)gy * w + gx)) : (uint8_t)0;
+    }
+    __syncthreads();
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
-    auto A = [&](int dx, int dy) -> int { return (int)RB_A(__ldg(src + (size_t)(y + dy) * w + (x + dx))); };
+    auto A = [&](int dx, int dy) -> int { return (int)s_alpha[threadIdx.y + 1 + dy][threadIdx.x + 1 + dx]; };
     const int bx = (x == 0) ? 0 : (x == w - 1 ? 2 : 1);
     const int by = (y == 0) ? 0 : (y == h - 1 ? 2 : 1);
     const float F12 = 1.0f / 2.0f, F13 = 1.0f / 3.0f, F14 = 1.0f / 4.0f, F23 = 2.0f / 3.0f;

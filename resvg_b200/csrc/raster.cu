@@ -1149,6 +1149,67 @@ extern "C" int rb_draw_layer(rb_layer *dst, const rb_layer *src, int32_t x, int3
     return RB_OK;
 }
 
+// Region-wise composite for atlases (many small documents in one layer, rb_batch_set_viewport): for every rectangle i,
+// the w x h pixels of `src` at src_xy[i] are drawn onto `dst` at (x, y) with their own opacity — what render.rs:108-133
+// does per document when a group needs a layer of its own (sub-pixmap + draw_pixmap with the group's opacity), and what
+// filter/mod.rs does when it offsets / merges sub-images; one launch for all documents.
+struct LayerRect {
+    int32_t x, y, w, h, sx, sy;
+    float opacity;
+};
+__global__ void __launch_bounds__(256)
+k_draw_layer_rects(uint32_t *__restrict__ dst, int dw, const uint32_t *__restrict__ src, int sw, const LayerRect *__restrict__ rects,
+                   int blend)
+{
+    const LayerRect r = rects[blockIdx.z];
+    for (int y = blockIdx.y; y < r.h; y += gridDim.y) {
+        uint32_t *drow = dst + (size_t)(r.y + y) * dw + r.x;
+        const uint32_t *srow = src + (size_t)(r.sy + y) * sw + r.sx;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < r.w; i += gridDim.x * blockDim.x)
+            drow[i] = draw_layer_px(__ldg(srow + i), drow[i], r.opacity, blend);
+    }
+}
+
+extern "C" int rb_draw_layer_rects(rb_layer *dst, const rb_layer *src, int32_t n, const int32_t *rects, const int32_t *src_xy,
+                                   const float *opacity, int32_t blend_mode)
+{
+    if (!dst || !src || n < 0 || (n > 0 && (!rects || !opacity)) || blend_mode < 0 || blend_mode > 28 || dst->d == src->d)
+        return RB_ERR_INVALID;
+    if (n == 0 || blend_mode == RB_BLEND_DESTINATION) return RB_OK;
+    rb_ctx *ctx = dst->ctx;
+    std::vector<LayerRect> host;
+    host.reserve((size_t)n);
+    int max_w = 0, max_h = 0;
+    for (int32_t i = 0; i < n; i++) { // clip every rectangle to both layers
+        int64_t x = rects[4 * i], y = rects[4 * i + 1], w = rects[4 * i + 2], h = rects[4 * i + 3];
+        int64_t sx = src_xy ? src_xy[2 * i] : x, sy = src_xy ? src_xy[2 * i + 1] : y;
+        if (w <= 0 || h <= 0) continue;
+        int64_t cut = std::max<int64_t>(std::max<int64_t>(-x, -sx), 0);
+        x += cut; sx += cut; w -= cut;
+        cut = std::max<int64_t>(std::max<int64_t>(-y, -sy), 0);
+        y += cut; sy += cut; h -= cut;
+        w = std::min<int64_t>(w, std::min<int64_t>((int64_t)dst->w - x, (int64_t)src->w - sx));
+        h = std::min<int64_t>(h, std::min<int64_t>((int64_t)dst->h - y, (int64_t)src->h - sy));
+        if (w <= 0 || h <= 0) continue;
+        host.push_back(LayerRect{(int32_t)x, (int32_t)y, (int32_t)w, (int32_t)h, (int32_t)sx, (int32_t)sy, opacity[i]});
+        max_w = std::max(max_w, (int)w);
+        max_h = std::max(max_h, (int)h);
+    }
+    if (host.empty()) return RB_OK;
+    LayerRect *dev = nullptr;
+    RB_CUDA(ctx, cudaMallocAsync((void **)&dev, host.size() * sizeof(LayerRect), ctx->stream));
+    RB_CUDA(ctx, cudaMemcpyAsync(dev, host.data(), host.size() * sizeof(LayerRect), cudaMemcpyHostToDevice, ctx->stream));
+    for (size_t first = 0; first < host.size(); first += 65535) {
+        const unsigned cnt = (unsigned)std::min<size_t>(65535, host.size() - first);
+        dim3 grid((unsigned)std::min((max_w + 255) / 256, 16), (unsigned)std::min(max_h, 64), cnt);
+        k_draw_layer_rects<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(dst->d), (int)dst->w,
+                                                          reinterpret_cast<const uint32_t *>(src->d), (int)src->w, dev + first, blend_mode);
+        RB_LAUNCHED(ctx, "draw_layer_rects");
+    }
+    RB_CUDA(ctx, cudaFreeAsync(dev, ctx->stream));
+    return RB_OK;
+}
+
 // =================================================================================================
 // masks — tiny-skia mask.rs
 // =================================================================================================
@@ -1192,7 +1253,7 @@ __device__ __forceinline__ uint32_t mask_px(uint32_t p, int luminance, const flo
     if (!luminance) return av;
     float r = div255[RB_R(p)], g = div255[RB_G(p)], b = div255[RB_B(p)];
     const float a = div255[av];
-    if (av != 0) { r = __fdiv_rn(r, a); g = __fdiv_rn(g, a); b = __fdiv_rn(b, a); }
+    if (av != 0 && av != 255) { r = __fdiv_rn(r, a); g = __fdiv_rn(g, a); b = __fdiv_rn(b, a); } // x / 1.0 == x
     const float luma = r * 0.2126f + g * 0.7152f + b * 0.0722f; // Rec. 709 (pinned by masking/mask goldens)
     float v = (luma * a) * 255.0f;
     v = v < 0.0f ? 0.0f : (v > 255.0f ? 255.0f : v); // f32::clamp

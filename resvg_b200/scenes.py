@@ -41,18 +41,21 @@ def _gather_ranges(off, idx):
 
 
 def paths_scene(width=8192, height=8192, n_paths=100_000, seed=0x5EED0002, rmin=8.0, rmax=256.0, strokes=True,
-                stroke_wmin=0.5, stroke_wmax=16.0, dashed=0.1):
+                stroke_wmin=0.5, stroke_wmax=16.0, dashed=0.1, u=None, p_solid=0.5, p_linear=0.8):
     """C2 'paths8k': n_paths random closed paths; 70 % are filled, 20 % filled then stroked, 10 % stroked only
     (strokes=True), a fraction `dashed` of the strokes with a dash array of 2-4 intervals U[2, 32] (an odd list is
     repeated, as usvg does).  The returned arrays hold one entry per DRAW (a filled+stroked path is two entries).  Stroke
     width is log-uniform [stroke_wmin, stroke_wmax]; anti-aliased strokes of at most 1 px are hairlines for tiny-skia."""
-    u = splitmix64_uniform(seed, n_paths * STREAM).reshape(n_paths, STREAM)
+    if u is None:
+        u = splitmix64_uniform(seed, n_paths * STREAM).reshape(n_paths, STREAM)
+    else:  # caller-provided uniforms, one row of STREAM values per path (icons_docs: one SplitMix64 stream per document)
+        n_paths = len(u)
     cx = u[:, 0] * width
     cy = u[:, 1] * height
     radius = np.exp(np.log(rmin) + u[:, 2] * (np.log(rmax) - np.log(rmin)))
     n_seg = 3 + np.minimum((u[:, 3] * 10).astype(np.int64), 9)  # 3..12
     evenodd = (u[:, 4] < 0.5).astype(np.uint8)
-    paint_kind = np.where(u[:, 5] < 0.5, 0, np.where(u[:, 5] < 0.8, 1, 2)).astype(np.int32)  # solid/linear/radial
+    paint_kind = np.where(u[:, 5] < p_solid, 0, np.where(u[:, 5] < p_linear, 1, 2)).astype(np.int32)  # solid/linear/radial
     anti_alias = (u[:, 6] < 0.95).astype(np.int32)
 
     # segments: per segment one kind draw + 6 coordinate draws, starting at column 32
@@ -238,3 +241,47 @@ def subset(scene, n):
             out[k] = scene[k][:n].copy()
     out["stop_off"] = scene["stop_off"][: n + 1].copy()
     return out
+
+
+ICON_SEED = 0x5EED0005
+ICON_SIZE = 256
+ICON_HEAD = 8  # per-document uniforms drawn before the first path's row
+
+
+def icons_docs(first_doc, n_docs, size=ICON_SIZE):
+    """C5 'icons' (SURVEY.md section 8(d)): documents first_doc .. first_doc + n_docs - 1, each size x size px and seeded
+    ICON_SEED + i: 5-40 closed paths (radius log-U[4, 96], filled, 80 % solid / 10 % linear / 10 % radial, 95 % AA);
+    10 % of the documents put the second half of their paths into one group with opacity U[0.3, 0.9]; another 5 % wrap
+    everything into a group with a drop shadow (stdDeviation U[2, 4], dx = dy = 4, black at 50 %, sRGB).  Returns the
+    packed paths of all documents in document-local coordinates (the paths_scene layout) plus per-document tables:
+    doc_first (n_docs + 1 path offsets), group_first (first path of the opacity group or -1), group_opacity, shadow_sigma
+    (0 = none)."""
+    ids = np.arange(first_doc, first_doc + n_docs, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        seeds = np.uint64(ICON_SEED) + ids
+
+    def rows(seed_arr, start, count):
+        """count consecutive SplitMix64 uniforms per row, row r starting at output index start[r] of stream seed_arr[r]"""
+        with np.errstate(over="ignore"):
+            k = (start.astype(np.uint64)[:, None] + np.arange(1, count + 1, dtype=np.uint64)[None, :])
+            z = seed_arr[:, None] + k * _GAMMA
+            z = (z ^ (z >> np.uint64(30))) * _M1
+            z = (z ^ (z >> np.uint64(27))) * _M2
+            z = z ^ (z >> np.uint64(31))
+        return (z >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
+
+    head = rows(seeds, np.zeros(n_docs, np.uint64), ICON_HEAD)
+    n_paths = 5 + np.minimum((head[:, 0] * 36).astype(np.int64), 35)
+    doc_first = np.zeros(n_docs + 1, np.uint32)
+    doc_first[1:] = np.cumsum(n_paths)
+    doc_of = np.repeat(np.arange(n_docs), n_paths)
+    j = np.arange(int(doc_first[-1])) - doc_first[:-1].astype(np.int64)[doc_of]
+    u = rows(seeds[doc_of], (ICON_HEAD + j * STREAM).astype(np.uint64), STREAM)
+    sc = paths_scene(size, size, rmin=4.0, rmax=96.0, strokes=False, u=u, p_solid=0.8, p_linear=0.9)
+    grouped = head[:, 1] < 0.10
+    shadow = (head[:, 1] >= 0.10) & (head[:, 1] < 0.15)
+    sc.update(n_docs=n_docs, first_doc=first_doc, doc_first=doc_first, doc_of=doc_of.astype(np.int32), doc_size=size,
+              group_first=np.where(grouped, doc_first[:-1].astype(np.int64) + n_paths // 2, -1),
+              group_opacity=(0.3 + 0.6 * head[:, 2]).astype(np.float32),
+              shadow_sigma=np.where(shadow, 2.0 + 2.0 * head[:, 3], 0.0))
+    return sc

@@ -638,8 +638,11 @@ def _sized(be, layer, w, h):
 
 def _recolor(be, layer, color, opacity):
     """filter/mod.rs:606-617: every pixel becomes flood colour * (opacity.to_u8()/255 * alpha/255), premultiplied."""
-    arr = be.to_numpy(layer)
     a8 = to_u8_opacity(opacity)
+    if be.name == "gpu":
+        be.rb.filters.flood_alpha(color, a8, layer)
+        return
+    arr = be.to_numpy(layer)
     ca = f32(a8) / f32(255.0)
     al = np.clip(ca * (arr[..., 3].astype(np.float32) / f32(255.0)), 0, 1).astype(np.float32)
     out = np.empty_like(arr)
@@ -648,7 +651,4 @@ def _recolor(be, layer, color, opacity):
         pm = np.where(al == 1.0, c, np.clip(c * al, 0, 1)).astype(np.float32)
         out[..., i] = (pm * f32(255.0) + f32(0.5)).astype(np.uint8)
     out[..., 3] = (al * f32(255.0) + f32(0.5)).astype(np.uint8)
-    if be.name == "gpu":
-        layer.upload(out)
-    else:
-        layer[...] = out
+    layer[...] = out

@@ -80,6 +80,16 @@ def test_box_blur_radius_larger_than_image(ctx, oracle):
     assert_exact(_run(ctx, img, lambda f, l: f.box_blur(300.0, 2.0, l)), oracle.box_blur(300.0, 2.0, img))
 
 
+def test_box_blur_radius_sweep(ctx, oracle):
+    """Every box radius the integer-quotient passes can select (and the first ones beyond, which take the float kernels),
+    on dense random pixels, odd and even widths."""
+    for w, h in ((260, 70), (131, 33)):
+        img = random_premul(w, h, 11)
+        for sigma in [2.0 + 3.1 * k for k in range(0, 56)]:
+            assert_exact(_run(ctx, img, lambda f, l: f.box_blur(sigma, sigma * 0.7, l)), oracle.box_blur(sigma, sigma * 0.7, img),
+                         f"box sweep {sigma} {w}x{h}")
+
+
 def test_box_blur_large(ctx, oracle):
     img = random_premul(2048, 1024, 6, sparse=True)
     for s in (2.0, 8.0, 64.0):

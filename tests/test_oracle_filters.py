@@ -34,6 +34,22 @@ def _box_axis_numpy(img, r, axis):
     return np.clip(v, 0, 255).astype(np.uint8)
 
 
+def test_box_quantisation_equals_an_exact_integer_quotient():
+    """The identity the fast CUDA box-blur passes rely on (filters.cu, BOX2): for every radius r <= 127 and every
+    possible window sum, round(sum as f32 * (1.0 / d as f32)) with the reference's add/subtract-1.5*2^23 rounding
+    (box_blur.rs:148, 327-331) equals ((sum + r) * ceil(2^24 / d)) >> 24, d = 2r + 1."""
+    magic = np.float32(12582912.0)
+    for r in range(1, 128):
+        d = 2 * r + 1
+        sums = np.arange(0, 255 * d + 1, dtype=np.int64)
+        v = sums.astype(np.float32) * (np.float32(1.0) / np.float32(d))
+        ref = ((v + magic) - magic).astype(np.int64)
+        m = ((1 << 24) + d - 1) // d
+        prod = (sums + r) * m
+        assert prod.max() < 2**32 and 255 * d + r < 65536
+        assert np.array_equal(prod >> 24, ref), r
+
+
 def test_box_blur_matches_window_sum_formulation():
     for (w, h, sx, sy) in [(37, 23, 2.0, 2.0), (64, 9, 6.0, 3.0), (15, 40, 0.0, 4.0), (8, 8, 30.0, 30.0)]:
         img = random_premul(w, h, 1, sparse=True)
