@@ -30,6 +30,10 @@ WORKLOADS = {
     # name: (width, height, n_paths, seed)
     "paths8k": (8192, 8192, 100_000, 0x5EED0002),
     "paths2k": (2048, 2048, 6_000, 0x5EED0002),  # smoke-sized variant for quick checks (not a bench line)
+    # BASELINE configs[4] / C5: 100 000 documents of 256x256 px, 1024 per 8192x8192 atlas, sharded by atlas chunk over the GPUs
+    "icons": (8192, 8192, 100_000, 0x5EED0005),
+    # BASELINE configs[2] / C3 (ii): the filter chain over one 8192x8192 layer holding 1000 C2-style shapes
+    "filters8k": (8192, 8192, 1_000, 0x5EED0003),
 }
 
 
@@ -250,14 +254,315 @@ def kernel_table(rb, ctx, layer, W, H, peak, reps=3):
     return out
 
 
+ICON_CHUNK = 1024  # documents per atlas (32 x 32 cells of 256 px)
+
+
+def icon_chunks_for_rank(n_docs, rank, world):
+    """[(first_doc, n)] of the atlas chunks this rank renders: chunk c -> rank c mod world (document-parallel, no collective)."""
+    chunks = [(f, min(ICON_CHUNK, n_docs - f)) for f in range(0, n_docs, ICON_CHUNK)]
+    return chunks[rank::world]
+
+
+def run_icons(args, rank, local_rank, world, torch, dist):
+    """Workload `icons` (BASELINE configs[4]): a step = every one of the 100 000 documents rendered once.
+    value: all chunks' batches resident in HBM, kernels only, CUDA events.  e2e: record + host edge build + H2D + kernels +
+    D2H of every atlas into pinned memory through the C ABI, downloads overlapped with the next atlas (two atlases)."""
+    import resvg_b200 as rb
+    from resvg_b200 import documents, shard
+    W, H, n_docs, _ = WORKLOADS["icons"]
+    n_docs = int(args.docs) if args.docs else n_docs
+    ctx = rb.Context(local_rank)
+    n_threads = 0 if world == 1 else shard.host_threads(world)
+    mine = icon_chunks_for_rank(n_docs, rank, world)
+    t0 = time.perf_counter()
+    scs = [documents.prepare_chunk(f, n) for f, n in mine]  # synthetic documents: generated outside every timed region
+    gen_s = time.perf_counter() - t0
+    my_docs = sum(n for _, n in mine)
+    atl = [documents.IconAtlas(ctx), documents.IconAtlas(ctx)]
+    chunks = [atl[0].prepare(sc, n_threads) for sc in scs]
+    ctx.synchronize()
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ctx.synchronize()
+
+    def step():
+        for ch in chunks:
+            atl[0].run(ch)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        step()
+    ms_step = ctx.timer_end() / args.steps
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = ctx.launch_count - launches0
+
+    # dominant kernel (k_raster_warp) alone, and its algorithmic bytes from the kernel's own pixel counters
+    ms_kernel = ms_pre = 0.0
+    alg_bytes = 0
+    stats = dict(draws=0, edges=0, pairs=0, upload_bytes=0)
+    for ch in chunks:
+        for b in (ch["base"], ch["group"]):
+            if b is None:
+                continue
+            b.run()
+            pre, ras = ctx.last_run_ms()
+            ms_pre += pre
+            ms_kernel += ras
+            n_rmw, n_store = b.run_counting()
+            st = b.stats()
+            alg_bytes += 8 * n_rmw + 4 * n_store + 16 * st["edges"]
+            for k in stats:
+                stats[k] += st[k]
+    for ch in chunks:
+        atl[0].release(ch)
+    ctx.synchronize()
+
+    # end to end
+    pinned = [rb.PinnedBuffer(W * H * 4), rb.PinnedBuffer(W * H * 4)]
+    e2e_h2d = 0
+
+    def e2e_step():
+        nonlocal e2e_h2d
+        prev = [None, None]
+        h2d = 0
+        for c, sc in enumerate(scs):
+            a = atl[c & 1]
+            a.atlas.download_end()  # the download that last read this atlas
+            if prev[c & 1] is not None:
+                a.release(prev[c & 1])
+            ch = a.render(sc, n_threads)
+            a.atlas.download_begin(pinned[c & 1].array.ctypes.data)
+            h2d += ch["base"].stats()["upload_bytes"] + (ch["group"].stats()["upload_bytes"] if ch["group"] is not None else 0)
+            prev[c & 1] = ch
+        for k in (0, 1):
+            atl[k].atlas.download_end()
+            if prev[k] is not None:
+                atl[k].release(prev[k])
+        e2e_h2d = h2d
+
+    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ctx.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+
+    ms_step, ms_kernel, e2e_s = shard.max_over_ranks([ms_step, ms_kernel, e2e_s], world, f"cuda:{local_rank}")
+    if rank != 0:
+        return
+    total_mpx = n_docs * 256 * 256 / 1e6
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+    out = {
+        "metric": "Mpixels/s rendered", "value": total_mpx / (ms_step * 1e-3), "unit": "Mpx/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8/u16 fixed point + f32", "data": "synthetic",
+        "config": {"workload": "icons", "documents": n_docs, "document_px": [256, 256], "atlas": [W, H], "documents_per_atlas": ICON_CHUNK,
+                   "mix": "5-40 filled paths per document, radius log-U[4,96], 80% solid / 10% linear / 10% radial, 95% AA; "
+                          "10% of the documents with one opacity group, 5% with a drop shadow (sigma U[2,4])",
+                   "sharding": "atlas chunk c (1024 documents) -> GPU c mod N, no collective",
+                   "l2": "every atlas pass touches 2 x 256 MiB layers (> 126 MB L2); rank 0 holds %d chunks" % len(mine),
+                   "rank0": dict(stats, documents=my_docs, generate_s=round(gen_s, 2))},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_raster_warp", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes": alg_bytes,
+                     "kernel_ms": ms_kernel, "prepass_ms": ms_pre,
+                     "model": "8 B per blended px + 4 B per opaque-stored px + 16 B per line edge, summed over rank 0's batches"},
+        "e2e": {"value": total_mpx / e2e_s, "unit": "Mpx/s", "h2d_bytes_per_step": int(e2e_h2d),
+                "d2h_bytes_per_step": len(mine) * W * H * 4, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                "note": "per atlas: record + host edge build + H2D + kernels, D2H of the atlas overlapped with the next atlas"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from tests import icons_ref  # the CPU checker: cpu_baseline only
+        n_s = max(16, min(n_docs, int(args.cpu_sample) // 8))
+        sc = scs[0] if scs[0]["n_docs"] >= n_s else scs[0]
+        n_s = min(n_s, sc["n_docs"])
+        _, dt = icons_ref.render_docs(sc, icons_ref.prepare(sc), range(n_s))
+        out["cpu_baseline"] = {"value": n_s * 0.065536 / dt, "unit": "Mpx/s", "cores": 1, "kind": "port",
+                               "sample": f"documents 0..{n_s - 1} of the same batch, one at a time, {dt:.2f} s; oracle restatement of "
+                                         "the resvg/tiny-skia CPU path"}
+    print(json.dumps(out))
+
+
+def run_filters8k(args, rank, local_rank, world, torch, dist):
+    """Workload `filters8k` (BASELINE configs[2]): a step = the 10-primitive filter chain over one
+    8192x8192 layer (every rank its own layer).  value: layer resident; e2e: upload of the source layer, chain, download."""
+    import resvg_b200 as rb
+    from resvg_b200 import _ffi, scenes, shard
+    W, H, n_paths, seed = WORKLOADS["filters8k"]
+    ctx = rb.Context(local_rank)
+    scene = scenes.paths_scene(W, H, n_paths, shard.scene_seed(seed, rank))
+    scene["paints"] = scenes.to_paint_array(scene, _ffi.Paint)
+    scene["strokes"] = scenes.to_stroke_array(scene, _ffi.Stroke)
+    src = ctx.layer(W, H)
+    b = rb.Batch(src)
+    b.fill_paths(scene)
+    b.submit(0 if world == 1 else shard.host_threads(world))
+    b.close()
+    F = rb.filters
+    a, t, c = ctx.layer(W, H), ctx.layer(W, H), ctx.layer(W, H)
+    light = rb.make_light("distant", azimuth=45.0, elevation=60.0)
+    sharpen = [0, -1, 0, -1, 5, -1, 0, -1, 0]
+
+    def chain():
+        F.into_linear_rgb(a)
+        F.box_blur(8.0, 8.0, a)
+        F.morphology("dilate", 3.0, 3.0, a)
+        F.convolve_matrix(sharpen, 3, 3, 1, 1, 1.0, 0.0, "duplicate", False, a)
+        F.turbulence(0.0, 0.0, 1.0, 1.0, 0.02, 0.02, 3, 7, False, False, t)
+        F.multiply_alpha(t)
+        F.arithmetic(0.5, 0.5, 0.5, 0.0, a, t, c)
+        F.diffuse_lighting(5.0, 1.0, (255, 255, 255), light, c, a)
+        F.box_blur(64.0, 64.0, a)
+        F.into_srgb(a)
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ctx.synchronize()
+
+    def step():
+        a.copy_from(src)
+        chain()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        step()
+    ms_step = ctx.timer_end() / args.steps
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = ctx.launch_count - launches0
+    # the chain's dominant primitive alone: the two box blurs (20 of the chain's passes)
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        F.box_blur(8.0, 8.0, a)
+        F.box_blur(64.0, 64.0, a)
+    ms_blur = ctx.timer_end() / args.steps
+
+    host_src = src.download()
+    pin_in, pin_out = rb.PinnedBuffer(W * H * 4), rb.PinnedBuffer(W * H * 4)
+    pin_in.array[:] = host_src.reshape(-1)
+
+    def e2e_step():
+        a.upload_ptr(pin_in.array.ctypes.data)
+        chain()
+        a.download_ptr(pin_out.array.ctypes.data)
+
+    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ctx.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    ms_step, ms_blur, e2e_s = shard.max_over_ranks([ms_step, ms_blur, e2e_s], world, f"cuda:{local_rank}")
+    if rank != 0:
+        return
+    mpx = W * H / 1e6
+    peak, peak_src = measured_peaks()
+    blur_bytes = 160 * W * H  # 2 blurs x 10 passes x 8 B/px (the reference's pass structure)
+    out = {
+        "metric": "Mpixels/s rendered", "value": shard.aggregate_throughput(mpx, world, ms_step * 1e-3), "unit": "Mpx/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8 + f32/f64", "data": "synthetic",
+        "config": {"workload": "filters8k", "canvas": [W, H], "source": "1000 C2-style shapes (seed 0x5EED0003)",
+                   "chain": "linearRGB: blur 8 -> dilate 3 -> sharpen 3x3 -> arithmetic(0.5,0.5,0.5,0) with turbulence(0.02, 3 oct) -> "
+                            "diffuse lighting (distant 45/60, surfaceScale 5) -> blur 64 -> sRGB",
+                   "l2": "every pass streams 256 MiB layers (> 126 MB L2)", "sharding": "one layer per GPU, no collective"},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_box_blur_v2 + k_box_blur_h2 (20 of the chain's passes)",
+                     "achieved": blur_bytes / (ms_blur * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": blur_bytes / (ms_blur * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes": blur_bytes, "kernel_ms": ms_blur, "model": "8 B/px per box pass, 20 passes"},
+        "e2e": {"value": shard.aggregate_throughput(mpx, world, e2e_s), "unit": "Mpx/s", "h2d_bytes_per_step": W * H * 4,
+                "d2h_bytes_per_step": W * H * 4, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from tests import oracle_ffi as O  # the CPU checker: cpu_baseline only
+        n = 1024
+        img = np.ascontiguousarray(host_src[:n, :n])
+        t0 = time.perf_counter()
+        x = O.into_linear_rgb(img)
+        x = O.box_blur(8.0, 8.0, x)
+        x = O.morphology("dilate", 3.0, 3.0, x)
+        x = O.convolve_matrix(sharpen, 3, 3, 1, 1, 1.0, 0.0, "duplicate", False, x)
+        tb = O.multiply_alpha(O.turbulence(0.0, 0.0, 1.0, 1.0, 0.02, 0.02, 3, 7, False, False, n, n))
+        x = O.arithmetic(0.5, 0.5, 0.5, 0.0, x, tb)
+        x = O.diffuse_lighting(5.0, 1.0, (255, 255, 255), O.make_light("distant", azimuth=45.0, elevation=60.0), x)
+        x = O.into_srgb(O.box_blur(64.0, 64.0, x))
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n * n / 1e6 / dt, "unit": "Mpx/s", "cores": 1, "kind": "port",
+                               "sample": f"the same chain on the top-left {n}x{n} px of the source layer, {dt:.2f} s; oracle restatement"}
+    print(json.dumps(out))
+
+
+def run_reference_icons(args, cores):
+    """--impl reference --workload icons: the CPU checker renders documents one at a time on every host core (one document
+    stream per thread, as `resvg` would be run per file)."""
+    from resvg_b200 import scenes
+    from tests import icons_ref
+    n_docs = int(args.docs) if args.docs else WORKLOADS["icons"][2]
+    per = max(8, min(256, int(args.cpu_sample) // (8 * cores)))
+    sc = scenes.icons_docs(0, per * cores)
+    paints = icons_ref.prepare(sc)
+
+    def step():
+        ths = [threading.Thread(target=icons_ref.render_docs, args=(sc, paints, range(t * per, (t + 1) * per))) for t in range(cores)]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        return time.perf_counter() - t0
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    times = [step() for _ in range(max(1, min(args.steps, 3)))]
+    dt = statistics.mean(times)
+    v = per * cores * 0.065536 / dt
+    sample = f"{cores} threads x {per} documents (documents 0..{per * cores - 1} of the batch) per step, one document at a time"
+    print(json.dumps({
+        "impl": "reference", "metric": "Mpixels/s rendered", "value": v, "unit": "Mpx/s", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8/u16 fixed point + f32", "data": "synthetic",
+        "config": {"workload": "icons", "documents": n_docs, "document_px": [256, 256]},
+        "cpu_baseline": {"value": v, "unit": "Mpx/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path (oracle restatement; Rust cannot be built here) on all host cores."""
     if rank != 0:
         return
     from resvg_b200 import scenes
+    cores = min(os.cpu_count() or 1, 32)
+    if args.workload == "icons":
+        return run_reference_icons(args, cores)
+    if args.workload == "filters8k":
+        raise SystemExit("--impl reference: workload filters8k has a cpu_baseline in the ours arm only")
     R = oracle_lib()
     W, H, n_paths, seed = WORKLOADS[args.workload]
-    cores = min(os.cpu_count() or 1, 32)
     scs = [scenes.paths_scene(W, H, n_paths, seed + t) for t in range(min(cores, 4))]
     n_draws = scs[0]["n_paths"]
     n_sample = max(200, min(n_draws, int(args.cpu_sample)))
@@ -308,6 +613,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-table", action="store_true", help="skip the per-kernel roofline table of the filter / compositing kernels")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--docs", type=int, default=0, help="icons: number of documents (default: the 100 000 of the recipe)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -327,6 +633,12 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if args.workload in ("icons", "filters8k"):
+        (run_icons if args.workload == "icons" else run_filters8k)(args, rank, local_rank, world, torch, dist)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     import resvg_b200 as rb
     from resvg_b200 import _ffi, scenes, shard

@@ -63,6 +63,11 @@ void *rb_layer_device_ptr(rb_layer *layer);
 /* PixmapMut::from_bytes / Pixmap::data (c-api/lib.rs:887-890): host <-> device copies. */
 int rb_layer_upload(rb_layer *layer, const uint8_t *host_rgba);
 int rb_layer_download(rb_layer *layer, uint8_t *host_rgba);
+/* Asynchronous form: the copy is ordered after everything enqueued on the layer so far and runs on a copy stream of the
+ * context, so the next render (into another layer) overlaps it; host_rgba should be pinned (rb_host_alloc).  The layer must
+ * not be written, and host_rgba not read, until rb_layer_download_end has returned. */
+int rb_layer_download_begin(rb_layer *layer, uint8_t *host_rgba);
+int rb_layer_download_end(rb_layer *layer);
 /* Pixmap::fill(color) with an already premultiplied RGBA8 colour (filter/mod.rs:112, 824). */
 int rb_layer_fill(rb_layer *layer, uint8_t r, uint8_t g, uint8_t b, uint8_t a);
 /* Pixmap::clone (filter/mod.rs:531): dst and src must have equal size. */

@@ -141,6 +141,8 @@ SIGNATURES = {
                                   C.c_int32, _vp]),
     "rb_ctx_last_run_ms": (_i, [_vp, _vp]),
     "rb_batch_set_viewport": (_i, [_vp, C.c_int32, C.c_int32, _u32, _u32]),
+    "rb_layer_download_begin": (_i, [_vp, _vp]),
+    "rb_layer_download_end": (_i, [_vp]),
     "rb_batch_draw_documents": (_i, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, f32p]),
     "rb_draw_layer_rects": (_i, [_vp, _vp, C.c_int32, _vp, _vp, _vp, C.c_int32]),
     "rb_filter_box_blur_cells": (_i, [_vp, C.c_int32, _vp, _vp, _vp]),

@@ -137,6 +137,13 @@ class Layer:
     def download_ptr(self, ptr: int):
         self.ctx.check(lib.rb_layer_download(self._h, ptr), "download")
 
+    def download_begin(self, ptr: int):
+        """Asynchronous download into pinned host memory at `ptr` (rb_layer_download_begin); overlaps later renders."""
+        self.ctx.check(lib.rb_layer_download_begin(self._h, C.c_void_p(ptr)), "layer_download_begin")
+
+    def download_end(self):
+        self.ctx.check(lib.rb_layer_download_end(self._h), "layer_download_end")
+
     def fill(self, r: int, g: int, b: int, a: int):
         self.ctx.check(lib.rb_layer_fill(self._h, r, g, b, a), "fill")
 

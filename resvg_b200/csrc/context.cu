@@ -70,6 +70,7 @@ void rb_ctx_release(rb_ctx *ctx)
     for (auto &e : ctx->ev_run) if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -93,6 +94,7 @@ extern "C" int rb_ctx_create(int device, rb_ctx **out)
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return RB_ERR_CUDA; }
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RB_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RB_ERR_CUDA; }
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
     cudaEventCreateWithFlags(&ctx->staging_ev, cudaEventDisableTiming);
@@ -170,7 +172,8 @@ extern "C" int rb_layer_create(rb_ctx *ctx, uint32_t w, uint32_t h, rb_layer **o
     cudaSetDevice(ctx->device);
     RB_CUDA(ctx, cudaMallocAsync(&d, bytes, ctx->stream));
     RB_CUDA(ctx, cudaMemsetAsync(d, 0, bytes, ctx->stream));
-    rb_layer *l = new rb_layer{ctx, w, h, (uint8_t *)d};
+    rb_layer *l = new rb_layer();
+    l->ctx = ctx; l->w = w; l->h = h; l->d = (uint8_t *)d;
     rb_ctx_retain(ctx);
     *out = l;
     return RB_OK;
@@ -179,6 +182,9 @@ extern "C" int rb_layer_create(rb_ctx *ctx, uint32_t w, uint32_t h, rb_layer **o
 extern "C" void rb_layer_destroy(rb_layer *l)
 {
     if (!l) return;
+    if (l->dl_pending) cudaEventSynchronize(l->dl_done);
+    if (l->dl_ready) cudaEventDestroy(l->dl_ready);
+    if (l->dl_done) cudaEventDestroy(l->dl_done);
     cudaFreeAsync(l->d, l->ctx->stream);
     rb_ctx_release(l->ctx);
     delete l;
@@ -200,6 +206,36 @@ extern "C" int rb_layer_download(rb_layer *l, uint8_t *host)
     if (!l || !host) return RB_ERR_INVALID;
     RB_CUDA(l->ctx, cudaMemcpyAsync(host, l->d, (size_t)l->w * l->h * 4, cudaMemcpyDeviceToHost, l->ctx->stream));
     RB_CUDA(l->ctx, cudaStreamSynchronize(l->ctx->stream));
+    return RB_OK;
+}
+
+// Asynchronous download: the copy is ordered after everything enqueued on the layer so far and runs on the context's
+// copy stream, so the kernels of the NEXT render (into another layer) overlap it.  `host` should be pinned (rb_host_alloc).
+// The layer must not be written again, and `host` not read, before rb_layer_download_end has returned.
+extern "C" int rb_layer_download_begin(rb_layer *l, uint8_t *host)
+{
+    if (!l || !host) return RB_ERR_INVALID;
+    rb_ctx *ctx = l->ctx;
+    if (l->dl_pending) RB_CUDA(ctx, cudaEventSynchronize(l->dl_done));
+    if (!l->dl_ready) {
+        RB_CUDA(ctx, cudaEventCreateWithFlags(&l->dl_ready, cudaEventDisableTiming));
+        RB_CUDA(ctx, cudaEventCreateWithFlags(&l->dl_done, cudaEventDisableTiming));
+    }
+    RB_CUDA(ctx, cudaEventRecord(l->dl_ready, ctx->stream));
+    RB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, l->dl_ready, 0));
+    RB_CUDA(ctx, cudaMemcpyAsync(host, l->d, (size_t)l->w * l->h * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    RB_CUDA(ctx, cudaEventRecord(l->dl_done, ctx->copy_stream));
+    l->dl_pending = true;
+    return RB_OK;
+}
+
+extern "C" int rb_layer_download_end(rb_layer *l)
+{
+    if (!l) return RB_ERR_INVALID;
+    if (l->dl_pending) {
+        RB_CUDA(l->ctx, cudaEventSynchronize(l->dl_done));
+        l->dl_pending = false;
+    }
     return RB_OK;
 }
 

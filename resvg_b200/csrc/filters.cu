@@ -422,11 +422,12 @@ constexpr int BOX2_MAX_R = 120;
 
 __device__ __forceinline__ void box2_add(uint32_t &rb, uint32_t &ga, uint32_t p) { rb += p & 0x00ff00ffu; ga += (p >> 8) & 0x00ff00ffu; }
 __device__ __forceinline__ void box2_sub(uint32_t &rb, uint32_t &ga, uint32_t p) { rb -= p & 0x00ff00ffu; ga -= (p >> 8) & 0x00ff00ffu; }
-__device__ __forceinline__ uint32_t box2_out(uint32_t rb, uint32_t ga, uint32_t M)
+// M8 = M << 8, so that (n * M) >> 24 is the high word of n * M8: one IMAD.HI per channel.
+__device__ __forceinline__ uint32_t box2_out(uint32_t rb, uint32_t ga, uint32_t M8)
 {
-    const uint32_t r = ((rb & 0xffffu) * M) >> 24, b = ((rb >> 16) * M) >> 24;
-    const uint32_t g = ((ga & 0xffffu) * M) >> 24, a = ((ga >> 16) * M) >> 24;
-    return r | (g << 8) | (b << 16) | (a << 24);
+    const uint32_t r = __umulhi(rb & 0xffffu, M8), b = __umulhi(rb >> 16, M8);
+    const uint32_t g = __umulhi(ga & 0xffffu, M8), a = __umulhi(ga >> 16, M8);
+    return __byte_perm(__byte_perm(r, g, 0x0040), __byte_perm(b, a, 0x0040), 0x5410);
 }
 
 // Both kernels work on a list of CELLS: rectangles of the buffer that are blurred as if each were a pixmap of its own
@@ -436,7 +437,7 @@ struct BoxCell {
     int32_t x, y, w, h;
     int32_t rv[5], rh[5];
 };
-__device__ __forceinline__ uint32_t box2_magic(int r) { return ((1u << 24) + (uint32_t)(2 * r)) / (uint32_t)(2 * r + 1); } // ceil(2^24 / d)
+__device__ __forceinline__ uint32_t box2_magic(int r) { return (((1u << 24) + (uint32_t)(2 * r)) / (uint32_t)(2 * r + 1)) << 8; } // ceil(2^24 / d) << 8
 
 // Vertical: one thread = two adjacent columns (8-byte accesses; VEC2 needs even cell x / width / pitch) or one column,
 // over `rows` consecutive rows of the cell.  Radius 0 copies (the passes ping-pong between two buffers).
@@ -521,7 +522,21 @@ k_box_blur_h2(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int 
             in[box2_skew(i)] = (gx >= 0 && gx < w) ? __ldg(row + gx) : 0u;
         }
         __syncwarp();
-        {
+        if (per == 32) {
+            // j0 = 32 * lane: skew(j0 + m) = 33 * lane + m + (m >> 5) with m warp-uniform, so every address is the lane's
+            // base plus a uniform offset
+            const uint32_t *li = in + 33 * lane;
+            uint32_t *lo = out + 33 * lane;
+            uint32_t rb = bias, ga = bias;
+            for (int t = 0; t <= 2 * r; t++) box2_add(rb, ga, li[t + (t >> 5)]);
+#pragma unroll 8
+            for (int k = 0; k < 32; k++) {
+                const int m = k + 2 * r + 1;
+                lo[k] = box2_out(rb, ga, M);
+                box2_add(rb, ga, li[m + (m >> 5)]);
+                box2_sub(rb, ga, li[k]);
+            }
+        } else {
             const int j0 = lane * per; // this lane's outputs: j0 .. j0 + per - 1; output j sums in[j .. j + 2r]
             uint32_t rb = bias, ga = bias;
             for (int t = 0; t <= 2 * r; t++) box2_add(rb, ga, in[box2_skew(j0 + t)]);
@@ -1613,19 +1628,10 @@ __device__ __forceinline__ float rb_powf(float a, float b) { return (float)pow((
 
 __global__ void k_lighting(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h, LightParams P)
 {
-    // the CTA's 34x10 alpha footprint is staged once (the border variants below never touch a neighbour outside the image,
-    // so what is staged for those positions does not matter)
-    __shared__ uint8_t s_alpha[10][36];
-    for (int i = threadIdx.y * 32 + threadIdx.x; i < 340; i += 256) {
-        const int sy = i / 34, sx = i - sy * 34;
-        const int gx = (int)(blockIdx.x * 32) - 1 + sx, gy = (int)(blockIdx.y * 8) - 1 + sy;
-        s_alpha[sy][sx] = (gx >= 0 && gx < w && gy >= 0 && gy < h) ? (uint8_t)RB_A(__ldg(src + (size_t)gy * w + gx)) : (uint8_t)0;
-    }
-    __syncthreads();
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= w || y >= h) return;
-    auto A = [&](int dx, int dy) -> int { return (int)s_alpha[threadIdx.y + 1 + dy][threadIdx.x + 1 + dx]; };
+    auto A = [&](int dx, int dy) -> int { return (int)RB_A(__ldg(src + (size_t)(y + dy) * w + (x + dx))); };
     const int bx = (x == 0) ? 0 : (x == w - 1 ? 2 : 1);
     const int by = (y == 0) ? 0 : (y == h - 1 ? 2 : 1);
     const float F12 = 1.0f / 2.0f, F13 = 1.0f / 3.0f, F14 = 1.0f / 4.0f, F23 = 2.0f / 3.0f;

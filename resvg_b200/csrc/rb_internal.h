@@ -12,6 +12,7 @@
 struct rb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // device-to-host downloads that overlap the next render (rb_layer_download_begin)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_run[3] = {nullptr, nullptr, nullptr}; // last batch run: start, after the pre-pass, after the raster kernel
     std::string err;
@@ -39,6 +40,8 @@ struct rb_layer {
     rb_ctx *ctx;
     uint32_t w, h;
     uint8_t *d; // w*h*4 bytes, premultiplied RGBA8
+    cudaEvent_t dl_ready = nullptr, dl_done = nullptr; // rb_layer_download_begin / _end
+    bool dl_pending = false;
 };
 
 struct rb_mask {

@@ -89,7 +89,7 @@ def test_draw_layer_rects_equals_per_rect_draw_layer(ctx):
     import resvg_b200 as rb
     from tests.util import random_premul
     base, src = random_premul(96, 64, 1), random_premul(96, 64, 2, sparse=True)
-    rects = np.array([[0, 0, 32, 32], [40, 8, 17, 23], [64, 40, 32, 24], [90, 60, 20, 20], [5, 40, 0, 3]], np.int32)
+    rects = np.array([[0, 0, 32, 32], [40, 8, 17, 23], [64, 40, 32, 24], [90, 2, 20, 20], [5, 40, 0, 3]], np.int32)
     op = np.array([0.5, 1.0, 0.25, 0.8, 0.3], np.float32)
     dst = ctx.layer_from(base)
     s = ctx.layer_from(src)
