@@ -439,9 +439,76 @@ struct BoxCell {
 };
 __device__ __forceinline__ uint32_t box2_magic(int r) { return (((1u << 24) + (uint32_t)(2 * r)) / (uint32_t)(2 * r + 1)) << 8; } // ceil(2^24 / d) << 8
 
-// Vertical: one thread = two adjacent columns (8-byte accesses; VEC2 needs even cell x / width / pitch) or one column,
-// over `rows` consecutive rows of the cell.  Radius 0 copies (the passes ping-pong between two buffers).
-constexpr int BOX2V_THREADS = 128;
+// Vertical: one thread = one column of the cell over `rows` consecutive rows.  The 2r + 1 rows inside the window live in
+// a shared-memory ring (each thread only ever touches its own column of it, so there is no synchronisation), which makes
+// the pass read every source row once: re-reading the row that leaves the window from global memory missed L2 on full
+// 8192-wide layers (ncu: 558 MB read for a 268 MB layer) and eviction hints did not change that.  Loads are issued
+// BOX2V_AHEAD rows ahead of the sliding sum.  Radius 0 copies (the passes ping-pong between two buffers).
+constexpr int BOX2V_THREADS = 128, BOX2V_AHEAD = 8;
+__global__ void __launch_bounds__(BOX2V_THREADS)
+k_box_blur_v3(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int pitch, const BoxCell *__restrict__ cells, int it,
+              int rows)
+{
+    extern __shared__ uint32_t box_ring[]; // [2 * r_max + 1][BOX2V_THREADS]
+    const BoxCell c = cells[blockIdx.z];
+    const int r = c.rv[it], h = c.h;
+    const int x = blockIdx.x * BOX2V_THREADS + threadIdx.x;
+    const int y0 = blockIdx.y * rows, y1 = min(y0 + rows, h);
+    if (x >= c.w || y0 >= h) return;
+    const size_t org = (size_t)c.y * pitch + c.x + x;
+    const uint32_t *s = src + org;
+    uint32_t *d = dst + org;
+    if (r == 0) {
+        for (int y = y0; y < y1; y++) d[(size_t)y * pitch] = s[(size_t)y * pitch];
+        return;
+    }
+    uint32_t *ring = box_ring + threadIdx.x;
+    const int win = 2 * r + 1;
+    const uint32_t M = box2_magic(r);
+    const uint32_t bias = (uint32_t)r | ((uint32_t)r << 16);
+    uint32_t rb = bias, ga = bias;
+    // warm-up: rows y0 - r .. y0 + r fill slots 0 .. 2r (rows outside the cell are zeros)
+    for (int k0 = 0; k0 < win; k0 += BOX2V_AHEAD) {
+        uint32_t p[BOX2V_AHEAD];
+#pragma unroll
+        for (int k = 0; k < BOX2V_AHEAD; k++) {
+            const int yy = y0 - r + k0 + k;
+            p[k] = (k0 + k < win && yy >= 0 && yy < h) ? __ldg(s + (size_t)yy * pitch) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < BOX2V_AHEAD; k++)
+            if (k0 + k < win) {
+                ring[(k0 + k) * BOX2V_THREADS] = p[k];
+                box2_add(rb, ga, p[k]);
+            }
+    }
+    int slot = 0; // holds row y - r, the one leaving the window next
+    for (int yb = y0; yb < y1; yb += BOX2V_AHEAD) {
+        uint32_t p[BOX2V_AHEAD];
+#pragma unroll
+        for (int k = 0; k < BOX2V_AHEAD; k++) {
+            const int ya = yb + k + r + 1;
+            p[k] = (yb + k < y1 && ya < h) ? __ldg(s + (size_t)ya * pitch) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < BOX2V_AHEAD; k++) {
+            const int y = yb + k;
+            if (y < y1) {
+                d[(size_t)y * pitch] = box2_out(rb, ga, M);
+                const uint32_t old = ring[slot * BOX2V_THREADS];
+                ring[slot * BOX2V_THREADS] = p[k];
+                box2_add(rb, ga, p[k]);
+                box2_sub(rb, ga, old);
+                slot = slot + 1 == win ? 0 : slot + 1;
+            }
+        }
+    }
+}
+
+// Vertical pass for narrow windows (2r + 1 < BOX2V_RING_MIN): the row leaving the window is simply read again — it is
+// at most 15 rows behind and still in L2 — which is cheaper than keeping a ring.  One thread = two adjacent columns
+// (8-byte accesses; VEC2 needs even cell x / width / pitch) or one column.
+constexpr int BOX2V_RING_MIN = 16;
 template <bool VEC2>
 __global__ void __launch_bounds__(BOX2V_THREADS)
 k_box_blur_v2(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int pitch, const BoxCell *__restrict__ cells, int it,
@@ -566,6 +633,7 @@ static int box2_run_cells(rb_ctx *ctx, uint32_t *a, uint32_t *b, int pitch, cons
     static bool attr_set = false;
     if (!attr_set) {
         RB_CUDA(ctx, cudaFuncSetAttribute(k_box_blur_h2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        RB_CUDA(ctx, cudaFuncSetAttribute(k_box_blur_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * BOX2_MAX_R + 1) * BOX2V_THREADS * 4));
         attr_set = true;
     }
     int max_w = 0, max_h = 0;
@@ -584,11 +652,8 @@ static int box2_run_cells(rb_ctx *ctx, uint32_t *a, uint32_t *b, int pitch, cons
             rv = std::max(rv, (int)cells[i].rv[it]);
             rh = std::max(rh, (int)cells[i].rh[it]);
         }
-        if (rv > 0) {
-            // a chunk of `rows` rows pays 2r + 1 warm-up rows: keep that below ~1/6; then pick the column width per thread
-            // (8-byte or 4-byte accesses) that still puts ~1536 threads on every SM
-            int rows = 64;
-            while (rows < 512 && rows < 6 * (2 * rv + 1)) rows <<= 1;
+        if (rv > 0 && 2 * rv + 1 < BOX2V_RING_MIN) {
+            int rows = 128;
             const int chunks = (max_h + rows - 1) / rows;
             const bool two = vec2 && (long long)(max_w / 2) * chunks * n_cells >= 1536LL * ctx->sm_count;
             const int gx = (max_w / (two ? 2 : 1) + BOX2V_THREADS - 1) / BOX2V_THREADS;
@@ -596,6 +661,16 @@ static int box2_run_cells(rb_ctx *ctx, uint32_t *a, uint32_t *b, int pitch, cons
             if (two) k_box_blur_v2<true><<<grid, BOX2V_THREADS, 0, ctx->stream>>>(cur, other, pitch, dev_cells, it, rows);
             else k_box_blur_v2<false><<<grid, BOX2V_THREADS, 0, ctx->stream>>>(cur, other, pitch, dev_cells, it, rows);
             RB_LAUNCHED(ctx, "box_blur_v2");
+            std::swap(cur, other);
+        } else if (rv > 0) {
+            // a chunk of `rows` rows pays 2r + 1 warm-up rows: long chunks for wide windows, but enough CTAs for two per SM
+            int rows = 2 * rv + 1 >= 64 ? 512 : (2 * rv + 1 >= 16 ? 256 : 128);
+            const int gx = (max_w + BOX2V_THREADS - 1) / BOX2V_THREADS;
+            while (rows > 32 && (long long)gx * ((max_h + rows - 1) / rows) * n_cells < 2LL * ctx->sm_count) rows >>= 1;
+            const size_t smem = (size_t)(2 * rv + 1) * BOX2V_THREADS * 4;
+            dim3 grid(gx, (max_h + rows - 1) / rows, n_cells);
+            k_box_blur_v3<<<grid, BOX2V_THREADS, smem, ctx->stream>>>(cur, other, pitch, dev_cells, it, rows);
+            RB_LAUNCHED(ctx, "box_blur_v3");
             std::swap(cur, other);
         }
         if (rh > 0) {
@@ -1854,20 +1929,21 @@ __device__ __forceinline__ double tb_lerp(double t, double a, double b)
 
 __global__ void __launch_bounds__(256)
 k_turbulence(uint32_t *__restrict__ dst, int w, int h, const int *__restrict__ g_lat, const double *__restrict__ g_grad,
-             TurbParams P)
+             TurbParams P, int strip)
 {
-    extern __shared__ double s_grad[]; // 4*514*2 doubles, then 514 ints
+    extern __shared__ __align__(16) double s_grad[]; // 4*514*2 doubles (read as double2), then 514 ints
     int *s_lat = reinterpret_cast<int *>(s_grad + 4 * TB_BLEN * 2);
     for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 4 * TB_BLEN * 2; i += blockDim.x * blockDim.y)
         s_grad[i] = g_grad[i];
     for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < TB_BLEN; i += blockDim.x * blockDim.y) s_lat[i] = g_lat[i];
     __syncthreads();
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-
-    // turbulence.rs:47 — point in user space
-    const double px = __ddiv_rn(__dadd_rn((double)x, P.offset_x), P.sx);
+    // a CTA of 32 x 8 threads walks a strip of 32 x `strip` pixels (256 on large layers), so the 37 KB of tables are staged
+    // once per 8192 pixels instead of once per 256
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    const int y_end = min(h, (int)(blockIdx.y + 1) * strip);
+    const double px = __ddiv_rn(__dadd_rn((double)x, P.offset_x), P.sx); // turbulence.rs:47 — point in user space
+    for (int y = blockIdx.y * strip + threadIdx.y; y < y_end; y += blockDim.y) {
     const double py = __ddiv_rn(__dadd_rn((double)y, P.offset_y), P.sy);
     // turbulence.rs:158-195 — stitching set-up (identical for the four channels)
     double bfx = P.bfx, bfy = P.bfy;
@@ -1891,26 +1967,27 @@ k_turbulence(uint32_t *__restrict__ dst, int w, int h, const int *__restrict__ g
         wrap_x = __double2int_rz(__dadd_rn(__dadd_rn(__dmul_rn((double)x, bfx), (double)TB_PERLIN_N), (double)st_w));
         wrap_y = __double2int_rz(__dadd_rn(__dadd_rn(__dmul_rn((double)y, bfy), (double)TB_PERLIN_N), (double)st_h));
     }
-    uint32_t out[4];
-#pragma unroll 1
-    for (int ch = 0; ch < 4; ch++) {
-        const double *grad = s_grad + ch * TB_BLEN * 2;
-        double sum = 0.0;
+    // The reference evaluates the four channels one after the other (turbulence.rs:47-75), each running the octave loop of
+    // :158-222 over noise2 (:224-285).  Everything in noise2 except the gradient vectors is independent of the channel, so
+    // the loops are swapped here: per octave the lattice cell, the fractions and the s-curves are computed once and the four
+    // channels only differ in their gradient look-ups; every channel still performs the reference's operations in the
+    // reference's order.  `x / ratio` with ratio = 2^o is computed as x * 2^-o, which is the same number exactly.
+    double sum[4] = {0.0, 0.0, 0.0, 0.0};
+    {
         double vx = __dmul_rn(px, bfx), vy = __dmul_rn(py, bfy);
-        double ratio = 1.0;
+        double inv_ratio = 1.0;
         int sw = st_w, sh = st_h, wx = wrap_x, wy = wrap_y;
         for (int o = 0; o < P.octaves; o++) {
-            // noise2 — turbulence.rs:224-285
             double t = __dadd_rn(vx, (double)TB_PERLIN_N);
             int bx0 = __double2int_rz(t);
             int bx1 = (int)((unsigned)bx0 + 1u);
-            double rx0 = __dsub_rn(t, (double)__double2ll_rz(t));
-            double rx1 = __dsub_rn(rx0, 1.0);
+            const double rx0 = __dsub_rn(t, (double)__double2ll_rz(t));
+            const double rx1 = __dsub_rn(rx0, 1.0);
             t = __dadd_rn(vy, (double)TB_PERLIN_N);
             int by0 = __double2int_rz(t);
             int by1 = (int)((unsigned)by0 + 1u);
-            double ry0 = __dsub_rn(t, (double)__double2ll_rz(t));
-            double ry1 = __dsub_rn(ry0, 1.0);
+            const double ry0 = __dsub_rn(t, (double)__double2ll_rz(t));
+            const double ry1 = __dsub_rn(ry0, 1.0);
             if (P.stitch) {
                 if (bx0 >= wx) bx0 = (int)((unsigned)bx0 - (unsigned)sw);
                 if (bx1 >= wx) bx1 = (int)((unsigned)bx1 - (unsigned)sw);
@@ -1918,25 +1995,28 @@ k_turbulence(uint32_t *__restrict__ dst, int w, int h, const int *__restrict__ g
                 if (by1 >= wy) by1 = (int)((unsigned)by1 - (unsigned)sh);
             }
             bx0 &= 0xff; bx1 &= 0xff; by0 &= 0xff; by1 &= 0xff;
-            int i = s_lat[bx0], j = s_lat[bx1];
-            int b00 = s_lat[i + by0], b10 = s_lat[j + by0], b01 = s_lat[i + by1], b11 = s_lat[j + by1];
-            double sxc = tb_s_curve(rx0), syc = tb_s_curve(ry0);
-            const double *q = grad + b00 * 2;
-            double u = __dadd_rn(__dmul_rn(rx0, q[0]), __dmul_rn(ry0, q[1]));
-            q = grad + b10 * 2;
-            double v = __dadd_rn(__dmul_rn(rx1, q[0]), __dmul_rn(ry0, q[1]));
-            double a = tb_lerp(sxc, u, v);
-            q = grad + b01 * 2;
-            u = __dadd_rn(__dmul_rn(rx0, q[0]), __dmul_rn(ry1, q[1]));
-            q = grad + b11 * 2;
-            v = __dadd_rn(__dmul_rn(rx1, q[0]), __dmul_rn(ry1, q[1]));
-            double b = tb_lerp(sxc, u, v);
-            double nz = tb_lerp(syc, a, b);
-            if (P.fractal) sum = __dadd_rn(sum, __ddiv_rn(nz, ratio));
-            else sum = __dadd_rn(sum, __ddiv_rn(fabs(nz), ratio));
+            const int i = s_lat[bx0], j = s_lat[bx1];
+            const int b00 = s_lat[i + by0], b10 = s_lat[j + by0], b01 = s_lat[i + by1], b11 = s_lat[j + by1];
+            const double sxc = tb_s_curve(rx0), syc = tb_s_curve(ry0);
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++) {
+                const double2 *grad = reinterpret_cast<const double2 *>(s_grad) + ch * TB_BLEN;
+                double2 q = grad[b00];
+                double u = __dadd_rn(__dmul_rn(rx0, q.x), __dmul_rn(ry0, q.y));
+                q = grad[b10];
+                double v = __dadd_rn(__dmul_rn(rx1, q.x), __dmul_rn(ry0, q.y));
+                const double a = tb_lerp(sxc, u, v);
+                q = grad[b01];
+                u = __dadd_rn(__dmul_rn(rx0, q.x), __dmul_rn(ry1, q.y));
+                q = grad[b11];
+                v = __dadd_rn(__dmul_rn(rx1, q.x), __dmul_rn(ry1, q.y));
+                const double b = tb_lerp(sxc, u, v);
+                const double nz = tb_lerp(syc, a, b);
+                sum[ch] = __dadd_rn(sum[ch], __dmul_rn(P.fractal ? nz : fabs(nz), inv_ratio));
+            }
             vx = __dmul_rn(vx, 2.0);
             vy = __dmul_rn(vy, 2.0);
-            ratio = __dmul_rn(ratio, 2.0);
+            inv_ratio = __dmul_rn(inv_ratio, 0.5);
             if (P.stitch) {
                 sw = (int)((unsigned)sw * 2u);
                 wx = (int)(2u * (unsigned)wx - (unsigned)TB_PERLIN_N);
@@ -1944,10 +2024,15 @@ k_turbulence(uint32_t *__restrict__ dst, int w, int h, const int *__restrict__ g
                 wy = (int)(2u * (unsigned)wy - (unsigned)TB_PERLIN_N);
             }
         }
-        double n = P.fractal ? __ddiv_rn(__dadd_rn(__dmul_rn(sum, 255.0), 255.0), 2.0) : __dmul_rn(sum, 255.0);
+    }
+    uint32_t out[4];
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) {
+        const double n = P.fractal ? __dmul_rn(__dadd_rn(__dmul_rn(sum[ch], 255.0), 255.0), 0.5) : __dmul_rn(sum[ch], 255.0);
         out[ch] = rb_f2u8(rb_f32_bound(0.0f, (float)n, 255.0f) + 0.5f);
     }
     dst[(size_t)y * w + x] = rb_pack(out[0], out[1], out[2], out[3]);
+    }
 }
 
 // turbulence.rs:287-294
@@ -2020,9 +2105,11 @@ extern "C" int rb_filter_turbulence(rb_layer *dest, double offset_x, double offs
                                           (int)(grad_bytes + lat_bytes)));
         attr_set = true;
     }
-    dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+    int strip = 256;
+    while (strip > 8 && (long long)((w + 31) / 32) * ((h + strip - 1) / strip) < 4LL * ctx->sm_count) strip >>= 1;
+    dim3 block(32, 8), grid((w + 31) / 32, (h + strip - 1) / strip);
     k_turbulence<<<grid, block, grad_bytes + lat_bytes, ctx->stream>>>(reinterpret_cast<uint32_t *>(dest->d), w, h, dl,
-                                                                         dg, P);
+                                                                         dg, P, strip);
     RB_LAUNCHED(ctx, "turbulence");
     return RB_OK;
 }

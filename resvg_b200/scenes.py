@@ -7,6 +7,7 @@ neutral paint table into a ctypes array of the caller's paint struct (the librar
 struct in tests/bench).
 """
 import ctypes as C
+import math
 
 import numpy as np
 
@@ -285,3 +286,83 @@ def icons_docs(first_doc, n_docs, size=ICON_SIZE):
               group_opacity=(0.3 + 0.6 * head[:, 2]).astype(np.float32),
               shadow_sigma=np.where(shadow, 2.0 + 2.0 * head[:, 3], 0.0))
     return sc
+
+
+STACK_SEED = 0x5EED0004
+
+
+def stack_svg(size=4096, levels=64, seed=STACK_SEED, inset=None, shapes=10):
+    """C4 'stack4k'  as SVG text: `levels` nested groups on a size x size canvas; level k has opacity
+    U[0.85, 0.99] and, by k mod 4: 0 a luminance mask (a linear-gradient rectangle), 1 a clip-path (a circle; every 8th level
+    that circle is itself clipped by a nested clip-path), 2 a pattern-filled rectangle (tile 32-128 px holding 3 shapes),
+    3 nothing more; every level draws `shapes` C2-style closed paths (cubic / quad / line segments, solid or linear-gradient
+    fill, both fill rules) inside a box inset `inset` px per level (default size / 256, i.e. 16 px at 4096)."""
+    inset = size / 256.0 if inset is None else inset
+    per = 16 + shapes * 64
+    u = splitmix64_uniform(seed, levels * per).reshape(levels, per)
+    defs, body, tail = [], [], []
+    fmt = lambda v: f"{v:.3f}"
+
+    def shape(uu, x0, y0, x1, y1, ident):
+        """one closed path from 64 uniforms inside the box"""
+        w, h = x1 - x0, y1 - y0
+        cx, cy = x0 + uu[0] * w, y0 + uu[1] * h
+        r = math.exp(math.log(8.0) + uu[2] * (math.log(max(16.0, min(w, h) / 4)) - math.log(8.0)))
+        nseg = 3 + min(int(uu[3] * 6), 5)
+        pt = lambda a, b: f"{fmt(cx + r * (2 * a - 1))} {fmt(cy + r * (2 * b - 1))}"
+        d = ["M " + pt(uu[4], uu[5])]
+        k = 8
+        for _ in range(nseg):
+            kind = uu[k]
+            if kind < 0.5:
+                d.append(f"C {pt(uu[k + 1], uu[k + 2])} {pt(uu[k + 3], uu[k + 4])} {pt(uu[k + 5], uu[k + 6])}")
+            elif kind < 0.8:
+                d.append(f"Q {pt(uu[k + 1], uu[k + 2])} {pt(uu[k + 3], uu[k + 4])}")
+            else:
+                d.append(f"L {pt(uu[k + 1], uu[k + 2])}")
+            k += 7
+        d.append("Z")
+        col = "#%02x%02x%02x" % (int(uu[56] * 256), int(uu[57] * 256), int(uu[58] * 256))
+        rule = "evenodd" if uu[59] < 0.5 else "nonzero"
+        op = fmt(0.3 + 0.7 * uu[60])
+        if uu[61] < 0.25:
+            col2 = "#%02x%02x%02x" % (int(uu[62] * 256), int(uu[63] * 256), int(uu[6] * 256))
+            defs.append(f'<linearGradient id="g{ident}" gradientUnits="userSpaceOnUse" x1="{fmt(cx - r)}" y1="{fmt(cy - r)}" '
+                        f'x2="{fmt(cx + r)}" y2="{fmt(cy + r)}"><stop offset="0" stop-color="{col}"/>'
+                        f'<stop offset="1" stop-color="{col2}" stop-opacity="{op}"/></linearGradient>')
+            fill = f'url(#g{ident})'
+        else:
+            fill = col
+        return f'<path d="{" ".join(d)}" fill="{fill}" fill-opacity="{op}" fill-rule="{rule}"/>'
+
+    for k in range(levels):
+        x0 = y0 = inset * k
+        x1 = y1 = size - inset * k
+        w = x1 - x0
+        uu = u[k]
+        attrs = [f'opacity="{fmt(0.85 + 0.14 * uu[0])}"']
+        if k % 4 == 0:
+            defs.append(f'<linearGradient id="ml{k}" x1="0" y1="0" x2="1" y2="{fmt(uu[1])}"><stop offset="0" stop-color="white"/>'
+                        f'<stop offset="1" stop-color="#404040"/></linearGradient>'
+                        f'<mask id="m{k}" maskUnits="userSpaceOnUse" x="{fmt(x0)}" y="{fmt(y0)}" width="{fmt(w)}" height="{fmt(w)}">'
+                        f'<rect x="{fmt(x0)}" y="{fmt(y0)}" width="{fmt(w)}" height="{fmt(w)}" fill="url(#ml{k})"/></mask>')
+            attrs.append(f'mask="url(#m{k})"')
+        elif k % 4 == 1:
+            c, rad = (x0 + x1) / 2, w * (0.45 + 0.1 * uu[1])
+            nested = ""
+            if k % 8 == 1:
+                defs.append(f'<clipPath id="cc{k}"><rect x="{fmt(x0 + w * 0.05)}" y="{fmt(y0)}" width="{fmt(w * 0.9)}" height="{fmt(w)}"/></clipPath>')
+                nested = f' clip-path="url(#cc{k})"'
+            defs.append(f'<clipPath id="c{k}"{nested}><circle cx="{fmt(c)}" cy="{fmt(c)}" r="{fmt(rad)}"/></clipPath>')
+            attrs.append(f'clip-path="url(#c{k})"')
+        body.append(f'<g {" ".join(attrs)}>')
+        if k % 4 == 2:
+            tile = 32 + 96 * uu[1]
+            inner = "".join(shape(uu[16 + 64 * j:16 + 64 * (j + 1)] * 1.0, 0, 0, tile, tile, f"p{k}_{j}") for j in range(3))
+            defs.append(f'<pattern id="p{k}" patternUnits="userSpaceOnUse" width="{fmt(tile)}" height="{fmt(tile)}">{inner}</pattern>')
+            body.append(f'<rect x="{fmt(x0)}" y="{fmt(y0)}" width="{fmt(w)}" height="{fmt(w)}" fill="url(#p{k})" fill-opacity="0.5"/>')
+        for j in range(shapes):
+            body.append(shape(uu[16 + 64 * j:16 + 64 * (j + 1)], x0, y0, x1, y1, f"{k}_{j}"))
+        tail.append("</g>")
+    return (f'<svg xmlns="http://www.w3.org/2000/svg" width="{size}" height="{size}" viewBox="0 0 {size} {size}">'
+            f'<defs>{"".join(defs)}</defs>{"".join(body)}{"".join(tail)}</svg>')

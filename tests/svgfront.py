@@ -619,6 +619,7 @@ class Converter:
         self.doc = doc
         self.vb_w = self.vb_h = 100.0
         self.depth = 0
+        self.pattern_depth = 0
 
     # ---- root ----
     def convert(self):
@@ -651,7 +652,7 @@ class Converter:
         if d.attr(el, "display", inherit=False) == "none":
             return None
         self.depth += 1
-        if self.depth > 64:
+        if self.depth > 256:
             raise Unsupported("depth")
         try:
             ts = IDENT if is_root else ts_pre(parse_transform(el.attrib.get("transform")), extra_ts)
@@ -1055,13 +1056,13 @@ class Converter:
             n = [float(x) for x in re.findall(NUM, vb)]
             if len(n) == 4 and n[2] > 0 and n[3] > 0:
                 vbr = n
-        self.depth += 1
+        self.pattern_depth += 1  # nesting of patterns only (groups have their own guard)
         try:
-            if self.depth > 16:
+            if self.pattern_depth > 16:
                 raise Unsupported("pattern recursion")
             kids = [n for n in (self.node_for(ch) for ch in with_children) if n is not None]
         finally:
-            self.depth -= 1
+            self.pattern_depth -= 1
         if not kids:
             return None
         if units == "objectBoundingBox":
