@@ -20,10 +20,12 @@
 // Pointwise infrastructure: 4 pixels (one 16-byte vector) per thread per step, grid-stride.
 // =================================================================================================
 
-// i / 255.0f for i in 0..255, computed with IEEE division so it equals Rust's `c as f32 / 255.0`.
+// i / 255.0f for every byte value, computed once per device at context creation with the host's IEEE division (what
+// Rust's `c as f32 / 255.0` is); kernels copy it into shared memory instead of each CTA dividing 256 times.
+__device__ float g_div255[256];
 __device__ __forceinline__ void rb_fill_div255(float *lut)
 {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = __fdiv_rn((float)i, 255.0f);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = g_div255[i];
 }
 
 template <class Op>
@@ -212,6 +214,14 @@ __global__ void __launch_bounds__(256) k_px_table(uint32_t *__restrict__ px, siz
 
 int rb_filters_init(rb_ctx *ctx)
 {
+    {
+        float h_div255[256];
+        for (int i = 0; i < 256; i++) {
+            volatile float c = (float)i;
+            h_div255[i] = c / 255.0f;
+        }
+        RB_CUDA(ctx, cudaMemcpyToSymbol(g_div255, h_div255, sizeof(h_div255)));
+    }
     RB_CUDA(ctx, cudaMemcpyToSymbol(c_srgb_to_linear, h_srgb_to_linear, 256));
     RB_CUDA(ctx, cudaMemcpyToSymbol(c_linear_to_srgb, h_linear_to_srgb, 256));
     RB_CUDA(ctx, cudaMalloc((void **)&ctx->px_tables, 3 * PX_TABLE));
@@ -1642,22 +1652,60 @@ extern "C" int rb_filter_composite_arithmetic(rb_layer *dest, const rb_layer *sr
 // =================================================================================================
 // displacement_map.rs:15-62 — gather
 // =================================================================================================
-__global__ void k_displace(const uint32_t *__restrict__ src, const uint32_t *__restrict__ map,
-                           uint32_t *__restrict__ dst, int w, int h, int xch, int ych, float scale, float sx, float sy)
+__device__ __forceinline__ bool displace_src(uint32_t m, int x, int y, int w, int h, int xsh, int ysh, float scale, float sx, float sy,
+                                             const float *div255, size_t *at)
+{
+    const float dx = div255[(m >> xsh) & 0xffu] - 0.5f;
+    const float dy = div255[(m >> ysh) & 0xffu] - 0.5f;
+    // f32::round = half away from zero = roundf; `as i32` saturates (cvt.rzi.s32.f32), NaN -> 0
+    const int ox = __float2int_rz(roundf((float)x + dx * sx * scale));
+    const int oy = __float2int_rz(roundf((float)y + dy * sy * scale));
+    *at = (size_t)oy * w + ox;
+    return ox >= 0 && ox < w && oy >= 0 && oy < h;
+}
+
+// VEC: 4 pixels per thread (w % 4 == 0): one 16-byte load of the map, four gathers, one 16-byte store when all four
+// sources are inside the image (pixels whose source is outside keep the destination's contents).
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+k_displace(const uint32_t *__restrict__ src, const uint32_t *__restrict__ map, uint32_t *__restrict__ dst, int w, int h, int xch,
+           int ych, float scale, float sx, float sy)
 {
     __shared__ float div255[256];
     rb_fill_div255(div255);
     __syncthreads();
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-    uint32_t m = map[(size_t)y * w + x];
-    float dx = div255[(m >> (8 * xch)) & 0xffu] - 0.5f;
-    float dy = div255[(m >> (8 * ych)) & 0xffu] - 0.5f;
-    // f32::round = half away from zero = roundf; `as i32` saturates (cvt.rzi.s32.f32), NaN -> 0
-    int ox = __float2int_rz(roundf((float)x + dx * sx * scale));
-    int oy = __float2int_rz(roundf((float)y + dy * sy * scale));
-    if (ox >= 0 && ox < w && oy >= 0 && oy < h) dst[(size_t)y * w + x] = __ldg(src + (size_t)oy * w + ox);
+    const int xsh = 8 * xch, ysh = 8 * ych;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (y >= h) return;
+    if (VEC) {
+        const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        if (x >= w) return;
+        const size_t base = (size_t)y * w + x;
+        const uint4 m = *reinterpret_cast<const uint4 *>(map + base);
+        size_t a0, a1, a2, a3;
+        const bool v0 = displace_src(m.x, x, y, w, h, xsh, ysh, scale, sx, sy, div255, &a0);
+        const bool v1 = displace_src(m.y, x + 1, y, w, h, xsh, ysh, scale, sx, sy, div255, &a1);
+        const bool v2 = displace_src(m.z, x + 2, y, w, h, xsh, ysh, scale, sx, sy, div255, &a2);
+        const bool v3 = displace_src(m.w, x + 3, y, w, h, xsh, ysh, scale, sx, sy, div255, &a3);
+        uint4 o;
+        o.x = v0 ? __ldg(src + a0) : 0u;
+        o.y = v1 ? __ldg(src + a1) : 0u;
+        o.z = v2 ? __ldg(src + a2) : 0u;
+        o.w = v3 ? __ldg(src + a3) : 0u;
+        if (v0 && v1 && v2 && v3) {
+            *reinterpret_cast<uint4 *>(dst + base) = o;
+        } else {
+            if (v0) dst[base] = o.x;
+            if (v1) dst[base + 1] = o.y;
+            if (v2) dst[base + 2] = o.z;
+            if (v3) dst[base + 3] = o.w;
+        }
+    } else {
+        const int x = blockIdx.x * blockDim.x + threadIdx.x;
+        if (x >= w) return;
+        size_t a;
+        if (displace_src(map[(size_t)y * w + x], x, y, w, h, xsh, ysh, scale, sx, sy, div255, &a)) dst[(size_t)y * w + x] = __ldg(src + a);
+    }
 }
 
 extern "C" int rb_filter_displacement_map(rb_layer *dest, const rb_layer *src, const rb_layer *map, int xch, int ych,
@@ -1668,10 +1716,12 @@ extern "C" int rb_filter_displacement_map(rb_layer *dest, const rb_layer *src, c
     if (dest->d == src->d) return RB_ERR_INVALID;
     rb_ctx *ctx = dest->ctx;
     int w = (int)dest->w, h = (int)dest->h;
-    dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
-    k_displace<<<grid, block, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(src->d),
-                                                reinterpret_cast<const uint32_t *>(map->d),
-                                                reinterpret_cast<uint32_t *>(dest->d), w, h, xch, ych, scale, sx, sy);
+    dim3 block(32, 8);
+#define RB_DM_ARGS reinterpret_cast<const uint32_t *>(src->d), reinterpret_cast<const uint32_t *>(map->d), \
+    reinterpret_cast<uint32_t *>(dest->d), w, h, xch, ych, scale, sx, sy
+    if (w % 4 == 0) k_displace<true><<<dim3((w / 4 + 31) / 32, (h + 7) / 8), block, 0, ctx->stream>>>(RB_DM_ARGS);
+    else k_displace<false><<<dim3((w + 31) / 32, (h + 7) / 8), block, 0, ctx->stream>>>(RB_DM_ARGS);
+#undef RB_DM_ARGS
     RB_LAUNCHED(ctx, "displacement_map");
     return RB_OK;
 }
@@ -1682,6 +1732,7 @@ extern "C" int rb_filter_displacement_map(rb_layer *dest, const rb_layer *src, c
 struct LightParams {
     int specular;
     float surface_scale, constant, exponent;
+    float scale255; // surface_scale / 255.0 (IEEE division on the host, as the reference computes it per pixel)
     int exp_is_one;
     float lr, lg, lb; // lighting colour as f32 of the u8 channels
     int kind;
@@ -1701,7 +1752,11 @@ __device__ __forceinline__ float v3len(V3 a) { return __fsqrt_rn(a.x * a.x + a.y
 // (used by the reference on Linux) delivers; any residual difference is inside the 1/255 tolerance.
 __device__ __forceinline__ float rb_powf(float a, float b) { return (float)pow((double)a, (double)b); }
 
-__global__ void k_lighting(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h, LightParams P)
+// KIND (0 distant, 1 point, 2 spot) and SPECULAR are compile-time: six compact kernels instead of one that carries every
+// variant's registers and branches.
+template <int KIND, bool SPECULAR>
+__global__ void __launch_bounds__(256)
+k_lighting(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h, LightParams P)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y * blockDim.y + threadIdx.y;
@@ -1764,7 +1819,7 @@ __global__ void k_lighting(const uint32_t *__restrict__ src, uint32_t *__restric
 
     // light vector (lighting.rs:257-271)
     V3 lv = {P.lvx, P.lvy, P.lvz};
-    if (P.kind != 0) {
+    if (KIND != 0) {
         float nz = __fdiv_rn((float)A(0, 0), 255.0f) * P.surface_scale;
         V3 v = {P.x - (float)x, P.y - (float)y, P.z - nz};
         float len = v3len(v);
@@ -1777,7 +1832,7 @@ __global__ void k_lighting(const uint32_t *__restrict__ src, uint32_t *__restric
     }
     // light colour (lighting.rs:309-338)
     float cr = P.lr, cg = P.lg, cb = P.lb;
-    if (P.kind == 2) {
+    if (KIND == 2) {
         V3 dir = {P.dirx, P.diry, P.dirz};
         float mls = -v3dot(lv, dir);
         bool black = (mls <= 0.0f) || (P.has_cone && mls < P.cone_cos);
@@ -1793,11 +1848,11 @@ __global__ void k_lighting(const uint32_t *__restrict__ src, uint32_t *__restric
     // light factor (lighting.rs:141-153, 185-219)
     bool nzero = rb_approx_zero_ulps(nnx) && rb_approx_zero_ulps(nny);
     float factor;
-    if (!P.specular) {
+    if (!SPECULAR) {
         float k;
         if (nzero) k = lv.z;
         else {
-            float s = __fdiv_rn(P.surface_scale, 255.0f);
+            float s = P.scale255;
             float ax = nnx * s, ay = nny * s;
             ax *= fx;
             ay *= fy;
@@ -1813,7 +1868,7 @@ __global__ void k_lighting(const uint32_t *__restrict__ src, uint32_t *__restric
             float ndh;
             if (nzero) ndh = __fdiv_rn(hv.z, hl);
             else {
-                float s = __fdiv_rn(P.surface_scale, 255.0f);
+                float s = P.scale255;
                 float ax = nnx * s, ay = nny * s;
                 ax *= fx;
                 ay *= fy;
@@ -1827,7 +1882,7 @@ __global__ void k_lighting(const uint32_t *__restrict__ src, uint32_t *__restric
     uint32_t r = rb_f2u8(rb_f32_bound(0.0f, cr * factor, 255.0f) + 0.5f);
     uint32_t g = rb_f2u8(rb_f32_bound(0.0f, cg * factor, 255.0f) + 0.5f);
     uint32_t b = rb_f2u8(rb_f32_bound(0.0f, cb * factor, 255.0f) + 0.5f);
-    uint32_t a = P.specular ? max(max(r, g), b) : 255u;
+    uint32_t a = SPECULAR ? max(max(r, g), b) : 255u;
     dst[(size_t)y * w + x] = rb_pack(r, g, b, a);
 }
 
@@ -1854,6 +1909,10 @@ static int launch_lighting(rb_layer *dest, const rb_layer *src, int specular, fl
     memset(&P, 0, sizeof(P));
     P.specular = specular;
     P.surface_scale = surface_scale;
+    {
+        volatile float ss = surface_scale;
+        P.scale255 = ss / 255.0f;
+    }
     P.constant = constant;
     P.exponent = exponent;
     P.exp_is_one = h_approx_eq_ulps(exponent, 1.0f, 4) ? 1 : 0;
@@ -1886,8 +1945,17 @@ static int launch_lighting(rb_layer *dest, const rb_layer *src, int specular, fl
     rb_ctx *ctx = dest->ctx;
     int w = (int)dest->w, h = (int)dest->h;
     dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
-    k_lighting<<<grid, block, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(src->d),
-                                                reinterpret_cast<uint32_t *>(dest->d), w, h, P);
+#define RB_LT(K, S) k_lighting<K, S><<<grid, block, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(src->d), \
+                                                                     reinterpret_cast<uint32_t *>(dest->d), w, h, P)
+    switch (light->kind * 2 + (specular ? 1 : 0)) {
+    case 0: RB_LT(0, false); break;
+    case 1: RB_LT(0, true); break;
+    case 2: RB_LT(1, false); break;
+    case 3: RB_LT(1, true); break;
+    case 4: RB_LT(2, false); break;
+    default: RB_LT(2, true); break;
+    }
+#undef RB_LT
     RB_LAUNCHED(ctx, "lighting");
     return RB_OK;
 }
