@@ -453,8 +453,9 @@ __device__ __forceinline__ uint32_t box2_magic(int r) { return (((1u << 24) + (u
 // a shared-memory ring (each thread only ever touches its own column of it, so there is no synchronisation), which makes
 // the pass read every source row once: re-reading the row that leaves the window from global memory missed L2 on full
 // 8192-wide layers (ncu: 558 MB read for a 268 MB layer) and eviction hints did not change that.  Loads are issued
-// BOX2V_AHEAD rows ahead of the sliding sum.  Radius 0 copies (the passes ping-pong between two buffers).
-constexpr int BOX2V_THREADS = 128, BOX2V_AHEAD = 8;
+// BOX2V_AHEAD (8 or 16) rows ahead of the sliding sum.  Radius 0 copies (the passes ping-pong between two buffers).
+constexpr int BOX2V_THREADS = 128;
+template <int BOX2V_AHEAD>
 __global__ void __launch_bounds__(BOX2V_THREADS)
 k_box_blur_v3(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int pitch, const BoxCell *__restrict__ cells, int it,
               int rows)
@@ -551,13 +552,28 @@ k_box_blur_v2(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int 
         else box2_sub(rb0, ga0, p);
     };
     for (int yy = max(0, y0 - r); yy <= min(h - 1, y0 + r); yy++) add(__ldg(s2 + (size_t)yy * step));
-#pragma unroll 4
-    for (int y = y0; y < y1; y++) {
-        if constexpr (VEC2) d2[(size_t)y * step] = make_uint2(box2_out(rb0, ga0, M), box2_out(rb1, ga1, M));
-        else d2[(size_t)y * step] = box2_out(rb0, ga0, M);
-        const int ya = y + r + 1, ys = y - r;
-        if (ya < h) add(__ldg(s2 + (size_t)ya * step));
-        if (ys >= 0) sub(__ldg(s2 + (size_t)ys * step));
+    constexpr int AHEAD = 8; // rows whose entering / leaving pixels are requested before the sliding sums consume them
+    T zero;
+    if constexpr (VEC2) zero = make_uint2(0u, 0u); else zero = 0u;
+    for (int yb = y0; yb < y1; yb += AHEAD) {
+        T pa[AHEAD], ps[AHEAD];
+#pragma unroll
+        for (int k = 0; k < AHEAD; k++) {
+            const int ya = yb + k + r + 1, ys = yb + k - r;
+            const bool live = yb + k < y1;
+            pa[k] = (live && ya < h) ? __ldg(s2 + (size_t)ya * step) : zero;
+            ps[k] = (live && ys >= 0) ? __ldg(s2 + (size_t)ys * step) : zero;
+        }
+#pragma unroll
+        for (int k = 0; k < AHEAD; k++) {
+            const int y = yb + k;
+            if (y < y1) {
+                if constexpr (VEC2) d2[(size_t)y * step] = make_uint2(box2_out(rb0, ga0, M), box2_out(rb1, ga1, M));
+                else d2[(size_t)y * step] = box2_out(rb0, ga0, M);
+                add(pa[k]);
+                sub(ps[k]);
+            }
+        }
     }
 }
 
@@ -586,6 +602,8 @@ k_box_blur_h2(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int 
     const uint32_t M = box2_magic(r);
     const uint32_t bias = (uint32_t)r | ((uint32_t)r << 16);
     const size_t org = (size_t)c.y * pitch + c.x;
+    // 16-byte accesses for the body of the segment: whole segment inside the cell, rows and segment start 16-byte aligned
+    const bool vec = r > 0 && seg >= 128 && x0 + seg <= w && ((pitch | c.x) & 3) == 0;
     for (int y = blockIdx.y * rows + wid; y < row_end; y += BOX2H_WARPS) {
         const uint32_t *row = src + org + (size_t)y * pitch;
         uint32_t *orow = dst + org + (size_t)y * pitch;
@@ -594,9 +612,35 @@ k_box_blur_h2(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int 
                 if (x0 + i < w) orow[x0 + i] = row[x0 + i];
             continue;
         }
-        for (int i = lane; i < n_in; i += 32) {
-            const int gx = x0 - r + i;
-            in[box2_skew(i)] = (gx >= 0 && gx < w) ? __ldg(row + gx) : 0u;
+        if (vec) {
+            // body: seg pixels as 16-byte loads, all of a lane's loads in flight before the first shared-memory store;
+            // halo: r pixels on the left, r + 1 on the right, scalar
+            uint4 v[BOX2H_SEG / 128];
+#pragma unroll
+            for (int k = 0; k < BOX2H_SEG / 128; k++)
+                if (k * 128 < seg) v[k] = __ldg(reinterpret_cast<const uint4 *>(row + x0) + k * 32 + lane);
+#pragma unroll
+            for (int k = 0; k < BOX2H_SEG / 128; k++)
+                if (k * 128 < seg) {
+                    const int i = r + (k * 32 + lane) * 4;
+                    in[box2_skew(i)] = v[k].x;
+                    in[box2_skew(i + 1)] = v[k].y;
+                    in[box2_skew(i + 2)] = v[k].z;
+                    in[box2_skew(i + 3)] = v[k].w;
+                }
+            for (int i = lane; i < r; i += 32) {
+                const int gx = x0 - r + i;
+                in[box2_skew(i)] = gx >= 0 ? __ldg(row + gx) : 0u;
+            }
+            for (int i = r + seg + lane; i < n_in; i += 32) {
+                const int gx = x0 - r + i;
+                in[box2_skew(i)] = gx < w ? __ldg(row + gx) : 0u;
+            }
+        } else {
+            for (int i = lane; i < n_in; i += 32) {
+                const int gx = x0 - r + i;
+                in[box2_skew(i)] = (gx >= 0 && gx < w) ? __ldg(row + gx) : 0u;
+            }
         }
         __syncwarp();
         if (per == 32) {
@@ -626,9 +670,19 @@ k_box_blur_h2(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int 
             }
         }
         __syncwarp();
-        for (int i = lane; i < seg; i += 32) {
-            const int gx = x0 + i;
-            if (gx < w) orow[gx] = out[box2_skew(i)];
+        if (vec) {
+#pragma unroll
+            for (int k = 0; k < BOX2H_SEG / 128; k++)
+                if (k * 128 < seg) {
+                    const int i = (k * 32 + lane) * 4;
+                    reinterpret_cast<uint4 *>(orow + x0)[k * 32 + lane] =
+                        make_uint4(out[box2_skew(i)], out[box2_skew(i + 1)], out[box2_skew(i + 2)], out[box2_skew(i + 3)]);
+                }
+        } else {
+            for (int i = lane; i < seg; i += 32) {
+                const int gx = x0 + i;
+                if (gx < w) orow[gx] = out[box2_skew(i)];
+            }
         }
         __syncwarp();
     }
@@ -643,7 +697,8 @@ static int box2_run_cells(rb_ctx *ctx, uint32_t *a, uint32_t *b, int pitch, cons
     static bool attr_set = false;
     if (!attr_set) {
         RB_CUDA(ctx, cudaFuncSetAttribute(k_box_blur_h2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        RB_CUDA(ctx, cudaFuncSetAttribute(k_box_blur_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * BOX2_MAX_R + 1) * BOX2V_THREADS * 4));
+        RB_CUDA(ctx, cudaFuncSetAttribute(k_box_blur_v3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * BOX2_MAX_R + 1) * BOX2V_THREADS * 4));
+        RB_CUDA(ctx, cudaFuncSetAttribute(k_box_blur_v3<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * BOX2_MAX_R + 1) * BOX2V_THREADS * 4));
         attr_set = true;
     }
     int max_w = 0, max_h = 0;
@@ -679,7 +734,9 @@ static int box2_run_cells(rb_ctx *ctx, uint32_t *a, uint32_t *b, int pitch, cons
             while (rows > 32 && (long long)gx * ((max_h + rows - 1) / rows) * n_cells < 2LL * ctx->sm_count) rows >>= 1;
             const size_t smem = (size_t)(2 * rv + 1) * BOX2V_THREADS * 4;
             dim3 grid(gx, (max_h + rows - 1) / rows, n_cells);
-            k_box_blur_v3<<<grid, BOX2V_THREADS, smem, ctx->stream>>>(cur, other, pitch, dev_cells, it, rows);
+            // wide windows leave room for few CTAs per SM (the ring): more loads in flight per thread instead
+            if (2 * rv + 1 >= 64) k_box_blur_v3<16><<<grid, BOX2V_THREADS, smem, ctx->stream>>>(cur, other, pitch, dev_cells, it, rows);
+            else k_box_blur_v3<8><<<grid, BOX2V_THREADS, smem, ctx->stream>>>(cur, other, pitch, dev_cells, it, rows);
             RB_LAUNCHED(ctx, "box_blur_v3");
             std::swap(cur, other);
         }
