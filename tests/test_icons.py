@@ -145,3 +145,27 @@ def test_box_blur_cells_blurs_every_rectangle_as_its_own_pixmap(ctx, oracle, odd
     for (x, y, w, h), b in zip(rects[:2], [3.0, 5.0]):
         want[y:y + h, x:x + w] = oracle.box_blur(0.0, b, np.ascontiguousarray(img[y:y + h, x:x + w]))
     assert np.array_equal(l.download(), want)
+
+
+@pytest.mark.gpu
+def test_documents_do_not_depend_on_their_chunk_or_cell(ctx):
+    """Full-size atlases (32 x 32 cells): documents 1024..1151 rendered as the head of their own chunk and as part of a full
+    1024-document chunk at other cells of the atlas give the same pixels (opacity groups and drop shadows included)."""
+    from resvg_b200 import documents
+    atlas = documents.IconAtlas(ctx)  # 8192 x 8192
+    size = 256
+    sc_a = documents.prepare_chunk(1024 - 896, 1024)  # documents 128..1151: 1024.. sit at cells 896..1023
+    ch = atlas.render(sc_a)
+    full = atlas.atlas.download()
+    atlas.release(ch)
+    sc_b = documents.prepare_chunk(1024, 128)         # the same documents at cells 0..127
+    ch = atlas.render(sc_b)
+    part = atlas.atlas.download()
+    atlas.release(ch)
+    assert (sc_b["shadow_sigma"] > 0).any() and (sc_b["group_first"] >= 0).any()
+    for k in range(128):
+        ca, cb = 896 + k, k
+        a = full[(ca // 32) * size:(ca // 32 + 1) * size, (ca % 32) * size:(ca % 32 + 1) * size]
+        b = part[(cb // 32) * size:(cb // 32 + 1) * size, (cb % 32) * size:(cb % 32 + 1) * size]
+        assert np.array_equal(a, b), f"document {1024 + k}"
+    assert not part[4 * size:].any()

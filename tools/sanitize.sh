@@ -5,3 +5,7 @@ compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test
 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_filters_gpu.py -q -x -k "box or iir or helpers or morph or convolve" || exit 1
 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_raster_gpu.py -q -x \
     -k "structured or hairline or batch_painters or coverage_random_paths or viewports or masks" || exit 1
+# the atlas path (region composites, cell-aware blur, flood) and the remaining filter kernels
+compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_icons.py tests/test_stack.py -q -x -m gpu -k "not chunk_or_cell" || exit 1
+compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_filters_gpu.py -q -x -k "not (box or iir or helpers or morph or convolve)" || exit 1
+compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_filters_gpu.py tests/test_icons.py -q -x -m gpu -k "box or morph or convolve or cells" || exit 1
