@@ -613,6 +613,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-table", action="store_true", help="skip the per-kernel roofline table of the filter / compositing kernels")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--shard", default="documents", choices=["documents", "strips"],
+                    help="paths8k at N > 1: one scene per GPU (weak scaling, default) or ONE scene cut into N canvas strips (strong)")
     ap.add_argument("--docs", type=int, default=0, help="icons: number of documents (default: the 100 000 of the recipe)")
     args = ap.parse_args()
 
@@ -646,15 +648,19 @@ def main():
     W, H, n_paths, seed = WORKLOADS[args.workload]
     canvas_mpx = W * H / 1e6
     ctx = rb.Context(local_rank)
-    scene = scenes.paths_scene(W, H, n_paths, shard.scene_seed(seed, rank))  # every rank renders its own document
+    strips = args.shard == "strips"
+    y0, strip_rows = shard.strip_for_rank(H, rank, world) if strips else (0, H)
+    draw_ts = shard.strip_transform(y0) if strips else (1.0, 0.0, 0.0, 1.0, 0.0, 0.0)
+    # every rank renders its own document — or, with --shard strips, rows y0 .. y0 + strip_rows of the same document
+    scene = scenes.paths_scene(W, H, n_paths, seed if strips else shard.scene_seed(seed, rank))
     n_threads = 0 if world == 1 else shard.host_threads(world)
     scene["paints"] = scenes.to_paint_array(scene, _ffi.Paint)
     scene["strokes"] = scenes.to_stroke_array(scene, _ffi.Stroke)
     n_draws_in = scene["n_paths"]
 
-    layer = ctx.layer(W, H)
+    layer = ctx.layer(W, strip_rows)
     batch = rb.Batch(layer)
-    batch.fill_paths(scene)
+    batch.fill_paths(scene, draw_ts)
     batch.prepare(n_threads)  # host edge build + binning + H2D: inputs are resident in HBM before the timed region
     st = batch.stats()
     ctx.synchronize()
@@ -697,7 +703,7 @@ def main():
     alg_bytes = 8 * n_rmw + 4 * n_store + 16 * st["edges"]
 
     # end to end through the C ABI with host buffers: record + edge build + H2D + kernel + D2H, every step
-    pinned = rb.PinnedBuffer(W * H * 4)
+    pinned = rb.PinnedBuffer(W * strip_rows * 4)
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
     e2e_h2d = 0
 
@@ -708,7 +714,7 @@ def main():
         ta = time.perf_counter()
         layer.fill(0, 0, 0, 0)
         b = rb.Batch(layer)
-        b.fill_paths(scene)
+        b.fill_paths(scene, draw_ts)
         tb = time.perf_counter()
         b.submit(n_threads)
         tc = time.perf_counter()
@@ -739,14 +745,18 @@ def main():
         except Exception:
             pass
         out = {
-            "metric": "Mpixels/s rendered", "value": shard.aggregate_throughput(canvas_mpx, world, ms_step * 1e-3), "unit": "Mpx/s",
+            "metric": "Mpixels/s rendered", "value": shard.aggregate_throughput(canvas_mpx, 1 if strips else world, ms_step * 1e-3), "unit": "Mpx/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if strips else "weak", "vs_baseline": None,
             "dtype": "u8/u16 fixed point + f32", "data": "synthetic",
             "config": {"workload": args.workload, "canvas": [W, H], "paths": n_paths, "draw_calls": int(n_draws_in),
                        "mix": "70% fill / 20% fill+stroke / 10% stroke; nonzero+evenodd; 50% solid / 30% linear / 20% radial; 95% AA",
                        "stroke": "width log-U[0.5,16] px (<= 1 px: anti-aliased hairlines), miter/round/bevel joins, butt/round/square caps, 10% dashed (2-4 intervals U[2,32])",
-                       "sharding": "one scene (document) per GPU, no collective",
+                       "sharding": ("ONE scene cut into %d canvas strips of %d rows, every rank records the whole scene translated by its "
+                                    "strip origin (a strip is a pixmap of its own, like a DrawTiler tile: curves crossing a strip boundary are clipped "
+                                    "before flattening, so those paths differ slightly from the whole-canvas render); no collective, every rank "
+                                    "downloads its strip" % (world, strip_rows)) if strips
+                                   else "one scene (document) per GPU, no collective",
                        "l2": "inputs (256 MiB canvas + %.0f MiB edges/bins) exceed the 126 MB L2" % (st["upload_bytes"] / 2**20),
                        "draws": st["draws"], "line_edges": st["edges"], "draw_tile_pairs": st["pairs"], "tiles": st["tiles"]},
             "gpu_launches": launches,
@@ -755,8 +765,8 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes": alg_bytes, "kernel_ms": ms_kernel, "prepass_ms": ms_prepass,
                          "model": "8 B per blended px + 4 B per opaque-stored px + 16 B per line edge"},
-            "e2e": {"value": shard.aggregate_throughput(canvas_mpx, world, e2e_s), "unit": "Mpx/s", "h2d_bytes_per_step": int(e2e_h2d),
-                    "d2h_bytes_per_step": W * H * 4, "ms_per_step": e2e_s * 1e3, "record_ms": e2e_phase[0] / e2e_steps * 1e3,
+            "e2e": {"value": shard.aggregate_throughput(canvas_mpx, 1 if strips else world, e2e_s), "unit": "Mpx/s", "h2d_bytes_per_step": int(e2e_h2d),
+                    "d2h_bytes_per_step": W * strip_rows * 4, "ms_per_step": e2e_s * 1e3, "record_ms": e2e_phase[0] / e2e_steps * 1e3,
                     "host_build_and_enqueue_ms": e2e_phase[1] / e2e_steps * 1e3, "gpu_wait_and_d2h_ms": e2e_phase[2] / e2e_steps * 1e3,
                     "steps": e2e_steps},
         }

@@ -60,3 +60,23 @@ def gather_ints(values, world: int, device=None):
 def aggregate_throughput(units_per_rank: float, world: int, seconds: float) -> float:
     """Whole-job throughput under weak scaling: every rank processed `units_per_rank` in `seconds` (max over ranks)."""
     return world * units_per_rank / seconds
+
+
+def strip_for_rank(height: int, rank: int, world: int, align: int = 8):
+    """Canvas-strip sharding of ONE large canvas: rank r renders rows [y0, y0 + rows) of the
+    canvas into a layer of its own; strips are `align`-row aligned (the raster kernel's tile height), cover [0, height)
+    exactly once and differ in size by at most one aligned block.  Path rendering needs no halo: every rank records the
+    whole scene translated by -y0 and the rasteriser clips it to the strip, exactly as tiny-skia's DrawTiler renders the
+    tiles of a canvas larger than 8191 px."""
+    if world <= 0 or not (0 <= rank < world) or height <= 0:
+        raise ValueError("bad rank/world/height")
+    blocks = (height + align - 1) // align
+    lo = (blocks * rank) // world
+    hi = (blocks * (rank + 1)) // world
+    y0, y1 = lo * align, min(hi * align, height)
+    return y0, max(0, y1 - y0)
+
+
+def strip_transform(y0: int):
+    """The transform a rank passes with its draws so that canvas row y0 lands on row 0 of its strip layer."""
+    return (1.0, 0.0, 0.0, 1.0, 0.0, -float(y0))

@@ -542,18 +542,14 @@ def _apply_primitive(rd, p, k, cs, ts, region, subregion, get_input, source):
     if k == "tile":
         inp = get_input(p["in"])
         sub = (inp.region[0] - region[0], inp.region[1] - region[1], inp.region[2], inp.region[3])
-        arr = be.to_numpy(inp.layer)
-        ih, iw = arr.shape[:2]
+        iw, ih = be.size(inp.layer)
         x0, y0 = max(sub[0], 0), max(sub[1], 0)
         x1, y1 = min(sub[0] + sub[2], iw), min(sub[1] + sub[3], ih)
         if x1 <= x0 or y1 <= y0:
             raise _FilterError()
-        tile = np.ascontiguousarray(arr[y0:y1, x0:x1])
+        # Pixmap::clone_rect: the crop is a draw of the input at a negative offset onto a transparent layer (exact copy)
         tl = be.new_layer(x1 - x0, y1 - y0)
-        if be.name == "gpu":
-            tl.upload(tile)
-        else:
-            tl[...] = tile
+        be.draw_layer(tl, inp.layer, -x0, -y0)
         out = be.new_layer(rw, rh)
         spec = {"kind": "pattern", "layer": tl, "spread": "repeat", "quality": "bicubic", "opacity": 1.0,
                 "ts": (1.0, 0.0, 0.0, 1.0, float(sub[0]), float(sub[1]))}

@@ -28,6 +28,21 @@ def test_document_assignment_is_a_partition():
     assert shard.host_threads(1) >= shard.host_threads(2) >= 1
 
 
+def test_strips_partition_the_canvas():
+    for height in (8192, 4096, 300, 17, 8):
+        for world in (1, 2, 3, 4, 8):
+            rows = []
+            for r in range(world):
+                y0, n = shard.strip_for_rank(height, r, world)
+                assert y0 % 8 == 0 and n >= 0
+                rows += list(range(y0, y0 + n))
+            assert rows == list(range(height)), (height, world)
+    y0, n = shard.strip_for_rank(8192, 3, 8)
+    assert (y0, n) == (3072, 1024) and shard.strip_transform(y0) == (1.0, 0.0, 0.0, 1.0, 0.0, -3072.0)
+    with pytest.raises(ValueError):
+        shard.strip_for_rank(100, 2, 2)
+
+
 @pytest.mark.timeout(300)
 def test_two_ranks_gloo(tmp_path):
     import bench
