@@ -650,7 +650,7 @@ def main():
     ctx = rb.Context(local_rank)
     strips = args.shard == "strips"
     y0, strip_rows = shard.strip_for_rank(H, rank, world) if strips else (0, H)
-    draw_ts = shard.strip_transform(y0) if strips else (1.0, 0.0, 0.0, 1.0, 0.0, 0.0)
+    draw_vp = shard.strip_viewport(W, H, y0) if strips else None
     # every rank renders its own document — or, with --shard strips, rows y0 .. y0 + strip_rows of the same document
     scene = scenes.paths_scene(W, H, n_paths, seed if strips else shard.scene_seed(seed, rank))
     n_threads = 0 if world == 1 else shard.host_threads(world)
@@ -660,7 +660,9 @@ def main():
 
     layer = ctx.layer(W, strip_rows)
     batch = rb.Batch(layer)
-    batch.fill_paths(scene, draw_ts)
+    if draw_vp:
+        batch.set_viewport(*draw_vp)
+    batch.fill_paths(scene)
     batch.prepare(n_threads)  # host edge build + binning + H2D: inputs are resident in HBM before the timed region
     st = batch.stats()
     ctx.synchronize()
@@ -714,7 +716,9 @@ def main():
         ta = time.perf_counter()
         layer.fill(0, 0, 0, 0)
         b = rb.Batch(layer)
-        b.fill_paths(scene, draw_ts)
+        if draw_vp:
+            b.set_viewport(*draw_vp)
+        b.fill_paths(scene)
         tb = time.perf_counter()
         b.submit(n_threads)
         tc = time.perf_counter()
@@ -752,10 +756,10 @@ def main():
             "config": {"workload": args.workload, "canvas": [W, H], "paths": n_paths, "draw_calls": int(n_draws_in),
                        "mix": "70% fill / 20% fill+stroke / 10% stroke; nonzero+evenodd; 50% solid / 30% linear / 20% radial; 95% AA",
                        "stroke": "width log-U[0.5,16] px (<= 1 px: anti-aliased hairlines), miter/round/bevel joins, butt/round/square caps, 10% dashed (2-4 intervals U[2,32])",
-                       "sharding": ("ONE scene cut into %d canvas strips of %d rows, every rank records the whole scene translated by its "
-                                    "strip origin (a strip is a pixmap of its own, like a DrawTiler tile: curves crossing a strip boundary are clipped "
-                                    "before flattening, so those paths differ slightly from the whole-canvas render); no collective, every rank "
-                                    "downloads its strip" % (world, strip_rows)) if strips
+                       "sharding": ("ONE scene cut into %d canvas strips of %d rows: every rank records the whole scene with the document's "
+                                    "pixmap placed above its strip layer (rb_batch_set_viewport with a negative origin), so the strips hold "
+                                    "exactly the pixels of the whole-canvas render; no collective, every rank downloads its strip"
+                                    % (world, strip_rows)) if strips
                                    else "one scene (document) per GPU, no collective",
                        "l2": "inputs (256 MiB canvas + %.0f MiB edges/bins) exceed the 126 MB L2" % (st["upload_bytes"] / 2**20),
                        "draws": st["draws"], "line_edges": st["edges"], "draw_tile_pairs": st["pairs"], "tiles": st["tiles"]},

@@ -226,7 +226,10 @@ int rb_batch_fill_paths(rb_batch *batch, int32_t n_paths, const uint32_t *verb_o
 /* The draws recorded after this call are rendered as if the rectangle (x, y, w, h) of the target were a pixmap of its
  * own (what resvg::render gets for one document): coordinates are relative to its origin, nothing is drawn outside it.
  * One batch can thus render many small documents into one atlas layer (document-parallel thumbnailing, BASELINE
- * config 5).  w = h = 0 restores the whole target. */
+ * config 5).  The rectangle may reach beyond the target (negative x / y, larger than the target): the document is still
+ * clipped and flattened against its whole pixmap and only what falls inside the target is drawn, pixel for pixel what
+ * a render of the whole pixmap holds there — one GPU can thus render a strip of a large canvas (canvas-strip sharding,
+ * SURVEY 8(e)).  w = h = 0 restores the whole target. */
 int rb_batch_set_viewport(rb_batch *batch, int32_t x, int32_t y, uint32_t w, uint32_t h);
 /* Bulk form of { rb_batch_set_viewport; rb_batch_draw_paths } per document (BASELINE config 5: one resvg::render per
  * icon): document k owns doc_count[k] paths starting at doc_first[k] of the packed arrays (same layout and lifetime rules

@@ -372,12 +372,11 @@ int rb_batch_hair_build(const rb_batch *b, size_t begin, size_t end, int W, int 
         rb_paint paint = d.paint;
         paint.stops = d.stops;
         hairline_modulate_paint(&paint, coverage, stops_scaled);
+        // the viewport is the document's own pixmap; it may reach beyond the target (only what falls inside is drawn)
         int VX = 0, VY = 0, VW = W, VH = H;
         if (d.vp_w > 0) {
-            VX = d.vp_x; VY = d.vp_y;
-            if (VX < 0 || VY < 0 || VX >= W || VY >= H) continue;
-            VW = std::min(d.vp_w, W - VX);
-            VH = std::min(d.vp_h, H - VY);
+            VX = d.vp_x; VY = d.vp_y; VW = d.vp_w; VH = d.vp_h;
+            if (VX >= W || VY >= H || (int64_t)VX + VW <= 0 || (int64_t)VY + VH <= 0) continue;
         }
         for (int ty = 0; ty < VH; ty += kMaxDim) {
             for (int tx = 0; tx < VW; tx += kMaxDim) {
@@ -400,8 +399,11 @@ int rb_batch_hair_build(const rb_batch *b, size_t begin, size_t end, int W, int 
                 if (!rbh::prepare_paint(&paint, ctm, &P, out->stops)) continue;
                 const uint32_t pi = (uint32_t)out->paints.size();
                 out->paints.push_back(P);
-                for (const rbh::HairBlit &hb : blits)
-                    raw.push_back(Raw{(uint32_t)(hb.x + VX + tx), (uint32_t)(hb.y + VY + ty), hb.alpha, pi, VX + tx, VY + ty});
+                for (const rbh::HairBlit &hb : blits) {
+                    const int lx = hb.x + VX + tx, ly = hb.y + VY + ty;
+                    if (lx < 0 || ly < 0 || lx >= W || ly >= H) continue; // outside the target
+                    raw.push_back(Raw{(uint32_t)lx, (uint32_t)ly, hb.alpha, pi, VX + tx, VY + ty});
+                }
             }
         }
     }
@@ -460,12 +462,12 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
         while (i < b->spans[span_i].start) span_i--;
         const DrawSpan &sp = b->spans[span_i];
         // the rectangle of the target this draw is rendered into, as if it were a pixmap of its own
+        // (it may reach beyond the target: the draw is built against the whole viewport, so curves are clipped and
+        // flattened exactly as in a render of the whole document, and only the part inside the target is binned)
         int VX = 0, VY = 0, VW = W, VH = H;
         if (sp.vp_w > 0) {
             VX = sp.vp_x; VY = sp.vp_y; VW = sp.vp_w; VH = sp.vp_h;
-            if (VX < 0 || VY < 0 || VX >= W || VY >= H) continue;
-            VW = std::min(VW, W - VX);
-            VH = std::min(VH, H - VY);
+            if (VX >= W || VY >= H || (int64_t)VX + VW <= 0 || (int64_t)VY + VH <= 0) continue;
         }
         const RecordedDraw *rp;
         const uint8_t *verbs;
@@ -543,8 +545,15 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
                             p = out->tmp.data();
                             ctm = rbh::post_concat(ctm, tr);
                         }
+                        if (ox >= W || oy >= H || ox + tw <= 0 || oy + th <= 0) continue; // tile wholly outside the target
                         out->hblits.clear();
                         rbh::hairline_blits(verbs, n_verbs, &p[0].x, n_pts, r.stroke.cap, tw, th, out->hblits);
+                        if (ox < 0 || oy < 0 || ox + tw > W || oy + th > H) { // keep the blits that land inside the target
+                            size_t keep = 0;
+                            for (const rbh::HairBlit &hb : out->hblits)
+                                if (hb.x + ox >= 0 && hb.y + oy >= 0 && hb.x + ox < W && hb.y + oy < H) out->hblits[keep++] = hb;
+                            out->hblits.resize(keep);
+                        }
                         const size_t nb = out->hblits.size();
                         if (nb == 0 || nb >= (1u << 28)) continue;
                         int x0 = INT32_MAX, y0 = INT32_MAX, x1 = INT32_MIN, y1 = INT32_MIN;
@@ -669,6 +678,12 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
                                : rbh::build_draw(verbs, n_verbs, pts, n_pts, aa, tw, th, out->scratch, &g);
                 }
                 if (!ok) continue;
+                if (ox < 0 || oy < 0 || ox + tw > W || oy + th > H) { // blitter rectangle ∩ target (tile-local coordinates)
+                    const int cx0 = std::max(g.sect.x, -ox), cy0 = std::max(g.sect.y, -oy);
+                    const int cx1 = std::min(g.sect.x + g.sect.w, W - ox), cy1 = std::min(g.sect.y + g.sect.h, H - oy);
+                    if (cx1 <= cx0 || cy1 <= cy0) continue;
+                    g.sect.x = cx0; g.sect.y = cy0; g.sect.w = cx1 - cx0; g.sect.h = cy1 - cy0;
+                }
                 const size_t ne = out->scratch.size(), ncv = out->cscratch.size();
                 DevDraw d;
                 memset(&d, 0, sizeof(d));
@@ -1111,9 +1126,12 @@ extern "C" int rb_batch_stats(rb_batch *b, uint64_t stats[6])
 // The draws recorded after this call are rendered as if the rectangle (x, y, w, h) of the target were a pixmap of its
 // own: coordinates are relative to its origin and nothing is drawn outside it.  This is how many small documents are
 // rendered into one atlas layer by a single batch (document-parallel thumbnailing).  w == 0 restores the whole target.
+// The rectangle may reach beyond the target (negative x / y, or larger than it): the document is still built against
+// its whole pixmap and only what falls inside the target is drawn — this is how one rank renders a strip of a large
+// canvas with exactly the pixels of the whole-canvas render (canvas-strip sharding).
 extern "C" int rb_batch_set_viewport(rb_batch *b, int32_t x, int32_t y, uint32_t w, uint32_t h)
 {
-    if (!b || x < 0 || y < 0 || w > 0x7fffffffu || h > 0x7fffffffu || ((w == 0) != (h == 0))) return RB_ERR_INVALID;
+    if (!b || w > 0x3fffffffu || h > 0x3fffffffu || ((w == 0) != (h == 0)) || x < -0x3fffffff || y < -0x3fffffff) return RB_ERR_INVALID;
     b->vp_x = x; b->vp_y = y; b->vp_w = (int32_t)w; b->vp_h = (int32_t)h;
     return RB_OK;
 }

@@ -65,9 +65,10 @@ def aggregate_throughput(units_per_rank: float, world: int, seconds: float) -> f
 def strip_for_rank(height: int, rank: int, world: int, align: int = 8):
     """Canvas-strip sharding of ONE large canvas: rank r renders rows [y0, y0 + rows) of the
     canvas into a layer of its own; strips are `align`-row aligned (the raster kernel's tile height), cover [0, height)
-    exactly once and differ in size by at most one aligned block.  Path rendering needs no halo: every rank records the
-    whole scene translated by -y0 and the rasteriser clips it to the strip, exactly as tiny-skia's DrawTiler renders the
-    tiles of a canvas larger than 8191 px."""
+    exactly once and differ in size by at most one aligned block.  Path rendering needs no halo and no exchange: every
+    rank records the whole scene with `strip_viewport`, i.e. the document's pixmap placed y0 rows above its strip layer,
+    so every path is clipped and flattened against the WHOLE canvas and the strip receives exactly the pixels of the
+    whole-canvas render."""
     if world <= 0 or not (0 <= rank < world) or height <= 0:
         raise ValueError("bad rank/world/height")
     blocks = (height + align - 1) // align
@@ -77,6 +78,13 @@ def strip_for_rank(height: int, rank: int, world: int, align: int = 8):
     return y0, max(0, y1 - y0)
 
 
+def strip_viewport(width: int, height: int, y0: int):
+    """rb_batch_set_viewport arguments that place the width x height document so that its row y0 is row 0 of the strip layer."""
+    return (0, -int(y0), int(width), int(height))
+
+
 def strip_transform(y0: int):
-    """The transform a rank passes with its draws so that canvas row y0 lands on row 0 of its strip layer."""
+    """The DrawTiler-style alternative: translate the draws by -y0 and let the strip layer be the pixmap.  Curves crossing
+    a strip boundary are then clipped to the strip before flattening and differ slightly from the whole-canvas render;
+    kept for the test that documents the difference."""
     return (1.0, 0.0, 0.0, 1.0, 0.0, -float(y0))

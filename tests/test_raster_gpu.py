@@ -595,45 +595,50 @@ def test_batch_stroke_path_matches_host_stroker_plus_oracle_fill(ctx):
     assert_exact(l.download(), want, "stroke batch")
 
 
-def test_canvas_strips_stitch_like_draw_tiler_tiles(ctx):
-    """Canvas-strip sharding (shard.strip_for_rank): the same scene rendered strip by strip into layers of their own, every
-    draw translated by the strip's origin.  A strip is a pixmap of its own, so curves are clipped to IT before they are
-    flattened (tiny-skia edge_clipper.rs), exactly as DrawTiler does to the tiles of canvases larger than 8191 px: paths
-    that cross a strip boundary are flattened slightly differently than in the whole-canvas render (the CPU checker shows
-    the same dependence on the canvas height), everything else is identical.  Pinned here: the strips equal the CPU
-    checker's render of the same strips bit for bit on the integer pipeline, and only a small fraction of the canvas —
-    around boundary-crossing paths — differs from the whole-canvas render."""
-    import ctypes as C
-
+def test_canvas_strips_equal_the_whole_canvas(ctx):
+    """Canvas-strip sharding (shard.strip_for_rank / strip_viewport): the bench scene (fills, strokes, dashes, hairlines,
+    gradients) rendered strip by strip, the document's pixmap placed above each strip layer with a negative viewport
+    origin, is bit-identical to the whole-canvas render.  The DrawTiler-style alternative (translate the draws, let the
+    strip be the pixmap) is NOT: tiny-skia clips curves to the pixmap before flattening them, so paths crossing a strip
+    boundary change slightly — shown here so the difference stays documented."""
     import resvg_b200 as rb
     from resvg_b200 import _ffi, scenes, shard
 
     W, H = 1024, 1000
-    scene = scenes.paths_scene(W, H, 1500, 77, rmin=8.0, rmax=160.0, strokes=False)
-    scene["paint_kind"][:] = 0  # solid paints: the integer pipeline, bit-exact
-    scene["n_stops"][:] = 0
+    scene = scenes.paths_scene(W, H, 1500, 77, rmin=8.0, rmax=160.0)
     scene["paints"] = scenes.to_paint_array(scene, _ffi.Paint)
+    scene["strokes"] = scenes.to_stroke_array(scene, _ffi.Stroke)
     whole = ctx.layer(W, H)
     b = rb.Batch(whole)
     b.fill_paths(scene)
     b.submit()
     b.close()
     want = whole.download()
-    got = np.zeros_like(want)
-    world = 3
-    opaints = scenes.to_paint_array(scene, R.Paint)
-    for r in range(world):
-        y0, rows = shard.strip_for_rank(H, r, world)
-        strip = ctx.layer(W, rows)
-        b = rb.Batch(strip)
-        b.fill_paths(scene, ts=shard.strip_transform(y0))
-        b.submit()
-        b.close()
-        got[y0:y0 + rows] = strip.download()
-        ref = np.zeros((rows, W, 4), np.uint8)
-        R.lib.orc_fill_paths(ref.ctypes.data, W, rows, scene["n_paths"], scene["verb_off"].ctypes.data, scene["pt_off"].ctypes.data,
-                             scene["verbs"].ctypes.data, scene["pts"].ctypes.data, C.addressof(opaints), scene["rules"].ctypes.data,
-                             R.ts_arr(shard.strip_transform(y0)))
-        assert_exact(got[y0:y0 + rows], ref, f"strip {r} vs the checker's render of that strip")
-    differing = (np.abs(got.astype(np.int16) - want.astype(np.int16)).max(axis=2) > 0).mean()
-    assert differing < 0.03, differing
+    for world in (2, 3):
+        got, tiled = np.zeros_like(want), np.zeros_like(want)
+        for r in range(world):
+            y0, rows = shard.strip_for_rank(H, r, world)
+            strip = ctx.layer(W, rows)
+            b = rb.Batch(strip)
+            b.set_viewport(*shard.strip_viewport(W, H, y0))
+            b.fill_paths(scene)
+            b.submit()
+            b.close()
+            got[y0:y0 + rows] = strip.download()
+            strip.fill(0, 0, 0, 0)
+            b = rb.Batch(strip)
+            b.fill_paths(scene, ts=shard.strip_transform(y0))
+            b.submit()
+            b.close()
+            tiled[y0:y0 + rows] = strip.download()
+        assert_exact(got, want, f"{world} strips")
+        differing = (np.abs(tiled.astype(np.int16) - want.astype(np.int16)).max(axis=2) > 0).mean()
+        assert 0 < differing < 0.05, differing
+    # a viewport reaching beyond the target on every side: the middle of the document
+    mid = ctx.layer(500, 400)
+    b = rb.Batch(mid)
+    b.set_viewport(-300, -250, W, H)
+    b.fill_paths(scene)
+    b.submit()
+    b.close()
+    assert_exact(mid.download(), want[250:650, 300:800], "window in the middle of the document")

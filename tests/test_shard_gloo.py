@@ -38,7 +38,7 @@ def test_strips_partition_the_canvas():
                 rows += list(range(y0, y0 + n))
             assert rows == list(range(height)), (height, world)
     y0, n = shard.strip_for_rank(8192, 3, 8)
-    assert (y0, n) == (3072, 1024) and shard.strip_transform(y0) == (1.0, 0.0, 0.0, 1.0, 0.0, -3072.0)
+    assert (y0, n) == (3072, 1024) and shard.strip_viewport(8192, 8192, y0) == (0, -3072, 8192, 8192)
     with pytest.raises(ValueError):
         shard.strip_for_rank(100, 2, 2)
 
