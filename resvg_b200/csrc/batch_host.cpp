@@ -503,6 +503,39 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
         }
         const RecordedDraw &r = *rp;
         int n_verbs = (int)r.n_verbs, n_pts = (int)r.n_pts, rule = r.rule;
+        {
+            // Cull draws that cannot touch the target before any geometry work (stroking dominates the host build): the
+            // path lies inside the hull of its control points; a stroke reaches at most half its width times
+            // max(miter limit, sqrt 2) beyond it (miter tips / square caps); anti-aliasing adds at most a pixel.
+            float bx0 = INFINITY, by0 = INFINITY, bx1 = -INFINITY, by1 = -INFINITY;
+            bool finite = n_pts > 0;
+            for (int k = 0; k < n_pts; k++) {
+                const float x = rpts[k].x, y = rpts[k].y;
+                finite = finite && std::isfinite(x) && std::isfinite(y);
+                bx0 = std::min(bx0, x); bx1 = std::max(bx1, x);
+                by0 = std::min(by0, y); by1 = std::max(by1, y);
+            }
+            if (finite) {
+                if (r.is_stroke) { // stroke points are in local space: inflate there, then map the box
+                    const float reach = 0.5f * r.stroke.width * std::max(r.stroke.miter_limit, 1.4143f);
+                    if (std::isfinite(reach)) {
+                        rbh::Pt c[4] = {{bx0 - reach, by0 - reach}, {bx1 + reach, by0 - reach}, {bx0 - reach, by1 + reach}, {bx1 + reach, by1 + reach}};
+                        rbh::map_points(r.ctm, c, 4);
+                        bx0 = by0 = INFINITY; bx1 = by1 = -INFINITY;
+                        for (const rbh::Pt &q : c) {
+                            finite = finite && std::isfinite(q.x) && std::isfinite(q.y);
+                            bx0 = std::min(bx0, q.x); bx1 = std::max(bx1, q.x);
+                            by0 = std::min(by0, q.y); by1 = std::max(by1, q.y);
+                        }
+                    } else {
+                        finite = false;
+                    }
+                }
+                const float pad = 2.0f; // viewport-local window of the target: [-VX, W - VX) x [-VY, H - VY)
+                if (finite && (bx1 < (float)(-VX) - pad || by1 < (float)(-VY) - pad || bx0 > (float)(W - VX) + pad || by0 > (float)(H - VY) + pad))
+                    continue;
+            }
+        }
         if (r.is_stroke && b->n_hair) {
             const float coverage = rb_hairline_coverage(r.paint, r.stroke, r.ctm);
             if (coverage >= 0.0f) {
