@@ -109,6 +109,9 @@ typedef struct {
     float amplitude, exponent, offset;
 } rb_transfer_fn;
 int rb_filter_component_transfer(rb_layer *layer, const rb_transfer_fn funcs[4]);
+/* Rows / columns the box blur of this standard deviation reads beyond a pixel (sum of the five box radii,
+ * box_blur.rs:37-71): the halo a strip of a larger image needs for its own rows to equal the blur of the whole image. */
+int rb_filter_box_blur_reach(double sigma);
 /* box_blur::apply on n sub-pixmaps at once: rectangle i = rects[4i..4i+3] = (x, y, w, h) of the layer is blurred as a
  * pixmap of its own (windows clipped to it) with sigma_x[i], sigma_y[i]; everything else is untouched.  One launch per
  * pass for all rectangles (per-document filters on an atlas).  Rectangles must lie inside the layer and not overlap. */

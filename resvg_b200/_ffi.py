@@ -145,6 +145,7 @@ SIGNATURES = {
     "rb_layer_download_end": (_i, [_vp]),
     "rb_batch_draw_documents": (_i, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, f32p]),
     "rb_draw_layer_rects": (_i, [_vp, _vp, C.c_int32, _vp, _vp, _vp, C.c_int32]),
+    "rb_filter_box_blur_reach": (_i, [_d]),
     "rb_filter_box_blur_cells": (_i, [_vp, C.c_int32, _vp, _vp, _vp]),
     "rb_filter_flood_alpha": (_i, [_vp, _u8, _u8, _u8, _u8]),
     "rb_debug_host_expand": (None, [_i]),

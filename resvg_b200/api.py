@@ -244,6 +244,11 @@ class filters:
         src.ctx.check(lib.rb_filter_component_transfer(src._h, arr), "component_transfer")
 
     @staticmethod
+    def box_blur_reach(sigma: float) -> int:
+        """Halo (rows / columns) a strip needs for its own pixels to equal the box blur of the whole image."""
+        return int(lib.rb_filter_box_blur_reach(float(sigma)))
+
+    @staticmethod
     def box_blur_cells(rects, sigma_x, sigma_y, src: Layer):
         """box_blur::apply on every rectangle (x, y, w, h) of the layer as a pixmap of its own (rb_filter_box_blur_cells)."""
         r = np.ascontiguousarray(rects, np.int32).reshape(-1, 4)

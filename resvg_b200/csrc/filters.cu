@@ -843,6 +843,17 @@ extern "C" int rb_filter_box_blur(rb_layer *l, double sigma_x, double sigma_y)
     return RB_OK;
 }
 
+// Rows / columns of context the box blur of this standard deviation reads on either side of a pixel: the sum of the five
+// box radii (box_blur.rs:37-71).  A strip of a larger image blurred together with that many halo rows on each side holds,
+// in its own rows, exactly the pixels of the blurred whole image (canvas-strip sharding of filters).
+extern "C" int rb_filter_box_blur_reach(double sigma)
+{
+    int b[5], reach = 0;
+    create_box_gauss((float)sigma, b);
+    for (int i = 0; i < 5; i++) reach += (b[i] - 1) / 2;
+    return reach;
+}
+
 // Atlas form: rectangle i of the layer is blurred as a pixmap of its own (box_blur::apply on a sub-pixmap, windows
 // clipped to the rectangle) with its own standard deviations; pixels outside the rectangles are untouched.  One launch
 // per pass for all rectangles.  Rectangles must not overlap.

@@ -88,3 +88,15 @@ def strip_transform(y0: int):
     a strip boundary are then clipped to the strip before flattening and differ slightly from the whole-canvas render;
     kept for the test that documents the difference."""
     return (1.0, 0.0, 0.0, 1.0, 0.0, -float(y0))
+
+
+def strip_with_halo(height: int, rank: int, world: int, halo: int, align: int = 8):
+    """Rows a rank must hold to FILTER its strip of a large layer: its own rows plus `halo` rows of
+    context on either side, clipped to the image — the sum of the vertical reach of the chain's primitives (box blur:
+    filters.box_blur_reach(sigma); morphology: ceil(ry); convolve: rows - 1; lighting: 1; pointwise: 0).  Rendering
+    the halo redundantly replaces any exchange between the GPUs.  Returns (first_row, n_rows, offset of the strip's own first
+    row inside that block, own rows)."""
+    y0, rows = strip_for_rank(height, rank, world, align)
+    lo = max(0, y0 - halo)
+    hi = min(height, y0 + rows + halo)
+    return lo, hi - lo, y0 - lo, rows

@@ -284,3 +284,36 @@ def test_filter_chain_matches_oracle(ctx, oracle):
     ll = o.diffuse_lighting(5.0, 1.0, (255, 255, 255), o.make_light(kind="distant", azimuth=45.0, elevation=60.0), cc)
     ll = o.into_srgb(o.box_blur(64.0, 64.0, ll))
     assert_exact(got, ll, "filter chain")
+
+
+@pytest.mark.gpu
+def test_filter_chain_on_strips_with_halo_equals_the_whole_layer(ctx, oracle):
+    """Canvas-strip sharding of a filter chain (shard.strip_with_halo): every strip is filtered together with the halo rows
+    the chain reads (box blur: sum of its radii; dilate 3: 3 + 3; convolve 3x3: 2; lighting: 1) and its own rows are
+    bit-identical to the chain over the whole layer — redundant halo work instead of an exchange."""
+    import resvg_b200 as rb
+    from resvg_b200 import shard
+    F = rb.filters
+    W, H = 320, 1000
+    img = random_premul(W, H, 21, sparse=True)
+    light = rb.make_light("distant", azimuth=45.0, elevation=60.0)
+
+    def chain(l):
+        F.box_blur(3.0, 3.0, l)
+        F.morphology("dilate", 3.0, 3.0, l)
+        F.convolve_matrix([0, -1, 0, -1, 5, -1, 0, -1, 0], 3, 3, 1, 1, 1.0, 0.0, "duplicate", False, l)
+        out = ctx.layer(l.width, l.height)
+        F.diffuse_lighting(5.0, 1.0, (255, 255, 255), light, l, out)
+        F.box_blur(9.0, 9.0, out)
+        return out
+
+    want = chain(ctx.layer_from(img)).download()
+    halo = F.box_blur_reach(3.0) + 6 + 2 + 1 + F.box_blur_reach(9.0)
+    assert F.box_blur_reach(3.0) == sum((b - 1) // 2 for b in oracle.create_box_gauss(3.0))
+    for world in (2, 3):
+        got = np.zeros_like(want)
+        for r in range(world):
+            lo, n, off, rows = shard.strip_with_halo(H, r, world, halo)
+            part = chain(ctx.layer_from(np.ascontiguousarray(img[lo:lo + n]))).download()
+            got[lo + off:lo + off + rows] = part[off:off + rows]
+        assert_exact(got, want, f"{world} strips with a {halo}-row halo")

@@ -41,6 +41,9 @@ def test_strips_partition_the_canvas():
     assert (y0, n) == (3072, 1024) and shard.strip_viewport(8192, 8192, y0) == (0, -3072, 8192, 8192)
     with pytest.raises(ValueError):
         shard.strip_for_rank(100, 2, 2)
+    # strips with a filter halo: own rows unchanged, context clipped to the image
+    assert shard.strip_with_halo(1000, 0, 2, 40) == (0, 536, 0, 496)
+    assert shard.strip_with_halo(1000, 1, 2, 40) == (456, 544, 40, 504)
 
 
 @pytest.mark.timeout(300)
