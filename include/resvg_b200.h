@@ -188,7 +188,12 @@ typedef struct {
 } rb_paint;
 
 /* PixmapMut::fill_path(path, paint, rule, transform, None) — path.rs:73.  Host: transform, chop, clip, edge
- * build; device: coverage + shade + blend.  Equivalent to a one-draw batch. */
+ * build; device: coverage + shade + blend.  The draw is validated and recorded at once but executed lazily: consecutive
+ * rb_fill_path calls on a layer are collected and run as ONE batch (painter's order = call order) the next time any
+ * entry point reads or writes that layer (composite, filter, mask, copy, download, rb_layer_device_ptr, an explicit
+ * batch on it, rb_ctx_synchronize, rb_timer_end), so a traversal that issues fill after fill and then composites the
+ * layer pays one tile-kernel launch.  Draws with a pattern paint are executed immediately.  The path, paint and
+ * stops are copied; nothing the caller passed needs to outlive the call. */
 int rb_fill_path(rb_layer *layer, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
                  const rb_paint *paint, int32_t fill_rule, const float ts[6]);
 

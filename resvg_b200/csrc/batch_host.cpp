@@ -1022,6 +1022,9 @@ int rb_batch_record(rb_batch *b, const uint8_t *verbs, int32_t n_verbs, const fl
                     const rb_paint *paint, int32_t rule, const float ts[6])
 {
     if (!b || !verbs || !points || n_verbs <= 0 || n_points <= 0 || !paint) return RB_ERR_INVALID;
+    // a pattern's source layer must hold its final pixels before this draw runs: execute its pending immediate draws now,
+    // on the caller's thread (rb_layer_device_ptr flushes)
+    if (paint->shader == 3 && paint->pattern) (void)rb_layer_device_ptr(const_cast<rb_layer *>(paint->pattern));
     // validate the verb/point bookkeeping so the builder never reads past the arrays
     int need = 0;
     for (int i = 0; i < n_verbs; i++) {
@@ -1116,6 +1119,7 @@ extern "C" int rb_batch_draw_paths(rb_batch *b, int32_t n_paths, const uint32_t 
         if (vb <= va || pb <= pa) return RB_ERR_INVALID;
         if (paint.shader < 0 || paint.shader > 3 || paint.blend_mode < 0 || paint.blend_mode > 28) return RB_ERR_INVALID;
         if ((paint.shader == 1 || paint.shader == 2) && paint.n_stops > rbh::kMaxStops) return RB_ERR_UNSUPPORTED;
+        if (paint.shader == 3 && paint.pattern) (void)rb_layer_device_ptr(const_cast<rb_layer *>(paint.pattern));
         // the verb/point bookkeeping must be right or the builder would read past the arrays
         uint32_t need = 0;
         for (uint32_t k = va; k < vb; k++) {

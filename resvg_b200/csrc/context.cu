@@ -3,6 +3,8 @@
 #include <string.h>
 
 #include "common.cuh"
+#include <algorithm>
+
 #include "rb_internal.h"
 
 int rb_filters_init(rb_ctx *ctx);
@@ -124,6 +126,10 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 extern "C" int rb_ctx_synchronize(rb_ctx *ctx)
 {
     if (!ctx) return RB_ERR_INVALID;
+    while (!ctx->dirty.empty()) { // pending immediate draws are work the caller has issued
+        int st = rb_layer_flush(ctx->dirty.back());
+        if (st != RB_OK) return st;
+    }
     RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RB_OK;
 }
@@ -143,6 +149,10 @@ extern "C" int rb_timer_begin(rb_ctx *ctx)
 extern "C" int rb_timer_end(rb_ctx *ctx, float *ms)
 {
     if (!ctx || !ms) return RB_ERR_INVALID;
+    while (!ctx->dirty.empty()) { // the timed region covers the immediate draws issued inside it
+        int st = rb_layer_flush(ctx->dirty.back());
+        if (st != RB_OK) return st;
+    }
     RB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     RB_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
     RB_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
@@ -182,6 +192,12 @@ extern "C" int rb_layer_create(rb_ctx *ctx, uint32_t w, uint32_t h, rb_layer **o
 extern "C" void rb_layer_destroy(rb_layer *l)
 {
     if (!l) return;
+    if (l->pending) { // immediate draws nobody looked at: drop them
+        rb_batch_destroy(l->pending);
+        l->pending = nullptr;
+        auto &dv = l->ctx->dirty;
+        dv.erase(std::remove(dv.begin(), dv.end(), l), dv.end());
+    }
     if (l->dl_pending) cudaEventSynchronize(l->dl_done);
     if (l->dl_ready) cudaEventDestroy(l->dl_ready);
     if (l->dl_done) cudaEventDestroy(l->dl_done);
@@ -192,10 +208,16 @@ extern "C" void rb_layer_destroy(rb_layer *l)
 
 extern "C" uint32_t rb_layer_width(const rb_layer *l) { return l ? l->w : 0; }
 extern "C" uint32_t rb_layer_height(const rb_layer *l) { return l ? l->h : 0; }
-extern "C" void *rb_layer_device_ptr(rb_layer *l) { return l ? l->d : nullptr; }
+extern "C" void *rb_layer_device_ptr(rb_layer *l)
+{
+    if (!l) return nullptr;
+    if (l->pending && rb_layer_flush(l) != RB_OK) return nullptr;
+    return l->d;
+}
 
 extern "C" int rb_layer_upload(rb_layer *l, const uint8_t *host)
 {
+    RB_SYNC_LAYER(l);
     if (!l || !host) return RB_ERR_INVALID;
     RB_CUDA(l->ctx, cudaMemcpyAsync(l->d, host, (size_t)l->w * l->h * 4, cudaMemcpyHostToDevice, l->ctx->stream));
     return RB_OK;
@@ -203,6 +225,7 @@ extern "C" int rb_layer_upload(rb_layer *l, const uint8_t *host)
 
 extern "C" int rb_layer_download(rb_layer *l, uint8_t *host)
 {
+    RB_SYNC_LAYER(l);
     if (!l || !host) return RB_ERR_INVALID;
     RB_CUDA(l->ctx, cudaMemcpyAsync(host, l->d, (size_t)l->w * l->h * 4, cudaMemcpyDeviceToHost, l->ctx->stream));
     RB_CUDA(l->ctx, cudaStreamSynchronize(l->ctx->stream));
@@ -214,6 +237,7 @@ extern "C" int rb_layer_download(rb_layer *l, uint8_t *host)
 // The layer must not be written again, and `host` not read, before rb_layer_download_end has returned.
 extern "C" int rb_layer_download_begin(rb_layer *l, uint8_t *host)
 {
+    RB_SYNC_LAYER(l);
     if (!l || !host) return RB_ERR_INVALID;
     rb_ctx *ctx = l->ctx;
     if (l->dl_pending) RB_CUDA(ctx, cudaEventSynchronize(l->dl_done));
@@ -231,6 +255,7 @@ extern "C" int rb_layer_download_begin(rb_layer *l, uint8_t *host)
 
 extern "C" int rb_layer_download_end(rb_layer *l)
 {
+    RB_SYNC_LAYER(l);
     if (!l) return RB_ERR_INVALID;
     if (l->dl_pending) {
         RB_CUDA(l->ctx, cudaEventSynchronize(l->dl_done));
@@ -252,6 +277,7 @@ __global__ void __launch_bounds__(256) k_fill_u32(uint32_t *__restrict__ px, siz
 
 extern "C" int rb_layer_fill(rb_layer *l, uint8_t r, uint8_t g, uint8_t b, uint8_t a)
 {
+    RB_SYNC_LAYER(l);
     if (!l) return RB_ERR_INVALID;
     rb_ctx *ctx = l->ctx;
     size_t n = (size_t)l->w * l->h;
@@ -263,6 +289,8 @@ extern "C" int rb_layer_fill(rb_layer *l, uint8_t r, uint8_t g, uint8_t b, uint8
 
 extern "C" int rb_layer_copy(rb_layer *dst, const rb_layer *src)
 {
+    RB_SYNC_LAYER(dst);
+    RB_SYNC_LAYER(src);
     if (!dst || !src || dst->w != src->w || dst->h != src->h) return RB_ERR_INVALID;
     RB_CUDA(dst->ctx, cudaMemcpyAsync(dst->d, src->d, (size_t)src->w * src->h * 4, cudaMemcpyDeviceToDevice,
                                       dst->ctx->stream));

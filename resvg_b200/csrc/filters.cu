@@ -244,9 +244,14 @@ static int launch_px_table(rb_layer *l, int which, const char *name)
     return RB_OK;
 }
 
-extern "C" int rb_layer_multiply_alpha(rb_layer *l) { return launch_pointwise(l, OpMultiplyAlpha(), "multiply_alpha"); }
+extern "C" int rb_layer_multiply_alpha(rb_layer *l)
+{
+    RB_SYNC_LAYER(l);
+    return launch_pointwise(l, OpMultiplyAlpha(), "multiply_alpha");
+}
 extern "C" int rb_layer_demultiply_alpha(rb_layer *l)
 {
+    RB_SYNC_LAYER(l);
     int st = launch_px_table(l, 0, "demultiply_alpha");
     return st >= 0 ? st : launch_pointwise(l, OpDemultiplyAlpha(), "demultiply_alpha");
 }
@@ -266,8 +271,16 @@ static int launch_cs(rb_layer *l)
     RB_LAUNCHED(ctx, "cs_convert");
     return RB_OK;
 }
-extern "C" int rb_layer_into_linear_rgb(rb_layer *l) { return launch_cs<true>(l); }
-extern "C" int rb_layer_into_srgb(rb_layer *l) { return launch_cs<false>(l); }
+extern "C" int rb_layer_into_linear_rgb(rb_layer *l)
+{
+    RB_SYNC_LAYER(l);
+    return launch_cs<true>(l);
+}
+extern "C" int rb_layer_into_srgb(rb_layer *l)
+{
+    RB_SYNC_LAYER(l);
+    return launch_cs<false>(l);
+}
 
 // =================================================================================================
 // box_blur.rs — five iterations of (vertical box, horizontal box), every pass quantised to u8.
@@ -781,6 +794,7 @@ static void create_box_gauss(float sigma, int sizes[5])
 
 extern "C" int rb_filter_box_blur(rb_layer *l, double sigma_x, double sigma_y)
 {
+    RB_SYNC_LAYER(l);
     if (!l) return RB_ERR_INVALID;
     rb_ctx *ctx = l->ctx;
     int w = (int)l->w, h = (int)l->h;
@@ -859,6 +873,7 @@ extern "C" int rb_filter_box_blur_reach(double sigma)
 // per pass for all rectangles.  Rectangles must not overlap.
 extern "C" int rb_filter_box_blur_cells(rb_layer *l, int32_t n, const int32_t *rects, const double *sigma_x, const double *sigma_y)
 {
+    RB_SYNC_LAYER(l);
     if (!l || n < 0 || (n > 0 && (!rects || !sigma_x || !sigma_y))) return RB_ERR_INVALID;
     if (n == 0) return RB_OK;
     if (n > 65535) return RB_ERR_UNSUPPORTED;
@@ -1039,6 +1054,7 @@ static double powi_f64(double a, int b)
 
 extern "C" int rb_filter_iir_blur(rb_layer *l, double sigma_x, double sigma_y)
 {
+    RB_SYNC_LAYER(l);
     if (!l) return RB_ERR_INVALID;
     rb_ctx *ctx = l->ctx;
     int w = (int)l->w, h = (int)l->h;
@@ -1175,6 +1191,7 @@ static inline uint32_t f2u32_sat(float v)
 
 extern "C" int rb_filter_morphology(rb_layer *l, int op, float rx, float ry)
 {
+    RB_SYNC_LAYER(l);
     if (!l || (op != 0 && op != 1)) return RB_ERR_INVALID;
     rb_ctx *ctx = l->ctx;
     int w = (int)l->w, h = (int)l->h;
@@ -1407,6 +1424,7 @@ extern "C" int rb_filter_convolve_matrix(rb_layer *l, const float *kernel, uint3
                                          uint32_t target_x, uint32_t target_y, float divisor, float bias,
                                          int edge_mode, int preserve_alpha)
 {
+    RB_SYNC_LAYER(l);
     if (!l || !kernel || columns == 0 || rows == 0 || edge_mode < 0 || edge_mode > 2) return RB_ERR_INVALID;
     if ((size_t)columns * rows > 8192) return RB_ERR_UNSUPPORTED;
     rb_ctx *ctx = l->ctx;
@@ -1478,6 +1496,7 @@ struct OpLuminanceToAlpha {
 
 extern "C" int rb_filter_color_matrix(rb_layer *l, int kind, const float *params)
 {
+    RB_SYNC_LAYER(l);
     if (!l) return RB_ERR_INVALID;
     if (kind == 0) {
         if (!params) return RB_ERR_INVALID;
@@ -1592,6 +1611,7 @@ static uint8_t transfer_u8(const rb_transfer_fn &f, uint8_t cu)
 
 extern "C" int rb_filter_component_transfer(rb_layer *l, const rb_transfer_fn funcs[4])
 {
+    RB_SYNC_LAYER(l);
     if (!l || !funcs) return RB_ERR_INVALID;
     OpLut4 L;
     uint8_t lut[4][256];
@@ -1640,6 +1660,7 @@ __global__ void __launch_bounds__(256) k_alpha_lut(uint32_t *__restrict__ px, si
 
 extern "C" int rb_filter_flood_alpha(rb_layer *l, uint8_t r, uint8_t g, uint8_t b, uint8_t a)
 {
+    RB_SYNC_LAYER(l);
     if (!l) return RB_ERR_INVALID;
     AlphaLut L;
     volatile float cr = (float)r / 255.0f, cg = (float)g / 255.0f, cb = (float)b / 255.0f, ca = (float)a / 255.0f;
@@ -1706,6 +1727,9 @@ k_arithmetic(const uint32_t *__restrict__ s1, const uint32_t *__restrict__ s2, u
 extern "C" int rb_filter_composite_arithmetic(rb_layer *dest, const rb_layer *src1, const rb_layer *src2, float k1,
                                               float k2, float k3, float k4)
 {
+    RB_SYNC_LAYER(dest);
+    RB_SYNC_LAYER(src1);
+    RB_SYNC_LAYER(src2);
     if (!dest || !src1 || !src2) return RB_ERR_INVALID;
     if (src1->w != dest->w || src2->w != dest->w || src1->h != dest->h || src2->h != dest->h) return RB_ERR_INVALID;
     rb_ctx *ctx = dest->ctx;
@@ -1779,6 +1803,9 @@ k_displace(const uint32_t *__restrict__ src, const uint32_t *__restrict__ map, u
 extern "C" int rb_filter_displacement_map(rb_layer *dest, const rb_layer *src, const rb_layer *map, int xch, int ych,
                                           float scale, float sx, float sy)
 {
+    RB_SYNC_LAYER(dest);
+    RB_SYNC_LAYER(src);
+    RB_SYNC_LAYER(map);
     if (!dest || !src || !map || xch < 0 || xch > 3 || ych < 0 || ych > 3) return RB_ERR_INVALID;
     if (src->w != dest->w || map->w != dest->w || src->h != dest->h || map->h != dest->h) return RB_ERR_INVALID;
     if (dest->d == src->d) return RB_ERR_INVALID;
@@ -2032,12 +2059,16 @@ extern "C" int rb_filter_diffuse_lighting(rb_layer *dest, const rb_layer *src, f
                                           float diffuse_constant, uint8_t r, uint8_t g, uint8_t b,
                                           const rb_light_source *light)
 {
+    RB_SYNC_LAYER(dest);
+    RB_SYNC_LAYER(src);
     return launch_lighting(dest, src, 0, surface_scale, diffuse_constant, 1.0f, r, g, b, light);
 }
 extern "C" int rb_filter_specular_lighting(rb_layer *dest, const rb_layer *src, float surface_scale,
                                            float specular_constant, float specular_exponent, uint8_t r, uint8_t g,
                                            uint8_t b, const rb_light_source *light)
 {
+    RB_SYNC_LAYER(dest);
+    RB_SYNC_LAYER(src);
     return launch_lighting(dest, src, 1, surface_scale, specular_constant, specular_exponent, r, g, b, light);
 }
 
@@ -2220,6 +2251,7 @@ extern "C" int rb_filter_turbulence(rb_layer *dest, double offset_x, double offs
                                     double bfx, double bfy, uint32_t num_octaves, int32_t seed, int stitch_tiles,
                                     int fractal_noise)
 {
+    RB_SYNC_LAYER(dest);
     if (!dest) return RB_ERR_INVALID;
     rb_ctx *ctx = dest->ctx;
     int w = (int)dest->w, h = (int)dest->h;

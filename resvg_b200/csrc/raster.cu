@@ -817,6 +817,7 @@ static int batch_prepare_range(rb_batch *b, int32_t n_threads, size_t begin, siz
 
 extern "C" int rb_batch_prepare(rb_batch *b, int32_t n_threads)
 {
+    if (b && b->layer && b->layer->pending != b) RB_SYNC_LAYER(b->layer);
     int st = batch_prepare_range(b, n_threads, 0, 0);
     // hairline strokes + the fallback builder: only rb_batch_submit can interleave the two kinds of passes
     if (st == RB_NEEDS_RUN_SPLIT)
@@ -825,7 +826,11 @@ extern "C" int rb_batch_prepare(rb_batch *b, int32_t n_threads)
 }
 
 static int batch_run(rb_batch *b, unsigned long long *px_stats);
-extern "C" int rb_batch_run(rb_batch *b) { return batch_run(b, nullptr); }
+extern "C" int rb_batch_run(rb_batch *b)
+{
+    if (b && b->layer && b->layer->pending != b) RB_SYNC_LAYER(b->layer);
+    return batch_run(b, nullptr);
+}
 
 // Runs the batch once with the coverage counters on: out[0] = pixels read-modify-written (partial coverage or
 // non-opaque paint), out[1] = pixels stored without reading (full coverage, opaque solid).  Synchronises.
@@ -1012,6 +1017,7 @@ static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t 
 extern "C" int rb_batch_submit(rb_batch *b, int32_t n_threads)
 {
     if (!b) return RB_ERR_INVALID;
+    if (b->layer && b->layer->pending != b) RB_SYNC_LAYER(b->layer); // immediate draws issued before this batch come first
     uint64_t total[6] = {0, 0, 0, 0, 0, 0};
     int st = RB_OK;
     // Hairline strokes ride along as draws of their own kind (their blits are applied by the tile kernel), except with
@@ -1057,16 +1063,45 @@ static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t 
     return st;
 }
 
+// Immediate draws are collected per layer and executed as one batch by rb_layer_flush, which every entry point that
+// reads or writes a layer calls first (RB_SYNC_LAYER): a traversal that issues fill_path after fill_path on a layer and
+// then composites it pays one tile-kernel launch, as if it had recorded an explicit batch.  Painter's order is the call
+// order.  Draws with a pattern paint are executed at once (their source layer may be gone or changed by the next call).
+constexpr uint32_t RB_PENDING_MAX = 16384;
+
+int rb_layer_flush(rb_layer *l)
+{
+    if (!l || !l->pending) return RB_OK;
+    rb_batch *b = l->pending;
+    const uint32_t n = l->pending_n;
+    l->pending = nullptr;
+    l->pending_n = 0;
+    {
+        auto &dv = l->ctx->dirty;
+        dv.erase(std::remove(dv.begin(), dv.end(), l), dv.end());
+    }
+    int st = rb_batch_submit(b, n > 64 ? 0 : 1);
+    rb_batch_destroy(b);
+    return st;
+}
+
 extern "C" int rb_fill_path(rb_layer *layer, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
                             const rb_paint *paint, int32_t fill_rule, const float ts[6])
 {
-    rb_batch *b = nullptr;
-    int st = rb_batch_begin(layer, &b);
-    if (st != RB_OK) return st;
-    st = rb_batch_fill_path(b, verbs, n_verbs, points, n_points, paint, fill_rule, ts);
-    if (st == RB_OK) st = rb_batch_submit(b, 1);
-    rb_batch_destroy(b);
-    return st;
+    if (!layer || !paint) return RB_ERR_INVALID;
+    const bool pattern = paint->shader == 3;
+    if (pattern) RB_SYNC_LAYER(paint->pattern);
+    if (!layer->pending) {
+        int st = rb_batch_begin(layer, &layer->pending);
+        if (st != RB_OK) return st;
+        layer->pending_n = 0;
+        layer->ctx->dirty.push_back(layer);
+    }
+    int st = rb_batch_fill_path(layer->pending, verbs, n_verbs, points, n_points, paint, fill_rule, ts);
+    if (st != RB_OK) return st; // nothing was recorded
+    layer->pending_n++;
+    if (pattern || layer->pending_n >= RB_PENDING_MAX) return rb_layer_flush(layer);
+    return RB_OK;
 }
 
 extern "C" int rb_mask_fill_path(rb_mask *mask, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
@@ -1126,6 +1161,8 @@ k_draw_layer(uint32_t *__restrict__ dst, int dw, const uint32_t *__restrict__ sr
 
 extern "C" int rb_draw_layer(rb_layer *dst, const rb_layer *src, int32_t x, int32_t y, float opacity, int32_t blend_mode)
 {
+    RB_SYNC_LAYER(dst);
+    RB_SYNC_LAYER(src);
     if (!dst || !src || blend_mode < 0 || blend_mode > 28 || dst->d == src->d) return RB_ERR_INVALID;
     if (blend_mode == RB_BLEND_DESTINATION) return RB_OK;
     rb_ctx *ctx = dst->ctx;
@@ -1173,6 +1210,8 @@ k_draw_layer_rects(uint32_t *__restrict__ dst, int dw, const uint32_t *__restric
 extern "C" int rb_draw_layer_rects(rb_layer *dst, const rb_layer *src, int32_t n, const int32_t *rects, const int32_t *src_xy,
                                    const float *opacity, int32_t blend_mode)
 {
+    RB_SYNC_LAYER(dst);
+    RB_SYNC_LAYER(src);
     if (!dst || !src || n < 0 || (n > 0 && (!rects || !opacity)) || blend_mode < 0 || blend_mode > 28 || dst->d == src->d)
         return RB_ERR_INVALID;
     if (n == 0 || blend_mode == RB_BLEND_DESTINATION) return RB_OK;
@@ -1314,6 +1353,7 @@ __global__ void __launch_bounds__(256) k_apply_mask(uint32_t *__restrict__ px, c
 
 extern "C" int rb_mask_from_layer(rb_mask *m, const rb_layer *l, int32_t luminance)
 {
+    RB_SYNC_LAYER(l);
     if (!m || !l || m->w != l->w || m->h != l->h) return RB_ERR_INVALID;
     rb_ctx *ctx = m->ctx;
     size_t n = (size_t)m->w * m->h;
@@ -1332,6 +1372,7 @@ extern "C" int rb_mask_invert(rb_mask *m)
 }
 extern "C" int rb_layer_apply_mask(rb_layer *l, const rb_mask *m)
 {
+    RB_SYNC_LAYER(l);
     if (!m || !l) return RB_ERR_INVALID;
     if (m->w != l->w || m->h != l->h) return RB_OK; // tiny-skia: warn and return
     rb_ctx *ctx = l->ctx;

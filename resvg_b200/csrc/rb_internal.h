@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <string>
+#include <vector>
 
 #include "../../include/resvg_b200.h"
 
@@ -29,6 +30,7 @@ struct rb_ctx {
     bool staging_in_flight = false;
     // owner + every live layer / mask / batch: the context outlives them whatever the destruction order
     std::atomic<int> refs{1};
+    std::vector<struct rb_layer *> dirty; // layers holding pending immediate draws (rb_fill_path), flushed by rb_ctx_synchronize
 };
 
 void rb_ctx_retain(rb_ctx *ctx);
@@ -42,7 +44,23 @@ struct rb_layer {
     uint8_t *d; // w*h*4 bytes, premultiplied RGBA8
     cudaEvent_t dl_ready = nullptr, dl_done = nullptr; // rb_layer_download_begin / _end
     bool dl_pending = false;
+    // Draws issued with the immediate calls (rb_fill_path) are collected here and executed as ONE batch the next time
+    // anything else looks at or changes the layer (rb_layer_flush): consecutive fill_path calls of a traversal cost one
+    // tile-kernel launch instead of one each.
+    struct rb_batch *pending = nullptr;
+    uint32_t pending_n = 0;
 };
+
+// Executes the layer's pending immediate draws, if any.  Every entry point that reads or writes a layer calls it first.
+int rb_layer_flush(rb_layer *l);
+#define RB_SYNC_LAYER(l)                                                        \
+    do {                                                                        \
+        rb_layer *l__ = const_cast<rb_layer *>(l);                              \
+        if (l__ && l__->pending) {                                              \
+            int st__ = rb_layer_flush(l__);                                     \
+            if (st__ != RB_OK) return st__;                                     \
+        }                                                                       \
+    } while (0)
 
 struct rb_mask {
     rb_ctx *ctx;

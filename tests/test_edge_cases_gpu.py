@@ -174,3 +174,75 @@ def test_empty_batches_and_error_returns(ctx):
     b2.stroke_path([M, L], [(1, 1), (30, 20)], paint, -1.0)
     b2.submit()
     assert_exact(l.download(), want, "negative stroke width")
+
+
+def test_immediate_fills_are_collected_and_flushed_in_call_order(ctx):
+    """rb_fill_path records lazily: consecutive immediate draws on a layer run as one batch the next time the layer is
+    read or written.  Interleavings with explicit batches, composites, pattern paints (executed at once), masks, copies
+    and layer destruction must give the CPU checker's sequential result, with far fewer launches than draws."""
+    import resvg_b200 as rb
+
+    W, H = 150, 120
+    rng = SplitMix64(99)
+    shapes = []
+    for k in range(60):
+        cx, cy, r = rng.uniform(0, W), rng.uniform(0, H), rng.log_uniform(6, 50)
+        verbs, pts = random_path(rng, cx, cy, r)
+        spec = {"kind": "solid", "color": (rng.uniform(0, 1), rng.uniform(0, 1), rng.uniform(0, 1), rng.uniform(0.3, 1.0))}
+        shapes.append((verbs, pts, spec, "evenodd" if k % 3 == 0 else "nonzero"))
+    want = np.zeros((H, W, 4), np.uint8)
+    l = ctx.layer(W, H)
+    ctx.synchronize()
+    launches0 = ctx.launch_count
+    for verbs, pts, spec, rule in shapes[:40]:                       # 40 immediate draws ...
+        rb.fill_path(l, verbs, pts, rb.make_paint(spec), rule)
+        R.fill_path(want, verbs, pts, R.make_paint(spec), rule)
+    assert ctx.launch_count == launches0                              # ... nothing has run yet
+    b = rb.Batch(l)                                                   # an explicit batch recorded now, submitted later
+    for verbs, pts, spec, rule in shapes[40:50]:
+        b.fill_path(verbs, pts, rb.make_paint(spec), rule)
+    for verbs, pts, spec, rule in shapes[50:55]:                      # more immediate draws BEFORE the batch is submitted:
+        rb.fill_path(l, verbs, pts, rb.make_paint(spec), rule)        # they come first (call order of the executions)
+        R.fill_path(want, verbs, pts, R.make_paint(spec), rule)
+    b.submit()
+    for verbs, pts, spec, rule in shapes[40:50]:
+        R.fill_path(want, verbs, pts, R.make_paint(spec), rule)
+    b.close()
+    assert ctx.launch_count - launches0 < 40                          # two batches, not 55 one-draw batches
+    # a composite reads a layer with pending draws; the destination has pending draws of its own
+    top = ctx.layer(W, H)
+    top_want = np.zeros((H, W, 4), np.uint8)
+    for verbs, pts, spec, rule in shapes[55:]:
+        rb.fill_path(top, verbs, pts, rb.make_paint(spec), rule)
+        R.fill_path(top_want, verbs, pts, R.make_paint(spec), rule)
+    verbs, pts, spec, rule = shapes[0]
+    rb.fill_path(l, verbs, pts, rb.make_paint(spec), rule)
+    R.fill_path(want, verbs, pts, R.make_paint(spec), rule)
+    rb.draw_layer(l, top, 0, 0, 1.0, "source_over")
+    R.draw_pixmap(want, 0, 0, top_want, 1.0, "source_over")
+    # a pattern paint whose source layer has pending draws and is destroyed right after the call
+    tile = ctx.layer(16, 12)
+    tile_want = np.zeros((12, 16, 4), np.uint8)
+    tv, tp = [M, L, L, Z], [(1, 1), (15, 3), (6, 11)]
+    rb.fill_path(tile, tv, tp, rb.make_paint(PAINT), "nonzero")
+    R.fill_path(tile_want, tv, tp, R.make_paint(PAINT), "nonzero")
+    pspec = {"kind": "pattern", "layer": tile, "spread": "repeat", "quality": "nearest", "opacity": 1.0, "ts": (1, 0, 0, 1, 0, 0)}
+    verbs, pts, _, rule = shapes[1]
+    rb.fill_path(l, verbs, pts, rb.make_paint(pspec), rule)
+    tile.close()
+    R.fill_path(want, verbs, pts, R.make_paint(dict(pspec, pixmap=tile_want)), rule)
+    # clone, mask and download all see the pending draws
+    verbs, pts, spec, rule = shapes[2]
+    rb.fill_path(l, verbs, pts, rb.make_paint(spec), rule)
+    R.fill_path(want, verbs, pts, R.make_paint(spec), rule)
+    c = l.clone()
+    m = rb.Mask.from_layer(l, "alpha")
+    assert_exact(c.download(), want, "clone after immediate draws")
+    assert_exact(m.download(), want[..., 3], "mask after immediate draws")
+    assert_exact(l.download(), want, "download after immediate draws")
+    # a layer destroyed with pending draws: nothing runs, nothing breaks
+    dead = ctx.layer(64, 64)
+    rb.fill_path(dead, *shapes[3][:2], rb.make_paint(shapes[3][2]), "nonzero")
+    dead.close()
+    ctx.synchronize()
+    assert_exact(l.download(), want, "still intact")
