@@ -34,6 +34,8 @@ WORKLOADS = {
     "icons": (8192, 8192, 100_000, 0x5EED0005),
     # BASELINE configs[2] / C3 (ii): the filter chain over one 8192x8192 layer holding 1000 C2-style shapes
     "filters8k": (8192, 8192, 1_000, 0x5EED0003),
+    # BASELINE configs[3] / C4: 64 nested groups (opacity, luminance masks, clip-paths, patterns) on a 4096x4096 canvas
+    "stack4k": (4096, 4096, 64, 0x5EED0004),
 }
 
 
@@ -516,6 +518,109 @@ def run_filters8k(args, rank, local_rank, world, torch, dist):
     print(json.dumps(out))
 
 
+def run_stack4k(args, rank, local_rank, world, torch, dist):
+    """Workload `stack4k` (BASELINE configs[3]).  The document is SVG text (scenes.stack_svg); parsing it and
+    walking the tree (groups -> layers, clip-paths, masks, patterns: render.rs / clip.rs / mask.rs / path.rs) is HOST work that
+    stays in Rust in resvg; here the test-side Python front end (tests/svgfront.py) plays that role and drives the C ABI
+    call by call.  value: CUDA-event time from the first to the last launch of one traversal (it includes the gaps the
+    Python traversal leaves between launches); e2e: wall clock of traversal + download of the canvas."""
+    import resvg_b200 as rb
+    from resvg_b200 import scenes, shard
+    from tests import svgfront as F          # host front end stand-in (no pixel work)
+    from tests.backends import GpuBackend    # thin adapter: back-end interface -> C ABI calls
+    W, H, levels, seed = WORKLOADS["stack4k"]
+    ctx = rb.Context(local_rank)
+    tree = F.parse(scenes.stack_svg(W, levels, shard.scene_seed(seed, rank)))
+    be = GpuBackend(ctx)
+    renderer = F.Renderer(be)
+    ident = (1.0, 0.0, 0.0, 1.0, 0.0, 0.0)
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ctx.synchronize()
+
+    def step():
+        return renderer.render(tree, W, H, ident)
+
+    for _ in range(max(args.warmup, 3)):
+        step().close()
+    barrier()
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ctx.timer_begin()
+    for _ in range(args.steps):
+        step().close()
+    ms_step = ctx.timer_end() / args.steps
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = ctx.launch_count - launches0
+
+    # the traversal's most frequent full-layer kernel alone: the layer composite (draw_pixmap), 12 B/px
+    a, b2 = ctx.layer(W, H), ctx.layer(W, H)
+    rb.draw_layer(a, b2, 0, 0, 0.9, "source_over")
+    ctx.timer_begin()
+    for _ in range(10):
+        rb.draw_layer(a, b2, 0, 0, 0.9, "source_over")
+    ms_comp = ctx.timer_end() / 10
+
+    pinned = rb.PinnedBuffer(W * H * 4)
+    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+
+    def e2e_step():
+        l = step()
+        l.download_ptr(pinned.array.ctypes.data)
+        l.close()
+
+    e2e_step()
+    barrier()
+    h2d0 = ctx.h2d_bytes
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ctx.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    h2d = (ctx.h2d_bytes - h2d0) // e2e_steps
+    ms_step, ms_comp, e2e_s = shard.max_over_ranks([ms_step, ms_comp, e2e_s], world, f"cuda:{local_rank}")
+    if rank != 0:
+        return
+    mpx = W * H / 1e6
+    peak, peak_src = measured_peaks()
+    comp_bytes = 12 * W * H
+    out = {
+        "metric": "Mpixels/s rendered", "value": shard.aggregate_throughput(mpx, world, ms_step * 1e-3), "unit": "Mpx/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16 fixed point + f32", "data": "synthetic",
+        "config": {"workload": "stack4k", "canvas": [W, H], "levels": levels,
+                   "recipe": "level k: opacity U[0.85,0.99]; k%4=0 luminance mask (gradient rect), 1 clip-path (circle, every 8th nested), "
+                             "2 pattern-filled rect (tile 32-128 px), 3 plain; 10 C2-style shapes per level in a box inset 16 px per level",
+                   "host": "SVG parsing + tree traversal by the test-side Python front end (stand-in for usvg + render.rs), one C-ABI call per "
+                           "tiny-skia call; the device time includes the gaps it leaves",
+                   "l2": "64 MiB layers; every level allocates, composites and masks full layers (> 126 MB L2 across a level)",
+                   "sharding": "one document per GPU, no collective"},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_draw_layer (layer composite, the traversal's most frequent full-layer pass)",
+                     "achieved": comp_bytes / (ms_comp * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": comp_bytes / (ms_comp * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes": comp_bytes, "kernel_ms": ms_comp, "model": "12 B/px: source read, destination read + write"},
+        "e2e": {"value": shard.aggregate_throughput(mpx, world, e2e_s), "unit": "Mpx/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": W * H * 4, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from tests.backends import OracleBackend  # the CPU checker: cpu_baseline only
+        n = 1024
+        small = F.parse(scenes.stack_svg(n, levels, seed))
+        t0 = time.perf_counter()
+        F.Renderer(OracleBackend()).render(small, n, n, ident)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n * n / 1e6 / dt, "unit": "Mpx/s", "cores": 1, "kind": "port",
+                               "sample": f"the same recipe at {n}x{n} (1/16 of the pixels, same 64 levels) through the same front end, {dt:.2f} s; "
+                                         "oracle restatement of the resvg/tiny-skia CPU path"}
+    print(json.dumps(out))
+
+
 def run_reference_icons(args, cores):
     """--impl reference --workload icons: the CPU checker renders documents one at a time on every host core (one document
     stream per thread, as `resvg` would be run per file)."""
@@ -559,8 +664,8 @@ def run_reference(args, rank, world):
     cores = min(os.cpu_count() or 1, 32)
     if args.workload == "icons":
         return run_reference_icons(args, cores)
-    if args.workload == "filters8k":
-        raise SystemExit("--impl reference: workload filters8k has a cpu_baseline in the ours arm only")
+    if args.workload in ("filters8k", "stack4k"):
+        raise SystemExit("--impl reference: workloads filters8k / stack4k have a cpu_baseline in the ours arm only")
     R = oracle_lib()
     W, H, n_paths, seed = WORKLOADS[args.workload]
     scs = [scenes.paths_scene(W, H, n_paths, seed + t) for t in range(min(cores, 4))]
@@ -636,8 +741,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    if args.workload in ("icons", "filters8k"):
-        (run_icons if args.workload == "icons" else run_filters8k)(args, rank, local_rank, world, torch, dist)
+    if args.workload in ("icons", "filters8k", "stack4k"):
+        {"icons": run_icons, "filters8k": run_filters8k, "stack4k": run_stack4k}[args.workload](args, rank, local_rank, world, torch, dist)
         if world > 1:
             dist.destroy_process_group()
         return

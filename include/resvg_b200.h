@@ -50,6 +50,8 @@ int rb_timer_begin(rb_ctx *ctx);
 int rb_timer_end(rb_ctx *ctx, float *elapsed_ms); /* synchronises */
 /* Number of kernel launches issued through this context since creation (bench "gpu_launches"). */
 uint64_t rb_ctx_launch_count(rb_ctx *ctx);
+/* bytes copied host -> device so far by batches (edge / paint blocks) and layer / mask uploads */
+uint64_t rb_ctx_h2d_bytes(rb_ctx *ctx);
 /* Pinned host memory for upload/download staging. */
 int rb_host_alloc(size_t bytes, void **out);
 void rb_host_free(void *p);

@@ -83,6 +83,7 @@ SIGNATURES = {
     "rb_timer_begin": (_i, [_vp]),
     "rb_timer_end": (_i, [_vp, f32p]),
     "rb_ctx_launch_count": (C.c_uint64, [_vp]),
+    "rb_ctx_h2d_bytes": (C.c_uint64, [_vp]),
     "rb_host_alloc": (_i, [C.c_size_t, c_void_pp]),
     "rb_host_free": (None, [_vp]),
     "rb_layer_create": (_i, [_vp, _u32, _u32, c_void_pp]),

@@ -61,6 +61,10 @@ class Context:
         return int(lib.rb_ctx_launch_count(self._h))
 
     @property
+    def h2d_bytes(self) -> int:
+        return int(lib.rb_ctx_h2d_bytes(self._h))
+
+    @property
     def stream(self) -> int:
         return int(lib.rb_ctx_stream(self._h) or 0)
 

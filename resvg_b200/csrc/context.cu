@@ -138,6 +138,7 @@ extern "C" const char *rb_last_error(rb_ctx *ctx) { return ctx ? ctx->err.c_str(
 extern "C" void *rb_ctx_stream(rb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 extern "C" int rb_ctx_device(rb_ctx *ctx) { return ctx ? ctx->device : -1; }
 extern "C" uint64_t rb_ctx_launch_count(rb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t rb_ctx_h2d_bytes(rb_ctx *ctx) { return ctx ? ctx->h2d_bytes : 0; }
 
 extern "C" int rb_timer_begin(rb_ctx *ctx)
 {
@@ -220,6 +221,7 @@ extern "C" int rb_layer_upload(rb_layer *l, const uint8_t *host)
     RB_SYNC_LAYER(l);
     if (!l || !host) return RB_ERR_INVALID;
     RB_CUDA(l->ctx, cudaMemcpyAsync(l->d, host, (size_t)l->w * l->h * 4, cudaMemcpyHostToDevice, l->ctx->stream));
+    l->ctx->h2d_bytes += (size_t)l->w * l->h * 4;
     return RB_OK;
 }
 

@@ -806,6 +806,7 @@ static int batch_prepare_range(rb_batch *b, int32_t n_threads, size_t begin, siz
     RB_CUDA(ctx, cudaMallocAsync((void **)&dev, b->lay.total, ctx->stream));
     b->dev = dev;
     RB_CUDA(ctx, cudaMemcpyAsync(dev, blk, b->lay.total, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d_bytes += b->lay.total;
     RB_CUDA(ctx, cudaEventRecord(ctx->staging_ev, ctx->stream));
     ctx->staging_in_flight = true;
     if (!b->lay.wide) {
@@ -1281,6 +1282,7 @@ extern "C" int rb_mask_upload(rb_mask *m, const uint8_t *host)
 {
     if (!m || !host) return RB_ERR_INVALID;
     RB_CUDA(m->ctx, cudaMemcpyAsync(m->d, host, (size_t)m->w * m->h, cudaMemcpyHostToDevice, m->ctx->stream));
+    m->ctx->h2d_bytes += (size_t)m->w * m->h;
     return RB_OK;
 }
 

@@ -18,6 +18,7 @@ struct rb_ctx {
     cudaEvent_t ev_run[3] = {nullptr, nullptr, nullptr}; // last batch run: start, after the pre-pass, after the raster kernel
     std::string err;
     uint64_t launches = 0;
+    uint64_t h2d_bytes = 0; // bytes uploaded by batches and layer / mask uploads (rb_ctx_h2d_bytes)
     int sm_count = 148;
     // scratch reused by multi-pass filters (grown on demand, freed with the context)
     void *scratch = nullptr;
