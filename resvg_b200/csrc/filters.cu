@@ -1137,7 +1137,7 @@ __global__ void k_morph_pass(const uint32_t *__restrict__ src, uint32_t *__restr
 // amounts to), filters it horizontally into a second shared array and vertically from there: 8 B/px of HBM traffic
 // instead of 16, and every window tap is a shared-memory read.  Pixels are staged as two u16x2 words (r,b | g,a) because
 // sm_100 has a native 16x2 min/max (VIMNMX.U16x2) while the 8x4 form is emulated with seven logic instructions.
-constexpr int MORPH_TW = 64, MORPH_TH = 32, MORPH_MAXC = 16;
+constexpr int MORPH_TW = 64, MORPH_TH = 32, MORPH_MAXC = 16, MORPH_BIG = 256;
 __device__ __forceinline__ uint2 morph_mm(uint2 a, uint2 b, bool dilate)
 {
     return dilate ? make_uint2(__vmaxu2(a.x, b.x), __vmaxu2(a.y, b.y)) : make_uint2(__vminu2(a.x, b.x), __vminu2(a.y, b.y));
@@ -1202,23 +1202,36 @@ extern "C" int rb_filter_morphology(rb_layer *l, int op, float rx, float ry)
     int target_x = (int)f2u32_sat(floorf((float)columns / 2.0f));
     int target_y = (int)f2u32_sat(floorf((float)rows / 2.0f));
     size_t bytes = (size_t)w * h * 4;
-    if (columns >= 1 && rows >= 1 && columns <= (uint32_t)MORPH_MAXC && rows <= (uint32_t)MORPH_MAXC) {
-        // fused tile kernel; its output block becomes the layer's storage
-        uint32_t *out = nullptr;
-        RB_CUDA(ctx, cudaMallocAsync((void **)&out, bytes, ctx->stream));
-        const int SW = MORPH_TW + (int)columns - 1, SH = MORPH_TH + (int)rows - 1;
-        const size_t smem = (size_t)(SH * SW + SH * MORPH_TW) * 8;
-        dim3 grid((w + MORPH_TW - 1) / MORPH_TW, (h + MORPH_TH - 1) / MORPH_TH);
+    if (columns >= 1 && rows >= 1 && columns <= (uint32_t)MORPH_BIG && rows <= (uint32_t)MORPH_BIG) {
+        // Fused tile kernel; its output block becomes the layer's storage.  Windows wider than MORPH_MAXC are applied as a
+        // chain of windows of at most MORPH_MAXC: min / max over [a, b] of the min / max over [c, d] is the min / max over
+        // [a + c, b + d], also with the windows clipped to the image (between an in-image sample and the in-image centre
+        // there is always an in-image intermediate position), so the chain is exact: L = sum(L_i) - (n - 1), lo = sum(lo_i).
         static bool attr_set = false;
         if (!attr_set) {
             RB_CUDA(ctx, cudaFuncSetAttribute(k_morph_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             attr_set = true;
         }
-        k_morph_tile<<<grid, 256, smem, ctx->stream>>>(reinterpret_cast<const uint32_t *>(l->d), out, w, h, target_x,
-                                                       (int)columns, target_y, (int)rows, op == 1);
-        RB_LAUNCHED(ctx, "morph_tile");
-        RB_CUDA(ctx, cudaFreeAsync(l->d, ctx->stream));
-        l->d = reinterpret_cast<uint8_t *>(out);
+        int left_x = (int)columns, left_y = (int)rows, lo_x = target_x, lo_y = target_y; // window still to apply, offset still to apply
+        while (left_x > 0 || left_y > 0) {
+            // this pass: up to MORPH_MAXC taps per axis (a 1-tap window leaves the axis unchanged)
+            const int cxp = left_x > 0 ? std::min(left_x, MORPH_MAXC) : 1, cyp = left_y > 0 ? std::min(left_y, MORPH_MAXC) : 1;
+            const int lxp = std::min(lo_x, cxp - 1), lyp = std::min(lo_y, cyp - 1);
+            uint32_t *out = nullptr;
+            RB_CUDA(ctx, cudaMallocAsync((void **)&out, bytes, ctx->stream));
+            const int SW = MORPH_TW + cxp - 1, SH = MORPH_TH + cyp - 1;
+            const size_t smem = (size_t)(SH * SW + SH * MORPH_TW) * 8;
+            dim3 grid((w + MORPH_TW - 1) / MORPH_TW, (h + MORPH_TH - 1) / MORPH_TH);
+            k_morph_tile<<<grid, 256, smem, ctx->stream>>>(reinterpret_cast<const uint32_t *>(l->d), out, w, h, lxp, cxp, lyp, cyp, op == 1);
+            RB_LAUNCHED(ctx, "morph_tile");
+            RB_CUDA(ctx, cudaFreeAsync(l->d, ctx->stream));
+            l->d = reinterpret_cast<uint8_t *>(out);
+            // a window of c taps extends the applied window by c - 1; the first pass of an axis applies c taps outright
+            left_x = left_x > 0 ? (left_x == cxp ? 0 : left_x - (cxp - 1)) : 0;
+            left_y = left_y > 0 ? (left_y == cyp ? 0 : left_y - (cyp - 1)) : 0;
+            lo_x -= lxp;
+            lo_y -= lyp;
+        }
         return RB_OK;
     }
     void *scratch = nullptr;

@@ -115,6 +115,16 @@ def test_morphology(ctx, oracle, w, h, op, rx, ry):
                  f"morph {op} {rx},{ry}")
 
 
+def test_morphology_wide_windows_as_a_chain_of_tile_passes(ctx, oracle):
+    """Windows wider than the tile kernel's 16 taps are applied as a chain of narrower windows (exact for min / max, also at
+    the image borders); windows that reach the image size, odd sizes and different radii per axis included."""
+    for (w, h, rx, ry) in [(200, 120, 32.0, 32.0), (97, 61, 20.0, 9.0), (150, 40, 8.5, 60.0), (64, 64, 100.0, 3.0), (300, 9, 127.0, 1.0)]:
+        img = random_premul(w, h, 31, sparse=True)
+        for op in ("erode", "dilate"):
+            assert_exact(_run(ctx, img, lambda f, l: f.morphology(op, rx, ry, l)), oracle.morphology(op, rx, ry, img),
+                         f"morph {op} {rx},{ry} on {w}x{h}")
+
+
 KERNELS = {
     "sharpen3": ([0, -1, 0, -1, 5, -1, 0, -1, 0], 3, 3, 1, 1, 1.0, 0.0),
     "emboss3": ([-2, -1, 0, -1, 1, 1, 0, 1, 2], 3, 3, 1, 1, 1.0, 0.5),

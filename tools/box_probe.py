@@ -22,3 +22,8 @@ for oct_ in (1, 2, 3, 4):
     ctx.timer_begin()
     F.turbulence(0.0, 0.0, 1.0, 1.0, 0.02, 0.02, oct_, 7, False, False, a)
     print(f"turbulence {oct_} octaves: {ctx.timer_end():.3f} ms")
+for r in (1.0, 3.0, 8.0, 32.0):
+    F.morphology("dilate", r, r, a)
+    ctx.timer_begin()
+    F.morphology("dilate", r, r, a)
+    print(f"morphology dilate r={r:g}: {ctx.timer_end():.3f} ms")
