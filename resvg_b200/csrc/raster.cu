@@ -1125,16 +1125,19 @@ extern "C" int rb_mask_fill_path(rb_mask *mask, const uint8_t *verbs, int32_t n_
 // (gather is highp-only): s = src/255 [* opacity]; blend with dst/255; store round(clamp*255).
 // 12 B/px: src read, dst read, dst write.
 // =================================================================================================
+// SO: the blend mode is known to be SourceOver at compile time (every group composite of render.rs:133 with the default
+// mix-blend-mode), which folds blendf's mode dispatch away.
+template <bool SO = false>
 __device__ __forceinline__ uint32_t draw_layer_px(uint32_t sp, uint32_t dp, float opacity, int blend)
 {
     PF s = load_pf(sp);
     if (opacity != 1.0f) { s.r *= opacity; s.g *= opacity; s.b *= opacity; s.a *= opacity; }
-    return store_pf(blendf(blend, s, load_pf(dp)));
+    return store_pf(blendf(SO ? (int)RB_BLEND_SOURCE_OVER : blend, s, load_pf(dp)));
 }
 
 // grid.y strides over the rows of the clipped rectangle, threads run along x.  VEC: source and destination rows are
 // 16-byte aligned at x0 and the width is a multiple of 4 (the whole-layer composite of render.rs:133): 4 px per thread.
-template <bool VEC>
+template <bool VEC, bool SO>
 __global__ void __launch_bounds__(256)
 k_draw_layer(uint32_t *__restrict__ dst, int dw, const uint32_t *__restrict__ src, int sw, int x0, int y0, int x1, int y1,
              int ox, int oy, float opacity, int blend)
@@ -1147,15 +1150,15 @@ k_draw_layer(uint32_t *__restrict__ dst, int dw, const uint32_t *__restrict__ sr
             for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (w >> 2); i += gridDim.x * blockDim.x) {
                 const uint4 s4 = __ldg(reinterpret_cast<const uint4 *>(srow) + i);
                 uint4 d4 = reinterpret_cast<uint4 *>(drow)[i];
-                d4.x = draw_layer_px(s4.x, d4.x, opacity, blend);
-                d4.y = draw_layer_px(s4.y, d4.y, opacity, blend);
-                d4.z = draw_layer_px(s4.z, d4.z, opacity, blend);
-                d4.w = draw_layer_px(s4.w, d4.w, opacity, blend);
+                d4.x = draw_layer_px<SO>(s4.x, d4.x, opacity, blend);
+                d4.y = draw_layer_px<SO>(s4.y, d4.y, opacity, blend);
+                d4.z = draw_layer_px<SO>(s4.z, d4.z, opacity, blend);
+                d4.w = draw_layer_px<SO>(s4.w, d4.w, opacity, blend);
                 reinterpret_cast<uint4 *>(drow)[i] = d4;
             }
         } else {
             for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w; i += gridDim.x * blockDim.x)
-                drow[i] = draw_layer_px(__ldg(srow + i), drow[i], opacity, blend);
+                drow[i] = draw_layer_px<SO>(__ldg(srow + i), drow[i], opacity, blend);
         }
     }
 }
@@ -1180,8 +1183,11 @@ extern "C" int rb_draw_layer(rb_layer *dst, const rb_layer *src, int32_t x, int3
     dim3 grid((unsigned)std::min(std::max((per_row + 255) / 256, 1), 64), (unsigned)std::min(ch, 16384));
 #define RB_DL_ARGS reinterpret_cast<uint32_t *>(dst->d), (int)dst->w, reinterpret_cast<const uint32_t *>(src->d), (int)src->w, \
     (int)x0, (int)y0, (int)x1, (int)y1, x, y, opacity, blend
-    if (vec) k_draw_layer<true><<<grid, 256, 0, ctx->stream>>>(RB_DL_ARGS);
-    else k_draw_layer<false><<<grid, 256, 0, ctx->stream>>>(RB_DL_ARGS);
+    const bool so = blend == RB_BLEND_SOURCE_OVER;
+    if (vec && so) k_draw_layer<true, true><<<grid, 256, 0, ctx->stream>>>(RB_DL_ARGS);
+    else if (vec) k_draw_layer<true, false><<<grid, 256, 0, ctx->stream>>>(RB_DL_ARGS);
+    else if (so) k_draw_layer<false, true><<<grid, 256, 0, ctx->stream>>>(RB_DL_ARGS);
+    else k_draw_layer<false, false><<<grid, 256, 0, ctx->stream>>>(RB_DL_ARGS);
 #undef RB_DL_ARGS
     RB_LAUNCHED(ctx, "draw_layer");
     return RB_OK;
@@ -1195,6 +1201,7 @@ struct LayerRect {
     int32_t x, y, w, h, sx, sy;
     float opacity;
 };
+template <bool SO>
 __global__ void __launch_bounds__(256)
 k_draw_layer_rects(uint32_t *__restrict__ dst, int dw, const uint32_t *__restrict__ src, int sw, const LayerRect *__restrict__ rects,
                    int blend)
@@ -1204,7 +1211,7 @@ k_draw_layer_rects(uint32_t *__restrict__ dst, int dw, const uint32_t *__restric
         uint32_t *drow = dst + (size_t)(r.y + y) * dw + r.x;
         const uint32_t *srow = src + (size_t)(r.sy + y) * sw + r.sx;
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < r.w; i += gridDim.x * blockDim.x)
-            drow[i] = draw_layer_px(__ldg(srow + i), drow[i], r.opacity, blend);
+            drow[i] = draw_layer_px<SO>(__ldg(srow + i), drow[i], r.opacity, blend);
     }
 }
 
@@ -1242,8 +1249,12 @@ extern "C" int rb_draw_layer_rects(rb_layer *dst, const rb_layer *src, int32_t n
     for (size_t first = 0; first < host.size(); first += 65535) {
         const unsigned cnt = (unsigned)std::min<size_t>(65535, host.size() - first);
         dim3 grid((unsigned)std::min((max_w + 255) / 256, 16), (unsigned)std::min(max_h, 64), cnt);
-        k_draw_layer_rects<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(dst->d), (int)dst->w,
-                                                          reinterpret_cast<const uint32_t *>(src->d), (int)src->w, dev + first, blend_mode);
+        if (blend_mode == RB_BLEND_SOURCE_OVER)
+            k_draw_layer_rects<true><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(dst->d), (int)dst->w,
+                                                                    reinterpret_cast<const uint32_t *>(src->d), (int)src->w, dev + first, blend_mode);
+        else
+            k_draw_layer_rects<false><<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(dst->d), (int)dst->w,
+                                                                     reinterpret_cast<const uint32_t *>(src->d), (int)src->w, dev + first, blend_mode);
         RB_LAUNCHED(ctx, "draw_layer_rects");
     }
     RB_CUDA(ctx, cudaFreeAsync(dev, ctx->stream));
