@@ -655,7 +655,7 @@ class Converter:
         if self.depth > 256:
             raise Unsupported("depth")
         try:
-            ts = IDENT if is_root else ts_pre(parse_transform(el.attrib.get("transform")), extra_ts)
+            ts = IDENT if is_root else ts_pre(self.resolve_transform(el, el.attrib.get("transform")), extra_ts)
             kids = []
             src = children_of if children_of is not None else el
             for ch in src:
@@ -764,7 +764,7 @@ class Converter:
                 d.parent[target] = old_parent
         if child is None:
             return None
-        ts = ts_pre(parse_transform(el.attrib.get("transform")), ts_translate(x, y))
+        ts = ts_pre(self.resolve_transform(el, el.attrib.get("transform")), ts_translate(x, y))
         g = {"t": "g", "ts": list(ts), "children": [child]}
         self.group_effects(el, g)
         return g
@@ -876,7 +876,7 @@ class Converter:
                         st["dash"] = vals
                         st["dash_offset"] = _f(parse_length(d.attr(el, "stroke-dashoffset"), 0.0, ref=diag, font=font))
         node["stroke"] = st
-        ts = parse_transform(el.attrib.get("transform"))
+        ts = self.resolve_transform(el, el.attrib.get("transform"))
         g = {"t": "g", "ts": list(ts), "children": [node]}
         self.group_effects(el, g)
         if not g["children"]:
@@ -986,7 +986,7 @@ class Converter:
             return {"kind": "solid", "color": out[0][1:5]}
         units = ga("gradientUnits") or "objectBoundingBox"
         spread = ga("spreadMethod") or "pad"
-        gts = parse_transform(ga("gradientTransform"))
+        gts = self.resolve_transform(el, ga("gradientTransform"))
         obb = units == "objectBoundingBox"
 
         def coord(name, default, ref):
@@ -1038,7 +1038,7 @@ class Converter:
             return None
         units = ga("patternUnits") or "objectBoundingBox"
         cunits = ga("patternContentUnits") or "userSpaceOnUse"
-        pts = parse_transform(ga("patternTransform"))
+        pts = self.resolve_transform(el, ga("patternTransform"))
         W, H = self.vb_w, self.vb_h
 
         def num(name):
@@ -1097,11 +1097,40 @@ class Converter:
         r, bt = max(b[0] + b[2] for b in boxes), max(b[1] + b[3] for b in boxes)
         return (l, tp, r - l, bt - tp)
 
+    def resolve_transform(self, el, value):
+        """usvg converter.rs:1100-1127 resolve_transform: the transform attribute combined with `transform-origin`
+        (lengths in user space, percentages of the viewBox): translate(o) * transform * translate(-o)."""
+        ts = parse_transform(value)
+        origin = el.attrib.get("transform-origin") if el is not None else None
+        if not origin:
+            return ts
+        toks = origin.replace(",", " ").split()
+        kw_x = {"left": "0%", "center": "50%", "right": "100%"}
+        kw_y = {"top": "0%", "center": "50%", "bottom": "100%"}
+        x, y = "50%", "50%"
+        if len(toks) == 1:
+            t = toks[0]
+            if t in ("top", "bottom"):
+                y = kw_y[t]
+            else:
+                x = kw_x.get(t, t)
+        elif len(toks) >= 2:
+            a, b = toks[0], toks[1]
+            if a in ("top", "bottom") or b in ("left", "right"):
+                a, b = b, a
+            x, y = kw_x.get(a, a), kw_y.get(b, b)
+        try:
+            dx = _f(parse_length(x, 0.0, ref=self.vb_w))
+            dy = _f(parse_length(y, 0.0, ref=self.vb_h))
+        except Unsupported:
+            return ts
+        return ts_pre(ts_pre(ts_translate(dx, dy), ts), ts_translate(-dx, -dy))
+
     # ---- clipPath / mask ----
     def clip_for(self, el, bbox):
         d = self.doc
         units = el.attrib.get("clipPathUnits", "userSpaceOnUse")
-        ts = parse_transform(el.attrib.get("transform"))
+        ts = self.resolve_transform(el, el.attrib.get("transform"))
         if units == "objectBoundingBox":
             if bbox is None or not (bbox[2] > 0 and bbox[3] > 0):
                 return None
@@ -1214,7 +1243,9 @@ class Renderer:
 
     def render(self, scene, width, height, ts):
         layer = self.be.new_layer(width, height)
-        self.render_nodes(scene["root"], tuple(ts), layer, "source_over")
+        root = scene["root"]
+        # the root group carries the viewBox / preserveAspectRatio transform (usvg Tree::root_transform)
+        self.render_nodes(root, ts_pre(tuple(ts), tuple(root.get("ts", IDENT))), layer, "source_over")
         return layer
 
     def render_nodes(self, group, ts, layer, blend):

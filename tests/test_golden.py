@@ -1,7 +1,7 @@
 """Golden pinning.  tests/golden/scenes/*.json are scene trees produced by tests/svgfront.parse from the reference's
 regression corpus (crates/resvg/tests/tests/**.svg), *.png the reference's own golden renders (made by resvg itself).
 The script that generated them is tests/golden/make_fixtures.py; tests/golden/CORPUS_RESULTS.md has the whole-corpus
-table (810 goldens reproduced).
+table (861 goldens reproduced).
 
 CPU: the oracle must reproduce every golden at the reference's own criterion (±1 per demultiplied channel, zero
 differing pixels — crates/resvg/tests/integration/main.rs:151-226).
