@@ -25,7 +25,8 @@
 __device__ float g_div255[256];
 __device__ __forceinline__ void rb_fill_div255(float *lut)
 {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = g_div255[i];
+    // all threads of the CTA share the copy, whatever its shape (32 x 8 CTAs used to copy the table once per row)
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 256; i += blockDim.x * blockDim.y) lut[i] = g_div255[i];
 }
 
 template <class Op>
@@ -1419,6 +1420,7 @@ k_convolve_tile(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, in
 #pragma unroll
             for (int ox = 0; ox < COLS; ox++) {
                 const float kk = k[oy * COLS + ox];
+                if (kk == 0.0f) continue; // x * (+-0) = +-0 for the finite x = c / 255, and s + (+-0) leaves s as it is
                 nr[j] = nr[j] + v[ox].x * kk;
                 ng[j] = ng[j] + v[ox].y * kk;
                 nb[j] = nb[j] + v[ox].z * kk;
