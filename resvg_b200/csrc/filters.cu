@@ -1864,73 +1864,17 @@ __device__ __forceinline__ float rb_powf(float a, float b) { return (float)pow((
 
 // KIND (0 distant, 1 point, 2 spot) and SPECULAR are compile-time: six compact kernels instead of one that carries every
 // variant's registers and branches.
+// Everything after the surface normal: light vector, light colour, lighting factor, output pixel (lighting.rs:141-153,
+// 185-219, 257-338).  (nx, ny) = the integer Sobel sums, (fx, fy) their factors, ca = the centre pixel's alpha.
 template <int KIND, bool SPECULAR>
-__global__ void __launch_bounds__(256)
-k_lighting(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h, LightParams P)
+__device__ __forceinline__ uint32_t light_shade(int nx, int ny, float fx, float fy, int ca, int x, int y, const LightParams &P)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h) return;
-    auto A = [&](int dx, int dy) -> int { return (int)RB_A(__ldg(src + (size_t)(y + dy) * w + (x + dx))); };
-    const int bx = (x == 0) ? 0 : (x == w - 1 ? 2 : 1);
-    const int by = (y == 0) ? 0 : (y == h - 1 ? 2 : 1);
-    const float F12 = 1.0f / 2.0f, F13 = 1.0f / 3.0f, F14 = 1.0f / 4.0f, F23 = 2.0f / 3.0f;
-    float fx, fy;
-    int nx, ny;
-    // lighting.rs:340-485
-    if (bx == 0 && by == 0) {
-        int c = A(0, 0), r = A(1, 0), b = A(0, 1), br = A(1, 1);
-        fx = F23; fy = F23;
-        nx = -2 * c + 2 * r - b + br;
-        ny = -2 * c - r + 2 * b + br;
-    } else if (bx == 2 && by == 0) {
-        int l = A(-1, 0), c = A(0, 0), bl = A(-1, 1), b = A(0, 1);
-        fx = F23; fy = F23;
-        nx = -2 * l + 2 * c - bl + b;
-        ny = -l - 2 * c + bl + 2 * b;
-    } else if (bx == 0 && by == 2) {
-        int t = A(0, -1), tr = A(1, -1), c = A(0, 0), r = A(1, 0);
-        fx = F23; fy = F23;
-        nx = -t + tr - 2 * c + 2 * r;
-        ny = -2 * t - tr + 2 * c + r;
-    } else if (bx == 2 && by == 2) {
-        int tl = A(-1, -1), t = A(0, -1), l = A(-1, 0), c = A(0, 0);
-        fx = F23; fy = F23;
-        nx = -tl + t - 2 * l + 2 * c;
-        ny = -tl - 2 * t + l + 2 * c;
-    } else if (by == 0) {
-        int l = A(-1, 0), c = A(0, 0), r = A(1, 0), bl = A(-1, 1), b = A(0, 1), br = A(1, 1);
-        fx = F13; fy = F12;
-        nx = -2 * l + 2 * r - bl + br;
-        ny = -l - 2 * c - r + bl + 2 * b + br;
-    } else if (by == 2) {
-        int tl = A(-1, -1), t = A(0, -1), tr = A(1, -1), l = A(-1, 0), c = A(0, 0), r = A(1, 0);
-        fx = F13; fy = F12;
-        nx = -tl + tr - 2 * l + 2 * r;
-        ny = -tl - 2 * t - tr + l + 2 * c + r;
-    } else if (bx == 0) {
-        int t = A(0, -1), tr = A(1, -1), c = A(0, 0), r = A(1, 0), b = A(0, 1), br = A(1, 1);
-        fx = F12; fy = F13;
-        nx = -t + tr - 2 * c + 2 * r - b + br;
-        ny = -2 * t - tr + 2 * b + br;
-    } else if (bx == 2) {
-        int tl = A(-1, -1), t = A(0, -1), l = A(-1, 0), c = A(0, 0), bl = A(-1, 1), b = A(0, 1);
-        fx = F12; fy = F13;
-        nx = -tl + t - 2 * l + 2 * c - bl + b;
-        ny = -tl - 2 * t + bl + 2 * b;
-    } else {
-        int tl = A(-1, -1), t = A(0, -1), tr = A(1, -1), l = A(-1, 0), r = A(1, 0);
-        int bl = A(-1, 1), b = A(0, 1), br = A(1, 1);
-        fx = F14; fy = F14;
-        nx = -tl + tr - 2 * l + 2 * r - bl + br;
-        ny = -tl - 2 * t - tr + bl + 2 * b + br;
-    }
     float nnx = (float)(-nx), nny = (float)(-ny);
 
     // light vector (lighting.rs:257-271)
     V3 lv = {P.lvx, P.lvy, P.lvz};
     if (KIND != 0) {
-        float nz = __fdiv_rn((float)A(0, 0), 255.0f) * P.surface_scale;
+        float nz = __fdiv_rn((float)ca, 255.0f) * P.surface_scale;
         V3 v = {P.x - (float)x, P.y - (float)y, P.z - nz};
         float len = v3len(v);
         if (!rb_approx_zero_ulps(len)) {
@@ -1993,7 +1937,105 @@ k_lighting(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, 
     uint32_t g = rb_f2u8(rb_f32_bound(0.0f, cg * factor, 255.0f) + 0.5f);
     uint32_t b = rb_f2u8(rb_f32_bound(0.0f, cb * factor, 255.0f) + 0.5f);
     uint32_t a = SPECULAR ? max(max(r, g), b) : 255u;
-    dst[(size_t)y * w + x] = rb_pack(r, g, b, a);
+    return rb_pack(r, g, b, a);
+}
+
+
+// KIND (0 distant, 1 point, 2 spot) and SPECULAR are compile-time: six compact kernels instead of one that carries every
+// variant's registers and branches.
+template <int KIND, bool SPECULAR>
+__device__ __noinline__ uint32_t light_px(const uint32_t *__restrict__ src, int w, int h, int x, int y, const LightParams &P)
+{
+    auto A = [&](int dx, int dy) -> int { return (int)RB_A(__ldg(src + (size_t)(y + dy) * w + (x + dx))); };
+    const int bx = (x == 0) ? 0 : (x == w - 1 ? 2 : 1);
+    const int by = (y == 0) ? 0 : (y == h - 1 ? 2 : 1);
+    const float F12 = 1.0f / 2.0f, F13 = 1.0f / 3.0f, F14 = 1.0f / 4.0f, F23 = 2.0f / 3.0f;
+    float fx, fy;
+    int nx, ny;
+    // lighting.rs:340-485
+    if (bx == 0 && by == 0) {
+        int c = A(0, 0), r = A(1, 0), b = A(0, 1), br = A(1, 1);
+        fx = F23; fy = F23;
+        nx = -2 * c + 2 * r - b + br;
+        ny = -2 * c - r + 2 * b + br;
+    } else if (bx == 2 && by == 0) {
+        int l = A(-1, 0), c = A(0, 0), bl = A(-1, 1), b = A(0, 1);
+        fx = F23; fy = F23;
+        nx = -2 * l + 2 * c - bl + b;
+        ny = -l - 2 * c + bl + 2 * b;
+    } else if (bx == 0 && by == 2) {
+        int t = A(0, -1), tr = A(1, -1), c = A(0, 0), r = A(1, 0);
+        fx = F23; fy = F23;
+        nx = -t + tr - 2 * c + 2 * r;
+        ny = -2 * t - tr + 2 * c + r;
+    } else if (bx == 2 && by == 2) {
+        int tl = A(-1, -1), t = A(0, -1), l = A(-1, 0), c = A(0, 0);
+        fx = F23; fy = F23;
+        nx = -tl + t - 2 * l + 2 * c;
+        ny = -tl - 2 * t + l + 2 * c;
+    } else if (by == 0) {
+        int l = A(-1, 0), c = A(0, 0), r = A(1, 0), bl = A(-1, 1), b = A(0, 1), br = A(1, 1);
+        fx = F13; fy = F12;
+        nx = -2 * l + 2 * r - bl + br;
+        ny = -l - 2 * c - r + bl + 2 * b + br;
+    } else if (by == 2) {
+        int tl = A(-1, -1), t = A(0, -1), tr = A(1, -1), l = A(-1, 0), c = A(0, 0), r = A(1, 0);
+        fx = F13; fy = F12;
+        nx = -tl + tr - 2 * l + 2 * r;
+        ny = -tl - 2 * t - tr + l + 2 * c + r;
+    } else if (bx == 0) {
+        int t = A(0, -1), tr = A(1, -1), c = A(0, 0), r = A(1, 0), b = A(0, 1), br = A(1, 1);
+        fx = F12; fy = F13;
+        nx = -t + tr - 2 * c + 2 * r - b + br;
+        ny = -2 * t - tr + 2 * b + br;
+    } else if (bx == 2) {
+        int tl = A(-1, -1), t = A(0, -1), l = A(-1, 0), c = A(0, 0), bl = A(-1, 1), b = A(0, 1);
+        fx = F12; fy = F13;
+        nx = -tl + t - 2 * l + 2 * c - bl + b;
+        ny = -tl - 2 * t + bl + 2 * b;
+    } else {
+        int tl = A(-1, -1), t = A(0, -1), tr = A(1, -1), l = A(-1, 0), r = A(1, 0);
+        int bl = A(-1, 1), b = A(0, 1), br = A(1, 1);
+        fx = F14; fy = F14;
+        nx = -tl + tr - 2 * l + 2 * r - bl + br;
+        ny = -tl - 2 * t - tr + bl + 2 * b + br;
+    }
+    return light_shade<KIND, SPECULAR>(nx, ny, fx, fy, A(0, 0), x, y, P);
+}
+
+// One thread = 4 horizontally adjacent pixels.  Interior groups (no pixel on the image border) read their 3 x 6 alpha
+// neighbourhood with one 16-byte and two 4-byte loads per row and evaluate the interior normal (lighting.rs:457-476);
+// groups touching the border take the per-pixel routine with its nine variants.
+template <int KIND, bool SPECULAR>
+__global__ void __launch_bounds__(256)
+k_lighting(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h, LightParams P)
+{
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h) return;
+    if ((w & 3) == 0 && x >= 4 && x + 4 < w && y >= 1 && y + 1 < h) {
+        int al[3][6];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const uint32_t *row = src + (size_t)(y - 1 + r) * w + x;
+            const uint4 m = __ldg(reinterpret_cast<const uint4 *>(row));
+            al[r][0] = (int)RB_A(__ldg(row - 1));
+            al[r][1] = (int)RB_A(m.x); al[r][2] = (int)RB_A(m.y); al[r][3] = (int)RB_A(m.z); al[r][4] = (int)RB_A(m.w);
+            al[r][5] = (int)RB_A(__ldg(row + 4));
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int tl = al[0][k], t = al[0][k + 1], tr = al[0][k + 2], l = al[1][k], r = al[1][k + 2];
+            const int bl = al[2][k], b = al[2][k + 1], br = al[2][k + 2];
+            const int nx = -tl + tr - 2 * l + 2 * r - bl + br;
+            const int ny = -tl - 2 * t - tr + bl + 2 * b + br;
+            o[k] = light_shade<KIND, SPECULAR>(nx, ny, 1.0f / 4.0f, 1.0f / 4.0f, al[1][k + 1], x + k, y, P);
+        }
+        *reinterpret_cast<uint4 *>(dst + (size_t)y * w + x) = make_uint4(o[0], o[1], o[2], o[3]);
+        return;
+    }
+    for (int k = 0; k < 4 && x + k < w; k++) dst[(size_t)y * w + x + k] = light_px<KIND, SPECULAR>(src, w, h, x + k, y, P);
 }
 
 static bool h_approx_eq_ulps(float a, float b, int32_t ulps)
@@ -2054,7 +2096,7 @@ static int launch_lighting(rb_layer *dest, const rb_layer *src, int specular, fl
     }
     rb_ctx *ctx = dest->ctx;
     int w = (int)dest->w, h = (int)dest->h;
-    dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+    dim3 block(32, 8), grid(((w + 3) / 4 + 31) / 32, (h + 7) / 8);
 #define RB_LT(K, S) k_lighting<K, S><<<grid, block, 0, ctx->stream>>>(reinterpret_cast<const uint32_t *>(src->d), \
                                                                      reinterpret_cast<uint32_t *>(dest->d), w, h, P)
     switch (light->kind * 2 + (specular ? 1 : 0)) {
