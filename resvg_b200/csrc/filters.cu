@@ -1139,18 +1139,46 @@ __global__ void k_morph_pass(const uint32_t *__restrict__ src, uint32_t *__restr
 // instead of 16, and every window tap is a shared-memory read.  Pixels are staged as two u16x2 words (r,b | g,a) because
 // sm_100 has a native 16x2 min/max (VIMNMX.U16x2) while the 8x4 form is emulated with seven logic instructions.
 constexpr int MORPH_TW = 64, MORPH_TH = 32, MORPH_MAXC = 16, MORPH_BIG = 256;
-__device__ __forceinline__ uint2 morph_mm(uint2 a, uint2 b, bool dilate)
+template <bool DILATE>
+__device__ __forceinline__ uint2 morph_mm(uint2 a, uint2 b)
 {
-    return dilate ? make_uint2(__vmaxu2(a.x, b.x), __vmaxu2(a.y, b.y)) : make_uint2(__vminu2(a.x, b.x), __vminu2(a.y, b.y));
+    return DILATE ? make_uint2(__vmaxu2(a.x, b.x), __vmaxu2(a.y, b.y)) : make_uint2(__vminu2(a.x, b.x), __vminu2(a.y, b.y));
 }
+// out[k] = min / max over ld(k) .. ld(k + c - 1) for k = 0..3: four adjacent window positions share their middle
+// ld(3) .. ld(c - 1), so they cost c + 3 loads and c + 6 min/max instead of 4c each.
+template <bool DILATE, class Load>
+__device__ __forceinline__ void morph_win4(int c, Load ld, uint2 out[4])
+{
+    if (c >= 4) {
+        uint2 m = ld(3);
+        for (int t = 4; t < c; t++) m = morph_mm<DILATE>(m, ld(t));
+        const uint2 a0 = ld(0), a1 = ld(1), a2 = ld(2), r0 = ld(c), r1 = ld(c + 1), r2 = ld(c + 2);
+        const uint2 a12 = morph_mm<DILATE>(a1, a2), r01 = morph_mm<DILATE>(r0, r1);
+        out[0] = morph_mm<DILATE>(m, morph_mm<DILATE>(a0, a12));
+        out[1] = morph_mm<DILATE>(morph_mm<DILATE>(m, a12), r0);
+        out[2] = morph_mm<DILATE>(morph_mm<DILATE>(m, a2), r01);
+        out[3] = morph_mm<DILATE>(m, morph_mm<DILATE>(r01, r2));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint2 acc = ld(k);
+            for (int t = 1; t < c; t++) acc = morph_mm<DILATE>(acc, ld(k + t));
+            out[k] = acc;
+        }
+    }
+}
+
+template <bool DILATE>
 __global__ void __launch_bounds__(256)
-k_morph_tile(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h, int lox, int cx, int loy, int cy,
-             bool dilate)
+k_morph_tile(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w, int h, int lox, int cx, int loy, int cy)
 {
     extern __shared__ uint2 morph_sm[];
     const int SW = MORPH_TW + cx - 1, SH = MORPH_TH + cy - 1;
-    uint2 *A = morph_sm, *B = morph_sm + SH * SW;
-    const uint32_t iw = dilate ? 0u : 0x00ff00ffu;
+    // A: staged footprint, every row stored 4-way interleaved — pixel x at (x & 3) * G + (x >> 2) — so that the threads of
+    // the horizontal pass, which own 4 adjacent pixels each, read consecutive words; B: its output, row-major
+    const int G = (SW + 3) >> 2, AROW = 4 * G;
+    uint2 *A = morph_sm, *B = morph_sm + SH * AROW;
+    const uint32_t iw = DILATE ? 0u : 0x00ff00ffu;
     const uint2 ident = make_uint2(iw, iw);
     const int X0 = blockIdx.x * MORPH_TW, Y0 = blockIdx.y * MORPH_TH;
     {   // staging: 2 rows of 128 threads (SW <= 79)
@@ -1163,23 +1191,29 @@ k_morph_tile(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int w
                     const uint32_t p = __ldg(src + (size_t)gy * w + gx);
                     v = make_uint2(p & 0x00ff00ffu, (p >> 8) & 0x00ff00ffu);
                 }
-                A[sy * SW + sx] = v;
+                A[sy * AROW + (sx & 3) * G + (sx >> 2)] = v;
             }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < SH * MORPH_TW; i += 256) {
-        const uint2 *a = A + (i >> 6) * SW + (i & 63);
-        uint2 acc = ident;
-        for (int t = 0; t < cx; t++) acc = morph_mm(acc, a[t], dilate);
-        B[i] = acc;
+    for (int i = threadIdx.x; i < SH * (MORPH_TW / 4); i += 256) { // horizontal: thread = 4 adjacent pixels of one row
+        const int row = i >> 4, g = i & 15;
+        const uint2 *a = A + row * AROW + g;
+        uint2 o[4];
+        morph_win4<DILATE>(cx, [&](int t) { return a[(t & 3) * G + (t >> 2)]; }, o);
+        uint4 *bo = reinterpret_cast<uint4 *>(B + row * MORPH_TW + 4 * g);
+        bo[0] = make_uint4(o[0].x, o[0].y, o[1].x, o[1].y);
+        bo[1] = make_uint4(o[2].x, o[2].y, o[3].x, o[3].y);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < MORPH_TH * MORPH_TW; i += 256) {
-        const int y = i >> 6, x = i & 63;
-        const uint2 *b = B + i;
-        uint2 acc = ident;
-        for (int t = 0; t < cy; t++) acc = morph_mm(acc, b[t * MORPH_TW], dilate);
-        if (X0 + x < w && Y0 + y < h) dst[(size_t)(Y0 + y) * w + X0 + x] = acc.x | (acc.y << 8);
+    for (int i = threadIdx.x; i < (MORPH_TH / 4) * MORPH_TW; i += 256) { // vertical: thread = 4 vertically adjacent pixels
+        const int yg = i >> 6, x = i & 63;
+        const uint2 *b = B + (4 * yg) * MORPH_TW + x;
+        uint2 o[4];
+        morph_win4<DILATE>(cy, [&](int t) { return b[t * MORPH_TW]; }, o);
+        if (X0 + x < w)
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (Y0 + 4 * yg + k < h) dst[(size_t)(Y0 + 4 * yg + k) * w + X0 + x] = o[k].x | (o[k].y << 8);
     }
 }
 
@@ -1210,7 +1244,8 @@ extern "C" int rb_filter_morphology(rb_layer *l, int op, float rx, float ry)
         // there is always an in-image intermediate position), so the chain is exact: L = sum(L_i) - (n - 1), lo = sum(lo_i).
         static bool attr_set = false;
         if (!attr_set) {
-            RB_CUDA(ctx, cudaFuncSetAttribute(k_morph_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            RB_CUDA(ctx, cudaFuncSetAttribute(k_morph_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            RB_CUDA(ctx, cudaFuncSetAttribute(k_morph_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             attr_set = true;
         }
         int left_x = (int)columns, left_y = (int)rows, lo_x = target_x, lo_y = target_y; // window still to apply, offset still to apply
@@ -1221,9 +1256,10 @@ extern "C" int rb_filter_morphology(rb_layer *l, int op, float rx, float ry)
             uint32_t *out = nullptr;
             RB_CUDA(ctx, cudaMallocAsync((void **)&out, bytes, ctx->stream));
             const int SW = MORPH_TW + cxp - 1, SH = MORPH_TH + cyp - 1;
-            const size_t smem = (size_t)(SH * SW + SH * MORPH_TW) * 8;
+            const size_t smem = (size_t)(SH * 4 * ((SW + 3) / 4) + SH * MORPH_TW) * 8;
             dim3 grid((w + MORPH_TW - 1) / MORPH_TW, (h + MORPH_TH - 1) / MORPH_TH);
-            k_morph_tile<<<grid, 256, smem, ctx->stream>>>(reinterpret_cast<const uint32_t *>(l->d), out, w, h, lxp, cxp, lyp, cyp, op == 1);
+            if (op == 1) k_morph_tile<true><<<grid, 256, smem, ctx->stream>>>(reinterpret_cast<const uint32_t *>(l->d), out, w, h, lxp, cxp, lyp, cyp);
+            else k_morph_tile<false><<<grid, 256, smem, ctx->stream>>>(reinterpret_cast<const uint32_t *>(l->d), out, w, h, lxp, cxp, lyp, cyp);
             RB_LAUNCHED(ctx, "morph_tile");
             RB_CUDA(ctx, cudaFreeAsync(l->d, ctx->stream));
             l->d = reinterpret_cast<uint8_t *>(out);
