@@ -1,13 +1,19 @@
 #!/usr/bin/env python
 """bench.py — Mpixels/s rendered on the BASELINE.json workloads (resvg pixel hot path on B200).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload paths8k]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload paths8k|icons|filters8k|stack4k]
+                    [--shard documents|strips]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload `paths8k` (BASELINE.json configs[1]): one 8192x8192 canvas, 100k random cubic/quad/line
-paths, non-zero + even-odd, solid + linear + radial paints.  A *step* is one full render of the scene (clear + every
-path).  With N GPUs every rank renders its own scene (document-parallel, weak scaling, no collective on the data
-path); `value` = N * canvas Mpx / max-over-ranks device time.
+Default workload `paths8k` (BASELINE.json configs[1]): one 8192x8192 canvas, 100k random
+cubic/quad/line paths, non-zero + even-odd, fills + strokes (dashes, hairlines), solid + linear + radial paints.  A *step*
+is one full render of the scene (clear + every path).  With N GPUs every rank renders its own scene (document-parallel,
+weak scaling, no collective on the data path); `value` = N * canvas Mpx / max-over-ranks device time.  `--shard strips`
+cuts ONE scene into N canvas strips instead (strong scaling; the strips are bit-identical to the whole-canvas render).
+
+The other configurations print the same JSON line: `icons` (configs[4]: 100 000 documents of 256x256 rendered into
+atlases, sharded by atlas chunk), `filters8k` (configs[2]: the 10-primitive filter chain over an 8192x8192 layer) and
+`stack4k` (configs[3]: 64 nested groups with masks / clip-paths / patterns, traversal by the Python front end).
 
 Printed JSON keys follow the driver's contract; see DESIGN.md §Measurement for how each number is obtained.
 """
