@@ -22,7 +22,10 @@ constexpr int WT_W = 32;           // warp-tile width  (pixels)
 constexpr int WT_H = 8;            // warp-tile height (pixels)
 constexpr int WT_POS = WT_W * 4;   // sub-sample positions per row
 constexpr int WT_SUB = WT_H * 4;   // sub-scanlines per tile
-constexpr int WT_WARPS = 4;        // warps per CTA (independent of each other)
+// Warps per CTA.  The warps of a CTA never cooperate, so a CTA is one warp: with 4 warps per CTA a slot stayed occupied
+// until the slowest of the four tiles was finished (measured on the C2 scene: 21.9 ms with 4 warps x 6 CTAs, 18.5 ms with
+// 1 warp x up to 25 CTAs per SM at the same 80 registers).
+constexpr int WT_WARPS = 1;
 
 struct WarpTileSmem {
     int wsum[WT_H * WT_POS];        // packed net crossings: [pixel row][position], byte s = sub-row s
@@ -475,8 +478,10 @@ struct WarpDraw { // what one lane holds about one upcoming (draw, tile) pair
     uint32_t list_begin, n_list, paint;
 };
 
+// minimum resident CTAs per SM the compiler plans for (caps the registers at 80; 24 / 28 cost more spills, 18 / 16 lose
+// occupancy — all measured)
 #ifndef RW_MIN_CTAS
-#define RW_MIN_CTAS 6
+#define RW_MIN_CTAS 21
 #endif
 // HAIR: the batch holds hairline strokes (a second instantiation, so that batches without them run the leaner code).
 template <bool MASK, bool HAIR>
