@@ -70,7 +70,7 @@ def main():
         md.write("# resvg regression corpus through tests/svgfront.py + the CPU oracle\n\n")
         md.write("Criterion = the reference's own (tests/integration/main.rs:151-226): demultiplied RGBA, every channel within 1, "
                  "zero differing pixels.\n`not expressible` = the test-side front end does not cover the feature (text, raster "
-                 "images, markers, CSS, switch, nested svg, dashes, hairline strokes ...) — those need the Rust host.\n"
+                 "images, markers, CSS, switch, nested svg ...) — those need the Rust host.\n"
                  "`fail` = expressible but differing; the list below shows they are front-end (usvg) gaps such as "
                  "transform-origin or xlink precedence, not rasteriser/filter arithmetic.\n\n")
         md.write(f"**Total: {tot[0]} pass, {tot[1]} fail, {tot[2]} not expressible** (of {sum(tot)} golden pairs)\n\n")
