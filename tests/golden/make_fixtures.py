@@ -72,7 +72,7 @@ def main():
                  "zero differing pixels.\n`not expressible` = the test-side front end does not cover the feature (text, raster "
                  "images, markers, CSS, switch, nested svg ...) — those need the Rust host.\n"
                  "`fail` = expressible but differing; the list below shows they are front-end (usvg) gaps such as "
-                 "transform-origin or xlink precedence, not rasteriser/filter arithmetic.\n\n")
+                 "skewed filter regions or xlink precedence, not rasteriser/filter arithmetic.\n\n")
         md.write(f"**Total: {tot[0]} pass, {tot[1]} fail, {tot[2]} not expressible** (of {sum(tot)} golden pairs)\n\n")
         md.write("| directory | pass | fail | not expressible |\n|---|---|---|---|\n")
         for fam in sorted(stats):
