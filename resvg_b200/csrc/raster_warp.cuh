@@ -495,13 +495,14 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WarpTileSmem &S = s_all[wid];
     const uint32_t tile = blockIdx.x * WT_WARPS + wid;
+    if (tile >= n_wtiles) return;
+    const uint32_t d_begin = tile_off[tile], d_end = tile_off[tile + 1];
+    if (d_begin == d_end) return; // nothing touches this tile (most tiles of a sparse atlas)
     {
         uint4 *z = reinterpret_cast<uint4 *>(&S);
         for (int i = lane; i < (int)(sizeof(WarpTileSmem) / 16); i += 32) z[i] = make_uint4(0, 0, 0, 0);
     }
-    if (tile >= n_wtiles) return;
-    const uint32_t d_begin = tile_off[tile], d_end = tile_off[tile + 1];
-    if (d_begin == d_end) return;
+    __syncwarp();
     const int X0 = (int)(tile % (uint32_t)wtiles_x) * WT_W, Y0 = (int)(tile / (uint32_t)wtiles_x) * WT_H;
     const int prow = lane >> 2, pj = lane & 3; // this lane's pixels: row prow, columns 8 pj .. 8 pj + 7
 
