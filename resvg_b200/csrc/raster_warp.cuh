@@ -873,7 +873,7 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
                 const bool simple_hp = !MASK && P.kind == 1 && !P.lowp && (P.blend == 1 || P.blend == 3);
                 uint32_t sr = P.solid16[0], sg = P.solid16[1], sb = P.solid16[2], sa = P.solid16[3];
                 const bool src_over = P.blend == 3;
-#pragma unroll 1
+#pragma unroll 2
                 for (int q = 0; q < 8; q++) {
                     const uint32_t c = min(16u * (c0 & 0xffu) - (dec & 1u), 255u);
                     c0 = __funnelshift_r(c0, c1, 8);
