@@ -182,7 +182,8 @@ struct Worker {
     std::vector<uint32_t> hrank;
     std::vector<uint8_t> sverbs;
     bool wide = false, skipped_hair = false, has_hair = false;
-    void reset() { edges.clear(); draws.clear(); paints.clear(); stops.clear(); curves.clear(); wide = false; skipped_hair = false; has_hair = false; }
+    bool too_large = false; // a draw the device structures cannot index (reported as RB_ERR_UNSUPPORTED, never dropped)
+    void reset() { edges.clear(); draws.clear(); paints.clear(); stops.clear(); curves.clear(); wide = false; skipped_hair = false; has_hair = false; too_large = false; }
 };
 
 std::mutex g_pool_mu;
@@ -588,7 +589,9 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
                             out->hblits.resize(keep);
                         }
                         const size_t nb = out->hblits.size();
-                        if (nb == 0 || nb >= (1u << 28)) continue;
+                        if (nb == 0) continue;
+                        // blits carry the layer pixel as 16 + 16 bits and their rank in 28
+                        if (nb >= (1u << 28) || W > 65536 || H > 65536) { out->too_large = true; continue; }
                         int x0 = INT32_MAX, y0 = INT32_MAX, x1 = INT32_MIN, y1 = INT32_MIN;
                         for (const rbh::HairBlit &hb : out->hblits) {
                             x0 = std::min(x0, hb.x); x1 = std::max(x1, hb.x);
@@ -785,7 +788,7 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
                             slot += 1u << sh;
                         }
                     }
-                    if (slot >= (1u << 28)) continue; // meta keeps slot indices in 28 bits
+                    if (slot >= (1u << 28)) { out->too_large = true; continue; } // meta keeps slot indices in 28 bits
                     if (chains_may_exceed_packed_winding(out->ends)) out->wide = true;
                     d.edge_cnt = slot;                     // slots of this draw in the device edge array
                     d.edge_off = (uint32_t)ci->n_slots;    // chunk-relative slot base
@@ -865,6 +868,7 @@ int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threa
     }
     // hairline strokes are only drawn inline by the tile kernel fed with items; with the fallback builder the caller has
     // to cut the batch into fill runs and hairline runs (rb_batch_submit does)
+    for (auto &w : workers) if (w->too_large) return RB_ERR_UNSUPPORTED;
     for (auto &w : workers) if (w->skipped_hair) return RB_NEEDS_RUN_SPLIT;
     b->phases[0] = us_since(t0);
 #ifdef RB_HOST_PROFILE
@@ -1072,12 +1076,14 @@ extern "C" int rb_batch_fill_path(rb_batch *b, const uint8_t *verbs, int32_t n_v
 {
     if (paint && (paint->shader < 0 || paint->shader > 3 || paint->blend_mode < 0 || paint->blend_mode > 28)) return RB_ERR_INVALID;
     if (paint && (paint->shader == 1 || paint->shader == 2) && paint->n_stops > rbh::kMaxStops) return RB_ERR_UNSUPPORTED;
+    // a pattern that IS the target would have to be flushed (and so destroy this very batch) to be read
+    if (paint && b && paint->shader == 3 && (!paint->pattern || paint->pattern == b->layer)) return RB_ERR_INVALID;
     return rb_batch_record(b, verbs, n_verbs, points, n_points, paint, fill_rule, ts);
 }
 
 // PixmapMut::stroke_path(path, paint, stroke, transform, None) — path.rs:113.  Thin anti-aliased strokes that
-// tiny-skia draws as hairlines (both transformed stroke-width vectors no longer than 1 px) are not implemented yet
-// and are reported as RB_ERR_UNSUPPORTED instead of being drawn differently.
+// tiny-skia draws as hairlines (both transformed stroke-width vectors no longer than 1 px) are walked by hairline.cpp
+// and applied by the tile kernel as ordered blits (targets up to 65536 px per side).
 extern "C" int rb_batch_stroke_path(rb_batch *b, const uint8_t *verbs, int32_t n_verbs, const float *points,
                                     int32_t n_points, const rb_paint *paint, const rb_stroke *stroke, const float ts[6])
 {

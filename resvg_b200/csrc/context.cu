@@ -24,6 +24,13 @@ int rb_cuda_fail(rb_ctx *ctx, cudaError_t e, const char *what)
     return e == cudaErrorMemoryAllocation ? RB_ERR_OOM : RB_ERR_CUDA;
 }
 
+int rb_check_flags(rb_ctx *ctx)
+{
+    if (!ctx || !ctx->h_flags || !ctx->h_flags[0]) return RB_OK;
+    ctx->h_flags[0] = 0;
+    return rb_fail(ctx, RB_ERR_CUDA, "tile-row edge list overflow: edges were dropped by an earlier batch");
+}
+
 int rb_scratch(rb_ctx *ctx, size_t bytes, void **out)
 {
     if (bytes > ctx->scratch_bytes) {
@@ -68,6 +75,7 @@ void rb_ctx_release(rb_ctx *ctx)
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->px_tables) cudaFree(ctx->px_tables);
     if (ctx->staging) cudaFreeHost(ctx->staging);
+    if (ctx->h_flags) cudaFreeHost((void *)ctx->h_flags);
     if (ctx->staging_ev) cudaEventDestroy(ctx->staging_ev);
     for (auto &e : ctx->ev_run) if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -97,6 +105,13 @@ extern "C" int rb_ctx_create(int device, rb_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RB_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RB_ERR_CUDA; }
+    {
+        void *hf = nullptr;
+        if (cudaHostAlloc(&hf, 64, cudaHostAllocMapped) != cudaSuccess) { delete ctx; return RB_ERR_CUDA; }
+        memset(hf, 0, 64);
+        ctx->h_flags = (volatile unsigned int *)hf;
+        if (cudaHostGetDevicePointer((void **)&ctx->d_flags, hf, 0) != cudaSuccess) { delete ctx; return RB_ERR_CUDA; }
+    }
     cudaEventCreate(&ctx->ev0);
     cudaEventCreate(&ctx->ev1);
     cudaEventCreateWithFlags(&ctx->staging_ev, cudaEventDisableTiming);
@@ -125,13 +140,14 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 
 extern "C" int rb_ctx_synchronize(rb_ctx *ctx)
 {
+    rb_enter(ctx);
     if (!ctx) return RB_ERR_INVALID;
     while (!ctx->dirty.empty()) { // pending immediate draws are work the caller has issued
         int st = rb_layer_flush(ctx->dirty.back());
         if (st != RB_OK) return st;
     }
     RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return RB_OK;
+    return rb_check_flags(ctx);
 }
 
 extern "C" const char *rb_last_error(rb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -142,6 +158,7 @@ extern "C" uint64_t rb_ctx_h2d_bytes(rb_ctx *ctx) { return ctx ? ctx->h2d_bytes 
 
 extern "C" int rb_timer_begin(rb_ctx *ctx)
 {
+    rb_enter(ctx);
     if (!ctx) return RB_ERR_INVALID;
     RB_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     return RB_OK;
@@ -149,6 +166,7 @@ extern "C" int rb_timer_begin(rb_ctx *ctx)
 
 extern "C" int rb_timer_end(rb_ctx *ctx, float *ms)
 {
+    rb_enter(ctx);
     if (!ctx || !ms) return RB_ERR_INVALID;
     while (!ctx->dirty.empty()) { // the timed region covers the immediate draws issued inside it
         int st = rb_layer_flush(ctx->dirty.back());
@@ -157,7 +175,7 @@ extern "C" int rb_timer_end(rb_ctx *ctx, float *ms)
     RB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     RB_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
     RB_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
-    return RB_OK;
+    return rb_check_flags(ctx);
 }
 
 extern "C" int rb_host_alloc(size_t bytes, void **out)
@@ -174,6 +192,7 @@ extern "C" void rb_host_free(void *p)
 
 extern "C" int rb_layer_create(rb_ctx *ctx, uint32_t w, uint32_t h, rb_layer **out)
 {
+    rb_enter(ctx);
     if (!ctx || !out) return RB_ERR_INVALID;
     *out = nullptr;
     // tiny-skia Pixmap::new: zero size or a row wider than i32::MAX/4 fails.
@@ -218,6 +237,7 @@ extern "C" void *rb_layer_device_ptr(rb_layer *l)
 
 extern "C" int rb_layer_upload(rb_layer *l, const uint8_t *host)
 {
+    rb_enter(l ? l->ctx : nullptr);
     RB_SYNC_LAYER(l);
     if (!l || !host) return RB_ERR_INVALID;
     RB_CUDA(l->ctx, cudaMemcpyAsync(l->d, host, (size_t)l->w * l->h * 4, cudaMemcpyHostToDevice, l->ctx->stream));
@@ -227,11 +247,12 @@ extern "C" int rb_layer_upload(rb_layer *l, const uint8_t *host)
 
 extern "C" int rb_layer_download(rb_layer *l, uint8_t *host)
 {
+    rb_enter(l ? l->ctx : nullptr);
     RB_SYNC_LAYER(l);
     if (!l || !host) return RB_ERR_INVALID;
     RB_CUDA(l->ctx, cudaMemcpyAsync(host, l->d, (size_t)l->w * l->h * 4, cudaMemcpyDeviceToHost, l->ctx->stream));
     RB_CUDA(l->ctx, cudaStreamSynchronize(l->ctx->stream));
-    return RB_OK;
+    return rb_check_flags(l->ctx);
 }
 
 // Asynchronous download: the copy is ordered after everything enqueued on the layer so far and runs on the context's
@@ -239,6 +260,7 @@ extern "C" int rb_layer_download(rb_layer *l, uint8_t *host)
 // The layer must not be written again, and `host` not read, before rb_layer_download_end has returned.
 extern "C" int rb_layer_download_begin(rb_layer *l, uint8_t *host)
 {
+    rb_enter(l ? l->ctx : nullptr);
     RB_SYNC_LAYER(l);
     if (!l || !host) return RB_ERR_INVALID;
     rb_ctx *ctx = l->ctx;
@@ -257,6 +279,7 @@ extern "C" int rb_layer_download_begin(rb_layer *l, uint8_t *host)
 
 extern "C" int rb_layer_download_end(rb_layer *l)
 {
+    rb_enter(l ? l->ctx : nullptr);
     RB_SYNC_LAYER(l);
     if (!l) return RB_ERR_INVALID;
     if (l->dl_pending) {
@@ -279,6 +302,7 @@ __global__ void __launch_bounds__(256) k_fill_u32(uint32_t *__restrict__ px, siz
 
 extern "C" int rb_layer_fill(rb_layer *l, uint8_t r, uint8_t g, uint8_t b, uint8_t a)
 {
+    rb_enter(l ? l->ctx : nullptr);
     RB_SYNC_LAYER(l);
     if (!l) return RB_ERR_INVALID;
     rb_ctx *ctx = l->ctx;
@@ -291,6 +315,7 @@ extern "C" int rb_layer_fill(rb_layer *l, uint8_t r, uint8_t g, uint8_t b, uint8
 
 extern "C" int rb_layer_copy(rb_layer *dst, const rb_layer *src)
 {
+    rb_enter(dst ? dst->ctx : nullptr);
     RB_SYNC_LAYER(dst);
     RB_SYNC_LAYER(src);
     if (!dst || !src || dst->w != src->w || dst->h != src->h) return RB_ERR_INVALID;

@@ -247,11 +247,13 @@ static int launch_px_table(rb_layer *l, int which, const char *name)
 
 extern "C" int rb_layer_multiply_alpha(rb_layer *l)
 {
+    rb_enter(l ? l->ctx : nullptr);
     RB_SYNC_LAYER(l);
     return launch_pointwise(l, OpMultiplyAlpha(), "multiply_alpha");
 }
 extern "C" int rb_layer_demultiply_alpha(rb_layer *l)
 {
+    rb_enter(l ? l->ctx : nullptr);
     RB_SYNC_LAYER(l);
     int st = launch_px_table(l, 0, "demultiply_alpha");
     return st >= 0 ? st : launch_pointwise(l, OpDemultiplyAlpha(), "demultiply_alpha");
@@ -274,11 +276,13 @@ static int launch_cs(rb_layer *l)
 }
 extern "C" int rb_layer_into_linear_rgb(rb_layer *l)
 {
+    rb_enter(l ? l->ctx : nullptr);
     RB_SYNC_LAYER(l);
     return launch_cs<true>(l);
 }
 extern "C" int rb_layer_into_srgb(rb_layer *l)
 {
+    rb_enter(l ? l->ctx : nullptr);
     RB_SYNC_LAYER(l);
     return launch_cs<false>(l);
 }
@@ -708,12 +712,11 @@ k_box_blur_h2(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int 
 static int box2_run_cells(rb_ctx *ctx, uint32_t *a, uint32_t *b, int pitch, const BoxCell *cells, int n_cells, const BoxCell *dev_cells,
                           uint32_t **result)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(ctx->attr_bits & RB_ATTR_BOX)) {
         RB_CUDA(ctx, cudaFuncSetAttribute(k_box_blur_h2, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         RB_CUDA(ctx, cudaFuncSetAttribute(k_box_blur_v3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * BOX2_MAX_R + 1) * BOX2V_THREADS * 4));
         RB_CUDA(ctx, cudaFuncSetAttribute(k_box_blur_v3<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * BOX2_MAX_R + 1) * BOX2V_THREADS * 4));
-        attr_set = true;
+        ctx->attr_bits |= RB_ATTR_BOX;
     }
     int max_w = 0, max_h = 0;
     bool vec2 = (pitch % 2) == 0;
@@ -795,6 +798,7 @@ static void create_box_gauss(float sigma, int sizes[5])
 
 extern "C" int rb_filter_box_blur(rb_layer *l, double sigma_x, double sigma_y)
 {
+    rb_enter(l ? l->ctx : nullptr);
     RB_SYNC_LAYER(l);
     if (!l) return RB_ERR_INVALID;
     rb_ctx *ctx = l->ctx;
@@ -805,7 +809,7 @@ extern "C" int rb_filter_box_blur(rb_layer *l, double sigma_x, double sigma_y)
     create_box_gauss((float)sigma_y, bv);
 
     void *scratch = nullptr;
-    int st = rb_scratch(ctx, bytes + 256, &scratch);
+    int st = rb_scratch(ctx, ((bytes + 255) & ~(size_t)255) + sizeof(BoxCell), &scratch); // ping-pong plane + the cell record placed after it
     if (st != RB_OK) return st;
     uint32_t *cur = reinterpret_cast<uint32_t *>(l->d);
     uint32_t *other = reinterpret_cast<uint32_t *>(scratch);
@@ -874,6 +878,7 @@ extern "C" int rb_filter_box_blur_reach(double sigma)
 // per pass for all rectangles.  Rectangles must not overlap.
 extern "C" int rb_filter_box_blur_cells(rb_layer *l, int32_t n, const int32_t *rects, const double *sigma_x, const double *sigma_y)
 {
+    rb_enter(l ? l->ctx : nullptr);
     RB_SYNC_LAYER(l);
     if (!l || n < 0 || (n > 0 && (!rects || !sigma_x || !sigma_y))) return RB_ERR_INVALID;
     if (n == 0) return RB_OK;
@@ -1055,6 +1060,7 @@ static double powi_f64(double a, int b)
 
 extern "C" int rb_filter_iir_blur(rb_layer *l, double sigma_x, double sigma_y)
 {
+    rb_enter(l ? l->ctx : nullptr);
     RB_SYNC_LAYER(l);
     if (!l) return RB_ERR_INVALID;
     rb_ctx *ctx = l->ctx;
@@ -1226,6 +1232,7 @@ static inline uint32_t f2u32_sat(float v)
 
 extern "C" int rb_filter_morphology(rb_layer *l, int op, float rx, float ry)
 {
+    rb_enter(l ? l->ctx : nullptr);
     RB_SYNC_LAYER(l);
     if (!l || (op != 0 && op != 1)) return RB_ERR_INVALID;
     rb_ctx *ctx = l->ctx;
@@ -1242,11 +1249,10 @@ extern "C" int rb_filter_morphology(rb_layer *l, int op, float rx, float ry)
         // chain of windows of at most MORPH_MAXC: min / max over [a, b] of the min / max over [c, d] is the min / max over
         // [a + c, b + d], also with the windows clipped to the image (between an in-image sample and the in-image centre
         // there is always an in-image intermediate position), so the chain is exact: L = sum(L_i) - (n - 1), lo = sum(lo_i).
-        static bool attr_set = false;
-        if (!attr_set) {
+            if (!(ctx->attr_bits & RB_ATTR_MORPH)) {
             RB_CUDA(ctx, cudaFuncSetAttribute(k_morph_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             RB_CUDA(ctx, cudaFuncSetAttribute(k_morph_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            attr_set = true;
+            ctx->attr_bits |= RB_ATTR_MORPH;
         }
         int left_x = (int)columns, left_y = (int)rows, lo_x = target_x, lo_y = target_y; // window still to apply, offset still to apply
         while (left_x > 0 || left_y > 0) {
@@ -1475,6 +1481,7 @@ extern "C" int rb_filter_convolve_matrix(rb_layer *l, const float *kernel, uint3
                                          uint32_t target_x, uint32_t target_y, float divisor, float bias,
                                          int edge_mode, int preserve_alpha)
 {
+    rb_enter(l ? l->ctx : nullptr);
     RB_SYNC_LAYER(l);
     if (!l || !kernel || columns == 0 || rows == 0 || edge_mode < 0 || edge_mode > 2) return RB_ERR_INVALID;
     if ((size_t)columns * rows > 8192) return RB_ERR_UNSUPPORTED;
@@ -1547,6 +1554,7 @@ struct OpLuminanceToAlpha {
 
 extern "C" int rb_filter_color_matrix(rb_layer *l, int kind, const float *params)
 {
+    rb_enter(l ? l->ctx : nullptr);
     RB_SYNC_LAYER(l);
     if (!l) return RB_ERR_INVALID;
     if (kind == 0) {
@@ -1662,6 +1670,7 @@ static uint8_t transfer_u8(const rb_transfer_fn &f, uint8_t cu)
 
 extern "C" int rb_filter_component_transfer(rb_layer *l, const rb_transfer_fn funcs[4])
 {
+    rb_enter(l ? l->ctx : nullptr);
     RB_SYNC_LAYER(l);
     if (!l || !funcs) return RB_ERR_INVALID;
     OpLut4 L;
@@ -1711,6 +1720,7 @@ __global__ void __launch_bounds__(256) k_alpha_lut(uint32_t *__restrict__ px, si
 
 extern "C" int rb_filter_flood_alpha(rb_layer *l, uint8_t r, uint8_t g, uint8_t b, uint8_t a)
 {
+    rb_enter(l ? l->ctx : nullptr);
     RB_SYNC_LAYER(l);
     if (!l) return RB_ERR_INVALID;
     AlphaLut L;
@@ -1778,6 +1788,7 @@ k_arithmetic(const uint32_t *__restrict__ s1, const uint32_t *__restrict__ s2, u
 extern "C" int rb_filter_composite_arithmetic(rb_layer *dest, const rb_layer *src1, const rb_layer *src2, float k1,
                                               float k2, float k3, float k4)
 {
+    rb_enter(dest ? dest->ctx : nullptr);
     RB_SYNC_LAYER(dest);
     RB_SYNC_LAYER(src1);
     RB_SYNC_LAYER(src2);
@@ -1854,6 +1865,7 @@ k_displace(const uint32_t *__restrict__ src, const uint32_t *__restrict__ map, u
 extern "C" int rb_filter_displacement_map(rb_layer *dest, const rb_layer *src, const rb_layer *map, int xch, int ych,
                                           float scale, float sx, float sy)
 {
+    rb_enter(dest ? dest->ctx : nullptr);
     RB_SYNC_LAYER(dest);
     RB_SYNC_LAYER(src);
     RB_SYNC_LAYER(map);
@@ -2152,6 +2164,7 @@ extern "C" int rb_filter_diffuse_lighting(rb_layer *dest, const rb_layer *src, f
                                           float diffuse_constant, uint8_t r, uint8_t g, uint8_t b,
                                           const rb_light_source *light)
 {
+    rb_enter(dest ? dest->ctx : nullptr);
     RB_SYNC_LAYER(dest);
     RB_SYNC_LAYER(src);
     return launch_lighting(dest, src, 0, surface_scale, diffuse_constant, 1.0f, r, g, b, light);
@@ -2160,6 +2173,7 @@ extern "C" int rb_filter_specular_lighting(rb_layer *dest, const rb_layer *src, 
                                            float specular_constant, float specular_exponent, uint8_t r, uint8_t g,
                                            uint8_t b, const rb_light_source *light)
 {
+    rb_enter(dest ? dest->ctx : nullptr);
     RB_SYNC_LAYER(dest);
     RB_SYNC_LAYER(src);
     return launch_lighting(dest, src, 1, surface_scale, specular_constant, specular_exponent, r, g, b, light);
@@ -2344,6 +2358,7 @@ extern "C" int rb_filter_turbulence(rb_layer *dest, double offset_x, double offs
                                     double bfx, double bfy, uint32_t num_octaves, int32_t seed, int stitch_tiles,
                                     int fractal_noise)
 {
+    rb_enter(dest ? dest->ctx : nullptr);
     RB_SYNC_LAYER(dest);
     if (!dest) return RB_ERR_INVALID;
     rb_ctx *ctx = dest->ctx;
@@ -2360,11 +2375,10 @@ extern "C" int rb_filter_turbulence(rb_layer *dest, double offset_x, double offs
     RB_CUDA(ctx, cudaMemcpyAsync(dg, grad.data(), grad_bytes, cudaMemcpyHostToDevice, ctx->stream));
     RB_CUDA(ctx, cudaMemcpyAsync(dl, lat.data(), lat_bytes, cudaMemcpyHostToDevice, ctx->stream));
     TurbParams P{offset_x, offset_y, sx, sy, bfx, bfy, (int)num_octaves, stitch_tiles ? 1 : 0, fractal_noise ? 1 : 0};
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(ctx->attr_bits & RB_ATTR_TURB)) {
         RB_CUDA(ctx, cudaFuncSetAttribute(k_turbulence, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(grad_bytes + lat_bytes)));
-        attr_set = true;
+        ctx->attr_bits |= RB_ATTR_TURB;
     }
     int strip = 256;
     while (strip > 8 && (long long)((w + 31) / 32) * ((h + strip - 1) / strip) < 4LL * ctx->sm_count) strip >>= 1;

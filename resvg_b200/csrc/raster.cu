@@ -714,6 +714,7 @@ static rb_ctx *batch_ctx(const rb_batch *b) { return b->ctx ? b->ctx : (b->mask 
 
 extern "C" int rb_batch_begin(rb_layer *target, rb_batch **out)
 {
+    rb_enter(target ? target->ctx : nullptr);
     if (!target || !out) return RB_ERR_INVALID;
     rb_batch *b = new rb_batch();
     b->layer = target;
@@ -818,6 +819,7 @@ static int batch_prepare_range(rb_batch *b, int32_t n_threads, size_t begin, siz
 
 extern "C" int rb_batch_prepare(rb_batch *b, int32_t n_threads)
 {
+    rb_enter(b ? b->ctx : nullptr);
     if (b && b->layer && b->layer->pending != b) RB_SYNC_LAYER(b->layer);
     int st = batch_prepare_range(b, n_threads, 0, 0);
     // hairline strokes + the fallback builder: only rb_batch_submit can interleave the two kinds of passes
@@ -829,6 +831,7 @@ extern "C" int rb_batch_prepare(rb_batch *b, int32_t n_threads)
 static int batch_run(rb_batch *b, unsigned long long *px_stats);
 extern "C" int rb_batch_run(rb_batch *b)
 {
+    rb_enter(b ? b->ctx : nullptr);
     if (b && b->layer && b->layer->pending != b) RB_SYNC_LAYER(b->layer);
     return batch_run(b, nullptr);
 }
@@ -837,6 +840,7 @@ extern "C" int rb_batch_run(rb_batch *b)
 // non-opaque paint), out[1] = pixels stored without reading (full coverage, opaque solid).  Synchronises.
 extern "C" int rb_batch_run_counting(rb_batch *b, uint64_t out[2])
 {
+    rb_enter(b ? b->ctx : nullptr);
     if (!b || !out) return RB_ERR_INVALID;
     rb_ctx *ctx = batch_ctx(b);
     if (!ctx) return RB_ERR_INVALID;
@@ -855,9 +859,7 @@ extern "C" int rb_batch_run_counting(rb_batch *b, uint64_t out[2])
                         "blended px %llu, stored px %llu\n", h[2], h[3], h[4], h[5], h[6], h[7], h[0], h[1]);
     if (st == RB_OK && b->dev_scratch && !b->lay.wide) {
         // the list builder counts entries it had to drop (the host's capacity bound makes that impossible)
-        unsigned int dropped = 0;
-        RB_CUDA(ctx, cudaMemcpy(&dropped, b->dev_scratch + warp_scratch_layout(b->lay).o_flag, 4, cudaMemcpyDeviceToHost));
-        if (dropped) return rb_fail(ctx, RB_ERR_CUDA, "tile-row edge list overflow");
+        if (rb_check_flags(ctx) != RB_OK) return RB_ERR_CUDA;
     }
     return st;
 }
@@ -870,11 +872,10 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
     rb_ctx *ctx = mask_target ? b->mask->ctx : b->layer->ctx;
     const int W = (int)(mask_target ? b->mask->w : b->layer->w), H = (int)(mask_target ? b->mask->h : b->layer->h);
     void *target = mask_target ? (void *)b->mask->d : (void *)b->layer->d;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(ctx->attr_bits & RB_ATTR_WIDE)) {
         RB_CUDA(ctx, cudaFuncSetAttribute(k_raster_tiles_wide<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CNT_BYTES));
         RB_CUDA(ctx, cudaFuncSetAttribute(k_raster_tiles_wide<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CNT_BYTES));
-        attr_set = true;
+        ctx->attr_bits |= RB_ATTR_WIDE;
     }
     const BatchLayout &L = b->lay;
     if (!L.wide) {
@@ -885,7 +886,7 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
         // item mode: o_edges holds the uploaded line edges; the edge array proper is expanded into the scratch block
         const DevEdge *d_lines = (const DevEdge *)(b->dev + L.o_edges);
         DevEdge *d_edges = L.items ? (DevEdge *)(sc + ws.o_edges) : (DevEdge *)(b->dev + L.o_edges);
-        unsigned int *d_flag = (unsigned int *)(sc + ws.o_flag);
+        unsigned int *d_flag = ctx->d_flags; // sticky, host-mapped: surfaced by rb_check_flags at every sync point
         uint32_t *row_off = (uint32_t *)(sc + ws.o_row_off), *row_cnt = (uint32_t *)(sc + ws.o_row_cnt);
         uint32_t *row_cols = (uint32_t *)(sc + ws.o_row_cols);
         uint32_t *tile_off = (uint32_t *)(sc + ws.o_tile_off), *tile_pairs = (uint32_t *)(sc + ws.o_tile_pairs);
@@ -896,7 +897,6 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
         RB_CUDA(ctx, cudaEventRecord(ctx->ev_run[0], ctx->stream));
         RB_CUDA(ctx, cudaMemsetAsync(row_cnt, 0, ((size_t)L.wtiles_y + 2) * 4, ctx->stream));
         RB_CUDA(ctx, cudaMemsetAsync(tile_off, 0, ((size_t)n_wtiles + 2) * 4, ctx->stream));
-        RB_CUDA(ctx, cudaMemsetAsync(d_flag, 0, 4, ctx->stream));
         k_row_lists<<<n_draws, RL_THREADS, 0, ctx->stream>>>(d_draws, d_lines, (const rbh::CurveRec *)(b->dev + L.o_curves), d_edges, row_off,
                                                               row_edges, row_cols, L.items ? 1 : 0, d_flag);
         RB_LAUNCHED(ctx, "row_lists");
@@ -949,6 +949,7 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
 // Device time of the context's last batch run: ms[0] = binning + edge-list pre-pass, ms[1] = the raster kernel.
 extern "C" int rb_ctx_last_run_ms(rb_ctx *ctx, float ms[2])
 {
+    rb_enter(ctx);
     if (!ctx || !ms) return RB_ERR_INVALID;
     RB_CUDA(ctx, cudaEventSynchronize(ctx->ev_run[2]));
     RB_CUDA(ctx, cudaEventElapsedTime(&ms[0], ctx->ev_run[0], ctx->ev_run[1]));
@@ -1017,6 +1018,7 @@ static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t 
 // hairlines (k_hair_blits), executed in painter's order on the context's stream.
 extern "C" int rb_batch_submit(rb_batch *b, int32_t n_threads)
 {
+    rb_enter(b ? b->ctx : nullptr);
     if (!b) return RB_ERR_INVALID;
     if (b->layer && b->layer->pending != b) RB_SYNC_LAYER(b->layer); // immediate draws issued before this batch come first
     uint64_t total[6] = {0, 0, 0, 0, 0, 0};
@@ -1089,6 +1091,7 @@ int rb_layer_flush(rb_layer *l)
 extern "C" int rb_fill_path(rb_layer *layer, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
                             const rb_paint *paint, int32_t fill_rule, const float ts[6])
 {
+    rb_enter(layer ? layer->ctx : nullptr);
     if (!layer || !paint) return RB_ERR_INVALID;
     const bool pattern = paint->shader == 3;
     if (pattern) RB_SYNC_LAYER(paint->pattern);
@@ -1108,6 +1111,7 @@ extern "C" int rb_fill_path(rb_layer *layer, const uint8_t *verbs, int32_t n_ver
 extern "C" int rb_mask_fill_path(rb_mask *mask, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
                                  int32_t fill_rule, int32_t anti_alias, const float ts[6])
 {
+    rb_enter(mask ? mask->ctx : nullptr);
     if (!mask) return RB_ERR_INVALID;
     rb_batch b;
     b.mask = mask;
@@ -1165,6 +1169,7 @@ k_draw_layer(uint32_t *__restrict__ dst, int dw, const uint32_t *__restrict__ sr
 
 extern "C" int rb_draw_layer(rb_layer *dst, const rb_layer *src, int32_t x, int32_t y, float opacity, int32_t blend_mode)
 {
+    rb_enter(dst ? dst->ctx : nullptr);
     RB_SYNC_LAYER(dst);
     RB_SYNC_LAYER(src);
     if (!dst || !src || blend_mode < 0 || blend_mode > 28 || dst->d == src->d) return RB_ERR_INVALID;
@@ -1218,6 +1223,7 @@ k_draw_layer_rects(uint32_t *__restrict__ dst, int dw, const uint32_t *__restric
 extern "C" int rb_draw_layer_rects(rb_layer *dst, const rb_layer *src, int32_t n, const int32_t *rects, const int32_t *src_xy,
                                    const float *opacity, int32_t blend_mode)
 {
+    rb_enter(dst ? dst->ctx : nullptr);
     RB_SYNC_LAYER(dst);
     RB_SYNC_LAYER(src);
     if (!dst || !src || n < 0 || (n > 0 && (!rects || !opacity)) || blend_mode < 0 || blend_mode > 28 || dst->d == src->d)
@@ -1266,6 +1272,7 @@ extern "C" int rb_draw_layer_rects(rb_layer *dst, const rb_layer *src, int32_t n
 // =================================================================================================
 extern "C" int rb_mask_create(rb_ctx *ctx, uint32_t w, uint32_t h, rb_mask **out)
 {
+    rb_enter(ctx);
     if (!ctx || !out || w == 0 || h == 0) return RB_ERR_INVALID;
     void *d = nullptr;
     cudaSetDevice(ctx->device);
@@ -1284,6 +1291,7 @@ extern "C" void rb_mask_destroy(rb_mask *m)
 }
 extern "C" int rb_mask_download(rb_mask *m, uint8_t *host)
 {
+    rb_enter(m ? m->ctx : nullptr);
     if (!m || !host) return RB_ERR_INVALID;
     RB_CUDA(m->ctx, cudaMemcpyAsync(host, m->d, (size_t)m->w * m->h, cudaMemcpyDeviceToHost, m->ctx->stream));
     RB_CUDA(m->ctx, cudaStreamSynchronize(m->ctx->stream));
@@ -1291,6 +1299,7 @@ extern "C" int rb_mask_download(rb_mask *m, uint8_t *host)
 }
 extern "C" int rb_mask_upload(rb_mask *m, const uint8_t *host)
 {
+    rb_enter(m ? m->ctx : nullptr);
     if (!m || !host) return RB_ERR_INVALID;
     RB_CUDA(m->ctx, cudaMemcpyAsync(m->d, host, (size_t)m->w * m->h, cudaMemcpyHostToDevice, m->ctx->stream));
     m->ctx->h2d_bytes += (size_t)m->w * m->h;
@@ -1366,6 +1375,7 @@ __global__ void __launch_bounds__(256) k_apply_mask(uint32_t *__restrict__ px, c
 
 extern "C" int rb_mask_from_layer(rb_mask *m, const rb_layer *l, int32_t luminance)
 {
+    rb_enter(m ? m->ctx : nullptr);
     RB_SYNC_LAYER(l);
     if (!m || !l || m->w != l->w || m->h != l->h) return RB_ERR_INVALID;
     rb_ctx *ctx = m->ctx;
@@ -1376,6 +1386,7 @@ extern "C" int rb_mask_from_layer(rb_mask *m, const rb_layer *l, int32_t luminan
 }
 extern "C" int rb_mask_invert(rb_mask *m)
 {
+    rb_enter(m ? m->ctx : nullptr);
     if (!m) return RB_ERR_INVALID;
     rb_ctx *ctx = m->ctx;
     size_t n = (size_t)m->w * m->h;
@@ -1385,6 +1396,7 @@ extern "C" int rb_mask_invert(rb_mask *m)
 }
 extern "C" int rb_layer_apply_mask(rb_layer *l, const rb_mask *m)
 {
+    rb_enter(l ? l->ctx : nullptr);
     RB_SYNC_LAYER(l);
     if (!m || !l) return RB_ERR_INVALID;
     if (m->w != l->w || m->h != l->h) return RB_OK; // tiny-skia: warn and return

@@ -199,7 +199,7 @@ k_row_lists(const DevDraw *__restrict__ draws, const DevEdge *__restrict__ lines
             const DevEdge B = B0[i];
             const uint32_t at = cell_off[B.meta] + B.ypack;
             if (at < D.list_cap) out[at] = B;
-            else atomicAdd(overflow, 1u);
+            else *(volatile unsigned int *)overflow = 1u; // host-mapped sticky flag, checked at the next sync point
         }
         return;
     }
@@ -297,7 +297,7 @@ k_row_lists(const DevDraw *__restrict__ draws, const DevEdge *__restrict__ lines
         for (int r = ra; r <= rb; r++) {
             const uint32_t at = atomicAdd(&cnt[r], 1u);
             if (at < D.list_cap) out[at] = E;
-            else atomicAdd(overflow, 1u); // cannot happen: the host's bound covers every segment
+            else *(volatile unsigned int *)overflow = 1u; // cannot happen: the host's bound covers every segment
         }
     }
 }

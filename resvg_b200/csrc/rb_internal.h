@@ -20,6 +20,13 @@ struct rb_ctx {
     uint64_t launches = 0;
     uint64_t h2d_bytes = 0; // bytes uploaded by batches and layer / mask uploads (rb_ctx_h2d_bytes)
     int sm_count = 148;
+    // which opt-in kernel attributes (dynamic shared memory > 48 KB) have been set on THIS context's device: function
+    // attributes are per device, so a process-wide flag would leave a second GPU without them
+    uint32_t attr_bits = 0;
+    // sticky error flags written by kernels straight into mapped pinned host memory ([0]: a tile-row edge list entry was
+    // dropped because the host's capacity bound was short); read by rb_check_flags after a stream synchronisation
+    volatile unsigned int *h_flags = nullptr;
+    unsigned int *d_flags = nullptr;
     // scratch reused by multi-pass filters (grown on demand, freed with the context)
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
@@ -33,6 +40,14 @@ struct rb_ctx {
     std::atomic<int> refs{1};
     std::vector<struct rb_layer *> dirty; // layers holding pending immediate draws (rb_fill_path), flushed by rb_ctx_synchronize
 };
+
+// Every entry point that allocates or launches makes the context's device current first: the host (torch, a second
+// context) may have switched devices since the last call.
+static inline void rb_enter(const rb_ctx *ctx)
+{
+    if (ctx) cudaSetDevice(ctx->device);
+}
+enum { RB_ATTR_BOX = 1, RB_ATTR_MORPH = 2, RB_ATTR_TURB = 4, RB_ATTR_WIDE = 8, RB_ATTR_PXTABLE = 16 };
 
 void rb_ctx_retain(rb_ctx *ctx);
 void rb_ctx_release(rb_ctx *ctx);
@@ -70,6 +85,8 @@ struct rb_mask {
 };
 
 int rb_fail(rb_ctx *ctx, int code, const char *what);
+// After a synchronisation: RB_ERR_CUDA (and rb_last_error) if a kernel raised a sticky flag since the last check.
+int rb_check_flags(rb_ctx *ctx);
 int rb_cuda_fail(rb_ctx *ctx, cudaError_t e, const char *what);
 // Ensures ctx->scratch holds at least `bytes`; returns RB_OK or an error status.
 int rb_scratch(rb_ctx *ctx, size_t bytes, void **out);
