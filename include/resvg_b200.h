@@ -275,6 +275,18 @@ int rb_draw_layer(rb_layer *dst, const rb_layer *src, int32_t x, int32_t y, floa
 int rb_draw_layer_rects(rb_layer *dst, const rb_layer *src, int32_t n, const int32_t *rects, const int32_t *src_xy,
                         const float *opacity, int32_t blend_mode);
 
+/* PixmapMut::stroke_path, immediate form of rb_batch_stroke_path (path.rs:113): recorded lazily like rb_fill_path. */
+int rb_stroke_path(rb_layer *layer, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
+                   const rb_paint *paint, const rb_stroke *stroke, const float ts[6]);
+/* PixmapMut::fill_rect(Rect::from_xywh(x, y, w, h), paint, transform, None) — filter/mod.rs:474-497 (clearing outside a
+ * primitive subregion), :853 (feTile), image.rs:203 (raster images).  Integer rectangles under the identity and any
+ * rectangle under another transform (tiny-skia then fills PathBuilder::from_rect) are drawn; a fractional anti-aliased
+ * rectangle under the identity (tiny-skia's fill_rect_aa, never issued by resvg) is RB_ERR_UNSUPPORTED. */
+int rb_fill_rect(rb_layer *layer, float x, float y, float w, float h, const rb_paint *paint, const float ts[6]);
+/* Pixmap::clone_rect as PixmapExt::copy_region uses it (filter/mod.rs:104-108, feTile :849): the part of the rectangle
+ * inside `src` as a new layer; RB_ERR_INVALID when they do not intersect. */
+int rb_layer_clone_rect(const rb_layer *src, int32_t x, int32_t y, uint32_t w, uint32_t h, rb_layer **out);
+
 /* tiny_skia::Mask — clip.rs:25-27, mask.rs:17-45 */
 int rb_mask_create(rb_ctx *ctx, uint32_t width, uint32_t height, rb_mask **out); /* Mask::new (zeroed) */
 void rb_mask_destroy(rb_mask *mask);
@@ -283,9 +295,76 @@ int rb_mask_upload(rb_mask *mask, const uint8_t *host);
 int rb_mask_from_layer(rb_mask *mask, const rb_layer *layer, int32_t luminance); /* Mask::from_pixmap */
 int rb_mask_invert(rb_mask *mask);                                                /* Mask::invert */
 int rb_layer_apply_mask(rb_layer *layer, const rb_mask *mask);                    /* Pixmap::apply_mask */
+/* Mask::from_pixmap(mask_pixmap, Luminance | Alpha) + Pixmap::apply_mask fused (mask.rs:40-45), and
+ * Mask::from_pixmap(clip_pixmap, Alpha) + Mask::invert + Pixmap::apply_mask fused (clip.rs:25-27): the mask value is a
+ * function of the source pixel, so the u8 plane is never materialised.  Bit-identical to the three-call sequence. */
+int rb_layer_apply_mask_layer(rb_layer *layer, const rb_layer *mask_pixmap, int32_t luminance);
+int rb_layer_apply_clip_layer(rb_layer *layer, const rb_layer *clip_pixmap);
 /* Mask::fill_path(path, rule, anti_alias, transform) */
 int rb_mask_fill_path(rb_mask *mask, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
                       int32_t fill_rule, int32_t anti_alias, const float ts[6]);
+
+/* ------------------------------------------------------------------------------------------------
+ * Whole-tree rendering — resvg::render / resvg::render_node (crates/resvg/src/lib.rs:34-70) and the C API's resvg_render
+ * / resvg_render_node (crates/c-api/lib.rs:875-942).  The traversal of crates/resvg/src/{render,path,clip,mask,image}.rs
+ * and the filter executor of filter/mod.rs run inside the library (csrc/render.cpp, csrc/filter_exec.cpp) against
+ * device-resident layers: one call across the boundary per document.
+ *
+ * The usvg::Tree is handed over as a flat little-endian stream of 4-byte words ("RBT1") that the Rust shim writes once
+ * per tree by walking usvg's public accessors (INTEGRATION.md shows the writer):
+ *
+ *   stream := u32 0x31544252 ("RBT1")  TREE
+ *   TREE   := f32 width, f32 height (tree.size())  GROUP (tree.root())
+ *   STR    := u32 n, n bytes, zero padding to a multiple of 4
+ *   XF     := f32 sx, ky, kx, sy, tx, ty          RECT := f32 x, y, width, height        RGB := u32 r | g << 8 | b << 16
+ *   GROUP  := STR id, XF transform, f32 opacity, u32 blend_mode (usvg::BlendMode order), u32 isolate,
+ *             RECT layer_bounding_box, RECT abs_layer_bounding_box, u32 has_clip_path [CLIP], u32 has_mask [MASK],
+ *             u32 n_filters FILTER*, u32 n_children NODE*
+ *   NODE   := u32 0 GROUP (Node::Group, and Node::Text as text.flattened()) | u32 1 PATH | u32 2 IMAGE
+ *   PATH   := STR id, u32 visible, u32 paint_order (0 FillAndStroke, 1 StrokeAndFill), u32 anti_alias
+ *             (rendering_mode().use_shape_antialiasing()), u32 has_bbox, RECT abs_stroke_bounding_box,
+ *             u32 has_fill [PAINT, f32 opacity, u32 rule (0 NonZero, 1 EvenOdd)],
+ *             u32 has_stroke [PAINT, f32 opacity, f32 width, f32 miterlimit, u32 linecap, u32 linejoin, u32 n_dash, f32 dash*,
+ *             f32 dashoffset], u32 n_verbs, verbs (RB_VERB_*, padded to 4), u32 n_points, f32 x,y per point
+ *   PAINT  := u32 0 RGB | u32 1 f32 x1 y1 x2 y2 BASE | u32 2 f32 cx cy r fx fy fr BASE | u32 3 RECT rect, XF transform, GROUP root
+ *   BASE   := u32 spread_method, XF transform, u32 n_stops, { f32 offset, RGB, f32 opacity }*
+ *   IMAGE  := STR id, u32 visible, u32 quality (RB_QUALITY_* of image.rs:180-187), u32 has_bbox, RECT abs bounding box,
+ *             u32 0 TREE (ImageKind::SVG) | u32 1 u32 w, u32 h, w*h*4 bytes premultiplied RGBA8 (decoded by the host, image.rs:62-170)
+ *   CLIP   := XF transform, u32 has_clip_path [CLIP], GROUP root
+ *   MASK   := RECT rect, u32 kind (0 Luminance, 1 Alpha), u32 has_mask [MASK], GROUP root
+ *   FILTER := RECT rect, u32 n_primitives, PRIM*
+ *   INPUT  := u32 0 (SourceGraphic) | u32 1 (SourceAlpha) | u32 2 STR name (Reference)
+ *   PRIM   := RECT rect, u32 color_interpolation (0 sRGB, 1 linearRGB), STR result, u32 kind, then by kind:
+ *      0 Blend: u32 mode, INPUT in1, INPUT in2            1 DropShadow: INPUT, f32 dx dy std_dev_x std_dev_y, RGB, f32 opacity
+ *      2 Flood: RGB, f32 opacity                          3 GaussianBlur: INPUT, f32 std_dev_x std_dev_y
+ *      4 Offset: INPUT, f32 dx dy                         5 Composite: u32 op (over,in,out,atop,xor,arithmetic), f32 k1..k4, INPUT, INPUT
+ *      6 Merge: u32 n, INPUT*                             7 Tile: INPUT                     8 Image: GROUP root
+ *      9 ComponentTransfer: INPUT, 4 x { u32 type (rb_transfer_fn), u32 n, f32 values*, f32 slope intercept amplitude exponent offset }
+ *      10 ColorMatrix: INPUT, u32 kind, u32 n, f32 params*
+ *      11 ConvolveMatrix: INPUT, u32 columns rows target_x target_y, f32 divisor bias, u32 edge_mode, u32 preserve_alpha, u32 n, f32 kernel*
+ *      12 Morphology: INPUT, u32 op (0 erode, 1 dilate), f32 rx ry
+ *      13 DisplacementMap: INPUT in1, INPUT in2, f32 scale, u32 x_channel y_channel
+ *      14 Turbulence: f32 base_freq_x base_freq_y, u32 octaves, i32 seed, u32 stitch, u32 fractal_noise
+ *      15 DiffuseLighting / 16 SpecularLighting: INPUT, f32 surface_scale, constant, specular_exponent, RGB lighting_color,
+ *         LIGHT := u32 kind, f32 azimuth elevation x y z points_at_x points_at_y points_at_z specular_exponent, u32 has_cone, f32 cone
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rb_tree rb_tree;
+/* Parses and validates a stream into a host-side tree (no device work).  RB_ERR_INVALID: malformed. */
+int rb_tree_parse(const void *stream, size_t len, rb_tree **out);
+void rb_tree_destroy(rb_tree *tree);
+int rb_tree_size(const rb_tree *tree, float *width, float *height); /* resvg_get_image_size */
+/* usvg::Tree::node_by_id(id)?.abs_layer_bounding_box() — the pixmap size render_node expects (c-api/lib.rs:795-814);
+ * RB_ERR_INVALID: no such node, or a zero-sized one. */
+int rb_tree_node_bbox(const rb_tree *tree, const char *id, float out_xywh[4]);
+/* resvg::render(tree, transform, pixmap) — lib.rs:34-43.  Draws over the target's current content. */
+int rb_render(rb_ctx *ctx, const rb_tree *tree, const float ts[6], rb_layer *target);
+/* resvg::render_node(node, transform, pixmap) — lib.rs:55-70: the node is placed at -abs_layer_bounding_box.  RB_ERR_INVALID
+ * is the reference's None (unknown id / zero-sized node). */
+int rb_render_node(rb_ctx *ctx, const rb_tree *tree, const char *id, const float ts[6], rb_layer *target);
+/* One-shot form: parse + render + free (SURVEY 8(b) `rb_submit`). */
+int rb_submit(rb_ctx *ctx, const void *stream, size_t len, const float ts[6], rb_layer *target);
+/* resvg_render (c-api/lib.rs:875-893) over a HOST pixmap: upload (the caller's pixels are the canvas), render, download. */
+int rb_render_to_host(rb_ctx *ctx, const rb_tree *tree, const float ts[6], uint32_t width, uint32_t height, uint8_t *pixmap);
 
 /* ------------------------------------------------------------------------------------------------
  * Host geometry: tiny_skia_path::Path::stroke(&Stroke, res_scale) — the outline PixmapMut::stroke_path fills

@@ -153,6 +153,19 @@ SIGNATURES = {
     "rb_debug_batch_begin_host": (_i, [_u32, _u32, c_void_pp]),
     "rb_debug_batch_phases": (_i, [_vp, _vp]),
     "rb_debug_batch_block": (C.c_int64, [_vp, C.c_int32, _vp, C.c_uint64]),
+    "rb_stroke_path": (_i, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.POINTER(Paint), _vp, f32p]),
+    "rb_fill_rect": (_i, [_vp, _f, _f, _f, _f, C.POINTER(Paint), f32p]),
+    "rb_layer_clone_rect": (_i, [_vp, C.c_int32, C.c_int32, _u32, _u32, c_void_pp]),
+    "rb_layer_apply_mask_layer": (_i, [_vp, _vp, C.c_int32]),
+    "rb_layer_apply_clip_layer": (_i, [_vp, _vp]),
+    "rb_tree_parse": (_i, [C.c_char_p, C.c_size_t, c_void_pp]),
+    "rb_tree_destroy": (None, [_vp]),
+    "rb_tree_size": (_i, [_vp, f32p, f32p]),
+    "rb_tree_node_bbox": (_i, [_vp, C.c_char_p, f32p]),
+    "rb_render": (_i, [_vp, _vp, f32p, _vp]),
+    "rb_render_node": (_i, [_vp, _vp, C.c_char_p, f32p, _vp]),
+    "rb_submit": (_i, [_vp, C.c_char_p, C.c_size_t, f32p, _vp]),
+    "rb_render_to_host": (_i, [_vp, _vp, f32p, _u32, _u32, _vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -323,3 +323,24 @@ extern "C" int rb_layer_copy(rb_layer *dst, const rb_layer *src)
                                       dst->ctx->stream));
     return RB_OK;
 }
+
+// Pixmap::clone_rect (tiny-skia pixmap.rs) as filter/mod.rs:104-108 copy_region uses it: the part of the rectangle that
+// lies inside the layer becomes a new layer; RB_ERR_INVALID when they do not intersect (the reference's None).
+extern "C" int rb_layer_clone_rect(const rb_layer *src, int32_t x, int32_t y, uint32_t w, uint32_t h, rb_layer **out)
+{
+    rb_enter(src ? src->ctx : nullptr);
+    RB_SYNC_LAYER(src);
+    if (!src || !out || w == 0 || h == 0) return RB_ERR_INVALID;
+    *out = nullptr;
+    const int64_t x0 = std::max<int64_t>(x, 0), y0 = std::max<int64_t>(y, 0);
+    const int64_t x1 = std::min<int64_t>((int64_t)x + w, src->w), y1 = std::min<int64_t>((int64_t)y + h, src->h);
+    if (x1 <= x0 || y1 <= y0) return RB_ERR_INVALID;
+    rb_layer *l = nullptr;
+    int st = rb_layer_create(src->ctx, (uint32_t)(x1 - x0), (uint32_t)(y1 - y0), &l);
+    if (st != RB_OK) return st;
+    cudaError_t e = cudaMemcpy2DAsync(l->d, (size_t)l->w * 4, src->d + ((size_t)y0 * src->w + (size_t)x0) * 4, (size_t)src->w * 4,
+                                      (size_t)l->w * 4, l->h, cudaMemcpyDeviceToDevice, src->ctx->stream);
+    if (e != cudaSuccess) { rb_layer_destroy(l); return rb_cuda_fail(src->ctx, e, "clone_rect"); }
+    *out = l;
+    return RB_OK;
+}

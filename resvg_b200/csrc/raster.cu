@@ -1108,6 +1108,49 @@ extern "C" int rb_fill_path(rb_layer *layer, const uint8_t *verbs, int32_t n_ver
     return RB_OK;
 }
 
+// PixmapMut::stroke_path, immediate form: recorded into the layer's pending batch like rb_fill_path (painter's order =
+// call order); rb_batch_stroke_path holds the reference's logic (dash, hairline test, stroker).
+extern "C" int rb_stroke_path(rb_layer *layer, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
+                              const rb_paint *paint, const rb_stroke *stroke, const float ts[6])
+{
+    rb_enter(layer ? layer->ctx : nullptr);
+    if (!layer || !paint || !stroke) return RB_ERR_INVALID;
+    const bool pattern = paint->shader == 3;
+    if (pattern) RB_SYNC_LAYER(paint->pattern);
+    if (!layer->pending) {
+        int st = rb_batch_begin(layer, &layer->pending);
+        if (st != RB_OK) return st;
+        layer->pending_n = 0;
+        layer->ctx->dirty.push_back(layer);
+    }
+    const size_t before = layer->pending->n_total;
+    int st = rb_batch_stroke_path(layer->pending, verbs, n_verbs, points, n_points, paint, stroke, ts);
+    if (st != RB_OK) return st;
+    if (layer->pending->n_total != before) layer->pending_n++;
+    if (pattern || layer->pending_n >= RB_PENDING_MAX) return rb_layer_flush(layer);
+    return RB_OK;
+}
+
+// PixmapMut::fill_rect(rect, paint, transform, None) (tiny-skia painter.rs).  With the identity transform tiny-skia
+// blits the rectangle directly (scan::fill_rect / fill_rect_aa); otherwise it fills PathBuilder::from_rect(rect).  For
+// a rectangle with integer edges the direct blit and the path fill cover exactly the same pixels at full coverage, and
+// resvg only ever issues integer rectangles under the identity (filter/mod.rs:474-497, 853; image.rs:203) — a fractional
+// anti-aliased rectangle under the identity would need fill_rect_aa's own edge coverage and is reported as unsupported
+// rather than drawn with the path rasteriser's 4x4 coverage.
+extern "C" int rb_fill_rect(rb_layer *layer, float x, float y, float w, float h, const rb_paint *paint, const float ts[6])
+{
+    if (!layer || !paint) return RB_ERR_INVALID;
+    const float r = x + w, b = y + h; // Rect::from_xywh
+    if (!(std::isfinite(x) && std::isfinite(y) && std::isfinite(r) && std::isfinite(b)) || !(x <= r && y <= b)) return RB_ERR_INVALID;
+    const bool identity = !ts || (ts[0] == 1 && ts[1] == 0 && ts[2] == 0 && ts[3] == 1 && ts[4] == 0 && ts[5] == 0);
+    const bool integral = x == floorf(x) && y == floorf(y) && r == floorf(r) && b == floorf(b);
+    if (identity && paint->anti_alias && !integral && layer->w <= 8191 && layer->h <= 8191) return RB_ERR_UNSUPPORTED;
+    if (!(w > 0.0f && h > 0.0f)) return RB_OK; // an empty rectangle blits nothing
+    const uint8_t verbs[5] = {RB_VERB_MOVE, RB_VERB_LINE, RB_VERB_LINE, RB_VERB_LINE, RB_VERB_CLOSE};
+    const float pts[8] = {x, y, r, y, r, b, x, b};
+    return rb_fill_path(layer, verbs, 5, pts, 4, paint, RB_FILL_WINDING, ts);
+}
+
 extern "C" int rb_mask_fill_path(rb_mask *mask, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
                                  int32_t fill_rule, int32_t anti_alias, const float ts[6])
 {
@@ -1405,6 +1448,55 @@ extern "C" int rb_layer_apply_mask(rb_layer *l, const rb_mask *m)
     k_apply_mask<<<rb_grid_1d(ctx, (n + 3) / 4, 256), 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(l->d), m->d, n);
     RB_LAUNCHED(ctx, "apply_mask");
     return RB_OK;
+}
+
+// Mask::from_pixmap(src, kind) [+ Mask::invert()] + Pixmap::apply_mask in ONE pass: the mask value is a function of the
+// source pixel alone, so the u8 plane never has to exist.  12 B/px instead of 5 + (2) + 9.
+//   mode 0: alpha mask, 1: luminance mask (mask.rs:40-45), 2: inverted alpha mask (clip.rs:25-27)
+__global__ void __launch_bounds__(256) k_apply_layer_as_mask(uint32_t *__restrict__ px, const uint32_t *__restrict__ src, size_t n, int mode)
+{
+    __shared__ float div255[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) div255[i] = __fdiv_rn((float)i, 255.0f);
+    __syncthreads();
+    const int lum = mode == 1;
+    const uint32_t inv = mode == 2 ? 255u : 0u;
+    const size_t n4 = n >> 2, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        uint4 p = reinterpret_cast<uint4 *>(px)[i];
+        const uint4 s = reinterpret_cast<const uint4 *>(src)[i];
+        p.x = apply_mask_px(p.x, mask_px(s.x, lum, div255) ^ inv);
+        p.y = apply_mask_px(p.y, mask_px(s.y, lum, div255) ^ inv);
+        p.z = apply_mask_px(p.z, mask_px(s.z, lum, div255) ^ inv);
+        p.w = apply_mask_px(p.w, mask_px(s.w, lum, div255) ^ inv);
+        reinterpret_cast<uint4 *>(px)[i] = p;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const size_t i = (n4 << 2) + threadIdx.x;
+        px[i] = apply_mask_px(px[i], mask_px(src[i], lum, div255) ^ inv);
+    }
+}
+
+static int apply_layer_as_mask(rb_layer *l, const rb_layer *src, int mode)
+{
+    rb_enter(l ? l->ctx : nullptr);
+    RB_SYNC_LAYER(l);
+    RB_SYNC_LAYER(src);
+    if (!l || !src || l == src) return RB_ERR_INVALID;
+    if (src->w != l->w || src->h != l->h) return RB_OK; // Pixmap::apply_mask: size mismatch is a warning and a no-op
+    rb_ctx *ctx = l->ctx;
+    const size_t n = (size_t)l->w * l->h;
+    k_apply_layer_as_mask<<<rb_grid_1d(ctx, (n + 3) / 4, 256), 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(l->d),
+                                                                                     reinterpret_cast<const uint32_t *>(src->d), n, mode);
+    RB_LAUNCHED(ctx, "apply_layer_as_mask");
+    return RB_OK;
+}
+extern "C" int rb_layer_apply_mask_layer(rb_layer *layer, const rb_layer *mask_pixmap, int32_t luminance)
+{
+    return apply_layer_as_mask(layer, mask_pixmap, luminance ? 1 : 0);
+}
+extern "C" int rb_layer_apply_clip_layer(rb_layer *layer, const rb_layer *clip_pixmap)
+{
+    return apply_layer_as_mask(layer, clip_pixmap, 2);
 }
 
 // =================================================================================================

@@ -35,11 +35,9 @@ class OracleBackend:
 
     def stroke_hairline(self, l, verbs, pts, spec, ts, blend, width, cap, dash=None, dash_offset=0.0):
         """tiny-skia painter.rs stroke_path for a stroke treat_as_hairline accepts (anti-aliased, transformed width <= 1
-        px): dash, transform into device space, fold the hairline coverage into the paint's alpha, walk the segments
-        (shared host geometry, like the stroker) and blend every blit with the oracle's pipeline."""
-        import math
-
-        import resvg_b200 as rb
+        px): dash (unless the caller already did), transform into device space, fold the hairline coverage into the paint's alpha,
+        walk the segments (oracle/hairline.c) and blend every blit with the oracle's pipeline."""
+        from tests import geom
         f = np.float32
 
         def fast_len(x, y):
@@ -53,9 +51,10 @@ class OracleBackend:
         coverage = f((len0 + len1) * f(0.5))
         v, p = np.asarray(verbs, np.uint8), np.asarray(pts, np.float32).reshape(-1, 2)
         if dash:
+            import math
             sx, sy = math.hypot(ts[0], ts[2]), math.hypot(ts[1], ts[3])
             res = max(sx, sy) if (math.isfinite(sx) and math.isfinite(sy) and max(sx, sy) > 0) else 1.0
-            out = rb.dash_path(v, p, dash, dash_offset, res)
+            out = geom.dash_path(v, p, dash, dash_offset, res)
             if out is None:
                 return
             v, p = out
@@ -83,11 +82,19 @@ class OracleBackend:
         paint = self.R.make_paint(spec, blend, True)
         for ty in range(0, h, 8191):  # DrawTiler: the painter draws layers larger than 8191 px tile by tile
             for tx in range(0, wpx, 8191):
-                blits = rb.hairline_blits(v, dev - np.float32([tx, ty]), cap, min(wpx - tx, 8191), min(h - ty, 8191))
+                blits = geom.hairline_blits(v, dev - np.float32([tx, ty]), cap, min(wpx - tx, 8191), min(h - ty, 8191))
                 if len(blits):
                     blits[:, 0] += tx
                     blits[:, 1] += ty
                     self.R.blit_coverage(l, blits, paint, ts)
+
+    def upload(self, l, px):
+        l[...] = px
+
+    def fill_rect(self, l, x, y, w, h, spec, ts, blend="source_over", aa=True):
+        if spec["kind"] == "pattern":
+            spec = dict(spec, pixmap=spec["layer"])
+        self.R.fill_rect(l, x, y, w, h, self.R.make_paint(spec, blend, aa), ts)
 
     def draw_layer(self, dst, src, x, y, opacity=1.0, blend="source_over"):
         self.R.draw_pixmap(dst, x, y, src, opacity, blend)
@@ -165,11 +172,14 @@ class GpuBackend:
     def fill_path(self, l, verbs, pts, spec, rule, ts, blend="source_over", aa=True):
         self.rb.fill_path(l, verbs, pts, self.rb.make_paint(spec, blend, aa), rule, ts)
 
-    def stroke_hairline(self, l, verbs, pts, spec, ts, blend, width, cap, dash=None, dash_offset=0.0):
+    def stroke_hairline(self, l, verbs, pts, spec, ts, blend, width, cap):
         b = self.rb.Batch(l)
-        b.stroke_path(verbs, pts, self.rb.make_paint(spec, blend, True), width, 4.0, cap, "miter", ts, dash, dash_offset)
+        b.stroke_path(verbs, pts, self.rb.make_paint(spec, blend, True), width, 4.0, cap, "miter", ts)
         b.submit()
         b.close()
+
+    def upload(self, l, px):
+        l.upload(px)
 
     def draw_layer(self, dst, src, x, y, opacity=1.0, blend="source_over"):
         self.rb.draw_layer(dst, src, x, y, opacity, blend)

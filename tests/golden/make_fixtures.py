@@ -26,7 +26,7 @@ from tests.backends import OracleBackend  # noqa: E402
 
 CORPUS = "/root/reference/crates/resvg/tests/tests"
 OUT = os.path.join(ROOT, "tests", "golden", "scenes")
-PER_DIR = int(os.environ.get("PER_DIR", "4"))
+PER_DIR = int(os.environ.get("PER_DIR", "100000"))  # every reproduced golden is a fixture
 
 
 def main():

@@ -662,7 +662,7 @@ class Converter:
                 n = self.node_for(ch)
                 if n is not None:
                     kids.append(n)
-            g = {"t": "g", "ts": list(ts), "children": kids}
+            g = {"t": "g", "id": "" if is_root else el.attrib.get("id", ""), "ts": list(ts), "children": kids}
             self.group_effects(el, g)
             if not kids and not g.get("filters"):
                 return None
@@ -674,6 +674,8 @@ class Converter:
         d = self.doc
         g["opacity"] = opacity_val(d.attr(el, "opacity", inherit=False))
         blend = d.attr(el, "mix-blend-mode", inherit=False) or "normal"
+        if blend not in BLEND_MAP:
+            blend = "normal"
         g["blend"] = blend
         iso = d.attr(el, "isolation", inherit=False) == "isolate"
         bbox = self.node_bbox(g)
@@ -720,6 +722,7 @@ class Converter:
                     g["children"] = []
                 else:
                     g["filters"] = [f]
+        g["isolate_attr"] = bool(iso)
         g["isolate"] = bool(g["opacity"] != 1.0 or g["clip"] or g["mask"] or g["filters"] or blend != "normal" or iso)
 
     # ---- nodes ----
@@ -765,7 +768,7 @@ class Converter:
         if child is None:
             return None
         ts = ts_pre(self.resolve_transform(el, el.attrib.get("transform")), ts_translate(x, y))
-        g = {"t": "g", "ts": list(ts), "children": [child]}
+        g = {"t": "g", "id": el.attrib.get("id", ""), "ts": list(ts), "children": [child]}
         self.group_effects(el, g)
         return g
 
@@ -841,7 +844,7 @@ class Converter:
                 raise Unsupported("marker")
         bbox = tight_bounds(verbs, pts)
         vis = d.attr(el, "visibility") or "visible"
-        node = {"t": "path", "verbs": verbs, "pts": [list(p) for p in pts], "visible": vis == "visible", "bbox": bbox}
+        node = {"t": "path", "id": el.attrib.get("id", ""), "verbs": verbs, "pts": [list(p) for p in pts], "visible": vis == "visible", "bbox": bbox}
         sr = d.attr(el, "shape-rendering") or "geometricPrecision"
         node["aa"] = sr not in ("optimizeSpeed", "crispEdges")
         po = (d.attr(el, "paint-order") or "normal").split()
@@ -858,8 +861,12 @@ class Converter:
             else:
                 st["width"] = width
                 st["cap"] = d.attr(el, "stroke-linecap") or "butt"
+                if st["cap"] not in ("butt", "round", "square"):
+                    st["cap"] = "butt"
                 join = d.attr(el, "stroke-linejoin") or "miter"
                 st["join"] = {"arcs": "miter", "miter-clip": "miter-clip"}.get(join, join)
+                if st["join"] not in ("miter", "miter-clip", "round", "bevel"):
+                    st["join"] = "miter"
                 ml = float(d.attr(el, "stroke-miterlimit") or 4.0)
                 if ml < 1:
                     raise Unsupported("miterlimit < 1")
@@ -886,6 +893,8 @@ class Converter:
         return g
 
     def paint_for(self, el, prop, default, color, bbox):
+        """usvg style.rs resolve_fill / resolve_stroke + convert_paint: -> {"paint": usvg::Paint, "opacity": Opacity}.
+        A colour's alpha (and the single stop a degenerate gradient collapses to) is folded into the opacity."""
         d = self.doc
         v = d.attr(el, prop) or default
         op = opacity_val(d.attr(el, prop + "-opacity"))
@@ -896,10 +905,13 @@ class Converter:
             target = d.link(m.group(1))
             fallback = m.group(2).strip()
             if target is not None and _strip(target.tag) in ("linearGradient", "radialGradient"):
-                p = self.gradient_for(target, bbox, op)
+                p = self.gradient_for(target, bbox)
                 if p == "none":
                     return None
                 if p is not None:
+                    if p["kind"] == "color":
+                        sub = p.pop("sub_opacity")
+                        return {"paint": p, "opacity": _f(min(max(f32(sub) * f32(op), f32(0)), f32(1)))}
                     return {"paint": p, "opacity": op}
             elif target is not None and _strip(target.tag) == "pattern":
                 p = self.pattern_for(target, bbox)
@@ -920,8 +932,7 @@ class Converter:
         if c is None:
             return None
         a = _f(f32(op) * f32(c[3]))
-        return {"paint": {"kind": "solid", "color": [c[0] / 255.0, c[1] / 255.0, c[2] / 255.0, to_u8_opacity(a) / 255.0]},
-                "opacity": op}
+        return {"paint": {"kind": "color", "rgb": [int(c[0]), int(c[1]), int(c[2])]}, "opacity": a}
 
     # ---- gradients (usvg paint_server.rs) ----
     def _grad_chain(self, el):
@@ -935,7 +946,7 @@ class Converter:
                 break
         return chain
 
-    def gradient_for(self, el, bbox, opacity):
+    def gradient_for(self, el, bbox):
         d = self.doc
         chain = self._grad_chain(el)
         tag = _strip(el.tag)
@@ -980,12 +991,13 @@ class Converter:
                     o = p + np.finfo(np.float32).eps if float(p) + float(np.finfo(np.float32).eps) <= 1.0 else p
                     if o == p and len(out) >= 1:
                         out[-1][0] = float(p - np.finfo(np.float32).eps)
-            a = _f(f32(so) * f32(opacity))
-            out.append([float(o), col[0] / 255.0, col[1] / 255.0, col[2] / 255.0, to_u8_opacity(a) / 255.0])
+            out.append([float(o), int(col[0]), int(col[1]), int(col[2]), so])  # usvg::Stop: offset, color, opacity
         if len(out) == 1:
-            return {"kind": "solid", "color": out[0][1:5]}
+            return {"kind": "color", "rgb": out[0][1:4], "sub_opacity": out[0][4]}
         units = ga("gradientUnits") or "objectBoundingBox"
         spread = ga("spreadMethod") or "pad"
+        if spread not in ("pad", "reflect", "repeat"):
+            spread = "pad"
         gts = self.resolve_transform(el, ga("gradientTransform"))
         obb = units == "objectBoundingBox"
 
@@ -1014,7 +1026,7 @@ class Converter:
         fr = coord("fr", "0%", diag)
         if not r > 0:
             # 'A value of zero will cause the area to be painted as a single color using the last stop'
-            return {"kind": "solid", "color": out[-1][1:5]}
+            return {"kind": "color", "rgb": out[-1][1:4], "sub_opacity": out[-1][4]}
         return {"kind": "radial", "x0": fx, "y0": fy, "r0": fr, "x1": cx, "y1": cy, "r1": r, "stops": out, "spread": spread,
                 "ts": list(gts)}
 
@@ -1082,20 +1094,25 @@ class Converter:
         return {"kind": "pattern_tree", "rect": list(rect), "ts": list(pts), "root": root}
 
     # ---- bbox of a converted node (object bounding box, no stroke) ----
-    def node_bbox(self, n, ts=IDENT):
+    def node_bbox(self, n):
+        """usvg Group::calculate_object_bbox (tree/mod.rs:1850-1864): the union of the children's object bounding boxes
+        in the group's OWN coordinate system — child groups contribute their bbox mapped by their transform, the
+        group's own transform is not applied."""
         if n["t"] == "path":
-            b = n.get("bbox")
+            return n.get("bbox")
+        boxes = []
+        for c in n["children"]:
+            b = self.node_bbox(c)
             if b is None:
-                return None
-            return rect_transform(b, ts) if not ts_is_identity(ts) else b
-        t = ts_pre(ts, tuple(n["ts"]))
-        boxes = [self.node_bbox(c, t) for c in n["children"]]
-        boxes = [b for b in boxes if b is not None]
+                continue
+            if c["t"] != "path" and not ts_is_identity(tuple(c["ts"])):
+                b = rect_transform(b, tuple(c["ts"]))
+            boxes.append(b)
         if not boxes:
             return None
         l, tp = min(b[0] for b in boxes), min(b[1] for b in boxes)
-        r, bt = max(b[0] + b[2] for b in boxes), max(b[1] + b[3] for b in boxes)
-        return (l, tp, r - l, bt - tp)
+        r, bt = max(_f(f32(b[0]) + f32(b[2])) for b in boxes), max(_f(f32(b[1]) + f32(b[3])) for b in boxes)
+        return (l, tp, _f(f32(r) - f32(l)), _f(f32(bt) - f32(tp)))
 
     def resolve_transform(self, el, value):
         """usvg converter.rs:1100-1127 resolve_transform: the transform attribute combined with `transform-origin`
@@ -1168,7 +1185,7 @@ class Converter:
         """Inside a clipPath only geometry and clip-rule matter: fill = opaque black with rule = clip-rule."""
         if n["t"] == "path":
             rule = self.doc.attr(el, "clip-rule") or "nonzero"
-            n["fill"] = {"paint": {"kind": "solid", "color": [0.0, 0.0, 0.0, 1.0]}, "opacity": 1.0,
+            n["fill"] = {"paint": {"kind": "color", "rgb": [0, 0, 0]}, "opacity": 1.0,
                          "rule": "evenodd" if rule == "evenodd" else "nonzero"}
             n["stroke"] = None
         else:
@@ -1176,6 +1193,7 @@ class Converter:
             n["mask"] = None
             n["filters"] = []
             n["blend"] = "normal"
+            n["isolate_attr"] = False
             n["isolate"] = bool(n.get("clip"))
             for c in n["children"]:
                 self._clip_fixup(c, el if c["t"] == "path" and len(n["children"]) == 1 else el)
@@ -1223,11 +1241,118 @@ class Converter:
 
 
 def parse(svg_text):
-    return Converter(Doc(svg_text)).convert()
+    return finalize_scene(Converter(Doc(svg_text)).convert())
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# render traversal (crates/resvg/src/render.rs, path.rs, clip.rs, mask.rs)
+# bounding boxes (usvg tree/mod.rs: Path::new :1311-1354, Group::calculate_bounding_boxes :1866-1929)
+# ---------------------------------------------------------------------------------------------------------------------
+def _union(boxes):
+    """usvg BBox::expand over Rects given as (x, y, w, h); -> (l, t, r, b) or None."""
+    acc = None
+    for b in boxes:
+        l, t, r, bt = f32(b[0]), f32(b[1]), f32(b[0]) + f32(b[2]), f32(b[1]) + f32(b[3])
+        acc = (l, t, r, bt) if acc is None else (min(acc[0], l), min(acc[1], t), max(acc[2], r), max(acc[3], bt))
+    return acc
+
+
+def _non_zero(acc):
+    if acc is None:
+        return None
+    w, h = acc[2] - acc[0], acc[3] - acc[1]
+    if not (w > 0 and h > 0 and math.isfinite(float(w)) and math.isfinite(float(h))):
+        return None
+    return (float(acc[0]), float(acc[1]), float(w), float(h))
+
+
+def _rect_transform_nz(r, t):
+    b = rect_transform(r, t) if not ts_is_identity(t) else tuple(r)
+    if not (b[2] > 0 and b[3] > 0 and all(math.isfinite(v) for v in b)):
+        return None
+    return b
+
+
+def _stroke_bbox(verbs, pts, st):
+    """Path::calculate_stroke_bbox: the tight bounds of the outline at res_scale 1 (dashes ignored)."""
+    from tests import geom
+    out = geom.stroke_outline(verbs, pts, st["width"], st["miter"], st["cap"], st["join"], 1.0)
+    if out is None:
+        return None
+    v, q = out
+    return tight_bounds([int(x) for x in v], [(float(a), float(b)) for a, b in q])
+
+
+DEFAULT_LAYER_BBOX = (0.0, 0.0, 1.0, 1.0)
+
+
+def finalize_scene(scene):
+    """Fills in what usvg stores on every node once the tree is built: stroke / layer / absolute layer bounding boxes."""
+    _finalize_group(scene["root"], IDENT)
+    return scene
+
+
+def _finalize_paint_roots(n):
+    for key in ("fill", "stroke"):
+        pd = n.get(key)
+        if pd and pd["paint"]["kind"] == "pattern_tree":
+            _finalize_group(pd["paint"]["root"], IDENT)
+
+
+def _finalize_group(g, parent_abs):
+    abs_ts = ts_pre(parent_abs, tuple(g["ts"]))
+    layer = []
+    for c in g["children"]:
+        if c["t"] == "path":
+            bbox = c.get("bbox")
+            sb = (_stroke_bbox(c["verbs"], c["pts"], c["stroke"]) if c.get("stroke") else None) or bbox
+            c["stroke_bbox"] = list(sb) if sb else None
+            if sb is not None:
+                if ts_has_skew(abs_ts):
+                    tp = [ts_map(abs_ts, x, y) for x, y in c["pts"]]
+                    ab = tight_bounds(c["verbs"], tp)
+                    asb = (_stroke_bbox(c["verbs"], tp, c["stroke"]) if c.get("stroke") else None) or ab
+                else:
+                    asb = rect_transform(sb, abs_ts) if not ts_is_identity(abs_ts) else tuple(sb)
+                c["abs_bbox"] = list(asb) if asb else None
+                layer.append(sb)
+            _finalize_paint_roots(c)
+        elif c["t"] == "image":
+            c["abs_bbox"] = list(rect_transform(tuple(c["bbox"]), abs_ts)) if not ts_is_identity(abs_ts) else list(c["bbox"])
+            layer.append(tuple(c["bbox"]))
+            if c["kind"] == "svg":
+                finalize_scene(c["tree"])
+        else:
+            _finalize_group(c, abs_ts)
+            r = _rect_transform_nz(tuple(c["layer_bbox"]), tuple(c["ts"]))
+            if r is not None:
+                layer.append(r)
+    if g.get("clip"):
+        _finalize_group(g["clip"], IDENT)  # a clip dict is group-like (ts + children); its own "clip" is reached recursively
+    m = g.get("mask")
+    while m:
+        _finalize_group(m["root"], IDENT)
+        m = m.get("mask")
+    for f in g.get("filters") or []:
+        for prim in f["primitives"]:
+            if prim["kind"] == "image":
+                _finalize_group(prim["root"], IDENT)
+    lb = None
+    if g.get("filters"):
+        lb = _non_zero(_union([tuple(f["rect"]) for f in g["filters"]]))  # the filter region has priority
+    if lb is None and not g.get("filters"):
+        lb = _non_zero(_union(layer))
+    if lb is None:
+        g["layer_bbox"] = list(DEFAULT_LAYER_BBOX)
+        g["abs_layer_bbox"] = list(DEFAULT_LAYER_BBOX)
+    else:
+        g["layer_bbox"] = list(lb)
+        ab = _rect_transform_nz(lb, abs_ts)
+        g["abs_layer_bbox"] = list(ab) if ab else list(DEFAULT_LAYER_BBOX)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# render traversal (crates/resvg/src/lib.rs, render.rs, path.rs, clip.rs, mask.rs, image.rs) — the CHECKER's copy: it
+# drives the CPU oracle.  The product's traversal is resvg_b200/csrc/render.cpp behind rb_render.
 # ---------------------------------------------------------------------------------------------------------------------
 BLEND_MAP = {"normal": "source_over", "multiply": "multiply", "screen": "screen", "overlay": "overlay", "darken": "darken",
              "lighten": "lighten", "color-dodge": "color_dodge", "color-burn": "color_burn", "hard-light": "hard_light",
@@ -1235,78 +1360,126 @@ BLEND_MAP = {"normal": "source_over", "multiply": "multiply", "screen": "screen"
              "saturation": "saturation", "color": "color", "luminosity": "luminosity"}
 
 
+def max_filter_bbox(w, h):
+    """lib.rs:86-97"""
+    return (-2 * w, -2 * h, 5 * w, 5 * h)
+
+
+def _trunc_i32(v):
+    v = float(v)
+    if v != v:
+        return 0
+    return int(max(min(math.trunc(v), 2147483647), -2147483648))
+
+
 class Renderer:
     def __init__(self, backend):
         self.be = backend
-        import resvg_b200 as rb  # host-side stroker (shared geometry)
-        self.stroke_path = rb.stroke_path
 
-    def render(self, scene, width, height, ts):
-        layer = self.be.new_layer(width, height)
-        root = scene["root"]
-        # the root group carries the viewBox / preserveAspectRatio transform (usvg Tree::root_transform)
-        self.render_nodes(root, ts_pre(tuple(ts), tuple(root.get("ts", IDENT))), layer, "source_over")
+    # lib.rs:34-43
+    def render(self, scene, width, height, ts, layer=None):
+        if layer is None:
+            layer = self.be.new_layer(width, height)
+        lw, lh = self.be.size(layer)
+        self.max_bbox = max_filter_bbox(lw, lh)
+        self.render_group(scene["root"], tuple(ts), layer)  # scene root = the child of usvg's root that carries the viewBox transform
         return layer
 
-    def render_nodes(self, group, ts, layer, blend):
+    # lib.rs:55-70
+    def render_node_by_id(self, scene, node_id, ts, layer):
+        n = find_node(scene["root"], node_id)
+        if n is None:
+            return False
+        bbox = n.get("abs_layer_bbox") if n["t"] == "g" else n.get("abs_bbox")
+        if bbox is None or not (bbox[2] > 0 and bbox[3] > 0):
+            return False
+        lw, lh = self.be.size(layer)
+        self.max_bbox = max_filter_bbox(lw, lh)
+        self.render_node(n, ts_pre(tuple(ts), ts_translate(-bbox[0], -bbox[1])), layer)
+        return True
+
+    def render_nodes(self, group, ts, layer, blend="source_over"):
         for n in group["children"]:
             self.render_node(n, ts, layer, blend)
 
     def render_node(self, n, ts, layer, blend="source_over"):
         if n["t"] == "path":
             self.render_path(n, ts, layer, blend)
+        elif n["t"] == "image":
+            self.render_image(n, ts, layer)
         else:
             self.render_group(n, ts, layer)
 
-    def render_path(self, n, ts, layer, blend, fill_only=False):
+    # path.rs:6-24
+    def render_path(self, n, ts, layer, blend):
         if not n.get("visible", True):
             return
-        order = ["stroke", "fill"] if n.get("stroke_first") else ["fill", "stroke"]
-        for what in order:
-            if what == "fill":
-                self.fill_path(n, ts, layer, blend)
-            elif not fill_only:
-                self.stroke(n, ts, layer, blend)
+        if n.get("stroke_first"):
+            self.stroke(n, ts, layer, blend)
+            self.fill_path(n, ts, layer, blend)
+        else:
+            self.fill_path(n, ts, layer, blend)
+            self.stroke(n, ts, layer, blend)
 
+    # path.rs:26-75
     def fill_path(self, n, ts, layer, blend):
         f = n.get("fill")
         if not f:
             return
-        b = n.get("bbox")
         xs = [p[0] for p in n["pts"]]
         ys = [p[1] for p in n["pts"]]
         if max(xs) - min(xs) == 0.0 or max(ys) - min(ys) == 0.0:  # path.rs:36
             return
-        paint = self.resolve_paint(f["paint"], f.get("opacity", 1.0), ts)
+        paint = self.convert_paint(f["paint"], f.get("opacity", 1.0), ts)
         if paint is None:
             return
         self.be.fill_path(layer, n["verbs"], n["pts"], paint, f["rule"], ts, blend, n.get("aa", True))
 
-    def resolve_paint(self, paint, opacity, ts):
-        """path.rs:57-68 / 179-205: a pattern paint is pre-rendered into a tile pixmap."""
-        if paint["kind"] != "pattern_tree":
-            return paint
+    def convert_paint(self, paint, opacity, ts):
+        """path.rs:45-71 / 118-177 (colour, gradients) and 179-205 (a pattern is pre-rendered into a tile pixmap)."""
+        k = paint["kind"]
+        if k == "color":
+            r, g, b = paint["rgb"]
+            return {"kind": "solid", "color": [_f(f32(r) / f32(255)), _f(f32(g) / f32(255)), _f(f32(b) / f32(255)),
+                                               _f(f32(to_u8_opacity(opacity)) / f32(255))]}
+        if k in ("linear", "radial"):
+            stops = []
+            for o, r, g, b, so in paint["stops"]:
+                a = min(max(f32(so) * f32(opacity), f32(0)), f32(1))
+                stops.append([o, _f(f32(r) / f32(255)), _f(f32(g) / f32(255)), _f(f32(b) / f32(255)), _f(f32(to_u8_opacity(a)) / f32(255))])
+            return dict(paint, stops=stops)
         sx, sy = ts_get_scale(ts_pre(ts, tuple(paint["ts"])))
         rect = paint["rect"]
-        iw = int(math.floor(float(f32(rect[2]) * f32(sx)) + 0.5))
-        ih = int(math.floor(float(f32(rect[3]) * f32(sy)) + 0.5))
+        iw = _trunc_i32(math.floor(abs(float(f32(rect[2]) * f32(sx))) + 0.5))  # f32::round of a non-negative value
+        ih = _trunc_i32(math.floor(abs(float(f32(rect[3]) * f32(sy))) + 0.5))
         if iw <= 0 or ih <= 0:
             return None
         tile = self.be.new_layer(iw, ih)
-        self.render_nodes(paint["root"], ts_scale(sx, sy), tile, "source_over")
+        self.render_nodes(paint["root"], ts_scale(sx, sy), tile)
         pts = ts_pre(IDENT, tuple(paint["ts"]))
         pts = ts_pre(pts, ts_translate(rect[0], rect[1]))
         pts = ts_pre(pts, ts_scale(_f(f32(1.0) / f32(sx)), _f(f32(1.0) / f32(sy))))
         return {"kind": "pattern", "layer": tile, "spread": "repeat", "quality": "bicubic", "opacity": opacity, "ts": pts}
 
+    # path.rs:77-116 + tiny-skia painter.rs stroke_path
     def stroke(self, n, ts, layer, blend):
+        from tests import geom
         s = n.get("stroke")
         if not s:
+            return
+        paint = self.convert_paint(s["paint"], s.get("opacity", 1.0), ts)
+        if paint is None:
             return
         # painter.rs stroke_path: res_scale = compute_resolution_scale(ts); thin strokes take the hairline path
         sx = math.hypot(ts[0], ts[2])
         sy = math.hypot(ts[1], ts[3])
         res_scale = max(sx, sy) if (math.isfinite(sx) and math.isfinite(sy) and max(sx, sy) > 0) else 1.0
+        src_verbs, src_pts = n["verbs"], n["pts"]
+        if s.get("dash"):
+            dashed = geom.dash_path(src_verbs, src_pts, s["dash"], s.get("dash_offset", 0.0), res_scale)
+            if dashed is None:
+                return  # StrokeDash::new accepted the list (the front end filtered the others) but nothing is left
+            src_verbs, src_pts = dashed
         if n.get("aa", True):
             w = s["width"]
             v0 = (abs(ts[0] * w), abs(ts[1] * w))
@@ -1316,49 +1489,38 @@ class Renderer:
                 return max(v) + min(v) / 2.0
 
             if fast_len(v0) <= 1.0 and fast_len(v1) <= 1.0:
-                paint = self.resolve_paint(s["paint"], s.get("opacity", 1.0), ts)
-                if paint is not None:
-                    self.be.stroke_hairline(layer, n["verbs"], n["pts"], paint, ts, blend, s["width"], s["cap"],
-                                            s.get("dash"), s.get("dash_offset", 0.0))
+                self.be.stroke_hairline(layer, src_verbs, src_pts, paint, ts, blend, s["width"], s["cap"])
                 return
-        src_verbs, src_pts = n["verbs"], n["pts"]
-        if s.get("dash"):
-            import resvg_b200 as rb
-            dashed = rb.dash_path(src_verbs, src_pts, s["dash"], s.get("dash_offset", 0.0), res_scale)
-            if dashed is None:
-                return  # StrokeDash::new accepted the list (the front end filtered the others) but nothing is left
-            src_verbs, src_pts = dashed
-        out = self.stroke_path(src_verbs, src_pts, s["width"], s["miter"], s["cap"], s["join"], res_scale)
+        out = geom.stroke_outline(src_verbs, src_pts, s["width"], s["miter"], s["cap"], s["join"], res_scale)
         if out is None:
             return
         verbs, pts = out
-        paint = self.resolve_paint(s["paint"], s.get("opacity", 1.0), ts)
-        if paint is None:
-            return
         self.be.fill_path(layer, verbs, pts, paint, "nonzero", ts, blend, n.get("aa", True))
 
+    # render.rs:49-143
     def render_group(self, g, ts, layer):
         ts = ts_pre(ts, tuple(g["ts"]))
         if not g.get("isolate"):
-            self.render_nodes(g, ts, layer, "source_over")
+            self.render_nodes(g, ts, layer)
             return
-        lw, lh = self.be.size(layer)
-        if g.get("filters"):
-            from tests.svgfilters import filter_region
-            region = filter_region(g["filters"][0], ts)
-            if region is None:
-                return
-            ib = fit_to_rect(region, (-2 * lw, -2 * lh, 5 * lw, 5 * lh))  # ctx.max_bbox (lib.rs:86-97) of this canvas
-            if ib is None:
-                return
+        bbox = _rect_transform_nz(tuple(g["layer_bbox"]), ts)
+        if bbox is None:
+            return
+        bx, by, bw, bh = [f32(v) for v in bbox]
+        if not g.get("filters"):
+            ib = (_trunc_i32(math.floor(float(bx))) - 2, _trunc_i32(math.floor(float(by))) - 2,
+                  _trunc_i32(math.ceil(float(bw))) + 4, _trunc_i32(math.ceil(float(bh))) + 4)
         else:
-            # Any integer rectangle containing every pixel the group can touch gives the same pixels as the
-            # reference's tight bbox (the shift is an integer translate, render.rs:94-106); use the canvas.
-            ib = (0, 0, lw, lh)
-        shift = ts_translate(-float(ib[0]), -float(ib[1]))
-        lts = ts_pre(shift, ts)
+            ib = (_trunc_i32(math.floor(float(bx))), _trunc_i32(math.floor(float(by))),
+                  _trunc_i32(max(math.ceil(float(bw)), 1.0)), _trunc_i32(max(math.ceil(float(bh)), 1.0)))
+        ib = fit_to_rect(ib, self.max_bbox)
+        if ib is None:
+            return
+        dx = bx - (bx - f32(ib[0]))
+        dy = by - (by - f32(ib[1]))
+        lts = ts_pre(ts_translate(-dx, -dy), ts)
         sub = self.be.new_layer(ib[2], ib[3])
-        self.render_nodes(g, lts, sub, "source_over")
+        self.render_nodes(g, lts, sub)
         for f in g.get("filters", []):
             from tests.svgfilters import apply_filter
             apply_filter(self, f, lts, sub)
@@ -1385,7 +1547,7 @@ class Renderer:
             if n["t"] == "path":
                 if n.get("visible", True):
                     self.fill_path(n, ts, layer, mode)
-            else:
+            elif n["t"] == "g":
                 t = ts_pre(ts, tuple(n["ts"]))
                 if n.get("clip"):
                     w, h = self.be.size(layer)
@@ -1408,24 +1570,77 @@ class Renderer:
         x, y, rw, rh = f32(x), f32(y), f32(rw), f32(rh)
         rect_pts = [(float(x), float(y)), (float(x + rw), float(y)), (float(x + rw), float(y + rh)), (float(x), float(y + rh))]
         self.be.mask_fill_path(am, [M, L, L, L, Z], rect_pts, "nonzero", True, ts)
-        self.render_nodes(mask["root"], ts, ml, "source_over")
+        self.render_nodes(mask["root"], ts, ml)
         self.be.apply_mask(ml, am)
         if mask.get("mask"):
             self.apply_mask(mask["mask"], ts, layer)
         m = self.be.mask_from_layer(ml, mask["kind"])
         self.be.apply_mask(layer, m)
 
+    # ---- image.rs ----
+    def render_image(self, n, ts, layer):
+        if not n.get("visible", True):
+            return
+        w, h = self.be.size(layer)
+        if n["kind"] == "svg":  # render_vector, image.rs:37-54
+            sub = self.be.new_layer(w, h)
+            saved = self.max_bbox
+            Renderer(self.be).render(n["tree"], w, h, ts, sub)
+            self.max_bbox = saved
+            self.be.draw_layer(layer, sub, 0, 0, 1.0, "source_over")
+            return
+        # render_raster, image.rs:173-206: a Pad pattern of the decoded pixmap filled into its own rectangle
+        px = np.asarray(n["pixels"], np.uint8).reshape(n["h"], n["w"], 4)
+        raster = self.be.new_layer(n["w"], n["h"])
+        self.be.upload(raster, px)
+        spec = {"kind": "pattern", "layer": raster, "spread": "pad", "quality": n.get("quality", "bicubic"), "opacity": 1.0,
+                "ts": IDENT}
+        self.be.fill_rect(layer, 0.0, 0.0, float(n["w"]), float(n["h"]), spec, ts)
 
-def render_scene(scene, backend, target_width=300):
-    """tests/integration/main.rs render_inner: scale to width 300, render, return premultiplied RGBA8."""
+
+def find_node(group, node_id):
+    """usvg Tree::node_by_id: depth first."""
+    if not node_id:
+        return None
+    for n in group["children"]:
+        if n.get("id") == node_id:
+            return n
+        if n["t"] == "g":
+            r = find_node(n, node_id)
+            if r is not None:
+                return r
+    return None
+
+
+def target_for(scene, target_width=300):
+    """tests/integration/main.rs:75-87 (TestMode::Normal): scale to width 300 -> (pixmap w, h, render transform)."""
     w, h = scene["width"], scene["height"]
     iw, ih = max(1, int(round(w))), max(1, int(round(h)))  # Size::to_int_size
     pw = target_width
     ph = int(math.ceil(float(f32(pw) * f32(ih) / f32(iw))))
-    ts = ts_scale(_f(f32(pw) / f32(w)), _f(f32(ph) / f32(h)))
-    r = Renderer(backend)
-    layer = r.render(scene, pw, ph, ts)
+    return pw, ph, ts_scale(_f(f32(pw) / f32(w)), _f(f32(ph) / f32(h)))
+
+
+def render_scene(scene, backend, target_width=300):
+    """The checker's render: test-side traversal + the given back end (the CPU oracle); premultiplied RGBA8."""
+    pw, ph, ts = target_for(scene, target_width)
+    layer = Renderer(backend).render(scene, pw, ph, ts)
     return backend.to_numpy(layer)
+
+
+def render_scene_gpu(scene, ctx, target_width=300, via="tree"):
+    """The product's render: the scene is serialised (RBT1) and drawn by ONE rb_render / rb_submit call — traversal,
+    filter graph and pixels all inside libresvg_b200.so."""
+    import resvg_b200 as rb
+    pw, ph, ts = target_for(scene, target_width)
+    layer = ctx.layer(pw, ph)
+    if via == "submit":
+        rb.tree.submit(rb.tree.serialize(scene), ts, layer)
+    else:
+        tree = rb.tree.Tree(scene)
+        rb.tree.render(tree, ts, layer)
+        tree.close()
+    return layer.download()
 
 
 def demultiply_f64(px):

@@ -36,10 +36,10 @@ def test_stack_scene_structure_and_checker_render():
 @pytest.mark.gpu
 @pytest.mark.parametrize("size,levels,inset", [(512, 16, 8.0), (300, 8, 5.5)])
 def test_gpu_stack_matches_checker(ctx, size, levels, inset):
-    from tests.backends import GpuBackend, OracleBackend
+    from tests.backends import OracleBackend
     sc = _scene(size, levels, inset)
     want = F.render_scene(sc, OracleBackend(), size)
-    got = F.render_scene(sc, GpuBackend(ctx), size)
+    got = F.render_scene_gpu(sc, ctx, size, via="submit")
     d = np.abs(got.astype(np.int16) - want.astype(np.int16))
     # layer composites with opacity and luminance masks run in f32: one unit per stage
     assert d.max() <= 1, f"max |gpu - checker| = {d.max()}, {int((d > 1).sum())} bytes"
