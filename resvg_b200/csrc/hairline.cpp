@@ -49,9 +49,12 @@ inline uint32_t i32_to_alpha(int32_t a) { return (uint32_t)a & 0xffu; }
 struct Sink {
     std::vector<rbh::HairBlit> *out;
     int32_t w, h;
+    // the sub-clip of the line being walked: (line bounds + 1) ∩ clip when the line's bounds leave the clip — what the
+    // reference hands to do_anti_hairline and wraps the blitter in (RectClipBlitter); the whole clip otherwise
+    int64_t sl = 0, st = 0, sr = 0, sb = 0;
     void px(int64_t x, int64_t y, uint32_t a)
     {
-        if (a == 0 || x < 0 || y < 0 || x >= w || y >= h) return;
+        if (a == 0 || x < sl || y < st || x >= sr || y >= sb) return;
         out->push_back(rbh::HairBlit{(int32_t)x, (int32_t)y, a});
     }
     void anti_h2(int64_t x, int64_t y, uint32_t a0, uint32_t a1) { px(x, y, a0); px(x + 1, y, a1); }
@@ -144,17 +147,18 @@ FDot16 draw_line(Sink &s, Kind k, int32_t at, int32_t stop, FDot16 f, FDot16 slo
     }
 }
 
-// do_anti_hairline.  The reference narrows the walk to a sub-clip and wraps the blitter in a RectClipBlitter when the
-// line's bounds leave the clip; since the per-column values it then starts from are the ones stepping would reach
-// (fstart += slope * k), walking everything and dropping the pixels outside the clip (Sink::px) gives the same blits.
-void do_anti_hairline(Sink &s, FDot6 x0, FDot6 y0, FDot6 x1, FDot6 y1)
+// do_anti_hairline.  `clipped`: the line's bounds leave the clip and Sink::{sl,st,sr,sb} hold the sub-clip.  The reference
+// then starts the walk at the clip edge (fstart jumps by slope * skipped columns — NOT the same as stepping there, because
+// every step clamps the ordinate at 0), ends it at the far edge, and drops the remaining outside pixels in a RectClipBlitter
+// (Sink::px).
+void do_anti_hairline(Sink &s, FDot6 x0, FDot6 y0, FDot6 x1, FDot6 y1, bool clipped)
 {
     if (x0 == INT32_MIN || y0 == INT32_MIN || x1 == INT32_MIN || y1 == INT32_MIN) return; // any_bad_ints
     if (abs(x1 - x0) > (511 << 6) || abs(y1 - y0) > (511 << 6)) {
         // long lines are halved so that the FDot16 slope arithmetic cannot overflow
         const int32_t hx = (x0 >> 1) + (x1 >> 1), hy = (y0 >> 1) + (y1 >> 1);
-        do_anti_hairline(s, x0, y0, hx, hy);
-        do_anti_hairline(s, hx, hy, x1, y1);
+        do_anti_hairline(s, x0, y0, hx, hy, clipped);
+        do_anti_hairline(s, hx, hy, x1, y1, clipped);
         return;
     }
     int32_t scale_start, scale_stop, istart, istop;
@@ -173,6 +177,24 @@ void do_anti_hairline(Sink &s, FDot6 x0, FDot6 y0, FDot6 x1, FDot6 y1)
         }
         if (istop - istart == 1) { scale_start = x1 - x0; scale_stop = 0; } // within a single pixel
         else { scale_start = 64 - (x0 & 63); scale_stop = x1 & 63; }
+        if (clipped) {
+            if (istart >= s.sr || istop <= s.sl) return;
+            if (istart < s.sl) {
+                fstart = wadd(fstart, wmul(slope, (int32_t)(s.sl - istart)));
+                istart = (int32_t)s.sl;
+                scale_start = 64;
+                if (istop - istart == 1) { scale_start = ((x1 - 1) & 63) + 1; scale_stop = 0; } // contribution_64
+            }
+            if (istop > s.sr) { istop = (int32_t)s.sr; scale_stop = 0; } // the last column is not drawn
+            if (istart == istop) return;
+            // rows the walk can touch, outset by one; wholly outside the clip -> nothing to draw
+            int32_t top, bottom;
+            const FDot16 fend = wadd(fstart, wmul(istop - istart - 1, slope));
+            if (slope >= 0) { top = wadd(fstart, -F16_HALF) >> 16; bottom = (int32_t)(((int64_t)wadd(fend, F16_HALF) + 65535) >> 16); }
+            else { bottom = (int32_t)(((int64_t)wadd(fstart, F16_HALF) + 65535) >> 16); top = wadd(fend, -F16_HALF) >> 16; }
+            top -= 1; bottom += 1;
+            if (top >= s.sb || bottom <= s.st) return;
+        }
     } else { // mostly vertical
         if (y0 > y1) { std::swap(x0, x1); std::swap(y0, y1); }
         istart = fdot6_floor(y0);
@@ -189,6 +211,23 @@ void do_anti_hairline(Sink &s, FDot6 x0, FDot6 y0, FDot6 x1, FDot6 y1)
         }
         if (istop - istart == 1) { scale_start = y1 - y0; scale_stop = 0; }
         else { scale_start = 64 - (y0 & 63); scale_stop = y1 & 63; }
+        if (clipped) {
+            if (istart >= s.sb || istop <= s.st) return;
+            if (istart < s.st) {
+                fstart = wadd(fstart, wmul(slope, (int32_t)(s.st - istart)));
+                istart = (int32_t)s.st;
+                scale_start = 64;
+                if (istop - istart == 1) { scale_start = ((y1 - 1) & 63) + 1; scale_stop = 0; }
+            }
+            if (istop > s.sb) { istop = (int32_t)s.sb; scale_stop = 0; }
+            if (istart == istop) return;
+            int32_t left, right;
+            const FDot16 fend = wadd(fstart, wmul(istop - istart - 1, slope));
+            if (slope >= 0) { left = wadd(fstart, -F16_HALF) >> 16; right = (int32_t)(((int64_t)wadd(fend, F16_HALF) + 65535) >> 16); }
+            else { right = (int32_t)(((int64_t)wadd(fstart, F16_HALF) + 65535) >> 16); left = wadd(fend, -F16_HALF) >> 16; }
+            left -= 1; right += 1;
+            if (left >= s.sr || right <= s.sl) return;
+        }
     }
     // the first pixel(s) are scaled by scale_start, the last by scale_stop, the full spans in between are not
     fstart = draw_cap(s, kind, istart, fstart, slope, scale_start);
@@ -262,7 +301,12 @@ void anti_hair_lines(Sink &s, const P *pts, int n)
         const int64_t ir = (int64_t)fdot6_ceil(std::max(x0, x1)) + 1, ib = (int64_t)fdot6_ceil(std::max(y0, y1)) + 1;
         if (ir - il <= 0 || ib - it <= 0 || ir - il > INT32_MAX || ib - it > INT32_MAX) return; // IntRect::from_ltrb -> None
         if (il >= s.w || it >= s.h || ir <= 0 || ib <= 0) continue;
-        do_anti_hairline(s, x0, y0, x1, y1);
+        // the walk below visits every column / row of the line; pixels outside the sub-clip are dropped by Sink::px.  The
+        // border pairs that tiny-skia's unsigned coordinates shift inwards (max(1) - 1) are cut by it like any other pixel.
+        s.sl = std::max<int64_t>(il, 0); s.st = std::max<int64_t>(it, 0);
+        s.sr = std::min<int64_t>(ir, s.w); s.sb = std::min<int64_t>(ib, s.h);
+        const bool contained = il >= 0 && it >= 0 && ir <= s.w && ib <= s.h;
+        do_anti_hairline(s, x0, y0, x1, y1, !contained);
     }
 }
 

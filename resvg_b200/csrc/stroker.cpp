@@ -43,8 +43,8 @@ bool set_length(P &p, float x, float y, float length)
     double xx = x, yy = y;
     double dmag = sqrt(xx * xx + yy * yy);
     double dscale = (double)length / dmag;
-    x = (float)(x * dscale);
-    y = (float)(y * dscale);
+    x *= (float)dscale; // tiny-skia-path point.rs set_point_length: `x *= dscale as f32` (Skia's C++ multiplies in double)
+    y *= (float)dscale;
     if (!std::isfinite(x) || !std::isfinite(y) || (x == 0 && y == 0)) {
         p = {0, 0};
         return false;
@@ -242,14 +242,40 @@ int build_unit_arc(P u_start, P u_stop, bool ccw, float radius, P pivot, Conic o
             count++;
         }
     }
-    // rotate by u_start (sin = y, cos = x), flip for ccw, then scale by radius and translate to pivot
-    float sn = u_start.y, cs = u_start.x;
+    // Transform::from_sin_cos(u_start.y, u_start.x), pre_scale(1, -1) for ccw, post_concat(scale(radius) + translate(pivot)),
+    // then map_points: composed with tiny-skia's concat (f64 mul-add for the skewed case) before any point is touched
+    auto mam = [](float a, float b, float c, float d) { return (float)((double)a * (double)b + (double)c * (double)d); };
+    float m_sx = u_start.x, m_ky = u_start.y, m_kx = -u_start.y, m_sy = u_start.x; // rotation (has skew unless u_start.y == 0)
+    if (ccw) {
+        if (m_kx != 0 || m_ky != 0) { // concat(m, scale(1, -1)) through the general branch
+            float sx = mam(m_sx, 1.0f, m_kx, 0.0f), ky = mam(m_ky, 1.0f, m_sy, 0.0f), kx = mam(m_sx, 0.0f, m_kx, -1.0f), sy = mam(m_ky, 0.0f, m_sy, -1.0f);
+            m_sx = sx; m_ky = ky; m_kx = kx; m_sy = sy;
+        } else {
+            m_sy = m_sy * -1.0f;
+        }
+    }
+    float f_sx, f_ky, f_kx, f_sy, f_tx, f_ty;
+    const bool m_identity = m_sx == 1 && m_ky == 0 && m_kx == 0 && m_sy == 1;
+    const bool u_identity = radius == 1 && pivot.x == 0 && pivot.y == 0;
+    if (u_identity) { f_sx = m_sx; f_ky = m_ky; f_kx = m_kx; f_sy = m_sy; f_tx = 0; f_ty = 0; }
+    else if (m_identity) { f_sx = radius; f_ky = 0; f_kx = 0; f_sy = radius; f_tx = pivot.x; f_ty = pivot.y; }
+    else if (m_kx == 0 && m_ky == 0) { f_sx = radius * m_sx; f_ky = 0; f_kx = 0; f_sy = radius * m_sy; f_tx = radius * 0.0f + pivot.x; f_ty = radius * 0.0f + pivot.y; }
+    else {
+        f_sx = mam(radius, m_sx, 0.0f, m_ky); f_ky = mam(0.0f, m_sx, radius, m_ky);
+        f_kx = mam(radius, m_kx, 0.0f, m_sy); f_sy = mam(0.0f, m_kx, radius, m_sy);
+        f_tx = mam(radius, 0.0f, 0.0f, 0.0f) + pivot.x; f_ty = mam(0.0f, 0.0f, radius, 0.0f) + pivot.y;
+    }
+    const bool f_identity = f_sx == 1 && f_ky == 0 && f_kx == 0 && f_sy == 1 && f_tx == 0 && f_ty == 0;
     for (int i = 0; i < count; i++)
         for (int j = 0; j < 3; j++) {
             P p = out[i].p[j];
-            if (ccw) p.y = -p.y;
-            P r = {cs * p.x - sn * p.y, sn * p.x + cs * p.y};
-            out[i].p[j] = {r.x * radius + pivot.x, r.y * radius + pivot.y};
+            if (f_identity) continue;
+            if (f_kx == 0 && f_ky == 0) {
+                if (f_sx == 1 && f_sy == 1) out[i].p[j] = {p.x + f_tx, p.y + f_ty};
+                else out[i].p[j] = {p.x * f_sx + f_tx, p.y * f_sy + f_ty};
+            } else {
+                out[i].p[j] = {p.x * f_sx + p.y * f_kx + f_tx, p.x * f_ky + p.y * f_sy + f_ty};
+            }
         }
     return count;
 }
