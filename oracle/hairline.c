@@ -539,8 +539,9 @@ int32_t orc_path_hairline(const uint8_t *verbs, int32_t n_verbs, const float *po
         clip = &clip_rect;
         /* two scalar rects for culling cubics: hairlines may draw one pixel beyond their control points */
         outset_s.l = -1.0f; outset_s.t = -1.0f; outset_s.r = (float)clip_w + 1.0f; outset_s.b = (float)clip_h + 1.0f;
+        /* tiny-skia: `clip.inset(1, 1)?` — an IntRect cannot be empty, so a clip 2 px wide or high ends the whole stroke */
+        if (clip_w <= 2 || clip_h <= 2) return 0;
         inset_s.l = 1.0f; inset_s.t = 1.0f; inset_s.r = (float)clip_w - 1.0f; inset_s.b = (float)clip_h - 1.0f;
-        if (inset_s.l > inset_s.r || inset_s.t > inset_s.b) { inset_s.l = inset_s.t = inset_s.r = inset_s.b = 0.0f; }
         inset = &inset_s;
         outset = &outset_s;
     }
