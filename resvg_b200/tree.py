@@ -177,7 +177,12 @@ def _image(w, n):
         w.u32(0)
         _tree(w, n["tree"])
     else:
-        px = np.ascontiguousarray(n["pixels"], np.uint8).reshape(n["h"], n["w"], 4)
+        if "pixels_z" in n:  # deflate + base64 (the JSON form of a decoded pixmap)
+            import base64
+            import zlib
+            px = np.frombuffer(zlib.decompress(base64.b64decode(n["pixels_z"])), np.uint8).reshape(n["h"], n["w"], 4)
+        else:
+            px = np.ascontiguousarray(n["pixels"], np.uint8).reshape(n["h"], n["w"], 4)
         w.u32(1, n["w"], n["h"])
         w.raw(px.tobytes())
 

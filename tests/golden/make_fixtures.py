@@ -44,7 +44,7 @@ def main():
         if not os.path.exists(png):
             continue
         try:
-            scene = F.parse(open(svg, encoding="utf-8").read())
+            scene = F.parse(open(svg, encoding="utf-8").read(), os.path.dirname(svg))
             gold = np.array(Image.open(png).convert("RGBA"))
             out = F.render_scene(scene, be, 300)
             n = F.diff_pixels(out, gold)
@@ -84,5 +84,46 @@ def main():
     print("total", tot, "fixtures", sum(kept.values()))
 
 
+EXTRA_DIR = "/root/reference/crates/resvg/tests/extra"
+EXTRA_OUT = os.path.join(ROOT, "tests", "golden", "extra")
+# crates/resvg/tests/integration/extra.rs: (name, mode, argument)
+EXTRA = [("group-with-only-transform", "extra", 1.0), ("subpixel-rect-position", "extra", 1.0), ("transformed-rect", "extra", 1.0),
+         ("hidden-element", "extra", 1.0), ("simple-stroke", "extra", 1.0), ("fill-and-stroke", "extra", 1.0),
+         ("paint-order=stroke", "extra", 1.0), ("stroke-linecap=square", "extra", 1.0), ("miter-join-with-acute-angle", "extra", 1.0),
+         ("horizontal-line", "extra", 1.0), ("horizontal-line-no-stroke", "extra", 1.0), ("filter-region-precision", "extra", 10.0),
+         ("translate-outside-viewbox", "extra", 1.0), ("filter-on-empty-group", "node", "g1"),
+         ("filter-with-transform-on-shape", "node", "g1")]
+
+
+def make_extra():
+    """tests/integration/extra.rs: native-size renders, one at scale 10, two rendered by node id (resvg::render_node)."""
+    from tests.test_golden import render_extra_oracle
+    os.makedirs(EXTRA_OUT, exist_ok=True)
+    for f in glob.glob(os.path.join(EXTRA_OUT, "*")):
+        os.remove(f)
+    ok = 0
+    for name, mode, arg in EXTRA:
+        svg, png = os.path.join(EXTRA_DIR, name + ".svg"), os.path.join(EXTRA_DIR, name + ".png")
+        try:
+            scene = F.parse(open(svg, encoding="utf-8").read(), os.path.dirname(svg))
+        except F.Unsupported as e:
+            print("extra: not expressible", name, e)
+            continue
+        gold = np.array(Image.open(png).convert("RGBA"))
+        out = render_extra_oracle(scene, mode, arg)
+        n = F.diff_pixels(out, gold) if out is not None else -1
+        print(f"extra/{name}: {'pass' if n == 0 else f'FAIL ({n})'}")
+        if n == 0:
+            ok += 1
+            with open(os.path.join(EXTRA_OUT, name + ".json"), "w") as fjson:
+                json.dump({"mode": mode, "arg": arg, "scene": scene}, fjson, separators=(",", ":"))
+            shutil.copyfile(png, os.path.join(EXTRA_OUT, name + ".png"))
+    print("extra fixtures", ok, "of", len(EXTRA))
+
+
 if __name__ == "__main__":
-    main()
+    if "extra" in sys.argv[1:]:
+        make_extra()
+    else:
+        main()
+        make_extra()

@@ -33,7 +33,7 @@ def run(patterns, verbose=False):
         if not os.path.exists(png):
             continue
         try:
-            scene = F.parse(open(svg, encoding="utf-8").read())
+            scene = F.parse(open(svg, encoding="utf-8").read(), os.path.dirname(svg))
             gold = np.array(Image.open(png).convert("RGBA"))
             out = F.render_scene(scene, be, 300)
             n = F.diff_pixels(out, gold)

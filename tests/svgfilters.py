@@ -124,6 +124,7 @@ def convert_filter(conv, el, bbox):
                 break
         cs = d.attr(ch, "color-interpolation-filters", inherit=True) or "linearRGB"
         cs = "sRGB" if cs == "sRGB" else "linearRGB"
+        conv._fe_subregion = sub
         k = _convert_kind(conv, ch, tag, scale, resolve_input)
         if k is None:
             continue
@@ -194,7 +195,7 @@ def _convert_kind(conv, ch, tag, scale, resolve_input):
     if tag == "feTile":
         return {"kind": "tile", "in": resolve_input(ch, "in")}
     if tag == "feImage":
-        raise Unsupported("feImage")
+        return _convert_fe_image(conv, ch)
     if tag == "feComponentTransfer":
         funcs = {k: {"kind": "identity"} for k in "rgba"}
         for c in ch:
@@ -344,6 +345,31 @@ def _convert_kind(conv, ch, tag, scale, resolve_input):
         return {"kind": "specular", "in": resolve_input(ch, "in"), "surface_scale": fget("surfaceScale", 1.0),
                 "constant": fget("specularConstant", 1.0), "exponent": se, "color": color, "light": light}
     return None
+
+
+def _convert_fe_image(conv, ch):
+    """usvg parser/filter.rs:809-880: a link to an element becomes that element's subtree; anything else is loaded as an
+    image placed in the primitive subregion moved to the origin."""
+    dummy = {"kind": "flood", "color": [0, 0, 0], "opacity": 0.0}
+    href = ch.attrib.get("href")
+    if href is None:
+        return dict(dummy)
+    target = conv.doc.link(href) if href.startswith("#") else None
+    if href.startswith("#"):
+        if target is None:
+            return dict(dummy)
+        n = conv.node_for(target)
+        if n is None:
+            return dict(dummy)
+        if n["t"] == "g" and n["children"]:
+            n["id"] = n["children"][0].get("id", "")
+            n["children"][0]["id"] = ""
+        return {"kind": "image", "root": {"t": "g", "id": "", "ts": list(IDENT), "children": [n], "opacity": 1.0, "isolate": False}}
+    sub = conv._fe_subregion
+    g = conv.image_for(ch, rect_override=(0.0, 0.0, sub[2], sub[3]))
+    if g is None:
+        return dict(dummy)
+    return {"kind": "image", "root": {"t": "g", "id": "", "ts": list(IDENT), "children": [g], "opacity": 1.0, "isolate": False}}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -555,6 +581,15 @@ def _apply_primitive(rd, p, k, cs, ts, region, subregion, get_input, source):
                 "ts": (1.0, 0.0, 0.0, 1.0, float(sub[0]), float(sub[1]))}
         pts = [(0, 0), (rw, 0), (rw, rh), (0, rh)]
         be.fill_path(out, [M, L, L, L, Z], pts, spec, "nonzero", IDENT, "source_over", False)
+        return _Img(out, _full(be, out), "sRGB")
+    if k == "image":
+        # apply_image, mod.rs:870-897: the subtree rendered at the subregion's origin with the transform's scale only
+        out = be.new_layer(rw, rh)
+        sx, sy = ts_get_scale(ts)
+        saved = rd.max_bbox
+        rd.max_bbox = (0, 0, rw, rh)
+        rd.render_nodes(p["root"], (sx, 0.0, 0.0, sy, float(subregion[0]), float(subregion[1])), out)
+        rd.max_bbox = saved
         return _Img(out, _full(be, out), "sRGB")
     if k in ("component_transfer", "color_matrix"):
         img = _into_cs(be, get_input(p["in"]), cs)

@@ -147,7 +147,7 @@ INHERITED = {"fill", "fill-rule", "fill-opacity", "stroke", "stroke-width", "str
              "stroke-miterlimit", "stroke-dasharray", "stroke-dashoffset", "stroke-opacity", "clip-rule",
              "shape-rendering", "visibility", "paint-order", "color", "color-interpolation-filters", "marker-start",
              "marker-mid", "marker-end", "font-size"}
-UNSUPPORTED_ELEMS = {"text", "image", "feImage", "marker", "switch", "style", "a", "tspan", "textPath", "symbol",
+UNSUPPORTED_ELEMS = {"text", "marker", "switch", "style", "a", "tspan", "textPath", "symbol",
                      "foreignObject", "script", "animate", "set", "animateTransform", "filter-unsupported"}
 
 
@@ -530,7 +530,8 @@ def _strip(tag):
 
 
 class Doc:
-    def __init__(self, text):
+    def __init__(self, text, base_dir=None):
+        self.base_dir = base_dir
         self.root = ET.fromstring(text)
         self.ids = {}
         self.parent = {}
@@ -620,6 +621,7 @@ class Converter:
         self.vb_w = self.vb_h = 100.0
         self.depth = 0
         self.pattern_depth = 0
+        self.nested = False
 
     # ---- root ----
     def convert(self):
@@ -740,6 +742,8 @@ class Converter:
             return self.use_for(el)
         if tag in ("path", "rect", "circle", "ellipse", "line", "polyline", "polygon"):
             return self.shape_for(el)
+        if tag == "image":
+            return self.image_for(el)
         if tag.startswith("fe"):
             return None
         raise Unsupported(f"element {tag}")
@@ -891,6 +895,146 @@ class Converter:
         if ts_is_identity(ts) and not g["isolate"]:
             return node
         return g
+
+    # ---- images (usvg parser/image.rs) ----
+    QUALITY = {"optimizeQuality": "bicubic", "auto": "bicubic", "optimizeSpeed": "nearest", "smooth": "bilinear",
+               "high-quality": "bicubic", "crisp-edges": "nearest", "pixelated": "nearest"}
+
+    def load_image(self, href):
+        """get_href_data + decode (resvg image.rs:62-170): -> ("svg", scene) | ("raster", w, h, premultiplied RGBA8) | None"""
+        import base64
+        import gzip
+        import io
+        import os
+        from urllib.parse import unquote_to_bytes
+        if href is None:
+            return None
+        href = href.strip()
+        mime = None
+        if href.startswith("data:"):
+            head, _, payload = href[5:].partition(",")
+            mime = head.split(";")[0].strip().lower()
+            try:
+                data = base64.b64decode("".join(payload.split())) if ";base64" in head else unquote_to_bytes(payload)
+            except Exception:
+                return None
+        else:
+            if self.doc.base_dir is None:
+                raise Unsupported("external image without a resources dir")
+            path = os.path.join(self.doc.base_dir, href)
+            if not os.path.exists(path):
+                return None
+            data = open(path, "rb").read()
+        if data[:2] == b"\x1f\x8b":
+            try:
+                data = gzip.decompress(data)
+            except Exception:
+                return None
+        is_raster = data[:8] == b"\x89PNG\r\n\x1a\n" or data[:3] == b"\xff\xd8\xff" or data[:4] == b"GIF8" or (data[:4] == b"RIFF" and data[8:12] == b"WEBP")
+        if not is_raster:
+            if self.nested:
+                return None  # Tree::from_data_nested: images inside a sub-SVG image are not loaded
+            try:
+                text = data.decode("utf-8")
+                if "<svg" not in text:
+                    return None
+                return ("svg", parse(text, self.doc.base_dir, nested=True))
+            except Unsupported:
+                raise
+            except Exception:
+                return None
+        from PIL import Image as PILImage
+        try:
+            im = PILImage.open(io.BytesIO(data))
+            im.seek(0)
+            rgba = np.array(im.convert("RGBA"), dtype=np.uint8)
+        except Exception:
+            return None
+        a = rgba[..., 3:4].astype(np.float64) / 255.0
+        px = rgba.copy()
+        px[..., :3] = (rgba[..., :3].astype(np.float64) * a + 0.5).astype(np.uint8)  # rgba_to_pixmap, image.rs:160-170
+        return ("raster", int(rgba.shape[1]), int(rgba.shape[0]), px)
+
+    def image_for(self, el, rect_override=None):
+        d = self.doc
+        if d.attr(el, "display", inherit=False) == "none":
+            return None
+        vis = (d.attr(el, "visibility") or "visible") == "visible"
+        quality = self.QUALITY.get(d.attr(el, "image-rendering") or "optimizeQuality", "bicubic")
+        kind = self.load_image(el.attrib.get("href"))
+        if kind is None:
+            return None
+        if kind[0] == "svg":
+            aw, ah = f32(kind[1]["width"]), f32(kind[1]["height"])
+        else:
+            aw, ah = f32(kind[1]), f32(kind[2])
+        if rect_override is not None:
+            x, y, w, h = [f32(v) for v in rect_override]
+        else:
+            x = f32(parse_length(el.attrib.get("x"), 0.0, ref=self.vb_w))
+            y = f32(parse_length(el.attrib.get("y"), 0.0, ref=self.vb_h))
+            wa, ha = el.attrib.get("width"), el.attrib.get("height")
+            w = f32(parse_length(wa, float(aw), ref=self.vb_w))
+            h = f32(parse_length(ha, float(ah), ref=self.vb_h))
+            if wa is not None and ha is None:
+                h = ah * (w / aw)
+            elif wa is None and ha is not None:
+                w = aw * (h / ah)
+        if not (w > 0 and h > 0):
+            return None
+        par = (el.attrib.get("preserveAspectRatio") or "xMidYMid meet").split()
+        if par and par[0] == "defer":
+            par = par[1:]
+        align = par[0] if par else "xMidYMid"
+        slice_ = len(par) > 1 and par[1] == "slice"
+        # fit_view_box + aligned_pos
+        if align == "none":
+            vw, vh = w, h
+        else:
+            rw = h * aw / ah
+            with_h = (rw <= w) if slice_ else (rw >= w)
+            if not with_h:
+                vw, vh = rw, h
+            else:
+                vw, vh = w, w * ah / aw
+        ax = {"xMin": 0.0, "xMid": 0.5, "xMax": 1.0}.get(align[:4], 0.5) if align != "none" else 0.0
+        ay = {"YMin": 0.0, "YMid": 0.5, "YMax": 1.0}.get(align[4:], 0.5) if align != "none" else 0.0
+        dx, dy = w - vw, h - vh
+        vx = x + (dx / f32(2) if ax == 0.5 else (dx if ax == 1.0 else f32(0)))
+        vy = y + (dy / f32(2) if ay == 0.5 else (dy if ay == 1.0 else f32(0)))
+        image_ts = (_f(vw / aw), 0.0, 0.0, _f(vh / ah), _f(vx), _f(vy))
+        node = {"t": "image", "id": "", "visible": vis, "quality": quality, "bbox": [0.0, 0.0, float(aw), float(ah)]}
+        if kind[0] == "svg":
+            node.update(kind="svg", tree=kind[1])
+        else:
+            import base64
+            import zlib
+            # JSON-friendly: the decoded premultiplied RGBA8 pixmap, deflated and base64-encoded
+            node.update(kind="raster", w=kind[1], h=kind[2], pixels_z=base64.b64encode(zlib.compress(kind[3].tobytes(), 9)).decode())
+        g = {"t": "g", "id": el.attrib.get("id", "") if rect_override is None else "", "ts": list(image_ts), "children": [node],
+             "opacity": 1.0, "blend": "normal", "clip": None, "mask": None, "filters": [], "isolate_attr": False, "isolate": False}
+        if slice_:
+            # an image slice acts like a rectangular clip, unaffected by the image's own view box transform
+            rp = [(float(x), float(y)), (float(x + w), float(y)), (float(x + w), float(y + h)), (float(x), float(y + h))]
+            cp = {"t": "path", "id": "", "verbs": [M, L, L, L, Z], "pts": [list(q) for q in rp], "visible": True, "aa": True,
+                  "stroke_first": False, "bbox": [float(x), float(y), float(w), float(h)], "stroke": None,
+                  "fill": {"paint": {"kind": "color", "rgb": [0, 0, 0]}, "opacity": 1.0, "rule": "nonzero"}}
+            g2 = {"t": "g", "id": g["id"], "ts": list(IDENT), "children": [g], "opacity": 1.0, "blend": "normal",
+                  "clip": {"ts": list(IDENT), "children": [cp], "clip": None}, "mask": None, "filters": [], "isolate_attr": False,
+                  "isolate": True}
+            g["id"] = ""
+            g = g2
+        if rect_override is not None:
+            return g
+        # the <image> element itself goes through convert_group (opacity, clip-path, mask, filter, transform)
+        ts = self.resolve_transform(el, el.attrib.get("transform"))
+        outer = {"t": "g", "id": "", "ts": list(ts), "children": [g]}
+        self.group_effects(el, outer)
+        if not outer["children"]:
+            return None
+        if ts_is_identity(ts) and not outer["isolate"]:
+            return g
+        return outer
 
     def paint_for(self, el, prop, default, color, bbox):
         """usvg style.rs resolve_fill / resolve_stroke + convert_paint: -> {"paint": usvg::Paint, "opacity": Opacity}.
@@ -1098,14 +1242,14 @@ class Converter:
         """usvg Group::calculate_object_bbox (tree/mod.rs:1850-1864): the union of the children's object bounding boxes
         in the group's OWN coordinate system — child groups contribute their bbox mapped by their transform, the
         group's own transform is not applied."""
-        if n["t"] == "path":
-            return n.get("bbox")
+        if n["t"] in ("path", "image"):
+            return tuple(n["bbox"]) if n.get("bbox") else None
         boxes = []
         for c in n["children"]:
             b = self.node_bbox(c)
             if b is None:
                 continue
-            if c["t"] != "path" and not ts_is_identity(tuple(c["ts"])):
+            if c["t"] == "g" and not ts_is_identity(tuple(c["ts"])):
                 b = rect_transform(b, tuple(c["ts"]))
             boxes.append(b)
         if not boxes:
@@ -1240,8 +1384,11 @@ class Converter:
         return {"rect": list(rect), "kind": kind, "mask": nested, "root": root}
 
 
-def parse(svg_text):
-    return finalize_scene(Converter(Doc(svg_text)).convert())
+def parse(svg_text, base_dir=None, nested=False):
+    """`base_dir`: where relative image hrefs are resolved (usvg Options::resources_dir)."""
+    conv = Converter(Doc(svg_text, base_dir))
+    conv.nested = nested
+    return finalize_scene(conv.convert())
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -1471,8 +1618,8 @@ class Renderer:
         if paint is None:
             return
         # painter.rs stroke_path: res_scale = compute_resolution_scale(ts); thin strokes take the hairline path
-        sx = math.hypot(ts[0], ts[2])
-        sy = math.hypot(ts[1], ts[3])
+        sx = float(np.sqrt(f32(ts[0]) * f32(ts[0]) + f32(ts[2]) * f32(ts[2])))  # Point::length in f32
+        sy = float(np.sqrt(f32(ts[1]) * f32(ts[1]) + f32(ts[3]) * f32(ts[3])))
         res_scale = max(sx, sy) if (math.isfinite(sx) and math.isfinite(sy) and max(sx, sy) > 0) else 1.0
         src_verbs, src_pts = n["verbs"], n["pts"]
         if s.get("dash"):
@@ -1481,14 +1628,17 @@ class Renderer:
                 return  # StrokeDash::new accepted the list (the front end filtered the others) but nothing is left
             src_verbs, src_pts = dashed
         if n.get("aa", True):
-            w = s["width"]
-            v0 = (abs(ts[0] * w), abs(ts[1] * w))
-            v1 = (abs(ts[2] * w), abs(ts[3] * w))
+            # painter.rs treat_as_hairline, in f32: map (w, 0) and (0, w) by the transform without its translation
+            (p0x, p0y), (p1x, p1y) = ts_map((ts[0], ts[1], ts[2], ts[3], 0.0, 0.0), s["width"], 0.0), \
+                ts_map((ts[0], ts[1], ts[2], ts[3], 0.0, 0.0), 0.0, s["width"])
 
-            def fast_len(v):
-                return max(v) + min(v) / 2.0
+            def fast_len(x, y):
+                x, y = abs(f32(x)), abs(f32(y))
+                if x < y:
+                    x, y = y, x
+                return f32(x + y * f32(0.5))
 
-            if fast_len(v0) <= 1.0 and fast_len(v1) <= 1.0:
+            if fast_len(p0x, p0y) <= 1.0 and fast_len(p1x, p1y) <= 1.0:
                 self.be.stroke_hairline(layer, src_verbs, src_pts, paint, ts, blend, s["width"], s["cap"])
                 return
         out = geom.stroke_outline(src_verbs, src_pts, s["width"], s["miter"], s["cap"], s["join"], res_scale)
@@ -1590,12 +1740,21 @@ class Renderer:
             self.be.draw_layer(layer, sub, 0, 0, 1.0, "source_over")
             return
         # render_raster, image.rs:173-206: a Pad pattern of the decoded pixmap filled into its own rectangle
-        px = np.asarray(n["pixels"], np.uint8).reshape(n["h"], n["w"], 4)
+        px = image_pixels(n)
         raster = self.be.new_layer(n["w"], n["h"])
         self.be.upload(raster, px)
         spec = {"kind": "pattern", "layer": raster, "spread": "pad", "quality": n.get("quality", "bicubic"), "opacity": 1.0,
                 "ts": IDENT}
         self.be.fill_rect(layer, 0.0, 0.0, float(n["w"]), float(n["h"]), spec, ts)
+
+
+def image_pixels(n):
+    """The decoded pixmap of a raster image node: premultiplied RGBA8 (h, w, 4)."""
+    if "pixels_z" in n:
+        import base64
+        import zlib
+        return np.frombuffer(zlib.decompress(base64.b64decode(n["pixels_z"])), np.uint8).reshape(n["h"], n["w"], 4)
+    return np.asarray(n["pixels"], np.uint8).reshape(n["h"], n["w"], 4)
 
 
 def find_node(group, node_id):
