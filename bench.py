@@ -13,7 +13,12 @@ cuts ONE scene into N canvas strips instead (strong scaling; the strips are bit-
 
 The other configurations print the same JSON line: `icons` (configs[4]: 100 000 documents of 256x256 rendered into
 atlases, sharded by atlas chunk), `filters8k` (configs[2]: the 10-primitive filter chain over an 8192x8192 layer) and
-`stack4k` (configs[3]: 64 nested groups with masks / clip-paths / patterns, traversal by the Python front end).
+`stack4k` (configs[3]: 64 nested groups with masks / clip-paths / patterns: one rb_render call per document, traversal in
+C++ inside the library).  The default run (`paths8k`, N = 1) also carries them as sub-records under `configs`, and a
+`parity` block per record: the GPU result against the CPU checker's on the sample the cpu_baseline leg renders anyway.
+
+Nothing under tests/ or oracle/ is imported outside the cpu_baseline / parity legs and `--impl reference`; the reference
+arm imports nothing of resvg_b200 (its only native library is oracle/liboracle.so).
 
 Printed JSON keys follow the driver's contract; see DESIGN.md §Measurement for how each number is obtained.
 """
@@ -106,12 +111,22 @@ def oracle_lib():
     return R
 
 
+def parity_record(got, want, what):
+    """GPU result against the CPU checker's on the same input: the largest channel difference and how many pixels differ."""
+    d = np.abs(np.asarray(got).astype(np.int16) - np.asarray(want).astype(np.int16))
+    per_px = d.reshape(-1, 4).max(axis=1)
+    return {"max_abs": int(d.max()) if d.size else 0, "differing_px": int((per_px > 0).sum()), "px_over_1": int((per_px > 1).sum()),
+            "compared_px": int(per_px.size), "what": what}
+
+
 def prepare_sample(R, scene, n_sample):
     """Host geometry of the first n_sample draws for the CPU arm: dash / stroke / hairline-walk every stroke draw with the
-    same host code both arms use, and pack the outlines for the oracle's bulk fill.  Returns the prepared arrays and
-    t_geom, the seconds spent INSIDE the C geometry calls (the Python loop around them is not CPU-renderer work)."""
-    import resvg_b200 as rb
-    from resvg_b200 import scenes
+    ORACLE's own stroker, dasher and hairline walker (oracle/stroke.c, dash.c, hairline.c through tests/geom.py — nothing of
+    libresvg_b200.so), and pack the outlines for the oracle's bulk fill.  Returns the prepared arrays and t_geom, the seconds
+    spent INSIDE the C geometry calls (the Python loop around them is not CPU-renderer work)."""
+    from tests import geom as rb          # oracle geometry under the names used below
+    from tests import scenes_loader
+    scenes = scenes_loader.load()
     sub = scenes.subset(scene, n_sample)
     n = sub["n_paths"]
     w, h = scene["width"], scene["height"]
@@ -145,8 +160,8 @@ def prepare_sample(R, scene, n_sample):
                     hair[i] = (np.concatenate(parts) if parts else np.zeros((0, 3), np.int32),
                                np.float32((255 * scale) >> 8) / np.float32(255.0) if sw[i] != 1.0 else np.float32(1.0))
                 elif src is not None:
-                    out = rb.stroke_path(src[0], src[1], float(sw[i]), float(sub["stroke_miter"][i]),
-                                         caps[sub["stroke_cap"][i]], joins[sub["stroke_join"][i]], 1.0)
+                    out = rb.stroke_outline(src[0], src[1], float(sw[i]), float(sub["stroke_miter"][i]),
+                                            caps[sub["stroke_cap"][i]], joins[sub["stroke_join"][i]], 1.0)
                 t_geom += time.perf_counter() - t0
                 if out is None:
                     v, p = v[:0], p[:0]
@@ -397,11 +412,20 @@ def run_icons(args, rank, local_rank, world, torch, dist):
         n_s = max(16, min(n_docs, int(args.cpu_sample) // 8))
         sc = scs[0] if scs[0]["n_docs"] >= n_s else scs[0]
         n_s = min(n_s, sc["n_docs"])
-        _, dt = icons_ref.render_docs(sc, icons_ref.prepare(sc), range(n_s))
+        ref_docs, dt = icons_ref.render_docs(sc, icons_ref.prepare(sc), range(n_s))
         out["cpu_baseline"] = {"value": n_s * 0.065536 / dt, "unit": "Mpx/s", "cores": 1, "kind": "port",
                                "sample": f"documents 0..{n_s - 1} of the same batch, one at a time, {dt:.2f} s; oracle restatement of "
                                          "the resvg/tiny-skia CPU path"}
-    print(json.dumps(out))
+        # parity: the same documents out of the GPU atlas of chunk 0, cell by cell, against the checker's pixmaps
+        a = atl[0]
+        ch = a.render(scs[0], n_threads)
+        got = a.atlas.download()
+        a.release(ch)
+        n_p = min(n_s, 128)
+        out["parity"] = parity_record(np.stack([got[(k // a.cols) * 256:(k // a.cols) * 256 + 256, (k % a.cols) * 256:(k % a.cols) * 256 + 256]
+                                                for k in range(n_p)]), ref_docs[:n_p],
+                                      f"documents 0..{n_p - 1}: GPU atlas cells vs the CPU checker's per-document pixmaps")
+    return out
 
 
 def run_filters8k(args, rank, local_rank, world, torch, dist):
@@ -424,7 +448,7 @@ def run_filters8k(args, rank, local_rank, world, torch, dist):
     light = rb.make_light("distant", azimuth=45.0, elevation=60.0)
     sharpen = [0, -1, 0, -1, 5, -1, 0, -1, 0]
 
-    def chain():
+    def chain():  # reads a, t, c at call time: the parity leg re-points them at crop-sized layers
         F.into_linear_rgb(a)
         F.box_blur(8.0, 8.0, a)
         F.morphology("dilate", 3.0, 3.0, a)
@@ -521,25 +545,33 @@ def run_filters8k(args, rank, local_rank, world, torch, dist):
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": n * n / 1e6 / dt, "unit": "Mpx/s", "cores": 1, "kind": "port",
                                "sample": f"the same chain on the top-left {n}x{n} px of the source layer, {dt:.2f} s; oracle restatement"}
-    print(json.dumps(out))
+        # parity: the GPU chain over the same crop (a layer of its own) against the checker's result
+        a, t, c = ctx.layer_from(img), ctx.layer(n, n), ctx.layer(n, n)
+        chain()
+        out["parity"] = parity_record(a.download(), x, f"the chain over the top-left {n}x{n} crop of the source layer, GPU vs CPU checker")
+    return out
+
+
+def stack_tree_stream(name):
+    """The usvg tree of a stack document as the RBT1 stream the Rust shim would write (tools/make_stack_trees.py)."""
+    with open(os.path.join(ROOT, "resvg_b200", "data", name), "rb") as f:
+        return f.read()
 
 
 def run_stack4k(args, rank, local_rank, world, torch, dist):
-    """Workload `stack4k` (BASELINE configs[3]).  The document is SVG text (scenes.stack_svg); parsing it and
-    walking the tree (groups -> layers, clip-paths, masks, patterns: render.rs / clip.rs / mask.rs / path.rs) is HOST work that
-    stays in Rust in resvg; here the test-side Python front end (tests/svgfront.py) plays that role and drives the C ABI
-    call by call.  value: CUDA-event time from the first to the last launch of one traversal (it includes the gaps the
-    Python traversal leaves between launches); e2e: wall clock of traversal + download of the canvas."""
+    """Workload `stack4k` (BASELINE configs[3]): 64 nested groups with opacity, luminance masks, clip-paths
+    (every 8th nested) and pattern fills on a 4096x4096 canvas.  The document reaches the library as a usvg tree stream
+    (parsing SVG is usvg's job and stays on the host; the streams are committed, see stack_tree_stream) and ONE rb_render
+    call draws it: traversal (render.rs / clip.rs / mask.rs / path.rs), layers and every pixel inside libresvg_b200.so.
+    value: CUDA-event time of rb_render, tree resident; e2e: rb_submit from the host stream (parse + render) + download."""
     import resvg_b200 as rb
-    from resvg_b200 import scenes, shard
-    from tests import svgfront as F          # host front end stand-in (no pixel work)
-    from tests.backends import GpuBackend    # thin adapter: back-end interface -> C ABI calls
+    from resvg_b200 import shard
     W, H, levels, seed = WORKLOADS["stack4k"]
     ctx = rb.Context(local_rank)
-    tree = F.parse(scenes.stack_svg(W, levels, shard.scene_seed(seed, rank)))
-    be = GpuBackend(ctx)
-    renderer = F.Renderer(be)
+    blob = stack_tree_stream(f"stack4k_r{rank % 8}.rbt")
+    tree = rb.tree.Tree(blob)
     ident = (1.0, 0.0, 0.0, 1.0, 0.0, 0.0)
+    target = ctx.layer(W, H)
 
     def barrier():
         ctx.synchronize()
@@ -549,16 +581,17 @@ def run_stack4k(args, rank, local_rank, world, torch, dist):
         ctx.synchronize()
 
     def step():
-        return renderer.render(tree, W, H, ident)
+        target.fill(0, 0, 0, 0)
+        rb.tree.render(tree, ident, target)
 
     for _ in range(max(args.warmup, 3)):
-        step().close()
+        step()
     barrier()
     launches0 = ctx.launch_count
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ctx.timer_begin()
     for _ in range(args.steps):
-        step().close()
+        step()
     ms_step = ctx.timer_end() / args.steps
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -571,14 +604,15 @@ def run_stack4k(args, rank, local_rank, world, torch, dist):
     for _ in range(10):
         rb.draw_layer(a, b2, 0, 0, 0.9, "source_over")
     ms_comp = ctx.timer_end() / 10
+    a.close(); b2.close()
 
     pinned = rb.PinnedBuffer(W * H * 4)
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
 
     def e2e_step():
-        l = step()
-        l.download_ptr(pinned.array.ctypes.data)
-        l.close()
+        target.fill(0, 0, 0, 0)
+        rb.tree.submit(blob, ident, target)          # host stream -> parse -> traversal -> kernels
+        target.download_ptr(pinned.array.ctypes.data)
 
     e2e_step()
     barrier()
@@ -591,7 +625,7 @@ def run_stack4k(args, rank, local_rank, world, torch, dist):
     h2d = (ctx.h2d_bytes - h2d0) // e2e_steps
     ms_step, ms_comp, e2e_s = shard.max_over_ranks([ms_step, ms_comp, e2e_s], world, f"cuda:{local_rank}")
     if rank != 0:
-        return
+        return None
     mpx = W * H / 1e6
     peak, peak_src = measured_peaks()
     comp_bytes = 12 * W * H
@@ -602,36 +636,40 @@ def run_stack4k(args, rank, local_rank, world, torch, dist):
         "config": {"workload": "stack4k", "canvas": [W, H], "levels": levels,
                    "recipe": "level k: opacity U[0.85,0.99]; k%4=0 luminance mask (gradient rect), 1 clip-path (circle, every 8th nested), "
                              "2 pattern-filled rect (tile 32-128 px), 3 plain; 10 C2-style shapes per level in a box inset 16 px per level",
-                   "host": "SVG parsing + tree traversal by the test-side Python front end (stand-in for usvg + render.rs), one C-ABI call per "
-                           "tiny-skia call; the device time includes the gaps it leaves",
-                   "l2": "64 MiB layers; every level allocates, composites and masks full layers (> 126 MB L2 across a level)",
+                   "host": "the usvg tree arrives as an RBT1 stream (%d bytes); ONE rb_render call per document, traversal in C++ inside the library" % len(blob),
+                   "l2": "layers of up to 64 MiB; every level allocates, composites and masks its layer (> 126 MB L2 across a level)",
                    "sharding": "one document per GPU, no collective"},
         "gpu_launches": launches, "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_draw_layer (layer composite, the traversal's most frequent full-layer pass)",
                      "achieved": comp_bytes / (ms_comp * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": comp_bytes / (ms_comp * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes": comp_bytes, "kernel_ms": ms_comp, "model": "12 B/px: source read, destination read + write"},
-        "e2e": {"value": shard.aggregate_throughput(mpx, world, e2e_s), "unit": "Mpx/s", "h2d_bytes_per_step": int(h2d),
+        "e2e": {"value": shard.aggregate_throughput(mpx, world, e2e_s), "unit": "Mpx/s", "h2d_bytes_per_step": int(h2d) + len(blob),
                 "d2h_bytes_per_step": W * H * 4, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
     }
     if world == 1 and not args.no_cpu_baseline:
-        from tests.backends import OracleBackend  # the CPU checker: cpu_baseline only
+        from tests import svgfront as F               # the CPU checker's traversal: cpu_baseline / parity only
+        from tests.backends import OracleBackend
+        from tests import scenes_loader
         n = 1024
-        small = F.parse(scenes.stack_svg(n, levels, seed))
+        small = F.parse(scenes_loader.load().stack_svg(n, levels, seed))
         t0 = time.perf_counter()
-        F.Renderer(OracleBackend()).render(small, n, n, ident)
+        ref = F.render_scene(small, OracleBackend(), n)
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": n * n / 1e6 / dt, "unit": "Mpx/s", "cores": 1, "kind": "port",
-                               "sample": f"the same recipe at {n}x{n} (1/16 of the pixels, same 64 levels) through the same front end, {dt:.2f} s; "
+                               "sample": f"the same recipe at {n}x{n} (1/16 of the pixels, same 64 levels) through the checker's traversal, {dt:.2f} s; "
                                          "oracle restatement of the resvg/tiny-skia CPU path"}
-    print(json.dumps(out))
+        small_l = ctx.layer(n, n)
+        rb.tree.submit(stack_tree_stream("stack1k.rbt"), ident, small_l)
+        out["parity"] = parity_record(small_l.download(), ref, f"the same {n}x{n} document: rb_submit vs the CPU checker (f32 composites: <= 1)")
+    return out
 
 
 def run_reference_icons(args, cores):
     """--impl reference --workload icons: the CPU checker renders documents one at a time on every host core (one document
     stream per thread, as `resvg` would be run per file)."""
-    from resvg_b200 import scenes
     from tests import icons_ref
+    scenes = icons_ref.scenes
     n_docs = int(args.docs) if args.docs else WORKLOADS["icons"][2]
     per = max(8, min(256, int(args.cpu_sample) // (8 * cores)))
     sc = scenes.icons_docs(0, per * cores)
@@ -646,27 +684,30 @@ def run_reference_icons(args, cores):
             t.join()
         return time.perf_counter() - t0
 
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(args.warmup):
         step()
-    times = [step() for _ in range(max(1, min(args.steps, 3)))]
+    times = [step() for _ in range(args.steps)]
     dt = statistics.mean(times)
     v = per * cores * 0.065536 / dt
     sample = f"{cores} threads x {per} documents (documents 0..{per * cores - 1} of the batch) per step, one document at a time"
-    print(json.dumps({
+    return {
         "impl": "reference", "metric": "Mpixels/s rendered", "value": v, "unit": "Mpx/s", "n_gpus": args.gpus,
-        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "u8/u16 fixed point + f32", "data": "synthetic",
         "config": {"workload": "icons", "documents": n_docs, "document_px": [256, 256]},
         "cpu_baseline": {"value": v, "unit": "Mpx/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path (oracle restatement; Rust cannot be built here) on all host cores."""
+    """--impl reference: the reference's CPU path on all host cores.  The Rust reference cannot be built here, so this is the
+    oracle restatement ("port") — pixels by oracle/raster.c + filters.c, stroking / dashing / hairlines by oracle/stroke.c,
+    dash.c, hairline.c.  Nothing of the product is imported: the only native library this arm loads is oracle/liboracle.so."""
     if rank != 0:
-        return
-    from resvg_b200 import scenes
+        return None
+    from tests import scenes_loader
+    scenes = scenes_loader.load()
     cores = min(os.cpu_count() or 1, 32)
     if args.workload == "icons":
         return run_reference_icons(args, cores)
@@ -676,7 +717,9 @@ def run_reference(args, rank, world):
     W, H, n_paths, seed = WORKLOADS[args.workload]
     scs = [scenes.paths_scene(W, H, n_paths, seed + t) for t in range(min(cores, 4))]
     n_draws = scs[0]["n_paths"]
-    n_sample = max(200, min(n_draws, int(args.cpu_sample)))
+    # sized so that warmup + steps fit a few minutes: every thread renders the first n_sample draws on a full canvas
+    budget = max(1, args.steps + args.warmup)
+    n_sample = max(200, min(n_draws, int(args.cpu_sample), int(args.cpu_sample) * 13 // budget))
     canvases = [np.zeros((H, W, 4), np.uint8) for _ in range(cores)]
     # Host geometry (dash / stroke / hairline walk) is prepared once, outside the timed region, because the Python loop
     # around those C calls would serialise the threads on the GIL; the seconds spent INSIDE the C calls are added to
@@ -695,22 +738,22 @@ def run_reference(args, rank, world):
             t.join()
         return time.perf_counter() - t0 + t_geom
 
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(args.warmup):
         step()
-    times = [step() for _ in range(max(1, min(args.steps, 3)))]
+    times = [step() for _ in range(args.steps)]
     dt = statistics.mean(times)
     mpx = cores * (W * H / 1e6) * (n_sample / n_draws)
     v = mpx / dt
     sample = (f"{cores} threads x first {n_sample} of {n_draws} draws of the {W}x{H} scene per step (full canvas); value scaled by "
-              f"{n_sample}/{n_draws}; step = threaded oracle pixel work (wall) + {t_geom:.2f} s of host stroking/dashing per thread")
-    print(json.dumps({
+              f"{n_sample}/{n_draws}; step = threaded oracle pixel work (wall) + {t_geom:.2f} s of oracle stroking/dashing/hairline walking per thread")
+    return {
         "impl": "reference", "metric": "Mpixels/s rendered", "value": v, "unit": "Mpx/s", "n_gpus": args.gpus,
-        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16 fixed point + f32", "data": "synthetic",
-        "config": {"workload": args.workload, "canvas": [W, H], "paths": n_paths},
+        "config": {"workload": args.workload, "canvas": [W, H], "paths": n_paths, "draw_calls": int(n_draws)},
         "cpu_baseline": {"value": v, "unit": "Mpx/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }
 
 
 def main():
@@ -727,6 +770,8 @@ def main():
     ap.add_argument("--shard", default="documents", choices=["documents", "strips"],
                     help="paths8k at N > 1: one scene per GPU (weak scaling, default) or ONE scene cut into N canvas strips (strong)")
     ap.add_argument("--docs", type=int, default=0, help="icons: number of documents (default: the 100 000 of the recipe)")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="paths8k: skip the sub-records of the other BASELINE configurations (icons, filters8k, stack4k)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -734,7 +779,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        out = run_reference(args, rank, world)
+        if out is not None:
+            print(json.dumps(out))
         return
 
     import torch
@@ -748,7 +795,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     if args.workload in ("icons", "filters8k", "stack4k"):
-        {"icons": run_icons, "filters8k": run_filters8k, "stack4k": run_stack4k}[args.workload](args, rank, local_rank, world, torch, dist)
+        out = {"icons": run_icons, "filters8k": run_filters8k, "stack4k": run_stack4k}[args.workload](args, rank, local_rank, world, torch, dist)
+        if out is not None:
+            print(json.dumps(out))
         if world > 1:
             dist.destroy_process_group()
         return
@@ -890,11 +939,42 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             R = oracle_lib()
             n_sample = max(200, min(n_draws_in, int(args.cpu_sample)))
-            dt = cpu_render_sample(R, scene, n_sample)
+            ref_canvas = np.zeros((H, W, 4), np.uint8)
+            dt = cpu_render_sample(R, scene, n_sample, ref_canvas)
             out["cpu_baseline"] = {
                 "value": canvas_mpx / (dt * n_draws_in / n_sample), "unit": "Mpx/s", "cores": 1, "kind": "port",
                 "sample": f"first {n_sample} of {n_draws_in} draws of the same scene on the full canvas, {dt:.2f} s; "
-                          f"value = canvas Mpx / (t * {n_draws_in}/{n_sample}); oracle restatement of the resvg/tiny-skia CPU path"}
+                          f"value = canvas Mpx / (t * {n_draws_in}/{n_sample}); oracle restatement of the resvg/tiny-skia CPU path "
+                          "(pixels, stroker, dasher, hairline walker all oracle/)"}
+            # parity at BASELINE size: the same first n_sample draws rendered by the product through the C ABI, against the
+            # canvas the checker has just produced (each arm with its OWN stroker / dasher / hairline walker)
+            sub = scenes.subset(scene, n_sample)
+            sub["paints"] = scenes.to_paint_array(sub, _ffi.Paint)
+            sub["strokes"] = scenes.to_stroke_array(sub, _ffi.Stroke)
+            layer.fill(0, 0, 0, 0)
+            pb = rb.Batch(layer)
+            pb.fill_paths(sub)
+            pb.submit(n_threads)
+            pb.close()
+            out["parity"] = parity_record(layer.download(), ref_canvas,
+                                          f"first {n_sample} draws on the full {W}x{H} canvas: GPU (C ABI) vs CPU checker")
+            del ref_canvas
+        if world == 1 and not args.no_configs and args.workload == "paths8k":
+            # the other BASELINE configurations, each with its own value / e2e / roofline / cpu_baseline / parity
+            # (full recipes except icons, which renders 8 atlas chunks = 8192 documents here; `--workload icons` runs all 100 000)
+            batch.close()
+            layer.close()
+            sub_args = argparse.Namespace(**vars(args))
+            sub_args.steps, sub_args.warmup, sub_args.e2e_steps = max(3, min(args.steps, 5)), 3, 2
+            sub_args.cpu_sample = min(int(args.cpu_sample), 2048)
+            configs = {}
+            sub_args.docs = 8192
+            configs["icons"] = run_icons(sub_args, rank, local_rank, world, torch, dist)
+            sub_args.docs = 0
+            configs["filters8k"] = run_filters8k(sub_args, rank, local_rank, world, torch, dist)
+            configs["stack4k"] = run_stack4k(sub_args, rank, local_rank, world, torch, dist)
+            out["configs"] = configs
+            out["gpu_launches_note"] = "gpu_launches counts the timed paths8k steps only; every sub-record carries its own"
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -7,10 +7,12 @@ import time
 
 import numpy as np
 
-from resvg_b200 import scenes
 from tests import oracle_ffi as O
+from tests import scenes_loader
 from tests import oracle_raster as R
 from tests.svgfilters import _recolor
+
+scenes = scenes_loader.load()  # without importing the product package (bench.py --impl reference)
 
 
 class _Be:  # the slice of the back-end interface _recolor needs
