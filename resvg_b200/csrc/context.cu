@@ -49,6 +49,23 @@ int rb_scratch(rb_ctx *ctx, size_t bytes, void **out)
 
 int rb_staging(rb_ctx *ctx, size_t bytes, void **out)
 {
+    if (bytes <= rb_ctx::kStageSmall) {
+        rb_ctx::StageSlot &s = ctx->stage_ring[ctx->stage_next];
+        ctx->stage_next = (ctx->stage_next + 1) % rb_ctx::kStageSlots;
+        if (s.in_flight) {
+            RB_CUDA(ctx, cudaEventSynchronize(s.ev)); // recorded kStageSlots uploads ago: normally long done
+            s.in_flight = false;
+        }
+        if (!s.p) {
+            RB_CUDA(ctx, cudaHostAlloc(&s.p, rb_ctx::kStageSmall, cudaHostAllocDefault));
+            s.bytes = rb_ctx::kStageSmall;
+            RB_CUDA(ctx, cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+        }
+        ctx->staging_cur = &s;
+        *out = s.p;
+        return RB_OK;
+    }
+    ctx->staging_cur = nullptr;
     if (ctx->staging_in_flight) {
         RB_CUDA(ctx, cudaEventSynchronize(ctx->staging_ev));
         ctx->staging_in_flight = false;
@@ -65,6 +82,18 @@ int rb_staging(rb_ctx *ctx, size_t bytes, void **out)
     return RB_OK;
 }
 
+int rb_staging_mark(rb_ctx *ctx)
+{
+    if (ctx->staging_cur) {
+        RB_CUDA(ctx, cudaEventRecord(ctx->staging_cur->ev, ctx->stream));
+        ctx->staging_cur->in_flight = true;
+    } else {
+        RB_CUDA(ctx, cudaEventRecord(ctx->staging_ev, ctx->stream));
+        ctx->staging_in_flight = true;
+    }
+    return RB_OK;
+}
+
 void rb_ctx_retain(rb_ctx *ctx) { ctx->refs.fetch_add(1, std::memory_order_relaxed); }
 
 void rb_ctx_release(rb_ctx *ctx)
@@ -77,6 +106,10 @@ void rb_ctx_release(rb_ctx *ctx)
     if (ctx->staging) cudaFreeHost(ctx->staging);
     if (ctx->h_flags) cudaFreeHost((void *)ctx->h_flags);
     if (ctx->staging_ev) cudaEventDestroy(ctx->staging_ev);
+    for (auto &s : ctx->stage_ring) {
+        if (s.p) cudaFreeHost(s.p);
+        if (s.ev) cudaEventDestroy(s.ev);
+    }
     for (auto &e : ctx->ev_run) if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);

@@ -808,8 +808,7 @@ static int batch_prepare_range(rb_batch *b, int32_t n_threads, size_t begin, siz
     b->dev = dev;
     RB_CUDA(ctx, cudaMemcpyAsync(dev, blk, b->lay.total, cudaMemcpyHostToDevice, ctx->stream));
     ctx->h2d_bytes += b->lay.total;
-    RB_CUDA(ctx, cudaEventRecord(ctx->staging_ev, ctx->stream));
-    ctx->staging_in_flight = true;
+    { int st__ = rb_staging_mark(ctx); if (st__ != RB_OK) return st__; }
     if (!b->lay.wide) {
         const WarpScratch ws = warp_scratch_layout(b->lay);
         RB_CUDA(ctx, cudaMallocAsync((void **)&b->dev_scratch, ws.total, ctx->stream));
@@ -895,13 +894,22 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
         RowEnt *row_draws = (RowEnt *)(sc + ws.o_row_draws);
         const uint32_t n_draws = (uint32_t)L.n_draws, n_wtiles = (uint32_t)((size_t)L.wtiles_x * L.wtiles_y);
         RB_CUDA(ctx, cudaEventRecord(ctx->ev_run[0], ctx->stream));
+        // Small batches (a tree traversal records a handful of draws per layer) skip the binning pre-pass: the raster
+        // kernel then tests every draw of the batch against the tile itself (direct mode), which saves two memsets and
+        // eight launches per batch.
+        const bool direct = n_draws <= 32 && !getenv("RB_NO_DIRECT");
+        if (direct) {
+            k_row_lists<<<n_draws, RL_THREADS, 0, ctx->stream>>>(d_draws, d_lines, (const rbh::CurveRec *)(b->dev + L.o_curves), d_edges, row_off,
+                                                                  row_edges, row_cols, L.items ? 1 : 0, d_flag, L.wtiles_x, nullptr, nullptr, nullptr);
+            RB_LAUNCHED(ctx, "row_lists");
+            tile_off = nullptr;
+            tile_pairs = nullptr;
+        } else {
         RB_CUDA(ctx, cudaMemsetAsync(row_cnt, 0, ((size_t)L.wtiles_y + 2) * 4, ctx->stream));
         RB_CUDA(ctx, cudaMemsetAsync(tile_off, 0, ((size_t)n_wtiles + 2) * 4, ctx->stream));
         k_row_lists<<<n_draws, RL_THREADS, 0, ctx->stream>>>(d_draws, d_lines, (const rbh::CurveRec *)(b->dev + L.o_curves), d_edges, row_off,
-                                                              row_edges, row_cols, L.items ? 1 : 0, d_flag);
+                                                              row_edges, row_cols, L.items ? 1 : 0, d_flag, L.wtiles_x, boxes, row_cnt, tile_off);
         RB_LAUNCHED(ctx, "row_lists");
-        k_bin_count<<<(n_draws + 255) / 256, 256, 0, ctx->stream>>>(d_draws, n_draws, L.wtiles_x, row_cols, boxes, row_cnt, tile_off);
-        RB_LAUNCHED(ctx, "bin_count");
         uint32_t *scan_tmp = (uint32_t *)(sc + ws.o_scan);
         auto exclusive_scan = [&](uint32_t *a, uint32_t n) -> int {
             const uint32_t nb = (n + SCAN_PER_CTA - 1) / SCAN_PER_CTA;
@@ -922,10 +930,11 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
         RB_LAUNCHED(ctx, "bin_rows");
         k_bin_tiles<<<(n_wtiles + 7) / 8, 256, 0, ctx->stream>>>(row_draws, row_cnt, tile_off, L.wtiles_x, n_wtiles, tile_pairs);
         RB_LAUNCHED(ctx, "bin_tiles");
+        }
         RB_CUDA(ctx, cudaEventRecord(ctx->ev_run[1], ctx->stream));
         const unsigned grid = (n_wtiles + WT_WARPS - 1) / WT_WARPS;
 #define RB_WARP_ARGS target, W, H, L.wtiles_x, n_wtiles, tile_off, tile_pairs, d_draws, row_off, row_edges, d_edges,                   \
-    (const DevPaint *)(b->dev + L.o_paints), (const DevStop *)(b->dev + L.o_stops), px_stats
+    (const DevPaint *)(b->dev + L.o_paints), (const DevStop *)(b->dev + L.o_stops), px_stats, row_cols, n_draws
         if (mask_target) k_raster_warp<true, false><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
         else if (L.has_hair) k_raster_warp<false, true><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
         else k_raster_warp<false, false><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
@@ -999,8 +1008,7 @@ static int hair_run(rb_batch *b, size_t lo, size_t hi)
     cudaSetDevice(ctx->device);
     RB_CUDA(ctx, cudaMallocAsync((void **)&dev, total, ctx->stream));
     RB_CUDA(ctx, cudaMemcpyAsync(dev, h, total, cudaMemcpyHostToDevice, ctx->stream));
-    RB_CUDA(ctx, cudaEventRecord(ctx->staging_ev, ctx->stream));
-    ctx->staging_in_flight = true;
+    { int st__ = rb_staging_mark(ctx); if (st__ != RB_OK) return st__; }
     const uint32_t n = (uint32_t)hb.groups.size();
     k_hair_blits<<<(n + 127) / 128, 128, 0, ctx->stream>>>(reinterpret_cast<uint32_t *>(b->layer->d), (int)b->layer->w, (const HairGroup *)(dev + o_groups), n,
                                                         (const HairDevBlit *)(dev + o_blits), (const DevPaint *)(dev + o_paints),

@@ -130,8 +130,10 @@ __device__ __noinline__ bool exact_span_break_list(const DevEdge *__restrict__ a
 // ---- per-draw tile-row edge lists ----------------------------------------------------------------------------------
 // One CTA per draw.  Tile row r of a draw = layer pixel rows [8 (r0 + r), 8 (r0 + r) + 8); an edge is copied into the
 // list of every tile row its sub-scanline range touches (meta: bit 0 upward, bit 1 continuation, bits 4.. own slot).
+struct DrawBox { uint32_t rows, row_base; }; // r0 | r1 << 16 (inclusive warp-tile rows); where its row_cols entries start
 constexpr int RL_THREADS = 128;
 constexpr int RL_MAX_ROWS = 1026;
+constexpr int RL_LONG = 32, RL_LONG_Q = 32; // edges crossing >= RL_LONG tile rows are walked by the whole CTA (up to RL_LONG_Q per draw)
 
 __device__ __forceinline__ int draw_row_of(const DevDraw &D, int suby)
 {
@@ -145,15 +147,29 @@ __device__ __forceinline__ int draw_row_of(const DevDraw &D, int suby)
 __global__ void __launch_bounds__(RL_THREADS)
 k_row_lists(const DevDraw *__restrict__ draws, const DevEdge *__restrict__ lines, const rbh::CurveRec *__restrict__ curves,
             DevEdge *__restrict__ edges, uint32_t *__restrict__ row_off, DevEdge *__restrict__ row_edges, uint32_t *__restrict__ row_cols,
-            int items, unsigned int *__restrict__ overflow)
+            int items, unsigned int *__restrict__ overflow, int wtiles_x, DrawBox *__restrict__ boxes, uint32_t *__restrict__ row_cnt,
+            uint32_t *__restrict__ tile_cnt)
 {
     __shared__ uint32_t cnt[RL_MAX_ROWS + 2];
     __shared__ int xlo[RL_MAX_ROWS + 2], xhi[RL_MAX_ROWS + 2]; // extent of the crossings of each tile row, in pixels
     __shared__ uint32_t warp_tot[RL_THREADS / 32];
+    __shared__ uint32_t long_q[RL_LONG_Q], n_long;
     const DevDraw D = draws[blockIdx.x];
     const int tid = threadIdx.x, nr = (int)D.n_rows;
     DevEdge *E0 = edges + D.edge_off;
     for (int i = tid; i <= nr; i += RL_THREADS) { cnt[i] = 0; xlo[i] = INT_MAX; xhi[i] = INT_MIN; }
+    if (tid == 0 && boxes) boxes[blockIdx.x] = DrawBox{D.r0 | ((D.r0 + D.n_rows - 1) << 16), D.row_base};
+    // Binning counts (how many draws touch each warp-tile row / each warp tile) are taken here, by the threads that have
+    // just computed a row's column extent: a draw spanning the whole layer has hundreds of rows, which a thread-per-draw
+    // counting kernel walked serially (124 us per launch for full-layer draws on a 4096 x 4096 layer).
+    auto count_row = [&](int i, uint32_t cols) {
+        const uint32_t c0 = cols & 0xffffu, c1 = cols >> 16;
+        if (c0 > c1 || !row_cnt) return; // direct mode (<= 32 draws): no bin tables
+        const uint32_t r = D.r0 + (uint32_t)i;
+        atomicAdd(&row_cnt[r], 1u);
+        uint32_t *t = tile_cnt + (size_t)r * wtiles_x;
+        for (uint32_t c = c0; c <= c1; c++) atomicAdd(&t[c], 1u);
+    };
     if (D.rule == 2) {
         // A hairline stroke: `lines` holds its ordered blits (x | y << 16 in layer pixels, coverage, rank inside its
         // warp-tile cell, cell index).  The draw's list table has one entry per CELL of its bounding box (row-major,
@@ -192,8 +208,11 @@ k_row_lists(const DevDraw *__restrict__ draws, const DevEdge *__restrict__ lines
             if (tid == RL_THREADS - 1) cell_off[n_cells] = base;
         }
         __syncthreads();
-        for (int i = tid; i < nr; i += RL_THREADS)
-            row_cols[D.row_base + i] = xlo[i] <= xhi[i] ? ((uint32_t)(xlo[i] / WT_W) | ((uint32_t)(xhi[i] / WT_W) << 16)) : 1u;
+        for (int i = tid; i < nr; i += RL_THREADS) {
+            const uint32_t cols = xlo[i] <= xhi[i] ? ((uint32_t)(xlo[i] / WT_W) | ((uint32_t)(xhi[i] / WT_W) << 16)) : 1u;
+            row_cols[D.row_base + i] = cols;
+            count_row(i, cols);
+        }
         DevEdge *out = row_edges + D.list_off;
         for (uint32_t i = tid; i < D.line_cnt; i += RL_THREADS) {
             const DevEdge B = B0[i];
@@ -236,22 +255,38 @@ k_row_lists(const DevDraw *__restrict__ draws, const DevEdge *__restrict__ lines
         // Per tile row: how many edges touch it, and between which pixel columns they cross it.  Outside that extent the
         // winding is zero (contours are closed), so only the warp tiles inside it are paired with this draw.
         const int sub_lo = D.sy << D.shift, sub_hi = ((D.sy + D.sh) << D.shift) - 1; // sub-scanlines the blitter may touch
+        auto touch = [&](const DevEdge &E, int fy, int ly, int r) {
+            atomicAdd(&cnt[r], 1u);
+            // sub-scanlines of tile row r: layer pixel rows [8 (r0 + r), +8) in the draw's units
+            const int top = max(max((((int)(D.r0 + r) << 3) - D.oy) << D.shift, sub_lo), fy);
+            const int bot = min(min((((((int)(D.r0 + r) + 1) << 3) - D.oy) << D.shift) - 1, sub_hi), ly);
+            if (top > bot) return;
+            const int xa = (int)((uint32_t)E.x + (uint32_t)(top - fy) * (uint32_t)E.dx), xb = (int)((uint32_t)E.x + (uint32_t)(bot - fy) * (uint32_t)E.dx);
+            const int pa = (((int)((uint32_t)xa + 0x8000u) >> 16) >> D.shift), pb = (((int)((uint32_t)xb + 0x8000u) >> 16) >> D.shift);
+            atomicMin(&xlo[r], min(pa, pb));
+            atomicMax(&xhi[r], max(pa, pb));
+        };
+        // An edge that crosses many tile rows (the sides of a layer-sized rectangle: 512 rows on a 4096 px layer) is
+        // queued and walked by the whole CTA, rows strided over the threads, instead of by the one thread that owns it.
+        if (tid == 0) n_long = 0;
+        __syncthreads();
         for (uint32_t e = tid; e < D.edge_cnt; e += RL_THREADS) {
             const DevEdge E = E0[e];
             const int fy = (int)(E.ypack & 0xffffu), ly = (int)(E.ypack >> 16);
             if (fy > ly) continue; // empty slot
             const int ra = draw_row_of(D, fy), rb = draw_row_of(D, ly);
-            for (int r = ra; r <= rb; r++) {
-                atomicAdd(&cnt[r], 1u);
-                // sub-scanlines of tile row r: layer pixel rows [8 (r0 + r), +8) in the draw's units
-                const int top = max(max((((int)(D.r0 + r) << 3) - D.oy) << D.shift, sub_lo), fy);
-                const int bot = min(min((((((int)(D.r0 + r) + 1) << 3) - D.oy) << D.shift) - 1, sub_hi), ly);
-                if (top > bot) continue;
-                const int xa = (int)((uint32_t)E.x + (uint32_t)(top - fy) * (uint32_t)E.dx), xb = (int)((uint32_t)E.x + (uint32_t)(bot - fy) * (uint32_t)E.dx);
-                const int pa = (((int)((uint32_t)xa + 0x8000u) >> 16) >> D.shift), pb = (((int)((uint32_t)xb + 0x8000u) >> 16) >> D.shift);
-                atomicMin(&xlo[r], min(pa, pb));
-                atomicMax(&xhi[r], max(pa, pb));
+            if (rb - ra >= RL_LONG) {
+                const uint32_t q = atomicAdd(&n_long, 1u);
+                if (q < RL_LONG_Q) { long_q[q] = e; continue; }
             }
+            for (int r = ra; r <= rb; r++) touch(E, fy, ly, r);
+        }
+        __syncthreads();
+        for (uint32_t q = 0; q < min(n_long, (uint32_t)RL_LONG_Q); q++) {
+            const DevEdge E = E0[long_q[q]];
+            const int fy = (int)(E.ypack & 0xffffu), ly = (int)(E.ypack >> 16);
+            const int ra = draw_row_of(D, fy), rb = draw_row_of(D, ly);
+            for (int r = ra + tid; r <= rb; r += RL_THREADS) touch(E, fy, ly, r);
         }
     }
     __syncthreads();
@@ -263,6 +298,7 @@ k_row_lists(const DevDraw *__restrict__ draws, const DevEdge *__restrict__ lines
             if (px0 <= px1) cols = (uint32_t)((D.ox + px0) / WT_W) | ((uint32_t)((D.ox + px1) / WT_W) << 16);
         }
         row_cols[D.row_base + i] = cols;
+        count_row(i, cols);
     }
     // exclusive scan of cnt[0..nr) -> cnt; contiguous chunks per thread + warp shuffles
     {
@@ -288,43 +324,35 @@ k_row_lists(const DevDraw *__restrict__ draws, const DevEdge *__restrict__ lines
     for (int i = tid; i <= nr; i += RL_THREADS) row_off[D.row_base + i] = cnt[i];
     __syncthreads();
     DevEdge *out = row_edges + D.list_off;
+    auto put = [&](const DevEdge &E, int r) {
+        const uint32_t at = atomicAdd(&cnt[r], 1u);
+        if (at < D.list_cap) out[at] = E;
+        else *(volatile unsigned int *)overflow = 1u; // cannot happen: the host's bound covers every segment
+    };
     for (uint32_t e = tid; e < D.edge_cnt; e += RL_THREADS) {
         DevEdge E = E0[e];
         const int fy = (int)(E.ypack & 0xffffu), ly = (int)(E.ypack >> 16);
         if (fy > ly) continue;
         E.meta = (E.meta & 3u) | (e << 4);
         const int ra = draw_row_of(D, fy), rb = draw_row_of(D, ly);
-        for (int r = ra; r <= rb; r++) {
-            const uint32_t at = atomicAdd(&cnt[r], 1u);
-            if (at < D.list_cap) out[at] = E;
-            else *(volatile unsigned int *)overflow = 1u; // cannot happen: the host's bound covers every segment
+        if (rb - ra >= RL_LONG) {
+            bool queued = false;
+            for (uint32_t q = 0; q < min(n_long, (uint32_t)RL_LONG_Q); q++) queued = queued || long_q[q] == e;
+            if (queued) continue; // walked by the whole CTA below
         }
+        for (int r = ra; r <= rb; r++) put(E, r);
+    }
+    for (uint32_t q = 0; q < min(n_long, (uint32_t)RL_LONG_Q); q++) {
+        const uint32_t e = long_q[q];
+        DevEdge E = E0[e];
+        const int fy = (int)(E.ypack & 0xffffu), ly = (int)(E.ypack >> 16);
+        E.meta = (E.meta & 3u) | (e << 4);
+        const int ra = draw_row_of(D, fy), rb = draw_row_of(D, ly);
+        for (int r = ra + tid; r <= rb; r += RL_THREADS) put(E, r);
     }
 }
 
 // ---- binning draws into warp tiles (painter's order kept without sorting) ------------------------------------------
-struct DrawBox { uint32_t rows, row_base; }; // r0 | r1 << 16 (inclusive warp-tile rows); where its row_cols entries start
-
-// row_cols[row_base + r] = c0 | c1 << 16: the warp-tile columns of the draw's tile row r that can receive coverage
-// (from k_row_lists; c0 > c1 when the row is empty).
-__global__ void __launch_bounds__(256)
-k_bin_count(const DevDraw *__restrict__ draws, uint32_t n_draws, int wtiles_x, const uint32_t *__restrict__ row_cols,
-            DrawBox *__restrict__ boxes, uint32_t *__restrict__ row_cnt, uint32_t *__restrict__ tile_cnt)
-{
-    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= n_draws) return;
-    const DevDraw D = draws[d];
-    const uint32_t r0 = D.r0, r1 = D.r0 + D.n_rows - 1;
-    boxes[d] = DrawBox{r0 | (r1 << 16), D.row_base};
-    for (uint32_t r = r0; r <= r1; r++) {
-        const uint32_t cols = row_cols[D.row_base + (r - r0)];
-        const uint32_t c0 = cols & 0xffffu, c1 = cols >> 16;
-        if (c0 > c1) continue;
-        atomicAdd(&row_cnt[r], 1u);
-        uint32_t *t = tile_cnt + (size_t)r * wtiles_x;
-        for (uint32_t c = c0; c <= c1; c++) atomicAdd(&t[c], 1u);
-    }
-}
 
 // In-place exclusive scan of a[0..n), a[n] = total, in three small launches: every CTA scans 4096 consecutive
 // elements (coalesced 16-byte loads, 4 per thread) and publishes its sum; one CTA scans the sums; every CTA adds its
@@ -489,14 +517,32 @@ __global__ void __launch_bounds__(WT_WARPS * 32, RW_MIN_CTAS)
 k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_wtiles, const uint32_t *__restrict__ tile_off,
               const uint32_t *__restrict__ tile_pairs, const DevDraw *__restrict__ draws, const uint32_t *__restrict__ row_off,
               const DevEdge *__restrict__ row_edges, const DevEdge *__restrict__ edges, const DevPaint *__restrict__ paints,
-              const DevStop *__restrict__ stops, unsigned long long *__restrict__ px_stats)
+              const DevStop *__restrict__ stops, unsigned long long *__restrict__ px_stats, const uint32_t *__restrict__ row_cols,
+              uint32_t n_direct)
 {
     __shared__ WarpTileSmem s_all[WT_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WarpTileSmem &S = s_all[wid];
     const uint32_t tile = blockIdx.x * WT_WARPS + wid;
     if (tile >= n_wtiles) return;
-    const uint32_t d_begin = tile_off[tile], d_end = tile_off[tile + 1];
+    // Direct mode (tile_off == nullptr; batches of at most 32 draws — the per-layer batches of a tree traversal): no bin
+    // tables were built; the tile's list is every draw of the batch, each kept or dropped by its own row / column extent.
+    const bool direct = tile_off == nullptr;
+    uint32_t direct_mask = 0;
+    if (direct) {
+        bool hit = false;
+        if ((uint32_t)lane < n_direct) {
+            const DevDraw &D = draws[lane];
+            const uint32_t r = (tile / (uint32_t)wtiles_x) - D.r0, c = tile % (uint32_t)wtiles_x;
+            if (r < D.n_rows) {
+                const uint32_t cols = row_cols[D.row_base + r];
+                hit = (cols & 0xffffu) <= c && c <= (cols >> 16);
+            }
+        }
+        direct_mask = __ballot_sync(0xffffffffu, hit);
+        if (!direct_mask) return;
+    }
+    const uint32_t d_begin = direct ? 0u : tile_off[tile], d_end = direct ? n_direct : tile_off[tile + 1];
     if (d_begin == d_end) return; // nothing touches this tile (most tiles of a sparse atlas)
     {
         uint4 *z = reinterpret_cast<uint4 *>(&S);
@@ -548,8 +594,8 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
         WarpDraw mine;
         mine.flags = 0; mine.n_list = 0; mine.list_begin = 0; mine.tlx = 0; mine.tly = 0; mine.bounds = 0; mine.paint = 0;
         const int n_group = (int)min(32u, d_end - gbase);
-        if (lane < n_group) {
-            const DevDraw D = draws[tile_pairs[gbase + lane]];
+        if (lane < n_group && (!direct || ((direct_mask >> lane) & 1u))) {
+            const DevDraw D = draws[direct ? (uint32_t)lane : tile_pairs[gbase + lane]];
             const int tlx = X0 - D.ox, tly = Y0 - D.oy;
             const int py0 = max(0, D.sy - tly), py1 = min(WT_H, D.sy + D.sh - tly);
             const int pxa = max(0, D.sx - tlx), pxb = min(WT_W, D.sx + D.sw - tlx);
@@ -832,7 +878,7 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
                                     mx &= mx - 1;
                                     const uint32_t pixbit = 1u << (b & ~3);
                                     if (!(full3 & pixbit) || (brk & pixbit)) continue;
-                                    if (exact_span_break_list(edges, draws, tile_pairs[gbase + k], row_edges + list_begin, n_list,
+                                    if (exact_span_break_list(edges, draws, direct ? (uint32_t)k : tile_pairs[gbase + k], row_edges + list_begin, n_list,
                                                               row0 + prow * 4 + 3, col0 + 32 * pj + b, col0 + lo_pos))
                                         brk |= pixbit;
                                 }
@@ -892,19 +938,24 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
                                 const P16 g16 = shade16_gradient(P, stops, tlx + 8 * pj + q, tly + prow);
                                 sr = g16.r; sg = g16.g; sb = g16.b; sa = g16.a;
                             }
-                            uint32_t r, g, b2, a;
+                            // Two channels per multiply: R | B << 16 and G | A << 16 hold two 16-bit lanes whose products with an
+                            // 8-bit factor stay below 2^16, so (x * k + 0x00ff00ff) >> 8 & 0x00ff00ff IS div255 on both lanes
+                            // (bit-identical to the per-channel u16 pipeline, half the instructions).
+                            const uint32_t s_rb = sr | (sb << 16), s_ag = sg | (sa << 16);
+                            const uint32_t d_rb = d & 0x00ff00ffu, d_ag = (d >> 8) & 0x00ff00ffu;
+                            uint32_t o_rb, o_ag;
                             if (src_over) { // scale_1_float (coverage folded into the source), then source_over
-                                const uint32_t pr = c == 255 ? sr : div255(sr * c), pg = c == 255 ? sg : div255(sg * c);
-                                const uint32_t pb = c == 255 ? sb : div255(sb * c), pa = c == 255 ? sa : div255(sa * c);
-                                const uint32_t ia = 255 - pa;
-                                r = pr + div255(RB_R(d) * ia); g = pg + div255(RB_G(d) * ia);
-                                b2 = pb + div255(RB_B(d) * ia); a = pa + div255(RB_A(d) * ia);
+                                const uint32_t p_rb = c == 255 ? s_rb : (((s_rb * c + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
+                                const uint32_t p_ag = c == 255 ? s_ag : (((s_ag * c + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
+                                const uint32_t ia = 255 - (p_ag >> 16);
+                                o_rb = p_rb + (((d_rb * ia + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
+                                o_ag = p_ag + (((d_ag * ia + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
                             } else {        // Source: lerp_1_float(dst, src, coverage)
                                 const uint32_t ic = 255 - c;
-                                r = div255(RB_R(d) * ic + sr * c); g = div255(RB_G(d) * ic + sg * c);
-                                b2 = div255(RB_B(d) * ic + sb * c); a = div255(RB_A(d) * ic + sa * c);
+                                o_rb = (d_rb * ic + s_rb * c + 0x00ff00ffu) >> 8;
+                                o_ag = (d_ag * ic + s_ag * c + 0x00ff00ffu) >> 8;
                             }
-                            d = rb_pack(r & 0xffu, g & 0xffu, b2 & 0xffu, a & 0xffu);
+                            d = (o_rb & 0x00ff00ffu) | ((o_ag & 0x00ff00ffu) << 8); // the store truncates every lane to u8
                         } else if (simple_hp) {
                             n_partial++;
                             const PF dd = load_pf(d);

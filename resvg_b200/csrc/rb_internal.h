@@ -36,6 +36,15 @@ struct rb_ctx {
     size_t staging_bytes = 0;
     cudaEvent_t staging_ev = nullptr;
     bool staging_in_flight = false;
+    // Small uploads (the batches of a tree traversal: a few draws per layer) rotate through a ring of pinned slots, so that
+    // recording batch k + 1 does not wait for the GPU to have consumed batch k; `staging_cur` is the slot rb_staging handed
+    // out last, rb_staging_mark records the copy that reads it.
+    struct StageSlot { void *p = nullptr; size_t bytes = 0; cudaEvent_t ev = nullptr; bool in_flight = false; };
+    static constexpr int kStageSlots = 16;
+    static constexpr size_t kStageSmall = 1u << 20;
+    StageSlot stage_ring[kStageSlots];
+    int stage_next = 0;
+    StageSlot *staging_cur = nullptr; // nullptr: the large block
     // owner + every live layer / mask / batch: the context outlives them whatever the destruction order
     std::atomic<int> refs{1};
     std::vector<struct rb_layer *> dirty; // layers holding pending immediate draws (rb_fill_path), flushed by rb_ctx_synchronize
@@ -53,6 +62,8 @@ void rb_ctx_retain(rb_ctx *ctx);
 void rb_ctx_release(rb_ctx *ctx);
 // Pinned staging block of at least `bytes`, safe to overwrite (waits for the previous upload out of it).
 int rb_staging(rb_ctx *ctx, size_t bytes, void **out);
+// After enqueuing the copy that reads the block rb_staging returned last: records when it may be overwritten.
+int rb_staging_mark(rb_ctx *ctx);
 
 struct rb_layer {
     rb_ctx *ctx;
