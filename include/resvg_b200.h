@@ -88,8 +88,13 @@ int rb_layer_into_srgb(rb_layer *layer);        /* mod.rs:114-118 */
  * ---------------------------------------------------------------------------------------------- */
 /* box_blur::apply(sigma_x, sigma_y, src) — box_blur.rs:23 */
 int rb_filter_box_blur(rb_layer *layer, double sigma_x, double sigma_y);
-/* iir_blur::apply(sigma_x, sigma_y, src) — iir_blur.rs:47 */
+/* iir_blur::apply(sigma_x, sigma_y, src) — iir_blur.rs:47: strictly sequential f64 recurrences, bit-identical to the
+ * reference.  This is what the renderer calls (filter/mod.rs:605, 661). */
 int rb_filter_iir_blur(rb_layer *layer, double sigma_x, double sigma_y);
+/* The same cascade in f32 on register-resident line segments with halos: within 1/255 of the reference on the stage output
+ * (the tolerance BASELINE.json grants the IIR blur), ~10x faster.  Opt-in: a 1-level difference in a flat linearRGB area
+ * becomes many levels after the conversion to sRGB, so corpus parity needs the exact form. */
+int rb_filter_iir_blur_fast(rb_layer *layer, double sigma_x, double sigma_y);
 /* morphology::apply(operator, rx, ry, src) — morphology.rs:15.  op: 0 erode, 1 dilate */
 int rb_filter_morphology(rb_layer *layer, int op, float rx, float ry);
 /* convolve_matrix::apply(matrix, src) — convolve_matrix.rs:15.

@@ -101,6 +101,7 @@ SIGNATURES = {
     "rb_layer_into_srgb": (_i, [_vp]),
     "rb_filter_box_blur": (_i, [_vp, _d, _d]),
     "rb_filter_iir_blur": (_i, [_vp, _d, _d]),
+    "rb_filter_iir_blur_fast": (_i, [_vp, _d, _d]),
     "rb_filter_morphology": (_i, [_vp, _i, _f, _f]),
     "rb_filter_convolve_matrix": (_i, [_vp, f32p, _u32, _u32, _u32, _u32, _f, _f, _i, _i]),
     "rb_filter_color_matrix": (_i, [_vp, _i, f32p]),

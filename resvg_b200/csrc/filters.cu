@@ -1044,6 +1044,130 @@ __global__ void k_iir_store(const double *__restrict__ in, uint32_t *__restrict_
     }
 }
 
+// ---- the production IIR blur: the same cascade in f32, on register-resident line segments ---------------------------
+// north_star allows 1/255 on the IIR blur, which frees it from the sequential f64 order.  The recurrence y[i] = x[i] + nu y[i-1]
+// forgets its start at the rate nu^k (nu <= 0.268 for sigma < 2), so a line can be cut into segments that carry a halo:
+// a segment of IIR_L = 224 samples lives in the registers of ONE WARP (7 consecutive samples x 4 channels per lane) through
+// all 8 sweeps; every sweep is a local recurrence + a warp scan of the lane carries (operator Y_j = c_j + nu^7 Y_{j-1}) + a
+// fix-up.  Halo = 4 R samples per side, R = the reach at which nu^R < 1e-7: each of the 4 sweeps per direction spreads the
+// truncation error by R.  Segments that touch the image border start exactly there, with the reference's zero state.
+// Horizontal pass: u8 -> f32x4 (16 B/px intermediate, the reference keeps f64 between the axes); vertical pass: f32x4 -> u8
+// with post_scale and the truncating cast.  No f64 planes, no transposes: 40 B/px of traffic instead of ~1 KB/px.
+constexpr int IIR_PER_LANE = 7, IIR_L = 32 * IIR_PER_LANE;
+struct IirCoef { float p[IIR_PER_LANE + 1]; float m[5]; }; // p[k] = nu^k (k = 1..7), m[d] = nu^(7 * 2^d)
+
+__device__ __forceinline__ void iir_sweeps(float (&v)[IIR_PER_LANE][4], const IirCoef &C, int n_valid, int lane)
+{
+    const float nu = C.p[1];
+#pragma unroll 1
+    for (int step = 0; step < 4; step++) {
+        // rightwards: v[i] += nu * v[i-1]
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+#pragma unroll
+            for (int k = 1; k < IIR_PER_LANE; k++) v[k][c] = fmaf(nu, v[k - 1][c], v[k][c]);
+            float y = v[IIR_PER_LANE - 1][c];
+#pragma unroll
+            for (int d = 0; d < 5; d++) {
+                const float t = __shfl_up_sync(0xffffffffu, y, 1 << d);
+                if (lane >= (1 << d)) y = fmaf(C.m[d], t, y);
+            }
+            float carry = __shfl_up_sync(0xffffffffu, y, 1);
+            if (lane == 0) carry = 0.0f;
+#pragma unroll
+            for (int k = 0; k < IIR_PER_LANE; k++) v[k][c] = fmaf(C.p[k + 1], carry, v[k][c]);
+        }
+        // samples beyond the end of the line do not exist: keep them at zero so the leftward sweep starts with zero state
+#pragma unroll
+        for (int k = 0; k < IIR_PER_LANE; k++)
+            if (lane * IIR_PER_LANE + k >= n_valid) { v[k][0] = 0.0f; v[k][1] = 0.0f; v[k][2] = 0.0f; v[k][3] = 0.0f; }
+        // leftwards: v[i-1] += nu * v[i]
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+#pragma unroll
+            for (int k = IIR_PER_LANE - 2; k >= 0; k--) v[k][c] = fmaf(nu, v[k + 1][c], v[k][c]);
+            float y = v[0][c];
+#pragma unroll
+            for (int d = 0; d < 5; d++) {
+                const float t = __shfl_down_sync(0xffffffffu, y, 1 << d);
+                if (lane + (1 << d) < 32) y = fmaf(C.m[d], t, y);
+            }
+            float carry = __shfl_down_sync(0xffffffffu, y, 1);
+            if (lane == 31) carry = 0.0f;
+#pragma unroll
+            for (int k = 0; k < IIR_PER_LANE; k++) v[k][c] = fmaf(C.p[IIR_PER_LANE - k], carry, v[k][c]);
+        }
+    }
+}
+
+// Horizontal pass.  Warp = one row segment; block = 8 rows.  seg = interior samples per segment, halo = samples loaded on
+// either side.  blur = 0: conversion only (sigma_x == 0).
+__global__ void __launch_bounds__(256)
+k_iir_fast_h(const uint32_t *__restrict__ src, float4 *__restrict__ out, int w, int h, int seg, int halo, IirCoef C, int blur)
+{
+    const int lane = threadIdx.x & 31, y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (y >= h) return;
+    const int i0 = blockIdx.x * seg, i1 = min(i0 + seg, w);           // interior [i0, i1)
+    const int lo = max(i0 - halo, 0), hi = min(i1 + halo, w);           // loaded [lo, hi)
+    const uint32_t *row = src + (size_t)y * w;
+    float v[IIR_PER_LANE][4];
+#pragma unroll
+    for (int k = 0; k < IIR_PER_LANE; k++) {
+        const int x = lo + lane * IIR_PER_LANE + k;
+        const uint32_t p = x < hi ? row[x] : 0u;
+        v[k][0] = (float)RB_R(p) * (1.0f / 255.0f); v[k][1] = (float)RB_G(p) * (1.0f / 255.0f);
+        v[k][2] = (float)RB_B(p) * (1.0f / 255.0f); v[k][3] = (float)RB_A(p) * (1.0f / 255.0f);
+    }
+    if (blur) iir_sweeps(v, C, hi - lo, lane);
+    float4 *orow = out + (size_t)y * w;
+#pragma unroll
+    for (int k = 0; k < IIR_PER_LANE; k++) {
+        const int x = lo + lane * IIR_PER_LANE + k;
+        if (x >= i0 && x < i1) orow[x] = make_float4(v[k][0], v[k][1], v[k][2], v[k][3]);
+    }
+}
+
+// Vertical pass.  Block = IIR_VCOLS adjacent columns (one warp each) of one column segment, staged through shared memory so
+// that global accesses run along rows; pitch 9 float4 per 8 columns keeps the lanes' float4 accesses conflict-free.
+constexpr int IIR_VCOLS = 16, IIR_VPITCH = IIR_VCOLS + 1;
+__global__ void __launch_bounds__(IIR_VCOLS * 32)
+k_iir_fast_v(const float4 *__restrict__ in, uint32_t *__restrict__ dst, int w, int h, int seg, int halo, IirCoef C, int blur, float post_scale)
+{
+    extern __shared__ float4 tile[]; // [IIR_L][IIR_VPITCH]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * IIR_VCOLS;
+    const int i0 = blockIdx.y * seg, i1 = min(i0 + seg, h);
+    const int lo = max(i0 - halo, 0), hi = min(i1 + halo, h);
+    for (int t = threadIdx.x; t < IIR_L * IIR_VCOLS; t += IIR_VCOLS * 32) {
+        const int r = t / IIR_VCOLS, c = t % IIR_VCOLS;
+        const int yy = lo + r, xx = x0 + c;
+        tile[r * IIR_VPITCH + c] = (yy < hi && xx < w) ? in[(size_t)yy * w + xx] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    __syncthreads();
+    float v[IIR_PER_LANE][4];
+#pragma unroll
+    for (int k = 0; k < IIR_PER_LANE; k++) {
+        const float4 q = tile[(lane * IIR_PER_LANE + k) * IIR_VPITCH + wid];
+        v[k][0] = q.x; v[k][1] = q.y; v[k][2] = q.z; v[k][3] = q.w;
+    }
+    if (blur) iir_sweeps(v, C, hi - lo, lane);
+    __syncthreads();
+    uint32_t *otile = reinterpret_cast<uint32_t *>(tile); // [IIR_L][IIR_VCOLS + 1]
+#pragma unroll
+    for (int k = 0; k < IIR_PER_LANE; k++) {
+        // v *= post_scale; (v * 255.0) as u8 (iir_blur.rs:73-76, 137-139)
+        const uint32_t r = rb_f2u8(v[k][0] * post_scale * 255.0f), g = rb_f2u8(v[k][1] * post_scale * 255.0f);
+        const uint32_t b = rb_f2u8(v[k][2] * post_scale * 255.0f), a = rb_f2u8(v[k][3] * post_scale * 255.0f);
+        otile[(lane * IIR_PER_LANE + k) * (IIR_VCOLS + 1) + wid] = rb_pack(r, g, b, a);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < IIR_L * IIR_VCOLS; t += IIR_VCOLS * 32) {
+        const int r = t / IIR_VCOLS, c = t % IIR_VCOLS;
+        const int yy = lo + r, xx = x0 + c;
+        if (yy >= i0 && yy < i1 && xx < w) dst[(size_t)yy * w + xx] = otile[r * (IIR_VCOLS + 1) + c];
+    }
+}
+
 static double powi_f64(double a, int b)
 {
     // compiler-rt __powidf2, which Rust's f64::powi lowers to
@@ -1106,6 +1230,66 @@ extern "C" int rb_filter_iir_blur(rb_layer *l, double sigma_x, double sigma_y)
     }
     k_iir_store<<<rb_grid_1d(ctx, n, 256), 256, 0, ctx->stream>>>(A, px, n, post_scale);
     RB_LAUNCHED(ctx, "iir_store");
+    return RB_OK;
+}
+
+// The f32 segment kernels above: within 1/255 of iir_blur::apply on the STAGE output (BASELINE.json's tolerance for the IIR
+// blur), ten times faster than the sequential f64 form.  Opt-in, NOT what the renderer calls: the reference truncates
+// `(v * 255.0) as u8`, a flat area of value c comes out as exactly c or c - 1 depending on the last bit of its f64 sum, and
+// a following linearRGB -> sRGB conversion (filter/mod.rs:114-118) turns that one level into up to 13 — the corpus
+// criterion (+-1 on the final image) therefore needs the bit-exact rb_filter_iir_blur, which stays the default.
+// Sigmas of 2.5 and more (resvg switches to the box blur at 2) go to the exact kernels.
+extern "C" int rb_filter_iir_blur_fast(rb_layer *l, double sigma_x, double sigma_y)
+{
+    rb_enter(l ? l->ctx : nullptr);
+    RB_SYNC_LAYER(l);
+    if (!l) return RB_ERR_INVALID;
+    if (sigma_x >= 2.5 || sigma_y >= 2.5 || sigma_x != sigma_x || sigma_y != sigma_y) return rb_filter_iir_blur(l, sigma_x, sigma_y);
+    rb_ctx *ctx = l->ctx;
+    const int w = (int)l->w, h = (int)l->h;
+    const size_t n = (size_t)w * h;
+    const int steps = 4;
+    double lambda[2] = {1.0, 1.0}, dnu[2] = {1.0, 1.0};
+    const double sigma[2] = {sigma_x, sigma_y};
+    IirCoef C[2];
+    int halo[2] = {0, 0};
+    for (int a = 0; a < 2; a++) {
+        memset(&C[a], 0, sizeof(IirCoef));
+        if (!(sigma[a] > 0.0)) continue;
+        lambda[a] = (sigma[a] * sigma[a]) / (2.0 * (double)steps); // iir_blur.rs:142-146
+        dnu[a] = (1.0 + 2.0 * lambda[a] - sqrt(1.0 + 4.0 * lambda[a])) / (2.0 * lambda[a]);
+        double pw = 1.0;
+        for (int k = 0; k <= IIR_PER_LANE; k++) { C[a].p[k] = (float)pw; pw *= dnu[a]; }
+        double m = pow(dnu[a], (double)IIR_PER_LANE);
+        for (int d = 0; d < 5; d++) { C[a].m[d] = (float)m; m *= m; }
+        // reach R: nu^R < 1e-7; every one of the 4 sweeps per direction spreads the truncation error by R
+        int reach = dnu[a] > 0.0 ? (int)ceil(log(1e-7) / log(dnu[a])) : 1;
+        reach = std::max(1, std::min(reach, 20));
+        halo[a] = 4 * reach;
+    }
+    const double post_scale = powi_f64(sqrt(dnu[0] * dnu[1]) / sqrt(lambda[0] * lambda[1]), 2 * steps);
+    void *scratch = nullptr;
+    int st = rb_scratch(ctx, n * sizeof(float4), &scratch);
+    if (st != RB_OK) return st;
+    float4 *mid = reinterpret_cast<float4 *>(scratch);
+    uint32_t *px = reinterpret_cast<uint32_t *>(l->d);
+    {
+        const int seg = IIR_L - 2 * halo[0];
+        dim3 grid((w + seg - 1) / seg, (h + 7) / 8);
+        k_iir_fast_h<<<grid, 256, 0, ctx->stream>>>(px, mid, w, h, seg, halo[0], C[0], sigma_x > 0.0 ? 1 : 0);
+        RB_LAUNCHED(ctx, "iir_fast_h");
+    }
+    {
+        const int seg = IIR_L - 2 * halo[1];
+        const size_t smem = (size_t)IIR_L * IIR_VPITCH * sizeof(float4);
+        if (!(ctx->attr_bits & RB_ATTR_IIR)) {
+            RB_CUDA(ctx, cudaFuncSetAttribute(k_iir_fast_v, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->attr_bits |= RB_ATTR_IIR;
+        }
+        dim3 grid((w + IIR_VCOLS - 1) / IIR_VCOLS, (h + seg - 1) / seg);
+        k_iir_fast_v<<<grid, IIR_VCOLS * 32, smem, ctx->stream>>>(mid, px, w, h, seg, halo[1], C[1], sigma_y > 0.0 ? 1 : 0, (float)post_scale);
+        RB_LAUNCHED(ctx, "iir_fast_v");
+    }
     return RB_OK;
 }
 

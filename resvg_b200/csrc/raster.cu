@@ -730,10 +730,7 @@ static void batch_release(rb_batch *b)
         cudaFreeAsync(b->dev, batch_ctx(b)->stream);
         b->dev = nullptr;
     }
-    if (b->dev_scratch) {
-        cudaFreeAsync(b->dev_scratch, batch_ctx(b)->stream);
-        b->dev_scratch = nullptr;
-    }
+    b->dev_scratch = nullptr; // carved out of the same allocation as `dev`
     if (b->host_block) {
         free(b->host_block);
         b->host_block = nullptr;
@@ -803,16 +800,16 @@ static int batch_prepare_range(rb_batch *b, int32_t n_threads, size_t begin, siz
     if (st == RB_NEEDS_RUN_SPLIT) return st;
     if (st != RB_OK) return rb_fail(ctx, st, "batch host build failed");
     if (!blk || b->lay.n_draws == 0) return RB_OK;
+    // one stream-ordered allocation holds the uploaded block and, behind it, the device-built lists and bins
+    const size_t block_bytes = (b->lay.total + 255) & ~(size_t)255;
+    const size_t scratch_bytes = b->lay.wide ? 0 : warp_scratch_layout(b->lay).total;
     uint8_t *dev = nullptr;
-    RB_CUDA(ctx, cudaMallocAsync((void **)&dev, b->lay.total, ctx->stream));
+    RB_CUDA(ctx, cudaMallocAsync((void **)&dev, block_bytes + scratch_bytes, ctx->stream));
     b->dev = dev;
     RB_CUDA(ctx, cudaMemcpyAsync(dev, blk, b->lay.total, cudaMemcpyHostToDevice, ctx->stream));
     ctx->h2d_bytes += b->lay.total;
     { int st__ = rb_staging_mark(ctx); if (st__ != RB_OK) return st__; }
-    if (!b->lay.wide) {
-        const WarpScratch ws = warp_scratch_layout(b->lay);
-        RB_CUDA(ctx, cudaMallocAsync((void **)&b->dev_scratch, ws.total, ctx->stream));
-    }
+    if (!b->lay.wide) b->dev_scratch = dev + block_bytes;
     return RB_OK;
 }
 
@@ -893,7 +890,8 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
         DrawBox *boxes = (DrawBox *)(sc + ws.o_boxes);
         RowEnt *row_draws = (RowEnt *)(sc + ws.o_row_draws);
         const uint32_t n_draws = (uint32_t)L.n_draws, n_wtiles = (uint32_t)((size_t)L.wtiles_x * L.wtiles_y);
-        RB_CUDA(ctx, cudaEventRecord(ctx->ev_run[0], ctx->stream));
+        const bool time_run = n_draws > 32; // rb_ctx_last_run_ms is about the large batches; small ones skip the event records
+        if (time_run) RB_CUDA(ctx, cudaEventRecord(ctx->ev_run[0], ctx->stream));
         // Small batches (a tree traversal records a handful of draws per layer) skip the binning pre-pass: the raster
         // kernel then tests every draw of the batch against the tile itself (direct mode), which saves two memsets and
         // eight launches per batch.
@@ -931,16 +929,23 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
         k_bin_tiles<<<(n_wtiles + 7) / 8, 256, 0, ctx->stream>>>(row_draws, row_cnt, tile_off, L.wtiles_x, n_wtiles, tile_pairs);
         RB_LAUNCHED(ctx, "bin_tiles");
         }
-        RB_CUDA(ctx, cudaEventRecord(ctx->ev_run[1], ctx->stream));
-        const unsigned grid = (n_wtiles + WT_WARPS - 1) / WT_WARPS;
+        if (time_run) RB_CUDA(ctx, cudaEventRecord(ctx->ev_run[1], ctx->stream));
+        unsigned grid = (n_wtiles + WT_WARPS - 1) / WT_WARPS;
+        if (direct) grid = std::min(grid, (unsigned)(ctx->sm_count * RW_MIN_CTAS * 2)); // warps stride over the tiles
 #define RB_WARP_ARGS target, W, H, L.wtiles_x, n_wtiles, tile_off, tile_pairs, d_draws, row_off, row_edges, d_edges,                   \
     (const DevPaint *)(b->dev + L.o_paints), (const DevStop *)(b->dev + L.o_stops), px_stats, row_cols, n_draws
-        if (mask_target) k_raster_warp<true, false><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
-        else if (L.has_hair) k_raster_warp<false, true><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
-        else k_raster_warp<false, false><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
+        if (direct) {
+            if (mask_target) k_raster_warp<true, false, true><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
+            else if (L.has_hair) k_raster_warp<false, true, true><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
+            else k_raster_warp<false, false, true><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
+        } else {
+            if (mask_target) k_raster_warp<true, false, false><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
+            else if (L.has_hair) k_raster_warp<false, true, false><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
+            else k_raster_warp<false, false, false><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
+        }
 #undef RB_WARP_ARGS
         RB_LAUNCHED(ctx, "raster_warp");
-        RB_CUDA(ctx, cudaEventRecord(ctx->ev_run[2], ctx->stream));
+        if (time_run) RB_CUDA(ctx, cudaEventRecord(ctx->ev_run[2], ctx->stream));
         return RB_OK;
     }
     const unsigned n_tile_ids = (unsigned)L.n_tile_ids;

@@ -512,36 +512,14 @@ struct WarpDraw { // what one lane holds about one upcoming (draw, tile) pair
 #define RW_MIN_CTAS 21
 #endif
 // HAIR: the batch holds hairline strokes (a second instantiation, so that batches without them run the leaner code).
-template <bool MASK, bool HAIR>
-__global__ void __launch_bounds__(WT_WARPS * 32, RW_MIN_CTAS)
-k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_wtiles, const uint32_t *__restrict__ tile_off,
-              const uint32_t *__restrict__ tile_pairs, const DevDraw *__restrict__ draws, const uint32_t *__restrict__ row_off,
-              const DevEdge *__restrict__ row_edges, const DevEdge *__restrict__ edges, const DevPaint *__restrict__ paints,
-              const DevStop *__restrict__ stops, unsigned long long *__restrict__ px_stats, const uint32_t *__restrict__ row_cols,
-              uint32_t n_direct)
+template <bool MASK, bool HAIR, bool direct>
+__device__ __forceinline__ void
+raster_warp_tile(WarpTileSmem &S, const uint32_t tile, const uint32_t direct_mask, void *__restrict__ target, int W, int H,
+                 int wtiles_x, const uint32_t *__restrict__ tile_off, const uint32_t *__restrict__ tile_pairs, const DevDraw *__restrict__ draws,
+                 const uint32_t *__restrict__ row_off, const DevEdge *__restrict__ row_edges, const DevEdge *__restrict__ edges,
+                 const DevPaint *__restrict__ paints, const DevStop *__restrict__ stops, unsigned long long *__restrict__ px_stats, uint32_t n_direct)
 {
-    __shared__ WarpTileSmem s_all[WT_WARPS];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    WarpTileSmem &S = s_all[wid];
-    const uint32_t tile = blockIdx.x * WT_WARPS + wid;
-    if (tile >= n_wtiles) return;
-    // Direct mode (tile_off == nullptr; batches of at most 32 draws — the per-layer batches of a tree traversal): no bin
-    // tables were built; the tile's list is every draw of the batch, each kept or dropped by its own row / column extent.
-    const bool direct = tile_off == nullptr;
-    uint32_t direct_mask = 0;
-    if (direct) {
-        bool hit = false;
-        if ((uint32_t)lane < n_direct) {
-            const DevDraw &D = draws[lane];
-            const uint32_t r = (tile / (uint32_t)wtiles_x) - D.r0, c = tile % (uint32_t)wtiles_x;
-            if (r < D.n_rows) {
-                const uint32_t cols = row_cols[D.row_base + r];
-                hit = (cols & 0xffffu) <= c && c <= (cols >> 16);
-            }
-        }
-        direct_mask = __ballot_sync(0xffffffffu, hit);
-        if (!direct_mask) return;
-    }
+    const int lane = threadIdx.x & 31;
     const uint32_t d_begin = direct ? 0u : tile_off[tile], d_end = direct ? n_direct : tile_off[tile + 1];
     if (d_begin == d_end) return; // nothing touches this tile (most tiles of a sparse atlas)
     {
@@ -1022,5 +1000,45 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
                 }
             }
         }
+    }
+}
+
+// One warp per 32x8 tile.  Binned mode: one tile per warp (the grid covers the tile table).  Direct mode (tile_off ==
+// nullptr; batches of at most 32 draws — the per-layer batches of a tree traversal): no bin tables were built, a tile's list
+// is every draw of the batch, each kept or dropped by its own row / column extent; the grid is a few CTAs per SM and every
+// warp strides over the tiles, so that the (many) tiles nothing touches cost one load instead of a CTA launch.
+template <bool MASK, bool HAIR, bool DIRECT>
+__global__ void __launch_bounds__(WT_WARPS * 32, RW_MIN_CTAS)
+k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_wtiles, const uint32_t *__restrict__ tile_off,
+              const uint32_t *__restrict__ tile_pairs, const DevDraw *__restrict__ draws, const uint32_t *__restrict__ row_off,
+              const DevEdge *__restrict__ row_edges, const DevEdge *__restrict__ edges, const DevPaint *__restrict__ paints,
+              const DevStop *__restrict__ stops, unsigned long long *__restrict__ px_stats, const uint32_t *__restrict__ row_cols,
+              uint32_t n_direct)
+{
+    __shared__ WarpTileSmem s_all[WT_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    WarpTileSmem &S = s_all[wid];
+    if (!DIRECT) {
+        const uint32_t tile = blockIdx.x * WT_WARPS + wid;
+        if (tile < n_wtiles)
+            raster_warp_tile<MASK, HAIR, false>(S, tile, 0u, target, W, H, wtiles_x, tile_off, tile_pairs, draws, row_off, row_edges, edges, paints,
+                                                stops, px_stats, 0u);
+        return;
+    }
+    // direct mode: lane d keeps draw d's tile-row range
+    uint32_t my_r0 = 0, my_nr = 0, my_base = 0;
+    if ((uint32_t)lane < n_direct) { my_r0 = draws[lane].r0; my_nr = draws[lane].n_rows; my_base = draws[lane].row_base; }
+    for (uint32_t tile = blockIdx.x * WT_WARPS + wid; tile < n_wtiles; tile += gridDim.x * WT_WARPS) {
+        const uint32_t r = tile / (uint32_t)wtiles_x - my_r0, c = tile % (uint32_t)wtiles_x;
+        bool hit = false;
+        if (r < my_nr) {
+            const uint32_t cols = row_cols[my_base + r];
+            hit = (cols & 0xffffu) <= c && c <= (cols >> 16);
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+        if (mask)
+            raster_warp_tile<MASK, HAIR, true>(S, tile, mask, target, W, H, wtiles_x, nullptr, nullptr, draws, row_off, row_edges, edges, paints,
+                                               stops, px_stats, n_direct);
+        __syncwarp();
     }
 }

@@ -56,7 +56,7 @@ static inline void rb_enter(const rb_ctx *ctx)
 {
     if (ctx) cudaSetDevice(ctx->device);
 }
-enum { RB_ATTR_BOX = 1, RB_ATTR_MORPH = 2, RB_ATTR_TURB = 4, RB_ATTR_WIDE = 8, RB_ATTR_PXTABLE = 16 };
+enum { RB_ATTR_BOX = 1, RB_ATTR_MORPH = 2, RB_ATTR_TURB = 4, RB_ATTR_WIDE = 8, RB_ATTR_PXTABLE = 16, RB_ATTR_IIR = 32 };
 
 void rb_ctx_retain(rb_ctx *ctx);
 void rb_ctx_release(rb_ctx *ctx);
