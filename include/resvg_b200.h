@@ -406,6 +406,10 @@ int rb_debug_build_edges(const uint8_t *verbs, int32_t n_verbs, const float *poi
                          int32_t *out_meta /* optional: {prev segment index | -1, inserts-before flag} per edge */,
                          int32_t max_edges, int32_t geom[7]);
 
+/* Tuning hook: with RB_PROFILE=1 in the environment the library accumulates host-side phase timers (host build, upload,
+ * launches, layer create / destroy, recording, composites); this prints them to stderr (reset_only == 0) and clears them. */
+void rb_debug_profile(int reset_only);
+
 /* Test hook: expand curves into line edges on the host (as the fallback path does) instead of on the device. */
 void rb_debug_host_expand(int on);
 

@@ -154,6 +154,7 @@ SIGNATURES = {
     "rb_debug_batch_begin_host": (_i, [_u32, _u32, c_void_pp]),
     "rb_debug_batch_phases": (_i, [_vp, _vp]),
     "rb_debug_batch_block": (C.c_int64, [_vp, C.c_int32, _vp, C.c_uint64]),
+    "rb_debug_profile": (None, [_i]),
     "rb_stroke_path": (_i, [_vp, _vp, C.c_int32, _vp, C.c_int32, C.POINTER(Paint), _vp, f32p]),
     "rb_fill_rect": (_i, [_vp, _f, _f, _f, _f, C.POINTER(Paint), f32p]),
     "rb_layer_clone_rect": (_i, [_vp, C.c_int32, C.c_int32, _u32, _u32, c_void_pp]),

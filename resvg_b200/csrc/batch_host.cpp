@@ -21,6 +21,7 @@
 
 #include "batch.h"
 #include "hairline.h"
+#include "rb_internal.h"
 
 extern "C" int rb_path_stroke(const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points, float width,
                               float miter_limit, int32_t cap, int32_t join, float res_scale, uint8_t **out_verbs,
@@ -1025,6 +1026,7 @@ int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threa
 int rb_batch_record(rb_batch *b, const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
                     const rb_paint *paint, int32_t rule, const float ts[6])
 {
+    rb_prof_scope prof__(RB_T_RECORD);
     if (!b || !verbs || !points || n_verbs <= 0 || n_points <= 0 || !paint) return RB_ERR_INVALID;
     // a pattern's source layer must hold its final pixels before this draw runs: execute its pending immediate draws now,
     // on the caller's thread (rb_layer_device_ptr flushes)

@@ -1,5 +1,7 @@
 // context.cu — context, device memory and host<->device plumbing of the resvg_b200 C ABI.
 #include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -23,6 +25,11 @@ int rb_cuda_fail(rb_ctx *ctx, cudaError_t e, const char *what)
     }
     return e == cudaErrorMemoryAllocation ? RB_ERR_OOM : RB_ERR_CUDA;
 }
+
+rb_host_prof g_rb_prof = {{0}, {0}, false};
+static double rb_now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+rb_prof_scope::rb_prof_scope(int kind) : k(kind), t0(g_rb_prof.on ? rb_now() : 0.0) {}
+rb_prof_scope::~rb_prof_scope() { if (g_rb_prof.on) { g_rb_prof.t[k] += rb_now() - t0; g_rb_prof.n[k]++; } }
 
 int rb_check_flags(rb_ctx *ctx)
 {
@@ -99,6 +106,11 @@ void rb_ctx_retain(rb_ctx *ctx) { ctx->refs.fetch_add(1, std::memory_order_relax
 void rb_ctx_release(rb_ctx *ctx)
 {
     if (ctx->refs.fetch_sub(1, std::memory_order_acq_rel) != 1) return;
+    if (g_rb_prof.on) {
+        static const char *names[6] = {"host build", "alloc + upload", "run (launches)", "layer create/destroy", "record", "composite/mask/filter calls"};
+        for (int i = 0; i < 6; i++)
+            fprintf(stderr, "[rb profile] %-28s %9.3f ms  %8llu calls\n", names[i], g_rb_prof.t[i] * 1e3, (unsigned long long)g_rb_prof.n[i]);
+    }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
@@ -130,6 +142,7 @@ extern "C" int rb_ctx_create(int device, rb_ctx **out)
         return RB_ERR_CUDA;
     }
     if (device < 0 || device >= count) return RB_ERR_INVALID;
+    g_rb_prof.on = getenv("RB_PROFILE") != nullptr;
     rb_ctx *ctx = new rb_ctx();
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return RB_ERR_CUDA; }
@@ -225,6 +238,7 @@ extern "C" void rb_host_free(void *p)
 
 extern "C" int rb_layer_create(rb_ctx *ctx, uint32_t w, uint32_t h, rb_layer **out)
 {
+    rb_prof_scope prof__(RB_T_LAYER);
     rb_enter(ctx);
     if (!ctx || !out) return RB_ERR_INVALID;
     *out = nullptr;
@@ -244,6 +258,7 @@ extern "C" int rb_layer_create(rb_ctx *ctx, uint32_t w, uint32_t h, rb_layer **o
 
 extern "C" void rb_layer_destroy(rb_layer *l)
 {
+    rb_prof_scope prof__(RB_T_LAYER);
     if (!l) return;
     if (l->pending) { // immediate draws nobody looked at: drop them
         rb_batch_destroy(l->pending);
@@ -376,4 +391,15 @@ extern "C" int rb_layer_clone_rect(const rb_layer *src, int32_t x, int32_t y, ui
     if (e != cudaSuccess) { rb_layer_destroy(l); return rb_cuda_fail(src->ctx, e, "clone_rect"); }
     *out = l;
     return RB_OK;
+}
+
+// Test / tuning hook: clears the RB_PROFILE phase timers (e.g. after warm-up) and prints them on demand.
+extern "C" void rb_debug_profile(int reset_only)
+{
+    if (!reset_only && g_rb_prof.on) {
+        static const char *names[6] = {"host build", "alloc + upload", "run (launches)", "layer create/destroy", "record", "composite/mask/filter calls"};
+        for (int i = 0; i < 6; i++)
+            fprintf(stderr, "[rb profile] %-28s %9.3f ms  %8llu calls\n", names[i], g_rb_prof.t[i] * 1e3, (unsigned long long)g_rb_prof.n[i]);
+    }
+    for (int i = 0; i < 8; i++) { g_rb_prof.t[i] = 0.0; g_rb_prof.n[i] = 0; }
 }

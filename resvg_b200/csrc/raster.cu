@@ -795,8 +795,10 @@ static int batch_prepare_range(rb_batch *b, int32_t n_threads, size_t begin, siz
     const int W = (int)(mask_target ? b->mask->w : b->layer->w), H = (int)(mask_target ? b->mask->h : b->layer->h);
     cudaSetDevice(ctx->device);
     StageReq req{ctx, RB_OK};
-    int st = rb_batch_host_build(b, W, H, mask_target, n_threads, stage_pinned, &req, &blk, begin, end);
+    int st;
+    { rb_prof_scope prof__(RB_T_BUILD); st = rb_batch_host_build(b, W, H, mask_target, n_threads, stage_pinned, &req, &blk, begin, end); }
     if (req.status != RB_OK) return req.status;
+    rb_prof_scope prof_up__(RB_T_UPLOAD);
     if (st == RB_NEEDS_RUN_SPLIT) return st;
     if (st != RB_OK) return rb_fail(ctx, st, "batch host build failed");
     if (!blk || b->lay.n_draws == 0) return RB_OK;
@@ -862,6 +864,7 @@ extern "C" int rb_batch_run_counting(rb_batch *b, uint64_t out[2])
 
 static int batch_run(rb_batch *b, unsigned long long *px_stats)
 {
+    rb_prof_scope prof__(RB_T_RUN);
     if (!b) return RB_ERR_INVALID;
     if (!b->dev || b->lay.n_draws == 0) return RB_OK; // nothing to draw
     const bool mask_target = b->mask != nullptr;
@@ -1225,6 +1228,7 @@ k_draw_layer(uint32_t *__restrict__ dst, int dw, const uint32_t *__restrict__ sr
 
 extern "C" int rb_draw_layer(rb_layer *dst, const rb_layer *src, int32_t x, int32_t y, float opacity, int32_t blend_mode)
 {
+    rb_prof_scope prof__(RB_T_COMPOSITE);
     rb_enter(dst ? dst->ctx : nullptr);
     RB_SYNC_LAYER(dst);
     RB_SYNC_LAYER(src);

@@ -95,6 +95,15 @@ struct rb_mask {
     uint8_t *d; // w*h bytes
 };
 
+// Host-side phase timers (RB_PROFILE=1 prints them when a context is destroyed): where a traversal's wall time goes.
+struct rb_host_prof { double t[8]; uint64_t n[8]; bool on; };
+extern rb_host_prof g_rb_prof;
+enum { RB_T_BUILD = 0, RB_T_UPLOAD = 1, RB_T_RUN = 2, RB_T_LAYER = 3, RB_T_RECORD = 4, RB_T_COMPOSITE = 5 };
+struct rb_prof_scope {
+    int k; double t0;
+    explicit rb_prof_scope(int kind);
+    ~rb_prof_scope();
+};
 int rb_fail(rb_ctx *ctx, int code, const char *what);
 // After a synchronisation: RB_ERR_CUDA (and rb_last_error) if a kernel raised a sticky flag since the last check.
 int rb_check_flags(rb_ctx *ctx);

@@ -10,6 +10,7 @@ target = ctx.layer(4096, 4096)
 for _ in range(3):
     rb.tree.render(tree, ident, target)
 ctx.synchronize()
+rb._ffi.lib.rb_debug_profile(1)
 for _ in range(3):
     l0 = ctx.launch_count
     ctx.timer_begin()
@@ -19,3 +20,4 @@ for _ in range(3):
     ms = ctx.timer_end()
     t2 = time.perf_counter()
     print(f"host enqueue {1e3*(t1-t0):.2f} ms, device span {ms:.2f} ms, wall {1e3*(t2-t0):.2f} ms, launches {ctx.launch_count-l0}")
+rb._ffi.lib.rb_debug_profile(0)
