@@ -28,6 +28,18 @@ def test_document_assignment_is_a_partition():
     assert shard.host_threads(1) >= shard.host_threads(2) >= 1
 
 
+def test_corpus_files_are_partitioned_by_file():
+    """C1 (the regression corpus) shards by file: file i -> rank i mod N; every fixture is rendered exactly once."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "scenes", "*.json")))
+    assert len(files) >= 850
+    for world in (1, 2, 4, 8):
+        got = sorted(i for r in range(world) for i in shard.documents_for_rank(len(files), r, world))
+        assert got == list(range(len(files)))
+        sizes = [len(shard.documents_for_rank(len(files), r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+
+
 def test_strips_partition_the_canvas():
     for height in (8192, 4096, 300, 17, 8):
         for world in (1, 2, 3, 4, 8):
@@ -73,3 +85,17 @@ def test_two_ranks_gloo(tmp_path):
     assert rep["ms"] == 15.0  # max over ranks, not rank 0's 10 ms
     assert rep["value"] == pytest.approx(2 * (W * H / 1e6) / 15e-3)
     assert rep["docs"] == [[0, 2, 4, 6], [1, 3, 5, -1]]
+    # corpus by file: 16 fixtures over 2 ranks, all reproduce their golden, and the per-rank checksums equal a serial run's
+    import glob
+    import json as _json
+    from tests import svgfront as F
+    from tests.backends import OracleBackend
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "scenes", "*.json")))[:16]
+    serial = []
+    for r in range(2):
+        crc = 0
+        for i in range(r, 16, 2):
+            with open(files[i]) as f:
+                crc = zlib.crc32(F.render_scene(_json.load(f), OracleBackend(), 300).tobytes(), crc)
+        serial.append([8, crc])
+    assert rep["corpus"] == serial
