@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "batch.h"
+#include "fill_core.h"
 #include "hairline.h"
 #include "rb_internal.h"
 
@@ -760,36 +761,12 @@ void build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, bool
                     // slots of the device-side edge array in emission order: one per line, 2^shift per curve
                     const size_t co = out->curves.size();
                     out->curves.resize(co + ncv);
-                    rbh::CurveRec *cdst = out->curves.data() + co;
-                    const rbh::CurveRec *csrc = out->cscratch.data();
                     out->ends.clear();
-                    uint32_t slot = 0;
-                    size_t il = 0, ic = 0;
-                    while (il < ne || ic < ncv) {
-                        if (ic >= ncv || (il < ne && src[il].order < csrc[ic].item)) {
-                            const rbh::Edge &e = src[il];
-                            DevEdge de;
-                            de.x = e.x; de.dx = e.dx;
-                            de.ypack = ((uint32_t)e.first_y & 0xffffu) | ((uint32_t)e.last_y << 16);
-                            de.meta = (e.winding < 0 ? 1u : 0u) | (slot << 4);
-                            dst[il++] = de;
-                            n_list += (size_t)(row_of(e.last_y) - row_of(e.first_y) + 1);
-                            out->ends.push_back(e.first_y); out->ends.push_back(e.last_y);
-                            slot += 1;
-                        } else {
-                            rbh::CurveRec c = csrc[ic];
-                            const int sh = (int)((c.info >> 4) & 0xfu);
-                            const int ylast = (c.info & 1u) ? c.p[7] : c.p[5];
-                            const int32_t top = (c.p[1] + 32) >> 6, bot = (ylast + 32) >> 6;
-                            c.item = slot;
-                            cdst[ic++] = c;
-                            // its segments partition [top, bot): at most one extra list entry per tile-row boundary
-                            n_list += ((size_t)1 << sh) + (size_t)(row_of(bot - 1) - row_of(top)) + 2;
-                            out->ends.push_back(top); out->ends.push_back(bot - 1);
-                            slot += 1u << sh;
-                        }
-                    }
-                    if (slot >= (1u << 28)) { out->too_large = true; continue; } // meta keeps slot indices in 28 bits
+                    struct Ends { std::vector<int32_t> *v; void operator()(int32_t a, int32_t b) { v->push_back(a); v->push_back(b); } } ends{&out->ends};
+                    const geo::fl::Packed po = geo::fl::pack_items(src, ne, out->cscratch.data(), ncv, dst, out->curves.data() + co, g.shift, oy, r0, nr, ends);
+                    n_list = po.n_list;
+                    const uint32_t slot = po.slots;
+                    if (po.too_large) { out->too_large = true; continue; }
                     if (chains_may_exceed_packed_winding(out->ends)) out->wide = true;
                     d.edge_cnt = slot;                     // slots of this draw in the device edge array
                     d.edge_off = (uint32_t)ci->n_slots;    // chunk-relative slot base

@@ -1,0 +1,146 @@
+// geom_common.h — what the path-geometry cores (stroker_core.h, dasher_core.h, hairline_core.h, fill_core.h) share.
+//
+// Every core is ONE source compiled twice: by g++ into the host builder (batch_host.cpp and the rb_path_* exports, with
+// std::vector storage) and by nvcc into the device geometry kernels (geo.cu, with heap-backed DVec storage), so the two
+// sides cannot drift apart: the CPU test-suite that pins the host geometry against the independent CPU checker pins the device code too,
+// and the GPU tests compare the two builds bit for bit.  Both compilers run without FMA contraction (-fmad=false /
+// -ffp-contract=off) and with IEEE division and square root.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define GEO_HD __host__ __device__
+#else
+#define GEO_HD
+#endif
+
+namespace geo {
+
+struct P {
+    float x, y;
+};
+GEO_HD inline P operator+(P a, P b) { return P{a.x + b.x, a.y + b.y}; }
+GEO_HD inline P operator-(P a, P b) { return P{a.x - b.x, a.y - b.y}; }
+GEO_HD inline P operator-(P a) { return P{-a.x, -a.y}; }
+GEO_HD inline P operator*(P a, float s) { return P{a.x * s, a.y * s}; }
+GEO_HD inline bool operator==(P a, P b) { return a.x == b.x && a.y == b.y; }
+GEO_HD inline bool operator!=(P a, P b) { return !(a == b); }
+
+template <class T> GEO_HD inline T gmin(T a, T b) { return b < a ? b : a; } // std::min
+template <class T> GEO_HD inline T gmax(T a, T b) { return a < b ? b : a; } // std::max
+template <class T> GEO_HD inline void gswap(T &a, T &b) { T t = a; a = b; b = t; }
+GEO_HD inline bool gfinite(float v) { return fabsf(v) <= 3.402823466e+38f; } // false for NaN and +-inf
+GEO_HD inline bool gfinite(double v) { return fabs(v) <= 1.7976931348623157e+308; }
+GEO_HD inline bool finite(P a) { return gfinite(a.x) && gfinite(a.y); }
+
+// Rust `as i32` casts: truncate, saturate, NaN -> 0
+GEO_HD inline int32_t f2i(float v)
+{
+    if (v != v) return 0;
+    if (v >= 2147483648.0f) return INT32_MAX;
+    if (v <= -2147483648.0f) return INT32_MIN;
+    return (int32_t)v;
+}
+GEO_HD inline int32_t d2i(double v)
+{
+    if (v != v) return 0;
+    if (v >= 2147483647.0) return INT32_MAX;
+    if (v <= -2147483648.0) return INT32_MIN;
+    return (int32_t)v;
+}
+
+// Transcendentals of the stroker's cubic solver (path_geometry.rs solve_cubic_poly).  The host calls glibc, whose acosf /
+// cosf are correctly rounded in all but astronomically rare cases; the device evaluates in double and rounds once,
+// which gives the same float (CUDA's double acos / cos are within 2 ulp of the double result).  cbrtf likewise.
+GEO_HD inline float g_acosf(float v)
+{
+#if defined(__CUDA_ARCH__)
+    return (float)acos((double)v);
+#else
+    return acosf(v);
+#endif
+}
+GEO_HD inline float g_cosf(float v)
+{
+#if defined(__CUDA_ARCH__)
+    return (float)cos((double)v);
+#else
+    return cosf(v);
+#endif
+}
+GEO_HD inline float g_cbrtf(float v)
+{
+#if defined(__CUDA_ARCH__)
+    return (float)cbrt((double)v);
+#else
+    return cbrtf(v);
+#endif
+}
+
+// ---- storage ---------------------------------------------------------------------------------------------------------------
+// The cores are templates over the vector type: std::vector on the host, DVec on the device.  DVec grows like a vector
+// but takes its chunks from a bump heap in global memory shared by the whole launch (one atomicAdd per growth; a chunk
+// that has been outgrown is simply abandoned).  When the heap runs out the push is dropped and the launch-wide flag is
+// raised: the host discards the launch's results and repeats it with a larger heap (geo.cu).  Everything here stays
+// memory-safe after a dropped push; the results are garbage that nobody reads.
+struct GeoHeap {
+    uint8_t *base;
+    unsigned long long *cursor; // bytes handed out so far
+    unsigned long long size;
+    unsigned int *overflow;
+};
+constexpr uint32_t kHeapAlign = 80; // lcm(sizeof(DevEdge) = 16, sizeof(CurveRec) = 40): element offsets from the base stay integral
+
+#if defined(__CUDACC__)
+template <class T> struct DVec {
+    T *p;
+    uint32_t n, cap;
+    GeoHeap *h;
+    __device__ void init(GeoHeap *heap, uint32_t reserve_hint)
+    {
+        h = heap; p = nullptr; n = 0; cap = 0;
+        grow_to(reserve_hint < 8 ? 8 : reserve_hint);
+    }
+    __device__ bool ok() const { return p != nullptr; }
+    __device__ void grow_to(uint32_t want)
+    {
+        const unsigned long long bytes = (((unsigned long long)want * sizeof(T) + kHeapAlign - 1) / kHeapAlign) * kHeapAlign;
+        const unsigned long long off = atomicAdd(h->cursor, bytes);
+        if (off + bytes > h->size) { *(volatile unsigned int *)h->overflow = 1u; return; }
+        T *np = reinterpret_cast<T *>(h->base + off);
+        for (uint32_t i = 0; i < n; i++) np[i] = p[i];
+        p = np;
+        cap = want;
+    }
+    __device__ void push_back(const T &v)
+    {
+        if (n == cap) grow_to(cap * 2);
+        if (n < cap) p[n++] = v;
+    }
+    __device__ void pop_back() { if (n) n--; }
+    __device__ T &back() { return p[n ? n - 1 : 0]; }
+    __device__ const T &back() const { return p[n ? n - 1 : 0]; }
+    __device__ T &operator[](size_t i) { return p[i]; }
+    __device__ const T &operator[](size_t i) const { return p[i]; }
+    __device__ size_t size() const { return n; }
+    __device__ bool empty() const { return n == 0; }
+    __device__ void clear() { n = 0; }
+    __device__ void resize(size_t m) // shrink, or grow with zero-filled elements
+    {
+        if (m > cap) grow_to((uint32_t)m);
+        if (m > cap) return;
+        for (size_t i = n; i < m; i++) memset(&p[i], 0, sizeof(T));
+        n = (uint32_t)m;
+    }
+    __device__ T *data() { return p; }
+    __device__ const T *data() const { return p; }
+};
+#endif
+
+// Path verbs (include/resvg_b200.h RB_VERB_*)
+enum { V_MOVE = 0, V_LINE = 1, V_QUAD = 2, V_CUBIC = 3, V_CLOSE = 4 };
+
+} // namespace geo

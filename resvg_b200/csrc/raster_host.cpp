@@ -8,6 +8,7 @@
 #include "raster_host.h"
 
 #include "edge_math.h"
+#include "fill_core.h"
 #ifdef RB_HOST_PROFILE
 #include <x86intrin.h>
 #include <atomic>
@@ -118,492 +119,12 @@ void map_points(const Xform &t, Pt *p, int n)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// curve chopping (tiny-skia-path path_geometry.rs)
+// curve chopping, edge emission, clipping, the fill_path front end: fill_core.h (shared with the device)
 // ---------------------------------------------------------------------------------------------------
-static inline float lerpf(float a, float b, float t) { return a + (b - a) * t; }
-static inline Pt lerp(Pt a, Pt b, float t) { return Pt{lerpf(a.x, b.x, t), lerpf(a.y, b.y, t)}; }
-
-static bool unit_divide(float numer, float denom, float *ratio)
-{
-    if (numer < 0) { numer = -numer; denom = -denom; }
-    if (denom == 0 || numer == 0 || numer >= denom) return false;
-    float r = numer / denom;
-    if (!(r > 0.0f && r < 1.0f)) return false;
-    *ratio = r;
-    return true;
-}
-
-static int unit_quad_roots(float a, float b, float c, float roots[2])
-{
-    if (a == 0) return unit_divide(-c, b, roots) ? 1 : 0;
-    double dr = (double)b * b - 4.0 * (double)a * c;
-    if (dr < 0) return 0;
-    float r = (float)sqrt(dr);
-    if (!std::isfinite(r)) return 0;
-    float q = (b < 0) ? -(b - r) / 2 : -(b + r) / 2;
-    int n = 0;
-    if (unit_divide(q, a, roots + n)) n++;
-    if (unit_divide(c, q, roots + n)) n++;
-    if (n == 2) {
-        if (roots[0] > roots[1]) std::swap(roots[0], roots[1]);
-        else if (roots[0] == roots[1]) n = 1;
-    }
-    return n;
-}
-
-static void split_quad(const Pt s[3], float t, Pt d[5])
-{
-    Pt p01 = lerp(s[0], s[1], t), p12 = lerp(s[1], s[2], t);
-    d[0] = s[0]; d[1] = p01; d[2] = lerp(p01, p12, t); d[3] = p12; d[4] = s[2];
-}
-static void split_cubic(const Pt s[4], float t, Pt d[7])
-{
-    Pt ab = lerp(s[0], s[1], t), bc = lerp(s[1], s[2], t), cd = lerp(s[2], s[3], t);
-    Pt abc = lerp(ab, bc, t), bcd = lerp(bc, cd, t);
-    d[0] = s[0]; d[1] = ab; d[2] = abc; d[3] = lerp(abc, bcd, t); d[4] = bcd; d[5] = cd; d[6] = s[3];
-}
-
-template <int AXIS> static inline float &ax(Pt &p) { return AXIS ? p.y : p.x; }
-template <int AXIS> static inline float axv(const Pt &p) { return AXIS ? p.y : p.x; }
-
-template <int AXIS> static int quad_extrema(const Pt s[3], Pt d[5])
-{
-    float a = axv<AXIS>(s[0]), b = axv<AXIS>(s[1]), c = axv<AXIS>(s[2]);
-    float ab = a - b, bc = b - c;
-    if (ab < 0) bc = -bc;
-    if (ab == 0 || bc < 0) { // not monotonic
-        float t;
-        if (unit_divide(a - b, a - b - b + c, &t)) {
-            split_quad(s, t, d);
-            ax<AXIS>(d[1]) = axv<AXIS>(d[2]);
-            ax<AXIS>(d[3]) = axv<AXIS>(d[2]);
-            return 1;
-        }
-        b = fabsf(a - b) < fabsf(b - c) ? a : c;
-    }
-    d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
-    ax<AXIS>(d[1]) = b;
-    return 0;
-}
-
-template <int AXIS> static int cubic_extrema(const Pt s[4], Pt d[10])
-{
-    float a = axv<AXIS>(s[0]), b = axv<AXIS>(s[1]), c = axv<AXIS>(s[2]), e = axv<AXIS>(s[3]);
-    float tv[2];
-    int roots = unit_quad_roots(e - a + 3 * (b - c), 2 * (a - b - b + c), b - a, tv);
-    if (roots == 0) { memcpy(d, s, 4 * sizeof(Pt)); return 0; }
-    Pt src[4];
-    memcpy(src, s, sizeof(src));
-    Pt *dst = d;
-    float t = tv[0];
-    for (int i = 0; i < roots; i++) {
-        split_cubic(src, t, dst);
-        if (i == roots - 1) break;
-        dst += 3;
-        memcpy(src, dst, sizeof(src));
-        if (!unit_divide(tv[i + 1] - tv[i], 1.0f - tv[i], &t)) {
-            dst[4] = dst[5] = dst[6] = src[3];
-            break;
-        }
-    }
-    ax<AXIS>(d[2]) = axv<AXIS>(d[3]);
-    ax<AXIS>(d[4]) = axv<AXIS>(d[3]);
-    if (roots == 2) {
-        ax<AXIS>(d[5]) = axv<AXIS>(d[6]);
-        ax<AXIS>(d[7]) = axv<AXIS>(d[6]);
-    }
-    return roots;
-}
-
-// ---------------------------------------------------------------------------------------------------
-// edge emission (tiny-skia edge.rs) — curves are expanded to their line edges immediately
-// ---------------------------------------------------------------------------------------------------
-struct Sink {
-    std::vector<Edge> *out;
-    size_t base;  // first edge of this draw
-    int shift;
-    std::vector<uint8_t> kinds; // per emitted edge: 0 = from a line, 1 = from a curve (combine_vertical only
-                                // ever looks at a preceding *line* edge)
-    // item mode: curves are recorded (FDot6 control points + subdivision count) instead of being expanded; `order`
-    // of a line / `item` of a curve is then the emission index shared by both kinds
-    std::vector<CurveRec> *curves = nullptr;
-    uint32_t n_items = 0;
-
-    uint32_t next_order() { return curves ? n_items++ : (uint32_t)(out->size() - base); }
-
-    // LineEdge::new / update tail: FDot6 end points, y0 <= y1
-    bool emit(int32_t x0, int32_t y0, int32_t x1, int32_t y1, int winding, Edge *e)
-    {
-        rbe::RawEdge r;
-        if (!rbe::line_edge(x0, y0, x1, y1, &r)) return false;
-        e->x = r.x;
-        e->dx = r.dx;
-        e->first_y = r.first_y;
-        e->last_y = r.last_y;
-        e->winding = winding;
-        e->prev = -1;
-        e->before = 0;
-        e->order = 0;
-        return true;
-    }
-
-    void line(Pt p0, Pt p1)
-    {
-        float scale = (float)(1 << (shift + 6));
-        int32_t x0 = f2i(p0.x * scale), y0 = f2i(p0.y * scale), x1 = f2i(p1.x * scale), y1 = f2i(p1.y * scale);
-        int w = 1;
-        if (y0 > y1) { std::swap(x0, x1); std::swap(y0, y1); w = -1; }
-        Edge e;
-        if (!emit(x0, y0, x1, y1, w, &e)) return;
-        if (e.dx == 0 && !kinds.empty() && kinds.back() == 0) {
-            int c = combine_vertical(e, out->back());
-            if (c == 2) { out->pop_back(); kinds.pop_back(); return; }
-            if (c == 1) return;
-        }
-        e.order = next_order();
-        out->push_back(e);
-        kinds.push_back(0);
-    }
-
-    // edge_builder.rs combine_vertical: 0 no, 1 partial, 2 total
-    static int combine_vertical(const Edge &edge, Edge &last)
-    {
-        if (last.dx != 0 || edge.x != last.x) return 0;
-        if (edge.winding == last.winding) {
-            if (edge.last_y + 1 == last.first_y) { last.first_y = edge.first_y; return 1; }
-            if (edge.first_y == last.last_y + 1) { last.last_y = edge.last_y; return 1; }
-            return 0;
-        }
-        if (edge.first_y == last.first_y) {
-            if (edge.last_y == last.last_y) return 2;
-            if (edge.last_y < last.last_y) { last.first_y = edge.last_y + 1; return 1; }
-            last.first_y = last.last_y + 1;
-            last.last_y = edge.last_y;
-            last.winding = edge.winding;
-            return 1;
-        }
-        if (edge.last_y == last.last_y) {
-            if (edge.first_y > last.first_y) last.last_y = edge.first_y - 1;
-            else {
-                last.last_y = last.first_y - 1;
-                last.first_y = edge.first_y;
-                last.winding = edge.winding;
-            }
-            return 1;
-        }
-        return 0;
-    }
-
-    void push_segment(const rbe::RawEdge &r, int w, int32_t *link)
-    {
-        Edge e;
-        e.x = r.x; e.dx = r.dx; e.first_y = r.first_y; e.last_y = r.last_y;
-        e.winding = w;
-        e.prev = *link;
-        e.before = 0;
-        e.order = (uint32_t)(out->size() - base);
-        *link = (int32_t)e.order;
-        out->push_back(e);
-        kinds.push_back(1);
-    }
-
-    // QuadraticEdge::new + every update(): emits one line edge per non-degenerate segment.
-    void quad(const Pt p[3])
-    {
-        float scale = (float)(1 << (shift + 6));
-        int32_t x0 = f2i(p[0].x * scale), y0 = f2i(p[0].y * scale), x1 = f2i(p[1].x * scale), y1 = f2i(p[1].y * scale);
-        int32_t x2 = f2i(p[2].x * scale), y2 = f2i(p[2].y * scale);
-        int w = 1;
-        if (y0 > y2) { std::swap(x0, x2); std::swap(y0, y2); w = -1; }
-        if (fdot6_round(y0) == fdot6_round(y2)) return;
-        const int sh = rbe::quad_shift(x0, y0, x1, y1, x2, y2, shift);
-        if (curves) {
-            CurveRec c;
-            c.p[0] = x0; c.p[1] = y0; c.p[2] = x1; c.p[3] = y1; c.p[4] = x2; c.p[5] = y2; c.p[6] = 0; c.p[7] = 0;
-            c.info = 0u | ((uint32_t)sh << 4) | (w < 0 ? 0x100u : 0u);
-            c.item = n_items++;
-            curves->push_back(c);
-            kinds.push_back(1);
-            return;
-        }
-        int32_t link = -1;
-        rbe::quad_expand(x0, y0, x1, y1, x2, y2, sh, [&](const rbe::RawEdge &r) { push_segment(r, w, &link); });
-    }
-
-    // CubicEdge::new + every update()
-    void cubic(const Pt p[4])
-    {
-        float scale = (float)(1 << (shift + 6));
-        int32_t x0 = f2i(p[0].x * scale), y0 = f2i(p[0].y * scale), x1 = f2i(p[1].x * scale), y1 = f2i(p[1].y * scale);
-        int32_t x2 = f2i(p[2].x * scale), y2 = f2i(p[2].y * scale), x3 = f2i(p[3].x * scale), y3 = f2i(p[3].y * scale);
-        int w = 1;
-        if (y0 > y3) { std::swap(x0, x3); std::swap(x1, x2); std::swap(y0, y3); std::swap(y1, y2); w = -1; }
-        if (fdot6_round(y0) == fdot6_round(y3)) return;
-        const int sh = rbe::cubic_shift(x0, y0, x1, y1, x2, y2, x3, y3);
-        if (curves) {
-            CurveRec c;
-            c.p[0] = x0; c.p[1] = y0; c.p[2] = x1; c.p[3] = y1; c.p[4] = x2; c.p[5] = y2; c.p[6] = x3; c.p[7] = y3;
-            c.info = 1u | ((uint32_t)sh << 4) | (w < 0 ? 0x100u : 0u);
-            c.item = n_items++;
-            curves->push_back(c);
-            kinds.push_back(1);
-            return;
-        }
-        int32_t link = -1;
-        rbe::cubic_expand(x0, y0, x1, y1, x2, y2, x3, y3, sh, [&](const rbe::RawEdge &r) { push_segment(r, w, &link); });
-    }
-};
-
-// ---------------------------------------------------------------------------------------------------
-// clipping against the tile rectangle (tiny-skia edge_clipper.rs / line_clipper.rs)
-// ---------------------------------------------------------------------------------------------------
-struct Clip { float l, t, r, b; };
-
-static float pin(double v, double a, double b)
-{
-    if (a > b) std::swap(a, b);
-    return (float)std::min(std::max(v, a), b);
-}
-static float cut_h(const Pt s[2], float y)
-{
-    float dy = s[1].y - s[0].y;
-    if (nearly_zero(dy)) return (s[0].x + s[1].x) * 0.5f;
-    double x0 = s[0].x, y0 = s[0].y, x1 = s[1].x, y1 = s[1].y;
-    return pin(x0 + ((double)y - y0) * (x1 - x0) / (y1 - y0), x0, x1);
-}
-static float cut_v(const Pt s[2], float x)
-{
-    float dx = s[1].x - s[0].x;
-    float y;
-    if (nearly_zero(dx)) y = (s[0].y + s[1].y) * 0.5f;
-    else {
-        double x0 = s[0].x, y0 = s[0].y, x1 = s[1].x, y1 = s[1].y;
-        y = (float)(y0 + ((double)x - x0) * (y1 - y0) / (x1 - x0));
-    }
-    float a = s[0].y, b = s[1].y;
-    if (a > b) std::swap(a, b);
-    return std::min(std::max(y, a), b);
-}
-
-struct Clipper {
-    Sink *sink;
-    Clip c;
-
-    void line(Pt p0, Pt p1)
-    {
-        const Pt pts[2] = {p0, p1};
-        int i0 = pts[0].y < pts[1].y ? 0 : 1, i1 = 1 - i0;
-        if (pts[i1].y <= c.t || pts[i0].y >= c.b) return;
-        Pt tmp[2] = {p0, p1};
-        if (pts[i0].y < c.t) tmp[i0] = Pt{cut_h(pts, c.t), c.t};
-        if (tmp[i1].y > c.b) tmp[i1] = Pt{cut_h(pts, c.b), c.b};
-        Pt res[4];
-        int n = 1;
-        bool rev;
-        if (pts[0].x < pts[1].x) { i0 = 0; i1 = 1; rev = false; } else { i0 = 1; i1 = 0; rev = true; }
-        if (tmp[i1].x <= c.l) {
-            res[0] = Pt{c.l, tmp[0].y}; res[1] = Pt{c.l, tmp[1].y}; rev = false;
-        } else if (tmp[i0].x >= c.r) {
-            res[0] = Pt{c.r, tmp[0].y}; res[1] = Pt{c.r, tmp[1].y}; rev = false;
-        } else {
-            Pt *r = res;
-            if (tmp[i0].x < c.l) {
-                *r++ = Pt{c.l, tmp[i0].y};
-                *r = Pt{c.l, cut_v(tmp, c.l)};
-            } else *r = tmp[i0];
-            r++;
-            if (tmp[i1].x > c.r) {
-                *r++ = Pt{c.r, cut_v(tmp, c.r)};
-                *r = Pt{c.r, tmp[i1].y};
-            } else *r = tmp[i1];
-            n = (int)(r - res);
-        }
-        if (rev) for (int i = n; i > 0; i--) sink->line(res[i], res[i - 1]);
-        else for (int i = 0; i < n; i++) sink->line(res[i], res[i + 1]);
-    }
-    void vline(float x, float y0, float y1, bool rev)
-    {
-        if (rev) std::swap(y0, y1);
-        sink->line(Pt{x, y0}, Pt{x, y1});
-    }
-    void put_quad(const Pt p[3], bool rev)
-    {
-        if (rev) { Pt r[3] = {p[2], p[1], p[0]}; sink->quad(r); } else sink->quad(p);
-    }
-    void put_cubic(const Pt p[4], bool rev)
-    {
-        if (rev) { Pt r[4] = {p[3], p[2], p[1], p[0]}; sink->cubic(r); } else sink->cubic(p);
-    }
-
-    static bool mono_quad_t(float c0, float c1, float c2, float target, float *t)
-    {
-        float roots[2];
-        if (unit_quad_roots(c0 - c1 - c1 + c2, 2 * (c1 - c0), c0 - target, roots)) { *t = roots[0]; return true; }
-        return false;
-    }
-
-    void mono_quad(const Pt src[3])
-    {
-        Pt p[3];
-        bool rev = src[0].y > src[2].y;
-        if (rev) { p[0] = src[2]; p[1] = src[1]; p[2] = src[0]; } else { p[0] = src[0]; p[1] = src[1]; p[2] = src[2]; }
-        if (p[2].y <= c.t || p[0].y >= c.b) return;
-        float t;
-        Pt tmp[5];
-        if (p[0].y < c.t) {
-            if (mono_quad_t(p[0].y, p[1].y, p[2].y, c.t, &t)) {
-                split_quad(p, t, tmp);
-                tmp[2].y = c.t;
-                tmp[3].y = std::max(tmp[3].y, c.t);
-                p[0] = tmp[2]; p[1] = tmp[3];
-            } else for (auto &q : p) if (q.y < c.t) q.y = c.t;
-        }
-        if (p[2].y > c.b) {
-            if (mono_quad_t(p[0].y, p[1].y, p[2].y, c.b, &t)) {
-                split_quad(p, t, tmp);
-                tmp[1].y = std::min(tmp[1].y, c.b);
-                tmp[2].y = c.b;
-                p[1] = tmp[1]; p[2] = tmp[2];
-            } else for (auto &q : p) if (q.y > c.b) q.y = c.b;
-        }
-        if (p[0].x > p[2].x) { std::swap(p[0], p[2]); rev = !rev; }
-        if (p[2].x <= c.l) { vline(c.l, p[0].y, p[2].y, rev); return; }
-        if (p[0].x >= c.r) { vline(c.r, p[0].y, p[2].y, rev); return; }
-        if (p[0].x < c.l) {
-            if (mono_quad_t(p[0].x, p[1].x, p[2].x, c.l, &t)) {
-                split_quad(p, t, tmp);
-                vline(c.l, tmp[0].y, tmp[2].y, rev);
-                tmp[2].x = c.l;
-                tmp[3].x = std::max(tmp[3].x, c.l);
-                p[0] = tmp[2]; p[1] = tmp[3];
-            } else { vline(c.l, p[0].y, p[2].y, rev); return; }
-        }
-        if (p[2].x > c.r) {
-            if (mono_quad_t(p[0].x, p[1].x, p[2].x, c.r, &t)) {
-                split_quad(p, t, tmp);
-                tmp[1].x = std::min(tmp[1].x, c.r);
-                tmp[2].x = c.r;
-                put_quad(tmp, rev);
-                vline(c.r, tmp[2].y, tmp[4].y, rev);
-            } else {
-                p[1].x = std::min(p[1].x, c.r);
-                p[2].x = std::min(p[2].x, c.r);
-                put_quad(p, rev);
-            }
-        } else put_quad(p, rev);
-    }
-
-    void quad(const Pt s[3])
-    {
-        float miny = std::min(std::min(s[0].y, s[1].y), s[2].y), maxy = std::max(std::max(s[0].y, s[1].y), s[2].y);
-        if (!(maxy > c.t && miny < c.b)) return;
-        Pt my[5];
-        int cy = quad_extrema<1>(s, my);
-        for (int y = 0; y <= cy; y++) {
-            Pt mx[5];
-            int cx = quad_extrema<0>(&my[y * 2], mx);
-            for (int x = 0; x <= cx; x++) mono_quad(&mx[x * 2]);
-        }
-    }
-
-    // mono_cubic_closest_t over one coordinate (stride 2 floats)
-    static float closest_t(const float *s, float x)
-    {
-        float t = 0.5f, last_t, best = t, step = 0.25f;
-        float d = s[0], a = s[6] + 3 * (s[2] - s[4]) - d, b = 3 * (s[4] - s[2] - s[2] + d), cc = 3 * (s[2] - d);
-        x -= d;
-        float closest = 3.402823466e+38f;
-        do {
-            float loc = ((a * t + b) * t + cc) * t;
-            float dist = fabsf(loc - x);
-            if (closest > dist) { closest = dist; best = t; }
-            last_t = t;
-            t += loc < x ? step : -step;
-            step *= 0.5f;
-        } while (closest > 0.25f && last_t != t);
-        return best;
-    }
-    static void chop_at(const Pt p[4], float v, int axis, Pt d[7]) { split_cubic(p, closest_t(axis ? &p[0].y : &p[0].x, v), d); }
-
-    void mono_cubic(const Pt src[4])
-    {
-        Pt p[4];
-        bool rev = src[0].y > src[3].y;
-        if (rev) { p[0] = src[3]; p[1] = src[2]; p[2] = src[1]; p[3] = src[0]; } else memcpy(p, src, sizeof(p));
-        if (p[3].y <= c.t || p[0].y >= c.b) return;
-        Pt tmp[7];
-        if (p[0].y < c.t) {
-            chop_at(p, c.t, 1, tmp);
-            if (tmp[3].y < c.t && tmp[4].y < c.t && tmp[5].y < c.t) {
-                Pt t2[4] = {tmp[3], tmp[4], tmp[5], tmp[6]};
-                chop_at(t2, c.t, 1, tmp);
-            }
-            tmp[3].y = c.t;
-            tmp[4].y = std::max(tmp[4].y, c.t);
-            p[0] = tmp[3]; p[1] = tmp[4]; p[2] = tmp[5];
-        }
-        if (p[3].y > c.b) {
-            chop_at(p, c.b, 1, tmp);
-            tmp[3].y = c.b;
-            tmp[2].y = std::min(tmp[2].y, c.b);
-            p[1] = tmp[1]; p[2] = tmp[2]; p[3] = tmp[3];
-        }
-        if (p[0].x > p[3].x) { std::swap(p[0], p[3]); std::swap(p[1], p[2]); rev = !rev; }
-        if (p[3].x <= c.l) { vline(c.l, p[0].y, p[3].y, rev); return; }
-        if (p[0].x >= c.r) { vline(c.r, p[0].y, p[3].y, rev); return; }
-        if (p[0].x < c.l) {
-            chop_at(p, c.l, 0, tmp);
-            vline(c.l, tmp[0].y, tmp[3].y, rev);
-            tmp[3].x = c.l;
-            tmp[4].x = std::max(tmp[4].x, c.l);
-            p[0] = tmp[3]; p[1] = tmp[4]; p[2] = tmp[5];
-        }
-        if (p[3].x > c.r) {
-            chop_at(p, c.r, 0, tmp);
-            tmp[3].x = c.r;
-            tmp[2].x = std::min(tmp[2].x, c.r);
-            put_cubic(tmp, rev);
-            vline(c.r, tmp[3].y, tmp[6].y, rev);
-        } else put_cubic(p, rev);
-    }
-
-    void cubic(const Pt s[4])
-    {
-        float minx = s[0].x, maxx = s[0].x, miny = s[0].y, maxy = s[0].y;
-        for (int i = 1; i < 4; i++) {
-            minx = std::min(minx, s[i].x); maxx = std::max(maxx, s[i].x);
-            miny = std::min(miny, s[i].y); maxy = std::max(maxy, s[i].y);
-        }
-        if (!(maxy > c.t && miny < c.b)) return;
-        const float limit = (float)(1 << 22);
-        if (minx < -limit || miny < -limit || maxx > limit || maxy > limit) { line(s[0], s[3]); return; }
-        Pt my[10];
-        int cy = cubic_extrema<1>(s, my);
-        for (int y = 0; y <= cy; y++) {
-            Pt mx[10];
-            int cx = cubic_extrema<0>(&my[y * 3], mx);
-            for (int x = 0; x <= cx; x++) mono_cubic(&mx[x * 3]);
-        }
-    }
-};
-
-// ---------------------------------------------------------------------------------------------------
-// build_draw: scan::path_aa::fill_path / scan::path::fill_path up to (not including) walk_edges
-// ---------------------------------------------------------------------------------------------------
-static bool sect(IRect a, IRect b, IRect *o)
-{
-    int64_t l = std::max(a.x, b.x), t = std::max(a.y, b.y);
-    int64_t r = std::min<int64_t>((int64_t)a.x + a.w, (int64_t)b.x + b.w);
-    int64_t bt = std::min<int64_t>((int64_t)a.y + a.h, (int64_t)b.y + b.h);
-    if (r <= l || bt <= t) return false;
-    *o = IRect{(int32_t)l, (int32_t)t, (int32_t)(r - l), (int32_t)(bt - t)};
-    return true;
-}
-static bool contains(IRect o, IRect in)
-{
-    return in.x >= o.x && in.y >= o.y && (int64_t)in.x + in.w <= (int64_t)o.x + o.w && (int64_t)in.y + in.h <= (int64_t)o.y + o.h;
-}
-static inline bool short_overflow(int32_t v, int s) { return ((int32_t)(int16_t)shl(v, s) >> s) != v; }
+template <class T> using HVec = std::vector<T>;
+typedef geo::fl::Sink<HVec> Sink;
+using geo::fl::walk_path;
+using geo::fl::finish_geom;
 
 #ifdef RB_HOST_PROFILE
 std::atomic<uint64_t> g_bd_prof[4];
@@ -611,109 +132,6 @@ std::atomic<uint64_t> g_bd_prof[4];
 #else
 #define BD_T(i)
 #endif
-// Shared front end of both builders: bounds and clip decisions of tiny-skia's fill_path (painter.rs, scan/path.rs,
-// scan/path_aa.rs), then PathEdgeIter + EdgeClipper feeding `sink`.  Returns false when nothing is to be drawn.
-static bool walk_path(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, bool anti_alias, int32_t cw, int32_t ch,
-                      Sink &sink, DrawGeom *g, IRect *ir_out, bool *inside_out)
-{
-    if (n_pts == 0) return false;
-    // tiny_skia_path::Path cannot hold a non-finite point (PathBuilder::finish fails): such a path is never drawn.
-    // min / max would silently skip a NaN, so every point is probed.
-    float l = pts[0].x, r = l, t = pts[0].y, b = t, probe = 0.0f;
-    for (int i = 0; i < n_pts; i++) {
-        l = std::min(l, pts[i].x); r = std::max(r, pts[i].x);
-        t = std::min(t, pts[i].y); b = std::max(b, pts[i].y);
-        probe += pts[i].x * 0.0f + pts[i].y * 0.0f; // NaN as soon as one coordinate is NaN or infinite
-    }
-    if (!(probe == 0.0f)) return false;
-    if (!(std::isfinite(l) && std::isfinite(r) && std::isfinite(t) && std::isfinite(b))) return false;
-    if (nearly_zero(r - l) || nearly_zero(b - t)) return false; // painter.rs: empty paths, h/v lines
-    const IRect clip{0, 0, cw, ch};
-    IRect ir;
-    int shift = anti_alias ? 2 : 0;
-    if (anti_alias) {
-        int32_t il = f2i(floorf(l)), it = f2i(floorf(t)), irr = f2i(ceilf(r)), ib = f2i(ceilf(b));
-        if ((int64_t)irr - il <= 0 || (int64_t)ib - it <= 0) return false;
-        ir = IRect{il, it, (int32_t)((int64_t)irr - il), (int32_t)((int64_t)ib - it)};
-        IRect s;
-        if (!sect(ir, clip, &s)) return false;
-        if (short_overflow(s.x, 2) || short_overflow(s.y, 2) || short_overflow(s.x + s.w, 2) || short_overflow(s.y + s.h, 2))
-            shift = 0; // cannot supersample: non-AA fallback
-        else if (cw > 32767 || ch > 32767) return false;
-    }
-    if (shift == 0) {
-        const double bias = 0.5 + 1.5 / 64.0; // conservative_round_to_int
-        int32_t il = d2i(ceil((double)l - bias)), it = d2i(ceil((double)t - bias));
-        int32_t irr = d2i(floor((double)r + bias)), ib = d2i(floor((double)b + bias));
-        if ((int64_t)irr - il <= 0 || (int64_t)ib - it <= 0) return false;
-        ir = IRect{il, it, (int32_t)((int64_t)irr - il), (int32_t)((int64_t)ib - it)};
-    }
-    IRect s;
-    if (!sect(ir, clip, &s)) return false;
-    const bool inside = ir.x >= 0 && ir.y >= 0 && contains(clip, ir);
-
-    sink.shift = shift;
-    Clipper cl{&sink, Clip{0.0f, 0.0f, (float)cw, (float)ch}};
-
-    // PathEdgeIter: every contour is closed implicitly
-    int pi = 0;
-    Pt move_to{0, 0}, last{0, 0};
-    bool open = false;
-    for (int vi = 0; vi <= n_verbs; vi++) {
-        int verb = vi < n_verbs ? verbs[vi] : 4;
-        if (verb == 0 || verb == 4) {
-            if (open) {
-                if (inside) sink.line(last, move_to); else cl.line(last, move_to);
-                open = false;
-            }
-            if (verb == 0) { move_to = pts[pi++]; last = move_to; } else last = move_to;
-            continue;
-        }
-        if (verb == 1) {
-            Pt p1 = pts[pi++];
-            if (inside) sink.line(last, p1); else cl.line(last, p1);
-            last = p1;
-        } else if (verb == 2) {
-            Pt q[3] = {last, pts[pi], pts[pi + 1]};
-            pi += 2;
-            if (inside) {
-                Pt m[5];
-                int n = quad_extrema<1>(q, m);
-                for (int i = 0; i <= n; i++) sink.quad(&m[i * 2]);
-            } else cl.quad(q);
-            last = q[2];
-        } else if (verb == 3) {
-            Pt q[4] = {last, pts[pi], pts[pi + 1], pts[pi + 2]};
-            pi += 3;
-            if (inside) {
-                Pt m[10];
-                int n = cubic_extrema<1>(q, m);
-                for (int i = 0; i <= n; i++) sink.cubic(&m[i * 3]);
-            } else cl.cubic(q);
-            last = q[3];
-        }
-        open = true;
-    }
-    g->sect = s;
-    g->shift = shift;
-    *ir_out = ir;
-    *inside_out = inside;
-    return true;
-}
-
-static bool finish_geom(const IRect &ir, bool inside, int32_t ch, DrawGeom *g)
-{
-    int32_t start_y = shl(ir.y, g->shift), stop_y = shl(ir.y + ir.h, g->shift);
-    if (!inside) {
-        start_y = std::max(start_y, 0);
-        stop_y = std::min(stop_y, shl(ch, g->shift));
-    }
-    if (start_y < 0 || stop_y <= start_y) return false;
-    g->start_y = start_y;
-    g->stop_y = stop_y;
-    return true;
-}
-
 bool build_draw(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, bool anti_alias, int32_t cw, int32_t ch,
                 std::vector<Edge> &out, DrawGeom *g)
 {
@@ -725,7 +143,8 @@ bool build_draw(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, boo
     sink.base = out.size();
     IRect ir;
     bool inside;
-    if (!walk_path(verbs, n_verbs, pts, n_pts, anti_alias, cw, ch, sink, g, &ir, &inside)) { out.resize(sink.base); return false; }
+    const geo::P *gp = reinterpret_cast<const geo::P *>(pts);
+    if (!walk_path(verbs, n_verbs, gp, n_pts, anti_alias, cw, ch, sink, g, &ir, &inside)) { out.resize(sink.base); return false; }
     BD_T(0);
     size_t n = out.size() - sink.base;
     {
@@ -774,18 +193,16 @@ bool build_draw(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, boo
 bool build_draw_items(const uint8_t *verbs, int n_verbs, const Pt *pts, int n_pts, bool anti_alias, int32_t cw, int32_t ch,
                       std::vector<Edge> &lines, std::vector<CurveRec> &curves, DrawGeom *g)
 {
-    Sink sink;
+    static thread_local Sink sink;
     sink.out = &lines;
     sink.base = lines.size();
     sink.curves = &curves;
+    sink.kinds.clear();
+    sink.n_items = 0;
     const size_t cbase = curves.size();
-    IRect ir;
-    bool inside;
-    bool ok = walk_path(verbs, n_verbs, pts, n_pts, anti_alias, cw, ch, sink, g, &ir, &inside);
-    // BasicEdgeBuilder::build: fewer than two edge objects (a curve is one) -> nothing to draw
-    if (ok && (lines.size() - sink.base) + (curves.size() - cbase) < 2) ok = false;
-    if (ok) ok = finish_geom(ir, inside, ch, g);
-    if (!ok) { lines.resize(sink.base); curves.resize(cbase); return false; }
+    if (cbase != 0) return false; // the builder's curve list is per draw
+    const geo::P *gp = reinterpret_cast<const geo::P *>(pts);
+    if (!geo::fl::build_items<HVec>(verbs, n_verbs, gp, n_pts, anti_alias, cw, ch, sink, g)) { lines.resize(sink.base); curves.resize(cbase); return false; }
     return true;
 }
 
