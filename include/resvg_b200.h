@@ -413,6 +413,14 @@ void rb_debug_profile(int reset_only);
 /* Test hook: expand curves into line edges on the host (as the fallback path does) instead of on the device. */
 void rb_debug_host_expand(int on);
 
+/* Path geometry (transform, dash, stroke, hairline walk, monotone chop, clip, edge set-up: path.rs:73,113 down to tiny-skia's
+ * edge builder) runs on the device for large batches on layers and on host threads otherwise.  Test / tuning hook:
+ * mode 0 = that default, 1 = on the device for every eligible batch, 2 = always on the host (the RB_GEO_MODE environment
+ * variable sets the initial mode).  rb_debug_geo_counts: out[0] = batch ranges built by the geometry kernels so far,
+ * out[1] = ranges they handed back to the host builder, out[2] = launches repeated with a larger heap. */
+void rb_debug_geo_mode(int mode);
+void rb_debug_geo_counts(uint64_t out[3]);
+
 /* Host-only batch (no target, no device work): records like any batch; rb_batch_prepare runs the host build (edges,
  * binning, block layout) for a width x height canvas and keeps the block on the host.  For the CPU test-suite and for
  * profiling the host half.  rb_debug_batch_phases: microseconds of the last host build — [0] edge build, [1] layout +

@@ -151,6 +151,8 @@ SIGNATURES = {
     "rb_filter_box_blur_cells": (_i, [_vp, C.c_int32, _vp, _vp, _vp]),
     "rb_filter_flood_alpha": (_i, [_vp, _u8, _u8, _u8, _u8]),
     "rb_debug_host_expand": (None, [_i]),
+    "rb_debug_geo_mode": (None, [_i]),
+    "rb_debug_geo_counts": (None, [_vp]),
     "rb_debug_batch_begin_host": (_i, [_u32, _u32, c_void_pp]),
     "rb_debug_batch_phases": (_i, [_vp, _vp]),
     "rb_debug_batch_block": (C.c_int64, [_vp, C.c_int32, _vp, C.c_uint64]),

@@ -110,11 +110,14 @@ struct rb_batch {
     BatchLayout lay;
     uint8_t *dev = nullptr;
     uint8_t *dev_scratch = nullptr; // row lists + warp-tile bins (device-built)
+    bool scratch_owned = false;     // dev_scratch is an allocation of its own (device geometry) rather than the tail of `dev`
     void *host_block = nullptr; // host-only batches: malloc'ed copy of the block
 };
 
 // rb_batch_host_build: the range holds hairline strokes the chosen builder cannot draw inline (internal status).
 enum { RB_NEEDS_RUN_SPLIT = 104 };
+// rb_geo_prepare: the range has to be built by the host builder (internal status).
+enum { RB_GEO_FALLBACK = 105 };
 
 // Staging allocator: returns `bytes` of host memory the block is assembled in (pinned, owned by the context; or
 // malloc'ed for host-only batches).

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "batch.h"
+#include "batch_geo.h"
 #include "fill_core.h"
 #include "hairline.h"
 #include "rb_internal.h"
@@ -996,6 +997,310 @@ int rb_batch_host_build(rb_batch *b, int W, int H, bool mask_target, int n_threa
     b->stats[3] = L.wide ? L.n_tile_ids : (size_t)L.wtiles_x * L.wtiles_y;
     b->stats[4] = L.total;
     b->stats[5] = b->phases[5] = us_since(t0);
+    return RB_OK;
+}
+
+// ---- device path geometry: the host half (batch_geo.h) ---------------------------------------------------------------------
+static int geo_mode_from_env()
+{
+    const char *e = getenv("RB_GEO_MODE");
+    return e ? atoi(e) : 0;
+}
+int g_geo_mode = geo_mode_from_env();
+std::atomic<uint64_t> g_geo_counts[3];
+extern "C" void rb_debug_geo_mode(int mode) { g_geo_mode = mode; }
+extern "C" void rb_debug_geo_counts(uint64_t out[3])
+{
+    if (out) for (int i = 0; i < 3; i++) out[i] = g_geo_counts[i].load();
+}
+// the debug hooks that select a builder variant only the host has
+bool rb_debug_host_only_builder() { return g_force_wide || g_host_expand; }
+
+namespace {
+
+struct GeoWorker {
+    std::vector<GeoTask> tasks;
+    std::vector<uint8_t> verbs;
+    std::vector<rbh::Pt> pts;
+    std::vector<float> dashes, hstops;
+    std::vector<DevPaint> paints;
+    std::vector<DevStop> stops;
+    void reset() { tasks.clear(); verbs.clear(); pts.clear(); dashes.clear(); paints.clear(); stops.clear(); }
+};
+struct GeoChunk {
+    int worker = 0;
+    size_t t0 = 0, nt = 0, v0 = 0, nv = 0, p0 = 0, np = 0, d0 = 0, nd = 0, pa0 = 0, npa = 0, s0 = 0, ns = 0; // ranges in the worker's vectors
+    size_t gt = 0, gv = 0, gp = 0, gd = 0, gpa = 0, gs = 0;                                                // global bases
+};
+
+std::mutex g_geo_pool_mu;
+std::vector<std::unique_ptr<GeoWorker>> g_geo_pool;
+
+// Cost class of a task for the heaviest-first task lists (log2 of the expected number of edge items).
+inline int cost_class(uint32_t hint)
+{
+    int c = 0;
+    while (hint > 1 && c < 23) { hint >>= 1; c++; }
+    return c;
+}
+
+void geo_build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, GeoWorker *out, GeoChunk *ci)
+{
+    ci->t0 = out->tasks.size(); ci->v0 = out->verbs.size(); ci->p0 = out->pts.size(); ci->d0 = out->dashes.size();
+    ci->pa0 = out->paints.size(); ci->s0 = out->stops.size();
+    size_t span_i = 0;
+    for (size_t i = begin; i < end; i++) {
+        while (i >= b->spans[span_i].start + b->spans[span_i].count) span_i++;
+        while (i < b->spans[span_i].start) span_i--;
+        const DrawSpan &sp = b->spans[span_i];
+        int VX = 0, VY = 0, VW = W, VH = H;
+        if (sp.vp_w > 0) {
+            VX = sp.vp_x; VY = sp.vp_y; VW = sp.vp_w; VH = sp.vp_h;
+            if (VX >= W || VY >= H || (int64_t)VX + VW <= 0 || (int64_t)VY + VH <= 0) continue;
+        }
+        // the draw's recorded form
+        const uint8_t *verbs;
+        const rbh::Pt *rpts;
+        const float *stops_src, *dash_src = nullptr;
+        uint32_t n_verbs, n_pts;
+        rb_paint paint;
+        rbh::Xform ctm;
+        bool is_stroke, map_fill = false;
+        rb_stroke stroke;
+        int rule;
+        memset(&stroke, 0, sizeof(stroke));
+        if (sp.bulk < 0) {
+            const RecordedDraw &r = b->recs[sp.first + (i - sp.start)];
+            verbs = b->verbs.data() + r.verb_off;
+            rpts = b->pts.data() + r.pt_off;
+            n_verbs = r.n_verbs; n_pts = r.n_pts;
+            paint = r.paint;
+            stops_src = r.n_stops ? b->stops.data() + r.stop_off : nullptr;
+            ctm = r.ctm;
+            is_stroke = r.is_stroke;
+            if (is_stroke) { stroke = r.stroke; dash_src = r.stroke.n_dash > 0 ? b->dashes.data() + r.dash_off : nullptr; }
+            rule = r.rule;
+        } else {
+            const BulkSeg &bs = b->bulk[(size_t)sp.bulk];
+            const size_t k = i - sp.start;
+            verbs = bs.verbs + bs.verb_off[k];
+            rpts = reinterpret_cast<const rbh::Pt *>(bs.points) + bs.point_off[k];
+            n_verbs = bs.verb_off[k + 1] - bs.verb_off[k];
+            n_pts = bs.point_off[k + 1] - bs.point_off[k];
+            paint = bs.paints[k];
+            stops_src = (paint.stops && paint.n_stops > 0) ? paint.stops : nullptr;
+            ctm = bs.ctm;
+            is_stroke = bs.strokes && bs.strokes[k].width > 0.0f;
+            if (is_stroke) { stroke = bs.strokes[k]; dash_src = stroke.n_dash > 0 ? stroke.dash_array : nullptr; }
+            rule = is_stroke ? 0 : (bs.fill_rules[k] ? 1 : 0);
+            map_fill = !is_stroke && !bs.ctm.is_identity(); // painter.rs: path.transform(ts), done by the device
+        }
+        if (stroke.n_dash > 0 && !dash_src) stroke.n_dash = 0;
+        // bounds of the draw in viewport coordinates (control-point hull, inflated by the stroke's reach): culls against
+        // the target and, per DrawTiler tile, against the tile
+        float bx0 = INFINITY, by0 = INFINITY, bx1 = -INFINITY, by1 = -INFINITY;
+        bool finite = n_pts > 0;
+        for (uint32_t k = 0; k < n_pts; k++) {
+            const float x = rpts[k].x, y = rpts[k].y;
+            finite = finite && std::isfinite(x) && std::isfinite(y);
+            bx0 = std::min(bx0, x); bx1 = std::max(bx1, x);
+            by0 = std::min(by0, y); by1 = std::max(by1, y);
+        }
+        if (finite && (is_stroke || map_fill)) {
+            const float reach = is_stroke ? 0.5f * stroke.width * std::max(stroke.miter_limit, 1.4143f) : 0.0f;
+            if (std::isfinite(reach)) {
+                rbh::Pt c[4] = {{bx0 - reach, by0 - reach}, {bx1 + reach, by0 - reach}, {bx0 - reach, by1 + reach}, {bx1 + reach, by1 + reach}};
+                rbh::map_points(ctm, c, 4);
+                bx0 = by0 = INFINITY; bx1 = by1 = -INFINITY;
+                for (const rbh::Pt &q : c) {
+                    finite = finite && std::isfinite(q.x) && std::isfinite(q.y);
+                    bx0 = std::min(bx0, q.x); bx1 = std::max(bx1, q.x);
+                    by0 = std::min(by0, q.y); by1 = std::max(by1, q.y);
+                }
+            } else finite = false;
+        }
+        const float pad = 2.0f;
+        if (finite && (bx1 < (float)(-VX) - pad || by1 < (float)(-VY) - pad || bx0 > (float)(W - VX) + pad || by0 > (float)(H - VY) + pad)) continue;
+        float coverage = -1.0f;
+        if (is_stroke && b->n_hair) coverage = rb_hairline_coverage(paint, stroke, ctm);
+        const bool hair = coverage >= 0.0f;
+        rb_paint pp = paint;
+        pp.stops = stops_src;
+        if (hair) hairline_modulate_paint(&pp, coverage, out->hstops);
+        // the draw's path data is copied once, however many tiles it touches
+        uint32_t voff = 0, poff = 0, doff = 0;
+        bool copied = false;
+        // expected edge items: a handful per segment; a stroke outline has two sides plus joins, a dashed one is cut up
+        uint32_t hint = n_verbs * 3 + 8;
+        if (is_stroke && !hair) {
+            hint = n_verbs * 24 + 16;
+            if (stroke.n_dash > 0) hint *= 4;
+        }
+        for (int ty = 0; ty < VH; ty += kMaxDim) {
+            for (int tx = 0; tx < VW; tx += kMaxDim) {
+                const int tw = std::min(VW - tx, kMaxDim), th = std::min(VH - ty, kMaxDim);
+                const int ox = VX + tx, oy = VY + ty; // tile origin inside the target
+                if (ox >= W || oy >= H || ox + tw <= 0 || oy + th <= 0) continue; // tile wholly outside the target
+                if (finite && (bx1 < (float)tx - pad || by1 < (float)ty - pad || bx0 > (float)(tx + tw) + pad || by0 > (float)(ty + th) + pad)) continue;
+                rbh::Xform tctm = ctm;
+                if (tx || ty) {
+                    rbh::Xform tr;
+                    tr.tx = -(float)tx;
+                    tr.ty = -(float)ty;
+                    tctm = rbh::post_concat(ctm, tr);
+                }
+                DevPaint P;
+                const size_t s_before = out->stops.size();
+                if (!rbh::prepare_paint(&pp, tctm, &P, out->stops)) continue;
+                if (out->stops.size() != s_before) P.stop_off = (uint32_t)(P.stop_off - ci->s0);
+                if (!copied) {
+                    voff = (uint32_t)(out->verbs.size() - ci->v0);
+                    poff = (uint32_t)(out->pts.size() - ci->p0);
+                    out->verbs.insert(out->verbs.end(), verbs, verbs + n_verbs);
+                    out->pts.insert(out->pts.end(), rpts, rpts + n_pts);
+                    if (stroke.n_dash > 0) {
+                        doff = (uint32_t)(out->dashes.size() - ci->d0);
+                        out->dashes.insert(out->dashes.end(), dash_src, dash_src + stroke.n_dash);
+                    }
+                    copied = true;
+                }
+                GeoTask t;
+                memset(&t, 0, sizeof(t));
+                t.verb_off = voff; t.n_verbs = n_verbs; t.pt_off = poff; t.n_pts = n_pts;
+                memcpy(t.ctm, &ctm, sizeof(float) * 6);
+                t.tile_tx = -(float)tx; t.tile_ty = -(float)ty;
+                t.tw = tw; t.th = th; t.ox = ox; t.oy = oy;
+                t.paint = (uint32_t)(out->paints.size() - ci->pa0);
+                out->paints.push_back(P);
+                t.flags = (is_stroke ? GT_STROKE : 0u) | (hair ? GT_HAIR : 0u) | (paint.anti_alias ? GT_AA : 0u) | (rule ? GT_EVENODD : 0u)
+                          | (stroke.n_dash > 0 ? GT_DASH : 0u) | ((is_stroke ? !ctm.is_identity() : map_fill) ? GT_MAP : 0u) | ((tx || ty) ? GT_TILE : 0u)
+                          | ((uint32_t)stroke.cap << GT_CAP_SHIFT) | ((uint32_t)stroke.join << GT_JOIN_SHIFT);
+                if (!is_stroke && !map_fill) { const rbh::Xform id; memcpy(t.ctm, &id, sizeof(float) * 6); }
+                t.width = stroke.width; t.miter = stroke.miter_limit; t.res_scale = is_stroke ? resolution_scale(ctm) : 1.0f;
+                t.dash_offset = stroke.dash_offset;
+                t.dash_off = doff; t.n_dash = (uint32_t)std::max(stroke.n_dash, 0);
+                t.hint = hint;
+                out->tasks.push_back(t);
+            }
+        }
+    }
+    ci->nt = out->tasks.size() - ci->t0; ci->nv = out->verbs.size() - ci->v0; ci->np = out->pts.size() - ci->p0;
+    ci->nd = out->dashes.size() - ci->d0; ci->npa = out->paints.size() - ci->pa0; ci->ns = out->stops.size() - ci->s0;
+}
+
+} // namespace
+
+int rb_geo_host_build(rb_batch *b, int W, int H, int n_threads, rb_stage_alloc alloc, void *user, void **block, GeoBlock *gb,
+                      size_t begin, size_t end)
+{
+    *block = nullptr;
+    *gb = GeoBlock();
+    if (end == 0 || end > b->n_total) end = b->n_total;
+    if (begin >= end) return RB_OK;
+    const size_t n = end - begin;
+    const size_t n_chunks = (n + kChunk - 1) / kChunk;
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min<int>(nt, (int)n_chunks));
+    std::vector<std::unique_ptr<GeoWorker>> workers;
+    {
+        std::lock_guard<std::mutex> g(g_geo_pool_mu);
+        for (int t = 0; t < nt; t++) {
+            if (g_geo_pool.empty()) workers.emplace_back(new GeoWorker());
+            else { workers.push_back(std::move(g_geo_pool.back())); g_geo_pool.pop_back(); }
+        }
+    }
+    struct Return {
+        std::vector<std::unique_ptr<GeoWorker>> &w;
+        ~Return()
+        {
+            std::lock_guard<std::mutex> g(g_geo_pool_mu);
+            for (auto &x : w) if (x) { x->reset(); if (g_geo_pool.size() < 256) g_geo_pool.push_back(std::move(x)); }
+        }
+    } give_back{workers};
+    std::vector<GeoChunk> chunks(n_chunks);
+    parallel_for(nt, n_chunks, [&](size_t c, int t) {
+        chunks[c].worker = t;
+        geo_build_chunk(b, begin + c * kChunk, begin + std::min(n, (c + 1) * kChunk), W, H, workers[(size_t)t].get(), &chunks[c]);
+    });
+    GeoBlock G;
+    for (auto &c : chunks) {
+        c.gt = G.n_tasks; c.gv = G.n_verbs; c.gp = G.n_pts; c.gd = G.n_dashes; c.gpa = G.n_paints; c.gs = G.n_stops;
+        G.n_tasks += c.nt; G.n_verbs += c.nv; G.n_pts += c.np; G.n_dashes += c.nd; G.n_paints += c.npa; G.n_stops += c.ns;
+    }
+    if (G.n_tasks == 0) return RB_OK;
+    if (G.n_tasks > 0x7ffffff0ull || G.n_verbs > 0xfffffff0ull || G.n_pts > 0xfffffff0ull) return RB_ERR_UNSUPPORTED;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t off = 0;
+    G.o_tasks = off;  off += al(G.n_tasks * sizeof(GeoTask));
+    G.o_paints = off; off += al(std::max<size_t>(G.n_paints, 1) * sizeof(DevPaint));
+    G.o_stops = off;  off += al(std::max<size_t>(G.n_stops, 1) * sizeof(DevStop));
+    G.o_lists = off;  off += al(G.n_tasks * 3 * sizeof(uint32_t)); // a dashed stroke is on three lists: dash, stroke, fill
+    G.o_dashes = off; off += al(std::max<size_t>(G.n_dashes, 1) * sizeof(float));
+    G.o_pts = off;    off += al(G.n_pts * sizeof(rbh::Pt));
+    G.o_verbs = off;  off += al(G.n_verbs);
+    G.total = off;
+    uint8_t *blk = (uint8_t *)alloc(user, G.total);
+    if (!blk) return RB_ERR_OOM;
+    GeoTask *o_tasks = (GeoTask *)(blk + G.o_tasks);
+    DevPaint *o_paints = (DevPaint *)(blk + G.o_paints);
+    DevStop *o_stops = (DevStop *)(blk + G.o_stops);
+    parallel_for(nt, n_chunks, [&](size_t ci, int) {
+        const GeoChunk &c = chunks[ci];
+        const GeoWorker &w = *workers[(size_t)c.worker];
+        if (c.nv) memcpy(blk + G.o_verbs + c.gv, w.verbs.data() + c.v0, c.nv);
+        if (c.np) memcpy(blk + G.o_pts + c.gp * sizeof(rbh::Pt), w.pts.data() + c.p0, c.np * sizeof(rbh::Pt));
+        if (c.nd) memcpy(blk + G.o_dashes + c.gd * sizeof(float), w.dashes.data() + c.d0, c.nd * sizeof(float));
+        if (c.ns) memcpy(o_stops + c.gs, w.stops.data() + c.s0, c.ns * sizeof(DevStop));
+        for (size_t k = 0; k < c.npa; k++) {
+            DevPaint p = w.paints[c.pa0 + k];
+            p.stop_off += (uint32_t)c.gs;
+            o_paints[c.gpa + k] = p;
+        }
+        for (size_t k = 0; k < c.nt; k++) {
+            GeoTask t = w.tasks[c.t0 + k];
+            t.verb_off += (uint32_t)c.gv; t.pt_off += (uint32_t)c.gp; t.dash_off += (uint32_t)c.gd; t.paint += (uint32_t)c.gpa;
+            o_tasks[c.gt + k] = t;
+        }
+    });
+    // task lists per kernel, heaviest first (counting sort over cost classes; ties keep painter's order)
+    {
+        uint32_t *lists = (uint32_t *)(blk + G.o_lists);
+        constexpr int NC = 24;
+        size_t cnt[4][NC];
+        memset(cnt, 0, sizeof(cnt));
+        auto kinds_of = [](const GeoTask &t, int k[3]) {
+            int m = 0;
+            if (t.flags & GT_DASH) k[m++] = 0;
+            k[m++] = (t.flags & GT_HAIR) ? 2 : ((t.flags & GT_STROKE) ? 1 : 3);
+            if ((t.flags & (GT_STROKE | GT_HAIR)) == GT_STROKE) k[m++] = 3; // an outline is filled
+            return m;
+        };
+        for (size_t i = 0; i < G.n_tasks; i++) {
+            int k[3];
+            const int m = kinds_of(o_tasks[i], k);
+            for (int j = 0; j < m; j++) cnt[k[j]][NC - 1 - cost_class(o_tasks[i].hint)]++;
+        }
+        size_t base[4][NC], run = 0;
+        size_t first[5];
+        for (int k = 0; k < 4; k++) {
+            first[k] = run;
+            for (int c = 0; c < NC; c++) { base[k][c] = run; run += cnt[k][c]; }
+        }
+        first[4] = run;
+        for (size_t i = 0; i < G.n_tasks; i++) {
+            int k[3];
+            const int m = kinds_of(o_tasks[i], k);
+            for (int j = 0; j < m; j++) lists[base[k[j]][NC - 1 - cost_class(o_tasks[i].hint)]++] = (uint32_t)i;
+        }
+        G.n_dash_l = first[1] - first[0]; G.n_stroke_l = first[2] - first[1]; G.n_hair_l = first[3] - first[2]; G.n_fill_l = first[4] - first[3];
+        G.has_hair = G.n_hair_l > 0;
+    }
+    // heap the geometry is expected to need: ~48 bytes per expected edge item plus the builders' chunks
+    size_t hint_bytes = 0;
+    for (size_t i = 0; i < G.n_tasks; i++) hint_bytes += (size_t)o_tasks[i].hint * 96 + 2048;
+    G.heap_hint = hint_bytes;
+    *gb = G;
+    *block = blk;
     return RB_OK;
 }
 

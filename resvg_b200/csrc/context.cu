@@ -117,6 +117,7 @@ void rb_ctx_release(rb_ctx *ctx)
     if (ctx->px_tables) cudaFree(ctx->px_tables);
     if (ctx->staging) cudaFreeHost(ctx->staging);
     if (ctx->h_flags) cudaFreeHost((void *)ctx->h_flags);
+    if (ctx->geo_pinned) cudaFreeHost(ctx->geo_pinned);
     if (ctx->staging_ev) cudaEventDestroy(ctx->staging_ev);
     for (auto &s : ctx->stage_ring) {
         if (s.p) cudaFreeHost(s.p);

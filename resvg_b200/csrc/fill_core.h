@@ -660,7 +660,7 @@ GEO_HD Packed pack_items(const Edge *src, size_t ne, const CurveRec *csrc, size_
     size_t il = 0, ic = 0;
     while (il < ne || ic < ncv) {
         if (ic >= ncv || (il < ne && src[il].order < csrc[ic].item)) {
-            const Edge &e = src[il];
+            const Edge e = src[il]; // by value: `dst` may be the same storage (the device packs in place)
             DevEdge de;
             de.x = e.x; de.dx = e.dx;
             de.ypack = ((uint32_t)e.first_y & 0xffffu) | ((uint32_t)e.last_y << 16);

@@ -1,0 +1,528 @@
+// geo.cu — device path geometry (crates/resvg/src/path.rs:73,113; tiny-skia painter.rs fill_path /
+// stroke_path): dashing, stroking, hairline walking and the fill front end (transform, y-monotone chop, clip, edge
+// set-up) as CUDA kernels, one thread per draw, running the SAME source as the host builder (geom_common.h).
+//
+// Pipeline of one batch range (all on the context's stream):
+//   k_geo_dash    thread per dashed stroke    Path::dash                                 -> the path to stroke / walk
+//   k_geo_stroke  thread per stroke           PathStroker::stroke (local coordinates)    -> the outline to fill
+//   k_geo_hair    thread per hairline stroke  hairline::stroke_path + hairline_aa        -> ordered blits, DevDraw
+//   k_geo_fill    thread per fill / outline   fill_path up to the walker                 -> line edges, curve records, DevDraw
+//   k_geo_wide    CTA per many-chain draw     exact bound of simultaneously active edges (packed winding range)
+// Every kernel takes its task indices from a list the host sorted heaviest first, so that the long draws (dashed strokes:
+// thousands of edges) start first and the short ones fill in behind them.  Dynamic storage comes from a bump heap
+// (geom_common.h DVec); a launch that exhausts it is repeated with a larger heap.  The kernels leave exactly the block
+// the host builder would have uploaded in item mode, so k_row_lists and everything after it run unchanged.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "batch.h"
+#include "batch_geo.h"
+#include "dasher_core.h"
+#include "fill_core.h"
+#include "hairline_core.h"
+#include "rb_internal.h"
+#include "stroker_core.h"
+
+using geo::DVec;
+using geo::GeoHeap;
+using geo::P;
+
+// The path a later stage consumes: status 0 = the recorded path, 1 = `verbs` / `pts` below, 2 = nothing is drawn.
+struct GeoMid {
+    const uint8_t *verbs;
+    const P *pts;
+    uint32_t n_verbs, n_pts;
+    uint32_t status, pad;
+};
+
+struct GeoArgs {
+    const GeoTask *tasks;
+    const uint8_t *verbs;
+    const P *pts;
+    const float *dashes;
+    GeoMid *mid;
+    DevDraw *draws;
+    GeoTotals *tot;
+    GeoHeap heap;
+    int W, H;
+};
+
+constexpr int GEO_THREADS = 64;
+// recursion guards (the device stack is GEO_STACK bytes per thread): deeper than this and the batch goes to the host builder
+constexpr int GEO_STACK = 12288;
+
+__device__ __forceinline__ void empty_draw(const GeoArgs &a, uint32_t ti, const GeoTask &t)
+{
+    DevDraw d;
+    memset(&d, 0, sizeof(d));
+    d.ox = t.ox; d.oy = t.oy;
+    d.shift = 2;
+    d.paint = t.paint;
+    d.r0 = 1; // r0 > r0 + n_rows - 1: the binning kernels never see it
+    d.n_rows = 0;
+    d.row_base = (uint32_t)atomicAdd(&a.tot->n_row_off, 1ull);
+    a.draws[ti] = d;
+}
+
+// ---- Path::dash ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEO_THREADS) k_geo_dash(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n)
+{
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n) return;
+    const uint32_t ti = list[li];
+    const GeoTask t = a.tasks[ti];
+    GeoHeap heap = a.heap;
+    geo::ds::DashOut<DVec> pb;
+    geo::ds::Contour<DVec> c;
+    pb.verbs.init(&heap, t.hint);
+    pb.pts.init(&heap, t.hint * 2);
+    pb.move_required = true;
+    pb.last_move = 0;
+    c.segs.init(&heap, t.n_verbs * 8);
+    c.pts.init(&heap, t.n_pts + 4);
+    GeoMid m;
+    m.verbs = nullptr; m.pts = nullptr; m.n_verbs = 0; m.n_pts = 0; m.status = 2; m.pad = 0;
+    if (pb.verbs.ok() && pb.pts.ok() && c.segs.ok() && c.pts.ok()) {
+        bool valid = false;
+        const bool ok = geo::ds::dash_path(pb, c, a.verbs + t.verb_off, (int)t.n_verbs, a.pts + t.pt_off, a.dashes + t.dash_off, (int)t.n_dash,
+                                           t.dash_offset, t.res_scale, &valid);
+        if (!valid) m.status = 0; // StrokeDash::new -> None: the stroke stays solid
+        else if (ok) {
+            m.verbs = pb.verbs.data(); m.pts = pb.pts.data();
+            m.n_verbs = (uint32_t)pb.verbs.size(); m.n_pts = (uint32_t)pb.pts.size();
+            m.status = 1;
+        }
+    }
+    a.mid[ti] = m;
+}
+
+// ---- PathStroker::stroke --------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEO_THREADS) k_geo_stroke(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n)
+{
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n) return;
+    const uint32_t ti = list[li];
+    const GeoTask t = a.tasks[ti];
+    const uint8_t *verbs = a.verbs + t.verb_off;
+    const P *pts = a.pts + t.pt_off;
+    int n_verbs = (int)t.n_verbs;
+    GeoMid m;
+    m.verbs = nullptr; m.pts = nullptr; m.n_verbs = 0; m.n_pts = 0; m.status = 2; m.pad = 0;
+    if (t.flags & GT_DASH) {
+        const GeoMid in = a.mid[ti];
+        if (in.status == 2) { a.mid[ti] = m; return; } // "path dashing failed": nothing is drawn
+        if (in.status == 1) { verbs = in.verbs; pts = in.pts; n_verbs = (int)in.n_verbs; }
+    }
+    GeoHeap heap = a.heap;
+    geo::sk::Stroker<DVec> s;
+    s.outer.verbs.init(&heap, t.hint);
+    s.outer.pts.init(&heap, t.hint * 2);
+    s.inner.verbs.init(&heap, t.hint / 2 + 8);
+    s.inner.pts.init(&heap, t.hint + 8);
+    s.cusper.verbs.init(&heap, 8);
+    s.cusper.pts.init(&heap, 8);
+    if (s.outer.verbs.ok() && s.outer.pts.ok() && s.inner.verbs.ok() && s.inner.pts.ok() && s.cusper.verbs.ok() && s.cusper.pts.ok()) {
+        s.reset();
+        if (geo::sk::stroke_path(s, verbs, n_verbs, pts, t.width, t.miter, (int)((t.flags >> GT_CAP_SHIFT) & 3u), (int)((t.flags >> GT_JOIN_SHIFT) & 3u),
+                                 t.res_scale)) {
+            m.verbs = s.outer.verbs.data(); m.pts = s.outer.pts.data();
+            m.n_verbs = (uint32_t)s.outer.verbs.size(); m.n_pts = (uint32_t)s.outer.pts.size();
+            m.status = 1;
+        }
+        if (s.too_deep) a.tot->deep = 1u;
+    }
+    a.mid[ti] = m;
+}
+
+// The path's points in device space relative to the DrawTiler tile: tiny-skia's path.transform(ts) (map_points: identity /
+// translate / scale + translate / affine, each its own expression) followed by the tile shift.
+struct MapPts {
+    const P *p;
+    float sx, ky, kx, sy, tx, ty, ttx, tty;
+    int mode; // 0 identity, 1 translate, 2 scale + translate, 3 affine
+    bool tile;
+    __device__ P operator[](int i) const
+    {
+        P q = p[i];
+        if (mode == 1) { q.x += tx; q.y += ty; }
+        else if (mode == 2) { q.x = q.x * sx + tx; q.y = q.y * sy + ty; }
+        else if (mode == 3) {
+            const float x = q.x * sx + q.y * kx + tx;
+            const float y = q.x * ky + q.y * sy + ty;
+            q.x = x; q.y = y;
+        }
+        if (tile) { q.x += ttx; q.y += tty; }
+        return q;
+    }
+};
+__device__ __forceinline__ MapPts map_for(const GeoTask &t, const P *p)
+{
+    MapPts m;
+    m.p = p;
+    m.sx = t.ctm[0]; m.ky = t.ctm[1]; m.kx = t.ctm[2]; m.sy = t.ctm[3]; m.tx = t.ctm[4]; m.ty = t.ctm[5];
+    m.ttx = t.tile_tx; m.tty = t.tile_ty;
+    m.tile = (t.flags & GT_TILE) != 0;
+    m.mode = 0;
+    if (t.flags & GT_MAP) {
+        const bool skew = m.kx != 0 || m.ky != 0, scale = m.sx != 1 || m.sy != 1;
+        m.mode = skew ? 3 : (scale ? 2 : ((m.tx != 0 || m.ty != 0) ? 1 : 0));
+    }
+    return m;
+}
+
+// ---- hairline strokes -----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEO_THREADS) k_geo_hair(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n)
+{
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n) return;
+    const uint32_t ti = list[li];
+    const GeoTask t = a.tasks[ti];
+    const uint8_t *verbs = a.verbs + t.verb_off;
+    const P *pts = a.pts + t.pt_off;
+    int n_verbs = (int)t.n_verbs, n_pts = (int)t.n_pts;
+    if (t.flags & GT_DASH) {
+        const GeoMid in = a.mid[ti];
+        if (in.status == 2) { empty_draw(a, ti, t); return; }
+        if (in.status == 1) { verbs = in.verbs; pts = in.pts; n_verbs = (int)in.n_verbs; n_pts = (int)in.n_pts; }
+    }
+    GeoHeap heap = a.heap;
+    DVec<geo::HairBlit> blits;
+    blits.init(&heap, t.hint * 16);
+    if (!blits.ok()) { empty_draw(a, ti, t); return; }
+    const MapPts mp = map_for(t, pts);
+    geo::hl::hairline_blits<DVec>(verbs, n_verbs, mp, n_pts, (int)((t.flags >> GT_CAP_SHIFT) & 3u), t.tw, t.th, blits);
+    const int W = a.W, H = a.H, ox = t.ox, oy = t.oy;
+    if (ox < 0 || oy < 0 || ox + t.tw > W || oy + t.th > H) { // keep the blits that land inside the target
+        uint32_t keep = 0;
+        for (uint32_t k = 0; k < blits.n; k++) {
+            const geo::HairBlit hb = blits.p[k];
+            if (hb.x + ox >= 0 && hb.y + oy >= 0 && hb.x + ox < W && hb.y + oy < H) blits.p[keep++] = hb;
+        }
+        blits.n = keep;
+    }
+    const uint32_t nb = blits.n;
+    if (nb == 0) { empty_draw(a, ti, t); return; }
+    if (nb >= (1u << 28)) { a.tot->too_large = 1u; empty_draw(a, ti, t); return; }
+    int x0 = INT32_MAX, y0 = INT32_MAX, x1 = INT32_MIN, y1 = INT32_MIN;
+    for (uint32_t k = 0; k < nb; k++) {
+        const geo::HairBlit hb = blits.p[k];
+        x0 = min(x0, hb.x); x1 = max(x1, hb.x);
+        y0 = min(y0, hb.y); y1 = max(y1, hb.y);
+    }
+    DevDraw d;
+    memset(&d, 0, sizeof(d));
+    d.ox = ox; d.oy = oy;
+    d.sx = x0; d.sy = y0; d.sw = x1 - x0 + 1; d.sh = y1 - y0 + 1;
+    d.shift = 2;
+    d.rule = 2; // hairline
+    d.paint = t.paint;
+    const int r0 = (oy + y0) >> 3, r1 = (oy + y1) >> 3, nr = r1 - r0 + 1;
+    const int c0 = (ox + x0) / 32, c1 = (ox + x1) / 32, ncols = c1 - c0 + 1;
+    // the draw's "tile rows" are its warp-tile CELLS (row-major over its bounding box); rank = order of the blit inside its cell
+    DVec<uint32_t> rank;
+    rank.init(&heap, (uint32_t)nr * (uint32_t)ncols);
+    DVec<DevEdge> out;
+    out.init(&heap, nb);
+    if (!rank.ok() || !out.ok()) { empty_draw(a, ti, t); return; }
+    rank.resize((size_t)nr * (size_t)ncols);
+    for (uint32_t k = 0; k < nb; k++) {
+        const geo::HairBlit hb = blits.p[k];
+        const uint32_t cell = (uint32_t)(((oy + hb.y) >> 3) - r0) * (uint32_t)ncols + (uint32_t)(((ox + hb.x) >> 5) - c0);
+        DevEdge e; // a blit in an edge-sized record: layer pixel, coverage, rank inside its cell, cell
+        e.x = (int32_t)((uint32_t)(hb.x + ox) | ((uint32_t)(hb.y + oy) << 16));
+        e.dx = (int32_t)hb.alpha;
+        e.ypack = rank.p[cell]++;
+        e.meta = cell;
+        out.p[k] = e;
+    }
+    d.curve_off = (uint32_t)c0; // hairline draws: first cell column / cells per row
+    d.curve_cnt = (uint32_t)ncols;
+    d.edge_off = 0;
+    d.edge_cnt = 0;
+    d.line_off = (uint32_t)(((const uint8_t *)out.p - heap.base) / sizeof(DevEdge));
+    d.line_cnt = nb;
+    d.r0 = (uint32_t)r0;
+    d.n_rows = (uint32_t)nr;
+    d.list_off = (uint32_t)atomicAdd(&a.tot->n_list, (unsigned long long)nb);
+    d.row_base = (uint32_t)atomicAdd(&a.tot->n_row_off, (unsigned long long)nr * (unsigned long long)ncols + 1ull);
+    d.list_cap = nb;
+    atomicAdd(&a.tot->n_row_ent, (unsigned long long)nr);
+    atomicAdd(&a.tot->n_wpairs, (unsigned long long)nr * (unsigned long long)ncols);
+    a.draws[ti] = d;
+}
+
+// ---- fill_path up to the scanline walker ------------------------------------------------------------------------------------------
+struct NoEnds {
+    uint32_t chains;
+    __device__ void operator()(int32_t, int32_t) { chains++; }
+};
+
+__global__ void __launch_bounds__(GEO_THREADS) k_geo_fill(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n, uint32_t *__restrict__ wide_q)
+{
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n) return;
+    const uint32_t ti = list[li];
+    const GeoTask t = a.tasks[ti];
+    const uint8_t *verbs = a.verbs + t.verb_off;
+    const P *pts = a.pts + t.pt_off;
+    int n_verbs = (int)t.n_verbs, n_pts = (int)t.n_pts;
+    int rule = (t.flags & GT_EVENODD) ? 1 : 0;
+    if (t.flags & GT_STROKE) {
+        const GeoMid in = a.mid[ti];
+        if (in.status != 1) { empty_draw(a, ti, t); return; }
+        verbs = in.verbs; pts = in.pts; n_verbs = (int)in.n_verbs; n_pts = (int)in.n_pts;
+        rule = 0;
+    }
+    GeoHeap heap = a.heap;
+    DVec<rbh::Edge> lines;
+    DVec<rbh::CurveRec> curves;
+    geo::fl::Sink<DVec> sink;
+    lines.init(&heap, t.hint);
+    curves.init(&heap, t.hint);
+    sink.kinds.init(&heap, t.hint * 2);
+    if (!lines.ok() || !curves.ok() || !sink.kinds.ok()) { empty_draw(a, ti, t); return; }
+    sink.out = &lines;
+    sink.base = 0;
+    sink.curves = &curves;
+    sink.n_items = 0;
+    const MapPts mp = map_for(t, pts);
+    rbh::DrawGeom g;
+    if (!geo::fl::build_items<DVec>(verbs, n_verbs, mp, n_pts, (t.flags & GT_AA) != 0, t.tw, t.th, sink, &g)) { empty_draw(a, ti, t); return; }
+    const int W = a.W, H = a.H, ox = t.ox, oy = t.oy;
+    if (ox < 0 || oy < 0 || ox + t.tw > W || oy + t.th > H) { // blitter rectangle ∩ target (tile-local coordinates)
+        const int cx0 = max(g.sect.x, -ox), cy0 = max(g.sect.y, -oy);
+        const int cx1 = min(g.sect.x + g.sect.w, W - ox), cy1 = min(g.sect.y + g.sect.h, H - oy);
+        if (cx1 <= cx0 || cy1 <= cy0) { empty_draw(a, ti, t); return; }
+        g.sect.x = cx0; g.sect.y = cy0; g.sect.w = cx1 - cx0; g.sect.h = cy1 - cy0;
+    }
+    const uint32_t ne = lines.n, ncv = curves.n;
+    DevDraw d;
+    memset(&d, 0, sizeof(d));
+    d.ox = ox; d.oy = oy;
+    d.sx = g.sect.x; d.sy = g.sect.y; d.sw = g.sect.w; d.sh = g.sect.h;
+    d.shift = g.shift;
+    d.rule = rule;
+    d.paint = t.paint;
+    const int r0 = (oy + g.sect.y) >> 3, r1 = (oy + g.sect.y + g.sect.h - 1) >> 3, nr = r1 - r0 + 1;
+    const int c0 = (ox + g.sect.x) / 32, c1 = (ox + g.sect.x + g.sect.w - 1) / 32;
+    // packed in place: a 16-byte DevEdge over the first half of each 32-byte Edge already consumed, curves where they are
+    NoEnds ends{0};
+    const geo::fl::Packed po = geo::fl::pack_items(lines.p, ne, curves.p, ncv, reinterpret_cast<DevEdge *>(lines.p), curves.p, g.shift, oy, r0, nr, ends);
+    if (po.too_large) { a.tot->too_large = 1u; empty_draw(a, ti, t); return; }
+    if (ends.chains >= 128u) wide_q[atomicAdd(&a.tot->n_wide_q, 1u)] = ti; // the exact bound is taken by k_geo_wide
+    d.edge_cnt = po.slots;
+    d.edge_off = (uint32_t)atomicAdd(&a.tot->n_slots, (unsigned long long)po.slots);
+    d.line_off = (uint32_t)(((const uint8_t *)lines.p - heap.base) / sizeof(DevEdge));
+    d.line_cnt = ne;
+    d.curve_off = (uint32_t)(((const uint8_t *)curves.p - heap.base) / sizeof(rbh::CurveRec));
+    d.curve_cnt = ncv;
+    d.r0 = (uint32_t)r0;
+    d.n_rows = (uint32_t)nr;
+    d.list_off = (uint32_t)atomicAdd(&a.tot->n_list, (unsigned long long)po.n_list);
+    d.row_base = (uint32_t)atomicAdd(&a.tot->n_row_off, (unsigned long long)nr + 1ull);
+    d.list_cap = (uint32_t)po.n_list;
+    atomicAdd(&a.tot->n_row_ent, (unsigned long long)nr);
+    atomicAdd(&a.tot->n_wpairs, (unsigned long long)nr * (unsigned long long)(c1 - c0 + 1));
+    a.draws[ti] = d;
+}
+
+// ---- packed winding range ------------------------------------------------------------------------------------------------------------
+// The tile kernel counts crossings in balanced base-256 digits: a draw is only safe there when fewer than 128 edges can
+// be active on one sub-scanline.  Chains (a line, or a whole curve) never overlap themselves in y, so the largest number of
+// chains covering one sub-scanline bounds it.  One CTA per queued draw: difference array over the draw's sub-scanlines in
+// shared memory, chunk by chunk, then a block scan for the running maximum.
+constexpr int GW_THREADS = 256, GW_CHUNK = 8192;
+__global__ void __launch_bounds__(GW_THREADS) k_geo_wide(GeoArgs a, const uint32_t *__restrict__ wide_q)
+{
+    __shared__ int diff[GW_CHUNK + 1];
+    __shared__ int warp_tot[GW_THREADS / 32], warp_max[GW_THREADS / 32];
+    __shared__ int worst_s;
+    const DevEdge *lines_base = reinterpret_cast<const DevEdge *>(a.heap.base);
+    const rbh::CurveRec *curves_base = reinterpret_cast<const rbh::CurveRec *>(a.heap.base);
+    const uint32_t nq = a.tot->n_wide_q;
+    const int tid = threadIdx.x;
+    for (uint32_t q = blockIdx.x; q < nq; q += gridDim.x) {
+        const DevDraw D = a.draws[wide_q[q]];
+        if (tid == 0) worst_s = 0;
+        // the chains' own range
+        int lo = INT32_MAX, hi = INT32_MIN;
+        for (uint32_t i = tid; i < D.line_cnt; i += GW_THREADS) {
+            const DevEdge E = lines_base[D.line_off + i];
+            lo = min(lo, (int)(E.ypack & 0xffffu)); hi = max(hi, (int)(E.ypack >> 16));
+        }
+        for (uint32_t i = tid; i < D.curve_cnt; i += GW_THREADS) {
+            const rbh::CurveRec C = curves_base[D.curve_off + i];
+            const int ylast = (C.info & 1u) ? C.p[7] : C.p[5];
+            lo = min(lo, (C.p[1] + 32) >> 6); hi = max(hi, ((ylast + 32) >> 6) - 1);
+        }
+        for (int d = 16; d >= 1; d >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, d)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, d)); }
+        if ((tid & 31) == 0) { warp_tot[tid >> 5] = lo; warp_max[tid >> 5] = hi; }
+        __syncthreads();
+        for (int w = 0; w < GW_THREADS / 32; w++) { lo = min(lo, warp_tot[w]); hi = max(hi, warp_max[w]); }
+        __syncthreads();
+        for (int base = lo; base <= hi; base += GW_CHUNK) {
+            const int top = min(base + GW_CHUNK - 1, hi); // chunk = [base, top]
+            for (int i = tid; i <= GW_CHUNK; i += GW_THREADS) diff[i] = 0;
+            __syncthreads();
+            auto add = [&](int f, int l) {
+                if (l < f || l < base || f > top) return;
+                atomicAdd(&diff[max(f, base) - base], 1);
+                atomicAdd(&diff[min(l, top) + 1 - base], -1);
+            };
+            for (uint32_t i = tid; i < D.line_cnt; i += GW_THREADS) {
+                const DevEdge E = lines_base[D.line_off + i];
+                add((int)(E.ypack & 0xffffu), (int)(E.ypack >> 16));
+            }
+            for (uint32_t i = tid; i < D.curve_cnt; i += GW_THREADS) {
+                const rbh::CurveRec C = curves_base[D.curve_off + i];
+                const int ylast = (C.info & 1u) ? C.p[7] : C.p[5];
+                add((C.p[1] + 32) >> 6, ((ylast + 32) >> 6) - 1);
+            }
+            __syncthreads();
+            // running sum over the chunk: contiguous pieces per thread, warp scan of the piece sums
+            const int per = GW_CHUNK / GW_THREADS;
+            int s = 0, mx_local = INT32_MIN, run = 0;
+            for (int k = 0; k < per; k++) s += diff[tid * per + k];
+            int incl = s;
+            for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if ((tid & 31) >= d) incl += v; }
+            if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+            __syncthreads();
+            int before = incl - s;
+            for (int w = 0; w < (tid >> 5); w++) before += warp_tot[w];
+            run = before; // sum of the chunk's entries before this thread's piece (entries cut at `base` already count from there)
+            for (int k = 0; k < per; k++) { run += diff[tid * per + k]; mx_local = max(mx_local, run); }
+            for (int d = 16; d >= 1; d >>= 1) mx_local = max(mx_local, __shfl_xor_sync(0xffffffffu, mx_local, d));
+            if ((tid & 31) == 0) warp_max[tid >> 5] = mx_local;
+            __syncthreads();
+            if (tid == 0) {
+                int m = worst_s;
+                for (int w = 0; w < GW_THREADS / 32; w++) m = max(m, warp_max[w]);
+                worst_s = m;
+            }
+            __syncthreads();
+        }
+        if (tid == 0 && worst_s >= 128) a.tot->wide = 1u;
+        __syncthreads();
+    }
+}
+
+// ---- host orchestration ----------------------------------------------------------------------------------------------------------
+struct StageReq2 { rb_ctx *ctx; int status; };
+static void *geo_stage_pinned(void *user, size_t bytes)
+{
+    StageReq2 *r = (StageReq2 *)user;
+    void *p = nullptr;
+    r->status = rb_staging(r->ctx, bytes, &p);
+    return r->status == RB_OK ? p : nullptr;
+}
+
+// Builds draws [begin, end) of the batch on the device.  On RB_OK, b->dev holds the block (b->lay describes it: item
+// mode, lines and curves addressed from the heap base) and the caller allocates the raster scratch.  RB_GEO_FALLBACK:
+// the range needs the host builder (a draw beyond the packed winding range, a recursion deeper than the device stack,
+// memory); nothing is left allocated.
+int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
+{
+    rb_ctx *ctx = b->layer->ctx;
+    const int W = (int)b->layer->w, H = (int)b->layer->h;
+    cudaSetDevice(ctx->device);
+    if (!(ctx->attr_bits & RB_ATTR_GEO)) {
+        RB_CUDA(ctx, cudaDeviceSetLimit(cudaLimitStackSize, GEO_STACK));
+        ctx->attr_bits |= RB_ATTR_GEO;
+    }
+    if (!ctx->geo_pinned) RB_CUDA(ctx, cudaHostAlloc(&ctx->geo_pinned, 4096, cudaHostAllocDefault));
+    StageReq2 req{ctx, RB_OK};
+    void *blk = nullptr;
+    GeoBlock G;
+    int st;
+    { rb_prof_scope prof__(RB_T_BUILD); st = rb_geo_host_build(b, W, H, n_threads, geo_stage_pinned, &req, &blk, &G, begin, end); }
+    if (req.status != RB_OK) return req.status;
+    if (st != RB_OK) return rb_fail(ctx, st, "geometry task build failed");
+    b->lay = BatchLayout();
+    if (!blk || G.n_tasks == 0) return RB_OK;
+    rb_prof_scope prof_up__(RB_T_UPLOAD);
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t n_tasks = G.n_tasks;
+    size_t heap_bytes = al(G.heap_hint + (64u << 20));
+    if (const char *e = getenv("RB_GEO_HEAP_BYTES")) heap_bytes = al((size_t)std::max(1024ll, atoll(e))); // tests: force heap retries
+    for (int attempt = 0; attempt < 6; attempt++, heap_bytes *= 8) {
+        // [uploaded block | DevDraw[] | GeoMid[] | wide queue | totals | heap]
+        const size_t o_draws = al(G.total), o_mid = o_draws + al(n_tasks * sizeof(DevDraw)), o_wq = o_mid + al(n_tasks * sizeof(GeoMid));
+        const size_t o_tot = o_wq + al(n_tasks * 4), o_heap = o_tot + 256, total = o_heap + heap_bytes + 65536;
+        uint8_t *dev = nullptr;
+        if (cudaMallocAsync((void **)&dev, total, ctx->stream) != cudaSuccess) {
+            cudaGetLastError();
+            return RB_GEO_FALLBACK;
+        }
+        if (attempt == 0) {
+            RB_CUDA(ctx, cudaMemcpyAsync(dev, blk, G.total, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->h2d_bytes += G.total;
+            { int st__ = rb_staging_mark(ctx); if (st__ != RB_OK) return st__; }
+        } else {
+            RB_CUDA(ctx, cudaMemcpyAsync(dev, b->dev, G.total, cudaMemcpyDeviceToDevice, ctx->stream));
+            RB_CUDA(ctx, cudaFreeAsync(b->dev, ctx->stream));
+        }
+        b->dev = dev;
+        RB_CUDA(ctx, cudaMemsetAsync(dev + o_tot, 0, 256, ctx->stream));
+        GeoArgs a;
+        a.tasks = (const GeoTask *)(dev + G.o_tasks);
+        a.verbs = dev + G.o_verbs;
+        a.pts = (const P *)(dev + G.o_pts);
+        a.dashes = (const float *)(dev + G.o_dashes);
+        a.mid = (GeoMid *)(dev + o_mid);
+        a.draws = (DevDraw *)(dev + o_draws);
+        a.tot = (GeoTotals *)(dev + o_tot);
+        a.heap.base = dev + o_heap;
+        a.heap.cursor = &a.tot->heap_cursor;
+        a.heap.size = heap_bytes;
+        a.heap.overflow = &a.tot->overflow;
+        a.W = W; a.H = H;
+        const uint32_t *lists = (const uint32_t *)(dev + G.o_lists);
+        const uint32_t nd = (uint32_t)G.n_dash_l, ns = (uint32_t)G.n_stroke_l, nh = (uint32_t)G.n_hair_l, nf = (uint32_t)G.n_fill_l;
+        auto grid = [](uint32_t n) { return (n + GEO_THREADS - 1) / GEO_THREADS; };
+        if (nd) { k_geo_dash<<<grid(nd), GEO_THREADS, 0, ctx->stream>>>(a, lists, nd); RB_LAUNCHED(ctx, "geo_dash"); }
+        if (ns) { k_geo_stroke<<<grid(ns), GEO_THREADS, 0, ctx->stream>>>(a, lists + nd, ns); RB_LAUNCHED(ctx, "geo_stroke"); }
+        if (nh) { k_geo_hair<<<grid(nh), GEO_THREADS, 0, ctx->stream>>>(a, lists + nd + ns, nh); RB_LAUNCHED(ctx, "geo_hair"); }
+        if (nf) {
+            k_geo_fill<<<grid(nf), GEO_THREADS, 0, ctx->stream>>>(a, lists + nd + ns + nh, nf, (uint32_t *)(dev + o_wq));
+            RB_LAUNCHED(ctx, "geo_fill");
+            k_geo_wide<<<std::min<uint32_t>(nf, (uint32_t)ctx->sm_count * 4u), GW_THREADS, 0, ctx->stream>>>(a, (const uint32_t *)(dev + o_wq));
+            RB_LAUNCHED(ctx, "geo_wide");
+        }
+        GeoTotals *ht = (GeoTotals *)ctx->geo_pinned;
+        RB_CUDA(ctx, cudaMemcpyAsync(ht, dev + o_tot, sizeof(GeoTotals), cudaMemcpyDeviceToHost, ctx->stream));
+        RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const GeoTotals T = *ht;
+        if (getenv("RB_GEO_DIAG"))
+            fprintf(stderr, "[geo] tasks %zu (dash %u stroke %u hair %u fill %u) upload %zu B heap %llu / %zu B slots %llu list %llu wide_q %u overflow %u wide %u\n",
+                    n_tasks, nd, ns, nh, nf, G.total, T.heap_cursor, heap_bytes, T.n_slots, T.n_list, T.n_wide_q, T.overflow, T.wide);
+        if (T.overflow) { g_geo_counts[2]++; continue; } // heap exhausted: again with eight times the heap
+        if (T.wide || T.too_large || T.deep) break;
+        if (T.n_slots > 0xfffffff0ull || T.n_list > 0xfffffff0ull || T.n_wpairs > 0xfffffff0ull || T.n_row_off > 0xfffffff0ull) break;
+        BatchLayout L;
+        L.items = true;
+        L.n_draws = n_tasks;
+        L.n_paints = G.n_paints; L.n_stops = G.n_stops;
+        L.o_draws = o_draws; L.o_paints = G.o_paints; L.o_stops = G.o_stops;
+        L.o_edges = o_heap; L.o_curves = o_heap;
+        L.total = G.total;
+        L.n_slots = (size_t)T.n_slots; L.n_list = (size_t)T.n_list; L.n_row_off = (size_t)T.n_row_off; L.n_row_ent = (size_t)T.n_row_ent;
+        L.n_wpairs = (size_t)T.n_wpairs;
+        L.has_hair = G.has_hair;
+        L.wtiles_x = (W + 31) / 32;
+        L.wtiles_y = (H + 7) / 8;
+        L.tiles_x = (W + TW - 1) / TW;
+        b->lay = L;
+        b->stats[0] = n_tasks; b->stats[1] = L.n_slots; b->stats[2] = L.n_wpairs; b->stats[3] = (size_t)L.wtiles_x * L.wtiles_y;
+        b->stats[4] = G.total; b->stats[5] = 0;
+        g_geo_counts[0]++;
+        return RB_OK;
+    }
+    if (b->dev) { cudaFreeAsync(b->dev, ctx->stream); b->dev = nullptr; }
+    b->lay = BatchLayout();
+    g_geo_counts[1]++;
+    return RB_GEO_FALLBACK;
+}

@@ -706,6 +706,9 @@ k_raster_tiles_wide(void *__restrict__ target, int W, int H, int tiles_x, const 
 
 
 #include "raster_warp.cuh"
+#include "batch_geo.h"
+int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end);
+bool rb_debug_host_only_builder();
 
 // =================================================================================================
 // batch: upload + launch (recording, edge building and binning live in batch_host.cpp)
@@ -730,7 +733,9 @@ static void batch_release(rb_batch *b)
         cudaFreeAsync(b->dev, batch_ctx(b)->stream);
         b->dev = nullptr;
     }
-    b->dev_scratch = nullptr; // carved out of the same allocation as `dev`
+    if (b->dev_scratch && b->scratch_owned) cudaFreeAsync(b->dev_scratch, batch_ctx(b)->stream);
+    b->dev_scratch = nullptr; // otherwise carved out of the same allocation as `dev`
+    b->scratch_owned = false;
     if (b->host_block) {
         free(b->host_block);
         b->host_block = nullptr;
@@ -794,6 +799,26 @@ static int batch_prepare_range(rb_batch *b, int32_t n_threads, size_t begin, siz
     rb_ctx *ctx = batch_ctx(b);
     const int W = (int)(mask_target ? b->mask->w : b->layer->w), H = (int)(mask_target ? b->mask->h : b->layer->h);
     cudaSetDevice(ctx->device);
+    // Device path geometry (geo.cu): large batches on layers are dashed / stroked / chopped / clipped by the geometry kernels
+    // from the raw paths; the host builder below remains for small batches (a tree traversal's handful of draws per layer
+    // is not worth a round trip), masks, and ranges the device hands back (RB_GEO_FALLBACK).
+    {
+        size_t n_range = (end == 0 || end > b->n_total ? b->n_total : end) - begin;
+        size_t geo_from = 4096;
+        if (const char *e = getenv("RB_GEO_FROM")) geo_from = (size_t)std::max(1, atoi(e));
+        const bool eligible = !mask_target && W <= 65536 && H <= 65536 && !rb_debug_host_only_builder();
+        if (eligible && g_geo_mode != 2 && (g_geo_mode == 1 || n_range >= geo_from)) {
+            int gst = rb_geo_prepare(b, n_threads, begin, end);
+            if (gst == RB_OK) {
+                if (!b->dev || b->lay.n_draws == 0) return RB_OK;
+                const size_t scratch_bytes = warp_scratch_layout(b->lay).total;
+                RB_CUDA(ctx, cudaMallocAsync((void **)&b->dev_scratch, scratch_bytes, ctx->stream));
+                b->scratch_owned = true;
+                return RB_OK;
+            }
+            if (gst != RB_GEO_FALLBACK) return gst;
+        }
+    }
     StageReq req{ctx, RB_OK};
     int st;
     { rb_prof_scope prof__(RB_T_BUILD); st = rb_batch_host_build(b, W, H, mask_target, n_threads, stage_pinned, &req, &blk, begin, end); }

@@ -30,6 +30,7 @@ struct rb_ctx {
     // scratch reused by multi-pass filters (grown on demand, freed with the context)
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
+    void *geo_pinned = nullptr;   // 4 KB of pinned memory the geometry kernels' totals are copied back into (geo.cu)
     uint8_t *px_tables = nullptr; // 3 x 64 KB: demultiply, into_linear_rgb, into_srgb as functions of (alpha, channel)
     // pinned host staging for batch uploads (grown on demand); staging_ev marks the last copy that read it
     void *staging = nullptr;
@@ -56,7 +57,7 @@ static inline void rb_enter(const rb_ctx *ctx)
 {
     if (ctx) cudaSetDevice(ctx->device);
 }
-enum { RB_ATTR_BOX = 1, RB_ATTR_MORPH = 2, RB_ATTR_TURB = 4, RB_ATTR_WIDE = 8, RB_ATTR_PXTABLE = 16, RB_ATTR_IIR = 32 };
+enum { RB_ATTR_BOX = 1, RB_ATTR_MORPH = 2, RB_ATTR_TURB = 4, RB_ATTR_WIDE = 8, RB_ATTR_PXTABLE = 16, RB_ATTR_IIR = 32, RB_ATTR_GEO = 64 };
 
 void rb_ctx_retain(rb_ctx *ctx);
 void rb_ctx_release(rb_ctx *ctx);

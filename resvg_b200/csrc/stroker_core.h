@@ -480,6 +480,7 @@ template <template <class> class Vec> struct Stroker {
     int stroke_type = 1; // 1 outer, -1 inner
     int recursion_depth = 0;
     bool found_tangents = false, join_completed = false;
+    bool too_deep = false; // device only: a recursion went past the device stack budget (the batch then goes to the host builder)
 
     // Back to the freshly constructed state, keeping the builders' storage.
     GEO_HD void reset()
@@ -807,6 +808,9 @@ template <template <class> class Vec> struct Stroker {
         if (r == Quad) { side().quad_to(qp.quad[1], qp.quad[2]); return true; }
         if (r == Degenerate) { side().line_to(qp.quad[2]); return true; }
         if (++recursion_depth > 11 * 3) return false;
+#if defined(__CUDA_ARCH__)
+        if (recursion_depth > 30) { too_deep = true; return false; }
+#endif
         QuadConstruct half;
         half.init_with_start(qp);
         if (!quad_stroke(q, half)) return false;
@@ -855,6 +859,9 @@ template <template <class> class Vec> struct Stroker {
         if (!finite(qp.quad[2])) return false;
         const int limits[2] = {5 * 3, 26 * 3};
         if (++recursion_depth > limits[found_tangents ? 1 : 0]) return false;
+#if defined(__CUDA_ARCH__)
+        if (recursion_depth > 30) { too_deep = true; return false; }
+#endif
         QuadConstruct half;
         if (!half.init_with_start(qp)) { side().line_to(qp.quad[2]); --recursion_depth; return true; }
         if (!cubic_stroke(c, half)) return false;
