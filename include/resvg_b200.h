@@ -420,6 +420,9 @@ void rb_debug_host_expand(int on);
  * out[1] = ranges they handed back to the host builder, out[2] = launches repeated with a larger heap. */
 void rb_debug_geo_mode(int mode);
 void rb_debug_geo_counts(uint64_t out[3]);
+/* Host-only batches (rb_debug_batch_begin_host): runs the host half of the device geometry path and reports out[0..7] =
+ * tasks, dashed, stroked, hairline, fill-list entries, bytes that would be uploaded, verbs, points. */
+int rb_debug_geo_host_stats(rb_batch *batch, uint64_t out[8]);
 
 /* Host-only batch (no target, no device work): records like any batch; rb_batch_prepare runs the host build (edges,
  * binning, block layout) for a width x height canvas and keeps the block on the host.  For the CPU test-suite and for

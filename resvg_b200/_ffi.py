@@ -153,6 +153,7 @@ SIGNATURES = {
     "rb_debug_host_expand": (None, [_i]),
     "rb_debug_geo_mode": (None, [_i]),
     "rb_debug_geo_counts": (None, [_vp]),
+    "rb_debug_geo_host_stats": (_i, [_vp, _vp]),
     "rb_debug_batch_begin_host": (_i, [_u32, _u32, c_void_pp]),
     "rb_debug_batch_phases": (_i, [_vp, _vp]),
     "rb_debug_batch_block": (C.c_int64, [_vp, C.c_int32, _vp, C.c_uint64]),

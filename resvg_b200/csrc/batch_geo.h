@@ -24,11 +24,14 @@ struct GeoTask {
     float width, miter, res_scale, dash_offset;
     uint32_t dash_off, n_dash;
     uint32_t hint;           // expected number of edge items (reserve hint, not a bound)
-    uint32_t pad;
+    int32_t sub;             // hairline strokes without dashes: the one verb this task walks (every verb is a draw of its own); -1: the whole path
+    uint32_t draw, n_draws;  // its DevDraw(s): one, except a dashed hairline, whose every dash is a draw of its own (n_draws = the bound below)
+    uint32_t max_units, pad; // dashed strokes: upper bound of the contours dashing can produce (GT_UNITS)
 };
-static_assert(sizeof(GeoTask) == 104, "GeoTask is uploaded as is");
+static_assert(sizeof(GeoTask) == 120, "GeoTask is uploaded as is");
 enum {
     GT_STROKE = 1, GT_HAIR = 2, GT_AA = 4, GT_EVENODD = 8, GT_DASH = 16, GT_MAP = 32, GT_TILE = 64,
+    GT_UNITS = 128, // a dashed stroke built dash by dash (one thread per output contour) rather than by one thread
     GT_CAP_SHIFT = 8, GT_JOIN_SHIFT = 10
 };
 
@@ -41,14 +44,18 @@ struct GeoTotals {
     unsigned int wide;       // some draw may exceed the packed winding range: the fallback builder has to take the batch
     unsigned int too_large;  // a draw the device structures cannot index
     unsigned int n_wide_q;   // draws queued for the exact winding bound
-    unsigned int deep;       // a recursion went deeper than the device stack allows: host fallback
-    unsigned int pad[3];
+    unsigned int deep;       // a recursion went deeper than the device stack allows (or a bound did not hold): host fallback
+    unsigned int n_units;    // output contours of the dashed strokes built in units
+    unsigned int pad[2];
 };
 
 // Host half (batch_geo.cpp): tasks, paints, stops and the raw path data of draws [begin, end), laid out in one staging
 // block.  Offsets are bytes from the block start.
 struct GeoBlock {
     size_t o_tasks = 0, o_verbs = 0, o_pts = 0, o_dashes = 0, o_paints = 0, o_stops = 0, total = 0;
+    size_t n_draws = 0;       // DevDraw entries (>= n_tasks: a dashed hairline reserves one per possible dash)
+    size_t max_units = 0;     // sum of the tasks' max_units
+    size_t n_units_l = 0;     // GT_UNITS tasks (their list follows the four others)
     size_t n_tasks = 0, n_verbs = 0, n_pts = 0, n_dashes = 0, n_paints = 0, n_stops = 0;
     // task indices per kernel, heaviest first: [dash | stroke | hair | fill]
     size_t o_lists = 0, n_dash_l = 0, n_stroke_l = 0, n_hair_l = 0, n_fill_l = 0;

@@ -1030,7 +1030,8 @@ struct GeoWorker {
 struct GeoChunk {
     int worker = 0;
     size_t t0 = 0, nt = 0, v0 = 0, nv = 0, p0 = 0, np = 0, d0 = 0, nd = 0, pa0 = 0, npa = 0, s0 = 0, ns = 0; // ranges in the worker's vectors
-    size_t gt = 0, gv = 0, gp = 0, gd = 0, gpa = 0, gs = 0;                                                // global bases
+    size_t n_draws = 0, max_units = 0;                                                                         // DevDraw entries / unit bound of this chunk
+    size_t gt = 0, gv = 0, gp = 0, gd = 0, gpa = 0, gs = 0, gdraw = 0;                                       // global bases
 };
 
 std::mutex g_geo_pool_mu;
@@ -1136,6 +1137,19 @@ void geo_build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, 
             hint = n_verbs * 24 + 16;
             if (stroke.n_dash > 0) hint *= 4;
         }
+        // A dashed stroke is built dash by dash on the device (one thread per output contour).  Bound of the contours
+        // dashing can produce: every contour is at most as long as its control polygon (plus the closing line, itself at
+        // most that long), and yields at most one dash per period of the pattern plus two.
+        uint32_t max_units = 0;
+        if (stroke.n_dash >= 2 && !(stroke.n_dash & 1)) {
+            double poly = 0.0, period = 0.0;
+            for (uint32_t k = 1; k < n_pts; k++) poly += hypot((double)rpts[k].x - rpts[k - 1].x, (double)rpts[k].y - rpts[k - 1].y);
+            for (int k = 0; k < stroke.n_dash; k++) period += dash_src[k];
+            if (std::isfinite(poly) && period > 0.0 && std::isfinite(period)) {
+                const double u = 2.0 * poly * (double)(stroke.n_dash >> 1) / period * 1.001 + 2.0 * (double)n_verbs + 4.0;
+                if (u < 8192.0) max_units = (uint32_t)u;
+            }
+        }
         for (int ty = 0; ty < VH; ty += kMaxDim) {
             for (int tx = 0; tx < VW; tx += kMaxDim) {
                 const int tw = std::min(VW - tx, kMaxDim), th = std::min(VH - ty, kMaxDim);
@@ -1180,6 +1194,29 @@ void geo_build_chunk(const rb_batch *b, size_t begin, size_t end, int W, int H, 
                 t.dash_offset = stroke.dash_offset;
                 t.dash_off = doff; t.n_dash = (uint32_t)std::max(stroke.n_dash, 0);
                 t.hint = hint;
+                t.sub = -1;
+                t.n_draws = 1;
+                static const int units_sel = getenv("RB_GEO_UNITS") ? atoi(getenv("RB_GEO_UNITS")) : 3; // tests: 1 strokes only, 2 hairlines only, 0 none
+                if (max_units && (units_sel & (hair ? 2 : 1))) {
+                    t.flags |= GT_UNITS;
+                    t.max_units = max_units;
+                    if (hair) t.n_draws = max_units; // every dash of a hairline is a draw of its own
+                }
+                if (hair && stroke.n_dash <= 0) {
+                    // a hairline's blits are those of its verbs, one after the other: every verb becomes a draw of its own
+                    // (same paint), so that a long path is walked by as many threads as it has segments
+                    t.hint = 64;
+                    for (uint32_t vi = 0; vi < n_verbs; vi++) {
+                        if (verbs[vi] == RB_VERB_MOVE) continue;
+                        t.sub = (int32_t)vi;
+                        t.draw = (uint32_t)ci->n_draws++;
+                        out->tasks.push_back(t);
+                    }
+                    continue;
+                }
+                t.draw = (uint32_t)ci->n_draws;
+                ci->n_draws += t.n_draws;
+                ci->max_units += t.max_units;
                 out->tasks.push_back(t);
             }
         }
@@ -1224,11 +1261,12 @@ int rb_geo_host_build(rb_batch *b, int W, int H, int n_threads, rb_stage_alloc a
     });
     GeoBlock G;
     for (auto &c : chunks) {
-        c.gt = G.n_tasks; c.gv = G.n_verbs; c.gp = G.n_pts; c.gd = G.n_dashes; c.gpa = G.n_paints; c.gs = G.n_stops;
+        c.gt = G.n_tasks; c.gv = G.n_verbs; c.gp = G.n_pts; c.gd = G.n_dashes; c.gpa = G.n_paints; c.gs = G.n_stops; c.gdraw = G.n_draws;
+        G.n_draws += c.n_draws; G.max_units += c.max_units;
         G.n_tasks += c.nt; G.n_verbs += c.nv; G.n_pts += c.np; G.n_dashes += c.nd; G.n_paints += c.npa; G.n_stops += c.ns;
     }
     if (G.n_tasks == 0) return RB_OK;
-    if (G.n_tasks > 0x7ffffff0ull || G.n_verbs > 0xfffffff0ull || G.n_pts > 0xfffffff0ull) return RB_ERR_UNSUPPORTED;
+    if (G.n_draws > 0x7ffffff0ull || G.max_units > 0x7ffffff0ull || G.n_tasks > 0x7ffffff0ull || G.n_verbs > 0xfffffff0ull || G.n_pts > 0xfffffff0ull) return RB_ERR_UNSUPPORTED;
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
     G.o_tasks = off;  off += al(G.n_tasks * sizeof(GeoTask));
@@ -1258,18 +1296,19 @@ int rb_geo_host_build(rb_batch *b, int W, int H, int n_threads, rb_stage_alloc a
         }
         for (size_t k = 0; k < c.nt; k++) {
             GeoTask t = w.tasks[c.t0 + k];
-            t.verb_off += (uint32_t)c.gv; t.pt_off += (uint32_t)c.gp; t.dash_off += (uint32_t)c.gd; t.paint += (uint32_t)c.gpa;
+            t.verb_off += (uint32_t)c.gv; t.pt_off += (uint32_t)c.gp; t.dash_off += (uint32_t)c.gd; t.paint += (uint32_t)c.gpa; t.draw += (uint32_t)c.gdraw;
             o_tasks[c.gt + k] = t;
         }
     });
     // task lists per kernel, heaviest first (counting sort over cost classes; ties keep painter's order)
     {
         uint32_t *lists = (uint32_t *)(blk + G.o_lists);
-        constexpr int NC = 24;
-        size_t cnt[4][NC];
+        constexpr int NC = 24, NL = 5; // lists: dash, stroke, hair, fill (one thread per task each), and the dashed strokes built in units
+        size_t cnt[NL][NC];
         memset(cnt, 0, sizeof(cnt));
         auto kinds_of = [](const GeoTask &t, int k[3]) {
             int m = 0;
+            if (t.flags & GT_UNITS) { k[m++] = 4; return m; }
             if (t.flags & GT_DASH) k[m++] = 0;
             k[m++] = (t.flags & GT_HAIR) ? 2 : ((t.flags & GT_STROKE) ? 1 : 3);
             if ((t.flags & (GT_STROKE | GT_HAIR)) == GT_STROKE) k[m++] = 3; // an outline is filled
@@ -1280,27 +1319,44 @@ int rb_geo_host_build(rb_batch *b, int W, int H, int n_threads, rb_stage_alloc a
             const int m = kinds_of(o_tasks[i], k);
             for (int j = 0; j < m; j++) cnt[k[j]][NC - 1 - cost_class(o_tasks[i].hint)]++;
         }
-        size_t base[4][NC], run = 0;
-        size_t first[5];
-        for (int k = 0; k < 4; k++) {
+        size_t base[NL][NC], run = 0;
+        size_t first[NL + 1];
+        for (int k = 0; k < NL; k++) {
             first[k] = run;
             for (int c = 0; c < NC; c++) { base[k][c] = run; run += cnt[k][c]; }
         }
-        first[4] = run;
+        first[NL] = run;
         for (size_t i = 0; i < G.n_tasks; i++) {
             int k[3];
             const int m = kinds_of(o_tasks[i], k);
             for (int j = 0; j < m; j++) lists[base[k[j]][NC - 1 - cost_class(o_tasks[i].hint)]++] = (uint32_t)i;
         }
         G.n_dash_l = first[1] - first[0]; G.n_stroke_l = first[2] - first[1]; G.n_hair_l = first[3] - first[2]; G.n_fill_l = first[4] - first[3];
-        G.has_hair = G.n_hair_l > 0;
+        G.n_units_l = first[5] - first[4];
+        G.has_hair = false;
+        for (size_t i = 0; i < G.n_tasks && !G.has_hair; i++) G.has_hair = (o_tasks[i].flags & GT_HAIR) != 0;
     }
     // heap the geometry is expected to need: ~48 bytes per expected edge item plus the builders' chunks
     size_t hint_bytes = 0;
-    for (size_t i = 0; i < G.n_tasks; i++) hint_bytes += (size_t)o_tasks[i].hint * 96 + 2048;
+    for (size_t i = 0; i < G.n_tasks; i++) hint_bytes += (o_tasks[i].flags & GT_UNITS) ? (size_t)o_tasks[i].max_units * 6144 + 8192 : (size_t)o_tasks[i].hint * 96 + 2048;
     G.heap_hint = hint_bytes;
     *gb = G;
     *block = blk;
+    return RB_OK;
+}
+
+// Host-only batches: runs the host half of the device geometry path (classification, culling, paints, task lists) and
+// reports out[0..7] = tasks, dashed, stroked, hairline, fill-list entries, uploaded bytes, verbs, points.  No device work.
+extern "C" int rb_debug_geo_host_stats(rb_batch *b, uint64_t out[8])
+{
+    if (!b || !out || b->host_w <= 0) return RB_ERR_INVALID;
+    void *blk = nullptr;
+    GeoBlock G;
+    int st = rb_geo_host_build(b, b->host_w, b->host_h, 0, [](void *, size_t bytes) { return malloc(bytes); }, nullptr, &blk, &G, 0, 0);
+    free(blk);
+    if (st != RB_OK) return st;
+    out[0] = G.n_tasks; out[1] = G.n_dash_l + G.n_units_l; out[2] = G.n_stroke_l; out[3] = G.n_hair_l; out[4] = G.n_fill_l; out[5] = G.total;
+    out[6] = G.n_verbs; out[7] = G.n_pts;
     return RB_OK;
 }
 

@@ -331,23 +331,26 @@ GEO_HD bool next_contour(const uint8_t *verbs, int n_verbs, const P *pts, int *v
 }
 
 
-// Path::dash into pb (which must be empty); `c` is scratch.  *spec_valid = StrokeDash::new accepted the specification
-// (a rejected one leaves the stroke solid).  Returns false when the specification is rejected or nothing is left.
-template <template <class> class Vec>
-GEO_HD bool dash_path(DashOut<Vec> &pb, Contour<Vec> &c, const uint8_t *verbs, int n_verbs, const P *pts, const float *dash_array, int n_dash,
-                      float dash_offset, float res_scale, bool *spec_valid)
+// StrokeDash::new + adjust_dash_offset + find_first_interval
+struct DashSpec {
+    bool valid;
+    float interval_len, first_len;
+    int first_index;
+};
+GEO_HD inline DashSpec dash_spec(const float *dash_array, int n_dash, float dash_offset)
 {
-    *spec_valid = false;
-    // StrokeDash::new
-    if (!gfinite(dash_offset)) return false;
-    if (n_dash < 2 || (n_dash & 1)) return false;
+    DashSpec sp;
+    sp.valid = false; sp.interval_len = 0.0f; sp.first_len = 0.0f; sp.first_index = 0;
+    if (!gfinite(dash_offset)) return sp;
+    if (n_dash < 2 || (n_dash & 1)) return sp;
     float interval_len = 0.0f;
     for (int i = 0; i < n_dash; i++) {
-        if (dash_array[i] < 0.0f) return false;
+        if (dash_array[i] < 0.0f) return sp;
         interval_len += dash_array[i];
     }
-    if (!gfinite(interval_len) || interval_len <= 0.0f) return false;
-    *spec_valid = true;
+    if (!gfinite(interval_len) || interval_len <= 0.0f) return sp;
+    sp.valid = true;
+    sp.interval_len = interval_len;
     // adjust_dash_offset
     float off = dash_offset;
     if (off < 0.0f) {
@@ -370,30 +373,56 @@ GEO_HD bool dash_path(DashOut<Vec> &pb, Contour<Vec> &c, const uint8_t *verbs, i
         }
         if (!found) { first_len = dash_array[0]; first_index = 0; }
     }
+    sp.first_len = first_len;
+    sp.first_index = first_index;
+    return sp;
+}
+
+// The "on" intervals dash_impl cuts out of one measured contour, in order: f(start_d, stop_d, start_with_move_to).  A call
+// without move_to continues the output contour of the previous call (a closed contour whose last dash runs into its first).
+template <class F>
+GEO_HD void dash_contour_ranges(const DashSpec &sp, const float *dash_array, int n_dash, float length, bool closed, F &f)
+{
+    bool skip_first = closed, added = false;
+    int index = sp.first_index;
+    float distance = 0.0f, d_len = sp.first_len;
+    while (distance < length) {
+        added = false;
+        if ((index & 1) == 0 && !skip_first) {
+            added = true;
+            f(distance, distance + d_len, true);
+        }
+        distance += d_len;
+        skip_first = false;
+        index += 1;
+        if (index == n_dash) index = 0;
+        d_len = dash_array[index];
+    }
+    // extend if we ended on a segment and need to join up with the (skipped) initial segment
+    if (closed && (sp.first_index & 1) == 0 && sp.first_len >= 0.0f) f(0.0f, sp.first_len, !added);
+}
+
+// Path::dash into pb (which must be empty); `c` is scratch.  *spec_valid = StrokeDash::new accepted the specification
+// (a rejected one leaves the stroke solid).  Returns false when the specification is rejected or nothing is left.
+template <template <class> class Vec>
+GEO_HD bool dash_path(DashOut<Vec> &pb, Contour<Vec> &c, const uint8_t *verbs, int n_verbs, const P *pts, const float *dash_array, int n_dash,
+                      float dash_offset, float res_scale, bool *spec_valid)
+{
+    const DashSpec sp = dash_spec(dash_array, n_dash, dash_offset);
+    *spec_valid = sp.valid;
+    if (!sp.valid) return false;
     const float tolerance = 0.5f * (1.0f / res_scale);
     int vi = 0, pi = 0;
     float dash_count = 0.0f;
+    struct Push {
+        Contour<Vec> *c;
+        DashOut<Vec> *pb;
+        GEO_HD void operator()(float a, float b, bool mv) { c->push_segment(a, b, mv, *pb); }
+    } push{&c, &pb};
     while (next_contour(verbs, n_verbs, pts, &vi, &pi, tolerance, &c)) {
-        bool skip_first = c.closed, added = false;
-        const float length = c.length;
-        int index = first_index;
-        dash_count += length * (float)(n_dash >> 1) / interval_len;
+        dash_count += c.length * (float)(n_dash >> 1) / sp.interval_len;
         if (dash_count > 1000000.0f) return false;
-        float distance = 0.0f, d_len = first_len;
-        while (distance < length) {
-            added = false;
-            if ((index & 1) == 0 && !skip_first) {
-                added = true;
-                c.push_segment(distance, distance + d_len, true, pb);
-            }
-            distance += d_len;
-            skip_first = false;
-            index += 1;
-            if (index == n_dash) index = 0;
-            d_len = dash_array[index];
-        }
-        // extend if we ended on a segment and need to join up with the (skipped) initial segment
-        if (c.closed && (first_index & 1) == 0 && first_len >= 0.0f) c.push_segment(0.0f, first_len, !added, pb);
+        dash_contour_ranges(sp, dash_array, n_dash, c.length, c.closed, push);
     }
     // PathBuilder::finish: nothing but move_to's is no path
     return pb.verbs.size() > 1;

@@ -177,7 +177,7 @@ template <template <class> class Vec> struct Sink {
     }
 
     // edge_builder.rs combine_vertical: 0 no, 1 partial, 2 total
-    GEO_HD int combine_vertical(const Edge &edge, Edge &last)
+    GEO_HD static int combine_vertical(const Edge &edge, Edge &last)
     {
         if (last.dx != 0 || edge.x != last.x) return 0;
         if (edge.winding == last.winding) {
@@ -518,20 +518,42 @@ GEO_HD inline bool short_overflow(int32_t v, int s) { return ((int32_t)(int16_t)
 
 // Shared front end of both builders: bounds and clip decisions of tiny-skia's fill_path (painter.rs, scan/path.rs,
 // scan/path_aa.rs), then PathEdgeIter + EdgeClipper feeding `sink`.  Returns false when nothing is to be drawn.
-template <class Sink, class Pts>
-GEO_HD bool walk_path(const uint8_t *verbs, int n_verbs, const Pts &pts, int n_pts, bool anti_alias, int32_t cw, int32_t ch,
-                      Sink &sink, DrawGeom *g, IRect *ir_out, bool *inside_out)
+// Bounds of a path's points, with the probe for non-finite coordinates (tiny_skia_path::Path cannot hold a non-finite
+// point — PathBuilder::finish fails — so such a path is never drawn; min / max would silently skip a NaN).
+struct PathBounds {
+    float l, t, r, b;
+    bool finite;
+};
+template <class Pts> GEO_HD PathBounds path_bounds(const Pts &pts, int n_pts)
 {
-    if (n_pts == 0) return false;
-    // tiny_skia_path::Path cannot hold a non-finite point (PathBuilder::finish fails): such a path is never drawn.
-    // min / max would silently skip a NaN, so every point is probed.
-    float l = pts[0].x, r = l, t = pts[0].y, b = t, probe = 0.0f;
+    PathBounds pb;
+    pb.l = pb.r = pb.t = pb.b = 0.0f;
+    pb.finite = false;
+    if (n_pts == 0) return pb;
+    const P p0 = pts[0];
+    float l = p0.x, r = l, t = p0.y, b = t, probe = 0.0f;
     for (int i = 0; i < n_pts; i++) {
-        l = gmin(l, pts[i].x); r = gmax(r, pts[i].x);
-        t = gmin(t, pts[i].y); b = gmax(b, pts[i].y);
-        probe += pts[i].x * 0.0f + pts[i].y * 0.0f; // NaN as soon as one coordinate is NaN or infinite
+        const P p = pts[i];
+        l = gmin(l, p.x); r = gmax(r, p.x);
+        t = gmin(t, p.y); b = gmax(b, p.y);
+        probe += p.x * 0.0f + p.y * 0.0f; // NaN as soon as one coordinate is NaN or infinite
     }
-    if (!(probe == 0.0f)) return false;
+    pb.l = l; pb.t = t; pb.r = r; pb.b = b;
+    pb.finite = probe == 0.0f;
+    return pb;
+}
+
+// The decisions tiny-skia's fill_path takes from the path's bounds (painter.rs, scan/path.rs, scan/path_aa.rs) before any
+// edge is built: the blitter rectangle, supersampling or not, whether the clipper is needed.  False: nothing is drawn.
+struct FillPlan {
+    IRect ir, sect;
+    int shift;
+    bool inside;
+};
+GEO_HD inline bool fill_plan(const PathBounds &pb, bool anti_alias, int32_t cw, int32_t ch, FillPlan *fp)
+{
+    if (!pb.finite) return false;
+    const float l = pb.l, t = pb.t, r = pb.r, b = pb.b;
     if (!(gfinite(l) && gfinite(r) && gfinite(t) && gfinite(b))) return false;
     if (nearly_zero(r - l) || nearly_zero(b - t)) return false; // painter.rs: empty paths, h/v lines
     const IRect clip{0, 0, cw, ch};
@@ -556,14 +578,21 @@ GEO_HD bool walk_path(const uint8_t *verbs, int n_verbs, const Pts &pts, int n_p
     }
     IRect s;
     if (!sect(ir, clip, &s)) return false;
-    const bool inside = ir.x >= 0 && ir.y >= 0 && contains(clip, ir);
+    fp->ir = ir;
+    fp->sect = s;
+    fp->shift = shift;
+    fp->inside = ir.x >= 0 && ir.y >= 0 && contains(clip, ir);
+    return true;
+}
 
-    sink.shift = shift;
+// PathEdgeIter + EdgeClipper feeding `sink` (every contour is closed implicitly).  `verbs` / `pts` may be any run of whole
+// contours of the path the plan was made for.
+template <class Sink, class Pts>
+GEO_HD void walk_verbs(const uint8_t *verbs, int n_verbs, const Pts &pts, bool inside, int32_t cw, int32_t ch, Sink &sink)
+{
     Clipper<Sink> cl;
     cl.sink = &sink;
     cl.c = Clip{0.0f, 0.0f, (float)cw, (float)ch};
-
-    // PathEdgeIter: every contour is closed implicitly
     int pi = 0;
     P move_to{0, 0}, last{0, 0};
     bool open = false;
@@ -602,10 +631,22 @@ GEO_HD bool walk_path(const uint8_t *verbs, int n_verbs, const Pts &pts, int n_p
         }
         open = true;
     }
-    g->sect = s;
-    g->shift = shift;
-    *ir_out = ir;
-    *inside_out = inside;
+}
+
+// Shared front end of both builders: plan, then the edges.  Returns false when nothing is to be drawn.
+template <class Sink, class Pts>
+GEO_HD bool walk_path(const uint8_t *verbs, int n_verbs, const Pts &pts, int n_pts, bool anti_alias, int32_t cw, int32_t ch,
+                      Sink &sink, DrawGeom *g, IRect *ir_out, bool *inside_out)
+{
+    if (n_pts == 0) return false;
+    FillPlan fp;
+    if (!fill_plan(path_bounds(pts, n_pts), anti_alias, cw, ch, &fp)) return false;
+    sink.shift = fp.shift;
+    walk_verbs(verbs, n_verbs, pts, fp.inside, cw, ch, sink);
+    g->sect = fp.sect;
+    g->shift = fp.shift;
+    *ir_out = fp.ir;
+    *inside_out = fp.inside;
     return true;
 }
 

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 
 #include "batch.h"
 #include "batch_geo.h"
@@ -32,11 +33,49 @@ using geo::GeoHeap;
 using geo::P;
 
 // The path a later stage consumes: status 0 = the recorded path, 1 = `verbs` / `pts` below, 2 = nothing is drawn.
+struct ContourRec { // one measured contour of a dashed stroke (dasher_core.h Contour), kept for the threads that cut its dashes
+    const geo::ds::Seg *segs;
+    const P *pts;
+    uint32_t n_segs, n_pts;
+    float length;
+    uint32_t closed;
+};
 struct GeoMid {
     const uint8_t *verbs;
     const P *pts;
     uint32_t n_verbs, n_pts;
     uint32_t status, pad;
+    // dashed strokes built in units (GT_UNITS)
+    const ContourRec *contours;
+    uint32_t unit_first, unit_count;
+    uint32_t plan_ok, n_list_row0;
+    geo::fl::FillPlan fp;   // stroke outlines: the fill decisions taken from the bounds of the WHOLE outline
+    rbh::IRect sect;        //   its blitter rectangle inside the target
+    int32_t r0, nr;         //   its warp-tile rows
+    geo::hl::Cull cull;     // hairlines: the culling decided from the bounds of the whole dashed path
+    DevEdge *out_lines;     // the outline's merged edge items
+    rbh::CurveRec *out_curves;
+};
+// One output contour of a dashed stroke: up to two "on" intervals of one measured contour (the second when the last dash of
+// a closed contour runs into its first).  contour == ~0u: the whole recorded path (dash specification rejected).
+struct GeoUnit {
+    uint32_t task, contour;
+    float a0, a1, b0, b1;
+    uint32_t has_b, local;
+};
+struct GeoPiece { // what the pipeline knows about a unit
+    const uint8_t *verbs; // its path: the dash (hairlines) or the outline of the dash (strokes)
+    const P *pts;
+    uint32_t n_verbs, n_pts;
+    float l, t, r, b;     // bounds of its points in device space
+    uint32_t finite, has_pts;
+    rbh::Edge *lines;     // its edge items (packed in place into DevEdge / slots local to the unit by k_geo_unit_fill)
+    rbh::CurveRec *curves;
+    uint32_t ne, ncv, slots, n_list;
+    uint32_t first_v, last_v; // its first / last item is a vertical line (what combine_vertical could merge across units)
+    int32_t first_x, last_x;
+    int32_t first_y0, first_y1, first_w, last_y0, last_y1, last_w;
+    uint32_t line_base, curve_base, slot_base, pad;
 };
 
 struct GeoArgs {
@@ -49,13 +88,16 @@ struct GeoArgs {
     GeoTotals *tot;
     GeoHeap heap;
     int W, H;
+    GeoUnit *units;
+    GeoPiece *pieces;
+    uint32_t max_units;
 };
 
 constexpr int GEO_THREADS = 64;
 // recursion guards (the device stack is GEO_STACK bytes per thread): deeper than this and the batch goes to the host builder
 constexpr int GEO_STACK = 12288;
 
-__device__ __forceinline__ void empty_draw(const GeoArgs &a, uint32_t ti, const GeoTask &t)
+__device__ __forceinline__ void empty_draw_at(const GeoArgs &a, uint32_t draw, const GeoTask &t)
 {
     DevDraw d;
     memset(&d, 0, sizeof(d));
@@ -65,8 +107,9 @@ __device__ __forceinline__ void empty_draw(const GeoArgs &a, uint32_t ti, const 
     d.r0 = 1; // r0 > r0 + n_rows - 1: the binning kernels never see it
     d.n_rows = 0;
     d.row_base = (uint32_t)atomicAdd(&a.tot->n_row_off, 1ull);
-    a.draws[ti] = d;
+    a.draws[draw] = d;
 }
+__device__ __forceinline__ void empty_draw(const GeoArgs &a, uint32_t, const GeoTask &t) { empty_draw_at(a, t.draw, t); }
 
 // ---- Path::dash ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GEO_THREADS) k_geo_dash(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n)
@@ -174,27 +217,10 @@ __device__ __forceinline__ MapPts map_for(const GeoTask &t, const P *p)
     return m;
 }
 
-// ---- hairline strokes -----------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEO_THREADS) k_geo_hair(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n)
+// The ordered blits of one hairline draw -> its DevDraw: blits outside the target dropped, bounding box, warp-tile cells, the
+// rank of every blit inside its cell (k_row_lists copies blit k of a cell to the cell's start + rank).
+__device__ void hair_emit(const GeoArgs &a, GeoHeap &heap, const GeoTask &t, uint32_t draw, DVec<geo::HairBlit> &blits)
 {
-    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
-    if (li >= n) return;
-    const uint32_t ti = list[li];
-    const GeoTask t = a.tasks[ti];
-    const uint8_t *verbs = a.verbs + t.verb_off;
-    const P *pts = a.pts + t.pt_off;
-    int n_verbs = (int)t.n_verbs, n_pts = (int)t.n_pts;
-    if (t.flags & GT_DASH) {
-        const GeoMid in = a.mid[ti];
-        if (in.status == 2) { empty_draw(a, ti, t); return; }
-        if (in.status == 1) { verbs = in.verbs; pts = in.pts; n_verbs = (int)in.n_verbs; n_pts = (int)in.n_pts; }
-    }
-    GeoHeap heap = a.heap;
-    DVec<geo::HairBlit> blits;
-    blits.init(&heap, t.hint * 16);
-    if (!blits.ok()) { empty_draw(a, ti, t); return; }
-    const MapPts mp = map_for(t, pts);
-    geo::hl::hairline_blits<DVec>(verbs, n_verbs, mp, n_pts, (int)((t.flags >> GT_CAP_SHIFT) & 3u), t.tw, t.th, blits);
     const int W = a.W, H = a.H, ox = t.ox, oy = t.oy;
     if (ox < 0 || oy < 0 || ox + t.tw > W || oy + t.th > H) { // keep the blits that land inside the target
         uint32_t keep = 0;
@@ -205,8 +231,8 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geo_hair(GeoArgs a, const uint3
         blits.n = keep;
     }
     const uint32_t nb = blits.n;
-    if (nb == 0) { empty_draw(a, ti, t); return; }
-    if (nb >= (1u << 28)) { a.tot->too_large = 1u; empty_draw(a, ti, t); return; }
+    if (nb == 0) { empty_draw_at(a, draw, t); return; }
+    if (nb >= (1u << 28)) { a.tot->too_large = 1u; empty_draw_at(a, draw, t); return; }
     int x0 = INT32_MAX, y0 = INT32_MAX, x1 = INT32_MIN, y1 = INT32_MIN;
     for (uint32_t k = 0; k < nb; k++) {
         const geo::HairBlit hb = blits.p[k];
@@ -227,7 +253,7 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geo_hair(GeoArgs a, const uint3
     rank.init(&heap, (uint32_t)nr * (uint32_t)ncols);
     DVec<DevEdge> out;
     out.init(&heap, nb);
-    if (!rank.ok() || !out.ok()) { empty_draw(a, ti, t); return; }
+    if (!rank.ok() || !out.ok()) { empty_draw_at(a, draw, t); return; }
     rank.resize((size_t)nr * (size_t)ncols);
     for (uint32_t k = 0; k < nb; k++) {
         const geo::HairBlit hb = blits.p[k];
@@ -252,7 +278,31 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geo_hair(GeoArgs a, const uint3
     d.list_cap = nb;
     atomicAdd(&a.tot->n_row_ent, (unsigned long long)nr);
     atomicAdd(&a.tot->n_wpairs, (unsigned long long)nr * (unsigned long long)ncols);
-    a.draws[ti] = d;
+    a.draws[draw] = d;
+}
+
+// ---- hairline strokes -----------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GEO_THREADS) k_geo_hair(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n)
+{
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n) return;
+    const uint32_t ti = list[li];
+    const GeoTask t = a.tasks[ti];
+    const uint8_t *verbs = a.verbs + t.verb_off;
+    const P *pts = a.pts + t.pt_off;
+    int n_verbs = (int)t.n_verbs, n_pts = (int)t.n_pts;
+    if (t.flags & GT_DASH) {
+        const GeoMid in = a.mid[ti];
+        if (in.status == 2) { empty_draw(a, ti, t); return; }
+        if (in.status == 1) { verbs = in.verbs; pts = in.pts; n_verbs = (int)in.n_verbs; n_pts = (int)in.n_pts; }
+    }
+    GeoHeap heap = a.heap;
+    DVec<geo::HairBlit> blits;
+    blits.init(&heap, (t.flags & GT_DASH) ? t.hint * 16 : 256u);
+    if (!blits.ok()) { empty_draw(a, ti, t); return; }
+    const MapPts mp = map_for(t, pts);
+    geo::hl::hairline_blits<DVec>(verbs, n_verbs, mp, n_pts, (int)((t.flags >> GT_CAP_SHIFT) & 3u), t.tw, t.th, blits, (t.flags & GT_DASH) ? -1 : t.sub);
+    hair_emit(a, heap, t, t.draw, blits);
 }
 
 // ---- fill_path up to the scanline walker ------------------------------------------------------------------------------------------
@@ -313,7 +363,7 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geo_fill(GeoArgs a, const uint3
     NoEnds ends{0};
     const geo::fl::Packed po = geo::fl::pack_items(lines.p, ne, curves.p, ncv, reinterpret_cast<DevEdge *>(lines.p), curves.p, g.shift, oy, r0, nr, ends);
     if (po.too_large) { a.tot->too_large = 1u; empty_draw(a, ti, t); return; }
-    if (ends.chains >= 128u) wide_q[atomicAdd(&a.tot->n_wide_q, 1u)] = ti; // the exact bound is taken by k_geo_wide
+    if (ends.chains >= 128u) wide_q[atomicAdd(&a.tot->n_wide_q, 1u)] = t.draw; // the exact bound is taken by k_geo_wide
     d.edge_cnt = po.slots;
     d.edge_off = (uint32_t)atomicAdd(&a.tot->n_slots, (unsigned long long)po.slots);
     d.line_off = (uint32_t)(((const uint8_t *)lines.p - heap.base) / sizeof(DevEdge));
@@ -327,7 +377,384 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geo_fill(GeoArgs a, const uint3
     d.list_cap = (uint32_t)po.n_list;
     atomicAdd(&a.tot->n_row_ent, (unsigned long long)nr);
     atomicAdd(&a.tot->n_wpairs, (unsigned long long)nr * (unsigned long long)(c1 - c0 + 1));
-    a.draws[ti] = d;
+    a.draws[t.draw] = d;
+}
+
+
+// ---- dashed strokes, dash by dash ---------------------------------------------------------------------------------------------
+// A dashed stroke is by far the longest draw (a hundred dashes, thousands of edges) and one thread per draw made the whole
+// launch wait for it.  Dashing cuts the path into independent open contours: the stroker treats every contour on its own,
+// and so does the fill front end up to one rule (combine_vertical looks at the last edge emitted, which may belong to the
+// previous contour — checked below).  So: k_geo_plan measures the contours of a dashed stroke and lists the dashes
+// ("units"); one thread per unit cuts the dash out, strokes it and takes its bounds (k_geo_unit_path); the fill decisions
+// are taken per draw from the bounds of all its units (k_geo_unit_bounds); one thread per unit builds its edges
+// (k_geo_unit_fill) or, for a hairline, walks it into a draw of its own (k_geo_unit_hair); k_geo_unit_merge lays the
+// units' edge items out one after the other and k_geo_unit_pack moves them there.
+struct CountRanges {
+    uint32_t n;
+    __device__ void operator()(float, float, bool mv) { if (mv || n == 0) n++; }
+};
+struct WriteRanges {
+    GeoUnit *units;
+    uint32_t task, contour, n;
+    __device__ void operator()(float a, float b, bool mv)
+    {
+        if (mv || n == 0) {
+            GeoUnit u;
+            u.task = task; u.contour = contour; u.a0 = a; u.a1 = b; u.b0 = 0.0f; u.b1 = 0.0f; u.has_b = 0; u.local = n;
+            units[n++] = u;
+        } else {
+            units[n - 1].b0 = a; units[n - 1].b1 = b; units[n - 1].has_b = 1;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(GEO_THREADS) k_geo_plan(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n)
+{
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n) return;
+    const uint32_t ti = list[li];
+    const GeoTask t = a.tasks[ti];
+    GeoMid m;
+    memset(&m, 0, sizeof(m));
+    m.status = 2;
+    const float *dash = a.dashes + t.dash_off;
+    const geo::ds::DashSpec sp = geo::ds::dash_spec(dash, (int)t.n_dash, t.dash_offset);
+    GeoHeap heap = a.heap;
+    uint32_t cnt = 0;
+    if (!sp.valid) {
+        // StrokeDash::new -> None: the stroke stays solid, one unit holding the recorded path
+        cnt = 1;
+        m.unit_first = atomicAdd(&a.tot->n_units, 1u);
+        GeoUnit u;
+        u.task = ti; u.contour = ~0u; u.a0 = u.a1 = u.b0 = u.b1 = 0.0f; u.has_b = 0; u.local = 0;
+        a.units[m.unit_first] = u;
+        m.unit_count = 1;
+        m.status = 1;
+    } else {
+        DVec<ContourRec> recs;
+        recs.init(&heap, 4);
+        const float tolerance = 0.5f * (1.0f / t.res_scale);
+        const uint8_t *verbs = a.verbs + t.verb_off;
+        const P *pts = a.pts + t.pt_off;
+        int vi = 0, pi = 0;
+        float dash_count = 0.0f;
+        bool ok = recs.ok();
+        while (ok) {
+            geo::ds::Contour<DVec> c;
+            c.segs.init(&heap, t.n_verbs * 8);
+            c.pts.init(&heap, t.n_pts + 4);
+            if (!c.segs.ok() || !c.pts.ok()) { ok = false; break; }
+            if (!geo::ds::next_contour(verbs, (int)t.n_verbs, pts, &vi, &pi, tolerance, &c)) break;
+            dash_count += c.length * (float)(t.n_dash >> 1) / sp.interval_len;
+            if (dash_count > 1000000.0f) { ok = false; break; } // dash_impl gives up: nothing is drawn
+            ContourRec r;
+            r.segs = c.segs.data(); r.pts = c.pts.data(); r.n_segs = (uint32_t)c.segs.size(); r.n_pts = (uint32_t)c.pts.size();
+            r.length = c.length; r.closed = c.closed ? 1u : 0u;
+            recs.push_back(r);
+            CountRanges cr{0};
+            geo::ds::dash_contour_ranges(sp, dash, (int)t.n_dash, c.length, c.closed, cr);
+            cnt += cr.n;
+        }
+        if (ok && cnt > t.max_units) { a.tot->deep = 1u; ok = false; } // the host's bound did not hold: the host builder takes the batch
+        if (ok && cnt > 0) {
+            m.unit_first = atomicAdd(&a.tot->n_units, cnt);
+            uint32_t at = m.unit_first;
+            for (uint32_t k = 0; k < recs.n; k++) {
+                WriteRanges wr{a.units + at, ti, k, 0};
+                geo::ds::dash_contour_ranges(sp, dash, (int)t.n_dash, recs.p[k].length, recs.p[k].closed != 0, wr);
+                for (uint32_t j = 0; j < wr.n; j++) a.units[at + j].local = at + j - m.unit_first;
+                at += wr.n;
+            }
+            m.unit_count = cnt;
+            m.contours = recs.data();
+            m.status = 1;
+        } else cnt = 0;
+    }
+    a.mid[ti] = m;
+    if (t.flags & GT_HAIR) { // every dash is a draw of its own: the reserved draws beyond the dashes there are stay empty
+        for (uint32_t k = cnt; k < t.n_draws; k++) empty_draw_at(a, t.draw + k, t);
+    } else if (cnt == 0) empty_draw(a, ti, t);
+}
+
+// The dash (hairlines) or its outline (strokes), and the bounds of its points in device space.
+__global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_path(GeoArgs a)
+{
+    const uint32_t ui = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ui >= a.tot->n_units) return;
+    const GeoUnit U = a.units[ui];
+    const GeoTask t = a.tasks[U.task];
+    GeoHeap heap = a.heap;
+    GeoPiece pc;
+    memset(&pc, 0, sizeof(pc));
+    const uint8_t *verbs = a.verbs + t.verb_off;
+    const P *pts = a.pts + t.pt_off;
+    int n_verbs = (int)t.n_verbs, n_pts = (int)t.n_pts;
+    bool ok = true;
+    if (U.contour != ~0u) {
+        const ContourRec r = a.mid[U.task].contours[U.contour];
+        geo::ds::Contour<DVec> c;
+        c.segs.p = const_cast<geo::ds::Seg *>(r.segs); c.segs.n = c.segs.cap = r.n_segs; c.segs.h = &heap;
+        c.pts.p = const_cast<P *>(r.pts); c.pts.n = c.pts.cap = r.n_pts; c.pts.h = &heap;
+        c.length = r.length; c.closed = r.closed != 0;
+        geo::ds::DashOut<DVec> pb;
+        pb.verbs.init(&heap, 16);
+        pb.pts.init(&heap, 40);
+        pb.move_required = true;
+        pb.last_move = 0;
+        ok = pb.verbs.ok() && pb.pts.ok();
+        if (ok) {
+            c.push_segment(U.a0, U.a1, true, pb);
+            if (U.has_b) c.push_segment(U.b0, U.b1, false, pb);
+            // The stroker ends every contour but the path's last through its move_to (finish_contour(false, false)) and the
+            // last one with finish_contour(false, last_is_line), which shapes a square cap after a line differently: a dash
+            // that is not the last one is followed by the next dash's move_to.
+            if (!(t.flags & GT_HAIR) && U.local + 1 != a.mid[U.task].unit_count) { pb.verbs.push_back(geo::V_MOVE); pb.pts.push_back(P{0.0f, 0.0f}); }
+            verbs = pb.verbs.data(); pts = pb.pts.data();
+            n_verbs = (int)pb.verbs.size(); n_pts = (int)pb.pts.size();
+        }
+    }
+    if (ok && !(t.flags & GT_HAIR)) {
+        geo::sk::Stroker<DVec> s;
+        s.outer.verbs.init(&heap, 48);
+        s.outer.pts.init(&heap, 96);
+        s.inner.verbs.init(&heap, 24);
+        s.inner.pts.init(&heap, 48);
+        s.cusper.verbs.init(&heap, 8);
+        s.cusper.pts.init(&heap, 8);
+        ok = s.outer.verbs.ok() && s.outer.pts.ok() && s.inner.verbs.ok() && s.inner.pts.ok() && s.cusper.verbs.ok() && s.cusper.pts.ok();
+        if (ok) {
+            s.reset();
+            ok = geo::sk::stroke_path(s, verbs, n_verbs, pts, t.width, t.miter, (int)((t.flags >> GT_CAP_SHIFT) & 3u), (int)((t.flags >> GT_JOIN_SHIFT) & 3u),
+                                      t.res_scale);
+            if (s.too_deep) a.tot->deep = 1u;
+            verbs = s.outer.verbs.data(); pts = s.outer.pts.data();
+            n_verbs = (int)s.outer.verbs.size(); n_pts = (int)s.outer.pts.size();
+        }
+    }
+    if (ok && n_pts > 0 && n_verbs > 1) {
+        pc.verbs = verbs; pc.pts = pts; pc.n_verbs = (uint32_t)n_verbs; pc.n_pts = (uint32_t)n_pts;
+        const MapPts mp = map_for(t, pts);
+        const geo::fl::PathBounds pb = geo::fl::path_bounds(mp, n_pts);
+        pc.l = pb.l; pc.t = pb.t; pc.r = pb.r; pc.b = pb.b;
+        pc.finite = pb.finite ? 1u : 0u;
+        pc.has_pts = 1u;
+    }
+    a.pieces[ui] = pc;
+}
+
+// Per dashed stroke: the bounds of all its units -> the decisions fill_path / stroke_hairline take from the whole path.
+__global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_bounds(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n)
+{
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n) return;
+    const uint32_t ti = list[li];
+    const GeoTask t = a.tasks[ti];
+    GeoMid *M = a.mid + ti;
+    if (M->status != 1) return;
+    bool any = false, finite = true;
+    float l = 0, tt = 0, r = 0, b = 0;
+    for (uint32_t k = 0; k < M->unit_count; k++) {
+        const GeoPiece *pc = a.pieces + M->unit_first + k;
+        if (!pc->has_pts) continue;
+        finite = finite && pc->finite != 0;
+        if (!any) { l = pc->l; tt = pc->t; r = pc->r; b = pc->b; any = true; }
+        else { l = geo::gmin(l, pc->l); tt = geo::gmin(tt, pc->t); r = geo::gmax(r, pc->r); b = geo::gmax(b, pc->b); }
+    }
+    uint32_t ok = 0;
+    if (any) {
+        if (t.flags & GT_HAIR) {
+            geo::hl::HairBounds hb;
+            hb.l = l; hb.t = tt; hb.r = r; hb.b = b; hb.finite = finite;
+            geo::hl::Cull cull;
+            if (geo::hl::hair_plan(hb, (int)((t.flags >> GT_CAP_SHIFT) & 3u), t.tw, t.th, &cull)) { M->cull = cull; ok = 1; }
+        } else {
+            geo::fl::PathBounds pb;
+            pb.l = l; pb.t = tt; pb.r = r; pb.b = b; pb.finite = finite;
+            geo::fl::FillPlan fp;
+            if (geo::fl::fill_plan(pb, (t.flags & GT_AA) != 0, t.tw, t.th, &fp)) {
+                rbh::IRect sc = fp.sect;
+                const int W = a.W, H = a.H, ox = t.ox, oy = t.oy;
+                bool vis = true;
+                if (ox < 0 || oy < 0 || ox + t.tw > W || oy + t.th > H) { // blitter rectangle ∩ target (tile-local coordinates)
+                    const int cx0 = max(sc.x, -ox), cy0 = max(sc.y, -oy);
+                    const int cx1 = min(sc.x + sc.w, W - ox), cy1 = min(sc.y + sc.h, H - oy);
+                    if (cx1 <= cx0 || cy1 <= cy0) vis = false;
+                    sc.x = cx0; sc.y = cy0; sc.w = cx1 - cx0; sc.h = cy1 - cy0;
+                }
+                rbh::DrawGeom g;
+                g.shift = fp.shift;
+                if (vis && geo::fl::finish_geom(fp.ir, fp.inside, t.th, &g)) {
+                    M->fp = fp;
+                    M->sect = sc;
+                    M->r0 = (oy + sc.y) >> 3;
+                    M->nr = ((oy + sc.y + sc.h - 1) >> 3) - M->r0 + 1;
+                    ok = 1;
+                }
+            }
+        }
+    }
+    M->plan_ok = ok;
+    if (!ok) {
+        if (t.flags & GT_HAIR) { for (uint32_t k = 0; k < M->unit_count; k++) empty_draw_at(a, t.draw + k, t); }
+        else empty_draw(a, ti, t);
+    }
+}
+
+// A dash of a hairline stroke: walked into a draw of its own.
+__global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_hair(GeoArgs a)
+{
+    const uint32_t ui = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ui >= a.tot->n_units) return;
+    const GeoUnit U = a.units[ui];
+    const GeoTask t = a.tasks[U.task];
+    if (!(t.flags & GT_HAIR)) return;
+    const GeoMid *M = a.mid + U.task;
+    if (!M->plan_ok) return; // its draws were emptied by k_geo_unit_bounds
+    const GeoPiece pc = a.pieces[ui];
+    const uint32_t draw = t.draw + U.local;
+    if (!pc.has_pts) { empty_draw_at(a, draw, t); return; }
+    GeoHeap heap = a.heap;
+    DVec<geo::HairBlit> blits;
+    blits.init(&heap, 128);
+    if (!blits.ok()) { empty_draw_at(a, draw, t); return; }
+    const MapPts mp = map_for(t, pc.pts);
+    geo::hl::hairline_walk<DVec>(pc.verbs, (int)pc.n_verbs, mp, (int)((t.flags >> GT_CAP_SHIFT) & 3u), t.tw, t.th, M->cull, blits);
+    hair_emit(a, heap, t, draw, blits);
+}
+
+// The edge items of one dash outline.
+__global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_fill(GeoArgs a)
+{
+    const uint32_t ui = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ui >= a.tot->n_units) return;
+    const GeoUnit U = a.units[ui];
+    const GeoTask t = a.tasks[U.task];
+    if (t.flags & GT_HAIR) return;
+    const GeoMid *M = a.mid + U.task;
+    GeoPiece *pc = a.pieces + ui;
+    if (!M->plan_ok || !pc->has_pts) return; // ne = ncv = 0
+    GeoHeap heap = a.heap;
+    DVec<rbh::Edge> lines;
+    DVec<rbh::CurveRec> curves;
+    geo::fl::Sink<DVec> sink;
+    lines.init(&heap, 32);
+    curves.init(&heap, 32);
+    sink.kinds.init(&heap, 64);
+    if (!lines.ok() || !curves.ok() || !sink.kinds.ok()) return;
+    sink.out = &lines;
+    sink.base = 0;
+    sink.curves = &curves;
+    sink.n_items = 0;
+    sink.shift = M->fp.shift;
+    const MapPts mp = map_for(t, pc->pts);
+    geo::fl::walk_verbs(pc->verbs, (int)pc->n_verbs, mp, M->fp.inside, t.tw, t.th, sink);
+    const uint32_t ne = lines.n, ncv = curves.n;
+    if (ne + ncv == 0) return;
+    // what combine_vertical could have merged with the neighbouring units' edges
+    const bool first_line = sink.kinds.p[0] == 0, last_line = sink.kinds.back() == 0;
+    pc->first_v = (first_line && lines.p[0].dx == 0) ? 1u : 0u;
+    pc->first_x = first_line ? lines.p[0].x : 0;
+    pc->last_v = (last_line && lines.back().dx == 0) ? 1u : 0u;
+    pc->last_x = last_line ? lines.back().x : 0;
+    if (first_line) { pc->first_y0 = lines.p[0].first_y; pc->first_y1 = lines.p[0].last_y; pc->first_w = lines.p[0].winding; }
+    if (last_line) { pc->last_y0 = lines.back().first_y; pc->last_y1 = lines.back().last_y; pc->last_w = lines.back().winding; }
+    NoEnds ends{0};
+    const geo::fl::Packed po = geo::fl::pack_items(lines.p, ne, curves.p, ncv, reinterpret_cast<DevEdge *>(lines.p), curves.p, M->fp.shift, t.oy, M->r0, M->nr, ends);
+    if (po.too_large) { a.tot->too_large = 1u; return; }
+    pc->lines = lines.p; pc->curves = curves.p;
+    pc->ne = ne; pc->ncv = ncv; pc->slots = po.slots; pc->n_list = (uint32_t)po.n_list;
+}
+
+// Per dashed stroke: its units' items one after the other -> the draw.
+__global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_merge(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n, uint32_t *__restrict__ wide_q)
+{
+    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= n) return;
+    const uint32_t ti = list[li];
+    const GeoTask t = a.tasks[ti];
+    if (t.flags & GT_HAIR) return;
+    GeoMid *M = a.mid + ti;
+    if (M->status != 1 || !M->plan_ok) return; // already an empty draw
+    uint32_t ne = 0, ncv = 0, slots = 0;
+    unsigned long long n_list = 0;
+    bool have_prev = false, prev_v = false;
+    int32_t prev_x = 0, prev_y0 = 0, prev_y1 = 0, prev_w = 0;
+    for (uint32_t k = 0; k < M->unit_count; k++) {
+        GeoPiece *pc = a.pieces + M->unit_first + k;
+        if (pc->ne + pc->ncv == 0) continue;
+        // scan/path: combine_vertical merges a new vertical line with the last edge emitted when that is a vertical line on
+        // the same x.  Across units nobody looked: hand the batch to the host builder if it could have happened.
+        if (have_prev && prev_v && pc->first_v && prev_x == pc->first_x) {
+            rbh::Edge e, last;
+            memset(&e, 0, sizeof(e)); memset(&last, 0, sizeof(last));
+            e.x = pc->first_x; e.first_y = pc->first_y0; e.last_y = pc->first_y1; e.winding = pc->first_w;
+            last.x = prev_x; last.first_y = prev_y0; last.last_y = prev_y1; last.winding = prev_w;
+            if (geo::fl::Sink<DVec>::combine_vertical(e, last) != 0) a.tot->deep = 1u;
+        }
+        have_prev = true; prev_v = pc->last_v != 0; prev_x = pc->last_x; prev_y0 = pc->last_y0; prev_y1 = pc->last_y1; prev_w = pc->last_w;
+        pc->line_base = ne; pc->curve_base = ncv; pc->slot_base = slots;
+        ne += pc->ne; ncv += pc->ncv; slots += pc->slots; n_list += pc->n_list;
+        if (slots >= (1u << 28)) { a.tot->too_large = 1u; empty_draw(a, ti, t); M->plan_ok = 0; return; }
+    }
+    if (ne + ncv < 2) { empty_draw(a, ti, t); M->plan_ok = 0; return; } // BasicEdgeBuilder::build: fewer than two edge objects
+    GeoHeap heap = a.heap;
+    DVec<DevEdge> out_l;
+    DVec<rbh::CurveRec> out_c;
+    out_l.init(&heap, ne);
+    out_c.init(&heap, ncv);
+    if (!out_l.ok() || !out_c.ok()) { empty_draw(a, ti, t); M->plan_ok = 0; return; }
+    M->out_lines = out_l.p;
+    M->out_curves = out_c.p;
+    const rbh::IRect sc = M->sect;
+    DevDraw d;
+    memset(&d, 0, sizeof(d));
+    d.ox = t.ox; d.oy = t.oy;
+    d.sx = sc.x; d.sy = sc.y; d.sw = sc.w; d.sh = sc.h;
+    d.shift = M->fp.shift;
+    d.rule = 0;
+    d.paint = t.paint;
+    const int c0 = (t.ox + sc.x) / 32, c1 = (t.ox + sc.x + sc.w - 1) / 32;
+    if (ne + ncv >= 128u) wide_q[atomicAdd(&a.tot->n_wide_q, 1u)] = t.draw;
+    d.edge_cnt = slots;
+    d.edge_off = (uint32_t)atomicAdd(&a.tot->n_slots, (unsigned long long)slots);
+    d.line_off = (uint32_t)(((const uint8_t *)out_l.p - heap.base) / sizeof(DevEdge));
+    d.line_cnt = ne;
+    d.curve_off = (uint32_t)(((const uint8_t *)out_c.p - heap.base) / sizeof(rbh::CurveRec));
+    d.curve_cnt = ncv;
+    d.r0 = (uint32_t)M->r0;
+    d.n_rows = (uint32_t)M->nr;
+    d.list_off = (uint32_t)atomicAdd(&a.tot->n_list, n_list);
+    d.row_base = (uint32_t)atomicAdd(&a.tot->n_row_off, (unsigned long long)M->nr + 1ull);
+    d.list_cap = (uint32_t)n_list;
+    if (n_list > 0xfffffff0ull) a.tot->too_large = 1u;
+    atomicAdd(&a.tot->n_row_ent, (unsigned long long)M->nr);
+    atomicAdd(&a.tot->n_wpairs, (unsigned long long)M->nr * (unsigned long long)(c1 - c0 + 1));
+    a.draws[t.draw] = d;
+}
+
+// Every unit moves its items to their place in the draw (slots become draw-wide).
+__global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_pack(GeoArgs a)
+{
+    const uint32_t ui = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ui >= a.tot->n_units) return;
+    const GeoUnit U = a.units[ui];
+    const GeoMid *M = a.mid + U.task;
+    const GeoPiece pc = a.pieces[ui];
+    if ((a.tasks[U.task].flags & GT_HAIR) || !M->plan_ok || pc.ne + pc.ncv == 0 || !M->out_lines) return;
+    const DevEdge *src = reinterpret_cast<const DevEdge *>(pc.lines);
+    DevEdge *dst = M->out_lines + pc.line_base;
+    for (uint32_t i = 0; i < pc.ne; i++) {
+        DevEdge e = src[i];
+        e.meta += pc.slot_base << 4;
+        dst[i] = e;
+    }
+    rbh::CurveRec *cd = M->out_curves + pc.curve_base;
+    for (uint32_t i = 0; i < pc.ncv; i++) {
+        rbh::CurveRec c = pc.curves[i];
+        c.item += pc.slot_base;
+        cd[i] = c;
+    }
 }
 
 // ---- packed winding range ------------------------------------------------------------------------------------------------------------
@@ -438,23 +865,31 @@ int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
     void *blk = nullptr;
     GeoBlock G;
     int st;
+    const bool diag = getenv("RB_GEO_DIAG") != nullptr;
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now_ms();
     { rb_prof_scope prof__(RB_T_BUILD); st = rb_geo_host_build(b, W, H, n_threads, geo_stage_pinned, &req, &blk, &G, begin, end); }
     if (req.status != RB_OK) return req.status;
     if (st != RB_OK) return rb_fail(ctx, st, "geometry task build failed");
     b->lay = BatchLayout();
     if (!blk || G.n_tasks == 0) return RB_OK;
     rb_prof_scope prof_up__(RB_T_UPLOAD);
+    const double t_built = now_ms();
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t n_tasks = G.n_tasks;
     size_t heap_bytes = al(G.heap_hint + (64u << 20));
     if (const char *e = getenv("RB_GEO_HEAP_BYTES")) heap_bytes = al((size_t)std::max(1024ll, atoll(e))); // tests: force heap retries
     for (int attempt = 0; attempt < 6; attempt++, heap_bytes *= 8) {
-        // [uploaded block | DevDraw[] | GeoMid[] | wide queue | totals | heap]
-        const size_t o_draws = al(G.total), o_mid = o_draws + al(n_tasks * sizeof(DevDraw)), o_wq = o_mid + al(n_tasks * sizeof(GeoMid));
-        const size_t o_tot = o_wq + al(n_tasks * 4), o_heap = o_tot + 256, total = o_heap + heap_bytes + 65536;
+        // [uploaded block | DevDraw[] | GeoMid[] | wide queue | units | pieces | totals | heap]
+        const size_t n_draws = G.n_draws, max_units = G.max_units;
+        const size_t o_draws = al(G.total), o_mid = o_draws + al(n_draws * sizeof(DevDraw)), o_wq = o_mid + al(n_tasks * sizeof(GeoMid));
+        const size_t o_units = o_wq + al(n_draws * 4), o_pieces = o_units + al((max_units + 1) * sizeof(GeoUnit));
+        const size_t o_tot = o_pieces + al((max_units + 1) * sizeof(GeoPiece)), o_heap = o_tot + 256, total = o_heap + heap_bytes + 65536;
         uint8_t *dev = nullptr;
         if (cudaMallocAsync((void **)&dev, total, ctx->stream) != cudaSuccess) {
             cudaGetLastError();
+            if (b->dev) { cudaFreeAsync(b->dev, ctx->stream); b->dev = nullptr; }
+            g_geo_counts[1]++;
             return RB_GEO_FALLBACK;
         }
         if (attempt == 0) {
@@ -480,31 +915,51 @@ int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
         a.heap.size = heap_bytes;
         a.heap.overflow = &a.tot->overflow;
         a.W = W; a.H = H;
+        a.units = (GeoUnit *)(dev + o_units);
+        a.pieces = (GeoPiece *)(dev + o_pieces);
+        a.max_units = (uint32_t)max_units;
         const uint32_t *lists = (const uint32_t *)(dev + G.o_lists);
-        const uint32_t nd = (uint32_t)G.n_dash_l, ns = (uint32_t)G.n_stroke_l, nh = (uint32_t)G.n_hair_l, nf = (uint32_t)G.n_fill_l;
-        auto grid = [](uint32_t n) { return (n + GEO_THREADS - 1) / GEO_THREADS; };
-        if (nd) { k_geo_dash<<<grid(nd), GEO_THREADS, 0, ctx->stream>>>(a, lists, nd); RB_LAUNCHED(ctx, "geo_dash"); }
-        if (ns) { k_geo_stroke<<<grid(ns), GEO_THREADS, 0, ctx->stream>>>(a, lists + nd, ns); RB_LAUNCHED(ctx, "geo_stroke"); }
-        if (nh) { k_geo_hair<<<grid(nh), GEO_THREADS, 0, ctx->stream>>>(a, lists + nd + ns, nh); RB_LAUNCHED(ctx, "geo_hair"); }
-        if (nf) {
-            k_geo_fill<<<grid(nf), GEO_THREADS, 0, ctx->stream>>>(a, lists + nd + ns + nh, nf, (uint32_t *)(dev + o_wq));
-            RB_LAUNCHED(ctx, "geo_fill");
-            k_geo_wide<<<std::min<uint32_t>(nf, (uint32_t)ctx->sm_count * 4u), GW_THREADS, 0, ctx->stream>>>(a, (const uint32_t *)(dev + o_wq));
+        const uint32_t nd = (uint32_t)G.n_dash_l, ns = (uint32_t)G.n_stroke_l, nh = (uint32_t)G.n_hair_l, nf = (uint32_t)G.n_fill_l, nu = (uint32_t)G.n_units_l;
+        const uint32_t *l_dash = lists, *l_stroke = l_dash + nd, *l_hair = l_stroke + ns, *l_fill = l_hair + nh, *l_units = l_fill + nf;
+        uint32_t *wide_q = (uint32_t *)(dev + o_wq);
+        auto grid = [](size_t n) { return (unsigned)((n + GEO_THREADS - 1) / GEO_THREADS); };
+        const unsigned g_units = grid(max_units);
+        if (nd) { k_geo_dash<<<grid(nd), GEO_THREADS, 0, ctx->stream>>>(a, l_dash, nd); RB_LAUNCHED(ctx, "geo_dash"); }
+        if (nu) {
+            k_geo_plan<<<grid(nu), GEO_THREADS, 0, ctx->stream>>>(a, l_units, nu); RB_LAUNCHED(ctx, "geo_plan");
+            k_geo_unit_path<<<g_units, GEO_THREADS, 0, ctx->stream>>>(a); RB_LAUNCHED(ctx, "geo_unit_path");
+            k_geo_unit_bounds<<<grid(nu), GEO_THREADS, 0, ctx->stream>>>(a, l_units, nu); RB_LAUNCHED(ctx, "geo_unit_bounds");
+        }
+        if (ns) { k_geo_stroke<<<grid(ns), GEO_THREADS, 0, ctx->stream>>>(a, l_stroke, ns); RB_LAUNCHED(ctx, "geo_stroke"); }
+        if (nh) { k_geo_hair<<<grid(nh), GEO_THREADS, 0, ctx->stream>>>(a, l_hair, nh); RB_LAUNCHED(ctx, "geo_hair"); }
+        if (nu) {
+            k_geo_unit_hair<<<g_units, GEO_THREADS, 0, ctx->stream>>>(a); RB_LAUNCHED(ctx, "geo_unit_hair");
+            k_geo_unit_fill<<<g_units, GEO_THREADS, 0, ctx->stream>>>(a); RB_LAUNCHED(ctx, "geo_unit_fill");
+        }
+        if (nf) { k_geo_fill<<<grid(nf), GEO_THREADS, 0, ctx->stream>>>(a, l_fill, nf, wide_q); RB_LAUNCHED(ctx, "geo_fill"); }
+        if (nu) {
+            k_geo_unit_merge<<<grid(nu), GEO_THREADS, 0, ctx->stream>>>(a, l_units, nu, wide_q); RB_LAUNCHED(ctx, "geo_unit_merge");
+            k_geo_unit_pack<<<g_units, GEO_THREADS, 0, ctx->stream>>>(a); RB_LAUNCHED(ctx, "geo_unit_pack");
+        }
+        if (nf || nu) {
+            k_geo_wide<<<std::min<uint32_t>((uint32_t)n_draws, (uint32_t)ctx->sm_count * 4u), GW_THREADS, 0, ctx->stream>>>(a, wide_q);
             RB_LAUNCHED(ctx, "geo_wide");
         }
         GeoTotals *ht = (GeoTotals *)ctx->geo_pinned;
         RB_CUDA(ctx, cudaMemcpyAsync(ht, dev + o_tot, sizeof(GeoTotals), cudaMemcpyDeviceToHost, ctx->stream));
+        const double t_enq = now_ms();
         RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         const GeoTotals T = *ht;
-        if (getenv("RB_GEO_DIAG"))
-            fprintf(stderr, "[geo] tasks %zu (dash %u stroke %u hair %u fill %u) upload %zu B heap %llu / %zu B slots %llu list %llu wide_q %u overflow %u wide %u\n",
-                    n_tasks, nd, ns, nh, nf, G.total, T.heap_cursor, heap_bytes, T.n_slots, T.n_list, T.n_wide_q, T.overflow, T.wide);
+        if (diag)
+            fprintf(stderr, "[geo] tasks %zu draws %zu (dash %u stroke %u hair %u fill %u units-tasks %u units %u / %zu) upload %zu B heap %llu / %zu B slots %llu list %llu wide_q %u overflow %u wide %u deep %u too_large %u | host %.2f ms, enqueue %.2f ms, wait %.2f ms\n",
+                    n_tasks, n_draws, nd, ns, nh, nf, nu, T.n_units, max_units, G.total, T.heap_cursor, heap_bytes, T.n_slots, T.n_list, T.n_wide_q, T.overflow, T.wide, T.deep, T.too_large,
+                    t_built - t_start, t_enq - t_built, now_ms() - t_enq);
         if (T.overflow) { g_geo_counts[2]++; continue; } // heap exhausted: again with eight times the heap
         if (T.wide || T.too_large || T.deep) break;
         if (T.n_slots > 0xfffffff0ull || T.n_list > 0xfffffff0ull || T.n_wpairs > 0xfffffff0ull || T.n_row_off > 0xfffffff0ull) break;
         BatchLayout L;
         L.items = true;
-        L.n_draws = n_tasks;
+        L.n_draws = n_draws;
         L.n_paints = G.n_paints; L.n_stops = G.n_stops;
         L.o_draws = o_draws; L.o_paints = G.o_paints; L.o_stops = G.o_stops;
         L.o_edges = o_heap; L.o_curves = o_heap;
@@ -516,7 +971,7 @@ int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
         L.wtiles_y = (H + 7) / 8;
         L.tiles_x = (W + TW - 1) / TW;
         b->lay = L;
-        b->stats[0] = n_tasks; b->stats[1] = L.n_slots; b->stats[2] = L.n_wpairs; b->stats[3] = (size_t)L.wtiles_x * L.wtiles_y;
+        b->stats[0] = n_draws; b->stats[1] = L.n_slots; b->stats[2] = L.n_wpairs; b->stats[3] = (size_t)L.wtiles_x * L.wtiles_y;
         b->stats[4] = G.total; b->stats[5] = 0;
         g_geo_counts[0]++;
         return RB_OK;

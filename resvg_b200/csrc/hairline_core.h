@@ -395,7 +395,7 @@ template <class Sink> GEO_HD void hair_cubic2(Sink &s, const P p[4])
     anti_hair_line(s, prev, p[3]);
 }
 GEO_HD inline float dot(P a, P b) { return a.x * b.x + a.y * b.y; }
-GEO_HD GEO_HD inline bool lt_90(P p0, P pivot, P p2) { return dot(p0 - pivot, p2 - pivot) >= 0.0f; }
+GEO_HD inline bool lt_90(P p0, P pivot, P p2) { return dot(p0 - pivot, p2 - pivot) >= 0.0f; }
 
 template <class Sink> GEO_HD void hair_cubic(Sink &s, const P p[4], const Cull &cull)
 {
@@ -476,37 +476,63 @@ GEO_HD inline void extend_pts(int cap, int prev_verb, int next_verb /* -1: none 
 
 // hairline::stroke_path_impl with line_proc = anti_hair_line_rgn.  `pts` are in device space relative to the clip
 // (0, 0, clip_w, clip_h); cap: 0 butt, 1 round, 2 square.
-template <template <class> class Vec, class Pts>
-GEO_HD void hairline_blits(const uint8_t *verbs, int n_verbs, const Pts &pts, int n_pts, int cap, int32_t clip_w, int32_t clip_h, Vec<HairBlit> &out)
+// only_verb >= 0: just the blits of that verb (the device walks the verbs of a path in parallel, one draw each: the blits of
+// a path are those of its verbs one after the other, and a verb's blits depend on its neighbours only through the points
+// carried along here).
+// Bounds of the whole path (with the probe for non-finite points): what stroke_path_impl decides culling from.
+struct HairBounds { float l, t, r, b; bool finite; };
+template <class Pts> GEO_HD HairBounds hair_bounds(const Pts &pts, int n_pts)
 {
-    if (n_pts <= 0 || n_verbs <= 0) return;
+    HairBounds hb;
+    hb.l = hb.t = hb.r = hb.b = 0.0f;
+    hb.finite = false;
+    if (n_pts <= 0) return hb;
+    const P p0 = pts[0];
+    float l = p0.x, t = p0.y, r = l, b = t, probe = 0.0f;
+    for (int i = 0; i < n_pts; i++) {
+        const P p = pts[i];
+        l = gmin(l, p.x); t = gmin(t, p.y); r = gmax(r, p.x); b = gmax(b, p.y);
+        probe += p.x * 0.0f + p.y * 0.0f; // a Path never holds a non-finite point
+    }
+    hb.l = l; hb.t = t; hb.r = r; hb.b = b;
+    hb.finite = probe == 0.0f;
+    return hb;
+}
+// false: nothing of the path is drawn
+GEO_HD inline bool hair_plan(const HairBounds &hb, int cap, int32_t clip_w, int32_t clip_h, Cull *cull)
+{
+    cull->on = false;
+    cull->inset = R{0, 0, 0, 0};
+    cull->outset = R{0, 0, 0, 0};
+    if (!hb.finite) return false;
+    const float l = hb.l, t = hb.t, r = hb.r, b = hb.b;
+    if (!(gfinite(l) && gfinite(t) && gfinite(r) && gfinite(b))) return false;
+    const float o = cap == 0 ? 1.0f : 2.0f;
+    const double fl = floor((double)l - o), ft = floor((double)t - o), cr = ceil((double)r + o), cb = ceil((double)b + o); // round_out
+    if (fl >= clip_w || ft >= clip_h || cr <= 0 || cb <= 0) return false;
+    if (!(fl >= 0 && ft >= 0 && cr <= clip_w && cb <= clip_h)) {
+        // per-segment culling rectangles: quick-accept inside the inset clip, quick-reject outside the outset clip
+        if (clip_w <= 2 || clip_h <= 2) return false; // inset(1, 1) -> None
+        cull->on = true;
+        cull->outset = R{-1.0f, -1.0f, (float)clip_w + 1.0f, (float)clip_h + 1.0f};
+        cull->inset = R{1.0f, 1.0f, (float)clip_w - 1.0f, (float)clip_h - 1.0f};
+    }
+    return true;
+}
+
+// The walk proper, for a path (or a run of whole contours of it) whose culling has been decided from the whole path.
+template <template <class> class Vec, class Pts>
+GEO_HD void hairline_walk(const uint8_t *verbs, int n_verbs, const Pts &pts, int cap, int32_t clip_w, int32_t clip_h, const Cull &cull,
+                          Vec<HairBlit> &out, int only_verb = -1)
+{
     HairSink<Vec> s;
     s.out = &out; s.w = clip_w; s.h = clip_h;
     s.sl = s.st = s.sr = s.sb = 0;
-    Cull cull{false, R{0, 0, 0, 0}, R{0, 0, 0, 0}};
-    {
-        float l = pts[0].x, t = pts[0].y, r = l, b = t, probe = 0.0f;
-        for (int i = 0; i < n_pts; i++) {
-            l = gmin(l, pts[i].x); t = gmin(t, pts[i].y); r = gmax(r, pts[i].x); b = gmax(b, pts[i].y);
-            probe += pts[i].x * 0.0f + pts[i].y * 0.0f; // a Path never holds a non-finite point
-        }
-        if (!(probe == 0.0f)) return;
-        if (!(gfinite(l) && gfinite(t) && gfinite(r) && gfinite(b))) return;
-        const float o = cap == 0 ? 1.0f : 2.0f;
-        const double fl = floor((double)l - o), ft = floor((double)t - o), cr = ceil((double)r + o), cb = ceil((double)b + o); // round_out
-        if (fl >= clip_w || ft >= clip_h || cr <= 0 || cb <= 0) return;
-        if (!(fl >= 0 && ft >= 0 && cr <= clip_w && cb <= clip_h)) {
-            // per-segment culling rectangles: quick-accept inside the inset clip, quick-reject outside the outset clip
-            if (clip_w <= 2 || clip_h <= 2) return; // inset(1, 1) -> None
-            cull.on = true;
-            cull.outset = R{-1.0f, -1.0f, (float)clip_w + 1.0f, (float)clip_h + 1.0f};
-            cull.inset = R{1.0f, 1.0f, (float)clip_w - 1.0f, (float)clip_h - 1.0f};
-        }
-    }
     int prev_verb = V_MOVE, pi = 0;
     P first_pt{0, 0}, last_pt{0, 0};
     for (int vi = 0; vi < n_verbs; vi++) {
         const int verb = verbs[vi];
+        const bool walk = only_verb < 0 || only_verb == vi;
         const int next_verb = vi + 1 < n_verbs ? verbs[vi + 1] : -1;
         P last_pt2 = last_pt;
         switch (verb) {
@@ -516,7 +542,7 @@ GEO_HD void hairline_blits(const uint8_t *verbs, int n_verbs, const Pts &pts, in
         case V_LINE: {
             P l[2] = {last_pt, pts[pi++]};
             if (cap != 0) extend_pts(cap, prev_verb, next_verb, l, 2);
-            anti_hair_lines(s, l, 2);
+            if (walk) anti_hair_lines(s, l, 2);
             last_pt = l[0];
             last_pt2 = l[1];
             break;
@@ -525,7 +551,7 @@ GEO_HD void hairline_blits(const uint8_t *verbs, int n_verbs, const Pts &pts, in
             P q[3] = {last_pt, pts[pi], pts[pi + 1]};
             pi += 2;
             if (cap != 0) extend_pts(cap, prev_verb, next_verb, q, 3);
-            hair_quad(s, q, cull, compute_quad_level(q));
+            if (walk) hair_quad(s, q, cull, compute_quad_level(q));
             last_pt = q[0];
             last_pt2 = q[2];
             break;
@@ -534,7 +560,7 @@ GEO_HD void hairline_blits(const uint8_t *verbs, int n_verbs, const Pts &pts, in
             P c[4] = {last_pt, pts[pi], pts[pi + 1], pts[pi + 2]};
             pi += 3;
             if (cap != 0) extend_pts(cap, prev_verb, next_verb, c, 4);
-            hair_cubic(s, c, cull);
+            if (walk) hair_cubic(s, c, cull);
             last_pt = c[0];
             last_pt2 = c[3];
             break;
@@ -542,7 +568,7 @@ GEO_HD void hairline_blits(const uint8_t *verbs, int n_verbs, const Pts &pts, in
         default: { // close
             P l[2] = {last_pt, first_pt};
             if (cap != 0 && prev_verb == V_MOVE) extend_pts(cap, prev_verb, next_verb, l, 2); // degenerate moveTo + close
-            anti_hair_lines(s, l, 2);
+            if (walk) anti_hair_lines(s, l, 2);
             last_pt2 = l[1];
             break;
         }
@@ -558,6 +584,16 @@ GEO_HD void hairline_blits(const uint8_t *verbs, int n_verbs, const Pts &pts, in
     }
 }
 
+
+template <template <class> class Vec, class Pts>
+GEO_HD void hairline_blits(const uint8_t *verbs, int n_verbs, const Pts &pts, int n_pts, int cap, int32_t clip_w, int32_t clip_h, Vec<HairBlit> &out,
+                           int only_verb = -1)
+{
+    if (n_pts <= 0 || n_verbs <= 0) return;
+    Cull cull;
+    if (!hair_plan(hair_bounds(pts, n_pts), cap, clip_w, clip_h, &cull)) return;
+    hairline_walk<Vec>(verbs, n_verbs, pts, cap, clip_w, clip_h, cull, out, only_verb);
+}
 
 } // namespace hl
 } // namespace geo

@@ -1092,6 +1092,9 @@ static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t 
     if (const char *e = getenv("RB_SUBMIT_SPLIT_FROM")) split_from = (size_t)std::max(1, atoi(e)); // tests
     if (n >= split_from && (b->layer || b->mask)) {
         parts = 8;
+        // with the geometry on the device there is no host build to overlap with the GPU, and one launch over all draws
+        // pays the long draws' latency once instead of once per part
+        if (b->layer && g_geo_mode != 2 && !rb_debug_host_only_builder()) parts = 1;
         if (const char *e = getenv("RB_SUBMIT_PARTS")) parts = (size_t)std::max(1, atoi(e));
     }
     int st = RB_OK;
