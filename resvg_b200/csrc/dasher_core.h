@@ -13,16 +13,16 @@
 namespace geo {
 namespace ds {
 
-GEO_HD inline float dist(P a, P b)
+GEO_HDI inline float dist(P a, P b)
 {
     const float dx = a.x - b.x, dy = a.y - b.y;
     return sqrtf(dx * dx + dy * dy);
 }
-GEO_HD inline float interp(float a, float b, float t) { return a + (b - a) * t; }
-GEO_HD inline P lerp(P a, P b, float t) { return P{interp(a.x, b.x, t), interp(a.y, b.y, t)}; }
+GEO_HDI inline float interp(float a, float b, float t) { return a + (b - a) * t; }
+GEO_HDI inline P lerp(P a, P b, float t) { return P{interp(a.x, b.x, t), interp(a.y, b.y, t)}; }
 
 // NormalizedF32Exclusive::new_bounded
-GEO_HD inline float bounded_t(float t)
+GEO_HDI inline float bounded_t(float t)
 {
     const float eps = 1.1920929e-7f;
     if (!(t > eps)) return eps;
@@ -78,13 +78,13 @@ template <template <class> class Vec> struct DashOut {
     GEO_HD void line_to(P p) { inject(); verbs.push_back(V_LINE); pts.push_back(p); }
     GEO_HD void quad_to(P a, P b) { inject(); verbs.push_back(V_QUAD); pts.push_back(a); pts.push_back(b); }
     GEO_HD void cubic_to(P a, P b, P c) { inject(); verbs.push_back(V_CUBIC); pts.push_back(a); pts.push_back(b); pts.push_back(c); }
-    GEO_HD bool last_point(P *p) const { if (pts.empty()) return false; *p = pts.back(); return true; }
+    GEO_HDI bool last_point(P *p) const { if (pts.empty()) return false; *p = pts.back(); return true; }
 };
 
 enum Kind { KLine = 0, KQuad = 1, KCubic = 2 };
 constexpr uint32_t MAX_T = 0x3FFFFFFF;
 struct Seg { float distance; uint32_t point_index; uint32_t t_value; int kind; };
-GEO_HD inline float scalar_t(const Seg &s) { return (float)s.t_value * (1.0f / (float)MAX_T); }
+GEO_HDI inline float scalar_t(const Seg &s) { return (float)s.t_value * (1.0f / (float)MAX_T); }
 
 template <template <class> class Vec> struct Contour {
     typedef DashOut<Vec> Out;
@@ -94,14 +94,14 @@ template <template <class> class Vec> struct Contour {
     bool closed = false;
     float tolerance = 0.5f;
 
-    GEO_HD static uint32_t t_span_big_enough(uint32_t span) { return span >> 10; }
-    GEO_HD bool quad_too_curvy(P a, P b, P c) const
+    GEO_HDI static uint32_t t_span_big_enough(uint32_t span) { return span >> 10; }
+    GEO_HDI bool quad_too_curvy(P a, P b, P c) const
     {
         const float dx = b.x * 0.5f - ((a.x + c.x) * 0.5f) * 0.5f, dy = b.y * 0.5f - ((a.y + c.y) * 0.5f) * 0.5f;
         return fmaxf(fabsf(dx), fabsf(dy)) > tolerance;
     }
-    GEO_HD bool cheap_exceeds(P pt, float x, float y) const { return fmaxf(fabsf(x - pt.x), fabsf(y - pt.y)) > tolerance; }
-    GEO_HD bool cubic_too_curvy(const P c[4]) const
+    GEO_HDI bool cheap_exceeds(P pt, float x, float y) const { return fmaxf(fabsf(x - pt.x), fabsf(y - pt.y)) > tolerance; }
+    GEO_HDI bool cubic_too_curvy(const P c[4]) const
     {
         return cheap_exceeds(c[1], interp(c[0].x, c[3].x, 1.0f / 3.0f), interp(c[0].y, c[3].y, 1.0f / 3.0f))
                || cheap_exceeds(c[2], interp(c[0].x, c[3].x, 2.0f / 3.0f), interp(c[0].y, c[3].y, 2.0f / 3.0f));
@@ -168,7 +168,7 @@ template <template <class> class Vec> struct Contour {
         *t = tv;
         return true;
     }
-    GEO_HD static void compute_pos(const P *p, int kind, float t, P *pos)
+    GEO_HDI static void compute_pos(const P *p, int kind, float t, P *pos)
     {
         if (kind == KLine) *pos = lerp(p[0], p[1], t);
         else if (kind == KQuad) *pos = eval_quad_at(p, t);

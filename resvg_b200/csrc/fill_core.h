@@ -26,15 +26,15 @@ using rbe::fdot6_round;
 using rbe::shl;
 
 constexpr float kNearlyZero = 1.0f / 4096.0f;
-GEO_HD inline bool nearly_zero(float v, float tol = kNearlyZero) { return fabsf(v) <= tol; }
+GEO_HDI inline bool nearly_zero(float v, float tol = kNearlyZero) { return fabsf(v) <= tol; }
 
 // ---------------------------------------------------------------------------------------------------
 // curve chopping (tiny-skia-path path_geometry.rs)
 // ---------------------------------------------------------------------------------------------------
-GEO_HD inline float lerpf(float a, float b, float t) { return a + (b - a) * t; }
-GEO_HD inline P lerp(P a, P b, float t) { return P{lerpf(a.x, b.x, t), lerpf(a.y, b.y, t)}; }
+GEO_HDI inline float lerpf(float a, float b, float t) { return a + (b - a) * t; }
+GEO_HDI inline P lerp(P a, P b, float t) { return P{lerpf(a.x, b.x, t), lerpf(a.y, b.y, t)}; }
 
-GEO_HD inline bool unit_divide(float numer, float denom, float *ratio)
+GEO_HDI inline bool unit_divide(float numer, float denom, float *ratio)
 {
     if (numer < 0) { numer = -numer; denom = -denom; }
     if (denom == 0 || numer == 0 || numer >= denom) return false;
@@ -74,8 +74,8 @@ GEO_HD inline void split_cubic(const P s[4], float t, P d[7])
     d[0] = s[0]; d[1] = ab; d[2] = abc; d[3] = lerp(abc, bcd, t); d[4] = bcd; d[5] = cd; d[6] = s[3];
 }
 
-template <int AXIS> GEO_HD inline float &ax(P &p) { return AXIS ? p.y : p.x; }
-template <int AXIS> GEO_HD inline float axv(const P &p) { return AXIS ? p.y : p.x; }
+template <int AXIS> GEO_HDI inline float &ax(P &p) { return AXIS ? p.y : p.x; }
+template <int AXIS> GEO_HDI inline float axv(const P &p) { return AXIS ? p.y : p.x; }
 
 template <int AXIS> GEO_HD int quad_extrema(const P s[3], P d[5])
 {
@@ -140,7 +140,7 @@ template <template <class> class Vec> struct Sink {
     Vec<CurveRec> *curves = nullptr;
     uint32_t n_items = 0;
 
-    GEO_HD uint32_t next_order() { return curves ? n_items++ : (uint32_t)(out->size() - base); }
+    GEO_HDI uint32_t next_order() { return curves ? n_items++ : (uint32_t)(out->size() - base); }
 
     // LineEdge::new / update tail: FDot6 end points, y0 <= y1
     GEO_HD bool emit(int32_t x0, int32_t y0, int32_t x1, int32_t y1, int winding, Edge *e)
@@ -270,7 +270,7 @@ template <template <class> class Vec> struct Sink {
 // ---------------------------------------------------------------------------------------------------
 struct Clip { float l, t, r, b; };
 
-GEO_HD inline float pin(double v, double a, double b)
+GEO_HDI inline float pin(double v, double a, double b)
 {
     if (a > b) gswap(a, b);
     return (float)gmin(gmax(v, a), b);
@@ -501,7 +501,7 @@ template <class Sink> struct Clipper {
 // ---------------------------------------------------------------------------------------------------
 // build_draw: scan::path_aa::fill_path / scan::path::fill_path up to (not including) walk_edges
 // ---------------------------------------------------------------------------------------------------
-GEO_HD inline bool sect(IRect a, IRect b, IRect *o)
+GEO_HDI inline bool sect(IRect a, IRect b, IRect *o)
 {
     int64_t l = gmax(a.x, b.x), t = gmax(a.y, b.y);
     int64_t r = gmin<int64_t>((int64_t)a.x + a.w, (int64_t)b.x + b.w);
@@ -510,11 +510,11 @@ GEO_HD inline bool sect(IRect a, IRect b, IRect *o)
     *o = IRect{(int32_t)l, (int32_t)t, (int32_t)(r - l), (int32_t)(bt - t)};
     return true;
 }
-GEO_HD inline bool contains(IRect o, IRect in)
+GEO_HDI inline bool contains(IRect o, IRect in)
 {
     return in.x >= o.x && in.y >= o.y && (int64_t)in.x + in.w <= (int64_t)o.x + o.w && (int64_t)in.y + in.h <= (int64_t)o.y + o.h;
 }
-GEO_HD inline bool short_overflow(int32_t v, int s) { return ((int32_t)(int16_t)shl(v, s) >> s) != v; }
+GEO_HDI inline bool short_overflow(int32_t v, int s) { return ((int32_t)(int16_t)shl(v, s) >> s) != v; }
 
 // Shared front end of both builders: bounds and clip decisions of tiny-skia's fill_path (painter.rs, scan/path.rs,
 // scan/path_aa.rs), then PathEdgeIter + EdgeClipper feeding `sink`.  Returns false when nothing is to be drawn.
@@ -687,7 +687,7 @@ struct Packed {
     size_t n_list;    // entries its tile-row edge lists can need
     bool too_large;   // slot indices would not fit DevEdge::meta
 };
-GEO_HD inline int tile_row_of(int32_t suby, int shift, int oy, int r0, int nr) { return gmin(gmax((((suby >> shift) + oy) >> 3) - r0, 0), nr - 1); }
+GEO_HDI inline int tile_row_of(int32_t suby, int shift, int oy, int r0, int nr) { return gmin(gmax((((suby >> shift) + oy) >> 3) - r0, 0), nr - 1); }
 
 // `ends` receives (first_y, last_y) of every chain: Ends::operator()(int32_t first, int32_t last).
 template <class Ends>

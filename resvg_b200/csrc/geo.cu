@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <vector>
 
 #include "batch.h"
 #include "batch_geo.h"
@@ -91,9 +92,18 @@ struct GeoArgs {
     GeoUnit *units;
     GeoPiece *pieces;
     uint32_t max_units;
+    uint32_t lane_shift;     // log2 of the lanes a task occupies (one of them works)
+    unsigned long long *dbg; // RB_GEO_TIMES: cycles per task of k_geo_stroke / k_geo_hair / k_geo_fill (3 arrays of n_tasks)
+    uint32_t n_tasks;
 };
 
+// The geometry code is one long data-dependent control flow per draw (recursive subdivision, clipping cases): the 32 lanes
+// of a warp would each take their own path and be executed one after the other, so a warp is no faster than a thread but
+// ties up 32 draws.  Every draw therefore gets a WARP of its own with lane 0 working: the same issue slots, but up to 32
+// times as many independent instruction streams per SM to hide latency with (measured on the 100 000-path scene: stroke
+// kernel 17.7 -> see DESIGN.md).
 constexpr int GEO_THREADS = 64;
+constexpr int GEO_TASKS_PER_CTA = GEO_THREADS / 32;
 // recursion guards (the device stack is GEO_STACK bytes per thread): deeper than this and the batch goes to the host builder
 constexpr int GEO_STACK = 12288;
 
@@ -114,7 +124,8 @@ __device__ __forceinline__ void empty_draw(const GeoArgs &a, uint32_t, const Geo
 // ---- Path::dash ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GEO_THREADS) k_geo_dash(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n)
 {
-    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> a.lane_shift;
+    if (threadIdx.x & ((1u << a.lane_shift) - 1u)) return; // 2^lane_shift lanes per task, one of them working: see GEO_THREADS
     if (li >= n) return;
     const uint32_t ti = list[li];
     const GeoTask t = a.tasks[ti];
@@ -146,10 +157,12 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geo_dash(GeoArgs a, const uint3
 // ---- PathStroker::stroke --------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GEO_THREADS) k_geo_stroke(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n)
 {
-    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> a.lane_shift;
+    if (threadIdx.x & ((1u << a.lane_shift) - 1u)) return; // 2^lane_shift lanes per task, one of them working: see GEO_THREADS
     if (li >= n) return;
     const uint32_t ti = list[li];
     const GeoTask t = a.tasks[ti];
+    struct Tm { const GeoArgs &a; uint32_t ti; long long t0; __device__ ~Tm() { if (a.dbg) a.dbg[0 * (size_t)a.n_tasks + ti] = (unsigned long long)(clock64() - t0); } } tm__{a, ti, clock64()};
     const uint8_t *verbs = a.verbs + t.verb_off;
     const P *pts = a.pts + t.pt_off;
     int n_verbs = (int)t.n_verbs;
@@ -284,10 +297,12 @@ __device__ void hair_emit(const GeoArgs &a, GeoHeap &heap, const GeoTask &t, uin
 // ---- hairline strokes -----------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GEO_THREADS) k_geo_hair(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n)
 {
-    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> a.lane_shift;
+    if (threadIdx.x & ((1u << a.lane_shift) - 1u)) return; // 2^lane_shift lanes per task, one of them working: see GEO_THREADS
     if (li >= n) return;
     const uint32_t ti = list[li];
     const GeoTask t = a.tasks[ti];
+    struct Tm { const GeoArgs &a; uint32_t ti; long long t0; __device__ ~Tm() { if (a.dbg) a.dbg[1 * (size_t)a.n_tasks + ti] = (unsigned long long)(clock64() - t0); } } tm__{a, ti, clock64()};
     const uint8_t *verbs = a.verbs + t.verb_off;
     const P *pts = a.pts + t.pt_off;
     int n_verbs = (int)t.n_verbs, n_pts = (int)t.n_pts;
@@ -313,10 +328,12 @@ struct NoEnds {
 
 __global__ void __launch_bounds__(GEO_THREADS) k_geo_fill(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n, uint32_t *__restrict__ wide_q)
 {
-    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> a.lane_shift;
+    if (threadIdx.x & ((1u << a.lane_shift) - 1u)) return; // 2^lane_shift lanes per task, one of them working: see GEO_THREADS
     if (li >= n) return;
     const uint32_t ti = list[li];
     const GeoTask t = a.tasks[ti];
+    struct Tm { const GeoArgs &a; uint32_t ti; long long t0; __device__ ~Tm() { if (a.dbg) a.dbg[2 * (size_t)a.n_tasks + ti] = (unsigned long long)(clock64() - t0); } } tm__{a, ti, clock64()};
     const uint8_t *verbs = a.verbs + t.verb_off;
     const P *pts = a.pts + t.pt_off;
     int n_verbs = (int)t.n_verbs, n_pts = (int)t.n_pts;
@@ -411,7 +428,8 @@ struct WriteRanges {
 
 __global__ void __launch_bounds__(GEO_THREADS) k_geo_plan(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n)
 {
-    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> a.lane_shift;
+    if (threadIdx.x & ((1u << a.lane_shift) - 1u)) return; // 2^lane_shift lanes per task, one of them working: see GEO_THREADS
     if (li >= n) return;
     const uint32_t ti = list[li];
     const GeoTask t = a.tasks[ti];
@@ -480,7 +498,8 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geo_plan(GeoArgs a, const uint3
 // The dash (hairlines) or its outline (strokes), and the bounds of its points in device space.
 __global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_path(GeoArgs a)
 {
-    const uint32_t ui = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t ui = (blockIdx.x * blockDim.x + threadIdx.x) >> a.lane_shift;
+    if (threadIdx.x & ((1u << a.lane_shift) - 1u)) return; // 2^lane_shift lanes per unit, one of them working: see GEO_THREADS
     if (ui >= a.tot->n_units) return;
     const GeoUnit U = a.units[ui];
     const GeoTask t = a.tasks[U.task];
@@ -546,7 +565,8 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_path(GeoArgs a)
 // Per dashed stroke: the bounds of all its units -> the decisions fill_path / stroke_hairline take from the whole path.
 __global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_bounds(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n)
 {
-    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> a.lane_shift;
+    if (threadIdx.x & ((1u << a.lane_shift) - 1u)) return; // 2^lane_shift lanes per task, one of them working: see GEO_THREADS
     if (li >= n) return;
     const uint32_t ti = list[li];
     const GeoTask t = a.tasks[ti];
@@ -604,7 +624,8 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_bounds(GeoArgs a, cons
 // A dash of a hairline stroke: walked into a draw of its own.
 __global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_hair(GeoArgs a)
 {
-    const uint32_t ui = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t ui = (blockIdx.x * blockDim.x + threadIdx.x) >> a.lane_shift;
+    if (threadIdx.x & ((1u << a.lane_shift) - 1u)) return; // 2^lane_shift lanes per unit, one of them working: see GEO_THREADS
     if (ui >= a.tot->n_units) return;
     const GeoUnit U = a.units[ui];
     const GeoTask t = a.tasks[U.task];
@@ -626,7 +647,8 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_hair(GeoArgs a)
 // The edge items of one dash outline.
 __global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_fill(GeoArgs a)
 {
-    const uint32_t ui = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t ui = (blockIdx.x * blockDim.x + threadIdx.x) >> a.lane_shift;
+    if (threadIdx.x & ((1u << a.lane_shift) - 1u)) return; // 2^lane_shift lanes per unit, one of them working: see GEO_THREADS
     if (ui >= a.tot->n_units) return;
     const GeoUnit U = a.units[ui];
     const GeoTask t = a.tasks[U.task];
@@ -669,7 +691,8 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_fill(GeoArgs a)
 // Per dashed stroke: its units' items one after the other -> the draw.
 __global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_merge(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n, uint32_t *__restrict__ wide_q)
 {
-    const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> a.lane_shift;
+    if (threadIdx.x & ((1u << a.lane_shift) - 1u)) return; // 2^lane_shift lanes per task, one of them working: see GEO_THREADS
     if (li >= n) return;
     const uint32_t ti = list[li];
     const GeoTask t = a.tasks[ti];
@@ -736,7 +759,8 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_merge(GeoArgs a, const
 // Every unit moves its items to their place in the draw (slots become draw-wide).
 __global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_pack(GeoArgs a)
 {
-    const uint32_t ui = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t ui = (blockIdx.x * blockDim.x + threadIdx.x) >> a.lane_shift;
+    if (threadIdx.x & ((1u << a.lane_shift) - 1u)) return; // 2^lane_shift lanes per unit, one of them working: see GEO_THREADS
     if (ui >= a.tot->n_units) return;
     const GeoUnit U = a.units[ui];
     const GeoMid *M = a.mid + U.task;
@@ -918,11 +942,18 @@ int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
         a.units = (GeoUnit *)(dev + o_units);
         a.pieces = (GeoPiece *)(dev + o_pieces);
         a.max_units = (uint32_t)max_units;
+        a.n_tasks = (uint32_t)n_tasks;
+        static const int lane_shift = getenv("RB_GEO_LANE_SHIFT") ? atoi(getenv("RB_GEO_LANE_SHIFT")) : 5;
+        a.lane_shift = (uint32_t)lane_shift;
+        a.dbg = nullptr;
+        unsigned long long *dbg = nullptr;
+        if (getenv("RB_GEO_TIMES")) { cudaMalloc((void **)&dbg, 3 * n_tasks * 8); cudaMemset(dbg, 0, 3 * n_tasks * 8); a.dbg = dbg; }
         const uint32_t *lists = (const uint32_t *)(dev + G.o_lists);
         const uint32_t nd = (uint32_t)G.n_dash_l, ns = (uint32_t)G.n_stroke_l, nh = (uint32_t)G.n_hair_l, nf = (uint32_t)G.n_fill_l, nu = (uint32_t)G.n_units_l;
         const uint32_t *l_dash = lists, *l_stroke = l_dash + nd, *l_hair = l_stroke + ns, *l_fill = l_hair + nh, *l_units = l_fill + nf;
         uint32_t *wide_q = (uint32_t *)(dev + o_wq);
-        auto grid = [](size_t n) { return (unsigned)((n + GEO_THREADS - 1) / GEO_THREADS); };
+        const size_t per_cta = (size_t)GEO_THREADS >> lane_shift;
+        auto grid = [&](size_t n) { return (unsigned)((n + per_cta - 1) / per_cta); };
         const unsigned g_units = grid(max_units);
         if (nd) { k_geo_dash<<<grid(nd), GEO_THREADS, 0, ctx->stream>>>(a, l_dash, nd); RB_LAUNCHED(ctx, "geo_dash"); }
         if (nu) {
@@ -950,6 +981,22 @@ int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
         const double t_enq = now_ms();
         RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         const GeoTotals T = *ht;
+        if (dbg) {
+            std::vector<unsigned long long> h(3 * n_tasks);
+            cudaMemcpy(h.data(), dbg, 3 * n_tasks * 8, cudaMemcpyDeviceToHost);
+            cudaFree(dbg);
+            const char *names[3] = {"stroke", "hair", "fill"};
+            for (int k = 0; k < 3; k++) {
+                std::vector<unsigned long long> v;
+                for (size_t i = 0; i < n_tasks; i++) if (h[k * n_tasks + i]) v.push_back(h[k * n_tasks + i]);
+                if (v.empty()) continue;
+                std::sort(v.begin(), v.end());
+                double sum = 0; for (auto x : v) sum += (double)x;
+                auto q = [&](double f) { return (double)v[std::min(v.size() - 1, (size_t)(f * v.size()))] / 1.9e3; };
+                fprintf(stderr, "[geo times] %s: n %zu, us: p50 %.0f p90 %.0f p99 %.0f p99.9 %.0f max %.0f, sum %.1f ms\n", names[k], v.size(), q(0.5), q(0.9), q(0.99), q(0.999),
+                        (double)v.back() / 1.9e3, sum / 1.9e6);
+            }
+        }
         if (diag)
             fprintf(stderr, "[geo] tasks %zu draws %zu (dash %u stroke %u hair %u fill %u units-tasks %u units %u / %zu) upload %zu B heap %llu / %zu B slots %llu list %llu wide_q %u overflow %u wide %u deep %u too_large %u | host %.2f ms, enqueue %.2f ms, wait %.2f ms\n",
                     n_tasks, n_draws, nd, ns, nh, nf, nu, T.n_units, max_units, G.total, T.heap_cursor, heap_bytes, T.n_slots, T.n_list, T.n_wide_q, T.overflow, T.wide, T.deep, T.too_large,

@@ -11,10 +11,16 @@
 #include <stdint.h>
 #include <string.h>
 
+// GEO_HD: a function of the cores.  On the device these are NOT inlined: the geometry code is a large tree of cases
+// (clipping, joins, caps, recursive subdivision) and inlining it into every call site produced kernels of more than a
+// megabyte of SASS, whose warps — each at a different point of it — spent most of their time waiting for instruction
+// fetches (ncu: 50-67 no-instruction stall cycles per issued instruction).  GEO_HDI: the small helpers that are inlined.
 #if defined(__CUDACC__)
-#define GEO_HD __host__ __device__
+#define GEO_HD __host__ __device__ __noinline__
+#define GEO_HDI __host__ __device__
 #else
 #define GEO_HD
+#define GEO_HDI
 #endif
 
 namespace geo {
@@ -22,29 +28,29 @@ namespace geo {
 struct P {
     float x, y;
 };
-GEO_HD inline P operator+(P a, P b) { return P{a.x + b.x, a.y + b.y}; }
-GEO_HD inline P operator-(P a, P b) { return P{a.x - b.x, a.y - b.y}; }
-GEO_HD inline P operator-(P a) { return P{-a.x, -a.y}; }
-GEO_HD inline P operator*(P a, float s) { return P{a.x * s, a.y * s}; }
-GEO_HD inline bool operator==(P a, P b) { return a.x == b.x && a.y == b.y; }
-GEO_HD inline bool operator!=(P a, P b) { return !(a == b); }
+GEO_HDI inline P operator+(P a, P b) { return P{a.x + b.x, a.y + b.y}; }
+GEO_HDI inline P operator-(P a, P b) { return P{a.x - b.x, a.y - b.y}; }
+GEO_HDI inline P operator-(P a) { return P{-a.x, -a.y}; }
+GEO_HDI inline P operator*(P a, float s) { return P{a.x * s, a.y * s}; }
+GEO_HDI inline bool operator==(P a, P b) { return a.x == b.x && a.y == b.y; }
+GEO_HDI inline bool operator!=(P a, P b) { return !(a == b); }
 
-template <class T> GEO_HD inline T gmin(T a, T b) { return b < a ? b : a; } // std::min
-template <class T> GEO_HD inline T gmax(T a, T b) { return a < b ? b : a; } // std::max
-template <class T> GEO_HD inline void gswap(T &a, T &b) { T t = a; a = b; b = t; }
-GEO_HD inline bool gfinite(float v) { return fabsf(v) <= 3.402823466e+38f; } // false for NaN and +-inf
-GEO_HD inline bool gfinite(double v) { return fabs(v) <= 1.7976931348623157e+308; }
-GEO_HD inline bool finite(P a) { return gfinite(a.x) && gfinite(a.y); }
+template <class T> GEO_HDI inline T gmin(T a, T b) { return b < a ? b : a; } // std::min
+template <class T> GEO_HDI inline T gmax(T a, T b) { return a < b ? b : a; } // std::max
+template <class T> GEO_HDI inline void gswap(T &a, T &b) { T t = a; a = b; b = t; }
+GEO_HDI inline bool gfinite(float v) { return fabsf(v) <= 3.402823466e+38f; } // false for NaN and +-inf
+GEO_HDI inline bool gfinite(double v) { return fabs(v) <= 1.7976931348623157e+308; }
+GEO_HDI inline bool finite(P a) { return gfinite(a.x) && gfinite(a.y); }
 
 // Rust `as i32` casts: truncate, saturate, NaN -> 0
-GEO_HD inline int32_t f2i(float v)
+GEO_HDI inline int32_t f2i(float v)
 {
     if (v != v) return 0;
     if (v >= 2147483648.0f) return INT32_MAX;
     if (v <= -2147483648.0f) return INT32_MIN;
     return (int32_t)v;
 }
-GEO_HD inline int32_t d2i(double v)
+GEO_HDI inline int32_t d2i(double v)
 {
     if (v != v) return 0;
     if (v >= 2147483647.0) return INT32_MAX;
@@ -55,7 +61,7 @@ GEO_HD inline int32_t d2i(double v)
 // Transcendentals of the stroker's cubic solver (path_geometry.rs solve_cubic_poly).  The host calls glibc, whose acosf /
 // cosf are correctly rounded in all but astronomically rare cases; the device evaluates in double and rounds once,
 // which gives the same float (CUDA's double acos / cos are within 2 ulp of the double result).  cbrtf likewise.
-GEO_HD inline float g_acosf(float v)
+GEO_HDI inline float g_acosf(float v)
 {
 #if defined(__CUDA_ARCH__)
     return (float)acos((double)v);
@@ -63,7 +69,7 @@ GEO_HD inline float g_acosf(float v)
     return acosf(v);
 #endif
 }
-GEO_HD inline float g_cosf(float v)
+GEO_HDI inline float g_cosf(float v)
 {
 #if defined(__CUDA_ARCH__)
     return (float)cos((double)v);
@@ -71,7 +77,7 @@ GEO_HD inline float g_cosf(float v)
     return cosf(v);
 #endif
 }
-GEO_HD inline float g_cbrtf(float v)
+GEO_HDI inline float g_cbrtf(float v)
 {
 #if defined(__CUDA_ARCH__)
     return (float)cbrt((double)v);
@@ -99,13 +105,13 @@ template <class T> struct DVec {
     T *p;
     uint32_t n, cap;
     GeoHeap *h;
-    __device__ void init(GeoHeap *heap, uint32_t reserve_hint)
+    __device__ __forceinline__ void init(GeoHeap *heap, uint32_t reserve_hint)
     {
         h = heap; p = nullptr; n = 0; cap = 0;
         grow_to(reserve_hint < 8 ? 8 : reserve_hint);
     }
-    __device__ bool ok() const { return p != nullptr; }
-    __device__ void grow_to(uint32_t want)
+    __device__ __forceinline__ bool ok() const { return p != nullptr; }
+    __device__ __noinline__ void grow_to(uint32_t want)
     {
         const unsigned long long bytes = (((unsigned long long)want * sizeof(T) + kHeapAlign - 1) / kHeapAlign) * kHeapAlign;
         const unsigned long long off = atomicAdd(h->cursor, bytes);
@@ -115,19 +121,19 @@ template <class T> struct DVec {
         p = np;
         cap = want;
     }
-    __device__ void push_back(const T &v)
+    __device__ __forceinline__ void push_back(const T &v)
     {
         if (n == cap) grow_to(cap * 2);
         if (n < cap) p[n++] = v;
     }
-    __device__ void pop_back() { if (n) n--; }
-    __device__ T &back() { return p[n ? n - 1 : 0]; }
-    __device__ const T &back() const { return p[n ? n - 1 : 0]; }
-    __device__ T &operator[](size_t i) { return p[i]; }
-    __device__ const T &operator[](size_t i) const { return p[i]; }
-    __device__ size_t size() const { return n; }
-    __device__ bool empty() const { return n == 0; }
-    __device__ void clear() { n = 0; }
+    __device__ __forceinline__ void pop_back() { if (n) n--; }
+    __device__ __forceinline__ T &back() { return p[n ? n - 1 : 0]; }
+    __device__ __forceinline__ const T &back() const { return p[n ? n - 1 : 0]; }
+    __device__ __forceinline__ T &operator[](size_t i) { return p[i]; }
+    __device__ __forceinline__ const T &operator[](size_t i) const { return p[i]; }
+    __device__ __forceinline__ size_t size() const { return n; }
+    __device__ __forceinline__ bool empty() const { return n == 0; }
+    __device__ __forceinline__ void clear() { n = 0; }
     __device__ void resize(size_t m) // shrink, or grow with zero-filled elements
     {
         if (m > cap) grow_to((uint32_t)m);
@@ -135,8 +141,8 @@ template <class T> struct DVec {
         for (size_t i = n; i < m; i++) memset(&p[i], 0, sizeof(T));
         n = (uint32_t)m;
     }
-    __device__ T *data() { return p; }
-    __device__ const T *data() const { return p; }
+    __device__ __forceinline__ T *data() { return p; }
+    __device__ __forceinline__ const T *data() const { return p; }
 };
 #endif
 

@@ -23,22 +23,22 @@ struct HairBlit { int32_t x, y; uint32_t alpha; };
 
 namespace hl {
 
-GEO_HD inline bool is_zero(P p) { return p.x == 0.0f && p.y == 0.0f; }
+GEO_HDI inline bool is_zero(P p) { return p.x == 0.0f && p.y == 0.0f; }
 
 typedef int32_t FDot6;
 typedef int32_t FDot16;
 constexpr FDot16 F16_HALF = 1 << 15, F16_ONE = 1 << 16;
 
-GEO_HD inline int32_t shl(int32_t v, int s) { return (int32_t)((uint32_t)v << s); }
-GEO_HD inline int32_t wmul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
-GEO_HD inline int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
-GEO_HD inline FDot6 fdot6_from_f32(float v) { return f2i(v * 64.0f); }
-GEO_HD inline int32_t fdot6_floor(FDot6 v) { return v >> 6; }
-GEO_HD inline int32_t fdot6_ceil(FDot6 v) { return wadd(v, 63) >> 6; }
-GEO_HD inline FDot16 fdot6_to_fdot16(FDot6 v) { return shl(v, 10); }
-GEO_HD inline FDot16 fast_div(FDot6 a, FDot6 b) { return shl(a, 16) / b; }
-GEO_HD inline uint32_t small_scale(uint32_t value, int32_t dot6) { return (uint32_t)(((int32_t)value * dot6) >> 6) & 0xffu; }
-GEO_HD inline uint32_t i32_to_alpha(int32_t a) { return (uint32_t)a & 0xffu; }
+GEO_HDI inline int32_t shl(int32_t v, int s) { return (int32_t)((uint32_t)v << s); }
+GEO_HDI inline int32_t wmul(int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); }
+GEO_HDI inline int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+GEO_HDI inline FDot6 fdot6_from_f32(float v) { return f2i(v * 64.0f); }
+GEO_HDI inline int32_t fdot6_floor(FDot6 v) { return v >> 6; }
+GEO_HDI inline int32_t fdot6_ceil(FDot6 v) { return wadd(v, 63) >> 6; }
+GEO_HDI inline FDot16 fdot6_to_fdot16(FDot6 v) { return shl(v, 10); }
+GEO_HDI inline FDot16 fast_div(FDot6 a, FDot6 b) { return shl(a, 16) / b; }
+GEO_HDI inline uint32_t small_scale(uint32_t value, int32_t dot6) { return (uint32_t)(((int32_t)value * dot6) >> 6) & 0xffu; }
+GEO_HDI inline uint32_t i32_to_alpha(int32_t a) { return (uint32_t)a & 0xffu; }
 
 template <template <class> class Vec> struct HairSink {
     Vec<HairBlit> *out;
@@ -46,13 +46,13 @@ template <template <class> class Vec> struct HairSink {
     // the sub-clip of the line being walked: (line bounds + 1) ∩ clip when the line's bounds leave the clip — what the
     // reference hands to do_anti_hairline and wraps the blitter in (RectClipBlitter); the whole clip otherwise
     int64_t sl = 0, st = 0, sr = 0, sb = 0;
-    GEO_HD void px(int64_t x, int64_t y, uint32_t a)
+    GEO_HDI void px(int64_t x, int64_t y, uint32_t a)
     {
         if (a == 0 || x < sl || y < st || x >= sr || y >= sb) return;
         out->push_back(HairBlit{(int32_t)x, (int32_t)y, a});
     }
-    GEO_HD void anti_h2(int64_t x, int64_t y, uint32_t a0, uint32_t a1) { px(x, y, a0); px(x + 1, y, a1); }
-    GEO_HD void anti_v2(int64_t x, int64_t y, uint32_t a0, uint32_t a1) { px(x, y, a0); px(x, y + 1, a1); }
+    GEO_HDI void anti_h2(int64_t x, int64_t y, uint32_t a0, uint32_t a1) { px(x, y, a0); px(x + 1, y, a1); }
+    GEO_HDI void anti_v2(int64_t x, int64_t y, uint32_t a0, uint32_t a1) { px(x, y, a0); px(x, y + 1, a1); }
     GEO_HD void v(int64_t x, int64_t y, int32_t height, uint32_t a) { for (int32_t i = 0; i < height; i++) px(x, y + i, a); }
     GEO_HD void hline(int64_t x, int64_t y, int32_t count, uint32_t a) { if (y < 0) return; for (int32_t i = 0; i < count; i++) px(x + i, y, a); }
 };
@@ -233,7 +233,7 @@ template <class Sink> GEO_HD void do_anti_hairline(Sink &s, FDot6 x0, FDot6 y0, 
 
 // ---- line_clipper::intersect ------------------------------------------------------------------------------------------------
 struct R { float l, t, r, b; };
-GEO_HD inline bool nested_lt(float a, float b, float dim) { return a <= b && (a < b || dim > 0.0f); }
+GEO_HDI inline bool nested_lt(float a, float b, float dim) { return a <= b && (a < b || dim > 0.0f); }
 GEO_HD inline float sect_with_horizontal(const P s[2], float y)
 {
     const float dx = s[1].x - s[0].x;
@@ -310,7 +310,7 @@ template <class Sink> GEO_HD void anti_hair_lines(Sink &s, const P *pts, int n)
 // ---- curves (hairline.rs) ----------------------------------------------------------------------------------------------------
 constexpr int MAX_QUAD_LEVEL = 5, MAX_CUBIC_LEVEL = 9;
 
-GEO_HD inline int sat_ceil_i32(float v) { return f2i(ceilf(v)); }
+GEO_HDI inline int sat_ceil_i32(float v) { return f2i(ceilf(v)); }
 GEO_HD inline uint32_t compute_int_quad_dist(const P p[3])
 {
     const float dx = fabsf((p[0].x + p[2].x) * 0.5f - p[1].x), dy = fabsf((p[0].y + p[2].y) * 0.5f - p[1].y);
@@ -324,8 +324,8 @@ GEO_HD inline int compute_quad_level(const P p[3])
     return gmin(level, MAX_QUAD_LEVEL);
 }
 struct Cull { bool on; R inset, outset; };
-GEO_HD inline bool overlaps(const R &a, const R &b) { return a.l < b.r && b.l < a.r && a.t < b.b && b.t < a.b; }     // geometric_overlap
-GEO_HD inline bool contains(const R &o, const R &i) { return o.l <= i.l && o.t <= i.t && o.r >= i.r && o.b >= i.b; } // geometric_contains
+GEO_HDI inline bool overlaps(const R &a, const R &b) { return a.l < b.r && b.l < a.r && a.t < b.b && b.t < a.b; }     // geometric_overlap
+GEO_HDI inline bool contains(const R &o, const R &i) { return o.l <= i.l && o.t <= i.t && o.r >= i.r && o.b >= i.b; } // geometric_contains
 
 template <class Sink> GEO_HD void hair_quad(Sink &s, const P p[3], const Cull &cull, int level)
 {
@@ -394,8 +394,8 @@ template <class Sink> GEO_HD void hair_cubic2(Sink &s, const P p[4])
     }
     anti_hair_line(s, prev, p[3]);
 }
-GEO_HD inline float dot(P a, P b) { return a.x * b.x + a.y * b.y; }
-GEO_HD inline bool lt_90(P p0, P pivot, P p2) { return dot(p0 - pivot, p2 - pivot) >= 0.0f; }
+GEO_HDI inline float dot(P a, P b) { return a.x * b.x + a.y * b.y; }
+GEO_HDI inline bool lt_90(P p0, P pivot, P p2) { return dot(p0 - pivot, p2 - pivot) >= 0.0f; }
 
 template <class Sink> GEO_HD void hair_cubic(Sink &s, const P p[4], const Cull &cull)
 {

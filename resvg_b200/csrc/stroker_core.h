@@ -14,16 +14,16 @@
 namespace geo {
 namespace sk {
 
-GEO_HD inline float dot(P a, P b) { return a.x * b.x + a.y * b.y; }
-GEO_HD inline float cross(P a, P b) { return a.x * b.y - a.y * b.x; }
-GEO_HD inline float len_sqd(P a) { return dot(a, a); }
-GEO_HD inline float dist_sqd(P a, P b) { return len_sqd(a - b); }
-GEO_HD inline P rot_cw(P a) { return {-a.y, a.x}; }
-GEO_HD inline P rot_ccw(P a) { return {a.y, -a.x}; }
+GEO_HDI inline float dot(P a, P b) { return a.x * b.x + a.y * b.y; }
+GEO_HDI inline float cross(P a, P b) { return a.x * b.y - a.y * b.x; }
+GEO_HDI inline float len_sqd(P a) { return dot(a, a); }
+GEO_HDI inline float dist_sqd(P a, P b) { return len_sqd(a - b); }
+GEO_HDI inline P rot_cw(P a) { return {-a.y, a.x}; }
+GEO_HDI inline P rot_ccw(P a) { return {a.y, -a.x}; }
 
 constexpr float kNearlyZero = 1.0f / 4096.0f;
 constexpr float kRoot2Over2 = 0.707106781f;
-GEO_HD inline bool nearly_zero(float v, float tol = kNearlyZero) { return fabsf(v) <= tol; }
+GEO_HDI inline bool nearly_zero(float v, float tol = kNearlyZero) { return fabsf(v) <= tol; }
 
 // Point::set_length / normalize (double precision magnitude, as tiny-skia-path point.rs)
 GEO_HD inline bool set_length(P &p, float x, float y, float length)
@@ -41,8 +41,8 @@ GEO_HD inline bool set_length(P &p, float x, float y, float length)
     return true;
 }
 GEO_HD inline bool set_length(P &p, float length) { return set_length(p, p.x, p.y, length); }
-GEO_HD inline bool normalize(P &p) { return set_length(p, p.x, p.y, 1.0f); }
-GEO_HD inline bool can_normalize(float dx, float dy) { return (gfinite(dx) && gfinite(dy)) && (dx != 0 || dy != 0); }
+GEO_HDI inline bool normalize(P &p) { return set_length(p, p.x, p.y, 1.0f); }
+GEO_HDI inline bool can_normalize(float dx, float dy) { return (gfinite(dx) && gfinite(dy)) && (dx != 0 || dy != 0); }
 
 // ---------------------------------------------------------------------------------------------------
 // PathBuilder subset (tiny-skia-path path_builder.rs)
@@ -53,8 +53,8 @@ template <template <class> class Vec> struct Builder {
     size_t last_move = 0;
     bool move_required = true;
 
-    GEO_HD void clear() { verbs.clear(); pts.clear(); last_move = 0; move_required = true; }
-    GEO_HD bool empty() const { return verbs.empty(); }
+    GEO_HDI void clear() { verbs.clear(); pts.clear(); last_move = 0; move_required = true; }
+    GEO_HDI bool empty() const { return verbs.empty(); }
     GEO_HD void move_to(float x, float y)
     {
         if (!verbs.empty() && verbs.back() == V_MOVE) pts.back() = {x, y};
@@ -80,7 +80,7 @@ template <template <class> class Vec> struct Builder {
         if (!verbs.empty() && verbs.back() != V_CLOSE) verbs.push_back(V_CLOSE);
         move_required = true;
     }
-    GEO_HD bool last_point(P *p) const { if (pts.empty()) return false; *p = pts.back(); return true; }
+    GEO_HDI bool last_point(P *p) const { if (pts.empty()) return false; *p = pts.back(); return true; }
     GEO_HD void set_last_point(P p) { if (pts.empty()) move_to(p.x, p.y); else pts.back() = p; }
 
     // conic -> quads (AutoConicToQuads, tolerance 0.25)
@@ -140,7 +140,7 @@ struct Conic {
         b.p[0] = m; b.p[1] = (wp1 + p[2]) * scale; b.p[2] = p[2]; b.w = nw;
     }
 };
-GEO_HD inline bool between(float a, float b, float c) { return (a - b) * (c - b) <= 0; }
+GEO_HDI inline bool between(float a, float b, float c) { return (a - b) * (c - b) <= 0; }
 
 GEO_HD inline P *subdivide(const Conic &src, P *out, int level)
 {
@@ -297,7 +297,7 @@ GEO_HD inline int unit_quad_roots(float a, float b, float c, float roots[2])
     }
     return n;
 }
-GEO_HD inline P eval_quad(const P q[3], float t)
+GEO_HDI inline P eval_quad(const P q[3], float t)
 {
     P a = q[2] - q[1] * 2.0f + q[0], b = (q[1] - q[0]) * 2.0f;
     return (a * t + b) * t + q[0];
@@ -309,12 +309,12 @@ GEO_HD inline P eval_quad_tangent(const P q[3], float t)
     P tt = a * t + b;
     return tt + tt;
 }
-GEO_HD inline P eval_cubic(const P c[4], float t)
+GEO_HDI inline P eval_cubic(const P c[4], float t)
 {
     P a = c[3] + (c[1] - c[2]) * 3.0f - c[0], b = (c[2] - c[1] * 2.0f + c[0]) * 3.0f, cc = (c[1] - c[0]) * 3.0f;
     return ((a * t + b) * t + cc) * t + c[0];
 }
-GEO_HD inline P eval_cubic_derivative(const P c[4], float t)
+GEO_HDI inline P eval_cubic_derivative(const P c[4], float t)
 {
     P a = c[3] + (c[1] - c[2]) * 3.0f - c[0], b = (c[2] - c[1] * 2.0f + c[0]) * 2.0f, cc = c[1] - c[0];
     return (a * t + b) * t + cc;
@@ -352,7 +352,7 @@ GEO_HD inline int cubic_inflections(const P c[4], float t[2])
     float cx = c[3].x + 3 * (c[1].x - c[2].x) - c[0].x, cy = c[3].y + 3 * (c[1].y - c[2].y) - c[0].y;
     return unit_quad_roots(bx * cy - by * cx, ax * cy - ay * cx, ax * by - ay * bx, t);
 }
-GEO_HD inline float pin01(float v) { return gmin(gmax(v, 0.0f), 1.0f); }
+GEO_HDI inline float pin01(float v) { return gmin(gmax(v, 0.0f), 1.0f); }
 GEO_HD inline int solve_cubic_poly(const float co[4], float t[3])
 {
     if (nearly_zero(co[0])) return unit_quad_roots(co[1], co[2], co[3], t);
@@ -427,19 +427,19 @@ struct QuadConstruct {
     P quad[3], tangent_start, tangent_end;
     float start_t, mid_t, end_t;
     bool start_set, end_set, opposite_tangents;
-    GEO_HD bool init(float s, float e)
+    GEO_HDI bool init(float s, float e)
     {
         start_t = s; mid_t = (s + e) * 0.5f; end_t = e;
         start_set = end_set = false;
         return start_t < mid_t && mid_t < end_t;
     }
-    GEO_HD bool init_with_start(const QuadConstruct &p)
+    GEO_HDI bool init_with_start(const QuadConstruct &p)
     {
         if (!init(p.start_t, p.mid_t)) return false;
         quad[0] = p.quad[0]; tangent_start = p.tangent_start; start_set = true;
         return true;
     }
-    GEO_HD bool init_with_end(const QuadConstruct &p)
+    GEO_HDI bool init_with_end(const QuadConstruct &p)
     {
         if (!init(p.mid_t, p.end_t)) return false;
         quad[2] = p.quad[2]; tangent_end = p.tangent_end; end_set = true;
@@ -458,10 +458,10 @@ GEO_HD inline float pt_to_line(P pt, P a, P b)
     }
     return dist_sqd(pt, a);
 }
-GEO_HD inline bool degenerate_vector(P v) { return !can_normalize(v.x, v.y); }
-GEO_HD inline bool is_clockwise(P before, P after) { return before.x * after.y > before.y * after.x; }
+GEO_HDI inline bool degenerate_vector(P v) { return !can_normalize(v.x, v.y); }
+GEO_HDI inline bool is_clockwise(P before, P after) { return before.x * after.y > before.y * after.x; }
 enum Angle { Nearly180, Sharp, Shallow, NearlyLine };
-GEO_HD inline Angle dot_to_angle(float d)
+GEO_HDI inline Angle dot_to_angle(float d)
 {
     if (d >= 0) return nearly_zero(1.0f - d) ? NearlyLine : Shallow;
     return nearly_zero(1.0f + d) ? Nearly180 : Sharp;
@@ -751,7 +751,7 @@ template <template <class> class Vec> struct Stroker {
         qp.opposite_tangents = dot(a_len, b_len) < 0;
         return Degenerate;
     }
-    GEO_HD static bool points_within_dist(P a, P b, float limit) { return dist_sqd(a, b) <= limit * limit; }
+    GEO_HDI static bool points_within_dist(P a, P b, float limit) { return dist_sqd(a, b) <= limit * limit; }
     GEO_HD static bool sharp_angle(const P q[3])
     {
         P smaller = q[1] - q[0], larger = q[1] - q[2];
@@ -791,7 +791,7 @@ template <template <class> class Vec> struct Stroker {
         if (points_within_dist(ray[0], qpnt, error)) return sharp_angle(qp.quad) ? Split : Quad;
         return Split;
     }
-    GEO_HD Builder &side() { return stroke_type == 1 ? outer : inner; }
+    GEO_HDI Builder &side() { return stroke_type == 1 ? outer : inner; }
     GEO_HD Result compare_quad_quad(const P q[3], QuadConstruct &qp)
     {
         if (!qp.start_set) { P t; quad_perp_ray(q, qp.start_t, &t, &qp.quad[0], &qp.tangent_start); qp.start_set = true; }

@@ -1,0 +1,86 @@
+"""Host half of the device geometry path (batch_host.cpp rb_geo_host_build): classification, culling, DrawTiler tiles,
+per-verb hairline tasks, unit bounds — no GPU needed (host-only batches)."""
+import ctypes as C
+
+import numpy as np
+
+from resvg_b200 import _ffi, scenes
+
+
+def _stats(w, h, scene, strokes=True, ts=None):
+    lib = _ffi.lib
+    paints = scenes.to_paint_array(scene, _ffi.Paint)
+    st = scenes.to_stroke_array(scene, _ffi.Stroke) if strokes else None
+    hnd = C.c_void_p()
+    assert lib.rb_debug_batch_begin_host(w, h, C.byref(hnd)) == 0
+    try:
+        t = (C.c_float * 6)(*ts) if ts is not None else None
+        assert lib.rb_batch_draw_paths(hnd, scene["n_paths"], scene["verb_off"].ctypes.data, scene["pt_off"].ctypes.data,
+                                       scene["verbs"].ctypes.data, scene["pts"].ctypes.data, C.addressof(paints),
+                                       scene["rules"].ctypes.data, C.addressof(st) if st is not None else None, t) == 0
+        out = (C.c_uint64 * 8)()
+        assert lib.rb_debug_geo_host_stats(hnd, out) == 0
+        return dict(zip(["tasks", "dashed", "stroked", "hair", "fill", "bytes", "verbs", "pts"], [int(v) for v in out]))
+    finally:
+        lib.rb_batch_destroy(hnd)
+
+
+def test_every_draw_becomes_a_task_and_strokes_are_classified():
+    w, h = 640, 480
+    scene = scenes.paths_scene(w, h, 900, 0xC2, rmin=6.0, rmax=120.0)
+    s = _stats(w, h, scene)
+    n_dashed = int(((scene["n_dash"] > 0) & (scene["stroke_width"] > 0)).sum())
+    n_strokes = int((scene["stroke_width"] > 0).sum())
+    assert s["dashed"] == n_dashed  # every dashed stroke is on the dash (or dash-unit) list
+    # hairlines without dashes are split into one task per drawing verb: more tasks than draws
+    assert s["tasks"] > scene["n_paths"] - 50 and s["hair"] > 0
+    assert s["stroked"] + s["dashed"] <= n_strokes
+    # every task that is filled: fills + stroke outlines (dashed outlines are filled by the unit kernels)
+    assert s["fill"] >= scene["n_paths"] - n_strokes
+    # raw path data is uploaded once per draw
+    assert s["verbs"] <= int(scene["verb_off"][-1]) and s["pts"] <= int(scene["pt_off"][-1])
+
+
+def test_draws_outside_the_target_are_culled():
+    w, h = 256, 256
+    scene = scenes.paths_scene(4096, 4096, 2000, 7, rmin=8.0, rmax=64.0, strokes=False)
+    s = _stats(w, h, scene, strokes=False)
+    inside = 0
+    for i in range(scene["n_paths"]):
+        p = scene["pts"][scene["pt_off"][i]:scene["pt_off"][i + 1]]
+        if p[:, 0].max() >= -2 and p[:, 1].max() >= -2 and p[:, 0].min() <= w + 2 and p[:, 1].min() <= h + 2:
+            inside += 1
+    assert s["tasks"] == inside and 0 < inside < 200
+
+
+def test_draw_tiler_tiles_get_their_own_tasks():
+    """A canvas wider than 8191 px: a draw crossing the tile boundary is one task per tile, all others one."""
+    w, h = 8300, 128
+    scene = scenes.paths_scene(w, h, 400, 0x7117, rmin=8.0, rmax=100.0, strokes=False)
+    s = _stats(w, h, scene, strokes=False)
+    crossing = 0
+    for i in range(scene["n_paths"]):
+        p = scene["pts"][scene["pt_off"][i]:scene["pt_off"][i + 1]]
+        if p[:, 0].min() <= 8191 + 2 and p[:, 0].max() >= 8191 - 2:
+            crossing += 1
+    assert s["tasks"] == scene["n_paths"] + crossing
+
+
+def test_upload_is_a_fraction_of_the_host_builders():
+    """The point of the device path: the raw paths are uploaded, not the edges."""
+    W, H = 2048, 2048
+    scene = scenes.paths_scene(W, H, 6000, 0x5EED0002)
+    s = _stats(W, H, scene)
+    lib = _ffi.lib
+    paints = scenes.to_paint_array(scene, _ffi.Paint)
+    st = scenes.to_stroke_array(scene, _ffi.Stroke)
+    hnd = C.c_void_p()
+    assert lib.rb_debug_batch_begin_host(W, H, C.byref(hnd)) == 0
+    assert lib.rb_batch_draw_paths(hnd, scene["n_paths"], scene["verb_off"].ctypes.data, scene["pt_off"].ctypes.data,
+                                   scene["verbs"].ctypes.data, scene["pts"].ctypes.data, C.addressof(paints),
+                                   scene["rules"].ctypes.data, C.addressof(st), None) == 0
+    assert lib.rb_batch_prepare(hnd, 0) == 0
+    stats = (C.c_uint64 * 6)()
+    lib.rb_batch_stats(hnd, stats)
+    lib.rb_batch_destroy(hnd)
+    assert s["bytes"] * 3 < int(stats[4])
