@@ -876,6 +876,7 @@ def main():
     e2e_h2d = 0
 
     e2e_phase = [0.0, 0.0, 0.0]  # seconds: record, host build + enqueue, wait for the GPU + D2H
+    e2e_geo = [0] * 6  # rb_debug_geo_counts after the last step
 
     def e2e_step():
         nonlocal e2e_h2d
@@ -889,6 +890,9 @@ def main():
         b.submit(n_threads)
         tc = time.perf_counter()
         e2e_h2d = b.stats()["upload_bytes"]
+        gc = (C.c_uint64 * 6)()
+        _ffi.lib.rb_debug_geo_counts(gc)
+        e2e_geo[:] = [int(v) for v in gc]
         b.close()
         layer.download_ptr(pinned.array.ctypes.data)  # synchronises
         td = time.perf_counter()
@@ -938,7 +942,12 @@ def main():
             "e2e": {"value": shard.aggregate_throughput(canvas_mpx, 1 if strips else world, e2e_s), "unit": "Mpx/s", "h2d_bytes_per_step": int(e2e_h2d),
                     "d2h_bytes_per_step": W * strip_rows * 4, "ms_per_step": e2e_s * 1e3, "record_ms": e2e_phase[0] / e2e_steps * 1e3,
                     "host_build_and_enqueue_ms": e2e_phase[1] / e2e_steps * 1e3, "gpu_wait_and_d2h_ms": e2e_phase[2] / e2e_steps * 1e3,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps,
+                    "geometry": {"where": "device" if e2e_geo[0] > 0 and e2e_geo[1] == 0 else "host",
+                                 "ranges_built_on_device": e2e_geo[0], "ranges_handed_to_host_builder": e2e_geo[1], "heap_retries": e2e_geo[2],
+                                 "device_geometry_ms": e2e_geo[3] / 1e3, "host_task_build_ms": e2e_geo[4] / 1e3, "tasks": e2e_geo[5],
+                                 "note": "dash / stroke / hairline walk / chop / clip / edge set-up run as CUDA kernels (geo.cu) from the raw "
+                                         "paths; host_build_and_enqueue_ms includes waiting for them (their totals size the raster scratch)"}},
         }
         if world == 1 and not args.no_kernel_table:
             out["kernels"] = kernel_table(rb, ctx, layer, W, H, peak)

@@ -417,9 +417,11 @@ void rb_debug_host_expand(int on);
  * edge builder) runs on the device for large batches on layers and on host threads otherwise.  Test / tuning hook:
  * mode 0 = that default, 1 = on the device for every eligible batch, 2 = always on the host (the RB_GEO_MODE environment
  * variable sets the initial mode).  rb_debug_geo_counts: out[0] = batch ranges built by the geometry kernels so far,
- * out[1] = ranges they handed back to the host builder, out[2] = launches repeated with a larger heap. */
+ * out[1] = ranges they handed back to the host builder, out[2] = launches repeated with a larger heap; of the last range
+ * built on the device: out[3] = microseconds the host waited for the geometry kernels, out[4] = microseconds of host task
+ * building, out[5] = geometry tasks. */
 void rb_debug_geo_mode(int mode);
-void rb_debug_geo_counts(uint64_t out[3]);
+void rb_debug_geo_counts(uint64_t out[6]);
 /* Host-only batches (rb_debug_batch_begin_host): runs the host half of the device geometry path and reports out[0..7] =
  * tasks, dashed, stroked, hairline, fill-list entries, bytes that would be uploaded, verbs, points. */
 int rb_debug_geo_host_stats(rb_batch *batch, uint64_t out[8]);

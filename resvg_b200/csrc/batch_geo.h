@@ -57,8 +57,8 @@ struct GeoBlock {
     size_t max_units = 0;     // sum of the tasks' max_units
     size_t n_units_l = 0;     // GT_UNITS tasks (their list follows the four others)
     size_t n_tasks = 0, n_verbs = 0, n_pts = 0, n_dashes = 0, n_paints = 0, n_stops = 0;
-    // task indices per kernel, heaviest first: [dash | stroke | hair | fill]
-    size_t o_lists = 0, n_dash_l = 0, n_stroke_l = 0, n_hair_l = 0, n_fill_l = 0;
+    // task indices per kernel, heaviest first: [dash | stroke | hair | fill (plain fills) | units | outline fills]
+    size_t o_lists = 0, n_dash_l = 0, n_stroke_l = 0, n_hair_l = 0, n_fill_l = 0, n_outline_l = 0;
     size_t heap_hint = 0; // bytes the geometry is expected to take from the heap
     bool has_hair = false;
 };
@@ -68,4 +68,4 @@ int rb_geo_host_build(rb_batch *b, int W, int H, int n_threads, rb_stage_alloc a
 // 0: device geometry for large batches on layers (default), 1: for every eligible batch, 2: never (host builder).
 extern int g_geo_mode;
 #include <atomic>
-extern std::atomic<uint64_t> g_geo_counts[3]; // ranges built on the device, ranges handed back, heap retries
+extern std::atomic<uint64_t> g_geo_counts[6]; // ranges built on the device, ranges handed back, heap retries; last range: device wait us, host build us, tasks

@@ -1007,11 +1007,11 @@ static int geo_mode_from_env()
     return e ? atoi(e) : 0;
 }
 int g_geo_mode = geo_mode_from_env();
-std::atomic<uint64_t> g_geo_counts[3];
+std::atomic<uint64_t> g_geo_counts[6];
 extern "C" void rb_debug_geo_mode(int mode) { g_geo_mode = mode; }
-extern "C" void rb_debug_geo_counts(uint64_t out[3])
+extern "C" void rb_debug_geo_counts(uint64_t out[6])
 {
-    if (out) for (int i = 0; i < 3; i++) out[i] = g_geo_counts[i].load();
+    if (out) for (int i = 0; i < 6; i++) out[i] = g_geo_counts[i].load();
 }
 // the debug hooks that select a builder variant only the host has
 bool rb_debug_host_only_builder() { return g_force_wide || g_host_expand; }
@@ -1303,7 +1303,7 @@ int rb_geo_host_build(rb_batch *b, int W, int H, int n_threads, rb_stage_alloc a
     // task lists per kernel, heaviest first (counting sort over cost classes; ties keep painter's order)
     {
         uint32_t *lists = (uint32_t *)(blk + G.o_lists);
-        constexpr int NC = 24, NL = 5; // lists: dash, stroke, hair, fill (one thread per task each), and the dashed strokes built in units
+        constexpr int NC = 24, NL = 6; // lists: dash, stroke, hair, plain fills, the dashed strokes built in units, outline fills
         size_t cnt[NL][NC];
         memset(cnt, 0, sizeof(cnt));
         auto kinds_of = [](const GeoTask &t, int k[3]) {
@@ -1311,7 +1311,7 @@ int rb_geo_host_build(rb_batch *b, int W, int H, int n_threads, rb_stage_alloc a
             if (t.flags & GT_UNITS) { k[m++] = 4; return m; }
             if (t.flags & GT_DASH) k[m++] = 0;
             k[m++] = (t.flags & GT_HAIR) ? 2 : ((t.flags & GT_STROKE) ? 1 : 3);
-            if ((t.flags & (GT_STROKE | GT_HAIR)) == GT_STROKE) k[m++] = 3; // an outline is filled
+            if ((t.flags & (GT_STROKE | GT_HAIR)) == GT_STROKE) k[m++] = 5; // an outline is filled
             return m;
         };
         for (size_t i = 0; i < G.n_tasks; i++) {
@@ -1333,6 +1333,7 @@ int rb_geo_host_build(rb_batch *b, int W, int H, int n_threads, rb_stage_alloc a
         }
         G.n_dash_l = first[1] - first[0]; G.n_stroke_l = first[2] - first[1]; G.n_hair_l = first[3] - first[2]; G.n_fill_l = first[4] - first[3];
         G.n_units_l = first[5] - first[4];
+        G.n_outline_l = first[6] - first[5];
         G.has_hair = false;
         for (size_t i = 0; i < G.n_tasks && !G.has_hair; i++) G.has_hair = (o_tasks[i].flags & GT_HAIR) != 0;
     }
@@ -1355,7 +1356,7 @@ extern "C" int rb_debug_geo_host_stats(rb_batch *b, uint64_t out[8])
     int st = rb_geo_host_build(b, b->host_w, b->host_h, 0, [](void *, size_t bytes) { return malloc(bytes); }, nullptr, &blk, &G, 0, 0);
     free(blk);
     if (st != RB_OK) return st;
-    out[0] = G.n_tasks; out[1] = G.n_dash_l + G.n_units_l; out[2] = G.n_stroke_l; out[3] = G.n_hair_l; out[4] = G.n_fill_l; out[5] = G.total;
+    out[0] = G.n_tasks; out[1] = G.n_dash_l + G.n_units_l; out[2] = G.n_stroke_l; out[3] = G.n_hair_l; out[4] = G.n_fill_l + G.n_outline_l; out[5] = G.total;
     out[6] = G.n_verbs; out[7] = G.n_pts;
     return RB_OK;
 }

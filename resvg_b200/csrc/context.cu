@@ -89,13 +89,14 @@ int rb_staging(rb_ctx *ctx, size_t bytes, void **out)
     return RB_OK;
 }
 
-int rb_staging_mark(rb_ctx *ctx)
+int rb_staging_mark(rb_ctx *ctx, cudaStream_t stream)
 {
+    if (!stream) stream = ctx->stream;
     if (ctx->staging_cur) {
-        RB_CUDA(ctx, cudaEventRecord(ctx->staging_cur->ev, ctx->stream));
+        RB_CUDA(ctx, cudaEventRecord(ctx->staging_cur->ev, stream));
         ctx->staging_cur->in_flight = true;
     } else {
-        RB_CUDA(ctx, cudaEventRecord(ctx->staging_ev, ctx->stream));
+        RB_CUDA(ctx, cudaEventRecord(ctx->staging_ev, stream));
         ctx->staging_in_flight = true;
     }
     return RB_OK;
@@ -118,6 +119,8 @@ void rb_ctx_release(rb_ctx *ctx)
     if (ctx->staging) cudaFreeHost(ctx->staging);
     if (ctx->h_flags) cudaFreeHost((void *)ctx->h_flags);
     if (ctx->geo_pinned) cudaFreeHost(ctx->geo_pinned);
+    for (auto &st : ctx->geo_streams) if (st) cudaStreamDestroy(st);
+    for (auto &ev : ctx->geo_events) if (ev) cudaEventDestroy(ev);
     if (ctx->staging_ev) cudaEventDestroy(ctx->staging_ev);
     for (auto &s : ctx->stage_ring) {
         if (s.p) cudaFreeHost(s.p);

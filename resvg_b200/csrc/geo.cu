@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geo_dash(GeoArgs a, const uint3
 }
 
 // ---- PathStroker::stroke --------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEO_THREADS) k_geo_stroke(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n)
+__global__ void __launch_bounds__(GEO_THREADS, 10) k_geo_stroke(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n)
 {
     const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> a.lane_shift;
     if (threadIdx.x & ((1u << a.lane_shift) - 1u)) return; // 2^lane_shift lanes per task, one of them working: see GEO_THREADS
@@ -295,7 +295,7 @@ __device__ void hair_emit(const GeoArgs &a, GeoHeap &heap, const GeoTask &t, uin
 }
 
 // ---- hairline strokes -----------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEO_THREADS) k_geo_hair(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n)
+__global__ void __launch_bounds__(GEO_THREADS, 10) k_geo_hair(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n)
 {
     const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> a.lane_shift;
     if (threadIdx.x & ((1u << a.lane_shift) - 1u)) return; // 2^lane_shift lanes per task, one of them working: see GEO_THREADS
@@ -326,7 +326,7 @@ struct NoEnds {
     __device__ void operator()(int32_t, int32_t) { chains++; }
 };
 
-__global__ void __launch_bounds__(GEO_THREADS) k_geo_fill(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n, uint32_t *__restrict__ wide_q)
+__global__ void __launch_bounds__(GEO_THREADS, 10) k_geo_fill(GeoArgs a, const uint32_t *__restrict__ list, uint32_t n, uint32_t *__restrict__ wide_q)
 {
     const uint32_t li = (blockIdx.x * blockDim.x + threadIdx.x) >> a.lane_shift;
     if (threadIdx.x & ((1u << a.lane_shift) - 1u)) return; // 2^lane_shift lanes per task, one of them working: see GEO_THREADS
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geo_plan(GeoArgs a, const uint3
 }
 
 // The dash (hairlines) or its outline (strokes), and the bounds of its points in device space.
-__global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_path(GeoArgs a)
+__global__ void __launch_bounds__(GEO_THREADS, 10) k_geo_unit_path(GeoArgs a)
 {
     const uint32_t ui = (blockIdx.x * blockDim.x + threadIdx.x) >> a.lane_shift;
     if (threadIdx.x & ((1u << a.lane_shift) - 1u)) return; // 2^lane_shift lanes per unit, one of them working: see GEO_THREADS
@@ -885,6 +885,14 @@ int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
         ctx->attr_bits |= RB_ATTR_GEO;
     }
     if (!ctx->geo_pinned) RB_CUDA(ctx, cudaHostAlloc(&ctx->geo_pinned, 4096, cudaHostAllocDefault));
+    // The geometry of a batch part runs on a stream of its own, so that it overlaps the raster kernel of the previous part
+    // (rb_batch_submit cuts a large batch into parts): the raster kernel is bound by instruction issue, the geometry kernels by
+    // latency and instruction fetch, and the host waits for the geometry stream only.  What this function leaves behind is
+    // used on the context's stream after that wait.
+    for (auto &st : ctx->geo_streams) if (!st) RB_CUDA(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto &ev : ctx->geo_events) if (!ev) RB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    static const bool own_stream = !(getenv("RB_GEO_OWN_STREAM") && atoi(getenv("RB_GEO_OWN_STREAM")) == 0);
+    cudaStream_t gs = own_stream ? ctx->geo_streams[0] : ctx->stream;
     StageReq2 req{ctx, RB_OK};
     void *blk = nullptr;
     GeoBlock G;
@@ -910,22 +918,22 @@ int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
         const size_t o_units = o_wq + al(n_draws * 4), o_pieces = o_units + al((max_units + 1) * sizeof(GeoUnit));
         const size_t o_tot = o_pieces + al((max_units + 1) * sizeof(GeoPiece)), o_heap = o_tot + 256, total = o_heap + heap_bytes + 65536;
         uint8_t *dev = nullptr;
-        if (cudaMallocAsync((void **)&dev, total, ctx->stream) != cudaSuccess) {
+        if (cudaMallocAsync((void **)&dev, total, gs) != cudaSuccess) {
             cudaGetLastError();
-            if (b->dev) { cudaFreeAsync(b->dev, ctx->stream); b->dev = nullptr; }
+            if (b->dev) { cudaFreeAsync(b->dev, gs); b->dev = nullptr; }
             g_geo_counts[1]++;
             return RB_GEO_FALLBACK;
         }
         if (attempt == 0) {
-            RB_CUDA(ctx, cudaMemcpyAsync(dev, blk, G.total, cudaMemcpyHostToDevice, ctx->stream));
+            RB_CUDA(ctx, cudaMemcpyAsync(dev, blk, G.total, cudaMemcpyHostToDevice, gs));
             ctx->h2d_bytes += G.total;
-            { int st__ = rb_staging_mark(ctx); if (st__ != RB_OK) return st__; }
+            { int st__ = rb_staging_mark(ctx, gs); if (st__ != RB_OK) return st__; }
         } else {
-            RB_CUDA(ctx, cudaMemcpyAsync(dev, b->dev, G.total, cudaMemcpyDeviceToDevice, ctx->stream));
-            RB_CUDA(ctx, cudaFreeAsync(b->dev, ctx->stream));
+            RB_CUDA(ctx, cudaMemcpyAsync(dev, b->dev, G.total, cudaMemcpyDeviceToDevice, gs));
+            RB_CUDA(ctx, cudaFreeAsync(b->dev, gs));
         }
         b->dev = dev;
-        RB_CUDA(ctx, cudaMemsetAsync(dev + o_tot, 0, 256, ctx->stream));
+        RB_CUDA(ctx, cudaMemsetAsync(dev + o_tot, 0, 256, gs));
         GeoArgs a;
         a.tasks = (const GeoTask *)(dev + G.o_tasks);
         a.verbs = dev + G.o_verbs;
@@ -943,7 +951,7 @@ int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
         a.pieces = (GeoPiece *)(dev + o_pieces);
         a.max_units = (uint32_t)max_units;
         a.n_tasks = (uint32_t)n_tasks;
-        static const int lane_shift = getenv("RB_GEO_LANE_SHIFT") ? atoi(getenv("RB_GEO_LANE_SHIFT")) : 5;
+        static const int lane_shift = getenv("RB_GEO_LANE_SHIFT") ? atoi(getenv("RB_GEO_LANE_SHIFT")) : 3;
         a.lane_shift = (uint32_t)lane_shift;
         a.dbg = nullptr;
         unsigned long long *dbg = nullptr;
@@ -955,31 +963,55 @@ int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
         const size_t per_cta = (size_t)GEO_THREADS >> lane_shift;
         auto grid = [&](size_t n) { return (unsigned)((n + per_cta - 1) / per_cta); };
         const unsigned g_units = grid(max_units);
-        if (nd) { k_geo_dash<<<grid(nd), GEO_THREADS, 0, ctx->stream>>>(a, l_dash, nd); RB_LAUNCHED(ctx, "geo_dash"); }
-        if (nu) {
-            k_geo_plan<<<grid(nu), GEO_THREADS, 0, ctx->stream>>>(a, l_units, nu); RB_LAUNCHED(ctx, "geo_plan");
-            k_geo_unit_path<<<g_units, GEO_THREADS, 0, ctx->stream>>>(a); RB_LAUNCHED(ctx, "geo_unit_path");
-            k_geo_unit_bounds<<<grid(nu), GEO_THREADS, 0, ctx->stream>>>(a, l_units, nu); RB_LAUNCHED(ctx, "geo_unit_bounds");
+        // Four chains that do not depend on each other — the dashed strokes built in units; stroke -> fill of the outlines;
+        // hairlines; plain fills — run side by side on streams of their own (every kernel here is bound by latency and
+        // instruction fetch, not by issue slots), joined before the winding check.
+        static const bool use_streams = getenv("RB_GEO_STREAMS") && atoi(getenv("RB_GEO_STREAMS")) != 0; // measured: no gain, every kernel fills the SMs' warp slots by itself
+        cudaStream_t s0 = gs, s1 = s0, s2 = s0, s3 = s0;
+        // dashed strokes beyond the unit bound (rare): dashed by one thread each, before anything that strokes or walks them
+        if (nd) { k_geo_dash<<<grid(nd), GEO_THREADS, 0, s0>>>(a, l_dash, nd); RB_LAUNCHED(ctx, "geo_dash"); }
+        if (use_streams) {
+            s1 = ctx->geo_streams[1]; s2 = ctx->geo_streams[2]; s3 = ctx->geo_streams[3];
+            RB_CUDA(ctx, cudaEventRecord(ctx->geo_events[0], s0));
+            RB_CUDA(ctx, cudaStreamWaitEvent(s1, ctx->geo_events[0], 0));
+            RB_CUDA(ctx, cudaStreamWaitEvent(s2, ctx->geo_events[0], 0));
+            RB_CUDA(ctx, cudaStreamWaitEvent(s3, ctx->geo_events[0], 0));
         }
-        if (ns) { k_geo_stroke<<<grid(ns), GEO_THREADS, 0, ctx->stream>>>(a, l_stroke, ns); RB_LAUNCHED(ctx, "geo_stroke"); }
-        if (nh) { k_geo_hair<<<grid(nh), GEO_THREADS, 0, ctx->stream>>>(a, l_hair, nh); RB_LAUNCHED(ctx, "geo_hair"); }
+        const uint32_t no = (uint32_t)G.n_outline_l;
+        const uint32_t *l_outline = l_units + nu;
+        // chain 1: the long strokes first
+        if (ns) { k_geo_stroke<<<grid(ns), GEO_THREADS, 0, s1>>>(a, l_stroke, ns); RB_LAUNCHED(ctx, "geo_stroke"); }
+        if (no) { k_geo_fill<<<grid(no), GEO_THREADS, 0, s1>>>(a, l_outline, no, wide_q); RB_LAUNCHED(ctx, "geo_fill_outlines"); }
+        // chain 2: dashed strokes, dash by dash
         if (nu) {
-            k_geo_unit_hair<<<g_units, GEO_THREADS, 0, ctx->stream>>>(a); RB_LAUNCHED(ctx, "geo_unit_hair");
-            k_geo_unit_fill<<<g_units, GEO_THREADS, 0, ctx->stream>>>(a); RB_LAUNCHED(ctx, "geo_unit_fill");
+            k_geo_plan<<<grid(nu), GEO_THREADS, 0, s2>>>(a, l_units, nu); RB_LAUNCHED(ctx, "geo_plan");
+            k_geo_unit_path<<<g_units, GEO_THREADS, 0, s2>>>(a); RB_LAUNCHED(ctx, "geo_unit_path");
+            k_geo_unit_bounds<<<grid(nu), GEO_THREADS, 0, s2>>>(a, l_units, nu); RB_LAUNCHED(ctx, "geo_unit_bounds");
+            k_geo_unit_hair<<<g_units, GEO_THREADS, 0, s2>>>(a); RB_LAUNCHED(ctx, "geo_unit_hair");
+            k_geo_unit_fill<<<g_units, GEO_THREADS, 0, s2>>>(a); RB_LAUNCHED(ctx, "geo_unit_fill");
+            k_geo_unit_merge<<<grid(nu), GEO_THREADS, 0, s2>>>(a, l_units, nu, wide_q); RB_LAUNCHED(ctx, "geo_unit_merge");
+            k_geo_unit_pack<<<g_units, GEO_THREADS, 0, s2>>>(a); RB_LAUNCHED(ctx, "geo_unit_pack");
         }
-        if (nf) { k_geo_fill<<<grid(nf), GEO_THREADS, 0, ctx->stream>>>(a, l_fill, nf, wide_q); RB_LAUNCHED(ctx, "geo_fill"); }
-        if (nu) {
-            k_geo_unit_merge<<<grid(nu), GEO_THREADS, 0, ctx->stream>>>(a, l_units, nu, wide_q); RB_LAUNCHED(ctx, "geo_unit_merge");
-            k_geo_unit_pack<<<g_units, GEO_THREADS, 0, ctx->stream>>>(a); RB_LAUNCHED(ctx, "geo_unit_pack");
+        // chain 3: hairlines
+        if (nh) {
+            k_geo_hair<<<grid(nh), GEO_THREADS, 0, s3>>>(a, l_hair, nh); RB_LAUNCHED(ctx, "geo_hair");
         }
-        if (nf || nu) {
-            k_geo_wide<<<std::min<uint32_t>((uint32_t)n_draws, (uint32_t)ctx->sm_count * 4u), GW_THREADS, 0, ctx->stream>>>(a, wide_q);
+        // chain 0: plain fills
+        if (nf) { k_geo_fill<<<grid(nf), GEO_THREADS, 0, s0>>>(a, l_fill, nf, wide_q); RB_LAUNCHED(ctx, "geo_fill"); }
+        if (use_streams) {
+            RB_CUDA(ctx, cudaEventRecord(ctx->geo_events[1], s1)); RB_CUDA(ctx, cudaStreamWaitEvent(s0, ctx->geo_events[1], 0));
+            RB_CUDA(ctx, cudaEventRecord(ctx->geo_events[2], s2)); RB_CUDA(ctx, cudaStreamWaitEvent(s0, ctx->geo_events[2], 0));
+            RB_CUDA(ctx, cudaEventRecord(ctx->geo_events[3], s3)); RB_CUDA(ctx, cudaStreamWaitEvent(s0, ctx->geo_events[3], 0));
+        }
+        if (nf || no || nu) {
+            k_geo_wide<<<std::min<uint32_t>((uint32_t)n_draws, (uint32_t)ctx->sm_count * 4u), GW_THREADS, 0, s0>>>(a, wide_q);
             RB_LAUNCHED(ctx, "geo_wide");
         }
         GeoTotals *ht = (GeoTotals *)ctx->geo_pinned;
-        RB_CUDA(ctx, cudaMemcpyAsync(ht, dev + o_tot, sizeof(GeoTotals), cudaMemcpyDeviceToHost, ctx->stream));
+        RB_CUDA(ctx, cudaMemcpyAsync(ht, dev + o_tot, sizeof(GeoTotals), cudaMemcpyDeviceToHost, gs));
         const double t_enq = now_ms();
-        RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        RB_CUDA(ctx, cudaStreamSynchronize(gs));
+        const double t_done = now_ms();
         const GeoTotals T = *ht;
         if (dbg) {
             std::vector<unsigned long long> h(3 * n_tasks);
@@ -998,8 +1030,8 @@ int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
             }
         }
         if (diag)
-            fprintf(stderr, "[geo] tasks %zu draws %zu (dash %u stroke %u hair %u fill %u units-tasks %u units %u / %zu) upload %zu B heap %llu / %zu B slots %llu list %llu wide_q %u overflow %u wide %u deep %u too_large %u | host %.2f ms, enqueue %.2f ms, wait %.2f ms\n",
-                    n_tasks, n_draws, nd, ns, nh, nf, nu, T.n_units, max_units, G.total, T.heap_cursor, heap_bytes, T.n_slots, T.n_list, T.n_wide_q, T.overflow, T.wide, T.deep, T.too_large,
+            fprintf(stderr, "[geo] tasks %zu draws %zu (dash %u stroke %u hair %u fill %u + %u units-tasks %u units %u / %zu) upload %zu B heap %llu / %zu B slots %llu list %llu wide_q %u overflow %u wide %u deep %u too_large %u | host %.2f ms, enqueue %.2f ms, wait %.2f ms\n",
+                    n_tasks, n_draws, nd, ns, nh, nf, no, nu, T.n_units, max_units, G.total, T.heap_cursor, heap_bytes, T.n_slots, T.n_list, T.n_wide_q, T.overflow, T.wide, T.deep, T.too_large,
                     t_built - t_start, t_enq - t_built, now_ms() - t_enq);
         if (T.overflow) { g_geo_counts[2]++; continue; } // heap exhausted: again with eight times the heap
         if (T.wide || T.too_large || T.deep) break;
@@ -1021,9 +1053,12 @@ int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
         b->stats[0] = n_draws; b->stats[1] = L.n_slots; b->stats[2] = L.n_wpairs; b->stats[3] = (size_t)L.wtiles_x * L.wtiles_y;
         b->stats[4] = G.total; b->stats[5] = 0;
         g_geo_counts[0]++;
+        g_geo_counts[3] = (uint64_t)((t_done - t_enq) * 1e3);
+        g_geo_counts[4] = (uint64_t)((t_built - t_start) * 1e3);
+        g_geo_counts[5] = n_tasks;
         return RB_OK;
     }
-    if (b->dev) { cudaFreeAsync(b->dev, ctx->stream); b->dev = nullptr; }
+    if (b->dev) { cudaFreeAsync(b->dev, gs); cudaStreamSynchronize(gs); b->dev = nullptr; }
     b->lay = BatchLayout();
     g_geo_counts[1]++;
     return RB_GEO_FALLBACK;

@@ -807,7 +807,14 @@ static int batch_prepare_range(rb_batch *b, int32_t n_threads, size_t begin, siz
         size_t geo_from = 4096;
         if (const char *e = getenv("RB_GEO_FROM")) geo_from = (size_t)std::max(1, atoi(e));
         const bool eligible = !mask_target && W <= 65536 && H <= 65536 && !rb_debug_host_only_builder();
-        if (eligible && g_geo_mode != 2 && (g_geo_mode == 1 || n_range >= geo_from)) {
+        // Which builder: the geometry kernels take ~0.35 us per draw of the 100 000-path scene (B200) and leave the host idle; the
+        // host builder takes ~8 core-us per draw but overlaps the raster kernel part by part.  With more than 16 host threads
+        // for this GPU the host builder finishes first; with fewer (several GPUs sharing the box's cores: one process per GPU)
+        // the device does.  RB_GEO_MODE / rb_debug_geo_mode override.
+        const int host_threads = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+        int geo_max_threads = 16;
+        if (const char *e = getenv("RB_GEO_MAX_HOST_THREADS")) geo_max_threads = atoi(e);
+        if (eligible && g_geo_mode != 2 && (g_geo_mode == 1 || (n_range >= geo_from && host_threads <= geo_max_threads))) {
             int gst = rb_geo_prepare(b, n_threads, begin, end);
             if (gst == RB_OK) {
                 if (!b->dev || b->lay.n_draws == 0) return RB_OK;
@@ -1092,9 +1099,14 @@ static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t 
     if (const char *e = getenv("RB_SUBMIT_SPLIT_FROM")) split_from = (size_t)std::max(1, atoi(e)); // tests
     if (n >= split_from && (b->layer || b->mask)) {
         parts = 8;
-        // with the geometry on the device there is no host build to overlap with the GPU, and one launch over all draws
-        // pays the long draws' latency once instead of once per part
-        if (b->layer && g_geo_mode != 2 && !rb_debug_host_only_builder()) parts = 1;
+        // with the geometry on the device there is no host build to overlap with the GPU, and every part would pay the latency
+        // of its longest draws again (measured: 1 part 66 ms, 2 parts 67, 4 parts 80, 8 parts 106 per 100 000-path scene)
+        {
+            const int host_threads = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+            int geo_max_threads = 16;
+            if (const char *e = getenv("RB_GEO_MAX_HOST_THREADS")) geo_max_threads = atoi(e);
+            if (b->layer && g_geo_mode != 2 && !rb_debug_host_only_builder() && (g_geo_mode == 1 || host_threads <= geo_max_threads)) parts = 1;
+        }
         if (const char *e = getenv("RB_SUBMIT_PARTS")) parts = (size_t)std::max(1, atoi(e));
     }
     int st = RB_OK;

@@ -31,6 +31,8 @@ struct rb_ctx {
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
     void *geo_pinned = nullptr;   // 4 KB of pinned memory the geometry kernels' totals are copied back into (geo.cu)
+    cudaStream_t geo_streams[4] = {nullptr, nullptr, nullptr, nullptr}; // [0]: the geometry kernels run beside the previous part's raster kernel; [1..3]: their independent chains (geo.cu)
+    cudaEvent_t geo_events[4] = {nullptr, nullptr, nullptr, nullptr};
     uint8_t *px_tables = nullptr; // 3 x 64 KB: demultiply, into_linear_rgb, into_srgb as functions of (alpha, channel)
     // pinned host staging for batch uploads (grown on demand); staging_ev marks the last copy that read it
     void *staging = nullptr;
@@ -64,7 +66,7 @@ void rb_ctx_release(rb_ctx *ctx);
 // Pinned staging block of at least `bytes`, safe to overwrite (waits for the previous upload out of it).
 int rb_staging(rb_ctx *ctx, size_t bytes, void **out);
 // After enqueuing the copy that reads the block rb_staging returned last: records when it may be overwritten.
-int rb_staging_mark(rb_ctx *ctx);
+int rb_staging_mark(rb_ctx *ctx, cudaStream_t stream = nullptr); // stream: the one the copy was enqueued on (default: the context's)
 
 struct rb_layer {
     rb_ctx *ctx;

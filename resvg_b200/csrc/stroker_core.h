@@ -26,7 +26,7 @@ constexpr float kRoot2Over2 = 0.707106781f;
 GEO_HDI inline bool nearly_zero(float v, float tol = kNearlyZero) { return fabsf(v) <= tol; }
 
 // Point::set_length / normalize (double precision magnitude, as tiny-skia-path point.rs)
-GEO_HD inline bool set_length(P &p, float x, float y, float length)
+GEO_HDI inline bool set_length(P &p, float x, float y, float length)
 {
     double xx = x, yy = y;
     double dmag = sqrt(xx * xx + yy * yy);
@@ -40,7 +40,7 @@ GEO_HD inline bool set_length(P &p, float x, float y, float length)
     p = {x, y};
     return true;
 }
-GEO_HD inline bool set_length(P &p, float length) { return set_length(p, p.x, p.y, length); }
+GEO_HDI inline bool set_length(P &p, float length) { return set_length(p, p.x, p.y, length); }
 GEO_HDI inline bool normalize(P &p) { return set_length(p, p.x, p.y, 1.0f); }
 GEO_HDI inline bool can_normalize(float dx, float dy) { return (gfinite(dx) && gfinite(dy)) && (dx != 0 || dy != 0); }
 
@@ -271,7 +271,7 @@ GEO_HD inline int build_unit_arc(P u_start, P u_stop, bool ccw, float radius, P 
 // ---------------------------------------------------------------------------------------------------
 // curve helpers (tiny-skia-path path_geometry.rs)
 // ---------------------------------------------------------------------------------------------------
-GEO_HD inline bool unit_divide(float numer, float denom, float *r)
+GEO_HDI inline bool unit_divide(float numer, float denom, float *r)
 {
     if (numer < 0) { numer = -numer; denom = -denom; }
     if (denom == 0 || numer == 0 || numer >= denom) return false;
@@ -280,7 +280,7 @@ GEO_HD inline bool unit_divide(float numer, float denom, float *r)
     *r = v;
     return true;
 }
-GEO_HD inline int unit_quad_roots(float a, float b, float c, float roots[2])
+GEO_HDI inline int unit_quad_roots(float a, float b, float c, float roots[2])
 {
     if (a == 0) return unit_divide(-c, b, roots) ? 1 : 0;
     double dr = (double)b * b - 4.0 * (double)a * c;
@@ -302,7 +302,7 @@ GEO_HDI inline P eval_quad(const P q[3], float t)
     P a = q[2] - q[1] * 2.0f + q[0], b = (q[1] - q[0]) * 2.0f;
     return (a * t + b) * t + q[0];
 }
-GEO_HD inline P eval_quad_tangent(const P q[3], float t)
+GEO_HDI inline P eval_quad_tangent(const P q[3], float t)
 {
     if ((t == 0 && q[0] == q[1]) || (t == 1 && q[1] == q[2])) return q[2] - q[0];
     P b = q[1] - q[0], a = q[2] - q[1] - b;
@@ -319,7 +319,7 @@ GEO_HDI inline P eval_cubic_derivative(const P c[4], float t)
     P a = c[3] + (c[1] - c[2]) * 3.0f - c[0], b = (c[2] - c[1] * 2.0f + c[0]) * 2.0f, cc = c[1] - c[0];
     return (a * t + b) * t + cc;
 }
-GEO_HD inline P eval_cubic_tangent(const P c[4], float t)
+GEO_HDI inline P eval_cubic_tangent(const P c[4], float t)
 {
     if ((t == 0 && c[0] == c[1]) || (t == 1 && c[2] == c[3])) {
         P tg = t == 0 ? c[2] - c[0] : c[3] - c[1];
@@ -328,7 +328,7 @@ GEO_HD inline P eval_cubic_tangent(const P c[4], float t)
     }
     return eval_cubic_derivative(c, t);
 }
-GEO_HD inline void chop_cubic(const P s[4], float t, P d[7])
+GEO_HDI inline void chop_cubic(const P s[4], float t, P d[7])
 {
     auto L = [&](P a, P b) { return P{a.x + (b.x - a.x) * t, a.y + (b.y - a.y) * t}; };
     P ab = L(s[0], s[1]), bc = L(s[1], s[2]), cd = L(s[2], s[3]);
@@ -447,7 +447,7 @@ struct QuadConstruct {
     }
 };
 
-GEO_HD inline float pt_to_line(P pt, P a, P b)
+GEO_HDI inline float pt_to_line(P pt, P a, P b)
 {
     P dxy = b - a, ab0 = pt - a;
     float numer = dot(dxy, ab0), denom = dot(dxy, dxy);
@@ -498,14 +498,14 @@ template <template <class> class Vec> struct Stroker {
         cusper.clear();
     }
 
-    GEO_HD bool set_normal_unitnormal(P before, P after, float scale, P &normal, P &unit)
+    GEO_HDI bool set_normal_unitnormal(P before, P after, float scale, P &normal, P &unit)
     {
         if (!set_length(unit, (after.x - before.x) * scale, (after.y - before.y) * scale, 1.0f)) return false;
         unit = rot_ccw(unit);
         normal = unit * radius;
         return true;
     }
-    GEO_HD bool set_normal_unitnormal2(P vec, P &normal, P &unit)
+    GEO_HDI bool set_normal_unitnormal2(P vec, P &normal, P &unit)
     {
         if (!set_length(unit, vec.x, vec.y, 1.0f)) return false;
         unit = rot_ccw(unit);
@@ -689,7 +689,7 @@ template <template <class> class Vec> struct Stroker {
     }
 
     // ---- quad / cubic offsetting ----
-    GEO_HD void set_ray_pts(P tp, P &dxy, P *on, P *tangent)
+    GEO_HDI void set_ray_pts(P tp, P &dxy, P *on, P *tangent)
     {
         if (!set_length(dxy, radius)) dxy = {radius, 0};
         float flip = (float)stroke_type;
@@ -697,14 +697,14 @@ template <template <class> class Vec> struct Stroker {
         on->y = tp.y - flip * dxy.x;
         if (tangent) { tangent->x = on->x + dxy.x; tangent->y = on->y + dxy.y; }
     }
-    GEO_HD void quad_perp_ray(const P q[3], float t, P *tp, P *on, P *tangent)
+    GEO_HDI void quad_perp_ray(const P q[3], float t, P *tp, P *on, P *tangent)
     {
         *tp = eval_quad(q, t);
         P dxy = eval_quad_tangent(q, t);
         if (dxy.x == 0 && dxy.y == 0) dxy = q[2] - q[0];
         set_ray_pts(*tp, dxy, on, tangent);
     }
-    GEO_HD void cubic_perp_ray(const P c[4], float t, P *tp, P *on, P *tangent)
+    GEO_HDI void cubic_perp_ray(const P c[4], float t, P *tp, P *on, P *tangent)
     {
         *tp = eval_cubic(c, t);
         P dxy = eval_cubic_tangent(c, t);
@@ -722,7 +722,7 @@ template <template <class> class Vec> struct Stroker {
         }
         set_ray_pts(*tp, dxy, on, tangent);
     }
-    GEO_HD Result intersect_ray(QuadConstruct &qp, bool want_ctrl)
+    GEO_HDI Result intersect_ray(QuadConstruct &qp, bool want_ctrl)
     {
         P start = qp.quad[0], end = qp.quad[2];
         P a_len = qp.tangent_start - start, b_len = qp.tangent_end - end;
@@ -752,7 +752,7 @@ template <template <class> class Vec> struct Stroker {
         return Degenerate;
     }
     GEO_HDI static bool points_within_dist(P a, P b, float limit) { return dist_sqd(a, b) <= limit * limit; }
-    GEO_HD static bool sharp_angle(const P q[3])
+    GEO_HDI static bool sharp_angle(const P q[3])
     {
         P smaller = q[1] - q[0], larger = q[1] - q[2];
         float sl = len_sqd(smaller), ll = len_sqd(larger);
@@ -760,7 +760,7 @@ template <template <class> class Vec> struct Stroker {
         if (!set_length(smaller, ll)) return false;
         return dot(smaller, larger) > 0;
     }
-    GEO_HD bool pt_in_quad_bounds(const P q[3], P pt)
+    GEO_HDI bool pt_in_quad_bounds(const P q[3], P pt)
     {
         float xmin = gmin(gmin(q[0].x, q[1].x), q[2].x);
         if (pt.x + inv_res_scale < xmin) return false;
@@ -772,7 +772,7 @@ template <template <class> class Vec> struct Stroker {
         if (pt.y - inv_res_scale > ymax) return false;
         return true;
     }
-    GEO_HD Result stroke_close_enough(const P stroke[3], const P ray[2], QuadConstruct &qp)
+    GEO_HDI Result stroke_close_enough(const P stroke[3], const P ray[2], QuadConstruct &qp)
     {
         P mid = eval_quad(stroke, 0.5f);
         if (points_within_dist(ray[0], mid, inv_res_scale)) return sharp_angle(qp.quad) ? Split : Quad;
@@ -792,7 +792,7 @@ template <template <class> class Vec> struct Stroker {
         return Split;
     }
     GEO_HDI Builder &side() { return stroke_type == 1 ? outer : inner; }
-    GEO_HD Result compare_quad_quad(const P q[3], QuadConstruct &qp)
+    GEO_HDI Result compare_quad_quad(const P q[3], QuadConstruct &qp)
     {
         if (!qp.start_set) { P t; quad_perp_ray(q, qp.start_t, &t, &qp.quad[0], &qp.tangent_start); qp.start_set = true; }
         if (!qp.end_set) { P t; quad_perp_ray(q, qp.end_t, &t, &qp.quad[2], &qp.tangent_end); qp.end_set = true; }
@@ -819,18 +819,18 @@ template <template <class> class Vec> struct Stroker {
         --recursion_depth;
         return true;
     }
-    GEO_HD void cubic_quad_ends(const P c[4], QuadConstruct &qp)
+    GEO_HDI void cubic_quad_ends(const P c[4], QuadConstruct &qp)
     {
         if (!qp.start_set) { P t; cubic_perp_ray(c, qp.start_t, &t, &qp.quad[0], &qp.tangent_start); qp.start_set = true; }
         if (!qp.end_set) { P t; cubic_perp_ray(c, qp.end_t, &t, &qp.quad[2], &qp.tangent_end); qp.end_set = true; }
     }
-    GEO_HD bool cubic_mid_on_line(const P c[4], const QuadConstruct &qp)
+    GEO_HDI bool cubic_mid_on_line(const P c[4], const QuadConstruct &qp)
     {
         P t, mid;
         cubic_perp_ray(c, qp.mid_t, &t, &mid, nullptr);
         return pt_to_line(mid, qp.quad[0], qp.quad[2]) < inv_res_scale_sq;
     }
-    GEO_HD Result compare_quad_cubic(const P c[4], QuadConstruct &qp)
+    GEO_HDI Result compare_quad_cubic(const P c[4], QuadConstruct &qp)
     {
         cubic_quad_ends(c, qp);
         Result r = intersect_ray(qp, true);

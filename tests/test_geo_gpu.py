@@ -25,9 +25,9 @@ def ctx():
 def _counts():
     from resvg_b200 import _ffi
 
-    out = (C.c_uint64 * 3)()
+    out = (C.c_uint64 * 6)()
     _ffi.lib.rb_debug_geo_counts(out)
-    return [int(v) for v in out]
+    return [int(v) for v in out][:3]
 
 
 def _render_scene(ctx, scene, w, h, mode, base=None, ts=None):
