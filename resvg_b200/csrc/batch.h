@@ -14,6 +14,7 @@
 struct rb_ctx;
 struct rb_layer;
 struct rb_mask;
+struct GeoPending;
 
 constexpr int TW = 64; // device tile width  (pixels)
 constexpr int TH = 16; // device tile height (pixels)
@@ -112,6 +113,7 @@ struct rb_batch {
     uint8_t *dev_scratch = nullptr; // row lists + warp-tile bins (device-built)
     bool scratch_owned = false;     // dev_scratch is an allocation of its own (device geometry) rather than the tail of `dev`
     void *host_block = nullptr; // host-only batches: malloc'ed copy of the block
+    struct GeoPending *geo = nullptr; // a geometry launch in flight (geo.cu rb_geo_begin / rb_geo_finish)
 };
 
 // rb_batch_host_build: the range holds hairline strokes the chosen builder cannot draw inline (internal status).

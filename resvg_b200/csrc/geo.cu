@@ -871,80 +871,63 @@ static void *geo_stage_pinned(void *user, size_t bytes)
     return r->status == RB_OK ? p : nullptr;
 }
 
-// Builds draws [begin, end) of the batch on the device.  On RB_OK, b->dev holds the block (b->lay describes it: item
-// mode, lines and curves addressed from the heap base) and the caller allocates the raster scratch.  RB_GEO_FALLBACK:
-// the range needs the host builder (a draw beyond the packed winding range, a recursion deeper than the device stack,
-// memory); nothing is left allocated.
-int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
-{
-    rb_ctx *ctx = b->layer->ctx;
-    const int W = (int)b->layer->w, H = (int)b->layer->h;
-    cudaSetDevice(ctx->device);
-    if (!(ctx->attr_bits & RB_ATTR_GEO)) {
-        RB_CUDA(ctx, cudaDeviceSetLimit(cudaLimitStackSize, GEO_STACK));
-        ctx->attr_bits |= RB_ATTR_GEO;
-    }
-    if (!ctx->geo_pinned) RB_CUDA(ctx, cudaHostAlloc(&ctx->geo_pinned, 4096, cudaHostAllocDefault));
-    // The geometry of a batch part runs on a stream of its own, so that it overlaps the raster kernel of the previous part
-    // (rb_batch_submit cuts a large batch into parts): the raster kernel is bound by instruction issue, the geometry kernels by
-    // latency and instruction fetch, and the host waits for the geometry stream only.  What this function leaves behind is
-    // used on the context's stream after that wait.
-    for (auto &st : ctx->geo_streams) if (!st) RB_CUDA(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    for (auto &ev : ctx->geo_events) if (!ev) RB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    static const bool own_stream = !(getenv("RB_GEO_OWN_STREAM") && atoi(getenv("RB_GEO_OWN_STREAM")) == 0);
-    cudaStream_t gs = own_stream ? ctx->geo_streams[0] : ctx->stream;
-    StageReq2 req{ctx, RB_OK};
-    void *blk = nullptr;
+// Builds draws [begin, end) of the batch on the device, in two steps so that the caller can do other work (build another
+// range on the host threads, rasterise it) while the geometry kernels run: rb_geo_begin builds the tasks, uploads them and
+// enqueues the kernels on the geometry stream; rb_geo_finish waits, repeats the launch with a larger heap if it ran out,
+// and on RB_OK leaves the block in b->dev (b->lay describes it: item mode, lines and curves addressed from the heap base) —
+// the caller allocates the raster scratch.  RB_GEO_FALLBACK: the range needs the host builder (a draw beyond the packed
+// winding range, a recursion deeper than the device stack, memory); nothing is left allocated.
+struct GeoPending {
     GeoBlock G;
-    int st;
-    const bool diag = getenv("RB_GEO_DIAG") != nullptr;
-    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double t_start = now_ms();
-    { rb_prof_scope prof__(RB_T_BUILD); st = rb_geo_host_build(b, W, H, n_threads, geo_stage_pinned, &req, &blk, &G, begin, end); }
-    if (req.status != RB_OK) return req.status;
-    if (st != RB_OK) return rb_fail(ctx, st, "geometry task build failed");
-    b->lay = BatchLayout();
-    if (!blk || G.n_tasks == 0) return RB_OK;
-    rb_prof_scope prof_up__(RB_T_UPLOAD);
-    const double t_built = now_ms();
+    void *blk = nullptr;      // pinned staging (first attempt only)
+    uint8_t *dev = nullptr;
+    size_t heap_bytes = 0, o_draws = 0, o_tot = 0, o_heap = 0;
+    int attempt = 0, W = 0, H = 0;
+    unsigned long long *dbg = nullptr;
+    double t_start = 0, t_built = 0, t_enq = 0;
+    cudaStream_t gs = nullptr;
+};
+static double geo_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+static int geo_enqueue(rb_ctx *ctx, GeoPending *gp)
+{
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    const size_t n_tasks = G.n_tasks;
-    size_t heap_bytes = al(G.heap_hint + (64u << 20));
-    if (const char *e = getenv("RB_GEO_HEAP_BYTES")) heap_bytes = al((size_t)std::max(1024ll, atoll(e))); // tests: force heap retries
-    for (int attempt = 0; attempt < 6; attempt++, heap_bytes *= 8) {
+    cudaStream_t gs = gp->gs;
+    const int W = gp->W, H = gp->H;
+    {
         // [uploaded block | DevDraw[] | GeoMid[] | wide queue | units | pieces | totals | heap]
-        const size_t n_draws = G.n_draws, max_units = G.max_units;
-        const size_t o_draws = al(G.total), o_mid = o_draws + al(n_draws * sizeof(DevDraw)), o_wq = o_mid + al(n_tasks * sizeof(GeoMid));
+        const size_t n_tasks = gp->G.n_tasks;
+        const size_t n_draws = gp->G.n_draws, max_units = gp->G.max_units;
+        const size_t o_draws = al(gp->G.total), o_mid = o_draws + al(n_draws * sizeof(DevDraw)), o_wq = o_mid + al(n_tasks * sizeof(GeoMid));
         const size_t o_units = o_wq + al(n_draws * 4), o_pieces = o_units + al((max_units + 1) * sizeof(GeoUnit));
-        const size_t o_tot = o_pieces + al((max_units + 1) * sizeof(GeoPiece)), o_heap = o_tot + 256, total = o_heap + heap_bytes + 65536;
+        const size_t o_tot = o_pieces + al((max_units + 1) * sizeof(GeoPiece)), o_heap = o_tot + 256, total = o_heap + gp->heap_bytes + 65536;
         uint8_t *dev = nullptr;
         if (cudaMallocAsync((void **)&dev, total, gs) != cudaSuccess) {
             cudaGetLastError();
-            if (b->dev) { cudaFreeAsync(b->dev, gs); b->dev = nullptr; }
-            g_geo_counts[1]++;
+            if (gp->dev) { cudaFreeAsync(gp->dev, gs); gp->dev = nullptr; }
             return RB_GEO_FALLBACK;
         }
-        if (attempt == 0) {
-            RB_CUDA(ctx, cudaMemcpyAsync(dev, blk, G.total, cudaMemcpyHostToDevice, gs));
-            ctx->h2d_bytes += G.total;
+        if (gp->attempt == 0) {
+            RB_CUDA(ctx, cudaMemcpyAsync(dev, gp->blk, gp->G.total, cudaMemcpyHostToDevice, gs));
+            ctx->h2d_bytes += gp->G.total;
             { int st__ = rb_staging_mark(ctx, gs); if (st__ != RB_OK) return st__; }
         } else {
-            RB_CUDA(ctx, cudaMemcpyAsync(dev, b->dev, G.total, cudaMemcpyDeviceToDevice, gs));
-            RB_CUDA(ctx, cudaFreeAsync(b->dev, gs));
+            RB_CUDA(ctx, cudaMemcpyAsync(dev, gp->dev, gp->G.total, cudaMemcpyDeviceToDevice, gs));
+            RB_CUDA(ctx, cudaFreeAsync(gp->dev, gs));
         }
-        b->dev = dev;
+        gp->dev = dev;
         RB_CUDA(ctx, cudaMemsetAsync(dev + o_tot, 0, 256, gs));
         GeoArgs a;
-        a.tasks = (const GeoTask *)(dev + G.o_tasks);
-        a.verbs = dev + G.o_verbs;
-        a.pts = (const P *)(dev + G.o_pts);
-        a.dashes = (const float *)(dev + G.o_dashes);
+        a.tasks = (const GeoTask *)(dev + gp->G.o_tasks);
+        a.verbs = dev + gp->G.o_verbs;
+        a.pts = (const P *)(dev + gp->G.o_pts);
+        a.dashes = (const float *)(dev + gp->G.o_dashes);
         a.mid = (GeoMid *)(dev + o_mid);
         a.draws = (DevDraw *)(dev + o_draws);
         a.tot = (GeoTotals *)(dev + o_tot);
         a.heap.base = dev + o_heap;
         a.heap.cursor = &a.tot->heap_cursor;
-        a.heap.size = heap_bytes;
+        a.heap.size = gp->heap_bytes;
         a.heap.overflow = &a.tot->overflow;
         a.W = W; a.H = H;
         a.units = (GeoUnit *)(dev + o_units);
@@ -956,8 +939,9 @@ int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
         a.dbg = nullptr;
         unsigned long long *dbg = nullptr;
         if (getenv("RB_GEO_TIMES")) { cudaMalloc((void **)&dbg, 3 * n_tasks * 8); cudaMemset(dbg, 0, 3 * n_tasks * 8); a.dbg = dbg; }
-        const uint32_t *lists = (const uint32_t *)(dev + G.o_lists);
-        const uint32_t nd = (uint32_t)G.n_dash_l, ns = (uint32_t)G.n_stroke_l, nh = (uint32_t)G.n_hair_l, nf = (uint32_t)G.n_fill_l, nu = (uint32_t)G.n_units_l;
+        gp->dbg = dbg;
+        const uint32_t *lists = (const uint32_t *)(dev + gp->G.o_lists);
+        const uint32_t nd = (uint32_t)gp->G.n_dash_l, ns = (uint32_t)gp->G.n_stroke_l, nh = (uint32_t)gp->G.n_hair_l, nf = (uint32_t)gp->G.n_fill_l, nu = (uint32_t)gp->G.n_units_l;
         const uint32_t *l_dash = lists, *l_stroke = l_dash + nd, *l_hair = l_stroke + ns, *l_fill = l_hair + nh, *l_units = l_fill + nf;
         uint32_t *wide_q = (uint32_t *)(dev + o_wq);
         const size_t per_cta = (size_t)GEO_THREADS >> lane_shift;
@@ -977,7 +961,7 @@ int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
             RB_CUDA(ctx, cudaStreamWaitEvent(s2, ctx->geo_events[0], 0));
             RB_CUDA(ctx, cudaStreamWaitEvent(s3, ctx->geo_events[0], 0));
         }
-        const uint32_t no = (uint32_t)G.n_outline_l;
+        const uint32_t no = (uint32_t)gp->G.n_outline_l;
         const uint32_t *l_outline = l_units + nu;
         // chain 1: the long strokes first
         if (ns) { k_geo_stroke<<<grid(ns), GEO_THREADS, 0, s1>>>(a, l_stroke, ns); RB_LAUNCHED(ctx, "geo_stroke"); }
@@ -1009,14 +993,74 @@ int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
         }
         GeoTotals *ht = (GeoTotals *)ctx->geo_pinned;
         RB_CUDA(ctx, cudaMemcpyAsync(ht, dev + o_tot, sizeof(GeoTotals), cudaMemcpyDeviceToHost, gs));
-        const double t_enq = now_ms();
+        gp->o_draws = o_draws; gp->o_tot = o_tot; gp->o_heap = o_heap;
+        gp->t_enq = geo_now_ms();
+    }
+    return RB_OK;
+}
+
+int rb_geo_begin(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
+{
+    rb_ctx *ctx = b->layer->ctx;
+    cudaSetDevice(ctx->device);
+    if (b->geo) { delete b->geo; b->geo = nullptr; }
+    if (!(ctx->attr_bits & RB_ATTR_GEO)) {
+        RB_CUDA(ctx, cudaDeviceSetLimit(cudaLimitStackSize, GEO_STACK));
+        ctx->attr_bits |= RB_ATTR_GEO;
+    }
+    if (!ctx->geo_pinned) RB_CUDA(ctx, cudaHostAlloc(&ctx->geo_pinned, 4096, cudaHostAllocDefault));
+    // The geometry runs on a stream of its own: the host waits for that stream only, and the context's stream is free to
+    // rasterise another range of the batch meanwhile (rb_batch_submit).  What rb_geo_finish leaves behind is used on the
+    // context's stream after that wait.
+    for (auto &st : ctx->geo_streams) if (!st) RB_CUDA(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto &ev : ctx->geo_events) if (!ev) RB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    static const bool own_stream = !(getenv("RB_GEO_OWN_STREAM") && atoi(getenv("RB_GEO_OWN_STREAM")) == 0);
+    GeoPending *gp = new GeoPending();
+    gp->gs = own_stream ? ctx->geo_streams[0] : ctx->stream;
+    gp->W = (int)b->layer->w; gp->H = (int)b->layer->h;
+    StageReq2 req{ctx, RB_OK};
+    int st;
+    gp->t_start = geo_now_ms();
+    { rb_prof_scope prof__(RB_T_BUILD); st = rb_geo_host_build(b, gp->W, gp->H, n_threads, geo_stage_pinned, &req, &gp->blk, &gp->G, begin, end); }
+    if (req.status != RB_OK) { delete gp; return req.status; }
+    if (st != RB_OK) { delete gp; return rb_fail(ctx, st, "geometry task build failed"); }
+    gp->t_built = geo_now_ms();
+    b->geo = gp;
+    if (!gp->blk || gp->G.n_tasks == 0) return RB_OK; // nothing to draw: rb_geo_finish reports an empty layout
+    rb_prof_scope prof_up__(RB_T_UPLOAD);
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    gp->heap_bytes = al(gp->G.heap_hint + (64u << 20));
+    if (const char *e = getenv("RB_GEO_HEAP_BYTES")) gp->heap_bytes = al((size_t)std::max(1024ll, atoll(e))); // tests: force heap retries
+    st = geo_enqueue(ctx, gp);
+    if (st != RB_OK) { delete gp; b->geo = nullptr; if (st == RB_GEO_FALLBACK) g_geo_counts[1]++; }
+    return st;
+}
+
+int rb_geo_finish(rb_batch *b)
+{
+    rb_ctx *ctx = b->layer->ctx;
+    GeoPending *gp = b->geo;
+    if (!gp) return RB_ERR_INVALID;
+    struct Drop { rb_batch *b; ~Drop() { delete b->geo; b->geo = nullptr; } } drop{b};
+    cudaSetDevice(ctx->device);
+    b->lay = BatchLayout();
+    if (!gp->blk || gp->G.n_tasks == 0) return RB_OK;
+    const bool diag = getenv("RB_GEO_DIAG") != nullptr;
+    cudaStream_t gs = gp->gs;
+    const GeoBlock &G = gp->G;
+    const size_t n_tasks = G.n_tasks, n_draws = G.n_draws;
+    const int W = gp->W, H = gp->H;
+    for (;;) {
+        const GeoTotals *ht = (const GeoTotals *)ctx->geo_pinned;
         RB_CUDA(ctx, cudaStreamSynchronize(gs));
-        const double t_done = now_ms();
+        const double t_done = geo_now_ms();
         const GeoTotals T = *ht;
-        if (dbg) {
+        if (gp->dbg) {
+            unsigned long long *dbg = gp->dbg;
             std::vector<unsigned long long> h(3 * n_tasks);
             cudaMemcpy(h.data(), dbg, 3 * n_tasks * 8, cudaMemcpyDeviceToHost);
             cudaFree(dbg);
+            gp->dbg = nullptr;
             const char *names[3] = {"stroke", "hair", "fill"};
             for (int k = 0; k < 3; k++) {
                 std::vector<unsigned long long> v;
@@ -1030,18 +1074,26 @@ int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
             }
         }
         if (diag)
-            fprintf(stderr, "[geo] tasks %zu draws %zu (dash %u stroke %u hair %u fill %u + %u units-tasks %u units %u / %zu) upload %zu B heap %llu / %zu B slots %llu list %llu wide_q %u overflow %u wide %u deep %u too_large %u | host %.2f ms, enqueue %.2f ms, wait %.2f ms\n",
-                    n_tasks, n_draws, nd, ns, nh, nf, no, nu, T.n_units, max_units, G.total, T.heap_cursor, heap_bytes, T.n_slots, T.n_list, T.n_wide_q, T.overflow, T.wide, T.deep, T.too_large,
-                    t_built - t_start, t_enq - t_built, now_ms() - t_enq);
-        if (T.overflow) { g_geo_counts[2]++; continue; } // heap exhausted: again with eight times the heap
-        if (T.wide || T.too_large || T.deep) break;
+            fprintf(stderr, "[geo] tasks %zu draws %zu (dash %zu stroke %zu hair %zu fill %zu + %zu units-tasks %zu units %u / %zu) upload %zu B heap %llu / %zu B slots %llu list %llu wide_q %u overflow %u wide %u deep %u too_large %u | host %.2f ms, enqueue %.2f ms, kernels done %.2f ms after the enqueue\n",
+                    n_tasks, n_draws, G.n_dash_l, G.n_stroke_l, G.n_hair_l, G.n_fill_l, G.n_outline_l, G.n_units_l, T.n_units, G.max_units, G.total, T.heap_cursor, gp->heap_bytes, T.n_slots,
+                    T.n_list, T.n_wide_q, T.overflow, T.wide, T.deep, T.too_large, gp->t_built - gp->t_start, gp->t_enq - gp->t_built, t_done - gp->t_enq);
+        if (T.overflow && gp->attempt < 5) { // heap exhausted: again with eight times the heap
+            g_geo_counts[2]++;
+            gp->attempt++;
+            gp->heap_bytes *= 8;
+            int st = geo_enqueue(ctx, gp);
+            if (st == RB_GEO_FALLBACK) break;
+            if (st != RB_OK) return st;
+            continue;
+        }
+        if (T.overflow || T.wide || T.too_large || T.deep) break;
         if (T.n_slots > 0xfffffff0ull || T.n_list > 0xfffffff0ull || T.n_wpairs > 0xfffffff0ull || T.n_row_off > 0xfffffff0ull) break;
         BatchLayout L;
         L.items = true;
         L.n_draws = n_draws;
         L.n_paints = G.n_paints; L.n_stops = G.n_stops;
-        L.o_draws = o_draws; L.o_paints = G.o_paints; L.o_stops = G.o_stops;
-        L.o_edges = o_heap; L.o_curves = o_heap;
+        L.o_draws = gp->o_draws; L.o_paints = G.o_paints; L.o_stops = G.o_stops;
+        L.o_edges = gp->o_heap; L.o_curves = gp->o_heap;
         L.total = G.total;
         L.n_slots = (size_t)T.n_slots; L.n_list = (size_t)T.n_list; L.n_row_off = (size_t)T.n_row_off; L.n_row_ent = (size_t)T.n_row_ent;
         L.n_wpairs = (size_t)T.n_wpairs;
@@ -1050,16 +1102,35 @@ int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
         L.wtiles_y = (H + 7) / 8;
         L.tiles_x = (W + TW - 1) / TW;
         b->lay = L;
+        b->dev = gp->dev;
+        gp->dev = nullptr;
         b->stats[0] = n_draws; b->stats[1] = L.n_slots; b->stats[2] = L.n_wpairs; b->stats[3] = (size_t)L.wtiles_x * L.wtiles_y;
         b->stats[4] = G.total; b->stats[5] = 0;
         g_geo_counts[0]++;
-        g_geo_counts[3] = (uint64_t)((t_done - t_enq) * 1e3);
-        g_geo_counts[4] = (uint64_t)((t_built - t_start) * 1e3);
+        g_geo_counts[3] = (uint64_t)((t_done - gp->t_enq) * 1e3);
+        g_geo_counts[4] = (uint64_t)((gp->t_built - gp->t_start) * 1e3);
         g_geo_counts[5] = n_tasks;
         return RB_OK;
     }
-    if (b->dev) { cudaFreeAsync(b->dev, gs); cudaStreamSynchronize(gs); b->dev = nullptr; }
-    b->lay = BatchLayout();
+    if (gp->dev) { cudaFreeAsync(gp->dev, gs); cudaStreamSynchronize(gs); gp->dev = nullptr; }
     g_geo_counts[1]++;
     return RB_GEO_FALLBACK;
+}
+
+// Releases a geometry launch nobody will finish (the batch is destroyed or prepared again).
+void rb_geo_abandon(rb_batch *b)
+{
+    GeoPending *gp = b->geo;
+    if (!gp) return;
+    if (gp->dev) { cudaStreamSynchronize(gp->gs); cudaFreeAsync(gp->dev, gp->gs); }
+    if (gp->dbg) cudaFree(gp->dbg);
+    delete gp;
+    b->geo = nullptr;
+}
+
+int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
+{
+    int st = rb_geo_begin(b, n_threads, begin, end);
+    if (st != RB_OK) return st;
+    return rb_geo_finish(b);
 }

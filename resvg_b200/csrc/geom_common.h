@@ -11,6 +11,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include "libm_compat.h"
+
 // GEO_HD: a function of the cores.  On the device these are NOT inlined: the geometry code is a large tree of cases
 // (clipping, joins, caps, recursive subdivision) and inlining it into every call site produced kernels of more than a
 // megabyte of SASS, whose warps — each at a different point of it — spent most of their time waiting for instruction
@@ -58,33 +60,13 @@ GEO_HDI inline int32_t d2i(double v)
     return (int32_t)v;
 }
 
-// Transcendentals of the stroker's cubic solver (path_geometry.rs solve_cubic_poly).  The host calls glibc, whose acosf /
-// cosf are correctly rounded in all but astronomically rare cases; the device evaluates in double and rounds once,
-// which gives the same float (CUDA's double acos / cos are within 2 ulp of the double result).  cbrtf likewise.
-GEO_HDI inline float g_acosf(float v)
-{
-#if defined(__CUDA_ARCH__)
-    return (float)acos((double)v);
-#else
-    return acosf(v);
-#endif
-}
-GEO_HDI inline float g_cosf(float v)
-{
-#if defined(__CUDA_ARCH__)
-    return (float)cos((double)v);
-#else
-    return cosf(v);
-#endif
-}
-GEO_HDI inline float g_cbrtf(float v)
-{
-#if defined(__CUDA_ARCH__)
-    return (float)cbrt((double)v);
-#else
-    return cbrtf(v);
-#endif
-}
+// Transcendentals of the cubic solver (path_geometry.rs solve_cubic_poly; Rust forwards f32::acos / cos / cbrt to the platform
+// libm): glibc's algorithms restated operation by operation (libm_compat.h), on BOTH sides — glibc 2.39's acosf / cosf /
+// cbrtf are not correctly rounded, so CUDA's own functions (or double evaluation rounded once) give other floats for a few
+// per cent of the arguments, which moved hairline cubics by a pixel here and there.
+GEO_HDI inline float g_acosf(float v) { return lmc::acosf_(v); }
+GEO_HDI inline float g_cosf(float v) { return lmc::cosf_(v); }
+GEO_HDI inline float g_cbrtf(float v) { return lmc::cbrtf_(v); }
 
 // ---- storage ---------------------------------------------------------------------------------------------------------------
 // The cores are templates over the vector type: std::vector on the host, DVec on the device.  DVec grows like a vector

@@ -708,6 +708,9 @@ k_raster_tiles_wide(void *__restrict__ target, int W, int H, int tiles_x, const 
 #include "raster_warp.cuh"
 #include "batch_geo.h"
 int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end);
+int rb_geo_begin(rb_batch *b, int32_t n_threads, size_t begin, size_t end);
+int rb_geo_finish(rb_batch *b);
+void rb_geo_abandon(rb_batch *b);
 bool rb_debug_host_only_builder();
 
 // =================================================================================================
@@ -747,6 +750,7 @@ extern "C" void rb_batch_destroy(rb_batch *b)
 {
     if (!b) return;
     rb_ctx *ctx = batch_ctx(b);
+    if (b->geo) rb_geo_abandon(b);
     batch_release(b);
     delete b;
     if (ctx) rb_ctx_release(ctx);
@@ -785,7 +789,7 @@ static void *stage_pinned(void *user, size_t bytes)
 static void *stage_malloc(void *, size_t bytes) { return malloc(bytes); }
 
 // Host build (threads) of draws [begin, end) into the context's pinned staging block, then ONE host-to-device copy.
-static int batch_prepare_range(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
+static int batch_prepare_range(rb_batch *b, int32_t n_threads, size_t begin, size_t end, bool allow_geo = true)
 {
     if (!b) return RB_ERR_INVALID;
     batch_release(b);
@@ -814,7 +818,7 @@ static int batch_prepare_range(rb_batch *b, int32_t n_threads, size_t begin, siz
         const int host_threads = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
         int geo_max_threads = 16;
         if (const char *e = getenv("RB_GEO_MAX_HOST_THREADS")) geo_max_threads = atoi(e);
-        if (eligible && g_geo_mode != 2 && (g_geo_mode == 1 || (n_range >= geo_from && host_threads <= geo_max_threads))) {
+        if (allow_geo && eligible && g_geo_mode != 2 && (g_geo_mode == 1 || (n_range >= geo_from && host_threads <= geo_max_threads))) {
             int gst = rb_geo_prepare(b, n_threads, begin, end);
             if (gst == RB_OK) {
                 if (!b->dev || b->lay.n_draws == 0) return RB_OK;
@@ -851,6 +855,7 @@ extern "C" int rb_batch_prepare(rb_batch *b, int32_t n_threads)
 {
     rb_enter(b ? b->ctx : nullptr);
     if (b && b->layer && b->layer->pending != b) RB_SYNC_LAYER(b->layer);
+    if (b && b->geo) rb_geo_abandon(b);
     int st = batch_prepare_range(b, n_threads, 0, 0);
     // hairline strokes + the fallback builder: only rb_batch_submit can interleave the two kinds of passes
     if (st == RB_NEEDS_RUN_SPLIT)
@@ -1090,6 +1095,24 @@ extern "C" int rb_batch_submit(rb_batch *b, int32_t n_threads)
     return st;
 }
 
+// Runs draws [lo, hi) through the host builder in `parts` consecutive parts (the GPU rasterises part k while the host
+// threads build part k + 1).
+static int submit_host_parts(rb_batch *b, int32_t n_threads, size_t lo0, size_t hi0, size_t parts, uint64_t total[6], size_t *stopped_at)
+{
+    const size_t n = hi0 - lo0;
+    int st = RB_OK;
+    for (size_t k = 0; k < parts && st == RB_OK; k++) {
+        const size_t lo = lo0 + n * k / parts, hi = lo0 + n * (k + 1) / parts;
+        if (lo >= hi) continue;
+        *stopped_at = lo;
+        st = batch_prepare_range(b, n_threads, lo, hi, /*allow_geo=*/false);
+        if (st == RB_OK) st = rb_batch_run(b);
+        for (int i = 0; i < 6; i++) total[i] += b->stats[i];
+        batch_release(b);
+    }
+    return st;
+}
+
 static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t last, uint64_t total[6], size_t *stopped_at)
 {
     const size_t n = last - first;
@@ -1099,25 +1122,58 @@ static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t 
     if (const char *e = getenv("RB_SUBMIT_SPLIT_FROM")) split_from = (size_t)std::max(1, atoi(e)); // tests
     if (n >= split_from && (b->layer || b->mask)) {
         parts = 8;
-        // with the geometry on the device there is no host build to overlap with the GPU, and every part would pay the latency
-        // of its longest draws again (measured: 1 part 66 ms, 2 parts 67, 4 parts 80, 8 parts 106 per 100 000-path scene)
-        {
-            const int host_threads = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
-            int geo_max_threads = 16;
-            if (const char *e = getenv("RB_GEO_MAX_HOST_THREADS")) geo_max_threads = atoi(e);
-            if (b->layer && g_geo_mode != 2 && !rb_debug_host_only_builder() && (g_geo_mode == 1 || host_threads <= geo_max_threads)) parts = 1;
-        }
         if (const char *e = getenv("RB_SUBMIT_PARTS")) parts = (size_t)std::max(1, atoi(e));
     }
+    // Who builds the geometry.  The geometry kernels (geo.cu) take ~0.35 us per draw of the 100 000-path scene on a B200 and
+    // pay the latency of their longest draws once per launch; the host builder takes ~8 core-us per draw and overlaps the
+    // raster kernel part by part.  Both at once: the host threads build (and the GPU rasterises) the FIRST draws of the
+    // batch while the geometry kernels, on their own stream, build the rest in one launch; the shares follow the two rates,
+    // so a box with many cores per GPU gives the host more and eight processes sharing the box's cores give it next to
+    // nothing.  RB_GEO_MODE / rb_debug_geo_mode: 1 = everything on the device, 2 = everything on the host.
+    size_t geo_from = 4096;
+    if (const char *e = getenv("RB_GEO_FROM")) geo_from = (size_t)std::max(1, atoi(e));
+    const bool geo_ok = b->layer && !b->mask && b->layer->w <= 65536 && b->layer->h <= 65536 && !rb_debug_host_only_builder() && g_geo_mode != 2
+                        && (g_geo_mode == 1 || n >= geo_from);
+    size_t split = last; // draws [split, last) go to the geometry kernels
+    if (geo_ok) {
+        const int host_threads = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+        double host_share = (host_threads / 8.3) / (host_threads / 8.3 + 2.9);
+        if (const char *e = getenv("RB_GEO_HOST_SHARE")) host_share = atof(e);
+        if (g_geo_mode == 1 || host_share < 0.12) host_share = 0.0; // not worth a second pipeline
+        host_share = std::min(host_share, 1.0);
+        split = first + (size_t)((double)n * host_share);
+        if (last - split < geo_from && g_geo_mode != 1) split = last;
+    }
     int st = RB_OK;
-    for (size_t k = 0; k < parts && st == RB_OK; k++) {
-        const size_t lo = first + n * k / parts, hi = first + n * (k + 1) / parts;
-        if (lo >= hi) continue;
-        *stopped_at = lo;
-        st = batch_prepare_range(b, n_threads, lo, hi);
-        if (st == RB_OK) st = rb_batch_run(b);
-        for (int i = 0; i < 6; i++) total[i] += b->stats[i];
+    bool geo_pending = false;
+    if (split < last) {
+        st = rb_geo_begin(b, n_threads, split, last);
+        if (st == RB_OK) geo_pending = true;
+        else if (st == RB_GEO_FALLBACK) { st = RB_OK; split = last; }
+        else return st;
+    }
+    if (split > first) {
+        const size_t host_parts = std::max<size_t>(1, parts * (split - first) / n);
+        st = submit_host_parts(b, n_threads, first, split, host_parts, total, stopped_at);
+        if (st != RB_OK) { if (geo_pending) rb_geo_abandon(b); return st; }
+    }
+    if (geo_pending) {
+        *stopped_at = split;
         batch_release(b);
+        st = rb_geo_finish(b);
+        if (st == RB_OK) {
+            if (b->dev && b->lay.n_draws) {
+                rb_ctx *ctx = batch_ctx(b);
+                const size_t scratch_bytes = warp_scratch_layout(b->lay).total;
+                RB_CUDA(ctx, cudaMallocAsync((void **)&b->dev_scratch, scratch_bytes, ctx->stream));
+                b->scratch_owned = true;
+                st = rb_batch_run(b);
+            }
+            for (int i = 0; i < 6; i++) total[i] += b->stats[i];
+            batch_release(b);
+        } else if (st == RB_GEO_FALLBACK) {
+            st = submit_host_parts(b, n_threads, split, last, std::max<size_t>(1, parts * (last - split) / n), total, stopped_at);
+        }
     }
     return st;
 }

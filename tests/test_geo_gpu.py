@@ -72,6 +72,41 @@ def test_bench_scene_device_geometry_equals_host_builder(ctx, seed, w, h, n):
     assert_exact(dev, host, "device geometry vs host builder")
 
 
+def test_full_size_scene_device_geometry_equals_host_builder(ctx):
+    """BASELINE.json's C2 scene at full size (8192 x 8192, 100 000 paths -> 120 087 draws, DrawTiler tiles, dashed strokes in
+    units, hairlines verb by verb): every pixel of the device build equals the host build, also when the two share the batch
+    (the default for large batches: the host threads build the first draws while the geometry kernels build the rest)."""
+    import zlib
+
+    import resvg_b200 as rb
+    from resvg_b200 import _ffi
+
+    w = h = 8192
+    scene = _scene(w, h, 100_000, 0x5EED0002)
+    l = ctx.layer(w, h)
+    pinned = rb.PinnedBuffer(w * h * 4)
+    crcs = {}
+    for name, mode in (("host", 2), ("device", 1), ("shared", 0)):
+        _ffi.lib.rb_debug_geo_mode(mode)
+        try:
+            before = _counts()
+            l.fill(0, 0, 0, 0)
+            b = rb.Batch(l)
+            b.fill_paths(scene)
+            b.submit()
+            b.close()
+            l.download_ptr(pinned.array.ctypes.data)
+            after = _counts()
+        finally:
+            _ffi.lib.rb_debug_geo_mode(0)
+        crcs[name] = zlib.crc32(pinned.array)
+        if name == "device":
+            assert after[0] - before[0] == 1 and after[1] == before[1], (before, after)
+    pinned.close()
+    l.close()
+    assert crcs["device"] == crcs["host"] and crcs["shared"] == crcs["host"], crcs
+
+
 def test_bench_scene_device_geometry_matches_checker(ctx):
     import bench
 

@@ -84,3 +84,17 @@ def test_upload_is_a_fraction_of_the_host_builders():
     lib.rb_batch_stats(hnd, stats)
     lib.rb_batch_destroy(hnd)
     assert s["bytes"] * 3 < int(stats[4])
+
+
+def test_libm_compat_matches_the_hosts_libm(tmp_path):
+    """libm_compat.h (acosf / cosf / cbrtf as glibc computes them, for the device) against the host's libm: every sampled
+    argument gives the identical float (tools/libm_compat_check.cpp: 22 M + 40 M + 80 M arguments)."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "lmc")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", os.path.join(root, "tools", "libm_compat_check.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert out.stdout.count(" 0 mismatches") == 3, out.stdout
