@@ -388,6 +388,7 @@ def run_icons(args, rank, local_rank, world, torch, dist):
     ctx.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
 
+    per_rank = shard.gather_floats([e2e_s * 1e3, e2e_phase[1] / e2e_steps * 1e3, e2e_phase[2] / e2e_steps * 1e3, e2e_geo[3] / 1e3], world, f"cuda:{local_rank}")
     ms_step, ms_kernel, e2e_s = shard.max_over_ranks([ms_step, ms_kernel, e2e_s], world, f"cuda:{local_rank}")
     if rank != 0:
         return
@@ -907,6 +908,7 @@ def main():
     ctx.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
 
+    per_rank = shard.gather_floats([e2e_s * 1e3, e2e_phase[1] / e2e_steps * 1e3, e2e_phase[2] / e2e_steps * 1e3, e2e_geo[3] / 1e3], world, f"cuda:{local_rank}")
     ms_step, ms_kernel, e2e_s = shard.max_over_ranks([ms_step, ms_kernel, e2e_s], world, f"cuda:{local_rank}")
 
     if rank == 0:
@@ -943,6 +945,8 @@ def main():
                     "d2h_bytes_per_step": W * strip_rows * 4, "ms_per_step": e2e_s * 1e3, "record_ms": e2e_phase[0] / e2e_steps * 1e3,
                     "host_build_and_enqueue_ms": e2e_phase[1] / e2e_steps * 1e3, "gpu_wait_and_d2h_ms": e2e_phase[2] / e2e_steps * 1e3,
                     "steps": e2e_steps,
+                    "per_rank_ms": {"e2e": [round(r[0], 2) for r in per_rank], "host_build_and_enqueue": [round(r[1], 2) for r in per_rank],
+                                    "gpu_wait_and_d2h": [round(r[2], 2) for r in per_rank], "device_geometry": [round(r[3], 2) for r in per_rank]},
                     "geometry": {"where": "device" if e2e_geo[0] > 0 and e2e_geo[1] == 0 else "host",
                                  "ranges_built_on_device": e2e_geo[0], "ranges_handed_to_host_builder": e2e_geo[1], "heap_retries": e2e_geo[2],
                                  "device_geometry_ms": e2e_geo[3] / 1e3, "host_task_build_ms": e2e_geo[4] / 1e3, "tasks": e2e_geo[5],

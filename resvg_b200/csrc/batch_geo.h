@@ -46,7 +46,8 @@ struct GeoTotals {
     unsigned int n_wide_q;   // draws queued for the exact winding bound
     unsigned int deep;       // a recursion went deeper than the device stack allows (or a bound did not hold): host fallback
     unsigned int n_units;    // output contours of the dashed strokes built in units
-    unsigned int pad[2];
+    unsigned int n_seq;      // dashed strokes whose edges were rebuilt by one thread (combine_vertical across units)
+    unsigned int pad[1];
 };
 
 // Host half (batch_geo.cpp): tasks, paints, stops and the raw path data of draws [begin, end), laid out in one staging

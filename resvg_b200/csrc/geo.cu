@@ -105,7 +105,7 @@ struct GeoArgs {
 constexpr int GEO_THREADS = 64;
 constexpr int GEO_TASKS_PER_CTA = GEO_THREADS / 32;
 // recursion guards (the device stack is GEO_STACK bytes per thread): deeper than this and the batch goes to the host builder
-constexpr int GEO_STACK = 12288;
+constexpr int GEO_STACK = 24576; // cubic_stroke recurses up to 78 levels of 232 bytes (the reference's own limit)
 
 __device__ __forceinline__ void empty_draw_at(const GeoArgs &a, uint32_t draw, const GeoTask &t)
 {
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(GEO_THREADS, 10) k_geo_stroke(GeoArgs a, const
             m.n_verbs = (uint32_t)s.outer.verbs.size(); m.n_pts = (uint32_t)s.outer.pts.size();
             m.status = 1;
         }
-        if (s.too_deep) a.tot->deep = 1u;
+        if (s.too_deep) atomicOr(&a.tot->deep, 1u);
     }
     a.mid[ti] = m;
 }
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geo_plan(GeoArgs a, const uint3
             geo::ds::dash_contour_ranges(sp, dash, (int)t.n_dash, c.length, c.closed, cr);
             cnt += cr.n;
         }
-        if (ok && cnt > t.max_units) { a.tot->deep = 1u; ok = false; } // the host's bound did not hold: the host builder takes the batch
+        if (ok && cnt > t.max_units) { atomicOr(&a.tot->deep, 2u); ok = false; } // the host's bound did not hold: the host builder takes the batch
         if (ok && cnt > 0) {
             m.unit_first = atomicAdd(&a.tot->n_units, cnt);
             uint32_t at = m.unit_first;
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(GEO_THREADS, 10) k_geo_unit_path(GeoArgs a)
             s.reset();
             ok = geo::sk::stroke_path(s, verbs, n_verbs, pts, t.width, t.miter, (int)((t.flags >> GT_CAP_SHIFT) & 3u), (int)((t.flags >> GT_JOIN_SHIFT) & 3u),
                                       t.res_scale);
-            if (s.too_deep) a.tot->deep = 1u;
+            if (s.too_deep) atomicOr(&a.tot->deep, 1u);
             verbs = s.outer.verbs.data(); pts = s.outer.pts.data();
             n_verbs = (int)s.outer.verbs.size(); n_pts = (int)s.outer.pts.size();
         }
@@ -701,24 +701,78 @@ __global__ void __launch_bounds__(GEO_THREADS) k_geo_unit_merge(GeoArgs a, const
     if (M->status != 1 || !M->plan_ok) return; // already an empty draw
     uint32_t ne = 0, ncv = 0, slots = 0;
     unsigned long long n_list = 0;
-    bool have_prev = false, prev_v = false;
+    bool have_prev = false, prev_v = false, sequential = false;
     int32_t prev_x = 0, prev_y0 = 0, prev_y1 = 0, prev_w = 0;
     for (uint32_t k = 0; k < M->unit_count; k++) {
         GeoPiece *pc = a.pieces + M->unit_first + k;
         if (pc->ne + pc->ncv == 0) continue;
-        // scan/path: combine_vertical merges a new vertical line with the last edge emitted when that is a vertical line on
-        // the same x.  Across units nobody looked: hand the batch to the host builder if it could have happened.
+        // edge_builder.rs combine_vertical merges a new vertical line with the last edge emitted when that is a vertical line
+        // on the same x with a matching end.  Across units nobody looked: if it would have happened, the draw's edges are
+        // built again below, by this thread, unit after unit into one list.
         if (have_prev && prev_v && pc->first_v && prev_x == pc->first_x) {
             rbh::Edge e, last;
             memset(&e, 0, sizeof(e)); memset(&last, 0, sizeof(last));
             e.x = pc->first_x; e.first_y = pc->first_y0; e.last_y = pc->first_y1; e.winding = pc->first_w;
             last.x = prev_x; last.first_y = prev_y0; last.last_y = prev_y1; last.winding = prev_w;
-            if (geo::fl::Sink<DVec>::combine_vertical(e, last) != 0) a.tot->deep = 1u;
+            if (geo::fl::Sink<DVec>::combine_vertical(e, last) != 0) sequential = true;
         }
         have_prev = true; prev_v = pc->last_v != 0; prev_x = pc->last_x; prev_y0 = pc->last_y0; prev_y1 = pc->last_y1; prev_w = pc->last_w;
         pc->line_base = ne; pc->curve_base = ncv; pc->slot_base = slots;
         ne += pc->ne; ncv += pc->ncv; slots += pc->slots; n_list += pc->n_list;
         if (slots >= (1u << 28)) { a.tot->too_large = 1u; empty_draw(a, ti, t); M->plan_ok = 0; return; }
+    }
+    if (sequential) {
+        GeoHeap heap = a.heap;
+        DVec<rbh::Edge> lines;
+        DVec<rbh::CurveRec> curves;
+        geo::fl::Sink<DVec> sink;
+        lines.init(&heap, ne + 16);
+        curves.init(&heap, ncv + 16);
+        sink.kinds.init(&heap, ne + ncv + 16);
+        M->plan_ok = 0; // the units' own lists are not used: k_geo_unit_pack skips this draw
+        if (!lines.ok() || !curves.ok() || !sink.kinds.ok()) { empty_draw(a, ti, t); return; }
+        sink.out = &lines;
+        sink.base = 0;
+        sink.curves = &curves;
+        sink.n_items = 0;
+        sink.shift = M->fp.shift;
+        for (uint32_t k = 0; k < M->unit_count; k++) {
+            const GeoPiece *pc = a.pieces + M->unit_first + k;
+            if (!pc->has_pts) continue;
+            const MapPts mp = map_for(t, pc->pts);
+            geo::fl::walk_verbs(pc->verbs, (int)pc->n_verbs, mp, M->fp.inside, t.tw, t.th, sink);
+        }
+        const uint32_t sne = lines.n, sncv = curves.n;
+        if (sne + sncv < 2) { empty_draw(a, ti, t); return; }
+        NoEnds ends{0};
+        const geo::fl::Packed po = geo::fl::pack_items(lines.p, sne, curves.p, sncv, reinterpret_cast<DevEdge *>(lines.p), curves.p, M->fp.shift, t.oy, M->r0, M->nr, ends);
+        if (po.too_large) { a.tot->too_large = 1u; empty_draw(a, ti, t); return; }
+        const rbh::IRect sc = M->sect;
+        DevDraw d;
+        memset(&d, 0, sizeof(d));
+        d.ox = t.ox; d.oy = t.oy;
+        d.sx = sc.x; d.sy = sc.y; d.sw = sc.w; d.sh = sc.h;
+        d.shift = M->fp.shift;
+        d.rule = 0;
+        d.paint = t.paint;
+        const int c0 = (t.ox + sc.x) / 32, c1 = (t.ox + sc.x + sc.w - 1) / 32;
+        if (ends.chains >= 128u) wide_q[atomicAdd(&a.tot->n_wide_q, 1u)] = t.draw;
+        d.edge_cnt = po.slots;
+        d.edge_off = (uint32_t)atomicAdd(&a.tot->n_slots, (unsigned long long)po.slots);
+        d.line_off = (uint32_t)(((const uint8_t *)lines.p - heap.base) / sizeof(DevEdge));
+        d.line_cnt = sne;
+        d.curve_off = (uint32_t)(((const uint8_t *)curves.p - heap.base) / sizeof(rbh::CurveRec));
+        d.curve_cnt = sncv;
+        d.r0 = (uint32_t)M->r0;
+        d.n_rows = (uint32_t)M->nr;
+        d.list_off = (uint32_t)atomicAdd(&a.tot->n_list, (unsigned long long)po.n_list);
+        d.row_base = (uint32_t)atomicAdd(&a.tot->n_row_off, (unsigned long long)M->nr + 1ull);
+        d.list_cap = (uint32_t)po.n_list;
+        atomicAdd(&a.tot->n_row_ent, (unsigned long long)M->nr);
+        atomicAdd(&a.tot->n_wpairs, (unsigned long long)M->nr * (unsigned long long)(c1 - c0 + 1));
+        atomicAdd(&a.tot->n_seq, 1u);
+        a.draws[t.draw] = d;
+        return;
     }
     if (ne + ncv < 2) { empty_draw(a, ti, t); M->plan_ok = 0; return; } // BasicEdgeBuilder::build: fewer than two edge objects
     GeoHeap heap = a.heap;
@@ -1074,9 +1128,9 @@ int rb_geo_finish(rb_batch *b)
             }
         }
         if (diag)
-            fprintf(stderr, "[geo] tasks %zu draws %zu (dash %zu stroke %zu hair %zu fill %zu + %zu units-tasks %zu units %u / %zu) upload %zu B heap %llu / %zu B slots %llu list %llu wide_q %u overflow %u wide %u deep %u too_large %u | host %.2f ms, enqueue %.2f ms, kernels done %.2f ms after the enqueue\n",
+            fprintf(stderr, "[geo] tasks %zu draws %zu (dash %zu stroke %zu hair %zu fill %zu + %zu units-tasks %zu units %u / %zu) upload %zu B heap %llu / %zu B slots %llu list %llu wide_q %u overflow %u wide %u deep %u too_large %u seq %u | host %.2f ms, enqueue %.2f ms, kernels done %.2f ms after the enqueue\n",
                     n_tasks, n_draws, G.n_dash_l, G.n_stroke_l, G.n_hair_l, G.n_fill_l, G.n_outline_l, G.n_units_l, T.n_units, G.max_units, G.total, T.heap_cursor, gp->heap_bytes, T.n_slots,
-                    T.n_list, T.n_wide_q, T.overflow, T.wide, T.deep, T.too_large, gp->t_built - gp->t_start, gp->t_enq - gp->t_built, t_done - gp->t_enq);
+                    T.n_list, T.n_wide_q, T.overflow, T.wide, T.deep, T.too_large, T.n_seq, gp->t_built - gp->t_start, gp->t_enq - gp->t_built, t_done - gp->t_enq);
         if (T.overflow && gp->attempt < 5) { // heap exhausted: again with eight times the heap
             g_geo_counts[2]++;
             gp->attempt++;

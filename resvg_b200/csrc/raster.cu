@@ -1130,7 +1130,10 @@ static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t 
     // batch while the geometry kernels, on their own stream, build the rest in one launch; the shares follow the two rates,
     // so a box with many cores per GPU gives the host more and eight processes sharing the box's cores give it next to
     // nothing.  RB_GEO_MODE / rb_debug_geo_mode: 1 = everything on the device, 2 = everything on the host.
-    size_t geo_from = 4096;
+    // a geometry launch costs a few milliseconds whatever its size (a dozen kernels, the latency of the longest draw, one
+    // round trip for the totals): with host threads to spare only large batches are worth it
+    const int host_threads_avail = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    size_t geo_from = host_threads_avail >= 8 ? 32768 : 4096;
     if (const char *e = getenv("RB_GEO_FROM")) geo_from = (size_t)std::max(1, atoi(e));
     const bool geo_ok = b->layer && !b->mask && b->layer->w <= 65536 && b->layer->h <= 65536 && !rb_debug_host_only_builder() && g_geo_mode != 2
                         && (g_geo_mode == 1 || n >= geo_from);

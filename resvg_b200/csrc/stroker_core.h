@@ -809,7 +809,7 @@ template <template <class> class Vec> struct Stroker {
         if (r == Degenerate) { side().line_to(qp.quad[2]); return true; }
         if (++recursion_depth > 11 * 3) return false;
 #if defined(__CUDA_ARCH__)
-        if (recursion_depth > 30) { too_deep = true; return false; }
+        if (recursion_depth > 80) { too_deep = true; return false; } // never: the limits above are lower (GEO_STACK holds 80 levels)
 #endif
         QuadConstruct half;
         half.init_with_start(qp);
@@ -860,7 +860,7 @@ template <template <class> class Vec> struct Stroker {
         const int limits[2] = {5 * 3, 26 * 3};
         if (++recursion_depth > limits[found_tangents ? 1 : 0]) return false;
 #if defined(__CUDA_ARCH__)
-        if (recursion_depth > 30) { too_deep = true; return false; }
+        if (recursion_depth > 80) { too_deep = true; return false; } // never: the limits above are lower (GEO_STACK holds 80 levels)
 #endif
         QuadConstruct half;
         if (!half.init_with_start(qp)) { side().line_to(qp.quad[2]); --recursion_depth; return true; }

@@ -57,6 +57,18 @@ def gather_ints(values, world: int, device=None):
     return [[int(v) for v in o.tolist()] for o in out]
 
 
+def gather_floats(values, world: int, device=None):
+    """All ranks' float tuples (per-rank timings), as a list indexed by rank."""
+    if world == 1:
+        return [[float(v) for v in values]]
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [[float(v) for v in o.tolist()] for o in out]
+
+
 def aggregate_throughput(units_per_rank: float, world: int, seconds: float) -> float:
     """Whole-job throughput under weak scaling: every rank processed `units_per_rank` in `seconds` (max over ranks)."""
     return world * units_per_rank / seconds

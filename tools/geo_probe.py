@@ -15,6 +15,7 @@ def main():
     wl = sys.argv[1] if len(sys.argv) > 1 else "paths8k"
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     W, H, n_paths, seed = bench.WORKLOADS[wl]
+    seed += int(sys.argv[3]) if len(sys.argv) > 3 else 0
     scene = scenes.paths_scene(W, H, n_paths, seed)
     scene["paints"] = scenes.to_paint_array(scene, _ffi.Paint)
     scene["strokes"] = scenes.to_stroke_array(scene, _ffi.Stroke)
