@@ -388,7 +388,6 @@ def run_icons(args, rank, local_rank, world, torch, dist):
     ctx.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
 
-    per_rank = shard.gather_floats([e2e_s * 1e3, e2e_phase[1] / e2e_steps * 1e3, e2e_phase[2] / e2e_steps * 1e3, e2e_geo[3] / 1e3], world, f"cuda:{local_rank}")
     ms_step, ms_kernel, e2e_s = shard.max_over_ranks([ms_step, ms_kernel, e2e_s], world, f"cuda:{local_rank}")
     if rank != 0:
         return

@@ -1235,6 +1235,7 @@ int rb_geo_host_build(rb_batch *b, int W, int H, int n_threads, rb_stage_alloc a
     if (end == 0 || end > b->n_total) end = b->n_total;
     if (begin >= end) return RB_OK;
     const size_t n = end - begin;
+    const auto t0g = Clock::now();
     const size_t n_chunks = (n + kChunk - 1) / kChunk;
     int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
     nt = std::max(1, std::min<int>(nt, (int)n_chunks));
@@ -1259,6 +1260,7 @@ int rb_geo_host_build(rb_batch *b, int W, int H, int n_threads, rb_stage_alloc a
         chunks[c].worker = t;
         geo_build_chunk(b, begin + c * kChunk, begin + std::min(n, (c + 1) * kChunk), W, H, workers[(size_t)t].get(), &chunks[c]);
     });
+    const auto t_chunks = Clock::now();
     GeoBlock G;
     for (auto &c : chunks) {
         c.gt = G.n_tasks; c.gv = G.n_verbs; c.gp = G.n_pts; c.gd = G.n_dashes; c.gpa = G.n_paints; c.gs = G.n_stops; c.gdraw = G.n_draws;
@@ -1341,6 +1343,7 @@ int rb_geo_host_build(rb_batch *b, int W, int H, int n_threads, rb_stage_alloc a
     size_t hint_bytes = 0;
     for (size_t i = 0; i < G.n_tasks; i++) hint_bytes += (o_tasks[i].flags & GT_UNITS) ? (size_t)o_tasks[i].max_units * 6144 + 8192 : (size_t)o_tasks[i].hint * 96 + 2048;
     G.heap_hint = hint_bytes;
+    if (getenv("RB_GEO_HOST_DIAG")) fprintf(stderr, "[geo host] chunks %.2f ms, layout + copy + lists %.2f ms\n", (double)std::chrono::duration_cast<std::chrono::microseconds>(t_chunks - t0g).count() / 1e3, (double)us_since(t_chunks) / 1e3);
     *gb = G;
     *block = blk;
     return RB_OK;
