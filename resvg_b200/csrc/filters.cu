@@ -706,6 +706,101 @@ k_box_blur_h2(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int 
     }
 }
 
+// Vertical + horizontal pass of one iteration in ONE launch, for the small radii SVG blurs mostly have (stdDeviation <= ~9:
+// r <= 8).  The reference quantises to u8 after every pass (box_blur.rs:74-82: vert into the back buffer, horz back into
+// the front buffer), so passes of the same axis cannot be merged, but a (vert, horz) PAIR can: a CTA stages a 128 x 32
+// output tile plus its halo (r_v rows above / below, r_h columns left / right, zero outside the cell like the reference's
+// default-pixel border) in shared memory, runs the vertical sliding sums into a second shared-memory plane — the
+// intermediate u8 image the reference keeps in its back buffer, only for this tile — and the horizontal ones from there.
+// Per iteration the layer is read once and written once: 40 B/px for the five iterations instead of 80 — but see the
+// measurement at the call site: opt-in only.
+constexpr int VH_TW = 128, VH_TH = 32, VH_THREADS = 256, VH_MAX_R = 8, VH_SEG = 16;
+__global__ void __launch_bounds__(VH_THREADS)
+k_box_blur_vh(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int pitch, const BoxCell *__restrict__ cells, int it, int rv_max,
+              int rh_max)
+{
+    extern __shared__ uint32_t vh_sm[];
+    const BoxCell c = cells[blockIdx.z];
+    const int rv = c.rv[it], rh = c.rh[it];
+    const int x0 = blockIdx.x * VH_TW, y0 = blockIdx.y * VH_TH;
+    if (x0 >= c.w || y0 >= c.h) return;
+    const int in_pitch = (VH_TW + 2 * rh_max) | 1; // odd: the horizontal phase walks rows with lane = row
+    const int in_h = VH_TH + 2 * rv_max;
+    uint32_t *in = vh_sm;                    // (VH_TH + 2 rv) rows x (VH_TW + 2 rh) columns staged from the source
+    uint32_t *mid = vh_sm + in_h * in_pitch; // VH_TH rows x (VH_TW + 2 rh) columns after the vertical pass
+    const int ew = VH_TW + 2 * rh, eh = VH_TH + 2 * rv;
+    const size_t org = (size_t)c.y * pitch + c.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int ry = warp; ry < eh; ry += VH_THREADS / 32) {
+        const int gy = y0 - rv + ry;
+        const bool row_in = gy >= 0 && gy < c.h;
+        const uint32_t *srow = src + org + (size_t)gy * pitch;
+        for (int rx = lane; rx < ew; rx += 32) {
+            const int gx = x0 - rh + rx;
+            in[ry * in_pitch + rx] = (row_in && gx >= 0 && gx < c.w) ? __ldg(srow + gx) : 0u;
+        }
+    }
+    __syncthreads();
+    // vertical: a column of the staged tile per thread, the tile's rows in two halves so that all threads have work
+    {
+        const uint32_t M = rv ? box2_magic(rv) : 0u;
+        const uint32_t bias = (uint32_t)rv | ((uint32_t)rv << 16);
+        for (int wi = threadIdx.x; wi < 2 * ew; wi += VH_THREADS) {
+            const int half = wi >= ew ? 1 : 0, col = wi - half * ew;
+            const int yb = half * (VH_TH / 2);
+            if (rv == 0) {
+                for (int y = yb; y < yb + VH_TH / 2; y++) mid[y * in_pitch + col] = in[y * in_pitch + col];
+                continue;
+            }
+            uint32_t rb = bias, ga = bias;
+            for (int k = 0; k <= 2 * rv; k++) box2_add(rb, ga, in[(yb + k) * in_pitch + col]);
+#pragma unroll 4
+            for (int y = yb; y < yb + VH_TH / 2; y++) {
+                mid[y * in_pitch + col] = box2_out(rb, ga, M);
+                if (y + 1 < yb + VH_TH / 2) {
+                    box2_add(rb, ga, in[(y + 2 * rv + 1) * in_pitch + col]);
+                    box2_sub(rb, ga, in[y * in_pitch + col]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // horizontal: lane = row, warp = a segment of VH_SEG output columns; results go back into the (now free) input plane
+    uint32_t *outp = in;
+    constexpr int out_pitch = VH_TW + 1;
+    {
+        const int row = lane;
+        const uint32_t M = rh ? box2_magic(rh) : 0u;
+        const uint32_t bias = (uint32_t)rh | ((uint32_t)rh << 16);
+        const uint32_t *mrow = mid + row * in_pitch;
+        for (int seg = warp; seg < VH_TW / VH_SEG; seg += VH_THREADS / 32) {
+            const int xb = seg * VH_SEG;
+            if (rh == 0) {
+                for (int j = 0; j < VH_SEG; j++) outp[row * out_pitch + xb + j] = mrow[xb + j];
+                continue;
+            }
+            uint32_t rb = bias, ga = bias;
+            for (int k = 0; k <= 2 * rh; k++) box2_add(rb, ga, mrow[xb + k]);
+#pragma unroll 4
+            for (int j = 0; j < VH_SEG; j++) {
+                outp[row * out_pitch + xb + j] = box2_out(rb, ga, M);
+                if (j + 1 < VH_SEG) {
+                    box2_add(rb, ga, mrow[xb + j + 2 * rh + 1]);
+                    box2_sub(rb, ga, mrow[xb + j]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int ry = warp; ry < VH_TH; ry += VH_THREADS / 32) {
+        const int gy = y0 + ry;
+        if (gy >= c.h) break;
+        uint32_t *drow = dst + org + (size_t)gy * pitch + x0;
+        for (int rx = lane; rx < VH_TW; rx += 32)
+            if (x0 + rx < c.w) drow[rx] = outp[ry * out_pitch + rx];
+    }
+}
+
 // Runs the 5 x (vertical, horizontal) passes over a list of cells, ping-ponging between `a` (holding the input) and `b`;
 // returns the buffer holding the result in *result.  `dev_cells` is the device copy of `cells`.  A pass whose radius is 0
 // in every cell is skipped (box_blur.rs:86-89 copies); in a pass some cells need, the others copy.
@@ -733,6 +828,20 @@ static int box2_run_cells(rb_ctx *ctx, uint32_t *a, uint32_t *b, int pitch, cons
         for (int i = 0; i < n_cells; i++) {
             rv = std::max(rv, (int)cells[i].rv[it]);
             rh = std::max(rh, (int)cells[i].rh[it]);
+        }
+        // opt-in (RB_BOX_VH=1): measured SLOWER than the two tuned single-axis passes on the B200 — 8192 x 8192, sigma 4: 1.79 ms
+        // against 1.41 ms for the five iterations; the tile kernel is bound by its shared-memory sliding sums (IPC ~1.4), not by the
+        // 40 B/px it moves
+        static const bool use_vh = getenv("RB_BOX_VH") && atoi(getenv("RB_BOX_VH")) != 0;
+        if (use_vh && rv > 0 && rh > 0 && rv <= VH_MAX_R && rh <= VH_MAX_R) {
+            // both passes of the iteration in one launch (k_box_blur_vh)
+            const int in_pitch = (VH_TW + 2 * rh) | 1;
+            const size_t smem = ((size_t)(VH_TH + 2 * rv) * in_pitch + (size_t)VH_TH * in_pitch) * 4;
+            dim3 grid((max_w + VH_TW - 1) / VH_TW, (max_h + VH_TH - 1) / VH_TH, n_cells);
+            k_box_blur_vh<<<grid, VH_THREADS, smem, ctx->stream>>>(cur, other, pitch, dev_cells, it, rv, rh);
+            RB_LAUNCHED(ctx, "box_blur_vh");
+            std::swap(cur, other);
+            continue;
         }
         if (rv > 0 && 2 * rv + 1 < BOX2V_RING_MIN) {
             int rows = 128;
