@@ -574,10 +574,14 @@ def run_stack4k(args, rank, local_rank, world, torch, dist):
     from resvg_b200 import shard
     W, H, levels, seed = WORKLOADS["stack4k"]
     ctx = rb.Context(local_rank)
-    blob = stack_tree_stream(f"stack4k_r{rank % 8}.rbt")
+    # --shard strips: ONE document, rank r renders rows strip_for_rank(H, r, world) of it (rb_render_strip:
+    # bit-identical to the whole render, tests/test_stack.py); otherwise one document per GPU
+    strips = args.shard == "strips"
+    y0, rows = shard.strip_for_rank(H, rank, world) if strips else (0, H)
+    blob = stack_tree_stream(f"stack4k_r{0 if strips else rank % 8}.rbt")
     tree = rb.tree.Tree(blob)
     ident = (1.0, 0.0, 0.0, 1.0, 0.0, 0.0)
-    target = ctx.layer(W, H)
+    target = ctx.layer(W, rows)
 
     def barrier():
         ctx.synchronize()
@@ -588,7 +592,10 @@ def run_stack4k(args, rank, local_rank, world, torch, dist):
 
     def step():
         target.fill(0, 0, 0, 0)
-        rb.tree.render(tree, ident, target)
+        if strips:
+            rb.tree.render_strip(tree, ident, W, H, y0, target)
+        else:
+            rb.tree.render(tree, ident, target)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -612,12 +619,17 @@ def run_stack4k(args, rank, local_rank, world, torch, dist):
     ms_comp = ctx.timer_end() / 10
     a.close(); b2.close()
 
-    pinned = rb.PinnedBuffer(W * H * 4)
+    pinned = rb.PinnedBuffer(W * rows * 4)
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
 
     def e2e_step():
         target.fill(0, 0, 0, 0)
-        rb.tree.submit(blob, ident, target)          # host stream -> parse -> traversal -> kernels
+        if strips:
+            t = rb.tree.Tree(blob)                   # host stream -> parse
+            rb.tree.render_strip(t, ident, W, H, y0, target)
+            t.close()
+        else:
+            rb.tree.submit(blob, ident, target)      # host stream -> parse -> traversal -> kernels
         target.download_ptr(pinned.array.ctypes.data)
 
     e2e_step()
@@ -636,22 +648,25 @@ def run_stack4k(args, rank, local_rank, world, torch, dist):
     peak, peak_src = measured_peaks()
     comp_bytes = 12 * W * H
     out = {
-        "metric": "Mpixels/s rendered", "value": shard.aggregate_throughput(mpx, world, ms_step * 1e-3), "unit": "Mpx/s",
+        "metric": "Mpixels/s rendered", "value": shard.aggregate_throughput(mpx, 1 if strips else world, ms_step * 1e-3), "unit": "Mpx/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8/u16 fixed point + f32", "data": "synthetic",
+        "scaling": "strong" if strips else "weak", "vs_baseline": None, "dtype": "u8/u16 fixed point + f32", "data": "synthetic",
         "config": {"workload": "stack4k", "canvas": [W, H], "levels": levels,
                    "recipe": "level k: opacity U[0.85,0.99]; k%4=0 luminance mask (gradient rect), 1 clip-path (circle, every 8th nested), "
                              "2 pattern-filled rect (tile 32-128 px), 3 plain; 10 C2-style shapes per level in a box inset 16 px per level",
                    "host": "the usvg tree arrives as an RBT1 stream (%d bytes); ONE rb_render call per document, traversal in C++ inside the library" % len(blob),
                    "l2": "layers of up to 64 MiB; every level allocates, composites and masks its layer (> 126 MB L2 across a level)",
-                   "sharding": "one document per GPU, no collective"},
+                   "sharding": ("ONE document cut into %d canvas strips (rb_render_strip): draws that reach the canvas directly are built against "
+                                "the whole canvas, isolated groups are rendered as in the whole render and composited shifted, groups that miss "
+                                "the strip are skipped; no halo, no collective, every rank downloads its strip" % world) if strips
+                               else "one document per GPU, no collective"},
         "gpu_launches": launches, "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "k_draw_layer (layer composite, the traversal's most frequent full-layer pass)",
                      "achieved": comp_bytes / (ms_comp * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": comp_bytes / (ms_comp * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes": comp_bytes, "kernel_ms": ms_comp, "model": "12 B/px: source read, destination read + write"},
-        "e2e": {"value": shard.aggregate_throughput(mpx, world, e2e_s), "unit": "Mpx/s", "h2d_bytes_per_step": int(h2d) + len(blob),
-                "d2h_bytes_per_step": W * H * 4, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
+        "e2e": {"value": shard.aggregate_throughput(mpx, 1 if strips else world, e2e_s), "unit": "Mpx/s", "h2d_bytes_per_step": int(h2d) + len(blob),
+                "d2h_bytes_per_step": W * rows * 4, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
     }
     if world == 1 and not args.no_cpu_baseline:
         from tests import svgfront as F               # the CPU checker's traversal: cpu_baseline / parity only

@@ -366,6 +366,11 @@ int rb_render(rb_ctx *ctx, const rb_tree *tree, const float ts[6], rb_layer *tar
 /* resvg::render_node(node, transform, pixmap) — lib.rs:55-70: the node is placed at -abs_layer_bounding_box.  RB_ERR_INVALID
  * is the reference's None (unknown id / zero-sized node). */
 int rb_render_node(rb_ctx *ctx, const rb_tree *tree, const char *id, const float ts[6], rb_layer *target);
+/* Canvas-strip sharding of ONE document across GPUs: renders rows [y0, y0 + height(target)) of the
+ * canvas_w x canvas_h render of `tree` into `target` (whose width must be canvas_w).  The strip holds exactly the pixels of
+ * the whole-canvas rb_render: draws that reach the target directly are clipped and flattened against the whole canvas,
+ * isolated groups are rendered as in the whole render (those that miss the strip are skipped) and composited shifted. */
+int rb_render_strip(rb_ctx *ctx, const rb_tree *tree, const float ts[6], uint32_t canvas_w, uint32_t canvas_h, int32_t y0, rb_layer *target);
 /* One-shot form: parse + render + free (SURVEY 8(b) `rb_submit`). */
 int rb_submit(rb_ctx *ctx, const void *stream, size_t len, const float ts[6], rb_layer *target);
 /* resvg_render (c-api/lib.rs:875-893) over a HOST pixmap: upload (the caller's pixels are the canvas), render, download. */

@@ -169,6 +169,7 @@ SIGNATURES = {
     "rb_tree_node_bbox": (_i, [_vp, C.c_char_p, f32p]),
     "rb_render": (_i, [_vp, _vp, f32p, _vp]),
     "rb_render_node": (_i, [_vp, _vp, C.c_char_p, f32p, _vp]),
+    "rb_render_strip": (_i, [_vp, _vp, f32p, _u32, _u32, C.c_int32, _vp]),
     "rb_submit": (_i, [_vp, C.c_char_p, C.c_size_t, f32p, _vp]),
     "rb_render_to_host": (_i, [_vp, _vp, f32p, _u32, _u32, _vp]),
 }

@@ -1215,6 +1215,7 @@ extern "C" int rb_fill_path(rb_layer *layer, const uint8_t *verbs, int32_t n_ver
         if (st != RB_OK) return st;
         layer->pending_n = 0;
         layer->ctx->dirty.push_back(layer);
+        if (layer->vp_w > 0) (void)rb_batch_set_viewport(layer->pending, layer->vp_x, layer->vp_y, (uint32_t)layer->vp_w, (uint32_t)layer->vp_h);
     }
     int st = rb_batch_fill_path(layer->pending, verbs, n_verbs, points, n_points, paint, fill_rule, ts);
     if (st != RB_OK) return st; // nothing was recorded
@@ -1237,6 +1238,7 @@ extern "C" int rb_stroke_path(rb_layer *layer, const uint8_t *verbs, int32_t n_v
         if (st != RB_OK) return st;
         layer->pending_n = 0;
         layer->ctx->dirty.push_back(layer);
+        if (layer->vp_w > 0) (void)rb_batch_set_viewport(layer->pending, layer->vp_x, layer->vp_y, (uint32_t)layer->vp_w, (uint32_t)layer->vp_h);
     }
     const size_t before = layer->pending->n_total;
     int st = rb_batch_stroke_path(layer->pending, verbs, n_verbs, points, n_points, paint, stroke, ts);

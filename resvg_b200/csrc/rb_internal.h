@@ -79,6 +79,9 @@ struct rb_layer {
     // tile-kernel launch instead of one each.
     struct rb_batch *pending = nullptr;
     uint32_t pending_n = 0;
+    // Canvas strips (rb_render_strip): the layer is a window of a larger pixmap placed at (vp_x, vp_y) relative to it; immediate
+    // draws are recorded with that viewport (rb_batch_set_viewport), i.e. built against the whole pixmap.  vp_w == 0: none.
+    int32_t vp_x = 0, vp_y = 0, vp_w = 0, vp_h = 0;
 };
 
 // Executes the layer's pending immediate draws, if any.  Every entry point that reads or writes a layer calls it first.

@@ -202,6 +202,10 @@ void Renderer::render_group(const rbt::Group &group, const Context &ctx, const X
         if (!int_rect_from_xywh(f2i(floorf(bbox.x)), f2i(floorf(bbox.y)), f2u(cw), f2u(ch), &r)) return;
         if (!fit_to_rect(r, ctx.max_bbox, &ibbox)) return;
     }
+    if (on_strip(pixmap)) { // canvas strips: a group whose layer misses the strip's rows draws nothing here
+        const int64_t top = ibbox.y, bottom = (int64_t)ibbox.y + ibbox.h;
+        if (bottom <= strip_y0 || top >= (int64_t)strip_y0 + rb_layer_height(strip)) return;
+    }
     // keep the sub-pixel phase of the layer (render.rs:94-106)
     float dx = bbox.x, dy = bbox.y;
     dx -= bbox.x - (float)ibbox.x;
@@ -222,7 +226,7 @@ void Renderer::render_group(const rbt::Group &group, const Context &ctx, const X
     if (group.clip_path) clip_apply(*group.clip_path, ts, sub.get());
     if (group.mask) mask_apply(*group.mask, ctx, ts, sub.get());
     if (status != RB_OK) return;
-    RBR_TRY(rb_draw_layer(pixmap, sub.get(), ibbox.x, ibbox.y, group.opacity, convert_blend_mode(group.blend_mode)));
+    RBR_TRY(rb_draw_layer(pixmap, sub.get(), ibbox.x, ibbox.y - (on_strip(pixmap) ? strip_y0 : 0), group.opacity, convert_blend_mode(group.blend_mode)));
 }
 
 // ---- path.rs ---------------------------------------------------------------------------------------------------------
@@ -452,10 +456,16 @@ void Renderer::render_image(const rbt::Image &image, const Xform &transform, rb_
 void Renderer::render_vector(const rbt::Tree &tree, const Xform &transform, rb_layer *pixmap)
 {
     Layer sub;
-    RBR_TRY(new_layer(rb_layer_width(pixmap), rb_layer_height(pixmap), &sub));
-    render_tree(tree, transform, sub.get());
+    const bool st = on_strip(pixmap); // canvas strips: the nested document is rendered on a canvas-sized layer as always
+    RBR_TRY(new_layer(st ? canvas_w : rb_layer_width(pixmap), st ? canvas_h : rb_layer_height(pixmap), &sub));
+    {
+        rb_layer *outer = strip;
+        strip = nullptr; // the nested tree's target is an ordinary layer
+        render_tree(tree, transform, sub.get());
+        strip = outer;
+    }
     if (status != RB_OK) return;
-    RBR_TRY(rb_draw_layer(pixmap, sub.get(), 0, 0, 1.0f, RB_BLEND_SOURCE_OVER));
+    RBR_TRY(rb_draw_layer(pixmap, sub.get(), 0, st ? -strip_y0 : 0, 1.0f, RB_BLEND_SOURCE_OVER));
 }
 
 // image.rs:173-206 (the decoders of image.rs:62-170 stay on the host: the stream carries premultiplied RGBA8)
@@ -483,7 +493,8 @@ void Renderer::render_raster(const rbt::Image &image, const Xform &transform, rb
 // lib.rs:34-43
 void Renderer::render_tree(const rbt::Tree &tree, const Xform &transform, rb_layer *pixmap)
 {
-    const Context ctx{max_filter_bbox(rb_layer_width(pixmap), rb_layer_height(pixmap))};
+    const bool st = on_strip(pixmap);
+    const Context ctx{max_filter_bbox(st ? canvas_w : rb_layer_width(pixmap), st ? canvas_h : rb_layer_height(pixmap))};
     render_nodes(tree.root, ctx, transform, pixmap);
 }
 
@@ -572,6 +583,26 @@ extern "C" int rb_render(rb_ctx *ctx, const rb_tree *tree, const float ts[6], rb
     rbr::Renderer r(ctx);
     r.render_tree(*tree->t, ts ? rbh::Xform::from(ts) : rbh::Xform(), target);
     return r.status;
+}
+
+// Canvas-strip sharding of a tree: rows [y0, y0 + height of target) of the canvas_w x canvas_h render.
+extern "C" int rb_render_strip(rb_ctx *ctx, const rb_tree *tree, const float ts[6], uint32_t canvas_w, uint32_t canvas_h, int32_t y0, rb_layer *target)
+{
+    if (!ctx || !tree || !target || canvas_w == 0 || canvas_h == 0 || y0 < 0 || rb_layer_width(target) != canvas_w
+        || (uint64_t)y0 + rb_layer_height(target) > canvas_h)
+        return RB_ERR_INVALID;
+    int st = rb_layer_flush(target);
+    if (st != RB_OK) return st;
+    rbr::Renderer r(ctx);
+    r.strip = target;
+    r.strip_y0 = y0;
+    r.canvas_w = canvas_w;
+    r.canvas_h = canvas_h;
+    target->vp_x = 0; target->vp_y = -y0; target->vp_w = (int32_t)canvas_w; target->vp_h = (int32_t)canvas_h;
+    r.render_tree(*tree->t, ts ? rbh::Xform::from(ts) : rbh::Xform(), target);
+    st = rb_layer_flush(target); // the draws recorded with the strip's viewport
+    target->vp_x = target->vp_y = target->vp_w = target->vp_h = 0;
+    return r.status != RB_OK ? r.status : st;
 }
 
 extern "C" int rb_render_node(rb_ctx *ctx, const rb_tree *tree, const char *id, const float ts[6], rb_layer *target)

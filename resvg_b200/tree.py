@@ -336,6 +336,12 @@ def render(tree: Tree, ts, layer):
     layer.ctx.check(lib.rb_render(layer.ctx._h, tree._h, _ts6(ts), layer._h), "rb_render")
 
 
+def render_strip(tree: Tree, ts, canvas_w: int, canvas_h: int, y0: int, layer):
+    """Rows [y0, y0 + layer.height) of the canvas_w x canvas_h render of `tree` (rb_render_strip: canvas-strip sharding of one
+    document across GPUs, bit-identical to the whole-canvas render)."""
+    layer.ctx.check(lib.rb_render_strip(layer.ctx._h, tree._h, _ts6(ts), canvas_w, canvas_h, y0, layer._h), "rb_render_strip")
+
+
 def render_node(tree: Tree, node_id: str, ts, layer) -> bool:
     """resvg::render_node(node, transform, pixmap) -> False for the reference's None."""
     st = lib.rb_render_node(layer.ctx._h, tree._h, node_id.encode(), _ts6(ts), layer._h)

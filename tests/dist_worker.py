@@ -51,9 +51,18 @@ def main():
             ccrc = zlib.crc32(img.tobytes(), ccrc)
             passed += F.diff_pixels(img, np.array(Image.open(files[i][:-5] + ".png").convert("RGBA"))) == 0
         corpus = shard.gather_ints([passed, ccrc], world)
+        # one document cut into canvas strips: rank r owns rows strip_for_rank(height, r, world) of the render
+        # (on a GPU: rb_render_strip; here the checker renders the document and keeps the rank's rows); the strips tile the
+        # canvas and only their checksums cross ranks
+        from resvg_b200 import scenes as _scenes
+        from tests import svgfront as _F
+        doc = _F.parse(_scenes.stack_svg(96, 6, inset=3.0, shapes=3))
+        whole = _F.render_scene(doc, OracleBackend(), 96)
+        y0, rows = shard.strip_for_rank(whole.shape[0], rank, world)
+        strips = shard.gather_ints([y0, rows, zlib.crc32(np.ascontiguousarray(whole[y0:y0 + rows]).tobytes())], world)
         if rank == 0:
             with open(out_path, "w") as f:
-                json.dump({"world": world, "per_rank": per_rank, "ms": ms, "render_s": real, "docs": all_docs, "corpus": corpus,
+                json.dump({"world": world, "per_rank": per_rank, "ms": ms, "render_s": real, "docs": all_docs, "corpus": corpus, "strips": strips,
                            "value": shard.aggregate_throughput(W * H / 1e6, world, ms * 1e-3)}, f)
     finally:
         dist.destroy_process_group()

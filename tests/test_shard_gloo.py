@@ -99,3 +99,12 @@ def test_two_ranks_gloo(tmp_path):
                 crc = zlib.crc32(F.render_scene(_json.load(f), OracleBackend(), 300).tobytes(), crc)
         serial.append([8, crc])
     assert rep["corpus"] == serial
+    # one document in canvas strips: the ranks' rows tile the canvas, their checksums are those of the whole render's rows
+    doc = F.parse(scenes.stack_svg(96, 6, inset=3.0, shapes=3))
+    whole = F.render_scene(doc, OracleBackend(), 96)
+    want_strips = []
+    for r in range(2):
+        y0, rows = shard.strip_for_rank(whole.shape[0], r, 2)
+        want_strips.append([y0, rows, zlib.crc32(np.ascontiguousarray(whole[y0:y0 + rows]).tobytes())])
+    assert rep["strips"] == want_strips
+    assert want_strips[0][0] == 0 and want_strips[0][1] == want_strips[1][0] and want_strips[1][0] + want_strips[1][1] == whole.shape[0]

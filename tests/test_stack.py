@@ -44,3 +44,63 @@ def test_gpu_stack_matches_checker(ctx, size, levels, inset):
     # layer composites with opacity and luminance masks run in f32: one unit per stage
     assert d.max() <= 1, f"max |gpu - checker| = {d.max()}, {int((d > 1).sum())} bytes"
     assert (d > 0).mean() < 0.02
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size,levels,inset,cuts", [(512, 16, 8.0, (0, 200, 328, 512)), (300, 8, 5.5, (0, 8, 96, 300))])
+def test_gpu_tree_rendered_in_canvas_strips_equals_the_whole_render(ctx, size, levels, inset, cuts):
+    """one document cut into canvas strips (rb_render_strip, one strip per GPU) — nested groups with opacity,
+    luminance masks, clip-paths and patterns crossing the cuts — holds exactly the pixels of the whole-canvas rb_render."""
+    import resvg_b200 as rb
+
+    sc = _scene(size, levels, inset)
+    pw, ph, ts = F.target_for(sc, size)
+    tree = rb.tree.Tree(sc)
+    whole = ctx.layer(pw, ph)
+    rb.tree.render(tree, ts, whole)
+    want = whole.download()
+    got = np.zeros_like(want)
+    rows = [min(c, ph) for c in cuts]
+    for y0, y1 in zip(rows[:-1], rows[1:]):
+        strip = ctx.layer(pw, y1 - y0)
+        rb.tree.render_strip(tree, ts, pw, ph, y0, strip)
+        got[y0:y1] = strip.download()
+    tree.close()
+    assert rows[-1] == ph
+    assert np.array_equal(got, want), f"{int((got != want).any(axis=-1).sum())} pixels differ between the strips and the whole render"
+
+
+@pytest.mark.gpu
+def test_gpu_corpus_scenes_in_strips(ctx):
+    """The same on fixtures of the regression corpus that carry filters, masks, clip-paths and nested svg images."""
+    import glob
+    import json
+    import os
+
+    import resvg_b200 as rb
+
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scenes")
+    names = sorted(glob.glob(os.path.join(root, "*.json")))
+    picked = [n for n in names if any(k in os.path.basename(n) for k in ("feGaussianBlur", "mask__", "clipPath__", "pattern__", "image__", "opacity"))][::7][:40]
+    assert len(picked) >= 20
+    checked = 0
+    for n in picked:
+        with open(n) as f:
+            sc = json.load(f)
+        pw, ph, ts = F.target_for(sc, 300)
+        if ph < 24:
+            continue
+        tree = rb.tree.Tree(sc)
+        whole = ctx.layer(pw, ph)
+        rb.tree.render(tree, ts, whole)
+        want = whole.download()
+        got = np.zeros_like(want)
+        cut = (ph // 3) | 1
+        for y0, y1 in ((0, cut), (cut, ph)):
+            strip = ctx.layer(pw, y1 - y0)
+            rb.tree.render_strip(tree, ts, pw, ph, y0, strip)
+            got[y0:y1] = strip.download()
+        tree.close()
+        assert np.array_equal(got, want), f"{os.path.basename(n)}: {int((got != want).any(axis=-1).sum())} pixels differ"
+        checked += 1
+    assert checked >= 20
