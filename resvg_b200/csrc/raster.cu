@@ -1279,6 +1279,7 @@ extern "C" int rb_mask_fill_path(rb_mask *mask, const uint8_t *verbs, int32_t n_
     memset(&paint, 0, sizeof(paint));
     paint.anti_alias = anti_alias;
     paint.blend_mode = RB_BLEND_SOURCE_OVER;
+    if (mask->vp_w > 0) { b.vp_x = mask->vp_x; b.vp_y = mask->vp_y; b.vp_w = mask->vp_w; b.vp_h = mask->vp_h; }
     int st = rb_batch_record(&b, verbs, n_verbs, points, n_points, &paint, fill_rule, ts);
     if (st != RB_OK) return st;
     return rb_batch_submit(&b, 1);

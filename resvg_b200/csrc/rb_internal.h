@@ -99,6 +99,7 @@ struct rb_mask {
     rb_ctx *ctx;
     uint32_t w, h;
     uint8_t *d; // w*h bytes
+    int32_t vp_x = 0, vp_y = 0, vp_w = 0, vp_h = 0; // a window of a larger mask, like rb_layer's (canvas strips)
 };
 
 // Host-side phase timers (RB_PROFILE=1 prints them when a context is destroyed): where a traversal's wall time goes.

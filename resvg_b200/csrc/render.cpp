@@ -145,6 +145,22 @@ int Renderer::new_layer(uint32_t w, uint32_t h, Layer *out)
     return RB_OK;
 }
 
+// rows [y0, y0 + height) of a virtual full_w x full_h pixmap; an ordinary layer is the window of itself
+struct Win { bool on; int32_t y0; uint32_t full_w, full_h; };
+static Win window_of(const rb_layer *l)
+{
+    if (l->vp_w > 0) return Win{true, -l->vp_y, (uint32_t)l->vp_w, (uint32_t)l->vp_h};
+    return Win{false, 0, l->w, l->h};
+}
+
+int Renderer::new_layer_like(const rb_layer *like, Layer *out)
+{
+    int st = new_layer(like->w, like->h, out);
+    if (st != RB_OK) return st;
+    (*out)->vp_x = like->vp_x; (*out)->vp_y = like->vp_y; (*out)->vp_w = like->vp_w; (*out)->vp_h = like->vp_h;
+    return RB_OK;
+}
+
 // A failed device call ends the traversal: the status is kept and every later step is skipped.
 #define RBR_TRY(call)                          \
     do {                                       \
@@ -202,9 +218,14 @@ void Renderer::render_group(const rbt::Group &group, const Context &ctx, const X
         if (!int_rect_from_xywh(f2i(floorf(bbox.x)), f2i(floorf(bbox.y)), f2u(cw), f2u(ch), &r)) return;
         if (!fit_to_rect(r, ctx.max_bbox, &ibbox)) return;
     }
-    if (on_strip(pixmap)) { // canvas strips: a group whose layer misses the strip's rows draws nothing here
-        const int64_t top = ibbox.y, bottom = (int64_t)ibbox.y + ibbox.h;
-        if (bottom <= strip_y0 || top >= (int64_t)strip_y0 + rb_layer_height(strip)) return;
+    // canvas strips: inside a window only the rows of the group's layer that can reach it are rendered
+    const Win win = window_of(pixmap);
+    int32_t sub_top = ibbox.y;
+    uint32_t sub_rows = ibbox.h;
+    if (win.on) {
+        const int64_t t = std::max<int64_t>(ibbox.y, win.y0), b = std::min<int64_t>((int64_t)ibbox.y + ibbox.h, (int64_t)win.y0 + rb_layer_height(pixmap));
+        if (b <= t) return; // the group misses the window
+        if (group.filters.empty()) { sub_top = (int32_t)t; sub_rows = (uint32_t)(b - t); } // a filter reads beyond its rows: whole layer
     }
     // keep the sub-pixel phase of the layer (render.rs:94-106)
     float dx = bbox.x, dy = bbox.y;
@@ -214,9 +235,10 @@ void Renderer::render_group(const rbt::Group &group, const Context &ctx, const X
 
     Layer sub;
     {
-        int st = new_layer(ibbox.w, ibbox.h, &sub);
+        int st = new_layer(ibbox.w, sub_rows, &sub);
         if (st == RB_ERR_OOM || st == RB_ERR_INVALID) return; // "Failed to allocate a group layer": the group is skipped
         if (st != RB_OK) { fail(st); return; }
+        if (sub_rows != ibbox.h) { sub->vp_x = 0; sub->vp_y = -(sub_top - ibbox.y); sub->vp_w = (int32_t)ibbox.w; sub->vp_h = (int32_t)ibbox.h; }
     }
     render_nodes(group, ctx, ts, sub.get());
     for (const rbt::Filter &f : group.filters) {
@@ -226,7 +248,7 @@ void Renderer::render_group(const rbt::Group &group, const Context &ctx, const X
     if (group.clip_path) clip_apply(*group.clip_path, ts, sub.get());
     if (group.mask) mask_apply(*group.mask, ctx, ts, sub.get());
     if (status != RB_OK) return;
-    RBR_TRY(rb_draw_layer(pixmap, sub.get(), ibbox.x, ibbox.y - (on_strip(pixmap) ? strip_y0 : 0), group.opacity, convert_blend_mode(group.blend_mode)));
+    RBR_TRY(rb_draw_layer(pixmap, sub.get(), ibbox.x, sub_top - win.y0, group.opacity, convert_blend_mode(group.blend_mode)));
 }
 
 // ---- path.rs ---------------------------------------------------------------------------------------------------------
@@ -364,7 +386,7 @@ void Renderer::clip_apply(const rbt::ClipPath &clip, const Xform &transform, rb_
 {
     if (status != RB_OK) return;
     Layer clip_pixmap;
-    RBR_TRY(new_layer(rb_layer_width(pixmap), rb_layer_height(pixmap), &clip_pixmap));
+    RBR_TRY(new_layer_like(pixmap, &clip_pixmap));
     RBR_TRY(rb_layer_fill(clip_pixmap.get(), 0, 0, 0, 255)); // Color::BLACK
     clip_draw_children(*clip.root, RB_BLEND_CLEAR, rbh::pre_concat(transform, clip.ts), clip_pixmap.get());
     if (clip.clip_path) clip_apply(*clip.clip_path, transform, pixmap);
@@ -396,7 +418,7 @@ void Renderer::clip_draw_children(const rbt::Group &parent, int mode, const Xfor
 void Renderer::clip_group(const rbt::Group &children, const rbt::ClipPath &clip, const Xform &transform, rb_layer *pixmap)
 {
     Layer clip_pixmap;
-    RBR_TRY(new_layer(rb_layer_width(pixmap), rb_layer_height(pixmap), &clip_pixmap));
+    RBR_TRY(new_layer_like(pixmap, &clip_pixmap));
     clip_draw_children(children, RB_BLEND_SOURCE_OVER, transform, clip_pixmap.get());
     clip_apply(clip, transform, clip_pixmap.get());
     if (status != RB_OK) return;
@@ -415,7 +437,7 @@ void Renderer::mask_apply(const rbt::Mask &mask, const Context &ctx, const Xform
     }
     const uint32_t w = rb_layer_width(pixmap), h = rb_layer_height(pixmap);
     Layer mask_pixmap;
-    RBR_TRY(new_layer(w, h, &mask_pixmap));
+    RBR_TRY(new_layer_like(pixmap, &mask_pixmap));
     {
         // the mask content is clipped by mask.rect()
         MaskHolder alpha_mask;
@@ -423,6 +445,7 @@ void Renderer::mask_apply(const rbt::Mask &mask, const Context &ctx, const Xform
             rb_mask *m = nullptr;
             RBR_TRY(rb_mask_create(rb, w, h, &m));
             alpha_mask.reset(m);
+            m->vp_x = pixmap->vp_x; m->vp_y = pixmap->vp_y; m->vp_w = pixmap->vp_w; m->vp_h = pixmap->vp_h;
         }
         const Rect &r = mask.rect;
         const float right = r.x + r.w, bottom = r.y + r.h; // to_rect()
@@ -456,16 +479,11 @@ void Renderer::render_image(const rbt::Image &image, const Xform &transform, rb_
 void Renderer::render_vector(const rbt::Tree &tree, const Xform &transform, rb_layer *pixmap)
 {
     Layer sub;
-    const bool st = on_strip(pixmap); // canvas strips: the nested document is rendered on a canvas-sized layer as always
-    RBR_TRY(new_layer(st ? canvas_w : rb_layer_width(pixmap), st ? canvas_h : rb_layer_height(pixmap), &sub));
-    {
-        rb_layer *outer = strip;
-        strip = nullptr; // the nested tree's target is an ordinary layer
-        render_tree(tree, transform, sub.get());
-        strip = outer;
-    }
+    const Win win = window_of(pixmap); // inside a window the nested document is still rendered on a layer of the whole size
+    RBR_TRY(new_layer(win.full_w, win.full_h, &sub));
+    render_tree(tree, transform, sub.get());
     if (status != RB_OK) return;
-    RBR_TRY(rb_draw_layer(pixmap, sub.get(), 0, st ? -strip_y0 : 0, 1.0f, RB_BLEND_SOURCE_OVER));
+    RBR_TRY(rb_draw_layer(pixmap, sub.get(), 0, -win.y0, 1.0f, RB_BLEND_SOURCE_OVER));
 }
 
 // image.rs:173-206 (the decoders of image.rs:62-170 stay on the host: the stream carries premultiplied RGBA8)
@@ -493,8 +511,8 @@ void Renderer::render_raster(const rbt::Image &image, const Xform &transform, rb
 // lib.rs:34-43
 void Renderer::render_tree(const rbt::Tree &tree, const Xform &transform, rb_layer *pixmap)
 {
-    const bool st = on_strip(pixmap);
-    const Context ctx{max_filter_bbox(st ? canvas_w : rb_layer_width(pixmap), st ? canvas_h : rb_layer_height(pixmap))};
+    const Win win = window_of(pixmap);
+    const Context ctx{max_filter_bbox(win.full_w, win.full_h)};
     render_nodes(tree.root, ctx, transform, pixmap);
 }
 
@@ -594,10 +612,6 @@ extern "C" int rb_render_strip(rb_ctx *ctx, const rb_tree *tree, const float ts[
     int st = rb_layer_flush(target);
     if (st != RB_OK) return st;
     rbr::Renderer r(ctx);
-    r.strip = target;
-    r.strip_y0 = y0;
-    r.canvas_w = canvas_w;
-    r.canvas_h = canvas_h;
     target->vp_x = 0; target->vp_y = -y0; target->vp_w = (int32_t)canvas_w; target->vp_h = (int32_t)canvas_h;
     r.render_tree(*tree->t, ts ? rbh::Xform::from(ts) : rbh::Xform(), target);
     st = rb_layer_flush(target); // the draws recorded with the strip's viewport

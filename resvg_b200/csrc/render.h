@@ -41,14 +41,12 @@ struct Renderer {
     rb_ctx *rb;
     int status = RB_OK; // first device error; once set the traversal unwinds without issuing more work
     explicit Renderer(rb_ctx *c) : rb(c) {}
-    // Canvas strips (rb_render_strip): `strip` is the target, holding rows [strip_y0, strip_y0 + its height) of the
-    // canvas_w x canvas_h render.  Draws that go straight to the target are built against the whole canvas (the layer's
-    // viewport), isolated groups are rendered exactly as in the whole-canvas render and composited with the rows shifted;
-    // groups that miss the strip are skipped.  The strip holds exactly the pixels of the whole-canvas render.
-    rb_layer *strip = nullptr;
-    int32_t strip_y0 = 0;
-    uint32_t canvas_w = 0, canvas_h = 0;
-    bool on_strip(const rb_layer *p) const { return strip && p == strip; }
+    // Canvas strips (rb_render_strip): a layer may be a WINDOW — rows [y0, y0 + its height) — of a larger
+    // virtual pixmap (rb_layer::vp_*).  Draws into a window are built against the whole virtual pixmap (the batch viewport),
+    // an isolated group inside a window gets a window of its own layer (the rows that can reach the parent's window), its
+    // clip / mask pixmaps the same window; a group with filters is rendered whole (a filter reads beyond its rows) and
+    // composited shifted; groups that miss the window are skipped.  Every pixel equals the whole-canvas render's.
+    int new_layer_like(const rb_layer *like, Layer *out);
 
     void fail(int st);
     int new_layer(uint32_t w, uint32_t h, Layer *out);
