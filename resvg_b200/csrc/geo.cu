@@ -940,6 +940,11 @@ struct GeoPending {
     unsigned long long *dbg = nullptr;
     double t_start = 0, t_built = 0, t_enq = 0;
     cudaStream_t gs = nullptr;
+    // several launches of one batch may be in flight (rb_batch_submit enqueues the sub-ranges of its device share one after
+    // the other): a FIFO hanging off rb_batch::geo, each with its own slot of the pinned totals and its own completion event
+    GeoPending *next = nullptr;
+    int slot = 0;
+    cudaEvent_t done = nullptr;
 };
 static double geo_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -1045,8 +1050,9 @@ static int geo_enqueue(rb_ctx *ctx, GeoPending *gp)
             k_geo_wide<<<std::min<uint32_t>((uint32_t)n_draws, (uint32_t)ctx->sm_count * 4u), GW_THREADS, 0, s0>>>(a, wide_q);
             RB_LAUNCHED(ctx, "geo_wide");
         }
-        GeoTotals *ht = (GeoTotals *)ctx->geo_pinned;
+        GeoTotals *ht = (GeoTotals *)((uint8_t *)ctx->geo_pinned + 128 * gp->slot);
         RB_CUDA(ctx, cudaMemcpyAsync(ht, dev + o_tot, sizeof(GeoTotals), cudaMemcpyDeviceToHost, gs));
+        RB_CUDA(ctx, cudaEventRecord(gp->done, gs));
         gp->o_draws = o_draws; gp->o_tot = o_tot; gp->o_heap = o_heap;
         gp->t_enq = geo_now_ms();
     }
@@ -1057,7 +1063,6 @@ int rb_geo_begin(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
 {
     rb_ctx *ctx = b->layer->ctx;
     cudaSetDevice(ctx->device);
-    if (b->geo) { delete b->geo; b->geo = nullptr; }
     if (!(ctx->attr_bits & RB_ATTR_GEO)) {
         RB_CUDA(ctx, cudaDeviceSetLimit(cudaLimitStackSize, GEO_STACK));
         ctx->attr_bits |= RB_ATTR_GEO;
@@ -1071,22 +1076,38 @@ int rb_geo_begin(rb_batch *b, int32_t n_threads, size_t begin, size_t end)
     static const bool own_stream = !(getenv("RB_GEO_OWN_STREAM") && atoi(getenv("RB_GEO_OWN_STREAM")) == 0);
     GeoPending *gp = new GeoPending();
     gp->gs = own_stream ? ctx->geo_streams[0] : ctx->stream;
+    {
+        int n_pending = 0;
+        for (GeoPending *q = b->geo; q; q = q->next) n_pending++;
+        if (n_pending >= 16) { delete gp; return RB_GEO_FALLBACK; }
+        static std::atomic<int> slot_counter{0};
+        gp->slot = slot_counter.fetch_add(1) & 15;
+        for (GeoPending *q = b->geo; q; q = q->next) if (q->slot == gp->slot) { gp->slot = (gp->slot + 1) & 15; q = b->geo; }
+    }
+    if (cudaEventCreateWithFlags(&gp->done, cudaEventDisableTiming) != cudaSuccess) { delete gp; return RB_ERR_CUDA; }
     gp->W = (int)b->layer->w; gp->H = (int)b->layer->h;
     StageReq2 req{ctx, RB_OK};
     int st;
     gp->t_start = geo_now_ms();
     { rb_prof_scope prof__(RB_T_BUILD); st = rb_geo_host_build(b, gp->W, gp->H, n_threads, geo_stage_pinned, &req, &gp->blk, &gp->G, begin, end); }
-    if (req.status != RB_OK) { delete gp; return req.status; }
-    if (st != RB_OK) { delete gp; return rb_fail(ctx, st, "geometry task build failed"); }
+    if (req.status != RB_OK) { cudaEventDestroy(gp->done); delete gp; return req.status; }
+    if (st != RB_OK) { cudaEventDestroy(gp->done); delete gp; return rb_fail(ctx, st, "geometry task build failed"); }
     gp->t_built = geo_now_ms();
-    b->geo = gp;
+    auto unlink = [&]() { // on failure: take gp out of the FIFO again
+        if (b->geo == gp) b->geo = gp->next;
+        else for (GeoPending *q = b->geo; q; q = q->next) if (q->next == gp) { q->next = gp->next; break; }
+        cudaEventDestroy(gp->done);
+        delete gp;
+    };
+    if (!b->geo) b->geo = gp;
+    else { GeoPending *q = b->geo; while (q->next) q = q->next; q->next = gp; }
     if (!gp->blk || gp->G.n_tasks == 0) return RB_OK; // nothing to draw: rb_geo_finish reports an empty layout
     rb_prof_scope prof_up__(RB_T_UPLOAD);
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     gp->heap_bytes = al(gp->G.heap_hint + (64u << 20));
     if (const char *e = getenv("RB_GEO_HEAP_BYTES")) gp->heap_bytes = al((size_t)std::max(1024ll, atoll(e))); // tests: force heap retries
     st = geo_enqueue(ctx, gp);
-    if (st != RB_OK) { delete gp; b->geo = nullptr; if (st == RB_GEO_FALLBACK) g_geo_counts[1]++; }
+    if (st != RB_OK) { unlink(); if (st == RB_GEO_FALLBACK) g_geo_counts[1]++; }
     return st;
 }
 
@@ -1095,7 +1116,7 @@ int rb_geo_finish(rb_batch *b)
     rb_ctx *ctx = b->layer->ctx;
     GeoPending *gp = b->geo;
     if (!gp) return RB_ERR_INVALID;
-    struct Drop { rb_batch *b; ~Drop() { delete b->geo; b->geo = nullptr; } } drop{b};
+    struct Drop { rb_batch *b; GeoPending *gp; ~Drop() { b->geo = gp->next; if (gp->done) cudaEventDestroy(gp->done); delete gp; } } drop{b, gp}; // pops the head
     cudaSetDevice(ctx->device);
     b->lay = BatchLayout();
     if (!gp->blk || gp->G.n_tasks == 0) return RB_OK;
@@ -1105,8 +1126,8 @@ int rb_geo_finish(rb_batch *b)
     const size_t n_tasks = G.n_tasks, n_draws = G.n_draws;
     const int W = gp->W, H = gp->H;
     for (;;) {
-        const GeoTotals *ht = (const GeoTotals *)ctx->geo_pinned;
-        RB_CUDA(ctx, cudaStreamSynchronize(gs));
+        const GeoTotals *ht = (const GeoTotals *)((const uint8_t *)ctx->geo_pinned + 128 * gp->slot);
+        RB_CUDA(ctx, cudaEventSynchronize(gp->done));
         const double t_done = geo_now_ms();
         const GeoTotals T = *ht;
         if (gp->dbg) {
@@ -1174,12 +1195,13 @@ int rb_geo_finish(rb_batch *b)
 // Releases a geometry launch nobody will finish (the batch is destroyed or prepared again).
 void rb_geo_abandon(rb_batch *b)
 {
-    GeoPending *gp = b->geo;
-    if (!gp) return;
-    if (gp->dev) { cudaStreamSynchronize(gp->gs); cudaFreeAsync(gp->dev, gp->gs); }
-    if (gp->dbg) cudaFree(gp->dbg);
-    delete gp;
-    b->geo = nullptr;
+    while (GeoPending *gp = b->geo) {
+        b->geo = gp->next;
+        if (gp->dev) { cudaStreamSynchronize(gp->gs); cudaFreeAsync(gp->dev, gp->gs); }
+        if (gp->dbg) cudaFree(gp->dbg);
+        if (gp->done) cudaEventDestroy(gp->done);
+        delete gp;
+    }
 }
 
 int rb_geo_prepare(rb_batch *b, int32_t n_threads, size_t begin, size_t end)

@@ -1147,38 +1147,55 @@ static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t 
         split = first + (size_t)((double)n * host_share);
         if (last - split < geo_from && g_geo_mode != 1) split = last;
     }
+    // The device share goes out in one launch (RB_GEO_SUBRANGES: in a few consecutive ones, each enqueued as soon as its tasks
+    // exist — kept for experiments, see below).
     int st = RB_OK;
-    bool geo_pending = false;
-    if (split < last) {
-        st = rb_geo_begin(b, n_threads, split, last);
-        if (st == RB_OK) geo_pending = true;
-        else if (st == RB_GEO_FALLBACK) { st = RB_OK; split = last; }
-        else return st;
+    size_t subs = 1;
+    {
+        const int host_threads = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+        (void)host_threads; // measured with 4 host threads: 1 / 2 / 3 / 4 launches = 65 / 66 / 75 / 84 ms per scene — every launch
+                            // pays the latency of its longest draws, which outweighs starting the GPU earlier
+        if (const char *e = getenv("RB_GEO_SUBRANGES")) subs = (size_t)std::max(1, std::min(8, atoi(e)));
     }
+    struct Sub { size_t lo, hi; bool pending; };
+    std::vector<Sub> sub_ranges;
+    for (size_t k = 0; k < subs && split < last; k++) {
+        Sub sr{split + (last - split) * k / subs, split + (last - split) * (k + 1) / subs, false};
+        if (sr.lo >= sr.hi) continue;
+        st = rb_geo_begin(b, n_threads, sr.lo, sr.hi);
+        if (st == RB_OK) sr.pending = true;
+        else if (st != RB_GEO_FALLBACK) { rb_geo_abandon(b); return st; }
+        sub_ranges.push_back(sr);
+    }
+    st = RB_OK;
     if (split > first) {
         const size_t host_parts = std::max<size_t>(1, parts * (split - first) / n);
         st = submit_host_parts(b, n_threads, first, split, host_parts, total, stopped_at);
-        if (st != RB_OK) { if (geo_pending) rb_geo_abandon(b); return st; }
+        if (st != RB_OK) { rb_geo_abandon(b); return st; }
     }
-    if (geo_pending) {
-        *stopped_at = split;
-        batch_release(b);
-        st = rb_geo_finish(b);
-        if (st == RB_OK) {
-            if (b->dev && b->lay.n_draws) {
-                rb_ctx *ctx = batch_ctx(b);
-                const size_t scratch_bytes = warp_scratch_layout(b->lay).total;
-                RB_CUDA(ctx, cudaMallocAsync((void **)&b->dev_scratch, scratch_bytes, ctx->stream));
-                b->scratch_owned = true;
-                st = rb_batch_run(b);
-            }
-            for (int i = 0; i < 6; i++) total[i] += b->stats[i];
+    for (const Sub &sr : sub_ranges) {
+        *stopped_at = sr.lo;
+        int gst = RB_GEO_FALLBACK;
+        if (sr.pending) {
             batch_release(b);
-        } else if (st == RB_GEO_FALLBACK) {
-            st = submit_host_parts(b, n_threads, split, last, std::max<size_t>(1, parts * (last - split) / n), total, stopped_at);
+            gst = rb_geo_finish(b);
+            if (gst == RB_OK) {
+                if (b->dev && b->lay.n_draws) {
+                    rb_ctx *ctx = batch_ctx(b);
+                    const size_t scratch_bytes = warp_scratch_layout(b->lay).total;
+                    RB_CUDA(ctx, cudaMallocAsync((void **)&b->dev_scratch, scratch_bytes, ctx->stream));
+                    b->scratch_owned = true;
+                    gst = rb_batch_run(b);
+                }
+                for (int i = 0; i < 6; i++) total[i] += b->stats[i];
+                batch_release(b);
+            }
         }
+        if (gst == RB_GEO_FALLBACK)
+            gst = submit_host_parts(b, n_threads, sr.lo, sr.hi, std::max<size_t>(1, parts * (sr.hi - sr.lo) / n), total, stopped_at);
+        if (gst != RB_OK) { rb_geo_abandon(b); return gst; }
     }
-    return st;
+    return RB_OK;
 }
 
 // Immediate draws are collected per layer and executed as one batch by rb_layer_flush, which every entry point that

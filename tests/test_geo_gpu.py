@@ -103,7 +103,7 @@ def test_full_size_scene_device_geometry_equals_host_builder(ctx, seed_offset):
             _ffi.lib.rb_debug_geo_mode(0)
         crcs[name] = zlib.crc32(pinned.array)
         if name == "device":
-            assert after[0] - before[0] == 1 and after[1] == before[1], (before, after)
+            assert after[0] - before[0] >= 1 and after[1] == before[1], (before, after)
     pinned.close()
     l.close()
     assert crcs["device"] == crcs["host"] and crcs["shared"] == crcs["host"], crcs

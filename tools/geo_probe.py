@@ -16,6 +16,7 @@ def main():
     steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     W, H, n_paths, seed = bench.WORKLOADS[wl]
     seed += int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    threads = int(sys.argv[4]) if len(sys.argv) > 4 else 0
     scene = scenes.paths_scene(W, H, n_paths, seed)
     scene["paints"] = scenes.to_paint_array(scene, _ffi.Paint)
     scene["strokes"] = scenes.to_stroke_array(scene, _ffi.Stroke)
@@ -26,7 +27,7 @@ def main():
         t0 = time.perf_counter()
         b = rb.Batch(layer)
         b.fill_paths(scene)
-        b.submit(0)
+        b.submit(threads)
         b.close()
         ctx.synchronize()
         print(f"step {s}: {1e3 * (time.perf_counter() - t0):.1f} ms", file=sys.stderr)
