@@ -430,6 +430,13 @@ void rb_debug_geo_counts(uint64_t out[6]);
 /* Host-only batches (rb_debug_batch_begin_host): runs the host half of the device geometry path and reports out[0..7] =
  * tasks, dashed, stroked, hairline, fill-list entries, bytes that would be uploaded, verbs, points. */
 int rb_debug_geo_host_stats(rb_batch *batch, uint64_t out[8]);
+/* The dash-by-dash decomposition the geometry kernels use for a dashed stroke, run on the host with the same code: the
+ * outline of the dashed path built one dash at a time (outputs malloc'ed, rb_path_free).  Tests compare it with
+ * rb_path_dash followed by rb_path_stroke. */
+int rb_debug_stroke_dashed_in_units(const uint8_t *verbs, int32_t n_verbs, const float *points, int32_t n_points,
+                                    const float *dash_array, int32_t n_dash, float dash_offset, float width, float miter_limit,
+                                    int32_t cap, int32_t join, float res_scale, uint8_t **out_verbs, int32_t *out_n_verbs,
+                                    float **out_points, int32_t *out_n_points);
 
 /* Host-only batch (no target, no device work): records like any batch; rb_batch_prepare runs the host build (edges,
  * binning, block layout) for a width x height canvas and keeps the block on the host.  For the CPU test-suite and for

@@ -154,6 +154,8 @@ SIGNATURES = {
     "rb_debug_geo_mode": (None, [_i]),
     "rb_debug_geo_counts": (None, [_vp]),
     "rb_debug_geo_host_stats": (_i, [_vp, _vp]),
+    "rb_debug_stroke_dashed_in_units": (_i, [_vp, C.c_int32, _vp, C.c_int32, _vp, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32,
+                                         C.c_float, _vp, _vp, _vp, _vp]),
     "rb_debug_batch_begin_host": (_i, [_u32, _u32, c_void_pp]),
     "rb_debug_batch_phases": (_i, [_vp, _vp]),
     "rb_debug_batch_block": (C.c_int64, [_vp, C.c_int32, _vp, C.c_uint64]),

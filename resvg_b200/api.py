@@ -601,3 +601,25 @@ def stroke_path(verbs, pts, width, miter_limit=4.0, cap="butt", join="miter", re
         lib.rb_path_free(ov)
         lib.rb_path_free(op)
     return out_v, out_p
+
+
+def stroke_dashed_in_units(verbs, pts, dash_array, dash_offset, width, miter_limit=4.0, cap="butt", join="miter", res_scale=1.0):
+    """The outline of a dashed stroke built dash by dash, as the geometry kernels do it (rb_debug_stroke_dashed_in_units:
+    the same code on the host) → (verbs, points) or None.  Equals stroke_path(*dash_path(...)) — that is what the test checks."""
+    v, p = _path(verbs, pts)
+    arr, ptr = _f32(dash_array)
+    ov, op = C.c_void_p(), C.c_void_p()
+    nv, np_ = C.c_int32(), C.c_int32()
+    st = lib.rb_debug_stroke_dashed_in_units(v.ctypes.data, len(v), p.ctypes.data, len(p), C.cast(ptr, C.c_void_p), arr.size, float(dash_offset),
+                                             float(width), float(miter_limit), CAPS[cap] if isinstance(cap, str) else int(cap),
+                                             JOINS[join] if isinstance(join, str) else int(join), float(res_scale),
+                                             C.byref(ov), C.byref(nv), C.byref(op), C.byref(np_))
+    if st != 0:
+        return None
+    try:
+        out_v = np.ctypeslib.as_array((C.c_uint8 * nv.value).from_address(ov.value)).copy()
+        out_p = np.ctypeslib.as_array((C.c_float * (np_.value * 2)).from_address(op.value)).copy().reshape(-1, 2)
+    finally:
+        lib.rb_path_free(ov)
+        lib.rb_path_free(op)
+    return out_v, out_p

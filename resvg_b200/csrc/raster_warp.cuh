@@ -156,6 +156,15 @@ k_row_lists(const DevDraw *__restrict__ draws, const DevEdge *__restrict__ lines
     __shared__ uint32_t long_q[RL_LONG_Q], n_long;
     const DevDraw D = draws[blockIdx.x];
     const int tid = threadIdx.x, nr = (int)D.n_rows;
+    if (nr == 0) {
+        // an empty draw (the geometry kernels keep one DevDraw per task: culled paths, strokes that come out empty, the
+        // reserved draws of a dashed hairline beyond its dashes): no rows, no lists, never binned
+        if (tid == 0) {
+            if (boxes) boxes[blockIdx.x] = DrawBox{D.r0 | ((D.r0 + D.n_rows - 1) << 16), D.row_base};
+            row_off[D.row_base] = 0;
+        }
+        return;
+    }
     DevEdge *E0 = edges + D.edge_off;
     for (int i = tid; i <= nr; i += RL_THREADS) { cnt[i] = 0; xlo[i] = INT_MAX; xhi[i] = INT_MIN; }
     if (tid == 0 && boxes) boxes[blockIdx.x] = DrawBox{D.r0 | ((D.r0 + D.n_rows - 1) << 16), D.row_base};

@@ -98,3 +98,43 @@ def test_libm_compat_matches_the_hosts_libm(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert out.stdout.count(" 0 mismatches") == 3, out.stdout
+
+
+def test_dashed_stroke_built_dash_by_dash_equals_dash_then_stroke():
+    """The decomposition the geometry kernels use for dashed strokes (one thread per dash: cut it out, stroke it alone, a
+    non-last dash followed by the next one's move_to) against dash-then-stroke of the whole path, over random open and
+    closed paths, every cap and join: identical verbs and bit-identical points."""
+    import resvg_b200 as rb
+    from resvg_b200 import api
+    from tests.pathgen import SplitMix64, random_path
+
+    rng = SplitMix64(0xDA5E)
+    caps, joins = ["butt", "round", "square"], ["miter", "miter-clip", "round", "bevel"]
+    checked = 0
+    for it in range(400):
+        cx, cy, r = rng.uniform(0, 300), rng.uniform(0, 300), rng.log_uniform(8, 150)
+        verbs, pts = random_path(rng, cx, cy, r)
+        verbs = list(verbs)
+        pts = [tuple(p) for p in pts]
+        if it % 3 == 0 and verbs and verbs[-1] == 4:  # an open contour as well
+            verbs = verbs[:-1]
+        if it % 5 == 0:  # a second contour
+            verbs += [0, 1, 2]
+            pts += [(cx + 3.0, cy - 7.5), (cx + r, cy + 2.0), (cx + 0.5 * r, cy + r), (cx - r, cy + 0.25 * r)]
+        n = 2 * int(rng.uniform(1, 3.99))
+        dash = [rng.uniform(0.5, 30.0) for _ in range(n)]
+        off = rng.uniform(-40.0, 80.0)
+        width = rng.log_uniform(1.2, 20.0)
+        cap, join = caps[it % 3], joins[(it // 3) % 4]
+        res = rng.uniform(0.5, 3.0)
+        d = rb.dash_path(verbs, pts, dash, off, res)
+        want = rb.stroke_path(d[0], d[1], width, 4.0, cap, join, res) if d is not None else None
+        got = api.stroke_dashed_in_units(verbs, pts, dash, off, width, 4.0, cap, join, res)
+        if want is None:
+            assert got is None
+            continue
+        assert got is not None, (it, cap, join)
+        assert np.array_equal(got[0], want[0]), (it, cap, join, len(got[0]), len(want[0]))
+        assert got[1].tobytes() == want[1].tobytes(), (it, cap, join)
+        checked += 1
+    assert checked > 350
