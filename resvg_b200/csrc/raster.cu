@@ -221,6 +221,57 @@ __device__ __forceinline__ uint32_t store_pf(PF o) { return rb_pack(unnorm(o.r),
 // =================================================================================================
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 
+// What the two-point-conical and tiling stages need of a paint, read once (a row of pixels shares it).
+struct GradGeom {
+    int geom, spread;
+    uint32_t fl; // 1 focal_on_circle, 2 well_behaved, 4 smaller, 8 negate_x, 16 !natively_focal, 32 swapped, 64 pad_x1
+    float p0, p1, conc_scale, conc_bias;
+};
+__device__ __forceinline__ GradGeom grad_geom(const DevPaint &P)
+{
+    GradGeom g;
+    g.geom = P.geom; g.spread = P.spread;
+    g.fl = (P.focal_on_circle ? 1u : 0u) | (P.well_behaved ? 2u : 0u) | (P.smaller ? 4u : 0u) | (P.negate_x ? 8u : 0u) |
+           (P.natively_focal ? 0u : 16u) | (P.swapped ? 32u : 0u) | (P.pad_x1 ? 64u : 0u);
+    g.p0 = P.p0; g.p1 = P.p1; g.conc_scale = P.conc_scale; g.conc_bias = P.conc_bias;
+    return g;
+}
+
+// t of a gradient at the (already transformed) point (x, y): the two-point-conical stage, then the tiling stage
+__device__ __forceinline__ float gradient_t_at(const GradGeom &G, float x, float y, bool &masked)
+{
+    masked = false;
+    float t = x;
+    switch (G.geom) {
+    case 0: break;
+    case 1: t = __fsqrt_rn(x * x + y * y); break;
+    case 4: t = __fsqrt_rn(x * x + y * y); t = t * G.conc_scale + G.conc_bias; break;
+    case 3:
+        t = x + __fsqrt_rn(G.p0 - y * y);
+        if (t != t) { masked = true; t = 0.0f; }
+        break;
+    default:
+        if (G.fl & 1u) t = x + __fdiv_rn(y * y, x);
+        else if (G.fl & 2u) t = __fsqrt_rn(x * x + y * y) - x * G.p0;
+        else if (G.fl & 4u) t = -__fsqrt_rn(x * x - y * y) - x * G.p0;
+        else t = __fsqrt_rn(x * x - y * y) - x * G.p0;
+        if (!(G.fl & 2u) && (t <= 0.0f || t != t)) { masked = true; t = 0.0f; }
+        if (G.fl & 8u) t = -t;
+        if (G.fl & 16u) t = t + G.p1;
+        if (G.fl & 32u) t = 1.0f - t;
+        break;
+    }
+    if (G.spread == 1) {
+        float v = (t - 1.0f) - two(floorf((t - 1.0f) * 0.5f)) - 1.0f;
+        t = clamp01(fabsf(v));
+    } else if (G.spread == 2) {
+        t = clamp01(t - floorf(t));
+    } else if (G.fl & 64u) {
+        t = clamp01(t);
+    }
+    return t;
+}
+
 __device__ __noinline__ float gradient_t(const DevPaint &P, int px, int py, bool &masked)
 {
     float x = (float)px + 0.5f, y = (float)py + 0.5f;
@@ -229,55 +280,40 @@ __device__ __noinline__ float gradient_t(const DevPaint &P, int px, int py, bool
         float ny = mad(x, P.ts[1], mad(y, P.ts[3], P.ts[5]));
         x = nx; y = ny;
     }
-    masked = false;
-    float t = x;
-    switch (P.geom) {
-    case 0: break;
-    case 1: t = __fsqrt_rn(x * x + y * y); break;
-    case 4: t = __fsqrt_rn(x * x + y * y); t = t * P.conc_scale + P.conc_bias; break;
-    case 3:
-        t = x + __fsqrt_rn(P.p0 - y * y);
-        if (t != t) { masked = true; t = 0.0f; }
-        break;
-    default:
-        if (P.focal_on_circle) t = x + __fdiv_rn(y * y, x);
-        else if (P.well_behaved) t = __fsqrt_rn(x * x + y * y) - x * P.p0;
-        else if (P.smaller) t = -__fsqrt_rn(x * x - y * y) - x * P.p0;
-        else t = __fsqrt_rn(x * x - y * y) - x * P.p0;
-        if (!P.well_behaved && (t <= 0.0f || t != t)) { masked = true; t = 0.0f; }
-        if (P.negate_x) t = -t;
-        if (!P.natively_focal) t = t + P.p1;
-        if (P.swapped) t = 1.0f - t;
-        break;
-    }
-    if (P.spread == 1) {
-        float v = (t - 1.0f) - two(floorf((t - 1.0f) * 0.5f)) - 1.0f;
-        t = clamp01(fabsf(v));
-    } else if (P.spread == 2) {
-        t = clamp01(t - floorf(t));
-    } else if (P.pad_x1) {
-        t = clamp01(t);
-    }
-    return t;
+    const GradGeom G = grad_geom(P);
+    return gradient_t_at(G, x, y, masked);
 }
 
-__device__ __forceinline__ PF gradient_color(const DevPaint &P, const DevStop *__restrict__ stops, float t)
+// colour(t): interval search over the first `len` thresholds (t0s holds +inf beyond the paint's own count; len <= 1: one
+// interval), then t * f + b of that interval
+__device__ __forceinline__ PF gradient_color_at(const float *__restrict__ t0s, const DevStop *__restrict__ st, int len, float t)
 {
-    const DevStop *st = stops + P.stop_off;
     int idx = 0;
-    if (!P.two_stop) {
-        if (P.len <= 8) {
-            const float4 a = *reinterpret_cast<const float4 *>(P.t0s), b = *reinterpret_cast<const float4 *>(P.t0s + 4);
-            idx = (t >= a.y) + (t >= a.z) + (t >= a.w) + (t >= b.x) + (t >= b.y) + (t >= b.z) + (t >= b.w);
+    if (len > 1) {
+        if (len <= 12) {
+            const float4 a = *reinterpret_cast<const float4 *>(t0s);
+            idx = (t >= a.y) + (t >= a.z) + (t >= a.w);
+            if (len > 4) {
+                const float4 b = *reinterpret_cast<const float4 *>(t0s + 4);
+                idx += (t >= b.x) + (t >= b.y) + (t >= b.z) + (t >= b.w);
+                if (len > 8) {
+                    const float4 c = *reinterpret_cast<const float4 *>(t0s + 8);
+                    idx += (t >= c.x) + (t >= c.y) + (t >= c.z) + (t >= c.w);
+                }
+            }
         } else {
 #pragma unroll 1
-            for (int i = 1; i < P.len; i++) idx += (t >= st[i].t0) ? 1 : 0;
+            for (int i = 1; i < len; i++) idx += (t >= st[i].t0) ? 1 : 0;
         }
     }
     const float4 f = *reinterpret_cast<const float4 *>(st[idx].f);
     const float4 b = *reinterpret_cast<const float4 *>(st[idx].b);
     PF c = {mad(t, f.x, b.x), mad(t, f.y, b.y), mad(t, f.z, b.z), mad(t, f.w, b.w)};
     return c;
+}
+__device__ __forceinline__ PF gradient_color(const DevPaint &P, const DevStop *__restrict__ stops, float t)
+{
+    return gradient_color_at(P.t0s, stops + P.stop_off, P.two_stop ? 1 : P.len, t);
 }
 
 __device__ __forceinline__ float ulp_sub(float v) { return __uint_as_float(__float_as_uint(v) - 1u); }
@@ -379,6 +415,82 @@ __device__ __forceinline__ PF shadef(const DevPaint &P, const DevStop *__restric
     if (P.kind == 0) { PF c = {P.premul[0], P.premul[1], P.premul[2], P.premul[3]}; return c; }
     if (P.kind == 2) return shade_pattern(P, x, y);
     return shadef_gradient(P, stops, x, y);
+}
+
+// The lane's eight pixels of one (draw, tile) pair under a gradient with Source / SourceOver, u16 or f32 pipeline: ONE call
+// per pair, so that what does not change along the row (the y half of the transform) is computed once and the per-pixel code
+// is a compact loop of its own.  c0 / c1 / dec: the coverage words of k_raster_warp; px: the pixels, in and out.
+struct Px8 { uint32_t v[8]; };
+__device__ __noinline__ void blend_row_gradient(const DevPaint &P, const DevStop *__restrict__ stops, Px8 &px, uint32_t c0, uint32_t c1,
+                                                uint32_t dec, int x0, int py)
+{
+    // everything the row shares is read here, once (the stores into px could alias the paint as far as the compiler knows)
+    const bool lowp = P.lowp != 0, src_over = P.blend == 3, memset_ok = P.has_memset != 0, has_ts = P.has_ts != 0;
+    const bool premul_after = P.premul_after != 0;
+    const uint32_t memset_color = P.memset_color;
+    const GradGeom G = grad_geom(P);
+    const float *__restrict__ t0s = P.t0s;
+    const DevStop *__restrict__ st = stops + P.stop_off;
+    const int len = P.two_stop ? 1 : P.len;
+    const float y = (float)py + 0.5f;
+    const float ts0 = P.ts[0], ts1 = P.ts[1];
+    const float hx = mad(y, P.ts[2], P.ts[4]), hy = mad(y, P.ts[3], P.ts[5]);
+#pragma unroll 1
+    for (int q = 0; q < 8; q++) {
+        const uint32_t c = min(16u * (c0 & 0xffu) - (dec & 1u), 255u);
+        c0 = __funnelshift_r(c0, c1, 8);
+        c1 >>= 8;
+        dec >>= 4;
+        if (!c) continue;
+        if (c == 255 && memset_ok) { px.v[q] = memset_color; continue; }
+        const uint32_t d = px.v[q];
+        float x = (float)(x0 + q) + 0.5f, yy = y;
+        if (has_ts) {
+            const float nx = mad(x, ts0, hx), ny = mad(x, ts1, hy);
+            x = nx; yy = ny;
+        }
+        bool masked;
+        const float t = gradient_t_at(G, x, yy, masked);
+        PF sc = gradient_color_at(t0s, st, len, t);
+        if (lowp) {
+            uint32_t sr = __float2uint_rz(clamp01(sc.r) * 255.0f + 0.5f), sg = __float2uint_rz(clamp01(sc.g) * 255.0f + 0.5f);
+            uint32_t sb = __float2uint_rz(clamp01(sc.b) * 255.0f + 0.5f), sa = __float2uint_rz(clamp01(sc.a) * 255.0f + 0.5f);
+            if (premul_after) { sr = div255(sr * sa); sg = div255(sg * sa); sb = div255(sb * sa); }
+            // two channels per multiply, as in k_raster_warp's solid-colour code
+            const uint32_t s_rb = sr | (sb << 16), s_ag = sg | (sa << 16);
+            const uint32_t d_rb = d & 0x00ff00ffu, d_ag = (d >> 8) & 0x00ff00ffu;
+            uint32_t o_rb, o_ag;
+            if (src_over) { // scale_1_float (coverage folded into the source), then source_over
+                const uint32_t p_rb = c == 255 ? s_rb : (((s_rb * c + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
+                const uint32_t p_ag = c == 255 ? s_ag : (((s_ag * c + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
+                const uint32_t ia = 255 - (p_ag >> 16);
+                o_rb = p_rb + (((d_rb * ia + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
+                o_ag = p_ag + (((d_ag * ia + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
+            } else {        // Source: lerp_1_float(dst, src, coverage)
+                const uint32_t ic = 255 - c;
+                o_rb = (d_rb * ic + s_rb * c + 0x00ff00ffu) >> 8;
+                o_ag = (d_ag * ic + s_ag * c + 0x00ff00ffu) >> 8;
+            }
+            px.v[q] = (o_rb & 0x00ff00ffu) | ((o_ag & 0x00ff00ffu) << 8); // the store truncates every lane to u8
+        } else {
+            if (premul_after) { sc.r *= sc.a; sc.g *= sc.a; sc.b *= sc.a; }
+            if (masked) sc.r = sc.g = sc.b = sc.a = 0.0f;
+            const PF dd = load_pf(d);
+            PF o;
+            const float cf = (float)c * (1.0f / 255.0f);
+            if (src_over) { // scale_1_float, then source_over: d * (1 - sa) + s
+                if (c != 255) { sc.r *= cf; sc.g *= cf; sc.b *= cf; sc.a *= cf; }
+                const float ia = 1.0f - sc.a;
+                o.r = mad(dd.r, ia, sc.r); o.g = mad(dd.g, ia, sc.g); o.b = mad(dd.b, ia, sc.b); o.a = mad(dd.a, ia, sc.a);
+            } else if (c == 255) {
+                o = sc;
+            } else {        // Source: lerp_1_float(dst, src, coverage)
+                o.r = mad(sc.r - dd.r, cf, dd.r); o.g = mad(sc.g - dd.g, cf, dd.g);
+                o.b = mad(sc.b - dd.b, cf, dd.b); o.a = mad(sc.a - dd.a, cf, dd.a);
+            }
+            px.v[q] = store_pf(o);
+        }
+    }
 }
 
 // RasterPipelineBlitter: full-coverage pixels run the blit_rect program, others blit_anti_h.
@@ -880,18 +992,18 @@ extern "C" int rb_batch_run_counting(rb_batch *b, uint64_t out[2])
     rb_ctx *ctx = batch_ctx(b);
     if (!ctx) return RB_ERR_INVALID;
     unsigned long long *d = nullptr;
-    RB_CUDA(ctx, cudaMallocAsync((void **)&d, 64, ctx->stream));
-    RB_CUDA(ctx, cudaMemsetAsync(d, 0, 64, ctx->stream));
+    RB_CUDA(ctx, cudaMallocAsync((void **)&d, 128, ctx->stream));
+    RB_CUDA(ctx, cudaMemsetAsync(d, 0, 128, ctx->stream));
     int st = batch_run(b, d);
-    unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    RB_CUDA(ctx, cudaMemcpyAsync(h, d, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long h[16] = {0};
+    RB_CUDA(ctx, cudaMemcpyAsync(h, d, 128, cudaMemcpyDeviceToHost, ctx->stream));
     RB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     RB_CUDA(ctx, cudaFreeAsync(d, ctx->stream));
     out[0] = h[0];
     out[1] = h[1];
     if (getenv("RB_RASTER_DIAG"))
         fprintf(stderr, "[raster diag] pairs %llu, skipped(bounds/empty) %llu, skipped(no span) %llu, with coverage %llu, list entries %llu, crossings %llu, "
-                        "blended px %llu, stored px %llu\n", h[2], h[3], h[4], h[5], h[6], h[7], h[0], h[1]);
+                        "blended px %llu, stored px %llu, pairs without a crossing edge %llu\n", h[2], h[3], h[4], h[5], h[6], h[7], h[0], h[1], h[8]);
     if (st == RB_OK && b->dev_scratch && !b->lay.wide) {
         // the list builder counts entries it had to drop (the host's capacity bound makes that impossible)
         if (rb_check_flags(ctx) != RB_OK) return RB_ERR_CUDA;

@@ -316,7 +316,7 @@ static bool setup_stops(DevPaint *o, const float *in, int n_in, int spread, bool
     for (int k = 0; k < 4; k++) { F[len][k] = 0.0f; B[len][k] = c_l[k]; }
     T[len++] = t_l;
     o->len = len;
-    for (int i = 0; i < 8; i++) o->t0s[i] = i < len ? T[i] : INFINITY;
+    for (int i = 0; i < 12; i++) o->t0s[i] = i < len ? T[i] : INFINITY;
     flush(len);
     return true;
 }

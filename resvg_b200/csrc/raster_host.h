@@ -97,7 +97,7 @@ struct DevPaint {
     int32_t focal_on_circle, well_behaved, swapped, natively_focal, negate_x, smaller;
     float conc_scale, conc_bias;
     uint32_t stop_off;   // first entry of this gradient in the pooled DevStop array
-    alignas(16) float t0s[8]; // t0 of the first 8 intervals (+inf beyond len): the interval search reads these, not the pool
+    alignas(16) float t0s[12]; // t0 of the first 12 intervals (+inf beyond len): the interval search reads these, not the pool
     // pattern
     const uint8_t *pix;
     uint32_t pw, ph;

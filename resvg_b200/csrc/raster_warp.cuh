@@ -520,6 +520,10 @@ struct WarpDraw { // what one lane holds about one upcoming (draw, tile) pair
 #ifndef RW_MIN_CTAS
 #define RW_MIN_CTAS 21
 #endif
+#ifndef RW_BLEND_UNROLL
+#define RW_BLEND_UNROLL 2
+#endif
+constexpr int kBlendUnroll = RW_BLEND_UNROLL;
 // HAIR: the batch holds hairline strokes (a second instantiation, so that batches without them run the leaner code).
 template <bool MASK, bool HAIR, bool direct>
 __device__ __forceinline__ void
@@ -728,6 +732,7 @@ raster_warp_tile(WarpTileSmem &S, const uint32_t tile, const uint32_t direct_mas
                         n = 0;
                     }
                 }
+                if (!__any_sync(0xffffffffu, n > 0)) continue; // interior / exterior rows: nothing to scatter from this chunk
                 int incl = n;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -735,7 +740,7 @@ raster_warp_tile(WarpTileSmem &S, const uint32_t tile, const uint32_t direct_mas
                     if (lane >= d) incl += u;
                 }
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
-                if (total) did = true;
+                did = true;
                 if (px_stats && lane == 0) atomicAdd(px_stats + 7, (unsigned long long)total);
                 const uint32_t ysup = (uint32_t)ys | (upbit << 16);
 #pragma unroll 1
@@ -893,78 +898,70 @@ raster_warp_tile(WarpTileSmem &S, const uint32_t tile, const uint32_t direct_mas
             if (lane < 16) reinterpret_cast<uint4 *>(S.dmask)[lane] = make_uint4(0, 0, 0, 0);
             __syncwarp();
 
-            // ---- blend: the lane's 8 pixels rotate through one copy of the code ---------------------------------------------------
+            // ---- blend ----------------------------------------------------------------------------------------------------------
             if (px_stats && __any_sync(0xffffffffu, (c0 | c1) != 0) && lane == 0) atomicAdd(px_stats + 5, 1ull);
             if (c0 | c1) {
                 const DevPaint &P = paints[paint_idx];
                 const bool memset_ok = !MASK && P.has_memset != 0;
                 const uint32_t memset_color = P.memset_color;
-                // u16 pipeline with Source / SourceOver over a solid colour or a gradient: the common programs, kept inline
-                const bool simple = !MASK && P.kind != 2 && P.lowp && (P.blend == 1 || P.blend == 3);
-                const bool is_solid = P.kind == 0;
-                // f32 pipeline with Source / SourceOver over a gradient (two-point conical gradients are f32-only)
-                const bool simple_hp = !MASK && P.kind == 1 && !P.lowp && (P.blend == 1 || P.blend == 3);
-                uint32_t sr = P.solid16[0], sg = P.solid16[1], sb = P.solid16[2], sa = P.solid16[3];
+                const bool plain = !MASK && P.kind != 2 && (P.blend == 1 || P.blend == 3); // Source / SourceOver, no pattern
                 const bool src_over = P.blend == 3;
-#pragma unroll 2
-                for (int q = 0; q < 8; q++) {
-                    const uint32_t c = min(16u * (c0 & 0xffu) - (dec & 1u), 255u);
-                    c0 = __funnelshift_r(c0, c1, 8);
-                    c1 >>= 8;
-                    dec >>= 4;
-                    uint32_t d = dst0;
-                    if (c) {
-                        if (MASK) {
-                            d = c == 255 ? 255u : div255(d * (255 - c) + 255u * c);
-                        } else if (c == 255 && memset_ok) {
-                            d = memset_color;
-                            n_full++;
-                        } else if (simple) {
-                            n_partial++;
-                            if (!is_solid) {
-                                const P16 g16 = shade16_gradient(P, stops, tlx + 8 * pj + q, tly + prow);
-                                sr = g16.r; sg = g16.g; sb = g16.b; sa = g16.a;
-                            }
-                            // Two channels per multiply: R | B << 16 and G | A << 16 hold two 16-bit lanes whose products with an
-                            // 8-bit factor stay below 2^16, so (x * k + 0x00ff00ff) >> 8 & 0x00ff00ff IS div255 on both lanes
-                            // (bit-identical to the per-channel u16 pipeline, half the instructions).
-                            const uint32_t s_rb = sr | (sb << 16), s_ag = sg | (sa << 16);
-                            const uint32_t d_rb = d & 0x00ff00ffu, d_ag = (d >> 8) & 0x00ff00ffu;
-                            uint32_t o_rb, o_ag;
-                            if (src_over) { // scale_1_float (coverage folded into the source), then source_over
-                                const uint32_t p_rb = c == 255 ? s_rb : (((s_rb * c + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
-                                const uint32_t p_ag = c == 255 ? s_ag : (((s_ag * c + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
-                                const uint32_t ia = 255 - (p_ag >> 16);
-                                o_rb = p_rb + (((d_rb * ia + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
-                                o_ag = p_ag + (((d_ag * ia + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
-                            } else {        // Source: lerp_1_float(dst, src, coverage)
-                                const uint32_t ic = 255 - c;
-                                o_rb = (d_rb * ic + s_rb * c + 0x00ff00ffu) >> 8;
-                                o_ag = (d_ag * ic + s_ag * c + 0x00ff00ffu) >> 8;
-                            }
-                            d = (o_rb & 0x00ff00ffu) | ((o_ag & 0x00ff00ffu) << 8); // the store truncates every lane to u8
-                        } else if (simple_hp) {
-                            n_partial++;
-                            const PF dd = load_pf(d);
-                            PF sc = shadef_gradient(P, stops, tlx + 8 * pj + q, tly + prow), o;
-                            const float cf = (float)c * (1.0f / 255.0f);
-                            if (src_over) { // scale_1_float, then source_over: d * (1 - sa) + s
-                                if (c != 255) { sc.r *= cf; sc.g *= cf; sc.b *= cf; sc.a *= cf; }
-                                const float ia = 1.0f - sc.a;
-                                o.r = mad(dd.r, ia, sc.r); o.g = mad(dd.g, ia, sc.g); o.b = mad(dd.b, ia, sc.b); o.a = mad(dd.a, ia, sc.a);
-                            } else if (c == 255) {
-                                o = sc;
-                            } else {        // Source: lerp_1_float(dst, src, coverage)
-                                o.r = mad(sc.r - dd.r, cf, dd.r); o.g = mad(sc.g - dd.g, cf, dd.g);
-                                o.b = mad(sc.b - dd.b, cf, dd.b); o.a = mad(sc.a - dd.a, cf, dd.a);
-                            }
-                            d = store_pf(o);
-                        } else {
-                            n_partial++;
-                            d = blend_pixel(P, stops, d, c, tlx + 8 * pj + q, tly + prow);
-                        }
+                if (px_stats && !MASK) { // the counters of rb_batch_run_counting (kept out of the blend code proper)
+                    uint32_t a0 = c0, a1 = c1, dd = dec;
+                    for (int q = 0; q < 8; q++) {
+                        const uint32_t c = min(16u * (a0 & 0xffu) - (dd & 1u), 255u);
+                        a0 = __funnelshift_r(a0, a1, 8); a1 >>= 8; dd >>= 4;
+                        if (c == 255 && memset_ok) n_full++;
+                        else if (c) n_partial++;
                     }
-                    dst0 = dst1; dst1 = dst2; dst2 = dst3; dst3 = dst4; dst4 = dst5; dst5 = dst6; dst6 = dst7; dst7 = d;
+                }
+                if (plain && P.kind == 1) {
+                    // a gradient, u16 or f32 pipeline: one call shades and blends the lane's eight pixels
+                    Px8 t;
+                    t.v[0] = dst0; t.v[1] = dst1; t.v[2] = dst2; t.v[3] = dst3; t.v[4] = dst4; t.v[5] = dst5; t.v[6] = dst6; t.v[7] = dst7;
+                    blend_row_gradient(P, stops, t, c0, c1, dec, tlx + 8 * pj, tly + prow);
+                    dst0 = t.v[0]; dst1 = t.v[1]; dst2 = t.v[2]; dst3 = t.v[3]; dst4 = t.v[4]; dst5 = t.v[5]; dst6 = t.v[6]; dst7 = t.v[7];
+                } else {
+                    // solid colours in the u16 pipeline inline, masks inline, everything else through blend_pixel; the lane's
+                    // 8 pixels rotate through one copy of the code
+                    const bool solid16 = plain && P.kind == 0 && P.lowp;
+                    // Two channels per multiply: R | B << 16 and G | A << 16 hold two 16-bit lanes whose products with an
+                    // 8-bit factor stay below 2^16, so (x * k + 0x00ff00ff) >> 8 & 0x00ff00ff IS div255 on both lanes
+                    // (bit-identical to the per-channel u16 pipeline, half the instructions).
+                    const uint32_t s_rb = P.solid16[0] | (P.solid16[2] << 16), s_ag = P.solid16[1] | (P.solid16[3] << 16);
+#pragma unroll kBlendUnroll
+                    for (int q = 0; q < 8; q++) {
+                        const uint32_t c = min(16u * (c0 & 0xffu) - (dec & 1u), 255u);
+                        c0 = __funnelshift_r(c0, c1, 8);
+                        c1 >>= 8;
+                        dec >>= 4;
+                        uint32_t d = dst0;
+                        if (c) {
+                            if (MASK) {
+                                d = c == 255 ? 255u : div255(d * (255 - c) + 255u * c);
+                            } else if (c == 255 && memset_ok) {
+                                d = memset_color;
+                            } else if (solid16) {
+                                const uint32_t d_rb = d & 0x00ff00ffu, d_ag = (d >> 8) & 0x00ff00ffu;
+                                uint32_t o_rb, o_ag;
+                                if (src_over) { // scale_1_float (coverage folded into the source), then source_over
+                                    const uint32_t p_rb = c == 255 ? s_rb : (((s_rb * c + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
+                                    const uint32_t p_ag = c == 255 ? s_ag : (((s_ag * c + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
+                                    const uint32_t ia = 255 - (p_ag >> 16);
+                                    o_rb = p_rb + (((d_rb * ia + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
+                                    o_ag = p_ag + (((d_ag * ia + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
+                                } else {        // Source: lerp_1_float(dst, src, coverage)
+                                    const uint32_t ic = 255 - c;
+                                    o_rb = (d_rb * ic + s_rb * c + 0x00ff00ffu) >> 8;
+                                    o_ag = (d_ag * ic + s_ag * c + 0x00ff00ffu) >> 8;
+                                }
+                                d = (o_rb & 0x00ff00ffu) | ((o_ag & 0x00ff00ffu) << 8); // the store truncates every lane to u8
+                            } else {
+                                d = blend_pixel(P, stops, d, c, tlx + 8 * pj + q, tly + prow);
+                            }
+                        }
+                        dst0 = dst1; dst1 = dst2; dst2 = dst3; dst3 = dst4; dst4 = dst5; dst5 = dst6; dst6 = dst7; dst7 = d;
+                    }
                 }
             }
         }

@@ -25,7 +25,7 @@ for x in rows:
     if x[0] in ("Function Name", "Line No"): continue
     if x[0] != "" and x[2] == "-":
         line = (cur, int(x[0]))
-        try: per[(cur, int(x[0]), x[1][:80])] = (int(x[7]), int(x[6]))
+        try: per[(cur, int(x[0]), x[1][:80])] = (int(x[7]), int(x[6]), [int(x[c]) if x[c].isdigit() else 0 for c in ci])
         except ValueError: pass
         for j, c in enumerate(ci):
             try: pf[cur][j] += int(x[c])
@@ -35,5 +35,5 @@ tot = sum(v[0] for v in per.values())
 print("total inst %.2f G; static SASS per file: %s" % (tot / 1e9, dict(static)))
 print(cols)
 for k, v in pf.items(): print(" ", k, v)
-for (f, l, s), (n, smp) in sorted(per.items(), key=lambda kv: -kv[1][0])[:N]:
-    print(f"{f}:{l:4d} {n/1e6:9.1f}M {100*n/tot:5.1f}% samp {smp:7d}  {s}")
+for (f, l, s), (n, smp, st) in sorted(per.items(), key=lambda kv: -kv[1][0])[:N]:
+    print(f"{f}:{l:4d} {n/1e6:9.1f}M {100*n/tot:5.1f}% samp {smp:7d}  {s}   ## " + " ".join(str(v) for v in st[1:]))
