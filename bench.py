@@ -890,6 +890,7 @@ def main():
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
     e2e_h2d = 0
 
+    banded_download = os.environ.get("RB_BENCH_PLAIN_DOWNLOAD") != "1"
     e2e_phase = [0.0, 0.0, 0.0]  # seconds: record, host build + enqueue, wait for the GPU + D2H
     e2e_geo = [0] * 6  # rb_debug_geo_counts after the last step
 
@@ -902,14 +903,20 @@ def main():
             b.set_viewport(*draw_vp)
         b.fill_paths(scene)
         tb = time.perf_counter()
-        b.submit(n_threads)
+        if banded_download:
+            b.submit_download(pinned.array.ctypes.data, n_threads)  # the download overlaps the last raster launch, band by band
+        else:
+            b.submit(n_threads)
         tc = time.perf_counter()
         e2e_h2d = b.stats()["upload_bytes"]
         gc = (C.c_uint64 * 6)()
         _ffi.lib.rb_debug_geo_counts(gc)
         e2e_geo[:] = [int(v) for v in gc]
         b.close()
-        layer.download_ptr(pinned.array.ctypes.data)  # synchronises
+        if banded_download:
+            layer.download_end()  # synchronises
+        else:
+            layer.download_ptr(pinned.array.ctypes.data)  # synchronises
         td = time.perf_counter()
         e2e_phase[0] += tb - ta; e2e_phase[1] += tc - tb; e2e_phase[2] += td - tc
 
@@ -959,6 +966,9 @@ def main():
                     "d2h_bytes_per_step": W * strip_rows * 4, "ms_per_step": e2e_s * 1e3, "record_ms": e2e_phase[0] / e2e_steps * 1e3,
                     "host_build_and_enqueue_ms": e2e_phase[1] / e2e_steps * 1e3, "gpu_wait_and_d2h_ms": e2e_phase[2] / e2e_steps * 1e3,
                     "steps": e2e_steps,
+                    "download": ("rb_batch_submit_download: the last raster launch runs in bands of tile rows, each copied out while the next "
+                                 "is rendered; rb_layer_download_end waits") if banded_download
+                                else "rb_batch_submit, then rb_layer_download",
                     "per_rank_ms": {"e2e": [round(r[0], 2) for r in per_rank], "host_build_and_enqueue": [round(r[1], 2) for r in per_rank],
                                     "gpu_wait_and_d2h": [round(r[2], 2) for r in per_rank], "device_geometry": [round(r[3], 2) for r in per_rank]},
                     "geometry": {"where": "device" if e2e_geo[0] > 0 and e2e_geo[1] == 0 else "host",

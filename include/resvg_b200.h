@@ -255,6 +255,14 @@ int rb_batch_draw_documents(rb_batch *batch, int32_t n_docs, const int32_t *view
                             const rb_stroke *strokes, const float ts[6]);
 /* Builds edges on host threads (n_threads <= 0: all cores), uploads, launches, frees the device copy. */
 int rb_batch_submit(rb_batch *batch, int32_t n_threads);
+/* rb_batch_submit, then rb_layer_download_begin(layer, host) (w * h * 4 bytes; pinned memory from rb_host_alloc lets the
+ * copy overlap): what resvg::render does with its host pixmap target (crates/resvg/src/lib.rs:34-53).  The last raster
+ * launch of the submit runs in bands of tile rows and every finished band is copied out while the next one is rendered.
+ * Returns once everything is enqueued; rb_layer_download_end(layer) waits for the pixels, which are those of
+ * rb_batch_submit + rb_layer_download. */
+int rb_batch_submit_download(rb_batch *batch, int32_t n_threads, uint8_t *host);
+/* Tests: how many rb_batch_submit_download calls overlapped their download with the last raster launch so far. */
+uint64_t rb_debug_banded_downloads(void);
 /* Split form: prepare = host edge build + binning + upload (device copy stays resident in the batch);
  * run = the kernel launch only, repeatable (e.g. after clearing the layer). */
 int rb_batch_prepare(rb_batch *batch, int32_t n_threads);

@@ -118,6 +118,8 @@ SIGNATURES = {
     "rb_batch_draw_paths": (_i, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, f32p]),
     "rb_batch_fill_paths": (_i, [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, f32p]),
     "rb_batch_submit": (_i, [_vp, C.c_int32]),
+    "rb_batch_submit_download": (_i, [_vp, C.c_int32, _vp]),
+    "rb_debug_banded_downloads": (C.c_uint64, []),
     "rb_batch_prepare": (_i, [_vp, C.c_int32]),
     "rb_batch_run": (_i, [_vp]),
     "rb_batch_run_counting": (_i, [_vp, C.POINTER(C.c_uint64)]),

@@ -445,6 +445,12 @@ class Batch:
     def submit(self, n_threads: int = 0):
         self.layer.ctx.check(lib.rb_batch_submit(self._h, n_threads), "batch_submit")
 
+    def submit_download(self, ptr: int, n_threads: int = 0):
+        """submit(), then the layer into host memory at `ptr` (w * h * 4 bytes, pinned for the overlap): the bands of the last
+        raster launch are copied out while the next band is rendered (rb_batch_submit_download).  Returns once everything is
+        enqueued; `layer.download_end()` waits for the pixels."""
+        self.layer.ctx.check(lib.rb_batch_submit_download(self._h, n_threads, C.c_void_p(ptr)), "batch_submit_download")
+
     def prepare(self, n_threads: int = 0):
         self.layer.ctx.check(lib.rb_batch_prepare(self._h, n_threads), "batch_prepare")
 

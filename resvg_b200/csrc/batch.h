@@ -114,6 +114,11 @@ struct rb_batch {
     bool scratch_owned = false;     // dev_scratch is an allocation of its own (device geometry) rather than the tail of `dev`
     void *host_block = nullptr; // host-only batches: malloc'ed copy of the block
     struct GeoPending *geo = nullptr; // a geometry launch in flight (geo.cu rb_geo_begin / rb_geo_finish)
+    // rb_batch_submit_download: the host pixmap the layer goes to.  The LAST raster launch of the submit is cut into bands of
+    // tile rows and every band is copied out (context's copy stream) while the next one is rendered.
+    uint8_t *dl_host = nullptr;
+    bool dl_arm = false;  // the next batch_run is the submit's last one
+    bool dl_done = false; // the banded copies were enqueued
 };
 
 // rb_batch_host_build: the range holds hairline strokes the chosen builder cannot draw inline (internal status).

@@ -127,6 +127,7 @@ void rb_ctx_release(rb_ctx *ctx)
         if (s.ev) cudaEventDestroy(s.ev);
     }
     for (auto &e : ctx->ev_run) if (e) cudaEventDestroy(e);
+    if (ctx->ev_band) cudaEventDestroy(ctx->ev_band);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -166,6 +167,7 @@ extern "C" int rb_ctx_create(int device, rb_ctx **out)
     cudaEventCreate(&ctx->ev1);
     cudaEventCreateWithFlags(&ctx->staging_ev, cudaEventDisableTiming);
     for (auto &e : ctx->ev_run) cudaEventCreate(&e);
+    cudaEventCreateWithFlags(&ctx->ev_band, cudaEventDisableTiming);
     // Keep freed layer memory in the stream-ordered pool: isolated groups allocate one layer each
     // (render.rs:108), so layer create/destroy must not hit the driver.
     cudaMemPool_t pool;

@@ -23,6 +23,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <thread>
 #include <vector>
@@ -975,6 +976,7 @@ extern "C" int rb_batch_prepare(rb_batch *b, int32_t n_threads)
     return st;
 }
 
+static std::atomic<uint64_t> g_banded_downloads{0};
 static int batch_run(rb_batch *b, unsigned long long *px_stats);
 extern "C" int rb_batch_run(rb_batch *b)
 {
@@ -1085,7 +1087,53 @@ static int batch_run(rb_batch *b, unsigned long long *px_stats)
         unsigned grid = (n_wtiles + WT_WARPS - 1) / WT_WARPS;
         if (direct) grid = std::min(grid, (unsigned)(ctx->sm_count * RW_MIN_CTAS * 2)); // warps stride over the tiles
 #define RB_WARP_ARGS target, W, H, L.wtiles_x, n_wtiles, tile_off, tile_pairs, d_draws, row_off, row_edges, d_edges,                   \
-    (const DevPaint *)(b->dev + L.o_paints), (const DevStop *)(b->dev + L.o_stops), px_stats, row_cols, n_draws
+    (const DevPaint *)(b->dev + L.o_paints), (const DevStop *)(b->dev + L.o_stops), px_stats, row_cols, n_draws, tile0
+        uint32_t tile0 = 0;
+        if (b->dl_arm && b->dl_host && !direct && !mask_target && !px_stats && b->layer) {
+            // The submit's last launch, the layer is wanted on the host: render it in bands of tile rows, top to bottom, and
+            // copy every finished band out on the copy stream while the next one is rendered (the tiles of a band are
+            // complete once its launch is: every draw of the batch that touches them is in their lists).
+            b->dl_arm = false;
+            int bands = 6;
+            if (const char *e = getenv("RB_DL_BANDS")) bands = std::max(1, std::min(32, atoi(e)));
+            bands = std::min(bands, L.wtiles_y);
+            const bool diag = getenv("RB_DL_DIAG") != nullptr;
+            std::vector<cudaEvent_t> evs; // diag: kernel start/end and copy start/end per band
+            auto mark = [&](cudaStream_t s) { if (!diag) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); evs.push_back(e); };
+            mark(ctx->stream);
+            for (int k = 0; k < bands; k++) {
+                const int ty0 = (int)((int64_t)L.wtiles_y * k / bands), ty1 = (int)((int64_t)L.wtiles_y * (k + 1) / bands);
+                if (ty0 >= ty1) continue;
+                tile0 = (uint32_t)ty0 * (uint32_t)L.wtiles_x;
+                const unsigned bgrid = (unsigned)(ty1 - ty0) * (unsigned)L.wtiles_x;
+                if (L.has_hair) k_raster_warp<false, true, false><<<bgrid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
+                else k_raster_warp<false, false, false><<<bgrid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
+                RB_LAUNCHED(ctx, "raster_warp");
+                const int y0 = ty0 * WT_H, y1 = std::min(H, ty1 * WT_H);
+                RB_CUDA(ctx, cudaEventRecord(ctx->ev_band, ctx->stream));
+                mark(ctx->stream);
+                RB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_band, 0));
+                mark(ctx->copy_stream);
+                RB_CUDA(ctx, cudaMemcpyAsync(b->dl_host + (size_t)y0 * W * 4, (const uint8_t *)target + (size_t)y0 * W * 4, (size_t)(y1 - y0) * W * 4,
+                                             cudaMemcpyDeviceToHost, ctx->copy_stream));
+                mark(ctx->copy_stream);
+            }
+            if (diag) {
+                cudaStreamSynchronize(ctx->copy_stream);
+                cudaStreamSynchronize(ctx->stream);
+                fprintf(stderr, "[dl diag] per band: kernel end, copy start, copy end (ms after the first launch)\n");
+                for (size_t i = 1; i + 2 < evs.size() + 1; i += 3) {
+                    float a = 0, c0 = 0, c1 = 0;
+                    cudaEventElapsedTime(&a, evs[0], evs[i]); cudaEventElapsedTime(&c0, evs[0], evs[i + 1]); cudaEventElapsedTime(&c1, evs[0], evs[i + 2]);
+                    fprintf(stderr, "[dl diag]   %.2f  %.2f  %.2f\n", a, c0, c1);
+                }
+                for (auto e : evs) cudaEventDestroy(e);
+            }
+            b->dl_done = true;
+            g_banded_downloads++;
+            if (time_run) RB_CUDA(ctx, cudaEventRecord(ctx->ev_run[2], ctx->stream));
+            return RB_OK;
+        }
         if (direct) {
             if (mask_target) k_raster_warp<true, false, true><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
             else if (L.has_hair) k_raster_warp<false, true, true><<<grid, WT_WARPS * 32, 0, ctx->stream>>>(RB_WARP_ARGS);
@@ -1194,6 +1242,7 @@ extern "C" int rb_batch_submit(rb_batch *b, int32_t n_threads)
     st = submit_fill_run(b, n_threads, 0, b->n_total, total, &resume);
     if (st == RB_NEEDS_RUN_SPLIT) {
         st = RB_OK;
+        b->dl_host = nullptr; // fill runs and hairline runs alternate from here on: the caller downloads afterwards
         size_t i = resume; // everything before was drawn already
         while (i < b->n_total && st == RB_OK) {
             const bool hair = rb_batch_draw_is_hairline(b, i);
@@ -1207,9 +1256,42 @@ extern "C" int rb_batch_submit(rb_batch *b, int32_t n_threads)
     return st;
 }
 
+// how many rb_batch_submit_download calls took the banded path so far (tests)
+extern "C" uint64_t rb_debug_banded_downloads(void) { return g_banded_downloads.load(); }
+
+// rb_batch_submit followed by rb_layer_download_begin(layer, host), with the download of the finished bands of the layer
+// overlapping the rendering of the rest (resvg::render's target is a host pixmap: crates/resvg/src/lib.rs:34).  `host`:
+// w * h * 4 bytes, pinned (rb_host_alloc) for the overlap to happen.  Returns once everything is enqueued;
+// rb_layer_download_end(layer) waits for the pixels.
+extern "C" int rb_batch_submit_download(rb_batch *b, int32_t n_threads, uint8_t *host)
+{
+    rb_enter(b ? b->ctx : nullptr);
+    if (!b || !host || !b->layer) return RB_ERR_INVALID;
+    rb_layer *l = b->layer;
+    rb_ctx *ctx = l->ctx;
+    if (l->dl_pending) { RB_CUDA(ctx, cudaEventSynchronize(l->dl_done)); l->dl_pending = false; }
+    b->dl_host = host;
+    b->dl_arm = false;
+    b->dl_done = false;
+    int st = rb_batch_submit(b, n_threads);
+    const bool banded = b->dl_done;
+    b->dl_host = nullptr;
+    b->dl_done = false;
+    if (st != RB_OK) return st;
+    if (!banded) return rb_layer_download_begin(l, host); // nothing to draw, a small (direct) batch, the any-winding fallback
+    if (!l->dl_ready) {
+        RB_CUDA(ctx, cudaEventCreateWithFlags(&l->dl_ready, cudaEventDisableTiming));
+        RB_CUDA(ctx, cudaEventCreateWithFlags(&l->dl_done, cudaEventDisableTiming));
+    }
+    RB_CUDA(ctx, cudaEventRecord(l->dl_done, ctx->copy_stream)); // after the last band's copy
+    l->dl_pending = true;
+    return RB_OK;
+}
+
 // Runs draws [lo, hi) through the host builder in `parts` consecutive parts (the GPU rasterises part k while the host
 // threads build part k + 1).
-static int submit_host_parts(rb_batch *b, int32_t n_threads, size_t lo0, size_t hi0, size_t parts, uint64_t total[6], size_t *stopped_at)
+static int submit_host_parts(rb_batch *b, int32_t n_threads, size_t lo0, size_t hi0, size_t parts, uint64_t total[6], size_t *stopped_at,
+                             bool tail = false) // tail: the range ends the whole submit (see rb_batch::dl_arm)
 {
     const size_t n = hi0 - lo0;
     int st = RB_OK;
@@ -1218,7 +1300,9 @@ static int submit_host_parts(rb_batch *b, int32_t n_threads, size_t lo0, size_t 
         if (lo >= hi) continue;
         *stopped_at = lo;
         st = batch_prepare_range(b, n_threads, lo, hi, /*allow_geo=*/false);
+        b->dl_arm = tail && hi == hi0 && b->dl_host && st == RB_OK;
         if (st == RB_OK) st = rb_batch_run(b);
+        b->dl_arm = false;
         for (int i = 0; i < 6; i++) total[i] += b->stats[i];
         batch_release(b);
     }
@@ -1269,6 +1353,7 @@ static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t 
                             // pays the latency of its longest draws, which outweighs starting the GPU earlier
         if (const char *e = getenv("RB_GEO_SUBRANGES")) subs = (size_t)std::max(1, std::min(8, atoi(e)));
     }
+    const bool whole_tail = b->dl_host != nullptr && last == b->n_total; // this run ends the submit: its last launch is banded
     struct Sub { size_t lo, hi; bool pending; };
     std::vector<Sub> sub_ranges;
     for (size_t k = 0; k < subs && split < last; k++) {
@@ -1282,11 +1367,12 @@ static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t 
     st = RB_OK;
     if (split > first) {
         const size_t host_parts = std::max<size_t>(1, parts * (split - first) / n);
-        st = submit_host_parts(b, n_threads, first, split, host_parts, total, stopped_at);
+        st = submit_host_parts(b, n_threads, first, split, host_parts, total, stopped_at, whole_tail && sub_ranges.empty());
         if (st != RB_OK) { rb_geo_abandon(b); return st; }
     }
     for (const Sub &sr : sub_ranges) {
         *stopped_at = sr.lo;
+        const bool sub_tail = whole_tail && &sr == &sub_ranges.back();
         int gst = RB_GEO_FALLBACK;
         if (sr.pending) {
             batch_release(b);
@@ -1297,14 +1383,16 @@ static int submit_fill_run(rb_batch *b, int32_t n_threads, size_t first, size_t 
                     const size_t scratch_bytes = warp_scratch_layout(b->lay).total;
                     RB_CUDA(ctx, cudaMallocAsync((void **)&b->dev_scratch, scratch_bytes, ctx->stream));
                     b->scratch_owned = true;
+                    b->dl_arm = sub_tail;
                     gst = rb_batch_run(b);
+                    b->dl_arm = false;
                 }
                 for (int i = 0; i < 6; i++) total[i] += b->stats[i];
                 batch_release(b);
             }
         }
         if (gst == RB_GEO_FALLBACK)
-            gst = submit_host_parts(b, n_threads, sr.lo, sr.hi, std::max<size_t>(1, parts * (sr.hi - sr.lo) / n), total, stopped_at);
+            gst = submit_host_parts(b, n_threads, sr.lo, sr.hi, std::max<size_t>(1, parts * (sr.hi - sr.lo) / n), total, stopped_at, sub_tail);
         if (gst != RB_OK) { rb_geo_abandon(b); return gst; }
     }
     return RB_OK;

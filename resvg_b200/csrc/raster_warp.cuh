@@ -1019,13 +1019,13 @@ k_raster_warp(void *__restrict__ target, int W, int H, int wtiles_x, uint32_t n_
               const uint32_t *__restrict__ tile_pairs, const DevDraw *__restrict__ draws, const uint32_t *__restrict__ row_off,
               const DevEdge *__restrict__ row_edges, const DevEdge *__restrict__ edges, const DevPaint *__restrict__ paints,
               const DevStop *__restrict__ stops, unsigned long long *__restrict__ px_stats, const uint32_t *__restrict__ row_cols,
-              uint32_t n_direct)
+              uint32_t n_direct, uint32_t tile0)
 {
     __shared__ WarpTileSmem s_all[WT_WARPS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WarpTileSmem &S = s_all[wid];
     if (!DIRECT) {
-        const uint32_t tile = blockIdx.x * WT_WARPS + wid;
+        const uint32_t tile = tile0 + blockIdx.x * WT_WARPS + wid; // tile0: first tile of this launch (banded runs)
         if (tile < n_wtiles)
             raster_warp_tile<MASK, HAIR, false>(S, tile, 0u, target, W, H, wtiles_x, tile_off, tile_pairs, draws, row_off, row_edges, edges, paints,
                                                 stops, px_stats, 0u);

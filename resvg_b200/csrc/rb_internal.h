@@ -15,6 +15,7 @@ struct rb_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr; // device-to-host downloads that overlap the next render (rb_layer_download_begin)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_band = nullptr; // a band of the last raster launch is complete (rb_batch_submit_download)
     cudaEvent_t ev_run[3] = {nullptr, nullptr, nullptr}; // last batch run: start, after the pre-pass, after the raster kernel
     std::string err;
     uint64_t launches = 0;

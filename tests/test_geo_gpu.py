@@ -229,3 +229,34 @@ def test_many_overlapping_loops_fall_back_to_the_host_builder(ctx):
         _ffi.lib.rb_debug_geo_mode(0)
     assert after[1] - before[1] == 1, (before, after)
     assert_exact(got, want, "wide draw through the fallback")
+
+
+@pytest.mark.parametrize("mode,w,h,n", [(0, 2048, 1536, 40000), (1, 1500, 1100, 6000), (2, 1500, 1100, 40000), (0, 300, 200, 20), (0, 640, 483, 900)])
+def test_submit_download_equals_submit_then_download(ctx, mode, w, h, n):
+    """rb_batch_submit_download (the last raster launch in bands of tile rows, every band copied out while the next one is
+    rendered) against rb_batch_submit + rb_layer_download: the same bytes — on the hybrid path (host parts, then the device
+    range), on the device-only and host-only paths, on a batch too small to be binned and on a height that is no multiple
+    of the tile height; the canvas starts from random pixels so that an untouched band is noticed too."""
+    import resvg_b200 as rb
+    from resvg_b200 import _ffi
+
+    scene = _scene(w, h, n, 0xBA2D + mode)
+    base = random_premul(w, h, 5)
+    want, _ = _render_scene(ctx, scene, w, h, mode, base=base)
+    _ffi.lib.rb_debug_geo_mode(mode)
+    try:
+        l = ctx.layer_from(base)
+        b = rb.Batch(l)
+        b.fill_paths(scene)
+        pinned = rb.PinnedBuffer(w * h * 4)
+        pinned.array[:] = 0x5A
+        banded0 = int(_ffi.lib.rb_debug_banded_downloads())
+        b.submit_download(pinned.array.ctypes.data)
+        l.download_end()
+        assert int(_ffi.lib.rb_debug_banded_downloads()) - banded0 == (1 if n > 32 else 0)  # <= 32 draws: no bins, plain download
+        got = np.array(pinned.array, copy=True).reshape(h, w, 4)
+        after = l.download()
+    finally:
+        _ffi.lib.rb_debug_geo_mode(0)
+    assert_exact(got, want, "submit_download vs submit + download")
+    assert_exact(after, want, "the layer after submit_download")
