@@ -418,81 +418,8 @@ __device__ __forceinline__ PF shadef(const DevPaint &P, const DevStop *__restric
     return shadef_gradient(P, stops, x, y);
 }
 
-// The lane's eight pixels of one (draw, tile) pair under a gradient with Source / SourceOver, u16 or f32 pipeline: ONE call
-// per pair, so that what does not change along the row (the y half of the transform) is computed once and the per-pixel code
-// is a compact loop of its own.  c0 / c1 / dec: the coverage words of k_raster_warp; px: the pixels, in and out.
+// k_raster_warp hands the pixels of a lane to blend_tile_gradient (raster_warp.cuh) in this form
 struct Px8 { uint32_t v[8]; };
-__device__ __noinline__ void blend_row_gradient(const DevPaint &P, const DevStop *__restrict__ stops, Px8 &px, uint32_t c0, uint32_t c1,
-                                                uint32_t dec, int x0, int py)
-{
-    // everything the row shares is read here, once (the stores into px could alias the paint as far as the compiler knows)
-    const bool lowp = P.lowp != 0, src_over = P.blend == 3, memset_ok = P.has_memset != 0, has_ts = P.has_ts != 0;
-    const bool premul_after = P.premul_after != 0;
-    const uint32_t memset_color = P.memset_color;
-    const GradGeom G = grad_geom(P);
-    const float *__restrict__ t0s = P.t0s;
-    const DevStop *__restrict__ st = stops + P.stop_off;
-    const int len = P.two_stop ? 1 : P.len;
-    const float y = (float)py + 0.5f;
-    const float ts0 = P.ts[0], ts1 = P.ts[1];
-    const float hx = mad(y, P.ts[2], P.ts[4]), hy = mad(y, P.ts[3], P.ts[5]);
-#pragma unroll 1
-    for (int q = 0; q < 8; q++) {
-        const uint32_t c = min(16u * (c0 & 0xffu) - (dec & 1u), 255u);
-        c0 = __funnelshift_r(c0, c1, 8);
-        c1 >>= 8;
-        dec >>= 4;
-        if (!c) continue;
-        if (c == 255 && memset_ok) { px.v[q] = memset_color; continue; }
-        const uint32_t d = px.v[q];
-        float x = (float)(x0 + q) + 0.5f, yy = y;
-        if (has_ts) {
-            const float nx = mad(x, ts0, hx), ny = mad(x, ts1, hy);
-            x = nx; yy = ny;
-        }
-        bool masked;
-        const float t = gradient_t_at(G, x, yy, masked);
-        PF sc = gradient_color_at(t0s, st, len, t);
-        if (lowp) {
-            uint32_t sr = __float2uint_rz(clamp01(sc.r) * 255.0f + 0.5f), sg = __float2uint_rz(clamp01(sc.g) * 255.0f + 0.5f);
-            uint32_t sb = __float2uint_rz(clamp01(sc.b) * 255.0f + 0.5f), sa = __float2uint_rz(clamp01(sc.a) * 255.0f + 0.5f);
-            if (premul_after) { sr = div255(sr * sa); sg = div255(sg * sa); sb = div255(sb * sa); }
-            // two channels per multiply, as in k_raster_warp's solid-colour code
-            const uint32_t s_rb = sr | (sb << 16), s_ag = sg | (sa << 16);
-            const uint32_t d_rb = d & 0x00ff00ffu, d_ag = (d >> 8) & 0x00ff00ffu;
-            uint32_t o_rb, o_ag;
-            if (src_over) { // scale_1_float (coverage folded into the source), then source_over
-                const uint32_t p_rb = c == 255 ? s_rb : (((s_rb * c + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
-                const uint32_t p_ag = c == 255 ? s_ag : (((s_ag * c + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
-                const uint32_t ia = 255 - (p_ag >> 16);
-                o_rb = p_rb + (((d_rb * ia + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
-                o_ag = p_ag + (((d_ag * ia + 0x00ff00ffu) >> 8) & 0x00ff00ffu);
-            } else {        // Source: lerp_1_float(dst, src, coverage)
-                const uint32_t ic = 255 - c;
-                o_rb = (d_rb * ic + s_rb * c + 0x00ff00ffu) >> 8;
-                o_ag = (d_ag * ic + s_ag * c + 0x00ff00ffu) >> 8;
-            }
-            px.v[q] = (o_rb & 0x00ff00ffu) | ((o_ag & 0x00ff00ffu) << 8); // the store truncates every lane to u8
-        } else {
-            if (premul_after) { sc.r *= sc.a; sc.g *= sc.a; sc.b *= sc.a; }
-            if (masked) sc.r = sc.g = sc.b = sc.a = 0.0f;
-            const PF dd = load_pf(d);
-            PF o;
-            const float cf = (float)c * (1.0f / 255.0f);
-            if (src_over) { // scale_1_float, then source_over: d * (1 - sa) + s
-                if (c != 255) { sc.r *= cf; sc.g *= cf; sc.b *= cf; sc.a *= cf; }
-                const float ia = 1.0f - sc.a;
-                o.r = mad(dd.r, ia, sc.r); o.g = mad(dd.g, ia, sc.g); o.b = mad(dd.b, ia, sc.b); o.a = mad(dd.a, ia, sc.a);
-            } else if (c == 255) {
-                o = sc;
-            } else {        // Source: lerp_1_float(dst, src, coverage)
-                o.r = mad(sc.r - dd.r, cf, dd.r); o.g = mad(sc.g - dd.g, cf, dd.g);
-                o.b = mad(sc.b - dd.b, cf, dd.b); o.a = mad(sc.a - dd.a, cf, dd.a);
-            }
-            px.v[q] = store_pf(o);
-        }
-    }
-}
 
 // RasterPipelineBlitter: full-coverage pixels run the blit_rect program, others blit_anti_h.
 __device__ __noinline__ uint32_t blend_pixel(const DevPaint &P, const DevStop *__restrict__ stops, uint32_t dst, uint32_t cov,
