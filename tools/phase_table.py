@@ -6,7 +6,7 @@ def find(s, after=0):
     for i, l in enumerate(src):
         if i >= after and s in l: return i + 1
     raise KeyError(s)
-marks = [("setup / load dst", find("struct WarpDraw")), ("group prep", find("---- every lane prepares")), ("pair header", find("for (int k = 0; k < n_group")),
+marks = [("blend_tile_gradient", find("void blend_tile_gradient(")), ("setup / load dst", find("struct WarpDraw")), ("group prep", find("---- every lane prepares")), ("pair header", find("for (int k = 0; k < n_group")),
          ("hair", find("---- hairline stroke:")), ("pair bounds", find("const uint32_t bounds = __shfl_sync")), ("scatter", find("---- scatter")),
          ("backdrop", find("winding every sub-scanline starts")), ("scan", find("---- scan:")), ("coverage", find("---- coverage:")),
          ("clear", find("---- clear the marks")), ("blend (inline)", find("---- blend")), ("store / wrapper", find("    if (px_stats) {", find("---- blend")))]
@@ -15,9 +15,12 @@ def rfind(s):
     for i, l in enumerate(rsrc):
         if s in l: return i + 1
     raise KeyError(s)
-rmarks = [("R helpers", 1), ("R gradient t", rfind("float gradient_t_at(")), ("R gradient colour", rfind("PF gradient_color(")), ("R pattern", rfind("float ulp_sub(")),
-          ("R old gradient fns", rfind("P16 shade16_gradient(")), ("R blend_row_gradient", rfind("void blend_row_gradient(")), ("R blend_pixel", rfind("uint32_t blend_pixel(")),
-          ("R rest", rfind("uint32_t blend_pixel(") + 60)]
+def rfind_opt(s):
+    try: return rfind(s)
+    except KeyError: return None
+rmarks = [m for m in [("R helpers", 1), ("R gradient t", rfind_opt("float gradient_t_at(")), ("R gradient colour", rfind_opt("PF gradient_color_at(")),
+          ("R pattern", rfind_opt("float ulp_sub(")), ("R per-pixel gradient fns", rfind_opt("P16 shade16_gradient(")),
+          ("R blend_pixel", rfind_opt("uint32_t blend_pixel(")), ("R rest", rfind("uint32_t blend_pixel(") + 60)] if m[1]]
 def phase(marks, ln):
     name = marks[0][0]
     for n, a in marks:
@@ -28,7 +31,7 @@ for l in open(sys.argv[1]):
     m = re.match(r'(\S+):\s*(\d+)\s+([\d.]+)M\s+[\d.]+% samp\s+(\d+)', l)
     if not m: continue
     f, ln, n, s = m.group(1), int(m.group(2)), float(m.group(3)), int(m.group(4))
-    if f == 'raster_warp.cuh': key = phase(marks, ln) if ln >= marks[0][1] else "exact_span_break_list etc."
+    if f == 'raster_warp.cuh': key = phase(marks, ln) if ln >= marks[0][1] else "k_row_lists / exact_span_break_list etc."
     elif f == 'raster.cu': key = phase(rmarks, ln)
     else: key = f
     tot[key] += n; samp[key] += s
