@@ -12,3 +12,6 @@ compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/tes
 # the geometry kernels (geo.cu): every case but the 8192 x 8192 ones, and the raster tests with every batch on the device
 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_geo_gpu.py -q -x -k "not full_size and not draw_tiler" || exit 1
 RB_GEO_MODE=1 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_raster_gpu.py -q -x -k "hairline or dashed or viewports or bench_scene_bulk" || exit 1
+# the dealt-out gradient blend (shared-memory staging in k_raster_warp) and the banded download
+compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_raster_gpu.py -q -x -k "test_gradients or radial_and_focal or bench_scene_bulk" || exit 1
+compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_geo_gpu.py -q -x -k "submit_download and 1500" || exit 1
