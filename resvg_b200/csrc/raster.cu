@@ -1204,7 +1204,10 @@ extern "C" int rb_batch_submit_download(rb_batch *b, int32_t n_threads, uint8_t 
     const bool banded = b->dl_done;
     b->dl_host = nullptr;
     b->dl_done = false;
-    if (st != RB_OK) return st;
+    if (st != RB_OK) {
+        if (banded) cudaStreamSynchronize(ctx->copy_stream); // nothing may still be writing into `host` once the error is out
+        return st;
+    }
     if (!banded) return rb_layer_download_begin(l, host); // nothing to draw, a small (direct) batch, the any-winding fallback
     if (!l->dl_ready) {
         RB_CUDA(ctx, cudaEventCreateWithFlags(&l->dl_ready, cudaEventDisableTiming));
