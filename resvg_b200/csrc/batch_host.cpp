@@ -1302,6 +1302,7 @@ int rb_geo_host_build(rb_batch *b, int W, int H, int n_threads, rb_stage_alloc a
             o_tasks[c.gt + k] = t;
         }
     });
+    const auto t_copy = Clock::now();
     // task lists per kernel, heaviest first (counting sort over cost classes; ties keep painter's order)
     {
         uint32_t *lists = (uint32_t *)(blk + G.o_lists);
@@ -1339,11 +1340,12 @@ int rb_geo_host_build(rb_batch *b, int W, int H, int n_threads, rb_stage_alloc a
         G.has_hair = false;
         for (size_t i = 0; i < G.n_tasks && !G.has_hair; i++) G.has_hair = (o_tasks[i].flags & GT_HAIR) != 0;
     }
+    const auto t_lists = Clock::now();
     // heap the geometry is expected to need: ~48 bytes per expected edge item plus the builders' chunks
     size_t hint_bytes = 0;
     for (size_t i = 0; i < G.n_tasks; i++) hint_bytes += (o_tasks[i].flags & GT_UNITS) ? (size_t)o_tasks[i].max_units * 6144 + 8192 : (size_t)o_tasks[i].hint * 96 + 2048;
     G.heap_hint = hint_bytes;
-    if (getenv("RB_GEO_HOST_DIAG")) fprintf(stderr, "[geo host] chunks %.2f ms, layout + copy + lists %.2f ms\n", (double)std::chrono::duration_cast<std::chrono::microseconds>(t_chunks - t0g).count() / 1e3, (double)us_since(t_chunks) / 1e3);
+    if (getenv("RB_GEO_HOST_DIAG")) fprintf(stderr, "[geo host] chunks %.2f ms, layout + copy %.2f ms, lists %.2f ms, heap hint %.2f ms\n", (double)std::chrono::duration_cast<std::chrono::microseconds>(t_chunks - t0g).count() / 1e3, (double)std::chrono::duration_cast<std::chrono::microseconds>(t_copy - t_chunks).count() / 1e3, (double)std::chrono::duration_cast<std::chrono::microseconds>(t_lists - t_copy).count() / 1e3, (double)us_since(t_lists) / 1e3);
     *gb = G;
     *block = blk;
     return RB_OK;
